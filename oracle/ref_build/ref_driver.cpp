@@ -1,0 +1,200 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into the product.
+//
+// Small command line driver around the UNMODIFIED reference IO/builder sources
+// (compiled in place from /root/reference by oracle/ref_build/Makefile into
+// oracle/_ref/).  It is used (a) to pin the C restatement in oracle/ against the
+// real reference at arbitrary sizes and (b) to generate the golden fixtures in
+// tests/golden/ (see tests/golden/make_golden.py).
+//
+//   ref_driver convert <in.raw> <sx> <sy> <sz> <u8|u16> <brick> <overlap>
+//                      <median 0|1> <clamp 0|1> <out.bin> [hist 0|1]
+//     runs TOCBlock::FlatDataToBrickedLOD (-> ExtendedOctreeConverter::Convert,
+//     Tuvok/IO/UVF/TOCBlock.cpp:135, ExtendedOctreeConverter.cpp:128), then
+//     Histogram1DDataBlock::Compute / Histogram2DDataBlock::Compute and dumps
+//     everything in a flat little-endian format (see dump layout below).
+//   ref_driver uvfinfo <file.uvf> <out.bin>
+//     opens a UVF (MD5 verified) and dumps the first RasterDataBlock brick, the
+//     1D histogram and the global min/max (used for DemoData/c60.uvf).
+//   ref_driver tf1d <file.1dt> <out.bin>   dumps size + GetByteArray (RGBA8)
+//
+// Dump layout of `convert` (all little endian):
+//   char[8] "TVKREF1\0"; u32 lodCount;
+//   per LOD: u64 lodSize[3]; u64 brickCount[3]; f64 aspect[3];
+//   u64 totalBricks; per brick (ToC order): u64 size[3]; f64 min; f64 max;
+//   then per brick: raw voxels (size.volume()*bytesPerVoxel);
+//   u64 n1; u64 hist1d[n1]; f32 maxGrad; u64 nx; u64 ny; u64 hist2d[nx*ny]
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <memory>
+#include <chrono>
+
+#include "Controller/Controller.h"
+#include "IO/UVF/UVF.h"
+#include "IO/UVF/TOCBlock.h"
+#include "IO/UVF/MaxMinDataBlock.h"
+#include "IO/UVF/Histogram1DDataBlock.h"
+#include "IO/UVF/Histogram2DDataBlock.h"
+#include "IO/UVF/RasterDataBlock.h"
+#include "IO/TransferFunction1D.h"
+#include "Basics/LargeRAWFile.h"
+
+using namespace tuvok;
+
+template <typename T> static void put(FILE* f, const T& v) { fwrite(&v, sizeof(T), 1, f); }
+
+static int do_convert(int argc, char** argv) {
+  if (argc < 12) { fprintf(stderr, "convert: not enough arguments\n"); return 2; }
+  const std::string in = argv[2];
+  const uint64_t sx = strtoull(argv[3], 0, 10), sy = strtoull(argv[4], 0, 10), sz = strtoull(argv[5], 0, 10);
+  const bool u16 = !strcmp(argv[6], "u16");
+  const uint64_t brick = strtoull(argv[7], 0, 10);
+  const uint32_t overlap = (uint32_t)strtoul(argv[8], 0, 10);
+  const bool median = atoi(argv[9]) != 0, clamp = atoi(argv[10]) != 0;
+  const std::string out = argv[11];
+  const bool hist = (argc > 12) ? atoi(argv[12]) != 0 : true;
+  const std::string tmp = out + ".octree.tmp";
+
+  LargeRAWFile_ptr src(new LargeRAWFile(in));
+  if (!src->Open(false)) { fprintf(stderr, "cannot open %s\n", in.c_str()); return 1; }
+
+  std::shared_ptr<MaxMinDataBlock> mm(new MaxMinDataBlock(1));
+  TOCBlock toc(UVF::ms_ulReaderVersion);
+  auto t0 = std::chrono::steady_clock::now();
+  bool ok = toc.FlatDataToBrickedLOD(src, tmp,
+      u16 ? ExtendedOctree::CT_UINT16 : ExtendedOctree::CT_UINT8, 1,
+      UINT64VECTOR3(sx, sy, sz), DOUBLEVECTOR3(1, 1, 1),
+      UINT64VECTOR3(brick, brick, brick), overlap, median, clamp,
+      size_t(1) << 31, mm, &Controller::Debug::Out(), CT_NONE, 0, LT_SCANLINE);
+  auto t1 = std::chrono::steady_clock::now();
+  if (!ok) { fprintf(stderr, "conversion failed\n"); return 1; }
+  fprintf(stderr, "REF_CONVERT_SECONDS %.6f\n", std::chrono::duration<double>(t1 - t0).count());
+
+  FILE* f = fopen(out.c_str(), "wb");
+  if (!f) return 1;
+  fwrite("TVKREF1\0", 1, 8, f);
+  const uint32_t lods = (uint32_t)toc.GetLoDCount();
+  put(f, lods);
+  uint64_t total = 0;
+  for (uint32_t l = 0; l < lods; ++l) {
+    UINT64VECTOR3 s = toc.GetLODDomainSize(l), b = toc.GetBrickCount(l);
+    DOUBLEVECTOR3 a = toc.GetBrickAspect(UINT64VECTOR4(0, 0, 0, l));
+    put(f, s.x); put(f, s.y); put(f, s.z);
+    put(f, b.x); put(f, b.y); put(f, b.z);
+    put(f, a.x); put(f, a.y); put(f, a.z);
+    total += b.volume();
+  }
+  put(f, total);
+  size_t idx = 0;
+  for (uint32_t l = 0; l < lods; ++l) {
+    UINT64VECTOR3 b = toc.GetBrickCount(l);
+    for (uint64_t z = 0; z < b.z; ++z) for (uint64_t y = 0; y < b.y; ++y) for (uint64_t x = 0; x < b.x; ++x) {
+      UINT64VECTOR3 s = toc.GetBrickSize(UINT64VECTOR4(x, y, z, l));
+      put(f, s.x); put(f, s.y); put(f, s.z);
+      const MinMaxBlock& v = mm->GetValue(idx++, 0);
+      put(f, v.minScalar); put(f, v.maxScalar);
+    }
+  }
+  const size_t bpv = u16 ? 2 : 1;
+  std::vector<uint8_t> buf(brick * brick * brick * bpv);
+  for (uint32_t l = 0; l < lods; ++l) {
+    UINT64VECTOR3 b = toc.GetBrickCount(l);
+    for (uint64_t z = 0; z < b.z; ++z) for (uint64_t y = 0; y < b.y; ++y) for (uint64_t x = 0; x < b.x; ++x) {
+      UINT64VECTOR4 c(x, y, z, l);
+      UINT64VECTOR3 s = toc.GetBrickSize(c);
+      toc.GetData(buf.data(), c);
+      fwrite(buf.data(), 1, size_t(s.volume()) * bpv, f);
+    }
+  }
+  if (hist) {
+    Histogram1DDataBlock h1;
+    auto t2 = std::chrono::steady_clock::now();
+    h1.Compute(&toc, 0);
+    auto t3 = std::chrono::steady_clock::now();
+    const std::vector<uint64_t>& bins = h1.GetHistogram();
+    uint64_t n1 = bins.size();
+    put(f, n1);
+    fwrite(bins.data(), 8, bins.size(), f);
+    Histogram2DDataBlock h2;
+    h2.Compute(&toc, 0, bins.size(), mm->GetGlobalValue().maxScalar);
+    auto t4 = std::chrono::steady_clock::now();
+    fprintf(stderr, "REF_HIST1D_SECONDS %.6f\nREF_HIST2D_SECONDS %.6f\n",
+            std::chrono::duration<double>(t3 - t2).count(), std::chrono::duration<double>(t4 - t3).count());
+    float mg = h2.GetMaxGradMagnitude();
+    put(f, mg);
+    const std::vector<std::vector<uint64_t>>& b2 = h2.GetHistogram();
+    uint64_t nx = b2.size(), ny = nx ? b2[0].size() : 0;
+    put(f, nx); put(f, ny);
+    for (uint64_t i = 0; i < nx; ++i) fwrite(b2[i].data(), 8, ny, f);
+  } else {
+    uint64_t z = 0; float zf = 0; put(f, z); put(f, zf); put(f, z); put(f, z);
+  }
+  fclose(f);
+  remove(tmp.c_str());
+  return 0;
+}
+
+static int do_uvfinfo(int argc, char** argv) {
+  if (argc < 4) return 2;
+  std::string fn(argv[2]);
+  UVF uvf(std::wstring(fn.begin(), fn.end()));
+  std::string err;
+  if (!uvf.Open(false, true, false, &err)) { fprintf(stderr, "open failed: %s\n", err.c_str()); return 1; }
+  FILE* f = fopen(argv[3], "wb");
+  fwrite("TVKUVF1\0", 1, 8, f);
+  const RasterDataBlock* rdb = NULL; const Histogram1DDataBlock* h1 = NULL; const MaxMinDataBlock* mm = NULL;
+  const Histogram2DDataBlock* h2 = NULL;
+  for (uint64_t i = 0; i < uvf.GetDataBlockCount(); ++i) {
+    const DataBlock* b = uvf.GetDataBlock(i).get();
+    if (!rdb) rdb = dynamic_cast<const RasterDataBlock*>(b);
+    if (!h1) h1 = dynamic_cast<const Histogram1DDataBlock*>(b);
+    if (!h2) h2 = dynamic_cast<const Histogram2DDataBlock*>(b);
+    if (!mm) mm = dynamic_cast<const MaxMinDataBlock*>(b);
+  }
+  if (!rdb || !h1 || !mm) { fprintf(stderr, "missing blocks\n"); return 1; }
+  std::vector<uint64_t> lod(1, 0), brick(3, 0);
+  std::vector<uint64_t> bs = rdb->GetBrickSize(lod, brick);
+  uint64_t dom[3] = {rdb->ulDomainSize[0], rdb->ulDomainSize[1], rdb->ulDomainSize[2]};
+  fwrite(dom, 8, 3, f);
+  uint64_t bsz[3] = {bs[0], bs[1], bs[2]};
+  fwrite(bsz, 8, 3, f);
+  uint64_t bits = rdb->ulElementBitSize[0][0];
+  put(f, bits);
+  std::vector<unsigned char> data;
+  rdb->GetData(data, lod, brick);
+  uint64_t n = data.size(); put(f, n);
+  fwrite(data.data(), 1, data.size(), f);
+  const std::vector<uint64_t>& bins = h1->GetHistogram();
+  uint64_t n1 = bins.size(); put(f, n1); fwrite(bins.data(), 8, n1, f);
+  double mn = mm->GetGlobalValue().minScalar, mx = mm->GetGlobalValue().maxScalar;
+  put(f, mn); put(f, mx);
+  float mg = h2 ? h2->GetMaxGradMagnitude() : 0.0f; put(f, mg);
+  fclose(f);
+  uvf.Close();
+  return 0;
+}
+
+static int do_tf1d(int argc, char** argv) {
+  if (argc < 4) return 2;
+  const std::string tfn(argv[2]);
+  TransferFunction1D tf(tfn);
+  std::vector<unsigned char> bytes;
+  tf.GetByteArray(bytes);
+  FILE* f = fopen(argv[3], "wb");
+  uint64_t n = tf.GetSize(); put(f, n);
+  fwrite(bytes.data(), 1, bytes.size(), f);
+  uint64_t lo = tf.GetNonZeroLimits().x; uint64_t hi = tf.GetNonZeroLimits().y;
+  put(f, lo); put(f, hi);
+  fclose(f);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) { fprintf(stderr, "usage: ref_driver convert|uvfinfo|tf1d ...\n"); return 2; }
+  if (!strcmp(argv[1], "convert")) return do_convert(argc, argv);
+  if (!strcmp(argv[1], "uvfinfo")) return do_uvfinfo(argc, argv);
+  if (!strcmp(argv[1], "tf1d")) return do_tf1d(argc, argv);
+  return 2;
+}
