@@ -1,0 +1,248 @@
+"""Thin object wrapper over the kernel-level C ABI (include/tvk_cuda.h).
+
+Only marshals numpy arrays into the C calls; all arithmetic happens in
+libtvk_cuda.so.  The AbstrRenderer-shaped host lives in csrc/host/ (C++) and is
+exposed through imagevis3d_b200.renderer.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class TvkContext:
+    def __init__(self, device=0):
+        self.lib = L.load()
+        self.h = C.c_void_p()
+        rc = self.lib.tvk_create(C.c_int(device), C.byref(self.h))
+        if rc != L.TVK_OK:
+            raise L.TvkError("tvk_create(device=%d) failed with status %d (no CUDA device?)" % (device, rc))
+        self.total_bricks = 0
+        self.build_info = None
+
+    def close(self):
+        if self.h:
+            self.lib.tvk_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        L.check(self.h, rc, what)
+
+    def synchronize(self):
+        self._ck(self.lib.tvk_device_synchronize(self.h), "tvk_device_synchronize")
+
+    # ------------------------------------------------------------------ pool
+    def pool_create(self, volume_size, max_brick_size, overlap, bytes_per_voxel, capacity, lod_count,
+                    sampler=L.SAMPLER_EXACT):
+        d = L.PoolDesc()
+        d.volume_size[:] = [int(v) for v in volume_size]
+        d.max_brick_size[:] = [int(v) for v in max_brick_size]
+        d.overlap = overlap
+        d.bytes_per_voxel = bytes_per_voxel
+        d.pool_capacity[:] = [int(v) for v in capacity]
+        d.lod_count = lod_count
+        d.sampler = sampler
+        self._ck(self.lib.tvk_pool_create(self.h, C.byref(d)), "tvk_pool_create")
+        n = C.c_uint32()
+        self._ck(self.lib.tvk_pool_total_bricks(self.h, C.byref(n)), "tvk_pool_total_bricks")
+        self.total_bricks = n.value
+        self.pool_desc = d
+        return n.value
+
+    def pool_upload_host(self, slots, bricks):
+        """bricks: list of C-contiguous numpy arrays [z][y][x] (host memory)."""
+        n = len(slots)
+        slot = np.asarray(slots, np.uint32)
+        src = (C.c_void_p * n)(*[b.ctypes.data for b in bricks])
+        sizes = np.asarray([[b.shape[2], b.shape[1], b.shape[0]] for b in bricks], np.uint32).reshape(-1)
+        self._ck(self.lib.tvk_pool_upload_bricks(self.h, C.c_uint32(n), _p(slot), src, _p(sizes), C.c_int(0)),
+                 "tvk_pool_upload_bricks")
+        self._ck(self.lib.tvk_pool_upload_wait(self.h), "tvk_pool_upload_wait")
+
+    def pool_upload_device(self, slots, dptrs, sizes3):
+        n = len(slots)
+        slot = np.asarray(slots, np.uint32)
+        src = (C.c_void_p * n)(*[int(p) for p in dptrs])
+        sizes = np.ascontiguousarray(sizes3, np.uint32).reshape(-1)
+        self._ck(self.lib.tvk_pool_upload_bricks(self.h, C.c_uint32(n), _p(slot), src, _p(sizes), C.c_int(1)),
+                 "tvk_pool_upload_bricks")
+        self._ck(self.lib.tvk_pool_upload_wait(self.h), "tvk_pool_upload_wait")
+
+    def set_metadata(self, meta):
+        meta = np.ascontiguousarray(meta, np.uint32)
+        self._ck(self.lib.tvk_pool_set_metadata(self.h, _p(meta), C.c_uint32(meta.size)), "tvk_pool_set_metadata")
+
+    def patch_metadata(self, idx, val):
+        idx = np.ascontiguousarray(idx, np.uint32)
+        val = np.ascontiguousarray(val, np.uint32)
+        self._ck(self.lib.tvk_pool_patch_metadata(self.h, C.c_uint32(idx.size), _p(idx), _p(val)),
+                 "tvk_pool_patch_metadata")
+
+    def get_metadata(self):
+        meta = np.zeros(self.total_bricks, np.uint32)
+        self._ck(self.lib.tvk_pool_get_metadata(self.h, _p(meta), C.c_uint32(meta.size)), "tvk_pool_get_metadata")
+        return meta
+
+    # ------------------------------------------------------------ visibility
+    def set_minmax(self, minmax, grad_minmax=None):
+        mm = np.ascontiguousarray(minmax, np.float64)
+        g = None if grad_minmax is None else np.ascontiguousarray(grad_minmax, np.float64)
+        self._ck(self.lib.tvk_visibility_set_minmax(self.h, _p(mm), _p(g) if g is not None else None,
+                                                    C.c_uint32(mm.shape[0])), "tvk_visibility_set_minmax")
+
+    def recompute_visibility(self, mode, smin, smax=0.0, gmin=0.0, gmax=0.0):
+        v = L.Visibility(mode, smin, smax, gmin, gmax)
+        counts = np.zeros(4, np.uint32)
+        self._ck(self.lib.tvk_visibility_recompute(self.h, C.byref(v), _p(counts)), "tvk_visibility_recompute")
+        return counts
+
+    # ------------------------------------------------------------------- TFs
+    def set_tf1d(self, rgba):
+        rgba = np.ascontiguousarray(rgba, np.uint8)
+        self._ck(self.lib.tvk_set_tf1d(self.h, _p(rgba), C.c_uint32(rgba.shape[0])), "tvk_set_tf1d")
+
+    def set_tf2d(self, rgba):
+        rgba = np.ascontiguousarray(rgba, np.uint8)   # [h][w][4]
+        self._ck(self.lib.tvk_set_tf2d(self.h, _p(rgba), C.c_uint32(rgba.shape[1]), C.c_uint32(rgba.shape[0])),
+                 "tvk_set_tf2d")
+
+    # --------------------------------------------------------------- raycast
+    def raycast(self, params):
+        self._ck(self.lib.tvk_raycast_subframe(self.h, C.byref(params)), "tvk_raycast_subframe")
+        self._wh = (params.width, params.height)
+
+    def read_requests(self, cap=4096):
+        out = np.zeros((cap, 4), np.uint32)
+        n = C.c_uint32()
+        self._ck(self.lib.tvk_read_requests(self.h, _p(out), C.c_uint32(cap), C.byref(n)), "tvk_read_requests")
+        return out[:n.value].copy()
+
+    def read_image(self):
+        w, h = self._wh
+        img = np.zeros((h, w, 4), np.float32)
+        self._ck(self.lib.tvk_read_image(self.h, _p(img)), "tvk_read_image")
+        return img
+
+    def read_resume(self):
+        w, h = self._wh
+        pos = np.zeros((h, w, 4), np.float32)
+        col = np.zeros((h, w, 4), np.float32)
+        self._ck(self.lib.tvk_read_resume(self.h, _p(pos), _p(col)), "tvk_read_resume")
+        return pos, col
+
+    def stats(self, reset=False):
+        s = L.Stats()
+        self._ck(self.lib.tvk_get_stats(self.h, C.byref(s), C.c_int(1 if reset else 0)), "tvk_get_stats")
+        return s
+
+    def probe_lod(self, depth, lod_factor, wse):
+        depth = np.ascontiguousarray(depth, np.float32)
+        out = np.zeros(depth.size, np.uint32)
+        self._ck(self.lib.tvk_probe_lod(self.h, _p(depth), C.c_uint32(depth.size), C.c_float(lod_factor),
+                                        C.c_float(wse), _p(out)), "tvk_probe_lod")
+        return out
+
+    def probe_brick_index(self, xyz, lod):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        lod = np.ascontiguousarray(lod, np.uint32)
+        idx = np.zeros(lod.size, np.uint32)
+        ser = np.zeros(lod.size, np.uint32)
+        self._ck(self.lib.tvk_probe_brick_index(self.h, _p(xyz), _p(lod), C.c_uint32(lod.size), _p(idx), _p(ser)),
+                 "tvk_probe_brick_index")
+        return idx, ser
+
+    # --------------------------------------------------------------- builder
+    @staticmethod
+    def build_plan(volume_size, brick=64, overlap=2, bpv=1):
+        d = L.BuildDesc()
+        d.volume_size[:] = [int(v) for v in volume_size]
+        d.brick_size, d.overlap, d.bytes_per_voxel = brick, overlap, bpv
+        info = L.BuildInfo()
+        rc = L.load().tvk_build_plan(C.byref(d), C.byref(info))
+        if rc != L.TVK_OK:
+            raise L.TvkError("tvk_build_plan failed with status %d" % rc)
+        return info
+
+    def build_octree(self, raw=None, brick=64, overlap=2, median=False, clamp=False, raw_dptr=None,
+                     volume_size=None, bpv=None):
+        d = L.BuildDesc()
+        if raw is not None:
+            raw = np.ascontiguousarray(raw)
+            volume_size = raw.shape[::-1]
+            bpv = raw.dtype.itemsize
+            ptr, on_dev = C.c_void_p(raw.ctypes.data), 0
+        else:
+            ptr, on_dev = C.c_void_p(int(raw_dptr)), 1
+        d.volume_size[:] = [int(v) for v in volume_size]
+        d.brick_size, d.overlap, d.bytes_per_voxel = brick, overlap, bpv
+        d.use_median, d.clamp_to_edge = int(median), int(clamp)
+        info = L.BuildInfo()
+        self._ck(self.lib.tvk_build_octree(self.h, C.byref(d), ptr, C.c_int(on_dev), C.byref(info)), "tvk_build_octree")
+        self.build_info = info
+        self.build_bpv = bpv
+        return info
+
+    def build_toc(self):
+        n = int(self.build_info.total_bricks)
+        off = np.zeros(n, np.uint64)
+        sizes = np.zeros((n, 3), np.uint32)
+        self._ck(self.lib.tvk_build_get_toc(self.h, _p(off), _p(sizes), C.c_uint64(n)), "tvk_build_get_toc")
+        return off, sizes
+
+    def build_minmax(self):
+        n = int(self.build_info.total_bricks)
+        mm = np.zeros((n, 2), np.float64)
+        self._ck(self.lib.tvk_build_get_minmax(self.h, _p(mm), C.c_uint64(n)), "tvk_build_get_minmax")
+        return mm
+
+    def build_bricks(self, offset=0, nbytes=None):
+        nbytes = int(self.build_info.total_bytes) - offset if nbytes is None else nbytes
+        out = np.zeros(nbytes, np.uint8)
+        self._ck(self.lib.tvk_build_get_bricks(self.h, _p(out), C.c_uint64(offset), C.c_uint64(nbytes)),
+                 "tvk_build_get_bricks")
+        return out
+
+    def build_store_ptr(self):
+        p = C.c_void_p()
+        self._ck(self.lib.tvk_build_store_device_ptr(self.h, C.byref(p)), "tvk_build_store_device_ptr")
+        return p.value
+
+    def build_hist1d(self):
+        cap = 1 << (8 * self.build_bpv)
+        bins = np.zeros(cap, np.uint64)
+        n = C.c_uint32()
+        self._ck(self.lib.tvk_build_hist1d(self.h, _p(bins), C.c_uint32(cap), C.byref(n)), "tvk_build_hist1d")
+        return bins[:n.value].copy()
+
+    def build_hist2d(self, bins_x, max_nonzero):
+        bins = np.zeros((bins_x, 256), np.uint64)
+        mg = C.c_float()
+        self._ck(self.lib.tvk_build_hist2d(self.h, C.c_uint32(bins_x), C.c_double(max_nonzero), _p(bins), C.byref(mg)),
+                 "tvk_build_hist2d")
+        return bins, mg.value
+
+    def build_release(self):
+        self._ck(self.lib.tvk_build_release(self.h), "tvk_build_release")
+
+    # ------------------------------------------------------------ compositor
+    def composite_ordered(self, dptrs, pixels, out_dptr):
+        n = len(dptrs)
+        arr = (C.c_void_p * n)(*[int(p) for p in dptrs])
+        self._ck(self.lib.tvk_composite_ordered(self.h, arr, C.c_uint32(n), C.c_uint64(pixels), C.c_void_p(int(out_dptr))),
+                 "tvk_composite_ordered")
+
+    def image_device_ptr(self):
+        p = C.c_void_p()
+        self._ck(self.lib.tvk_image_device_ptr(self.h, C.byref(p)), "tvk_image_device_ptr")
+        return p.value

@@ -1,0 +1,508 @@
+// K2 -- ExtendedOctree / UVF brick-and-LOD builder as streaming kernels (sm_100a).
+//
+// Replaces ExtendedOctreeConverter::Convert (Tuvok/IO/UVF/ExtendedOctree/
+// ExtendedOctreeConverter.cpp:128-280) and the histogram blocks:
+//   plan              ExtendedOctree::ComputeMetadata / ComputeBrickSize (ExtendedOctree.cpp:188-285)
+//   downsample_kernel ComputeHierarchy -> DownsampleBrick -> DownsampleBricktoBrick
+//                     (ExtendedOctreeConverter.inc:1-398), VolumeTools::Filter (VolumeTools.h:168-262)
+//   cut_bricks_kernel PermuteInputData/GetInputBrick (.cpp:1381-1414,288-373) for LOD 0,
+//                     FillOverlap/CopyBrickToBrick (.cpp:1203-1372,1153-1181) for LOD >= 1,
+//                     ComputeBrickStats (.inc:408-444) fused in
+//   hist1d_kernel     Histogram1DDataBlock::Compute (IO/UVF/Histogram1DDataBlock.cpp:60-160)
+//   grad_*_kernel     Histogram2DDataBlock::ComputeTemplate (IO/UVF/Histogram2DDataBlock.cpp:348-455)
+//
+// The reference works brick by brick through an LRU file cache; the result is
+// nevertheless a pure function of GLOBAL voxel coordinates, which is what lets
+// the work stream:
+//  * the inner region of every LOD-(l+1) brick is the 2x2x2 (edge: 4/2/1 tap)
+//    reduction of LOD-l voxels 2g..2g+1 -- valid because the inner brick size is
+//    even, so child bricks never straddle a parent voxel.  We therefore keep a
+//    flat volume per LOD in HBM (total 1/7 of the input) and reduce flat->flat;
+//  * every brick voxel, ghost cells included, is then a gather from the flat
+//    volume of its LOD.  LOD 0 follows GetInputBrick's linear-file-offset reads
+//    (a scan line of a next-to-last brick may run into the following row when the
+//    last brick is thinner than the overlap).  LOD >= 1 follows FillOverlap's
+//    fixed order of 10 neighbour copies: resolve_overlap() replays "which copy
+//    wrote this ghost voxel last, and had its source brick been completed yet",
+//    which reproduces the reference's zeroed corner ghosts bit for bit.
+// Algorithmic bytes per input voxel: read bpv + write 1.2136*(8/7)*bpv (bricks)
+// + 1/7*bpv (pyramid) -- DESIGN.md, "K2".
+#include "tvk_internal.h"
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+
+static const uint64_t kBrickAlign = 256;   // device store: every brick starts 256 B aligned
+
+extern "C" int tvk_build_plan(const tvk_build_desc* d, tvk_build_info* info) {
+  if (!d || !info) return TVK_ERR_INVALID;
+  if (d->brick_size <= 2 * d->overlap || (d->bytes_per_voxel != 1 && d->bytes_per_voxel != 2)) return TVK_ERR_INVALID;
+  for (int a = 0; a < 3; ++a) if (d->volume_size[a] == 0) return TVK_ERR_INVALID;
+  memset(info, 0, sizeof(*info));
+  const uint32_t usable = d->brick_size - 2 * d->overlap;
+  uint32_t v[3] = {d->volume_size[0], d->volume_size[1], d->volume_size[2]};
+  uint32_t n = 0;
+  do {
+    if (n > 0)
+      for (int a = 0; a < 3; ++a) if (v[a] > 1) v[a] = (uint32_t)std::ceil(v[a] / 2.0);
+    if (n >= TVK_MAX_LOD) return TVK_ERR_UNSUPPORTED;
+    for (int a = 0; a < 3; ++a) {
+      info->lod_size[n][a] = v[a];
+      info->lod_bricks[n][a] = (uint32_t)std::ceil((double)v[a] / (double)usable);
+    }
+    ++n;
+  } while (v[0] > 1 || v[1] > 1 || v[2] > 1);
+  info->lod_count = n;
+  uint64_t off = 0;
+  for (uint32_t l = 0; l < n; ++l) {
+    info->lod_offset[l] = off;
+    off += (uint64_t)info->lod_bricks[l][0] * info->lod_bricks[l][1] * info->lod_bricks[l][2];
+  }
+  info->total_bricks = off;
+  return TVK_OK;
+}
+
+struct BuildConst {
+  uint32_t lod_size[TVK_MAX_LOD][3];
+  uint32_t lod_bricks[TVK_MAX_LOD][3];
+  uint32_t brick, overlap, core;
+};
+
+__host__ __device__ inline uint32_t brick_dim(const BuildConst& bc, uint32_t lod, int axis, uint32_t coord) {
+  const bool last = coord >= bc.lod_bricks[lod][axis] - 1;
+  const uint32_t rem = bc.lod_size[lod][axis] % bc.core;
+  return (last && rem) ? (2 * bc.overlap + rem) : bc.brick;
+}
+
+// ------------------------------------------------------------------ filters
+template <typename T> __device__ __forceinline__ void order2(T& a, T& b) { if (a > b) { T t = a; a = b; b = t; } }
+template <typename T> __device__ __forceinline__ void insert4(T& a, T& b, T& c, T& d, T& p) {
+  if (p > c) { order2(d, p); }
+  else if (p < b) { d = c; c = b; b = p; order2(a, b); }
+  else { d = c; c = p; }
+}
+template <typename T, bool MEDIAN> __device__ __forceinline__ T filter8(T a, T b, T c, T d, T e, T f, T g, T h) {
+  if (MEDIAN) {
+    order2(a, b); order2(c, d); order2(a, c); order2(b, d); order2(b, c);
+    insert4(a, b, c, d, e);
+    insert4(a, b, c, d, f);
+    const T m = d < g ? d : g;
+    return m > c ? m : c;
+  }
+  // T((double sum)/8.0): the sum is exact, the quotient truncates toward zero
+  return (T)(((uint32_t)a + b + c + d + e + f + g + h) >> 3);
+}
+template <typename T, bool MEDIAN> __device__ __forceinline__ T filter4(T a, T b, T c, T d) {
+  if (MEDIAN) { order2(a, b); order2(b, c); return a > b ? a : b; }
+  return (T)(((uint32_t)a + b + c + d) >> 2);
+}
+template <typename T, bool MEDIAN> __device__ __forceinline__ T filter2(T a, T b) {
+  if (MEDIAN) return a;
+  return (T)(((uint32_t)a + b) >> 1);
+}
+
+// flat LOD l -> flat LOD l+1; one thread per output voxel, x fastest (coalesced:
+// a warp reads 64 consecutive input voxels from each of 4 rows).
+template <typename T, bool MEDIAN>
+__global__ void __launch_bounds__(256) downsample_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                          uint32_t sx, uint32_t sy, uint32_t sz,
+                                                          uint32_t dx, uint32_t dy, uint32_t dz) {
+  const uint64_t n = (uint64_t)dx * dy * dz;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t x = (uint32_t)(i % dx), y = (uint32_t)((i / dx) % dy), z = (uint32_t)(i / ((uint64_t)dx * dy));
+    // an axis of extent 1 is not reduced any further (ExtendedOctree.cpp:204-217)
+    const uint32_t x0 = (sx > 1) ? 2 * x : x, y0 = (sy > 1) ? 2 * y : y, z0 = (sz > 1) ? 2 * z : z;
+    const bool hx = (sx > 1) && (x0 + 1 < sx), hy = (sy > 1) && (y0 + 1 < sy), hz = (sz > 1) && (z0 + 1 < sz);
+    const uint64_t rs = sx, ss = (uint64_t)sx * sy;
+    const T* p = src + x0 + y0 * rs + z0 * ss;
+    T out;
+    // argument order = p0..p7 of DownsampleBricktoBrick: p1 = +z, p2 = +y, p3 = +y+z, p4.. = +x
+    if (hx && hy && hz) out = filter8<T, MEDIAN>(p[0], p[ss], p[rs], p[rs + ss], p[1], p[1 + ss], p[1 + rs], p[1 + rs + ss]);
+    else if (!hx && hy && hz) out = filter4<T, MEDIAN>(p[0], p[ss], p[rs], p[rs + ss]);
+    else if (hx && !hy && hz) out = filter4<T, MEDIAN>(p[0], p[ss], p[1], p[1 + ss]);
+    else if (hx && hy && !hz) out = filter4<T, MEDIAN>(p[0], p[rs], p[1], p[1 + rs]);
+    else if (!hx && !hy && hz) out = filter2<T, MEDIAN>(p[0], p[ss]);
+    else if (hx && !hy && !hz) out = filter2<T, MEDIAN>(p[0], p[1]);
+    else if (!hx && hy && !hz) out = filter2<T, MEDIAN>(p[0], p[rs]);
+    else out = p[0];
+    dst[i] = out;
+  }
+}
+
+// FillOverlap replay for one ghost voxel of brick (bx,by,bz) at LOD >= 1.
+// Returns true and the global voxel coordinate to gather, or false for "zero".
+__device__ __forceinline__ bool resolve_overlap(const BuildConst& bc, uint32_t lod, int bx, int by, int bz,
+                                                int i, int j, int k, uint32_t& gx, uint32_t& gy, uint32_t& gz) {
+  const int o = (int)bc.overlap;
+  const int nbx = (int)bc.lod_bricks[lod][0], nby = (int)bc.lod_bricks[lod][1], nbz = (int)bc.lod_bricks[lod][2];
+  bool processed = true;
+#pragma unroll 1
+  for (int iter = 0; iter < 8; ++iter) {
+    const int tx = (int)brick_dim(bc, lod, 0, bx), ty = (int)brick_dim(bc, lod, 1, by), tz = (int)brick_dim(bc, lod, 2, bz);
+    const int cx = (i < o) ? -1 : (i >= tx - o ? 1 : 0);
+    const int cy = (j < o) ? -1 : (j >= ty - o ? 1 : 0);
+    const int cz = (k < o) ? -1 : (k >= tz - o ? 1 : 0);
+    if (cx == 0 && cy == 0 && cz == 0) {
+      gx = (uint32_t)(bx * (int)bc.core + i - o);
+      gy = (uint32_t)(by * (int)bc.core + j - o);
+      gz = (uint32_t)(bz * (int)bc.core + k - o);
+      return true;
+    }
+    if (!processed) return false;       // ghost cell of a brick FillOverlap had not reached yet: still zero
+    const bool R = bx < nbx - 1, B = by < nby - 1, K = bz < nbz - 1, L = bx > 0, T = by > 0, F = bz > 0;
+    // last writer first: ops 10..1 of FillOverlap (.cpp:1234-1340)
+    if (R && B && K && cx == 1 && cy == 1 && cz == 1) { i = o + (i - (tx - o)); j = o + (j - (ty - o)); k = o + (k - (tz - o)); bx++; by++; bz++; processed = false; }
+    else if (B && K && cy == 1 && cz == 1) { j = o + (j - (ty - o)); k = o + (k - (tz - o)); by++; bz++; processed = false; }
+    else if (R && K && cx == 1 && cz == 1) { i = o + (i - (tx - o)); k = o + (k - (tz - o)); bx++; bz++; processed = false; }
+    else if (R && B && cx == 1 && cy == 1) { i = o + (i - (tx - o)); j = o + (j - (ty - o)); bx++; by++; processed = false; }
+    else if (F && cz == -1) { bz--; k = (int)brick_dim(bc, lod, 2, bz) - 2 * o + k; }
+    else if (T && cy == -1) { by--; j = (int)brick_dim(bc, lod, 1, by) - 2 * o + j; }
+    else if (L && cx == -1) { bx--; i = (int)brick_dim(bc, lod, 0, bx) - 2 * o + i; }
+    else if (K && cz == 1) { k = o + (k - (tz - o)); bz++; processed = false; }
+    else if (B && cy == 1) { j = o + (j - (ty - o)); by++; processed = false; }
+    else if (R && cx == 1) { i = o + (i - (tx - o)); bx++; processed = false; }
+    else return false;                  // no copy ever touches it: DownsampleBrick's memset
+  }
+  return false;
+}
+
+// One CTA per (brick, z-chunk): gathers the brick (ghost cells included) from the
+// flat LOD volume into the store and reduces min/max over the whole brick.
+template <typename T>
+__global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ flat, uint8_t* __restrict__ store,
+                                                          const uint64_t* __restrict__ offsets, uint64_t first_brick,
+                                                          uint32_t lod, const __grid_constant__ BuildConst bc,
+                                                          uint32_t* __restrict__ mn, uint32_t* __restrict__ mx) {
+  const uint32_t nbx = bc.lod_bricks[lod][0], nby = bc.lod_bricks[lod][1];
+  const uint32_t b = blockIdx.x;
+  const int bx = (int)(b % nbx), by = (int)((b / nbx) % nby), bz = (int)(b / (nbx * nby));
+  const uint32_t tx = brick_dim(bc, lod, 0, bx), ty = brick_dim(bc, lod, 1, by), tz = brick_dim(bc, lod, 2, bz);
+  const uint32_t sx = bc.lod_size[lod][0], sy = bc.lod_size[lod][1], sz = bc.lod_size[lod][2];
+  const uint64_t nvox = (uint64_t)sx * sy * sz;
+  T* dst = reinterpret_cast<T*>(store + offsets[first_brick + b]);
+  const uint32_t total = tx * ty * tz;
+  const int o = (int)bc.overlap;
+  uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+  for (uint32_t v = blockIdx.y * blockDim.x + threadIdx.x; v < total; v += gridDim.y * blockDim.x) {
+    const int i = (int)(v % tx), j = (int)((v / tx) % ty), k = (int)(v / (tx * ty));
+    T val = 0;
+    if (lod == 0) {
+      // GetInputBrick: rows/lines that exist in the copy loops, addressed by linear offset
+      const int nbz = (int)bc.lod_bricks[0][2];
+      const bool fx = bx == 0, fy = by == 0, fz = bz == 0;
+      const bool lx = bx == (int)nbx - 1, ly = by == (int)nby - 1, lz = bz == nbz - 1;
+      const bool in_x = i >= (fx ? o : 0) && i < (int)tx - (lx ? o : 0);
+      const bool in_y = j >= (fy ? o : 0) && j < (int)ty - (ly ? o : 0);
+      const bool in_z = k >= (fz ? o : 0) && k < (int)tz - (lz ? o : 0);
+      if (in_x && in_y && in_z) {
+        const uint64_t lin = (uint64_t)(bx * (int)bc.core - o + i) + (uint64_t)(by * (int)bc.core - o + j) * sx +
+                             (uint64_t)(bz * (int)bc.core - o + k) * sx * sy;
+        if (lin < nvox) val = flat[lin];
+      }
+    } else {
+      uint32_t gx, gy, gz;
+      if (resolve_overlap(bc, lod, bx, by, bz, i, j, k, gx, gy, gz)) val = flat[gx + (uint64_t)gy * sx + (uint64_t)gz * sx * sy];
+    }
+    dst[v] = val;
+    lo = min(lo, (uint32_t)val);
+    hi = max(hi, (uint32_t)val);
+  }
+  for (int s = 16; s > 0; s >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+  }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) {
+    atomicMin(mn + first_brick + b, lo);
+    atomicMax(mx + first_brick + b, hi);
+  }
+}
+
+__global__ void minmax_to_double_kernel(const uint32_t* mn, const uint32_t* mx, double* out, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { out[2 * i] = (double)mn[i]; out[2 * i + 1] = (double)mx[i]; }
+}
+
+// exact histogram of the raw volume (== LOD-0 inner voxels); per-CTA shared
+// histogram for 8 bit, warp-aggregated global atomics for 16 bit
+template <typename T>
+__global__ void __launch_bounds__(256) hist1d_kernel(const T* __restrict__ raw, uint64_t n, unsigned long long* __restrict__ bins) {
+  if (sizeof(T) == 1) {
+    __shared__ unsigned int sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+      atomicAdd(&sh[raw[i]], 1u);
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&bins[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+  } else {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (n + stride - 1) / stride;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint64_t r = 0; r < rounds; ++r, i += stride) {
+      const bool act = i < n;
+      const unsigned am = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        const uint32_t v = raw[i];
+        const unsigned peers = __match_any_sync(am, v);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&bins[v], (unsigned long long)__popc(peers));
+      }
+    }
+  }
+}
+
+// Histogram2DDataBlock::ComputeGradient on the raw volume: the +-1 neighbours of an
+// inner LOD-0 brick voxel are the raw neighbours, zero outside the domain.
+// All arithmetic in fp64 with explicit round-to-nearest ops (no FMA contraction)
+// so that it matches the reference's x86-64 doubles bit for bit.
+template <typename T>
+__device__ __forceinline__ double grad_mag(const T* __restrict__ raw, uint32_t x, uint32_t y, uint32_t z,
+                                           uint32_t sx, uint32_t sy, uint32_t sz, double norm2) {
+  const uint64_t rs = sx, ss = (uint64_t)sx * sy;
+  const uint64_t c = x + y * rs + z * ss;
+  const double l = x > 0 ? (double)raw[c - 1] : 0.0, r = x + 1 < sx ? (double)raw[c + 1] : 0.0;
+  const double t = y > 0 ? (double)raw[c - rs] : 0.0, b = y + 1 < sy ? (double)raw[c + rs] : 0.0;
+  const double f = z > 0 ? (double)raw[c - ss] : 0.0, k = z + 1 < sz ? (double)raw[c + ss] : 0.0;
+  const double gx = __ddiv_rn(__dsub_rn(l, r), norm2), gy = __ddiv_rn(__dsub_rn(t, b), norm2), gz = __ddiv_rn(__dsub_rn(f, k), norm2);
+  return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), __dmul_rn(gz, gz)));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) grad_max_kernel(const T* __restrict__ raw, uint32_t sx, uint32_t sy, uint32_t sz,
+                                                        double norm2, unsigned long long* __restrict__ out_bits) {
+  const uint64_t n = (uint64_t)sx * sy * sz;
+  double m = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t x = (uint32_t)(i % sx), y = (uint32_t)((i / sx) % sy), z = (uint32_t)(i / ((uint64_t)sx * sy));
+    const double g = grad_mag(raw, x, y, z, sx, sy, sz, norm2);
+    if (g > m) m = g;
+  }
+  unsigned long long bits = (unsigned long long)__double_as_longlong(m);   // non-negative doubles order like integers
+  for (int s = 16; s > 0; s >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, bits, s);
+    bits = o > bits ? o : bits;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, bits);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) hist2d_kernel(const T* __restrict__ raw, uint32_t sx, uint32_t sy, uint32_t sz,
+                                                      double norm2, double max_grad, uint32_t bins_x, double max_nonzero,
+                                                      unsigned long long* __restrict__ bins) {
+  const uint64_t n = (uint64_t)sx * sy * sz;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t rounds = (n + stride - 1) / stride;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint64_t r = 0; r < rounds; ++r, i += stride) {
+    const bool act = i < n;
+    const unsigned am = __ballot_sync(0xffffffffu, act);
+    if (!act) continue;
+    const uint32_t x = (uint32_t)(i % sx), y = (uint32_t)((i / sx) % sy), z = (uint32_t)(i / ((uint64_t)sx * sy));
+    const double g = grad_mag(raw, x, y, z, sx, sy, sz, norm2);
+    // size_t(len/max*255.0f); NaN (constant volume) -> 0 here, undefined in the reference
+    const double q = __dmul_rn(__ddiv_rn(g, max_grad), 255.0);
+    uint32_t gi = (q >= 255.0) ? 255u : ((q > 0.0) ? (uint32_t)q : 0u);
+    const double v = (double)raw[i];
+    uint32_t vi = (max_nonzero <= (double)(bins_x - 1)) ? (uint32_t)raw[i]
+                                                         : (uint32_t)__ddiv_rn(__dmul_rn(v, (double)(bins_x - 1)), max_nonzero);
+    if (vi > bins_x - 1) vi = bins_x - 1;
+    const uint32_t bin = vi * 256u + gi;
+    const unsigned peers = __match_any_sync(am, bin);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&bins[bin], (unsigned long long)__popc(peers));
+  }
+}
+
+static void release(tvk_ctx* c) {
+  BuildState& b = c->build;
+  cudaFree(b.d_store); cudaFree(b.d_offsets); cudaFree(b.d_sizes); cudaFree(b.d_minmax); cudaFree(b.d_hist1d);
+  for (uint32_t l = 0; l < TVK_MAX_LOD; ++l) {
+    if (l > 0 || b.own_lod0) cudaFree(b.d_lod[l]);
+    b.d_lod[l] = nullptr;
+  }
+  b = BuildState();
+}
+
+extern "C" int tvk_build_release(tvk_ctx* c) {
+  if (!c) return TVK_ERR_INVALID;
+  cudaSetDevice(c->device);
+  release(c);
+  return TVK_OK;
+}
+
+template <typename T>
+static int run_build(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms) {
+  const tvk_build_info& info = b.info;
+  cudaStream_t st = c->stream;
+  // flat pyramid
+  for (uint32_t l = 1; l < info.lod_count; ++l) {
+    const uint64_t n = (uint64_t)info.lod_size[l][0] * info.lod_size[l][1] * info.lod_size[l][2];
+    TVK_CHECK_CUDA(c, cudaMalloc(&b.d_lod[l], n * sizeof(T)));
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 16);
+    const uint32_t* s = info.lod_size[l - 1];
+    const uint32_t* d = info.lod_size[l];
+    if (b.desc.use_median)
+      downsample_kernel<T, true><<<blocks, 256, 0, st>>>((const T*)b.d_lod[l - 1], (T*)b.d_lod[l], s[0], s[1], s[2], d[0], d[1], d[2]);
+    else
+      downsample_kernel<T, false><<<blocks, 256, 0, st>>>((const T*)b.d_lod[l - 1], (T*)b.d_lod[l], s[0], s[1], s[2], d[0], d[1], d[2]);
+    c->launches++;
+  }
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  // bricks + stats
+  uint32_t *d_mn = nullptr, *d_mx = nullptr;
+  TVK_CHECK_CUDA(c, cudaMallocAsync(&d_mn, sizeof(uint32_t) * info.total_bricks, st));
+  TVK_CHECK_CUDA(c, cudaMallocAsync(&d_mx, sizeof(uint32_t) * info.total_bricks, st));
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(d_mn, 0xFF, sizeof(uint32_t) * info.total_bricks, st));
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(d_mx, 0, sizeof(uint32_t) * info.total_bricks, st));
+  for (uint32_t l = 0; l < info.lod_count; ++l) {
+    const uint64_t nb = (uint64_t)info.lod_bricks[l][0] * info.lod_bricks[l][1] * info.lod_bricks[l][2];
+    // a few z-chunks per brick when there are few bricks, to fill the machine
+    const unsigned chunks = nb >= (uint64_t)sms * 4 ? 2 : 16;
+    cut_bricks_kernel<T><<<dim3((unsigned)nb, chunks), 256, 0, st>>>((const T*)b.d_lod[l], (uint8_t*)b.d_store, b.d_offsets,
+                                                                  info.lod_offset[l], l, bc, d_mn, d_mx);
+    c->launches++;
+  }
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  minmax_to_double_kernel<<<(unsigned)((info.total_bricks + 255) / 256), 256, 0, st>>>(d_mn, d_mx, b.d_minmax, info.total_bricks);
+  c->launches++;
+  // 1-D histogram
+  const uint32_t range = 1u << (8 * sizeof(T));
+  TVK_CHECK_CUDA(c, cudaMalloc(&b.d_hist1d, sizeof(unsigned long long) * range));
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(b.d_hist1d, 0, sizeof(unsigned long long) * range, st));
+  const uint64_t n0 = (uint64_t)info.lod_size[0][0] * info.lod_size[0][1] * info.lod_size[0][2];
+  hist1d_kernel<T><<<(unsigned)std::min<uint64_t>((n0 + 255) / 256, (uint64_t)sms * 8), 256, 0, st>>>((const T*)b.d_lod[0], n0, b.d_hist1d);
+  c->launches++;
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  TVK_CHECK_CUDA(c, cudaFreeAsync(d_mn, st));
+  TVK_CHECK_CUDA(c, cudaFreeAsync(d_mx, st));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(st));
+  return TVK_OK;
+}
+
+extern "C" int tvk_build_octree(tvk_ctx* c, const tvk_build_desc* d, const void* raw, int raw_on_device, tvk_build_info* info_out) {
+  if (!c || !d || !raw) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  if (d->clamp_to_edge) TVK_FAIL(c, TVK_ERR_UNSUPPORTED, "clamp-to-edge borders are not built yet (reference default is off)");
+  tvk_build_info info;
+  if (tvk_build_plan(d, &info) != TVK_OK) TVK_FAIL(c, TVK_ERR_INVALID, "bad build description");
+  if ((d->brick_size - 2 * d->overlap) % 2) TVK_FAIL(c, TVK_ERR_UNSUPPORTED, "odd inner brick size");
+  release(c);
+  BuildState& b = c->build;
+  b.desc = *d;
+  b.info = info;
+  BuildConst bc{};
+  memcpy(bc.lod_size, info.lod_size, sizeof(bc.lod_size));
+  memcpy(bc.lod_bricks, info.lod_bricks, sizeof(bc.lod_bricks));
+  bc.brick = d->brick_size; bc.overlap = d->overlap; bc.core = d->brick_size - 2 * d->overlap;
+  // ToC
+  b.offsets.resize(info.total_bricks);
+  b.sizes.resize(3 * info.total_bricks);
+  uint64_t off = 0, i = 0;
+  for (uint32_t l = 0; l < info.lod_count; ++l)
+    for (uint32_t z = 0; z < info.lod_bricks[l][2]; ++z)
+      for (uint32_t y = 0; y < info.lod_bricks[l][1]; ++y)
+        for (uint32_t x = 0; x < info.lod_bricks[l][0]; ++x, ++i) {
+          const uint32_t s[3] = {brick_dim(bc, l, 0, x), brick_dim(bc, l, 1, y), brick_dim(bc, l, 2, z)};
+          b.offsets[i] = off;
+          b.sizes[3 * i] = s[0]; b.sizes[3 * i + 1] = s[1]; b.sizes[3 * i + 2] = s[2];
+          off += ((uint64_t)s[0] * s[1] * s[2] * d->bytes_per_voxel + kBrickAlign - 1) / kBrickAlign * kBrickAlign;
+        }
+  b.info.total_bytes = off;
+  int sms = 0;
+  TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  const uint64_t n0 = (uint64_t)d->volume_size[0] * d->volume_size[1] * d->volume_size[2];
+  if (raw_on_device) { b.d_lod[0] = const_cast<void*>(raw); b.own_lod0 = false; }
+  else {
+    TVK_CHECK_CUDA(c, cudaMalloc(&b.d_lod[0], n0 * d->bytes_per_voxel));
+    b.own_lod0 = true;
+    TVK_CHECK_CUDA(c, cudaMemcpyAsync(b.d_lod[0], raw, n0 * d->bytes_per_voxel, cudaMemcpyHostToDevice, c->stream));
+  }
+  TVK_CHECK_CUDA(c, cudaMalloc(&b.d_store, off));
+  TVK_CHECK_CUDA(c, cudaMalloc(&b.d_offsets, sizeof(uint64_t) * info.total_bricks));
+  TVK_CHECK_CUDA(c, cudaMalloc(&b.d_sizes, sizeof(uint32_t) * 3 * info.total_bricks));
+  TVK_CHECK_CUDA(c, cudaMalloc(&b.d_minmax, sizeof(double) * 2 * info.total_bricks));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(b.d_offsets, b.offsets.data(), sizeof(uint64_t) * info.total_bricks, cudaMemcpyHostToDevice, c->stream));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(b.d_sizes, b.sizes.data(), sizeof(uint32_t) * 3 * info.total_bricks, cudaMemcpyHostToDevice, c->stream));
+  int rc = (d->bytes_per_voxel == 1) ? run_build<uint8_t>(c, b, bc, sms) : run_build<uint16_t>(c, b, bc, sms);
+  if (rc) { release(c); return rc; }
+  b.valid = true;
+  if (info_out) *info_out = b.info;
+  return TVK_OK;
+}
+
+extern "C" int tvk_build_get_toc(tvk_ctx* c, uint64_t* offsets, uint32_t* sizes3, uint64_t n) {
+  if (!c || !c->build.valid || n != c->build.info.total_bricks) return TVK_ERR_INVALID;
+  if (offsets) memcpy(offsets, c->build.offsets.data(), sizeof(uint64_t) * n);
+  if (sizes3) memcpy(sizes3, c->build.sizes.data(), sizeof(uint32_t) * 3 * n);
+  return TVK_OK;
+}
+
+extern "C" int tvk_build_get_minmax(tvk_ctx* c, double* minmax2, uint64_t n) {
+  if (!c || !c->build.valid || !minmax2 || n != c->build.info.total_bricks) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  TVK_CHECK_CUDA(c, cudaMemcpy(minmax2, c->build.d_minmax, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost));
+  return TVK_OK;
+}
+
+extern "C" int tvk_build_get_bricks(tvk_ctx* c, void* host_dst, uint64_t offset, uint64_t bytes) {
+  if (!c || !c->build.valid || !host_dst || offset + bytes > c->build.info.total_bytes) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  TVK_CHECK_CUDA(c, cudaMemcpy(host_dst, (const uint8_t*)c->build.d_store + offset, bytes, cudaMemcpyDeviceToHost));
+  return TVK_OK;
+}
+
+extern "C" int tvk_build_store_device_ptr(tvk_ctx* c, void** dptr) {
+  if (!c || !c->build.valid || !dptr) return TVK_ERR_INVALID;
+  *dptr = c->build.d_store;
+  return TVK_OK;
+}
+
+extern "C" int tvk_build_hist1d(tvk_ctx* c, uint64_t* bins, uint32_t cap, uint32_t* n) {
+  if (!c || !c->build.valid || !bins || !n) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  const uint32_t range = 1u << (8 * c->build.desc.bytes_per_voxel);
+  std::vector<unsigned long long> h(range);
+  TVK_CHECK_CUDA(c, cudaMemcpy(h.data(), c->build.d_hist1d, sizeof(unsigned long long) * range, cudaMemcpyDeviceToHost));
+  uint32_t size = 0;
+  for (uint32_t i = 0; i < range; ++i) if (h[i]) size = i + 1;    // trim after the last non-zero bin
+  if (size > cap) TVK_FAIL(c, TVK_ERR_INVALID, "histogram buffer too small");
+  for (uint32_t i = 0; i < size; ++i) bins[i] = h[i];
+  *n = size;
+  return TVK_OK;
+}
+
+template <typename T>
+static int run_hist2d(tvk_ctx* c, uint32_t bins_x, double max_nonzero, uint64_t* bins, float* max_grad, int sms) {
+  BuildState& b = c->build;
+  const uint32_t* s = b.info.lod_size[0];
+  const uint64_t n = (uint64_t)s[0] * s[1] * s[2];
+  const double norm2 = (sizeof(T) == 1 ? 255.0 : 65535.0) * 2;
+  unsigned long long *d_bits = nullptr, *d_bins = nullptr;
+  TVK_CHECK_CUDA(c, cudaMalloc(&d_bits, sizeof(unsigned long long)));
+  TVK_CHECK_CUDA(c, cudaMalloc(&d_bins, sizeof(unsigned long long) * 256 * bins_x));
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(d_bits, 0, sizeof(unsigned long long), c->stream));
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(d_bins, 0, sizeof(unsigned long long) * 256 * bins_x, c->stream));
+  const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 16);
+  grad_max_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_bits);
+  c->launches++;
+  unsigned long long bits = 0;
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(&bits, d_bits, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  double mg;
+  memcpy(&mg, &bits, sizeof(mg));
+  hist2d_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, mg, bins_x, max_nonzero, d_bins);
+  c->launches++;
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(bins, d_bins, sizeof(unsigned long long) * 256 * bins_x, cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(d_bits); cudaFree(d_bins);
+  *max_grad = (float)mg;
+  return TVK_OK;
+}
+
+extern "C" int tvk_build_hist2d(tvk_ctx* c, uint32_t bins_x, double max_nonzero_value, uint64_t* bins, float* max_grad_magnitude) {
+  if (!c || !c->build.valid || !bins || !max_grad_magnitude || bins_x == 0) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  int sms = 0;
+  TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  return c->build.desc.bytes_per_voxel == 1 ? run_hist2d<uint8_t>(c, bins_x, max_nonzero_value, bins, max_grad_magnitude, sms)
+                                            : run_hist2d<uint16_t>(c, bins_x, max_nonzero_value, bins, max_grad_magnitude, sms);
+}

@@ -1,0 +1,387 @@
+// Context, brick pool (storage + pager upload path), metadata table and transfer
+// functions behind include/tvk_cuda.h.
+//
+// HBM layout of the pool (replaces the GL 3-D texture of GLVolumePool.cpp:864-870):
+//   TVK_SAMPLER_EXACT : one linear array [pool_dim.z][pool_dim.y][pool_dim.x] of
+//                       UNORM8/16 voxels; slot (sx,sy,sz) starts at voxel
+//                       (sx,sy,sz)*max_brick_size -- identical addressing to the
+//                       reference's texture so the shader constants carry over.
+//   TVK_SAMPLER_TEX3D : the same voxels in a cudaArray (surface-writable) bound
+//                       to a normalised-float, linear-filter texture object.
+// Brick upload = contiguous DMA (pinned host -> staging ring in HBM, side stream)
+// followed by a placement kernel that scatters each brick into its slot with
+// 16-byte accesses; the reference does one synchronous glTexSubImage3D per brick
+// from pageable memory (GLVolumePool.cpp:673-717).
+#include "tvk_internal.h"
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+
+// ---------------------------------------------------------------------------
+// host tables: GLVolumePool.cpp:82-117 (GetLoDSize, GetFloatBrickLayout,
+// GetBrickLayout) and the LoD offset table of the ctor (:222-230)
+// ---------------------------------------------------------------------------
+void tvk_compute_pool_const(const tvk_pool_desc& d, PoolConst& pc) {
+  memset(&pc, 0, sizeof(pc));
+  pc.lod_count = d.lod_count;
+  pc.bpv = d.bytes_per_voxel;
+  uint32_t inner[3], base[3];
+  for (int a = 0; a < 3; ++a) {
+    inner[a] = d.max_brick_size[a] - 2 * d.overlap;
+    base[a] = (uint32_t)std::ceil((double)d.volume_size[a] / inner[a]);
+  }
+  uint32_t off = 0;
+  for (uint32_t l = 0; l < d.lod_count; ++l) {
+    const uint32_t pw = 1u << l;
+    for (int a = 0; a < 3; ++a) {
+      float f = (float)d.volume_size[a] / (float)inner[a];
+      f /= (float)pw;
+      if ((float)(uint32_t)f == f) f -= f * FLT_EPSILON;   // the epsilon nudge, :99-104
+      pc.lod_layout[l][a] = f;
+      pc.lod_bricks[l][a] = (uint32_t)std::ceil((double)base[a] / pw);
+    }
+    pc.lod_layout_x[l] = (uint32_t)std::ceil(pc.lod_layout[l][0]);
+    pc.lod_layout_xy[l] = (uint32_t)std::ceil(pc.lod_layout[l][0]) * (uint32_t)std::ceil(pc.lod_layout[l][1]);
+    pc.lod_offset[l] = off;
+    off += pc.lod_bricks[l][0] * pc.lod_bricks[l][1] * pc.lod_bricks[l][2];
+  }
+  pc.total_bricks = pc.lod_offset[d.lod_count - 1] + 1;    // m_iTotalBrickCount, :877
+  for (int a = 0; a < 3; ++a) {
+    pc.l0_bricks[a] = pc.lod_bricks[0][a];
+    pc.capacity[a] = d.pool_capacity[a];
+    pc.max_brick[a] = d.max_brick_size[a];
+    pc.pool_dim[a] = d.pool_capacity[a] * d.max_brick_size[a];
+    pc.pool_size[a] = (float)pc.pool_dim[a];
+    pc.overlap_tc[a] = (float)(d.max_brick_size[a] - inner[a]) / (2.0f * pc.pool_size[a]);
+    pc.volume_size[a] = (float)d.volume_size[a];
+  }
+}
+
+extern "C" int tvk_create(int device, tvk_ctx** out) {
+  if (!out) return TVK_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return TVK_ERR_CUDA;
+  tvk_ctx* c = new tvk_ctx();
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->render_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaMalloc(&c->d_tile_counter, 64) != cudaSuccess ||
+      cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMalloc(&c->d_counts, 4 * sizeof(uint32_t)) != cudaSuccess) {
+    delete c;
+    return TVK_ERR_CUDA;
+  }
+  cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
+  *out = c;
+  return TVK_OK;
+}
+
+static void free_frame(tvk_ctx* c) {
+  cudaFree(c->d_image); c->d_image = nullptr;
+  for (int i = 0; i < 2; ++i) { cudaFree(c->d_pos[i]); cudaFree(c->d_aux[i]); c->d_pos[i] = c->d_aux[i] = nullptr; }
+  c->width = c->height = 0;
+}
+
+extern "C" void tvk_destroy(tvk_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  tvk_build_release(c);
+  tvk_pool_destroy(c);
+  free_frame(c);
+  cudaFree(c->d_tf); cudaFree(c->d_hash); cudaFree(c->d_tile_counter); cudaFree(c->d_stats); cudaFree(c->d_counts);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->copy_done); cudaEventDestroy(c->render_done);
+  cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+extern "C" const char* tvk_last_error(const tvk_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+extern "C" int tvk_device_synchronize(tvk_ctx* c) {
+  if (!c) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TVK_OK;
+}
+
+int tvk_ensure_frame(tvk_ctx* c, uint32_t w, uint32_t h, uint32_t hash_size) {
+  if (w == 0 || h == 0) TVK_FAIL(c, TVK_ERR_INVALID, "zero-sized render target");
+  if (c->width != w || c->height != h) {
+    free_frame(c);
+    const size_t bytes = (size_t)w * h * sizeof(float4);
+    TVK_CHECK_CUDA(c, cudaMalloc(&c->d_image, bytes));
+    for (int i = 0; i < 2; ++i) {
+      TVK_CHECK_CUDA(c, cudaMalloc(&c->d_pos[i], bytes));
+      TVK_CHECK_CUDA(c, cudaMalloc(&c->d_aux[i], bytes));
+    }
+    c->width = w; c->height = h; c->cur = 0;
+  }
+  if (c->hash_size != hash_size) {
+    cudaFree(c->d_hash); c->d_hash = nullptr;
+    TVK_CHECK_CUDA(c, cudaMalloc(&c->d_hash, sizeof(uint32_t) * hash_size));
+    c->hash_size = hash_size;
+  }
+  return TVK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// pool
+// ---------------------------------------------------------------------------
+extern "C" int tvk_pool_create(tvk_ctx* c, const tvk_pool_desc* d) {
+  if (!c || !d) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  if (d->bytes_per_voxel != 1 && d->bytes_per_voxel != 2) TVK_FAIL(c, TVK_ERR_UNSUPPORTED, "only 8/16 bit single component volumes");
+  if (d->lod_count == 0 || d->lod_count > TVK_MAX_LOD) TVK_FAIL(c, TVK_ERR_INVALID, "bad lod_count");
+  for (int a = 0; a < 3; ++a)
+    if (d->max_brick_size[a] <= 2 * d->overlap || d->pool_capacity[a] == 0 || d->volume_size[a] == 0)
+      TVK_FAIL(c, TVK_ERR_INVALID, "bad pool description");
+  if (d->sampler != TVK_SAMPLER_EXACT && d->sampler != TVK_SAMPLER_TEX3D) TVK_FAIL(c, TVK_ERR_INVALID, "bad sampler");
+  tvk_pool_destroy(c);
+  c->pdesc = *d;
+  tvk_compute_pool_const(*d, c->pc);
+  const size_t voxels = (size_t)c->pc.pool_dim[0] * c->pc.pool_dim[1] * c->pc.pool_dim[2];
+  if (d->sampler == TVK_SAMPLER_EXACT) {
+    TVK_CHECK_CUDA(c, cudaMalloc(&c->d_pool, voxels * d->bytes_per_voxel));
+    TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_pool, 0, voxels * d->bytes_per_voxel, c->stream));
+  } else {
+    cudaChannelFormatDesc fd = cudaCreateChannelDesc(8 * d->bytes_per_voxel, 0, 0, 0, cudaChannelFormatKindUnsigned);
+    TVK_CHECK_CUDA(c, cudaMalloc3DArray(&c->pool_array, &fd,
+                                        make_cudaExtent(c->pc.pool_dim[0], c->pc.pool_dim[1], c->pc.pool_dim[2]),
+                                        cudaArraySurfaceLoadStore));
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = c->pool_array;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 1;
+    TVK_CHECK_CUDA(c, cudaCreateTextureObject(&c->pool_tex, &rd, &td, nullptr));
+  }
+  TVK_CHECK_CUDA(c, cudaMalloc(&c->d_meta, sizeof(uint32_t) * c->pc.total_bricks));
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_meta, 0, sizeof(uint32_t) * c->pc.total_bricks, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->has_pool = true;
+  return TVK_OK;
+}
+
+extern "C" int tvk_pool_destroy(tvk_ctx* c) {
+  if (!c) return TVK_ERR_INVALID;
+  cudaSetDevice(c->device);
+  if (c->pool_tex) { cudaDestroyTextureObject(c->pool_tex); c->pool_tex = 0; }
+  if (c->pool_array) { cudaFreeArray(c->pool_array); c->pool_array = nullptr; }
+  cudaFree(c->d_pool); c->d_pool = nullptr;
+  cudaFree(c->d_meta); c->d_meta = nullptr;
+  cudaFree(c->d_minmax); c->d_minmax = nullptr;
+  cudaFree(c->d_gminmax); c->d_gminmax = nullptr;
+  c->n_minmax = 0;
+  c->has_pool = false;
+  return TVK_OK;
+}
+
+extern "C" int tvk_pool_total_bricks(const tvk_ctx* c, uint32_t* out) {
+  if (!c || !out || !c->has_pool) return TVK_ERR_INVALID;
+  *out = c->pc.total_bricks;
+  return TVK_OK;
+}
+
+// Placement kernel: one CTA row-group per brick; copies brick b (tightly packed,
+// x fastest) into its pool slot.  VEC = bytes moved per thread access.
+struct PlaceJob {
+  const uint8_t* src;
+  uint32_t slot;
+  uint32_t sx, sy, sz;   // voxels
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) place_bricks_linear(const PlaceJob* __restrict__ jobs, uint8_t* __restrict__ pool,
+                                                            const __grid_constant__ PoolConst pc) {
+  const PlaceJob j = jobs[blockIdx.x];
+  const uint32_t bpv = pc.bpv;
+  const uint32_t row_bytes = j.sx * bpv;
+  const uint32_t units = row_bytes / VEC;                 // per row
+  const uint32_t rows = j.sy * j.sz;
+  const uint32_t s0 = j.slot % pc.capacity[0], s1 = (j.slot / pc.capacity[0]) % pc.capacity[1],
+                 s2 = j.slot / (pc.capacity[0] * pc.capacity[1]);
+  const size_t px = (size_t)pc.pool_dim[0] * bpv, pxy = px * pc.pool_dim[1];
+  uint8_t* dst0 = pool + (size_t)s0 * pc.max_brick[0] * bpv + (size_t)s1 * pc.max_brick[1] * px + (size_t)s2 * pc.max_brick[2] * pxy;
+  const uint32_t total = units * rows;
+  for (uint32_t i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
+    const uint32_t r = i / units, u = i - r * units;
+    const uint32_t y = r % j.sy, z = r / j.sy;
+    const uint8_t* s = j.src + (size_t)r * row_bytes + (size_t)u * VEC;
+    uint8_t* d = dst0 + (size_t)y * px + (size_t)z * pxy + (size_t)u * VEC;
+    if (VEC == 16) *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(s);
+    else *d = *s;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) place_bricks_surface(const PlaceJob* __restrict__ jobs, cudaSurfaceObject_t surf,
+                                                             const __grid_constant__ PoolConst pc) {
+  const PlaceJob j = jobs[blockIdx.x];
+  const uint32_t s0 = j.slot % pc.capacity[0], s1 = (j.slot / pc.capacity[0]) % pc.capacity[1],
+                 s2 = j.slot / (pc.capacity[0] * pc.capacity[1]);
+  const uint32_t total = j.sx * j.sy * j.sz;
+  const T* src = reinterpret_cast<const T*>(j.src);
+  for (uint32_t i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
+    const uint32_t x = i % j.sx, y = (i / j.sx) % j.sy, z = i / (j.sx * j.sy);
+    surf3Dwrite(src[i], surf, (int)((s0 * pc.max_brick[0] + x) * sizeof(T)), (int)(s1 * pc.max_brick[1] + y),
+                (int)(s2 * pc.max_brick[2] + z));
+  }
+}
+
+static int place_batch(tvk_ctx* c, std::vector<PlaceJob>& jobs, cudaStream_t st) {
+  if (jobs.empty()) return TVK_OK;
+  const uint32_t bpv = c->pc.bpv;
+  std::stable_partition(jobs.begin(), jobs.end(), [bpv](const PlaceJob& j) {
+    return !(((uintptr_t)j.src & 15) || ((j.sx * bpv) & 15));
+  });
+  PlaceJob* d_jobs = nullptr;
+  TVK_CHECK_CUDA(c, cudaMallocAsync(&d_jobs, sizeof(PlaceJob) * jobs.size(), st));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(PlaceJob) * jobs.size(), cudaMemcpyHostToDevice, st));
+  const dim3 grid((unsigned)jobs.size(), 8);
+  if (c->pdesc.sampler == TVK_SAMPLER_EXACT) {
+    // jobs arrive sorted: [0, nvec) can move 16 B per access, the rest go byte-wise
+    size_t nvec = 0;
+    while (nvec < jobs.size() && !(((uintptr_t)jobs[nvec].src & 15) || ((jobs[nvec].sx * c->pc.bpv) & 15))) ++nvec;
+    if (nvec) place_bricks_linear<16><<<dim3((unsigned)nvec, 8), 256, 0, st>>>(d_jobs, (uint8_t*)c->d_pool, c->pc);
+    if (nvec < jobs.size()) {
+      place_bricks_linear<1><<<dim3((unsigned)(jobs.size() - nvec), 8), 256, 0, st>>>(d_jobs + nvec, (uint8_t*)c->d_pool, c->pc);
+      c->launches++;
+    }
+  } else {
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = c->pool_array;
+    cudaSurfaceObject_t surf = 0;
+    TVK_CHECK_CUDA(c, cudaCreateSurfaceObject(&surf, &rd));
+    if (c->pc.bpv == 1) place_bricks_surface<uint8_t><<<grid, 256, 0, st>>>(d_jobs, surf, c->pc);
+    else place_bricks_surface<uint16_t><<<grid, 256, 0, st>>>(d_jobs, surf, c->pc);
+    TVK_CHECK_CUDA(c, cudaStreamSynchronize(st));
+    cudaDestroySurfaceObject(surf);
+  }
+  c->launches++;
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  TVK_CHECK_CUDA(c, cudaFreeAsync(d_jobs, st));
+  return TVK_OK;
+}
+
+extern "C" int tvk_pool_upload_bricks(tvk_ctx* c, uint32_t n, const uint32_t* slot, const void* const* src,
+                                      const uint32_t* sizes, int on_device) {
+  if (!c || !c->has_pool || (n && (!slot || !src || !sizes))) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  const uint32_t nslots = c->pc.capacity[0] * c->pc.capacity[1] * c->pc.capacity[2];
+  for (uint32_t i = 0; i < n; ++i) {
+    if (slot[i] >= nslots) TVK_FAIL(c, TVK_ERR_INVALID, "slot out of range");
+    for (int a = 0; a < 3; ++a)
+      if (sizes[3 * i + a] == 0 || sizes[3 * i + a] > c->pc.max_brick[a]) TVK_FAIL(c, TVK_ERR_INVALID, "brick larger than a pool slot");
+  }
+  cudaStream_t st = c->copy_stream;
+  // the side stream must not overwrite slots a ray-march in flight still samples
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->render_done, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamWaitEvent(st, c->render_done, 0));
+  if (on_device) {
+    std::vector<PlaceJob> jobs(n);
+    for (uint32_t i = 0; i < n; ++i) jobs[i] = PlaceJob{(const uint8_t*)src[i], slot[i], sizes[3 * i], sizes[3 * i + 1], sizes[3 * i + 2]};
+    int rc = place_batch(c, jobs, st);
+    if (rc) return rc;
+  } else {
+    // staging ring in HBM: contiguous DMA per brick, then one placement launch per batch
+    const size_t slot_bytes = (size_t)c->pc.max_brick[0] * c->pc.max_brick[1] * c->pc.max_brick[2] * c->pc.bpv;
+    const uint32_t batch = 256;
+    uint8_t* staging = nullptr;
+    const uint32_t cap = std::min(n, batch);
+    if (cap) TVK_CHECK_CUDA(c, cudaMallocAsync(&staging, slot_bytes * cap, st));
+    for (uint32_t b0 = 0; b0 < n; b0 += batch) {
+      const uint32_t bn = std::min(batch, n - b0);
+      std::vector<PlaceJob> jobs(bn);
+      for (uint32_t i = 0; i < bn; ++i) {
+        const uint32_t k = b0 + i;
+        const size_t bytes = (size_t)sizes[3 * k] * sizes[3 * k + 1] * sizes[3 * k + 2] * c->pc.bpv;
+        TVK_CHECK_CUDA(c, cudaMemcpyAsync(staging + slot_bytes * i, src[k], bytes, cudaMemcpyHostToDevice, st));
+        jobs[i] = PlaceJob{staging + slot_bytes * i, slot[k], sizes[3 * k], sizes[3 * k + 1], sizes[3 * k + 2]};
+      }
+      int rc = place_batch(c, jobs, st);
+      if (rc) return rc;
+    }
+    if (staging) TVK_CHECK_CUDA(c, cudaFreeAsync(staging, st));
+  }
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->copy_done, st));
+  return TVK_OK;
+}
+
+extern "C" int tvk_pool_upload_wait(tvk_ctx* c) {
+  if (!c) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  // later work on the render stream sees the placed bricks; the host may reuse its buffers
+  TVK_CHECK_CUDA(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  return TVK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// metadata
+// ---------------------------------------------------------------------------
+__global__ void patch_meta_kernel(uint32_t* __restrict__ meta, const uint32_t* __restrict__ idx,
+                                  const uint32_t* __restrict__ val, uint32_t n, uint32_t total) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && idx[i] < total) meta[idx[i]] = val[i];
+}
+
+extern "C" int tvk_pool_set_metadata(tvk_ctx* c, const uint32_t* meta, uint32_t n) {
+  if (!c || !c->has_pool || !meta || n != c->pc.total_bricks) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_meta, meta, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TVK_OK;
+}
+
+extern "C" int tvk_pool_patch_metadata(tvk_ctx* c, uint32_t n, const uint32_t* brick_index, const uint32_t* value) {
+  if (!c || !c->has_pool || (n && (!brick_index || !value))) return TVK_ERR_INVALID;
+  if (!n) return TVK_OK;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  uint32_t* d = nullptr;
+  TVK_CHECK_CUDA(c, cudaMallocAsync(&d, sizeof(uint32_t) * 2 * n, c->stream));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(d, brick_index, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(d + n, value, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
+  patch_meta_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_meta, d, d + n, n, c->pc.total_bricks);
+  c->launches++;
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  TVK_CHECK_CUDA(c, cudaFreeAsync(d, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));   // host arrays may be reused by the caller
+  return TVK_OK;
+}
+
+extern "C" int tvk_pool_get_metadata(tvk_ctx* c, uint32_t* meta, uint32_t n) {
+  if (!c || !c->has_pool || !meta || n != c->pc.total_bricks) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(meta, c->d_meta, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TVK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// transfer functions (RGBA8, fetched NEAREST in the kernels)
+// ---------------------------------------------------------------------------
+static int set_tf(tvk_ctx* c, const uint8_t* rgba, uint32_t w, uint32_t h) {
+  if (!c || !rgba || w == 0 || h == 0) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  if ((size_t)w * h != (size_t)c->tf_w * c->tf_h) {
+    cudaFree(c->d_tf); c->d_tf = nullptr;
+    TVK_CHECK_CUDA(c, cudaMalloc(&c->d_tf, sizeof(uchar4) * (size_t)w * h));
+  }
+  c->tf_w = w; c->tf_h = h;
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf, rgba, sizeof(uchar4) * (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TVK_OK;
+}
+extern "C" int tvk_set_tf1d(tvk_ctx* c, const uint8_t* rgba, uint32_t n) { return set_tf(c, rgba, n, 1); }
+extern "C" int tvk_set_tf2d(tvk_ctx* c, const uint8_t* rgba, uint32_t w, uint32_t h) { return set_tf(c, rgba, w, h); }

@@ -1,0 +1,96 @@
+// Internal definitions shared by the CUDA translation units behind include/tvk_cuda.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "tvk_cuda.h"
+
+// Constants the reference bakes into the generated GLSL (GLVolumePool.cpp:346-483,
+// GLHashTable.cpp:112-135); passed to the kernels as one __grid_constant__ struct.
+struct PoolConst {
+  uint32_t lod_count;
+  uint32_t total_bricks;
+  float    lod_layout[TVK_MAX_LOD][3];   // vLODLayout
+  uint32_t lod_layout_x[TVK_MAX_LOD];    // iLODLayoutSize.x
+  uint32_t lod_layout_xy[TVK_MAX_LOD];   // iLODLayoutSize.y
+  uint32_t lod_offset[TVK_MAX_LOD];      // vLODOffset
+  uint32_t lod_bricks[TVK_MAX_LOD][3];   // integer GetBrickLayout (host tables)
+  uint32_t l0_bricks[3];                 // hash Serialize strides
+  uint32_t capacity[3];                  // poolCapacity
+  uint32_t max_brick[3];                 // maxTotalBrickSize
+  uint32_t pool_dim[3];                  // iPoolSize (voxels)
+  float    pool_size[3];                 // vec3(iPoolSize)
+  float    overlap_tc[3];                // "overlap" in pool tex coords
+  float    volume_size[3];               // volumeSize
+  uint32_t bpv;
+};
+
+struct BuildState {
+  tvk_build_desc desc{};
+  tvk_build_info info{};
+  std::vector<uint64_t> offsets;     // byte offset per brick
+  std::vector<uint32_t> sizes;       // 3 per brick
+  void*     d_store = nullptr;       // brick store
+  uint64_t* d_offsets = nullptr;
+  uint32_t* d_sizes = nullptr;
+  double*   d_minmax = nullptr;      // 2 per brick
+  unsigned long long* d_hist1d = nullptr;
+  void*     d_lod[TVK_MAX_LOD] = {}; // flat LOD volumes (lod 0 = raw when raw_on_device)
+  bool      own_lod0 = false;
+  bool      valid = false;
+};
+
+struct tvk_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;       // render / builder stream
+  cudaStream_t copy_stream = nullptr;  // pager side stream
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, copy_done = nullptr, render_done = nullptr;
+  std::string err;
+
+  // pool
+  bool has_pool = false;
+  tvk_pool_desc pdesc{};
+  PoolConst pc{};
+  void* d_pool = nullptr;              // linear pool (TVK_SAMPLER_EXACT)
+  cudaArray_t pool_array = nullptr;    // 3-D array (TVK_SAMPLER_TEX3D)
+  cudaTextureObject_t pool_tex = 0;
+  uint32_t* d_meta = nullptr;
+  double* d_minmax = nullptr;
+  double* d_gminmax = nullptr;
+  uint32_t n_minmax = 0;
+  uint32_t* d_counts = nullptr;
+
+  // transfer functions
+  uchar4* d_tf = nullptr;
+  uint32_t tf_w = 0, tf_h = 0;
+
+  // frame state
+  uint32_t width = 0, height = 0;
+  float4* d_image = nullptr;           // accRayColor / composed iso image
+  float4* d_pos[2] = {nullptr, nullptr};   // rayStartPoint ping-pong
+  float4* d_aux[2] = {nullptr, nullptr};   // rayStartColor (iso: normal) ping-pong
+  int cur = 0;
+  uint32_t* d_hash = nullptr;
+  uint32_t hash_size = 0;
+  uint32_t* d_tile_counter = nullptr;
+  unsigned long long* d_stats = nullptr;   // samples, rays, brick steps
+  float last_raycast_ms = 0.f;
+  uint32_t launches = 0;
+
+  BuildState build;
+};
+
+#define TVK_CHECK_CUDA(ctx, call)                                                       \
+  do {                                                                                  \
+    cudaError_t _e = (call);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e);                  \
+      return (_e == cudaErrorMemoryAllocation) ? TVK_ERR_NOMEM : TVK_ERR_CUDA;          \
+    }                                                                                   \
+  } while (0)
+
+#define TVK_FAIL(ctx, code, msg) do { (ctx)->err = (msg); return (code); } while (0)
+
+void tvk_compute_pool_const(const tvk_pool_desc& d, PoolConst& pc);
+int  tvk_ensure_frame(tvk_ctx* ctx, uint32_t w, uint32_t h, uint32_t hash_size);

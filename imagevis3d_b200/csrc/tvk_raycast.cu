@@ -1,0 +1,739 @@
+// K1 -- persistent-warp ray-march kernel (sm_100a).
+//
+// Replaces, in one launch per sub-frame, what the reference does with two raster
+// passes and a fragment shader (paths relative to /root/reference/Tuvok/):
+//   ray entry / exit      GLGridLeaper::FillRayEntryBuffer + bbox back faces
+//                         (Renderer/GL/GLGridLeaper.cpp:579-620,835-843)          -> ray_setup()
+//   traversal             Shaders/GLGridLeaper-blend.glsl:65-228, -iso.glsl:68-200 -> march_*()
+//   page-table walk       generated GLSL, Renderer/GL/GLVolumePool.cpp:484-656    -> get_brick()
+//   request table         generated GLSL, Renderer/GL/GLHashTable.cpp:136-182     -> hash_report()
+//   sample -> colour      Shaders/GLGridLeaper-Method-{1D,1D-L,2D,2D-L,iso}.glsl,
+//                         GLGridLeaper-GradientTools.glsl, lighting.glsl, Compositing.glsl
+//   iso shading           Shaders/Compose-FS.glsl:47-75 (fused into the epilogue)
+//
+// Execution model: a persistent grid (CTAs x 4 warps, sized from the SM count);
+// every warp repeatedly claims an 8x4 pixel tile from a global counter, so
+// early-terminated / empty-space tiles cost nothing and the tail is balanced.
+// Neighbouring rays of a tile walk the same bricks, so their 2x2x2 voxel
+// footprints share L1 lines.  The page table (<= 6 MB) and the transfer function
+// stay L2/L1 resident.  Ray state (resume pos / colour) lives in HBM as float4
+// planes and is updated in place: each pixel only ever touches its own entry.
+#include "tvk_internal.h"
+#include <cmath>
+
+struct RayParams {
+  tvk_raycast_params p;
+  PoolConst pc;
+  const void* pool;
+  cudaTextureObject_t tex;
+  const uint32_t* meta;
+  const uchar4* tf;
+  uint32_t tf_w, tf_h;
+  uint32_t* hash;
+  float4* pos;      // rayStartPoint / rayResumePos
+  float4* aux;      // rayStartColor / rayResumeColor (iso: normal)
+  float4* image;    // accRayColor (iso: composed image)
+  uint32_t* tile_counter;
+  unsigned long long* stats;
+  uint32_t tiles_x, tiles_y;
+};
+
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ float len3(f3 v) { return sqrtf(v.x * v.x + v.y * v.y + v.z * v.z); }
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
+// v' = v*M, FLOATMATRIX4 memory order (Basics/Vectors.h:434)
+__device__ __forceinline__ float4 xform(const float* m, f3 v, float w) {
+  float4 o;
+  o.x = v.x * m[0] + v.y * m[4] + v.z * m[8] + w * m[12];
+  o.y = v.x * m[1] + v.y * m[5] + v.z * m[9] + w * m[13];
+  o.z = v.x * m[2] + v.y * m[6] + v.z * m[10] + w * m[14];
+  o.w = v.x * m[3] + v.y * m[7] + v.z * m[11] + w * m[15];
+  return o;
+}
+
+// ComputeLOD, GLVolumePool.cpp:653-656.  log2 is evaluated in fp64 and rounded
+// to fp32 so that the truncation agrees with a correctly rounded log2f on the
+// CPU side (bit-exact LOD selection); negative / NaN saturate to 0 like NVIDIA's
+// GLSL uint().
+__device__ __forceinline__ uint32_t compute_lod(float dist, float lod_factor, float wse, uint32_t max_lod) {
+  const float x = lod_factor * (-dist) / wse;
+  const float v = (float)log2((double)x);
+  const uint32_t l = (v > 0.0f) ? ((v >= 4294967296.0f) ? 0xFFFFFFFFu : (uint32_t)v) : 0u;
+  return min(l, max_lod);
+}
+
+__device__ __forceinline__ uint4 brick_coords(const PoolConst& pc, f3 p, uint32_t lod) {
+  return make_uint4((uint32_t)(p.x * pc.lod_layout[lod][0]), (uint32_t)(p.y * pc.lod_layout[lod][1]),
+                    (uint32_t)(p.z * pc.lod_layout[lod][2]), lod);
+}
+__device__ __forceinline__ uint32_t brick_index(const PoolConst& pc, uint4 bc) {
+  return pc.lod_offset[bc.w] + bc.x + bc.y * pc.lod_layout_x[bc.w] + bc.z * pc.lod_layout_xy[bc.w];
+}
+__device__ __forceinline__ uint32_t serialize(const PoolConst& pc, uint4 bc) {
+  return 1u + bc.x + bc.y * pc.l0_bricks[0] + bc.z * pc.l0_bricks[0] * pc.l0_bricks[1] +
+         bc.w * pc.l0_bricks[0] * pc.l0_bricks[1] * pc.l0_bricks[2];
+}
+
+// Hash(), GLHashTable.cpp:170-182.  A plain read first: once a brick is in the
+// table (the common case: thousands of rays report the same brick) no atomic is
+// issued at all; semantics are those of the CAS loop.
+__device__ __forceinline__ void hash_report(const RayParams& rp, uint4 bc) {
+  const uint32_t serial = serialize(rp.pc, bc);
+  for (uint32_t rehash = 0; rehash < rp.p.rehash_count; ++rehash) {
+    const uint32_t h = (serial + rehash) % rp.p.hash_table_size;
+    uint32_t cur = *reinterpret_cast<volatile uint32_t*>(rp.hash + h);
+    if (cur == serial) return;
+    if (cur == 0u) {
+      cur = atomicCAS(rp.hash + h, 0u, serial);
+      if (cur == 0u || cur == serial) return;
+    }
+  }
+}
+
+struct BrickHit {
+  f3 pool_entry, pool_exit, norm_exit, scale, trans;
+  uint4 bc;
+  bool empty, found;
+};
+
+// GetBrick, GLVolumePool.cpp:552-620
+__device__ __forceinline__ void get_brick(const RayParams& rp, f3 entry, uint32_t& lod, f3 dir, BrickHit& b) {
+  const PoolConst& pc = rp.pc;
+  const uint32_t max_lod = pc.lod_count - 1;
+  const f3 e = mk3(clamp01(entry.x), clamp01(entry.y), clamp01(entry.z));
+  b.found = true;
+  b.bc = brick_coords(pc, e, lod);
+  uint32_t info = __ldg(rp.meta + brick_index(pc, b.bc));
+  if (info == TVK_BI_MISSING) {
+    const uint32_t start = lod;
+    hash_report(rp, b.bc);
+    b.found = false;
+    do {
+      lod++;
+      b.bc = brick_coords(pc, e, lod);
+      info = __ldg(rp.meta + brick_index(pc, b.bc));
+      if (info == TVK_BI_MISSING) {
+        const uint32_t s = rp.p.missing_strategy;
+        if (s == TVK_MBS_REQUEST_ALL || (s == TVK_MBS_SKIP_ONE_LEVEL && start + 1 == lod) ||
+            (s == TVK_MBS_SKIP_TWO_LEVELS && start + 2 == lod))
+          hash_report(rp, b.bc);
+      }
+    } while (info == TVK_BI_MISSING && lod < max_lod);   // the coarsest brick is pinned resident
+  }
+  b.empty = (info <= TVK_BI_EMPTY);
+  if (b.empty) {
+    for (uint32_t l = lod + 1; l < max_lod; ++l) {
+      const uint4 lbc = brick_coords(pc, e, l);
+      const uint32_t linfo = __ldg(rp.meta + brick_index(pc, lbc));
+      if (linfo == TVK_BI_CHILD_EMPTY) { b.bc = lbc; info = linfo; lod = l; }
+      else break;
+    }
+  }
+  const float lx = pc.lod_layout[b.bc.w][0], ly = pc.lod_layout[b.bc.w][1], lz = pc.lod_layout[b.bc.w][2];
+  const f3 c0 = mk3((float)b.bc.x / lx, (float)b.bc.y / ly, (float)b.bc.z / lz);
+  const f3 c1 = mk3((float)(b.bc.x + 1) / lx, (float)(b.bc.y + 1) / ly, (float)(b.bc.z + 1) / lz);
+  // BrickExit: side = step(0, 1/dir)
+  const float dvx = 1.0f / dir.x, dvy = 1.0f / dir.y, dvz = 1.0f / dir.z;
+  const float tx = ((dvx >= 0.0f ? c1.x : c0.x) - e.x) * dvx;
+  const float ty = ((dvy >= 0.0f ? c1.y : c0.y) - e.y) * dvy;
+  const float tz = ((dvz >= 0.0f ? c1.z : c0.z) - e.z) * dvz;
+  const float tmin = fminf(fminf(fminf(INFINITY, tx), ty), tz);   // fminf drops NaN (0*inf)
+  b.norm_exit = mk3(e.x + tmin * dir.x, e.y + tmin * dir.y, e.z + tmin * dir.z);
+  if (b.empty) return;
+  const uint32_t idx = info - TVK_BI_FLAG_COUNT;
+  const uint32_t s0 = idx % pc.capacity[0], s1 = (idx / pc.capacity[0]) % pc.capacity[1],
+                 s2 = idx / (pc.capacity[0] * pc.capacity[1]);
+  {
+    const uint32_t v = s0 * pc.max_brick[0];
+    const float p0 = (float)v / pc.pool_size[0] + pc.overlap_tc[0];
+    const float p1 = (float)(v + pc.max_brick[0]) / pc.pool_size[0] - pc.overlap_tc[0];
+    b.scale.x = (p1 - p0) / (c1.x - c0.x);
+    b.trans.x = p0 - c0.x * b.scale.x;
+  }
+  {
+    const uint32_t v = s1 * pc.max_brick[1];
+    const float p0 = (float)v / pc.pool_size[1] + pc.overlap_tc[1];
+    const float p1 = (float)(v + pc.max_brick[1]) / pc.pool_size[1] - pc.overlap_tc[1];
+    b.scale.y = (p1 - p0) / (c1.y - c0.y);
+    b.trans.y = p0 - c0.y * b.scale.y;
+  }
+  {
+    const uint32_t v = s2 * pc.max_brick[2];
+    const float p0 = (float)v / pc.pool_size[2] + pc.overlap_tc[2];
+    const float p1 = (float)(v + pc.max_brick[2]) / pc.pool_size[2] - pc.overlap_tc[2];
+    b.scale.z = (p1 - p0) / (c1.z - c0.z);
+    b.trans.z = p0 - c0.z * b.scale.z;
+  }
+  b.pool_entry = mk3(e.x * b.scale.x + b.trans.x, e.y * b.scale.y + b.trans.y, e.z * b.scale.z + b.trans.z);
+  b.pool_exit = mk3(b.norm_exit.x * b.scale.x + b.trans.x, b.norm_exit.y * b.scale.y + b.trans.y,
+                    b.norm_exit.z * b.scale.z + b.trans.z);
+}
+
+// texture(volumePool, p).r -- GL_LINEAR, CLAMP_TO_EDGE, UNORM8/16.
+template <int BPV, bool TEX>
+__device__ __forceinline__ float sample_pool(const RayParams& rp, f3 p) {
+  if (TEX) {
+    return tex3D<float>(rp.tex, p.x, p.y, p.z);
+  } else {
+    const PoolConst& pc = rp.pc;
+    const float u = p.x * pc.pool_size[0] - 0.5f, v = p.y * pc.pool_size[1] - 0.5f, w = p.z * pc.pool_size[2] - 0.5f;
+    const float fu = floorf(u), fv = floorf(v), fw = floorf(w);
+    const int x = (int)fu, y = (int)fv, z = (int)fw;
+    const float a = u - fu, b = v - fv, g = w - fw;
+    const int mx = (int)pc.pool_dim[0] - 1, my = (int)pc.pool_dim[1] - 1, mz = (int)pc.pool_dim[2] - 1;
+    const int x0 = min(max(x, 0), mx), x1 = min(max(x + 1, 0), mx);
+    const int y0 = min(max(y, 0), my), y1 = min(max(y + 1, 0), my);
+    const int z0 = min(max(z, 0), mz), z1 = min(max(z + 1, 0), mz);
+    const size_t sx = pc.pool_dim[0], sxy = sx * pc.pool_dim[1];
+    const size_t r00 = (size_t)y0 * sx + (size_t)z0 * sxy, r10 = (size_t)y1 * sx + (size_t)z0 * sxy;
+    const size_t r01 = (size_t)y0 * sx + (size_t)z1 * sxy, r11 = (size_t)y1 * sx + (size_t)z1 * sxy;
+    float c000, c100, c010, c110, c001, c101, c011, c111;
+    if (BPV == 1) {
+      const uint8_t* d = static_cast<const uint8_t*>(rp.pool);
+      const float k = 1.0f / 255.0f;
+      c000 = (float)__ldg(d + r00 + x0) * k; c100 = (float)__ldg(d + r00 + x1) * k;
+      c010 = (float)__ldg(d + r10 + x0) * k; c110 = (float)__ldg(d + r10 + x1) * k;
+      c001 = (float)__ldg(d + r01 + x0) * k; c101 = (float)__ldg(d + r01 + x1) * k;
+      c011 = (float)__ldg(d + r11 + x0) * k; c111 = (float)__ldg(d + r11 + x1) * k;
+    } else {
+      const uint16_t* d = static_cast<const uint16_t*>(rp.pool);
+      const float k = 1.0f / 65535.0f;
+      c000 = (float)__ldg(d + r00 + x0) * k; c100 = (float)__ldg(d + r00 + x1) * k;
+      c010 = (float)__ldg(d + r10 + x0) * k; c110 = (float)__ldg(d + r10 + x1) * k;
+      c001 = (float)__ldg(d + r01 + x0) * k; c101 = (float)__ldg(d + r01 + x1) * k;
+      c011 = (float)__ldg(d + r11 + x0) * k; c111 = (float)__ldg(d + r11 + x1) * k;
+    }
+    const float c00 = c000 + a * (c100 - c000), c10 = c010 + a * (c110 - c010);
+    const float c01 = c001 + a * (c101 - c001), c11 = c011 + a * (c111 - c011);
+    const float c0 = c00 + b * (c10 - c00), c1 = c01 + b * (c11 - c01);
+    return c0 + g * (c1 - c0);
+  }
+}
+
+__device__ __forceinline__ int nearest_index(float s, uint32_t n) {
+  const float f = floorf(s * (float)n);
+  if (!(f > 0.0f)) return 0;
+  return f >= (float)n ? (int)n - 1 : (int)f;
+}
+__device__ __forceinline__ float4 tf_fetch(const RayParams& rp, int i) {
+  const uchar4 t = __ldg(rp.tf + i);
+  const float k = 1.0f / 255.0f;
+  return make_float4((float)t.x * k, (float)t.y * k, (float)t.z * k, (float)t.w * k);
+}
+
+// ComputeGradient, GLGridLeaper-GradientTools.glsl:6-16 (y sign flipped there)
+template <int BPV, bool TEX>
+__device__ __forceinline__ f3 gradient(const RayParams& rp, f3 p) {
+  const float dx = 1.0f / rp.pc.pool_size[0], dy = 1.0f / rp.pc.pool_size[1], dz = 1.0f / rp.pc.pool_size[2];
+  const float xp = sample_pool<BPV, TEX>(rp, mk3(p.x + dx, p.y, p.z)), xm = sample_pool<BPV, TEX>(rp, mk3(p.x - dx, p.y, p.z));
+  const float yp = sample_pool<BPV, TEX>(rp, mk3(p.x, p.y - dy, p.z)), ym = sample_pool<BPV, TEX>(rp, mk3(p.x, p.y + dy, p.z));
+  const float zp = sample_pool<BPV, TEX>(rp, mk3(p.x, p.y, p.z + dz)), zm = sample_pool<BPV, TEX>(rp, mk3(p.x, p.y, p.z - dz));
+  return mk3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
+}
+
+__device__ __forceinline__ float pow8(float x) { x *= x; x *= x; return x * x; }
+
+// Lighting, lighting.glsl:33-43
+__device__ __forceinline__ f3 lighting(const tvk_raycast_params& p, f3 pos, f3 n, f3 diffuse) {
+  f3 v = mk3(p.model_eye_pos[0] - pos.x, p.model_eye_pos[1] - pos.y, p.model_eye_pos[2] - pos.z);
+  float l = len3(v);
+  v = mk3(v.x / l, v.y / l, v.z / l);
+  const float d = dot3(n, v);
+  f3 r = mk3(v.x - 2.0f * d * n.x, v.y - 2.0f * d * n.y, v.z - 2.0f * d * n.z);
+  l = len3(r);
+  r = mk3(r.x / l, r.y / l, r.z / l);
+  const f3 L = mk3(p.model_light_dir[0], p.model_light_dir[1], p.model_light_dir[2]);
+  const float ndl = fmaxf(fabsf(dot3(n, L)), 0.0f);
+  const float spec = pow8(fmaxf(dot3(r, L), 0.0f));
+  return mk3(clamp01(p.light_ambient[0] + diffuse.x * ndl + p.light_specular[0] * spec),
+             clamp01(p.light_ambient[1] + diffuse.y * ndl + p.light_specular[1] * spec),
+             clamp01(p.light_ambient[2] + diffuse.z * ndl + p.light_specular[2] * spec));
+}
+
+// ComputeColorFromVolume, GLGridLeaper-Method-{1D,1D-L,2D,2D-L}.glsl
+template <int MODE, bool LIT, int BPV, bool TEX>
+__device__ __forceinline__ float4 color_from_volume(const RayParams& rp, f3 pc, f3 scale, f3 trans) {
+  const tvk_raycast_params& p = rp.p;
+  const float data = sample_pool<BPV, TEX>(rp, pc);
+  float4 col;
+  f3 n;
+  if (MODE == TVK_RM_1DTRANS) {
+    col = tf_fetch(rp, nearest_index(data * p.trans_scale, rp.tf_w));
+    if (LIT) {
+      const f3 g = gradient<BPV, TEX>(rp, pc);
+      n = mk3(g.x * p.domain_scale[0], g.y * p.domain_scale[1], g.z * p.domain_scale[2]);
+      const float l = len3(n);
+      if (l > 0.0f) n = mk3(n.x / l, n.y / l, n.z / l);
+    }
+  } else {
+    const f3 g = gradient<BPV, TEX>(rp, pc);
+    const float gm = len3(g);
+    col = tf_fetch(rp, nearest_index(1.0f - gm * p.gradient_scale, rp.tf_h) * (int)rp.tf_w +
+                           nearest_index(data * p.trans_scale, rp.tf_w));
+    if (LIT) {
+      const f3 gn = (gm > 0.0f) ? mk3(g.x / gm, g.y / gm, g.z / gm) : g;
+      n = mk3(p.domain_scale[0] * gn.x, p.domain_scale[1] * gn.y, p.domain_scale[2] * gn.z);
+    }
+  }
+  if (LIT) {
+    const f3 mp = mk3((pc.x - trans.x) / scale.x, (pc.y - trans.y) / scale.y, (pc.z - trans.z) / scale.z);
+    const f3 lit = lighting(p, mp, n, mk3(col.x * p.light_diffuse[0], col.y * p.light_diffuse[1], col.z * p.light_diffuse[2]));
+    col.x = lit.x; col.y = lit.y; col.z = lit.z;
+  }
+  return col;
+}
+
+// Analytic ray set-up (pixel-centre ray against the unit box in normalised volume
+// coordinates); same arithmetic as oracle ray_setup().
+__device__ __forceinline__ bool ray_setup(const tvk_raycast_params& p, uint32_t px, uint32_t py, float4& entry, float4& exitp) {
+  const f3 ndc = mk3(((float)px + 0.5f) / (float)p.width * 2.0f - 1.0f, ((float)py + 0.5f) / (float)p.height * 2.0f - 1.0f, -1.0f);
+  const float4 n4 = xform(p.inv_projection, ndc, 1.0f);
+  const f3 n = mk3(n4.x / n4.w, n4.y / n4.w, n4.z / n4.w);
+  const float4 O = xform(p.eye_to_model, mk3(0.f, 0.f, 0.f), 1.0f);
+  const float4 D = xform(p.eye_to_model, n, 0.0f);
+  float s0 = -INFINITY, s1 = INFINITY;
+  const float o[3] = {O.x, O.y, O.z}, d[3] = {D.x, D.y, D.z};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (d[a] == 0.0f) {
+      if (o[a] < 0.0f || o[a] > 1.0f) return false;
+      continue;
+    }
+    const float inv = 1.0f / d[a];
+    float ta = (0.0f - o[a]) * inv, tb = (1.0f - o[a]) * inv;
+    if (ta > tb) { const float t = ta; ta = tb; tb = t; }
+    s0 = fmaxf(s0, ta);
+    s1 = fminf(s1, tb);
+  }
+  if (p.clip_enabled) {
+    const float dn = p.clip_plane[0] * D.x + p.clip_plane[1] * D.y + p.clip_plane[2] * D.z;
+    const float on = p.clip_plane[0] * O.x + p.clip_plane[1] * O.y + p.clip_plane[2] * O.z + p.clip_plane[3];
+    if (dn == 0.0f) { if (on > 0.0f) return false; }
+    else {
+      const float t = -on / dn;
+      if (dn > 0.0f) s1 = fminf(s1, t); else s0 = fmaxf(s0, t);
+    }
+  }
+  const float se = fmaxf(s0, 1.0f);
+  if (!(s1 > se)) return false;
+  const f3 pe = mk3(n.x * se, n.y * se, n.z * se), px1 = mk3(n.x * s1, n.y * s1, n.z * s1);
+  float4 t4 = xform(p.eye_to_model, pe, 1.0f);
+  entry = make_float4(t4.x, t4.y, t4.z, pe.z);
+  t4 = xform(p.eye_to_model, px1, 1.0f);
+  exitp = make_float4(t4.x, t4.y, t4.z, px1.z);
+  return true;
+}
+
+struct Counters { unsigned long long samples, bricks; };
+
+// GLGridLeaper-blend.glsl main()
+template <int MODE, bool LIT, int BPV, bool TEX>
+__device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, float4& pos, float4& col, float4& acc, Counters& cn) {
+  const tvk_raycast_params& p = rp.p;
+  const PoolConst& pc = rp.pc;
+  acc = col;
+  const f3 entry = mk3(pos.x, pos.y, pos.z);
+  const float entry_depth = pos.w, exit_depth = exitp.w;
+  const f3 dir = mk3(exitp.x - entry.x, exitp.y - entry.y, exitp.z - entry.z);
+  const float ray_len = len3(dir);
+  f3 vdir = mk3(dir.x * pc.volume_size[0], dir.y * pc.volume_size[1], dir.z * pc.volume_size[2]);
+  const float vl = len3(vdir);
+  const float den = 2.0f * p.sample_rate_modifier;
+  vdir = mk3(vdir.x / vl / pc.pool_size[0] / den, vdir.y / vl / pc.pool_size[1] / den, vdir.z / vl / pc.pool_size[2] / den);
+  const float step_size = len3(vdir);
+  float t = 0.0f;
+  bool optimal = true;
+  const float voxel_size = 0.125f / 2000.0f;
+  f3 cur = entry;
+  uint4 last_bc = make_uint4(0, 0, 0, 9999);
+  const float oc = 1.0f / p.sample_rate_modifier;
+  if (ray_len > voxel_size) {
+    for (uint32_t j = 0; j < 100; ++j) {
+      const float depth = entry_depth * (1.0f - t) + exit_depth * t;
+      uint32_t lod = compute_lod(depth, p.lod_factor, p.level_zero_wse, pc.lod_count - 1);
+      BrickHit b;
+      get_brick(rp, cur, lod, dir, b);
+      cn.bricks++;
+      if (!b.found && optimal) {
+        optimal = false;
+        pos = make_float4(cur.x, cur.y, cur.z, depth);
+        col = acc;
+      }
+      if (!b.empty && (last_bc.x != b.bc.x || last_bc.y != b.bc.y || last_bc.z != b.bc.z || last_bc.w != b.bc.w)) {
+        int steps = (int)ceilf(len3(mk3(b.pool_exit.x - b.pool_entry.x, b.pool_exit.y - b.pool_entry.y, b.pool_exit.z - b.pool_entry.z)) / step_size);
+        const int s2 = (int)ceilf(len3(mk3((exitp.x - cur.x) * b.scale.x, (exitp.y - cur.y) * b.scale.y, (exitp.z - cur.z) * b.scale.z)) / step_size);
+        steps = min(steps, s2);
+        f3 q = b.pool_entry;
+        for (int i = 0; i < steps; ++i) {
+          float4 s = color_from_volume<MODE, LIT, BPV, TEX>(rp, q, b.scale, b.trans);
+          cn.samples++;
+          s.w = (oc == 1.0f) ? 1.0f - (1.0f - s.w) : 1.0f - powf(1.0f - s.w, oc);
+          const float w = (1.0f - acc.w) * s.w;       // UnderCompositing, Compositing.glsl:33-38
+          acc.x += s.x * w; acc.y += s.y * w; acc.z += s.z * w;
+          acc.w += s.w * (1.0f - acc.w);
+          if (acc.w > 0.99f) {
+            if (optimal) { pos.w = 1000.0f; col = acc; }
+            return;
+          }
+          q = mk3(q.x + vdir.x, q.y + vdir.y, q.z + vdir.z);
+        }
+        cur = mk3((q.x - b.trans.x) / b.scale.x, (q.y - b.trans.y) / b.scale.y, (q.z - b.trans.z) / b.scale.z);
+      } else {
+        cur = mk3(b.norm_exit.x + voxel_size * dir.x / ray_len, b.norm_exit.y + voxel_size * dir.y / ray_len,
+                  b.norm_exit.z + voxel_size * dir.z / ray_len);
+      }
+      last_bc = b.bc;
+      t = len3(mk3(entry.x - b.norm_exit.x, entry.y - b.norm_exit.y, entry.z - b.norm_exit.z)) / ray_len;
+      if (t > 0.9999f) break;
+    }
+  }
+  if (optimal) { pos.w = 1000.0f; col = acc; }
+}
+
+// GLGridLeaper-iso.glsl main() + GLGridLeaper-Method-iso.glsl
+template <int BPV, bool TEX>
+__device__ __forceinline__ void march_ray_iso(const RayParams& rp, float4 exitp, float4& pos, float4& nrm, float4& hit, float4& hitn, Counters& cn) {
+  const tvk_raycast_params& p = rp.p;
+  const PoolConst& pc = rp.pc;
+  hit = make_float4(0.f, 0.f, 0.f, 0.f);
+  hitn = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (floorf(pos.w) == 1000.0f) return;
+  if (floorf(pos.w) == 500.0f) {
+    const float4 h4 = xform(p.model_to_eye, mk3(pos.x, pos.y, pos.z), 1.0f);
+    hit = make_float4(h4.x, h4.y, h4.z, pos.w - floorf(pos.w) + 1.0f);
+    hitn = nrm;
+    return;
+  }
+  const f3 entry = mk3(pos.x, pos.y, pos.z);
+  const float entry_depth = pos.w, exit_depth = exitp.w;
+  const f3 dir = mk3(exitp.x - entry.x, exitp.y - entry.y, exitp.z - entry.z);
+  const float ray_len = len3(dir);
+  f3 vdir = mk3(dir.x * pc.volume_size[0], dir.y * pc.volume_size[1], dir.z * pc.volume_size[2]);
+  const float vl = len3(vdir);
+  const float den = 2.0f * p.sample_rate_modifier;
+  vdir = mk3(vdir.x / vl / pc.pool_size[0] / den, vdir.y / vl / pc.pool_size[1] / den, vdir.z / vl / pc.pool_size[2] / den);
+  const float step_size = len3(vdir);
+  float t = 0.0f;
+  bool optimal = true;
+  const float voxel_size = 0.125f / 2000.0f;
+  f3 cur = entry;
+  uint4 last_bc = make_uint4(0, 0, 0, 9999);
+  if (ray_len > voxel_size) {
+    for (uint32_t j = 0; j < 100; ++j) {
+      const float depth = entry_depth * (1.0f - t) + exit_depth * t;
+      uint32_t lod = compute_lod(depth, p.lod_factor, p.level_zero_wse, pc.lod_count - 1);
+      BrickHit b;
+      get_brick(rp, cur, lod, dir, b);
+      cn.bricks++;
+      if (!b.found && optimal) {
+        optimal = false;
+        pos = make_float4(cur.x, cur.y, cur.z, depth);
+      }
+      if (!b.empty && (last_bc.x != b.bc.x || last_bc.y != b.bc.y || last_bc.z != b.bc.z || last_bc.w != b.bc.w)) {
+        int steps = (int)ceilf(len3(mk3(b.pool_exit.x - b.pool_entry.x, b.pool_exit.y - b.pool_entry.y, b.pool_exit.z - b.pool_entry.z)) / step_size);
+        const int s2 = (int)ceilf(len3(mk3((exitp.x - cur.x) * b.scale.x, (exitp.y - cur.y) * b.scale.y, (exitp.z - cur.z) * b.scale.z)) / step_size);
+        steps = min(steps, s2);
+        f3 q = b.pool_entry;
+        for (int i = 0; i < steps; ++i) {
+          cn.samples++;
+          if (sample_pool<BPV, TEX>(rp, q) >= p.isoval) {
+            f3 rd = mk3(vdir.x / 2.0f, vdir.y / 2.0f, vdir.z / 2.0f);       // RefineIsosurface
+            q = mk3(q.x - rd.x, q.y - rd.y, q.z - rd.z);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+              rd = mk3(rd.x / 2.0f, rd.y / 2.0f, rd.z / 2.0f);
+              if (sample_pool<BPV, TEX>(rp, q) >= p.isoval) q = mk3(q.x - rd.x, q.y - rd.y, q.z - rd.z);
+              else q = mk3(q.x + rd.x, q.y + rd.y, q.z + rd.z);
+            }
+            cur = mk3((q.x - b.trans.x) / b.scale.x, (q.y - b.trans.y) / b.scale.y, (q.z - b.trans.z) / b.scale.z);
+            const float4 h4 = xform(p.model_to_eye, cur, 1.0f);
+            hit = make_float4(h4.x, h4.y, h4.z, 2.0f);                       // color.r + 1
+            const f3 g = gradient<BPV, TEX>(rp, q);
+            f3 n = mk3(g.x * p.domain_scale[0], g.y * p.domain_scale[1], g.z * p.domain_scale[2]);
+            const float l = len3(n);
+            if (l > 0.0f) n = mk3(n.x / l, n.y / l, n.z / l);
+            const float4 n4 = xform(p.model_view_it, n, 0.0f);
+            hitn = make_float4(n4.x, n4.y, n4.z, 513.0f);                    // floor(color.g*512)+color.b
+            if (optimal) pos.w = 499.0f + hit.w;                             // TerminateRay; xyz untouched
+            nrm = hitn;
+            return;
+          }
+          q = mk3(q.x + vdir.x, q.y + vdir.y, q.z + vdir.z);
+        }
+        cur = mk3((q.x - b.trans.x) / b.scale.x, (q.y - b.trans.y) / b.scale.y, (q.z - b.trans.z) / b.scale.z);
+      } else {
+        cur = mk3(b.norm_exit.x + voxel_size * dir.x / ray_len, b.norm_exit.y + voxel_size * dir.y / ray_len,
+                  b.norm_exit.z + voxel_size * dir.z / ray_len);
+      }
+      last_bc = b.bc;
+      t = len3(mk3(entry.x - b.norm_exit.x, entry.y - b.norm_exit.y, entry.z - b.norm_exit.z)) / ray_len;
+      if (t > 0.9999f) break;
+    }
+  }
+  if (optimal) pos.w = 1000.0f;
+  nrm = hitn;
+}
+
+// Compose-FS.glsl:47-75 with the uniforms of GLRenderer::ComposeSurfaceImage (:2763-2811)
+__device__ __forceinline__ float4 compose_iso(const tvk_raycast_params& p, float4 hit, float4 hitn) {
+  if (hit.w == 0.0f) return make_float4(0.f, 0.f, 0.f, 0.f);
+  const f3 n = mk3(hitn.x, hitn.y, fabsf(hitn.z));
+  f3 v = mk3(0.0f - hit.x, 0.0f - hit.y, 0.0f - hit.z);
+  float l = len3(v);
+  v = mk3(v.x / l, v.y / l, v.z / l);
+  const float d = dot3(n, v);
+  f3 r = mk3(v.x - 2.0f * d * n.x, v.y - 2.0f * d * n.y, v.z - 2.0f * d * n.z);
+  l = len3(r);
+  r = mk3(r.x / l, r.y / l, r.z / l);
+  const f3 L = mk3(p.compose_light_dir[0], p.compose_light_dir[1], p.compose_light_dir[2]);
+  const float ndl = fmaxf(fabsf(dot3(n, mk3(-L.x, -L.y, -L.z))), 0.0f);
+  const float spec = pow8(fmaxf(dot3(r, L), 0.0f));
+  return make_float4(clamp01(p.light_ambient[0] + p.light_diffuse[0] * p.iso_color[0] * ndl + p.light_specular[0] * spec),
+                     clamp01(p.light_ambient[1] + p.light_diffuse[1] * p.iso_color[1] * ndl + p.light_specular[1] * spec),
+                     clamp01(p.light_ambient[2] + p.light_diffuse[2] * p.iso_color[2] * ndl + p.light_specular[2] * spec), 1.0f);
+}
+
+template <int MODE, bool LIT, int BPV, bool TEX>
+__global__ void __launch_bounds__(128) raycast_kernel(const __grid_constant__ RayParams rp) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t ntiles = rp.tiles_x * rp.tiles_y;
+  Counters cn;
+  cn.samples = 0; cn.bricks = 0;
+  unsigned long long nrays = 0;
+  for (;;) {
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(rp.tile_counter, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= ntiles) break;
+    const uint32_t px = (tile % rp.tiles_x) * 8u + (lane & 7u), py = (tile / rp.tiles_x) * 4u + (lane >> 3);
+    if (px >= rp.p.width || py >= rp.p.height) continue;
+    const size_t i = (size_t)py * rp.p.width + px;
+    float4 entry, exitp;
+    if (!ray_setup(rp.p, px, py, entry, exitp)) {
+      if (rp.p.new_view) {
+        rp.image[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rp.aux[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rp.pos[i] = make_float4(0.f, 0.f, 0.f, 1000.0f);
+      }
+      continue;
+    }
+    float4 pos, aux;
+    if (rp.p.new_view) { pos = entry; aux = make_float4(0.f, 0.f, 0.f, 0.f); }
+    else { pos = rp.pos[i]; }
+    nrays++;
+    if (MODE == TVK_RM_ISOSURFACE) {
+      if (!rp.p.new_view) {
+        if (floorf(pos.w) == 1000.0f) continue;      // finished without a hit: image stays 0
+        aux = rp.aux[i];
+      }
+      float4 hit, hitn;
+      march_ray_iso<BPV, TEX>(rp, exitp, pos, aux, hit, hitn, cn);
+      rp.image[i] = compose_iso(rp.p, hit, hitn);
+    } else {
+      if (!rp.p.new_view) {
+        if (pos.w == 1000.0f) continue;              // finished: image already holds rayResumeColor
+        aux = rp.aux[i];
+      }
+      float4 acc;
+      march_ray<MODE, LIT, BPV, TEX>(rp, exitp, pos, aux, acc, cn);
+      rp.image[i] = acc;
+    }
+    rp.pos[i] = pos;
+    rp.aux[i] = aux;
+  }
+  if (rp.p.count_samples) {
+    for (int o = 16; o > 0; o >>= 1) {
+      cn.samples += __shfl_down_sync(0xffffffffu, cn.samples, o);
+      cn.bricks += __shfl_down_sync(0xffffffffu, cn.bricks, o);
+      nrays += __shfl_down_sync(0xffffffffu, nrays, o);
+    }
+    if (lane == 0) {
+      atomicAdd(rp.stats + 0, cn.samples);
+      atomicAdd(rp.stats + 1, nrays);
+      atomicAdd(rp.stats + 2, cn.bricks);
+    }
+  }
+}
+
+typedef void (*raycast_fn)(const RayParams);
+
+template <int BPV, bool TEX>
+static raycast_fn pick_kernel(uint32_t mode, bool lit) {
+  if (mode == TVK_RM_ISOSURFACE) return raycast_kernel<TVK_RM_ISOSURFACE, false, BPV, TEX>;
+  if (mode == TVK_RM_1DTRANS) return lit ? raycast_kernel<TVK_RM_1DTRANS, true, BPV, TEX> : raycast_kernel<TVK_RM_1DTRANS, false, BPV, TEX>;
+  return lit ? raycast_kernel<TVK_RM_2DTRANS, true, BPV, TEX> : raycast_kernel<TVK_RM_2DTRANS, false, BPV, TEX>;
+}
+
+extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
+  if (!c || !p) return TVK_ERR_INVALID;
+  if (!c->has_pool) TVK_FAIL(c, TVK_ERR_INVALID, "no brick pool");
+  if (p->render_mode > TVK_RM_ISOSURFACE) TVK_FAIL(c, TVK_ERR_INVALID, "bad render mode");
+  if (p->render_mode != TVK_RM_ISOSURFACE && !c->d_tf) TVK_FAIL(c, TVK_ERR_INVALID, "no transfer function");
+  if (p->render_mode == TVK_RM_1DTRANS && c->tf_h != 1) TVK_FAIL(c, TVK_ERR_INVALID, "1D mode needs a 1D transfer function");
+  if (p->hash_table_size == 0 || p->rehash_count == 0) TVK_FAIL(c, TVK_ERR_INVALID, "bad hash table parameters");
+  if (!(p->sample_rate_modifier > 0.0f)) TVK_FAIL(c, TVK_ERR_INVALID, "bad sample rate modifier");
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  const bool fresh = (c->width != p->width || c->height != p->height);
+  int rc = tvk_ensure_frame(c, p->width, p->height, p->hash_table_size);
+  if (rc) return rc;
+  if (fresh && !p->new_view) TVK_FAIL(c, TVK_ERR_INVALID, "first sub-frame after a resize must be a new view");
+
+  RayParams rp;
+  rp.p = *p;
+  rp.pc = c->pc;
+  rp.pool = c->d_pool;
+  rp.tex = c->pool_tex;
+  rp.meta = c->d_meta;
+  rp.tf = c->d_tf;
+  rp.tf_w = c->tf_w; rp.tf_h = c->tf_h;
+  rp.hash = c->d_hash;
+  rp.pos = c->d_pos[0]; rp.aux = c->d_aux[0]; rp.image = c->d_image;
+  rp.tile_counter = c->d_tile_counter;
+  rp.stats = c->d_stats;
+  rp.tiles_x = (p->width + 7) / 8; rp.tiles_y = (p->height + 3) / 4;
+
+  const bool tex = c->pdesc.sampler == TVK_SAMPLER_TEX3D;
+  raycast_fn fn;
+  if (c->pc.bpv == 1) fn = tex ? pick_kernel<1, true>(p->render_mode, p->lighting != 0) : pick_kernel<1, false>(p->render_mode, p->lighting != 0);
+  else fn = tex ? pick_kernel<2, true>(p->render_mode, p->lighting != 0) : pick_kernel<2, false>(p->render_mode, p->lighting != 0);
+
+  int sms = 0, per_sm = 0;
+  TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  TVK_CHECK_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 128, 0));
+  if (per_sm < 1) per_sm = 1;
+  const uint32_t ntiles = rp.tiles_x * rp.tiles_y;
+  uint32_t grid = (uint32_t)(sms * per_sm);
+  if (grid > (ntiles + 3) / 4) grid = (ntiles + 3) / 4;
+  if (grid < 1) grid = 1;
+
+  // GLHashTable::ClearData (:106-110) + tile counter reset, then the march; timed with events
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_hash, 0, sizeof(uint32_t) * p->hash_table_size, c->stream));
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(uint32_t), c->stream));
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  fn<<<grid, 128, 0, c->stream>>>(rp);
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  c->launches++;
+  return TVK_OK;
+}
+
+extern "C" int tvk_read_requests(tvk_ctx* c, uint32_t* xyzl, uint32_t cap, uint32_t* count) {
+  if (!c || !count || (cap && !xyzl) || !c->d_hash || !c->has_pool) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  std::vector<uint32_t> h(c->hash_size);
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(h.data(), c->d_hash, sizeof(uint32_t) * c->hash_size, cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  // GLHashTable::GetData + Int2Vector (GLHashTable.cpp:65-77,90-104)
+  const uint32_t* B = c->pc.l0_bricks;
+  const uint32_t vol = B[0] * B[1] * B[2];
+  uint32_t n = 0;
+  for (uint32_t i = 0; i < c->hash_size && n < cap; ++i) {
+    if (!h[i]) continue;
+    uint32_t idx = h[i] - 1;
+    uint32_t* o = xyzl + 4 * n++;
+    o[3] = idx / vol; idx -= o[3] * vol;
+    o[2] = idx / (B[0] * B[1]); idx -= o[2] * (B[0] * B[1]);
+    o[1] = idx / B[0]; idx -= o[1] * B[0];
+    o[0] = idx;
+  }
+  *count = n;
+  return TVK_OK;
+}
+
+extern "C" int tvk_read_image(tvk_ctx* c, float* rgba) {
+  if (!c || !rgba || !c->d_image) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(rgba, c->d_image, sizeof(float4) * (size_t)c->width * c->height, cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TVK_OK;
+}
+
+extern "C" int tvk_read_resume(tvk_ctx* c, float* pos, float* color) {
+  if (!c || !c->d_image) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  const size_t bytes = sizeof(float4) * (size_t)c->width * c->height;
+  if (pos) TVK_CHECK_CUDA(c, cudaMemcpyAsync(pos, c->d_pos[0], bytes, cudaMemcpyDeviceToHost, c->stream));
+  if (color) TVK_CHECK_CUDA(c, cudaMemcpyAsync(color, c->d_aux[0], bytes, cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TVK_OK;
+}
+
+extern "C" int tvk_image_device_ptr(tvk_ctx* c, void** dptr) {
+  if (!c || !dptr || !c->d_image) return TVK_ERR_INVALID;
+  *dptr = c->d_image;
+  return TVK_OK;
+}
+
+extern "C" int tvk_get_stats(tvk_ctx* c, tvk_stats* out, int reset) {
+  if (!c || !out) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  unsigned long long h[3];
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  if (reset) TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_stats, 0, sizeof(h), c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  if (c->launches && cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_raycast_ms = ms;
+  (void)cudaGetLastError();
+  out->samples = h[0]; out->rays = h[1]; out->brick_steps = h[2];
+  out->last_raycast_ms = c->last_raycast_ms;
+  out->launches = c->launches;
+  return TVK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// bit-exactness probes
+// ---------------------------------------------------------------------------
+__global__ void probe_lod_kernel(const float* depth, uint32_t n, float lod_factor, float wse, uint32_t max_lod, uint32_t* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = compute_lod(depth[i], lod_factor, wse, max_lod);
+}
+__global__ void probe_index_kernel(const float* xyz, const uint32_t* lod, uint32_t n, const __grid_constant__ PoolConst pc,
+                                   uint32_t* index_out, uint32_t* serial_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const f3 e = mk3(clamp01(xyz[3 * i]), clamp01(xyz[3 * i + 1]), clamp01(xyz[3 * i + 2]));
+  const uint4 bc = brick_coords(pc, e, lod[i]);
+  index_out[i] = brick_index(pc, bc);
+  serial_out[i] = serialize(pc, bc);
+}
+
+extern "C" int tvk_probe_lod(tvk_ctx* c, const float* depth, uint32_t n, float lod_factor, float wse, uint32_t* lod_out) {
+  if (!c || !c->has_pool || !depth || !lod_out) return TVK_ERR_INVALID;
+  if (!n) return TVK_OK;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  float* d_in = nullptr; uint32_t* d_out = nullptr;
+  TVK_CHECK_CUDA(c, cudaMalloc(&d_in, sizeof(float) * n));
+  TVK_CHECK_CUDA(c, cudaMalloc(&d_out, sizeof(uint32_t) * n));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_in, depth, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+  probe_lod_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_in, n, lod_factor, wse, c->pc.lod_count - 1, d_out);
+  c->launches++;
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(lod_out, d_out, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(d_in); cudaFree(d_out);
+  return TVK_OK;
+}
+
+extern "C" int tvk_probe_brick_index(tvk_ctx* c, const float* norm_xyz, const uint32_t* lod, uint32_t n,
+                                     uint32_t* index_out, uint32_t* serial_out) {
+  if (!c || !c->has_pool || !norm_xyz || !lod || !index_out || !serial_out) return TVK_ERR_INVALID;
+  if (!n) return TVK_OK;
+  for (uint32_t i = 0; i < n; ++i) if (lod[i] >= c->pc.lod_count) TVK_FAIL(c, TVK_ERR_INVALID, "lod out of range");
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  float* d_xyz = nullptr; uint32_t *d_lod = nullptr, *d_i = nullptr, *d_s = nullptr;
+  TVK_CHECK_CUDA(c, cudaMalloc(&d_xyz, sizeof(float) * 3 * n));
+  TVK_CHECK_CUDA(c, cudaMalloc(&d_lod, sizeof(uint32_t) * n));
+  TVK_CHECK_CUDA(c, cudaMalloc(&d_i, sizeof(uint32_t) * n));
+  TVK_CHECK_CUDA(c, cudaMalloc(&d_s, sizeof(uint32_t) * n));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_xyz, norm_xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_lod, lod, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
+  probe_index_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_xyz, d_lod, n, c->pc, d_i, d_s);
+  c->launches++;
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(index_out, d_i, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(serial_out, d_s, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(d_xyz); cudaFree(d_lod); cudaFree(d_i); cudaFree(d_s);
+  return TVK_OK;
+}

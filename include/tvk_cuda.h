@@ -1,0 +1,255 @@
+/*
+ * tvk_cuda.h -- C ABI of the B200-native bricked ray-caster that replaces the
+ * GLSL/GL hot path of Tuvok (ImageVis3D).
+ *
+ * Everything here is plain C: opaque handle, POD structs, caller-owned buffers,
+ * int status returns (0 = TVK_OK), no exceptions, no torch / C++ types.  A
+ * `CudaGridLeaper : AbstrRenderer` binds these entry points
+ * instead of the GL objects the reference uses.  Each entry point names the
+ * reference interface it replaces (paths relative to /root/reference/).
+ *
+ * Conventions shared with the reference:
+ *   - matrices are FLOATMATRIX4 memory order (m11,m12,...,m44), row-vector
+ *     convention v' = v*M (Tuvok/Basics/Vectors.h:434,936)
+ *   - brick ids are (x,y,z,lod); the 1-D index is
+ *     lodOffset[lod] + x + y*Lx + z*Lx*Ly (GLVolumePool.cpp:288-303)
+ *   - metadata values: 0 MISSING, 1 CHILD_EMPTY, 2 EMPTY, >=3 pool slot + 3
+ *     (GLVolumePool.h:62-72)
+ *   - images are RGBA32F, row 0 = bottom row (GL window convention)
+ */
+#ifndef TVK_CUDA_H
+#define TVK_CUDA_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TVK_OK               0
+#define TVK_ERR_INVALID      1   /* bad argument / state                      */
+#define TVK_ERR_CUDA         2   /* a CUDA runtime call failed                */
+#define TVK_ERR_NOMEM        3   /* allocation failed                         */
+#define TVK_ERR_UNSUPPORTED  4   /* valid in the reference, not built yet     */
+
+#define TVK_BI_MISSING      0u
+#define TVK_BI_CHILD_EMPTY  1u
+#define TVK_BI_EMPTY        2u
+#define TVK_BI_FLAG_COUNT   3u
+
+#define TVK_MAX_LOD 16
+
+/* AbstrRenderer::ERenderMode (Tuvok/Renderer/AbstrRenderer.h:142-147) */
+#define TVK_RM_1DTRANS     0
+#define TVK_RM_2DTRANS     1
+#define TVK_RM_ISOSURFACE  2
+
+/* GLVolumePool::MissingBrickStrategy (GLVolumePool.h:81-87) */
+#define TVK_MBS_ONLY_NEEDED     0
+#define TVK_MBS_REQUEST_ALL     1
+#define TVK_MBS_SKIP_ONE_LEVEL  2
+#define TVK_MBS_SKIP_TWO_LEVELS 3
+
+/* pool sampler back-ends (both give GL_LINEAR / CLAMP_TO_EDGE semantics) */
+#define TVK_SAMPLER_EXACT  0   /* fp32 trilinear from linear HBM (oracle arithmetic) */
+#define TVK_SAMPLER_TEX3D  1   /* cudaArray + hardware filtering (1.8 fixed-point weights) */
+
+typedef struct tvk_ctx tvk_ctx;
+
+/* ------------------------------------------------------------------ context */
+/* replaces tuvok::Context / BatchContext (Renderer/Context.h:46-59,
+ * BatchRenderer/BatchContext.h:47-66): one context = one device + streams. */
+int  tvk_create(int device, tvk_ctx** out);
+void tvk_destroy(tvk_ctx* ctx);
+const char* tvk_last_error(const tvk_ctx* ctx);
+int  tvk_device_synchronize(tvk_ctx* ctx);
+
+/* --------------------------------------------------------------- brick pool */
+/* replaces GLVolumePool ctor + CreateGLResources (GLVolumePool.cpp:119-259,
+ * 864-910) and the shader constants baked by GetShaderFragment (:317-483). */
+typedef struct tvk_pool_desc {
+  uint32_t volume_size[3];     /* LOD-0 domain size in voxels (m_volumeSize)            */
+  uint32_t max_brick_size[3];  /* total brick size incl. overlap (m_maxTotalBrickSize)  */
+  uint32_t overlap;            /* ghost voxels per side                                 */
+  uint32_t bytes_per_voxel;    /* 1 (UNORM8) or 2 (UNORM16), single component           */
+  uint32_t pool_capacity[3];   /* slots per axis; pool voxels = capacity*max_brick_size */
+  uint32_t lod_count;          /* LargestSingleBrickLOD+1 (GLVolumePool.cpp:132)        */
+  uint32_t sampler;            /* TVK_SAMPLER_*                                          */
+} tvk_pool_desc;
+
+int tvk_pool_create(tvk_ctx* ctx, const tvk_pool_desc* desc);
+int tvk_pool_destroy(tvk_ctx* ctx);
+/* total bricks over the lod_count pool levels (m_iTotalBrickCount) */
+int tvk_pool_total_bricks(const tvk_ctx* ctx, uint32_t* out);
+
+/* replaces GLVolumePool::UploadBrick -> glTexSubImage3D (GLVolumePool.cpp:673-717).
+ * Copies n bricks (x-fastest voxels, sizes[3*i..] voxels each, possibly smaller
+ * than max_brick_size) into pool slots slot[i] (linear slot index
+ * x + y*Cx + z*Cx*Cy) on the pager's side stream.  src pointers may be pinned
+ * host memory (asynchronous DMA) or device memory (on_device != 0).
+ * Metadata is NOT touched; patch it with tvk_pool_patch_metadata once
+ * tvk_pool_upload_wait() has returned. */
+int tvk_pool_upload_bricks(tvk_ctx* ctx, uint32_t n, const uint32_t* slot,
+                           const void* const* src, const uint32_t* sizes,
+                           int on_device);
+int tvk_pool_upload_wait(tvk_ctx* ctx);
+
+/* replaces UploadMetadataTexture / UploadMetadataTexel (GLVolumePool.cpp:912-953) */
+int tvk_pool_set_metadata(tvk_ctx* ctx, const uint32_t* meta, uint32_t n);
+int tvk_pool_patch_metadata(tvk_ctx* ctx, uint32_t n, const uint32_t* brick_index,
+                            const uint32_t* value);
+int tvk_pool_get_metadata(tvk_ctx* ctx, uint32_t* meta, uint32_t n);
+
+/* ---------------------------------------------------------------- visibility */
+/* replaces GLVolumePool::RecomputeVisibility (+ForBrickPool, +ForOctree)
+ * (GLVolumePool.cpp:1580-1718, 992-1018, 1021-1359).  minmax holds
+ * {min,max} doubles per brick in pool index order (m_vMinMaxScalar);
+ * grad_minmax may be NULL (then -DBL_MAX/+DBL_MAX as written by the TOC path,
+ * ExtendedOctreeConverter.cpp:954-1000). */
+int tvk_visibility_set_minmax(tvk_ctx* ctx, const double* minmax,
+                              const double* grad_minmax, uint32_t n);
+typedef struct tvk_visibility {
+  uint32_t render_mode;        /* TVK_RM_*                                         */
+  double   smin, smax;         /* 1D/2D TF non-zero value range; iso: smin = iso   */
+  double   gmin, gmax;         /* 2D TF gradient range                             */
+} tvk_visibility;
+/* Recomputes every metadata entry on the device: entries >= FLAG_COUNT
+ * (resident) keep their slot if the brick contains data, else become EMPTY;
+ * all others are derived bottom-up from the min/max table.
+ * counts[4] = (processed, inner EMPTY, inner CHILD_EMPTY, leaf empty) as
+ * vEmptyBrickCount; may be NULL. */
+int tvk_visibility_recompute(tvk_ctx* ctx, const tvk_visibility* vis, uint32_t* counts);
+
+/* --------------------------------------------------------- transfer functions */
+/* replaces GLRenderer::Changed1DTrans/Changed2DTrans texture upload
+ * (GLRenderer.cpp:465-472, GPUMemMan.cpp:421-427): RGBA8, NEAREST, clamp. */
+int tvk_set_tf1d(tvk_ctx* ctx, const uint8_t* rgba, uint32_t n);
+int tvk_set_tf2d(tvk_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t h);
+
+/* ------------------------------------------------------------------ ray-march */
+/* replaces GLGridLeaper::Raycast + SetupRaycastShader + FillRayEntryBuffer
+ * (GLGridLeaper.cpp:754-870, 690-752, 579-620) and the shaders
+ * GLGridLeaper-blend.glsl / -iso.glsl / Method-*.glsl / Compose-FS.glsl. */
+typedef struct tvk_raycast_params {
+  uint32_t width, height;          /* render target size                              */
+  float eye_to_model[16];          /* mEyeToModel (GLGridLeaper.cpp:560-573)          */
+  float model_to_eye[16];          /* its inverse (iso: mModelToEye)                  */
+  float model_view_it[16];         /* MV^-1 uploaded transposed (iso: mModelViewIT)   */
+  float inv_projection[16];        /* m_mProjection^-1 (near-plane / pixel rays)      */
+  float lod_factor;                /* CullingLOD::GetLoDFactor (CullingLOD.cpp:65-66) */
+  float level_zero_wse;            /* fLevelZeroWorldSpaceError (GLVolumePool.cpp:801)*/
+  float sample_rate_modifier;
+  float trans_scale;               /* fTransScale (GLRenderer.cpp:1813-1819)          */
+  float gradient_scale;            /* fGradientScale (GLGridLeaper.cpp:728-732)       */
+  float isoval;                    /* fIsoval, normalised                             */
+  uint32_t render_mode;            /* TVK_RM_*                                        */
+  uint32_t lighting;               /* m_bUseLighting                                  */
+  float light_ambient[3];
+  float light_diffuse[3];
+  float light_specular[3];
+  float model_light_dir[3];        /* vModelSpaceLightDir                             */
+  float model_eye_pos[3];          /* vModelSpaceEyePos                               */
+  float domain_scale[3];           /* vDomainScale = 1/(scale/min(scale))             */
+  float iso_color[3];              /* Compose-FS: vLightDiffuse*isoColor              */
+  float compose_light_dir[3];      /* Compose-FS vLightDir (eye space)                */
+  uint32_t new_view;               /* 1: rr.isBlank -> recompute ray entry, clear     */
+  uint32_t missing_strategy;       /* TVK_MBS_* (default SKIP_TWO_LEVELS)             */
+  uint32_t rehash_count;           /* GLHashTable rehash count (default 10)           */
+  uint32_t hash_table_size;        /* GLHashTable size (default 509)                  */
+  uint32_t clip_enabled;           /* clip plane (model space, normalised coords)     */
+  float clip_plane[4];
+  uint32_t count_samples;          /* accumulate executed samples into the stats      */
+} tvk_raycast_params;
+
+/* One sub-frame = one GLGridLeaper::Render3DRegion pass: clears the request
+ * table, marches all unfinished rays, leaves image + resume state on device. */
+int tvk_raycast_subframe(tvk_ctx* ctx, const tvk_raycast_params* p);
+
+/* replaces GLHashTable::GetData (GLHashTable.cpp:90-110): compacted requests in
+ * table order, 4 uint32 (x,y,z,lod) each.  *count <= cap. */
+int tvk_read_requests(tvk_ctx* ctx, uint32_t* xyzl, uint32_t cap, uint32_t* count);
+
+/* replaces glReadPixels on m_pFBO3DImage (float RGBA, premultiplied; for iso
+ * mode this is the Compose-FS shaded image).  rgba = width*height*4 floats. */
+int tvk_read_image(tvk_ctx* ctx, float* rgba);
+/* resume buffers, for tests: rayResumePos / rayResumeColor (iso: hit normal) */
+int tvk_read_resume(tvk_ctx* ctx, float* pos, float* color);
+/* device pointer of the current image (for the sort-last compositor / interop) */
+int tvk_image_device_ptr(tvk_ctx* ctx, void** dptr);
+
+typedef struct tvk_stats {
+  uint64_t samples;        /* executed ComputeColorFromVolume / GetVolumeHit calls  */
+  uint64_t rays;           /* rays that entered the volume                          */
+  uint64_t brick_steps;    /* GetBrick calls                                        */
+  float    last_raycast_ms;/* CUDA-event time of the last ray-march launch          */
+  uint32_t launches;       /* kernels launched by this context since creation       */
+} tvk_stats;
+int tvk_get_stats(tvk_ctx* ctx, tvk_stats* out, int reset);
+
+/* bit-exactness probes used by the parity tests (R3, R2, R5 of SURVEY 8a):
+ * evaluate ComputeLOD / ComputeBrickCoords+GetBrickIndex / hash Serialize on
+ * the device for n inputs. */
+int tvk_probe_lod(tvk_ctx* ctx, const float* depth, uint32_t n, float lod_factor,
+                  float level_zero_wse, uint32_t* lod_out);
+int tvk_probe_brick_index(tvk_ctx* ctx, const float* norm_xyz, const uint32_t* lod,
+                          uint32_t n, uint32_t* index_out, uint32_t* serial_out);
+
+/* ------------------------------------------------------------------- builder */
+/* replaces ExtendedOctreeConverter::Convert (ExtendedOctreeConverter.cpp:128-280:
+ * PermuteInputData, ComputeHierarchy/DownsampleBrick, FillOverlap,
+ * ComputeBrickStats) + Histogram1DDataBlock::Compute +
+ * Histogram2DDataBlock::Compute, as streaming kernels over a volume resident
+ * in HBM.  Output bricks use the ExtendedOctree ToC order and sizes. */
+typedef struct tvk_build_desc {
+  uint32_t volume_size[3];
+  uint32_t brick_size;         /* cubic max brick size incl. overlap (default 64) */
+  uint32_t overlap;            /* default 2                                        */
+  uint32_t bytes_per_voxel;    /* 1 or 2 (unsigned)                                */
+  uint32_t use_median;         /* 0 mean (default) / 1 median                      */
+  uint32_t clamp_to_edge;      /* 0 (default) / 1                                  */
+} tvk_build_desc;
+
+typedef struct tvk_build_info {
+  uint32_t lod_count;                      /* all LODs down to 1x1x1            */
+  uint32_t lod_size[TVK_MAX_LOD][3];       /* voxels                            */
+  uint32_t lod_bricks[TVK_MAX_LOD][3];     /* brick counts                      */
+  uint64_t lod_offset[TVK_MAX_LOD];        /* first ToC index of each LOD       */
+  uint64_t total_bricks;
+  uint64_t total_bytes;                    /* size of the brick store           */
+} tvk_build_info;
+
+/* metadata only (ExtendedOctree::ComputeMetadata, ExtendedOctree.cpp:188-243) */
+int tvk_build_plan(const tvk_build_desc* desc, tvk_build_info* info);
+
+/* Runs the whole builder.  raw: the x-fastest input volume (host pointer, or
+ * device pointer if raw_on_device).  On return the context owns a device
+ * resident "brick store" (all bricks, ToC order, tightly packed), a min/max
+ * table and the histograms; fetch them with the getters below. */
+int tvk_build_octree(tvk_ctx* ctx, const tvk_build_desc* desc, const void* raw,
+                     int raw_on_device, tvk_build_info* info);
+/* per brick: offset into the store (bytes) and size in voxels */
+int tvk_build_get_toc(tvk_ctx* ctx, uint64_t* offsets, uint32_t* sizes3, uint64_t n);
+int tvk_build_get_minmax(tvk_ctx* ctx, double* minmax2, uint64_t n);
+int tvk_build_get_bricks(tvk_ctx* ctx, void* host_dst, uint64_t offset, uint64_t bytes);
+int tvk_build_store_device_ptr(tvk_ctx* ctx, void** dptr);
+/* 1-D histogram of LOD-0 inner voxels, 2^bits bins, *n = trimmed size
+ * (Histogram1DDataBlock.cpp:60-160) */
+int tvk_build_hist1d(tvk_ctx* ctx, uint64_t* bins, uint32_t cap, uint32_t* n);
+/* 2-D histogram (value x gradient magnitude), bins_x * 256 entries
+ * (Histogram2DDataBlock.cpp:348-455) */
+int tvk_build_hist2d(tvk_ctx* ctx, uint32_t bins_x, double max_nonzero_value,
+                     uint64_t* bins, float* max_grad_magnitude);
+int tvk_build_release(tvk_ctx* ctx);
+
+/* -------------------------------------------------------- sort-last compositor */
+/* new in this build (no reference counterpart): ordered "under"
+ * blend of n premultiplied RGBA32F partial images, front-to-back in the given
+ * order, using Compositing.glsl:33-38 arithmetic for premultiplied input. */
+int tvk_composite_ordered(tvk_ctx* ctx, const void* const* partial_dptrs, uint32_t n,
+                          uint64_t pixels, void* out_dptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVK_CUDA_H */

@@ -1,0 +1,449 @@
+"""TEST INFRASTRUCTURE ONLY -- restatement of the reference's HOST side of the
+GLGridLeaper path in numpy (fp32 where the reference uses float):
+
+  look_at / perspective / inverse     Tuvok/Basics/Vectors.h:1250-1277,1042-1140
+  camera -> raycast parameters        Tuvok/Renderer/GL/GLRenderer.cpp:864-920 (SetViewPort,
+                                      ComputeViewAndProjection), GLGridLeaper.cpp:560-573
+                                      (ComputeEyeToModelMatrix), :690-752 (SetupRaycastShader)
+  lod_factor                          Tuvok/Renderer/CullingLOD.cpp:57-67
+  pool sizing                         Tuvok/Renderer/GPUMemMan/GPUMemMan.cpp:766-844
+  OraclePool (slots, LRU, metadata)   Tuvok/Renderer/GL/GLVolumePool.cpp:673-778,955-959,
+                                      992-1018,1720-1789; GLVolumePool.h:25-60
+  render loop                         GLGridLeaper::Render3DRegion (GLGridLeaper.cpp:914-1154)
+
+Used by tests/ (and smoke()/bench cpu legs) to drive liboracle.so; never imported by
+the product package.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import oracle as O
+
+f32 = np.float32
+
+# ---------------------------------------------------------------- ctypes mirrors of include/tvk_cuda.h
+TVK_MAX_LOD = 16
+
+
+class RaycastParams(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32),
+                ("eye_to_model", C.c_float * 16), ("model_to_eye", C.c_float * 16),
+                ("model_view_it", C.c_float * 16), ("inv_projection", C.c_float * 16),
+                ("lod_factor", C.c_float), ("level_zero_wse", C.c_float), ("sample_rate_modifier", C.c_float),
+                ("trans_scale", C.c_float), ("gradient_scale", C.c_float), ("isoval", C.c_float),
+                ("render_mode", C.c_uint32), ("lighting", C.c_uint32),
+                ("light_ambient", C.c_float * 3), ("light_diffuse", C.c_float * 3), ("light_specular", C.c_float * 3),
+                ("model_light_dir", C.c_float * 3), ("model_eye_pos", C.c_float * 3), ("domain_scale", C.c_float * 3),
+                ("iso_color", C.c_float * 3), ("compose_light_dir", C.c_float * 3),
+                ("new_view", C.c_uint32), ("missing_strategy", C.c_uint32), ("rehash_count", C.c_uint32),
+                ("hash_table_size", C.c_uint32), ("clip_enabled", C.c_uint32), ("clip_plane", C.c_float * 4),
+                ("count_samples", C.c_uint32)]
+
+
+class Visibility(C.Structure):
+    _fields_ = [("render_mode", C.c_uint32), ("smin", C.c_double), ("smax", C.c_double),
+                ("gmin", C.c_double), ("gmax", C.c_double)]
+
+
+class OrcPool(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("bpv", C.c_uint32), ("volume_size", C.c_uint32 * 3),
+                ("max_brick", C.c_uint32 * 3), ("overlap", C.c_uint32), ("capacity", C.c_uint32 * 3),
+                ("lod_count", C.c_uint32), ("meta", C.c_void_p)]
+
+
+# ---------------------------------------------------------------- matrices (row-vector convention v' = v @ M)
+def look_at(eye, at, up):
+    eye, at, up = [np.asarray(v, f32) for v in (eye, at, up)]
+    F = at - eye
+    U = up.copy()
+    S = np.cross(F, U).astype(f32)
+    U = np.cross(S, F).astype(f32)
+    F = F / f32(np.sqrt(f32(np.dot(F, F))))
+    U = U / f32(np.sqrt(f32(np.dot(U, U))))
+    S = S / f32(np.sqrt(f32(np.dot(S, S))))
+    m = np.zeros((4, 4), f32)
+    m[0, :3] = [S[0], U[0], -F[0]]
+    m[1, :3] = [S[1], U[1], -F[1]]
+    m[2, :3] = [S[2], U[2], -F[2]]
+    m[3] = [-f32(np.dot(S, eye)), -f32(np.dot(U, eye)), f32(np.dot(F, eye)), 1]
+    return m
+
+
+def perspective(fovy_deg, aspect, n, f):
+    fovy = f32(f32(fovy_deg) * f32(3.14159265358979323846 / 180.0))
+    cotan = f32(1.0 / math.tan(float(fovy) / 2.0))
+    aspect, n, f = f32(aspect), f32(n), f32(f)
+    m = np.zeros((4, 4), f32)
+    m[0, 0] = cotan / aspect
+    m[1, 1] = cotan
+    m[2, 2] = -(f + n) / (f - n)
+    m[2, 3] = -1
+    m[3, 2] = f32(-2) * (f * n) / (f - n)
+    return m
+
+
+def inverse(m):
+    # the reference uses a cofactor expansion in fp32; a float64 inverse rounded to
+    # fp32 is within a few ulp, and images are compared with a tolerance.  Both the
+    # oracle and the CUDA path are always fed the SAME parameter struct.
+    return np.linalg.inv(m.astype(np.float64)).astype(f32)
+
+
+def translation(x, y, z):
+    m = np.eye(4, dtype=f32)
+    m[3, :3] = [x, y, z]
+    return m
+
+
+def scaling(x, y, z):
+    return np.diag(np.asarray([x, y, z, 1], f32))
+
+
+def rotation_y(angle):
+    c, s = f32(math.cos(angle)), f32(math.sin(angle))
+    m = np.eye(4, dtype=f32)
+    m[0, 0], m[0, 2], m[2, 0], m[2, 2] = c, -s, s, c
+    return m
+
+
+def rotation_x(angle):
+    c, s = f32(math.cos(angle)), f32(math.sin(angle))
+    m = np.eye(4, dtype=f32)
+    m[1, 1], m[1, 2], m[2, 1], m[2, 2] = c, s, -s, c
+    return m
+
+
+def lod_factor(fovy_deg, pixels_y, sse=1.0):
+    """CullingLOD::SetScreenParams, CullingLOD.cpp:65-66 (tan evaluated in double as ::tan)."""
+    arg = f32(f32(fovy_deg) * f32(f32(f32(3.1416) / f32(180.0)) / f32(2.0)))
+    return f32(f32(f32(2.0) * f32(math.tan(float(arg)))) * f32(sse) / f32(float(pixels_y)))
+
+
+class Camera:
+    """Defaults of AbstrRenderer.cpp:64-69,71-172."""
+
+    def __init__(self):
+        self.eye = np.array([0, 0, 1.6], f32)
+        self.at = np.array([0, 0, 0], f32)
+        self.up = np.array([0, 1, 0], f32)
+        self.fov, self.znear, self.zfar = 50.0, 0.01, 1000.0
+        self.rotation = np.eye(4, dtype=f32)
+        self.translation = np.eye(4, dtype=f32)
+        self.light_dir = np.array([0, 0, -1], f32)
+        self.ambient = np.array([1, 1, 1, 0.1], f32)
+        self.diffuse = np.array([1, 1, 1, 1], f32)
+        self.specular = np.array([1, 1, 1, 1], f32)
+        self.iso_color = np.array([0.5, 0.5, 0.5], f32)
+
+
+def raycast_params(cam, width, height, domain_size, scale=(1, 1, 1), render_mode=0, lighting=False,
+                   sample_rate=1.0, trans_scale=1.0, gradient_scale=1.0, isoval=0.5, new_view=True,
+                   strategy=3, rehash=10, hash_size=509, count_samples=True):
+    p = RaycastParams()
+    p.width, p.height = width, height
+    dom = np.asarray(domain_size, f32)
+    sc = np.asarray(scale, f32)
+    extent = dom * sc
+    extent = extent / extent.max()                      # GetVolumeAABB, AbstrRenderer.cpp:1102-1109
+    aspect = f32(width) / f32(height)
+    view = look_at(cam.eye, cam.at, cam.up)
+    proj = perspective(cam.fov, aspect, cam.znear, cam.zfar)
+    mv = (cam.rotation @ cam.translation @ view).astype(f32)     # GLRenderer.cpp:627
+    emm = (inverse(mv) @ translation(0, 0, 0) @ scaling(*(f32(1) / extent)) @ translation(0.5, 0.5, 0.5)).astype(f32)
+    p.eye_to_model[:] = emm.reshape(-1).tolist()
+    p.model_to_eye[:] = inverse(emm).reshape(-1).tolist()
+    p.model_view_it[:] = inverse(mv).T.reshape(-1).tolist()
+    p.inv_projection[:] = inverse(proj).reshape(-1).tolist()
+    p.lod_factor = float(lod_factor(cam.fov, height))
+    p.level_zero_wse = float((extent / dom).max())     # GLVolumePool.cpp:801
+    p.sample_rate_modifier = sample_rate
+    p.trans_scale, p.gradient_scale, p.isoval = trans_scale, gradient_scale, isoval
+    p.render_mode, p.lighting = render_mode, int(lighting)
+    a = cam.ambient[:3] * cam.ambient[3]
+    d = cam.diffuse[:3] * cam.diffuse[3]
+    s = cam.specular[:3] * cam.specular[3]
+    p.light_ambient[:] = a.tolist()
+    p.light_diffuse[:] = d.tolist()
+    p.light_specular[:] = s.tolist()
+    ld = (np.append(cam.light_dir, f32(0)) @ emm)[:3]
+    ld = ld / f32(np.sqrt(f32(np.dot(ld, ld))))
+    p.model_light_dir[:] = ld.tolist()
+    p.model_eye_pos[:] = (np.append(cam.eye, f32(1)) @ emm)[:3].tolist()   # sic: world eye through eye->model
+    vs = sc / sc.min()
+    p.domain_scale[:] = (f32(1) / vs).tolist()
+    p.iso_color[:] = cam.iso_color.tolist()
+    p.compose_light_dir[:] = cam.light_dir.tolist()
+    p.new_view = int(new_view)
+    p.missing_strategy, p.rehash_count, p.hash_table_size = strategy, rehash, hash_size
+    p.clip_enabled = 0
+    p.count_samples = int(count_samples)
+    return p
+
+
+# ---------------------------------------------------------------- transfer functions
+def tf1d_std(n, center=0.5, inv_gradient=0.5):
+    """TransferFunction1D::SetStdFunction (TransferFunction1D.cpp:74-112) -> float table [n][4]."""
+    t = np.zeros((n, 4), f32)
+    ic = int((n - 1) * f32(min(max(0.0, center), 1.0)))
+    ig = int((n - 1) * f32(min(max(0.0, inv_gradient), 1.0)))
+    start = 0 if ig // 2 > ic else ic - ig // 2
+    end = n if ig // 2 + ic > n else ic + ig // 2
+    for i in range(start, end):
+        x = f32(float(i - ic + ig // 2) / float(ig))
+        t[i, :] = f32(3) * x * x - f32(2) * x * x * x
+    t[end:, :] = 1
+    return t
+
+
+def tf_bytes(table):
+    """TransferFunction1D::GetByteArray (TransferFunction1D.cpp:311-328): truncation, not rounding."""
+    return (np.clip(np.asarray(table, f32), 0, 1) * f32(255)).astype(np.uint8)
+
+
+def tf_nonzero_limits(table):
+    """ComputeNonZeroLimits (TransferFunction1D.cpp:362-370)."""
+    nz = np.nonzero(np.asarray(table)[:, 3] != 0)[0]
+    return (len(table), 0) if nz.size == 0 else (int(nz[0]), int(nz[-1]))
+
+
+# ---------------------------------------------------------------- pool
+def largest_single_brick_lod(plan):
+    for l in range(plan.lod_count):
+        if plan.lod_bricks[l][0] * plan.lod_bricks[l][1] * plan.lod_bricks[l][2] == 1:
+            return l
+    return plan.lod_count - 1
+
+
+def pool_layout(vol, max_brick, overlap, lod_count):
+    lay = np.zeros((lod_count, 3), f32)
+    off = np.zeros(lod_count, np.uint32)
+    bricks = np.zeros((lod_count, 3), np.uint32)
+    total = C.c_uint32()
+    O.lib().orc_pool_layout((C.c_uint32 * 3)(*vol), (C.c_uint32 * 3)(*max_brick), C.c_uint32(overlap),
+                            C.c_uint32(lod_count), lay.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
+                            bricks.ctypes.data_as(C.c_void_p), C.byref(total))
+    return lay, off, bricks, total.value
+
+
+class OraclePool:
+    """GLVolumePool bookkeeping + a numpy pool texture, fed from an oracle octree (O.build_octree)."""
+
+    def __init__(self, oct, capacity):
+        self.oct = oct
+        p = oct["plan"]
+        self.vol = tuple(int(v) for v in oct["vol"])
+        self.bpv = oct["bpv"]
+        self.overlap = oct["overlap"]
+        self.max_brick = tuple(int(v) for v in oct["sizes"].max(axis=0))   # GetMaxUsedBrickSizes
+        self.lod_count = largest_single_brick_lod(p) + 1
+        self.capacity = tuple(capacity)
+        self.layout, self.lod_offset, self.lod_bricks, self.total = pool_layout(self.vol, self.max_brick, self.overlap, self.lod_count)
+        dims = [self.capacity[a] * self.max_brick[a] for a in range(3)]
+        self.data = np.zeros((dims[2], dims[1], dims[0]), np.uint8 if self.bpv == 1 else np.uint16)
+        self.meta = np.zeros(self.total, np.uint32)
+        nslots = capacity[0] * capacity[1] * capacity[2]
+        self.slot_brick = -np.ones(nslots, np.int64)
+        self.slot_time = np.zeros(nslots, np.uint64)
+        self.slot_orig = np.zeros(nslots, np.uint64)
+        self.time = 2
+        self.insert_pos = 0
+        self.order = np.arange(nslots)
+        # min/max in POOL index order: m_vMinMaxScalar[i] = MaxMinForKey(IndexFrom4D(GetVectorBrickID(i)))
+        # (GLVolumePool.cpp:232-239)
+        self.minmax = np.zeros((self.total, 2), np.float64)
+        for i in range(self.total):
+            x, y, z, lod = self.index_to_xyzl(i)
+            b = p.lod_bricks[lod]
+            if x >= b[0] or y >= b[1] or z >= b[2]:
+                raise ValueError("pool layout and octree layout disagree at LOD %d" % lod)
+            self.minmax[i] = oct["minmax"][self.toc_index(x, y, z, lod)]
+        self.vis = None
+
+    # brick ids ----------------------------------------------------------------
+    def brick_index(self, x, y, z, lod):
+        b = self.lod_bricks[lod]
+        return int(self.lod_offset[lod]) + x + y * int(b[0]) + z * int(b[0]) * int(b[1])
+
+    def toc_index(self, x, y, z, lod):
+        p = self.oct["plan"]
+        b = p.lod_bricks[lod]
+        return int(p.lod_offset[lod]) + x + y * int(b[0]) + z * int(b[0]) * int(b[1])
+
+    def index_to_xyzl(self, idx):
+        lod = int(np.searchsorted(self.lod_offset, idx, side="right") - 1)
+        r = idx - int(self.lod_offset[lod])
+        b = self.lod_bricks[lod]
+        return r % int(b[0]), (r // int(b[0])) % int(b[1]), r // (int(b[0]) * int(b[1])), lod
+
+    # uploads ------------------------------------------------------------------
+    def _write_slot(self, slot, brick):
+        cx, cy, _ = self.capacity
+        s = (slot % cx, (slot // cx) % cy, slot // (cx * cy))
+        o = [s[a] * self.max_brick[a] for a in range(3)]
+        self.data[o[2]:o[2] + brick.shape[0], o[1]:o[1] + brick.shape[1], o[0]:o[0] + brick.shape[2]] = brick
+
+    def _upload(self, idx, slot, time):
+        """UploadBrick(iBrickID, ..., iInsertPos, iTimeOfCreation), GLVolumePool.cpp:673-717."""
+        if self.slot_time[slot] > 1:                      # ContainsVisibleBrick
+            self.meta[self.slot_brick[slot]] = 0
+        self.slot_brick[slot] = idx
+        self.slot_time[slot] = time
+        self.meta[idx] = slot + 3
+        x, y, z, lod = self.index_to_xyzl(idx)
+        self._write_slot(slot, O.brick(self.oct, self.toc_index(x, y, z, lod)))
+
+    def upload_first_brick(self):
+        """UploadFirstBrick, :763-766: coarsest brick into the LAST slot, pinned forever."""
+        self._upload(int(self.lod_offset[-1]), len(self.slot_brick) - 1, np.iinfo(np.uint64).max)
+
+    def prepare_for_paging(self):
+        self.order = np.argsort(self.slot_time, kind="stable")     # PoolSorter (stable tie-break = slot order)
+        self.insert_pos = 0
+
+    def upload_requests(self, requests):
+        """UploadBricks -> UploadBricksToBrickPoolT (:1720-1789,1362-1393); visibility is up to date."""
+        paged = 0
+        if len(requests):
+            self.prepare_for_paging()
+            for x, y, z, lod in requests:
+                if self.insert_pos >= len(self.slot_brick) - 1:
+                    break
+                slot = int(self.order[self.insert_pos])
+                self._upload(self.brick_index(int(x), int(y), int(z), int(lod)), slot, self.time)
+                self.time += 1
+                self.insert_pos += 1
+                paged += 1
+        return paged
+
+    # visibility ---------------------------------------------------------------
+    def recompute_visibility(self, mode, smin, smax=0.0, gmin=0.0, gmax=0.0):
+        """RecomputeVisibility (:1580-1718) incl. the slot FlagEmpty/Restore of ForBrickPool (:992-1018)."""
+        v = Visibility(mode, smin, smax, gmin, gmax)
+        self.vis = v
+        for slot in range(len(self.slot_brick)):
+            idx = self.slot_brick[slot]
+            if idx < 0:
+                continue
+            lo, hi = self.minmax[idx]
+            if mode == 2:
+                cd = smin >= lo and smin <= hi
+            else:
+                cd = smax >= lo and smin <= hi
+            contained = self.slot_time[slot] > 1
+            if cd:
+                if not contained:
+                    self.slot_time[slot] = self.slot_orig[slot]      # Restore
+                self.meta[idx] = slot + 3
+            else:
+                if contained:
+                    self.slot_orig[slot] = self.slot_time[slot]      # FlagEmpty
+                    self.slot_time[slot] = 1
+                self.meta[idx] = 2
+        # everything that is not resident-and-visible is recomputed by orc_visibility
+        keep = self.meta.copy()
+        keep[keep < 3] = 0
+        counts = np.zeros(4, np.uint32)
+        O.lib().orc_visibility((C.c_uint32 * 3)(*self.vol), (C.c_uint32 * 3)(*self.max_brick), C.c_uint32(self.overlap),
+                               C.c_uint32(self.lod_count), C.byref(v), self.minmax.ctypes.data_as(C.c_void_p), None,
+                               keep.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p))
+        self.meta = keep
+        return counts
+
+    def c_pool(self):
+        cp = OrcPool()
+        cp.data = self.data.ctypes.data
+        cp.bpv = self.bpv
+        cp.volume_size[:] = self.vol
+        cp.max_brick[:] = self.max_brick
+        cp.overlap = self.overlap
+        cp.capacity[:] = self.capacity
+        cp.lod_count = self.lod_count
+        cp.meta = self.meta.ctypes.data
+        return cp
+
+
+class OracleFrame:
+    """Resume buffers + request table of one view."""
+
+    def __init__(self, w, h, hash_size=509):
+        self.pos = np.zeros((h, w, 4), f32)
+        self.aux = np.zeros((h, w, 4), f32)
+        self.image = np.zeros((h, w, 4), f32)
+        self.hash = np.zeros(hash_size, np.uint32)
+        self.stats = np.zeros(3, np.uint64)
+
+
+def raycast(params, pool, tf_rgba8, frame):
+    tf = np.ascontiguousarray(tf_rgba8, np.uint8)
+    tf_w, tf_h = (tf.shape[0], 1) if tf.ndim == 2 else (tf.shape[1], tf.shape[0])
+    cp = pool.c_pool()
+    rc = O.lib().orc_raycast(C.byref(params), C.byref(cp), tf.ctypes.data_as(C.c_void_p), C.c_uint32(tf_w), C.c_uint32(tf_h),
+                             frame.pos.ctypes.data_as(C.c_void_p), frame.aux.ctypes.data_as(C.c_void_p),
+                             frame.image.ctypes.data_as(C.c_void_p), frame.hash.ctypes.data_as(C.c_void_p),
+                             frame.stats.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return frame.image
+
+
+def read_requests(pool, frame, cap=4096):
+    out = np.zeros((cap, 4), np.uint32)
+    n = O.lib().orc_read_requests(frame.hash.ctypes.data_as(C.c_void_p), C.c_uint32(frame.hash.size),
+                                  (C.c_uint32 * 3)(*[int(v) for v in pool.lod_bricks[0]]),
+                                  out.ctypes.data_as(C.c_void_p), C.c_uint32(cap))
+    return out[:n].copy()
+
+
+def render_converged(params, pool, tf_rgba8, max_subframes=200):
+    """paint() until converged (GLGridLeaper.cpp:872-890,914-1154).  Returns (image, subframes, paged)."""
+    frame = OracleFrame(params.width, params.height, params.hash_table_size)
+    params.new_view = 1
+    paged = 0
+    total_samples = 0
+    for sub in range(max_subframes):
+        raycast(params, pool, tf_rgba8, frame)
+        total_samples += int(frame.stats[0])
+        params.new_view = 0
+        req = read_requests(pool, frame)
+        if len(req) == 0:
+            return frame.image.copy(), sub + 1, paged, total_samples
+        paged += pool.upload_requests(req)
+    raise RuntimeError("oracle render did not converge")
+
+
+def psnr(a, b, peak=1.0):
+    mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+    return float("inf") if mse == 0 else 10.0 * math.log10(peak * peak / mse)
+
+
+# ---------------------------------------------------------------- synthetic volumes (UVFReader/DataSource.h)
+def synth_sphere(size, dtype=np.uint8):
+    """UVFReader/DataSource.h:361-372 'sphere': v = T(max(0,(0.5-|0.5-p/size|)*max*2))."""
+    sx, sy, sz = size
+    z, y, x = np.meshgrid(np.arange(sz), np.arange(sy), np.arange(sx), indexing="ij")
+    fx, fy, fz = f32(0.5) - x.astype(f32) / f32(sx), f32(0.5) - y.astype(f32) / f32(sy), f32(0.5) - z.astype(f32) / f32(sz)
+    d = np.sqrt(fx * fx + fy * fy + fz * fz).astype(f32)
+    mx = f32(np.iinfo(dtype).max)
+    return np.maximum(f32(0), (f32(0.5) - d) * mx * f32(2)).astype(dtype)
+
+
+def synth_noise(size, dtype=np.uint8, seed=1, maxval=None):
+    rng = np.random.default_rng(seed)
+    hi = int(np.iinfo(dtype).max if maxval is None else maxval)
+    return rng.integers(0, hi + 1, size=size[::-1]).astype(dtype)
+
+
+def synth_blobs(size, dtype=np.uint8, seed=3):
+    """smooth multi-blob field (sum of gaussians), a harder target than the sphere for LOD/visibility tests"""
+    sx, sy, sz = size
+    rng = np.random.default_rng(seed)
+    z, y, x = np.meshgrid(np.linspace(0, 1, sz, dtype=f32), np.linspace(0, 1, sy, dtype=f32),
+                          np.linspace(0, 1, sx, dtype=f32), indexing="ij")
+    v = np.zeros((sz, sy, sx), f32)
+    for _ in range(6):
+        c = rng.random(3).astype(f32) * f32(0.6) + f32(0.2)
+        r = f32(0.08 + 0.12 * rng.random())
+        v += np.exp(-((x - c[0]) ** 2 + (y - c[1]) ** 2 + (z - c[2]) ** 2) / (r * r)).astype(f32)
+    v = np.clip(v / v.max(), 0, 1)
+    return (v * f32(np.iinfo(dtype).max)).astype(dtype)

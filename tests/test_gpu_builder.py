@@ -1,0 +1,79 @@
+"""GPU: K2 builder kernels against the golden vectors of the reference and the oracle (bit-exact)."""
+import numpy as np
+import pytest
+
+from oracle import host as H
+from oracle import oracle as O
+from tests.util import cuda_store_tight, golden_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(tvk, raw, brick, overlap, median, ref_store, ref_sizes, ref_minmax, ref_h1=None, ref_h2=None, ref_mg=None):
+    info = tvk.build_octree(raw, brick, overlap, median=bool(median))
+    store, sizes = cuda_store_tight(tvk)
+    assert (sizes == ref_sizes).all()
+    assert store.size == ref_store.size
+    bad = np.nonzero(store != ref_store)[0]
+    assert bad.size == 0, "first mismatching byte %d of %d" % (bad[0], store.size)
+    assert (tvk.build_minmax() == ref_minmax).all()
+    if ref_h1 is not None:
+        h1 = tvk.build_hist1d()
+        assert h1.size == ref_h1.size and (h1 == ref_h1).all()
+        h2, mg = tvk.build_hist2d(len(h1), float(ref_minmax[:, 1].max()))
+        assert np.float32(mg) == np.float32(ref_mg)
+        assert (h2 == ref_h2).all()
+    tvk.build_release()
+    return info
+
+
+@pytest.mark.parametrize("case", range(7))
+def test_builder_matches_reference_golden(tvk, case):
+    g = golden_cases()[case]
+    brick, overlap, median = [int(v) for v in g["params"]]
+    _compare(tvk, g["raw"], brick, overlap, median, g["store"], g["sizes"], g["minmax"], g["hist1d"], g["hist2d"], g["max_grad"])
+
+
+@pytest.mark.parametrize("vol,dtype,brick,overlap,median", [
+    ((61, 47, 33), np.uint8, 12, 2, False), ((49, 9, 5), np.uint8, 12, 2, True), ((97, 97, 97), np.uint16, 20, 2, False),
+    ((130, 121, 64), np.uint8, 64, 2, False), ((200, 150, 100), np.uint16, 64, 2, True), ((50, 26, 14), np.uint16, 16, 4, False)])
+def test_builder_matches_oracle(tvk, vol, dtype, brick, overlap, median):
+    raw = H.synth_noise(vol, dtype, seed=sum(vol), maxval=255 if dtype == np.uint8 else 4095)
+    oc = O.build_octree(raw, brick, overlap, median)
+    h1 = O.hist1d(oc)
+    h2, mg = O.hist2d(oc, len(h1), oc["minmax"][:, 1].max())
+    _compare(tvk, raw, brick, overlap, median, oc["store"], oc["sizes"], oc["minmax"], h1, h2, mg)
+
+
+def test_builder_rejects_unsupported(tvk):
+    from imagevis3d_b200._lib import TvkError
+    raw = np.zeros((8, 8, 8), np.uint8)
+    with pytest.raises(TvkError):
+        tvk.build_octree(raw, 64, 2, clamp=True)
+    with pytest.raises(TvkError):
+        tvk.build_octree(raw, 4, 2)
+
+
+def test_builder_full_size_properties(tvk):
+    """512^3 uint8 (BASELINE config 2 size): size-independent properties instead of a CPU re-run."""
+    vol = (512, 512, 512)
+    raw = H.synth_sphere(vol, np.uint8)
+    info = tvk.build_octree(raw, 64, 2)
+    assert info.total_bricks == 890 and info.lod_count == 10
+    h1 = tvk.build_hist1d()
+    assert h1.sum() == 512 ** 3                                   # every voxel counted once
+    assert (h1 == np.bincount(raw.reshape(-1), minlength=256)[:len(h1)]).all()
+    mm = tvk.build_minmax()
+    assert mm[:729, 1].max() == raw.max() and mm[:, 0].min() == 0
+    off, sizes = tvk.build_toc()
+    # brick (4,4,4) of LOD 0 is the raw sub-volume [238..302)^3
+    i = 4 + 4 * 9 + 4 * 81
+    n = int(np.prod(sizes[i]))
+    b = tvk.build_bricks(int(off[i]), n).reshape(64, 64, 64)
+    assert (b == raw[238:302, 238:302, 238:302]).all()
+    # mean filter: LOD 1 inner voxel == floor(mean of the 8 children)
+    j = int(info.lod_offset[1])
+    b1 = tvk.build_bricks(int(off[j]), int(np.prod(sizes[j]))).reshape(64, 64, 64)
+    blk = raw[:120, :120, :120].astype(np.uint32).reshape(60, 2, 60, 2, 60, 2).sum(axis=(1, 3, 5)) // 8
+    assert (b1[2:62, 2:62, 2:62] == blk).all()
+    tvk.build_release()

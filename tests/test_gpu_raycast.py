@@ -1,0 +1,210 @@
+"""GPU: K1 ray-march kernel against the CPU restatement of the GLGridLeaper shaders.
+
+Tolerance (BASELINE.json north_star): PSNR >= 45 dB and max per-channel error <= 2/255 on the
+converged float image; brick requests (the integer side) must agree."""
+import numpy as np
+import pytest
+
+from oracle import host as H
+from oracle import oracle as O
+from tests.util import image_errors, lockstep_render
+
+pytestmark = pytest.mark.gpu
+
+PSNR_MIN = 45.0
+MAX_ERR = 2.0 / 255.0
+
+
+@pytest.fixture(scope="module")
+def oct_u8():
+    return O.build_octree(H.synth_blobs((150, 131, 97), np.uint8), 20, 2)
+
+
+@pytest.fixture(scope="module")
+def oct_u16():
+    return O.build_octree(H.synth_blobs((120, 100, 90), np.uint16, seed=9), 20, 2)
+
+
+def _tf(n, center=0.3, inv=0.3, alpha=0.15):
+    t = H.tf1d_std(n, center, inv)
+    t[:, 3] *= alpha
+    t[:, 0] *= 0.9
+    t[:, 2] *= 0.6
+    return t
+
+
+def _cold_pool(oc, capacity, mode, lo, hi):
+    pool = H.OraclePool(oc, capacity)
+    pool.upload_first_brick()
+    pool.recompute_visibility(mode, lo, hi, -1e308, 1e308)
+    return pool
+
+
+def _check(r, expect_paging=True):
+    psnr, err = image_errors(r["cuda"], r["oracle"])
+    assert r["oracle"].max() > 0.05, "oracle image is empty: the test would be vacuous"
+    assert psnr >= PSNR_MIN, "PSNR %.2f dB" % psnr
+    assert err <= MAX_ERR, "max channel error %.5f" % err
+    assert r["rays_cuda"] == r["rays_oracle"]
+    assert r["req_mismatch"] <= max(1, r["req_total"] // 200), r
+    assert abs(r["samples_cuda"] - r["samples_oracle"]) <= max(64, r["samples_oracle"] // 1000)
+    if expect_paging:
+        assert r["subframes"] > 1 and r["req_total"] > 0
+
+
+@pytest.mark.parametrize("lighting", [False, True])
+def test_1d_tf_progressive_u8(tvk, oct_u8, lighting):
+    tf = _tf(256)
+    lo, hi = H.tf_nonzero_limits(tf)
+    pool = _cold_pool(oct_u8, (8, 8, 8), 0, float(lo), float(hi))
+    cam = H.Camera()
+    cam.rotation = H.rotation_y(0.6) @ H.rotation_x(0.3)
+    p = H.raycast_params(cam, 203, 149, oct_u8["vol"], lighting=lighting)
+    _check(lockstep_render(tvk, p, pool, H.tf_bytes(tf)))
+
+
+def test_1d_tf_u16_sample_rate_and_scale(tvk, oct_u16):
+    tf = _tf(4096, 0.25, 0.2, 0.3)
+    lo, hi = H.tf_nonzero_limits(tf)
+    maxv = float(oct_u16["minmax"][:, 1].max())
+    scale = maxv / 4095.0
+    pool = _cold_pool(oct_u16, (7, 7, 7), 0, lo * scale, hi * scale)
+    cam = H.Camera()
+    cam.rotation = H.rotation_y(-0.9)
+    p = H.raycast_params(cam, 160, 120, oct_u16["vol"], sample_rate=1.7, trans_scale=65535.0 / maxv)
+    _check(lockstep_render(tvk, p, pool, H.tf_bytes(tf)))
+
+
+@pytest.mark.parametrize("lighting", [False, True])
+def test_2d_tf_u16(tvk, oct_u16, lighting):
+    n = 256
+    v = np.linspace(0, 1, n, dtype=np.float32)
+    g = np.linspace(0, 1, 256, dtype=np.float32)
+    tf2 = np.zeros((256, n, 4), np.float32)                       # [gradient row][value]
+    tf2[..., 0] = v[None, :]
+    tf2[..., 1] = g[:, None]
+    tf2[..., 2] = 0.5
+    tf2[..., 3] = np.clip((v[None, :] - 0.2) * 0.6, 0, 1) * (0.3 + 0.7 * g[:, None])
+    tfb = (np.clip(tf2, 0, 1) * np.float32(255)).astype(np.uint8)
+    maxv = float(oct_u16["minmax"][:, 1].max())
+    pool = _cold_pool(oct_u16, (7, 7, 7), 1, 0.2 * maxv, maxv)
+    cam = H.Camera()
+    cam.rotation = H.rotation_x(0.5) @ H.rotation_y(0.4)
+    p = H.raycast_params(cam, 144, 112, oct_u16["vol"], render_mode=1, lighting=lighting,
+                         trans_scale=65535.0 / maxv, gradient_scale=8.0)
+    _check(lockstep_render(tvk, p, pool, tfb))
+
+
+def test_isosurface_u8(tvk, oct_u8):
+    pool = _cold_pool(oct_u8, (8, 8, 8), 2, 100.0, 0.0)
+    cam = H.Camera()
+    cam.rotation = H.rotation_y(2.1) @ H.rotation_x(-0.4)
+    p = H.raycast_params(cam, 180, 140, oct_u8["vol"], render_mode=2, isoval=100.0 / 256.0)
+    r = lockstep_render(tvk, p, pool, H.tf_bytes(_tf(256)))
+    # a hit/miss flip on a silhouette pixel is a full-scale error; bound their NUMBER instead
+    d = np.abs(r["cuda"] - r["oracle"]).max(axis=2)
+    assert r["oracle"][..., 3].sum() > 500
+    assert (d > MAX_ERR).sum() <= max(4, int(0.002 * d.size)), (d > MAX_ERR).sum()
+    assert r["req_mismatch"] <= max(1, r["req_total"] // 200)
+
+
+def test_sparse_tf_skips_empty_space(tvk, oct_u8):
+    tf = np.zeros((256, 4), np.float32)
+    tf[96:161] = [1.0, 0.6, 0.2, 0.08]
+    pool = _cold_pool(oct_u8, (8, 8, 8), 0, 96.0, 160.0)
+    n_empty = int((pool.meta == 1).sum() + (pool.meta == 2).sum())
+    assert n_empty > 10
+    cam = H.Camera()
+    p = H.raycast_params(cam, 128, 128, oct_u8["vol"])
+    r = lockstep_render(tvk, p, pool, H.tf_bytes(tf))
+    _check(r)
+
+
+def test_early_ray_termination(tvk, oct_u8):
+    tf = _tf(256, 0.1, 0.1, 1.0)                                  # opaque almost everywhere
+    lo, hi = H.tf_nonzero_limits(tf)
+    pool = _cold_pool(oct_u8, (8, 8, 8), 0, float(lo), float(hi))
+    p = H.raycast_params(H.Camera(), 128, 96, oct_u8["vol"])
+    r = lockstep_render(tvk, p, pool, H.tf_bytes(tf))
+    _check(r)
+    assert r["cuda"][..., 3].max() > 0.99
+
+
+def test_eye_inside_volume_and_miss(tvk, oct_u8):
+    tf = _tf(256)
+    lo, hi = H.tf_nonzero_limits(tf)
+    pool = _cold_pool(oct_u8, (8, 8, 8), 0, float(lo), float(hi))
+    cam = H.Camera()
+    cam.eye = np.array([0.05, 0.02, 0.2], np.float32)             # inside the unit box: near-plane entry
+    p = H.raycast_params(cam, 96, 80, oct_u8["vol"])
+    _check(lockstep_render(tvk, p, pool, H.tf_bytes(tf)), expect_paging=False)
+    cam = H.Camera()
+    cam.at = np.array([0, 0, 5.0], np.float32)                    # looking away: no ray hits the box
+    p = H.raycast_params(cam, 64, 48, oct_u8["vol"])
+    pool = _cold_pool(oct_u8, (8, 8, 8), 0, float(lo), float(hi))
+    r = lockstep_render(tvk, p, pool, H.tf_bytes(tf))
+    assert r["rays_cuda"] == 0 and r["cuda"].max() == 0.0 and r["subframes"] == 1
+
+
+def test_small_pool_pages_and_still_converges(tvk, oct_u8):
+    """Pool far smaller than the working set: bricks get evicted (LRU) and re-requested."""
+    tf = _tf(256)
+    lo, hi = H.tf_nonzero_limits(tf)
+    pool = _cold_pool(oct_u8, (3, 3, 2), 0, float(lo), float(hi))
+    cam = H.Camera()
+    cam.eye = np.array([0, 0, 3.2], np.float32)                   # far away: coarse LODs suffice
+    p = H.raycast_params(cam, 96, 72, oct_u8["vol"])
+    _check(lockstep_render(tvk, p, pool, H.tf_bytes(tf)), expect_paging=False)
+
+
+def test_tex3d_sampler_reports_its_error(tvk, oct_u8):
+    """Hardware trilinear (9-bit weights): measured against the fp32 oracle; must stay in tolerance to be usable."""
+    tf = _tf(256)
+    lo, hi = H.tf_nonzero_limits(tf)
+    pool = _cold_pool(oct_u8, (8, 8, 8), 0, float(lo), float(hi))
+    cam = H.Camera()
+    cam.rotation = H.rotation_y(0.6) @ H.rotation_x(0.3)
+    p = H.raycast_params(cam, 203, 149, oct_u8["vol"])
+    r = lockstep_render(tvk, p, pool, H.tf_bytes(tf), sampler=1)
+    psnr, err = image_errors(r["cuda"], r["oracle"])
+    print("TEX3D sampler: PSNR %.2f dB, max err %.5f (%.2f/255)" % (psnr, err, err * 255))
+    assert psnr >= 40.0 and err <= 4.0 / 255.0
+
+
+def test_api_errors(tvk, oct_u8):
+    from imagevis3d_b200._lib import TvkError
+    p = H.raycast_params(H.Camera(), 64, 48, oct_u8["vol"])
+    from tests.util import to_cuda_params
+    q = to_cuda_params(p)
+    q.hash_table_size = 0
+    with pytest.raises(TvkError):
+        tvk.raycast(q)
+    q = to_cuda_params(p)
+    q.sample_rate_modifier = 0.0
+    with pytest.raises(TvkError):
+        tvk.raycast(q)
+    q = to_cuda_params(p)
+    q.render_mode = 7
+    with pytest.raises(TvkError):
+        tvk.raycast(q)
+
+
+def test_compositor_matches_oracle(tvk):
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(3)
+    n, pix = 4, 64 * 48
+    parts = []
+    for _ in range(n):
+        a = rng.uniform(0, 1, (pix, 1)).astype(np.float32)
+        rgb = rng.uniform(0, 1, (pix, 3)).astype(np.float32) * a
+        parts.append(np.ascontiguousarray(np.concatenate([rgb, a], axis=1)))
+    want = np.zeros((pix, 4), np.float32)
+    arr = (C.c_void_p * n)(*[p.ctypes.data for p in parts])
+    O.lib().orc_composite_ordered(arr, C.c_uint32(n), C.c_uint64(pix), want.ctypes.data_as(C.c_void_p))
+    dev = [torch.from_numpy(p).cuda() for p in parts]
+    out = torch.zeros((pix, 4), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    tvk.composite_ordered([d.data_ptr() for d in dev], pix, out.data_ptr())
+    got = out.cpu().numpy()
+    assert np.abs(got - want).max() <= 1e-6

@@ -1,0 +1,121 @@
+"""Helpers shared by the parity tests (test infrastructure)."""
+import os
+import struct
+import zlib
+
+import numpy as np
+
+from oracle import host as H
+from oracle import oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_cases():
+    z = np.load(os.path.join(GOLDEN, "builder_cases.npz"))
+    out = []
+    for i in range(int(z["n_cases"])):
+        k = "c%d_" % i
+        out.append({n: z[k + n] for n in ("raw", "params", "lod_size", "lod_bricks", "lod_aspect", "sizes", "minmax",
+                                           "store", "hist1d", "hist2d", "max_grad")})
+    return out
+
+
+def write_png(path, img8):
+    h, w, c = img8.shape
+    raw = b"".join(b"\x00" + img8[y].tobytes() for y in range(h))
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6 if c == 4 else 2, 0, 0, 0))
+                + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b""))
+
+
+def cuda_store_tight(ctx):
+    """Brick store of the CUDA builder re-packed tightly in ToC order (the oracle's layout)."""
+    off, sizes = ctx.build_toc()
+    blob = ctx.build_bricks()
+    bpv = ctx.build_bpv
+    parts = []
+    for o, s in zip(off, sizes):
+        n = int(s[0]) * int(s[1]) * int(s[2]) * bpv
+        parts.append(blob[int(o):int(o) + n])
+    return np.concatenate(parts), sizes
+
+
+def mirror_pool(ctx, pool, sampler=0):
+    """Creates the CUDA pool with the oracle pool's geometry and copies its residency state."""
+    ctx.pool_create(pool.vol, pool.max_brick, pool.overlap, pool.bpv, pool.capacity, pool.lod_count, sampler)
+    assert ctx.total_bricks == pool.total
+    sync_pool(ctx, pool, set())
+
+
+def sync_pool(ctx, pool, already):
+    """Uploads every resident slot whose (slot, brick) pair is not in `already`, then the metadata."""
+    slots, bricks = [], []
+    for slot, idx in enumerate(pool.slot_brick):
+        if idx < 0 or (slot, int(idx)) in already:
+            continue
+        x, y, z, lod = pool.index_to_xyzl(int(idx))
+        slots.append(slot)
+        bricks.append(np.ascontiguousarray(O.brick(pool.oct, pool.toc_index(x, y, z, lod))))
+        already.add((slot, int(idx)))
+    if slots:
+        ctx.pool_upload_host(slots, bricks)
+    ctx.set_metadata(pool.meta)
+    return already
+
+
+def to_cuda_params(p):
+    """oracle RaycastParams -> product RaycastParams (same C layout)."""
+    import ctypes as C
+    from imagevis3d_b200 import _lib as L
+    q = L.RaycastParams()
+    assert C.sizeof(q) == C.sizeof(p)
+    C.memmove(C.byref(q), C.byref(p), C.sizeof(p))
+    return q
+
+
+def image_errors(a, b):
+    d = np.abs(a.astype(np.float64) - b.astype(np.float64))
+    return H.psnr(a, b), float(d.max())
+
+
+def lockstep_render(tvk, params, pool, tf_rgba8, sampler=0, max_subframes=100):
+    """Renders one view to convergence with the oracle and the CUDA path side by side.  Paging
+    decisions are taken by the oracle's pool manager from the ORACLE's requests and mirrored to
+    the device, so that both always march through identical pool states.  Returns a dict."""
+    mirror = set()
+    tvk.pool_create(pool.vol, pool.max_brick, pool.overlap, pool.bpv, pool.capacity, pool.lod_count, sampler)
+    sync_pool(tvk, pool, mirror)
+    if tf_rgba8.ndim == 2:
+        tvk.set_tf1d(tf_rgba8)
+    else:
+        tvk.set_tf2d(tf_rgba8)
+    frame = H.OracleFrame(params.width, params.height, params.hash_table_size)
+    params.new_view = 1
+    tvk.stats(reset=True)
+    req_mismatch, req_total, subframes, samples_o = 0, 0, 0, 0
+    for sub in range(max_subframes):
+        H.raycast(params, pool, tf_rgba8, frame)
+        samples_o += int(frame.stats[0])
+        tvk.raycast(to_cuda_params(params))
+        params.new_view = 0
+        subframes += 1
+        req_o = {tuple(int(v) for v in r) for r in H.read_requests(pool, frame)}
+        req_c = {tuple(int(v) for v in r) for r in tvk.read_requests()}
+        req_total += len(req_o | req_c)
+        req_mismatch += len(req_o ^ req_c)
+        if not req_o and not req_c:
+            break
+        pool.upload_requests(H.read_requests(pool, frame) if req_o else np.array(sorted(req_c), np.uint32))
+        sync_pool(tvk, pool, mirror)
+    else:
+        raise AssertionError("did not converge")
+    img_c = tvk.read_image()
+    pos_c, aux_c = tvk.read_resume()
+    st = tvk.stats()
+    return dict(cuda=img_c, oracle=frame.image.copy(), subframes=subframes, req_total=req_total,
+                req_mismatch=req_mismatch, samples_cuda=int(st.samples), samples_oracle=samples_o,
+                pos_cuda=pos_c, pos_oracle=frame.pos.copy(), rays_cuda=int(st.rays), rays_oracle=int(frame.stats[2]))
