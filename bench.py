@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- ray samples/s and ms/frame of the bricked ray-march hot path.
+
+Workload at N=1 (BASELINE.json configs[1]): synthetic 512^3 uint8 volume (the reference's own
+"sphere" generator, UVFReader/DataSource.h:361-372, plus a deterministic ripple so that rays do
+not all terminate at the same depth), bricked 64/overlap 2 by the CUDA builder, fully resident
+brick pool, 1D transfer function + early ray termination, 1920x1080, one converged frame per
+step on an orbiting camera (every step is a new view).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 (torchrun, one rank per GPU): sort-last.  Every rank owns one 512^3 z-slab of a
+512x512x(512*N) volume (weak scaling), renders its partial image, the partial images are
+exchanged as scan-line stripes (all_to_all over NCCL/NVLink), blended in depth order by the
+compositor kernel and gathered on rank 0.
+
+--impl reference times the CPU restatement of the reference's GLSL ray-marcher (oracle/, OpenMP
+on all host cores) because the reference's GL path cannot run here (no libGL/Mesa/Qt; see
+DESIGN.md); it is a reported baseline, not the target.
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VOL = (512, 512, 512)
+WIDTH, HEIGHT = 1920, 1080
+BRICK, OVERLAP = 64, 2
+BYTES_PER_SAMPLE = 1.2136 * 1 / 2.0     # 1.2136*bpv/(2*sampleRateModifier), uint8, srm 1
+BYTES_PER_RAY = 16.0                    # RGBA32F result write
+CPU_SAMPLE = (480, 270)                 # bounded CPU sample: same view at 1/16 of the rays
+
+
+def peaks():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def bench_tf():
+    """TransferFunction1D::SetStdFunction(0.5,0.5) colours with a 10x thinner alpha."""
+    from_oracle = False
+    n = 256
+    t = np.zeros((n, 4), np.float32)
+    ic, ig = int((n - 1) * 0.5), int((n - 1) * 0.5)
+    start, end = ic - ig // 2, ic + ig // 2
+    for i in range(start, end):
+        x = np.float32(float(i - ic + ig // 2) / float(ig))
+        t[i, :] = np.float32(3) * x * x - np.float32(2) * x * x * x
+    t[end:, :] = 1
+    t[:, 3] *= np.float32(0.1)
+    t[:, 1] *= np.float32(0.8)
+    rgba = (np.clip(t, 0, 1) * np.float32(255)).astype(np.uint8)     # GetByteArray truncation
+    nz = np.nonzero(t[:, 3] != 0)[0]
+    return rgba, float(nz[0]), float(nz[-1])
+
+
+def volume_numpy(size, z0=0, zn=None, ztotal=None):
+    """sphere + ripple, uint8, [z][y][x]; z0/zn select a slab of a volume ztotal deep."""
+    sx, sy, sz = size
+    ztotal = sz if ztotal is None else ztotal
+    zn = sz if zn is None else zn
+    f = np.float32
+    x = (f(0.5) - np.arange(sx, dtype=f) / f(sx))[None, None, :]
+    y = (f(0.5) - np.arange(sy, dtype=f) / f(sy))[None, :, None]
+    z = (f(0.5) - (np.arange(zn, dtype=f) + f(z0)) / f(ztotal))[:, None, None]
+    d = np.sqrt(x * x + y * y + z * z)
+    v = np.maximum(f(0), (f(0.5) - d) * f(255) * f(2))
+    rip = f(18) * np.sin(x * f(40)) * np.sin(y * f(34)) * np.sin(z * f(46))
+    return np.clip(v + rip * (v > 0), 0, 255).astype(np.uint8)
+
+
+def volume_torch(size, device, z0=0, zn=None, ztotal=None):
+    import torch
+    sx, sy, sz = size
+    ztotal = sz if ztotal is None else ztotal
+    zn = sz if zn is None else zn
+    x = (0.5 - torch.arange(sx, device=device, dtype=torch.float32) / sx)[None, None, :]
+    y = (0.5 - torch.arange(sy, device=device, dtype=torch.float32) / sy)[None, :, None]
+    z = (0.5 - (torch.arange(zn, device=device, dtype=torch.float32) + z0) / ztotal)[:, None, None]
+    d = torch.sqrt(x * x + y * y + z * z)
+    v = torch.clamp((0.5 - d) * 255.0 * 2.0, min=0)
+    rip = 18.0 * torch.sin(x * 40.0) * torch.sin(y * 34.0) * torch.sin(z * 46.0)
+    return torch.clamp(v + rip * (v > 0), 0, 255).to(torch.uint8).contiguous()
+
+
+class ClockSampler(threading.Thread):
+    Q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 7 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 7 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def camera_for_step(H, k, steps, n_slabs=1):
+    cam = H.Camera()
+    ang = 0.35 + 2.0 * math.pi * (k % max(steps, 1)) / max(steps, 1)
+    cam.rotation = H.rotation_y(ang) @ H.rotation_x(0.35)
+    return cam
+
+
+# --------------------------------------------------------------------------- CPU arm
+def oracle_setup(z0=0, ztotal=None):
+    from oracle import host as H
+    from oracle import oracle as O
+    vol = volume_numpy(VOL, z0=z0, ztotal=ztotal)
+    oc = O.build_octree(vol, BRICK, OVERLAP)
+    pool = H.OraclePool(oc, (10, 10, 9))
+    pool.upload_first_brick()
+    req = []
+    for i in range(pool.total - 1):
+        req.append(pool.index_to_xyzl(i))
+    pool.upload_requests(req)
+    return H, O, oc, pool
+
+
+def cpu_frame(H, pool, tf_rgba, lo, hi, k, steps, w, h):
+    pool.recompute_visibility(0, lo, hi)
+    p = H.raycast_params(camera_for_step(H, k, steps), w, h, pool.vol)
+    frame = H.OracleFrame(w, h)
+    t0 = time.perf_counter()
+    H.raycast(p, pool, tf_rgba, frame)
+    dt = time.perf_counter() - t0
+    return int(frame.stats[0]), int(frame.stats[2]), dt, frame
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    H, O, oc, pool = oracle_setup()
+    tf_rgba, lo, hi = bench_tf()
+    cores = os.cpu_count() or 1
+    w, h = CPU_SAMPLE
+    for k in range(args.warmup):
+        cpu_frame(H, pool, tf_rgba, lo, hi, k, args.steps, w, h)
+    samples, secs = 0, 0.0
+    for k in range(args.steps):
+        s, r, dt, _ = cpu_frame(H, pool, tf_rgba, lo, hi, k, args.steps, w, h)
+        samples += s
+        secs += dt
+    value = samples / secs
+    sample = "same volume/TF/orbit, %dx%d rays per step (1/16 of 1920x1080)" % (w, h)
+    line = {"impl": "reference", "metric": "ray samples/s", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(n):
+    return {"workload": "synthetic %dx%dx%d uint8 (sphere+ripple), brick 64/overlap 2, 1D-TF + ERT, %dx%d, "
+                        "1 converged frame/step, orbiting camera" % (VOL[0], VOL[1], VOL[2] * n, WIDTH, HEIGHT),
+            "volume": [VOL[0], VOL[1], VOL[2] * n], "resolution": [WIDTH, HEIGHT], "render_mode": "1D-TF",
+            "lighting": False, "sample_rate_modifier": 1.0, "sampler": os.environ.get("TVK_SAMPLER", "exact"),
+            "l2": "inputs larger than L2 (236 MB pool) + 256 MB L2 flush between steps",
+            "parallelism": "single GPU" if n == 1 else "sort-last z-slabs x%d + direct-send compositing" % n}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_gpu(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    from imagevis3d_b200 import _lib as L
+    from imagevis3d_b200.context import TvkContext
+    from imagevis3d_b200 import hostmath as HM
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    tvk = TvkContext(local)
+    sampler = L.SAMPLER_TEX3D if os.environ.get("TVK_SAMPLER", "exact") == "tex3d" else L.SAMPLER_EXACT
+
+    # ---- untimed set-up: synthesize the slab in HBM, build bricks, fill the pool
+    raw = volume_torch(VOL, dev, z0=rank * VOL[2], ztotal=VOL[2] * world)
+    torch.cuda.synchronize()
+    t_b0 = time.perf_counter()
+    info = tvk.build_octree(raw_dptr=raw.data_ptr(), volume_size=VOL, bpv=1, brick=BRICK, overlap=OVERLAP)
+    t_build = time.perf_counter() - t_b0
+    off, sizes = tvk.build_toc()
+    mm = tvk.build_minmax()
+    lod_count = next(l for l in range(info.lod_count)
+                     if info.lod_bricks[l][0] * info.lod_bricks[l][1] * info.lod_bricks[l][2] == 1) + 1
+    cap = (10, 10, 9)
+    total = tvk.pool_create(VOL, (BRICK,) * 3, OVERLAP, 1, cap, lod_count, sampler)
+    store = tvk.build_store_ptr()
+    slots = np.arange(total, dtype=np.uint32)
+    slots[total - 1] = cap[0] * cap[1] * cap[2] - 1          # coarsest brick pinned in the last slot
+    tvk.pool_upload_device(slots, [store + int(o) for o in off[:total]], sizes[:total])
+    tvk.set_metadata(slots + 3)
+    tvk.set_minmax(mm[:total])
+    tf_rgba, lo, hi = bench_tf()
+    tvk.set_tf1d(tf_rgba)
+    tvk.recompute_visibility(0, lo, hi)
+
+    # host copies for the e2e leg (pinned) and the CPU baseline
+    blob = torch.empty(int(info.total_bytes), dtype=torch.uint8, pin_memory=True)
+    tvk._ck(tvk.lib.tvk_build_get_bricks(tvk.h, C.c_void_p(blob.data_ptr()), C.c_uint64(0), C.c_uint64(blob.numel())), "get_bricks")
+    meta_host = tvk.get_metadata()
+    img_host = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32, pin_memory=True)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def params_for(k):
+        cam = camera_for_step(HM, k, args.steps)
+        if world == 1:
+            return HM.raycast_params(cam, WIDTH, HEIGHT, VOL)
+        return HM.raycast_params(cam, WIDTH, HEIGHT, VOL, slab=(rank, world))
+
+    def step(k):
+        tvk.raycast(params_for(k))
+
+    # ---- warm-up
+    for k in range(args.warmup):
+        flush.zero_()
+        torch.cuda.synchronize()
+        step(k)
+        tvk.synchronize()
+    tvk.stats(reset=True)
+    assert len(tvk.read_requests()) == 0, "pool is not fully resident: frame would not be converged"
+
+    # ---- timed region (device time from CUDA events around each step's launch)
+    sampler_thread = ClockSampler(local)
+    sampler_thread.start()
+    time.sleep(0.3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    kernel_ms = 0.0
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        step(k)
+        tvk.synchronize()
+        kernel_ms += tvk.stats().last_raycast_ms
+    torch.cuda.synchronize()
+    wall_s = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    st = tvk.stats()
+    clocks = sampler_thread.stop()
+    samples, rays = int(st.samples), int(st.rays)
+
+    # ---- e2e: host buffers in, host image out, every step (pager upload + march + read-back)
+    h2d = int(sum(int(np.prod(s)) for s in sizes[:total])) + 4 * total
+    d2h = HEIGHT * WIDTH * 16
+    srcs = [blob.data_ptr() + int(o) for o in off[:total]]
+    n = len(srcs)
+    src_arr = (C.c_void_p * n)(*srcs)
+    slot_arr = np.ascontiguousarray(slots, np.uint32)
+    size_arr = np.ascontiguousarray(sizes[:total], np.uint32).reshape(-1)
+
+    def e2e_step(k):
+        tvk._ck(tvk.lib.tvk_pool_upload_bricks(tvk.h, C.c_uint32(n), slot_arr.ctypes.data_as(C.c_void_p), src_arr,
+                                               size_arr.ctypes.data_as(C.c_void_p), C.c_int(0)), "upload")
+        tvk._ck(tvk.lib.tvk_pool_upload_wait(tvk.h), "wait")
+        tvk.set_metadata(meta_host)
+        tvk.raycast(params_for(k))
+        tvk._ck(tvk.lib.tvk_read_image(tvk.h, C.c_void_p(img_host.data_ptr())), "read_image")
+
+    e2e_step(0)
+    tvk.stats(reset=True)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for k in range(args.steps):
+        e2e_step(k)
+    tvk.synchronize()
+    e2e_s = time.perf_counter() - t1
+    e2e_samples = int(tvk.stats().samples)
+
+    # ---- reduce over ranks
+    if world > 1:
+        t = torch.tensor([kernel_ms, wall_s, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kernel_ms, wall_s, e2e_s = [float(v) for v in t.tolist()]
+        c = torch.tensor([samples, rays, e2e_samples], device=dev, dtype=torch.int64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        samples, rays, e2e_samples = [int(v) for v in c.tolist()]
+    if rank != 0:
+        tvk.close()
+        return
+
+    peak, peak_src = peaks()
+    ms_step = kernel_ms / args.steps
+    value = samples / (kernel_ms * 1e-3)
+    alg_bytes = (samples * BYTES_PER_SAMPLE + rays * BYTES_PER_RAY) / args.steps / world
+    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    line = {"metric": "ray samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "samples_per_step": samples / args.steps, "rays_per_step": rays / args.steps,
+            "wall_ms_per_step_incl_l2_flush": 1e3 * wall_s / args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "0.6068 B/sample + 16 B/ray (SURVEY 8d); the kernel is L1/TEX-issue bound, see DESIGN.md"},
+            "e2e": {"value": e2e_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": args.steps, "clocks": clocks, "builder_ms_untimed": 1e3 * t_build}
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample
+    if world == 1 and not args.no_cpu:
+        from oracle import host as H
+        oc_like = dict(plan=None)
+        pool = build_oracle_pool_from_store(H, info, off, sizes, blob.numpy(), mm, total, cap, lod_count, slots, meta_host)
+        w, h = CPU_SAMPLE
+        p = H.raycast_params(camera_for_step(H, 0, args.steps), w, h, VOL)
+        frame = H.OracleFrame(w, h)
+        tc = time.perf_counter()
+        H.raycast(p, pool, tf_rgba, frame)
+        dt = time.perf_counter() - tc
+        line["cpu_baseline"] = {"value": int(frame.stats[0]) / dt, "unit": "samples/s", "cores": os.cpu_count() or 1,
+                                "kind": "port", "sample": "step 0 view at %dx%d (1/16 of the rays), %.1f s" % (w, h, dt)}
+    print(json.dumps(line))
+    tvk.close()
+
+
+def build_oracle_pool_from_store(H, info, off, sizes, blob, mm, total, cap, lod_count, slots, meta):
+    """Host copy of the device pool for the CPU baseline (bricks come from the CUDA builder, which the
+    tests prove bit-identical to the oracle builder)."""
+    class P:
+        pass
+    pool = P()
+    pool.vol, pool.bpv, pool.overlap, pool.max_brick, pool.lod_count, pool.capacity = VOL, 1, OVERLAP, (BRICK,) * 3, lod_count, cap
+    pool.layout, pool.lod_offset, pool.lod_bricks, pool.total = H.pool_layout(VOL, pool.max_brick, OVERLAP, lod_count)
+    pool.data = np.zeros((cap[2] * BRICK, cap[1] * BRICK, cap[0] * BRICK), np.uint8)
+    for i in range(total):
+        s = sizes[i]
+        b = blob[int(off[i]):int(off[i]) + int(np.prod(s))].reshape(int(s[2]), int(s[1]), int(s[0]))
+        sl = int(slots[i])
+        o = ((sl % cap[0]) * BRICK, ((sl // cap[0]) % cap[1]) * BRICK, (sl // (cap[0] * cap[1])) * BRICK)
+        pool.data[o[2]:o[2] + b.shape[0], o[1]:o[1] + b.shape[1], o[0]:o[0] + b.shape[2]] = b
+    pool.meta = np.ascontiguousarray(meta, np.uint32)
+    pool.c_pool = lambda: H.OraclePool.c_pool(pool)
+    return pool
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    run_gpu(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -241,9 +241,12 @@ __global__ void __launch_bounds__(256) place_bricks_surface(const PlaceJob* __re
 static int place_batch(tvk_ctx* c, std::vector<PlaceJob>& jobs, cudaStream_t st) {
   if (jobs.empty()) return TVK_OK;
   const uint32_t bpv = c->pc.bpv;
-  std::stable_partition(jobs.begin(), jobs.end(), [bpv](const PlaceJob& j) {
-    return !(((uintptr_t)j.src & 15) || ((j.sx * bpv) & 15));
-  });
+  // 16-byte accesses need 16 B aligned sources, rows AND pool slots (slot pitch = max_brick.x*bpv)
+  const bool slot_aligned = ((c->pc.max_brick[0] * bpv) & 15) == 0;
+  auto can_vec = [bpv, slot_aligned](const PlaceJob& j) {
+    return slot_aligned && !(((uintptr_t)j.src & 15) || ((j.sx * bpv) & 15));
+  };
+  std::stable_partition(jobs.begin(), jobs.end(), can_vec);
   PlaceJob* d_jobs = nullptr;
   TVK_CHECK_CUDA(c, cudaMallocAsync(&d_jobs, sizeof(PlaceJob) * jobs.size(), st));
   TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(PlaceJob) * jobs.size(), cudaMemcpyHostToDevice, st));
@@ -251,7 +254,7 @@ static int place_batch(tvk_ctx* c, std::vector<PlaceJob>& jobs, cudaStream_t st)
   if (c->pdesc.sampler == TVK_SAMPLER_EXACT) {
     // jobs arrive sorted: [0, nvec) can move 16 B per access, the rest go byte-wise
     size_t nvec = 0;
-    while (nvec < jobs.size() && !(((uintptr_t)jobs[nvec].src & 15) || ((jobs[nvec].sx * c->pc.bpv) & 15))) ++nvec;
+    while (nvec < jobs.size() && can_vec(jobs[nvec])) ++nvec;
     if (nvec) place_bricks_linear<16><<<dim3((unsigned)nvec, 8), 256, 0, st>>>(d_jobs, (uint8_t*)c->d_pool, c->pc);
     if (nvec < jobs.size()) {
       place_bricks_linear<1><<<dim3((unsigned)(jobs.size() - nvec), 8), 256, 0, st>>>(d_jobs + nvec, (uint8_t*)c->d_pool, c->pc);

@@ -59,7 +59,7 @@ def test_builder_full_size_properties(tvk):
     vol = (512, 512, 512)
     raw = H.synth_sphere(vol, np.uint8)
     info = tvk.build_octree(raw, 64, 2)
-    assert info.total_bricks == 890 and info.lod_count == 10
+    assert info.total_bricks == 895 and info.lod_count == 10 and info.lod_offset[4] + 1 == 890
     h1 = tvk.build_hist1d()
     assert h1.sum() == 512 ** 3                                   # every voxel counted once
     assert (h1 == np.bincount(raw.reshape(-1), minlength=256)[:len(h1)]).all()
