@@ -38,7 +38,8 @@ WIDTH, HEIGHT = 1920, 1080
 BRICK, OVERLAP = 64, 2
 BYTES_PER_SAMPLE = 1.2136 * 1 / 2.0     # 1.2136*bpv/(2*sampleRateModifier), uint8, srm 1
 BYTES_PER_RAY = 16.0                    # RGBA32F result write
-CPU_SAMPLE = (480, 270)                 # bounded CPU sample: same view at 1/16 of the rays
+CPU_SAMPLE = (1920, 1080)               # the CPU arm renders full frames (a frame is < 1 s on 16 cores)
+CPU_STEPS = 8                           # bounded: this many steps of the orbit
 
 
 def peaks():
@@ -179,7 +180,7 @@ def run_reference(args, rank):
         samples += s
         secs += dt
     value = samples / secs
-    sample = "same volume/TF/orbit, %dx%d rays per step (1/16 of 1920x1080)" % (w, h)
+    sample = "same volume/TF/orbit, full %dx%d frames, %d steps" % (w, h, args.steps)
     line = {"impl": "reference", "metric": "ray samples/s", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -349,13 +350,19 @@ def run_gpu(args, rank, world):
         oc_like = dict(plan=None)
         pool = build_oracle_pool_from_store(H, info, off, sizes, blob.numpy(), mm, total, cap, lod_count, slots, meta_host)
         w, h = CPU_SAMPLE
-        p = H.raycast_params(camera_for_step(H, 0, args.steps), w, h, VOL)
         frame = H.OracleFrame(w, h)
-        tc = time.perf_counter()
-        H.raycast(p, pool, tf_rgba, frame)
-        dt = time.perf_counter() - tc
-        line["cpu_baseline"] = {"value": int(frame.stats[0]) / dt, "unit": "samples/s", "cores": os.cpu_count() or 1,
-                                "kind": "port", "sample": "step 0 view at %dx%d (1/16 of the rays), %.1f s" % (w, h, dt)}
+        nsteps = min(CPU_STEPS, args.steps)
+        cs, dt = 0, 0.0
+        for k in range(-1, nsteps):                       # k = -1: untimed warm-up frame
+            p = H.raycast_params(camera_for_step(H, max(k, 0), args.steps), w, h, VOL)
+            tc = time.perf_counter()
+            H.raycast(p, pool, tf_rgba, frame)
+            if k >= 0:
+                dt += time.perf_counter() - tc
+                cs += int(frame.stats[0])
+        line["cpu_baseline"] = {"value": cs / dt, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "first %d steps of the same orbit at full %dx%d, %.1f s of CPU work"
+                                          % (nsteps, w, h, dt)}
     print(json.dumps(line))
     tvk.close()
 

@@ -78,6 +78,12 @@ extern "C" int tvk_create(int device, tvk_ctx** out) {
     return TVK_ERR_CUDA;
   }
   cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
+  // keep stream-ordered allocations (pager staging ring, job lists) cached between frames
+  cudaMemPool_t mp;
+  if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
   *out = c;
   return TVK_OK;
 }
@@ -306,11 +312,22 @@ extern "C" int tvk_pool_upload_bricks(tvk_ctx* c, uint32_t n, const uint32_t* sl
     for (uint32_t b0 = 0; b0 < n; b0 += batch) {
       const uint32_t bn = std::min(batch, n - b0);
       std::vector<PlaceJob> jobs(bn);
-      for (uint32_t i = 0; i < bn; ++i) {
-        const uint32_t k = b0 + i;
-        const size_t bytes = (size_t)sizes[3 * k] * sizes[3 * k + 1] * sizes[3 * k + 2] * c->pc.bpv;
-        TVK_CHECK_CUDA(c, cudaMemcpyAsync(staging + slot_bytes * i, src[k], bytes, cudaMemcpyHostToDevice, st));
-        jobs[i] = PlaceJob{staging + slot_bytes * i, slot[k], sizes[3 * k], sizes[3 * k + 1], sizes[3 * k + 2]};
+      for (uint32_t i = 0; i < bn;) {
+        // full-size bricks that are contiguous in host memory go out as ONE DMA
+        uint32_t run = 1;
+        size_t bytes = (size_t)sizes[3 * (b0 + i)] * sizes[3 * (b0 + i) + 1] * sizes[3 * (b0 + i) + 2] * c->pc.bpv;
+        if (bytes == slot_bytes)
+          while (i + run < bn &&
+                 (const uint8_t*)src[b0 + i + run] == (const uint8_t*)src[b0 + i] + slot_bytes * run &&
+                 (size_t)sizes[3 * (b0 + i + run)] * sizes[3 * (b0 + i + run) + 1] * sizes[3 * (b0 + i + run) + 2] * c->pc.bpv == slot_bytes)
+            ++run;
+        if (run > 1) bytes = slot_bytes * run;
+        TVK_CHECK_CUDA(c, cudaMemcpyAsync(staging + slot_bytes * i, src[b0 + i], bytes, cudaMemcpyHostToDevice, st));
+        for (uint32_t r = 0; r < run; ++r) {
+          const uint32_t k = b0 + i + r;
+          jobs[i + r] = PlaceJob{staging + slot_bytes * (i + r), slot[k], sizes[3 * k], sizes[3 * k + 1], sizes[3 * k + 2]};
+        }
+        i += run;
       }
       int rc = place_batch(c, jobs, st);
       if (rc) return rc;

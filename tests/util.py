@@ -96,10 +96,11 @@ def lockstep_render(tvk, params, pool, tf_rgba8, sampler=0, max_subframes=100):
     frame = H.OracleFrame(params.width, params.height, params.hash_table_size)
     params.new_view = 1
     tvk.stats(reset=True)
-    req_mismatch, req_total, subframes, samples_o = 0, 0, 0, 0
+    req_mismatch, req_total, subframes, samples_o, rays_o = 0, 0, 0, 0, 0
     for sub in range(max_subframes):
         H.raycast(params, pool, tf_rgba8, frame)
         samples_o += int(frame.stats[0])
+        rays_o += int(frame.stats[2])
         tvk.raycast(to_cuda_params(params))
         params.new_view = 0
         subframes += 1
@@ -118,4 +119,4 @@ def lockstep_render(tvk, params, pool, tf_rgba8, sampler=0, max_subframes=100):
     st = tvk.stats()
     return dict(cuda=img_c, oracle=frame.image.copy(), subframes=subframes, req_total=req_total,
                 req_mismatch=req_mismatch, samples_cuda=int(st.samples), samples_oracle=samples_o,
-                pos_cuda=pos_c, pos_oracle=frame.pos.copy(), rays_cuda=int(st.rays), rays_oracle=int(frame.stats[2]))
+                pos_cuda=pos_c, pos_oracle=frame.pos.copy(), rays_cuda=int(st.rays), rays_oracle=rays_o)
