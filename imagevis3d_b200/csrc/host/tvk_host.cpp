@@ -1,0 +1,851 @@
+// C++ host of the B200 ray-caster (see tvk_host.h).  Pure host code: every device
+// operation is a call into the C ABI of include/tvk_cuda.h.
+#include "tvk_host.h"
+#include <cuda_runtime_api.h>   // only cudaHostAlloc/cudaFreeHost for the pinned out-of-core store
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+
+namespace tvk {
+
+// ---------------------------------------------------------------------------- math
+float Vec3::length() const { return std::sqrt(x * x + y * y + z * z); }
+Vec3 Vec3::normalized() const { const float l = length(); return Vec3(x / l, y / l, z / l); }
+
+Matrix4::Matrix4() { for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.0f : 0.0f; }
+
+Matrix4 Matrix4::operator*(const Matrix4& o) const {      // Vectors.h:936-946
+  Matrix4 r;
+  for (int x = 0; x < 16; x += 4)
+    for (int y = 0; y < 4; ++y)
+      r.m[x + y] = m[0 + x] * o.m[0 + y] + m[1 + x] * o.m[4 + y] + m[2 + x] * o.m[8 + y] + m[3 + x] * o.m[12 + y];
+  return r;
+}
+
+Matrix4 Matrix4::transposed() const {
+  Matrix4 r;
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) r.m[4 * i + j] = m[4 * j + i];
+  return r;
+}
+
+// General 4x4 inverse by cofactors (the reference expands the same adjugate in
+// fp32, Vectors.h:1042-1140; we accumulate in double and round once).
+Matrix4 Matrix4::inverse() const {
+  double a[16], inv[16];
+  for (int i = 0; i < 16; ++i) a[i] = m[i];
+  inv[0] = a[5] * a[10] * a[15] - a[5] * a[11] * a[14] - a[9] * a[6] * a[15] + a[9] * a[7] * a[14] + a[13] * a[6] * a[11] - a[13] * a[7] * a[10];
+  inv[4] = -a[4] * a[10] * a[15] + a[4] * a[11] * a[14] + a[8] * a[6] * a[15] - a[8] * a[7] * a[14] - a[12] * a[6] * a[11] + a[12] * a[7] * a[10];
+  inv[8] = a[4] * a[9] * a[15] - a[4] * a[11] * a[13] - a[8] * a[5] * a[15] + a[8] * a[7] * a[13] + a[12] * a[5] * a[11] - a[12] * a[7] * a[9];
+  inv[12] = -a[4] * a[9] * a[14] + a[4] * a[10] * a[13] + a[8] * a[5] * a[14] - a[8] * a[6] * a[13] - a[12] * a[5] * a[10] + a[12] * a[6] * a[9];
+  inv[1] = -a[1] * a[10] * a[15] + a[1] * a[11] * a[14] + a[9] * a[2] * a[15] - a[9] * a[3] * a[14] - a[13] * a[2] * a[11] + a[13] * a[3] * a[10];
+  inv[5] = a[0] * a[10] * a[15] - a[0] * a[11] * a[14] - a[8] * a[2] * a[15] + a[8] * a[3] * a[14] + a[12] * a[2] * a[11] - a[12] * a[3] * a[10];
+  inv[9] = -a[0] * a[9] * a[15] + a[0] * a[11] * a[13] + a[8] * a[1] * a[15] - a[8] * a[3] * a[13] - a[12] * a[1] * a[11] + a[12] * a[3] * a[9];
+  inv[13] = a[0] * a[9] * a[14] - a[0] * a[10] * a[13] - a[8] * a[1] * a[14] + a[8] * a[2] * a[13] + a[12] * a[1] * a[10] - a[12] * a[2] * a[9];
+  inv[2] = a[1] * a[6] * a[15] - a[1] * a[7] * a[14] - a[5] * a[2] * a[15] + a[5] * a[3] * a[14] + a[13] * a[2] * a[7] - a[13] * a[3] * a[6];
+  inv[6] = -a[0] * a[6] * a[15] + a[0] * a[7] * a[14] + a[4] * a[2] * a[15] - a[4] * a[3] * a[14] - a[12] * a[2] * a[7] + a[12] * a[3] * a[6];
+  inv[10] = a[0] * a[5] * a[15] - a[0] * a[7] * a[13] - a[4] * a[1] * a[15] + a[4] * a[3] * a[13] + a[12] * a[1] * a[7] - a[12] * a[3] * a[5];
+  inv[14] = -a[0] * a[5] * a[14] + a[0] * a[6] * a[13] + a[4] * a[1] * a[14] - a[4] * a[2] * a[13] - a[12] * a[1] * a[6] + a[12] * a[2] * a[5];
+  inv[3] = -a[1] * a[6] * a[11] + a[1] * a[7] * a[10] + a[5] * a[2] * a[11] - a[5] * a[3] * a[10] - a[9] * a[2] * a[7] + a[9] * a[3] * a[6];
+  inv[7] = a[0] * a[6] * a[11] - a[0] * a[7] * a[10] - a[4] * a[2] * a[11] + a[4] * a[3] * a[10] + a[8] * a[2] * a[7] - a[8] * a[3] * a[6];
+  inv[11] = -a[0] * a[5] * a[11] + a[0] * a[7] * a[9] + a[4] * a[1] * a[11] - a[4] * a[3] * a[9] - a[8] * a[1] * a[7] + a[8] * a[3] * a[5];
+  inv[15] = a[0] * a[5] * a[10] - a[0] * a[6] * a[9] - a[4] * a[1] * a[10] + a[4] * a[2] * a[9] + a[8] * a[1] * a[6] - a[8] * a[2] * a[5];
+  const double det = a[0] * inv[0] + a[1] * inv[4] + a[2] * inv[8] + a[3] * inv[12];
+  Matrix4 r;
+  for (int i = 0; i < 16; ++i) r.m[i] = (float)(inv[i] / det);
+  return r;
+}
+
+Matrix4 Matrix4::Translation(float x, float y, float z) { Matrix4 r; r.m[12] = x; r.m[13] = y; r.m[14] = z; return r; }
+Matrix4 Matrix4::Scaling(float x, float y, float z) { Matrix4 r; r.m[0] = x; r.m[5] = y; r.m[10] = z; return r; }
+Matrix4 Matrix4::RotationX(double a) {                      // Vectors.h:984-992
+  Matrix4 r; const float c = (float)std::cos(a), s = (float)std::sin(a);
+  r.m[5] = c; r.m[6] = s; r.m[9] = -s; r.m[10] = c; return r;
+}
+Matrix4 Matrix4::RotationY(double a) {
+  Matrix4 r; const float c = (float)std::cos(a), s = (float)std::sin(a);
+  r.m[0] = c; r.m[2] = -s; r.m[8] = s; r.m[10] = c; return r;
+}
+Matrix4 Matrix4::RotationZ(double a) {
+  Matrix4 r; const float c = (float)std::cos(a), s = (float)std::sin(a);
+  r.m[0] = c; r.m[1] = s; r.m[4] = -s; r.m[5] = c; return r;
+}
+Matrix4 Matrix4::LookAt(const Vec3& eye, const Vec3& at, const Vec3& up) {    // Vectors.h:1250-1265
+  Vec3 F = at - eye, U = up;
+  Vec3 S = F.cross(U);
+  U = S.cross(F);
+  F = F.normalized(); U = U.normalized(); S = S.normalized();
+  Matrix4 r;
+  r.m[0] = S.x; r.m[4] = S.y; r.m[8] = S.z; r.m[12] = -S.dot(eye);
+  r.m[1] = U.x; r.m[5] = U.y; r.m[9] = U.z; r.m[13] = -U.dot(eye);
+  r.m[2] = -F.x; r.m[6] = -F.y; r.m[10] = -F.z; r.m[14] = F.dot(eye);
+  r.m[3] = 0; r.m[7] = 0; r.m[11] = 0; r.m[15] = 1;
+  return r;
+}
+Matrix4 Matrix4::Perspective(float fovy, float aspect, float n, float f) {    // Vectors.h:1267-1277
+  fovy = fovy * float(3.14159265358979323846 / 180.0);
+  const float cotan = float(1.0 / std::tan(double(fovy) / 2.0));
+  Matrix4 r;
+  for (int i = 0; i < 16; ++i) r.m[i] = 0;
+  r.m[0] = cotan / aspect; r.m[5] = cotan;
+  r.m[10] = -(f + n) / (f - n); r.m[14] = -2.0f * (f * n) / (f - n);
+  r.m[11] = -1.0f;
+  return r;
+}
+void Matrix4::transform(const float v[4], float out[4]) const {
+  for (int j = 0; j < 4; ++j) out[j] = v[0] * m[j] + v[1] * m[4 + j] + v[2] * m[8 + j] + v[3] * m[12 + j];
+}
+
+// ---------------------------------------------------------------------------- TransferFunction1D
+void TransferFunction1D::Set(const float* rgba, size_t n) { m_color.assign(rgba, rgba + 4 * n); ComputeNonZeroLimits(); }
+
+bool TransferFunction1D::Load(const std::string& filename) {                  // TransferFunction1D.cpp:279-293
+  std::ifstream f(filename.c_str());
+  if (!f.is_open()) return false;
+  uint32_t n = 0;
+  f >> n;
+  if (!f || n == 0) return false;
+  m_color.assign(4 * (size_t)n, 0.0f);
+  for (size_t i = 0; i < 4 * (size_t)n; ++i) if (!(f >> m_color[i])) return false;
+  ComputeNonZeroLimits();
+  return true;
+}
+bool TransferFunction1D::Save(const std::string& filename) const {
+  std::ofstream f(filename.c_str());
+  if (!f.is_open()) return false;
+  f << GetSize() << "\n";
+  for (size_t i = 0; i < GetSize(); ++i)
+    f << m_color[4 * i] << " " << m_color[4 * i + 1] << " " << m_color[4 * i + 2] << " " << m_color[4 * i + 3] << "\n";
+  return true;
+}
+static float Smoothstep(float x) { return 3 * x * x - 2 * x * x * x; }
+void TransferFunction1D::SetStdFunction(float c, float g, int comp) {        // TransferFunction1D.cpp:81-112
+  const size_t n = GetSize();
+  if (!n) return;
+  const size_t ic = size_t((n - 1) * float(std::min<float>(std::max<float>(0, c), 1)));
+  const size_t ig = size_t((n - 1) * float(std::min<float>(std::max<float>(0, g), 1)));
+  const size_t start = (ig / 2 > ic) ? 0 : ic - (ig / 2);
+  const size_t end = (ig / 2 + ic > n) ? n : ic + (ig / 2);
+  for (size_t i = 0; i < start; ++i) m_color[4 * i + comp] = 0;
+  for (size_t i = start; i < end; ++i) m_color[4 * i + comp] = Smoothstep(float(i - ic + (ig / 2)) / float(ig));
+  for (size_t i = end; i < n; ++i) m_color[4 * i + comp] = 1;
+}
+void TransferFunction1D::SetStdFunction(float c, float g) {
+  for (int k = 0; k < 4; ++k) SetStdFunction(c, g, k);
+  ComputeNonZeroLimits();
+}
+void TransferFunction1D::GetByteArray(std::vector<uint8_t>& out, uint8_t used) const {   // :311-328 (truncates)
+  out.resize(m_color.size());
+  for (size_t i = 0; i < m_color.size(); ++i)
+    out[i] = (uint8_t)(std::max(0.0f, std::min(m_color[i], 1.0f)) * used);
+}
+void TransferFunction1D::ComputeNonZeroLimits() {                                        // :362-370
+  m_lo = GetSize(); m_hi = 0;
+  for (size_t i = 0; i < GetSize(); ++i)
+    if (m_color[4 * i + 3] != 0) { m_lo = std::min<uint64_t>(m_lo, i); m_hi = i; }
+}
+
+// ---------------------------------------------------------------------------- BrickedVolume
+uint32_t BrickedVolume::LargestSingleBrickLOD() const {
+  for (uint32_t l = 0; l < info.lod_count; ++l)
+    if ((uint64_t)info.lod_bricks[l][0] * info.lod_bricks[l][1] * info.lod_bricks[l][2] == 1) return l;
+  return info.lod_count - 1;
+}
+void BrickedVolume::MaxUsedBrickSizes(uint32_t out[3]) const {
+  out[0] = out[1] = out[2] = 0;
+  for (size_t i = 0; i < sizes.size() / 3; ++i) for (int a = 0; a < 3; ++a) out[a] = std::max(out[a], sizes[3 * i + a]);
+}
+uint64_t BrickedVolume::TocIndex(uint32_t x, uint32_t y, uint32_t z, uint32_t lod) const {
+  return info.lod_offset[lod] + x + (uint64_t)y * info.lod_bricks[lod][0] + (uint64_t)z * info.lod_bricks[lod][0] * info.lod_bricks[lod][1];
+}
+void BrickedVolume::Range(double& lo, double& hi) const {
+  const uint64_t n0 = (uint64_t)info.lod_bricks[0][0] * info.lod_bricks[0][1] * info.lod_bricks[0][2];
+  lo = minmax[0]; hi = minmax[1];
+  for (uint64_t i = 1; i < n0; ++i) { lo = std::min(lo, minmax[2 * i]); hi = std::max(hi, minmax[2 * i + 1]); }
+}
+
+// ---------------------------------------------------------------------------- BrickPool
+void BrickPool::ComputePoolCapacity(const BrickedVolume& v, uint64_t gpuMem, uint32_t max3d, uint32_t cap[3]) {
+  uint32_t bs[3];
+  v.MaxUsedBrickSizes(bs);
+  // the layout the GPU memory allows (GPUMemMan.cpp:780-803)
+  const uint64_t maxVoxels = gpuMem / v.bpv;
+  const uint64_t r3 = (uint64_t)std::pow((double)maxVoxels, 1.0 / 3.0);
+  uint64_t gx = uint64_t(((float)r3 / bs[0]) + 0.5f) * bs[0];
+  if (gx > max3d) gx = (max3d / bs[0]) * bs[0];
+  if (gx < bs[0]) gx = bs[0];
+  uint64_t gy = ((maxVoxels / (gx * gx)) / bs[1]) * bs[1];
+  if (gy > max3d) gy = (max3d / bs[1]) * bs[1];
+  if (gy < bs[1]) gy = bs[1];
+  uint64_t gz = ((maxVoxels / (gx * gy)) / bs[2]) * bs[2];
+  if (gz > max3d) gz = (max3d / bs[2]) * bs[2];
+  if (gz < bs[2]) gz = bs[2];
+  // the layout the dataset needs (:805-826)
+  const uint64_t nb = v.info.total_bricks;                 // GetTotalBrickCount: all LODs of the file
+  const uint64_t r3b = (uint64_t)std::pow((double)nb, 1.0 / 3.0);
+  uint64_t dx = (uint64_t)bs[0] * std::max<uint64_t>(r3b, 1);
+  if (dx > max3d) dx = (max3d / bs[0]) * bs[0];
+  uint64_t dy = bs[1] * (uint64_t)std::ceil(float(nb) / ((dx / bs[0]) * (dx / bs[0])));
+  if (dy > max3d) dy = (max3d / bs[1]) * bs[1];
+  uint64_t dz = bs[2] * (uint64_t)std::ceil(float(nb) / ((dx / bs[0]) * (dy / bs[1])));
+  if (dz > max3d) dz = (max3d / bs[2]) * bs[2];
+  const bool useDataset = (dx * dy * dz) < (gx * gy * gz);
+  cap[0] = (uint32_t)((useDataset ? dx : gx) / bs[0]);
+  cap[1] = (uint32_t)((useDataset ? dy : gy) / bs[1]);
+  cap[2] = (uint32_t)((useDataset ? dz : gz) / bs[2]);
+}
+
+int BrickPool::Create(const uint32_t capacity[3], uint32_t sampler) {
+  tvk_pool_desc d{};
+  m_vol->MaxUsedBrickSizes(m_maxBrick);
+  for (int a = 0; a < 3; ++a) { d.volume_size[a] = m_vol->domain[a]; d.max_brick_size[a] = m_maxBrick[a]; d.pool_capacity[a] = m_cap[a] = capacity[a]; }
+  d.overlap = m_vol->overlap;
+  d.bytes_per_voxel = m_vol->bpv;
+  d.lod_count = m_lodCount = m_vol->LargestSingleBrickLOD() + 1;
+  d.sampler = sampler;
+  int rc = tvk_pool_create(m_ctx, &d);
+  if (rc) return rc;
+  rc = tvk_pool_total_bricks(m_ctx, &m_total);
+  if (rc) return rc;
+  // GetBrickLayout / LoD offset table (GLVolumePool.cpp:109-117,222-230)
+  m_lodOffset.assign(m_lodCount, 0);
+  m_lodBricks.assign(3 * m_lodCount, 0);
+  uint32_t off = 0;
+  for (uint32_t l = 0; l < m_lodCount; ++l) {
+    for (int a = 0; a < 3; ++a) {
+      const uint32_t inner = m_maxBrick[a] - 2 * m_vol->overlap;
+      const uint32_t base = (uint32_t)std::ceil((double)m_vol->domain[a] / inner);
+      m_lodBricks[3 * l + a] = (uint32_t)std::ceil((double)base / (1u << l));
+    }
+    m_lodOffset[l] = off;
+    off += m_lodBricks[3 * l] * m_lodBricks[3 * l + 1] * m_lodBricks[3 * l + 2];
+  }
+  // m_vMinMaxScalar: dataset min/max in pool index order (:232-239)
+  m_minmax.assign(2 * (size_t)m_total, 0.0);
+  for (uint32_t i = 0; i < m_total; ++i) {
+    uint32_t c[4];
+    BrickCoords(i, c);
+    if (c[0] >= m_vol->info.lod_bricks[c[3]][0] || c[1] >= m_vol->info.lod_bricks[c[3]][1] || c[2] >= m_vol->info.lod_bricks[c[3]][2])
+      return TVK_ERR_UNSUPPORTED;      // pool layout and octree layout disagree (reference would mis-index)
+    const uint64_t t = m_vol->TocIndex(c[0], c[1], c[2], c[3]);
+    m_minmax[2 * i] = m_vol->minmax[2 * t];
+    m_minmax[2 * i + 1] = m_vol->minmax[2 * t + 1];
+  }
+  rc = tvk_visibility_set_minmax(m_ctx, m_minmax.data(), nullptr, m_total);
+  if (rc) return rc;
+  const uint32_t nslots = capacity[0] * capacity[1] * capacity[2];
+  m_slots.assign(nslots, PoolSlot());
+  for (uint32_t i = 0; i < nslots; ++i) m_slots[i].pos = i;
+  m_time = 2; m_insertPos = 0; m_uploadedBytes = 0;
+  return TVK_OK;
+}
+
+uint32_t BrickPool::BrickIndex(uint32_t x, uint32_t y, uint32_t z, uint32_t lod) const {
+  return m_lodOffset[lod] + x + y * m_lodBricks[3 * lod] + z * m_lodBricks[3 * lod] * m_lodBricks[3 * lod + 1];
+}
+void BrickPool::BrickCoords(uint32_t index, uint32_t c[4]) const {
+  uint32_t lod = (uint32_t)(std::upper_bound(m_lodOffset.begin(), m_lodOffset.end(), index) - m_lodOffset.begin()) - 1;
+  const uint32_t bx = m_lodBricks[3 * lod], by = m_lodBricks[3 * lod + 1];
+  index -= m_lodOffset[lod];
+  c[0] = index % bx; c[1] = (index % (bx * by)) / bx; c[2] = index / (bx * by); c[3] = lod;
+}
+bool BrickPool::IsBrickResident(uint32_t x, uint32_t y, uint32_t z, uint32_t lod) const {
+  const int32_t id = (int32_t)BrickIndex(x, y, z, lod);
+  for (const PoolSlot& s : m_slots) if (s.brick == id) return true;
+  return false;
+}
+
+void BrickPool::PrepareForPaging() {
+  // std::sort by m_iTimeOfCreation (:946-959); stable here so that ties are deterministic
+  std::stable_sort(m_slots.begin(), m_slots.end(), [](const PoolSlot& a, const PoolSlot& b) { return a.time < b.time; });
+  m_insertPos = 0;
+}
+
+int BrickPool::UploadFirstBrick() {
+  // coarsest brick -> last slot, time = UINT64_MAX so that it is never evicted (:763-766)
+  const uint32_t idx = m_lodOffset[m_lodCount - 1];
+  uint32_t c[4];
+  BrickCoords(idx, c);
+  const uint64_t t = m_vol->TocIndex(c[0], c[1], c[2], c[3]);
+  PoolSlot& s = m_slots[m_slots.size() - 1];
+  s.brick = (int32_t)idx; s.time = UINT64_MAX;
+  const void* src = m_vol->host_store ? (const void*)(m_vol->host_store + m_vol->offsets[t])
+                                      : (const void*)((const uint8_t*)m_vol->device_store + m_vol->offsets[t]);
+  int rc = tvk_pool_upload_bricks(m_ctx, 1, &s.pos, &src, &m_vol->sizes[3 * t], m_vol->host_store ? 0 : 1);
+  if (rc) return rc;
+  rc = tvk_pool_upload_wait(m_ctx);
+  if (rc) return rc;
+  const uint32_t val = s.pos + TVK_BI_FLAG_COUNT;
+  return tvk_pool_patch_metadata(m_ctx, 1, &idx, &val);
+}
+
+int BrickPool::UploadBricks(const std::vector<uint32_t>& xyzl, uint32_t& paged) {
+  paged = 0;
+  const size_t n = xyzl.size() / 4;
+  if (!n) return TVK_OK;
+  PrepareForPaging();
+  std::vector<uint32_t> slot, sizes, pidx, pval;
+  std::vector<const void*> src;
+  for (size_t i = 0; i < n; ++i) {
+    // "in this frame we already replaced all bricks (except the single low-res brick)" (:768-778)
+    if (m_insertPos >= m_slots.size() - 1) break;
+    const uint32_t* b = &xyzl[4 * i];
+    if (b[3] >= m_lodCount || b[0] >= m_lodBricks[3 * b[3]] || b[1] >= m_lodBricks[3 * b[3] + 1] || b[2] >= m_lodBricks[3 * b[3] + 2])
+      return TVK_ERR_INVALID;
+    const uint32_t idx = BrickIndex(b[0], b[1], b[2], b[3]);
+    PoolSlot& s = m_slots[m_insertPos];
+    if (s.ContainsVisibleBrick()) { pidx.push_back((uint32_t)s.brick); pval.push_back(TVK_BI_MISSING); }   // evicted
+    s.brick = (int32_t)idx;
+    s.time = m_time++;
+    pidx.push_back(idx); pval.push_back(s.pos + TVK_BI_FLAG_COUNT);
+    const uint64_t t = m_vol->TocIndex(b[0], b[1], b[2], b[3]);
+    slot.push_back(s.pos);
+    src.push_back(m_vol->host_store ? (const void*)(m_vol->host_store + m_vol->offsets[t])
+                                    : (const void*)((const uint8_t*)m_vol->device_store + m_vol->offsets[t]));
+    for (int a = 0; a < 3; ++a) sizes.push_back(m_vol->sizes[3 * t + a]);
+    m_uploadedBytes += (uint64_t)m_vol->sizes[3 * t] * m_vol->sizes[3 * t + 1] * m_vol->sizes[3 * t + 2] * m_vol->bpv;
+    ++m_insertPos;
+    ++paged;
+  }
+  int rc = tvk_pool_upload_bricks(m_ctx, (uint32_t)slot.size(), slot.data(), src.data(), sizes.data(), m_vol->host_store ? 0 : 1);
+  if (rc) return rc;
+  rc = tvk_pool_upload_wait(m_ctx);
+  if (rc) return rc;
+  // a slot can be evicted and re-filled within one pass only across passes, so later patches win
+  return tvk_pool_patch_metadata(m_ctx, (uint32_t)pidx.size(), pidx.data(), pval.data());
+}
+
+bool BrickPool::ContainsData(const tvk_visibility& v, uint32_t i) const {     // :963-989
+  const double lo = m_minmax[2 * i], hi = m_minmax[2 * i + 1];
+  switch (v.render_mode) {
+    case TVK_RM_1DTRANS: return v.smax >= lo && v.smin <= hi;
+    case TVK_RM_2DTRANS: return (v.smax >= lo && v.smin <= hi) && (v.gmax >= -DBL_MAX && v.gmin <= DBL_MAX);
+    default: return v.smin >= lo && v.smin <= hi;
+  }
+}
+
+int BrickPool::RecomputeVisibility(const tvk_visibility& vis, uint32_t counts[4]) {
+  // RecomputeVisibilityForBrickPool (:992-1018): slot bookkeeping on the host; the resident
+  // entries are (re)written so that a brick flagged EMPTY earlier gets its slot back
+  std::vector<uint32_t> pidx, pval;
+  for (PoolSlot& s : m_slots) {
+    if (!s.WasEverUsed()) continue;
+    const bool cd = ContainsData(vis, (uint32_t)s.brick), had = s.ContainsVisibleBrick();
+    if (cd) { if (!had) s.Restore(); pidx.push_back((uint32_t)s.brick); pval.push_back(s.pos + TVK_BI_FLAG_COUNT); }
+    else { if (had) s.FlagEmpty(); pidx.push_back((uint32_t)s.brick); pval.push_back(TVK_BI_EMPTY); }
+  }
+  int rc = tvk_pool_patch_metadata(m_ctx, (uint32_t)pidx.size(), pidx.data(), pval.data());
+  if (rc) return rc;
+  // RecomputeVisibilityForOctree (:1021-1359) on the device
+  return tvk_visibility_recompute(m_ctx, &vis, counts);
+}
+
+// ---------------------------------------------------------------------------- CudaGridLeaper
+CudaGridLeaper::CudaGridLeaper() : m_tf1d(256) { m_tf1d.SetStdFunction(); }
+CudaGridLeaper::~CudaGridLeaper() { Cleanup(); }
+
+bool CudaGridLeaper::Fail(const std::string& what, int rc) {
+  m_err = what + " (status " + std::to_string(rc) + (m_ctx ? std::string("): ") + tvk_last_error(m_ctx) : ")");
+  return false;
+}
+
+bool CudaGridLeaper::Initialize(int device) {
+  if (m_ctx) return true;
+  const int rc = tvk_create(device, &m_ctx);
+  if (rc) { m_ctx = nullptr; return Fail("tvk_create", rc); }
+  return true;
+}
+
+void CudaGridLeaper::Cleanup() {
+  delete m_pool; m_pool = nullptr;
+  if (m_vol) { if (m_vol->host_store) cudaFreeHost(m_vol->host_store); delete m_vol; m_vol = nullptr; }
+  if (m_ctx) { tvk_destroy(m_ctx); m_ctx = nullptr; }
+}
+
+bool CudaGridLeaper::LoadRawVolume(const void* raw, const uint32_t size[3], uint32_t bpv, const float scale[3],
+                                   uint32_t brickSize, uint32_t overlap, bool median, bool outOfCore,
+                                   uint64_t gpuMemBytes, bool computeHist2D) {
+  if (!m_ctx) { m_err = "renderer not initialised"; return false; }
+  delete m_pool; m_pool = nullptr;
+  if (m_vol) { if (m_vol->host_store) cudaFreeHost(m_vol->host_store); delete m_vol; m_vol = nullptr; }
+  tvk_build_desc d{};
+  for (int a = 0; a < 3; ++a) d.volume_size[a] = size[a];
+  d.brick_size = brickSize; d.overlap = overlap; d.bytes_per_voxel = bpv; d.use_median = median ? 1 : 0;
+  BrickedVolume* v = new BrickedVolume();
+  int rc = tvk_build_octree(m_ctx, &d, raw, 0, &v->info);
+  if (rc) { delete v; return Fail("tvk_build_octree", rc); }
+  for (int a = 0; a < 3; ++a) { v->domain[a] = size[a]; v->scale[a] = scale ? scale[a] : 1.0f; }
+  v->bpv = bpv; v->brick_size = brickSize; v->overlap = overlap;
+  const uint64_t n = v->info.total_bricks;
+  v->offsets.resize(n); v->sizes.resize(3 * n); v->minmax.resize(2 * n);
+  rc = tvk_build_get_toc(m_ctx, v->offsets.data(), v->sizes.data(), n);
+  if (!rc) rc = tvk_build_get_minmax(m_ctx, v->minmax.data(), n);
+  if (rc) { delete v; return Fail("tvk_build_get_*", rc); }
+  v->hist1d.resize(1u << (8 * bpv));
+  uint32_t hn = 0;
+  rc = tvk_build_hist1d(m_ctx, v->hist1d.data(), (uint32_t)v->hist1d.size(), &hn);
+  if (rc) { delete v; return Fail("tvk_build_hist1d", rc); }
+  v->hist1d.resize(hn);
+  // RAWConverter caps the 1-D histogram (= TF size) at 4096 bins (Quantize.h:429-578)
+  uint32_t tfSize = std::max<uint32_t>(1, std::min<uint32_t>(hn, 4096));
+  if (computeHist2D) {
+    double lo, hi;
+    v->Range(lo, hi);
+    std::vector<uint64_t> h2((size_t)tfSize * 256);
+    rc = tvk_build_hist2d(m_ctx, tfSize, hi, h2.data(), &v->max_grad_magnitude);
+    if (rc) { delete v; return Fail("tvk_build_hist2d", rc); }
+  }
+  v->store_bytes = v->info.total_bytes;
+  if (outOfCore) {
+    if (cudaHostAlloc((void**)&v->host_store, v->store_bytes, cudaHostAllocDefault) != cudaSuccess) {
+      delete v; m_err = "cudaHostAlloc failed for the out-of-core brick store"; return false;
+    }
+    rc = tvk_build_get_bricks(m_ctx, v->host_store, 0, v->store_bytes);
+    if (rc) { cudaFreeHost(v->host_store); delete v; return Fail("tvk_build_get_bricks", rc); }
+    tvk_build_release(m_ctx);
+  } else {
+    rc = tvk_build_store_device_ptr(m_ctx, &v->device_store);
+    if (rc) { delete v; return Fail("tvk_build_store_device_ptr", rc); }
+  }
+  m_vol = v;
+  // pool sizing: dataset-sized unless a GPU memory budget is given (GPUMemMan.cpp:766-844)
+  uint32_t cap[3];
+  uint32_t bs[3];
+  v->MaxUsedBrickSizes(bs);
+  const uint64_t need = (uint64_t)bs[0] * bs[1] * bs[2] * bpv * (v->info.total_bricks + 8);
+  BrickPool::ComputePoolCapacity(*v, gpuMemBytes ? gpuMemBytes : need, 16384, cap);
+  m_pool = new BrickPool(m_ctx, v);
+  rc = m_pool->Create(cap, m_sampler);
+  if (rc) return Fail("pool create", rc);
+  rc = m_pool->UploadFirstBrick();
+  if (rc) return Fail("UploadFirstBrick", rc);
+  // AbstrRenderer::LoadFile tail (:245-261): default iso value = half the range; TF sized like the histogram
+  double lo, hi;
+  v->Range(lo, hi);
+  m_isoValue = float(hi - lo) / 2.0f;
+  m_tf1d.Resize(tfSize);
+  m_tf1d.SetStdFunction();
+  m_visValid = false;
+  Changed1DTrans();
+  ScheduleCompleteRedraw();
+  return true;
+}
+
+void CudaGridLeaper::Resize(uint32_t w, uint32_t h) { m_w = w; m_h = h; ScheduleCompleteRedraw(); }
+
+bool CudaGridLeaper::SetRendermode(int mode) {
+  if (mode < RM_1DTRANS || mode > RM_ISOSURFACE) { m_err = "invalid render mode"; return false; }
+  if (mode == RM_2DTRANS && !m_has2d) { m_err = "no 2D transfer function set"; return false; }
+  m_mode = mode;
+  RecomputeBrickVisibility(false);
+  ScheduleCompleteRedraw();
+  return true;
+}
+void CudaGridLeaper::SetUseLighting(bool b) { m_lighting = b; ScheduleCompleteRedraw(); }
+void CudaGridLeaper::SetSampleRateModifier(float f) { m_sampleRate = f; ScheduleCompleteRedraw(); }
+void CudaGridLeaper::SetFoV(float f) { m_fov = f; ScheduleCompleteRedraw(); }
+void CudaGridLeaper::SetViewPos(const Vec3& p) { m_at = m_at + (p - m_eye); m_eye = p; ScheduleCompleteRedraw(); }   // AbstrRenderer.cpp:1587-1591
+void CudaGridLeaper::SetViewDir(const Vec3& d) { m_at = d + m_eye; ScheduleCompleteRedraw(); }                       // :1603-1606
+void CudaGridLeaper::SetUpDir(const Vec3& u) { m_up = u; ScheduleCompleteRedraw(); }
+void CudaGridLeaper::ResetViewPos() { m_at = Vec3(0, 0, 0); m_eye = Vec3(0, 0, 1.6f); ScheduleCompleteRedraw(); }
+void CudaGridLeaper::ResetViewDir() { m_at = Vec3(0, 0, 0); ScheduleCompleteRedraw(); }
+void CudaGridLeaper::ResetUpDir() { m_up = Vec3(0, 1, 0); ScheduleCompleteRedraw(); }
+void CudaGridLeaper::SetViewParameters(float angle, float znear, float zfar, const Vec3& eye, const Vec3& ref, const Vec3& up) {
+  m_fov = angle; m_znear = znear; m_zfar = zfar; m_eye = eye; m_at = ref; m_up = up;
+  ScheduleCompleteRedraw();
+}
+void CudaGridLeaper::SetRotation4x4(const Matrix4& m) { m_rotation = m; ScheduleCompleteRedraw(); }
+void CudaGridLeaper::SetTranslation4x4(const Matrix4& m) { m_translation = m; ScheduleCompleteRedraw(); }
+void CudaGridLeaper::SetIsoValue(float v) { m_isoValue = v; RecomputeBrickVisibility(false); ScheduleCompleteRedraw(); }
+void CudaGridLeaper::SetIsoValueRelative(float rel) {           // AbstrRenderer.cpp:395-410
+  double lo = 0, hi = 0;
+  if (m_vol) m_vol->Range(lo, hi);
+  SetIsoValue(float(lo) + rel * float(hi - lo));
+}
+void CudaGridLeaper::SetIsosurfaceColor(const Vec3& c) { m_isoColor = c; ScheduleCompleteRedraw(); }
+void CudaGridLeaper::SetLightColors(const float a[4], const float d[4], const float s[4], const Vec3& dir) {
+  memcpy(m_ambient, a, 16); memcpy(m_diffuse, d, 16); memcpy(m_specular, s, 16); m_lightDir = dir;
+  ScheduleCompleteRedraw();
+}
+
+bool CudaGridLeaper::Set1DTrans(const std::vector<uint8_t>& rgba) {          // GLRenderer::Set1DTrans
+  if (rgba.size() % 4 || rgba.empty()) { m_err = "1D transfer function must be RGBA8"; return false; }
+  std::vector<float> f(rgba.size());
+  for (size_t i = 0; i < rgba.size(); ++i) f[i] = rgba[i] / 255.0f;
+  m_tf1d.Set(f.data(), rgba.size() / 4);
+  int rc = tvk_set_tf1d(m_ctx, rgba.data(), (uint32_t)(rgba.size() / 4));
+  if (rc) return Fail("tvk_set_tf1d", rc);
+  RecomputeBrickVisibility(false);
+  ScheduleCompleteRedraw();
+  return true;
+}
+
+void CudaGridLeaper::Changed1DTrans() {                                      // GLGridLeaper.cpp:632-635
+  if (!m_ctx) return;
+  std::vector<uint8_t> bytes;
+  m_tf1d.ComputeNonZeroLimits();
+  m_tf1d.GetByteArray(bytes);
+  if (m_mode != RM_2DTRANS || !m_has2d) tvk_set_tf1d(m_ctx, bytes.data(), (uint32_t)m_tf1d.GetSize());
+  RecomputeBrickVisibility(false);
+  ScheduleCompleteRedraw();
+}
+
+bool CudaGridLeaper::Set2DTrans(const uint8_t* rgba, uint32_t w, uint32_t h, double nz[4]) {
+  // the swatch rasterisation of TransferFunction2D needs Qt (TransferFunction2D.cpp:294-361);
+  // the renderer takes the rasterised RGBA8 table and its non-zero limits instead
+  if (!rgba || !w || !h) { m_err = "bad 2D transfer function"; return false; }
+  int rc = tvk_set_tf2d(m_ctx, rgba, w, h);
+  if (rc) return Fail("tvk_set_tf2d", rc);
+  m_has2d = true;
+  for (int i = 0; i < 4; ++i) m_tf2dLimits[i] = nz[i];
+  if (m_mode == RM_2DTRANS) RecomputeBrickVisibility(false);
+  ScheduleCompleteRedraw();
+  return true;
+}
+
+bool CudaGridLeaper::RecomputeBrickVisibility(bool force) {                  // GLGridLeaper.cpp:647-688
+  if (!m_pool || !m_vol) return false;
+  double lo, hi;
+  m_vol->Range(lo, hi);
+  const double maxValue = (lo > hi) ? double(m_tf1d.GetSize()) : hi;
+  const double rescale = maxValue / double(m_tf1d.GetSize() - 1);
+  tvk_visibility v{};
+  v.render_mode = (uint32_t)m_mode;
+  if (m_mode == RM_1DTRANS) { v.smin = double(m_tf1d.NonZeroMin()) * rescale; v.smax = double(m_tf1d.NonZeroMax()) * rescale; }
+  else if (m_mode == RM_2DTRANS) {
+    v.smin = m_tf2dLimits[0] * rescale; v.smax = m_tf2dLimits[1] * rescale; v.gmin = m_tf2dLimits[2]; v.gmax = m_tf2dLimits[3];
+  } else v.smin = m_isoValue;
+  // VisibilityState::NeedsUpdate (VisibilityState.h:15-50)
+  if (!force && m_visValid && v.render_mode == m_lastVis.render_mode && v.smin == m_lastVis.smin && v.smax == m_lastVis.smax &&
+      v.gmin == m_lastVis.gmin && v.gmax == m_lastVis.gmax)
+    return true;
+  uint32_t counts[4];
+  const int rc = m_pool->RecomputeVisibility(v, counts);
+  if (rc) return Fail("RecomputeVisibility", rc);
+  m_lastVis = v; m_visValid = true;
+  return true;
+}
+
+bool CudaGridLeaper::RecalcVisibility() { const bool ok = RecomputeBrickVisibility(true); ScheduleCompleteRedraw(); return ok; }
+
+void CudaGridLeaper::ClearWorkingSet() {                                     // GLVolumePool::PH_Reset (:261-284)
+  if (!m_pool || !m_vol) return;
+  const uint32_t* cap = m_pool->Capacity();
+  const uint32_t c[3] = {cap[0], cap[1], cap[2]};
+  BrickPool* np = new BrickPool(m_ctx, m_vol);
+  if (np->Create(c, m_sampler) == TVK_OK && np->UploadFirstBrick() == TVK_OK) { delete m_pool; m_pool = np; }
+  else delete np;
+  m_visValid = false;
+  RecomputeBrickVisibility(true);
+  ScheduleCompleteRedraw();
+}
+
+bool CudaGridLeaper::ComputeRaycastParams(tvk_raycast_params& p) {
+  if (!m_vol || !m_w || !m_h) { m_err = "no dataset / render target"; return false; }
+  memset(&p, 0, sizeof(p));
+  p.width = m_w; p.height = m_h;
+  // GetVolumeAABB (AbstrRenderer.cpp:1102-1109)
+  float ext[3], mx = 0;
+  for (int a = 0; a < 3; ++a) { ext[a] = float(m_vol->domain[a]) * m_vol->scale[a]; mx = std::max(mx, ext[a]); }
+  for (int a = 0; a < 3; ++a) ext[a] /= mx;
+  // GLRenderer::ComputeViewAndProjection (:888-920) and Paint (:627)
+  const float aspect = float(m_w) / float(m_h);
+  const Matrix4 view = Matrix4::LookAt(m_eye, m_at, m_up);
+  const Matrix4 proj = Matrix4::Perspective(m_fov, aspect, m_znear, m_zfar);
+  const Matrix4 mv = m_rotation * m_translation * view;
+  // ComputeEyeToModelMatrix (GLGridLeaper.cpp:560-573), centre = 0
+  const Matrix4 emm = mv.inverse() * Matrix4::Translation(0, 0, 0) * Matrix4::Scaling(1.0f / ext[0], 1.0f / ext[1], 1.0f / ext[2]) *
+                      Matrix4::Translation(0.5f, 0.5f, 0.5f);
+  memcpy(p.eye_to_model, emm.m, 64);
+  memcpy(p.model_to_eye, emm.inverse().m, 64);
+  memcpy(p.model_view_it, mv.inverse().transposed().m, 64);
+  memcpy(p.inv_projection, proj.inverse().m, 64);
+  // CullingLOD::SetScreenParams (CullingLOD.cpp:65-66), screen space error 1
+  p.lod_factor = 2.0f * (float)tan(m_fov * ((3.1416f / 180.0f) / 2.0f)) * 1.0f / float(m_h);
+  float wse = 0;
+  for (int a = 0; a < 3; ++a) wse = std::max(wse, ext[a] / float(m_vol->domain[a]));   // GLVolumePool.cpp:801
+  p.level_zero_wse = wse;
+  p.sample_rate_modifier = m_sampleRate;
+  // CalculateScaling (GLRenderer.cpp:1813-1819) / MaxValue (AbstrRenderer.cpp:860-866)
+  double lo, hi;
+  m_vol->Range(lo, hi);
+  const double maxValue = (lo > hi) ? double(m_tf1d.GetSize()) : hi;
+  const uint32_t iMax = (1u << (8 * m_vol->bpv)) - 1;
+  p.trans_scale = float(iMax / maxValue);
+  p.gradient_scale = (m_vol->max_grad_magnitude == 0) ? 1.0f : 1.0f / m_vol->max_grad_magnitude;
+  p.isoval = float(m_isoValue / double(1u << (8 * m_vol->bpv)));       // GetNormalizedIsovalue
+  p.render_mode = (uint32_t)m_mode;
+  p.lighting = (m_lighting && m_mode != RM_ISOSURFACE) ? 1u : 0u;
+  float smin = std::min(m_vol->scale[0], std::min(m_vol->scale[1], m_vol->scale[2]));
+  for (int a = 0; a < 3; ++a) {
+    p.light_ambient[a] = m_ambient[a] * m_ambient[3];
+    p.light_diffuse[a] = m_diffuse[a] * m_diffuse[3];
+    p.light_specular[a] = m_specular[a] * m_specular[3];
+    p.domain_scale[a] = 1.0f / (m_vol->scale[a] / smin);
+  }
+  const float l4[4] = {m_lightDir.x, m_lightDir.y, m_lightDir.z, 0.0f}, e4[4] = {m_eye.x, m_eye.y, m_eye.z, 1.0f};
+  float o[4];
+  emm.transform(l4, o);
+  const Vec3 ml = Vec3(o[0], o[1], o[2]).normalized();
+  p.model_light_dir[0] = ml.x; p.model_light_dir[1] = ml.y; p.model_light_dir[2] = ml.z;
+  emm.transform(e4, o);                                 // sic: the world-space eye through eye->model (:735)
+  p.model_eye_pos[0] = o[0]; p.model_eye_pos[1] = o[1]; p.model_eye_pos[2] = o[2];
+  p.iso_color[0] = m_isoColor.x; p.iso_color[1] = m_isoColor.y; p.iso_color[2] = m_isoColor.z;
+  p.compose_light_dir[0] = m_lightDir.x; p.compose_light_dir[1] = m_lightDir.y; p.compose_light_dir[2] = m_lightDir.z;
+  p.new_view = m_blank ? 1u : 0u;
+  p.missing_strategy = m_strategy; p.rehash_count = m_rehash; p.hash_table_size = m_hashSize;
+  p.clip_enabled = 0;
+  p.count_samples = 1;
+  return true;
+}
+
+bool CudaGridLeaper::Paint() {                                               // GLGridLeaper::Render3DRegion (:914-1154)
+  if (!m_ctx || !m_vol || !m_pool) { m_err = "Paint() without dataset"; return false; }
+  if (!m_w || !m_h) { m_err = "Paint() on a zero-sized target"; return false; }
+  if (!m_visValid) RecomputeBrickVisibility(true);
+  tvk_raycast_params p;
+  if (!ComputeRaycastParams(p)) return false;
+  if (m_blank) { m_perf.frames += 1; }
+  int rc = tvk_raycast_subframe(m_ctx, &p);
+  if (rc) return Fail("tvk_raycast_subframe", rc);
+  m_blank = false;
+  m_perf.subframes += 1;
+  std::vector<uint32_t> req(4 * (size_t)m_hashSize);
+  uint32_t n = 0;
+  rc = tvk_read_requests(m_ctx, req.data(), m_hashSize, &n);
+  if (rc) return Fail("tvk_read_requests", rc);
+  req.resize(4 * (size_t)n);
+  if (n) {
+    uint32_t paged = 0;
+    rc = m_pool->UploadBricks(req, paged);
+    if (rc) return Fail("UploadBricks", rc);
+    m_perf.paged_bricks += paged;
+    m_perf.uploaded_bytes = (double)m_pool->UploadedBytes();
+  }
+  tvk_stats st;
+  if (tvk_get_stats(m_ctx, &st, 0) == TVK_OK) { m_perf.raycast_ms += st.last_raycast_ms; m_perf.samples = (double)st.samples; }
+  m_converged = (n == 0);
+  return true;
+}
+
+bool CudaGridLeaper::CheckForRedraw() const { return m_w && m_h && (!m_converged || m_blank); }
+
+bool CudaGridLeaper::PaintUntilConverged(uint32_t maxSub, uint32_t& subframes) {
+  subframes = 0;
+  do {
+    if (!Paint()) return false;
+    ++subframes;
+  } while (!m_converged && subframes < maxSub);
+  return m_converged;
+}
+
+bool CudaGridLeaper::GetFrameFloat(std::vector<float>& out) {
+  if (!m_ctx || !m_w || !m_h) return false;
+  out.resize((size_t)m_w * m_h * 4);
+  const int rc = tvk_read_image(m_ctx, out.data());
+  return rc ? Fail("tvk_read_image", rc) : true;
+}
+
+bool CudaGridLeaper::GetFrameRGBA8(std::vector<uint8_t>& out) {
+  std::vector<float> f;
+  if (!GetFrameFloat(f)) return false;
+  out.resize(f.size());
+  // glReadPixels(GL_RGBA, GL_UNSIGNED_BYTE): clamp, scale, round to nearest; then the vertical flip of
+  // FrameCapture::SaveImage (FrameCapture.h:90-98)
+  for (uint32_t y = 0; y < m_h; ++y) {
+    const float* src = &f[(size_t)(m_h - 1 - y) * m_w * 4];
+    uint8_t* dst = &out[(size_t)y * m_w * 4];
+    for (uint32_t i = 0; i < m_w * 4; ++i) {
+      const float c = std::min(1.0f, std::max(0.0f, src[i]));
+      dst[i] = (uint8_t)(c * 255.0f + 0.5f);
+    }
+  }
+  return true;
+}
+
+// minimal, dependency-free PNG writer (stored deflate blocks)
+static uint32_t crc32_buf(uint32_t crc, const uint8_t* d, size_t n) {
+  static uint32_t table[256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; table[i] = c; }
+    init = true;
+  }
+  crc = ~crc;
+  for (size_t i = 0; i < n; ++i) crc = table[(crc ^ d[i]) & 0xFF] ^ (crc >> 8);
+  return ~crc;
+}
+static void put_be32(std::vector<uint8_t>& v, uint32_t x) { v.push_back(x >> 24); v.push_back(x >> 16); v.push_back(x >> 8); v.push_back(x); }
+static void png_chunk(std::vector<uint8_t>& out, const char* type, const std::vector<uint8_t>& data) {
+  put_be32(out, (uint32_t)data.size());
+  std::vector<uint8_t> td(type, type + 4);
+  td.insert(td.end(), data.begin(), data.end());
+  out.insert(out.end(), td.begin(), td.end());
+  put_be32(out, crc32_buf(0, td.data(), td.size()));
+}
+static bool write_png(const std::string& fn, uint32_t w, uint32_t h, const std::vector<uint8_t>& rgba) {
+  std::vector<uint8_t> raw;
+  raw.reserve((size_t)h * (w * 4 + 1));
+  for (uint32_t y = 0; y < h; ++y) { raw.push_back(0); raw.insert(raw.end(), rgba.begin() + (size_t)y * w * 4, rgba.begin() + (size_t)(y + 1) * w * 4); }
+  std::vector<uint8_t> z;
+  z.push_back(0x78); z.push_back(0x01);
+  uint32_t a = 1, b = 0;
+  for (size_t off = 0; off < raw.size();) {
+    const size_t n = std::min<size_t>(65535, raw.size() - off);
+    z.push_back(off + n == raw.size() ? 1 : 0);
+    z.push_back(n & 0xFF); z.push_back(n >> 8); z.push_back(~n & 0xFF); z.push_back((~n >> 8) & 0xFF);
+    z.insert(z.end(), raw.begin() + off, raw.begin() + off + n);
+    for (size_t i = 0; i < n; ++i) { a = (a + raw[off + i]) % 65521; b = (b + a) % 65521; }
+    off += n;
+  }
+  put_be32(z, (b << 16) | a);
+  std::vector<uint8_t> out = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+  std::vector<uint8_t> ihdr;
+  put_be32(ihdr, w); put_be32(ihdr, h);
+  ihdr.push_back(8); ihdr.push_back(6); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);
+  png_chunk(out, "IHDR", ihdr);
+  png_chunk(out, "IDAT", z);
+  png_chunk(out, "IEND", std::vector<uint8_t>());
+  FILE* f = fopen(fn.c_str(), "wb");
+  if (!f) return false;
+  const bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+  fclose(f);
+  return ok;
+}
+
+bool CudaGridLeaper::CaptureSingleFrame(const std::string& filename, bool preserveTransparency) {
+  std::vector<uint8_t> img;
+  if (!GetFrameRGBA8(img)) return false;
+  // FrameCapture.h:129-156: with transparency the colour is de-multiplied, without it alpha = 255
+  for (size_t i = 0; i < img.size(); i += 4) {
+    if (preserveTransparency) {
+      const uint8_t a = img[i + 3];
+      for (int k = 0; k < 3; ++k) img[i + k] = a ? (uint8_t)std::min(255, int(0.5f + img[i + k] / (a / 255.0f))) : 0;
+    } else img[i + 3] = 255;
+  }
+  if (!write_png(filename, m_w, m_h, img)) { m_err = "cannot write " + filename; return false; }
+  return true;
+}
+
+}  // namespace tvk
+
+// ============================================================================ C wrapper (include/tvk_renderer.h)
+#include "tvk_renderer.h"
+using tvk::CudaGridLeaper;
+using tvk::Matrix4;
+using tvk::Vec3;
+
+#define R(h) (reinterpret_cast<CudaGridLeaper*>(h))
+
+extern "C" {
+tvkr_renderer* tvkr_create(int device) {
+  CudaGridLeaper* r = new CudaGridLeaper();
+  if (!r->Initialize(device)) { delete r; return nullptr; }
+  return reinterpret_cast<tvkr_renderer*>(r);
+}
+void tvkr_destroy(tvkr_renderer* h) { delete R(h); }
+const char* tvkr_last_error(tvkr_renderer* h) { return h ? R(h)->LastError() : "null renderer"; }
+int tvkr_load_raw_volume(tvkr_renderer* h, const void* raw, const uint32_t size[3], uint32_t bpv, const float scale[3],
+                         uint32_t brick, uint32_t overlap, int median, int out_of_core, uint64_t gpu_mem_bytes, int hist2d) {
+  return h && R(h)->LoadRawVolume(raw, size, bpv, scale, brick, overlap, median != 0, out_of_core != 0, gpu_mem_bytes, hist2d != 0) ? 0 : 1;
+}
+int tvkr_resize(tvkr_renderer* h, uint32_t w, uint32_t hh) { if (!h) return 1; R(h)->Resize(w, hh); return 0; }
+int tvkr_set_render_mode(tvkr_renderer* h, int mode) { return h && R(h)->SetRendermode(mode) ? 0 : 1; }
+int tvkr_set_lighting_enabled(tvkr_renderer* h, int on) { if (!h) return 1; R(h)->SetUseLighting(on != 0); return 0; }
+int tvkr_set_sample_rate_modifier(tvkr_renderer* h, float f) { if (!h) return 1; R(h)->SetSampleRateModifier(f); return 0; }
+int tvkr_set_fov(tvkr_renderer* h, float f) { if (!h) return 1; R(h)->SetFoV(f); return 0; }
+int tvkr_set_view_pos(tvkr_renderer* h, const float p[3]) { if (!h) return 1; R(h)->SetViewPos(Vec3(p[0], p[1], p[2])); return 0; }
+int tvkr_set_view_dir(tvkr_renderer* h, const float p[3]) { if (!h) return 1; R(h)->SetViewDir(Vec3(p[0], p[1], p[2])); return 0; }
+int tvkr_set_up_dir(tvkr_renderer* h, const float p[3]) { if (!h) return 1; R(h)->SetUpDir(Vec3(p[0], p[1], p[2])); return 0; }
+int tvkr_set_view_parameters(tvkr_renderer* h, float angle, float znear, float zfar, const float eye[3], const float ref[3], const float up[3]) {
+  if (!h) return 1;
+  R(h)->SetViewParameters(angle, znear, zfar, Vec3(eye[0], eye[1], eye[2]), Vec3(ref[0], ref[1], ref[2]), Vec3(up[0], up[1], up[2]));
+  return 0;
+}
+int tvkr_set_rotation4x4(tvkr_renderer* h, const float m[16]) { if (!h) return 1; Matrix4 t; memcpy(t.m, m, 64); R(h)->SetRotation4x4(t); return 0; }
+int tvkr_set_translation4x4(tvkr_renderer* h, const float m[16]) { if (!h) return 1; Matrix4 t; memcpy(t.m, m, 64); R(h)->SetTranslation4x4(t); return 0; }
+int tvkr_set_iso_value(tvkr_renderer* h, float v) { if (!h) return 1; R(h)->SetIsoValue(v); return 0; }
+int tvkr_set_iso_value_relative(tvkr_renderer* h, float v) { if (!h) return 1; R(h)->SetIsoValueRelative(v); return 0; }
+int tvkr_set_isosurface_color(tvkr_renderer* h, const float c[3]) { if (!h) return 1; R(h)->SetIsosurfaceColor(Vec3(c[0], c[1], c[2])); return 0; }
+int tvkr_set_1d_trans(tvkr_renderer* h, const uint8_t* rgba, uint32_t n) {
+  if (!h || !rgba) return 1;
+  return R(h)->Set1DTrans(std::vector<uint8_t>(rgba, rgba + 4 * (size_t)n)) ? 0 : 1;
+}
+int tvkr_set_1d_trans_float(tvkr_renderer* h, const float* rgba, uint32_t n) {
+  if (!h || !rgba) return 1;
+  R(h)->Get1DTrans().Set(rgba, n);
+  R(h)->Changed1DTrans();
+  return 0;
+}
+int tvkr_load_1d_trans(tvkr_renderer* h, const char* filename) {
+  if (!h || !filename || !R(h)->Get1DTrans().Load(filename)) return 1;
+  R(h)->Changed1DTrans();
+  return 0;
+}
+int tvkr_set_2d_trans(tvkr_renderer* h, const uint8_t* rgba, uint32_t w, uint32_t hh, const double nz_limits[4]) {
+  double nz[4] = {nz_limits[0], nz_limits[1], nz_limits[2], nz_limits[3]};
+  return h && R(h)->Set2DTrans(rgba, w, hh, nz) ? 0 : 1;
+}
+int tvkr_set_state(tvkr_renderer* h, uint32_t strategy, uint32_t hash_size, uint32_t rehash, uint32_t sampler) {
+  if (!h || hash_size == 0 || rehash == 0 || strategy > TVK_MBS_SKIP_TWO_LEVELS || sampler > TVK_SAMPLER_TEX3D) return 1;
+  R(h)->SetMissingBrickStrategy(strategy); R(h)->SetHashTable(hash_size, rehash); R(h)->SetSampler(sampler);
+  return 0;
+}
+int tvkr_paint(tvkr_renderer* h) { return h && R(h)->Paint() ? 0 : 1; }
+int tvkr_check_for_redraw(tvkr_renderer* h) { return h && R(h)->CheckForRedraw() ? 1 : 0; }
+int tvkr_converged(tvkr_renderer* h) { return h && R(h)->Converged() ? 1 : 0; }
+int tvkr_paint_until_converged(tvkr_renderer* h, uint32_t max_subframes, uint32_t* subframes) {
+  uint32_t s = 0;
+  const bool ok = h && R(h)->PaintUntilConverged(max_subframes, s);
+  if (subframes) *subframes = s;
+  return ok ? 0 : 1;
+}
+int tvkr_clear_working_set(tvkr_renderer* h) { if (!h) return 1; R(h)->ClearWorkingSet(); return 0; }
+int tvkr_recalc_visibility(tvkr_renderer* h) { return h && R(h)->RecalcVisibility() ? 0 : 1; }
+int tvkr_get_frame_rgba8(tvkr_renderer* h, uint8_t* out) {
+  std::vector<uint8_t> v;
+  if (!h || !out || !R(h)->GetFrameRGBA8(v)) return 1;
+  memcpy(out, v.data(), v.size());
+  return 0;
+}
+int tvkr_get_frame_float(tvkr_renderer* h, float* out) {
+  if (!h || !out) return 1;
+  return tvk_read_image(R(h)->Context(), out) == TVK_OK ? 0 : 1;
+}
+int tvkr_capture_single_frame(tvkr_renderer* h, const char* filename, int preserve_transparency) {
+  return h && filename && R(h)->CaptureSingleFrame(filename, preserve_transparency != 0) ? 0 : 1;
+}
+int tvkr_get_raycast_params(tvkr_renderer* h, tvk_raycast_params* p) { return h && p && R(h)->ComputeRaycastParams(*p) ? 0 : 1; }
+int tvkr_get_dataset_info(tvkr_renderer* h, tvkr_dataset_info* o) {
+  if (!h || !o || !R(h)->Volume()) return 1;
+  const tvk::BrickedVolume* v = R(h)->Volume();
+  memset(o, 0, sizeof(*o));
+  for (int a = 0; a < 3; ++a) { o->domain[a] = v->domain[a]; o->pool_capacity[a] = R(h)->Pool()->Capacity()[a]; }
+  o->lod_count = R(h)->Pool()->LodCount();
+  o->total_bricks = R(h)->Pool()->TotalBricks();
+  o->tf_size = (uint32_t)R(h)->Get1DTrans().GetSize();
+  v->Range(o->range[0], o->range[1]);
+  o->max_grad_magnitude = v->max_grad_magnitude;
+  o->iso_value = R(h)->GetIsoValue();
+  o->out_of_core = v->host_store ? 1 : 0;
+  return 0;
+}
+int tvkr_get_pool_slots(tvkr_renderer* h, int32_t* brick, uint64_t* time, uint32_t cap, uint32_t* n) {
+  if (!h || !R(h)->Pool() || !n) return 1;
+  const std::vector<tvk::PoolSlot>& s = R(h)->Pool()->Slots();
+  *n = (uint32_t)s.size();
+  if (cap < s.size()) return 1;
+  // reported in POSITION order (the vector itself is kept in LRU order after a paging pass)
+  for (const tvk::PoolSlot& p : s) { if (brick) brick[p.pos] = p.brick; if (time) time[p.pos] = p.time; }
+  return 0;
+}
+int tvkr_get_perf(tvkr_renderer* h, double out[6]) {
+  if (!h || !out) return 1;
+  const tvk::PerfCounters& p = R(h)->Perf();
+  out[0] = p.subframes; out[1] = p.raycast_ms; out[2] = p.paged_bricks; out[3] = p.uploaded_bytes; out[4] = p.samples; out[5] = p.frames;
+  return 0;
+}
+tvk_ctx* tvkr_context(tvkr_renderer* h) { return h ? R(h)->Context() : nullptr; }
+}

@@ -1,0 +1,240 @@
+// C++ host of the B200 ray-caster: the AbstrRenderer-shaped class a Tuvok build
+// registers as a new EVolumeRendererType.  It owns no CUDA
+// code: everything device-side goes through the C ABI of include/tvk_cuda.h.
+//
+// Reference counterparts (paths relative to /root/reference/Tuvok/):
+//   Matrix4 / Vec3          Basics/Vectors.h (row-vector convention, BuildLookAt :1250,
+//                           Perspective :1267, inverse :1042)
+//   TransferFunction1D      IO/TransferFunction1D.{h,cpp}
+//   BrickedVolume           what GLGridLeaper needs from LinearIndexDataset / UVFDataset
+//                           (IO/LinearIndexDataset.h:14-27, IO/uvfDataset.cpp:590-596,1120-1199)
+//   BrickPool               Renderer/GL/GLVolumePool.{h,cpp} bookkeeping (slots, LRU,
+//                           UploadBricks, RecomputeVisibility) + GPUMemMan::GetVolumePool sizing
+//   CudaGridLeaper          Renderer/AbstrRenderer.{h,cpp} state + Renderer/GL/GLGridLeaper.cpp
+//                           frame loop (Render3DRegion :914-1154) + GLRenderer camera set-up
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "tvk_cuda.h"
+
+namespace tvk {
+
+struct Vec3 {
+  float x = 0, y = 0, z = 0;
+  Vec3() {}
+  Vec3(float x_, float y_, float z_) : x(x_), y(y_), z(z_) {}
+  Vec3 operator+(const Vec3& o) const { return Vec3(x + o.x, y + o.y, z + o.z); }
+  Vec3 operator-(const Vec3& o) const { return Vec3(x - o.x, y - o.y, z - o.z); }
+  Vec3 operator*(float s) const { return Vec3(x * s, y * s, z * s); }
+  float dot(const Vec3& o) const { return x * o.x + y * o.y + z * o.z; }
+  Vec3 cross(const Vec3& o) const { return Vec3(y * o.z - z * o.y, z * o.x - x * o.z, x * o.y - y * o.x); }
+  float length() const;
+  Vec3 normalized() const;
+};
+
+// FLOATMATRIX4: memory order m11..m44, v' = v*M
+struct Matrix4 {
+  float m[16];
+  Matrix4();                                     // identity
+  Matrix4 operator*(const Matrix4& o) const;
+  Matrix4 inverse() const;
+  Matrix4 transposed() const;
+  static Matrix4 Translation(float x, float y, float z);
+  static Matrix4 Scaling(float x, float y, float z);
+  static Matrix4 RotationX(double a);
+  static Matrix4 RotationY(double a);
+  static Matrix4 RotationZ(double a);
+  static Matrix4 LookAt(const Vec3& eye, const Vec3& at, const Vec3& up);
+  static Matrix4 Perspective(float fovy, float aspect, float n, float f);
+  void transform(const float v[4], float out[4]) const;   // v*M
+};
+
+class TransferFunction1D {
+ public:
+  explicit TransferFunction1D(size_t n = 0) : m_color(4 * n, 0.0f) { ComputeNonZeroLimits(); }
+  size_t GetSize() const { return m_color.size() / 4; }
+  void Resize(size_t n) { m_color.resize(4 * n, 0.0f); ComputeNonZeroLimits(); }
+  bool Load(const std::string& filename);                  // ".1dt" text format
+  bool Save(const std::string& filename) const;
+  void Set(const float* rgba, size_t n);
+  void SetStdFunction(float center = 0.5f, float invGradient = 0.5f);
+  void GetByteArray(std::vector<uint8_t>& out, uint8_t usedRange = 255) const;
+  void ComputeNonZeroLimits();
+  uint64_t NonZeroMin() const { return m_lo; }
+  uint64_t NonZeroMax() const { return m_hi; }
+  std::vector<float>& ColorData() { return m_color; }
+
+ private:
+  void SetStdFunction(float center, float invGradient, int component);
+  std::vector<float> m_color;     // r g b a per entry
+  uint64_t m_lo = 0, m_hi = 0;
+};
+
+// A bricked multi-resolution volume in ExtendedOctree layout (ToC order).
+// Brick payloads live EITHER in the device brick store left by tvk_build_octree
+// (in-core) OR in one pinned host allocation (out-of-core paging source).
+struct BrickedVolume {
+  uint32_t domain[3] = {0, 0, 0};
+  float    scale[3] = {1, 1, 1};
+  uint32_t bpv = 1, brick_size = 64, overlap = 2;
+  tvk_build_info info{};
+  std::vector<uint64_t> offsets;        // bytes, per brick
+  std::vector<uint32_t> sizes;          // 3 per brick
+  std::vector<double>   minmax;         // 2 per brick
+  std::vector<uint64_t> hist1d;
+  float    max_grad_magnitude = 0.0f;   // 0 = unknown (2-D histogram not computed)
+  uint8_t* host_store = nullptr;        // pinned (cudaHostAlloc) when out of core
+  void*    device_store = nullptr;      // owned by the tvk_ctx build state when in core
+  uint64_t store_bytes = 0;
+
+  uint32_t LargestSingleBrickLOD() const;                 // uvfDataset.cpp:590-596
+  void     MaxUsedBrickSizes(uint32_t out[3]) const;      // GetMaxUsedBrickSizes
+  uint64_t TocIndex(uint32_t x, uint32_t y, uint32_t z, uint32_t lod) const;
+  void     Range(double& lo, double& hi) const;           // ComputeRange, uvfDataset.cpp:1120-1181
+};
+
+struct PoolSlot {                        // PoolSlotData, GLVolumePool.h:25-60
+  int32_t  brick = -1;
+  uint64_t time = 0, orig_time = 0;
+  uint32_t pos = 0;                      // linear slot index = position in pool
+  bool WasEverUsed() const { return brick != -1; }
+  bool ContainsVisibleBrick() const { return time > 1; }
+  void FlagEmpty() { orig_time = time; time = 1; }
+  void Restore() { time = orig_time; }
+};
+
+class BrickPool {
+ public:
+  BrickPool(tvk_ctx* ctx, const BrickedVolume* vol) : m_ctx(ctx), m_vol(vol) {}
+  // GPUMemMan::GetVolumePool (GPUMemMan.cpp:766-844); max3d = GL_MAX_3D_TEXTURE_SIZE stand-in
+  static void ComputePoolCapacity(const BrickedVolume& v, uint64_t gpuMemBytes, uint32_t max3d, uint32_t cap[3]);
+  int  Create(const uint32_t capacity[3], uint32_t sampler);
+  int  UploadFirstBrick();                                       // :763-766
+  int  UploadBricks(const std::vector<uint32_t>& xyzl, uint32_t& paged);   // :1720-1789
+  int  RecomputeVisibility(const tvk_visibility& vis, uint32_t counts[4]); // :1580-1718
+  bool IsBrickResident(uint32_t x, uint32_t y, uint32_t z, uint32_t lod) const;
+  uint32_t BrickIndex(uint32_t x, uint32_t y, uint32_t z, uint32_t lod) const;   // GetIntegerBrickID
+  void     BrickCoords(uint32_t index, uint32_t xyzl[4]) const;                  // GetVectorBrickID
+  uint32_t LodCount() const { return m_lodCount; }
+  uint32_t TotalBricks() const { return m_total; }
+  const std::vector<PoolSlot>& Slots() const { return m_slots; }
+  const uint32_t* Capacity() const { return m_cap; }
+  const uint32_t* MaxBrick() const { return m_maxBrick; }
+  uint64_t UploadedBytes() const { return m_uploadedBytes; }
+
+ private:
+  bool ContainsData(const tvk_visibility& vis, uint32_t index) const;
+  void PrepareForPaging();                                        // :955-959
+  tvk_ctx* m_ctx;
+  const BrickedVolume* m_vol;
+  uint32_t m_cap[3] = {0, 0, 0}, m_maxBrick[3] = {0, 0, 0};
+  uint32_t m_lodCount = 0, m_total = 0;
+  std::vector<uint32_t> m_lodOffset;
+  std::vector<uint32_t> m_lodBricks;     // 3 per lod
+  std::vector<double>   m_minmax;        // pool index order
+  std::vector<PoolSlot> m_slots;
+  uint64_t m_time = 2;                   // m_iTimeOfCreation
+  size_t   m_insertPos = 0;
+  uint64_t m_uploadedBytes = 0;
+};
+
+enum ERenderMode { RM_1DTRANS = 0, RM_2DTRANS = 1, RM_ISOSURFACE = 2 };
+enum ERendererTarget { RT_INTERACTIVE = 0, RT_CAPTURE = 1, RT_HEADLESS = 2 };
+
+struct PerfCounters {                     // subset of Basics/PerfCounter.h:7-44 we can fill
+  double subframes = 0, raycast_ms = 0, paged_bricks = 0, uploaded_bytes = 0, samples = 0, frames = 0;
+};
+
+class CudaGridLeaper {
+ public:
+  CudaGridLeaper();
+  ~CudaGridLeaper();
+
+  // --- life cycle (AbstrRenderer::LoadFile / Initialize / Resize / Cleanup)
+  bool Initialize(int device);
+  // raw x-fastest volume in host memory -> K2 builder -> bricked volume.  out_of_core moves the
+  // brick store to pinned host memory and sizes the pool by gpuMemBytes (0 = whole dataset).
+  bool LoadRawVolume(const void* raw, const uint32_t size[3], uint32_t bytesPerVoxel, const float scale[3],
+                     uint32_t brickSize, uint32_t overlap, bool median, bool outOfCore, uint64_t gpuMemBytes,
+                     bool computeHist2D);
+  void Resize(uint32_t w, uint32_t h);
+  void Cleanup();
+  const char* LastError() const { return m_err.c_str(); }
+
+  // --- state (names of AbstrRenderer.h; Lua: setRenderMode, setViewPos, ...)
+  bool SetRendermode(int mode);
+  int  GetRendermode() const { return m_mode; }
+  void SetUseLighting(bool b);
+  void SetSampleRateModifier(float f);
+  void SetFoV(float f);
+  void SetViewPos(const Vec3& p);
+  void SetViewDir(const Vec3& d);
+  void SetUpDir(const Vec3& u);
+  void ResetViewPos(); void ResetViewDir(); void ResetUpDir();
+  void SetViewParameters(float angle, float znear, float zfar, const Vec3& eye, const Vec3& ref, const Vec3& up);
+  void SetRotation4x4(const Matrix4& m);        // first 3-D render region (RenderRegion.cpp:51-127)
+  void SetTranslation4x4(const Matrix4& m);
+  void SetIsoValue(float v);
+  void SetIsoValueRelative(float v);
+  double GetIsoValue() const { return m_isoValue; }
+  void SetIsosurfaceColor(const Vec3& c);
+  void SetLightColors(const float ambient[4], const float diffuse[4], const float specular[4], const Vec3& lightDir);
+  bool Set1DTrans(const std::vector<uint8_t>& rgba);           // AbstrRenderer.h:189 (pure virtual there)
+  TransferFunction1D& Get1DTrans() { return m_tf1d; }
+  void Changed1DTrans();                                        // tuvok.gpu.changed1DTrans
+  bool Set2DTrans(const uint8_t* rgba, uint32_t w, uint32_t h, double nzLimits[4]);
+  void SetRendererTarget(int t) { m_target = t; }
+  void SetMissingBrickStrategy(uint32_t s) { m_strategy = s; ScheduleCompleteRedraw(); }
+  void SetHashTable(uint32_t size, uint32_t rehash) { m_hashSize = size; m_rehash = rehash; }
+  void SetSampler(uint32_t s) { m_sampler = s; }
+  void ScheduleCompleteRedraw() { m_blank = true; m_converged = false; }
+
+  // --- frame loop
+  bool Paint();                      // one sub-frame (GLGridLeaper::Render3DRegion)
+  bool CheckForRedraw() const;       // GLGridLeaper.cpp:872-890
+  bool Converged() const { return m_converged; }        // PH_Converged
+  bool PaintUntilConverged(uint32_t maxSubframes, uint32_t& subframes);
+  void ClearWorkingSet();            // PH_ClearWorkingSet: pool back to the pinned coarsest brick
+  bool RecalcVisibility();           // PH_RecalculateVisibility
+  // GLFrameCapture.cpp:47-86 + FrameCapture.h:83-159: RGBA8, top row first
+  bool GetFrameRGBA8(std::vector<uint8_t>& out);
+  bool GetFrameFloat(std::vector<float>& out);             // premultiplied RGBA32F, bottom row first
+  bool CaptureSingleFrame(const std::string& filename, bool preserveTransparency);
+
+  // --- introspection used by tests / the C wrapper
+  bool ComputeRaycastParams(tvk_raycast_params& p);
+  const BrickedVolume* Volume() const { return m_vol; }
+  BrickPool* Pool() { return m_pool; }
+  tvk_ctx* Context() { return m_ctx; }
+  PerfCounters& Perf() { return m_perf; }
+  uint32_t Width() const { return m_w; }
+  uint32_t Height() const { return m_h; }
+
+ private:
+  bool Fail(const std::string& what, int rc);
+  bool RecomputeBrickVisibility(bool force);            // GLGridLeaper.cpp:632-688
+  tvk_ctx* m_ctx = nullptr;
+  BrickedVolume* m_vol = nullptr;
+  BrickPool* m_pool = nullptr;
+  std::string m_err;
+  uint32_t m_w = 0, m_h = 0;
+  int m_mode = RM_1DTRANS, m_target = RT_INTERACTIVE;
+  bool m_lighting = true;                                // AbstrRenderer.cpp:81
+  float m_sampleRate = 1.0f, m_fov = 50.0f, m_znear = 0.01f, m_zfar = 1000.0f;
+  Vec3 m_eye{0, 0, 1.6f}, m_at{0, 0, 0}, m_up{0, 1, 0};
+  Matrix4 m_rotation, m_translation;
+  Vec3 m_lightDir{0, 0, -1}, m_isoColor{0.5f, 0.5f, 0.5f};
+  float m_ambient[4] = {1, 1, 1, 0.1f}, m_diffuse[4] = {1, 1, 1, 1}, m_specular[4] = {1, 1, 1, 1};
+  double m_isoValue = 0.5;
+  TransferFunction1D m_tf1d;
+  bool m_has2d = false;
+  double m_tf2dLimits[4] = {0, 0, 0, 0};
+  uint32_t m_strategy = TVK_MBS_SKIP_TWO_LEVELS, m_hashSize = 509, m_rehash = 10, m_sampler = TVK_SAMPLER_EXACT;
+  bool m_blank = true, m_converged = false;
+  tvk_visibility m_lastVis{};
+  bool m_visValid = false;
+  PerfCounters m_perf;
+};
+
+}  // namespace tvk

@@ -1,0 +1,217 @@
+"""Python mirror of the renderer's Lua surface (tuvok.renderer.*), bound to the C++ host
+class tvk::CudaGridLeaper through include/tvk_renderer.h.
+
+Method names, argument meaning and error behaviour follow the Lua registrations of the
+reference (Tuvok/Renderer/AbstrRenderer.cpp:1793-2267, RenderRegion.cpp:51-127) so that
+LuaScripts/BatchRenderer.lua reads 1:1:
+
+    r = Renderer()                      # tuvok.renderer.new(types.CUDA_GridLeaper, ...) + initialize
+    r.loadRawVolume(vol)                # loadDataset (in-memory raw volume -> K2 builder)
+    r.resize((1024, 1024)); r.setRendererTarget(RT_HEADLESS)
+    while not r.converged(): r.paint()  # repeat paint() until converged()
+    r.captureSingleFrame("out.png", True)
+    r.cleanup()
+
+There is no CPU fallback: constructing a Renderer without the CUDA library or a GPU raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+RM_1DTRANS, RM_2DTRANS, RM_ISOSURFACE = 0, 1, 2
+RT_INTERACTIVE, RT_CAPTURE, RT_HEADLESS = 0, 1, 2
+
+
+class DatasetInfo(C.Structure):
+    _fields_ = [("domain", C.c_uint32 * 3), ("pool_capacity", C.c_uint32 * 3), ("lod_count", C.c_uint32),
+                ("total_bricks", C.c_uint32), ("tf_size", C.c_uint32), ("range", C.c_double * 2),
+                ("max_grad_magnitude", C.c_float), ("iso_value", C.c_double), ("out_of_core", C.c_uint32)]
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+class Renderer:
+    def __init__(self, device=0):
+        self._lib = L.load()
+        self._lib.tvkr_create.restype = C.c_void_p
+        self._lib.tvkr_last_error.restype = C.c_char_p
+        self._lib.tvkr_context.restype = C.c_void_p
+        self._h = self._lib.tvkr_create(C.c_int(device))
+        if not self._h:
+            raise L.TvkError("tvk::CudaGridLeaper::Initialize failed (no CUDA device %d?)" % device)
+        self._h = C.c_void_p(self._h)
+        self._size = (0, 0)
+        self._target = RT_INTERACTIVE
+
+    # -- helpers
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise L.TvkError("%s failed: %s" % (what, self._lib.tvkr_last_error(self._h).decode()))
+
+    def cleanup(self):
+        if self._h:
+            self._lib.tvkr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.cleanup()
+        except Exception:
+            pass
+
+    # -- dataset
+    def loadRawVolume(self, volume, scale=(1, 1, 1), brick_size=64, overlap=2, median=False, out_of_core=False,
+                      gpu_mem_bytes=0, hist2d=False):
+        vol = np.ascontiguousarray(volume)
+        if vol.dtype not in (np.uint8, np.uint16) or vol.ndim != 3:
+            raise L.TvkError("loadRawVolume: only 3-D uint8/uint16 volumes")
+        size = (C.c_uint32 * 3)(vol.shape[2], vol.shape[1], vol.shape[0])
+        self._ck(self._lib.tvkr_load_raw_volume(self._h, vol.ctypes.data_as(C.c_void_p), size, C.c_uint32(vol.dtype.itemsize),
+                                                _f3(scale), C.c_uint32(brick_size), C.c_uint32(overlap), C.c_int(int(median)),
+                                                C.c_int(int(out_of_core)), C.c_uint64(int(gpu_mem_bytes)), C.c_int(int(hist2d))),
+                 "loadRawVolume")
+        return True
+
+    def datasetInfo(self):
+        d = DatasetInfo()
+        self._ck(self._lib.tvkr_get_dataset_info(self._h, C.byref(d)), "datasetInfo")
+        return d
+
+    # -- state (Lua names)
+    def resize(self, wh):
+        self._size = (int(wh[0]), int(wh[1]))
+        self._ck(self._lib.tvkr_resize(self._h, C.c_uint32(self._size[0]), C.c_uint32(self._size[1])), "resize")
+
+    def setRendererTarget(self, t):
+        self._target = t
+
+    def setRenderMode(self, mode):
+        self._ck(self._lib.tvkr_set_render_mode(self._h, C.c_int(mode)), "setRenderMode")
+
+    def setLightingEnabled(self, on):
+        self._ck(self._lib.tvkr_set_lighting_enabled(self._h, C.c_int(int(on))), "setLightingEnabled")
+
+    def setSampleRateModifier(self, f):
+        self._ck(self._lib.tvkr_set_sample_rate_modifier(self._h, C.c_float(f)), "setSampleRateModifier")
+
+    def setFoV(self, f):
+        self._ck(self._lib.tvkr_set_fov(self._h, C.c_float(f)), "setFoV")
+
+    def setViewPos(self, p):
+        self._ck(self._lib.tvkr_set_view_pos(self._h, _f3(p)), "setViewPos")
+
+    def setViewDir(self, d):
+        self._ck(self._lib.tvkr_set_view_dir(self._h, _f3(d)), "setViewDir")
+
+    def setUpDir(self, u):
+        self._ck(self._lib.tvkr_set_up_dir(self._h, _f3(u)), "setUpDir")
+
+    def setViewParameters(self, angle, znear, zfar, eye, ref, up):
+        self._ck(self._lib.tvkr_set_view_parameters(self._h, C.c_float(angle), C.c_float(znear), C.c_float(zfar),
+                                                    _f3(eye), _f3(ref), _f3(up)), "setViewParameters")
+
+    def setRotation4x4(self, m):
+        a = np.ascontiguousarray(m, np.float32).reshape(16)
+        self._ck(self._lib.tvkr_set_rotation4x4(self._h, a.ctypes.data_as(C.c_void_p)), "setRotation4x4")
+
+    def setTranslation4x4(self, m):
+        a = np.ascontiguousarray(m, np.float32).reshape(16)
+        self._ck(self._lib.tvkr_set_translation4x4(self._h, a.ctypes.data_as(C.c_void_p)), "setTranslation4x4")
+
+    def setIsoValue(self, v):
+        self._ck(self._lib.tvkr_set_iso_value(self._h, C.c_float(v)), "setIsoValue")
+
+    def setIsoValueRelative(self, v):
+        self._ck(self._lib.tvkr_set_iso_value_relative(self._h, C.c_float(v)), "setIsoValueRelative")
+
+    def setIsosurfaceColor(self, rgb):
+        self._ck(self._lib.tvkr_set_isosurface_color(self._h, _f3(rgb)), "setIsosurfaceColor")
+
+    def set1DTrans(self, rgba8):
+        a = np.ascontiguousarray(rgba8, np.uint8)
+        self._ck(self._lib.tvkr_set_1d_trans(self._h, a.ctypes.data_as(C.c_void_p), C.c_uint32(a.shape[0])), "set1DTrans")
+
+    def set1DTransFloat(self, table):
+        """edit through the get1DTrans() proxy + tuvok.gpu.changed1DTrans"""
+        a = np.ascontiguousarray(table, np.float32)
+        self._ck(self._lib.tvkr_set_1d_trans_float(self._h, a.ctypes.data_as(C.c_void_p), C.c_uint32(a.shape[0])),
+                 "changed1DTrans")
+
+    def load1DTrans(self, filename):
+        self._ck(self._lib.tvkr_load_1d_trans(self._h, filename.encode()), "load1DTrans")
+
+    def set2DTrans(self, rgba8, nz_limits):
+        a = np.ascontiguousarray(rgba8, np.uint8)           # [256 gradient rows][value bins][4]
+        nz = (C.c_double * 4)(*[float(v) for v in nz_limits])
+        self._ck(self._lib.tvkr_set_2d_trans(self._h, a.ctypes.data_as(C.c_void_p), C.c_uint32(a.shape[1]),
+                                             C.c_uint32(a.shape[0]), nz), "changed2DTrans")
+
+    def setState(self, brick_strategy=3, hash_table_size=509, rehash_count=10, sampler=0):
+        """tuvok.state.brickStrategy / hashTableSize / rehashCount"""
+        self._ck(self._lib.tvkr_set_state(self._h, C.c_uint32(brick_strategy), C.c_uint32(hash_table_size),
+                                          C.c_uint32(rehash_count), C.c_uint32(sampler)), "setState")
+
+    # -- frame loop
+    def paint(self):
+        self._ck(self._lib.tvkr_paint(self._h), "paint")
+        return True
+
+    def checkForRedraw(self):
+        return bool(self._lib.tvkr_check_for_redraw(self._h))
+
+    def converged(self):
+        return bool(self._lib.tvkr_converged(self._h))
+
+    def paintUntilConverged(self, max_subframes=1000):
+        n = C.c_uint32()
+        rc = self._lib.tvkr_paint_until_converged(self._h, C.c_uint32(max_subframes), C.byref(n))
+        self._ck(rc, "paint")
+        return n.value
+
+    def clearWorkingSet(self):
+        self._ck(self._lib.tvkr_clear_working_set(self._h), "clearWorkingSet")
+
+    def recalcVisibility(self):
+        self._ck(self._lib.tvkr_recalc_visibility(self._h), "recalcVisibility")
+
+    def captureSingleFrame(self, filename, preserve_transparency=False):
+        self._ck(self._lib.tvkr_capture_single_frame(self._h, filename.encode(), C.c_int(int(preserve_transparency))),
+                 "captureSingleFrame")
+        return True
+
+    def frameRGBA8(self):
+        w, h = self._size
+        out = np.zeros((h, w, 4), np.uint8)
+        self._ck(self._lib.tvkr_get_frame_rgba8(self._h, out.ctypes.data_as(C.c_void_p)), "frameRGBA8")
+        return out
+
+    def frameFloat(self):
+        w, h = self._size
+        out = np.zeros((h, w, 4), np.float32)
+        self._ck(self._lib.tvkr_get_frame_float(self._h, out.ctypes.data_as(C.c_void_p)), "frameFloat")
+        return out
+
+    # -- introspection
+    def raycastParams(self):
+        p = L.RaycastParams()
+        self._ck(self._lib.tvkr_get_raycast_params(self._h, C.byref(p)), "raycastParams")
+        return p
+
+    def poolSlots(self):
+        info = self.datasetInfo()
+        n = info.pool_capacity[0] * info.pool_capacity[1] * info.pool_capacity[2]
+        brick = np.zeros(n, np.int32)
+        time = np.zeros(n, np.uint64)
+        cnt = C.c_uint32()
+        self._ck(self._lib.tvkr_get_pool_slots(self._h, brick.ctypes.data_as(C.c_void_p), time.ctypes.data_as(C.c_void_p),
+                                               C.c_uint32(n), C.byref(cnt)), "poolSlots")
+        return brick, time
+
+    def perf(self):
+        out = (C.c_double * 6)()
+        self._ck(self._lib.tvkr_get_perf(self._h, out), "perf")
+        return dict(zip(("subframes", "raycast_ms", "paged_bricks", "uploaded_bytes", "samples", "frames"), list(out)))

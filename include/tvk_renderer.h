@@ -1,0 +1,99 @@
+/*
+ * tvk_renderer.h -- C handle API of the C++ host class tvk::CudaGridLeaper
+ * (imagevis3d_b200/csrc/host/tvk_host.h), for callers that cannot include C++
+ * (the Python mirror, ctypes tests, a Lua binding).  One function per
+ * AbstrRenderer / Lua method the reference's scripts use; the Lua name each
+ * replaces is given (registrations: Tuvok/Renderer/AbstrRenderer.cpp:1793-2267,
+ * Tuvok/Renderer/RenderRegion.cpp:51-127).  Return 0 = success, non-zero =
+ * failure (tvkr_last_error gives the T_ERROR-style message); predicates return
+ * 0/1.
+ */
+#ifndef TVK_RENDERER_H
+#define TVK_RENDERER_H
+
+#include "tvk_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tvkr_renderer tvkr_renderer;
+
+typedef struct tvkr_dataset_info {
+  uint32_t domain[3];
+  uint32_t pool_capacity[3];
+  uint32_t lod_count;          /* pool LODs = LargestSingleBrickLOD + 1 */
+  uint32_t total_bricks;
+  uint32_t tf_size;            /* 1-D transfer function size = 1-D histogram size (<= 4096) */
+  double   range[2];           /* UVFDataset::ComputeRange */
+  float    max_grad_magnitude;
+  double   iso_value;
+  uint32_t out_of_core;
+} tvkr_dataset_info;
+
+/* tuvok.renderer.new(...) + renderer.initialize(ctx) : MasterController::RequestNewVolumeRenderer
+ * (MasterController.cpp:144-215), GLGridLeaper::Initialize (GLGridLeaper.cpp:247-316) */
+tvkr_renderer* tvkr_create(int device);
+/* renderer.cleanup() + deleteClass */
+void tvkr_destroy(tvkr_renderer* r);
+const char* tvkr_last_error(tvkr_renderer* r);
+
+/* renderer.loadDataset(...) for an in-memory raw volume: runs the K2 builder
+ * (the reference converts to UVF first: IOManager::ConvertDataset, IOManager.cpp:1061).
+ * out_of_core: brick store in pinned host memory, pool sized by gpu_mem_bytes
+ * (tuvok.state.gpuMem; 0 = the whole dataset fits). */
+int tvkr_load_raw_volume(tvkr_renderer* r, const void* raw, const uint32_t size[3], uint32_t bytes_per_voxel,
+                         const float scale[3], uint32_t brick_size, uint32_t overlap, int use_median,
+                         int out_of_core, uint64_t gpu_mem_bytes, int compute_hist2d);
+int tvkr_get_dataset_info(tvkr_renderer* r, tvkr_dataset_info* out);
+
+int tvkr_resize(tvkr_renderer* r, uint32_t w, uint32_t h);                      /* renderer.resize({w,h})       */
+int tvkr_set_render_mode(tvkr_renderer* r, int mode);                           /* renderer.setRenderMode       */
+int tvkr_set_lighting_enabled(tvkr_renderer* r, int on);                        /* renderer.setLightingEnabled  */
+int tvkr_set_sample_rate_modifier(tvkr_renderer* r, float f);                   /* renderer.setSampleRateModifier */
+int tvkr_set_fov(tvkr_renderer* r, float fov_deg);                              /* renderer.setFoV              */
+int tvkr_set_view_pos(tvkr_renderer* r, const float p[3]);                      /* renderer.setViewPos          */
+int tvkr_set_view_dir(tvkr_renderer* r, const float d[3]);                      /* renderer.setViewDir          */
+int tvkr_set_up_dir(tvkr_renderer* r, const float u[3]);                        /* renderer.setUpDir            */
+/* AbstrRenderer::SetViewParameters (AbstrRenderer.h:250-261, C++ only in the reference) */
+int tvkr_set_view_parameters(tvkr_renderer* r, float angle, float znear, float zfar, const float eye[3],
+                             const float ref[3], const float up[3]);
+int tvkr_set_rotation4x4(tvkr_renderer* r, const float m[16]);                  /* region.setRotation4x4        */
+int tvkr_set_translation4x4(tvkr_renderer* r, const float m[16]);               /* region.setTranslation4x4     */
+int tvkr_set_iso_value(tvkr_renderer* r, float v);                              /* renderer.setIsoValue         */
+int tvkr_set_iso_value_relative(tvkr_renderer* r, float v);                     /* renderer.setIsoValueRelative */
+int tvkr_set_isosurface_color(tvkr_renderer* r, const float rgb[3]);            /* renderer.setIsosurfaceColor  */
+/* AbstrRenderer::Set1DTrans (AbstrRenderer.h:189): RGBA8 table */
+int tvkr_set_1d_trans(tvkr_renderer* r, const uint8_t* rgba, uint32_t n);
+/* renderer.get1DTrans() proxy edit + tuvok.gpu.changed1DTrans */
+int tvkr_set_1d_trans_float(tvkr_renderer* r, const float* rgba, uint32_t n);
+int tvkr_load_1d_trans(tvkr_renderer* r, const char* filename_1dt);
+/* 2-D TF as a rasterised RGBA8 table (w = value bins, h = 256 gradient bins) + its non-zero
+ * limits (TransferFunction2D::GetNonZeroLimits); + tuvok.gpu.changed2DTrans */
+int tvkr_set_2d_trans(tvkr_renderer* r, const uint8_t* rgba, uint32_t w, uint32_t h, const double nz_limits[4]);
+/* tuvok.state.brickStrategy / hashTableSize / rehashCount (MasterController.cpp:458-496) + sampler */
+int tvkr_set_state(tvkr_renderer* r, uint32_t brick_strategy, uint32_t hash_table_size, uint32_t rehash_count,
+                   uint32_t sampler);
+
+int tvkr_paint(tvkr_renderer* r);                                               /* renderer.paint               */
+int tvkr_check_for_redraw(tvkr_renderer* r);                                    /* renderer.checkForRedraw      */
+int tvkr_converged(tvkr_renderer* r);                                           /* renderer.converged           */
+int tvkr_paint_until_converged(tvkr_renderer* r, uint32_t max_subframes, uint32_t* subframes);
+int tvkr_clear_working_set(tvkr_renderer* r);                                   /* renderer.clearWorkingSet     */
+int tvkr_recalc_visibility(tvkr_renderer* r);                                   /* renderer.recalcVisibility    */
+/* renderer.captureSingleFrame(file, preserveTransparency): PNG */
+int tvkr_capture_single_frame(tvkr_renderer* r, const char* filename, int preserve_transparency);
+/* glReadPixels equivalents: RGBA8 top row first / premultiplied RGBA32F bottom row first */
+int tvkr_get_frame_rgba8(tvkr_renderer* r, uint8_t* out);
+int tvkr_get_frame_float(tvkr_renderer* r, float* out);
+
+/* introspection for tests */
+int tvkr_get_raycast_params(tvkr_renderer* r, tvk_raycast_params* out);
+int tvkr_get_pool_slots(tvkr_renderer* r, int32_t* brick, uint64_t* time, uint32_t cap, uint32_t* n);
+int tvkr_get_perf(tvkr_renderer* r, double out[6]);     /* tuvok.perf: subframes, raycast ms, paged bricks, uploaded bytes, samples, frames */
+tvk_ctx* tvkr_context(tvkr_renderer* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVK_RENDERER_H */

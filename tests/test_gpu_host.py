@@ -1,0 +1,156 @@
+"""GPU: the C++ host (tvk::CudaGridLeaper through include/tvk_renderer.h and the Python mirror of
+the Lua surface) against the oracle's independent restatement of the reference host code."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import host as H
+from oracle import oracle as O
+from tests.util import image_errors
+
+pytestmark = pytest.mark.gpu
+
+
+def _tf(n):
+    t = H.tf1d_std(n, 0.3, 0.3)
+    t[:, 3] *= 0.15
+    t[:, 2] *= 0.5
+    return t
+
+
+def _oracle_converged(vol, brick, tf, cam, w, h, capacity, **kw):
+    oc = O.build_octree(vol, brick, 2)
+    pool = H.OraclePool(oc, capacity)
+    pool.upload_first_brick()
+    mode = kw.get("render_mode", 0)
+    maxv = float(oc["minmax"][:int(np.prod(oc["plan"].lod_bricks[0][:])), 1].max())
+    if mode == 0:
+        lo, hi = H.tf_nonzero_limits(tf)
+        resc = maxv / (len(tf) - 1)
+        pool.recompute_visibility(0, lo * resc, hi * resc)
+    else:
+        pool.recompute_visibility(2, kw["iso"])
+    bits = 8 * vol.dtype.itemsize
+    p = H.raycast_params(cam, w, h, oc["vol"], trans_scale=((1 << bits) - 1) / maxv, isoval=kw.get("iso", 0) / float(1 << bits), **{k: v for k, v in kw.items() if k not in ("iso",)})
+    img, subs, paged, _ = H.render_converged(p, pool, H.tf_bytes(tf))
+    return img, p, pool, subs
+
+
+def _params_close(a, b):
+    for name, ctype in a._fields_:
+        va, vb = getattr(a, name), getattr(b, name)
+        if hasattr(va, "__len__"):
+            assert np.allclose(np.array(va[:], np.float64), np.array(vb[:], np.float64), rtol=2e-5, atol=2e-6), name
+        elif isinstance(va, float):
+            assert abs(va - vb) <= 2e-6 + 2e-5 * abs(vb), name
+        else:
+            assert va == vb, name
+
+
+@pytest.mark.parametrize("lighting", [False, True])
+def test_renderer_matches_oracle_end_to_end(lighting):
+    from imagevis3d_b200.renderer import Renderer, RT_HEADLESS
+    vol = H.synth_blobs((150, 131, 97), np.uint8)
+    r = Renderer(0)
+    r.loadRawVolume(vol, brick_size=20)
+    info = r.datasetInfo()
+    assert info.tf_size == int(vol.max()) + 1 and list(info.domain) == [150, 131, 97]
+    tf = _tf(info.tf_size)
+    r.set1DTransFloat(tf)
+    r.setLightingEnabled(lighting)
+    r.resize((203, 149))
+    r.setRendererTarget(RT_HEADLESS)
+    rot = H.rotation_y(0.6) @ H.rotation_x(0.3)
+    r.setRotation4x4(rot)
+    cam = H.Camera()
+    cam.rotation = rot
+    cap = tuple(info.pool_capacity)
+    want, p_o, pool_o, subs_o = _oracle_converged(vol, 20, tf, cam, 203, 149, cap, lighting=lighting)
+    p_c = r.raycastParams()
+    _params_close(p_c, p_o)
+    assert r.checkForRedraw()
+    subs = r.paintUntilConverged()
+    assert r.converged() and not r.checkForRedraw()
+    assert subs == subs_o
+    got = r.frameFloat()
+    psnr, err = image_errors(got, want)
+    assert psnr >= 45.0 and err <= 2.0 / 255.0, (psnr, err)
+    # same working set as the oracle's GLVolumePool restatement
+    bricks, times = r.poolSlots()
+    assert set(bricks[bricks >= 0].tolist()) == set(pool_o.slot_brick[pool_o.slot_brick >= 0].tolist())
+    assert times.max() == np.iinfo(np.uint64).max            # the coarsest brick is pinned
+    # 8-bit capture path: glReadPixels rounding + vertical flip
+    rgba = r.frameRGBA8()
+    ref8 = (np.clip(want[::-1], 0, 1) * 255.0 + 0.5).astype(np.uint8)
+    assert np.abs(rgba.astype(int) - ref8.astype(int)).max() <= 2
+    out = "/tmp/tvk_capture_%d.png" % int(lighting)
+    r.captureSingleFrame(out, True)
+    assert open(out, "rb").read(8) == b"\x89PNG\r\n\x1a\n" and os.path.getsize(out) > 203 * 149 * 4
+    perf = r.perf()
+    assert perf["subframes"] == subs and perf["paged_bricks"] > 0
+    # a view change restarts the progressive frame; a TF change re-evaluates visibility
+    r.setViewPos((0.0, 0.2, 1.9))
+    assert r.checkForRedraw() and not r.converged()
+    r.paintUntilConverged()
+    sparse = np.zeros_like(tf)
+    sparse[100:140] = [1, 0.5, 0.2, 0.1]
+    r.set1DTransFloat(sparse)
+    r.paintUntilConverged()
+    cam2 = H.Camera()
+    cam2.rotation = rot
+    cam2.at = cam2.at + (np.array([0.0, 0.2, 1.9], np.float32) - cam2.eye)
+    cam2.eye = np.array([0.0, 0.2, 1.9], np.float32)
+    want2, _, _, _ = _oracle_converged(vol, 20, sparse, cam2, 203, 149, cap, lighting=lighting)
+    psnr, err = image_errors(r.frameFloat(), want2)
+    assert psnr >= 45.0 and err <= 2.0 / 255.0, (psnr, err)
+    r.cleanup()
+
+
+def test_renderer_isosurface_and_out_of_core():
+    from imagevis3d_b200.renderer import Renderer, RM_ISOSURFACE
+    vol = H.synth_blobs((120, 100, 90), np.uint16, seed=9)
+    r = Renderer(0)
+    # pool budget of 40 bricks of 20^3 uint16 -> bricks stream from pinned host memory
+    r.loadRawVolume(vol, brick_size=20, out_of_core=True, gpu_mem_bytes=40 * 20 ** 3 * 2)
+    info = r.datasetInfo()
+    assert info.out_of_core == 1
+    nslots = int(np.prod(info.pool_capacity[:]))
+    assert nslots < info.total_bricks
+    assert abs(info.iso_value - float(info.range[1] - info.range[0]) / 2.0) < 1.0
+    r.resize((160, 120))
+    r.setRenderMode(RM_ISOSURFACE)
+    r.setIsoValue(20000.0)
+    r.setViewPos((0.0, 0.0, 3.0))            # far enough that the working set fits the small pool
+    subs = r.paintUntilConverged(200)
+    assert r.converged()
+    cam = H.Camera()
+    cam.eye = np.array([0, 0, 3.0], np.float32)
+    want, _, _, _ = _oracle_converged(vol, 20, _tf(4096), cam, 160, 120, tuple(info.pool_capacity), render_mode=2, iso=20000.0)
+    got = r.frameFloat()
+    d = np.abs(got - want).max(axis=2)
+    assert want[..., 3].sum() > 50
+    assert (d > 2.0 / 255.0).sum() <= max(4, int(0.002 * d.size))
+    r.clearWorkingSet()
+    bricks, _ = r.poolSlots()
+    assert (bricks >= 0).sum() == 1
+    r.cleanup()
+
+
+def test_renderer_error_behaviour():
+    from imagevis3d_b200._lib import TvkError
+    from imagevis3d_b200.renderer import Renderer
+    r = Renderer(0)
+    with pytest.raises(TvkError):
+        r.paint()                                   # Paint() without dataset returns false
+    with pytest.raises(TvkError):
+        r.loadRawVolume(np.zeros((4, 4, 4), np.float32))
+    r.loadRawVolume(H.synth_blobs((40, 40, 40), np.uint8), brick_size=20)
+    with pytest.raises(TvkError):
+        r.paint()                                   # zero-sized target
+    with pytest.raises(TvkError):
+        r.setRenderMode(7)
+    with pytest.raises(TvkError):
+        r.setRenderMode(1)                          # 2D mode without a 2D transfer function
+    r.cleanup()
