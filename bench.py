@@ -214,7 +214,7 @@ def run_gpu(args, rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     tvk = TvkContext(local)
-    sampler = L.SAMPLER_TEX3D if os.environ.get("TVK_SAMPLER", "exact") == "tex3d" else L.SAMPLER_EXACT
+    sampler = {"exact": L.SAMPLER_EXACT, "tex3d": L.SAMPLER_TEX3D, "q4": L.SAMPLER_EXACT_Q4}[os.environ.get("TVK_SAMPLER", "exact")]
 
     # ---- untimed set-up: synthesize the slab in HBM, build bricks, fill the pool
     raw = volume_torch(VOL, dev, z0=rank * VOL[2], ztotal=VOL[2] * world)

@@ -789,7 +789,7 @@ int tvkr_set_2d_trans(tvkr_renderer* h, const uint8_t* rgba, uint32_t w, uint32_
   return h && R(h)->Set2DTrans(rgba, w, hh, nz) ? 0 : 1;
 }
 int tvkr_set_state(tvkr_renderer* h, uint32_t strategy, uint32_t hash_size, uint32_t rehash, uint32_t sampler) {
-  if (!h || hash_size == 0 || rehash == 0 || strategy > TVK_MBS_SKIP_TWO_LEVELS || sampler > TVK_SAMPLER_TEX3D) return 1;
+  if (!h || hash_size == 0 || rehash == 0 || strategy > TVK_MBS_SKIP_TWO_LEVELS || sampler > TVK_SAMPLER_EXACT_Q4) return 1;
   R(h)->SetMissingBrickStrategy(strategy); R(h)->SetHashTable(hash_size, rehash); R(h)->SetSampler(sampler);
   return 0;
 }

@@ -148,14 +148,15 @@ extern "C" int tvk_pool_create(tvk_ctx* c, const tvk_pool_desc* d) {
   for (int a = 0; a < 3; ++a)
     if (d->max_brick_size[a] <= 2 * d->overlap || d->pool_capacity[a] == 0 || d->volume_size[a] == 0)
       TVK_FAIL(c, TVK_ERR_INVALID, "bad pool description");
-  if (d->sampler != TVK_SAMPLER_EXACT && d->sampler != TVK_SAMPLER_TEX3D) TVK_FAIL(c, TVK_ERR_INVALID, "bad sampler");
+  if (d->sampler > TVK_SAMPLER_EXACT_Q4) TVK_FAIL(c, TVK_ERR_INVALID, "bad sampler");
   tvk_pool_destroy(c);
   c->pdesc = *d;
   tvk_compute_pool_const(*d, c->pc);
   const size_t voxels = (size_t)c->pc.pool_dim[0] * c->pc.pool_dim[1] * c->pc.pool_dim[2];
-  if (d->sampler == TVK_SAMPLER_EXACT) {
-    TVK_CHECK_CUDA(c, cudaMalloc(&c->d_pool, voxels * d->bytes_per_voxel));
-    TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_pool, 0, voxels * d->bytes_per_voxel, c->stream));
+  if (d->sampler == TVK_SAMPLER_EXACT || d->sampler == TVK_SAMPLER_EXACT_Q4) {
+    const size_t elem = (d->sampler == TVK_SAMPLER_EXACT_Q4 ? 4 : 1) * (size_t)d->bytes_per_voxel;
+    TVK_CHECK_CUDA(c, cudaMalloc(&c->d_pool, voxels * elem));
+    TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_pool, 0, voxels * elem, c->stream));
   } else {
     cudaChannelFormatDesc fd = cudaCreateChannelDesc(8 * d->bytes_per_voxel, 0, 0, 0, cudaChannelFormatKindUnsigned);
     TVK_CHECK_CUDA(c, cudaMalloc3DArray(&c->pool_array, &fd,
@@ -229,6 +230,30 @@ __global__ void __launch_bounds__(256) place_bricks_linear(const PlaceJob* __res
   }
 }
 
+// TVK_SAMPLER_EXACT_Q4: pool element (x,y,z) = { v(x,y,z), v(x,y+1,z), v(x,y,z+1), v(x,y+1,z+1) }
+// (y+1 / z+1 clamped inside the brick; the clamped copies are never sampled with weight > 0).
+template <typename T, typename T4>
+__global__ void __launch_bounds__(256) place_bricks_q4(const PlaceJob* __restrict__ jobs, T4* __restrict__ pool,
+                                                        const __grid_constant__ PoolConst pc) {
+  const PlaceJob j = jobs[blockIdx.x];
+  const uint32_t s0 = j.slot % pc.capacity[0], s1 = (j.slot / pc.capacity[0]) % pc.capacity[1],
+                 s2 = j.slot / (pc.capacity[0] * pc.capacity[1]);
+  const size_t px = pc.pool_dim[0], pxy = px * pc.pool_dim[1];
+  T4* dst0 = pool + (size_t)s0 * pc.max_brick[0] + (size_t)s1 * pc.max_brick[1] * px + (size_t)s2 * pc.max_brick[2] * pxy;
+  const T* src = reinterpret_cast<const T*>(j.src);
+  const uint32_t total = j.sx * j.sy * j.sz;
+  for (uint32_t i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
+    const uint32_t x = i % j.sx, y = (i / j.sx) % j.sy, z = i / (j.sx * j.sy);
+    const uint32_t y1 = min(y + 1, j.sy - 1), z1 = min(z + 1, j.sz - 1);
+    T4 q;
+    q.x = src[x + j.sx * (y + j.sy * z)];
+    q.y = src[x + j.sx * (y1 + j.sy * z)];
+    q.z = src[x + j.sx * (y + j.sy * z1)];
+    q.w = src[x + j.sx * (y1 + j.sy * z1)];
+    dst0[(size_t)x + (size_t)y * px + (size_t)z * pxy] = q;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) place_bricks_surface(const PlaceJob* __restrict__ jobs, cudaSurfaceObject_t surf,
                                                              const __grid_constant__ PoolConst pc) {
@@ -257,7 +282,10 @@ static int place_batch(tvk_ctx* c, std::vector<PlaceJob>& jobs, cudaStream_t st)
   TVK_CHECK_CUDA(c, cudaMallocAsync(&d_jobs, sizeof(PlaceJob) * jobs.size(), st));
   TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(PlaceJob) * jobs.size(), cudaMemcpyHostToDevice, st));
   const dim3 grid((unsigned)jobs.size(), 8);
-  if (c->pdesc.sampler == TVK_SAMPLER_EXACT) {
+  if (c->pdesc.sampler == TVK_SAMPLER_EXACT_Q4) {
+    if (c->pc.bpv == 1) place_bricks_q4<uint8_t, uchar4><<<grid, 256, 0, st>>>(d_jobs, (uchar4*)c->d_pool, c->pc);
+    else place_bricks_q4<uint16_t, ushort4><<<grid, 256, 0, st>>>(d_jobs, (ushort4*)c->d_pool, c->pc);
+  } else if (c->pdesc.sampler == TVK_SAMPLER_EXACT) {
     // jobs arrive sorted: [0, nvec) can move 16 B per access, the rest go byte-wise
     size_t nvec = 0;
     while (nvec < jobs.size() && can_vec(jobs[nvec])) ++nvec;

@@ -189,7 +189,7 @@ struct Taps {
 // gradient taps one texel further) never leaves the slot -- 2 ghost voxels per side --
 // so this equals GL_CLAMP_TO_EDGE for every position the march can produce, and it lets
 // the eight loads share one address.
-template <int BPV>
+template <int BPV, int SAMP>
 __device__ __forceinline__ void fetch_taps(const RayParams& rp, f3 p, Taps& t) {
   const PoolConst& pc = rp.pc;
   const float M = 12582912.0f;   // 1.5 * 2^23
@@ -202,7 +202,26 @@ __device__ __forceinline__ void fetch_taps(const RayParams& rp, f3 p, Taps& t) {
   z = min(max(z, 0), (int)pc.pool_dim[2] - 2);
   const size_t sx = pc.pool_dim[0], sxy = sx * pc.pool_dim[1];
   const size_t o = (size_t)x + (size_t)y * sx + (size_t)z * sxy;
-  if (BPV == 1) {
+  if (SAMP == TVK_SAMPLER_EXACT_Q4) {
+    // two loads: the (y,z) quads of columns x and x+1
+    if (BPV == 1) {
+      const uint32_t* d = static_cast<const uint32_t*>(rp.pool) + o;
+      const uint32_t q0 = __ldg(d), q1 = __ldg(d + 1);
+      t.v[0] = __uint_as_float(__byte_perm(q0, 0x4B000000u, 0x7650)) - 8388608.0f;
+      t.v[2] = __uint_as_float(__byte_perm(q0, 0x4B000000u, 0x7651)) - 8388608.0f;
+      t.v[4] = __uint_as_float(__byte_perm(q0, 0x4B000000u, 0x7652)) - 8388608.0f;
+      t.v[6] = __uint_as_float(__byte_perm(q0, 0x4B000000u, 0x7653)) - 8388608.0f;
+      t.v[1] = __uint_as_float(__byte_perm(q1, 0x4B000000u, 0x7650)) - 8388608.0f;
+      t.v[3] = __uint_as_float(__byte_perm(q1, 0x4B000000u, 0x7651)) - 8388608.0f;
+      t.v[5] = __uint_as_float(__byte_perm(q1, 0x4B000000u, 0x7652)) - 8388608.0f;
+      t.v[7] = __uint_as_float(__byte_perm(q1, 0x4B000000u, 0x7653)) - 8388608.0f;
+    } else {
+      const uint2* d = static_cast<const uint2*>(rp.pool) + o;
+      const uint2 q0 = __ldg(d), q1 = __ldg(d + 1);
+      t.v[0] = u2f(q0.x & 0xFFFFu); t.v[2] = u2f(q0.x >> 16); t.v[4] = u2f(q0.y & 0xFFFFu); t.v[6] = u2f(q0.y >> 16);
+      t.v[1] = u2f(q1.x & 0xFFFFu); t.v[3] = u2f(q1.x >> 16); t.v[5] = u2f(q1.y & 0xFFFFu); t.v[7] = u2f(q1.y >> 16);
+    }
+  } else if (BPV == 1) {
     const uint8_t* d = static_cast<const uint8_t*>(rp.pool) + o;
     const uint8_t *d1 = d + sx, *d2 = d + sxy, *d3 = d2 + sx;
     const uint32_t r0 = __ldg(d), r1 = __ldg(d + 1), r2 = __ldg(d1), r3 = __ldg(d1 + 1);
@@ -229,13 +248,13 @@ __device__ __forceinline__ float filter_taps(const Taps& t) {
 }
 
 // texture(volumePool, p).r -- GL_LINEAR, CLAMP_TO_EDGE, UNORM8/16.
-template <int BPV, bool TEX>
+template <int BPV, int SAMP>
 __device__ __forceinline__ float sample_pool(const RayParams& rp, f3 p) {
-  if (TEX) {
+  if (SAMP == TVK_SAMPLER_TEX3D) {
     return tex3D<float>(rp.tex, p.x, p.y, p.z);
   } else {
     Taps t;
-    fetch_taps<BPV>(rp, p, t);
+    fetch_taps<BPV, SAMP>(rp, p, t);
     return filter_taps<BPV>(t);
   }
 }
@@ -252,12 +271,12 @@ __device__ __forceinline__ float4 tf_fetch(const RayParams& rp, int i) {
 }
 
 // ComputeGradient, GLGridLeaper-GradientTools.glsl:6-16 (y sign flipped there)
-template <int BPV, bool TEX>
+template <int BPV, int SAMP>
 __device__ __forceinline__ f3 gradient(const RayParams& rp, f3 p) {
   const float dx = 1.0f / rp.pc.pool_size[0], dy = 1.0f / rp.pc.pool_size[1], dz = 1.0f / rp.pc.pool_size[2];
-  const float xp = sample_pool<BPV, TEX>(rp, mk3(p.x + dx, p.y, p.z)), xm = sample_pool<BPV, TEX>(rp, mk3(p.x - dx, p.y, p.z));
-  const float yp = sample_pool<BPV, TEX>(rp, mk3(p.x, p.y - dy, p.z)), ym = sample_pool<BPV, TEX>(rp, mk3(p.x, p.y + dy, p.z));
-  const float zp = sample_pool<BPV, TEX>(rp, mk3(p.x, p.y, p.z + dz)), zm = sample_pool<BPV, TEX>(rp, mk3(p.x, p.y, p.z - dz));
+  const float xp = sample_pool<BPV, SAMP>(rp, mk3(p.x + dx, p.y, p.z)), xm = sample_pool<BPV, SAMP>(rp, mk3(p.x - dx, p.y, p.z));
+  const float yp = sample_pool<BPV, SAMP>(rp, mk3(p.x, p.y - dy, p.z)), ym = sample_pool<BPV, SAMP>(rp, mk3(p.x, p.y + dy, p.z));
+  const float zp = sample_pool<BPV, SAMP>(rp, mk3(p.x, p.y, p.z + dz)), zm = sample_pool<BPV, SAMP>(rp, mk3(p.x, p.y, p.z - dz));
   return mk3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
 }
 
@@ -282,7 +301,7 @@ __device__ __forceinline__ f3 lighting(const tvk_raycast_params& p, f3 pos, f3 n
 
 // ComputeColorFromVolume, GLGridLeaper-Method-{1D,1D-L,2D,2D-L}.glsl; `data` is the
 // already filtered centre sample (fetched one iteration ahead by the march loop).
-template <int MODE, bool LIT, int BPV, bool TEX>
+template <int MODE, bool LIT, int BPV, int SAMP>
 __device__ __forceinline__ float4 color_from_volume(const RayParams& rp, float data, f3 pc, f3 scale, f3 trans) {
   const tvk_raycast_params& p = rp.p;
   float4 col;
@@ -290,13 +309,13 @@ __device__ __forceinline__ float4 color_from_volume(const RayParams& rp, float d
   if (MODE == TVK_RM_1DTRANS) {
     col = __ldg(rp.tf_f + nearest_index(data * p.trans_scale, rp.tf_w));
     if (LIT) {
-      const f3 g = gradient<BPV, TEX>(rp, pc);
+      const f3 g = gradient<BPV, SAMP>(rp, pc);
       n = mk3(g.x * p.domain_scale[0], g.y * p.domain_scale[1], g.z * p.domain_scale[2]);
       const float l = len3(n);
       if (l > 0.0f) n = mk3(n.x / l, n.y / l, n.z / l);
     }
   } else {
-    const f3 g = gradient<BPV, TEX>(rp, pc);
+    const f3 g = gradient<BPV, SAMP>(rp, pc);
     const float gm = len3(g);
     col = tf_fetch(rp, nearest_index(1.0f - gm * p.gradient_scale, rp.tf_h) * (int)rp.tf_w +
                            nearest_index(data * p.trans_scale, rp.tf_w));
@@ -357,7 +376,7 @@ __device__ __forceinline__ bool ray_setup(const tvk_raycast_params& p, uint32_t 
 struct Counters { unsigned long long samples, bricks; };
 
 // GLGridLeaper-blend.glsl main()
-template <int MODE, bool LIT, int BPV, bool TEX>
+template <int MODE, bool LIT, int BPV, int SAMP>
 __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, float4& pos, float4& col, float4& acc, Counters& cn) {
   const tvk_raycast_params& p = rp.p;
   const PoolConst& pc = rp.pc;
@@ -399,19 +418,19 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
         Taps cur_t;
         float cur_tex = 0.0f;
         if (steps > 0) {
-          if (TEX) cur_tex = tex3D<float>(rp.tex, q.x, q.y, q.z);
-          else fetch_taps<BPV>(rp, q, cur_t);
+          if (SAMP == TVK_SAMPLER_TEX3D) cur_tex = tex3D<float>(rp.tex, q.x, q.y, q.z);
+          else fetch_taps<BPV, SAMP>(rp, q, cur_t);
         }
         for (int i = 0; i < steps; ++i) {
           const f3 qn = mk3(q.x + vdir.x, q.y + vdir.y, q.z + vdir.z);
           Taps nxt_t;
           float nxt_tex = 0.0f;
           if (i + 1 < steps) {
-            if (TEX) nxt_tex = tex3D<float>(rp.tex, qn.x, qn.y, qn.z);
-            else fetch_taps<BPV>(rp, qn, nxt_t);
+            if (SAMP == TVK_SAMPLER_TEX3D) nxt_tex = tex3D<float>(rp.tex, qn.x, qn.y, qn.z);
+            else fetch_taps<BPV, SAMP>(rp, qn, nxt_t);
           }
-          const float data = TEX ? cur_tex : filter_taps<BPV>(cur_t);
-          float4 s = color_from_volume<MODE, LIT, BPV, TEX>(rp, data, q, b.scale, b.trans);
+          const float data = (SAMP == TVK_SAMPLER_TEX3D) ? cur_tex : filter_taps<BPV>(cur_t);
+          float4 s = color_from_volume<MODE, LIT, BPV, SAMP>(rp, data, q, b.scale, b.trans);
           cn.samples++;
           s.w = (oc == 1.0f) ? 1.0f - (1.0f - s.w) : 1.0f - powf(1.0f - s.w, oc);
           const float w = (1.0f - acc.w) * s.w;       // UnderCompositing, Compositing.glsl:33-38
@@ -422,7 +441,7 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
             return;
           }
           q = qn;
-          if (TEX) cur_tex = nxt_tex; else cur_t = nxt_t;
+          if (SAMP == TVK_SAMPLER_TEX3D) cur_tex = nxt_tex; else cur_t = nxt_t;
         }
         cur = mk3((q.x - b.trans.x) / b.scale.x, (q.y - b.trans.y) / b.scale.y, (q.z - b.trans.z) / b.scale.z);
       } else {
@@ -438,7 +457,7 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
 }
 
 // GLGridLeaper-iso.glsl main() + GLGridLeaper-Method-iso.glsl
-template <int BPV, bool TEX>
+template <int BPV, int SAMP>
 __device__ __forceinline__ void march_ray_iso(const RayParams& rp, float4 exitp, float4& pos, float4& nrm, float4& hit, float4& hitn, Counters& cn) {
   const tvk_raycast_params& p = rp.p;
   const PoolConst& pc = rp.pc;
@@ -483,19 +502,19 @@ __device__ __forceinline__ void march_ray_iso(const RayParams& rp, float4 exitp,
         f3 q = b.pool_entry;
         for (int i = 0; i < steps; ++i) {
           cn.samples++;
-          if (sample_pool<BPV, TEX>(rp, q) >= p.isoval) {
+          if (sample_pool<BPV, SAMP>(rp, q) >= p.isoval) {
             f3 rd = mk3(vdir.x / 2.0f, vdir.y / 2.0f, vdir.z / 2.0f);       // RefineIsosurface
             q = mk3(q.x - rd.x, q.y - rd.y, q.z - rd.z);
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
               rd = mk3(rd.x / 2.0f, rd.y / 2.0f, rd.z / 2.0f);
-              if (sample_pool<BPV, TEX>(rp, q) >= p.isoval) q = mk3(q.x - rd.x, q.y - rd.y, q.z - rd.z);
+              if (sample_pool<BPV, SAMP>(rp, q) >= p.isoval) q = mk3(q.x - rd.x, q.y - rd.y, q.z - rd.z);
               else q = mk3(q.x + rd.x, q.y + rd.y, q.z + rd.z);
             }
             cur = mk3((q.x - b.trans.x) / b.scale.x, (q.y - b.trans.y) / b.scale.y, (q.z - b.trans.z) / b.scale.z);
             const float4 h4 = xform(p.model_to_eye, cur, 1.0f);
             hit = make_float4(h4.x, h4.y, h4.z, 2.0f);                       // color.r + 1
-            const f3 g = gradient<BPV, TEX>(rp, q);
+            const f3 g = gradient<BPV, SAMP>(rp, q);
             f3 n = mk3(g.x * p.domain_scale[0], g.y * p.domain_scale[1], g.z * p.domain_scale[2]);
             const float l = len3(n);
             if (l > 0.0f) n = mk3(n.x / l, n.y / l, n.z / l);
@@ -540,7 +559,7 @@ __device__ __forceinline__ float4 compose_iso(const tvk_raycast_params& p, float
                      clamp01(p.light_ambient[2] + p.light_diffuse[2] * p.iso_color[2] * ndl + p.light_specular[2] * spec), 1.0f);
 }
 
-template <int MODE, bool LIT, int BPV, bool TEX>
+template <int MODE, bool LIT, int BPV, int SAMP>
 __global__ void __launch_bounds__(128) raycast_kernel(const __grid_constant__ RayParams rp) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t ntiles = rp.tiles_x * rp.tiles_y;
@@ -574,7 +593,7 @@ __global__ void __launch_bounds__(128) raycast_kernel(const __grid_constant__ Ra
         aux = rp.aux[i];
       }
       float4 hit, hitn;
-      march_ray_iso<BPV, TEX>(rp, exitp, pos, aux, hit, hitn, cn);
+      march_ray_iso<BPV, SAMP>(rp, exitp, pos, aux, hit, hitn, cn);
       rp.image[i] = compose_iso(rp.p, hit, hitn);
     } else {
       if (!rp.p.new_view) {
@@ -582,7 +601,7 @@ __global__ void __launch_bounds__(128) raycast_kernel(const __grid_constant__ Ra
         aux = rp.aux[i];
       }
       float4 acc;
-      march_ray<MODE, LIT, BPV, TEX>(rp, exitp, pos, aux, acc, cn);
+      march_ray<MODE, LIT, BPV, SAMP>(rp, exitp, pos, aux, acc, cn);
       rp.image[i] = acc;
     }
     rp.pos[i] = pos;
@@ -604,11 +623,17 @@ __global__ void __launch_bounds__(128) raycast_kernel(const __grid_constant__ Ra
 
 typedef void (*raycast_fn)(const RayParams);
 
-template <int BPV, bool TEX>
+template <int BPV, int SAMP>
 static raycast_fn pick_kernel(uint32_t mode, bool lit) {
-  if (mode == TVK_RM_ISOSURFACE) return raycast_kernel<TVK_RM_ISOSURFACE, false, BPV, TEX>;
-  if (mode == TVK_RM_1DTRANS) return lit ? raycast_kernel<TVK_RM_1DTRANS, true, BPV, TEX> : raycast_kernel<TVK_RM_1DTRANS, false, BPV, TEX>;
-  return lit ? raycast_kernel<TVK_RM_2DTRANS, true, BPV, TEX> : raycast_kernel<TVK_RM_2DTRANS, false, BPV, TEX>;
+  if (mode == TVK_RM_ISOSURFACE) return raycast_kernel<TVK_RM_ISOSURFACE, false, BPV, SAMP>;
+  if (mode == TVK_RM_1DTRANS) return lit ? raycast_kernel<TVK_RM_1DTRANS, true, BPV, SAMP> : raycast_kernel<TVK_RM_1DTRANS, false, BPV, SAMP>;
+  return lit ? raycast_kernel<TVK_RM_2DTRANS, true, BPV, SAMP> : raycast_kernel<TVK_RM_2DTRANS, false, BPV, SAMP>;
+}
+template <int BPV>
+static raycast_fn pick_sampler(uint32_t sampler, uint32_t mode, bool lit) {
+  if (sampler == TVK_SAMPLER_TEX3D) return pick_kernel<BPV, TVK_SAMPLER_TEX3D>(mode, lit);
+  if (sampler == TVK_SAMPLER_EXACT_Q4) return pick_kernel<BPV, TVK_SAMPLER_EXACT_Q4>(mode, lit);
+  return pick_kernel<BPV, TVK_SAMPLER_EXACT>(mode, lit);
 }
 
 extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
@@ -640,10 +665,8 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   rp.stats = c->d_stats;
   rp.tiles_x = (p->width + 7) / 8; rp.tiles_y = (p->height + 3) / 4;
 
-  const bool tex = c->pdesc.sampler == TVK_SAMPLER_TEX3D;
-  raycast_fn fn;
-  if (c->pc.bpv == 1) fn = tex ? pick_kernel<1, true>(p->render_mode, p->lighting != 0) : pick_kernel<1, false>(p->render_mode, p->lighting != 0);
-  else fn = tex ? pick_kernel<2, true>(p->render_mode, p->lighting != 0) : pick_kernel<2, false>(p->render_mode, p->lighting != 0);
+  const raycast_fn fn = (c->pc.bpv == 1) ? pick_sampler<1>(c->pdesc.sampler, p->render_mode, p->lighting != 0)
+                                         : pick_sampler<2>(c->pdesc.sampler, p->render_mode, p->lighting != 0);
 
   int sms = 0, per_sm = 0;
   TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));

@@ -54,6 +54,8 @@ extern "C" {
 /* pool sampler back-ends (both give GL_LINEAR / CLAMP_TO_EDGE semantics) */
 #define TVK_SAMPLER_EXACT  0   /* fp32 trilinear from linear HBM (oracle arithmetic) */
 #define TVK_SAMPLER_TEX3D  1   /* cudaArray + hardware filtering (1.8 fixed-point weights) */
+#define TVK_SAMPLER_EXACT_Q4 2 /* EXACT arithmetic; pool stored as (y,z) 2x2 quads per voxel: 4x the
+                                  memory, 2 loads per sample instead of 8 (same results as EXACT)   */
 
 typedef struct tvk_ctx tvk_ctx;
 

@@ -171,6 +171,45 @@ def test_tex3d_sampler_reports_its_error(tvk, oct_u8):
     assert psnr >= 40.0 and err <= 4.0 / 255.0
 
 
+@pytest.mark.parametrize("which", ["u8_lit", "u16_2d", "u8_iso"])
+def test_quad_packed_pool_is_exact_too(tvk, oct_u8, oct_u16, which):
+    """TVK_SAMPLER_EXACT_Q4 (pool stored as 2x2 (y,z) quads, 2 loads per sample) must give the EXACT results."""
+    if which == "u8_lit":
+        tf = _tf(256)
+        lo, hi = H.tf_nonzero_limits(tf)
+        pool = _cold_pool(oct_u8, (8, 8, 8), 0, float(lo), float(hi))
+        cam = H.Camera()
+        cam.rotation = H.rotation_y(0.6) @ H.rotation_x(0.3)
+        p = H.raycast_params(cam, 203, 149, oct_u8["vol"], lighting=True)
+        _check(lockstep_render(tvk, p, pool, H.tf_bytes(tf), sampler=2))
+    elif which == "u16_2d":
+        n = 256
+        v = np.linspace(0, 1, n, dtype=np.float32)
+        g = np.linspace(0, 1, 256, dtype=np.float32)
+        tf2 = np.zeros((256, n, 4), np.float32)
+        tf2[..., 0] = v[None, :]
+        tf2[..., 1] = g[:, None]
+        tf2[..., 2] = 0.5
+        tf2[..., 3] = np.clip((v[None, :] - 0.2) * 0.6, 0, 1) * (0.3 + 0.7 * g[:, None])
+        tfb = (np.clip(tf2, 0, 1) * np.float32(255)).astype(np.uint8)
+        maxv = float(oct_u16["minmax"][:, 1].max())
+        pool = _cold_pool(oct_u16, (7, 7, 7), 1, 0.2 * maxv, maxv)
+        cam = H.Camera()
+        cam.rotation = H.rotation_x(0.5) @ H.rotation_y(0.4)
+        p = H.raycast_params(cam, 144, 112, oct_u16["vol"], render_mode=1, lighting=True,
+                             trans_scale=65535.0 / maxv, gradient_scale=8.0)
+        _check(lockstep_render(tvk, p, pool, tfb, sampler=2))
+    else:
+        pool = _cold_pool(oct_u8, (8, 8, 8), 2, 100.0, 0.0)
+        cam = H.Camera()
+        cam.rotation = H.rotation_y(2.1) @ H.rotation_x(-0.4)
+        p = H.raycast_params(cam, 180, 140, oct_u8["vol"], render_mode=2, isoval=100.0 / 256.0)
+        r = lockstep_render(tvk, p, pool, H.tf_bytes(_tf(256)), sampler=2)
+        d = np.abs(r["cuda"] - r["oracle"]).max(axis=2)
+        assert r["oracle"][..., 3].sum() > 500
+        assert (d > MAX_ERR).sum() <= max(4, int(0.002 * d.size))
+
+
 def test_api_errors(tvk, oct_u8):
     from imagevis3d_b200._lib import TvkError
     p = H.raycast_params(H.Camera(), 64, 48, oct_u8["vol"])
