@@ -597,6 +597,7 @@ bool CudaGridLeaper::ComputeRaycastParams(tvk_raycast_params& p) {
   p.new_view = m_blank ? 1u : 0u;
   p.missing_strategy = m_strategy; p.rehash_count = m_rehash; p.hash_table_size = m_hashSize;
   p.clip_enabled = 0;
+  for (int a = 0; a < 3; ++a) { p.box_min[a] = 0.0f; p.box_max[a] = 1.0f; }
   p.count_samples = 1;
   return true;
 }

@@ -25,6 +25,7 @@ struct RayParams {
   tvk_raycast_params p;
   PoolConst pc;
   const void* pool;
+  uint32_t elem_bytes;   // bytes per pool element (bpv, or 4*bpv for the quad-packed pool)
   cudaTextureObject_t tex;
   const uint32_t* meta;
   const uchar4* tf;
@@ -94,9 +95,18 @@ __device__ __forceinline__ void hash_report(const RayParams& rp, uint4 bc) {
   }
 }
 
+// Where the current brick lives in the pool: pointer to the slot's first element and the slot's
+// origin in pool voxels (pre-biased by the floor-trick constant), so that tap addresses are one
+// 64-bit base + a 32-bit in-slot offset.
+struct SlotCtx {
+  const uint8_t* base;
+  int ox, oy, oz;
+};
+
 struct BrickHit {
   f3 pool_entry, pool_exit, norm_exit, scale, trans;
   uint4 bc;
+  SlotCtx slot;
   bool empty, found;
 };
 
@@ -148,6 +158,12 @@ __device__ __forceinline__ void get_brick(const RayParams& rp, f3 entry, uint32_
   const uint32_t s0 = idx % pc.capacity[0], s1 = (idx / pc.capacity[0]) % pc.capacity[1],
                  s2 = idx / (pc.capacity[0] * pc.capacity[1]);
   {
+    const uint32_t vx = s0 * pc.max_brick[0], vy = s1 * pc.max_brick[1], vz = s2 * pc.max_brick[2];
+    const size_t sx = pc.pool_dim[0], sxy = sx * pc.pool_dim[1];
+    b.slot.base = static_cast<const uint8_t*>(rp.pool) + ((size_t)vx + (size_t)vy * sx + (size_t)vz * sxy) * rp.elem_bytes;
+    b.slot.ox = 0x4B400000 + (int)vx; b.slot.oy = 0x4B400000 + (int)vy; b.slot.oz = 0x4B400000 + (int)vz;
+  }
+  {
     const uint32_t v = s0 * pc.max_brick[0];
     const float p0 = (float)v / pc.pool_size[0] + pc.overlap_tc[0];
     const float p1 = (float)(v + pc.max_brick[0]) / pc.pool_size[0] - pc.overlap_tc[0];
@@ -188,24 +204,24 @@ struct Taps {
 // The base voxel is clamped to [0, dim-2]: inside a brick the footprint (and the
 // gradient taps one texel further) never leaves the slot -- 2 ghost voxels per side --
 // so this equals GL_CLAMP_TO_EDGE for every position the march can produce, and it lets
-// the eight loads share one address.
+// the eight loads share one address.  (The clamp is applied to the in-slot coordinate.)
 template <int BPV, int SAMP>
-__device__ __forceinline__ void fetch_taps(const RayParams& rp, f3 p, Taps& t) {
+__device__ __forceinline__ void fetch_taps(const RayParams& rp, const SlotCtx& sl, f3 p, Taps& t) {
   const PoolConst& pc = rp.pc;
   const float M = 12582912.0f;   // 1.5 * 2^23
   const float u = p.x * pc.pool_size[0] - 0.5f, v = p.y * pc.pool_size[1] - 0.5f, w = p.z * pc.pool_size[2] - 0.5f;
   const float tu = __fadd_rd(u, M), tv = __fadd_rd(v, M), tw = __fadd_rd(w, M);
   t.a = u - (tu - M); t.b = v - (tv - M); t.g = w - (tw - M);
-  int x = __float_as_int(tu) - 0x4B400000, y = __float_as_int(tv) - 0x4B400000, z = __float_as_int(tw) - 0x4B400000;
-  x = min(max(x, 0), (int)pc.pool_dim[0] - 2);
-  y = min(max(y, 0), (int)pc.pool_dim[1] - 2);
-  z = min(max(z, 0), (int)pc.pool_dim[2] - 2);
-  const size_t sx = pc.pool_dim[0], sxy = sx * pc.pool_dim[1];
-  const size_t o = (size_t)x + (size_t)y * sx + (size_t)z * sxy;
+  // in-slot voxel coordinates of the footprint's base corner
+  const int x = min(max(__float_as_int(tu) - sl.ox, 0), (int)pc.max_brick[0] - 2);
+  const int y = min(max(__float_as_int(tv) - sl.oy, 0), (int)pc.max_brick[1] - 2);
+  const int z = min(max(__float_as_int(tw) - sl.oz, 0), (int)pc.max_brick[2] - 2);
+  const uint32_t sx = pc.pool_dim[0], sxy = sx * pc.pool_dim[1];
+  const uint32_t o = (uint32_t)x + (uint32_t)y * sx + (uint32_t)z * sxy;
   if (SAMP == TVK_SAMPLER_EXACT_Q4) {
     // two loads: the (y,z) quads of columns x and x+1
     if (BPV == 1) {
-      const uint32_t* d = static_cast<const uint32_t*>(rp.pool) + o;
+      const uint32_t* d = reinterpret_cast<const uint32_t*>(sl.base) + o;
       const uint32_t q0 = __ldg(d), q1 = __ldg(d + 1);
       t.v[0] = __uint_as_float(__byte_perm(q0, 0x4B000000u, 0x7650)) - 8388608.0f;
       t.v[2] = __uint_as_float(__byte_perm(q0, 0x4B000000u, 0x7651)) - 8388608.0f;
@@ -216,20 +232,20 @@ __device__ __forceinline__ void fetch_taps(const RayParams& rp, f3 p, Taps& t) {
       t.v[5] = __uint_as_float(__byte_perm(q1, 0x4B000000u, 0x7652)) - 8388608.0f;
       t.v[7] = __uint_as_float(__byte_perm(q1, 0x4B000000u, 0x7653)) - 8388608.0f;
     } else {
-      const uint2* d = static_cast<const uint2*>(rp.pool) + o;
+      const uint2* d = reinterpret_cast<const uint2*>(sl.base) + o;
       const uint2 q0 = __ldg(d), q1 = __ldg(d + 1);
       t.v[0] = u2f(q0.x & 0xFFFFu); t.v[2] = u2f(q0.x >> 16); t.v[4] = u2f(q0.y & 0xFFFFu); t.v[6] = u2f(q0.y >> 16);
       t.v[1] = u2f(q1.x & 0xFFFFu); t.v[3] = u2f(q1.x >> 16); t.v[5] = u2f(q1.y & 0xFFFFu); t.v[7] = u2f(q1.y >> 16);
     }
   } else if (BPV == 1) {
-    const uint8_t* d = static_cast<const uint8_t*>(rp.pool) + o;
+    const uint8_t* d = sl.base + o;
     const uint8_t *d1 = d + sx, *d2 = d + sxy, *d3 = d2 + sx;
     const uint32_t r0 = __ldg(d), r1 = __ldg(d + 1), r2 = __ldg(d1), r3 = __ldg(d1 + 1);
     const uint32_t r4 = __ldg(d2), r5 = __ldg(d2 + 1), r6 = __ldg(d3), r7 = __ldg(d3 + 1);
     t.v[0] = u2f(r0); t.v[1] = u2f(r1); t.v[2] = u2f(r2); t.v[3] = u2f(r3);
     t.v[4] = u2f(r4); t.v[5] = u2f(r5); t.v[6] = u2f(r6); t.v[7] = u2f(r7);
   } else {
-    const uint16_t* d = static_cast<const uint16_t*>(rp.pool) + o;
+    const uint16_t* d = reinterpret_cast<const uint16_t*>(sl.base) + o;
     const uint16_t *d1 = d + sx, *d2 = d + sxy, *d3 = d2 + sx;
     const uint32_t r0 = __ldg(d), r1 = __ldg(d + 1), r2 = __ldg(d1), r3 = __ldg(d1 + 1);
     const uint32_t r4 = __ldg(d2), r5 = __ldg(d2 + 1), r6 = __ldg(d3), r7 = __ldg(d3 + 1);
@@ -249,12 +265,12 @@ __device__ __forceinline__ float filter_taps(const Taps& t) {
 
 // texture(volumePool, p).r -- GL_LINEAR, CLAMP_TO_EDGE, UNORM8/16.
 template <int BPV, int SAMP>
-__device__ __forceinline__ float sample_pool(const RayParams& rp, f3 p) {
+__device__ __forceinline__ float sample_pool(const RayParams& rp, const SlotCtx& sl, f3 p) {
   if (SAMP == TVK_SAMPLER_TEX3D) {
     return tex3D<float>(rp.tex, p.x, p.y, p.z);
   } else {
     Taps t;
-    fetch_taps<BPV, SAMP>(rp, p, t);
+    fetch_taps<BPV, SAMP>(rp, sl, p, t);
     return filter_taps<BPV>(t);
   }
 }
@@ -272,11 +288,11 @@ __device__ __forceinline__ float4 tf_fetch(const RayParams& rp, int i) {
 
 // ComputeGradient, GLGridLeaper-GradientTools.glsl:6-16 (y sign flipped there)
 template <int BPV, int SAMP>
-__device__ __forceinline__ f3 gradient(const RayParams& rp, f3 p) {
+__device__ __forceinline__ f3 gradient(const RayParams& rp, const SlotCtx& sl, f3 p) {
   const float dx = 1.0f / rp.pc.pool_size[0], dy = 1.0f / rp.pc.pool_size[1], dz = 1.0f / rp.pc.pool_size[2];
-  const float xp = sample_pool<BPV, SAMP>(rp, mk3(p.x + dx, p.y, p.z)), xm = sample_pool<BPV, SAMP>(rp, mk3(p.x - dx, p.y, p.z));
-  const float yp = sample_pool<BPV, SAMP>(rp, mk3(p.x, p.y - dy, p.z)), ym = sample_pool<BPV, SAMP>(rp, mk3(p.x, p.y + dy, p.z));
-  const float zp = sample_pool<BPV, SAMP>(rp, mk3(p.x, p.y, p.z + dz)), zm = sample_pool<BPV, SAMP>(rp, mk3(p.x, p.y, p.z - dz));
+  const float xp = sample_pool<BPV, SAMP>(rp, sl, mk3(p.x + dx, p.y, p.z)), xm = sample_pool<BPV, SAMP>(rp, sl, mk3(p.x - dx, p.y, p.z));
+  const float yp = sample_pool<BPV, SAMP>(rp, sl, mk3(p.x, p.y - dy, p.z)), ym = sample_pool<BPV, SAMP>(rp, sl, mk3(p.x, p.y + dy, p.z));
+  const float zp = sample_pool<BPV, SAMP>(rp, sl, mk3(p.x, p.y, p.z + dz)), zm = sample_pool<BPV, SAMP>(rp, sl, mk3(p.x, p.y, p.z - dz));
   return mk3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
 }
 
@@ -302,20 +318,20 @@ __device__ __forceinline__ f3 lighting(const tvk_raycast_params& p, f3 pos, f3 n
 // ComputeColorFromVolume, GLGridLeaper-Method-{1D,1D-L,2D,2D-L}.glsl; `data` is the
 // already filtered centre sample (fetched one iteration ahead by the march loop).
 template <int MODE, bool LIT, int BPV, int SAMP>
-__device__ __forceinline__ float4 color_from_volume(const RayParams& rp, float data, f3 pc, f3 scale, f3 trans) {
+__device__ __forceinline__ float4 color_from_volume(const RayParams& rp, const SlotCtx& sl, float data, f3 pc, f3 scale, f3 trans) {
   const tvk_raycast_params& p = rp.p;
   float4 col;
   f3 n;
   if (MODE == TVK_RM_1DTRANS) {
     col = __ldg(rp.tf_f + nearest_index(data * p.trans_scale, rp.tf_w));
     if (LIT) {
-      const f3 g = gradient<BPV, SAMP>(rp, pc);
+      const f3 g = gradient<BPV, SAMP>(rp, sl, pc);
       n = mk3(g.x * p.domain_scale[0], g.y * p.domain_scale[1], g.z * p.domain_scale[2]);
       const float l = len3(n);
       if (l > 0.0f) n = mk3(n.x / l, n.y / l, n.z / l);
     }
   } else {
-    const f3 g = gradient<BPV, SAMP>(rp, pc);
+    const f3 g = gradient<BPV, SAMP>(rp, sl, pc);
     const float gm = len3(g);
     col = tf_fetch(rp, nearest_index(1.0f - gm * p.gradient_scale, rp.tf_h) * (int)rp.tf_w +
                            nearest_index(data * p.trans_scale, rp.tf_w));
@@ -345,11 +361,11 @@ __device__ __forceinline__ bool ray_setup(const tvk_raycast_params& p, uint32_t 
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     if (d[a] == 0.0f) {
-      if (o[a] < 0.0f || o[a] > 1.0f) return false;
+      if (o[a] < p.box_min[a] || o[a] > p.box_max[a]) return false;
       continue;
     }
     const float inv = 1.0f / d[a];
-    float ta = (0.0f - o[a]) * inv, tb = (1.0f - o[a]) * inv;
+    float ta = (p.box_min[a] - o[a]) * inv, tb = (p.box_max[a] - o[a]) * inv;
     if (ta > tb) { const float t = ta; ta = tb; tb = t; }
     s0 = fmaxf(s0, ta);
     s1 = fminf(s1, tb);
@@ -413,36 +429,51 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
         const int s2 = (int)ceilf(len3(mk3((exitp.x - cur.x) * b.scale.x, (exitp.y - cur.y) * b.scale.y, (exitp.z - cur.z) * b.scale.z)) / step_size);
         steps = min(steps, s2);
         f3 q = b.pool_entry;
-        // software pipeline: the voxel footprint of sample i+1 is requested before sample i is
-        // classified and composited, so the L1 latency overlaps the dependent TF fetch + blend
-        Taps cur_t;
-        float cur_tex = 0.0f;
-        if (steps > 0) {
-          if (SAMP == TVK_SAMPLER_TEX3D) cur_tex = tex3D<float>(rp.tex, q.x, q.y, q.z);
-          else fetch_taps<BPV, SAMP>(rp, q, cur_t);
+        // Two samples per trip: both footprints (and both TF fetches) are in flight together, which
+        // doubles the memory-level parallelism of a ray without any register rotation.  Samples are
+        // still classified, counted and composited strictly in order, with the ERT test after each.
+        const bool pairwise = (MODE == TVK_RM_1DTRANS) && !LIT;
+        int i = 0;
+#define TVK_COMPOSITE(S)                                                                     \
+        {                                                                                    \
+          cn.samples++;                                                                      \
+          (S).w = (oc == 1.0f) ? 1.0f - (1.0f - (S).w) : 1.0f - powf(1.0f - (S).w, oc);      \
+          const float w_ = (1.0f - acc.w) * (S).w;    /* UnderCompositing, Compositing.glsl:33-38 */ \
+          acc.x += (S).x * w_; acc.y += (S).y * w_; acc.z += (S).z * w_;                      \
+          acc.w += (S).w * (1.0f - acc.w);                                                   \
+          if (acc.w > 0.99f) {                                                               \
+            if (optimal) { pos.w = 1000.0f; col = acc; }                                     \
+            return;                                                                          \
+          }                                                                                  \
         }
-        for (int i = 0; i < steps; ++i) {
-          const f3 qn = mk3(q.x + vdir.x, q.y + vdir.y, q.z + vdir.z);
-          Taps nxt_t;
-          float nxt_tex = 0.0f;
-          if (i + 1 < steps) {
-            if (SAMP == TVK_SAMPLER_TEX3D) nxt_tex = tex3D<float>(rp.tex, qn.x, qn.y, qn.z);
-            else fetch_taps<BPV, SAMP>(rp, qn, nxt_t);
+        if (pairwise) {
+          for (; i + 1 < steps; i += 2) {
+            const f3 q1 = mk3(q.x + vdir.x, q.y + vdir.y, q.z + vdir.z);
+            float d0, d1;
+            if (SAMP == TVK_SAMPLER_TEX3D) {
+              d0 = tex3D<float>(rp.tex, q.x, q.y, q.z);
+              d1 = tex3D<float>(rp.tex, q1.x, q1.y, q1.z);
+            } else {
+              Taps ta, tb;
+              fetch_taps<BPV, SAMP>(rp, b.slot, q, ta);
+              fetch_taps<BPV, SAMP>(rp, b.slot, q1, tb);
+              d0 = filter_taps<BPV>(ta);
+              d1 = filter_taps<BPV>(tb);
+            }
+            float4 s0 = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, d0, q, b.scale, b.trans);
+            float4 s1 = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, d1, q1, b.scale, b.trans);
+            TVK_COMPOSITE(s0)
+            TVK_COMPOSITE(s1)
+            q = mk3(q1.x + vdir.x, q1.y + vdir.y, q1.z + vdir.z);
           }
-          const float data = (SAMP == TVK_SAMPLER_TEX3D) ? cur_tex : filter_taps<BPV>(cur_t);
-          float4 s = color_from_volume<MODE, LIT, BPV, SAMP>(rp, data, q, b.scale, b.trans);
-          cn.samples++;
-          s.w = (oc == 1.0f) ? 1.0f - (1.0f - s.w) : 1.0f - powf(1.0f - s.w, oc);
-          const float w = (1.0f - acc.w) * s.w;       // UnderCompositing, Compositing.glsl:33-38
-          acc.x += s.x * w; acc.y += s.y * w; acc.z += s.z * w;
-          acc.w += s.w * (1.0f - acc.w);
-          if (acc.w > 0.99f) {
-            if (optimal) { pos.w = 1000.0f; col = acc; }
-            return;
-          }
-          q = qn;
-          if (SAMP == TVK_SAMPLER_TEX3D) cur_tex = nxt_tex; else cur_t = nxt_t;
         }
+        for (; i < steps; ++i) {
+          const float data = sample_pool<BPV, SAMP>(rp, b.slot, q);
+          float4 s0 = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, data, q, b.scale, b.trans);
+          TVK_COMPOSITE(s0)
+          q = mk3(q.x + vdir.x, q.y + vdir.y, q.z + vdir.z);
+        }
+#undef TVK_COMPOSITE
         cur = mk3((q.x - b.trans.x) / b.scale.x, (q.y - b.trans.y) / b.scale.y, (q.z - b.trans.z) / b.scale.z);
       } else {
         cur = mk3(b.norm_exit.x + voxel_size * dir.x / ray_len, b.norm_exit.y + voxel_size * dir.y / ray_len,
@@ -502,19 +533,19 @@ __device__ __forceinline__ void march_ray_iso(const RayParams& rp, float4 exitp,
         f3 q = b.pool_entry;
         for (int i = 0; i < steps; ++i) {
           cn.samples++;
-          if (sample_pool<BPV, SAMP>(rp, q) >= p.isoval) {
+          if (sample_pool<BPV, SAMP>(rp, b.slot, q) >= p.isoval) {
             f3 rd = mk3(vdir.x / 2.0f, vdir.y / 2.0f, vdir.z / 2.0f);       // RefineIsosurface
             q = mk3(q.x - rd.x, q.y - rd.y, q.z - rd.z);
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
               rd = mk3(rd.x / 2.0f, rd.y / 2.0f, rd.z / 2.0f);
-              if (sample_pool<BPV, SAMP>(rp, q) >= p.isoval) q = mk3(q.x - rd.x, q.y - rd.y, q.z - rd.z);
+              if (sample_pool<BPV, SAMP>(rp, b.slot, q) >= p.isoval) q = mk3(q.x - rd.x, q.y - rd.y, q.z - rd.z);
               else q = mk3(q.x + rd.x, q.y + rd.y, q.z + rd.z);
             }
             cur = mk3((q.x - b.trans.x) / b.scale.x, (q.y - b.trans.y) / b.scale.y, (q.z - b.trans.z) / b.scale.z);
             const float4 h4 = xform(p.model_to_eye, cur, 1.0f);
             hit = make_float4(h4.x, h4.y, h4.z, 2.0f);                       // color.r + 1
-            const f3 g = gradient<BPV, SAMP>(rp, q);
+            const f3 g = gradient<BPV, SAMP>(rp, b.slot, q);
             f3 n = mk3(g.x * p.domain_scale[0], g.y * p.domain_scale[1], g.z * p.domain_scale[2]);
             const float l = len3(n);
             if (l > 0.0f) n = mk3(n.x / l, n.y / l, n.z / l);
@@ -644,6 +675,9 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   if (p->render_mode == TVK_RM_1DTRANS && c->tf_h != 1) TVK_FAIL(c, TVK_ERR_INVALID, "1D mode needs a 1D transfer function");
   if (p->hash_table_size == 0 || p->rehash_count == 0) TVK_FAIL(c, TVK_ERR_INVALID, "bad hash table parameters");
   if (!(p->sample_rate_modifier > 0.0f)) TVK_FAIL(c, TVK_ERR_INVALID, "bad sample rate modifier");
+  for (int a = 0; a < 3; ++a)
+    if (!(p->box_min[a] >= 0.0f && p->box_max[a] <= 1.0f && p->box_min[a] < p->box_max[a]))
+      TVK_FAIL(c, TVK_ERR_INVALID, "bad clip box (box_min/box_max must be a sub-box of the unit cube)");
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
   const bool fresh = (c->width != p->width || c->height != p->height);
   int rc = tvk_ensure_frame(c, p->width, p->height, p->hash_table_size);
@@ -654,6 +688,7 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   rp.p = *p;
   rp.pc = c->pc;
   rp.pool = c->d_pool;
+  rp.elem_bytes = c->pc.bpv * (c->pdesc.sampler == TVK_SAMPLER_EXACT_Q4 ? 4u : 1u);
   rp.tex = c->pool_tex;
   rp.meta = c->d_meta;
   rp.tf = c->d_tf;

@@ -161,6 +161,8 @@ typedef struct tvk_raycast_params {
   uint32_t hash_table_size;        /* GLHashTable size (default 509)                  */
   uint32_t clip_enabled;           /* clip plane (model space, normalised coords)     */
   float clip_plane[4];
+  float box_min[3];                /* rays are clipped to this sub-box of the unit cube (normalised   */
+  float box_max[3];                /* volume coords): {0,0,0}-{1,1,1}, or a sort-last partition       */
   uint32_t count_samples;          /* accumulate executed samples into the stats      */
 } tvk_raycast_params;
 

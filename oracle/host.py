@@ -39,7 +39,7 @@ class RaycastParams(C.Structure):
                 ("iso_color", C.c_float * 3), ("compose_light_dir", C.c_float * 3),
                 ("new_view", C.c_uint32), ("missing_strategy", C.c_uint32), ("rehash_count", C.c_uint32),
                 ("hash_table_size", C.c_uint32), ("clip_enabled", C.c_uint32), ("clip_plane", C.c_float * 4),
-                ("count_samples", C.c_uint32)]
+                ("box_min", C.c_float * 3), ("box_max", C.c_float * 3), ("count_samples", C.c_uint32)]
 
 
 class Visibility(C.Structure):
@@ -140,7 +140,7 @@ class Camera:
 
 def raycast_params(cam, width, height, domain_size, scale=(1, 1, 1), render_mode=0, lighting=False,
                    sample_rate=1.0, trans_scale=1.0, gradient_scale=1.0, isoval=0.5, new_view=True,
-                   strategy=3, rehash=10, hash_size=509, count_samples=True):
+                   strategy=3, rehash=10, hash_size=509, count_samples=True, slab=None):
     p = RaycastParams()
     p.width, p.height = width, height
     dom = np.asarray(domain_size, f32)
@@ -152,12 +152,22 @@ def raycast_params(cam, width, height, domain_size, scale=(1, 1, 1), render_mode
     proj = perspective(cam.fov, aspect, cam.znear, cam.zfar)
     mv = (cam.rotation @ cam.translation @ view).astype(f32)     # GLRenderer.cpp:627
     emm = (inverse(mv) @ translation(0, 0, 0) @ scaling(*(f32(1) / extent)) @ translation(0.5, 0.5, 0.5)).astype(f32)
+    box_min, box_max = [0.0, 0.0, 0.0], [1.0, 1.0, 1.0]
+    wse = float((extent / dom).max())
+    if slab is not None:
+        # sort-last partition: this rank holds voxels [zs, ze) of the global volume (its own slab
+        # [z0, z1) plus a halo) as ITS volume; map global normalised coords to the local ones and
+        # clip the rays to the slab proper.  domain_size is the GLOBAL size here.
+        ld = np.asarray(slab["local_dims"], f32)
+        zs, z0, z1 = float(slab["zs"]), float(slab["z0"]), float(slab["z1"])
+        emm = (emm @ scaling(dom[0] / ld[0], dom[1] / ld[1], dom[2] / ld[2]) @ translation(0, 0, -zs / float(ld[2]))).astype(f32)
+        box_min[2], box_max[2] = (z0 - zs) / float(ld[2]), (z1 - zs) / float(ld[2])
     p.eye_to_model[:] = emm.reshape(-1).tolist()
     p.model_to_eye[:] = inverse(emm).reshape(-1).tolist()
     p.model_view_it[:] = inverse(mv).T.reshape(-1).tolist()
     p.inv_projection[:] = inverse(proj).reshape(-1).tolist()
     p.lod_factor = float(lod_factor(cam.fov, height))
-    p.level_zero_wse = float((extent / dom).max())     # GLVolumePool.cpp:801
+    p.level_zero_wse = wse                             # GLVolumePool.cpp:801 (global volume)
     p.sample_rate_modifier = sample_rate
     p.trans_scale, p.gradient_scale, p.isoval = trans_scale, gradient_scale, isoval
     p.render_mode, p.lighting = render_mode, int(lighting)
@@ -178,6 +188,8 @@ def raycast_params(cam, width, height, domain_size, scale=(1, 1, 1), render_mode
     p.new_view = int(new_view)
     p.missing_strategy, p.rehash_count, p.hash_table_size = strategy, rehash, hash_size
     p.clip_enabled = 0
+    p.box_min[:] = box_min
+    p.box_max[:] = box_max
     p.count_samples = int(count_samples)
     return p
 

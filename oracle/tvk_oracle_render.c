@@ -363,9 +363,9 @@ static int ray_setup(const tvk_raycast_params* p, uint32_t px, uint32_t py, floa
   float s0 = -INFINITY, s1 = INFINITY;
   for (int a = 0; a < 3; ++a) {
     const float inv = 1.0f / D[a];
-    float ta = (0.0f - O[a]) * inv, tb = (1.0f - O[a]) * inv;
+    float ta = (p->box_min[a] - O[a]) * inv, tb = (p->box_max[a] - O[a]) * inv;
     if (D[a] == 0.0f) {
-      if (O[a] < 0.0f || O[a] > 1.0f) return 0;
+      if (O[a] < p->box_min[a] || O[a] > p->box_max[a]) return 0;
       continue;
     }
     if (ta > tb) { const float t = ta; ta = tb; tb = t; }
