@@ -216,18 +216,24 @@ def run_gpu(args, rank, world):
     tvk = TvkContext(local)
     sampler = {"exact": L.SAMPLER_EXACT, "tex3d": L.SAMPLER_TEX3D, "q4": L.SAMPLER_EXACT_Q4}[os.environ.get("TVK_SAMPLER", "exact")]
 
-    # ---- untimed set-up: synthesize the slab in HBM, build bricks, fill the pool
-    raw = volume_torch(VOL, dev, z0=rank * VOL[2], ztotal=VOL[2] * world)
+    # ---- untimed set-up: synthesize the (slab of the) volume in HBM, build bricks, fill the pool
+    from imagevis3d_b200 import sortlast as SL
+    GLOBAL = (VOL[0], VOL[1], VOL[2] * world)
+    parts = SL.slab_partition(GLOBAL, world, halo=64)
+    part = parts[rank]
+    LOCAL = part["local_dims"] if world > 1 else VOL
+    raw = volume_torch(LOCAL, dev, z0=part["zs"], zn=LOCAL[2], ztotal=GLOBAL[2])
     torch.cuda.synchronize()
     t_b0 = time.perf_counter()
-    info = tvk.build_octree(raw_dptr=raw.data_ptr(), volume_size=VOL, bpv=1, brick=BRICK, overlap=OVERLAP)
+    info = tvk.build_octree(raw_dptr=raw.data_ptr(), volume_size=LOCAL, bpv=1, brick=BRICK, overlap=OVERLAP)
     t_build = time.perf_counter() - t_b0
     off, sizes = tvk.build_toc()
     mm = tvk.build_minmax()
     lod_count = next(l for l in range(info.lod_count)
                      if info.lod_bricks[l][0] * info.lod_bricks[l][1] * info.lod_bricks[l][2] == 1) + 1
-    cap = (10, 10, 9)
-    total = tvk.pool_create(VOL, (BRICK,) * 3, OVERLAP, 1, cap, lod_count, sampler)
+    total_needed = int(info.lod_offset[lod_count - 1]) + 1
+    cap = (10, 10, 9) if world == 1 else (11, 11, -(-total_needed // 121))
+    total = tvk.pool_create(LOCAL, (BRICK,) * 3, OVERLAP, 1, cap, lod_count, sampler)
     store = tvk.build_store_ptr()
     slots = np.arange(total, dtype=np.uint32)
     slots[total - 1] = cap[0] * cap[1] * cap[2] - 1          # coarsest brick pinned in the last slot
@@ -250,10 +256,29 @@ def run_gpu(args, rank, world):
         cam = camera_for_step(HM, k, args.steps)
         if world == 1:
             return HM.raycast_params(cam, WIDTH, HEIGHT, VOL)
-        return HM.raycast_params(cam, WIDTH, HEIGHT, VOL, slab=(rank, world))
+        return HM.raycast_params(cam, WIDTH, HEIGHT, GLOBAL, slab=part)
+
+    class _CAI:                      # zero-copy torch view of the renderer's device image
+        def __init__(self, ptr, shape):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+    def gpu_composite(stripes):
+        out = torch.empty_like(stripes[0])
+        torch.cuda.current_stream().synchronize()
+        tvk.composite_ordered([t.data_ptr() for t in stripes], stripes[0].shape[0] * stripes[0].shape[1], out.data_ptr())
+        return out
+
+    final_image = [None]
 
     def step(k):
         tvk.raycast(params_for(k))
+        if world > 1:
+            # sort-last: direct-send stripes over NCCL, ordered blend on the owner, gather
+            tvk.synchronize()
+            pg = HM.raycast_params(camera_for_step(HM, k, args.steps), WIDTH, HEIGHT, GLOBAL)
+            order = SL.depth_order(np.array(pg.eye_to_model[:]).reshape(4, 4), parts)
+            partial = torch.as_tensor(_CAI(tvk.image_device_ptr(), (HEIGHT, WIDTH, 4)), device=dev)
+            final_image[0] = SL.exchange_and_composite(partial, order, gpu_composite, world, rank)
 
     # ---- warm-up
     for k in range(args.warmup):
@@ -271,13 +296,16 @@ def run_gpu(args, rank, world):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    kernel_ms = 0.0
+    kernel_ms, step_s = 0.0, 0.0
     t0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
+        ts = time.perf_counter()
         step(k)
         tvk.synchronize()
+        torch.cuda.synchronize()
+        step_s += time.perf_counter() - ts
         kernel_ms += tvk.stats().last_raycast_ms
     torch.cuda.synchronize()
     wall_s = time.perf_counter() - t0
@@ -297,12 +325,19 @@ def run_gpu(args, rank, world):
     size_arr = np.ascontiguousarray(sizes[:total], np.uint32).reshape(-1)
 
     def e2e_step(k):
+        if world > 1:
+            tvk.set_metadata(meta_host)
         tvk._ck(tvk.lib.tvk_pool_upload_bricks(tvk.h, C.c_uint32(n), slot_arr.ctypes.data_as(C.c_void_p), src_arr,
                                                size_arr.ctypes.data_as(C.c_void_p), C.c_int(0)), "upload")
         tvk._ck(tvk.lib.tvk_pool_upload_wait(tvk.h), "wait")
         tvk.set_metadata(meta_host)
-        tvk.raycast(params_for(k))
-        tvk._ck(tvk.lib.tvk_read_image(tvk.h, C.c_void_p(img_host.data_ptr())), "read_image")
+        step(k)
+        if world > 1:
+            if rank == 0:
+                img_host.copy_(final_image[0])
+                torch.cuda.synchronize()
+        else:
+            tvk._ck(tvk.lib.tvk_read_image(tvk.h, C.c_void_p(img_host.data_ptr())), "read_image")
 
     e2e_step(0)
     tvk.stats(reset=True)
@@ -316,9 +351,9 @@ def run_gpu(args, rank, world):
 
     # ---- reduce over ranks
     if world > 1:
-        t = torch.tensor([kernel_ms, wall_s, e2e_s], device=dev, dtype=torch.float64)
+        t = torch.tensor([kernel_ms, wall_s, e2e_s, step_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        kernel_ms, wall_s, e2e_s = [float(v) for v in t.tolist()]
+        kernel_ms, wall_s, e2e_s, step_s = [float(v) for v in t.tolist()]
         c = torch.tensor([samples, rays, e2e_samples], device=dev, dtype=torch.int64)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         samples, rays, e2e_samples = [int(v) for v in c.tolist()]
@@ -328,11 +363,16 @@ def run_gpu(args, rank, world):
 
     peak, peak_src = peaks()
     ms_step = kernel_ms / args.steps
-    value = samples / (kernel_ms * 1e-3)
+    if world > 1:
+        # a step = render + exchange + blend + gather: the ray-march kernel alone is not the step
+        ms_frame = 1e3 * step_s / args.steps
+    else:
+        ms_frame = ms_step
+    value = samples / (ms_frame * 1e-3 * args.steps)
     alg_bytes = (samples * BYTES_PER_SAMPLE + rays * BYTES_PER_RAY) / args.steps / world
     achieved = alg_bytes / (ms_step * 1e-3) / 1e9
     line = {"metric": "ray samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_frame, "raycast_kernel_ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "samples_per_step": samples / args.steps, "rays_per_step": rays / args.steps,
             "wall_ms_per_step_incl_l2_flush": 1e3 * wall_s / args.steps,
@@ -342,7 +382,7 @@ def run_gpu(args, rank, world):
                          "note": "0.6068 B/sample + 16 B/ray (SURVEY 8d); the kernel is L1/TEX-issue bound, see DESIGN.md"},
             "e2e": {"value": e2e_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
-            "gpu_launches": args.steps, "clocks": clocks, "builder_ms_untimed": 1e3 * t_build}
+            "gpu_launches": args.steps * (1 if world == 1 else 2 * world), "clocks": clocks, "builder_ms_untimed": 1e3 * t_build}
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample
     if world == 1 and not args.no_cpu:
