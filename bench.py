@@ -191,11 +191,23 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+# N = 1: BASELINE configs[1].  N > 1: the sort-last configuration (configs[3]) scaled so that every GPU
+# still owns about 512^3 voxels: a near-cubic global volume of ~N*512^3 voxels, slab origins 64-aligned,
+# rendered at the 3840x2160 that configs[3] names.
+GLOBAL_BY_N = {1: (512, 512, 512), 2: (640, 640, 640), 4: (832, 832, 768), 8: (1024, 1024, 1024)}
+
+
+def global_config(n):
+    g = GLOBAL_BY_N.get(n, (512, 512, 512 * n))
+    return g, ((1920, 1080) if n == 1 else (3840, 2160))
+
+
 def workload_config(n):
+    g, (w, h) = global_config(n)
     return {"workload": "synthetic %dx%dx%d uint8 (sphere+ripple), brick 64/overlap 2, 1D-TF + ERT, %dx%d, "
-                        "1 converged frame/step, orbiting camera" % (VOL[0], VOL[1], VOL[2] * n, WIDTH, HEIGHT),
-            "volume": [VOL[0], VOL[1], VOL[2] * n], "resolution": [WIDTH, HEIGHT], "render_mode": "1D-TF",
-            "lighting": False, "sample_rate_modifier": 1.0, "sampler": os.environ.get("TVK_SAMPLER", "exact"),
+                        "1 converged frame/step, orbiting camera" % (g[0], g[1], g[2], w, h),
+            "volume": list(g), "resolution": [w, h], "render_mode": "1D-TF",
+            "lighting": False, "sample_rate_modifier": 1.0, "sampler": os.environ.get("TVK_SAMPLER", "q4"),
             "l2": "inputs larger than L2 (236 MB pool) + 256 MB L2 flush between steps",
             "parallelism": "single GPU" if n == 1 else "sort-last z-slabs x%d + direct-send compositing" % n}
 
@@ -208,17 +220,20 @@ def run_gpu(args, rank, world):
     from imagevis3d_b200.context import TvkContext
     from imagevis3d_b200 import hostmath as HM
 
+    global WIDTH, HEIGHT
+    GLOBAL, (WIDTH, HEIGHT) = global_config(world)
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     tvk = TvkContext(local)
-    sampler = {"exact": L.SAMPLER_EXACT, "tex3d": L.SAMPLER_TEX3D, "q4": L.SAMPLER_EXACT_Q4}[os.environ.get("TVK_SAMPLER", "exact")]
+    if world > 1:
+        tvk.set_stream(torch.cuda.current_stream().cuda_stream)   # K1, NCCL and the compositor stay stream-ordered
+    sampler = {"exact": L.SAMPLER_EXACT, "tex3d": L.SAMPLER_TEX3D, "q4": L.SAMPLER_EXACT_Q4}[os.environ.get("TVK_SAMPLER", "q4")]
 
     # ---- untimed set-up: synthesize the (slab of the) volume in HBM, build bricks, fill the pool
     from imagevis3d_b200 import sortlast as SL
-    GLOBAL = (VOL[0], VOL[1], VOL[2] * world)
     parts = SL.slab_partition(GLOBAL, world, halo=64)
     part = parts[rank]
     LOCAL = part["local_dims"] if world > 1 else VOL
@@ -232,7 +247,8 @@ def run_gpu(args, rank, world):
     lod_count = next(l for l in range(info.lod_count)
                      if info.lod_bricks[l][0] * info.lod_bricks[l][1] * info.lod_bricks[l][2] == 1) + 1
     total_needed = int(info.lod_offset[lod_count - 1]) + 1
-    cap = (10, 10, 9) if world == 1 else (11, 11, -(-total_needed // 121))
+    nbx, nby = int(info.lod_bricks[0][0]) + 1, int(info.lod_bricks[0][1]) + 1
+    cap = (10, 10, 9) if world == 1 else (nbx, nby, -(-total_needed // (nbx * nby)))
     total = tvk.pool_create(LOCAL, (BRICK,) * 3, OVERLAP, 1, cap, lod_count, sampler)
     store = tvk.build_store_ptr()
     slots = np.arange(total, dtype=np.uint32)
@@ -264,7 +280,6 @@ def run_gpu(args, rank, world):
 
     def gpu_composite(stripes):
         out = torch.empty_like(stripes[0])
-        torch.cuda.current_stream().synchronize()
         tvk.composite_ordered([t.data_ptr() for t in stripes], stripes[0].shape[0] * stripes[0].shape[1], out.data_ptr())
         return out
 
@@ -274,7 +289,6 @@ def run_gpu(args, rank, world):
         tvk.raycast(params_for(k))
         if world > 1:
             # sort-last: direct-send stripes over NCCL, ordered blend on the owner, gather
-            tvk.synchronize()
             pg = HM.raycast_params(camera_for_step(HM, k, args.steps), WIDTH, HEIGHT, GLOBAL)
             order = SL.depth_order(np.array(pg.eye_to_model[:]).reshape(4, 4), parts)
             partial = torch.as_tensor(_CAI(tvk.image_device_ptr(), (HEIGHT, WIDTH, 4)), device=dev)

@@ -39,6 +39,10 @@ class TvkContext:
     def _ck(self, rc, what):
         L.check(self.h, rc, what)
 
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); None = own stream"""
+        self._ck(self.lib.tvk_set_stream(self.h, C.c_void_p(cuda_stream)), "tvk_set_stream")
+
     def synchronize(self):
         self._ck(self.lib.tvk_device_synchronize(self.h), "tvk_device_synchronize")
 

@@ -417,7 +417,15 @@ bool CudaGridLeaper::LoadRawVolume(const void* raw, const uint32_t size[3], uint
   const uint64_t need = (uint64_t)bs[0] * bs[1] * bs[2] * bpv * (v->info.total_bricks + 8);
   BrickPool::ComputePoolCapacity(*v, gpuMemBytes ? gpuMemBytes : need, 16384, cap);
   m_pool = new BrickPool(m_ctx, v);
-  rc = m_pool->Create(cap, m_sampler);
+  uint32_t sampler = m_sampler;
+  if (sampler == kSamplerAuto) {
+    // the quad-packed pool needs 4x the bytes; take it when that is at most half of the free HBM
+    size_t freeB = 0, totalB = 0;
+    const uint64_t q4 = 4ull * bs[0] * bs[1] * bs[2] * bpv * cap[0] * cap[1] * cap[2];
+    sampler = (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess && q4 <= freeB / 2) ? TVK_SAMPLER_EXACT_Q4 : TVK_SAMPLER_EXACT;
+  }
+  m_activeSampler = sampler;
+  rc = m_pool->Create(cap, sampler);
   if (rc) return Fail("pool create", rc);
   rc = m_pool->UploadFirstBrick();
   if (rc) return Fail("UploadFirstBrick", rc);
@@ -535,7 +543,7 @@ void CudaGridLeaper::ClearWorkingSet() {                                     // 
   const uint32_t* cap = m_pool->Capacity();
   const uint32_t c[3] = {cap[0], cap[1], cap[2]};
   BrickPool* np = new BrickPool(m_ctx, m_vol);
-  if (np->Create(c, m_sampler) == TVK_OK && np->UploadFirstBrick() == TVK_OK) { delete m_pool; m_pool = np; }
+  if (np->Create(c, m_activeSampler) == TVK_OK && np->UploadFirstBrick() == TVK_OK) { delete m_pool; m_pool = np; }
   else delete np;
   m_visValid = false;
   RecomputeBrickVisibility(true);
@@ -790,7 +798,7 @@ int tvkr_set_2d_trans(tvkr_renderer* h, const uint8_t* rgba, uint32_t w, uint32_
   return h && R(h)->Set2DTrans(rgba, w, hh, nz) ? 0 : 1;
 }
 int tvkr_set_state(tvkr_renderer* h, uint32_t strategy, uint32_t hash_size, uint32_t rehash, uint32_t sampler) {
-  if (!h || hash_size == 0 || rehash == 0 || strategy > TVK_MBS_SKIP_TWO_LEVELS || sampler > TVK_SAMPLER_EXACT_Q4) return 1;
+  if (!h || hash_size == 0 || rehash == 0 || strategy > TVK_MBS_SKIP_TWO_LEVELS || (sampler > TVK_SAMPLER_EXACT_Q4 && sampler != tvk::kSamplerAuto)) return 1;
   R(h)->SetMissingBrickStrategy(strategy); R(h)->SetHashTable(hash_size, rehash); R(h)->SetSampler(sampler);
   return 0;
 }

@@ -139,6 +139,9 @@ class BrickPool {
   uint64_t m_uploadedBytes = 0;
 };
 
+// host-level choice: EXACT_Q4 when the 4x pool fits comfortably in free HBM, else EXACT
+static const uint32_t kSamplerAuto = 0xFFFFFFFFu;
+
 enum ERenderMode { RM_1DTRANS = 0, RM_2DTRANS = 1, RM_ISOSURFACE = 2 };
 enum ERendererTarget { RT_INTERACTIVE = 0, RT_CAPTURE = 1, RT_HEADLESS = 2 };
 
@@ -230,7 +233,8 @@ class CudaGridLeaper {
   TransferFunction1D m_tf1d;
   bool m_has2d = false;
   double m_tf2dLimits[4] = {0, 0, 0, 0};
-  uint32_t m_strategy = TVK_MBS_SKIP_TWO_LEVELS, m_hashSize = 509, m_rehash = 10, m_sampler = TVK_SAMPLER_EXACT;
+  uint32_t m_strategy = TVK_MBS_SKIP_TWO_LEVELS, m_hashSize = 509, m_rehash = 10, m_sampler = kSamplerAuto;
+  uint32_t m_activeSampler = TVK_SAMPLER_EXACT;
   bool m_blank = true, m_converged = false;
   tvk_visibility m_lastVis{};
   bool m_visValid = false;

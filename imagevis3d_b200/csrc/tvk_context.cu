@@ -77,6 +77,7 @@ extern "C" int tvk_create(int device, tvk_ctx** out) {
     delete c;
     return TVK_ERR_CUDA;
   }
+  c->own_stream = c->stream;
   cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
   // keep stream-ordered allocations (pager staging ring, job lists) cached between frames
   cudaMemPool_t mp;
@@ -103,11 +104,19 @@ extern "C" void tvk_destroy(tvk_ctx* c) {
   free_frame(c);
   cudaFree(c->d_tf); cudaFree(c->d_tf_f); cudaFree(c->d_hash); cudaFree(c->d_tile_counter); cudaFree(c->d_stats); cudaFree(c->d_counts);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->copy_done); cudaEventDestroy(c->render_done);
-  cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy_stream);
+  cudaStreamDestroy(c->own_stream); cudaStreamDestroy(c->copy_stream);
   delete c;
 }
 
 extern "C" const char* tvk_last_error(const tvk_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+extern "C" int tvk_set_stream(tvk_ctx* c, void* cuda_stream) {
+  if (!c) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+  return TVK_OK;
+}
 
 extern "C" int tvk_device_synchronize(tvk_ctx* c) {
   if (!c) return TVK_ERR_INVALID;

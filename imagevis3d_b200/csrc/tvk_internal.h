@@ -43,7 +43,8 @@ struct BuildState {
 
 struct tvk_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;       // render / builder stream
+  cudaStream_t stream = nullptr;       // render / builder stream (own_stream unless tvk_set_stream)
+  cudaStream_t own_stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // pager side stream
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, copy_done = nullptr, render_done = nullptr;
   std::string err;

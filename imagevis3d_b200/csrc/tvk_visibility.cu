@@ -107,12 +107,14 @@ extern "C" int tvk_visibility_recompute(tvk_ctx* c, const tvk_visibility* vis, u
 // (dst += (1-dst.a)*src, the premultiplied form of Compositing.glsl:33-38).
 // Pure streaming: 16 B/pixel read per partial, 16 B/pixel written.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) composite_kernel(const float4* const* __restrict__ partials, uint32_t n, uint64_t pixels,
+struct PartialList { const float4* p[64]; };
+
+__global__ void __launch_bounds__(256) composite_kernel(const __grid_constant__ PartialList partials, uint32_t n, uint64_t pixels,
                                                          float4* __restrict__ out) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += (uint64_t)gridDim.x * blockDim.x) {
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
     for (uint32_t k = 0; k < n; ++k) {
-      const float4 s = partials[k][i];
+      const float4 s = partials.p[k][i];
       const float w = 1.0f - d.w;
       d.x += w * s.x; d.y += w * s.y; d.z += w * s.z; d.w += w * s.w;
     }
@@ -120,20 +122,18 @@ __global__ void __launch_bounds__(256) composite_kernel(const float4* const* __r
   }
 }
 
+// Asynchronous: enqueued on the context's stream (see tvk_set_stream); the caller synchronises.
 extern "C" int tvk_composite_ordered(tvk_ctx* c, const void* const* partial_dptrs, uint32_t n, uint64_t pixels, void* out_dptr) {
   if (!c || !partial_dptrs || !out_dptr || n == 0 || n > 64) return TVK_ERR_INVALID;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
-  const float4** d_list = nullptr;
-  TVK_CHECK_CUDA(c, cudaMallocAsync(&d_list, sizeof(void*) * n, c->stream));
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_list, partial_dptrs, sizeof(void*) * n, cudaMemcpyHostToDevice, c->stream));
+  PartialList pl{};
+  for (uint32_t k = 0; k < n; ++k) pl.p[k] = static_cast<const float4*>(partial_dptrs[k]);
   int sms = 0;
   TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
   uint64_t blocks = (pixels + 255) / 256;
   if (blocks > (uint64_t)sms * 8) blocks = (uint64_t)sms * 8;
-  composite_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(d_list, n, pixels, (float4*)out_dptr);
+  composite_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(pl, n, pixels, (float4*)out_dptr);
   c->launches++;
   TVK_CHECK_CUDA(c, cudaGetLastError());
-  TVK_CHECK_CUDA(c, cudaFreeAsync(d_list, c->stream));
-  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
   return TVK_OK;
 }

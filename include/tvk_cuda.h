@@ -66,6 +66,10 @@ int  tvk_create(int device, tvk_ctx** out);
 void tvk_destroy(tvk_ctx* ctx);
 const char* tvk_last_error(const tvk_ctx* ctx);
 int  tvk_device_synchronize(tvk_ctx* ctx);
+/* Run all render / builder / compositor work of this context on an existing CUDA stream
+ * (e.g. the caller's, so that NCCL collectives and these kernels are ordered without host
+ * synchronisation).  cuda_stream is a cudaStream_t; NULL restores the context's own stream. */
+int  tvk_set_stream(tvk_ctx* ctx, void* cuda_stream);
 
 /* --------------------------------------------------------------- brick pool */
 /* replaces GLVolumePool ctor + CreateGLResources (GLVolumePool.cpp:119-259,
@@ -249,7 +253,8 @@ int tvk_build_release(tvk_ctx* ctx);
 /* -------------------------------------------------------- sort-last compositor */
 /* new in this build (no reference counterpart): ordered "under"
  * blend of n premultiplied RGBA32F partial images, front-to-back in the given
- * order, using Compositing.glsl:33-38 arithmetic for premultiplied input. */
+ * order, using Compositing.glsl:33-38 arithmetic for premultiplied input.
+ * Asynchronous on the context's stream (n <= 64); synchronise before reading out_dptr. */
 int tvk_composite_ordered(tvk_ctx* ctx, const void* const* partial_dptrs, uint32_t n,
                           uint64_t pixels, void* out_dptr);
 

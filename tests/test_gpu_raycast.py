@@ -245,5 +245,6 @@ def test_compositor_matches_oracle(tvk):
     out = torch.zeros((pix, 4), dtype=torch.float32, device="cuda")
     torch.cuda.synchronize()
     tvk.composite_ordered([d.data_ptr() for d in dev], pix, out.data_ptr())
+    tvk.synchronize()
     got = out.cpu().numpy()
     assert np.abs(got - want).max() <= 1e-6

@@ -64,6 +64,7 @@ def test_slabs_composite_like_one_volume(tvk, angle):
     out = torch.zeros((Hh, W, 4), dtype=torch.float32, device="cuda")
     torch.cuda.synchronize()
     tvk.composite_ordered([d.data_ptr() for d in dev], pix, out.data_ptr())
+    tvk.synchronize()
     got = out.cpu().numpy()
     psnr, err = image_errors(got, want)
     assert want.max() > 0.05 and psnr >= 45.0 and err <= 2.0 / 255.0, (psnr, err)
