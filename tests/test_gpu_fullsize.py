@@ -1,0 +1,103 @@
+"""GPU: BASELINE.json configs[2] at FULL size -- synthetic 2048^3 uint16 volume (17 GB), multi-LOD bricked
+(64^3 bricks, 49,597 pool bricks), 2D-TF with lighting and isosurface mode at 1920x1080.  A CPU re-run is
+out of reach at this size, so the builder is checked through size-independent properties (every voxel
+histogrammed once, bricks equal to the raw sub-volumes, truncating mean filter, min/max consistency) and the
+renderer through convergence / plausibility of the frames; small-size parity is in the other test files."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N = 2048
+
+
+def _volume_u16(dev):
+    import torch
+    out = torch.empty((N, N, N), dtype=torch.uint16, device=dev)
+    x = (0.5 - torch.arange(N, device=dev, dtype=torch.float32) / N)[None, None, :]
+    y = (0.5 - torch.arange(N, device=dev, dtype=torch.float32) / N)[None, :, None]
+    for z0 in range(0, N, 32):
+        z = (0.5 - (torch.arange(32, device=dev, dtype=torch.float32) + z0) / N)[:, None, None]
+        d = torch.sqrt(x * x + y * y + z * z)
+        v = torch.clamp((0.5 - d) * 65535.0 * 2.0, min=0)                      # UVFReader/DataSource.h sphere
+        rip = 4000.0 * torch.sin(x * 40.0) * torch.sin(y * 34.0) * torch.sin(z * 46.0)
+        out[z0:z0 + 32] = torch.clamp(v + rip * (v > 0), 0, 65535).to(torch.int32).to(torch.uint16)
+    return out
+
+
+def test_config3_2048_cubed_uint16():
+    import torch
+    from imagevis3d_b200 import _lib as L
+    from imagevis3d_b200 import hostmath as HM
+    from imagevis3d_b200.context import TvkContext
+    from imagevis3d_b200.scene import load_resident
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100 << 30:
+        pytest.skip("needs ~80 GB of free HBM")
+    dev = torch.device("cuda", 0)
+    raw = _volume_u16(dev)
+    torch.cuda.synchronize()
+    tvk = TvkContext(0)
+    sc = load_resident(tvk, raw.data_ptr(), (N, N, N), 2, sampler=L.SAMPLER_EXACT)
+    info = sc["info"]
+    assert info.total_bricks == 49602 and sc["total"] == 49597 and sc["lod_count"] == 7
+    # --- builder properties
+    h1 = tvk.build_hist1d()
+    assert int(h1.sum()) == N ** 3
+    mm = sc["minmax"]
+    rmax = int(raw.view(torch.int16).to(torch.int32).bitwise_and(0xFFFF).max())
+    assert mm[:42875, 1].max() == rmax and mm[:, 0].min() == 0 and len(h1) == rmax + 1
+    off, sizes = sc["offsets"], sc["sizes"]
+    rng = np.random.default_rng(7)
+    for bx, by, bz in [(17, 17, 17), (0, 0, 0), (34, 34, 34)] + [tuple(rng.integers(1, 34, 3)) for _ in range(3)]:
+        i = int(bx + 35 * by + 35 * 35 * bz)
+        s = [int(v) for v in sizes[i]]
+        b = tvk.build_bricks(int(off[i]), s[0] * s[1] * s[2] * 2).view(np.uint16).reshape(s[2], s[1], s[0])
+        lo = [60 * c - 2 for c in (bx, by, bz)]
+        ref = torch.zeros((s[2], s[1], s[0]), dtype=torch.int32, device=dev)
+        xs, ys, zs = [max(l, 0) for l in lo]
+        xe, ye, ze = [min(l + n, N) for l, n in zip(lo, s)]
+        sub = raw[zs:ze, ys:ye, xs:xe].view(torch.int16).to(torch.int32).bitwise_and(0xFFFF)
+        ref[zs - lo[2]:ze - lo[2], ys - lo[1]:ye - lo[1], xs - lo[0]:xe - lo[0]] = sub
+        assert (b.astype(np.int32) == ref.cpu().numpy()).all(), (bx, by, bz)
+        assert mm[i, 0] == b.min() and mm[i, 1] == b.max()
+    j = int(info.lod_offset[1]) + 5 + 18 * 5 + 18 * 18 * 5                 # LOD-1 brick (5,5,5): truncating mean of 8
+    b1 = tvk.build_bricks(int(off[j]), 64 ** 3 * 2).view(np.uint16).reshape(64, 64, 64)
+    blk = raw[600:720, 600:720, 600:720].view(torch.int16).to(torch.int64).bitwise_and(0xFFFF)
+    want = (blk.reshape(60, 2, 60, 2, 60, 2).sum(dim=(1, 3, 5)) // 8).cpu().numpy()
+    assert (b1[2:62, 2:62, 2:62].astype(np.int64) == want).all()
+
+    # --- isosurface frame (iso = half the range, AbstrRenderer.cpp:253-261)
+    cam = HM.Camera()
+    cam.rotation = HM.rotation_y(0.5) @ HM.rotation_x(0.3)
+    tvk.recompute_visibility(2, rmax / 2.0)
+    p = HM.raycast_params(cam, 1920, 1080, (N, N, N), render_mode=2, isoval=(rmax / 2.0) / 65536.0)
+    tvk.stats(reset=True)
+    tvk.raycast(p)
+    assert len(tvk.read_requests()) == 0                                   # fully resident: converged in one pass
+    img = tvk.read_image()
+    st = tvk.stats()
+    cover = float((img[..., 3] > 0).mean())
+    assert 0.05 < cover < 0.6 and img[..., :3].max() <= 1.0 and st.samples > 1e8
+    print("C3 iso: %.2f ms, %.0f M samples, coverage %.2f" % (st.last_raycast_ms, st.samples / 1e6, cover))
+
+    # --- 2D transfer function + lighting
+    v = np.linspace(0, 1, 4096, dtype=np.float32)
+    g = np.linspace(0, 1, 256, dtype=np.float32)
+    tf2 = np.zeros((256, 4096, 4), np.float32)
+    tf2[..., 0] = v[None, :]
+    tf2[..., 1] = 0.3 + 0.7 * g[:, None]
+    tf2[..., 2] = 0.4
+    tf2[..., 3] = np.clip((v[None, :] - 0.25) * 0.2, 0, 1) * (0.5 + 0.5 * g[:, None])
+    tvk.set_tf2d((np.clip(tf2, 0, 1) * np.float32(255)).astype(np.uint8))
+    tvk.recompute_visibility(1, 0.25 * rmax, float(rmax), -1e308, 1e308)
+    p = HM.raycast_params(cam, 1920, 1080, (N, N, N), render_mode=1, lighting=True, trans_scale=65535.0 / rmax,
+                          gradient_scale=40.0)
+    tvk.stats(reset=True)
+    tvk.raycast(p)
+    assert len(tvk.read_requests()) == 0
+    img = tvk.read_image()
+    st = tvk.stats()
+    assert img[..., 3].max() > 0.5 and np.isfinite(img).all() and st.samples > 1e8
+    print("C3 2D-TF lit: %.2f ms, %.0f M samples" % (st.last_raycast_ms, st.samples / 1e6))
+    tvk.close()
