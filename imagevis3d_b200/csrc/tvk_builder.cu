@@ -180,32 +180,54 @@ __global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ f
   const uint32_t sx = bc.lod_size[lod][0], sy = bc.lod_size[lod][1], sz = bc.lod_size[lod][2];
   const uint64_t nvox = (uint64_t)sx * sy * sz;
   T* dst = reinterpret_cast<T*>(store + offsets[first_brick + b]);
-  const uint32_t total = tx * ty * tz;
   const int o = (int)bc.overlap;
   uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-  for (uint32_t v = blockIdx.y * blockDim.x + threadIdx.x; v < total; v += gridDim.y * blockDim.x) {
-    const int i = (int)(v % tx), j = (int)((v / tx) % ty), k = (int)(v / (tx * ty));
-    T val = 0;
+  // A warp owns one brick row (j,k) at a time: everything that depends on (j,k) -- row validity,
+  // the source row pointer, ghost classification -- is warp-uniform and computed once per row; the
+  // lanes then stream x.  No per-voxel division, loads and stores are both unit-stride.
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.y * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.y * blockDim.x) >> 5;
+  const uint32_t rows = ty * tz;
+  const int nbz = (int)bc.lod_bricks[lod][2];
+  const bool fx = bx == 0, fy = by == 0, fz = bz == 0;
+  const bool lx = bx == (int)nbx - 1, ly = by == (int)nby - 1, lz = bz == nbz - 1;
+  for (uint32_t r = warp; r < rows; r += nwarps) {
+    const int j = (int)(r % ty), k = (int)(r / ty);
+    T* drow = dst + (size_t)r * tx;
     if (lod == 0) {
-      // GetInputBrick: rows/lines that exist in the copy loops, addressed by linear offset
-      const int nbz = (int)bc.lod_bricks[0][2];
-      const bool fx = bx == 0, fy = by == 0, fz = bz == 0;
-      const bool lx = bx == (int)nbx - 1, ly = by == (int)nby - 1, lz = bz == nbz - 1;
-      const bool in_x = i >= (fx ? o : 0) && i < (int)tx - (lx ? o : 0);
+      // GetInputBrick: rows/lines that exist in the copy loops, addressed by linear file offset
       const bool in_y = j >= (fy ? o : 0) && j < (int)ty - (ly ? o : 0);
       const bool in_z = k >= (fz ? o : 0) && k < (int)tz - (lz ? o : 0);
-      if (in_x && in_y && in_z) {
-        const uint64_t lin = (uint64_t)(bx * (int)bc.core - o + i) + (uint64_t)(by * (int)bc.core - o + j) * sx +
-                             (uint64_t)(bz * (int)bc.core - o + k) * sx * sy;
-        if (lin < nvox) val = flat[lin];
+      const int xa = fx ? o : 0, xb = (int)tx - (lx ? o : 0);
+      const uint64_t lin0 = (uint64_t)(int64_t)(bx * (int)bc.core - o) + (uint64_t)(by * (int)bc.core - o + j) * sx +
+                            (uint64_t)(bz * (int)bc.core - o + k) * sx * sy;      // wraps for i < xa only; never read there
+      for (int i = (int)lane; i < (int)tx; i += 32) {
+        T val = 0;
+        if (in_y && in_z && i >= xa && i < xb) {
+          const uint64_t lin = lin0 + (uint64_t)i;
+          if (lin < nvox) val = flat[lin];
+        }
+        drow[i] = val;
+        lo = min(lo, (uint32_t)val);
+        hi = max(hi, (uint32_t)val);
       }
     } else {
-      uint32_t gx, gy, gz;
-      if (resolve_overlap(bc, lod, bx, by, bz, i, j, k, gx, gy, gz)) val = flat[gx + (uint64_t)gy * sx + (uint64_t)gz * sx * sy];
+      const bool inner_row = j >= o && j < (int)ty - o && k >= o && k < (int)tz - o;
+      const T* srow = flat + (uint64_t)(by * (int)bc.core + j - o) * sx + (uint64_t)(bz * (int)bc.core + k - o) * sx * sy +
+                      (uint64_t)(int64_t)(bx * (int)bc.core - o);
+      for (int i = (int)lane; i < (int)tx; i += 32) {
+        T val = 0;
+        if (inner_row && i >= o && i < (int)tx - o) {
+          val = srow[i];
+        } else {
+          uint32_t gx, gy, gz;
+          if (resolve_overlap(bc, lod, bx, by, bz, i, j, k, gx, gy, gz)) val = flat[gx + (uint64_t)gy * sx + (uint64_t)gz * sx * sy];
+        }
+        drow[i] = val;
+        lo = min(lo, (uint32_t)val);
+        hi = max(hi, (uint32_t)val);
+      }
     }
-    dst[v] = val;
-    lo = min(lo, (uint32_t)val);
-    hi = max(hi, (uint32_t)val);
   }
   for (int s = 16; s > 0; s >>= 1) {
     lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, s));
@@ -227,13 +249,29 @@ __global__ void minmax_to_double_kernel(const uint32_t* mn, const uint32_t* mx, 
 template <typename T>
 __global__ void __launch_bounds__(256) hist1d_kernel(const T* __restrict__ raw, uint64_t n, unsigned long long* __restrict__ bins) {
   if (sizeof(T) == 1) {
-    __shared__ unsigned int sh[256];
-    sh[threadIdx.x] = 0;
+    // one private 256-bin histogram per warp (8 KB per CTA): smooth data sends a whole warp to a
+    // couple of bins, which a single shared table would serialise CTA-wide; 16-byte loads
+    __shared__ unsigned int sh[8][256];
+    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&sh[0][0])[i] = 0;
     __syncthreads();
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-      atomicAdd(&sh[raw[i]], 1u);
+    unsigned int* mine = sh[threadIdx.x >> 5];
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(raw);
+    const uint64_t nvec = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) ? n / 16 : 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
+      const uint4 q = reinterpret_cast<const uint4*>(p)[i];
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        atomicAdd(&mine[w[k] & 0xFFu], 1u); atomicAdd(&mine[(w[k] >> 8) & 0xFFu], 1u);
+        atomicAdd(&mine[(w[k] >> 16) & 0xFFu], 1u); atomicAdd(&mine[w[k] >> 24], 1u);
+      }
+    }
+    for (uint64_t i = nvec * 16 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+      atomicAdd(&mine[p[i]], 1u);
     __syncthreads();
-    if (sh[threadIdx.x]) atomicAdd(&bins[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+    unsigned int s = 0;
+    for (int w = 0; w < 8; ++w) s += sh[w][threadIdx.x];
+    if (s) atomicAdd(&bins[threadIdx.x], (unsigned long long)s);
   } else {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t rounds = (n + stride - 1) / stride;

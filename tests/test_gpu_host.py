@@ -179,3 +179,38 @@ def test_renderer_error_behaviour():
     with pytest.raises(TvkError):
         r.setRenderMode(1)                          # 2D mode without a 2D transfer function
     r.cleanup()
+
+
+@pytest.mark.parametrize("lighting", [True, False])
+def test_config1_c60_demo_dataset(lighting):
+    """BASELINE configs[0]: DemoData/c60.uvf (128^3 uint8, decoded by the reference's own UVF reader into
+    tests/golden/c60.npz) with c60.1dt, 1D-TF ray-cast at 1024x1024, lighting on (the reference default) and
+    off.  c60.uvf is a legacy single-brick RasterDataBlock file; like DynamicBrickingDS would, we re-brick
+    it to 64^3 bricks for the ray-guided path."""
+    from imagevis3d_b200.renderer import Renderer, RT_HEADLESS
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c60.npz"))
+    vol = np.ascontiguousarray(z["brick"])                                # the single 128^3 brick == the whole domain
+    assert vol.shape == (128, 128, 128) and list(z["domain"]) == [128, 128, 128]
+    assert int(np.bincount(vol.reshape(-1), minlength=256)[0]) == int(z["hist1d"][0])   # same voxels the UVF histogrammed
+    tfb = np.ascontiguousarray(z["tf1d_rgba8"])
+    lo, hi = [int(v) for v in z["tf1d_nonzero"]]
+    r = Renderer(0)
+    r.loadRawVolume(vol, brick_size=64)
+    info = r.datasetInfo()
+    assert info.tf_size == 256 and info.range[1] == 255.0
+    r.set1DTrans(tfb)
+    r.setLightingEnabled(lighting)
+    r.resize((1024, 1024))
+    r.setRendererTarget(RT_HEADLESS)
+    subs = r.paintUntilConverged()
+    got = r.frameFloat()
+    oc = O.build_octree(vol, 64, 2)
+    pool = H.OraclePool(oc, tuple(info.pool_capacity))
+    pool.upload_first_brick()
+    pool.recompute_visibility(0, lo * 255.0 / 255.0, hi * 255.0 / 255.0)
+    p = H.raycast_params(H.Camera(), 1024, 1024, oc["vol"], lighting=lighting, trans_scale=1.0)
+    want, subs_o, _, _ = H.render_converged(p, pool, tfb)
+    psnr, err = image_errors(got, want)
+    assert want[..., 3].max() > 0.3 and subs == subs_o
+    assert psnr >= 45.0 and err <= 2.0 / 255.0, (psnr, err)
+    r.cleanup()
