@@ -12,7 +12,9 @@ LIB = os.path.join(HERE, "libtvk_cuda.so")
 
 CU_SOURCES = ["tvk_context.cu", "tvk_raycast.cu", "tvk_visibility.cu", "tvk_builder.cu"]
 CPP_SOURCES = ["host/tvk_host.cpp"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+# -fmad=false: multiply-adds are fused only where the source says fmaf(), so that the ray-marcher
+# rounds exactly like the CPU oracle (see the floating-point contract in tvk_raycast.cu)
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
               "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 

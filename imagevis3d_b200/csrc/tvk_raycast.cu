@@ -42,17 +42,20 @@ struct RayParams {
 
 struct f3 { float x, y, z; };
 __device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
-__device__ __forceinline__ float len3(f3 v) { return sqrtf(v.x * v.x + v.y * v.y + v.z * v.z); }
-__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// Floating-point contract (shared with oracle/tvk_oracle_render.c): this file is compiled with
+// -fmad=false, so the ONLY fused multiply-adds are the explicit fmaf() calls, and they sit exactly
+// where the oracle has them.  Every other operation is a single IEEE fp32 op in the oracle's order.
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ float len3(f3 v) { return sqrtf(dot3(v, v)); }
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 
 // v' = v*M, FLOATMATRIX4 memory order (Basics/Vectors.h:434)
 __device__ __forceinline__ float4 xform(const float* m, f3 v, float w) {
   float4 o;
-  o.x = v.x * m[0] + v.y * m[4] + v.z * m[8] + w * m[12];
-  o.y = v.x * m[1] + v.y * m[5] + v.z * m[9] + w * m[13];
-  o.z = v.x * m[2] + v.y * m[6] + v.z * m[10] + w * m[14];
-  o.w = v.x * m[3] + v.y * m[7] + v.z * m[11] + w * m[15];
+  o.x = fmaf(w, m[12], fmaf(v.z, m[8], fmaf(v.y, m[4], v.x * m[0])));
+  o.y = fmaf(w, m[13], fmaf(v.z, m[9], fmaf(v.y, m[5], v.x * m[1])));
+  o.z = fmaf(w, m[14], fmaf(v.z, m[10], fmaf(v.y, m[6], v.x * m[2])));
+  o.w = fmaf(w, m[15], fmaf(v.z, m[11], fmaf(v.y, m[7], v.x * m[3])));
   return o;
 }
 
@@ -152,7 +155,7 @@ __device__ __forceinline__ void get_brick(const RayParams& rp, f3 entry, uint32_
   const float ty = ((dvy >= 0.0f ? c1.y : c0.y) - e.y) * dvy;
   const float tz = ((dvz >= 0.0f ? c1.z : c0.z) - e.z) * dvz;
   const float tmin = fminf(fminf(fminf(INFINITY, tx), ty), tz);   // fminf drops NaN (0*inf)
-  b.norm_exit = mk3(e.x + tmin * dir.x, e.y + tmin * dir.y, e.z + tmin * dir.z);
+  b.norm_exit = mk3(fmaf(tmin, dir.x, e.x), fmaf(tmin, dir.y, e.y), fmaf(tmin, dir.z, e.z));
   if (b.empty) return;
   const uint32_t idx = info - TVK_BI_FLAG_COUNT;
   const uint32_t s0 = idx % pc.capacity[0], s1 = (idx / pc.capacity[0]) % pc.capacity[1],
@@ -168,25 +171,25 @@ __device__ __forceinline__ void get_brick(const RayParams& rp, f3 entry, uint32_
     const float p0 = (float)v / pc.pool_size[0] + pc.overlap_tc[0];
     const float p1 = (float)(v + pc.max_brick[0]) / pc.pool_size[0] - pc.overlap_tc[0];
     b.scale.x = (p1 - p0) / (c1.x - c0.x);
-    b.trans.x = p0 - c0.x * b.scale.x;
+    b.trans.x = fmaf(-c0.x, b.scale.x, p0);
   }
   {
     const uint32_t v = s1 * pc.max_brick[1];
     const float p0 = (float)v / pc.pool_size[1] + pc.overlap_tc[1];
     const float p1 = (float)(v + pc.max_brick[1]) / pc.pool_size[1] - pc.overlap_tc[1];
     b.scale.y = (p1 - p0) / (c1.y - c0.y);
-    b.trans.y = p0 - c0.y * b.scale.y;
+    b.trans.y = fmaf(-c0.y, b.scale.y, p0);
   }
   {
     const uint32_t v = s2 * pc.max_brick[2];
     const float p0 = (float)v / pc.pool_size[2] + pc.overlap_tc[2];
     const float p1 = (float)(v + pc.max_brick[2]) / pc.pool_size[2] - pc.overlap_tc[2];
     b.scale.z = (p1 - p0) / (c1.z - c0.z);
-    b.trans.z = p0 - c0.z * b.scale.z;
+    b.trans.z = fmaf(-c0.z, b.scale.z, p0);
   }
-  b.pool_entry = mk3(e.x * b.scale.x + b.trans.x, e.y * b.scale.y + b.trans.y, e.z * b.scale.z + b.trans.z);
-  b.pool_exit = mk3(b.norm_exit.x * b.scale.x + b.trans.x, b.norm_exit.y * b.scale.y + b.trans.y,
-                    b.norm_exit.z * b.scale.z + b.trans.z);
+  b.pool_entry = mk3(fmaf(e.x, b.scale.x, b.trans.x), fmaf(e.y, b.scale.y, b.trans.y), fmaf(e.z, b.scale.z, b.trans.z));
+  b.pool_exit = mk3(fmaf(b.norm_exit.x, b.scale.x, b.trans.x), fmaf(b.norm_exit.y, b.scale.y, b.trans.y),
+                    fmaf(b.norm_exit.z, b.scale.z, b.trans.z));
 }
 
 // Exact small-integer -> float without the quarter-rate I2F pipe: OR the value into the
@@ -209,7 +212,7 @@ template <int BPV, int SAMP>
 __device__ __forceinline__ void fetch_taps(const RayParams& rp, const SlotCtx& sl, f3 p, Taps& t) {
   const PoolConst& pc = rp.pc;
   const float M = 12582912.0f;   // 1.5 * 2^23
-  const float u = p.x * pc.pool_size[0] - 0.5f, v = p.y * pc.pool_size[1] - 0.5f, w = p.z * pc.pool_size[2] - 0.5f;
+  const float u = fmaf(p.x, pc.pool_size[0], -0.5f), v = fmaf(p.y, pc.pool_size[1], -0.5f), w = fmaf(p.z, pc.pool_size[2], -0.5f);
   const float tu = __fadd_rd(u, M), tv = __fadd_rd(v, M), tw = __fadd_rd(w, M);
   t.a = u - (tu - M); t.b = v - (tv - M); t.g = w - (tw - M);
   // in-slot voxel coordinates of the footprint's base corner
@@ -257,10 +260,10 @@ __device__ __forceinline__ void fetch_taps(const RayParams& rp, const SlotCtx& s
 // Filter half: fp32 trilinear on the raw values, then the UNORM scale.
 template <int BPV>
 __device__ __forceinline__ float filter_taps(const Taps& t) {
-  const float c00 = t.v[0] + t.a * (t.v[1] - t.v[0]), c10 = t.v[2] + t.a * (t.v[3] - t.v[2]);
-  const float c01 = t.v[4] + t.a * (t.v[5] - t.v[4]), c11 = t.v[6] + t.a * (t.v[7] - t.v[6]);
-  const float c0 = c00 + t.b * (c10 - c00), c1 = c01 + t.b * (c11 - c01);
-  return (c0 + t.g * (c1 - c0)) * (BPV == 1 ? 1.0f / 255.0f : 1.0f / 65535.0f);
+  const float c00 = fmaf(t.a, t.v[1] - t.v[0], t.v[0]), c10 = fmaf(t.a, t.v[3] - t.v[2], t.v[2]);
+  const float c01 = fmaf(t.a, t.v[5] - t.v[4], t.v[4]), c11 = fmaf(t.a, t.v[7] - t.v[6], t.v[6]);
+  const float c0 = fmaf(t.b, c10 - c00, c00), c1 = fmaf(t.b, c11 - c01, c01);
+  return fmaf(t.g, c1 - c0, c0) * (BPV == 1 ? 1.0f / 255.0f : 1.0f / 65535.0f);
 }
 
 // texture(volumePool, p).r -- GL_LINEAR, CLAMP_TO_EDGE, UNORM8/16.
@@ -303,16 +306,16 @@ __device__ __forceinline__ f3 lighting(const tvk_raycast_params& p, f3 pos, f3 n
   f3 v = mk3(p.model_eye_pos[0] - pos.x, p.model_eye_pos[1] - pos.y, p.model_eye_pos[2] - pos.z);
   float l = len3(v);
   v = mk3(v.x / l, v.y / l, v.z / l);
-  const float d = dot3(n, v);
-  f3 r = mk3(v.x - 2.0f * d * n.x, v.y - 2.0f * d * n.y, v.z - 2.0f * d * n.z);
+  const float d2 = 2.0f * dot3(n, v);
+  f3 r = mk3(fmaf(-d2, n.x, v.x), fmaf(-d2, n.y, v.y), fmaf(-d2, n.z, v.z));
   l = len3(r);
   r = mk3(r.x / l, r.y / l, r.z / l);
   const f3 L = mk3(p.model_light_dir[0], p.model_light_dir[1], p.model_light_dir[2]);
   const float ndl = fmaxf(fabsf(dot3(n, L)), 0.0f);
   const float spec = pow8(fmaxf(dot3(r, L), 0.0f));
-  return mk3(clamp01(p.light_ambient[0] + diffuse.x * ndl + p.light_specular[0] * spec),
-             clamp01(p.light_ambient[1] + diffuse.y * ndl + p.light_specular[1] * spec),
-             clamp01(p.light_ambient[2] + diffuse.z * ndl + p.light_specular[2] * spec));
+  return mk3(clamp01(fmaf(p.light_specular[0], spec, fmaf(diffuse.x, ndl, p.light_ambient[0]))),
+             clamp01(fmaf(p.light_specular[1], spec, fmaf(diffuse.y, ndl, p.light_ambient[1]))),
+             clamp01(fmaf(p.light_specular[2], spec, fmaf(diffuse.z, ndl, p.light_ambient[2]))));
 }
 
 // ComputeColorFromVolume, GLGridLeaper-Method-{1D,1D-L,2D,2D-L}.glsl; `data` is the
@@ -333,7 +336,7 @@ __device__ __forceinline__ float4 color_from_volume(const RayParams& rp, const S
   } else {
     const f3 g = gradient<BPV, SAMP>(rp, sl, pc);
     const float gm = len3(g);
-    col = tf_fetch(rp, nearest_index(1.0f - gm * p.gradient_scale, rp.tf_h) * (int)rp.tf_w +
+    col = tf_fetch(rp, nearest_index(fmaf(-gm, p.gradient_scale, 1.0f), rp.tf_h) * (int)rp.tf_w +
                            nearest_index(data * p.trans_scale, rp.tf_w));
     if (LIT) {
       const f3 gn = (gm > 0.0f) ? mk3(g.x / gm, g.y / gm, g.z / gm) : g;
@@ -351,7 +354,7 @@ __device__ __forceinline__ float4 color_from_volume(const RayParams& rp, const S
 // Analytic ray set-up (pixel-centre ray against the unit box in normalised volume
 // coordinates); same arithmetic as oracle ray_setup().
 __device__ __forceinline__ bool ray_setup(const tvk_raycast_params& p, uint32_t px, uint32_t py, float4& entry, float4& exitp) {
-  const f3 ndc = mk3(((float)px + 0.5f) / (float)p.width * 2.0f - 1.0f, ((float)py + 0.5f) / (float)p.height * 2.0f - 1.0f, -1.0f);
+  const f3 ndc = mk3(fmaf(((float)px + 0.5f) / (float)p.width, 2.0f, -1.0f), fmaf(((float)py + 0.5f) / (float)p.height, 2.0f, -1.0f), -1.0f);
   const float4 n4 = xform(p.inv_projection, ndc, 1.0f);
   const f3 n = mk3(n4.x / n4.w, n4.y / n4.w, n4.z / n4.w);
   const float4 O = xform(p.eye_to_model, mk3(0.f, 0.f, 0.f), 1.0f);
@@ -371,8 +374,9 @@ __device__ __forceinline__ bool ray_setup(const tvk_raycast_params& p, uint32_t 
     s1 = fminf(s1, tb);
   }
   if (p.clip_enabled) {
-    const float dn = p.clip_plane[0] * D.x + p.clip_plane[1] * D.y + p.clip_plane[2] * D.z;
-    const float on = p.clip_plane[0] * O.x + p.clip_plane[1] * O.y + p.clip_plane[2] * O.z + p.clip_plane[3];
+    const f3 cp = mk3(p.clip_plane[0], p.clip_plane[1], p.clip_plane[2]);
+    const float dn = dot3(cp, mk3(D.x, D.y, D.z));
+    const float on = dot3(cp, mk3(O.x, O.y, O.z)) + p.clip_plane[3];
     if (dn == 0.0f) { if (on > 0.0f) return false; }
     else {
       const float t = -on / dn;
@@ -414,7 +418,7 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
   const float oc = 1.0f / p.sample_rate_modifier;
   if (ray_len > voxel_size) {
     for (uint32_t j = 0; j < 100; ++j) {
-      const float depth = entry_depth * (1.0f - t) + exit_depth * t;
+      const float depth = fmaf(exit_depth, t, entry_depth * (1.0f - t));
       uint32_t lod = compute_lod(depth, p.lod_factor, p.level_zero_wse, pc.lod_count - 1);
       BrickHit b;
       get_brick(rp, cur, lod, dir, b);
@@ -439,8 +443,8 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
           cn.samples++;                                                                      \
           (S).w = (oc == 1.0f) ? 1.0f - (1.0f - (S).w) : 1.0f - powf(1.0f - (S).w, oc);      \
           const float w_ = (1.0f - acc.w) * (S).w;    /* UnderCompositing, Compositing.glsl:33-38 */ \
-          acc.x += (S).x * w_; acc.y += (S).y * w_; acc.z += (S).z * w_;                      \
-          acc.w += (S).w * (1.0f - acc.w);                                                   \
+          acc.x = fmaf((S).x, w_, acc.x); acc.y = fmaf((S).y, w_, acc.y); acc.z = fmaf((S).z, w_, acc.z); \
+          acc.w = fmaf((S).w, 1.0f - acc.w, acc.w);                                          \
           if (acc.w > 0.99f) {                                                               \
             if (optimal) { pos.w = 1000.0f; col = acc; }                                     \
             return;                                                                          \
@@ -517,7 +521,7 @@ __device__ __forceinline__ void march_ray_iso(const RayParams& rp, float4 exitp,
   uint4 last_bc = make_uint4(0, 0, 0, 9999);
   if (ray_len > voxel_size) {
     for (uint32_t j = 0; j < 100; ++j) {
-      const float depth = entry_depth * (1.0f - t) + exit_depth * t;
+      const float depth = fmaf(exit_depth, t, entry_depth * (1.0f - t));
       uint32_t lod = compute_lod(depth, p.lod_factor, p.level_zero_wse, pc.lod_count - 1);
       BrickHit b;
       get_brick(rp, cur, lod, dir, b);
@@ -578,20 +582,20 @@ __device__ __forceinline__ float4 compose_iso(const tvk_raycast_params& p, float
   f3 v = mk3(0.0f - hit.x, 0.0f - hit.y, 0.0f - hit.z);
   float l = len3(v);
   v = mk3(v.x / l, v.y / l, v.z / l);
-  const float d = dot3(n, v);
-  f3 r = mk3(v.x - 2.0f * d * n.x, v.y - 2.0f * d * n.y, v.z - 2.0f * d * n.z);
+  const float d2 = 2.0f * dot3(n, v);
+  f3 r = mk3(fmaf(-d2, n.x, v.x), fmaf(-d2, n.y, v.y), fmaf(-d2, n.z, v.z));
   l = len3(r);
   r = mk3(r.x / l, r.y / l, r.z / l);
   const f3 L = mk3(p.compose_light_dir[0], p.compose_light_dir[1], p.compose_light_dir[2]);
   const float ndl = fmaxf(fabsf(dot3(n, mk3(-L.x, -L.y, -L.z))), 0.0f);
   const float spec = pow8(fmaxf(dot3(r, L), 0.0f));
-  return make_float4(clamp01(p.light_ambient[0] + p.light_diffuse[0] * p.iso_color[0] * ndl + p.light_specular[0] * spec),
-                     clamp01(p.light_ambient[1] + p.light_diffuse[1] * p.iso_color[1] * ndl + p.light_specular[1] * spec),
-                     clamp01(p.light_ambient[2] + p.light_diffuse[2] * p.iso_color[2] * ndl + p.light_specular[2] * spec), 1.0f);
+  return make_float4(clamp01(fmaf(p.light_specular[0], spec, fmaf(p.light_diffuse[0] * p.iso_color[0], ndl, p.light_ambient[0]))),
+                     clamp01(fmaf(p.light_specular[1], spec, fmaf(p.light_diffuse[1] * p.iso_color[1], ndl, p.light_ambient[1]))),
+                     clamp01(fmaf(p.light_specular[2], spec, fmaf(p.light_diffuse[2] * p.iso_color[2], ndl, p.light_ambient[2]))), 1.0f);
 }
 
 template <int MODE, bool LIT, int BPV, int SAMP>
-__global__ void __launch_bounds__(128) raycast_kernel(const __grid_constant__ RayParams rp) {
+__global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? 5 : 3) raycast_kernel(const __grid_constant__ RayParams rp) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t ntiles = rp.tiles_x * rp.tiles_y;
   Counters cn;

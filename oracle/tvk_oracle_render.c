@@ -16,6 +16,12 @@
  * transfer-function fetches, and is the arbiter the CUDA images are held to
  * (PSNR >= 45 dB, max channel error <= 2/255).
  *
+ * Floating-point contract: every operation below is a single IEEE-754 fp32 operation (add, sub,
+ * mul, div, sqrt, fma) in a fixed order -- fmaf() where a multiply-add is fused, nothing else is
+ * contracted (-ffp-contract=off) -- and the CUDA kernel issues the same operations in the same
+ * order (nvcc -fmad=false + explicit fmaf).  The two therefore agree bit for bit except where
+ * powf/log2 enter (sample-rate modifier != 1, LOD boundaries).
+ *
  * Restated items (paths relative to /root/reference/Tuvok/):
  *   orc_pool_layout     GetLoDSize/GetFloatBrickLayout/GetBrickLayout, LoD offset
  *                       table                Renderer/GL/GLVolumePool.cpp:82-117,222-230
@@ -222,7 +228,7 @@ static int get_brick(ctx_t* c, const float entry_in[3], uint32_t* lod, const flo
     const float t = (corner - e[a]) * div;
     tmin = fminf(tmin, t);                                /* NaN (0*inf) is ignored */
   }
-  for (int a = 0; a < 3; ++a) norm_exit[a] = e[a] + tmin * dir[a];
+  for (int a = 0; a < 3; ++a) norm_exit[a] = fmaf(tmin, dir[a], e[a]);
   if (*empty) return found;
   /* InfoToCoords + BrickPoolCoords + NormCoordsToPoolCoords */
   const uint32_t idx = info - TVK_BI_FLAG_COUNT;
@@ -233,9 +239,9 @@ static int get_brick(ctx_t* c, const float entry_in[3], uint32_t* lod, const flo
     const float pc0 = (float)vp / c->pool_size[a] + c->overlap_tc[a];
     const float pc1 = (float)(vp + c->pool->max_brick[a]) / c->pool_size[a] - c->overlap_tc[a];
     scale[a] = (pc1 - pc0) / (c1[a] - c0[a]);
-    trans[a] = pc0 - c0[a] * scale[a];
-    pool_entry[a] = e[a] * scale[a] + trans[a];
-    pool_exit[a] = norm_exit[a] * scale[a] + trans[a];
+    trans[a] = fmaf(-c0[a], scale[a], pc0);
+    pool_entry[a] = fmaf(e[a], scale[a], trans[a]);
+    pool_exit[a] = fmaf(norm_exit[a], scale[a], trans[a]);
   }
   return found;
 }
@@ -247,11 +253,11 @@ static inline float voxel(const ctx_t* c, int x, int y, int z) {
   y = y < 0 ? 0 : (y >= sy ? sy - 1 : y);
   z = z < 0 ? 0 : (z >= sz ? sz - 1 : z);
   const size_t i = (size_t)x + (size_t)sx * ((size_t)y + (size_t)sy * (size_t)z);
-  return c->pool->bpv == 1 ? (float)((const uint8_t*)c->pool->data)[i] * (1.0f / 255.0f)
-                           : (float)((const uint16_t*)c->pool->data)[i] * (1.0f / 65535.0f);
+  return c->pool->bpv == 1 ? (float)((const uint8_t*)c->pool->data)[i] : (float)((const uint16_t*)c->pool->data)[i];
 }
+/* trilinear filter on the raw texel values, then the UNORM scale (1/255 or 1/65535) */
 static float sample_pool(const ctx_t* c, const float p[3]) {
-  const float u = p[0] * c->pool_size[0] - 0.5f, v = p[1] * c->pool_size[1] - 0.5f, w = p[2] * c->pool_size[2] - 0.5f;
+  const float u = fmaf(p[0], c->pool_size[0], -0.5f), v = fmaf(p[1], c->pool_size[1], -0.5f), w = fmaf(p[2], c->pool_size[2], -0.5f);
   const float fu = floorf(u), fv = floorf(v), fw = floorf(w);
   const int x = (int)fu, y = (int)fv, z = (int)fw;
   const float a = u - fu, b = v - fv, g = w - fw;
@@ -259,10 +265,10 @@ static float sample_pool(const ctx_t* c, const float p[3]) {
   const float c010 = voxel(c, x, y + 1, z), c110 = voxel(c, x + 1, y + 1, z);
   const float c001 = voxel(c, x, y, z + 1), c101 = voxel(c, x + 1, y, z + 1);
   const float c011 = voxel(c, x, y + 1, z + 1), c111 = voxel(c, x + 1, y + 1, z + 1);
-  const float c00 = c000 + a * (c100 - c000), c10 = c010 + a * (c110 - c010);
-  const float c01 = c001 + a * (c101 - c001), c11 = c011 + a * (c111 - c011);
-  const float c0 = c00 + b * (c10 - c00), c1 = c01 + b * (c11 - c01);
-  return c0 + g * (c1 - c0);
+  const float c00 = fmaf(a, c100 - c000, c000), c10 = fmaf(a, c110 - c010, c010);
+  const float c01 = fmaf(a, c101 - c001, c001), c11 = fmaf(a, c111 - c011, c011);
+  const float c0 = fmaf(b, c10 - c00, c00), c1 = fmaf(b, c11 - c01, c01);
+  return fmaf(g, c1 - c0, c0) * (c->pool->bpv == 1 ? 1.0f / 255.0f : 1.0f / 65535.0f);
 }
 
 /* texture(transferFunction, s): RGBA8, GL_NEAREST, clamp to edge */
@@ -280,8 +286,9 @@ static void tf_fetch2d(const ctx_t* c, float s, float g, float out[4]) {
   for (int k = 0; k < 4; ++k) out[k] = (float)t[k] * (1.0f / 255.0f);
 }
 
-static inline float len3(const float v[3]) { return sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
-static inline float dot3(const float a[3], const float b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static inline float dot3(const float a[3], const float b[3]) { return fmaf(a[2], b[2], fmaf(a[1], b[1], a[0] * b[0])); }
+static inline float len3(const float v[3]) { return sqrtf(dot3(v, v)); }
+static inline float pow8(float x) { x *= x; x *= x; return x * x; }
 
 /* ComputeGradient, GLGridLeaper-GradientTools.glsl:6-16 (note the y sign) */
 static void gradient(const ctx_t* c, const float p[3], float g[3]) {
@@ -303,14 +310,14 @@ static void lighting(const ctx_t* c, const float pos[3], const float n[3], const
   float l = len3(v);
   for (int a = 0; a < 3; ++a) v[a] /= l;
   /* reflect(I,N) = I - 2*dot(N,I)*N */
-  const float d = dot3(n, v);
-  float r[3] = {v[0] - 2.0f * d * n[0], v[1] - 2.0f * d * n[1], v[2] - 2.0f * d * n[2]};
+  const float d2 = 2.0f * dot3(n, v);
+  float r[3] = {fmaf(-d2, n[0], v[0]), fmaf(-d2, n[1], v[1]), fmaf(-d2, n[2], v[2])};
   l = len3(r);
   for (int a = 0; a < 3; ++a) r[a] /= l;
   const float ndl = fmaxf(fabsf(dot3(n, p->model_light_dir)), 0.0f);
-  const float spec = powf(fmaxf(dot3(r, p->model_light_dir), 0.0f), 8.0f);
+  const float spec = pow8(fmaxf(dot3(r, p->model_light_dir), 0.0f));   /* pow(x, 8.0) */
   for (int a = 0; a < 3; ++a)
-    out[a] = clampf(p->light_ambient[a] + diffuse[a] * ndl + p->light_specular[a] * spec, 0.0f, 1.0f);
+    out[a] = clampf(fmaf(p->light_specular[a], spec, fmaf(diffuse[a], ndl, p->light_ambient[a])), 0.0f, 1.0f);
 }
 
 /* ComputeColorFromVolume for the four scalar variants */
@@ -332,7 +339,7 @@ static void color_from_volume(const ctx_t* c, const float pc[3], const float mod
     float g[3];
     gradient(c, pc, g);
     const float gm = len3(g);
-    tf_fetch2d(c, data * p->trans_scale, 1.0f - gm * p->gradient_scale, col);
+    tf_fetch2d(c, data * p->trans_scale, fmaf(-gm, p->gradient_scale, 1.0f), col);
     if (p->lighting) {
       float n[3];
       for (int a = 0; a < 3; ++a) n[a] = p->domain_scale[a] * ((gm > 0) ? g[a] / gm : g[a]);
@@ -344,15 +351,15 @@ static void color_from_volume(const ctx_t* c, const float pc[3], const float mod
 
 /* v' = v*M, FLOATMATRIX4 memory order (Vectors.h:434) */
 static void xform_point(const float m[16], const float v[3], float w, float out[4]) {
-  for (int j = 0; j < 4; ++j) out[j] = v[0] * m[j] + v[1] * m[4 + j] + v[2] * m[8 + j] + w * m[12 + j];
+  for (int j = 0; j < 4; ++j) out[j] = fmaf(w, m[12 + j], fmaf(v[2], m[8 + j], fmaf(v[1], m[4 + j], v[0] * m[j])));
 }
 
 /* Analytic ray set-up for pixel (px,py): replaces the rasterised near-plane quad
  * and bbox faces (GLGridLeaper.cpp:579-620, 835-843).  Returns 0 if the ray
  * misses the box.  entry/exit = (normalised volume coords, eye-space z). */
 static int ray_setup(const tvk_raycast_params* p, uint32_t px, uint32_t py, float entry[4], float exitp[4]) {
-  const float ndc[3] = {((float)px + 0.5f) / (float)p->width * 2.0f - 1.0f,
-                        ((float)py + 0.5f) / (float)p->height * 2.0f - 1.0f, -1.0f};
+  const float ndc[3] = {fmaf(((float)px + 0.5f) / (float)p->width, 2.0f, -1.0f),
+                        fmaf(((float)py + 0.5f) / (float)p->height, 2.0f, -1.0f), -1.0f};
   float n4[4];
   xform_point(p->inv_projection, ndc, 1.0f, n4);
   const float n[3] = {n4[0] / n4[3], n4[1] / n4[3], n4[2] / n4[3]};   /* near-plane point, eye space */
@@ -374,8 +381,8 @@ static int ray_setup(const tvk_raycast_params* p, uint32_t px, uint32_t py, floa
   }
   if (p->clip_enabled) {
     /* keep the half space dot(plane.xyz, x) + plane.w <= 0 ... (model space) */
-    const float dn = p->clip_plane[0] * D[0] + p->clip_plane[1] * D[1] + p->clip_plane[2] * D[2];
-    const float on = p->clip_plane[0] * O[0] + p->clip_plane[1] * O[1] + p->clip_plane[2] * O[2] + p->clip_plane[3];
+    const float dn = dot3(p->clip_plane, D);
+    const float on = dot3(p->clip_plane, O) + p->clip_plane[3];
     if (dn == 0.0f) { if (on > 0.0f) return 0; }
     else {
       const float t = -on / dn;
@@ -396,8 +403,8 @@ static int ray_setup(const tvk_raycast_params* p, uint32_t px, uint32_t py, floa
 
 static void under(const float src[4], float dst[4]) {   /* Compositing.glsl:33-38 */
   const float w = (1.0f - dst[3]) * src[3];
-  dst[0] += src[0] * w; dst[1] += src[1] * w; dst[2] += src[2] * w;
-  dst[3] += src[3] * (1.0f - dst[3]);
+  dst[0] = fmaf(src[0], w, dst[0]); dst[1] = fmaf(src[1], w, dst[1]); dst[2] = fmaf(src[2], w, dst[2]);
+  dst[3] = fmaf(src[3], 1.0f - dst[3], dst[3]);
 }
 
 /* GLGridLeaper-blend.glsl main().  pos/col: in = rayStartPoint/rayStartColor,
@@ -423,7 +430,7 @@ static void march_ray(ctx_t* c, const float exitp[4], float pos[4], float col[4]
   const float oc = 1.0f / p->sample_rate_modifier;
   if (ray_len > voxel_size) {
     for (uint32_t j = 0; j < 100; ++j) {
-      const float depth = entry_depth * (1.0f - t) + exit_depth * t;   /* mix */
+      const float depth = fmaf(exit_depth, t, entry_depth * (1.0f - t));   /* mix */
       uint32_t lod = compute_lod(depth, p->lod_factor, p->level_zero_wse, c->L.lod_count - 1);
       float pe[3], px[3], nexit[3], scale[3], trans[3];
       uint32_t bc[4];
@@ -497,7 +504,7 @@ static void march_ray_iso(ctx_t* c, const float exitp[4], float pos[4], float nr
   uint32_t last_bc[4] = {0, 0, 0, 9999};
   if (ray_len > voxel_size) {
     for (uint32_t j = 0; j < 100; ++j) {
-      const float depth = entry_depth * (1.0f - t) + exit_depth * t;
+      const float depth = fmaf(exit_depth, t, entry_depth * (1.0f - t));
       uint32_t lod = compute_lod(depth, p->lod_factor, p->level_zero_wse, c->L.lod_count - 1);
       float pe[3], px[3], nexit[3], scale[3], trans[3];
       uint32_t bc[4];
@@ -572,16 +579,16 @@ static void compose_iso(const tvk_raycast_params* p, const float hit[4], const f
   float v[3] = {0.0f - hit[0], 0.0f - hit[1], 0.0f - hit[2]};
   float l = len3(v);
   for (int a = 0; a < 3; ++a) v[a] /= l;
-  const float d = dot3(n, v);
-  float r[3] = {v[0] - 2.0f * d * n[0], v[1] - 2.0f * d * n[1], v[2] - 2.0f * d * n[2]};
+  const float d2 = 2.0f * dot3(n, v);
+  float r[3] = {fmaf(-d2, n[0], v[0]), fmaf(-d2, n[1], v[1]), fmaf(-d2, n[2], v[2])};
   l = len3(r);
   for (int a = 0; a < 3; ++a) r[a] /= l;
   const float* L = p->compose_light_dir;
   const float negL[3] = {-L[0], -L[1], -L[2]};
   const float ndl = fmaxf(fabsf(dot3(n, negL)), 0.0f);
-  const float spec = powf(fmaxf(dot3(r, L), 0.0f), 8.0f);
+  const float spec = pow8(fmaxf(dot3(r, L), 0.0f));
   for (int a = 0; a < 3; ++a)
-    out[a] = clampf(p->light_ambient[a] + p->light_diffuse[a] * p->iso_color[a] * ndl + p->light_specular[a] * spec, 0.0f, 1.0f);
+    out[a] = clampf(fmaf(p->light_specular[a], spec, fmaf(p->light_diffuse[a] * p->iso_color[a], ndl, p->light_ambient[a])), 0.0f, 1.0f);
   out[3] = 1.0f;
 }
 

@@ -70,6 +70,7 @@ def test_config3_2048_cubed_uint16():
     # --- isosurface frame (iso = half the range, AbstrRenderer.cpp:253-261)
     cam = HM.Camera()
     cam.rotation = HM.rotation_y(0.5) @ HM.rotation_x(0.3)
+    tvk.set_metadata(sc["slots"] + 3)               # (the host class re-flags resident slots itself)
     tvk.recompute_visibility(2, rmax / 2.0)
     p = HM.raycast_params(cam, 1920, 1080, (N, N, N), render_mode=2, isoval=(rmax / 2.0) / 65536.0)
     tvk.stats(reset=True)
@@ -90,6 +91,7 @@ def test_config3_2048_cubed_uint16():
     tf2[..., 2] = 0.4
     tf2[..., 3] = np.clip((v[None, :] - 0.25) * 0.2, 0, 1) * (0.5 + 0.5 * g[:, None])
     tvk.set_tf2d((np.clip(tf2, 0, 1) * np.float32(255)).astype(np.uint8))
+    tvk.set_metadata(sc["slots"] + 3)
     tvk.recompute_visibility(1, 0.25 * rmax, float(rmax), -1e308, 1e308)
     p = HM.raycast_params(cam, 1920, 1080, (N, N, N), render_mode=1, lighting=True, trans_scale=65535.0 / rmax,
                           gradient_scale=40.0)

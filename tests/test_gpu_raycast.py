@@ -42,6 +42,8 @@ def _cold_pool(oc, capacity, mode, lo, hi):
 
 def _check(r, expect_paging=True):
     psnr, err = image_errors(r["cuda"], r["oracle"])
+    print("PSNR %.1f dB, max err %.3g, identical pixels %.4f, requests %d (mismatch %d)" % (
+        psnr, err, float((r["cuda"] == r["oracle"]).all(axis=2).mean()), r["req_total"], r["req_mismatch"]))
     assert r["oracle"].max() > 0.05, "oracle image is empty: the test would be vacuous"
     assert psnr >= PSNR_MIN, "PSNR %.2f dB" % psnr
     assert err <= MAX_ERR, "max channel error %.5f" % err
