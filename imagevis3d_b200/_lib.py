@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtvk_cuda.so")
+LIB_PATH = os.environ.get("TVK_CUDA_LIB") or os.path.join(_HERE, "libtvk_cuda.so")   # override: kernel-variant sweeps
 TVK_MAX_LOD = 16
 
 TVK_OK, TVK_ERR_INVALID, TVK_ERR_CUDA, TVK_ERR_NOMEM, TVK_ERR_UNSUPPORTED = 0, 1, 2, 3, 4

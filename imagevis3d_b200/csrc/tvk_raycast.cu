@@ -21,6 +21,21 @@
 #include "tvk_internal.h"
 #include <cmath>
 
+// Tuning knobs of the 1D-TF sample loop (swept on a B200, see profiles/README.md): samples in flight
+// per ray and resident CTAs per SM, for the hardware-filtered and the exact (LDG) samplers.
+#ifndef TVK_NB_TEX
+#define TVK_NB_TEX 8
+#endif
+#ifndef TVK_NB_LDG
+#define TVK_NB_LDG 4
+#endif
+#ifndef TVK_OCC_TEX
+#define TVK_OCC_TEX 6
+#endif
+#ifndef TVK_OCC_LDG
+#define TVK_OCC_LDG 4
+#endif
+
 struct RayParams {
   tvk_raycast_params p;
   PoolConst pc;
@@ -393,10 +408,11 @@ __device__ __forceinline__ bool ray_setup(const tvk_raycast_params& p, uint32_t 
   return true;
 }
 
-struct Counters { unsigned long long samples, bricks; };
+// per-ray counters (a ray takes <= 100 bricks); the kernel folds them into 64-bit totals after each ray
+struct Counters { uint32_t samples, bricks; };
 
 // GLGridLeaper-blend.glsl main()
-template <int MODE, bool LIT, int BPV, int SAMP>
+template <int MODE, bool LIT, int BPV, int SAMP, bool SRM1>
 __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, float4& pos, float4& col, float4& acc, Counters& cn) {
   const tvk_raycast_params& p = rp.p;
   const PoolConst& pc = rp.pc;
@@ -433,15 +449,16 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
         const int s2 = (int)ceilf(len3(mk3((exitp.x - cur.x) * b.scale.x, (exitp.y - cur.y) * b.scale.y, (exitp.z - cur.z) * b.scale.z)) / step_size);
         steps = min(steps, s2);
         f3 q = b.pool_entry;
-        // Two samples per trip: both footprints (and both TF fetches) are in flight together, which
-        // doubles the memory-level parallelism of a ray without any register rotation.  Samples are
+        // NB samples per trip: their footprints (and then their TF fetches) are in flight together, which
+        // multiplies the memory-level parallelism of a ray without any register rotation.  Samples are
         // still classified, counted and composited strictly in order, with the ERT test after each.
-        const bool pairwise = (MODE == TVK_RM_1DTRANS) && !LIT;
+        // The hardware-filtered path needs one register per sample in flight, so it batches deeper.
+        const int NB = ((MODE == TVK_RM_1DTRANS) && !LIT) ? (SAMP == TVK_SAMPLER_TEX3D ? TVK_NB_TEX : TVK_NB_LDG) : 1;
         int i = 0;
 #define TVK_COMPOSITE(S)                                                                     \
         {                                                                                    \
           cn.samples++;                                                                      \
-          (S).w = (oc == 1.0f) ? 1.0f - (1.0f - (S).w) : 1.0f - powf(1.0f - (S).w, oc);      \
+          (S).w = (SRM1 || oc == 1.0f) ? 1.0f - (1.0f - (S).w) : 1.0f - powf(1.0f - (S).w, oc); \
           const float w_ = (1.0f - acc.w) * (S).w;    /* UnderCompositing, Compositing.glsl:33-38 */ \
           acc.x = fmaf((S).x, w_, acc.x); acc.y = fmaf((S).y, w_, acc.y); acc.z = fmaf((S).z, w_, acc.z); \
           acc.w = fmaf((S).w, 1.0f - acc.w, acc.w);                                          \
@@ -450,25 +467,29 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
             return;                                                                          \
           }                                                                                  \
         }
-        if (pairwise) {
-          for (; i + 1 < steps; i += 2) {
-            const f3 q1 = mk3(q.x + vdir.x, q.y + vdir.y, q.z + vdir.z);
-            float d0, d1;
+        if (NB > 1) {
+          for (; i + NB <= steps; i += NB) {
+            f3 qs[NB];
+            float d[NB];
+            qs[0] = q;
+#pragma unroll
+            for (int k = 1; k < NB; ++k) qs[k] = mk3(qs[k - 1].x + vdir.x, qs[k - 1].y + vdir.y, qs[k - 1].z + vdir.z);
             if (SAMP == TVK_SAMPLER_TEX3D) {
-              d0 = tex3D<float>(rp.tex, q.x, q.y, q.z);
-              d1 = tex3D<float>(rp.tex, q1.x, q1.y, q1.z);
+#pragma unroll
+              for (int k = 0; k < NB; ++k) d[k] = tex3D<float>(rp.tex, qs[k].x, qs[k].y, qs[k].z);
             } else {
-              Taps ta, tb;
-              fetch_taps<BPV, SAMP>(rp, b.slot, q, ta);
-              fetch_taps<BPV, SAMP>(rp, b.slot, q1, tb);
-              d0 = filter_taps<BPV>(ta);
-              d1 = filter_taps<BPV>(tb);
+              Taps tp[NB];
+#pragma unroll
+              for (int k = 0; k < NB; ++k) fetch_taps<BPV, SAMP>(rp, b.slot, qs[k], tp[k]);
+#pragma unroll
+              for (int k = 0; k < NB; ++k) d[k] = filter_taps<BPV>(tp[k]);
             }
-            float4 s0 = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, d0, q, b.scale, b.trans);
-            float4 s1 = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, d1, q1, b.scale, b.trans);
-            TVK_COMPOSITE(s0)
-            TVK_COMPOSITE(s1)
-            q = mk3(q1.x + vdir.x, q1.y + vdir.y, q1.z + vdir.z);
+            float4 sc[NB];
+#pragma unroll
+            for (int k = 0; k < NB; ++k) sc[k] = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, d[k], qs[k], b.scale, b.trans);
+#pragma unroll
+            for (int k = 0; k < NB; ++k) TVK_COMPOSITE(sc[k])
+            q = mk3(qs[NB - 1].x + vdir.x, qs[NB - 1].y + vdir.y, qs[NB - 1].z + vdir.z);
           }
         }
         for (; i < steps; ++i) {
@@ -594,14 +615,18 @@ __device__ __forceinline__ float4 compose_iso(const tvk_raycast_params& p, float
                      clamp01(fmaf(p.light_specular[2], spec, fmaf(p.light_diffuse[2] * p.iso_color[2], ndl, p.light_ambient[2]))), 1.0f);
 }
 
-template <int MODE, bool LIT, int BPV, int SAMP>
-__global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? 5 : 3) raycast_kernel(const __grid_constant__ RayParams rp) {
+// SRM1: sampleRateModifier == 1 known at compile time (the opacity correction is then the identity
+// 1-(1-a) and the pow path is not even compiled in); instantiated for the 1D-TF kernels only.
+template <int MODE, bool LIT, int BPV, int SAMP, bool SRM1>
+__global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP == TVK_SAMPLER_TEX3D ? TVK_OCC_TEX : TVK_OCC_LDG) : 3) raycast_kernel(const __grid_constant__ RayParams rp) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t ntiles = rp.tiles_x * rp.tiles_y;
   Counters cn;
   cn.samples = 0; cn.bricks = 0;
-  unsigned long long nrays = 0;
+  unsigned long long nrays = 0, nsamples = 0, nbricks = 0;
   for (;;) {
+    nsamples += cn.samples; nbricks += cn.bricks;
+    cn.samples = 0; cn.bricks = 0;
     uint32_t tile = 0;
     if (lane == 0) tile = atomicAdd(rp.tile_counter, 1u);
     tile = __shfl_sync(0xffffffffu, tile, 0);
@@ -636,7 +661,7 @@ __global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? 5 : 3)
         aux = rp.aux[i];
       }
       float4 acc;
-      march_ray<MODE, LIT, BPV, SAMP>(rp, exitp, pos, aux, acc, cn);
+      march_ray<MODE, LIT, BPV, SAMP, SRM1>(rp, exitp, pos, aux, acc, cn);
       rp.image[i] = acc;
     }
     rp.pos[i] = pos;
@@ -644,14 +669,14 @@ __global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? 5 : 3)
   }
   if (rp.p.count_samples) {
     for (int o = 16; o > 0; o >>= 1) {
-      cn.samples += __shfl_down_sync(0xffffffffu, cn.samples, o);
-      cn.bricks += __shfl_down_sync(0xffffffffu, cn.bricks, o);
+      nsamples += __shfl_down_sync(0xffffffffu, nsamples, o);
+      nbricks += __shfl_down_sync(0xffffffffu, nbricks, o);
       nrays += __shfl_down_sync(0xffffffffu, nrays, o);
     }
     if (lane == 0) {
-      atomicAdd(rp.stats + 0, cn.samples);
+      atomicAdd(rp.stats + 0, nsamples);
       atomicAdd(rp.stats + 1, nrays);
-      atomicAdd(rp.stats + 2, cn.bricks);
+      atomicAdd(rp.stats + 2, nbricks);
     }
   }
 }
@@ -659,16 +684,19 @@ __global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? 5 : 3)
 typedef void (*raycast_fn)(const RayParams);
 
 template <int BPV, int SAMP>
-static raycast_fn pick_kernel(uint32_t mode, bool lit) {
-  if (mode == TVK_RM_ISOSURFACE) return raycast_kernel<TVK_RM_ISOSURFACE, false, BPV, SAMP>;
-  if (mode == TVK_RM_1DTRANS) return lit ? raycast_kernel<TVK_RM_1DTRANS, true, BPV, SAMP> : raycast_kernel<TVK_RM_1DTRANS, false, BPV, SAMP>;
-  return lit ? raycast_kernel<TVK_RM_2DTRANS, true, BPV, SAMP> : raycast_kernel<TVK_RM_2DTRANS, false, BPV, SAMP>;
+static raycast_fn pick_kernel(uint32_t mode, bool lit, bool srm1) {
+  if (mode == TVK_RM_ISOSURFACE) return raycast_kernel<TVK_RM_ISOSURFACE, false, BPV, SAMP, false>;
+  if (mode == TVK_RM_1DTRANS) {
+    if (srm1) return lit ? raycast_kernel<TVK_RM_1DTRANS, true, BPV, SAMP, true> : raycast_kernel<TVK_RM_1DTRANS, false, BPV, SAMP, true>;
+    return lit ? raycast_kernel<TVK_RM_1DTRANS, true, BPV, SAMP, false> : raycast_kernel<TVK_RM_1DTRANS, false, BPV, SAMP, false>;
+  }
+  return lit ? raycast_kernel<TVK_RM_2DTRANS, true, BPV, SAMP, false> : raycast_kernel<TVK_RM_2DTRANS, false, BPV, SAMP, false>;
 }
 template <int BPV>
-static raycast_fn pick_sampler(uint32_t sampler, uint32_t mode, bool lit) {
-  if (sampler == TVK_SAMPLER_TEX3D) return pick_kernel<BPV, TVK_SAMPLER_TEX3D>(mode, lit);
-  if (sampler == TVK_SAMPLER_EXACT_Q4) return pick_kernel<BPV, TVK_SAMPLER_EXACT_Q4>(mode, lit);
-  return pick_kernel<BPV, TVK_SAMPLER_EXACT>(mode, lit);
+static raycast_fn pick_sampler(uint32_t sampler, uint32_t mode, bool lit, bool srm1) {
+  if (sampler == TVK_SAMPLER_TEX3D) return pick_kernel<BPV, TVK_SAMPLER_TEX3D>(mode, lit, srm1);
+  if (sampler == TVK_SAMPLER_EXACT_Q4) return pick_kernel<BPV, TVK_SAMPLER_EXACT_Q4>(mode, lit, srm1);
+  return pick_kernel<BPV, TVK_SAMPLER_EXACT>(mode, lit, srm1);
 }
 
 extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
@@ -704,8 +732,9 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   rp.stats = c->d_stats;
   rp.tiles_x = (p->width + 7) / 8; rp.tiles_y = (p->height + 3) / 4;
 
-  const raycast_fn fn = (c->pc.bpv == 1) ? pick_sampler<1>(c->pdesc.sampler, p->render_mode, p->lighting != 0)
-                                         : pick_sampler<2>(c->pdesc.sampler, p->render_mode, p->lighting != 0);
+  const bool srm1 = (1.0f / p->sample_rate_modifier == 1.0f);
+  const raycast_fn fn = (c->pc.bpv == 1) ? pick_sampler<1>(c->pdesc.sampler, p->render_mode, p->lighting != 0, srm1)
+                                         : pick_sampler<2>(c->pdesc.sampler, p->render_mode, p->lighting != 0, srm1);
 
   int sms = 0, per_sm = 0;
   TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
