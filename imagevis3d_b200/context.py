@@ -236,6 +236,12 @@ class TvkContext:
                  "tvk_build_hist2d")
         return bins, mg.value
 
+    def build_last_ms(self):
+        """CUDA-event time of the builder kernels of the last build_octree (ms)."""
+        ms = C.c_float()
+        self._ck(self.lib.tvk_build_last_ms(self.h, C.byref(ms)), "tvk_build_last_ms")
+        return ms.value
+
     def build_release(self):
         self._ck(self.lib.tvk_build_release(self.h), "tvk_build_release")
 

@@ -129,6 +129,130 @@ __global__ void __launch_bounds__(256) downsample_kernel(const T* __restrict__ s
   }
 }
 
+
+// ------------------------------------------------------------------ 16-byte vector helpers
+// The streaming kernels move 16 bytes per thread.  Brick rows start at x = bx*core - overlap, so the
+// source of a destination chunk is almost never 16-byte aligned: load16() reads the (up to) five
+// aligned 32-bit words that cover [byte_off, byte_off+16) and funnel-shifts them into place.  Bytes
+// before the array or at/after nbytes read as zero (GetInputBrick's "offset past the end of the file").
+__device__ __forceinline__ uint32_t load_word_guarded(const uint8_t* __restrict__ base, int64_t w, uint64_t nbytes) {
+  if (w < 0) return 0u;
+  const uint64_t b = (uint64_t)w * 4u;
+  if (b + 4u <= nbytes) return __ldg(reinterpret_cast<const uint32_t*>(base + b));
+  uint32_t v = 0u;
+  for (uint32_t k = 0; k < 4u; ++k) if (b + k < nbytes) v |= (uint32_t)__ldg(base + b + k) << (8u * k);
+  return v;
+}
+__device__ __forceinline__ uint4 load16(const uint8_t* __restrict__ base, int64_t byte_off, uint64_t nbytes) {
+  const int64_t w0 = byte_off >> 2;
+  const uint32_t sh = ((uint32_t)byte_off & 3u) * 8u;
+  uint32_t w[5];
+  if (byte_off >= 0 && (uint64_t)(w0 * 4 + 20) <= nbytes) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(base) + w0;
+    if (((uint32_t)byte_off & 15u) == 0u) return __ldg(reinterpret_cast<const uint4*>(p));
+#pragma unroll
+    for (int k = 0; k < 5; ++k) w[k] = __ldg(p + k);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) w[k] = load_word_guarded(base, w0 + k, nbytes);
+  }
+  return make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh),
+                    __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh));
+}
+// CB = 16, 8 or 4 bytes at an arbitrary byte offset, zero-extended to a uint4
+template <int CB>
+__device__ __forceinline__ uint4 load_chunk(const uint8_t* __restrict__ base, int64_t byte_off, uint64_t nbytes) {
+  if (CB == 16) return load16(base, byte_off, nbytes);
+  constexpr int NW = CB / 4;
+  const int64_t w0 = byte_off >> 2;
+  const uint32_t sh = ((uint32_t)byte_off & 3u) * 8u;
+  uint32_t w[NW + 1];
+  if (byte_off >= 0 && (uint64_t)(w0 * 4 + 4 * (NW + 1)) <= nbytes) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(base) + w0;
+#pragma unroll
+    for (int k = 0; k <= NW; ++k) w[k] = __ldg(p + k);
+  } else {
+#pragma unroll
+    for (int k = 0; k <= NW; ++k) w[k] = load_word_guarded(base, w0 + k, nbytes);
+  }
+  uint4 v = make_uint4(__funnelshift_r(w[0], w[1], sh), 0u, 0u, 0u);
+  if (NW == 2) v.y = __funnelshift_r(w[1], w[NW], sh);
+  return v;
+}
+// keep bytes [lo, hi) of one 32-bit word whose first byte has index `first`
+__device__ __forceinline__ uint32_t keep_bytes(uint32_t v, int first, int lo, int hi) {
+  const int a = lo - first, b = hi - first;
+  if (a >= 4 || b <= 0) return 0u;
+  uint32_t m = 0xFFFFFFFFu;
+  if (a > 0) m &= 0xFFFFFFFFu << (8 * a);
+  if (b < 4) m &= 0xFFFFFFFFu >> (8 * (4 - b));
+  return v & m;
+}
+__device__ __forceinline__ uint4 keep16(uint4 v, int lo, int hi) {
+  return make_uint4(keep_bytes(v.x, 0, lo, hi), keep_bytes(v.y, 4, lo, hi), keep_bytes(v.z, 8, lo, hi), keep_bytes(v.w, 12, lo, hi));
+}
+template <typename T> __device__ __forceinline__ uint32_t vec_get(const uint4& v, int e) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  if (sizeof(T) == 1) return (w[e >> 2] >> (8 * (e & 3))) & 0xFFu;
+  return (w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
+}
+template <typename T> __device__ __forceinline__ void vec_set(uint4& v, int e, uint32_t val) {
+  const int wi = (sizeof(T) == 1) ? (e >> 2) : (e >> 1);
+  const uint32_t s = (sizeof(T) == 1) ? val << (8 * (e & 3)) : val << (16 * (e & 1));
+  if (wi == 0) v.x |= s; else if (wi == 1) v.y |= s; else if (wi == 2) v.z |= s; else v.w |= s;
+}
+template <typename T> __device__ __forceinline__ void vec_minmax(const uint4& v, uint32_t& pmn, uint32_t& pmx) {
+  if (sizeof(T) == 1) {
+    pmn = __vminu4(__vminu4(pmn, v.x), __vminu4(__vminu4(v.y, v.z), v.w));
+    pmx = __vmaxu4(__vmaxu4(pmx, v.x), __vmaxu4(__vmaxu4(v.y, v.z), v.w));
+  } else {
+    pmn = __vminu2(__vminu2(pmn, v.x), __vminu2(__vminu2(v.y, v.z), v.w));
+    pmx = __vmaxu2(__vmaxu2(pmx, v.x), __vmaxu2(__vmaxu2(v.y, v.z), v.w));
+  }
+}
+
+// flat LOD l -> flat LOD l+1, 16 bytes of each of the (up to) four source rows per thread, 8 bytes
+// out.  Requires 16-byte aligned source rows (sx*sizeof(T) % 16 == 0), which also makes the
+// destination rows 8-byte aligned and every x pair complete.
+template <typename T, bool MEDIAN>
+__global__ void __launch_bounds__(256) downsample_vec_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                              uint32_t sx, uint32_t sy, uint32_t sz,
+                                                              uint32_t dx, uint32_t dy, uint32_t dz) {
+  constexpr int E = 16 / sizeof(T), V = E / 2;
+  const uint32_t ncx = sx / E;
+  const uint64_t n = (uint64_t)ncx * dy * dz;
+  const uint64_t rs = sx, ss = (uint64_t)sx * sy;
+  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t cx = (uint32_t)(idx % ncx);
+    const uint64_t row = idx / ncx;
+    const uint32_t y = (uint32_t)(row % dy), z = (uint32_t)(row / dy);
+    const uint32_t y0 = (sy > 1) ? 2 * y : y, z0 = (sz > 1) ? 2 * z : z;
+    const bool hy = (sy > 1) && (y0 + 1 < sy), hz = (sz > 1) && (z0 + 1 < sz);
+    const T* p = src + (uint64_t)cx * E + y0 * rs + z0 * ss;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+    uint4 b = a, c = a, d = a;
+    if (hz) b = __ldg(reinterpret_cast<const uint4*>(p + ss));
+    if (hy) c = __ldg(reinterpret_cast<const uint4*>(p + rs));
+    if (hy && hz) d = __ldg(reinterpret_cast<const uint4*>(p + rs + ss));
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int m = 0; m < V; ++m) {
+      const T a0 = (T)vec_get<T>(a, 2 * m), a1 = (T)vec_get<T>(a, 2 * m + 1);
+      const T b0 = (T)vec_get<T>(b, 2 * m), b1 = (T)vec_get<T>(b, 2 * m + 1);
+      const T c0 = (T)vec_get<T>(c, 2 * m), c1 = (T)vec_get<T>(c, 2 * m + 1);
+      const T d0 = (T)vec_get<T>(d, 2 * m), d1 = (T)vec_get<T>(d, 2 * m + 1);
+      T r;
+      // p0..p7 of DownsampleBricktoBrick: p1 = +z, p2 = +y, p3 = +y+z, p4.. = +x
+      if (hy && hz) r = filter8<T, MEDIAN>(a0, b0, c0, d0, a1, b1, c1, d1);
+      else if (hz) r = filter4<T, MEDIAN>(a0, b0, a1, b1);
+      else if (hy) r = filter4<T, MEDIAN>(a0, c0, a1, c1);
+      else r = filter2<T, MEDIAN>(a0, a1);
+      vec_set<T>(o, m, (uint32_t)r);
+    }
+    *reinterpret_cast<uint2*>(dst + (uint64_t)cx * V + (uint64_t)y * dx + (uint64_t)z * dx * dy) = make_uint2(o.x, o.y);
+  }
+}
+
 // FillOverlap replay for one ghost voxel of brick (bx,by,bz) at LOD >= 1.
 // Returns true and the global voxel coordinate to gather, or false for "zero".
 __device__ __forceinline__ bool resolve_overlap(const BuildConst& bc, uint32_t lod, int bx, int by, int bz,
@@ -172,10 +296,11 @@ template <typename T>
 __global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ flat, uint8_t* __restrict__ store,
                                                           const uint64_t* __restrict__ offsets, uint64_t first_brick,
                                                           uint32_t lod, const __grid_constant__ BuildConst bc,
-                                                          uint32_t* __restrict__ mn, uint32_t* __restrict__ mx) {
+                                                          uint32_t* __restrict__ mn, uint32_t* __restrict__ mx,
+                                                          uint32_t x_first, uint32_t x_count) {
   const uint32_t nbx = bc.lod_bricks[lod][0], nby = bc.lod_bricks[lod][1];
-  const uint32_t b = blockIdx.x;
-  const int bx = (int)(b % nbx), by = (int)((b / nbx) % nby), bz = (int)(b / (nbx * nby));
+  const int bx = (int)(x_first + blockIdx.x % x_count), by = (int)((blockIdx.x / x_count) % nby), bz = (int)(blockIdx.x / (x_count * nby));
+  const uint32_t b = (uint32_t)bx + (uint32_t)by * nbx + (uint32_t)bz * nbx * nby;
   const uint32_t tx = brick_dim(bc, lod, 0, bx), ty = brick_dim(bc, lod, 1, by), tz = brick_dim(bc, lod, 2, bz);
   const uint32_t sx = bc.lod_size[lod][0], sy = bc.lod_size[lod][1], sz = bc.lod_size[lod][2];
   const uint64_t nvox = (uint64_t)sx * sy * sz;
@@ -239,9 +364,154 @@ __global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ f
   }
 }
 
-__global__ void minmax_to_double_kernel(const uint32_t* mn, const uint32_t* mx, double* out, uint64_t n) {
+// Vector form of cut_bricks_kernel: a thread produces one aligned CB-byte chunk (16, 8 or 4 bytes,
+// whatever divides the brick's row length) per trip, so loads and stores are word-granular.
+//  * LOD 0: the chunk is CB bytes at a linear file offset, masked to the x range GetInputBrick copies;
+//  * LOD >= 1: the FillOverlap replay of resolve_overlap() has a closed form (checked exhaustively
+//    against the replay; needs core >= overlap): with P / M the number of axes on which the voxel is a
+//    high / low ghost, the voxel is ZERO iff its global coordinate lies outside the LOD's domain or
+//    (P == 2 and M == 1) -- a diagonal two-axis copy runs before the low-side copies and finds the
+//    third axis still unfilled -- and otherwise it is the voxel at its global coordinate.  Along a row
+//    that is a domain mask plus "drop the low-x ghosts if both y and z are high ghosts" / "drop the
+//    high-x ghosts if one of y,z is a high and the other a low ghost".
+// Min/max accumulate packed (vminu4 / vminu2) and unpack once per thread.
+// The grid covers the bricks bx in [x_first, x_first + x_count) of every brick row, so that the
+// full-width bricks and the (narrower) last column get a kernel each, without idle CTAs.
+template <int CB> struct Chunk;
+template <> struct Chunk<16> { typedef uint4 type; };
+template <> struct Chunk<8> { typedef uint2 type; };
+template <> struct Chunk<4> { typedef uint32_t type; };
+
+template <typename T, int CB>
+__global__ void __launch_bounds__(256) cut_bricks_vec_kernel(const T* __restrict__ flat, uint8_t* __restrict__ store,
+                                                              const uint64_t* __restrict__ offsets, uint64_t first_brick,
+                                                              uint32_t lod, const __grid_constant__ BuildConst bc,
+                                                              uint32_t* __restrict__ mn, uint32_t* __restrict__ mx,
+                                                              uint32_t x_first, uint32_t x_count) {
+  constexpr int E = CB / (int)sizeof(T), NW = CB / 4;
+  const uint32_t nbx = bc.lod_bricks[lod][0], nby = bc.lod_bricks[lod][1];
+  const int nbz = (int)bc.lod_bricks[lod][2];
+  const int bx = (int)(x_first + blockIdx.x % x_count), by = (int)((blockIdx.x / x_count) % nby), bz = (int)(blockIdx.x / (x_count * nby));
+  const uint32_t b = (uint32_t)bx + (uint32_t)by * nbx + (uint32_t)bz * nbx * nby;
+  const uint32_t tx = brick_dim(bc, lod, 0, bx), ty = brick_dim(bc, lod, 1, by), tz = brick_dim(bc, lod, 2, bz);
+  const uint32_t sx = bc.lod_size[lod][0], sy = bc.lod_size[lod][1], sz = bc.lod_size[lod][2];
+  const uint64_t nbytes = (uint64_t)sx * sy * sz * sizeof(T);
+  const uint8_t* fb = reinterpret_cast<const uint8_t*>(flat);
+  typename Chunk<CB>::type* dst = reinterpret_cast<typename Chunk<CB>::type*>(store + offsets[first_brick + b]);
+  const int o = (int)bc.overlap, core = (int)bc.core;
+  const bool fx = bx == 0, fy = by == 0, fz = bz == 0;
+  const bool lx = bx == (int)nbx - 1, ly = by == (int)nby - 1, lz = bz == nbz - 1;
+  const uint32_t cpr = tx / E, nchunks = cpr * ty * tz;
+  uint32_t pmn = 0xFFFFFFFFu, pmx = 0u;
+  for (uint32_t c = blockIdx.y * blockDim.x + threadIdx.x; c < nchunks; c += gridDim.y * blockDim.x) {
+    const uint32_t r = c / cpr;
+    const int i0 = (int)(c - r * cpr) * E, j = (int)(r % ty), k = (int)(r / ty);
+    int lo, hi;            // element range of the row that is copied; everything else stays zero
+    bool row_ok;
+    if (lod == 0) {
+      row_ok = j >= (fy ? o : 0) && j < (int)ty - (ly ? o : 0) && k >= (fz ? o : 0) && k < (int)tz - (lz ? o : 0);
+      lo = fx ? o : 0; hi = (int)tx - (lx ? o : 0);
+    } else {
+      const int gy = by * core + j - o, gz = bz * core + k - o;
+      row_ok = gy >= 0 && gy < (int)sy && gz >= 0 && gz < (int)sz;
+      const int py = j >= (int)ty - o, pz = k >= (int)tz - o, my = j < o, mz = k < o;
+      lo = max(0, o - bx * core); hi = min((int)tx, (int)sx - bx * core + o);      // the domain along x
+      if (py + pz == 2) lo = max(lo, o);                                            // P == 2, M == 1 at the low-x ghosts
+      if (py + pz == 1 && my + mz == 1) hi = min(hi, (int)tx - o);                  // ... and at the high-x ghosts
+    }
+    lo = max(lo, i0); hi = min(hi, i0 + E);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row_ok && lo < hi) {
+      const int64_t lin = (int64_t)(bx * core - o + i0) + (int64_t)(by * core - o + j) * sx + (int64_t)(bz * core - o + k) * sx * sy;
+      v = load_chunk<CB>(fb, lin * (int64_t)sizeof(T), nbytes);
+      if (lo > i0 || hi < i0 + E) v = keep16(v, (lo - i0) * (int)sizeof(T), (hi - i0) * (int)sizeof(T));
+    }
+    if (NW == 4) reinterpret_cast<uint4*>(dst)[c] = v;
+    else if (NW == 2) reinterpret_cast<uint2*>(dst)[c] = make_uint2(v.x, v.y);
+    else reinterpret_cast<uint32_t*>(dst)[c] = v.x;
+    if (NW == 4) vec_minmax<T>(v, pmn, pmx);
+    else if (NW == 2) vec_minmax<T>(make_uint4(v.x, v.y, v.x, v.y), pmn, pmx);
+    else vec_minmax<T>(make_uint4(v.x, v.x, v.x, v.x), pmn, pmx);
+  }
+  uint32_t lo, hi;
+  if (sizeof(T) == 1) {
+    lo = min(min(pmn & 0xFFu, (pmn >> 8) & 0xFFu), min((pmn >> 16) & 0xFFu, pmn >> 24));
+    hi = max(max(pmx & 0xFFu, (pmx >> 8) & 0xFFu), max((pmx >> 16) & 0xFFu, pmx >> 24));
+  } else {
+    lo = min(pmn & 0xFFFFu, pmn >> 16);
+    hi = max(pmx & 0xFFFFu, pmx >> 16);
+  }
+  for (int s = 16; s > 0; s >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+  }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) {
+    atomicMin(mn + first_brick + b, lo);
+    atomicMax(mx + first_brick + b, hi);
+  }
+}
+
+__global__ void minmax_to_double_kernel(const uint32_t* mn, const uint32_t* mx, double* out, uint64_t n, uint32_t* gmax) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { out[2 * i] = (double)mn[i]; out[2 * i + 1] = (double)mx[i]; }
+  uint32_t m = 0;
+  if (i < n) { out[2 * i] = (double)mn[i]; out[2 * i + 1] = (double)mx[i]; m = mx[i]; }
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(gmax, m);
+}
+
+// 16-bit histogram, one pass per window of HIST_WINDOW bins: every CTA (one per SM, 1024 threads)
+// counts its share of the volume into a private 128 KB shared-memory table and adds the non-zero
+// entries to the global bins at the end, so the atomics that smooth data aims at a handful of bins
+// never leave the SM.  Eight voxels per 16-byte load; equal neighbours are run-length merged and a
+// warp that sees one single value issues one atomic.  A window above the volume's maximum (known from
+// the brick min/max table, read on the device) returns at once.
+#define HIST_WINDOW 32768u
+__global__ void __launch_bounds__(1024, 1) hist16_window_kernel(const uint16_t* __restrict__ raw, uint64_t n, uint32_t lo,
+                                                                 const uint32_t* __restrict__ gmax,
+                                                                 unsigned long long* __restrict__ bins) {
+  extern __shared__ uint32_t sh[];
+  if (lo > *gmax) return;
+  for (uint32_t i = threadIdx.x; i < HIST_WINDOW; i += blockDim.x) sh[i] = 0u;
+  __syncthreads();
+  const uint64_t head = min((unsigned long long)n, (unsigned long long)(((16u - (reinterpret_cast<uintptr_t>(raw) & 15u)) & 15u) / 2u));   // voxels before 16-byte alignment
+  const uint64_t nvec = (n - head) / 8u;
+  const uint4* pv = reinterpret_cast<const uint4*>(raw + head);
+  const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, gstride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t rounds = (nvec + gstride - 1) / gstride;
+  uint64_t i = gtid;
+  for (uint64_t r = 0; r < rounds; ++r, i += gstride) {
+    const bool act = i < nvec;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (act) q = __ldg(pv + i);
+    const uint32_t v0 = q.x & 0xFFFFu;
+    const bool uni = act && q.x == (v0 | (v0 << 16)) && q.y == q.x && q.z == q.x && q.w == q.x;
+    const uint32_t first = __shfl_sync(0xffffffffu, v0, 0);      // (outside the &&: every lane must take part)
+    if (__all_sync(0xffffffffu, uni && v0 == first)) {
+      if ((threadIdx.x & 31) == 0 && v0 - lo < HIST_WINDOW) atomicAdd(&sh[v0 - lo], 256u);
+      continue;
+    }
+    if (!act) continue;
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t cur = v0, cnt = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const uint32_t v = (w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
+      if (v == cur) { cnt++; }
+      else {
+        if (cur - lo < HIST_WINDOW) atomicAdd(&sh[cur - lo], cnt);
+        cur = v; cnt = 1;
+      }
+    }
+    if (cur - lo < HIST_WINDOW) atomicAdd(&sh[cur - lo], cnt);
+  }
+  // unaligned head and the tail
+  for (uint64_t t = gtid; t < head; t += gstride) { const uint32_t v = raw[t]; if (v - lo < HIST_WINDOW) atomicAdd(&sh[v - lo], 1u); }
+  for (uint64_t t = head + nvec * 8u + gtid; t < n; t += gstride) { const uint32_t v = raw[t]; if (v - lo < HIST_WINDOW) atomicAdd(&sh[v - lo], 1u); }
+  __syncthreads();
+  for (uint32_t t = threadIdx.x; t < HIST_WINDOW; t += blockDim.x) {
+    const uint32_t cnt = sh[t];
+    if (cnt) atomicAdd(&bins[lo + t], (unsigned long long)cnt);
+  }
 }
 
 // exact histogram of the raw volume (== LOD-0 inner voxels); per-CTA shared
@@ -370,48 +640,95 @@ template <typename T>
 static int run_build(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms) {
   const tvk_build_info& info = b.info;
   cudaStream_t st = c->stream;
-  // flat pyramid
+  constexpr uint32_t E = 16 / sizeof(T);
+  // all allocations first, so that the event-timed region below holds kernels only
   for (uint32_t l = 1; l < info.lod_count; ++l) {
     const uint64_t n = (uint64_t)info.lod_size[l][0] * info.lod_size[l][1] * info.lod_size[l][2];
     TVK_CHECK_CUDA(c, cudaMalloc(&b.d_lod[l], n * sizeof(T)));
-    const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 16);
+  }
+  uint32_t *d_mn = nullptr, *d_mx = nullptr;
+  TVK_CHECK_CUDA(c, cudaMalloc(&d_mn, sizeof(uint32_t) * (2 * info.total_bricks + 1)));
+  d_mx = d_mn + info.total_bricks;
+  uint32_t* d_gmax = d_mx + info.total_bricks;
+  const uint32_t range = 1u << (8 * sizeof(T));
+  TVK_CHECK_CUDA(c, cudaMalloc(&b.d_hist1d, sizeof(unsigned long long) * range));
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->bev0, st));
+  // flat pyramid
+  for (uint32_t l = 1; l < info.lod_count; ++l) {
     const uint32_t* s = info.lod_size[l - 1];
     const uint32_t* d = info.lod_size[l];
-    if (b.desc.use_median)
-      downsample_kernel<T, true><<<blocks, 256, 0, st>>>((const T*)b.d_lod[l - 1], (T*)b.d_lod[l], s[0], s[1], s[2], d[0], d[1], d[2]);
-    else
-      downsample_kernel<T, false><<<blocks, 256, 0, st>>>((const T*)b.d_lod[l - 1], (T*)b.d_lod[l], s[0], s[1], s[2], d[0], d[1], d[2]);
+    const bool vec = (s[0] % E) == 0 && (reinterpret_cast<uintptr_t>(b.d_lod[l - 1]) & 15) == 0;
+    const uint64_t n = vec ? (uint64_t)(s[0] / E) * d[1] * d[2] : (uint64_t)d[0] * d[1] * d[2];
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 32);
+    const T* src = (const T*)b.d_lod[l - 1];
+    T* dst = (T*)b.d_lod[l];
+    if (vec) {
+      if (b.desc.use_median) downsample_vec_kernel<T, true><<<blocks, 256, 0, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2]);
+      else downsample_vec_kernel<T, false><<<blocks, 256, 0, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2]);
+    } else {
+      if (b.desc.use_median) downsample_kernel<T, true><<<blocks, 256, 0, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2]);
+      else downsample_kernel<T, false><<<blocks, 256, 0, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2]);
+    }
     c->launches++;
   }
   TVK_CHECK_CUDA(c, cudaGetLastError());
   // bricks + stats
-  uint32_t *d_mn = nullptr, *d_mx = nullptr;
-  TVK_CHECK_CUDA(c, cudaMallocAsync(&d_mn, sizeof(uint32_t) * info.total_bricks, st));
-  TVK_CHECK_CUDA(c, cudaMallocAsync(&d_mx, sizeof(uint32_t) * info.total_bricks, st));
   TVK_CHECK_CUDA(c, cudaMemsetAsync(d_mn, 0xFF, sizeof(uint32_t) * info.total_bricks, st));
-  TVK_CHECK_CUDA(c, cudaMemsetAsync(d_mx, 0, sizeof(uint32_t) * info.total_bricks, st));
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(d_mx, 0, sizeof(uint32_t) * (info.total_bricks + 1), st));
   for (uint32_t l = 0; l < info.lod_count; ++l) {
-    const uint64_t nb = (uint64_t)info.lod_bricks[l][0] * info.lod_bricks[l][1] * info.lod_bricks[l][2];
-    // a few z-chunks per brick when there are few bricks, to fill the machine
-    const unsigned chunks = nb >= (uint64_t)sms * 4 ? 2 : 16;
-    cut_bricks_kernel<T><<<dim3((unsigned)nb, chunks), 256, 0, st>>>((const T*)b.d_lod[l], (uint8_t*)b.d_store, b.d_offsets,
-                                                                  info.lod_offset[l], l, bc, d_mn, d_mx);
+    // one launch for the full-width bricks, one for the last column if it is narrower
+    const uint32_t nbx = info.lod_bricks[l][0];
+    const uint32_t last_tx = brick_dim(bc, l, 0, nbx - 1);
+    const uint32_t groups[2][3] = {{0u, last_tx == bc.brick ? nbx : nbx - 1, bc.brick}, {nbx - 1, last_tx == bc.brick ? 0u : 1u, last_tx}};
+    for (int g = 0; g < 2; ++g) {
+      const uint32_t x_first = groups[g][0], x_count = groups[g][1], tx = groups[g][2];
+      if (!x_count) continue;
+      const uint64_t nb = (uint64_t)x_count * info.lod_bricks[l][1] * info.lod_bricks[l][2];
+      // a few z-chunks per brick when there are few bricks, to fill the machine
+      const unsigned chunks = nb >= (uint64_t)sms * 8 ? 2 : (nb >= (uint64_t)sms ? 8 : 32);
+      const dim3 grid((unsigned)nb, chunks);
+      const uint32_t row_bytes = tx * (uint32_t)sizeof(T);
+      // word-granular path: needs a 4-byte aligned volume, and core >= overlap for the closed-form ghosts
+      const bool vec = (reinterpret_cast<uintptr_t>(b.d_lod[l]) & 3) == 0 && bc.core >= bc.overlap && row_bytes % 4 == 0;
+      const T* src = (const T*)b.d_lod[l];
+      uint8_t* store = (uint8_t*)b.d_store;
+      if (vec && row_bytes % 16 == 0)
+        cut_bricks_vec_kernel<T, 16><<<grid, 256, 0, st>>>(src, store, b.d_offsets, info.lod_offset[l], l, bc, d_mn, d_mx, x_first, x_count);
+      else if (vec && row_bytes % 8 == 0)
+        cut_bricks_vec_kernel<T, 8><<<grid, 256, 0, st>>>(src, store, b.d_offsets, info.lod_offset[l], l, bc, d_mn, d_mx, x_first, x_count);
+      else if (vec)
+        cut_bricks_vec_kernel<T, 4><<<grid, 256, 0, st>>>(src, store, b.d_offsets, info.lod_offset[l], l, bc, d_mn, d_mx, x_first, x_count);
+      else
+        cut_bricks_kernel<T><<<grid, 256, 0, st>>>(src, store, b.d_offsets, info.lod_offset[l], l, bc, d_mn, d_mx, x_first, x_count);
+      c->launches++;
+    }
+  }
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  minmax_to_double_kernel<<<(unsigned)((info.total_bricks + 255) / 256), 256, 0, st>>>(d_mn, d_mx, b.d_minmax, info.total_bricks, d_gmax);
+  c->launches++;
+  // 1-D histogram
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(b.d_hist1d, 0, sizeof(unsigned long long) * range, st));
+  const uint64_t n0 = (uint64_t)info.lod_size[0][0] * info.lod_size[0][1] * info.lod_size[0][2];
+  if (sizeof(T) == 2 && n0 >= (1u << 18)) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      TVK_CHECK_CUDA(c, cudaFuncSetAttribute(hist16_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HIST_WINDOW * sizeof(uint32_t))));
+      attr_set = true;
+    }
+    for (uint32_t lo = 0; lo < range; lo += HIST_WINDOW) {
+      hist16_window_kernel<<<sms, 1024, HIST_WINDOW * sizeof(uint32_t), st>>>((const uint16_t*)b.d_lod[0], n0, lo, d_gmax, b.d_hist1d);
+      c->launches++;
+    }
+  } else {
+    hist1d_kernel<T><<<(unsigned)std::min<uint64_t>((n0 + 255) / 256, (uint64_t)sms * 8), 256, 0, st>>>((const T*)b.d_lod[0], n0, b.d_hist1d);
     c->launches++;
   }
   TVK_CHECK_CUDA(c, cudaGetLastError());
-  minmax_to_double_kernel<<<(unsigned)((info.total_bricks + 255) / 256), 256, 0, st>>>(d_mn, d_mx, b.d_minmax, info.total_bricks);
-  c->launches++;
-  // 1-D histogram
-  const uint32_t range = 1u << (8 * sizeof(T));
-  TVK_CHECK_CUDA(c, cudaMalloc(&b.d_hist1d, sizeof(unsigned long long) * range));
-  TVK_CHECK_CUDA(c, cudaMemsetAsync(b.d_hist1d, 0, sizeof(unsigned long long) * range, st));
-  const uint64_t n0 = (uint64_t)info.lod_size[0][0] * info.lod_size[0][1] * info.lod_size[0][2];
-  hist1d_kernel<T><<<(unsigned)std::min<uint64_t>((n0 + 255) / 256, (uint64_t)sms * 8), 256, 0, st>>>((const T*)b.d_lod[0], n0, b.d_hist1d);
-  c->launches++;
-  TVK_CHECK_CUDA(c, cudaGetLastError());
-  TVK_CHECK_CUDA(c, cudaFreeAsync(d_mn, st));
-  TVK_CHECK_CUDA(c, cudaFreeAsync(d_mx, st));
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->bev1, st));
   TVK_CHECK_CUDA(c, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->bev0, c->bev1) == cudaSuccess) b.kernels_ms = ms;
+  cudaFree(d_mn);
   return TVK_OK;
 }
 
@@ -484,6 +801,12 @@ extern "C" int tvk_build_get_bricks(tvk_ctx* c, void* host_dst, uint64_t offset,
   if (!c || !c->build.valid || !host_dst || offset + bytes > c->build.info.total_bytes) return TVK_ERR_INVALID;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
   TVK_CHECK_CUDA(c, cudaMemcpy(host_dst, (const uint8_t*)c->build.d_store + offset, bytes, cudaMemcpyDeviceToHost));
+  return TVK_OK;
+}
+
+extern "C" int tvk_build_last_ms(tvk_ctx* c, float* kernels_ms) {
+  if (!c || !c->build.valid || !kernels_ms) return TVK_ERR_INVALID;
+  *kernels_ms = c->build.kernels_ms;
   return TVK_OK;
 }
 

@@ -69,6 +69,7 @@ extern "C" int tvk_create(int device, tvk_ctx** out) {
       cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+      cudaEventCreate(&c->bev0) != cudaSuccess || cudaEventCreate(&c->bev1) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->render_done, cudaEventDisableTiming) != cudaSuccess ||
       cudaMalloc(&c->d_tile_counter, 64) != cudaSuccess ||
@@ -103,7 +104,7 @@ extern "C" void tvk_destroy(tvk_ctx* c) {
   tvk_pool_destroy(c);
   free_frame(c);
   cudaFree(c->d_tf); cudaFree(c->d_tf_f); cudaFree(c->d_hash); cudaFree(c->d_tile_counter); cudaFree(c->d_stats); cudaFree(c->d_counts);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->copy_done); cudaEventDestroy(c->render_done);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->bev0); cudaEventDestroy(c->bev1); cudaEventDestroy(c->copy_done); cudaEventDestroy(c->render_done);
   cudaStreamDestroy(c->own_stream); cudaStreamDestroy(c->copy_stream);
   delete c;
 }

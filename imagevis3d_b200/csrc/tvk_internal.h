@@ -39,6 +39,7 @@ struct BuildState {
   void*     d_lod[TVK_MAX_LOD] = {}; // flat LOD volumes (lod 0 = raw when raw_on_device)
   bool      own_lod0 = false;
   bool      valid = false;
+  float     kernels_ms = 0.f;        // CUDA-event time of the builder kernels of the last tvk_build_octree
 };
 
 struct tvk_ctx {
@@ -46,7 +47,7 @@ struct tvk_ctx {
   cudaStream_t stream = nullptr;       // render / builder stream (own_stream unless tvk_set_stream)
   cudaStream_t own_stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // pager side stream
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, copy_done = nullptr, render_done = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, copy_done = nullptr, render_done = nullptr, bev0 = nullptr, bev1 = nullptr;
   std::string err;
 
   // pool

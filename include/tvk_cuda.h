@@ -241,6 +241,9 @@ int tvk_build_get_toc(tvk_ctx* ctx, uint64_t* offsets, uint32_t* sizes3, uint64_
 int tvk_build_get_minmax(tvk_ctx* ctx, double* minmax2, uint64_t n);
 int tvk_build_get_bricks(tvk_ctx* ctx, void* host_dst, uint64_t offset, uint64_t bytes);
 int tvk_build_store_device_ptr(tvk_ctx* ctx, void** dptr);
+/* CUDA-event time (ms) of the builder kernels of the last tvk_build_octree (allocations and the
+ * host->device copy of the raw volume excluded) */
+int tvk_build_last_ms(tvk_ctx* ctx, float* kernels_ms);
 /* 1-D histogram of LOD-0 inner voxels, 2^bits bins, *n = trimmed size
  * (Histogram1DDataBlock.cpp:60-160) */
 int tvk_build_hist1d(tvk_ctx* ctx, uint64_t* bins, uint32_t cap, uint32_t* n);

@@ -45,6 +45,28 @@ def test_builder_matches_oracle(tvk, vol, dtype, brick, overlap, median):
     _compare(tvk, raw, brick, overlap, median, oc["store"], oc["sizes"], oc["minmax"], h1, h2, mg)
 
 
+@pytest.mark.parametrize("kind", ["noise", "smooth", "flat"])
+def test_builder_u16_full_range_histogram(tvk, kind):
+    """Full-range 16-bit volumes take the windowed shared-memory histogram (two 32768-bin passes)."""
+    vol = (128, 96, 72)
+    if kind == "noise":
+        raw = H.synth_noise(vol, np.uint16, seed=5, maxval=65535)
+    elif kind == "smooth":
+        raw = (H.synth_sphere(vol, np.uint8).astype(np.uint32) * 257).astype(np.uint16)
+    else:
+        raw = np.full(vol[::-1], 40000, np.uint16)
+        raw[:, :, :7] = 3
+    oc = O.build_octree(raw, 64, 2, False)
+    tvk.build_octree(raw, 64, 2)
+    store, sizes = cuda_store_tight(tvk)
+    assert (store == oc["store"]).all() and (tvk.build_minmax() == oc["minmax"]).all()
+    h1 = tvk.build_hist1d()
+    ref = np.bincount(raw.reshape(-1), minlength=65536)
+    ref = ref[:np.nonzero(ref)[0][-1] + 1]
+    assert h1.size == ref.size and (h1 == ref).all()
+    tvk.build_release()
+
+
 def test_builder_rejects_unsupported(tvk):
     from imagevis3d_b200._lib import TvkError
     raw = np.zeros((8, 8, 8), np.uint8)
