@@ -60,6 +60,16 @@ class BuildInfo(C.Structure):
                 ("total_bricks", C.c_uint64), ("total_bytes", C.c_uint64)]
 
 
+class QuantizeResult(C.Structure):
+    _fields_ = [("out_bits", C.c_uint32), ("generated", C.c_uint32), ("hist_size", C.c_uint32), ("bin_count", C.c_uint32),
+                ("device_ms", C.c_float)]
+
+
+# TVK_DT_* codes by numpy dtype name
+DTYPE_CODES = {"int8": 0, "uint8": 1, "int16": 2, "uint16": 3, "int32": 4, "uint32": 5, "float32": 6, "int64": 7,
+               "uint64": 8, "float64": 9}
+
+
 # every symbol include/tvk_cuda.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "tvk_create", "tvk_destroy", "tvk_last_error", "tvk_device_synchronize", "tvk_set_stream",
@@ -69,7 +79,7 @@ EXPORTS = [
     "tvk_raycast_subframe", "tvk_read_requests", "tvk_read_image", "tvk_read_resume", "tvk_image_device_ptr",
     "tvk_get_stats", "tvk_probe_lod", "tvk_probe_brick_index",
     "tvk_build_plan", "tvk_build_octree", "tvk_build_get_toc", "tvk_build_get_minmax", "tvk_build_get_bricks",
-    "tvk_build_store_device_ptr", "tvk_build_hist1d", "tvk_build_hist2d", "tvk_build_release", "tvk_build_last_ms",
+    "tvk_build_store_device_ptr", "tvk_build_hist1d", "tvk_build_hist2d", "tvk_build_release", "tvk_build_last_ms", "tvk_quantize",
     "tvk_composite_ordered",
 ]
 

@@ -245,6 +245,35 @@ class TvkContext:
     def build_release(self):
         self._ck(self.lib.tvk_build_release(self.h), "tvk_build_release")
 
+    # ---------------------------------------------------------- quantisation
+    def quantize(self, data=None, to8bit=False, src_dptr=None, dtype=None, count=None, dst_dptr=None):
+        """RAWConverter's quantize() on the device.  data: numpy array (copied up), or src_dptr/dtype/count
+        for a volume already in HBM.  Returns dict(out_bits, generated, hist, device_ms, data): `data` is the
+        quantised stream fetched back unless dst_dptr (a caller-owned device buffer of 2*count bytes) is given."""
+        import torch
+        if data is not None:
+            data = np.ascontiguousarray(data).reshape(-1)
+            dtype, count = data.dtype, data.size
+            src, on_dev = _p(data), 0
+        else:
+            src, on_dev = C.c_void_p(int(src_dptr)), 1
+        code = L.DTYPE_CODES[np.dtype(dtype).name]
+        own = None
+        if dst_dptr is None:
+            own = torch.empty(2 * int(count) + 16, dtype=torch.uint8, device="cuda")
+            dst_dptr = own.data_ptr()
+        hist = np.zeros(4096, np.uint64)
+        r = L.QuantizeResult()
+        self._ck(self.lib.tvk_quantize(self.h, C.c_uint32(code), C.c_uint64(int(count)), src, C.c_int(on_dev),
+                                       C.c_int(1 if to8bit else 0), C.c_void_p(int(dst_dptr)), _p(hist), C.byref(r)), "tvk_quantize")
+        out = dict(out_bits=int(r.out_bits), generated=bool(r.generated), device_ms=float(r.device_ms),
+                   hist=hist[:r.hist_size].copy() if r.hist_size else None, bin_count=int(r.bin_count), data=None)
+        if own is not None and r.generated:
+            nb = int(count) * (r.out_bits // 8)
+            raw = own[:nb].cpu().numpy()
+            out["data"] = raw.copy() if r.out_bits == 8 else raw.view(np.uint16).copy()
+        return out
+
     # ------------------------------------------------------------ compositor
     def composite_ordered(self, dptrs, pixels, out_dptr):
         n = len(dptrs)

@@ -253,6 +253,34 @@ int tvk_build_hist2d(tvk_ctx* ctx, uint32_t bins_x, double max_nonzero_value,
                      uint64_t* bins, float* max_grad_magnitude);
 int tvk_build_release(tvk_ctx* ctx);
 
+/* --------------------------------------------------------------- quantisation */
+/* replaces the reference's pre-bricking passes over the raw input: the dispatcher quantize()
+ * (IO/RAWConverter.cpp:196-352) with Quantize<T,U> / BinningQuantize<T,U> (IO/Quantize.h:429-686),
+ * AbstrConverter::Process8Bits and ::QuantizeTo8Bit (IO/AbstrConverter.cpp:75-246), for one component
+ * and one time step.  Input element types: */
+#define TVK_DT_I8  0
+#define TVK_DT_U8  1
+#define TVK_DT_I16 2
+#define TVK_DT_U16 3
+#define TVK_DT_I32 4
+#define TVK_DT_U32 5
+#define TVK_DT_F32 6
+#define TVK_DT_I64 7
+#define TVK_DT_U64 8
+#define TVK_DT_F64 9
+typedef struct tvk_quantize_result {
+  uint32_t out_bits;    /* component size after the call: 8 or 16                                     */
+  uint32_t generated;   /* 1: dst holds the quantised stream (uint8 / uint16); 0: the input is used   */
+                        /*    as it is (the reference returns its source file in that case)           */
+  uint32_t hist_size;   /* bins written to hist; 0 = none (Histogram1DDataBlock::Compute runs later)  */
+  uint32_t bin_count;   /* iBinCount of Quantize<T,U> (unsigned integer inputs; diagnostic)           */
+  float    device_ms;   /* CUDA-event time of all passes                                              */
+} tvk_quantize_result;
+/* src: n elements (host pointer, or 16-byte aligned device pointer if src_on_device).
+ * dst_device: 16-byte aligned device buffer of at least 2*n bytes.  hist: host, 4096 entries. */
+int tvk_quantize(tvk_ctx* ctx, uint32_t type, uint64_t n, const void* src, int src_on_device,
+                 int to8bit, void* dst_device, uint64_t* hist, tvk_quantize_result* result);
+
 /* -------------------------------------------------------- sort-last compositor */
 /* new in this build (no reference counterpart): ordered "under"
  * blend of n premultiplied RGBA32F partial images, front-to-back in the given

@@ -15,7 +15,7 @@ ORC_MAX_LOD = 32
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("tvk_oracle_builder.c", "tvk_oracle_render.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("tvk_oracle_builder.c", "tvk_oracle_render.c", "tvk_oracle_quantize.c", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -104,6 +104,58 @@ def brick(oct, i):
     o = int(oct["offsets"][i])
     dt = np.uint8 if oct["bpv"] == 1 else np.uint16
     return oct["store"][o:o + n].view(dt).reshape(int(s[2]), int(s[1]), int(s[0]))
+
+
+# ---------------------------------------------------------------- quantisation (B5)
+QUANT_TYPES = {"i8": (0, np.int8), "u8": (1, np.uint8), "i16": (2, np.int16), "u16": (3, np.uint16), "i32": (4, np.int32),
+               "u32": (5, np.uint32), "f32": (6, np.float32), "i64": (7, np.int64), "u64": (8, np.uint64), "f64": (9, np.float64)}
+
+
+class QuantResult(C.Structure):
+    _fields_ = [("out_bits", C.c_uint32), ("generated", C.c_uint32), ("hist_size", C.c_uint32), ("bin_count", C.c_uint32)]
+
+
+def quantize(data, to8bit=False):
+    """RAWConverter.cpp quantize() on a 1-D numpy array.  Returns dict(out_bits, generated, data, hist):
+    `data` is the quantised stream (uint8/uint16) if generated, else the input itself; `hist` is None
+    when the reference leaves the histogram to Histogram1DDataBlock::Compute."""
+    data = np.ascontiguousarray(data).reshape(-1)
+    code = [c for c, (k, dt) in QUANT_TYPES.items() if np.dtype(dt) == data.dtype][0]
+    out = np.zeros(2 * data.size, np.uint8)
+    hist = np.zeros(4096, np.uint64)
+    r = QuantResult()
+    rc = lib().orc_quantize(data.ctypes.data_as(C.c_void_p), C.c_uint32(QUANT_TYPES[code][0]), C.c_uint64(data.size),
+                            C.c_int(1 if to8bit else 0), out.ctypes.data_as(C.c_void_p), hist.ctypes.data_as(C.c_void_p), C.byref(r))
+    if rc:
+        raise ValueError("orc_quantize failed (%d)" % rc)
+    if r.generated:
+        q = out[:data.size].copy() if r.out_bits == 8 else out.view(np.uint16)[:data.size].copy()
+    else:
+        q = data
+    return dict(out_bits=int(r.out_bits), generated=bool(r.generated), data=q,
+                hist=hist[:r.hist_size].copy() if r.hist_size else None, bin_count=int(r.bin_count))
+
+
+def ref_quantize(data, to8bit=False, tmpdir=None):
+    """The same through the reference's own templates (oracle/_ref/ref_driver quantize)."""
+    import tempfile
+    data = np.ascontiguousarray(data).reshape(-1)
+    code = [c for c, (k, dt) in QUANT_TYPES.items() if np.dtype(dt) == data.dtype][0]
+    with tempfile.TemporaryDirectory(dir=tmpdir) as td:
+        fi, fo = os.path.join(td, "in.raw"), os.path.join(td, "out.bin")
+        data.tofile(fi)
+        subprocess.check_call([ref_driver_path(), "quantize", fi, code, str(data.size), "1" if to8bit else "0", fo],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        buf = open(fo, "rb").read()
+    bits, gen = [int(v) for v in np.frombuffer(buf, np.uint32, 2, 0)]
+    nb = int(np.frombuffer(buf, np.uint64, 1, 8)[0])
+    raw = np.frombuffer(buf, np.uint8, nb, 16)
+    o = 16 + nb
+    nh = int(np.frombuffer(buf, np.uint64, 1, o)[0])
+    hist = np.frombuffer(buf, np.uint64, nh, o + 8).copy() if nh else None
+    # (Quantize<T,U> pre-sizes its output file to bytes*sizeof(U); only the first `size` elements are data)
+    q = (raw.copy() if bits == 8 else raw.view(np.uint16).copy())[:data.size] if gen else data
+    return dict(out_bits=bits, generated=bool(gen), data=q, hist=hist)
 
 
 # ---------------------------------------------------------------- reference dumps

@@ -16,6 +16,11 @@
 //     opens a UVF (MD5 verified) and dumps the first RasterDataBlock brick, the
 //     1D histogram and the global min/max (used for DemoData/c60.uvf).
 //   ref_driver tf1d <file.1dt> <out.bin>   dumps size + GetByteArray (RGBA8)
+//   ref_driver quantize <in.raw> <i8|u8|i16|u16|i32|u32|f32|i64|u64|f64> <elements> <to8bit 0|1> <out.bin>
+//     calls the reference's Quantize<T,U> / BinningQuantize<T,U> / AbstrConverter::Process8Bits /
+//     QuantizeTo8Bit templates (IO/Quantize.h, IO/AbstrConverter.cpp) in the order of the file-static
+//     dispatcher quantize() of IO/RAWConverter.cpp:196-352 (one component, one time step) and dumps
+//     u32 outBits; u32 generated; u64 nbytes; data; u64 nh; u64 hist[nh]
 //
 // Dump layout of `convert` (all little endian):
 //   char[8] "TVKREF1\0"; u32 lodCount;
@@ -24,6 +29,7 @@
 //   then per brick: raw voxels (size.volume()*bytesPerVoxel);
 //   u64 n1; u64 hist1d[n1]; f32 maxGrad; u64 nx; u64 ny; u64 hist2d[nx*ny]
 #include <cstdio>
+#include <list>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -40,6 +46,8 @@
 #include "IO/UVF/RasterDataBlock.h"
 #include "IO/TransferFunction1D.h"
 #include "Basics/LargeRAWFile.h"
+#include "IO/AbstrConverter.h"
+#include "IO/Quantize.h"
 
 using namespace tuvok;
 
@@ -191,10 +199,93 @@ static int do_tf1d(int argc, char** argv) {
   return 0;
 }
 
+static int do_quantize(int argc, char** argv) {
+  if (argc < 7) { fprintf(stderr, "quantize: not enough arguments\n"); return 2; }
+  const std::string in = argv[2], type = argv[3], out = argv[6];
+  const uint64_t n = strtoull(argv[4], 0, 10);
+  const bool to8 = atoi(argv[5]) != 0;
+  const std::string tmp = out + ".quantized.tmp";
+  LargeRAWFile src(in);
+  src.Open(false);
+  if (!src.IsOpen()) return 3;
+  const bool fp = type[0] == 'f', sgn = type[0] == 'i' || fp;
+  unsigned bits = (unsigned)atoi(type.c_str() + 1);
+  Histogram1DDataBlock h;
+  BStreamDescriptor bsd;
+  bsd.elements = n; bsd.components = 1; bsd.width = bits / 8; bsd.is_signed = sgn; bsd.fp = fp;
+  bsd.big_endian = EndianConvert::IsBigEndian(); bsd.timesteps = 1;
+  bool target = false;
+  if (to8 && bits > 8) {
+    target = AbstrConverter::QuantizeTo8Bit(src, tmp, bits, n, sgn, fp, &h);
+    bits = 8;
+  } else {
+    size_t bc = 0;
+    switch (bits) {
+      case 8: target = AbstrConverter::Process8Bits(src, tmp, n, sgn, &h); break;
+      case 16:
+        if (sgn) target = Quantize<short, unsigned short>(src, bsd, tmp, &h);
+        else {
+          target = Quantize<unsigned short, unsigned short>(src, bsd, tmp, &h, &bc);
+          if (bc > 0 && bc <= 256) target = BinningQuantize<unsigned short, unsigned char>(src, tmp, n, bits, &h);
+        }
+        break;
+      case 32:
+        if (fp) target = BinningQuantize<float, unsigned short>(src, tmp, n, bits, &h);
+        else {
+          bool binned = false;
+          if (sgn) target = Quantize<int32_t, unsigned short>(src, bsd, tmp, &h);
+          else {
+            target = Quantize<uint32_t, unsigned short>(src, bsd, tmp, &h, &bc);
+            if (bc > 0 && bc <= 256) { target = BinningQuantize<uint32_t, unsigned char>(src, tmp, n, bits, &h); binned = true; }
+          }
+          if (!binned) bits = 16;
+        }
+        break;
+      case 64:
+        if (fp) target = BinningQuantize<double, unsigned short>(src, tmp, n, bits, &h);
+        else {
+          bool binned = false;
+          if (sgn) target = Quantize<int64_t, unsigned short>(src, bsd, tmp, &h);
+          else {
+            target = Quantize<uint64_t, unsigned short>(src, bsd, tmp, &h, &bc);
+            if (bc > 0 && bc <= 256) { target = BinningQuantize<uint64_t, unsigned char>(src, tmp, n, bits, &h); binned = true; }
+          }
+          if (!binned) bits = 16;
+        }
+        break;
+      default: return 2;
+    }
+  }
+  src.Close();
+  FILE* f = fopen(out.c_str(), "wb");
+  if (!f) return 3;
+  put<uint32_t>(f, bits);
+  put<uint32_t>(f, target ? 1u : 0u);
+  {
+    FILE* d = fopen((target ? tmp : in).c_str(), "rb");
+    std::vector<unsigned char> buf;
+    if (d) {
+      fseek(d, 0, SEEK_END); const long sz = ftell(d); fseek(d, 0, SEEK_SET);
+      buf.resize((size_t)sz);
+      if (sz && fread(buf.data(), 1, (size_t)sz, d) != (size_t)sz) return 3;
+      fclose(d);
+    }
+    put<uint64_t>(f, (uint64_t)buf.size());
+    if (!buf.empty()) fwrite(buf.data(), 1, buf.size(), f);
+  }
+  const std::vector<uint64_t>& hist = h.GetHistogram();
+  put<uint64_t>(f, (uint64_t)hist.size());
+  if (!hist.empty()) fwrite(hist.data(), sizeof(uint64_t), hist.size(), f);
+  fclose(f);
+  remove(tmp.c_str());
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) { fprintf(stderr, "usage: ref_driver convert|uvfinfo|tf1d ...\n"); return 2; }
   if (!strcmp(argv[1], "convert")) return do_convert(argc, argv);
   if (!strcmp(argv[1], "uvfinfo")) return do_uvfinfo(argc, argv);
   if (!strcmp(argv[1], "tf1d")) return do_tf1d(argc, argv);
+  if (!strcmp(argv[1], "quantize")) return do_quantize(argc, argv);
   return 2;
 }

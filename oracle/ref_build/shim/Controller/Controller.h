@@ -9,6 +9,8 @@
 #define TUVOK_STACK_TIMER_H
 #endif
 
+#include <list>
+#include <string>
 #include "Basics/PerfCounter.h"
 #include "DebugOut/AbstrDebugOut.h"
 #include "DebugOut/ConsoleOut.h"
@@ -23,8 +25,15 @@ public:
   unsigned GetNumberOfCPUs() const { return 1; }
 };
 
+class ShimIOMan {
+public:
+  unsigned long long GetIncoresize() const { return 1ull << 20; }
+};
+
 class ShimMasterController {
 public:
+  ShimIOMan* IOMan() { return nullptr; }                    // AbstrConverter::GetIncoreSize -> DEFAULT_INCORESIZE
+  const ShimIOMan& IOMan() const { static ShimIOMan m; return m; }
   void IncrementPerfCounter(enum PerfCounter, double) {}
   AbstrDebugOut* DebugOut() { static ConsoleOut out; static bool once = (out.SetOutput(true, false, false, false), true); (void)once; return &out; }
   const AbstrDebugOut* DebugOut() const { return const_cast<ShimMasterController*>(this)->DebugOut(); }
