@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtvk_cuda.so")
 
 CU_SOURCES = ["tvk_context.cu", "tvk_raycast.cu", "tvk_visibility.cu", "tvk_builder.cu", "tvk_quantize.cu"]
-CPP_SOURCES = ["host/tvk_host.cpp"]
+CPP_SOURCES = ["host/tvk_host.cpp", "host/tvk_uvf.cpp"]
 # -fmad=false: multiply-adds are fused only where the source says fmaf(), so that the ray-marcher
 # rounds exactly like the CPU oracle (see the floating-point contract in tvk_raycast.cu)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
@@ -37,7 +37,7 @@ def needs_build():
         return True
     t = os.path.getmtime(LIB)
     deps = sources() + [os.path.join(CSRC, "tvk_internal.h"), os.path.join(ROOT, "include", "tvk_cuda.h"),
-                        os.path.join(ROOT, "include", "tvk_renderer.h"), os.path.join(CSRC, "host", "tvk_host.h")]
+                        os.path.join(ROOT, "include", "tvk_renderer.h"), os.path.join(ROOT, "include", "tvk_uvf.h"), os.path.join(CSRC, "host", "tvk_host.h")]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
@@ -60,7 +60,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
         if verbose:
             sys.stderr.write(out.decode())
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lz"]
     subprocess.check_call(cmd)
     return LIB
 

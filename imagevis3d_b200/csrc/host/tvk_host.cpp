@@ -1,6 +1,7 @@
 // C++ host of the B200 ray-caster (see tvk_host.h).  Pure host code: every device
 // operation is a call into the C ABI of include/tvk_cuda.h.
 #include "tvk_host.h"
+#include "tvk_uvf.h"
 #include <cuda_runtime_api.h>   // only cudaHostAlloc/cudaFreeHost for the pinned out-of-core store
 #include <algorithm>
 #include <cfloat>
@@ -409,6 +410,13 @@ bool CudaGridLeaper::LoadRawVolume(const void* raw, const uint32_t size[3], uint
     rc = tvk_build_store_device_ptr(m_ctx, &v->device_store);
     if (rc) { delete v; return Fail("tvk_build_store_device_ptr", rc); }
   }
+  return FinishLoad(v, gpuMemBytes, tfSize);
+}
+
+// pool set-up + AbstrRenderer::LoadFile tail, shared by the raw-volume and the UVF loaders
+bool CudaGridLeaper::FinishLoad(BrickedVolume* v, uint64_t gpuMemBytes, uint32_t tfSize) {
+  const uint32_t bpv = v->bpv;
+  int rc;
   m_vol = v;
   // pool sizing: dataset-sized unless a GPU memory budget is given (GPUMemMan.cpp:766-844)
   uint32_t cap[3];
@@ -438,6 +446,96 @@ bool CudaGridLeaper::LoadRawVolume(const void* raw, const uint32_t size[3], uint
   m_visValid = false;
   Changed1DTrans();
   ScheduleCompleteRedraw();
+  return true;
+}
+
+// renderer.loadDataset(file.uvf): UVFDataset::Open (uvfDataset.cpp:83-216) through the reader of tvk_uvf.h.
+// The bricks are read (and inflated) once into pinned host memory, which is the pager's source.
+bool CudaGridLeaper::LoadDataset(const std::string& uvfFile, uint64_t gpuMemBytes, bool verifyChecksum) {
+  if (!m_ctx) { m_err = "renderer not initialised"; return false; }
+  char err[256] = {0};
+  tvk_uvf* u = nullptr;
+  if (tvk_uvf_open(uvfFile.c_str(), verifyChecksum ? 1 : 0, &u, err, sizeof(err))) { m_err = std::string("UVF open failed: ") + err; return false; }
+  tvk_uvf_info ui;
+  tvk_uvf_get_info(u, &ui);
+  if (ui.toc_block < 0 || (ui.vol.component_type != TVK_UVF_CT_UINT8 && ui.vol.component_type != TVK_UVF_CT_UINT16) ||
+      ui.maxmin_bricks != ui.total_bricks) {
+    tvk_uvf_close(u);
+    m_err = "UVF file has no 8/16-bit unsigned TOC block with a matching max/min block (legacy RasterDataBlock files need rebricking)";
+    return false;
+  }
+  delete m_pool; m_pool = nullptr;
+  if (m_vol) { if (m_vol->host_store) cudaFreeHost(m_vol->host_store); delete m_vol; m_vol = nullptr; }
+  tvk_build_release(m_ctx);
+  BrickedVolume* v = new BrickedVolume();
+  v->bpv = ui.vol.component_type == TVK_UVF_CT_UINT16 ? 2 : 1;
+  v->brick_size = (uint32_t)ui.vol.brick_size[0]; v->overlap = ui.vol.overlap;
+  tvk_build_desc d{};
+  for (int a = 0; a < 3; ++a) { v->domain[a] = d.volume_size[a] = (uint32_t)ui.vol.volume_size[a]; v->scale[a] = (float)ui.vol.aspect[a]; }
+  d.brick_size = v->brick_size; d.overlap = v->overlap; d.bytes_per_voxel = v->bpv;
+  tvk_build_plan(&d, &v->info);
+  const uint64_t n = ui.total_bricks;
+  v->offsets.resize(n); v->sizes.resize(3 * n); v->minmax.resize(2 * n);
+  tvk_uvf_get_toc(u, nullptr, nullptr, nullptr, v->sizes.data(), n);
+  uint64_t off = 0;
+  for (uint64_t i = 0; i < n; ++i) {          // same 256-byte brick alignment as the builder's store
+    v->offsets[i] = off;
+    off += ((uint64_t)v->sizes[3 * i] * v->sizes[3 * i + 1] * v->sizes[3 * i + 2] * v->bpv + 255) / 256 * 256;
+  }
+  v->store_bytes = v->info.total_bytes = off;
+  std::vector<double> mm4(4 * n);
+  tvk_uvf_get_minmax(u, mm4.data(), n);
+  for (uint64_t i = 0; i < n; ++i) { v->minmax[2 * i] = mm4[4 * i]; v->minmax[2 * i + 1] = mm4[4 * i + 1]; }
+  v->hist1d.resize(ui.hist1d_size);
+  if (ui.hist1d_size) tvk_uvf_get_hist1d(u, v->hist1d.data(), ui.hist1d_size);
+  v->max_grad_magnitude = ui.max_grad_magnitude;
+  if (cudaHostAlloc((void**)&v->host_store, v->store_bytes, cudaHostAllocDefault) != cudaSuccess) {
+    tvk_uvf_close(u); delete v; m_err = "cudaHostAlloc failed for the brick store"; return false;
+  }
+  const int rc = tvk_uvf_read_bricks(u, 0, n, v->host_store, v->offsets.data());
+  if (rc) { m_err = std::string("UVF brick read failed: ") + tvk_uvf_last_error(u); tvk_uvf_close(u); cudaFreeHost(v->host_store); delete v; return false; }
+  tvk_uvf_close(u);
+  const uint32_t tfSize = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)v->hist1d.size(), 4096));
+  return FinishLoad(v, gpuMemBytes, tfSize);
+}
+
+// writes the loaded volume as a UVF v5 file stock ImageVis3D opens (tvk_uvf_write)
+bool CudaGridLeaper::SaveUVF(const std::string& uvfFile, uint32_t compression, uint32_t level) {
+  if (!m_ctx || !m_vol) { m_err = "no dataset"; return false; }
+  const BrickedVolume& v = *m_vol;
+  std::vector<uint8_t> tmp;
+  const uint8_t* store = v.host_store;
+  if (!store) {
+    tmp.resize(v.store_bytes);
+    const int rc = tvk_build_get_bricks(m_ctx, tmp.data(), 0, v.store_bytes);
+    if (rc) return Fail("tvk_build_get_bricks", rc);
+    store = tmp.data();
+  }
+  const uint32_t tfSize = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)v.hist1d.size(), 4096));
+  std::vector<uint64_t> h2;
+  float mg = v.max_grad_magnitude;
+  if (!v.host_store) {                        // the builder state is alive: the 2-D histogram comes from it
+    double lo, hi;
+    v.Range(lo, hi);
+    h2.resize((size_t)tfSize * 256);
+    const int rc = tvk_build_hist2d(m_ctx, tfSize, hi, h2.data(), &mg);
+    if (rc) return Fail("tvk_build_hist2d", rc);
+  }
+  tvk_uvf_write_desc w{};
+  w.vol.component_type = v.bpv == 2 ? TVK_UVF_CT_UINT16 : TVK_UVF_CT_UINT8;
+  w.vol.component_count = 1;
+  for (int a = 0; a < 3; ++a) { w.vol.volume_size[a] = v.domain[a]; w.vol.aspect[a] = v.scale[a]; w.vol.brick_size[a] = v.brick_size; }
+  w.vol.overlap = v.overlap; w.vol.compression = compression; w.vol.compression_level = level;
+  w.total_bricks = v.info.total_bricks;
+  w.brick_offsets = v.offsets.data(); w.brick_sizes = v.sizes.data(); w.store = store; w.minmax = v.minmax.data();
+  w.hist1d = v.hist1d.data(); w.hist1d_size = v.hist1d.size();
+  if (!h2.empty()) { w.hist2d = h2.data(); w.hist2d_x = tfSize; w.hist2d_y = 256; }
+  w.max_grad_magnitude = mg;
+  const char* keys[3] = {"Source Endianness", "Source Type", "Source Bitwidth"};
+  const char* vals[3] = {"little", "integer", v.bpv == 2 ? "16" : "8"};
+  w.kv_keys = keys; w.kv_values = vals; w.kv_count = 3;
+  char err[256] = {0};
+  if (tvk_uvf_write(uvfFile.c_str(), &w, err, sizeof(err))) { m_err = err; return false; }
   return true;
 }
 
@@ -759,6 +857,12 @@ const char* tvkr_last_error(tvkr_renderer* h) { return h ? R(h)->LastError() : "
 int tvkr_load_raw_volume(tvkr_renderer* h, const void* raw, const uint32_t size[3], uint32_t bpv, const float scale[3],
                          uint32_t brick, uint32_t overlap, int median, int out_of_core, uint64_t gpu_mem_bytes, int hist2d) {
   return h && R(h)->LoadRawVolume(raw, size, bpv, scale, brick, overlap, median != 0, out_of_core != 0, gpu_mem_bytes, hist2d != 0) ? 0 : 1;
+}
+int tvkr_load_dataset(tvkr_renderer* h, const char* uvf_file, uint64_t gpu_mem_bytes, int verify_checksum) {
+  return h && uvf_file && R(h)->LoadDataset(uvf_file, gpu_mem_bytes, verify_checksum != 0) ? 0 : 1;
+}
+int tvkr_save_uvf(tvkr_renderer* h, const char* uvf_file, uint32_t compression, uint32_t level) {
+  return h && uvf_file && R(h)->SaveUVF(uvf_file, compression, level) ? 0 : 1;
 }
 int tvkr_resize(tvkr_renderer* h, uint32_t w, uint32_t hh) { if (!h) return 1; R(h)->Resize(w, hh); return 0; }
 int tvkr_set_render_mode(tvkr_renderer* h, int mode) { return h && R(h)->SetRendermode(mode) ? 0 : 1; }

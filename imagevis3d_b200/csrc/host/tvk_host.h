@@ -161,6 +161,10 @@ class CudaGridLeaper {
   bool LoadRawVolume(const void* raw, const uint32_t size[3], uint32_t bytesPerVoxel, const float scale[3],
                      uint32_t brickSize, uint32_t overlap, bool median, bool outOfCore, uint64_t gpuMemBytes,
                      bool computeHist2D);
+  // renderer.loadDataset(file.uvf): a UVF with a TOC block (8/16-bit unsigned); bricks go to pinned host memory
+  bool LoadDataset(const std::string& uvfFile, uint64_t gpuMemBytes, bool verifyChecksum);
+  // the loaded volume as a UVF v5 file (TOC, histograms, max/min, key/values, MD5); compression: TVK_UVF_COMP_*
+  bool SaveUVF(const std::string& uvfFile, uint32_t compression, uint32_t level);
   void Resize(uint32_t w, uint32_t h);
   void Cleanup();
   const char* LastError() const { return m_err.c_str(); }
@@ -216,6 +220,7 @@ class CudaGridLeaper {
 
  private:
   bool Fail(const std::string& what, int rc);
+  bool FinishLoad(BrickedVolume* v, uint64_t gpuMemBytes, uint32_t tfSize);
   bool RecomputeBrickVisibility(bool force);            // GLGridLeaper.cpp:632-688
   tvk_ctx* m_ctx = nullptr;
   BrickedVolume* m_vol = nullptr;

@@ -76,6 +76,16 @@ class Renderer:
                  "loadRawVolume")
         return True
 
+    def loadDataset(self, filename, gpu_mem_bytes=0, verify=True):
+        """renderer.loadDataset("file.uvf") -- UVF v5 with a TOC block (tvkr_load_dataset)"""
+        self._ck(self._lib.tvkr_load_dataset(self._h, filename.encode(), C.c_uint64(int(gpu_mem_bytes)), C.c_int(int(verify))),
+                 "loadDataset")
+        return True
+
+    def saveUVF(self, filename, compression=0, level=1):
+        self._ck(self._lib.tvkr_save_uvf(self._h, filename.encode(), C.c_uint32(compression), C.c_uint32(level)), "saveUVF")
+        return True
+
     def datasetInfo(self):
         d = DatasetInfo()
         self._ck(self._lib.tvkr_get_dataset_info(self._h, C.byref(d)), "datasetInfo")

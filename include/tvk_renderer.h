@@ -45,6 +45,13 @@ const char* tvkr_last_error(tvkr_renderer* r);
 int tvkr_load_raw_volume(tvkr_renderer* r, const void* raw, const uint32_t size[3], uint32_t bytes_per_voxel,
                          const float scale[3], uint32_t brick_size, uint32_t overlap, int use_median,
                          int out_of_core, uint64_t gpu_mem_bytes, int compute_hist2d);
+/* renderer.loadDataset("file.uvf") (AbstrRenderer::LoadFile, AbstrRenderer.cpp:215-263 -> UVFDataset::Open,
+ * uvfDataset.cpp:83-216): a UVF v5 file with a TOC block; bricks are read (zlib / lz4 inflated) into pinned
+ * host memory and paged from there.  gpu_mem_bytes as above. */
+int tvkr_load_dataset(tvkr_renderer* r, const char* uvf_file, uint64_t gpu_mem_bytes, int verify_checksum);
+/* what IOManager::ConvertDataset leaves on disk (RAWConverter::ConvertRAWDataset, RAWConverter.cpp:412-681):
+ * the loaded volume as a UVF v5 file; compression = TVK_UVF_COMP_NONE / _ZLIB (tvk_uvf.h) */
+int tvkr_save_uvf(tvkr_renderer* r, const char* uvf_file, uint32_t compression, uint32_t level);
 int tvkr_get_dataset_info(tvkr_renderer* r, tvkr_dataset_info* out);
 
 int tvkr_resize(tvkr_renderer* r, uint32_t w, uint32_t h);                      /* renderer.resize({w,h})       */

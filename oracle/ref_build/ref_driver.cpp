@@ -48,10 +48,50 @@
 #include "Basics/LargeRAWFile.h"
 #include "IO/AbstrConverter.h"
 #include "IO/Quantize.h"
+#include "IO/UVF/KeyValuePairDataBlock.h"
+#include "Basics/nonstd.h"
 
 using namespace tuvok;
 
 template <typename T> static void put(FILE* f, const T& v) { fwrite(&v, sizeof(T), 1, f); }
+
+// header + per-brick sizes / min / max + brick payloads of a TOC block (TVKREF1 layout, see above)
+static void dump_octree(FILE* f, const TOCBlock& toc, const MaxMinDataBlock& mmb, size_t bpv, uint64_t brick) {
+  const MaxMinDataBlock* mm = &mmb;
+  fwrite("TVKREF1\0", 1, 8, f);
+  const uint32_t lods = (uint32_t)toc.GetLoDCount();
+  put(f, lods);
+  uint64_t total = 0;
+  for (uint32_t l = 0; l < lods; ++l) {
+    UINT64VECTOR3 s = toc.GetLODDomainSize(l), b = toc.GetBrickCount(l);
+    DOUBLEVECTOR3 a = toc.GetBrickAspect(UINT64VECTOR4(0, 0, 0, l));
+    put(f, s.x); put(f, s.y); put(f, s.z);
+    put(f, b.x); put(f, b.y); put(f, b.z);
+    put(f, a.x); put(f, a.y); put(f, a.z);
+    total += b.volume();
+  }
+  put(f, total);
+  size_t idx = 0;
+  for (uint32_t l = 0; l < lods; ++l) {
+    UINT64VECTOR3 b = toc.GetBrickCount(l);
+    for (uint64_t z = 0; z < b.z; ++z) for (uint64_t y = 0; y < b.y; ++y) for (uint64_t x = 0; x < b.x; ++x) {
+      UINT64VECTOR3 s = toc.GetBrickSize(UINT64VECTOR4(x, y, z, l));
+      put(f, s.x); put(f, s.y); put(f, s.z);
+      const MinMaxBlock& v = mm->GetValue(idx++, 0);
+      put(f, v.minScalar); put(f, v.maxScalar);
+    }
+  }
+  std::vector<uint8_t> buf(brick * brick * brick * bpv);
+  for (uint32_t l = 0; l < lods; ++l) {
+    UINT64VECTOR3 b = toc.GetBrickCount(l);
+    for (uint64_t z = 0; z < b.z; ++z) for (uint64_t y = 0; y < b.y; ++y) for (uint64_t x = 0; x < b.x; ++x) {
+      UINT64VECTOR4 c(x, y, z, l);
+      UINT64VECTOR3 s = toc.GetBrickSize(c);
+      toc.GetData(buf.data(), c);
+      fwrite(buf.data(), 1, size_t(s.volume()) * bpv, f);
+    }
+  }
+}
 
 static int do_convert(int argc, char** argv) {
   if (argc < 12) { fprintf(stderr, "convert: not enough arguments\n"); return 2; }
@@ -82,40 +122,7 @@ static int do_convert(int argc, char** argv) {
 
   FILE* f = fopen(out.c_str(), "wb");
   if (!f) return 1;
-  fwrite("TVKREF1\0", 1, 8, f);
-  const uint32_t lods = (uint32_t)toc.GetLoDCount();
-  put(f, lods);
-  uint64_t total = 0;
-  for (uint32_t l = 0; l < lods; ++l) {
-    UINT64VECTOR3 s = toc.GetLODDomainSize(l), b = toc.GetBrickCount(l);
-    DOUBLEVECTOR3 a = toc.GetBrickAspect(UINT64VECTOR4(0, 0, 0, l));
-    put(f, s.x); put(f, s.y); put(f, s.z);
-    put(f, b.x); put(f, b.y); put(f, b.z);
-    put(f, a.x); put(f, a.y); put(f, a.z);
-    total += b.volume();
-  }
-  put(f, total);
-  size_t idx = 0;
-  for (uint32_t l = 0; l < lods; ++l) {
-    UINT64VECTOR3 b = toc.GetBrickCount(l);
-    for (uint64_t z = 0; z < b.z; ++z) for (uint64_t y = 0; y < b.y; ++y) for (uint64_t x = 0; x < b.x; ++x) {
-      UINT64VECTOR3 s = toc.GetBrickSize(UINT64VECTOR4(x, y, z, l));
-      put(f, s.x); put(f, s.y); put(f, s.z);
-      const MinMaxBlock& v = mm->GetValue(idx++, 0);
-      put(f, v.minScalar); put(f, v.maxScalar);
-    }
-  }
-  const size_t bpv = u16 ? 2 : 1;
-  std::vector<uint8_t> buf(brick * brick * brick * bpv);
-  for (uint32_t l = 0; l < lods; ++l) {
-    UINT64VECTOR3 b = toc.GetBrickCount(l);
-    for (uint64_t z = 0; z < b.z; ++z) for (uint64_t y = 0; y < b.y; ++y) for (uint64_t x = 0; x < b.x; ++x) {
-      UINT64VECTOR4 c(x, y, z, l);
-      UINT64VECTOR3 s = toc.GetBrickSize(c);
-      toc.GetData(buf.data(), c);
-      fwrite(buf.data(), 1, size_t(s.volume()) * bpv, f);
-    }
-  }
+  dump_octree(f, toc, *mm, u16 ? 2 : 1, brick);
   if (hist) {
     Histogram1DDataBlock h1;
     auto t2 = std::chrono::steady_clock::now();
@@ -196,6 +203,97 @@ static int do_tf1d(int argc, char** argv) {
   uint64_t lo = tf.GetNonZeroLimits().x; uint64_t hi = tf.GetNonZeroLimits().y;
   put(f, lo); put(f, hi);
   fclose(f);
+  return 0;
+}
+
+// ref_driver writeuvf <in.raw> <sx> <sy> <sz> <u8|u16> <brick> <overlap> <median> <compression> <level> <out.uvf>
+//   the file assembly of RAWConverter::ConvertRAWDataset (IO/RAWConverter.cpp:527-681) for an input that
+//   needs no quantisation: TOC block, 1-D / 2-D histogram, max/min, key/value block, MD5.
+static int do_writeuvf(int argc, char** argv) {
+  if (argc < 13) return 2;
+  const std::string in = argv[2], out = argv[12];
+  const uint64_t sx = strtoull(argv[3], 0, 10), sy = strtoull(argv[4], 0, 10), sz = strtoull(argv[5], 0, 10);
+  const bool u16 = !strcmp(argv[6], "u16");
+  const uint64_t brick = strtoull(argv[7], 0, 10);
+  const uint32_t overlap = (uint32_t)strtoul(argv[8], 0, 10);
+  const bool median = atoi(argv[9]) != 0;
+  const uint32_t comp = (uint32_t)atoi(argv[10]), level = (uint32_t)atoi(argv[11]);
+  const std::string tmp = out + ".octree.tmp";
+  LargeRAWFile_ptr src(new LargeRAWFile(in));
+  if (!src->Open(false)) return 1;
+  UVF uvfFile(std::wstring(out.begin(), out.end()));
+  GlobalHeader gh;
+  gh.bIsBigEndian = EndianConvert::IsBigEndian();
+  gh.ulChecksumSemanticsEntry = UVFTables::CS_MD5;
+  uvfFile.SetGlobalHeader(gh);
+  std::shared_ptr<MaxMinDataBlock> mm(new MaxMinDataBlock(1));
+  std::shared_ptr<Histogram2DDataBlock> h2(new Histogram2DDataBlock());
+  std::shared_ptr<TOCBlock> toc(new TOCBlock(UVF::ms_ulReaderVersion));
+  toc->strBlockID = "Volume converted by ImageVis3D";
+  if (!toc->FlatDataToBrickedLOD(src, tmp, u16 ? ExtendedOctree::CT_UINT16 : ExtendedOctree::CT_UINT8, 1,
+                                 UINT64VECTOR3(sx, sy, sz), DOUBLEVECTOR3(1, 1, 1), UINT64VECTOR3(brick, brick, brick), overlap,
+                                 median, false, size_t(1) << 31, mm, &Controller::Debug::Out(), COMPRESSION_TYPE(comp), level,
+                                 LT_SCANLINE)) return 1;
+  if (!uvfFile.AddDataBlock(toc)) return 1;
+  Histogram1DDataBlock h1;
+  if (!h1.Compute(toc.get(), 0)) return 1;
+  if (!h2->Compute(toc.get(), 0, h1.GetHistogram().size(), mm->GetGlobalValue().maxScalar)) return 1;
+  uvfFile.AddDataBlock(std::shared_ptr<Histogram1DDataBlock>(&h1, nonstd::null_deleter()));
+  uvfFile.AddDataBlock(h2);
+  uvfFile.AddDataBlock(mm);
+  std::shared_ptr<KeyValuePairDataBlock> meta(new KeyValuePairDataBlock());
+  meta->AddPair("Source Endianness", "little");
+  meta->AddPair("Source Type", "integer");
+  meta->AddPair("Source Bitwidth", u16 ? "16" : "8");
+  uvfFile.AddDataBlock(meta);
+  uvfFile.Create();
+  uvfFile.Close();
+  src->Close();
+  return 0;
+}
+
+// ref_driver readuvf <file.uvf> <out.bin>: UVF::Open with checksum verification, then the TVKREF1 dump of
+// the first TOC block with the file's own histogram / max-min blocks, followed by u64 nkv and, per pair,
+// u64 len, key, u64 len, value.
+static int do_readuvf(int argc, char** argv) {
+  if (argc < 4) return 2;
+  std::string fn(argv[2]);
+  UVF uvf(std::wstring(fn.begin(), fn.end()));
+  std::string err;
+  if (!uvf.Open(true, true, false, &err)) { fprintf(stderr, "open failed: %s\n", err.c_str()); return 1; }
+  const TOCBlock* toc = NULL; const Histogram1DDataBlock* h1 = NULL; const MaxMinDataBlock* mm = NULL;
+  const Histogram2DDataBlock* h2 = NULL; const KeyValuePairDataBlock* kv = NULL;
+  for (uint64_t i = 0; i < uvf.GetDataBlockCount(); ++i) {
+    const DataBlock* b = uvf.GetDataBlock(i).get();
+    if (!toc) toc = dynamic_cast<const TOCBlock*>(b);
+    if (!h1) h1 = dynamic_cast<const Histogram1DDataBlock*>(b);
+    if (!h2) h2 = dynamic_cast<const Histogram2DDataBlock*>(b);
+    if (!mm) mm = dynamic_cast<const MaxMinDataBlock*>(b);
+    if (!kv) kv = dynamic_cast<const KeyValuePairDataBlock*>(b);
+  }
+  if (!toc || !h1 || !h2 || !mm || !kv) { fprintf(stderr, "missing blocks\n"); return 1; }
+  FILE* f = fopen(argv[3], "wb");
+  if (!f) return 1;
+  dump_octree(f, *toc, *mm, toc->GetComponentTypeSize(), toc->GetMaxBrickSize().x);
+  const std::vector<uint64_t>& bins = h1->GetHistogram();
+  uint64_t n1 = bins.size();
+  put(f, n1);
+  fwrite(bins.data(), 8, bins.size(), f);
+  float mg = h2->GetMaxGradMagnitude();
+  put(f, mg);
+  const std::vector<std::vector<uint64_t>>& b2 = h2->GetHistogram();
+  uint64_t nx = b2.size(), ny = nx ? b2[0].size() : 0;
+  put(f, nx); put(f, ny);
+  for (uint64_t i = 0; i < nx; ++i) fwrite(b2[i].data(), 8, ny, f);
+  uint64_t nkv = kv->GetKeyCount();
+  put(f, nkv);
+  for (uint64_t i = 0; i < nkv; ++i) {
+    const std::string k = kv->GetKeyByIndex(i), v = kv->GetValueByIndex(i);
+    uint64_t l = k.size(); put(f, l); fwrite(k.data(), 1, k.size(), f);
+    l = v.size(); put(f, l); fwrite(v.data(), 1, v.size(), f);
+  }
+  fclose(f);
+  uvf.Close();
   return 0;
 }
 
@@ -287,5 +385,7 @@ int main(int argc, char** argv) {
   if (!strcmp(argv[1], "uvfinfo")) return do_uvfinfo(argc, argv);
   if (!strcmp(argv[1], "tf1d")) return do_tf1d(argc, argv);
   if (!strcmp(argv[1], "quantize")) return do_quantize(argc, argv);
+  if (!strcmp(argv[1], "writeuvf")) return do_writeuvf(argc, argv);
+  if (!strcmp(argv[1], "readuvf")) return do_readuvf(argc, argv);
   return 2;
 }

@@ -1,0 +1,118 @@
+"""CPU: the UVF v5 writer / reader (include/tvk_uvf.h, host code) against the reference.
+ * a UVF written by the REFERENCE (tests/golden/ref_*.uvf, made by tests/golden/make_golden_uvf.py from
+   oracle/_ref/ref_driver writeuvf = the block assembly of RAWConverter::ConvertRAWDataset) is read by our
+   reader and compared with the oracle's octree; and our writer, fed the oracle's arrays, must reproduce that
+   file BYTE FOR BYTE (uncompressed and zlib);
+ * where oracle/_ref exists (build container) the reference's own UVF::Open(verify) + TOCBlock::GetData read
+   the files our writer produced."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from imagevis3d_b200 import uvf as U
+from oracle import host as H
+from oracle import oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CASES = {"ref_u8_none": ((50, 41, 33), np.uint8, 16, 2, 0, 0), "ref_u8_zlib": ((50, 41, 33), np.uint8, 16, 2, 1, 1),
+         "ref_u16_zlib": ((37, 20, 45), np.uint16, 20, 2, 1, 1), "ref_u8_lz4": ((50, 41, 33), np.uint8, 16, 2, 3, 1)}
+
+
+def case_volume(name):
+    vol, dt, brick, overlap, comp, level = CASES[name]
+    raw = H.synth_blobs(vol, dt, seed=7) if comp else H.synth_noise(vol, dt, seed=4)
+    if dt == np.uint16:
+        raw = (H.synth_blobs(vol, np.uint8, seed=7).astype(np.uint16) + 300)   # < 4096: no quantisation in the reference flow
+    return raw
+
+
+def golden_file(name, tmp_path):
+    """the fixtures are committed gzip-compressed (their 2-D histogram blocks are mostly zeros)"""
+    import gzip
+    out = os.path.join(str(tmp_path), name + ".uvf")
+    with gzip.open(os.path.join(GOLD, name + ".uvf.gz"), "rb") as f:
+        open(out, "wb").write(f.read())
+    return out
+
+
+def _oracle_parts(raw, brick, overlap):
+    oc = O.build_octree(raw, brick, overlap)
+    h1 = O.hist1d(oc)
+    h2, mg = O.hist2d(oc, len(h1), oc["minmax"][:, 1].max())
+    tight = np.concatenate([[0], np.cumsum(oc["sizes"].astype(np.uint64).prod(axis=1) * oc["bpv"])]).astype(np.uint64)
+    return oc, h1, h2, mg, tight
+
+
+def test_md5_known_answers():
+    import hashlib
+    for msg in (b"", b"a", b"abc", b"message digest", bytes(range(256)) * 37):
+        assert U.md5(msg) == hashlib.md5(msg).digest()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_reader_on_reference_written_file(name, tmp_path):
+    vol, dt, brick, overlap, comp, level = CASES[name]
+    raw = case_volume(name)
+    oc, h1, h2, mg, tight = _oracle_parts(raw, brick, overlap)
+    with U.UvfFile(golden_file(name, tmp_path), verify=True) as f:
+        i = f.info
+        assert i.uvf_version == 5 and i.checksum_ok == 1 and i.toc_block == 0 and i.octree_version == 2
+        assert list(i.block_semantics[:i.block_count]) == [9, 5, 6, 7, 4]     # TOC, Hist1D, Hist2D, MaxMin, KeyValue
+        assert list(i.vol.volume_size) == list(vol) and list(i.vol.brick_size) == [brick] * 3 and i.vol.overlap == overlap
+        assert i.total_bricks == oc["plan"].total_bricks and i.lod_count == oc["plan"].lod_count
+        off, ln, c, sizes = f.toc()
+        assert (sizes == oc["sizes"]).all()
+        if comp:
+            assert (c == comp).any()
+        assert (f.read_bricks() == oc["store"]).all()
+        mm = f.minmax()
+        assert (mm[:, :2] == oc["minmax"]).all() and (mm[:, 2] == -np.finfo(np.float64).max).all()
+        assert (f.hist1d() == h1).all() and (f.hist2d() == h2).all()
+        assert np.float32(i.max_grad_magnitude) == np.float32(mg)
+        assert f.kv() == [("Source Endianness", "little"), ("Source Type", "integer"), ("Source Bitwidth", str(8 * raw.dtype.itemsize))]
+
+
+@pytest.mark.parametrize("name", ["ref_u8_none", "ref_u8_zlib", "ref_u16_zlib"])
+def test_writer_reproduces_reference_file_byte_for_byte(name, tmp_path):
+    vol, dt, brick, overlap, comp, level = CASES[name]
+    raw = case_volume(name)
+    oc, h1, h2, mg, tight = _oracle_parts(raw, brick, overlap)
+    out = str(tmp_path / "ours.uvf")
+    U.write_uvf(out, vol, raw.dtype.itemsize, brick, overlap, tight[:-1], oc["sizes"], oc["store"], oc["minmax"], h1, h2, mg,
+                compression=comp, level=level)
+    ours, ref = open(out, "rb").read(), open(golden_file(name, tmp_path), "rb").read()
+    assert len(ours) == len(ref)
+    assert ours == ref
+
+
+def test_reader_rejects_corruption(tmp_path):
+    from imagevis3d_b200._lib import TvkError
+    data = bytearray(open(golden_file("ref_u8_none", tmp_path), "rb").read())
+    data[len(data) // 2] ^= 0x40
+    bad = str(tmp_path / "bad.uvf")
+    open(bad, "wb").write(bytes(data))
+    with pytest.raises(TvkError):
+        U.UvfFile(bad, verify=True)
+    U.UvfFile(bad, verify=False).close()          # like the reference, unverified opens do not look at the payload
+    open(bad, "wb").write(b"not a uvf file at all, not even close ........................")
+    with pytest.raises(TvkError):
+        U.UvfFile(bad)
+    with pytest.raises(TvkError):
+        U.UvfFile(str(tmp_path / "missing.uvf"))
+
+
+@pytest.mark.skipif(O.ref_driver_path() is None, reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("comp", [0, 1])
+def test_reference_reads_our_file(comp, tmp_path):
+    vol, brick, overlap = (70, 33, 29), 32, 2
+    raw = H.synth_blobs(vol, np.uint8, seed=9)
+    oc, h1, h2, mg, tight = _oracle_parts(raw, brick, overlap)
+    out = str(tmp_path / "ours.uvf")
+    U.write_uvf(out, vol, 1, brick, overlap, tight[:-1], oc["sizes"], oc["store"], oc["minmax"], h1, h2, mg, compression=comp, level=3)
+    dump = str(tmp_path / "dump.bin")
+    subprocess.check_call([O.ref_driver_path(), "readuvf", out, dump])       # UVF::Open(verify = true) checks our MD5
+    r = O.parse_ref_convert(dump, 1)
+    assert (r["store"] == oc["store"]).all() and (r["minmax"] == oc["minmax"]).all()
+    assert (r["hist1d"] == h1).all() and (r["hist2d"] == h2).all() and np.float32(r["max_grad"]) == np.float32(mg)
