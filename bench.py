@@ -229,7 +229,11 @@ def run_gpu(args, rank, world):
         dist.init_process_group("nccl", device_id=dev)
     tvk = TvkContext(local)
     if world > 1:
-        tvk.set_stream(torch.cuda.current_stream().cuda_stream)   # K1, NCCL and the compositor stay stream-ordered
+        # K1, NCCL and the compositor stay stream-ordered on ONE explicit stream (torch's legacy default stream has
+        # handle 0, which tvk_set_stream reads as "use your own stream")
+        work_stream = torch.cuda.Stream(device=dev)
+        torch.cuda.set_stream(work_stream)
+        tvk.set_stream(work_stream.cuda_stream)
     sampler = {"exact": L.SAMPLER_EXACT, "tex3d": L.SAMPLER_TEX3D, "q4": L.SAMPLER_EXACT_Q4}[os.environ.get("TVK_SAMPLER", "q4")]
 
     # ---- untimed set-up: synthesize the (slab of the) volume in HBM, build bricks, fill the pool
@@ -284,13 +288,35 @@ def run_gpu(args, rank, world):
         return out
 
     final_image = [None]
+    # sort-last exchange: fused into the kernels over NVLink peer memory (CUDA IPC); TVK_EXCHANGE=nccl selects the
+    # collective-based direct send instead, which is also the fall-back when peer mapping is not possible
+    exchange_kind, fused = "none", None
+    if world > 1:
+        exchange_kind = os.environ.get("TVK_EXCHANGE", "p2p-fused")
+        if exchange_kind == "p2p-fused":
+            ok = torch.ones(1, device=dev)
+            try:
+                fused = SL.FusedExchange(tvk, world, rank, WIDTH, HEIGHT, dist)
+            except Exception as e:            # noqa: BLE001 -- any failure to map peers demotes ALL ranks together
+                sys.stderr.write("rank %d: fused exchange unavailable (%s)\n" % (rank, e))
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                fused, exchange_kind = None, "nccl"
 
     def step(k):
-        tvk.raycast(params_for(k))
-        if world > 1:
-            # sort-last: direct-send stripes over NCCL, ordered blend on the owner, gather
-            pg = HM.raycast_params(camera_for_step(HM, k, args.steps), WIDTH, HEIGHT, GLOBAL)
-            order = SL.depth_order(np.array(pg.eye_to_model[:]).reshape(4, 4), parts)
+        if world == 1:
+            tvk.raycast(params_for(k))
+            return
+        pg = HM.raycast_params(camera_for_step(HM, k, args.steps), WIDTH, HEIGHT, GLOBAL)
+        order = SL.depth_order(np.array(pg.eye_to_model[:]).reshape(4, 4), parts)
+        if fused is not None:
+            # K1 sends its stripes while it marches; stripe blend waits on arrival flags; result lands on rank 0
+            ptr = fused.render(params_for(k), order)
+            final_image[0] = torch.as_tensor(_CAI(ptr, (HEIGHT, WIDTH, 4)), device=dev)
+        else:
+            # direct-send stripes over NCCL, ordered blend on the owner, gather
+            tvk.raycast(params_for(k))
             partial = torch.as_tensor(_CAI(tvk.image_device_ptr(), (HEIGHT, WIDTH, 4)), device=dev)
             final_image[0] = SL.exchange_and_composite(partial, order, gpu_composite, world, rank)
 
@@ -302,6 +328,8 @@ def run_gpu(args, rank, world):
         tvk.synchronize()
     tvk.stats(reset=True)
     assert len(tvk.read_requests()) == 0, "pool is not fully resident: frame would not be converged"
+    if fused is not None:
+        assert not tvk.exchange_timed_out(), "sort-last exchange timed out during warm-up"
 
     # ---- timed region (device time from CUDA events around each step's launch)
     sampler_thread = ClockSampler(local)
@@ -396,7 +424,12 @@ def run_gpu(args, rank, world):
                          "note": "0.6068 B/sample + 16 B/ray (SURVEY 8d); the kernel is L1/TEX-issue bound, see DESIGN.md"},
             "e2e": {"value": e2e_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
-            "gpu_launches": args.steps * (1 if world == 1 else 2 * world), "clocks": clocks, "builder_ms_untimed": 1e3 * t_build}
+            "gpu_launches": args.steps * (1 if world == 1 else (2 * world if fused is not None else 2 * world)), "clocks": clocks,
+            "builder_ms_untimed": 1e3 * t_build}
+    if world > 1:
+        line["config"]["exchange"] = exchange_kind
+        if fused is not None:
+            line["exchange_timed_out"] = bool(tvk.exchange_timed_out())
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample
     if world == 1 and not args.no_cpu:

@@ -281,6 +281,49 @@ class TvkContext:
         self._ck(self.lib.tvk_composite_ordered(self.h, arr, C.c_uint32(n), C.c_uint64(pixels), C.c_void_p(int(out_dptr))),
                  "tvk_composite_ordered")
 
+    # ------------------------------------------- sort-last exchange over peer memory
+    def exchange_create(self, world, rank, width, height):
+        """returns the 64-byte CUDA IPC handle of this rank's exchange region"""
+        h = C.create_string_buffer(64)
+        self._ck(self.lib.tvk_exchange_create(self.h, C.c_uint32(world), C.c_uint32(rank), C.c_uint32(width), C.c_uint32(height), h),
+                 "tvk_exchange_create")
+        self._xchg_world = world
+        return h.raw
+
+    def exchange_open_peers(self, handles):
+        buf = b"".join(handles)
+        assert len(buf) == 64 * self._xchg_world
+        self._ck(self.lib.tvk_exchange_open_peers(self.h, C.c_char_p(buf)), "tvk_exchange_open_peers")
+
+    def exchange_local_base(self):
+        p = C.c_void_p()
+        self._ck(self.lib.tvk_exchange_local_base(self.h, C.byref(p)), "tvk_exchange_local_base")
+        return p.value
+
+    def exchange_set_peers(self, bases):
+        arr = (C.c_void_p * len(bases))(*[int(b) for b in bases])
+        self._ck(self.lib.tvk_exchange_set_peers(self.h, arr), "tvk_exchange_set_peers")
+
+    def exchange_begin_frame(self, frame_id):
+        self._ck(self.lib.tvk_exchange_begin_frame(self.h, C.c_uint32(frame_id)), "tvk_exchange_begin_frame")
+
+    def exchange_composite(self, order, frame_id):
+        arr = (C.c_uint32 * len(order))(*[int(o) for o in order])
+        self._ck(self.lib.tvk_exchange_composite(self.h, arr, C.c_uint32(frame_id)), "tvk_exchange_composite")
+
+    def exchange_final(self, frame_id):
+        p = C.c_void_p()
+        self._ck(self.lib.tvk_exchange_final(self.h, C.c_uint32(frame_id), C.byref(p)), "tvk_exchange_final")
+        return p.value
+
+    def exchange_timed_out(self):
+        t = C.c_uint32()
+        self._ck(self.lib.tvk_exchange_status(self.h, C.byref(t)), "tvk_exchange_status")
+        return bool(t.value)
+
+    def exchange_destroy(self):
+        self._ck(self.lib.tvk_exchange_destroy(self.h), "tvk_exchange_destroy")
+
     def image_device_ptr(self):
         p = C.c_void_p()
         self._ck(self.lib.tvk_image_device_ptr(self.h, C.byref(p)), "tvk_image_device_ptr")

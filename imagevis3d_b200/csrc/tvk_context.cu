@@ -79,6 +79,7 @@ extern "C" int tvk_create(int device, tvk_ctx** out) {
     return TVK_ERR_CUDA;
   }
   c->own_stream = c->stream;
+  cudaMemset(c->d_tile_counter, 0, 64);
   cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
   // keep stream-ordered allocations (pager staging ring, job lists) cached between frames
   cudaMemPool_t mp;
@@ -100,6 +101,7 @@ extern "C" void tvk_destroy(tvk_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  tvk_exchange_destroy(c);
   tvk_build_release(c);
   tvk_pool_destroy(c);
   free_frame(c);

@@ -42,6 +42,22 @@ struct BuildState {
   float     kernels_ms = 0.f;        // CUDA-event time of the builder kernels of the last tvk_build_octree
 };
 
+// sort-last exchange over peer memory (tvk_exchange.cu)
+#define TVK_XCHG_MAX_WORLD 16
+struct ExchangeState {
+  uint32_t world = 0, rank = 0, width = 0, height = 0, rows = 0;
+  void* local = nullptr;                          // this rank's region (cudaMalloc)
+  void* base[TVK_XCHG_MAX_WORLD] = {};            // every rank's region as seen from this device
+  uint32_t* flags[TVK_XCHG_MAX_WORLD] = {};
+  bool ipc_opened[TVK_XCHG_MAX_WORLD] = {};
+  uint32_t send_frame = 0;                        // != 0: the next ray-march launch also sends its stripes
+};
+struct ExchangeSend {                             // what K1 needs; world == 0: local image only
+  float4* recv[TVK_XCHG_MAX_WORLD];               // owner r's buffer for this rank's stripe (rows*W pixels)
+  uint32_t* flag[TVK_XCHG_MAX_WORLD];             // owner r's arrival flag for this rank
+  uint32_t world, rank, rows, frame;
+};
+
 struct tvk_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;       // render / builder stream (own_stream unless tvk_set_stream)
@@ -82,6 +98,7 @@ struct tvk_ctx {
   uint32_t launches = 0;
 
   BuildState build;
+  ExchangeState xchg;
 };
 
 #define TVK_CHECK_CUDA(ctx, call)                                                       \
@@ -97,3 +114,4 @@ struct tvk_ctx {
 
 void tvk_compute_pool_const(const tvk_pool_desc& d, PoolConst& pc);
 int  tvk_ensure_frame(tvk_ctx* ctx, uint32_t w, uint32_t h, uint32_t hash_size);
+void tvk_exchange_fill(const tvk_ctx* ctx, ExchangeSend& s);

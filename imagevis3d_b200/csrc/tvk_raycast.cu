@@ -53,6 +53,7 @@ struct RayParams {
   uint32_t* tile_counter;
   unsigned long long* stats;
   uint32_t tiles_x, tiles_y;
+  ExchangeSend xs;       // sort-last: finished pixels also go to the stripe owner's receive buffer (peer store)
 };
 
 struct f3 { float x, y, z; };
@@ -615,6 +616,16 @@ __device__ __forceinline__ float4 compose_iso(const tvk_raycast_params& p, float
                      clamp01(fmaf(p.light_specular[2], spec, fmaf(p.light_diffuse[2] * p.iso_color[2], ndl, p.light_ambient[2]))), 1.0f);
 }
 
+// Result store.  With the sort-last exchange active the pixel also goes, by a peer store over NVLink, into the
+// receive buffer of the rank that owns its scan-line stripe -- while the warp moves on to its next tile.
+__device__ __forceinline__ void store_pixel(const RayParams& rp, uint32_t px, uint32_t py, size_t i, float4 v) {
+  rp.image[i] = v;
+  if (rp.xs.world) {
+    const uint32_t owner = py / rp.xs.rows;
+    rp.xs.recv[owner][(size_t)(py - owner * rp.xs.rows) * rp.p.width + px] = v;
+  }
+}
+
 // SRM1: sampleRateModifier == 1 known at compile time (the opacity correction is then the identity
 // 1-(1-a) and the pow path is not even compiled in); instantiated for the 1D-TF kernels only.
 template <int MODE, bool LIT, int BPV, int SAMP, bool SRM1>
@@ -637,7 +648,7 @@ __global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP 
     float4 entry, exitp;
     if (!ray_setup(rp.p, px, py, entry, exitp)) {
       if (rp.p.new_view) {
-        rp.image[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        store_pixel(rp, px, py, i, make_float4(0.f, 0.f, 0.f, 0.f));
         rp.aux[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         rp.pos[i] = make_float4(0.f, 0.f, 0.f, 1000.0f);
       }
@@ -654,7 +665,7 @@ __global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP 
       }
       float4 hit, hitn;
       march_ray_iso<BPV, SAMP>(rp, exitp, pos, aux, hit, hitn, cn);
-      rp.image[i] = compose_iso(rp.p, hit, hitn);
+      store_pixel(rp, px, py, i, compose_iso(rp.p, hit, hitn));
     } else {
       if (!rp.p.new_view) {
         if (pos.w == 1000.0f) continue;              // finished: image already holds rayResumeColor
@@ -662,7 +673,7 @@ __global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP 
       }
       float4 acc;
       march_ray<MODE, LIT, BPV, SAMP, SRM1>(rp, exitp, pos, aux, acc, cn);
-      rp.image[i] = acc;
+      store_pixel(rp, px, py, i, acc);
     }
     rp.pos[i] = pos;
     rp.aux[i] = aux;
@@ -677,6 +688,20 @@ __global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP 
       atomicAdd(rp.stats + 0, nsamples);
       atomicAdd(rp.stats + 1, nrays);
       atomicAdd(rp.stats + 2, nbricks);
+    }
+  }
+  if (rp.xs.world) {
+    // all peer stores of this CTA are performed system-wide; the last CTA to retire raises this rank's
+    // arrival flag on every stripe owner
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned prev = atomicAdd(rp.tile_counter + 1, 1u);
+      if (prev == gridDim.x - 1) {
+        rp.tile_counter[1] = 0u;
+        __threadfence_system();
+        for (uint32_t o = 0; o < rp.xs.world; ++o) *reinterpret_cast<volatile uint32_t*>(rp.xs.flag[o]) = rp.xs.frame;
+      }
     }
   }
 }
@@ -731,6 +756,9 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   rp.tile_counter = c->d_tile_counter;
   rp.stats = c->d_stats;
   rp.tiles_x = (p->width + 7) / 8; rp.tiles_y = (p->height + 3) / 4;
+  tvk_exchange_fill(c, rp.xs);
+  if (rp.xs.world && (c->xchg.width != p->width || c->xchg.height != p->height))
+    TVK_FAIL(c, TVK_ERR_INVALID, "exchange was created for another image size");
 
   const bool srm1 = (1.0f / p->sample_rate_modifier == 1.0f);
   const raycast_fn fn = (c->pc.bpv == 1) ? pick_sampler<1>(c->pdesc.sampler, p->render_mode, p->lighting != 0, srm1)

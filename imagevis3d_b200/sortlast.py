@@ -8,8 +8,10 @@ rank g owns scan-line stripe g, one all_to_all moves every foreign stripe to its
 over NVSwitch), the owner blends its N stripes front to back with the compositor kernel and the
 finished stripes are gathered.  Bytes on the wire per rank: (N-1)/N * W*H*16 B each way.
 
-This module is backend agnostic (nccl on GPUs, gloo in the CPU tests): the blend itself is
-passed in as a callable.
+exchange_and_composite() is backend agnostic (nccl on GPUs, gloo in the CPU tests): the blend itself is
+passed in as a callable.  FusedExchange is the B200 path: the same direct send, but the ray-march kernel
+itself stores each finished pixel into the owner's buffer over NVLink peer memory and the compositor waits
+on arrival flags -- no collective call on the data path (csrc/tvk_exchange.cu).
 """
 import math
 
@@ -67,3 +69,26 @@ def exchange_and_composite(partial, order, composite, world, rank):
     full = torch.empty((world, rows, w, 4), dtype=partial.dtype, device=partial.device)
     dist.all_gather(list(full.unbind(0)), mine)               # (gloo has no all_gather_into_tensor)
     return full.view(hp, w, 4)[:h]
+
+
+class FusedExchange:
+    """Direct-send compositing fused into the kernels over CUDA-IPC peer memory (one process per GPU).
+    `dist` is torch.distributed (only used once, to swap the 64-byte IPC handles)."""
+
+    def __init__(self, tvk, world, rank, width, height, dist=None):
+        self.tvk, self.world, self.rank, self.frame = tvk, world, rank, 0
+        handle = tvk.exchange_create(world, rank, width, height)
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, handle)
+            tvk.exchange_open_peers(handles)
+            dist.barrier()                       # every rank has mapped every region before the first peer store
+
+    def render(self, params, order):
+        """march + send, then blend this rank's stripe; returns the device pointer of the finished H x W
+        image (complete on rank 0 once the stream has passed this call; other ranks hold their own stripe)."""
+        self.frame += 1
+        self.tvk.exchange_begin_frame(self.frame)
+        self.tvk.raycast(params)
+        self.tvk.exchange_composite(order, self.frame)
+        return self.tvk.exchange_final(self.frame)

@@ -289,6 +289,27 @@ int tvk_quantize(tvk_ctx* ctx, uint32_t type, uint64_t n, const void* src, int s
 int tvk_composite_ordered(tvk_ctx* ctx, const void* const* partial_dptrs, uint32_t n,
                           uint64_t pixels, void* out_dptr);
 
+/* ---------------------------------------------- sort-last exchange over peer memory */
+/* Direct-send compositing fused into the kernels (no reference counterpart): rank r owns scan-line
+ * stripe r.  After tvk_exchange_begin_frame the next tvk_raycast_subframe stores every finished pixel into the
+ * stripe owner's receive buffer with peer stores (NVLink), tvk_exchange_composite blends the `world` partial
+ * stripes of this rank front to back (order[k] = rank of the k-th nearest slab) once they have all arrived and
+ * sends the result to rank 0, tvk_exchange_final orders rank 0's stream behind the arrival of all stripes.
+ * One process per GPU: exchange the 64-byte handle of tvk_exchange_create between the ranks and pass all of
+ * them (rank order) to tvk_exchange_open_peers.  Several ranks inside one process (tests): pass the pointers of
+ * tvk_exchange_local_base to tvk_exchange_set_peers.  frame_id >= 1, the same on all ranks, +1 per frame.
+ * Waits are bounded (4 s): tvk_exchange_status reports a time-out instead of a hang.  world <= 16. */
+int tvk_exchange_create(tvk_ctx* ctx, uint32_t world, uint32_t rank, uint32_t width, uint32_t height,
+                        void* ipc_handle64);
+int tvk_exchange_open_peers(tvk_ctx* ctx, const void* handles);
+int tvk_exchange_set_peers(tvk_ctx* ctx, void* const* bases);
+int tvk_exchange_local_base(tvk_ctx* ctx, void** base);
+int tvk_exchange_begin_frame(tvk_ctx* ctx, uint32_t frame_id);
+int tvk_exchange_composite(tvk_ctx* ctx, const uint32_t* order, uint32_t frame_id);
+int tvk_exchange_final(tvk_ctx* ctx, uint32_t frame_id, void** final_dptr);
+int tvk_exchange_status(tvk_ctx* ctx, uint32_t* timed_out);
+int tvk_exchange_destroy(tvk_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

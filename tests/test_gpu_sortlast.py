@@ -80,3 +80,55 @@ def test_clip_box_validation(tvk):
     p.box_min[2], p.box_max[2] = 0.6, 0.4
     with pytest.raises(TvkError):
         tvk.raycast(p)
+
+
+@pytest.mark.parametrize("world,angle", [(3, 0.3), (3, 3.5), (4, 1.9)])
+def test_fused_exchange_equals_separate_compositor(world, angle):
+    """The fused direct-send path (K1 peer stores + arrival flags + stripe compositor, csrc/tvk_exchange.cu)
+    with the ranks emulated inside one process on one GPU: its image must equal, bit for bit, the ordered
+    compositor applied to the ranks' partial images -- over several frames (both buffer parities)."""
+    import torch
+    from imagevis3d_b200.context import TvkContext
+    from tests.util import resident_pool, to_cuda_params
+    G = (64, 64, 64 * world)
+    vol = H.synth_blobs(G, np.uint8, seed=23)
+    parts = SL.slab_partition(G, world, halo=32)
+    tf = _tf()
+    lo, hi = H.tf_nonzero_limits(tf)
+    W, Hh = 161, 123                                   # height not divisible by the world size
+    ctxs = []
+    for r, part in enumerate(parts):
+        t = TvkContext(0)
+        resident_pool(t, np.ascontiguousarray(vol[part["zs"]:part["ze"]]), 20, H.tf_bytes(tf), float(lo), float(hi))
+        t.exchange_create(world, r, W, Hh)
+        ctxs.append(t)
+    bases = [t.exchange_local_base() for t in ctxs]
+    for t in ctxs:
+        t.exchange_set_peers(bases)
+    for frame in range(1, 4):
+        cam = H.Camera()
+        cam.rotation = H.rotation_y(angle + 0.2 * frame) @ H.rotation_x(0.25)
+        pg = H.raycast_params(cam, W, Hh, G)
+        order = SL.depth_order(np.array(pg.eye_to_model[:]).reshape(4, 4), parts)
+        partial = []
+        for r, t in enumerate(ctxs):
+            t.exchange_begin_frame(frame)
+            t.raycast(to_cuda_params(H.raycast_params(cam, W, Hh, G, slab=parts[r])))
+            t.synchronize()
+            partial.append(torch.from_numpy(t.read_image()).cuda())
+        for t in ctxs:
+            t.exchange_composite(order, frame)
+        final = ctxs[0].exchange_final(frame)
+        for t in ctxs:
+            assert not t.exchange_timed_out()
+        class _CAI:
+            def __init__(self, ptr, shape):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+        got = torch.as_tensor(_CAI(final, (Hh, W, 4)), device="cuda").cpu().numpy()
+        want = torch.zeros((Hh, W, 4), dtype=torch.float32, device="cuda")
+        ctxs[0].composite_ordered([partial[r].data_ptr() for r in order], W * Hh, want.data_ptr())
+        ctxs[0].synchronize()
+        want = want.cpu().numpy()
+        assert want.max() > 0.05 and np.array_equal(got, want), frame
+    for t in ctxs:
+        t.close()

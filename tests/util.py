@@ -120,3 +120,28 @@ def lockstep_render(tvk, params, pool, tf_rgba8, sampler=0, max_subframes=100):
     return dict(cuda=img_c, oracle=frame.image.copy(), subframes=subframes, req_total=req_total,
                 req_mismatch=req_mismatch, samples_cuda=int(st.samples), samples_oracle=samples_o,
                 pos_cuda=pos_c, pos_oracle=frame.pos.copy(), rays_cuda=int(st.rays), rays_oracle=rays_o)
+
+
+def resident_pool(tvk, vol, brick, tf_rgba8, lo, hi, sampler=0):
+    """Builds the octree of `vol` with the CUDA builder and makes EVERY pool brick resident (slot i = brick i,
+    coarsest brick in the last slot), with 1D-TF visibility for the value range [lo, hi]."""
+    dims = vol.shape[::-1]
+    info = tvk.build_octree(vol, brick, 2)
+    off, sizes = tvk.build_toc()
+    mm = tvk.build_minmax()
+    lod_count = next(l for l in range(info.lod_count)
+                     if info.lod_bricks[l][0] * info.lod_bricks[l][1] * info.lod_bricks[l][2] == 1) + 1
+    total = int(info.lod_offset[lod_count - 1]) + 1
+    nbx, nby = int(info.lod_bricks[0][0]) + 1, int(info.lod_bricks[0][1]) + 1
+    cap = (nbx, nby, -(-total // (nbx * nby)))
+    mb = tuple(int(v) for v in sizes[:total].max(axis=0))
+    assert tvk.pool_create(dims, mb, 2, vol.dtype.itemsize, cap, lod_count, sampler) == total
+    store = tvk.build_store_ptr()
+    slots = np.arange(total, dtype=np.uint32)
+    slots[total - 1] = cap[0] * cap[1] * cap[2] - 1
+    tvk.pool_upload_device(slots, [store + int(o) for o in off[:total]], sizes[:total])
+    tvk.set_metadata(slots + 3)
+    tvk.set_minmax(mm[:total])
+    tvk.set_tf1d(tf_rgba8)
+    tvk.recompute_visibility(0, lo, hi)
+    tvk.build_release()
