@@ -44,11 +44,18 @@ def main():
             tvk.synchronize()
             best = min(best, time.perf_counter() - t0)
             kbest = min(kbest, tvk.build_last_ms() * 1e-3)
+            if it == 0:
+                h1 = tvk.build_hist1d()
+                tvk.synchronize()
+                t2 = time.perf_counter()
+                tvk.build_hist2d(min(len(h1), 4096), float(tvk.build_minmax()[:, 1].max()))
+                h2_ms = 1e3 * (time.perf_counter() - t2)
+                h2_kernel_ms = tvk.build_hist2d_last_ms()
             tvk.build_release()
         n = dims[0] * dims[1] * dims[2]
         print(json.dumps({"bench": "builder", "volume": list(dims), "bpv": bpv, "wall_ms_incl_alloc": 1e3 * best,
                           "kernels_ms": 1e3 * kbest, "voxels_per_s": n / kbest,
-                          "algorithmic_GBps": 2.387 * bpv * n / kbest / 1e9,
+                          "algorithmic_GBps": 2.387 * bpv * n / kbest / 1e9, "hist2d_wall_ms": h2_ms, "hist2d_kernels_ms": h2_kernel_ms,
                           "note": "kernels_ms = CUDA events around pyramid + brick cut + min/max + 1-D histogram"}), flush=True)
         del raw
         torch.cuda.empty_cache()

@@ -242,6 +242,11 @@ class TvkContext:
         self._ck(self.lib.tvk_build_last_ms(self.h, C.byref(ms)), "tvk_build_last_ms")
         return ms.value
 
+    def build_hist2d_last_ms(self):
+        ms = C.c_float()
+        self._ck(self.lib.tvk_build_hist2d_last_ms(self.h, C.byref(ms)), "tvk_build_hist2d_last_ms")
+        return ms.value
+
     def build_release(self):
         self._ck(self.lib.tvk_build_release(self.h), "tvk_build_release")
 

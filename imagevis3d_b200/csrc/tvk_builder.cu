@@ -574,49 +574,138 @@ __device__ __forceinline__ double grad_mag(const T* __restrict__ raw, uint32_t x
   return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), __dmul_rn(gz, gz)));
 }
 
+// The fp64 chain of grad_mag() (3 divisions + a square root per voxel, twice over the volume) is what the
+// reference evaluates, and it must be matched bit for bit -- but it is needed for very few voxels:
+//  * the gradient length is, up to ~4 ulp, sqrt(S)/norm2 with the INTEGER S = dx^2+dy^2+dz^2 of the three
+//    central differences; two different S differ by a relative 1/S >= 7.7e-11, far beyond the rounding noise,
+//    so the maximum length is attained at a voxel with the maximum S.  Pass 1 therefore runs in integers and
+//    evaluates the fp64 chain only for voxels that tie or beat the thread's current best S;
+//  * the gradient bin floor(len/max*255) follows from S/Smax in fp32 whenever that estimate is not within
+//    1e-3 of a bin boundary (fp32 error < 1e-4); only the boundary cases run the exact fp64 chain.
+template <typename T>
+__device__ __forceinline__ unsigned long long grad_s(const T* __restrict__ raw, uint32_t x, uint32_t y, uint32_t z,
+                                                     uint32_t sx, uint32_t sy, uint32_t sz) {
+  const uint64_t rs = sx, ss = (uint64_t)sx * sy;
+  const uint64_t c = x + y * rs + z * ss;
+  const long long l = x > 0 ? (long long)raw[c - 1] : 0, r = x + 1 < sx ? (long long)raw[c + 1] : 0;
+  const long long t = y > 0 ? (long long)raw[c - rs] : 0, b = y + 1 < sy ? (long long)raw[c + rs] : 0;
+  const long long f = z > 0 ? (long long)raw[c - ss] : 0, k = z + 1 < sz ? (long long)raw[c + ss] : 0;
+  return (unsigned long long)((l - r) * (l - r) + (t - b) * (t - b) + (f - k) * (f - k));
+}
+
+// the same S with everything that depends on (y,z) hoisted out of the row loop: pointers to the four
+// neighbouring rows (nullptr outside the domain) and 32-bit arithmetic (a difference is < 2^16)
+template <typename T> struct RowCtx { const T *line, *up, *down, *front, *back; };
+template <typename T>
+__device__ __forceinline__ RowCtx<T> row_ctx(const T* __restrict__ raw, uint32_t y, uint32_t z, uint32_t sx, uint32_t sy, uint32_t sz) {
+  const uint64_t rs = sx, ss = (uint64_t)sx * sy;
+  RowCtx<T> r;
+  r.line = raw + y * rs + z * ss;
+  r.up = y > 0 ? r.line - rs : nullptr; r.down = y + 1 < sy ? r.line + rs : nullptr;
+  r.front = z > 0 ? r.line - ss : nullptr; r.back = z + 1 < sz ? r.line + ss : nullptr;
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ unsigned long long grad_s_row(const RowCtx<T>& r, uint32_t x, uint32_t sx, unsigned long long* key = nullptr) {
+  const int l = x > 0 ? (int)r.line[x - 1] : 0, rr = x + 1 < sx ? (int)r.line[x + 1] : 0;
+  const int t = r.up ? (int)r.up[x] : 0, b = r.down ? (int)r.down[x] : 0;
+  const int f = r.front ? (int)r.front[x] : 0, k = r.back ? (int)r.back[x] : 0;
+  const int dx = l - rr, dy = t - b, dz = f - k;
+  // the fp64 length depends on (|dx|,|dy|,|dz|) only: this key identifies it
+  if (key) *key = (unsigned long long)abs(dx) | ((unsigned long long)abs(dy) << 17) | ((unsigned long long)abs(dz) << 34);
+  if (sizeof(T) == 1) return (unsigned long long)(unsigned)(dx * dx + dy * dy + dz * dz);
+  return (unsigned long long)(unsigned)(dx * dx) + (unsigned)(dy * dy) + (unsigned)(dz * dz);
+}
+
+struct GradBest { unsigned long long s; unsigned long long len_bits; };
+
 template <typename T>
 __global__ void __launch_bounds__(256) grad_max_kernel(const T* __restrict__ raw, uint32_t sx, uint32_t sy, uint32_t sz,
-                                                        double norm2, unsigned long long* __restrict__ out_bits) {
-  const uint64_t n = (uint64_t)sx * sy * sz;
-  double m = 0.0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t x = (uint32_t)(i % sx), y = (uint32_t)((i / sx) % sy), z = (uint32_t)(i / ((uint64_t)sx * sy));
-    const double g = grad_mag(raw, x, y, z, sx, sy, sz, norm2);
-    if (g > m) m = g;
+                                                        double norm2, GradBest* __restrict__ partial) {
+  // a warp walks one row (y,z) at a time, 32 voxels per trip: no per-voxel index division
+  const uint32_t rows = sy * sz, lane = threadIdx.x & 31u;
+  unsigned long long best_s = 0, best_bits = 0, last_key = ~0ull;
+  for (uint32_t row = blockIdx.x * 8u + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8u) {
+    const uint32_t y = row % sy, z = row / sy;
+    const RowCtx<T> rc = row_ctx(raw, y, z, sx, sy, sz);
+    for (uint32_t x = lane; x < sx; x += 32u) {
+      unsigned long long key;
+      const unsigned long long s = grad_s_row(rc, x, sx, &key);
+      if (s == 0 || s < best_s || key == last_key) continue;      // (a tie with the triple just evaluated adds nothing)
+      last_key = key;
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(grad_mag(raw, x, y, z, sx, sy, sz, norm2));
+      if (s > best_s) { best_s = s; best_bits = bits; }
+      else if (bits > best_bits) best_bits = bits;          // non-negative doubles order like integers
+    }
   }
-  unsigned long long bits = (unsigned long long)__double_as_longlong(m);   // non-negative doubles order like integers
-  for (int s = 16; s > 0; s >>= 1) {
-    const unsigned long long o = __shfl_xor_sync(0xffffffffu, bits, s);
-    bits = o > bits ? o : bits;
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long os = __shfl_xor_sync(0xffffffffu, best_s, o), ob = __shfl_xor_sync(0xffffffffu, best_bits, o);
+    if (os > best_s || (os == best_s && ob > best_bits)) { best_s = os; best_bits = ob; }
   }
-  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, bits);
+  __shared__ GradBest sh[8];
+  if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5].s = best_s; sh[threadIdx.x >> 5].len_bits = best_bits; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    GradBest g = sh[0];
+    for (int w = 1; w < 8; ++w) if (sh[w].s > g.s || (sh[w].s == g.s && sh[w].len_bits > g.len_bits)) g = sh[w];
+    partial[blockIdx.x] = g;
+  }
+}
+
+// value -> histogram column, exactly as Histogram2DDataBlock.cpp:432-435 computes it (one fp64 mul + div per VALUE)
+__global__ void hist2d_value_lut_kernel(uint32_t range, uint32_t bins_x, double max_nonzero, uint16_t* __restrict__ lut) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= range) return;
+  uint32_t vi = (max_nonzero <= (double)(bins_x - 1)) ? v : (uint32_t)__ddiv_rn(__dmul_rn((double)v, (double)(bins_x - 1)), max_nonzero);
+  if (vi > bins_x - 1) vi = bins_x - 1;
+  lut[v] = (uint16_t)vi;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) hist2d_kernel(const T* __restrict__ raw, uint32_t sx, uint32_t sy, uint32_t sz,
-                                                      double norm2, double max_grad, uint32_t bins_x, double max_nonzero,
+                                                      double norm2, double max_grad, unsigned long long smax, float inv_smax,
+                                                      const uint16_t* __restrict__ vlut,
                                                       unsigned long long* __restrict__ bins) {
-  const uint64_t n = (uint64_t)sx * sy * sz;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  const uint64_t rounds = (n + stride - 1) / stride;
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (uint64_t r = 0; r < rounds; ++r, i += stride) {
-    const bool act = i < n;
-    const unsigned am = __ballot_sync(0xffffffffu, act);
-    if (!act) continue;
-    const uint32_t x = (uint32_t)(i % sx), y = (uint32_t)((i / sx) % sy), z = (uint32_t)(i / ((uint64_t)sx * sy));
-    const double g = grad_mag(raw, x, y, z, sx, sy, sz, norm2);
-    // size_t(len/max*255.0f); NaN (constant volume) -> 0 here, undefined in the reference
-    const double q = __dmul_rn(__ddiv_rn(g, max_grad), 255.0);
-    uint32_t gi = (q >= 255.0) ? 255u : ((q > 0.0) ? (uint32_t)q : 0u);
-    const double v = (double)raw[i];
-    uint32_t vi = (max_nonzero <= (double)(bins_x - 1)) ? (uint32_t)raw[i]
-                                                         : (uint32_t)__ddiv_rn(__dmul_rn(v, (double)(bins_x - 1)), max_nonzero);
-    if (vi > bins_x - 1) vi = bins_x - 1;
-    const uint32_t bin = vi * 256u + gi;
-    const unsigned peers = __match_any_sync(am, bin);
-    if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&bins[bin], (unsigned long long)__popc(peers));
+  // a warp's votes for one bin go out as one atomic; a leader whose bin repeats from trip to trip (the empty
+  // background sends every warp to bin 0) keeps counting in a register and flushes when the bin changes
+  uint32_t pend_bin = 0xFFFFFFFFu, pend_cnt = 0;
+  const uint32_t rows = sy * sz, lane = threadIdx.x & 31u;
+  for (uint32_t row = blockIdx.x * 8u + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8u) {
+    const uint32_t y = row % sy, z = row / sy;
+    const RowCtx<T> rc = row_ctx(raw, y, z, sx, sy, sz);
+    const T* line = rc.line;
+    for (uint32_t x0 = 0; x0 < sx; x0 += 32u) {
+      const uint32_t x = x0 + lane;
+      const bool act = x < sx;
+      const unsigned am = __ballot_sync(0xffffffffu, act);
+      if (!act) continue;
+      const unsigned long long s = grad_s_row(rc, x, sx);
+      uint32_t gi = 0;
+      if (s != 0) {
+        const float q = 255.0f * sqrtf((float)s * inv_smax);
+        const float fl = floorf(q);
+        // S < Smax: the length is below the maximum by a relative 0.5/Smax >= 3.8e-11, so len/max*255 < 255 in fp64
+        // too and everything from 254.5 up lands in bin 254; only ties with the maximum need the exact chain there
+        if (s != smax && q >= 254.5f) gi = 254u;
+        else if (s != smax && q - fl > 1e-3f && fl + 1.0f - q > 1e-3f) gi = (uint32_t)fl;
+        else {
+          // size_t(len/max*255.0f); NaN (constant volume) -> 0 here, undefined in the reference
+          const double e = __dmul_rn(__ddiv_rn(grad_mag(raw, x, y, z, sx, sy, sz, norm2), max_grad), 255.0);
+          gi = (e >= 255.0) ? 255u : ((e > 0.0) ? (uint32_t)e : 0u);
+        }
+      }
+      const uint32_t bin = (uint32_t)vlut[line[x]] * 256u + gi;
+      const unsigned peers = __match_any_sync(am, bin);
+      if (lane == (unsigned)(__ffs(peers) - 1)) {
+        if (bin == pend_bin) pend_cnt += __popc(peers);
+        else {
+          if (pend_cnt) atomicAdd(&bins[pend_bin], (unsigned long long)pend_cnt);
+          pend_bin = bin; pend_cnt = __popc(peers);
+        }
+      }
+    }
   }
+  if (pend_cnt) atomicAdd(&bins[pend_bin], (unsigned long long)pend_cnt);
 }
 
 static void release(tvk_ctx* c) {
@@ -810,6 +899,12 @@ extern "C" int tvk_build_last_ms(tvk_ctx* c, float* kernels_ms) {
   return TVK_OK;
 }
 
+extern "C" int tvk_build_hist2d_last_ms(tvk_ctx* c, float* kernels_ms) {
+  if (!c || !c->build.valid || !kernels_ms) return TVK_ERR_INVALID;
+  *kernels_ms = c->build.hist2d_ms;
+  return TVK_OK;
+}
+
 extern "C" int tvk_build_store_device_ptr(tvk_ctx* c, void** dptr) {
   if (!c || !c->build.valid || !dptr) return TVK_ERR_INVALID;
   *dptr = c->build.d_store;
@@ -836,25 +931,36 @@ static int run_hist2d(tvk_ctx* c, uint32_t bins_x, double max_nonzero, uint64_t*
   const uint32_t* s = b.info.lod_size[0];
   const uint64_t n = (uint64_t)s[0] * s[1] * s[2];
   const double norm2 = (sizeof(T) == 1 ? 255.0 : 65535.0) * 2;
-  unsigned long long *d_bits = nullptr, *d_bins = nullptr;
-  TVK_CHECK_CUDA(c, cudaMalloc(&d_bits, sizeof(unsigned long long)));
+  const uint32_t range = 1u << (8 * sizeof(T));
+  const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)s[1] * s[2] + 7) / 8, (uint64_t)sms * 16);
+  GradBest* d_part = nullptr;
+  unsigned long long* d_bins = nullptr;
+  uint16_t* d_lut = nullptr;
+  TVK_CHECK_CUDA(c, cudaMalloc(&d_part, sizeof(GradBest) * blocks));
   TVK_CHECK_CUDA(c, cudaMalloc(&d_bins, sizeof(unsigned long long) * 256 * bins_x));
-  TVK_CHECK_CUDA(c, cudaMemsetAsync(d_bits, 0, sizeof(unsigned long long), c->stream));
+  TVK_CHECK_CUDA(c, cudaMalloc(&d_lut, sizeof(uint16_t) * range));
   TVK_CHECK_CUDA(c, cudaMemsetAsync(d_bins, 0, sizeof(unsigned long long) * 256 * bins_x, c->stream));
-  const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 16);
-  grad_max_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_bits);
-  c->launches++;
-  unsigned long long bits = 0;
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(&bits, d_bits, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->bev0, c->stream));
+  grad_max_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_part);
+  hist2d_value_lut_kernel<<<(range + 255) / 256, 256, 0, c->stream>>>(range, bins_x, max_nonzero, d_lut);
+  c->launches += 2;
+  std::vector<GradBest> part(blocks);
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(part.data(), d_part, sizeof(GradBest) * blocks, cudaMemcpyDeviceToHost, c->stream));
   TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  GradBest g = part[0];
+  for (unsigned i = 1; i < blocks; ++i) if (part[i].s > g.s || (part[i].s == g.s && part[i].len_bits > g.len_bits)) g = part[i];
   double mg;
-  memcpy(&mg, &bits, sizeof(mg));
-  hist2d_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, mg, bins_x, max_nonzero, d_bins);
+  memcpy(&mg, &g.len_bits, sizeof(mg));
+  const float inv_smax = g.s ? 1.0f / (float)g.s : 0.0f;
+  hist2d_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, mg, g.s, inv_smax, d_lut, d_bins);
   c->launches++;
   TVK_CHECK_CUDA(c, cudaGetLastError());
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->bev1, c->stream));
   TVK_CHECK_CUDA(c, cudaMemcpyAsync(bins, d_bins, sizeof(unsigned long long) * 256 * bins_x, cudaMemcpyDeviceToHost, c->stream));
   TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
-  cudaFree(d_bits); cudaFree(d_bins);
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->bev0, c->bev1) == cudaSuccess) b.hist2d_ms = ms;
+  cudaFree(d_part); cudaFree(d_bins); cudaFree(d_lut);
   *max_grad = (float)mg;
   return TVK_OK;
 }

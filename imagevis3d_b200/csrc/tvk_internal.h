@@ -40,6 +40,7 @@ struct BuildState {
   bool      own_lod0 = false;
   bool      valid = false;
   float     kernels_ms = 0.f;        // CUDA-event time of the builder kernels of the last tvk_build_octree
+  float     hist2d_ms = 0.f;         // ... and of the last tvk_build_hist2d
 };
 
 // sort-last exchange over peer memory (tvk_exchange.cu)

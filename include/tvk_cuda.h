@@ -244,6 +244,8 @@ int tvk_build_store_device_ptr(tvk_ctx* ctx, void** dptr);
 /* CUDA-event time (ms) of the builder kernels of the last tvk_build_octree (allocations and the
  * host->device copy of the raw volume excluded) */
 int tvk_build_last_ms(tvk_ctx* ctx, float* kernels_ms);
+/* the same for the last tvk_build_hist2d (max-gradient pass + binning pass) */
+int tvk_build_hist2d_last_ms(tvk_ctx* ctx, float* kernels_ms);
 /* 1-D histogram of LOD-0 inner voxels, 2^bits bins, *n = trimmed size
  * (Histogram1DDataBlock.cpp:60-160) */
 int tvk_build_hist1d(tvk_ctx* ctx, uint64_t* bins, uint32_t cap, uint32_t* n);
