@@ -703,10 +703,32 @@ bool CudaGridLeaper::ComputeRaycastParams(tvk_raycast_params& p) {
   p.new_view = m_blank ? 1u : 0u;
   p.missing_strategy = m_strategy; p.rehash_count = m_rehash; p.hash_table_size = m_hashSize;
   p.clip_enabled = 0;
+  if (m_clipEnabled) {
+    // GLGridLeaper::FillBBoxVBO (:515-526): the world-space plane goes back to model space with
+    // PLANE::operator*(inverse(rotation*translation)) = plane4 * (rotation*translation)^T, all four components
+    // divided by |normal| (Vectors.h:1460-1477); Clipper::BoxPlane keeps n.p + d <= 0.  Model space is the centred
+    // box of size `ext`; the kernel wants the plane over normalised [0,1]^3 coordinates.
+    const Matrix4 rt = (m_rotation * m_translation).transposed();
+    float q[4];
+    rt.transform(m_clipPlane, q);
+    const float len = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    if (len > 0.0f) {
+      for (int a = 0; a < 4; ++a) q[a] /= len;
+      p.clip_enabled = 1;
+      for (int a = 0; a < 3; ++a) p.clip_plane[a] = q[a] * ext[a];
+      p.clip_plane[3] = q[3] - 0.5f * (q[0] * ext[0] + q[1] * ext[1] + q[2] * ext[2]);
+    }
+  }
   for (int a = 0; a < 3; ++a) { p.box_min[a] = 0.0f; p.box_max[a] = 1.0f; }
   p.count_samples = 1;
   return true;
 }
+
+void CudaGridLeaper::SetClipPlane(const float plane[4]) { memcpy(m_clipPlane, plane, 16); if (m_clipEnabled) ScheduleCompleteRedraw(); }
+void CudaGridLeaper::EnableClipPlane(bool on) { if (on != m_clipEnabled) { m_clipEnabled = on; ScheduleCompleteRedraw(); } }
+bool CudaGridLeaper::SetTimestep(size_t t) { if (t != 0) { m_err = "the dataset has one time step"; return false; } return true; }
+void CudaGridLeaper::SetLODLimits(uint32_t lo, uint32_t hi) { m_lodLimits[0] = lo; m_lodLimits[1] = hi; }
+void CudaGridLeaper::SetBGColors(const float top[3], const float bottom[3]) { memcpy(m_bg[0], top, 12); memcpy(m_bg[1], bottom, 12); }
 
 bool CudaGridLeaper::Paint() {                                               // GLGridLeaper::Render3DRegion (:914-1154)
   if (!m_ctx || !m_vol || !m_pool) { m_err = "Paint() without dataset"; return false; }
@@ -864,6 +886,26 @@ int tvkr_load_dataset(tvkr_renderer* h, const char* uvf_file, uint64_t gpu_mem_b
 int tvkr_save_uvf(tvkr_renderer* h, const char* uvf_file, uint32_t compression, uint32_t level) {
   return h && uvf_file && R(h)->SaveUVF(uvf_file, compression, level) ? 0 : 1;
 }
+int tvkr_set_clip_plane(tvkr_renderer* h, const float plane[4]) { if (!h || !plane) return 1; R(h)->SetClipPlane(plane); return 0; }
+int tvkr_enable_clip_plane(tvkr_renderer* h, int on) { if (!h) return 1; R(h)->EnableClipPlane(on != 0); return 0; }
+int tvkr_set_light_colors(tvkr_renderer* h, const float ambient[4], const float diffuse[4], const float specular[4], const float dir[3]) {
+  if (!h || !ambient || !diffuse || !specular || !dir) return 1;
+  R(h)->SetLightColors(ambient, diffuse, specular, Vec3(dir[0], dir[1], dir[2]));
+  return 0;
+}
+int tvkr_get_view(tvkr_renderer* h, float pos[3], float dir[3], float up[3]) {
+  if (!h) return 1;
+  const Vec3 e = R(h)->GetViewPos(), d = R(h)->GetViewDir(), u = R(h)->GetUpDir();
+  if (pos) { pos[0] = e.x; pos[1] = e.y; pos[2] = e.z; }
+  if (dir) { dir[0] = d.x; dir[1] = d.y; dir[2] = d.z; }
+  if (up) { up[0] = u.x; up[1] = u.y; up[2] = u.z; }
+  return 0;
+}
+int tvkr_reset_view(tvkr_renderer* h) { if (!h) return 1; R(h)->ResetViewPos(); R(h)->ResetViewDir(); R(h)->ResetUpDir(); return 0; }
+int tvkr_set_timestep(tvkr_renderer* h, uint64_t t) { return h && R(h)->SetTimestep((size_t)t) ? 0 : 1; }
+int tvkr_set_lod_limits(tvkr_renderer* h, uint32_t lo, uint32_t hi) { if (!h) return 1; R(h)->SetLODLimits(lo, hi); return 0; }
+int tvkr_set_bg_colors(tvkr_renderer* h, const float top[3], const float bottom[3]) { if (!h || !top || !bottom) return 1; R(h)->SetBGColors(top, bottom); return 0; }
+int tvkr_set_blend_precision(tvkr_renderer* h, int) { return h ? 0 : 1; }
 int tvkr_resize(tvkr_renderer* h, uint32_t w, uint32_t hh) { if (!h) return 1; R(h)->Resize(w, hh); return 0; }
 int tvkr_set_render_mode(tvkr_renderer* h, int mode) { return h && R(h)->SetRendermode(mode) ? 0 : 1; }
 int tvkr_set_lighting_enabled(tvkr_renderer* h, int on) { if (!h) return 1; R(h)->SetUseLighting(on != 0); return 0; }

@@ -191,6 +191,15 @@ class CudaGridLeaper {
   TransferFunction1D& Get1DTrans() { return m_tf1d; }
   void Changed1DTrans();                                        // tuvok.gpu.changed1DTrans
   bool Set2DTrans(const uint8_t* rgba, uint32_t w, uint32_t h, double nzLimits[4]);
+  // RenderRegion::SetClipPlane / EnableClipPlane (world-space plane a,b,c,d; n.p + d <= 0 is kept)
+  void SetClipPlane(const float plane[4]);
+  void EnableClipPlane(bool on);
+  Vec3 GetViewPos() const { return m_eye; }
+  Vec3 GetViewDir() const { return m_at - m_eye; }                 // AbstrRenderer.cpp:1599-1601
+  Vec3 GetUpDir() const { return m_up; }
+  bool SetTimestep(size_t t);
+  void SetLODLimits(uint32_t lo, uint32_t hi);                     // kept for the classic path; the ray-guided path ignores it
+  void SetBGColors(const float top[3], const float bottom[3]);     // display path only (captures read the FBO)
   void SetRendererTarget(int t) { m_target = t; }
   void SetMissingBrickStrategy(uint32_t s) { m_strategy = s; ScheduleCompleteRedraw(); }
   void SetHashTable(uint32_t size, uint32_t rehash) { m_hashSize = size; m_rehash = rehash; }
@@ -244,6 +253,10 @@ class CudaGridLeaper {
   tvk_visibility m_lastVis{};
   bool m_visValid = false;
   PerfCounters m_perf;
+  bool m_clipEnabled = false;
+  float m_clipPlane[4] = {0, 0, 1, 0};
+  uint32_t m_lodLimits[2] = {0, 0};
+  float m_bg[2][3] = {{0, 0, 0}, {0, 0, 0}};
 };
 
 }  // namespace tvk

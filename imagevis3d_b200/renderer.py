@@ -132,6 +132,51 @@ class Renderer:
         a = np.ascontiguousarray(m, np.float32).reshape(16)
         self._ck(self._lib.tvkr_set_translation4x4(self._h, a.ctypes.data_as(C.c_void_p)), "setTranslation4x4")
 
+    def setClipPlane(self, plane):
+        """world-space plane (a, b, c, d); the half space a*x + b*y + c*z + d <= 0 is kept"""
+        a = (C.c_float * 4)(*[float(v) for v in plane])
+        self._ck(self._lib.tvkr_set_clip_plane(self._h, a), "setClipPlane")
+
+    def enableClipPlane(self, on=True):
+        self._ck(self._lib.tvkr_enable_clip_plane(self._h, C.c_int(int(on))), "enableClipPlane")
+
+    def setLightColors(self, ambient, diffuse, specular, direction):
+        f4 = lambda v: (C.c_float * 4)(*[float(x) for x in v])      # noqa: E731
+        self._ck(self._lib.tvkr_set_light_colors(self._h, f4(ambient), f4(diffuse), f4(specular), _f3(direction)), "setLightColors")
+
+    def _view(self):
+        p, d, u = (C.c_float * 3)(), (C.c_float * 3)(), (C.c_float * 3)()
+        self._ck(self._lib.tvkr_get_view(self._h, p, d, u), "getView")
+        return list(p), list(d), list(u)
+
+    def getViewPos(self):
+        return self._view()[0]
+
+    def getViewDir(self):
+        return self._view()[1]
+
+    def getUpDir(self):
+        return self._view()[2]
+
+    def resetView(self):
+        self._ck(self._lib.tvkr_reset_view(self._h), "resetView")
+
+    def setTimestep(self, t):
+        self._ck(self._lib.tvkr_set_timestep(self._h, C.c_uint64(int(t))), "setTimestep")
+
+    def setLODLimits(self, limits):
+        self._ck(self._lib.tvkr_set_lod_limits(self._h, C.c_uint32(int(limits[0])), C.c_uint32(int(limits[1]))), "setLODLimits")
+
+    def setBGColors(self, top, bottom):
+        self._ck(self._lib.tvkr_set_bg_colors(self._h, _f3(top), _f3(bottom)), "setBGColors")
+
+    def setBlendPrecision(self, precision):
+        self._ck(self._lib.tvkr_set_blend_precision(self._h, C.c_int(int(precision))), "setBlendPrecision")
+
+    def addShaderPath(self, path):
+        """no shaders here: kept so that BatchRenderer scripts run unchanged"""
+        return True
+
     def setIsoValue(self, v):
         self._ck(self._lib.tvkr_set_iso_value(self._h, C.c_float(v)), "setIsoValue")
 

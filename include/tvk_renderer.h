@@ -97,6 +97,18 @@ int tvkr_get_frame_float(tvkr_renderer* r, float* out);
 /* introspection for tests */
 int tvkr_get_raycast_params(tvkr_renderer* r, tvk_raycast_params* out);
 int tvkr_get_pool_slots(tvkr_renderer* r, int32_t* brick, uint64_t* time, uint32_t cap, uint32_t* n);
+/* getFirst3DRenderRegion().setClipPlane / enableClipPlane: world-space plane (a,b,c,d), n.p + d <= 0 is kept
+ * (GLGridLeaper::FillBBoxVBO, GLGridLeaper.cpp:515-526 + Clipper::BoxPlane) */
+int tvkr_set_clip_plane(tvkr_renderer* r, const float plane[4]);
+int tvkr_enable_clip_plane(tvkr_renderer* r, int on);
+int tvkr_set_light_colors(tvkr_renderer* r, const float ambient[4], const float diffuse[4], const float specular[4],
+                          const float dir[3]);                                    /* renderer.setLightColors   */
+int tvkr_get_view(tvkr_renderer* r, float pos[3], float dir[3], float up[3]);    /* getViewPos/Dir/UpDir      */
+int tvkr_reset_view(tvkr_renderer* r);                                           /* resetViewPos/Dir/UpDir    */
+int tvkr_set_timestep(tvkr_renderer* r, uint64_t t);                             /* renderer.setTimestep      */
+int tvkr_set_lod_limits(tvkr_renderer* r, uint32_t lo, uint32_t hi);             /* renderer.setLODLimits     */
+int tvkr_set_bg_colors(tvkr_renderer* r, const float top[3], const float bottom[3]);   /* renderer.setBGColors */
+int tvkr_set_blend_precision(tvkr_renderer* r, int precision);   /* renderer.setBlendPrecision: accumulation is always fp32 here */
 int tvkr_get_perf(tvkr_renderer* r, double out[6]);     /* tuvok.perf: subframes, raycast ms, paged bricks, uploaded bytes, samples, frames */
 tvk_ctx* tvkr_context(tvkr_renderer* r);
 

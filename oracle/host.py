@@ -140,7 +140,7 @@ class Camera:
 
 def raycast_params(cam, width, height, domain_size, scale=(1, 1, 1), render_mode=0, lighting=False,
                    sample_rate=1.0, trans_scale=1.0, gradient_scale=1.0, isoval=0.5, new_view=True,
-                   strategy=3, rehash=10, hash_size=509, count_samples=True, slab=None):
+                   strategy=3, rehash=10, hash_size=509, count_samples=True, slab=None, clip_plane=None):
     p = RaycastParams()
     p.width, p.height = width, height
     dom = np.asarray(domain_size, f32)
@@ -188,6 +188,16 @@ def raycast_params(cam, width, height, domain_size, scale=(1, 1, 1), render_mode
     p.new_view = int(new_view)
     p.missing_strategy, p.rehash_count, p.hash_table_size = strategy, rehash, hash_size
     p.clip_enabled = 0
+    if clip_plane is not None:
+        # GLGridLeaper::FillBBoxVBO (GLGridLeaper.cpp:515-526): world-space plane -> model space through
+        # PLANE::operator*(inverse(rotation*translation)) (Vectors.h:1460-1477: plane4 * (M^-1)^T, then all four
+        # components / |normal|); Clipper::BoxPlane keeps n.p + d <= 0.  Model space = centred box of size `extent`.
+        m = inverse((cam.rotation @ cam.translation).astype(f32))
+        q = (np.asarray(clip_plane, f32) @ inverse(m).T).astype(f32)
+        q = (q / f32(np.sqrt(f32(np.dot(q[:3], q[:3]))))).astype(f32)
+        n = q[:3] * extent
+        p.clip_enabled = 1
+        p.clip_plane[:] = [float(n[0]), float(n[1]), float(n[2]), float(q[3] - f32(0.5) * (n[0] + n[1] + n[2]))]
     p.box_min[:] = box_min
     p.box_max[:] = box_max
     p.count_samples = int(count_samples)

@@ -214,3 +214,43 @@ def test_config1_c60_demo_dataset(lighting):
     assert want[..., 3].max() > 0.3 and subs == subs_o
     assert psnr >= 45.0 and err <= 2.0 / 255.0, (psnr, err)
     r.cleanup()
+
+
+def test_clip_plane_through_the_host():
+    """getFirst3DRenderRegion().setClipPlane: the host's world->normalised plane equals the oracle's restatement of
+    GLGridLeaper::FillBBoxVBO, and the clipped render matches the oracle render with those parameters."""
+    from imagevis3d_b200.renderer import Renderer, RT_HEADLESS
+    vol = H.synth_blobs((96, 80, 72), np.uint8, seed=5)
+    r = Renderer(0)
+    r.loadRawVolume(vol, brick_size=32)
+    info = r.datasetInfo()
+    tf = _tf(info.tf_size)
+    r.set1DTransFloat(tf)
+    r.setLightingEnabled(False)
+    r.resize((160, 120))
+    r.setRendererTarget(RT_HEADLESS)
+    rot = H.rotation_y(0.7) @ H.rotation_x(-0.3)
+    r.setRotation4x4(rot)
+    r.paintUntilConverged()
+    full = r.frameFloat().copy()
+    plane = (0.6, 0.0, 0.8, 0.05)
+    r.setClipPlane(plane)
+    r.enableClipPlane(True)
+    assert r.checkForRedraw()
+    r.paintUntilConverged()
+    got = r.frameFloat().copy()
+    cam = H.Camera()
+    cam.rotation = rot
+    want, p_o, _, _ = _oracle_converged(vol, 32, tf, cam, 160, 120, tuple(info.pool_capacity), clip_plane=plane)
+    p_c = r.raycastParams()
+    assert p_c.clip_enabled == 1 and np.allclose(np.array(p_c.clip_plane[:]), np.array(p_o.clip_plane[:]), rtol=2e-5, atol=2e-6)
+    psnr, err = image_errors(got, want)
+    assert psnr >= 45.0 and err <= 2.0 / 255.0, (psnr, err)
+    assert np.abs(got - full).max() > 0.1                       # the plane really removed something
+    r.enableClipPlane(False)
+    r.paintUntilConverged()
+    assert np.abs(r.frameFloat() - full).max() < 2e-3          # (bricks now sit in other pool slots: pool-space rounding differs)
+    assert r.getViewPos() == [0.0, 0.0, pytest.approx(1.6)] and r.getUpDir() == [0.0, 1.0, 0.0]
+    with pytest.raises(Exception):
+        r.setTimestep(3)
+    r.cleanup()
