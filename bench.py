@@ -404,6 +404,12 @@ def run_gpu(args, rank, world):
         return
 
     peak, peak_src = peaks()
+    traffic = None
+    try:        # DRAM bytes per launch of this kernel from the committed ncu --set full capture (N=1 workload only)
+        if world == 1:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))[os.environ.get("TVK_SAMPLER", "q4")]["dram_bytes_per_launch"]
+    except Exception:       # noqa: BLE001
+        traffic = None
     ms_step = kernel_ms / args.steps
     if world > 1:
         # a step = render + exchange + blend + gather: the ray-march kernel alone is not the step
@@ -419,7 +425,7 @@ def run_gpu(args, rank, world):
             "samples_per_step": samples / args.steps, "rays_per_step": rays / args.steps,
             "wall_ms_per_step_incl_l2_flush": 1e3 * wall_s / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "0.6068 B/sample + 16 B/ray (SURVEY 8d); the kernel is L1/TEX-issue bound, see DESIGN.md"},
             "e2e": {"value": e2e_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
