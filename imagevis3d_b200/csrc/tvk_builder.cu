@@ -253,6 +253,97 @@ __global__ void __launch_bounds__(256) downsample_vec_kernel(const T* __restrict
   }
 }
 
+// The LOD 0 -> 1 reduction reads every raw voxel exactly once, 16 bytes at a time -- so it also counts the 1-D
+// histogram on the way (Histogram1DDataBlock::Compute is a histogram of exactly these voxels), which saves one full
+// read of the volume.  One CTA of 1024 threads per SM; the table lives in shared memory: 32 per-warp 256-bin tables
+// for 8-bit data, one 32768-bin window [0, 32768) for 16-bit data (values above it are counted afterwards by
+// hist16_window_kernel, which returns at once when the volume has none).
+#define HIST_WINDOW 32768u
+template <typename T>
+__device__ __forceinline__ void hist_add16(const uint4& q, unsigned int* __restrict__ table) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+  if (sizeof(T) == 1) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(&table[w[k] & 0xFFu], 1u); atomicAdd(&table[(w[k] >> 8) & 0xFFu], 1u);
+      atomicAdd(&table[(w[k] >> 16) & 0xFFu], 1u); atomicAdd(&table[w[k] >> 24], 1u);
+    }
+  } else {
+    uint32_t cur = w[0] & 0xFFFFu, cnt = 0;        // equal neighbours are merged into one atomic
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const uint32_t v = (w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
+      if (v == cur) cnt++;
+      else {
+        if (cur < HIST_WINDOW) atomicAdd(&table[cur], cnt);
+        cur = v; cnt = 1;
+      }
+    }
+    if (cur < HIST_WINDOW) atomicAdd(&table[cur], cnt);
+  }
+}
+
+template <typename T, bool MEDIAN>
+__global__ void __launch_bounds__(1024, 1) downsample_hist_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                                  uint32_t sx, uint32_t sy, uint32_t sz,
+                                                                  uint32_t dx, uint32_t dy, uint32_t dz,
+                                                                  unsigned long long* __restrict__ bins) {
+  extern __shared__ unsigned int hsm[];
+  constexpr uint32_t TABLE = sizeof(T) == 1 ? 32u * 256u : HIST_WINDOW;
+  for (uint32_t i = threadIdx.x; i < TABLE; i += blockDim.x) hsm[i] = 0u;
+  __syncthreads();
+  unsigned int* mine = sizeof(T) == 1 ? hsm + (threadIdx.x >> 5) * 256u : hsm;
+  constexpr int E = 16 / sizeof(T), V = E / 2;
+  const uint32_t ncx = sx / E;
+  const uint64_t n = (uint64_t)ncx * dy * dz;
+  const uint64_t rs = sx, ss = (uint64_t)sx * sy;
+  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t cx = (uint32_t)(idx % ncx);
+    const uint64_t row = idx / ncx;
+    const uint32_t y = (uint32_t)(row % dy), z = (uint32_t)(row / dy);
+    const uint32_t y0 = (sy > 1) ? 2 * y : y, z0 = (sz > 1) ? 2 * z : z;
+    const bool hy = (sy > 1) && (y0 + 1 < sy), hz = (sz > 1) && (z0 + 1 < sz);
+    const T* p = src + (uint64_t)cx * E + y0 * rs + z0 * ss;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+    uint4 b = a, c = a, d = a;
+    if (hz) b = __ldg(reinterpret_cast<const uint4*>(p + ss));
+    if (hy) c = __ldg(reinterpret_cast<const uint4*>(p + rs));
+    if (hy && hz) d = __ldg(reinterpret_cast<const uint4*>(p + rs + ss));
+    hist_add16<T>(a, mine);                      // only rows that exist: the stand-ins b = c = d = a are not counted
+    if (hz) hist_add16<T>(b, mine);
+    if (hy) hist_add16<T>(c, mine);
+    if (hy && hz) hist_add16<T>(d, mine);
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int m = 0; m < V; ++m) {
+      const T a0 = (T)vec_get<T>(a, 2 * m), a1 = (T)vec_get<T>(a, 2 * m + 1);
+      const T b0 = (T)vec_get<T>(b, 2 * m), b1 = (T)vec_get<T>(b, 2 * m + 1);
+      const T c0 = (T)vec_get<T>(c, 2 * m), c1 = (T)vec_get<T>(c, 2 * m + 1);
+      const T d0 = (T)vec_get<T>(d, 2 * m), d1 = (T)vec_get<T>(d, 2 * m + 1);
+      T r;
+      if (hy && hz) r = filter8<T, MEDIAN>(a0, b0, c0, d0, a1, b1, c1, d1);
+      else if (hz) r = filter4<T, MEDIAN>(a0, b0, a1, b1);
+      else if (hy) r = filter4<T, MEDIAN>(a0, c0, a1, c1);
+      else r = filter2<T, MEDIAN>(a0, a1);
+      vec_set<T>(o, m, (uint32_t)r);
+    }
+    *reinterpret_cast<uint2*>(dst + (uint64_t)cx * V + (uint64_t)y * dx + (uint64_t)z * dx * dy) = make_uint2(o.x, o.y);
+  }
+  __syncthreads();
+  if (sizeof(T) == 1) {
+    for (uint32_t b = threadIdx.x; b < 256u; b += blockDim.x) {
+      unsigned int s = 0;
+      for (uint32_t w = 0; w < 32u; ++w) s += hsm[w * 256u + b];
+      if (s) atomicAdd(&bins[b], (unsigned long long)s);
+    }
+  } else {
+    for (uint32_t b = threadIdx.x; b < HIST_WINDOW; b += blockDim.x) {
+      const unsigned int s = hsm[b];
+      if (s) atomicAdd(&bins[b], (unsigned long long)s);
+    }
+  }
+}
+
 // FillOverlap replay for one ghost voxel of brick (bx,by,bz) at LOD >= 1.
 // Returns true and the global voxel coordinate to gather, or false for "zero".
 __device__ __forceinline__ bool resolve_overlap(const BuildConst& bc, uint32_t lod, int bx, int by, int bz,
@@ -465,7 +556,6 @@ __global__ void minmax_to_double_kernel(const uint32_t* mn, const uint32_t* mx, 
 // never leave the SM.  Eight voxels per 16-byte load; equal neighbours are run-length merged and a
 // warp that sees one single value issues one atomic.  A window above the volume's maximum (known from
 // the brick min/max table, read on the device) returns at once.
-#define HIST_WINDOW 32768u
 __global__ void __launch_bounds__(1024, 1) hist16_window_kernel(const uint16_t* __restrict__ raw, uint64_t n, uint32_t lo,
                                                                  const uint32_t* __restrict__ gmax,
                                                                  unsigned long long* __restrict__ bins) {
@@ -743,6 +833,7 @@ static int run_build(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms) {
   TVK_CHECK_CUDA(c, cudaMalloc(&b.d_hist1d, sizeof(unsigned long long) * range));
   TVK_CHECK_CUDA(c, cudaEventRecord(c->bev0, st));
   // flat pyramid
+  bool hist_fused = false;
   for (uint32_t l = 1; l < info.lod_count; ++l) {
     const uint32_t* s = info.lod_size[l - 1];
     const uint32_t* d = info.lod_size[l];
@@ -751,7 +842,21 @@ static int run_build(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms) {
     const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 32);
     const T* src = (const T*)b.d_lod[l - 1];
     T* dst = (T*)b.d_lod[l];
-    if (vec) {
+    // LOD 0 -> 1 also counts the 1-D histogram (bins [0, 32768) for 16-bit data)
+    const bool fuse_hist = vec && l == 1 && ((uint64_t)s[0] * s[1] * s[2]) >= (1u << 18);
+    if (fuse_hist) {
+      const size_t smem = sizeof(unsigned int) * (sizeof(T) == 1 ? 32u * 256u : HIST_WINDOW);
+      static bool attr_set = false;
+      if (!attr_set) {
+        TVK_CHECK_CUDA(c, cudaFuncSetAttribute(downsample_hist_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TVK_CHECK_CUDA(c, cudaFuncSetAttribute(downsample_hist_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      TVK_CHECK_CUDA(c, cudaMemsetAsync(b.d_hist1d, 0, sizeof(unsigned long long) * range, st));
+      if (b.desc.use_median) downsample_hist_kernel<T, true><<<sms, 1024, smem, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2], b.d_hist1d);
+      else downsample_hist_kernel<T, false><<<sms, 1024, smem, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2], b.d_hist1d);
+      hist_fused = true;
+    } else if (vec) {
       if (b.desc.use_median) downsample_vec_kernel<T, true><<<blocks, 256, 0, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2]);
       else downsample_vec_kernel<T, false><<<blocks, 256, 0, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2]);
     } else {
@@ -795,20 +900,20 @@ static int run_build(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms) {
   TVK_CHECK_CUDA(c, cudaGetLastError());
   minmax_to_double_kernel<<<(unsigned)((info.total_bricks + 255) / 256), 256, 0, st>>>(d_mn, d_mx, b.d_minmax, info.total_bricks, d_gmax);
   c->launches++;
-  // 1-D histogram
-  TVK_CHECK_CUDA(c, cudaMemsetAsync(b.d_hist1d, 0, sizeof(unsigned long long) * range, st));
+  // 1-D histogram: whatever the fused LOD 0 -> 1 pass did not count
   const uint64_t n0 = (uint64_t)info.lod_size[0][0] * info.lod_size[0][1] * info.lod_size[0][2];
+  if (!hist_fused) TVK_CHECK_CUDA(c, cudaMemsetAsync(b.d_hist1d, 0, sizeof(unsigned long long) * range, st));
   if (sizeof(T) == 2 && n0 >= (1u << 18)) {
     static bool attr_set = false;
     if (!attr_set) {
       TVK_CHECK_CUDA(c, cudaFuncSetAttribute(hist16_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HIST_WINDOW * sizeof(uint32_t))));
       attr_set = true;
     }
-    for (uint32_t lo = 0; lo < range; lo += HIST_WINDOW) {
+    for (uint32_t lo = hist_fused ? HIST_WINDOW : 0u; lo < range; lo += HIST_WINDOW) {
       hist16_window_kernel<<<sms, 1024, HIST_WINDOW * sizeof(uint32_t), st>>>((const uint16_t*)b.d_lod[0], n0, lo, d_gmax, b.d_hist1d);
       c->launches++;
     }
-  } else {
+  } else if (!hist_fused) {
     hist1d_kernel<T><<<(unsigned)std::min<uint64_t>((n0 + 255) / 256, (uint64_t)sms * 8), 256, 0, st>>>((const T*)b.d_lod[0], n0, b.d_hist1d);
     c->launches++;
   }
