@@ -60,6 +60,19 @@ class BuildInfo(C.Structure):
                 ("total_bricks", C.c_uint64), ("total_bytes", C.c_uint64)]
 
 
+class ClassicBrick(C.Structure):
+    _fields_ = [("center", C.c_float * 3), ("extension", C.c_float * 3), ("eye_to_tex", C.c_float * 16),
+                ("ray_step", C.c_float), ("voxels", C.c_uint32 * 3), ("store_offset", C.c_uint64)]
+
+
+class ClassicParams(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("inv_model_view", C.c_float * 16),
+                ("normal_matrix", C.c_float * 9), ("inv_projection", C.c_float * 16), ("step_scale", C.c_float),
+                ("trans_scale", C.c_float), ("lighting", C.c_uint32), ("light_ambient", C.c_float * 3),
+                ("light_diffuse", C.c_float * 3), ("light_specular", C.c_float * 3), ("light_dir", C.c_float * 3),
+                ("domain_scale", C.c_float * 3), ("bytes_per_voxel", C.c_uint32)]
+
+
 class QuantizeResult(C.Structure):
     _fields_ = [("out_bits", C.c_uint32), ("generated", C.c_uint32), ("hist_size", C.c_uint32), ("bin_count", C.c_uint32),
                 ("device_ms", C.c_float)]
@@ -80,7 +93,7 @@ EXPORTS = [
     "tvk_get_stats", "tvk_probe_lod", "tvk_probe_brick_index",
     "tvk_build_plan", "tvk_build_octree", "tvk_build_get_toc", "tvk_build_get_minmax", "tvk_build_get_bricks",
     "tvk_build_store_device_ptr", "tvk_build_hist1d", "tvk_build_hist2d", "tvk_build_release", "tvk_build_last_ms", "tvk_build_hist2d_last_ms", "tvk_quantize",
-    "tvk_composite_ordered",
+    "tvk_composite_ordered", "tvk_raycast_classic",
     "tvk_exchange_create", "tvk_exchange_open_peers", "tvk_exchange_set_peers", "tvk_exchange_local_base",
     "tvk_exchange_begin_frame", "tvk_exchange_composite", "tvk_exchange_final", "tvk_exchange_status", "tvk_exchange_destroy",
 ]

@@ -730,7 +730,184 @@ bool CudaGridLeaper::SetTimestep(size_t t) { if (t != 0) { m_err = "the dataset 
 void CudaGridLeaper::SetLODLimits(uint32_t lo, uint32_t hi) { m_lodLimits[0] = lo; m_lodLimits[1] = hi; }
 void CudaGridLeaper::SetBGColors(const float top[3], const float bottom[3]) { memcpy(m_bg[0], top, 12); memcpy(m_bg[1], bottom, 12); }
 
+// ---------------------------------------------------------------------------------------------------------
+// Classic per-brick ray-caster (EVolumeRendererType OPENGL_RAYCASTER): AbstrRenderer::PlanFrame /
+// ComputeMinLODForCurrentView / BuildSubFrameBrickList / RegionNeedsBrick / ContainsData / brick_distance
+// (AbstrRenderer.cpp:1125-1212,789-803,999-1100,874-920,953-997,808-841), CullingLOD::Update / IsVisible /
+// GetLODLevel (CullingLOD.cpp:89-160), the brick metadata of UVFDataset::ComputeMetadataTOC / GetTextCoords
+// (uvfDataset.cpp:242-288,1747-1774) and the per-brick uniforms of GLRaycaster::SetBrickDepShaderVars /
+// ComputeEyeToTextureMatrix (GLRaycaster.cpp:239-300,589-612).  The final sub-frame of a view (LOD =
+// m_iMinLODForCurrentView, or 0 for RT_CAPTURE) is rendered in one launch of tvk_raycast_classic.
+bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_classic_brick>& bricks, uint32_t& lodOut) {
+  if (!m_vol || !m_w || !m_h) { m_err = "no dataset / render target"; return false; }
+  if (m_mode != RM_1DTRANS) { m_err = "the classic ray-caster is built for 1D transfer functions"; return false; }
+  const BrickedVolume& v = *m_vol;
+  memset(&p, 0, sizeof(p));
+  bricks.clear();
+  const float aspect = float(m_w) / float(m_h);
+  const Matrix4 view = Matrix4::LookAt(m_eye, m_at, m_up);
+  const Matrix4 proj = Matrix4::Perspective(m_fov, aspect, m_znear, m_zfar);
+  const Matrix4 mv = m_rotation * m_translation * view;
+  const Matrix4 invMv = mv.inverse();
+  float dom0[3], ext[3], mx = 0;
+  for (int a = 0; a < 3; ++a) { dom0[a] = float(v.domain[a]); ext[a] = dom0[a] * v.scale[a]; mx = std::max(mx, ext[a]); }
+  for (int a = 0; a < 3; ++a) ext[a] /= mx;
+  // ComputeMinLODForCurrentView
+  float wse = 0;
+  for (int a = 0; a < 3; ++a) wse = std::max(wse, ext[a] / dom0[a]);
+  const float c4[4] = {0, 0, 0, 1};
+  float o4[4];
+  mv.transform(c4, o4);
+  const float fz = std::max(m_znear, -o4[2]);
+  const float lodFactor = 2.0f * (float)tan(m_fov * ((3.1416f / 180.0f) / 2.0f)) * 1.0f / float(m_h);
+  const int level = (int)floor(log(lodFactor * fz / wse) / log(2.0f));
+  const int lodCount = (int)v.info.lod_count;
+  const int minLod = std::min(std::max(level, (int)m_lodLimits[1]), lodCount - 1);
+  const uint32_t lod = (m_target == RT_CAPTURE) ? 0u : (uint32_t)minLod;
+  lodOut = lod;
+  // CullingLOD::Update: planes from modelView * projection
+  const Matrix4 mvp = mv * proj;
+  float planes[6][4];
+  const int cols[6] = {0, 0, 1, 1, 2, 2};
+  const float sgn[6] = {-1, 1, -1, 1, 1, -1};
+  for (int k = 0; k < 6; ++k)
+    for (int r = 0; r < 4; ++r) planes[k][r] = sgn[k] * mvp.m[4 * r + cols[k]] + mvp.m[4 * r + 3];
+  // per-LOD aspect (ExtendedOctree::ComputeMetadata, ExtendedOctree.cpp:188-243)
+  double asp[3] = {1, 1, 1};
+  {
+    uint64_t s[3] = {v.domain[0], v.domain[1], v.domain[2]};
+    for (uint32_t l = 1; l <= lod; ++l) {
+      for (int a = 0; a < 3; ++a)
+        if (s[a] > 1) {
+          const uint64_t n = (s[a] + 1) / 2;
+          asp[a] *= (s[a] % 2) ? (double)((float)s[a] / (float)n) : 2.0;
+          s[a] = n;
+        }
+      const double m = std::max(asp[0], std::max(asp[1], asp[2]));
+      for (int a = 0; a < 3; ++a) asp[a] /= m;
+    }
+  }
+  const uint32_t* nb = v.info.lod_bricks[lod];
+  float dl[3], nds[3], maxval = 0;
+  for (int a = 0; a < 3; ++a) { dl[a] = float(v.info.lod_size[lod][a]); nds[a] = dl[a] * float(asp[a]); maxval = std::max(maxval, nds[a]); }
+  for (int a = 0; a < 3; ++a) nds[a] /= maxval;
+  float vscale[3], corr = 0, dmax = std::max(dom0[0], std::max(dom0[1], dom0[2]));
+  for (int a = 0; a < 3; ++a) corr = std::max(corr, v.scale[a] * dom0[a] / dmax);
+  for (int a = 0; a < 3; ++a) vscale[a] = v.scale[a] / corr;
+  const uint32_t core = v.brick_size - 2 * v.overlap;
+  std::vector<float> extAxis[3], corner[3];
+  for (int a = 0; a < 3; ++a) {
+    float acc = 0;
+    for (uint32_t c = 0; c < nb[a]; ++c) {
+      const bool last = c >= nb[a] - 1;
+      const uint32_t rem = v.info.lod_size[lod][a] % core;
+      const uint32_t size = (last && rem) ? 2 * v.overlap + rem : v.brick_size;
+      const float e = float(size - 2 * v.overlap) * float(asp[a]) / maxval;
+      extAxis[a].push_back(e);
+      corner[a].push_back(acc);
+      acc += e;
+    }
+  }
+  // ContainsData (1D): the TF's non-zero index range scaled to data values
+  double lo, hi;
+  v.Range(lo, hi);
+  const double maxValue = (lo > hi) ? double(m_tf1d.GetSize()) : hi;
+  const double resc = maxValue / double(m_tf1d.GetSize() - 1);
+  const double smin = double(m_tf1d.NonZeroMin()) * resc, smax = double(m_tf1d.NonZeroMax()) * resc;
+  struct Item { float dist; uint64_t idx; tvk_classic_brick b; };
+  std::vector<Item> items;
+  for (uint32_t x = 0; x < nb[0]; ++x)
+    for (uint32_t y = 0; y < nb[1]; ++y)
+      for (uint32_t z = 0; z < nb[2]; ++z) {
+        const uint64_t idx = v.info.lod_offset[lod] + x + (uint64_t)y * nb[0] + (uint64_t)z * nb[0] * nb[1];
+        const uint32_t bc[3] = {x, y, z};
+        float be[3], bcn[3];
+        for (int a = 0; a < 3; ++a) {
+          const float e = extAxis[a][bc[a]];
+          const float cen = (corner[a][bc[a]] + e / 2.0f) - nds[a] * 0.5f;
+          be[a] = e * vscale[a]; bcn[a] = cen * vscale[a];
+        }
+        bool vis = true;
+        for (int k = 0; k < 6 && vis; ++k) {
+          const float* pl = planes[k];
+          if (pl[0] * bcn[0] + pl[1] * bcn[1] + pl[2] * bcn[2] + pl[3] <=
+              -(0.5f * be[0] * fabsf(pl[0]) + 0.5f * be[1] * fabsf(pl[1]) + 0.5f * be[2] * fabsf(pl[2]))) vis = false;
+        }
+        if (!vis) continue;
+        if (!(smax >= v.minmax[2 * idx] && smin <= v.minmax[2 * idx + 1])) continue;     // bIsEmpty: never drawn
+        Item it;
+        memset(&it.b, 0, sizeof(it.b));
+        float tmin[3], tmax[3], rs = FLT_MAX;
+        for (int a = 0; a < 3; ++a) {
+          const float n = float(v.sizes[3 * idx + a]);
+          tmin[a] = float(v.overlap) / n;
+          tmax[a] = (1.0f - tmin[a]) * float(asp[a]);
+          rs = std::min(rs, be[a] * (1.0f / n) * 0.5f * 1.0f / m_sampleRate);
+          it.b.center[a] = bcn[a]; it.b.extension[a] = be[a]; it.b.voxels[a] = v.sizes[3 * idx + a];
+        }
+        it.b.ray_step = rs;
+        it.b.store_offset = v.offsets[idx];
+        float dist = FLT_MAX;
+        for (int sx = -1; sx <= 1; sx += 2) for (int sy = -1; sy <= 1; sy += 2) for (int sz = -1; sz <= 1; sz += 2) {
+          const float pt[4] = {bcn[0] + float(sx) * be[0] * 0.4999f, bcn[1] + float(sy) * be[1] * 0.4999f, bcn[2] + float(sz) * be[2] * 0.4999f, 1.0f};
+          float e4[4];
+          mv.transform(pt, e4);
+          dist = std::min(dist, sqrtf(e4[0] * e4[0] + e4[1] * e4[1] + e4[2] * e4[2]));
+        }
+        it.dist = dist; it.idx = idx;
+        // ComputeEyeToTextureMatrix(p1 = max point, t1 = max coords, p2 = min point, t2 = min coords)
+        float p1[3], p2[3];
+        for (int a = 0; a < 3; ++a) { p1[a] = bcn[a] + be[a] / 2.0f; p2[a] = bcn[a] - be[a] / 2.0f; }
+        const Matrix4 tm = invMv * Matrix4::Translation(-p1[0], -p1[1], -p1[2]) *
+                           Matrix4::Scaling((tmin[0] - tmax[0]) / (p2[0] - p1[0]), (tmin[1] - tmax[1]) / (p2[1] - p1[1]), (tmin[2] - tmax[2]) / (p2[2] - p1[2])) *
+                           Matrix4::Translation(tmax[0], tmax[1], tmax[2]);
+        memcpy(it.b.eye_to_tex, tm.m, 64);
+        items.push_back(it);
+      }
+  std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.dist < b.dist || (a.dist == b.dist && a.idx < b.idx); });
+  for (const Item& it : items) bricks.push_back(it.b);
+  p.width = m_w; p.height = m_h;
+  memcpy(p.inv_model_view, invMv.m, 64);
+  const Matrix4 nmT = invMv.transposed();
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) p.normal_matrix[3 * r + c] = nmT.m[4 * r + c];
+  memcpy(p.inv_projection, proj.inverse().m, 64);
+  float ratio = 0;
+  for (int a = 0; a < 3; ++a) ratio = std::max(ratio, dom0[a] / dl[a]);
+  p.step_scale = 1.0f / m_sampleRate * ratio;
+  const uint32_t iMax = (1u << (8 * v.bpv)) - 1;
+  p.trans_scale = float(iMax / maxValue);
+  p.lighting = m_lighting ? 1u : 0u;
+  for (int a = 0; a < 3; ++a) {
+    p.light_ambient[a] = m_ambient[a] * m_ambient[3];
+    p.light_diffuse[a] = m_diffuse[a] * m_diffuse[3];
+    p.light_specular[a] = m_specular[a] * m_specular[3];
+    p.domain_scale[a] = 1.0f / v.scale[a];
+  }
+  p.light_dir[0] = m_lightDir.x; p.light_dir[1] = m_lightDir.y; p.light_dir[2] = m_lightDir.z;
+  p.bytes_per_voxel = v.bpv;
+  return true;
+}
+
+bool CudaGridLeaper::PaintClassic() {
+  if (!m_ctx || !m_vol) { m_err = "Paint() without dataset"; return false; }
+  if (!m_vol->device_store) { m_err = "the classic ray-caster needs the brick store in device memory (load in core)"; return false; }
+  tvk_classic_params p;
+  std::vector<tvk_classic_brick> bricks;
+  uint32_t lod = 0;
+  if (!PlanClassicFrame(p, bricks, lod)) return false;
+  if (m_blank) m_perf.frames += 1;
+  const int rc = tvk_raycast_classic(m_ctx, &p, bricks.data(), (uint32_t)bricks.size(), m_vol->device_store);
+  if (rc) return Fail("tvk_raycast_classic", rc);
+  m_blank = false;
+  m_perf.subframes += 1;
+  tvk_stats st;
+  if (tvk_get_stats(m_ctx, &st, 0) == TVK_OK) { m_perf.raycast_ms += st.last_raycast_ms; m_perf.samples = (double)st.samples; }
+  m_converged = true;
+  return true;
+}
+
 bool CudaGridLeaper::Paint() {                                               // GLGridLeaper::Render3DRegion (:914-1154)
+  if (m_classic) return PaintClassic();
   if (!m_ctx || !m_vol || !m_pool) { m_err = "Paint() without dataset"; return false; }
   if (!m_w || !m_h) { m_err = "Paint() on a zero-sized target"; return false; }
   if (!m_visValid) RecomputeBrickVisibility(true);
@@ -885,6 +1062,15 @@ int tvkr_load_dataset(tvkr_renderer* h, const char* uvf_file, uint64_t gpu_mem_b
 }
 int tvkr_save_uvf(tvkr_renderer* h, const char* uvf_file, uint32_t compression, uint32_t level) {
   return h && uvf_file && R(h)->SaveUVF(uvf_file, compression, level) ? 0 : 1;
+}
+int tvkr_set_renderer_type(tvkr_renderer* h, int type) { if (!h || type < 0 || type > 1) return 1; R(h)->SetClassic(type == 1); return 0; }
+int tvkr_plan_classic_frame(tvkr_renderer* h, tvk_classic_params* p, tvk_classic_brick* bricks, uint32_t cap, uint32_t* n, uint32_t* lod) {
+  if (!h || !p || !n || !lod) return 1;
+  std::vector<tvk_classic_brick> b;
+  if (!R(h)->PlanClassicFrame(*p, b, *lod)) return 1;
+  *n = (uint32_t)b.size();
+  if (bricks) { if (b.size() > cap) return 1; memcpy(bricks, b.data(), sizeof(tvk_classic_brick) * b.size()); }
+  return 0;
 }
 int tvkr_set_clip_plane(tvkr_renderer* h, const float plane[4]) { if (!h || !plane) return 1; R(h)->SetClipPlane(plane); return 0; }
 int tvkr_enable_clip_plane(tvkr_renderer* h, int on) { if (!h) return 1; R(h)->EnableClipPlane(on != 0); return 0; }

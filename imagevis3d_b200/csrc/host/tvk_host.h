@@ -206,8 +206,13 @@ class CudaGridLeaper {
   void SetSampler(uint32_t s) { m_sampler = s; }
   void ScheduleCompleteRedraw() { m_blank = true; m_converged = false; }
 
+  // --- renderer type: false = ray-guided GLGridLeaper path (default), true = classic per-brick GLRaycaster path
+  void SetClassic(bool on) { m_classic = on; ScheduleCompleteRedraw(); }
+  bool PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_classic_brick>& bricks, uint32_t& lod);
+  bool PaintClassic();
+
   // --- frame loop
-  bool Paint();                      // one sub-frame (GLGridLeaper::Render3DRegion)
+  bool Paint();                      // one sub-frame (GLGridLeaper::Render3DRegion, or the classic path's final sub-frame)
   bool CheckForRedraw() const;       // GLGridLeaper.cpp:872-890
   bool Converged() const { return m_converged; }        // PH_Converged
   bool PaintUntilConverged(uint32_t maxSubframes, uint32_t& subframes);
@@ -253,6 +258,7 @@ class CudaGridLeaper {
   tvk_visibility m_lastVis{};
   bool m_visValid = false;
   PerfCounters m_perf;
+  bool m_classic = false;
   bool m_clipEnabled = false;
   float m_clipPlane[4] = {0, 0, 1, 0};
   uint32_t m_lodLimits[2] = {0, 0};

@@ -1,0 +1,176 @@
+// Classic per-brick ray-caster (see tvk_raycast_classic in include/tvk_cuda.h for the
+// reference functions and shaders it replaces).  One thread per pixel walks the host-sorted brick list of one
+// level of detail front to back: analytic ray / brick-box intersection instead of the two rasterised passes
+// per brick, the fragment shader's march inside the brick, and the frame buffer's "under" blend in registers --
+// one launch per frame instead of 2 draws + glFinish per brick.  Floating-point contract as in tvk_raycast.cu
+// (-fmad=false, explicit fmaf where the oracle has it).
+#include "tvk_internal.h"
+#include <cuda_fp16.h>
+
+struct ClassicArgs {
+  tvk_classic_params p;
+  const tvk_classic_brick* bricks;
+  uint32_t nbricks;
+  const uint8_t* store;
+  const float4* tf_f;
+  uint32_t tf_w;
+  float4* image;
+  unsigned long long* stats;
+};
+
+__device__ __forceinline__ float c_dot3(float ax, float ay, float az, float bx, float by, float bz) { return fmaf(az, bz, fmaf(ay, by, ax * bx)); }
+__device__ __forceinline__ float c_clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+// v' = (v, w) * M, FLOATMATRIX4 memory order
+__device__ __forceinline__ float4 c_xform(const float* m, float x, float y, float z, float w) {
+  float4 o;
+  o.x = fmaf(w, m[12], fmaf(z, m[8], fmaf(y, m[4], x * m[0])));
+  o.y = fmaf(w, m[13], fmaf(z, m[9], fmaf(y, m[5], x * m[1])));
+  o.z = fmaf(w, m[14], fmaf(z, m[10], fmaf(y, m[6], x * m[2])));
+  o.w = fmaf(w, m[15], fmaf(z, m[11], fmaf(y, m[7], x * m[3])));
+  return o;
+}
+
+// texture3D(texVolume, t).x on the brick's own texture: GL_LINEAR, CLAMP_TO_EDGE, UNORM8/16
+template <int BPV>
+__device__ __forceinline__ float brick_sample(const uint8_t* __restrict__ data, const uint32_t vox[3], float tx, float ty, float tz) {
+  const float u = fmaf(tx, (float)vox[0], -0.5f), v = fmaf(ty, (float)vox[1], -0.5f), w = fmaf(tz, (float)vox[2], -0.5f);
+  const float fu = floorf(u), fv = floorf(v), fw = floorf(w);
+  const float a = u - fu, b = v - fv, g = w - fw;
+  const int mx = (int)vox[0] - 1, my = (int)vox[1] - 1, mz = (int)vox[2] - 1;
+  // (int) of a float beyond the int range is clamped by the conversion; NaN -> 0
+  const int x0 = min(max((int)fu, 0), mx), x1 = min(max((int)fu + 1, 0), mx);
+  const int y0 = min(max((int)fv, 0), my), y1 = min(max((int)fv + 1, 0), my);
+  const int z0 = min(max((int)fw, 0), mz), z1 = min(max((int)fw + 1, 0), mz);
+  const size_t sx = vox[0], sxy = (size_t)vox[0] * vox[1];
+#define TVK_VOX(X, Y, Z) (BPV == 1 ? (float)data[(X) + (Y) * sx + (Z) * sxy] : (float)reinterpret_cast<const uint16_t*>(data)[(X) + (Y) * sx + (Z) * sxy])
+  const float v000 = TVK_VOX(x0, y0, z0), v100 = TVK_VOX(x1, y0, z0), v010 = TVK_VOX(x0, y1, z0), v110 = TVK_VOX(x1, y1, z0);
+  const float v001 = TVK_VOX(x0, y0, z1), v101 = TVK_VOX(x1, y0, z1), v011 = TVK_VOX(x0, y1, z1), v111 = TVK_VOX(x1, y1, z1);
+#undef TVK_VOX
+  const float c00 = fmaf(a, v100 - v000, v000), c10 = fmaf(a, v110 - v010, v010);
+  const float c01 = fmaf(a, v101 - v001, v001), c11 = fmaf(a, v111 - v011, v011);
+  const float c0 = fmaf(b, c10 - c00, c00), c1 = fmaf(b, c11 - c01, c01);
+  return fmaf(g, c1 - c0, c0) * (BPV == 1 ? 1.0f / 255.0f : 1.0f / 65535.0f);
+}
+
+template <int BPV, bool LIT>
+__global__ void __launch_bounds__(128) classic_kernel(const __grid_constant__ ClassicArgs a) {
+  // 8x4 pixel tiles per warp, as in K1, so that neighbouring rays share cache lines
+  const uint32_t lane = threadIdx.x & 31u, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t tiles_x = (a.p.width + 7) / 8;
+  const uint32_t px = (warp % tiles_x) * 8u + (lane & 7u), py = (warp / tiles_x) * 4u + (lane >> 3);
+  if (px >= a.p.width || py >= a.p.height) return;
+  const tvk_classic_params& p = a.p;
+  const float nx = fmaf(((float)px + 0.5f) / (float)p.width, 2.0f, -1.0f), ny = fmaf(((float)py + 0.5f) / (float)p.height, 2.0f, -1.0f);
+  const float4 n4 = c_xform(p.inv_projection, nx, ny, -1.0f, 1.0f);
+  const float ex = n4.x / n4.w, ey = n4.y / n4.w, ez = n4.z / n4.w;          // near-plane point in eye space
+  const float4 O = c_xform(p.inv_model_view, 0.f, 0.f, 0.f, 1.0f);
+  const float4 D = c_xform(p.inv_model_view, ex, ey, ez, 0.0f);
+  const float o[3] = {O.x, O.y, O.z}, d[3] = {D.x, D.y, D.z};
+  float4 dst = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned long long nsamples = 0;
+  for (uint32_t bi = 0; bi < a.nbricks; ++bi) {
+    const tvk_classic_brick& b = a.bricks[bi];
+    float s0 = -INFINITY, s1 = INFINITY;
+    bool miss = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float lo = b.center[k] - b.extension[k] / 2.0f, hi = b.center[k] + b.extension[k] / 2.0f;
+      if (d[k] == 0.0f) { if (o[k] < lo || o[k] > hi) miss = true; continue; }
+      const float inv = 1.0f / d[k];
+      float ta = (lo - o[k]) * inv, tb = (hi - o[k]) * inv;
+      if (ta > tb) { const float t = ta; ta = tb; tb = t; }
+      s0 = fmaxf(s0, ta); s1 = fminf(s1, tb);
+    }
+    const float se = fmaxf(s0, 1.0f);                       // front face, or the near plane if that lies behind it
+    if (miss || !(s1 > se)) continue;
+    // ray entry through the RGBA16F buffer, ray exit from the interpolated varying
+    const float enx = __half2float(__float2half_rn(ex * se)), eny = __half2float(__float2half_rn(ey * se)), enz = __half2float(__float2half_rn(ez * se));
+    const float xx = ex * s1, xy = ey * s1, xz = ez * s1;
+    const float4 te = c_xform(b.eye_to_tex, enx, eny, enz, 1.0f), tx = c_xform(b.eye_to_tex, xx, xy, xz, 1.0f);
+    float dx = xx - enx, dy = xy - eny, dz = xz - enz;
+    const float len = sqrtf(c_dot3(dx, dy, dz, dx, dy, dz));
+    const int steps = (int)(len / b.ray_step) + 1;
+    const float q = len / b.ray_step;
+    const float itx = (tx.x - te.x) / q, ity = (tx.y - te.y) / q, itz = (tx.z - te.z) / q;
+    dx /= len; dy /= len; dz /= len;
+    const float ix = dx * b.ray_step, iy = dy * b.ray_step, iz = dz * b.ray_step;
+    const uint8_t* data = a.store + b.store_offset;
+    float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ptx = te.x, pty = te.y, ptz = te.z, pex = enx, pey = eny, pez = enz;
+    for (int i = 0; i < steps; ++i) {
+      const float v = brick_sample<BPV>(data, b.voxels, ptx, pty, ptz);
+      const int ti = min(max(__float2int_rz(v * p.trans_scale * (float)a.tf_w), 0), (int)a.tf_w - 1);
+      float4 c = __ldg(a.tf_f + ti);
+      nsamples++;
+      if (LIT) {
+        const float hx = 1.0f / (float)b.voxels[0], hy = 1.0f / (float)b.voxels[1], hz = 1.0f / (float)b.voxels[2];
+        // ComputeGradient, Volume3D.glsl (y sign flipped there)
+        const float gxp = brick_sample<BPV>(data, b.voxels, ptx + hx, pty, ptz), gxm = brick_sample<BPV>(data, b.voxels, ptx - hx, pty, ptz);
+        const float gyp = brick_sample<BPV>(data, b.voxels, ptx, pty - hy, ptz), gym = brick_sample<BPV>(data, b.voxels, ptx, pty + hy, ptz);
+        const float gzp = brick_sample<BPV>(data, b.voxels, ptx, pty, ptz + hz), gzm = brick_sample<BPV>(data, b.voxels, ptx, pty, ptz - hz);
+        const float gx = (gxm - gxp) / 2.0f * p.domain_scale[0], gy = (gyp - gym) / 2.0f * p.domain_scale[1], gz = (gzm - gzp) / 2.0f * p.domain_scale[2];
+        // gl_NormalMatrix * g
+        float Nx = fmaf(gz, p.normal_matrix[6], fmaf(gy, p.normal_matrix[3], gx * p.normal_matrix[0]));
+        float Ny = fmaf(gz, p.normal_matrix[7], fmaf(gy, p.normal_matrix[4], gx * p.normal_matrix[1]));
+        float Nz = fmaf(gz, p.normal_matrix[8], fmaf(gy, p.normal_matrix[5], gx * p.normal_matrix[2]));
+        const float nl = sqrtf(c_dot3(Nx, Ny, Nz, Nx, Ny, Nz));
+        if (nl > 0.0f) { Nx /= nl; Ny /= nl; Nz /= nl; }
+        // Lighting(vec3(0), position, ...), lighting.glsl
+        float vx = 0.0f - pex, vy = 0.0f - pey, vz = 0.0f - pez;
+        float l = sqrtf(c_dot3(vx, vy, vz, vx, vy, vz));
+        vx /= l; vy /= l; vz /= l;
+        const float d2 = 2.0f * c_dot3(Nx, Ny, Nz, vx, vy, vz);
+        float rx = fmaf(-d2, Nx, vx), ry = fmaf(-d2, Ny, vy), rz = fmaf(-d2, Nz, vz);
+        l = sqrtf(c_dot3(rx, ry, rz, rx, ry, rz));
+        rx /= l; ry /= l; rz /= l;
+        const float ndl = fmaxf(fabsf(c_dot3(Nx, Ny, Nz, p.light_dir[0], p.light_dir[1], p.light_dir[2])), 0.0f);
+        float sp = fmaxf(c_dot3(rx, ry, rz, p.light_dir[0], p.light_dir[1], p.light_dir[2]), 0.0f);
+        sp *= sp; sp *= sp; sp *= sp;
+        c.x = c_clamp01(fmaf(p.light_specular[0], sp, fmaf(p.light_diffuse[0] * c.x, ndl, p.light_ambient[0])));
+        c.y = c_clamp01(fmaf(p.light_specular[1], sp, fmaf(p.light_diffuse[1] * c.y, ndl, p.light_ambient[1])));
+        c.z = c_clamp01(fmaf(p.light_specular[2], sp, fmaf(p.light_diffuse[2] * c.z, ndl, p.light_ambient[2])));
+      }
+      c.w = (p.step_scale == 1.0f) ? 1.0f - (1.0f - c.w) : 1.0f - powf(1.0f - c.w, p.step_scale);
+      const float wgt = (1.0f - col.w) * c.w;             // UnderCompositing, Compositing.glsl:33-38
+      col.x = fmaf(c.x, wgt, col.x); col.y = fmaf(c.y, wgt, col.y); col.z = fmaf(c.z, wgt, col.z);
+      col.w = fmaf(c.w, 1.0f - col.w, col.w);
+      pex += ix; pey += iy; pez += iz;
+      ptx += itx; pty += ity; ptz += itz;
+      if (col.w >= 0.99f) break;
+    }
+    const float k = 1.0f - dst.w;                          // frame buffer blend: ONE_MINUS_DST_ALPHA, ONE
+    dst.x = fmaf(col.x, k, dst.x); dst.y = fmaf(col.y, k, dst.y); dst.z = fmaf(col.z, k, dst.z); dst.w = fmaf(col.w, k, dst.w);
+  }
+  a.image[(size_t)py * p.width + px] = dst;
+  for (int s = 16; s > 0; s >>= 1) nsamples += __shfl_down_sync(__activemask(), nsamples, s);
+  if (lane == 0 && a.stats) atomicAdd(a.stats, nsamples);
+}
+
+extern "C" int tvk_raycast_classic(tvk_ctx* c, const tvk_classic_params* p, const tvk_classic_brick* bricks, uint32_t n, const void* store) {
+  if (!c || !p || (n && !bricks) || !store) return TVK_ERR_INVALID;
+  if (!c->d_tf || c->tf_h != 1) TVK_FAIL(c, TVK_ERR_INVALID, "the classic ray-caster needs a 1D transfer function");
+  if (p->bytes_per_voxel != 1 && p->bytes_per_voxel != 2) TVK_FAIL(c, TVK_ERR_INVALID, "bad voxel size");
+  if (!p->width || !p->height) TVK_FAIL(c, TVK_ERR_INVALID, "bad image size");
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  int rc = tvk_ensure_frame(c, p->width, p->height, c->hash_size ? c->hash_size : 509);
+  if (rc) return rc;
+  tvk_classic_brick* d_bricks = nullptr;
+  TVK_CHECK_CUDA(c, cudaMallocAsync(&d_bricks, sizeof(tvk_classic_brick) * (n ? n : 1), c->stream));
+  if (n) TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_bricks, bricks, sizeof(tvk_classic_brick) * n, cudaMemcpyHostToDevice, c->stream));
+  ClassicArgs a;
+  a.p = *p; a.bricks = d_bricks; a.nbricks = n; a.store = static_cast<const uint8_t*>(store);
+  a.tf_f = c->d_tf_f; a.tf_w = c->tf_w; a.image = c->d_image; a.stats = c->d_stats;
+  const uint32_t tiles = ((p->width + 7) / 8) * ((p->height + 3) / 4);
+  const uint32_t blocks = (tiles + 3) / 4;
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  if (p->bytes_per_voxel == 1) {
+    if (p->lighting) classic_kernel<1, true><<<blocks, 128, 0, c->stream>>>(a); else classic_kernel<1, false><<<blocks, 128, 0, c->stream>>>(a);
+  } else {
+    if (p->lighting) classic_kernel<2, true><<<blocks, 128, 0, c->stream>>>(a); else classic_kernel<2, false><<<blocks, 128, 0, c->stream>>>(a);
+  }
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  c->launches++;
+  TVK_CHECK_CUDA(c, cudaFreeAsync(d_bricks, c->stream));
+  return TVK_OK;
+}

@@ -132,6 +132,18 @@ class Renderer:
         a = np.ascontiguousarray(m, np.float32).reshape(16)
         self._ck(self._lib.tvkr_set_translation4x4(self._h, a.ctypes.data_as(C.c_void_p)), "setTranslation4x4")
 
+    def setRendererType(self, classic):
+        """False: ray-guided (OpenGL_GridLeaper-like, default); True: classic per-brick (OpenGL_Raycaster-like)"""
+        self._ck(self._lib.tvkr_set_renderer_type(self._h, C.c_int(1 if classic else 0)), "setRendererType")
+
+    def planClassicFrame(self, cap=65536):
+        from . import _lib
+        p = _lib.ClassicParams()
+        arr = (_lib.ClassicBrick * cap)()
+        n, lod = C.c_uint32(), C.c_uint32()
+        self._ck(self._lib.tvkr_plan_classic_frame(self._h, C.byref(p), arr, C.c_uint32(cap), C.byref(n), C.byref(lod)), "planClassicFrame")
+        return p, [arr[i] for i in range(n.value)], lod.value
+
     def setClipPlane(self, plane):
         """world-space plane (a, b, c, d); the half space a*x + b*y + c*z + d <= 0 is kept"""
         a = (C.c_float * 4)(*[float(v) for v in plane])

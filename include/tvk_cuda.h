@@ -291,6 +291,38 @@ int tvk_quantize(tvk_ctx* ctx, uint32_t type, uint64_t n, const void* src, int s
 int tvk_composite_ordered(tvk_ctx* ctx, const void* const* partial_dptrs, uint32_t n,
                           uint64_t pixels, void* out_dptr);
 
+/* ------------------------------------------------- classic per-brick ray-caster */
+/* replaces GLRaycaster::Render3DPreLoop / Render3DInLoop / SetBrickDepShaderVars / RenderBox /
+ * ComputeEyeToTextureMatrix (Renderer/GL/GLRaycaster.cpp:239-300,327-479,589-612) with the shaders
+ * GLRaycaster-1D-FS.glsl / GLRaycaster-1D-light-FS.glsl (+ VRender1D[Lit].glsl, Volume3D.glsl, lighting.glsl,
+ * Compositing.glsl) and the frame buffer's ONE_MINUS_DST_ALPHA / ONE blend (GLRenderer.cpp:152-153): the bricks
+ * of ONE level of detail, sorted front to back by the host (AbstrRenderer::BuildSubFrameBrickList), are marched
+ * one after the other for every pixel.  Like the reference, ray entry points pass through half precision (the
+ * RGBA16F entry buffer, GLRaycaster.cpp:97) and early ray termination works per brick.  1D transfer function,
+ * with or without lighting; bricks are read from a device-resident brick store (tvk_build_store_device_ptr). */
+typedef struct tvk_classic_brick {
+  float center[3], extension[3];     /* Brick::vCenter / vExtension                                  */
+  float eye_to_tex[16];              /* ComputeEyeToTextureMatrix for this brick (row-vector order)   */
+  float ray_step;                    /* fRayStepsize (SetBrickDepShaderVars)                          */
+  uint32_t voxels[3];                /* brick size incl. overlap                                      */
+  uint64_t store_offset;             /* byte offset of the brick in the store                         */
+} tvk_classic_brick;
+typedef struct tvk_classic_params {
+  uint32_t width, height;
+  float inv_model_view[16];          /* renderRegion.modelView^-1                                     */
+  float normal_matrix[9];            /* gl_NormalMatrix = (modelView^-1)^T, upper 3x3, row-vector use */
+  float inv_projection[16];
+  float step_scale;                  /* fStepScale (opacity correction exponent)                      */
+  float trans_scale;                 /* fTransScale                                                   */
+  uint32_t lighting;
+  float light_ambient[3], light_diffuse[3], light_specular[3], light_dir[3];
+  float domain_scale[3];             /* vDomainScale = 1 / scale                                      */
+  uint32_t bytes_per_voxel;
+} tvk_classic_params;
+/* bricks: host array, front to back.  Result: the context's image (tvk_read_image). */
+int tvk_raycast_classic(tvk_ctx* ctx, const tvk_classic_params* p, const tvk_classic_brick* bricks, uint32_t n,
+                        const void* store_dptr);
+
 /* ---------------------------------------------- sort-last exchange over peer memory */
 /* Direct-send compositing fused into the kernels (no reference counterpart): rank r owns scan-line
  * stripe r.  After tvk_exchange_begin_frame the next tvk_raycast_subframe stores every finished pixel into the

@@ -97,6 +97,13 @@ int tvkr_get_frame_float(tvkr_renderer* r, float* out);
 /* introspection for tests */
 int tvkr_get_raycast_params(tvkr_renderer* r, tvk_raycast_params* out);
 int tvkr_get_pool_slots(tvkr_renderer* r, int32_t* brick, uint64_t* time, uint32_t cap, uint32_t* n);
+/* tuvok.renderer.new(type, ...): 0 = OpenGL_GridLeaper-like ray-guided path (default), 1 = OpenGL_Raycaster-like classic
+ * per-brick path (MasterController::RequestNewVolumeRenderer, MasterController.cpp:144-215).  The classic path
+ * renders the final sub-frame of a view (AbstrRenderer::PlanFrame's last LOD) per paint(), 1D-TF modes, in-core data. */
+int tvkr_set_renderer_type(tvkr_renderer* r, int type);
+/* the classic path's frame plan, for tests: parameters, front-to-back brick list (cap entries), chosen LOD */
+int tvkr_plan_classic_frame(tvkr_renderer* r, tvk_classic_params* p, tvk_classic_brick* bricks, uint32_t cap,
+                            uint32_t* n, uint32_t* lod);
 /* getFirst3DRenderRegion().setClipPlane / enableClipPlane: world-space plane (a,b,c,d), n.p + d <= 0 is kept
  * (GLGridLeaper::FillBBoxVBO, GLGridLeaper.cpp:515-526 + Clipper::BoxPlane) */
 int tvkr_set_clip_plane(tvkr_renderer* r, const float plane[4]);

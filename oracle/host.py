@@ -469,3 +469,144 @@ def synth_blobs(size, dtype=np.uint8, seed=3):
         v += np.exp(-((x - c[0]) ** 2 + (y - c[1]) ** 2 + (z - c[2]) ** 2) / (r * r)).astype(f32)
     v = np.clip(v / v.max(), 0, 1)
     return (v * f32(np.iinfo(dtype).max)).astype(dtype)
+
+
+# ---------------------------------------------------------------- classic per-brick ray-caster (R12 / R13)
+class ClassicBrick(C.Structure):                     # tvk_classic_brick (include/tvk_cuda.h)
+    _fields_ = [("center", C.c_float * 3), ("extension", C.c_float * 3), ("eye_to_tex", C.c_float * 16),
+                ("ray_step", C.c_float), ("voxels", C.c_uint32 * 3), ("store_offset", C.c_uint64)]
+
+
+class ClassicParams(C.Structure):                    # tvk_classic_params
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("inv_model_view", C.c_float * 16),
+                ("normal_matrix", C.c_float * 9), ("inv_projection", C.c_float * 16), ("step_scale", C.c_float),
+                ("trans_scale", C.c_float), ("lighting", C.c_uint32), ("light_ambient", C.c_float * 3),
+                ("light_diffuse", C.c_float * 3), ("light_specular", C.c_float * 3), ("light_dir", C.c_float * 3),
+                ("domain_scale", C.c_float * 3), ("bytes_per_voxel", C.c_uint32)]
+
+
+def classic_plan(oc, cam, width, height, tf_limits, lighting=False, sample_rate=1.0, scale=(1, 1, 1), trans_scale=1.0,
+                 capture=False, lod=None):
+    """What AbstrRenderer::PlanFrame / BuildSubFrameBrickList (AbstrRenderer.cpp:1125-1212, 999-1100) and
+    GLRaycaster::SetBrickDepShaderVars / ComputeEyeToTextureMatrix hand to the shaders for the FINAL sub-frame of a
+    view: (ClassicParams, [ClassicBrick...] front to back, lod).  oc: oracle octree (tight store offsets)."""
+    plan = oc["plan"]
+    dom0 = np.array([int(v) for v in plan.lod_size[0]], f32)
+    sc = np.asarray(scale, f32)
+    aspect = f32(width) / f32(height)
+    view = look_at(cam.eye, cam.at, cam.up)
+    proj = perspective(cam.fov, aspect, cam.znear, cam.zfar)
+    mv = (cam.rotation @ cam.translation @ view).astype(f32)
+    # --- ComputeMinLODForCurrentView (:789-803) + CullingLOD::GetLODLevel (CullingLOD.cpp:128-141)
+    extent = dom0 * sc
+    extent = (extent / extent.max()).astype(f32)
+    wse = f32((extent / dom0).max())
+    zc = f32((np.array([0, 0, 0, 1], f32) @ mv)[2])
+    fz = max(f32(cam.znear), f32(-zc))
+    lf = lod_factor(cam.fov, height)
+    level = int(math.floor(f32(f32(math.log(float(f32(lf * fz / wse)))) / f32(math.log(2.0)))))
+    min_lod = min(max(level, 0), plan.lod_count - 1)
+    if lod is None:
+        lod = 0 if capture else min_lod
+    # --- frustum planes (CullingLOD::Update, :89-126), model matrix = identity
+    mvp = (mv @ proj).astype(f32)
+    planes = []
+    for col, sign in ((0, -1), (0, 1), (1, -1), (1, 1), (2, 1), (2, -1)):
+        planes.append(np.array([sign * mvp[r, col] + mvp[r, 3] for r in range(4)], f32))
+    # --- brick metadata of this LOD (UVFDataset::ComputeMetadataTOC, uvfDataset.cpp:242-288)
+    nb = [int(v) for v in plan.lod_bricks[lod]]
+    dl = np.array([int(v) for v in plan.lod_size[lod]], f32)
+    asp = np.array([float(v) for v in plan.lod_aspect[lod]], f32)
+    nds = (dl * asp).astype(f32)
+    maxval = f32(nds.max())
+    nds = (nds / maxval).astype(f32)
+    overlap, brick = oc["overlap"], oc["brick"]
+    first = int(plan.lod_offset[lod])
+    vscale = sc.copy()
+    corrected = (sc * dom0 / f32(dom0.max())).astype(f32)
+    vscale = (vscale / f32(corrected.max())).astype(f32)
+    tight = np.concatenate([[0], np.cumsum(oc["sizes"].astype(np.uint64).prod(axis=1) * oc["bpv"])]).astype(np.uint64)
+    maxv = float(oc["minmax"][:int(np.prod([int(v) for v in plan.lod_bricks[0]])), 1].max())
+    lo_i, hi_i, tf_n = tf_limits
+    resc = maxv / float(tf_n - 1)
+    out = []
+    corner = np.zeros(3, f32)
+    ext_axis = []
+    for a in range(3):                                # extents along an axis depend on the brick coordinate only
+        e = []
+        for c in range(nb[a]):
+            last = c >= nb[a] - 1
+            rem = int(dl[a]) % (brick - 2 * overlap)
+            size = (2 * overlap + rem) if (last and rem) else brick
+            e.append(f32(f32(size - 2 * overlap) * asp[a] / maxval))
+        ext_axis.append(e)
+    inv_mv = inverse(mv)
+    for x in range(nb[0]):
+        for y in range(nb[1]):
+            for z in range(nb[2]):
+                idx = first + x + y * nb[0] + z * nb[0] * nb[1]
+                ext = np.array([ext_axis[0][x], ext_axis[1][y], ext_axis[2][z]], f32)
+                cor = np.array([sum(ext_axis[0][:x], f32(0)), sum(ext_axis[1][:y], f32(0)), sum(ext_axis[2][:z], f32(0))], f32)
+                center = ((cor + ext / f32(2)) - nds * f32(0.5)).astype(f32)
+                b_ext, b_cen = (ext * vscale).astype(f32), (center * vscale).astype(f32)
+                # RegionNeedsBrick (:874-920): frustum, then data range
+                half = f32(0.5) * b_ext
+                vis = all(float(pl[0] * b_cen[0] + pl[1] * b_cen[1] + pl[2] * b_cen[2] + pl[3]) >
+                          -float(half[0] * abs(pl[0]) + half[1] * abs(pl[1]) + half[2] * abs(pl[2])) for pl in planes)
+                if not vis:
+                    continue
+                mn, mx = oc["minmax"][idx]
+                if not (hi_i * resc >= mn and lo_i * resc <= mx):
+                    continue                          # bIsEmpty: stays in the reference's list but is never drawn
+                vox = oc["sizes"][idx].astype(np.uint32)
+                tmin = (f32(overlap) / vox.astype(f32)).astype(f32)
+                tmax = ((f32(1) - tmin) * asp).astype(f32)
+                # brick_distance (:808-841)
+                dist = None
+                for sx in (-1, 1):
+                    for sy in (-1, 1):
+                        for sz in (-1, 1):
+                            cpt = (b_cen + np.array([sx, sy, sz], f32) * b_ext * f32(0.4999)).astype(f32)
+                            e4 = (np.append(cpt, f32(1)) @ mv)[:3]
+                            dd = f32(np.sqrt(f32(np.dot(e4, e4))))
+                            dist = dd if dist is None else min(dist, dd)
+                p1, p2 = (b_cen + b_ext / f32(2)).astype(f32), (b_cen - b_ext / f32(2)).astype(f32)
+                tm = (inv_mv @ translation(*(-p1)) @ scaling(*((tmin - tmax) / (p2 - p1))) @ translation(*tmax)).astype(f32)
+                cb = ClassicBrick()
+                cb.center[:] = b_cen.tolist(); cb.extension[:] = b_ext.tolist()
+                cb.eye_to_tex[:] = tm.reshape(-1).tolist()
+                cb.ray_step = float((b_ext * (f32(1) / vox.astype(f32)) * f32(0.5) * f32(1.0) / f32(sample_rate)).min())
+                cb.voxels[:] = [int(v) for v in vox]
+                cb.store_offset = int(tight[idx])
+                out.append((float(dist), idx, cb))
+    out.sort(key=lambda t: (t[0], t[1]))
+    p = ClassicParams()
+    p.width, p.height = width, height
+    p.inv_model_view[:] = inv_mv.reshape(-1).tolist()
+    p.normal_matrix[:] = inv_mv.T[:3, :3].reshape(-1).tolist()
+    p.inv_projection[:] = inverse(proj).reshape(-1).tolist()
+    p.step_scale = float(f32(1.0) / f32(sample_rate) * f32((dom0 / dl).max()))
+    p.trans_scale = trans_scale
+    p.lighting = int(lighting)
+    p.light_ambient[:] = (cam.ambient[:3] * cam.ambient[3]).tolist()
+    p.light_diffuse[:] = (cam.diffuse[:3] * cam.diffuse[3]).tolist()
+    p.light_specular[:] = (cam.specular[:3] * cam.specular[3]).tolist()
+    p.light_dir[:] = cam.light_dir.tolist()
+    p.domain_scale[:] = (f32(1) / sc).tolist()
+    p.bytes_per_voxel = oc["bpv"]
+    return p, [t[2] for t in out], lod
+
+
+def classic_render(p, bricks, store_tight, tf_rgba8):
+    """orc_raycast_classic: (image [H][W][4] float32, samples)"""
+    from . import oracle as O
+    arr = (ClassicBrick * max(len(bricks), 1))(*bricks)
+    img = np.zeros((p.height, p.width, 4), f32)
+    n = C.c_uint64()
+    tf = np.ascontiguousarray(tf_rgba8, np.uint8)
+    st = np.ascontiguousarray(store_tight, np.uint8)
+    rc = O.lib().orc_raycast_classic(C.byref(p), arr, C.c_uint32(len(bricks)), st.ctypes.data_as(C.c_void_p),
+                                     tf.ctypes.data_as(C.c_void_p), C.c_uint32(tf.shape[0]), img.ctypes.data_as(C.c_void_p), C.byref(n))
+    if rc:
+        raise ValueError("orc_raycast_classic failed")
+    return img, int(n.value)

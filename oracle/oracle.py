@@ -15,7 +15,7 @@ ORC_MAX_LOD = 32
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("tvk_oracle_builder.c", "tvk_oracle_render.c", "tvk_oracle_quantize.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("tvk_oracle_builder.c", "tvk_oracle_render.c", "tvk_oracle_quantize.c", "tvk_oracle_classic.c", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so

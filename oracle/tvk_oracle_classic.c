@@ -1,0 +1,178 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's CLASSIC per-brick ray-caster (SURVEY 8a rows
+ * R12): what GLRaycaster draws for one sub-frame, pixel by pixel.
+ *
+ * Follows, under /root/reference/Tuvok/:
+ *   Renderer/GL/GLRaycaster.cpp:383-479   Render3DPreLoop / Render3DInLoop (near-plane pass, front faces into the
+ *                                         RGBA16F entry buffer :97, back faces with the ray-cast shader)
+ *   Renderer/GL/GLRaycaster.cpp:239-300   SetBrickDepShaderVars (fRayStepsize, fStepScale, vVoxelStepsize)
+ *   Renderer/GL/GLRaycaster.cpp:589-612   ComputeEyeToTextureMatrix (computed by the caller, see oracle/host.py)
+ *   Shaders/GLRaycaster-1D-FS.glsl:51-82, GLRaycaster-1D-light-FS.glsl:83-134   main()
+ *   Shaders/VRender1D.glsl, VRender1DLit.glsl, Volume3D.glsl (sampleVolume, ComputeGradient, ComputeNormal),
+ *   Shaders/lighting.glsl, Shaders/Compositing.glsl:33-38
+ *   Renderer/GL/GLRenderer.cpp:152-153    frame-buffer blend ONE_MINUS_DST_ALPHA / ONE between bricks
+ * Parity status: "parity unpinned" like the ray-guided restatement (the reference's pixels need an OpenGL driver).
+ * Restatement choices: brick faces are intersected analytically with the pixel-centre ray instead of being
+ * rasterised; a brick whose front face lies behind the near plane starts at the near plane (the reference reads
+ * whatever the previous brick left in the entry buffer there); the entry point is rounded to half precision as the
+ * RGBA16F buffer does, the exit point is not (it is an interpolated varying).
+ * Floating-point contract as in tvk_oracle_render.c.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include "tvk_cuda.h"
+
+static float half_round(float f) {          /* float -> IEEE binary16 (round to nearest even) -> float */
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = x & 0x80000000u;
+  x &= 0x7FFFFFFFu;
+  if (x >= 0x7F800000u) return f;                              /* inf / nan */
+  if (x >= 0x477FF000u) { x = 0x7F800000u | sign; memcpy(&f, &x, 4); return f; }   /* rounds to >= 65520 -> inf */
+  float a;
+  memcpy(&a, &x, 4);
+  if (x < 0x38800000u) {                                       /* below 2^-14: half subnormal, quantum 2^-24 */
+    const float q = 5.9604644775390625e-08f;
+    a = rintf(a / q) * q;
+  } else {
+    const uint32_t rem = x & 0x1FFFu, base = x & ~0x1FFFu;     /* keep 10 mantissa bits */
+    uint32_t r = base;
+    if (rem > 0x1000u || (rem == 0x1000u && (base & 0x2000u))) r += 0x2000u;
+    memcpy(&a, &r, 4);
+  }
+  uint32_t y;
+  memcpy(&y, &a, 4);
+  y |= sign;
+  memcpy(&a, &y, 4);
+  return a;
+}
+
+static inline float dot3c(float ax, float ay, float az, float bx, float by, float bz) { return fmaf(az, bz, fmaf(ay, by, ax * bx)); }
+static inline float clamp01c(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+static void xformc(const float* m, float x, float y, float z, float w, float o[4]) {
+  o[0] = fmaf(w, m[12], fmaf(z, m[8], fmaf(y, m[4], x * m[0])));
+  o[1] = fmaf(w, m[13], fmaf(z, m[9], fmaf(y, m[5], x * m[1])));
+  o[2] = fmaf(w, m[14], fmaf(z, m[10], fmaf(y, m[6], x * m[2])));
+  o[3] = fmaf(w, m[15], fmaf(z, m[11], fmaf(y, m[7], x * m[3])));
+}
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static inline int f2i_sat(float f) {          /* (int)f with the saturation CUDA's conversion has; NaN -> 0 */
+  if (!(f == f)) return 0;
+  if (f >= 2147483648.0f) return 2147483647;
+  if (f <= -2147483648.0f) return -2147483647 - 1;
+  return (int)f;
+}
+
+static float brick_sample(const uint8_t* data, uint32_t bpv, const uint32_t vox[3], float tx, float ty, float tz) {
+  const float u = fmaf(tx, (float)vox[0], -0.5f), v = fmaf(ty, (float)vox[1], -0.5f), w = fmaf(tz, (float)vox[2], -0.5f);
+  const float fu = floorf(u), fv = floorf(v), fw = floorf(w);
+  const float a = u - fu, b = v - fv, g = w - fw;
+  const int mx = (int)vox[0] - 1, my = (int)vox[1] - 1, mz = (int)vox[2] - 1;
+  const int x0 = clampi(f2i_sat(fu), 0, mx), x1 = clampi(f2i_sat(fu) == 2147483647 ? 2147483647 : f2i_sat(fu) + 1, 0, mx);
+  const int y0 = clampi(f2i_sat(fv), 0, my), y1 = clampi(f2i_sat(fv) == 2147483647 ? 2147483647 : f2i_sat(fv) + 1, 0, my);
+  const int z0 = clampi(f2i_sat(fw), 0, mz), z1 = clampi(f2i_sat(fw) == 2147483647 ? 2147483647 : f2i_sat(fw) + 1, 0, mz);
+  const size_t sx = vox[0], sxy = (size_t)vox[0] * vox[1];
+#define VOX(X, Y, Z) (bpv == 1 ? (float)data[(X) + (Y) * sx + (Z) * sxy] : (float)((const uint16_t*)data)[(X) + (Y) * sx + (Z) * sxy])
+  const float v000 = VOX(x0, y0, z0), v100 = VOX(x1, y0, z0), v010 = VOX(x0, y1, z0), v110 = VOX(x1, y1, z0);
+  const float v001 = VOX(x0, y0, z1), v101 = VOX(x1, y0, z1), v011 = VOX(x0, y1, z1), v111 = VOX(x1, y1, z1);
+#undef VOX
+  const float c00 = fmaf(a, v100 - v000, v000), c10 = fmaf(a, v110 - v010, v010);
+  const float c01 = fmaf(a, v101 - v001, v001), c11 = fmaf(a, v111 - v011, v011);
+  const float c0 = fmaf(b, c10 - c00, c00), c1 = fmaf(b, c11 - c01, c01);
+  return fmaf(g, c1 - c0, c0) * (bpv == 1 ? 1.0f / 255.0f : 1.0f / 65535.0f);
+}
+
+int orc_raycast_classic(const tvk_classic_params* p, const tvk_classic_brick* bricks, uint32_t n, const uint8_t* store,
+                        const uint8_t* tf_rgba8, uint32_t tf_n, float* image, uint64_t* samples_out) {
+  if (!p || (n && !bricks) || !store || !tf_rgba8 || !image) return 1;
+  uint64_t total = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : total)
+  for (int64_t py = 0; py < (int64_t)p->height; ++py) {
+    for (uint32_t px = 0; px < p->width; ++px) {
+      const float nx = fmaf(((float)px + 0.5f) / (float)p->width, 2.0f, -1.0f), ny = fmaf(((float)py + 0.5f) / (float)p->height, 2.0f, -1.0f);
+      float n4[4], O[4], D[4];
+      xformc(p->inv_projection, nx, ny, -1.0f, 1.0f, n4);
+      const float ex = n4[0] / n4[3], ey = n4[1] / n4[3], ez = n4[2] / n4[3];
+      xformc(p->inv_model_view, 0.f, 0.f, 0.f, 1.0f, O);
+      xformc(p->inv_model_view, ex, ey, ez, 0.0f, D);
+      float dst[4] = {0.f, 0.f, 0.f, 0.f};
+      for (uint32_t bi = 0; bi < n; ++bi) {
+        const tvk_classic_brick* b = &bricks[bi];
+        float s0 = -INFINITY, s1 = INFINITY;
+        int miss = 0;
+        for (int k = 0; k < 3; ++k) {
+          const float lo = b->center[k] - b->extension[k] / 2.0f, hi = b->center[k] + b->extension[k] / 2.0f;
+          if (D[k] == 0.0f) { if (O[k] < lo || O[k] > hi) miss = 1; continue; }
+          const float inv = 1.0f / D[k];
+          float ta = (lo - O[k]) * inv, tb = (hi - O[k]) * inv;
+          if (ta > tb) { const float t = ta; ta = tb; tb = t; }
+          s0 = fmaxf(s0, ta); s1 = fminf(s1, tb);
+        }
+        const float se = fmaxf(s0, 1.0f);
+        if (miss || !(s1 > se)) continue;
+        const float enx = half_round(ex * se), eny = half_round(ey * se), enz = half_round(ez * se);
+        const float xx = ex * s1, xy = ey * s1, xz = ez * s1;
+        float te[4], tx[4];
+        xformc(b->eye_to_tex, enx, eny, enz, 1.0f, te);
+        xformc(b->eye_to_tex, xx, xy, xz, 1.0f, tx);
+        float dx = xx - enx, dy = xy - eny, dz = xz - enz;
+        const float len = sqrtf(dot3c(dx, dy, dz, dx, dy, dz));
+        const int steps = f2i_sat(len / b->ray_step) + 1;
+        const float q = len / b->ray_step;
+        const float itx = (tx[0] - te[0]) / q, ity = (tx[1] - te[1]) / q, itz = (tx[2] - te[2]) / q;
+        dx /= len; dy /= len; dz /= len;
+        const float ix = dx * b->ray_step, iy = dy * b->ray_step, iz = dz * b->ray_step;
+        const uint8_t* data = store + b->store_offset;
+        float col[4] = {0.f, 0.f, 0.f, 0.f};
+        float ptx = te[0], pty = te[1], ptz = te[2], pex = enx, pey = eny, pez = enz;
+        for (int i = 0; i < steps; ++i) {
+          const float v = brick_sample(data, p->bytes_per_voxel, b->voxels, ptx, pty, ptz);
+          const int ti = clampi(f2i_sat(v * p->trans_scale * (float)tf_n), 0, (int)tf_n - 1);
+          float c[4];
+          for (int k = 0; k < 4; ++k) c[k] = (float)tf_rgba8[4 * ti + k] * (1.0f / 255.0f);
+          total++;
+          if (p->lighting) {
+            const float hx = 1.0f / (float)b->voxels[0], hy = 1.0f / (float)b->voxels[1], hz = 1.0f / (float)b->voxels[2];
+            const uint32_t bpv = p->bytes_per_voxel;
+            const float gxp = brick_sample(data, bpv, b->voxels, ptx + hx, pty, ptz), gxm = brick_sample(data, bpv, b->voxels, ptx - hx, pty, ptz);
+            const float gyp = brick_sample(data, bpv, b->voxels, ptx, pty - hy, ptz), gym = brick_sample(data, bpv, b->voxels, ptx, pty + hy, ptz);
+            const float gzp = brick_sample(data, bpv, b->voxels, ptx, pty, ptz + hz), gzm = brick_sample(data, bpv, b->voxels, ptx, pty, ptz - hz);
+            const float gx = (gxm - gxp) / 2.0f * p->domain_scale[0], gy = (gyp - gym) / 2.0f * p->domain_scale[1], gz = (gzm - gzp) / 2.0f * p->domain_scale[2];
+            float Nx = fmaf(gz, p->normal_matrix[6], fmaf(gy, p->normal_matrix[3], gx * p->normal_matrix[0]));
+            float Ny = fmaf(gz, p->normal_matrix[7], fmaf(gy, p->normal_matrix[4], gx * p->normal_matrix[1]));
+            float Nz = fmaf(gz, p->normal_matrix[8], fmaf(gy, p->normal_matrix[5], gx * p->normal_matrix[2]));
+            const float nl = sqrtf(dot3c(Nx, Ny, Nz, Nx, Ny, Nz));
+            if (nl > 0.0f) { Nx /= nl; Ny /= nl; Nz /= nl; }
+            float vx = 0.0f - pex, vy = 0.0f - pey, vz = 0.0f - pez;
+            float l = sqrtf(dot3c(vx, vy, vz, vx, vy, vz));
+            vx /= l; vy /= l; vz /= l;
+            const float d2 = 2.0f * dot3c(Nx, Ny, Nz, vx, vy, vz);
+            float rx = fmaf(-d2, Nx, vx), ry = fmaf(-d2, Ny, vy), rz = fmaf(-d2, Nz, vz);
+            l = sqrtf(dot3c(rx, ry, rz, rx, ry, rz));
+            rx /= l; ry /= l; rz /= l;
+            const float ndl = fmaxf(fabsf(dot3c(Nx, Ny, Nz, p->light_dir[0], p->light_dir[1], p->light_dir[2])), 0.0f);
+            float sp = fmaxf(dot3c(rx, ry, rz, p->light_dir[0], p->light_dir[1], p->light_dir[2]), 0.0f);
+            sp *= sp; sp *= sp; sp *= sp;
+            c[0] = clamp01c(fmaf(p->light_specular[0], sp, fmaf(p->light_diffuse[0] * c[0], ndl, p->light_ambient[0])));
+            c[1] = clamp01c(fmaf(p->light_specular[1], sp, fmaf(p->light_diffuse[1] * c[1], ndl, p->light_ambient[1])));
+            c[2] = clamp01c(fmaf(p->light_specular[2], sp, fmaf(p->light_diffuse[2] * c[2], ndl, p->light_ambient[2])));
+          }
+          c[3] = (p->step_scale == 1.0f) ? 1.0f - (1.0f - c[3]) : 1.0f - powf(1.0f - c[3], p->step_scale);
+          const float wgt = (1.0f - col[3]) * c[3];
+          col[0] = fmaf(c[0], wgt, col[0]); col[1] = fmaf(c[1], wgt, col[1]); col[2] = fmaf(c[2], wgt, col[2]);
+          col[3] = fmaf(c[3], 1.0f - col[3], col[3]);
+          pex += ix; pey += iy; pez += iz;
+          ptx += itx; pty += ity; ptz += itz;
+          if (col[3] >= 0.99f) break;
+        }
+        const float k = 1.0f - dst[3];
+        dst[0] = fmaf(col[0], k, dst[0]); dst[1] = fmaf(col[1], k, dst[1]); dst[2] = fmaf(col[2], k, dst[2]); dst[3] = fmaf(col[3], k, dst[3]);
+      }
+      float* o = image + 4 * ((size_t)py * p->width + px);
+      o[0] = dst[0]; o[1] = dst[1]; o[2] = dst[2]; o[3] = dst[3];
+    }
+  }
+  if (samples_out) *samples_out = total;
+  return 0;
+}

@@ -109,7 +109,9 @@ static int quantize_tu(const void* in, uint32_t type, uint64_t n, uint32_t out_w
   minmax_of(in, type, n, &mn8, &mx8);
   /* unsigned data that already fits needs no processing */
   if (!is_signed_type(type) && kWidth[type] <= (hsz == 256 ? 1u : 2u)) {
-    const uint32_t mxv = type == DT_U8 ? *(uint8_t*)&mx8 : *(uint16_t*)&mx8;
+    uint16_t mx16;
+    memcpy(&mx16, &mx8, 2);
+    const uint32_t mxv = type == DT_U8 ? (uint32_t)(mx16 & 0xFFu) : (uint32_t)mx16;
     if (mxv < hsz) {
       if (bin_count) {
         memset(hist, 0, sizeof(uint64_t) * hsz);
