@@ -458,6 +458,20 @@ bool CudaGridLeaper::LoadDataset(const std::string& uvfFile, uint64_t gpuMemByte
   if (tvk_uvf_open(uvfFile.c_str(), verifyChecksum ? 1 : 0, &u, err, sizeof(err))) { m_err = std::string("UVF open failed: ") + err; return false; }
   tvk_uvf_info ui;
   tvk_uvf_get_info(u, &ui);
+  if (ui.toc_block < 0 && ui.rdb_block >= 0 && !ui.rdb_signed) {
+    // legacy RasterDataBlock file (e.g. DemoData/c60.uvf: one 128^3 brick): stitch the finest level back together
+    // and re-brick it for the ray-guided path, as IOManager::LoadRebrickedDataset / DynamicBrickingDS do
+    // (IOManager.cpp:1281-1320, IO/DynamicBrickingDS.cpp) -- here by running the K2 builder on the volume
+    const uint32_t size[3] = {(uint32_t)ui.rdb_domain[0], (uint32_t)ui.rdb_domain[1], (uint32_t)ui.rdb_domain[2]};
+    const uint32_t bpv = ui.rdb_bits / 8;
+    std::vector<uint8_t> flat((size_t)size[0] * size[1] * size[2] * bpv);
+    const int rc = tvk_uvf_read_rdb_volume(u, flat.data(), flat.size());
+    const std::string why = rc ? tvk_uvf_last_error(u) : "";
+    tvk_uvf_close(u);
+    if (rc) { m_err = "RasterDataBlock read failed: " + why; return false; }
+    const float scale[3] = {1, 1, 1};
+    return LoadRawVolume(flat.data(), size, bpv, scale, 64, 2, false, false, gpuMemBytes, true);
+  }
   if (ui.toc_block < 0 || (ui.vol.component_type != TVK_UVF_CT_UINT8 && ui.vol.component_type != TVK_UVF_CT_UINT16) ||
       ui.maxmin_bricks != ui.total_bricks) {
     tvk_uvf_close(u);

@@ -357,6 +357,7 @@ struct tvk_uvf {
   std::vector<uint64_t> hist1d, hist2d;
   std::vector<std::pair<std::string, std::string>> kv;
   uint32_t bpv = 0;
+  uint64_t rdb_data_pos = 0;                  // file offset of the finest level's first brick
 };
 
 namespace {
@@ -381,6 +382,7 @@ extern "C" int tvk_uvf_open(const char* path, int verify, tvk_uvf** out, char* e
   tvk_uvf* u = new tvk_uvf();
   u->f = f;
   u->info.toc_block = -1;
+  u->info.rdb_block = -1;
   auto fail = [&](const std::string& m, int code) { set_err(err, errlen, m); tvk_uvf_close(u); return code; };
   Rd r{f};
   char magic[8];
@@ -448,6 +450,46 @@ extern "C" int tvk_uvf_open(const char* path, int verify, tvk_uvf** out, char* e
       }
       if (!r.ok) return fail("truncated brick table", TVK_ERR_INVALID);
       v.compression = u->t_comp[0];
+    } else if (sem == BS_REG_NDIM_GRID && u->info.rdb_block < 0) {
+      // RasterDataBlock::GetHeaderFromFile (RasterDataBlock.cpp:154-208); only 3-D scalar 8/16-bit grids are decoded
+      const uint64_t dims = r.get<uint64_t>();
+      bool usable = r.ok && dims == 3;
+      uint64_t dom[3] = {0, 0, 0}, brick[3] = {0, 0, 0}, ovl[3] = {0, 0, 0}, groups[3] = {0, 0, 0};
+      if (usable) {
+        for (int a = 0; a < 3; ++a) (void)r.get<uint64_t>();                 // domain semantics
+        for (int a = 0; a < 16; ++a) (void)r.get<double>();                  // (n+1)^2 domain transformation
+        for (int a = 0; a < 3; ++a) dom[a] = r.get<uint64_t>();
+        for (int a = 0; a < 3; ++a) brick[a] = r.get<uint64_t>();
+        for (int a = 0; a < 3; ++a) ovl[a] = r.get<uint64_t>();
+        for (int a = 0; a < 3; ++a) (void)r.get<uint64_t>();                 // LOD decimation factors
+        for (int a = 0; a < 3; ++a) groups[a] = r.get<uint64_t>();
+        uint64_t lodIdx = 1;
+        for (int a = 0; a < 3; ++a) if (groups[a] >= lodIdx) lodIdx = groups[a] + 1;
+        uint64_t levels = 0;
+        for (uint64_t i = 0; i < lodIdx; ++i) levels = std::max<uint64_t>(levels, r.get<uint64_t>());
+        const uint64_t edim = r.get<uint64_t>();
+        usable = r.ok && edim == 1;
+        if (usable) {
+          const uint64_t esize = r.get<uint64_t>();
+          usable = r.ok && esize == 1;
+          if (usable) {
+            (void)r.get<uint64_t>();                                          // element semantic
+            const uint64_t bits = r.get<uint64_t>();
+            (void)r.get<uint64_t>();                                          // mantissa
+            const uint8_t sgn = r.get<uint8_t>();
+            const uint64_t toData = r.get<uint64_t>();
+            usable = r.ok && (bits == 8 || bits == 16);
+            for (int a = 0; a < 3; ++a) usable = usable && dom[a] > 0 && brick[a] > ovl[a];
+            if (usable) {
+              u->info.rdb_block = (int32_t)bi;
+              u->info.rdb_bits = (uint32_t)bits; u->info.rdb_signed = sgn ? 1u : 0u; u->info.rdb_lod_levels = levels;
+              for (int a = 0; a < 3; ++a) { u->info.rdb_domain[a] = dom[a]; u->info.rdb_brick[a] = brick[a]; u->info.rdb_overlap[a] = ovl[a]; }
+              u->rdb_data_pos = (uint64_t)ftello(f) + toData;
+            }
+          }
+        }
+      }
+      r.ok = true;                                                            // an undecodable grid block is skipped, not fatal
     } else if (sem == BS_HIST1D && u->hist1d.empty()) {
       const uint64_t n = r.get<uint64_t>();
       if (!r.ok || n > (1u << 24)) return fail("corrupt 1D histogram", TVK_ERR_INVALID);
@@ -533,6 +575,46 @@ extern "C" int tvk_uvf_read_bricks(tvk_uvf* u, uint64_t first, uint64_t count, v
     else { u->err = "brick compression not supported (lzma / bzip2)"; return TVK_ERR_UNSUPPORTED; }
     if (!ok) { u->err = "brick decompression failed"; return TVK_ERR_INVALID; }
   }
+  return TVK_OK;
+}
+
+// RasterDataBlock::ComputeBricks (RasterDataBlock.cpp:321-349): brick sizes along one axis
+static std::vector<uint64_t> rdb_axis_bricks(uint64_t size, uint64_t brick, uint64_t overlap) {
+  std::vector<uint64_t> v;
+  if (size <= brick) { v.push_back(size); return v; }
+  do {
+    if (size + overlap <= brick) { v.push_back(size); break; }
+    v.push_back(brick);
+    size = size + overlap - brick;
+  } while (size > overlap);
+  return v;
+}
+
+extern "C" int tvk_uvf_read_rdb_volume(tvk_uvf* u, void* dst, uint64_t dst_bytes) {
+  if (!u || !dst || u->info.rdb_block < 0) return TVK_ERR_INVALID;
+  const tvk_uvf_info& i = u->info;
+  const uint64_t bpe = i.rdb_bits / 8;
+  if (dst_bytes != i.rdb_domain[0] * i.rdb_domain[1] * i.rdb_domain[2] * bpe) { u->err = "destination size does not match the domain"; return TVK_ERR_INVALID; }
+  std::vector<uint64_t> bs[3];
+  for (int a = 0; a < 3; ++a) bs[a] = rdb_axis_bricks(i.rdb_domain[a], i.rdb_brick[a], i.rdb_overlap[a]);
+  // finest level first in the block; bricks in Cartesian-product order, x fastest (:289-312, :365-391)
+  if (fseeko(u->f, (off_t)u->rdb_data_pos, SEEK_SET)) { u->err = "seek failed"; return TVK_ERR_INVALID; }
+  uint8_t* out = static_cast<uint8_t*>(dst);
+  std::vector<uint8_t> buf;
+  for (size_t kz = 0; kz < bs[2].size(); ++kz)
+    for (size_t ky = 0; ky < bs[1].size(); ++ky)
+      for (size_t kx = 0; kx < bs[0].size(); ++kx) {
+        const uint64_t sx = bs[0][kx], sy = bs[1][ky], sz = bs[2][kz];
+        buf.resize((size_t)(sx * sy * sz * bpe));
+        if (fread(buf.data(), 1, buf.size(), u->f) != buf.size()) { u->err = "short read in RasterDataBlock"; return TVK_ERR_INVALID; }
+        // brick k starts at k * (brickSize - overlap); neighbouring bricks share `overlap` voxels (identical data)
+        const uint64_t ox = kx * (i.rdb_brick[0] - i.rdb_overlap[0]), oy = ky * (i.rdb_brick[1] - i.rdb_overlap[1]),
+                       oz = kz * (i.rdb_brick[2] - i.rdb_overlap[2]);
+        for (uint64_t z = 0; z < sz; ++z)
+          for (uint64_t y = 0; y < sy; ++y)
+            memcpy(out + ((ox) + (oy + y) * i.rdb_domain[0] + (oz + z) * i.rdb_domain[0] * i.rdb_domain[1]) * bpe,
+                   buf.data() + (y + z * sy) * sx * bpe, (size_t)(sx * bpe));
+      }
   return TVK_OK;
 }
 

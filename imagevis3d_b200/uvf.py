@@ -31,7 +31,10 @@ class UvfInfo(C.Structure):
                 ("toc_block", C.c_int32), ("vol", UvfVolume), ("octree_version", C.c_uint32), ("lod_count", C.c_uint32),
                 ("total_bricks", C.c_uint64), ("store_bytes", C.c_uint64), ("hist1d_size", C.c_uint64),
                 ("hist2d_x", C.c_uint64), ("hist2d_y", C.c_uint64), ("max_grad_magnitude", C.c_float),
-                ("maxmin_bricks", C.c_uint64), ("kv_count", C.c_uint32), ("checksum_ok", C.c_uint32)]
+                ("maxmin_bricks", C.c_uint64), ("kv_count", C.c_uint32), ("checksum_ok", C.c_uint32),
+                ("rdb_block", C.c_int32), ("rdb_bits", C.c_uint32), ("rdb_signed", C.c_uint32),
+                ("rdb_domain", C.c_uint64 * 3), ("rdb_brick", C.c_uint64 * 3), ("rdb_overlap", C.c_uint64 * 3),
+                ("rdb_lod_levels", C.c_uint64)]
 
 
 def _p(a):
@@ -127,6 +130,14 @@ class UvfFile:
         nbytes = int(sizes[first:first + count].astype(np.uint64).prod(axis=1).sum()) * bpv
         out = np.zeros(nbytes, np.uint8)
         self._ck(self.lib.tvk_uvf_read_bricks(self.h, C.c_uint64(first), C.c_uint64(count), _p(out), None), "tvk_uvf_read_bricks")
+        return out
+
+    def read_rdb_volume(self):
+        """finest level of a legacy RasterDataBlock file as a [z][y][x] array"""
+        i = self.info
+        dt = np.uint8 if i.rdb_bits == 8 else np.uint16
+        out = np.zeros((int(i.rdb_domain[2]), int(i.rdb_domain[1]), int(i.rdb_domain[0])), dt)
+        self._ck(self.lib.tvk_uvf_read_rdb_volume(self.h, _p(out), C.c_uint64(out.nbytes)), "tvk_uvf_read_rdb_volume")
         return out
 
     def minmax(self):

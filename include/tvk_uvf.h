@@ -84,6 +84,10 @@ typedef struct tvk_uvf_info {
   uint64_t maxmin_bricks;
   uint32_t kv_count;
   uint32_t checksum_ok;             /* 1 verified, 0 not verified (verify_checksum = 0)     */
+  /* legacy RasterDataBlock (UVF versions < 5, e.g. DemoData/c60.uvf): finest level only    */
+  int32_t  rdb_block;               /* index of the first 3-D scalar RasterDataBlock, -1 if none */
+  uint32_t rdb_bits, rdb_signed;    /* element width (8 / 16) and signedness                */
+  uint64_t rdb_domain[3], rdb_brick[3], rdb_overlap[3], rdb_lod_levels;
 } tvk_uvf_info;
 
 int  tvk_uvf_open(const char* path, int verify_checksum, tvk_uvf** out, char* err, size_t errlen);
@@ -95,6 +99,10 @@ int  tvk_uvf_get_toc(const tvk_uvf* u, uint64_t* file_offsets, uint64_t* lengths
 /* ExtendedOctree::GetBrickData for bricks [first, first+count): decompressed, each written at
  * dst + dst_offsets[i] (i relative to `first`); dst_offsets == NULL packs them tightly. */
 int  tvk_uvf_read_bricks(tvk_uvf* u, uint64_t first, uint64_t count, void* dst, const uint64_t* dst_offsets);
+/* RasterDataBlock::GetData over all bricks of the finest level, stitched back into the flat x-fastest volume
+ * (rdb_domain voxels of rdb_bits/8 bytes): what DynamicBrickingDS (IO/DynamicBrickingDS.cpp) starts from when it
+ * re-bricks a legacy / large-brick file for the ray-guided renderer. */
+int  tvk_uvf_read_rdb_volume(tvk_uvf* u, void* dst, uint64_t dst_bytes);
 int  tvk_uvf_get_minmax(const tvk_uvf* u, double* minmax4, uint64_t n);   /* min, max, minGrad, maxGrad per brick */
 int  tvk_uvf_get_hist1d(const tvk_uvf* u, uint64_t* bins, uint64_t n);
 int  tvk_uvf_get_hist2d(const tvk_uvf* u, uint64_t* bins, uint64_t n);

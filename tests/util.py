@@ -145,3 +145,45 @@ def resident_pool(tvk, vol, brick, tf_rgba8, lo, hi, sampler=0):
     tvk.set_tf1d(tf_rgba8)
     tvk.recompute_visibility(0, lo, hi)
     tvk.build_release()
+
+
+def write_rdb_uvf(path, vol, brick=256, overlap=4, block_id="Qvis data volume converted by ImageVis3D"):
+    """TEST HELPER: writes a legacy (UVF version 2) file with one single-LOD RasterDataBlock, the layout
+    RasterDataBlock::CopyHeaderToFile / ComputeBricks give it (Tuvok/IO/UVF/RasterDataBlock.cpp:210-260,321-349;
+    DemoData/c60.uvf is such a file) plus an MD5 checksum -- so that the legacy reader can be tested where
+    /root/reference (and with it DemoData) does not exist."""
+    import hashlib
+    import struct
+    vol = np.ascontiguousarray(vol)
+    dz, dy, dx = vol.shape
+    bits = 8 * vol.dtype.itemsize
+
+    def axis(size):
+        out = []
+        if size <= brick:
+            return [size]
+        while True:
+            if size + overlap <= brick:
+                out.append(size)
+                break
+            out.append(brick)
+            size = size + overlap - brick
+            if size <= overlap:
+                break
+        return out
+    ax = [axis(dx), axis(dy), axis(dz)]
+    payload = bytearray()
+    step = brick - overlap
+    for kz, sz in enumerate(ax[2]):
+        for ky, sy in enumerate(ax[1]):
+            for kx, sx in enumerate(ax[0]):
+                payload += vol[kz * step:kz * step + sz, ky * step:ky * step + sy, kx * step:kx * step + sx].tobytes()
+    q = lambda *v: struct.pack("<%dQ" % len(v), *v)        # noqa: E731
+    hdr = q(3) + q(1, 2, 3) + struct.pack("<16d", *np.eye(4).reshape(-1)) + q(dx, dy, dz) + q(brick, brick, brick)
+    hdr += q(overlap, overlap, overlap) + q(2, 2, 2) + q(0, 0, 0) + q(1) + q(1) + q(1) + q(0) + q(bits) + q(bits) + b"\x00" + q(0)
+    bid = block_id.encode()
+    block = q(len(bid)) + bid + q(1) + q(0) + q(0) + hdr + bytes(payload)          # last block: offsetToNext = 0
+    body = q(0) + block                                                             # offsetToFirstDataBlock + blocks
+    digest = hashlib.md5(body).digest()
+    with open(path, "wb") as f:
+        f.write(b"UVF-DATA" + b"\x00" + q(2) + q(2) + q(16) + digest + body)
