@@ -266,6 +266,77 @@ __global__ void __launch_bounds__(256) place_bricks_q4(const PlaceJob* __restric
   }
 }
 
+// Vector form of place_bricks_q4 for bricks whose rows are a multiple of four voxels: a thread builds four
+// consecutive quads from four voxels of each of the rows (y,z), (y+1,z), (y,z+1), (y+1,z+1) -- four 4/8-byte
+// loads, one (u8) or two (u16) 16-byte stores, no per-voxel division.
+template <typename T>
+__global__ void __launch_bounds__(256) place_bricks_q4_vec(const PlaceJob* __restrict__ jobs, void* __restrict__ pool_v,
+                                                            const __grid_constant__ PoolConst pc) {
+  const PlaceJob j = jobs[blockIdx.x];
+  const uint32_t s0 = j.slot % pc.capacity[0], s1 = (j.slot / pc.capacity[0]) % pc.capacity[1],
+                 s2 = j.slot / (pc.capacity[0] * pc.capacity[1]);
+  const size_t px = pc.pool_dim[0], pxy = px * pc.pool_dim[1];
+  const size_t base = (size_t)s0 * pc.max_brick[0] + (size_t)s1 * pc.max_brick[1] * px + (size_t)s2 * pc.max_brick[2] * pxy;   // in quads
+  const uint32_t gx = j.sx / 4, rows = j.sy * j.sz, total = gx * rows;
+  for (uint32_t i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
+    const uint32_t r = i / gx, x = (i - r * gx) * 4;
+    const uint32_t y = r % j.sy, z = r / j.sy;
+    const uint32_t y1 = min(y + 1, j.sy - 1), z1 = min(z + 1, j.sz - 1);
+    const size_t quad = base + x + (size_t)y * px + (size_t)z * pxy;
+    if (sizeof(T) == 1) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(j.src);
+      const uint32_t a = src[(x + j.sx * (y + j.sy * z)) >> 2], b = src[(x + j.sx * (y1 + j.sy * z)) >> 2];
+      const uint32_t c = src[(x + j.sx * (y + j.sy * z1)) >> 2], d = src[(x + j.sx * (y1 + j.sy * z1)) >> 2];
+      // quad k = { a.byte[k], b.byte[k], c.byte[k], d.byte[k] }
+      const uint32_t ab0 = __byte_perm(a, b, 0x5140), ab1 = __byte_perm(a, b, 0x7362);     // a0 b0 a1 b1 | a2 b2 a3 b3
+      const uint32_t cd0 = __byte_perm(c, d, 0x5140), cd1 = __byte_perm(c, d, 0x7362);
+      uint4 o;
+      o.x = __byte_perm(ab0, cd0, 0x5410); o.y = __byte_perm(ab0, cd0, 0x7632);
+      o.z = __byte_perm(ab1, cd1, 0x5410); o.w = __byte_perm(ab1, cd1, 0x7632);
+      reinterpret_cast<uint4*>(static_cast<uchar4*>(pool_v) + quad)[0] = o;
+    } else {
+      const uint2* src = reinterpret_cast<const uint2*>(j.src);
+      const uint2 a = src[(x + j.sx * (y + j.sy * z)) >> 2], b = src[(x + j.sx * (y1 + j.sy * z)) >> 2];
+      const uint2 c = src[(x + j.sx * (y + j.sy * z1)) >> 2], d = src[(x + j.sx * (y1 + j.sy * z1)) >> 2];
+      // quad k = { a.half[k], b.half[k], c.half[k], d.half[k] } (8 bytes each)
+      uint4 o0, o1;
+      o0.x = __byte_perm(a.x, b.x, 0x5410); o0.y = __byte_perm(c.x, d.x, 0x5410);
+      o0.z = __byte_perm(a.x, b.x, 0x7632); o0.w = __byte_perm(c.x, d.x, 0x7632);
+      o1.x = __byte_perm(a.y, b.y, 0x5410); o1.y = __byte_perm(c.y, d.y, 0x5410);
+      o1.z = __byte_perm(a.y, b.y, 0x7632); o1.w = __byte_perm(c.y, d.y, 0x7632);
+      uint4* dst = reinterpret_cast<uint4*>(static_cast<ushort4*>(pool_v) + quad);
+      dst[0] = o0; dst[1] = o1;
+    }
+  }
+}
+
+// Pager gather: pulls the bricks of one batch out of PINNED host memory straight over PCIe (zero-copy loads,
+// 16 bytes per thread, every SM issuing) into the staging area -- one launch instead of one cudaMemcpyAsync per
+// brick, whose set-up cost is comparable to the 5 us a 256 KB brick takes on the wire.
+struct GatherJob {
+  const uint8_t* src;      // device alias of the pinned host address
+  uint8_t* dst;            // staging
+  uint64_t bytes;
+};
+__global__ void __launch_bounds__(256) gather_from_host_kernel(const GatherJob* __restrict__ jobs) {
+  const GatherJob j = jobs[blockIdx.x];
+  const uint64_t tid = (uint64_t)blockIdx.y * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.y * blockDim.x;
+  if (((reinterpret_cast<uintptr_t>(j.src) | reinterpret_cast<uintptr_t>(j.dst)) & 15) == 0) {
+    const uint64_t nv = j.bytes / 16;
+    const uint4* s = reinterpret_cast<const uint4*>(j.src);
+    uint4* d = reinterpret_cast<uint4*>(j.dst);
+    uint64_t i = tid;
+    for (; i + 3 * nth < nv; i += 4 * nth) {            // four loads in flight per thread
+      const uint4 a = __ldcs(s + i), b = __ldcs(s + i + nth), c = __ldcs(s + i + 2 * nth), e = __ldcs(s + i + 3 * nth);
+      d[i] = a; d[i + nth] = b; d[i + 2 * nth] = c; d[i + 3 * nth] = e;
+    }
+    for (; i < nv; i += nth) d[i] = __ldcs(s + i);
+    for (uint64_t k = nv * 16 + tid; k < j.bytes; k += nth) j.dst[k] = j.src[k];
+  } else {
+    for (uint64_t k = tid; k < j.bytes; k += nth) j.dst[k] = j.src[k];
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) place_bricks_surface(const PlaceJob* __restrict__ jobs, cudaSurfaceObject_t surf,
                                                              const __grid_constant__ PoolConst pc) {
@@ -295,8 +366,24 @@ static int place_batch(tvk_ctx* c, std::vector<PlaceJob>& jobs, cudaStream_t st)
   TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(PlaceJob) * jobs.size(), cudaMemcpyHostToDevice, st));
   const dim3 grid((unsigned)jobs.size(), 8);
   if (c->pdesc.sampler == TVK_SAMPLER_EXACT_Q4) {
-    if (c->pc.bpv == 1) place_bricks_q4<uint8_t, uchar4><<<grid, 256, 0, st>>>(d_jobs, (uchar4*)c->d_pool, c->pc);
-    else place_bricks_q4<uint16_t, ushort4><<<grid, 256, 0, st>>>(d_jobs, (ushort4*)c->d_pool, c->pc);
+    // jobs with rows of a multiple of four voxels (and a source aligned to four voxels) take the vector kernel
+    auto q4_vec = [bpv, &c](const PlaceJob& j) {
+      return (j.sx & 3) == 0 && (((uintptr_t)j.src) & (4 * bpv - 1)) == 0 && (c->pc.max_brick[0] & 3) == 0;
+    };
+    std::vector<PlaceJob> sorted(jobs);
+    const size_t nv = std::stable_partition(sorted.begin(), sorted.end(), q4_vec) - sorted.begin();
+    TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_jobs, sorted.data(), sizeof(PlaceJob) * sorted.size(), cudaMemcpyHostToDevice, st));
+    // (a cudaMemcpyAsync from pageable memory returns once the source has been staged: the locals may go)
+    if (nv) {
+      if (bpv == 1) place_bricks_q4_vec<uint8_t><<<dim3((unsigned)nv, 8), 256, 0, st>>>(d_jobs, c->d_pool, c->pc);
+      else place_bricks_q4_vec<uint16_t><<<dim3((unsigned)nv, 8), 256, 0, st>>>(d_jobs, c->d_pool, c->pc);
+    }
+    if (nv < sorted.size()) {
+      const dim3 g2((unsigned)(sorted.size() - nv), 8);
+      if (bpv == 1) place_bricks_q4<uint8_t, uchar4><<<g2, 256, 0, st>>>(d_jobs + nv, (uchar4*)c->d_pool, c->pc);
+      else place_bricks_q4<uint16_t, ushort4><<<g2, 256, 0, st>>>(d_jobs + nv, (ushort4*)c->d_pool, c->pc);
+      if (nv) c->launches++;
+    }
   } else if (c->pdesc.sampler == TVK_SAMPLER_EXACT) {
     // jobs arrive sorted: [0, nvec) can move 16 B per access, the rest go byte-wise
     size_t nvec = 0;
@@ -349,9 +436,35 @@ extern "C" int tvk_pool_upload_bricks(tvk_ctx* c, uint32_t n, const uint32_t* sl
     uint8_t* staging = nullptr;
     const uint32_t cap = std::min(n, batch);
     if (cap) TVK_CHECK_CUDA(c, cudaMallocAsync(&staging, slot_bytes * cap, st));
+    // zero-copy gather when every source is pinned, device-mapped host memory; else one DMA per (run of) brick(s)
+    std::vector<const uint8_t*> alias(n, nullptr);
+    bool mapped = true;
+    for (uint32_t i = 0; i < n && mapped; ++i) {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, src[i]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) { mapped = false; (void)cudaGetLastError(); }
+      else alias[i] = static_cast<const uint8_t*>(at.devicePointer);
+    }
     for (uint32_t b0 = 0; b0 < n; b0 += batch) {
       const uint32_t bn = std::min(batch, n - b0);
       std::vector<PlaceJob> jobs(bn);
+      if (mapped) {
+        std::vector<GatherJob> gj(bn);
+        for (uint32_t i = 0; i < bn; ++i) {
+          const uint32_t k = b0 + i;
+          gj[i] = GatherJob{alias[k], staging + slot_bytes * i, (uint64_t)sizes[3 * k] * sizes[3 * k + 1] * sizes[3 * k + 2] * c->pc.bpv};
+          jobs[i] = PlaceJob{staging + slot_bytes * i, slot[k], sizes[3 * k], sizes[3 * k + 1], sizes[3 * k + 2]};
+        }
+        GatherJob* d_gj = nullptr;
+        TVK_CHECK_CUDA(c, cudaMallocAsync(&d_gj, sizeof(GatherJob) * bn, st));
+        TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_gj, gj.data(), sizeof(GatherJob) * bn, cudaMemcpyHostToDevice, st));
+        gather_from_host_kernel<<<dim3(bn, 8), 256, 0, st>>>(d_gj);
+        c->launches++;
+        TVK_CHECK_CUDA(c, cudaGetLastError());
+        TVK_CHECK_CUDA(c, cudaFreeAsync(d_gj, st));
+        int rc = place_batch(c, jobs, st);
+        if (rc) return rc;
+        continue;
+      }
       for (uint32_t i = 0; i < bn;) {
         // full-size bricks that are contiguous in host memory go out as ONE DMA
         uint32_t run = 1;
