@@ -30,6 +30,7 @@
 #include "tvk_internal.h"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 static const uint64_t kBrickAlign = 256;   // device store: every brick starts 256 B aligned
@@ -542,6 +543,174 @@ __global__ void __launch_bounds__(256) cut_bricks_vec_kernel(const T* __restrict
   }
 }
 
+// ------------------------------------------------------------------ fused LOD-0 pass
+// One read of the raw volume produces everything LOD 0 contributes: the LOD-0 bricks (ghost layers and min/max
+// included), the 1-D histogram and the flat LOD-1 volume.  A thread owns, for one CB-byte x chunk of a brick,
+// the 2x2 rows (j, j+1) x (k, k+1): the brick's inner region starts at the (even) overlap and the inner size of
+// a brick is even, so those rows and the chunk's voxel pairs are exactly the 2x2x2 blocks of the reduction
+// (ghost rows / voxels pair up among themselves and are only copied).  Every raw voxel is an inner voxel of
+// exactly one brick, which makes the histogram and the LOD-1 volume complete.  Persistent: one CTA of 1024
+// threads per SM walks the bricks bx in [x_first, x_first + x_count) of the lattice; histogram table in shared
+// memory as in downsample_hist_kernel.  Needs an even overlap and LOD-0 extents > 1.
+// STATUS: bit-exact, ~35 % less DRAM traffic, but one 1024-thread CTA per SM at 64 registers leaves too few loads
+// in flight: 2048^3 u16 takes 25.0 ms fused vs 22.4 ms with the separate kernels.  Opt-in (TVK_BUILD_FUSED=1).
+template <typename T, int CB>
+__device__ __forceinline__ uint4 lod0_chunk(const uint8_t* __restrict__ fb, uint64_t nbytes, uint32_t sx, uint32_t sy,
+                                            int bx, int by, int bz, int core, int o, int i0, int j, int k,
+                                            bool row_ok, int xlo, int xhi) {
+  constexpr int E = CB / (int)sizeof(T);
+  const int lo = max(xlo, i0), hi = min(xhi, i0 + E);
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (row_ok && lo < hi) {
+    const int64_t lin = (int64_t)(bx * core - o + i0) + (int64_t)(by * core - o + j) * sx + (int64_t)(bz * core - o + k) * sx * sy;
+    v = load_chunk<CB>(fb, lin * (int64_t)sizeof(T), nbytes);
+    if (lo > i0 || hi < i0 + E) v = keep16(v, (lo - i0) * (int)sizeof(T), (hi - i0) * (int)sizeof(T));
+  }
+  return v;
+}
+template <int CB> __device__ __forceinline__ void store_chunk(void* dst, uint32_t c, const uint4& v) {
+  if (CB == 16) reinterpret_cast<uint4*>(dst)[c] = v;
+  else if (CB == 8) reinterpret_cast<uint2*>(dst)[c] = make_uint2(v.x, v.y);
+  else reinterpret_cast<uint32_t*>(dst)[c] = v.x;
+}
+template <typename T, int CB> __device__ __forceinline__ void chunk_minmax(const uint4& v, uint32_t& pmn, uint32_t& pmx) {
+  if (CB == 16) vec_minmax<T>(v, pmn, pmx);
+  else if (CB == 8) vec_minmax<T>(make_uint4(v.x, v.y, v.x, v.y), pmn, pmx);
+  else vec_minmax<T>(make_uint4(v.x, v.x, v.x, v.x), pmn, pmx);
+}
+// histogram of the chunk's elements [e_lo, e_hi)
+template <typename T, int CB>
+__device__ __forceinline__ void hist_add_range(const uint4& q, int e_lo, int e_hi, unsigned int* __restrict__ table) {
+  constexpr int E = CB / (int)sizeof(T);
+  if (sizeof(T) == 1) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) if (e >= e_lo && e < e_hi) atomicAdd(&table[vec_get<T>(q, e)], 1u);
+  } else {
+    uint32_t cur = 0xFFFFFFFFu, cnt = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if (e < e_lo || e >= e_hi) continue;
+      const uint32_t v = vec_get<T>(q, e);
+      if (v == cur) cnt++;
+      else {
+        if (cnt && cur < HIST_WINDOW) atomicAdd(&table[cur], cnt);
+        cur = v; cnt = 1;
+      }
+    }
+    if (cnt && cur < HIST_WINDOW) atomicAdd(&table[cur], cnt);
+  }
+}
+
+template <typename T, int CB, bool MEDIAN>
+__global__ void __launch_bounds__(1024, 1) lod0_fused_kernel(const T* __restrict__ raw, uint8_t* __restrict__ store,
+                                                             const uint64_t* __restrict__ offsets, const __grid_constant__ BuildConst bc,
+                                                             uint32_t* __restrict__ mn, uint32_t* __restrict__ mx,
+                                                             uint32_t x_first, uint32_t x_count, T* __restrict__ lod1,
+                                                             unsigned long long* __restrict__ bins) {
+  extern __shared__ unsigned int hsm[];
+  constexpr uint32_t TABLE = sizeof(T) == 1 ? 32u * 256u : HIST_WINDOW;
+  constexpr int E = CB / (int)sizeof(T);
+  for (uint32_t i = threadIdx.x; i < TABLE; i += blockDim.x) hsm[i] = 0u;
+  __syncthreads();
+  unsigned int* mine = sizeof(T) == 1 ? hsm + (threadIdx.x >> 5) * 256u : hsm;
+  const uint32_t nbx = bc.lod_bricks[0][0], nby = bc.lod_bricks[0][1], nbz = bc.lod_bricks[0][2];
+  const uint32_t sx = bc.lod_size[0][0], sy = bc.lod_size[0][1], sz = bc.lod_size[0][2];
+  const uint32_t dx = bc.lod_size[1][0], dy = bc.lod_size[1][1];
+  const uint64_t nbytes = (uint64_t)sx * sy * sz * sizeof(T);
+  const uint8_t* fb = reinterpret_cast<const uint8_t*>(raw);
+  const int o = (int)bc.overlap, core = (int)bc.core;
+  const uint32_t nbricks = x_count * nby * nbz;
+  for (uint32_t bi = blockIdx.x; bi < nbricks; bi += gridDim.x) {
+    const int bx = (int)(x_first + bi % x_count), by = (int)((bi / x_count) % nby), bz = (int)(bi / (x_count * nby));
+    const uint32_t b = (uint32_t)bx + (uint32_t)by * nbx + (uint32_t)bz * nbx * nby;
+    const uint32_t tx = brick_dim(bc, 0, 0, bx), ty = brick_dim(bc, 0, 1, by), tz = brick_dim(bc, 0, 2, bz);
+    void* dst = store + offsets[b];
+    const bool fx = bx == 0, fy = by == 0, fz = bz == 0;
+    const bool lx = bx == (int)nbx - 1, ly = by == (int)nby - 1, lz = bz == (int)nbz - 1;
+    const int xlo = fx ? o : 0, xhi = (int)tx - (lx ? o : 0);
+    const uint32_t cpr = tx / E, jp_n = (ty + 1) / 2, kp_n = (tz + 1) / 2, units = cpr * jp_n * kp_n;
+    uint32_t pmn = 0xFFFFFFFFu, pmx = 0u;
+    for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) {
+      const uint32_t cx = u % cpr, rp = u / cpr;
+      const int i0 = (int)cx * E, j = 2 * (int)(rp % jp_n), k = 2 * (int)(rp / jp_n);
+      const bool j1 = j + 1 < (int)ty, k1 = k + 1 < (int)tz;
+      auto ok = [&](int jj, int kk) {
+        return jj >= (fy ? o : 0) && jj < (int)ty - (ly ? o : 0) && kk >= (fz ? o : 0) && kk < (int)tz - (lz ? o : 0);
+      };
+      const uint4 a = lod0_chunk<T, CB>(fb, nbytes, sx, sy, bx, by, bz, core, o, i0, j, k, ok(j, k), xlo, xhi);
+      uint4 bq = a, c = a, d = a;
+      store_chunk<CB>(dst, cx + cpr * ((uint32_t)j + ty * (uint32_t)k), a);
+      chunk_minmax<T, CB>(a, pmn, pmx);
+      if (k1) { bq = lod0_chunk<T, CB>(fb, nbytes, sx, sy, bx, by, bz, core, o, i0, j, k + 1, ok(j, k + 1), xlo, xhi);
+                store_chunk<CB>(dst, cx + cpr * ((uint32_t)j + ty * (uint32_t)(k + 1)), bq); chunk_minmax<T, CB>(bq, pmn, pmx); }
+      if (j1) { c = lod0_chunk<T, CB>(fb, nbytes, sx, sy, bx, by, bz, core, o, i0, j + 1, k, ok(j + 1, k), xlo, xhi);
+                store_chunk<CB>(dst, cx + cpr * ((uint32_t)(j + 1) + ty * (uint32_t)k), c); chunk_minmax<T, CB>(c, pmn, pmx); }
+      if (j1 && k1) { d = lod0_chunk<T, CB>(fb, nbytes, sx, sy, bx, by, bz, core, o, i0, j + 1, k + 1, ok(j + 1, k + 1), xlo, xhi);
+                      store_chunk<CB>(dst, cx + cpr * ((uint32_t)(j + 1) + ty * (uint32_t)(k + 1)), d); chunk_minmax<T, CB>(d, pmn, pmx); }
+      // inner part: rows j / k inner?  (pairs never straddle the inner boundary: the overlap is even)
+      const bool inner_j = j >= o && j < (int)ty - o, inner_k = k >= o && k < (int)tz - o;
+      if (!inner_j || !inner_k) continue;
+      const bool hy = j + 1 < (int)ty - o, hz = k + 1 < (int)tz - o;
+      const int e_lo = max(o - i0, 0), e_hi = min((int)tx - o - i0, E);
+      if (e_lo >= e_hi) continue;
+      hist_add_range<T, CB>(a, e_lo, e_hi, mine);
+      if (hz) hist_add_range<T, CB>(bq, e_lo, e_hi, mine);
+      if (hy) hist_add_range<T, CB>(c, e_lo, e_hi, mine);
+      if (hy && hz) hist_add_range<T, CB>(d, e_lo, e_hi, mine);
+      const uint32_t Y = (uint32_t)(by * core + j - o) >> 1, Z = (uint32_t)(bz * core + k - o) >> 1;
+      T* orow = lod1 + (uint64_t)Y * dx + (uint64_t)Z * dx * dy;
+#pragma unroll
+      for (int m = 0; m < E / 2; ++m) {
+        const int e0 = 2 * m;
+        if (e0 < e_lo || e0 >= e_hi) continue;
+        const bool hx = e0 + 1 < e_hi;
+        const T a0 = (T)vec_get<T>(a, e0), a1 = (T)vec_get<T>(a, e0 + 1), b0 = (T)vec_get<T>(bq, e0), b1 = (T)vec_get<T>(bq, e0 + 1);
+        const T c0 = (T)vec_get<T>(c, e0), c1 = (T)vec_get<T>(c, e0 + 1), d0 = (T)vec_get<T>(d, e0), d1 = (T)vec_get<T>(d, e0 + 1);
+        T r;
+        // argument order = p0..p7 of DownsampleBricktoBrick (see downsample_kernel)
+        if (hx && hy && hz) r = filter8<T, MEDIAN>(a0, b0, c0, d0, a1, b1, c1, d1);
+        else if (!hx && hy && hz) r = filter4<T, MEDIAN>(a0, b0, c0, d0);
+        else if (hx && !hy && hz) r = filter4<T, MEDIAN>(a0, b0, a1, b1);
+        else if (hx && hy && !hz) r = filter4<T, MEDIAN>(a0, c0, a1, c1);
+        else if (!hx && !hy && hz) r = filter2<T, MEDIAN>(a0, b0);
+        else if (hx && !hy && !hz) r = filter2<T, MEDIAN>(a0, a1);
+        else if (!hx && hy && !hz) r = filter2<T, MEDIAN>(a0, c0);
+        else r = a0;
+        orow[(uint32_t)(bx * core + i0 + e0 - o) >> 1] = r;
+      }
+    }
+    uint32_t lo, hi;
+    if (sizeof(T) == 1) {
+      lo = min(min(pmn & 0xFFu, (pmn >> 8) & 0xFFu), min((pmn >> 16) & 0xFFu, pmn >> 24));
+      hi = max(max(pmx & 0xFFu, (pmx >> 8) & 0xFFu), max((pmx >> 16) & 0xFFu, pmx >> 24));
+    } else {
+      lo = min(pmn & 0xFFFFu, pmn >> 16);
+      hi = max(pmx & 0xFFFFu, pmx >> 16);
+    }
+    for (int s = 16; s > 0; s >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+    }
+    if ((threadIdx.x & 31) == 0 && lo <= hi) {
+      atomicMin(mn + b, lo);
+      atomicMax(mx + b, hi);
+    }
+  }
+  __syncthreads();
+  if (sizeof(T) == 1) {
+    for (uint32_t t = threadIdx.x; t < 256u; t += blockDim.x) {
+      unsigned int sum = 0;
+      for (uint32_t w = 0; w < 32u; ++w) sum += hsm[w * 256u + t];
+      if (sum) atomicAdd(&bins[t], (unsigned long long)sum);
+    }
+  } else {
+    for (uint32_t t = threadIdx.x; t < HIST_WINDOW; t += blockDim.x) {
+      const unsigned int sum = hsm[t];
+      if (sum) atomicAdd(&bins[t], (unsigned long long)sum);
+    }
+  }
+}
+
 __global__ void minmax_to_double_kernel(const uint32_t* mn, const uint32_t* mx, double* out, uint64_t n, uint32_t* gmax) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t m = 0;
@@ -832,9 +1001,52 @@ static int run_build(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms) {
   const uint32_t range = 1u << (8 * sizeof(T));
   TVK_CHECK_CUDA(c, cudaMalloc(&b.d_hist1d, sizeof(unsigned long long) * range));
   TVK_CHECK_CUDA(c, cudaEventRecord(c->bev0, st));
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(d_mn, 0xFF, sizeof(uint32_t) * info.total_bricks, st));
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(d_mx, 0, sizeof(uint32_t) * (info.total_bricks + 1), st));
+  bool hist_fused = false, lod0_fused = false;
+  // ---- fused LOD-0 pass: bricks + min/max + 1-D histogram + flat LOD 1 from ONE read of the raw volume
+  {
+    const uint32_t* s0 = info.lod_size[0];
+    const uint32_t nbx = info.lod_bricks[0][0];
+    const uint32_t last_tx = brick_dim(bc, 0, 0, nbx - 1);
+    const uint32_t groups[2][3] = {{0u, last_tx == bc.brick ? nbx : nbx - 1, bc.brick}, {nbx - 1, last_tx == bc.brick ? 0u : 1u, last_tx}};
+    bool can = info.lod_count >= 2 && s0[0] > 1 && s0[1] > 1 && s0[2] > 1 && (bc.overlap % 2) == 0 && bc.core >= bc.overlap &&
+               (reinterpret_cast<uintptr_t>(b.d_lod[0]) & 3) == 0 && (uint64_t)s0[0] * s0[1] * s0[2] >= (1u << 18) &&
+               getenv("TVK_BUILD_FUSED") != nullptr;    // opt-in: measured SLOWER than the separate kernels, see DESIGN.md
+    for (int g = 0; g < 2; ++g) if (groups[g][1] && (groups[g][2] * sizeof(T)) % 4 != 0) can = false;
+    if (can) {
+      const size_t smem = sizeof(unsigned int) * (sizeof(T) == 1 ? 32u * 256u : HIST_WINDOW);
+      TVK_CHECK_CUDA(c, cudaMemsetAsync(b.d_hist1d, 0, sizeof(unsigned long long) * range, st));
+      for (int g = 0; g < 2; ++g) {
+        const uint32_t x_first = groups[g][0], x_count = groups[g][1], row_bytes = groups[g][2] * (uint32_t)sizeof(T);
+        if (!x_count) continue;
+        const uint64_t nb = (uint64_t)x_count * info.lod_bricks[0][1] * info.lod_bricks[0][2];
+        const unsigned grid = (unsigned)std::min<uint64_t>(nb, (uint64_t)sms);
+        const T* src = (const T*)b.d_lod[0];
+        uint8_t* store = (uint8_t*)b.d_store;
+        T* l1 = (T*)b.d_lod[1];
+#define TVK_LAUNCH_FUSED(CBV)                                                                                                  \
+        do {                                                                                                                   \
+          if (b.desc.use_median) {                                                                                             \
+            TVK_CHECK_CUDA(c, cudaFuncSetAttribute(lod0_fused_kernel<T, CBV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            lod0_fused_kernel<T, CBV, true><<<grid, 1024, smem, st>>>(src, store, b.d_offsets, bc, d_mn, d_mx, x_first, x_count, l1, b.d_hist1d); \
+          } else {                                                                                                             \
+            TVK_CHECK_CUDA(c, cudaFuncSetAttribute(lod0_fused_kernel<T, CBV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            lod0_fused_kernel<T, CBV, false><<<grid, 1024, smem, st>>>(src, store, b.d_offsets, bc, d_mn, d_mx, x_first, x_count, l1, b.d_hist1d); \
+          }                                                                                                                    \
+        } while (0)
+        if (row_bytes % 16 == 0) TVK_LAUNCH_FUSED(16);
+        else if (row_bytes % 8 == 0) TVK_LAUNCH_FUSED(8);
+        else TVK_LAUNCH_FUSED(4);
+#undef TVK_LAUNCH_FUSED
+        c->launches++;
+      }
+      TVK_CHECK_CUDA(c, cudaGetLastError());
+      hist_fused = true; lod0_fused = true;
+    }
+  }
   // flat pyramid
-  bool hist_fused = false;
-  for (uint32_t l = 1; l < info.lod_count; ++l) {
+  for (uint32_t l = lod0_fused ? 2u : 1u; l < info.lod_count; ++l) {
     const uint32_t* s = info.lod_size[l - 1];
     const uint32_t* d = info.lod_size[l];
     const bool vec = (s[0] % E) == 0 && (reinterpret_cast<uintptr_t>(b.d_lod[l - 1]) & 15) == 0;
@@ -867,9 +1079,7 @@ static int run_build(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms) {
   }
   TVK_CHECK_CUDA(c, cudaGetLastError());
   // bricks + stats
-  TVK_CHECK_CUDA(c, cudaMemsetAsync(d_mn, 0xFF, sizeof(uint32_t) * info.total_bricks, st));
-  TVK_CHECK_CUDA(c, cudaMemsetAsync(d_mx, 0, sizeof(uint32_t) * (info.total_bricks + 1), st));
-  for (uint32_t l = 0; l < info.lod_count; ++l) {
+  for (uint32_t l = lod0_fused ? 1u : 0u; l < info.lod_count; ++l) {
     // one launch for the full-width bricks, one for the last column if it is narrower
     const uint32_t nbx = info.lod_bricks[l][0];
     const uint32_t last_tx = brick_dim(bc, l, 0, nbx - 1);

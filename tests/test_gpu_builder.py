@@ -99,3 +99,21 @@ def test_builder_full_size_properties(tvk):
     blk = raw[:120, :120, :120].astype(np.uint32).reshape(60, 2, 60, 2, 60, 2).sum(axis=(1, 3, 5)) // 8
     assert (b1[2:62, 2:62, 2:62] == blk).all()
     tvk.build_release()
+
+
+@pytest.mark.parametrize("vol,dtype,median", [((130, 121, 64), np.uint8, False), ((200, 150, 100), np.uint16, True), ((96, 96, 96), np.uint16, False)])
+def test_fused_lod0_pass_is_bit_exact(vol, dtype, median, monkeypatch):
+    """TVK_BUILD_FUSED=1: bricks + min/max + 1-D histogram + LOD 1 from one read of the raw volume (opt-in path)."""
+    from imagevis3d_b200.context import TvkContext
+    monkeypatch.setenv("TVK_BUILD_FUSED", "1")
+    t = TvkContext(0)
+    raw = H.synth_noise(vol, dtype, seed=sum(vol), maxval=255 if dtype == np.uint8 else 50000)
+    oc = O.build_octree(raw, 64, 2, median)
+    t.build_octree(raw, 64, 2, median=median)
+    store, sizes = cuda_store_tight(t)
+    assert (store == oc["store"]).all() and (t.build_minmax() == oc["minmax"]).all()
+    h1 = t.build_hist1d()
+    ref = np.bincount(raw.reshape(-1), minlength=1 << (8 * raw.dtype.itemsize))
+    ref = ref[:np.nonzero(ref)[0][-1] + 1]
+    assert h1.size == ref.size and (h1 == ref).all()
+    t.close()
