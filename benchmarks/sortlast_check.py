@@ -35,11 +35,11 @@ def main():
     work_stream = torch.cuda.Stream(device=dev)      # (the legacy default stream's handle 0 would mean "own stream")
     torch.cuda.set_stream(work_stream)
     tvk.set_stream(work_stream.cuda_stream)
-    G = (256, 256, 128 * world)
+    G = (256, 256, 128 * world) if os.environ.get("TVK_PARTITION", "blocks") == "slabs" else (256 * (2 if world >= 2 else 1), 256 * (2 if world >= 4 else 1), 256 * max(world // 4, 1))
     W, Hh = 1283, 717                              # neither divisible by the world size nor by the tile size
-    parts = SL.slab_partition(G, world, halo=64)
+    parts = SL.slab_partition(G, world, halo=64) if os.environ.get("TVK_PARTITION", "blocks") == "slabs" else SL.block_partition(G, world, halo=64)
     part = parts[rank]
-    raw = B.volume_torch(part["local_dims"], dev, z0=part["zs"], zn=part["local_dims"][2], ztotal=G[2]).cpu().numpy()
+    raw = B.volume_torch(part["local_dims"], dev, origin=part["s"], total=G).cpu().numpy()
     tf, lo, hi = B.bench_tf()
     resident_pool(tvk, raw, 64, tf, lo, hi, sampler=2)
     fused = SL.FusedExchange(tvk, world, rank, W, Hh, dist)

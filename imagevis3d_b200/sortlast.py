@@ -18,28 +18,74 @@ import math
 import numpy as np
 
 
+def _part(lo, hi, gdims, halo):
+    s = [max(0, lo[a] - halo) for a in range(3)]
+    e = [min(gdims[a], hi[a] + halo) for a in range(3)]
+    return dict(lo=tuple(lo), hi=tuple(hi), s=tuple(s), e=tuple(e), local_dims=tuple(e[a] - s[a] for a in range(3)),
+                global_dims=tuple(gdims), z0=lo[2], z1=hi[2], zs=s[2], ze=e[2])
+
+
 def slab_partition(global_dims, world, halo=64):
     """Splits [0, Gz) into `world` z-slabs.  Each rank also keeps `halo` voxels of its neighbours so
     that trilinear/gradient taps and the coarser LODs (up to log2(halo)-1) see real data at the cut.
-    Returns one dict per rank: z0,z1 = the slab proper, zs,ze = slab + halo, local_dims."""
+    Returns one dict per rank: lo/hi = the slab proper, s/e = slab + halo, local_dims (z0,z1,zs,ze: the z range)."""
     gx, gy, gz = [int(v) for v in global_dims]
-    out = []
-    for r in range(world):
-        z0, z1 = (gz * r) // world, (gz * (r + 1)) // world
-        zs, ze = max(0, z0 - halo), min(gz, z1 + halo)
-        out.append(dict(z0=z0, z1=z1, zs=zs, ze=ze, local_dims=(gx, gy, ze - zs), global_dims=(gx, gy, gz)))
-    return out
+    return [_part((0, 0, (gz * r) // world), (gx, gy, (gz * (r + 1)) // world), (gx, gy, gz), halo) for r in range(world)]
+
+
+def block_grid(global_dims, world):
+    """(px, py, pz) with px*py*pz == world: the longest block edge is halved until the factors are used up, so the
+    blocks stay as cubic as the volume allows (8 -> 2x2x2 for a cube)."""
+    grid, n, dims = [1, 1, 1], int(world), [float(v) for v in global_dims]
+    f = 2
+    factors = []
+    while n > 1:
+        while n % f == 0:
+            factors.append(f)
+            n //= f
+        f += 1
+    for f in sorted(factors, reverse=True):
+        a = max(range(3), key=lambda k: (dims[k] / grid[k], k))
+        grid[a] *= f
+    return tuple(grid)
+
+
+def block_partition(global_dims, world, halo=64, align=64):
+    """Convex boxes on a regular px x py x pz grid, one per rank (rank = ix + px*(iy + py*iz)), cut at multiples of
+    `align` voxels.  Compared with z-slabs a ray meets about world^(1/3) boxes instead of `world`, so the per-ray
+    set-up work a rank repeats for rays that only graze its part shrinks accordingly.  Same dict as slab_partition."""
+    g = [int(v) for v in global_dims]
+    px, py, pz = block_grid(g, world)
+    cuts = []
+    for a, p in enumerate((px, py, pz)):
+        c = [int(round(g[a] * i / p / align)) * align for i in range(p + 1)]
+        c[0], c[-1] = 0, g[a]
+        cuts.append(c)
+    parts = []
+    for iz in range(pz):
+        for iy in range(py):
+            for ix in range(px):
+                parts.append(_part((cuts[0][ix], cuts[1][iy], cuts[2][iz]), (cuts[0][ix + 1], cuts[1][iy + 1], cuts[2][iz + 1]), g, halo))
+    return parts
 
 
 def depth_order(eye_to_model_global, parts):
-    """Front-to-back order of the slabs for the eye of this view.  The slabs are stacked along one
-    axis, so sorting them by the distance of their centre plane from the eye's z is exact: a ray
-    travels monotonically in z and meets the slabs of its side in exactly this order."""
+    """Front-to-back order of the parts (slabs or grid boxes) for the eye of this view.  Along every axis a ray
+    moves monotonically, so it meets the parts in non-decreasing distance of their [lo, hi) interval from the eye's
+    coordinate on EACH axis; sorting by the tuple of the three per-axis distances is a linear extension of that
+    product order, hence a correct visibility order for every ray at once (ties are parts no ray can cross both)."""
     m = np.asarray(eye_to_model_global, np.float64).reshape(4, 4)
-    eye_z = float((np.array([0, 0, 0, 1.0]) @ m)[2])            # eye in global normalised coords
-    gz = float(parts[0]["global_dims"][2])
-    centres = [0.5 * (p["z0"] + p["z1"]) / gz for p in parts]
-    return sorted(range(len(parts)), key=lambda r: (abs(centres[r] - eye_z), r))
+    eye = (np.array([0, 0, 0, 1.0]) @ m)[:3]                    # eye in global normalised coords
+    g = [float(v) for v in parts[0]["global_dims"]]
+
+    def key(r):
+        p = parts[r]
+        k = []
+        for a in range(3):
+            lo, hi = p["lo"][a] / g[a], p["hi"][a] / g[a]
+            k.append(max(lo - eye[a], 0.0, eye[a] - hi))
+        return (k[0], k[1], k[2], r)
+    return sorted(range(len(parts)), key=key)
 
 
 def stripe_rows(height, world):

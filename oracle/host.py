@@ -159,9 +159,16 @@ def raycast_params(cam, width, height, domain_size, scale=(1, 1, 1), render_mode
         # [z0, z1) plus a halo) as ITS volume; map global normalised coords to the local ones and
         # clip the rays to the slab proper.  domain_size is the GLOBAL size here.
         ld = np.asarray(slab["local_dims"], f32)
-        zs, z0, z1 = float(slab["zs"]), float(slab["z0"]), float(slab["z1"])
-        emm = (emm @ scaling(dom[0] / ld[0], dom[1] / ld[1], dom[2] / ld[2]) @ translation(0, 0, -zs / float(ld[2]))).astype(f32)
-        box_min[2], box_max[2] = (z0 - zs) / float(ld[2]), (z1 - zs) / float(ld[2])
+        if "lo" in slab:                                    # box partition (slabs are boxes spanning x and y)
+            lo3, hi3, s3 = [np.asarray(slab[k], np.float64) for k in ("lo", "hi", "s")]
+        else:
+            lo3 = np.array([0, 0, slab["z0"]], np.float64)
+            hi3 = np.array([dom[0], dom[1], slab["z1"]], np.float64)
+            s3 = np.array([0, 0, slab["zs"]], np.float64)
+        emm = (emm @ scaling(dom[0] / ld[0], dom[1] / ld[1], dom[2] / ld[2]) @
+               translation(-s3[0] / float(ld[0]), -s3[1] / float(ld[1]), -s3[2] / float(ld[2]))).astype(f32)
+        for a in range(3):
+            box_min[a], box_max[a] = (lo3[a] - s3[a]) / float(ld[a]), (hi3[a] - s3[a]) / float(ld[a])
     p.eye_to_model[:] = emm.reshape(-1).tolist()
     p.model_to_eye[:] = inverse(emm).reshape(-1).tolist()
     p.model_view_it[:] = inverse(mv).T.reshape(-1).tolist()

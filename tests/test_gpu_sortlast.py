@@ -82,6 +82,46 @@ def test_clip_box_validation(tvk):
         tvk.raycast(p)
 
 
+@pytest.mark.parametrize("world,angle", [(4, 0.4), (8, 2.3)])
+def test_block_partition_composites_like_one_volume(tvk, world, angle):
+    """regular-grid boxes (sortlast.block_partition) instead of z-slabs: per-box renders composited in
+    depth_order reproduce the single-volume render (oracle), as the slab test above does."""
+    import torch
+    G = (128, 128, 128)
+    vol = H.synth_blobs(G, np.uint8, seed=29)
+    parts = SL.block_partition(G, world, halo=32, align=32)
+    tf = _tf()
+    lo, hi = H.tf_nonzero_limits(tf)
+    cam = H.Camera()
+    cam.rotation = H.rotation_y(angle) @ H.rotation_x(0.35)
+    W, Hh = 160, 120
+    oc = O.build_octree(vol, 20, 2)
+    pool = H.OraclePool(oc, (9, 9, 9))
+    pool.upload_first_brick()
+    pool.recompute_visibility(0, float(lo), float(hi))
+    p_global = H.raycast_params(cam, W, Hh, G)
+    whole, _, _, _ = H.render_converged(p_global, pool, H.tf_bytes(tf))
+    order = SL.depth_order(np.array(p_global.eye_to_model[:]).reshape(4, 4), parts)
+    partials = {}
+    for r, part in enumerate(parts):
+        local = np.ascontiguousarray(vol[part["s"][2]:part["e"][2], part["s"][1]:part["e"][1], part["s"][0]:part["e"][0]])
+        ocl = O.build_octree(local, 20, 2)
+        pl = H.OraclePool(ocl, (7, 7, 7))
+        pl.upload_first_brick()
+        pl.recompute_visibility(0, float(lo), float(hi))
+        res = lockstep_render(tvk, H.raycast_params(cam, W, Hh, G, slab=part), pl, H.tf_bytes(tf))
+        psnr, err = image_errors(res["cuda"], res["oracle"])
+        assert psnr >= 45.0 and err <= 2.0 / 255.0, (r, psnr, err)
+        partials[r] = res["cuda"]
+    dev = [torch.from_numpy(np.ascontiguousarray(partials[r])).cuda() for r in order]
+    out = torch.zeros((Hh, W, 4), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    tvk.composite_ordered([d.data_ptr() for d in dev], W * Hh, out.data_ptr())
+    tvk.synchronize()
+    psnr, err = image_errors(out.cpu().numpy(), whole)
+    assert whole.max() > 0.05 and psnr >= 38.0 and err <= 12.0 / 255.0, (psnr, err)
+
+
 @pytest.mark.parametrize("world,angle", [(3, 0.3), (3, 3.5), (4, 1.9)])
 def test_fused_exchange_equals_separate_compositor(world, angle):
     """The fused direct-send path (K1 peer stores + arrival flags + stripe compositor, csrc/tvk_exchange.cu)

@@ -64,3 +64,41 @@ def test_slab_partition_and_depth_order():
     o = SL.depth_order(eye, parts)
     assert o[0] == 2 and o.index(1) < o.index(0) and set(o) == {0, 1, 2, 3}
     assert SL.stripe_rows(1080, 8) == 135 and SL.stripe_rows(37, 2) == 19
+
+
+def test_block_partition_and_visibility_order():
+    """regular-grid boxes: cover the volume exactly, cuts at multiples of 64, and depth_order is a correct
+    front-to-back order -- checked by brute force: along random rays from the eye the boxes met must appear in
+    increasing position of the order."""
+    assert SL.block_grid((1024, 1024, 1024), 8) == (2, 2, 2) and SL.block_grid((1024, 512, 512), 2) == (2, 1, 1)
+    assert SL.block_grid((1024, 1024, 512), 4) == (2, 2, 1) and SL.block_grid((64, 64, 192), 3) == (1, 1, 3)
+    rng = np.random.default_rng(7)
+    for dims, world in [((1024, 1024, 1024), 8), ((1024, 1024, 512), 4), ((768, 512, 640), 6), ((512, 512, 512), 12)]:
+        parts = SL.block_partition(dims, world, halo=64)
+        assert len(parts) == world
+        vol = sum(int(np.prod(np.array(p["hi"]) - np.array(p["lo"]))) for p in parts)
+        assert vol == int(np.prod(dims))
+        for p in parts:
+            assert all(v % 64 == 0 or v == d for v, d in zip(p["lo"] + p["hi"], dims + dims))
+            assert all(p["s"][a] <= p["lo"][a] and p["hi"][a] <= p["e"][a] for a in range(3))
+        g = np.array(dims, np.float64)
+        for trial in range(40):
+            eye = rng.uniform(-1.5, 2.5, 3)
+            m = np.eye(4)
+            m[3, :3] = eye
+            order = SL.depth_order(m, parts)
+            pos = {r: i for i, r in enumerate(order)}
+            for ray in range(25):
+                target = rng.uniform(0, 1, 3)
+                d = target - eye
+                hits = []
+                for r, p in enumerate(parts):                       # slab test against the box in normalised coords
+                    lo, hi = np.array(p["lo"]) / g, np.array(p["hi"]) / g
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        t0, t1 = (lo - eye) / d, (hi - eye) / d
+                    tn, tf = np.minimum(t0, t1).max(), np.maximum(t0, t1).min()
+                    if tf > max(tn, 0.0) + 1e-9:
+                        hits.append((max(tn, 0.0), r))
+                hits.sort()
+                seq = [pos[r] for _, r in hits]
+                assert seq == sorted(seq), (dims, world, eye, hits, order)
