@@ -173,6 +173,13 @@ def cpu_frame(H, pool, tf_rgba, lo, hi, k, steps, w, h):
 def run_reference(args, rank):
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use every host core
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except OSError:
+        pass
     H, O, oc, pool = oracle_setup()
     tf_rgba, lo, hi = bench_tf()
     cores = os.cpu_count() or 1
@@ -232,8 +239,7 @@ def run_gpu(args, rank, world):
     dev = torch.device("cuda", local)
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) must not join it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     tvk = TvkContext(local)
     if world > 1:

@@ -214,7 +214,8 @@ __device__ __forceinline__ float u2f(uint32_t v) { return __uint_as_float(0x4B00
 
 // The 2x2x2 voxel footprint of one sample: raw values + lerp weights.
 struct Taps {
-  float v[8];       // 000 100 010 110 001 101 011 111 (x fastest)
+  float v[4];       // base taps 000 010 001 011 (the x = 0 corner of each x-edge)
+  float d[4];       // x-differences v(1,y,z) - v(0,y,z) of the same four edges
   float a, b, g;
 };
 
@@ -242,42 +243,43 @@ __device__ __forceinline__ void fetch_taps(const RayParams& rp, const SlotCtx& s
     if (BPV == 1) {
       const uint32_t* d = reinterpret_cast<const uint32_t*>(sl.base) + o;
       const uint32_t q0 = __ldg(d), q1 = __ldg(d + 1);
-      t.v[0] = __uint_as_float(__byte_perm(q0, 0x4B000000u, 0x7650)) - 8388608.0f;
-      t.v[2] = __uint_as_float(__byte_perm(q0, 0x4B000000u, 0x7651)) - 8388608.0f;
-      t.v[4] = __uint_as_float(__byte_perm(q0, 0x4B000000u, 0x7652)) - 8388608.0f;
-      t.v[6] = __uint_as_float(__byte_perm(q0, 0x4B000000u, 0x7653)) - 8388608.0f;
-      t.v[1] = __uint_as_float(__byte_perm(q1, 0x4B000000u, 0x7650)) - 8388608.0f;
-      t.v[3] = __uint_as_float(__byte_perm(q1, 0x4B000000u, 0x7651)) - 8388608.0f;
-      t.v[5] = __uint_as_float(__byte_perm(q1, 0x4B000000u, 0x7652)) - 8388608.0f;
-      t.v[7] = __uint_as_float(__byte_perm(q1, 0x4B000000u, 0x7653)) - 8388608.0f;
+      // the x-differences are taken on the biased values (2^23 + byte: the difference is exact either way), so only
+      // the four base taps need the bias removed
+      const float b0 = __uint_as_float(__byte_perm(q0, 0x4B000000u, 0x7650)), b1 = __uint_as_float(__byte_perm(q1, 0x4B000000u, 0x7650));
+      const float b2 = __uint_as_float(__byte_perm(q0, 0x4B000000u, 0x7651)), b3 = __uint_as_float(__byte_perm(q1, 0x4B000000u, 0x7651));
+      const float b4 = __uint_as_float(__byte_perm(q0, 0x4B000000u, 0x7652)), b5 = __uint_as_float(__byte_perm(q1, 0x4B000000u, 0x7652));
+      const float b6 = __uint_as_float(__byte_perm(q0, 0x4B000000u, 0x7653)), b7 = __uint_as_float(__byte_perm(q1, 0x4B000000u, 0x7653));
+      t.d[0] = b1 - b0; t.d[1] = b3 - b2; t.d[2] = b5 - b4; t.d[3] = b7 - b6;
+      t.v[0] = b0 - 8388608.0f; t.v[1] = b2 - 8388608.0f; t.v[2] = b4 - 8388608.0f; t.v[3] = b6 - 8388608.0f;
     } else {
       const uint2* d = reinterpret_cast<const uint2*>(sl.base) + o;
       const uint2 q0 = __ldg(d), q1 = __ldg(d + 1);
-      t.v[0] = u2f(q0.x & 0xFFFFu); t.v[2] = u2f(q0.x >> 16); t.v[4] = u2f(q0.y & 0xFFFFu); t.v[6] = u2f(q0.y >> 16);
-      t.v[1] = u2f(q1.x & 0xFFFFu); t.v[3] = u2f(q1.x >> 16); t.v[5] = u2f(q1.y & 0xFFFFu); t.v[7] = u2f(q1.y >> 16);
+      t.v[0] = u2f(q0.x & 0xFFFFu); t.v[1] = u2f(q0.x >> 16); t.v[2] = u2f(q0.y & 0xFFFFu); t.v[3] = u2f(q0.y >> 16);
+      t.d[0] = u2f(q1.x & 0xFFFFu) - t.v[0]; t.d[1] = u2f(q1.x >> 16) - t.v[1];
+      t.d[2] = u2f(q1.y & 0xFFFFu) - t.v[2]; t.d[3] = u2f(q1.y >> 16) - t.v[3];
     }
   } else if (BPV == 1) {
     const uint8_t* d = sl.base + o;
     const uint8_t *d1 = d + sx, *d2 = d + sxy, *d3 = d2 + sx;
     const uint32_t r0 = __ldg(d), r1 = __ldg(d + 1), r2 = __ldg(d1), r3 = __ldg(d1 + 1);
     const uint32_t r4 = __ldg(d2), r5 = __ldg(d2 + 1), r6 = __ldg(d3), r7 = __ldg(d3 + 1);
-    t.v[0] = u2f(r0); t.v[1] = u2f(r1); t.v[2] = u2f(r2); t.v[3] = u2f(r3);
-    t.v[4] = u2f(r4); t.v[5] = u2f(r5); t.v[6] = u2f(r6); t.v[7] = u2f(r7);
+    t.v[0] = u2f(r0); t.v[1] = u2f(r2); t.v[2] = u2f(r4); t.v[3] = u2f(r6);
+    t.d[0] = u2f(r1) - t.v[0]; t.d[1] = u2f(r3) - t.v[1]; t.d[2] = u2f(r5) - t.v[2]; t.d[3] = u2f(r7) - t.v[3];
   } else {
     const uint16_t* d = reinterpret_cast<const uint16_t*>(sl.base) + o;
     const uint16_t *d1 = d + sx, *d2 = d + sxy, *d3 = d2 + sx;
     const uint32_t r0 = __ldg(d), r1 = __ldg(d + 1), r2 = __ldg(d1), r3 = __ldg(d1 + 1);
     const uint32_t r4 = __ldg(d2), r5 = __ldg(d2 + 1), r6 = __ldg(d3), r7 = __ldg(d3 + 1);
-    t.v[0] = u2f(r0); t.v[1] = u2f(r1); t.v[2] = u2f(r2); t.v[3] = u2f(r3);
-    t.v[4] = u2f(r4); t.v[5] = u2f(r5); t.v[6] = u2f(r6); t.v[7] = u2f(r7);
+    t.v[0] = u2f(r0); t.v[1] = u2f(r2); t.v[2] = u2f(r4); t.v[3] = u2f(r6);
+    t.d[0] = u2f(r1) - t.v[0]; t.d[1] = u2f(r3) - t.v[1]; t.d[2] = u2f(r5) - t.v[2]; t.d[3] = u2f(r7) - t.v[3];
   }
 }
 
 // Filter half: fp32 trilinear on the raw values, then the UNORM scale.
 template <int BPV>
 __device__ __forceinline__ float filter_taps(const Taps& t) {
-  const float c00 = fmaf(t.a, t.v[1] - t.v[0], t.v[0]), c10 = fmaf(t.a, t.v[3] - t.v[2], t.v[2]);
-  const float c01 = fmaf(t.a, t.v[5] - t.v[4], t.v[4]), c11 = fmaf(t.a, t.v[7] - t.v[6], t.v[6]);
+  const float c00 = fmaf(t.a, t.d[0], t.v[0]), c10 = fmaf(t.a, t.d[1], t.v[1]);
+  const float c01 = fmaf(t.a, t.d[2], t.v[2]), c11 = fmaf(t.a, t.d[3], t.v[3]);
   const float c0 = fmaf(t.b, c10 - c00, c00), c1 = fmaf(t.b, c11 - c01, c01);
   return fmaf(t.g, c1 - c0, c0) * (BPV == 1 ? 1.0f / 255.0f : 1.0f / 65535.0f);
 }
