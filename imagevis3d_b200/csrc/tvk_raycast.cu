@@ -60,7 +60,11 @@ struct f3 { float x, y, z; };
 __device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
 // Floating-point contract (shared with oracle/tvk_oracle_render.c): this file is compiled with
 // -fmad=false, so the ONLY fused multiply-adds are the explicit fmaf() calls, and they sit exactly
-// where the oracle has them.  Every other operation is a single IEEE fp32 op in the oracle's order.
+// where the oracle has them.  Every other operation is a single IEEE fp32 op in the oracle's order -- with one
+// exception: the SHADING block (normalisations in lighting(), the normal, the model-space position) uses
+// rsqrtf / a per-brick reciprocal instead of IEEE sqrt + divisions (12 divisions and 3 square roots per lit
+// sample otherwise).  Nothing discrete depends on it -- transfer-function indices, LOD, brick walk and step
+// counts stay exact -- and the colour changes by ~2 ulp (the reference's GLSL normalize() is no more precise).
 __device__ __forceinline__ float dot3(f3 a, f3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
 __device__ __forceinline__ float len3(f3 v) { return sqrtf(dot3(v, v)); }
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
@@ -123,7 +127,7 @@ struct SlotCtx {
 };
 
 struct BrickHit {
-  f3 pool_entry, pool_exit, norm_exit, scale, trans;
+  f3 pool_entry, pool_exit, norm_exit, scale, trans, inv_scale;   // inv_scale: for the shading block only
   uint4 bc;
   SlotCtx slot;
   bool empty, found;
@@ -203,6 +207,7 @@ __device__ __forceinline__ void get_brick(const RayParams& rp, f3 entry, uint32_
     b.scale.z = (p1 - p0) / (c1.z - c0.z);
     b.trans.z = fmaf(-c0.z, b.scale.z, p0);
   }
+  b.inv_scale = mk3(1.0f / b.scale.x, 1.0f / b.scale.y, 1.0f / b.scale.z);
   b.pool_entry = mk3(fmaf(e.x, b.scale.x, b.trans.x), fmaf(e.y, b.scale.y, b.trans.y), fmaf(e.z, b.scale.z, b.trans.z));
   b.pool_exit = mk3(fmaf(b.norm_exit.x, b.scale.x, b.trans.x), fmaf(b.norm_exit.y, b.scale.y, b.trans.y),
                     fmaf(b.norm_exit.z, b.scale.z, b.trans.z));
@@ -317,17 +322,86 @@ __device__ __forceinline__ f3 gradient(const RayParams& rp, const SlotCtx& sl, f
   return mk3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
 }
 
+
+// Centre sample AND central-difference gradient from ONE shared footprint (quad-packed pool only).
+// gradient() above evaluates six more trilinear samples at +-1 texel, each with its own address arithmetic and
+// eight-tap footprint: 7 footprints = 14 quad loads and ~500 instructions per lit / 2D-TF sample.  All seven
+// share the fractional weights, and their footprints overlap: the union is a 4x2x2 + 2x4x2 + 2x2x4 cross of 32
+// voxels, which the (y,z)-quad layout delivers in 12 loads around one base address.  The CENTRE value is filtered
+// exactly as filter_taps does (x, then y, then z: it selects the transfer-function entry); the six offset samples
+// are filtered with the same weights in whatever order needs the fewest lerps, so the gradient differs from the
+// seven-sample evaluation by rounding only (~1e-7 relative; the image tolerance is 2/255).
+template <int BPV>
+__device__ __forceinline__ void unpack_quad(const void* __restrict__ base, uint32_t o, float q[4]) {
+  if (BPV == 1) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(base) + o);
+    q[0] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650)) - 8388608.0f;
+    q[1] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7651)) - 8388608.0f;
+    q[2] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7652)) - 8388608.0f;
+    q[3] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7653)) - 8388608.0f;
+  } else {
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(base) + o);
+    q[0] = u2f(w.x & 0xFFFFu); q[1] = u2f(w.x >> 16); q[2] = u2f(w.y & 0xFFFFu); q[3] = u2f(w.y >> 16);
+  }
+}
+__device__ __forceinline__ float lerpf(float t, float a, float b) { return fmaf(t, b - a, a); }
+
+template <int BPV>
+__device__ __forceinline__ void q4_center_gradient(const RayParams& rp, const SlotCtx& sl, f3 p, float& data, f3& grad) {
+  const PoolConst& pc = rp.pc;
+  const float M = 12582912.0f;   // 1.5 * 2^23
+  const float u = fmaf(p.x, pc.pool_size[0], -0.5f), v = fmaf(p.y, pc.pool_size[1], -0.5f), w = fmaf(p.z, pc.pool_size[2], -0.5f);
+  const float tu = __fadd_rd(u, M), tv = __fadd_rd(v, M), tw = __fadd_rd(w, M);
+  const float a = u - (tu - M), b = v - (tv - M), g = w - (tw - M);
+  const int mx = (int)pc.max_brick[0], my = (int)pc.max_brick[1], mz = (int)pc.max_brick[2];
+  const int x = min(max(__float_as_int(tu) - sl.ox, 0), mx - 2);
+  const int y = min(max(__float_as_int(tv) - sl.oy, 0), my - 2);
+  const int z = min(max(__float_as_int(tw) - sl.oz, 0), mz - 2);
+  const uint32_t sx = pc.pool_dim[0], sxy = sx * pc.pool_dim[1];
+  const uint32_t o = (uint32_t)x + (uint32_t)y * sx + (uint32_t)z * sxy;
+  const uint32_t oxm = o - (x > 0 ? 1u : 0u), oxp = o + (x + 2 < mx ? 2u : 1u);         // columns x-1 and x+2 (clamped)
+  const uint32_t dym = y > 0 ? sx : 0u, dyp = sx, dzm = z > 0 ? sxy : 0u, dzp = sxy;     // (y+1, z+1 <= dim-1 always)
+  float X0[4], X1[4], X2[4], X3[4], Ym0[4], Ym1[4], Yp0[4], Yp1[4], Zm0[4], Zm1[4], Zp0[4], Zp1[4];
+  unpack_quad<BPV>(sl.base, oxm, X0); unpack_quad<BPV>(sl.base, o, X1); unpack_quad<BPV>(sl.base, o + 1, X2); unpack_quad<BPV>(sl.base, oxp, X3);
+  unpack_quad<BPV>(sl.base, o - dym, Ym0); unpack_quad<BPV>(sl.base, o + 1 - dym, Ym1);
+  unpack_quad<BPV>(sl.base, o + dyp, Yp0); unpack_quad<BPV>(sl.base, o + 1 + dyp, Yp1);
+  unpack_quad<BPV>(sl.base, o - dzm, Zm0); unpack_quad<BPV>(sl.base, o + 1 - dzm, Zm1);
+  unpack_quad<BPV>(sl.base, o + dzp, Zp0); unpack_quad<BPV>(sl.base, o + 1 + dzp, Zp1);
+  const float scale = (BPV == 1 ? 1.0f / 255.0f : 1.0f / 65535.0f);
+  // centre: filter_taps order (quad = {v(y,z), v(y+1,z), v(y,z+1), v(y+1,z+1)})
+  const float c00 = fmaf(a, X2[0] - X1[0], X1[0]), c10 = fmaf(a, X2[1] - X1[1], X1[1]);
+  const float c01 = fmaf(a, X2[2] - X1[2], X1[2]), c11 = fmaf(a, X2[3] - X1[3], X1[3]);
+  const float c0 = fmaf(b, c10 - c00, c00), c1 = fmaf(b, c11 - c01, c01);
+  data = fmaf(g, c1 - c0, c0) * scale;
+  // x: bilinear (b, g) value of each of the four columns, then the two offset samples
+  const float B0 = lerpf(g, lerpf(b, X0[0], X0[1]), lerpf(b, X0[2], X0[3])), B1 = lerpf(g, lerpf(b, X1[0], X1[1]), lerpf(b, X1[2], X1[3]));
+  const float B2 = lerpf(g, lerpf(b, X2[0], X2[1]), lerpf(b, X2[2], X2[3])), B3 = lerpf(g, lerpf(b, X3[0], X3[1]), lerpf(b, X3[2], X3[3]));
+  const float txm = lerpf(a, B0, B1), txp = lerpf(a, B2, B3);
+  // y: rows y-1, y, y+1, y+2, each bilinear in (a, g)
+  const float R0 = lerpf(g, lerpf(a, y > 0 ? Ym0[0] : X1[0], y > 0 ? Ym1[0] : X2[0]), lerpf(a, y > 0 ? Ym0[2] : X1[2], y > 0 ? Ym1[2] : X2[2]));
+  const float R1 = lerpf(g, c00, c01), R2 = lerpf(g, c10, c11);
+  const float R3 = lerpf(g, lerpf(a, Yp0[1], Yp1[1]), lerpf(a, Yp0[3], Yp1[3]));
+  const float tym = lerpf(b, R0, R1), typ = lerpf(b, R2, R3);
+  // z: planes z-1, z, z+1, z+2, each bilinear in (a, b)
+  const float P0 = lerpf(b, lerpf(a, z > 0 ? Zm0[0] : X1[0], z > 0 ? Zm1[0] : X2[0]), lerpf(a, z > 0 ? Zm0[1] : X1[1], z > 0 ? Zm1[1] : X2[1]));
+  const float P1 = c0, P2 = c1;
+  const float P3 = lerpf(b, lerpf(a, Zp0[2], Zp1[2]), lerpf(a, Zp0[3], Zp1[3]));
+  const float tzm = lerpf(g, P0, P1), tzp = lerpf(g, P2, P3);
+  // ComputeGradient: (xm - xp, yp - ym, zm - zp) / 2 with yp = S(y - dy), ym = S(y + dy)  (GradientTools.glsl:6-16)
+  grad = mk3((txm - txp) * scale / 2.0f, (tym - typ) * scale / 2.0f, (tzm - tzp) * scale / 2.0f);
+}
+
 __device__ __forceinline__ float pow8(float x) { x *= x; x *= x; return x * x; }
 
 // Lighting, lighting.glsl:33-43
 __device__ __forceinline__ f3 lighting(const tvk_raycast_params& p, f3 pos, f3 n, f3 diffuse) {
   f3 v = mk3(p.model_eye_pos[0] - pos.x, p.model_eye_pos[1] - pos.y, p.model_eye_pos[2] - pos.z);
-  float l = len3(v);
-  v = mk3(v.x / l, v.y / l, v.z / l);
+  float il = rsqrtf(dot3(v, v));
+  v = mk3(v.x * il, v.y * il, v.z * il);
   const float d2 = 2.0f * dot3(n, v);
   f3 r = mk3(fmaf(-d2, n.x, v.x), fmaf(-d2, n.y, v.y), fmaf(-d2, n.z, v.z));
-  l = len3(r);
-  r = mk3(r.x / l, r.y / l, r.z / l);
+  il = rsqrtf(dot3(r, r));
+  r = mk3(r.x * il, r.y * il, r.z * il);
   const f3 L = mk3(p.model_light_dir[0], p.model_light_dir[1], p.model_light_dir[2]);
   const float ndl = fmaxf(fabsf(dot3(n, L)), 0.0f);
   const float spec = pow8(fmaxf(dot3(r, L), 0.0f));
@@ -339,30 +413,32 @@ __device__ __forceinline__ f3 lighting(const tvk_raycast_params& p, f3 pos, f3 n
 // ComputeColorFromVolume, GLGridLeaper-Method-{1D,1D-L,2D,2D-L}.glsl; `data` is the
 // already filtered centre sample (fetched one iteration ahead by the march loop).
 template <int MODE, bool LIT, int BPV, int SAMP>
-__device__ __forceinline__ float4 color_from_volume(const RayParams& rp, const SlotCtx& sl, float data, f3 pc, f3 scale, f3 trans) {
+__device__ __forceinline__ float4 color_from_volume(const RayParams& rp, const SlotCtx& sl, float data, f3 pc, f3 scale /* 1 / brick scale */, f3 trans,
+                                                     const f3* grad = nullptr) {
   const tvk_raycast_params& p = rp.p;
   float4 col;
   f3 n;
   if (MODE == TVK_RM_1DTRANS) {
     col = __ldg(rp.tf_f + nearest_index(data * p.trans_scale, rp.tf_w));
     if (LIT) {
-      const f3 g = gradient<BPV, SAMP>(rp, sl, pc);
+      const f3 g = grad ? *grad : gradient<BPV, SAMP>(rp, sl, pc);
       n = mk3(g.x * p.domain_scale[0], g.y * p.domain_scale[1], g.z * p.domain_scale[2]);
-      const float l = len3(n);
-      if (l > 0.0f) n = mk3(n.x / l, n.y / l, n.z / l);
+      const float d = dot3(n, n);
+      if (d > 0.0f) { const float il = rsqrtf(d); n = mk3(n.x * il, n.y * il, n.z * il); }
     }
   } else {
-    const f3 g = gradient<BPV, SAMP>(rp, sl, pc);
+    const f3 g = grad ? *grad : gradient<BPV, SAMP>(rp, sl, pc);
     const float gm = len3(g);
     col = tf_fetch(rp, nearest_index(fmaf(-gm, p.gradient_scale, 1.0f), rp.tf_h) * (int)rp.tf_w +
                            nearest_index(data * p.trans_scale, rp.tf_w));
     if (LIT) {
-      const f3 gn = (gm > 0.0f) ? mk3(g.x / gm, g.y / gm, g.z / gm) : g;
+      const float ig = 1.0f / gm;
+      const f3 gn = (gm > 0.0f) ? mk3(g.x * ig, g.y * ig, g.z * ig) : g;
       n = mk3(p.domain_scale[0] * gn.x, p.domain_scale[1] * gn.y, p.domain_scale[2] * gn.z);
     }
   }
   if (LIT) {
-    const f3 mp = mk3((pc.x - trans.x) / scale.x, (pc.y - trans.y) / scale.y, (pc.z - trans.z) / scale.z);
+    const f3 mp = mk3((pc.x - trans.x) * scale.x, (pc.y - trans.y) * scale.y, (pc.z - trans.z) * scale.z);   // scale = 1 / brick scale here
     const f3 lit = lighting(p, mp, n, mk3(col.x * p.light_diffuse[0], col.y * p.light_diffuse[1], col.z * p.light_diffuse[2]));
     col.x = lit.x; col.y = lit.y; col.z = lit.z;
   }
@@ -489,15 +565,23 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
             }
             float4 sc[NB];
 #pragma unroll
-            for (int k = 0; k < NB; ++k) sc[k] = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, d[k], qs[k], b.scale, b.trans);
+            for (int k = 0; k < NB; ++k) sc[k] = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, d[k], qs[k], b.inv_scale, b.trans);
 #pragma unroll
             for (int k = 0; k < NB; ++k) TVK_COMPOSITE(sc[k])
             q = mk3(qs[NB - 1].x + vdir.x, qs[NB - 1].y + vdir.y, qs[NB - 1].z + vdir.z);
           }
         }
         for (; i < steps; ++i) {
-          const float data = sample_pool<BPV, SAMP>(rp, b.slot, q);
-          float4 s0 = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, data, q, b.scale, b.trans);
+          float4 s0;
+          if (SAMP == TVK_SAMPLER_EXACT_Q4 && (LIT || MODE == TVK_RM_2DTRANS)) {
+            float data;
+            f3 g;
+            q4_center_gradient<BPV>(rp, b.slot, q, data, g);
+            s0 = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, data, q, b.inv_scale, b.trans, &g);
+          } else {
+            const float data = sample_pool<BPV, SAMP>(rp, b.slot, q);
+            s0 = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, data, q, b.inv_scale, b.trans);
+          }
           TVK_COMPOSITE(s0)
           q = mk3(q.x + vdir.x, q.y + vdir.y, q.z + vdir.z);
         }
