@@ -35,6 +35,9 @@
 #ifndef TVK_OCC_LDG
 #define TVK_OCC_LDG 4
 #endif
+#ifndef TVK_OCC_LIT
+#define TVK_OCC_LIT 4
+#endif
 
 struct RayParams {
   tvk_raycast_params p;
@@ -715,7 +718,7 @@ __device__ __forceinline__ void store_pixel(const RayParams& rp, uint32_t px, ui
 // SRM1: sampleRateModifier == 1 known at compile time (the opacity correction is then the identity
 // 1-(1-a) and the pow path is not even compiled in); instantiated for the 1D-TF kernels only.
 template <int MODE, bool LIT, int BPV, int SAMP, bool SRM1>
-__global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP == TVK_SAMPLER_TEX3D ? TVK_OCC_TEX : TVK_OCC_LDG) : 3) raycast_kernel(const __grid_constant__ RayParams rp) {
+__global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP == TVK_SAMPLER_TEX3D ? TVK_OCC_TEX : TVK_OCC_LDG) : TVK_OCC_LIT) raycast_kernel(const __grid_constant__ RayParams rp) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t ntiles = rp.tiles_x * rp.tiles_y;
   Counters cn;
