@@ -20,7 +20,10 @@
  * mul, div, sqrt, fma) in a fixed order -- fmaf() where a multiply-add is fused, nothing else is
  * contracted (-ffp-contract=off) -- and the CUDA kernel issues the same operations in the same
  * order (nvcc -fmad=false + explicit fmaf).  The two therefore agree bit for bit except where
- * powf/log2 enter (sample-rate modifier != 1, LOD boundaries).
+ * powf/log2 enter (sample-rate modifier != 1, LOD boundaries), and in the shading block of the
+ * lit / 2D-TF modes, where the kernel normalises with rsqrtf and multiplies by a per-brick
+ * reciprocal while this file keeps sqrtf and the divisions of the GLSL (tolerance 2e-3 in the tests,
+ * measured 3e-5).
  *
  * Restated items (paths relative to /root/reference/Tuvok/):
  *   orc_pool_layout     GetLoDSize/GetFloatBrickLayout/GetBrickLayout, LoD offset
