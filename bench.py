@@ -39,7 +39,7 @@ BRICK, OVERLAP = 64, 2
 BYTES_PER_SAMPLE = 1.2136 * 1 / 2.0     # 1.2136*bpv/(2*sampleRateModifier), uint8, srm 1
 BYTES_PER_RAY = 16.0                    # RGBA32F result write
 CPU_SAMPLE = (1920, 1080)               # the CPU arm renders full frames (a frame is < 1 s on 16 cores)
-CPU_STEPS = 8                           # bounded: this many steps of the orbit
+CPU_STEPS = 24                          # ~0.47 s per 1080p frame on 16 cores -> ~11 s of CPU work
 
 
 def peaks():
@@ -282,7 +282,7 @@ def run_gpu(args, rank, world):
     blob = torch.empty(int(info.total_bytes), dtype=torch.uint8, pin_memory=True)
     tvk._ck(tvk.lib.tvk_build_get_bricks(tvk.h, C.c_void_p(blob.data_ptr()), C.c_uint64(0), C.c_uint64(blob.numel())), "get_bricks")
     meta_host = tvk.get_metadata()
-    img_host = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32, pin_memory=True)
+    img8_host = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, pin_memory=True)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -380,7 +380,7 @@ def run_gpu(args, rank, world):
 
     # ---- e2e: host buffers in, host image out, every step (pager upload + march + read-back)
     h2d = int(sum(int(np.prod(s)) for s in sizes[:total])) + 4 * total
-    d2h = HEIGHT * WIDTH * 16
+    d2h = HEIGHT * WIDTH * 4        # the frame as glReadPixels(GL_RGBA, GL_UNSIGNED_BYTE) returns it (captureSingleFrame)
     srcs = [blob.data_ptr() + int(o) for o in off[:total]]
     n = len(srcs)
     src_arr = (C.c_void_p * n)(*srcs)
@@ -397,10 +397,10 @@ def run_gpu(args, rank, world):
         step(k)
         if world > 1:
             if rank == 0:
-                img_host.copy_(final_image[0])
+                img8_host.copy_((final_image[0].clamp(0.0, 1.0) * 255.0 + 0.5).to(torch.uint8))
                 torch.cuda.synchronize()
         else:
-            tvk._ck(tvk.lib.tvk_read_image(tvk.h, C.c_void_p(img_host.data_ptr())), "read_image")
+            tvk._ck(tvk.lib.tvk_read_image_rgba8(tvk.h, C.c_void_p(img8_host.data_ptr()), C.c_int(1)), "read_image_rgba8")
 
     e2e_step(0)
     tvk.stats(reset=True)
@@ -452,7 +452,8 @@ def run_gpu(args, rank, world):
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "0.6068 B/sample + 16 B/ray (SURVEY 8d); the kernel is L1/TEX-issue bound, see DESIGN.md"},
             "e2e": {"value": e2e_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "result": "RGBA8 frame (glReadPixels GL_UNSIGNED_BYTE, as captureSingleFrame reads it)"},
             "gpu_launches": args.steps * (1 if world == 1 else (2 * world if fused is not None else 2 * world)), "clocks": clocks,
             "builder_ms_untimed": 1e3 * t_build}
     if world > 1:

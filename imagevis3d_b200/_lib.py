@@ -89,7 +89,7 @@ EXPORTS = [
     "tvk_pool_create", "tvk_pool_destroy", "tvk_pool_total_bricks", "tvk_pool_upload_bricks",
     "tvk_pool_upload_wait", "tvk_pool_set_metadata", "tvk_pool_patch_metadata", "tvk_pool_get_metadata",
     "tvk_visibility_set_minmax", "tvk_visibility_recompute", "tvk_set_tf1d", "tvk_set_tf2d",
-    "tvk_raycast_subframe", "tvk_read_requests", "tvk_read_image", "tvk_read_resume", "tvk_image_device_ptr",
+    "tvk_raycast_subframe", "tvk_read_requests", "tvk_read_image", "tvk_read_image_rgba8", "tvk_read_resume", "tvk_image_device_ptr",
     "tvk_get_stats", "tvk_probe_lod", "tvk_probe_brick_index",
     "tvk_build_plan", "tvk_build_octree", "tvk_build_get_toc", "tvk_build_get_minmax", "tvk_build_get_bricks",
     "tvk_build_store_device_ptr", "tvk_build_hist1d", "tvk_build_hist2d", "tvk_build_release", "tvk_build_last_ms", "tvk_build_hist2d_last_ms", "tvk_quantize",

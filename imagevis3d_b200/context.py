@@ -138,6 +138,13 @@ class TvkContext:
         self._ck(self.lib.tvk_read_image(self.h, _p(img)), "tvk_read_image")
         return img
 
+    def read_image_rgba8(self, flip_rows=False, out=None):
+        """glReadPixels(GL_RGBA, GL_UNSIGNED_BYTE): converted on the device, [h][w][4] uint8."""
+        w, h = self._wh
+        img = np.empty((h, w, 4), np.uint8) if out is None else out
+        self._ck(self.lib.tvk_read_image_rgba8(self.h, _p(img), C.c_int(int(flip_rows))), "tvk_read_image_rgba8")
+        return img
+
     def read_resume(self):
         w, h = self._wh
         pos = np.zeros((h, w, 4), np.float32)

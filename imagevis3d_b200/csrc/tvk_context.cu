@@ -93,6 +93,7 @@ extern "C" int tvk_create(int device, tvk_ctx** out) {
 
 static void free_frame(tvk_ctx* c) {
   cudaFree(c->d_image); c->d_image = nullptr;
+  cudaFree(c->d_rgba8); c->d_rgba8 = nullptr;
   for (int i = 0; i < 2; ++i) { cudaFree(c->d_pos[i]); cudaFree(c->d_aux[i]); c->d_pos[i] = c->d_aux[i] = nullptr; }
   c->width = c->height = 0;
 }

@@ -88,6 +88,7 @@ struct tvk_ctx {
   // frame state
   uint32_t width = 0, height = 0;
   float4* d_image = nullptr;           // accRayColor / composed iso image
+  uchar4* d_rgba8 = nullptr;           // tvk_read_image_rgba8 staging (allocated on first use)
   float4* d_pos[2] = {nullptr, nullptr};   // rayStartPoint ping-pong
   float4* d_aux[2] = {nullptr, nullptr};   // rayStartColor (iso: normal) ping-pong
   int cur = 0;

@@ -904,6 +904,36 @@ extern "C" int tvk_read_image(tvk_ctx* c, float* rgba) {
   return TVK_OK;
 }
 
+// glReadPixels(GL_RGBA, GL_UNSIGNED_BYTE) of the float target: clamp to [0,1], scale by 255, round to nearest
+// (GLFrameCapture.cpp:47-86); flip = the row reversal FrameCapture::SaveImage applies (FrameCapture.h:90-98).
+__global__ void __launch_bounds__(256) image_to_rgba8_kernel(const float4* __restrict__ img, uchar4* __restrict__ out,
+                                                            uint32_t w, uint32_t h, int flip) {
+  const uint32_t n = w * h;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t y = i / w, x = i - y * w;
+    const float4 v = __ldcs(img + (size_t)(flip ? h - 1 - y : y) * w + x);
+    uchar4 o;
+    o.x = (unsigned char)(fminf(1.0f, fmaxf(0.0f, v.x)) * 255.0f + 0.5f);
+    o.y = (unsigned char)(fminf(1.0f, fmaxf(0.0f, v.y)) * 255.0f + 0.5f);
+    o.z = (unsigned char)(fminf(1.0f, fmaxf(0.0f, v.z)) * 255.0f + 0.5f);
+    o.w = (unsigned char)(fminf(1.0f, fmaxf(0.0f, v.w)) * 255.0f + 0.5f);
+    out[i] = o;
+  }
+}
+
+extern "C" int tvk_read_image_rgba8(tvk_ctx* c, uint8_t* rgba8, int flip_rows) {
+  if (!c || !rgba8 || !c->d_image) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)c->width * c->height;
+  if (!c->d_rgba8) TVK_CHECK_CUDA(c, cudaMalloc(&c->d_rgba8, n * sizeof(uchar4)));
+  const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
+  image_to_rgba8_kernel<<<blocks, 256, 0, c->stream>>>(c->d_image, c->d_rgba8, c->width, c->height, flip_rows);
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(rgba8, c->d_rgba8, n * sizeof(uchar4), cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TVK_OK;
+}
+
 extern "C" int tvk_read_resume(tvk_ctx* c, float* pos, float* color) {
   if (!c || !c->d_image) return TVK_ERR_INVALID;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));

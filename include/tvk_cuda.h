@@ -181,6 +181,10 @@ int tvk_read_requests(tvk_ctx* ctx, uint32_t* xyzl, uint32_t cap, uint32_t* coun
 /* replaces glReadPixels on m_pFBO3DImage (float RGBA, premultiplied; for iso
  * mode this is the Compose-FS shaded image).  rgba = width*height*4 floats. */
 int tvk_read_image(tvk_ctx* ctx, float* rgba);
+/* replaces glReadPixels(GL_RGBA, GL_UNSIGNED_BYTE) of the same target (GLFrameCapture.cpp:47-86): clamp, *255, round
+ * to nearest on the device, width*height*4 bytes copied back.  flip_rows != 0 returns the top row first
+ * (FrameCapture::SaveImage, FrameCapture.h:90-98). */
+int tvk_read_image_rgba8(tvk_ctx* ctx, uint8_t* rgba8, int flip_rows);
 /* resume buffers, for tests: rayResumePos / rayResumeColor (iso: hit normal) */
 int tvk_read_resume(tvk_ctx* ctx, float* pos, float* color);
 /* device pointer of the current image (for the sort-last compositor / interop) */

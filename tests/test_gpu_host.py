@@ -87,6 +87,9 @@ def test_renderer_matches_oracle_end_to_end(lighting):
     rgba = r.frameRGBA8()
     ref8 = (np.clip(want[::-1], 0, 1) * 255.0 + 0.5).astype(np.uint8)
     assert np.abs(rgba.astype(int) - ref8.astype(int)).max() <= 2
+    # the device-side conversion is the host formula applied to the float frame, bit for bit
+    own8 = (np.clip(got[::-1], np.float32(0), np.float32(1)) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
+    assert np.array_equal(rgba, own8)
     out = "/tmp/tvk_capture_%d.png" % int(lighting)
     r.captureSingleFrame(out, True)
     assert open(out, "rb").read(8) == b"\x89PNG\r\n\x1a\n" and os.path.getsize(out) > 203 * 149 * 4
