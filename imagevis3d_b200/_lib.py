@@ -70,7 +70,9 @@ class ClassicParams(C.Structure):
                 ("normal_matrix", C.c_float * 9), ("inv_projection", C.c_float * 16), ("step_scale", C.c_float),
                 ("trans_scale", C.c_float), ("lighting", C.c_uint32), ("light_ambient", C.c_float * 3),
                 ("light_diffuse", C.c_float * 3), ("light_specular", C.c_float * 3), ("light_dir", C.c_float * 3),
-                ("domain_scale", C.c_float * 3), ("bytes_per_voxel", C.c_uint32)]
+                ("domain_scale", C.c_float * 3), ("bytes_per_voxel", C.c_uint32), ("render_mode", C.c_uint32),
+                ("gradient_scale", C.c_float), ("isoval", C.c_float), ("proj_param", C.c_float * 2),
+                ("iso_color", C.c_float * 3)]
 
 
 class QuantizeResult(C.Structure):

@@ -558,6 +558,18 @@ void CudaGridLeaper::Resize(uint32_t w, uint32_t h) { m_w = w; m_h = h; Schedule
 bool CudaGridLeaper::SetRendermode(int mode) {
   if (mode < RM_1DTRANS || mode > RM_ISOSURFACE) { m_err = "invalid render mode"; return false; }
   if (mode == RM_2DTRANS && !m_has2d) { m_err = "no 2D transfer function set"; return false; }
+  // the device holds ONE table (texture unit 1 of the reference: 1D or 2D, GLGridLeaper.cpp:754-870): re-upload on a switch
+  if (m_ctx && mode != m_mode) {
+    if (mode == RM_2DTRANS) {
+      const int rc = tvk_set_tf2d(m_ctx, m_tf2dBytes.data(), m_tf2dW, m_tf2dH);
+      if (rc) return Fail("tvk_set_tf2d", rc);
+    } else if (m_mode == RM_2DTRANS && m_tf1d.GetSize()) {
+      std::vector<uint8_t> bytes;
+      m_tf1d.GetByteArray(bytes);
+      const int rc = tvk_set_tf1d(m_ctx, bytes.data(), (uint32_t)m_tf1d.GetSize());
+      if (rc) return Fail("tvk_set_tf1d", rc);
+    }
+  }
   m_mode = mode;
   RecomputeBrickVisibility(false);
   ScheduleCompleteRedraw();
@@ -595,8 +607,10 @@ bool CudaGridLeaper::Set1DTrans(const std::vector<uint8_t>& rgba) {          // 
   std::vector<float> f(rgba.size());
   for (size_t i = 0; i < rgba.size(); ++i) f[i] = rgba[i] / 255.0f;
   m_tf1d.Set(f.data(), rgba.size() / 4);
-  int rc = tvk_set_tf1d(m_ctx, rgba.data(), (uint32_t)(rgba.size() / 4));
-  if (rc) return Fail("tvk_set_tf1d", rc);
+  if (m_mode != RM_2DTRANS) {
+    int rc = tvk_set_tf1d(m_ctx, rgba.data(), (uint32_t)(rgba.size() / 4));
+    if (rc) return Fail("tvk_set_tf1d", rc);
+  }
   RecomputeBrickVisibility(false);
   ScheduleCompleteRedraw();
   return true;
@@ -616,8 +630,11 @@ bool CudaGridLeaper::Set2DTrans(const uint8_t* rgba, uint32_t w, uint32_t h, dou
   // the swatch rasterisation of TransferFunction2D needs Qt (TransferFunction2D.cpp:294-361);
   // the renderer takes the rasterised RGBA8 table and its non-zero limits instead
   if (!rgba || !w || !h) { m_err = "bad 2D transfer function"; return false; }
-  int rc = tvk_set_tf2d(m_ctx, rgba, w, h);
-  if (rc) return Fail("tvk_set_tf2d", rc);
+  m_tf2dBytes.assign(rgba, rgba + (size_t)w * h * 4); m_tf2dW = w; m_tf2dH = h;
+  if (m_mode == RM_2DTRANS) {                              // otherwise uploaded when the mode is switched to 2D
+    int rc = tvk_set_tf2d(m_ctx, rgba, w, h);
+    if (rc) return Fail("tvk_set_tf2d", rc);
+  }
   m_has2d = true;
   for (int i = 0; i < 4; ++i) m_tf2dLimits[i] = nz[i];
   if (m_mode == RM_2DTRANS) RecomputeBrickVisibility(false);
@@ -754,7 +771,6 @@ void CudaGridLeaper::SetBGColors(const float top[3], const float bottom[3]) { me
 // m_iMinLODForCurrentView, or 0 for RT_CAPTURE) is rendered in one launch of tvk_raycast_classic.
 bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_classic_brick>& bricks, uint32_t& lodOut) {
   if (!m_vol || !m_w || !m_h) { m_err = "no dataset / render target"; return false; }
-  if (m_mode != RM_1DTRANS) { m_err = "the classic ray-caster is built for 1D transfer functions"; return false; }
   const BrickedVolume& v = *m_vol;
   memset(&p, 0, sizeof(p));
   bricks.clear();
@@ -827,7 +843,10 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
   v.Range(lo, hi);
   const double maxValue = (lo > hi) ? double(m_tf1d.GetSize()) : hi;
   const double resc = maxValue / double(m_tf1d.GetSize() - 1);
-  const double smin = double(m_tf1d.NonZeroMin()) * resc, smax = double(m_tf1d.NonZeroMax()) * resc;
+  // AbstrRenderer::ContainsData (:953-995): 1D / 2D scalar limits (a TOC file's gradient limits are -/+DBL_MAX, so
+  // the 2D gradient test passes for every brick), isosurface: isovalue <= max
+  const double smin = (m_mode == RM_2DTRANS) ? m_tf2dLimits[0] * resc : double(m_tf1d.NonZeroMin()) * resc;
+  const double smax = (m_mode == RM_2DTRANS) ? m_tf2dLimits[1] * resc : double(m_tf1d.NonZeroMax()) * resc;
   struct Item { float dist; uint64_t idx; tvk_classic_brick b; };
   std::vector<Item> items;
   for (uint32_t x = 0; x < nb[0]; ++x)
@@ -848,7 +867,11 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
               -(0.5f * be[0] * fabsf(pl[0]) + 0.5f * be[1] * fabsf(pl[1]) + 0.5f * be[2] * fabsf(pl[2]))) vis = false;
         }
         if (!vis) continue;
-        if (!(smax >= v.minmax[2 * idx] && smin <= v.minmax[2 * idx + 1])) continue;     // bIsEmpty: never drawn
+        const bool contains = (m_mode == RM_ISOSURFACE) ? (m_isoValue <= v.minmax[2 * idx + 1])
+                            : (m_mode == RM_2DTRANS)  ? (smax >= v.minmax[2 * idx] && smin <= v.minmax[2 * idx + 1] &&
+                                                         m_tf2dLimits[3] >= -DBL_MAX && m_tf2dLimits[2] <= DBL_MAX)
+                                                      : (smax >= v.minmax[2 * idx] && smin <= v.minmax[2 * idx + 1]);
+        if (!contains) continue;                                                          // bIsEmpty: never drawn
         Item it;
         memset(&it.b, 0, sizeof(it.b));
         float tmin[3], tmax[3], rs = FLT_MAX;
@@ -899,6 +922,12 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
   }
   p.light_dir[0] = m_lightDir.x; p.light_dir[1] = m_lightDir.y; p.light_dir[2] = m_lightDir.z;
   p.bytes_per_voxel = v.bpv;
+  p.render_mode = (uint32_t)m_mode;
+  p.gradient_scale = (v.max_grad_magnitude == 0) ? 1.0f : 1.0f / v.max_grad_magnitude;   // GLRenderer.cpp:1840-1841
+  p.isoval = float(m_isoValue / double(1u << (8 * v.bpv)));                                // GetNormalizedIsovalue
+  p.proj_param[0] = m_zfar / (m_zfar - m_znear);                                           // CullingLOD::GetDepthScaleParams
+  p.proj_param[1] = m_zfar * m_znear / (m_znear - m_zfar);
+  p.iso_color[0] = m_isoColor.x; p.iso_color[1] = m_isoColor.y; p.iso_color[2] = m_isoColor.z;
   return true;
 }
 

@@ -247,6 +247,8 @@ class CudaGridLeaper {
   Vec3 m_eye{0, 0, 1.6f}, m_at{0, 0, 0}, m_up{0, 1, 0};
   Matrix4 m_rotation, m_translation;
   Vec3 m_lightDir{0, 0, -1}, m_isoColor{0.5f, 0.5f, 0.5f};
+  std::vector<uint8_t> m_tf2dBytes;                                   // host copy of the rasterised 2D table
+  uint32_t m_tf2dW = 0, m_tf2dH = 0;
   float m_ambient[4] = {1, 1, 1, 0.1f}, m_diffuse[4] = {1, 1, 1, 1}, m_specular[4] = {1, 1, 1, 1};
   double m_isoValue = 0.5;
   TransferFunction1D m_tf1d;

@@ -12,8 +12,9 @@ struct ClassicArgs {
   const tvk_classic_brick* bricks;
   uint32_t nbricks;
   const uint8_t* store;
-  const float4* tf_f;
-  uint32_t tf_w;
+  const float4* tf_f;                // 1D table as floats
+  const uchar4* tf;                  // RGBA8 table (2D: [tf_h][tf_w])
+  uint32_t tf_w, tf_h;
   float4* image;
   unsigned long long* stats;
 };
@@ -52,7 +53,48 @@ __device__ __forceinline__ float brick_sample(const uint8_t* __restrict__ data, 
   return fmaf(g, c1 - c0, c0) * (BPV == 1 ? 1.0f / 255.0f : 1.0f / 65535.0f);
 }
 
-template <int BPV, bool LIT>
+// ComputeGradient, Volume3D.glsl:43-53 (y sign flipped there)
+template <int BPV>
+__device__ __forceinline__ void brick_gradient(const uint8_t* __restrict__ data, const uint32_t vox[3], float tx, float ty, float tz, float g[3]) {
+  const float hx = 1.0f / (float)vox[0], hy = 1.0f / (float)vox[1], hz = 1.0f / (float)vox[2];
+  const float gxp = brick_sample<BPV>(data, vox, tx + hx, ty, tz), gxm = brick_sample<BPV>(data, vox, tx - hx, ty, tz);
+  const float gyp = brick_sample<BPV>(data, vox, tx, ty - hy, tz), gym = brick_sample<BPV>(data, vox, tx, ty + hy, tz);
+  const float gzp = brick_sample<BPV>(data, vox, tx, ty, tz + hz), gzm = brick_sample<BPV>(data, vox, tx, ty, tz - hz);
+  g[0] = (gxm - gxp) / 2.0f; g[1] = (gyp - gym) / 2.0f; g[2] = (gzm - gzp) / 2.0f;
+}
+
+// gl_NormalMatrix * (g * vDomainScale), "secure" normalisation (Volume3D.glsl:55-60, GLRaycaster-*-light-FS.glsl)
+__device__ __forceinline__ void classic_normal(const tvk_classic_params& p, const float g[3], float& Nx, float& Ny, float& Nz) {
+  const float gx = g[0] * p.domain_scale[0], gy = g[1] * p.domain_scale[1], gz = g[2] * p.domain_scale[2];
+  Nx = fmaf(gz, p.normal_matrix[6], fmaf(gy, p.normal_matrix[3], gx * p.normal_matrix[0]));
+  Ny = fmaf(gz, p.normal_matrix[7], fmaf(gy, p.normal_matrix[4], gx * p.normal_matrix[1]));
+  Nz = fmaf(gz, p.normal_matrix[8], fmaf(gy, p.normal_matrix[5], gx * p.normal_matrix[2]));
+  const float nl = sqrtf(c_dot3(Nx, Ny, Nz, Nx, Ny, Nz));
+  if (nl > 0.0f) { Nx /= nl; Ny /= nl; Nz /= nl; }
+}
+
+__device__ __forceinline__ int c_nearest(float s, uint32_t n) { return min(max(__float2int_rz(s * (float)n), 0), (int)n - 1); }
+
+// Compose-FS.glsl:49-75 with the uniforms of GLRenderer::ComposeSurfaceImage (GLRenderer.cpp:2763-2811)
+__device__ __forceinline__ float4 classic_compose(const tvk_classic_params& p, float4 hit, float nx, float ny, float nz) {
+  if (hit.w == 0.0f) return make_float4(0.f, 0.f, 0.f, 0.f);
+  nz = fabsf(nz);
+  float vx = 0.0f - hit.x, vy = 0.0f - hit.y, vz = 0.0f - hit.z;
+  float l = sqrtf(c_dot3(vx, vy, vz, vx, vy, vz));
+  vx /= l; vy /= l; vz /= l;
+  const float d2 = 2.0f * c_dot3(nx, ny, nz, vx, vy, vz);
+  float rx = fmaf(-d2, nx, vx), ry = fmaf(-d2, ny, vy), rz = fmaf(-d2, nz, vz);
+  l = sqrtf(c_dot3(rx, ry, rz, rx, ry, rz));
+  rx /= l; ry /= l; rz /= l;
+  const float ndl = fmaxf(fabsf(c_dot3(nx, ny, nz, -p.light_dir[0], -p.light_dir[1], -p.light_dir[2])), 0.0f);
+  float sp = fmaxf(c_dot3(rx, ry, rz, p.light_dir[0], p.light_dir[1], p.light_dir[2]), 0.0f);
+  sp *= sp; sp *= sp; sp *= sp;
+  return make_float4(c_clamp01(fmaf(p.light_specular[0], sp, fmaf(p.light_diffuse[0] * p.iso_color[0], ndl, p.light_ambient[0]))),
+                     c_clamp01(fmaf(p.light_specular[1], sp, fmaf(p.light_diffuse[1] * p.iso_color[1], ndl, p.light_ambient[1]))),
+                     c_clamp01(fmaf(p.light_specular[2], sp, fmaf(p.light_diffuse[2] * p.iso_color[2], ndl, p.light_ambient[2]))), 1.0f);
+}
+
+template <int BPV, int MODE, bool LIT>
 __global__ void __launch_bounds__(128) classic_kernel(const __grid_constant__ ClassicArgs a) {
   // 8x4 pixel tiles per warp, as in K1, so that neighbouring rays share cache lines
   const uint32_t lane = threadIdx.x & 31u, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -68,6 +110,9 @@ __global__ void __launch_bounds__(128) classic_kernel(const __grid_constant__ Cl
   const float o[3] = {O.x, O.y, O.z}, d[3] = {D.x, D.y, D.z};
   float4 dst = make_float4(0.f, 0.f, 0.f, 0.f);
   unsigned long long nsamples = 0;
+  // isosurface: the two hit targets and the depth buffer (cleared to 0 / 1.0, depth test GL_LESS)
+  float4 hit = make_float4(0.f, 0.f, 0.f, 0.f);
+  float hnx = 0.f, hny = 0.f, hnz = 0.f, best_depth = 1.0f;
   for (uint32_t bi = 0; bi < a.nbricks; ++bi) {
     const tvk_classic_brick& b = a.bricks[bi];
     float s0 = -INFINITY, s1 = INFINITY;
@@ -97,24 +142,56 @@ __global__ void __launch_bounds__(128) classic_kernel(const __grid_constant__ Cl
     const uint8_t* data = a.store + b.store_offset;
     float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
     float ptx = te.x, pty = te.y, ptz = te.z, pex = enx, pey = eny, pez = enz;
+    if (MODE == TVK_RM_ISOSURFACE) {                        // GLRaycaster-ISO-FS.glsl:56-104
+      bool found = false;
+      for (int i = 0; i < steps; ++i) {
+        const float v = brick_sample<BPV>(data, b.voxels, ptx, pty, ptz);
+        nsamples++;
+        if (v >= p.isoval) { found = true; break; }
+        ptx += itx; pty += ity; ptz += itz;
+      }
+      if (!found) continue;                                 // discard
+      // RefineIsosurface.glsl:37-53
+      float rx = itx / 2.0f, ry = ity / 2.0f, rz = itz / 2.0f;
+      ptx -= rx; pty -= ry; ptz -= rz;
+      for (int i = 0; i < 5; ++i) {
+        rx /= 2.0f; ry /= 2.0f; rz /= 2.0f;
+        const float v = brick_sample<BPV>(data, b.voxels, ptx, pty, ptz);
+        if (v >= p.isoval) { ptx -= rx; pty -= ry; ptz -= rz; } else { ptx += rx; pty += ry; ptz += rz; }
+      }
+      const float ltx = tx.x - te.x, lty = tx.y - te.y, ltz = tx.z - te.z;
+      const float len_tex = sqrtf(c_dot3(ltx, lty, ltz, ltx, lty, ltz));
+      const float hx = ptx - te.x, hy = pty - te.y, hz = ptz - te.z;
+      const float f = sqrtf(c_dot3(hx, hy, hz, hx, hy, hz)) / len_tex;
+      const float hpx = fmaf(xx, f, enx * (1.0f - f)), hpy = fmaf(xy, f, eny * (1.0f - f)), hpz = fmaf(xz, f, enz * (1.0f - f));
+      const float depth = c_clamp01(p.proj_param[0] + p.proj_param[1] / (0.0f - hpz));
+      if (depth < best_depth) {
+        best_depth = depth;
+        hit = make_float4(hpx, hpy, hpz, f);
+        float g[3];
+        brick_gradient<BPV>(data, b.voxels, ptx, pty, ptz, g);
+        classic_normal(p, g, hnx, hny, hnz);
+      }
+      continue;
+    }
     for (int i = 0; i < steps; ++i) {
       const float v = brick_sample<BPV>(data, b.voxels, ptx, pty, ptz);
-      const int ti = min(max(__float2int_rz(v * p.trans_scale * (float)a.tf_w), 0), (int)a.tf_w - 1);
-      float4 c = __ldg(a.tf_f + ti);
+      float4 c;
+      float g[3];
+      if (MODE == TVK_RM_2DTRANS || LIT) brick_gradient<BPV>(data, b.voxels, ptx, pty, ptz, g);
+      if (MODE == TVK_RM_2DTRANS) {                          // GLRaycaster-2D[-light]-FS.glsl
+        const float gm = sqrtf(c_dot3(g[0], g[1], g[2], g[0], g[1], g[2]));
+        const uchar4 t = __ldg(a.tf + (size_t)c_nearest(fmaf(-gm, p.gradient_scale, 1.0f), a.tf_h) * a.tf_w + c_nearest(v * p.trans_scale, a.tf_w));
+        const float k = 1.0f / 255.0f;
+        c = make_float4((float)t.x * k, (float)t.y * k, (float)t.z * k, (float)t.w * k);
+      } else {
+        const int ti = min(max(__float2int_rz(v * p.trans_scale * (float)a.tf_w), 0), (int)a.tf_w - 1);
+        c = __ldg(a.tf_f + ti);
+      }
       nsamples++;
       if (LIT) {
-        const float hx = 1.0f / (float)b.voxels[0], hy = 1.0f / (float)b.voxels[1], hz = 1.0f / (float)b.voxels[2];
-        // ComputeGradient, Volume3D.glsl (y sign flipped there)
-        const float gxp = brick_sample<BPV>(data, b.voxels, ptx + hx, pty, ptz), gxm = brick_sample<BPV>(data, b.voxels, ptx - hx, pty, ptz);
-        const float gyp = brick_sample<BPV>(data, b.voxels, ptx, pty - hy, ptz), gym = brick_sample<BPV>(data, b.voxels, ptx, pty + hy, ptz);
-        const float gzp = brick_sample<BPV>(data, b.voxels, ptx, pty, ptz + hz), gzm = brick_sample<BPV>(data, b.voxels, ptx, pty, ptz - hz);
-        const float gx = (gxm - gxp) / 2.0f * p.domain_scale[0], gy = (gyp - gym) / 2.0f * p.domain_scale[1], gz = (gzm - gzp) / 2.0f * p.domain_scale[2];
-        // gl_NormalMatrix * g
-        float Nx = fmaf(gz, p.normal_matrix[6], fmaf(gy, p.normal_matrix[3], gx * p.normal_matrix[0]));
-        float Ny = fmaf(gz, p.normal_matrix[7], fmaf(gy, p.normal_matrix[4], gx * p.normal_matrix[1]));
-        float Nz = fmaf(gz, p.normal_matrix[8], fmaf(gy, p.normal_matrix[5], gx * p.normal_matrix[2]));
-        const float nl = sqrtf(c_dot3(Nx, Ny, Nz, Nx, Ny, Nz));
-        if (nl > 0.0f) { Nx /= nl; Ny /= nl; Nz /= nl; }
+        float Nx, Ny, Nz;
+        classic_normal(p, g, Nx, Ny, Nz);
         // Lighting(vec3(0), position, ...), lighting.glsl
         float vx = 0.0f - pex, vy = 0.0f - pey, vz = 0.0f - pez;
         float l = sqrtf(c_dot3(vx, vy, vz, vx, vy, vz));
@@ -141,6 +218,7 @@ __global__ void __launch_bounds__(128) classic_kernel(const __grid_constant__ Cl
     const float k = 1.0f - dst.w;                          // frame buffer blend: ONE_MINUS_DST_ALPHA, ONE
     dst.x = fmaf(col.x, k, dst.x); dst.y = fmaf(col.y, k, dst.y); dst.z = fmaf(col.z, k, dst.z); dst.w = fmaf(col.w, k, dst.w);
   }
+  if (MODE == TVK_RM_ISOSURFACE) dst = classic_compose(p, hit, hnx, hny, hnz);
   a.image[(size_t)py * p.width + px] = dst;
   for (int s = 16; s > 0; s >>= 1) nsamples += __shfl_down_sync(__activemask(), nsamples, s);
   if (lane == 0 && a.stats) atomicAdd(a.stats, nsamples);
@@ -148,7 +226,10 @@ __global__ void __launch_bounds__(128) classic_kernel(const __grid_constant__ Cl
 
 extern "C" int tvk_raycast_classic(tvk_ctx* c, const tvk_classic_params* p, const tvk_classic_brick* bricks, uint32_t n, const void* store) {
   if (!c || !p || (n && !bricks) || !store) return TVK_ERR_INVALID;
-  if (!c->d_tf || c->tf_h != 1) TVK_FAIL(c, TVK_ERR_INVALID, "the classic ray-caster needs a 1D transfer function");
+  if (p->render_mode != TVK_RM_1DTRANS && p->render_mode != TVK_RM_2DTRANS && p->render_mode != TVK_RM_ISOSURFACE)
+    TVK_FAIL(c, TVK_ERR_INVALID, "bad render mode");
+  if (p->render_mode == TVK_RM_1DTRANS && (!c->d_tf || c->tf_h != 1)) TVK_FAIL(c, TVK_ERR_INVALID, "1D mode needs a 1D transfer function");
+  if (p->render_mode == TVK_RM_2DTRANS && (!c->d_tf || c->tf_h < 2)) TVK_FAIL(c, TVK_ERR_INVALID, "2D mode needs a 2D transfer function");
   if (p->bytes_per_voxel != 1 && p->bytes_per_voxel != 2) TVK_FAIL(c, TVK_ERR_INVALID, "bad voxel size");
   if (!p->width || !p->height) TVK_FAIL(c, TVK_ERR_INVALID, "bad image size");
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
@@ -159,15 +240,19 @@ extern "C" int tvk_raycast_classic(tvk_ctx* c, const tvk_classic_params* p, cons
   if (n) TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_bricks, bricks, sizeof(tvk_classic_brick) * n, cudaMemcpyHostToDevice, c->stream));
   ClassicArgs a;
   a.p = *p; a.bricks = d_bricks; a.nbricks = n; a.store = static_cast<const uint8_t*>(store);
-  a.tf_f = c->d_tf_f; a.tf_w = c->tf_w; a.image = c->d_image; a.stats = c->d_stats;
+  a.tf_f = c->d_tf_f; a.tf = c->d_tf; a.tf_w = c->tf_w; a.tf_h = c->tf_h; a.image = c->d_image; a.stats = c->d_stats;
   const uint32_t tiles = ((p->width + 7) / 8) * ((p->height + 3) / 4);
   const uint32_t blocks = (tiles + 3) / 4;
   TVK_CHECK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-  if (p->bytes_per_voxel == 1) {
-    if (p->lighting) classic_kernel<1, true><<<blocks, 128, 0, c->stream>>>(a); else classic_kernel<1, false><<<blocks, 128, 0, c->stream>>>(a);
-  } else {
-    if (p->lighting) classic_kernel<2, true><<<blocks, 128, 0, c->stream>>>(a); else classic_kernel<2, false><<<blocks, 128, 0, c->stream>>>(a);
-  }
+  typedef void (*classic_fn)(const ClassicArgs);
+  const bool lit = p->lighting != 0 && p->render_mode != TVK_RM_ISOSURFACE;
+  classic_fn fn;
+#define TVK_PICK(B) (p->render_mode == TVK_RM_ISOSURFACE ? classic_kernel<B, TVK_RM_ISOSURFACE, false> \
+                     : p->render_mode == TVK_RM_2DTRANS ? (lit ? classic_kernel<B, TVK_RM_2DTRANS, true> : classic_kernel<B, TVK_RM_2DTRANS, false>) \
+                                                        : (lit ? classic_kernel<B, TVK_RM_1DTRANS, true> : classic_kernel<B, TVK_RM_1DTRANS, false>))
+  fn = (p->bytes_per_voxel == 1) ? TVK_PICK(1) : TVK_PICK(2);
+#undef TVK_PICK
+  fn<<<blocks, 128, 0, c->stream>>>(a);
   TVK_CHECK_CUDA(c, cudaGetLastError());
   TVK_CHECK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   c->launches++;

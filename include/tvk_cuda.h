@@ -302,8 +302,11 @@ int tvk_composite_ordered(tvk_ctx* ctx, const void* const* partial_dptrs, uint32
  * Compositing.glsl) and the frame buffer's ONE_MINUS_DST_ALPHA / ONE blend (GLRenderer.cpp:152-153): the bricks
  * of ONE level of detail, sorted front to back by the host (AbstrRenderer::BuildSubFrameBrickList), are marched
  * one after the other for every pixel.  Like the reference, ray entry points pass through half precision (the
- * RGBA16F entry buffer, GLRaycaster.cpp:97) and early ray termination works per brick.  1D transfer function,
- * with or without lighting; bricks are read from a device-resident brick store (tvk_build_store_device_ptr). */
+ * RGBA16F entry buffer, GLRaycaster.cpp:97) and early ray termination works per brick.  Render modes: 1D and 2D
+ * transfer function with or without lighting (GLRaycaster-2D[-light]-FS.glsl), and the isosurface pass
+ * (GLRaycaster-ISO-FS.glsl + RefineIsosurface.glsl: per brick first hit, refined, kept if it passes the GL_LESS depth
+ * test against the hits of the bricks before it) followed by Compose-FS.glsl.  Bricks are read from a
+ * device-resident brick store (tvk_build_store_device_ptr). */
 typedef struct tvk_classic_brick {
   float center[3], extension[3];     /* Brick::vCenter / vExtension                                  */
   float eye_to_tex[16];              /* ComputeEyeToTextureMatrix for this brick (row-vector order)   */
@@ -322,6 +325,11 @@ typedef struct tvk_classic_params {
   float light_ambient[3], light_diffuse[3], light_specular[3], light_dir[3];
   float domain_scale[3];             /* vDomainScale = 1 / scale                                      */
   uint32_t bytes_per_voxel;
+  uint32_t render_mode;              /* TVK_RM_1DTRANS / TVK_RM_2DTRANS / TVK_RM_ISOSURFACE             */
+  float gradient_scale;              /* fGradientScale, 2D TF (GLRenderer.cpp:1840-1841)               */
+  float isoval;                      /* fIsoval = GetNormalizedIsovalue()                              */
+  float proj_param[2];               /* vProjParam (CullingLOD::GetDepthScaleParams, CullingLOD.cpp:69-72) */
+  float iso_color[3];                /* isosurface colour (ComposeSurfaceImage multiplies the diffuse by it) */
 } tvk_classic_params;
 /* bricks: host array, front to back.  Result: the context's image (tvk_read_image). */
 int tvk_raycast_classic(tvk_ctx* ctx, const tvk_classic_params* p, const tvk_classic_brick* bricks, uint32_t n,

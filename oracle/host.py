@@ -489,14 +489,19 @@ class ClassicParams(C.Structure):                    # tvk_classic_params
                 ("normal_matrix", C.c_float * 9), ("inv_projection", C.c_float * 16), ("step_scale", C.c_float),
                 ("trans_scale", C.c_float), ("lighting", C.c_uint32), ("light_ambient", C.c_float * 3),
                 ("light_diffuse", C.c_float * 3), ("light_specular", C.c_float * 3), ("light_dir", C.c_float * 3),
-                ("domain_scale", C.c_float * 3), ("bytes_per_voxel", C.c_uint32)]
+                ("domain_scale", C.c_float * 3), ("bytes_per_voxel", C.c_uint32), ("render_mode", C.c_uint32),
+                ("gradient_scale", C.c_float), ("isoval", C.c_float), ("proj_param", C.c_float * 2),
+                ("iso_color", C.c_float * 3)]
 
 
 def classic_plan(oc, cam, width, height, tf_limits, lighting=False, sample_rate=1.0, scale=(1, 1, 1), trans_scale=1.0,
-                 capture=False, lod=None):
+                 capture=False, lod=None, render_mode=0, gradient_scale=1.0, iso_value=None):
     """What AbstrRenderer::PlanFrame / BuildSubFrameBrickList (AbstrRenderer.cpp:1125-1212, 999-1100) and
     GLRaycaster::SetBrickDepShaderVars / ComputeEyeToTextureMatrix hand to the shaders for the FINAL sub-frame of a
-    view: (ClassicParams, [ClassicBrick...] front to back, lod).  oc: oracle octree (tight store offsets)."""
+    view: (ClassicParams, [ClassicBrick...] front to back, lod).  oc: oracle octree (tight store offsets).
+    render_mode 0/1/2 = 1D TF / 2D TF / isosurface (AbstrRenderer::ContainsData, :953-995): tf_limits = the scalar
+    non-zero limits of the active table with the 1D table's size (a TOC file's gradient limits are -/+DBL_MAX, so the
+    2D gradient test always passes); iso_value = the raw isovalue (m_fIsovalue)."""
     plan = oc["plan"]
     dom0 = np.array([int(v) for v in plan.lod_size[0]], f32)
     sc = np.asarray(scale, f32)
@@ -563,7 +568,11 @@ def classic_plan(oc, cam, width, height, tf_limits, lighting=False, sample_rate=
                 if not vis:
                     continue
                 mn, mx = oc["minmax"][idx]
-                if not (hi_i * resc >= mn and lo_i * resc <= mx):
+                if render_mode == 2:
+                    contains = float(iso_value) <= mx
+                else:
+                    contains = hi_i * resc >= mn and lo_i * resc <= mx
+                if not contains:
                     continue                          # bIsEmpty: stays in the reference's list but is never drawn
                 vox = oc["sizes"][idx].astype(np.uint32)
                 tmin = (f32(overlap) / vox.astype(f32)).astype(f32)
@@ -601,6 +610,13 @@ def classic_plan(oc, cam, width, height, tf_limits, lighting=False, sample_rate=
     p.light_dir[:] = cam.light_dir.tolist()
     p.domain_scale[:] = (f32(1) / sc).tolist()
     p.bytes_per_voxel = oc["bpv"]
+    p.render_mode = int(render_mode)
+    p.gradient_scale = float(gradient_scale)
+    if iso_value is not None:
+        p.isoval = float(f32(float(iso_value) / float(1 << (8 * oc["bpv"]))))       # GetNormalizedIsovalue
+    zn, zf = f32(cam.znear), f32(cam.zfar)
+    p.proj_param[:] = [float(f32(zf / f32(zf - zn))), float(f32(f32(zf * zn) / f32(zn - zf)))]
+    p.iso_color[:] = cam.iso_color.tolist()
     return p, [t[2] for t in out], lod
 
 
@@ -610,10 +626,12 @@ def classic_render(p, bricks, store_tight, tf_rgba8):
     arr = (ClassicBrick * max(len(bricks), 1))(*bricks)
     img = np.zeros((p.height, p.width, 4), f32)
     n = C.c_uint64()
-    tf = np.ascontiguousarray(tf_rgba8, np.uint8)
+    tf = np.ascontiguousarray(tf_rgba8, np.uint8)          # [n][4] (1D) or [h][w][4] (2D)
+    tf_w, tf_h = (tf.shape[0], 1) if tf.ndim == 2 else (tf.shape[1], tf.shape[0])
     st = np.ascontiguousarray(store_tight, np.uint8)
     rc = O.lib().orc_raycast_classic(C.byref(p), arr, C.c_uint32(len(bricks)), st.ctypes.data_as(C.c_void_p),
-                                     tf.ctypes.data_as(C.c_void_p), C.c_uint32(tf.shape[0]), img.ctypes.data_as(C.c_void_p), C.byref(n))
+                                     tf.ctypes.data_as(C.c_void_p), C.c_uint32(tf_w), C.c_uint32(tf_h),
+                                     img.ctypes.data_as(C.c_void_p), C.byref(n))
     if rc:
         raise ValueError("orc_raycast_classic failed")
     return img, int(n.value)

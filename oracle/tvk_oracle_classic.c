@@ -8,6 +8,11 @@
  *   Renderer/GL/GLRaycaster.cpp:239-300   SetBrickDepShaderVars (fRayStepsize, fStepScale, vVoxelStepsize)
  *   Renderer/GL/GLRaycaster.cpp:589-612   ComputeEyeToTextureMatrix (computed by the caller, see oracle/host.py)
  *   Shaders/GLRaycaster-1D-FS.glsl:51-82, GLRaycaster-1D-light-FS.glsl:83-134   main()
+ *   Shaders/GLRaycaster-2D-FS.glsl:52-94, GLRaycaster-2D-light-FS.glsl:62-117   main() (2D transfer function)
+ *   Shaders/GLRaycaster-ISO-FS.glsl:56-104, RefineIsosurface.glsl:37-53         first hit per brick, refined; the
+ *                                         hit survives if it passes the GL_LESS depth test (GLRenderer.cpp:139) against
+ *                                         the buffer cleared to 1.0 (GLRaycaster.cpp:391-394); depth compared in fp32
+ *   Shaders/Compose-FS.glsl:49-75, GLRenderer::ComposeSurfaceImage (GLRenderer.cpp:2763-2811)   isosurface shading
  *   Shaders/VRender1D.glsl, VRender1DLit.glsl, Volume3D.glsl (sampleVolume, ComputeGradient, ComputeNormal),
  *   Shaders/lighting.glsl, Shaders/Compositing.glsl:33-38
  *   Renderer/GL/GLRenderer.cpp:152-153    frame-buffer blend ONE_MINUS_DST_ALPHA / ONE between bricks
@@ -83,9 +88,49 @@ static float brick_sample(const uint8_t* data, uint32_t bpv, const uint32_t vox[
   return fmaf(g, c1 - c0, c0) * (bpv == 1 ? 1.0f / 255.0f : 1.0f / 65535.0f);
 }
 
+static void brick_gradient(const uint8_t* data, uint32_t bpv, const uint32_t vox[3], float tx, float ty, float tz, float g[3]) {
+  const float hx = 1.0f / (float)vox[0], hy = 1.0f / (float)vox[1], hz = 1.0f / (float)vox[2];
+  const float gxp = brick_sample(data, bpv, vox, tx + hx, ty, tz), gxm = brick_sample(data, bpv, vox, tx - hx, ty, tz);
+  const float gyp = brick_sample(data, bpv, vox, tx, ty - hy, tz), gym = brick_sample(data, bpv, vox, tx, ty + hy, tz);
+  const float gzp = brick_sample(data, bpv, vox, tx, ty, tz + hz), gzm = brick_sample(data, bpv, vox, tx, ty, tz - hz);
+  g[0] = (gxm - gxp) / 2.0f; g[1] = (gyp - gym) / 2.0f; g[2] = (gzm - gzp) / 2.0f;
+}
+
+static void classic_normal(const tvk_classic_params* p, const float g[3], float N[3]) {
+  const float gx = g[0] * p->domain_scale[0], gy = g[1] * p->domain_scale[1], gz = g[2] * p->domain_scale[2];
+  N[0] = fmaf(gz, p->normal_matrix[6], fmaf(gy, p->normal_matrix[3], gx * p->normal_matrix[0]));
+  N[1] = fmaf(gz, p->normal_matrix[7], fmaf(gy, p->normal_matrix[4], gx * p->normal_matrix[1]));
+  N[2] = fmaf(gz, p->normal_matrix[8], fmaf(gy, p->normal_matrix[5], gx * p->normal_matrix[2]));
+  const float nl = sqrtf(dot3c(N[0], N[1], N[2], N[0], N[1], N[2]));
+  if (nl > 0.0f) { N[0] /= nl; N[1] /= nl; N[2] /= nl; }
+}
+
+static inline int nearest_c(float s, uint32_t n) { return clampi(f2i_sat(s * (float)n), 0, (int)n - 1); }
+
+static void classic_compose(const tvk_classic_params* p, const float hit[4], const float hn[3], float out[4]) {
+  out[0] = out[1] = out[2] = out[3] = 0.0f;
+  if (hit[3] == 0.0f) return;
+  const float nx = hn[0], ny = hn[1], nz = fabsf(hn[2]);
+  float vx = 0.0f - hit[0], vy = 0.0f - hit[1], vz = 0.0f - hit[2];
+  float l = sqrtf(dot3c(vx, vy, vz, vx, vy, vz));
+  vx /= l; vy /= l; vz /= l;
+  const float d2 = 2.0f * dot3c(nx, ny, nz, vx, vy, vz);
+  float rx = fmaf(-d2, nx, vx), ry = fmaf(-d2, ny, vy), rz = fmaf(-d2, nz, vz);
+  l = sqrtf(dot3c(rx, ry, rz, rx, ry, rz));
+  rx /= l; ry /= l; rz /= l;
+  const float ndl = fmaxf(fabsf(dot3c(nx, ny, nz, -p->light_dir[0], -p->light_dir[1], -p->light_dir[2])), 0.0f);
+  float sp = fmaxf(dot3c(rx, ry, rz, p->light_dir[0], p->light_dir[1], p->light_dir[2]), 0.0f);
+  sp *= sp; sp *= sp; sp *= sp;
+  for (int k = 0; k < 3; ++k)
+    out[k] = clamp01c(fmaf(p->light_specular[k], sp, fmaf(p->light_diffuse[k] * p->iso_color[k], ndl, p->light_ambient[k])));
+  out[3] = 1.0f;
+}
+
+/* tf_rgba8: [tf_h][tf_w][4]; tf_h == 1 for the 1D modes */
 int orc_raycast_classic(const tvk_classic_params* p, const tvk_classic_brick* bricks, uint32_t n, const uint8_t* store,
-                        const uint8_t* tf_rgba8, uint32_t tf_n, float* image, uint64_t* samples_out) {
-  if (!p || (n && !bricks) || !store || !tf_rgba8 || !image) return 1;
+                        const uint8_t* tf_rgba8, uint32_t tf_n, uint32_t tf_h, float* image, uint64_t* samples_out) {
+  if (!p || (n && !bricks) || !store || !tf_rgba8 || !image || !tf_h) return 1;
+  const int lit = p->lighting && p->render_mode != TVK_RM_ISOSURFACE;
   uint64_t total = 0;
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : total)
   for (int64_t py = 0; py < (int64_t)p->height; ++py) {
@@ -97,6 +142,7 @@ int orc_raycast_classic(const tvk_classic_params* p, const tvk_classic_brick* br
       xformc(p->inv_model_view, 0.f, 0.f, 0.f, 1.0f, O);
       xformc(p->inv_model_view, ex, ey, ez, 0.0f, D);
       float dst[4] = {0.f, 0.f, 0.f, 0.f};
+      float hit[4] = {0.f, 0.f, 0.f, 0.f}, hn[3] = {0.f, 0.f, 0.f}, best_depth = 1.0f;
       for (uint32_t bi = 0; bi < n; ++bi) {
         const tvk_classic_brick* b = &bricks[bi];
         float s0 = -INFINITY, s1 = INFINITY;
@@ -126,24 +172,54 @@ int orc_raycast_classic(const tvk_classic_params* p, const tvk_classic_brick* br
         const uint8_t* data = store + b->store_offset;
         float col[4] = {0.f, 0.f, 0.f, 0.f};
         float ptx = te[0], pty = te[1], ptz = te[2], pex = enx, pey = eny, pez = enz;
+        const uint32_t bpv = p->bytes_per_voxel;
+        if (p->render_mode == TVK_RM_ISOSURFACE) {
+          int found = 0;
+          for (int i = 0; i < steps; ++i) {
+            const float v = brick_sample(data, bpv, b->voxels, ptx, pty, ptz);
+            total++;
+            if (v >= p->isoval) { found = 1; break; }
+            ptx += itx; pty += ity; ptz += itz;
+          }
+          if (!found) continue;
+          float rx = itx / 2.0f, ry = ity / 2.0f, rz = itz / 2.0f;
+          ptx -= rx; pty -= ry; ptz -= rz;
+          for (int i = 0; i < 5; ++i) {
+            rx /= 2.0f; ry /= 2.0f; rz /= 2.0f;
+            const float v = brick_sample(data, bpv, b->voxels, ptx, pty, ptz);
+            if (v >= p->isoval) { ptx -= rx; pty -= ry; ptz -= rz; } else { ptx += rx; pty += ry; ptz += rz; }
+          }
+          const float ltx = tx[0] - te[0], lty = tx[1] - te[1], ltz = tx[2] - te[2];
+          const float len_tex = sqrtf(dot3c(ltx, lty, ltz, ltx, lty, ltz));
+          const float hx = ptx - te[0], hy = pty - te[1], hz = ptz - te[2];
+          const float f = sqrtf(dot3c(hx, hy, hz, hx, hy, hz)) / len_tex;
+          const float hpx = fmaf(xx, f, enx * (1.0f - f)), hpy = fmaf(xy, f, eny * (1.0f - f)), hpz = fmaf(xz, f, enz * (1.0f - f));
+          const float depth = clamp01c(p->proj_param[0] + p->proj_param[1] / (0.0f - hpz));
+          if (depth < best_depth) {
+            best_depth = depth;
+            hit[0] = hpx; hit[1] = hpy; hit[2] = hpz; hit[3] = f;
+            float g[3];
+            brick_gradient(data, bpv, b->voxels, ptx, pty, ptz, g);
+            classic_normal(p, g, hn);
+          }
+          continue;
+        }
         for (int i = 0; i < steps; ++i) {
-          const float v = brick_sample(data, p->bytes_per_voxel, b->voxels, ptx, pty, ptz);
-          const int ti = clampi(f2i_sat(v * p->trans_scale * (float)tf_n), 0, (int)tf_n - 1);
-          float c[4];
+          const float v = brick_sample(data, bpv, b->voxels, ptx, pty, ptz);
+          float c[4], g[3];
+          const int two_d = p->render_mode == TVK_RM_2DTRANS;
+          if (two_d || lit) brick_gradient(data, bpv, b->voxels, ptx, pty, ptz, g);
+          size_t ti;
+          if (two_d) {
+            const float gm = sqrtf(dot3c(g[0], g[1], g[2], g[0], g[1], g[2]));
+            ti = (size_t)nearest_c(fmaf(-gm, p->gradient_scale, 1.0f), tf_h) * tf_n + nearest_c(v * p->trans_scale, tf_n);
+          } else ti = (size_t)clampi(f2i_sat(v * p->trans_scale * (float)tf_n), 0, (int)tf_n - 1);
           for (int k = 0; k < 4; ++k) c[k] = (float)tf_rgba8[4 * ti + k] * (1.0f / 255.0f);
           total++;
-          if (p->lighting) {
-            const float hx = 1.0f / (float)b->voxels[0], hy = 1.0f / (float)b->voxels[1], hz = 1.0f / (float)b->voxels[2];
-            const uint32_t bpv = p->bytes_per_voxel;
-            const float gxp = brick_sample(data, bpv, b->voxels, ptx + hx, pty, ptz), gxm = brick_sample(data, bpv, b->voxels, ptx - hx, pty, ptz);
-            const float gyp = brick_sample(data, bpv, b->voxels, ptx, pty - hy, ptz), gym = brick_sample(data, bpv, b->voxels, ptx, pty + hy, ptz);
-            const float gzp = brick_sample(data, bpv, b->voxels, ptx, pty, ptz + hz), gzm = brick_sample(data, bpv, b->voxels, ptx, pty, ptz - hz);
-            const float gx = (gxm - gxp) / 2.0f * p->domain_scale[0], gy = (gyp - gym) / 2.0f * p->domain_scale[1], gz = (gzm - gzp) / 2.0f * p->domain_scale[2];
-            float Nx = fmaf(gz, p->normal_matrix[6], fmaf(gy, p->normal_matrix[3], gx * p->normal_matrix[0]));
-            float Ny = fmaf(gz, p->normal_matrix[7], fmaf(gy, p->normal_matrix[4], gx * p->normal_matrix[1]));
-            float Nz = fmaf(gz, p->normal_matrix[8], fmaf(gy, p->normal_matrix[5], gx * p->normal_matrix[2]));
-            const float nl = sqrtf(dot3c(Nx, Ny, Nz, Nx, Ny, Nz));
-            if (nl > 0.0f) { Nx /= nl; Ny /= nl; Nz /= nl; }
+          if (lit) {
+            float N[3];
+            classic_normal(p, g, N);
+            const float Nx = N[0], Ny = N[1], Nz = N[2];
             float vx = 0.0f - pex, vy = 0.0f - pey, vz = 0.0f - pez;
             float l = sqrtf(dot3c(vx, vy, vz, vx, vy, vz));
             vx /= l; vy /= l; vz /= l;
@@ -169,6 +245,7 @@ int orc_raycast_classic(const tvk_classic_params* p, const tvk_classic_brick* br
         const float k = 1.0f - dst[3];
         dst[0] = fmaf(col[0], k, dst[0]); dst[1] = fmaf(col[1], k, dst[1]); dst[2] = fmaf(col[2], k, dst[2]); dst[3] = fmaf(col[3], k, dst[3]);
       }
+      if (p->render_mode == TVK_RM_ISOSURFACE) classic_compose(p, hit, hn, dst);
       float* o = image + 4 * ((size_t)py * p->width + px);
       o[0] = dst[0]; o[1] = dst[1]; o[2] = dst[2]; o[3] = dst[3];
     }

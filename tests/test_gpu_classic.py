@@ -81,7 +81,81 @@ def test_classic_kernel_matches_oracle(lighting, dtype):
     r.cleanup()
 
 
-def test_classic_plan_matches_oracle_host():
+def _tf2d(n):
+    v = np.linspace(0, 1, n, dtype=np.float32)
+    g = np.linspace(0, 1, 256, dtype=np.float32)
+    t = np.zeros((256, n, 4), np.float32)
+    t[..., 0] = v[None, :]
+    t[..., 1] = 0.2 + 0.8 * g[:, None]
+    t[..., 2] = 0.4
+    t[..., 3] = np.clip((v[None, :] - 0.3) * 0.5, 0, 1) * (0.3 + 0.7 * g[:, None])
+    return (np.clip(t, 0, 1) * np.float32(255)).astype(np.uint8)
+
+
+@pytest.mark.parametrize("lighting,dtype", [(False, np.uint8), (True, np.uint8), (True, np.uint16)])
+def test_classic_2d_transfer_function_matches_oracle(lighting, dtype):
+    """GLRaycaster-2D-FS.glsl / GLRaycaster-2D-light-FS.glsl"""
+    from imagevis3d_b200.renderer import Renderer, RT_HEADLESS
+    vol = H.synth_blobs((150, 131, 97), dtype)
+    r = Renderer(0)
+    r.loadRawVolume(vol, brick_size=32)
+    r.setRendererType(True)
+    info = r.datasetInfo()
+    tf2 = _tf2d(info.tf_size)
+    nzv = np.nonzero(tf2[..., 3].max(axis=0))[0]
+    r.set2DTrans(tf2, (float(nzv.min()), float(nzv.max()), 0.0, 1.0))
+    r.setRenderMode(1)
+    r.setLightingEnabled(lighting)
+    r.resize((203, 149))
+    r.setRendererTarget(RT_HEADLESS)
+    r.setRotation4x4(H.rotation_y(-0.8) @ H.rotation_x(0.5))
+    p, bricks, lod = r.planClassicFrame()
+    assert p.render_mode == 1 and len(bricks) > 20 and lod == 0
+    assert r.paintUntilConverged() == 1 and r.converged()
+    got = r.frameFloat()
+    q, ob = _to_oracle(p, bricks)
+    want, samples = H.classic_render(q, ob, _device_store(r), tf2)
+    psnr, err = image_errors(got, want)
+    assert want[..., 3].max() > 0.3 and psnr >= 45.0 and err <= 2.0 / 255.0, (psnr, err)
+    assert len(np.unique(want[..., 1].round(3))) > 50          # the gradient axis of the table is exercised
+    assert abs(r.perf()["samples"] - samples) <= samples * 1e-4
+    r.cleanup()
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+def test_classic_isosurface_matches_oracle(dtype):
+    """GLRaycaster-ISO-FS.glsl + RefineIsosurface.glsl + depth test + Compose-FS.glsl"""
+    from imagevis3d_b200.renderer import Renderer, RT_HEADLESS
+    vol = H.synth_blobs((150, 131, 97), dtype)
+    r = Renderer(0)
+    r.loadRawVolume(vol, brick_size=32)
+    r.setRendererType(True)
+    info = r.datasetInfo()
+    r.set1DTransFloat(_tf(info.tf_size))
+    r.setRenderMode(2)
+    r.setIsoValue(0.25 * float(vol.max()))
+    r.setIsosurfaceColor((0.9, 0.6, 0.3))
+    r.resize((203, 149))
+    r.setRendererTarget(RT_HEADLESS)
+    r.setRotation4x4(H.rotation_y(0.6) @ H.rotation_x(0.3))
+    p, bricks, lod = r.planClassicFrame()
+    assert p.render_mode == 2 and len(bricks) > 5 and lod == 0
+    assert r.paintUntilConverged() == 1 and r.converged()
+    got = r.frameFloat()
+    q, ob = _to_oracle(p, bricks)
+    want, samples = H.classic_render(q, ob, _device_store(r), H.tf_bytes(_tf(info.tf_size)))
+    cover = float((want[..., 3] > 0).mean())
+    assert 0.03 < cover < 0.95, cover
+    # a hit either exists in both images or in neither (same fp32 operations), up to a handful of silhouette pixels
+    assert float(((got[..., 3] > 0) != (want[..., 3] > 0)).mean()) <= 1e-3
+    psnr, err = image_errors(got, want)
+    assert psnr >= 45.0, (psnr, err)
+    assert abs(r.perf()["samples"] - samples) <= samples * 1e-4
+    r.cleanup()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_classic_plan_matches_oracle_host(mode):
     from imagevis3d_b200.renderer import Renderer, RT_HEADLESS
     vol = H.synth_blobs((150, 131, 97), np.uint8)
     r = Renderer(0)
@@ -90,6 +164,13 @@ def test_classic_plan_matches_oracle_host():
     info = r.datasetInfo()
     tf = _tf(info.tf_size)
     r.set1DTransFloat(tf)
+    if mode == 1:
+        tf2 = _tf2d(info.tf_size)
+        nzv = np.nonzero(tf2[..., 3].max(axis=0))[0]
+        r.set2DTrans(tf2, (float(nzv.min()), float(nzv.max()), 0.0, 1.0))
+    r.setRenderMode(mode)
+    iso = 0.7 * float(vol.max())
+    r.setIsoValue(iso)
     r.setLightingEnabled(True)
     r.resize((203, 149))
     r.setRendererTarget(RT_HEADLESS)
@@ -100,9 +181,15 @@ def test_classic_plan_matches_oracle_host():
     cam.rotation = rot
     oc = O.build_octree(vol, 32, 2)
     lo, hi = H.tf_nonzero_limits(tf)
+    if mode == 1:
+        lo, hi = int(nzv.min()), int(nzv.max())
     maxv = float(vol.max())
-    po, bo, lod_o = H.classic_plan(oc, cam, 203, 149, (lo, hi, len(tf)), lighting=True, trans_scale=255.0 / maxv)
+    po, bo, lod_o = H.classic_plan(oc, cam, 203, 149, (lo, hi, len(tf)), lighting=True, trans_scale=255.0 / maxv,
+                                   render_mode=mode, gradient_scale=p.gradient_scale, iso_value=iso)
     assert lod == lod_o and len(bricks) == len(bo)
+    if mode == 2:                                          # bricks below the isovalue are dropped
+        p0, b0, _ = H.classic_plan(oc, cam, 203, 149, (lo, hi, len(tf)), lighting=True, trans_scale=255.0 / maxv)
+        assert len(bo) < len(b0)
     for name, _ in po._fields_:
         a, b = getattr(p, name), getattr(po, name)
         if hasattr(a, "__len__"):
