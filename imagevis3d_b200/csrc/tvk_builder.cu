@@ -873,7 +873,10 @@ __device__ __forceinline__ unsigned long long grad_s_row(const RowCtx<T>& r, uin
   // the fp64 length depends on (|dx|,|dy|,|dz|) only: this key identifies it
   if (key) *key = (unsigned long long)abs(dx) | ((unsigned long long)abs(dy) << 17) | ((unsigned long long)abs(dz) << 34);
   if (sizeof(T) == 1) return (unsigned long long)(unsigned)(dx * dx + dy * dy + dz * dz);
-  return (unsigned long long)(unsigned)(dx * dx) + (unsigned)(dy * dy) + (unsigned)(dz * dz);
+  // 16-bit: a square reaches 2^32 - 2^17, beyond int -- multiply as unsigned (signed overflow is undefined and the
+  // compiler did sign-extend the wrapped product into the 64-bit sum)
+  const unsigned ux = (unsigned)abs(dx), uy = (unsigned)abs(dy), uz = (unsigned)abs(dz);
+  return (unsigned long long)ux * ux + (unsigned long long)uy * uy + (unsigned long long)uz * uz;
 }
 
 struct GradBest { unsigned long long s; unsigned long long len_bits; };
@@ -965,6 +968,215 @@ __global__ void __launch_bounds__(256) hist2d_kernel(const T* __restrict__ raw, 
     }
   }
   if (pend_cnt) atomicAdd(&bins[pend_bin], (unsigned long long)pend_cnt);
+}
+
+// ---- 4 voxels per thread (rows that are a multiple of 4 voxels long, base 4/8-byte aligned) --------------
+// One 4-/8-byte load per neighbouring row instead of one element load per neighbour and voxel, the three
+// central differences of all four voxels with SIMD-in-a-word |a-b|, S by dp4a (8-bit) / 32x32->64 multiplies.
+// Same decisions as the scalar kernels above; the voxels that need the exact fp64 chain are queued per warp
+// and evaluated 32 at a time, so a warp never runs the chain for a single lane.
+template <typename T> struct QuadOf;
+template <> struct QuadOf<uint8_t> { typedef uint32_t type; };
+template <> struct QuadOf<uint16_t> { typedef uint2 type; };
+__device__ __forceinline__ uint32_t quad_zero(uint32_t) { return 0u; }
+__device__ __forceinline__ uint2 quad_zero(uint2) { return make_uint2(0u, 0u); }
+template <typename T>
+__device__ __forceinline__ typename QuadOf<T>::type quad_load(const T* row, uint32_t q) {
+  typedef typename QuadOf<T>::type Q;
+  return row ? __ldg(reinterpret_cast<const Q*>(row) + q) : quad_zero(Q());
+}
+__device__ __forceinline__ uint32_t quad_shfl_up(uint32_t v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ uint32_t quad_shfl_down(uint32_t v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ uint2 quad_shfl_up(uint2 v) { return make_uint2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1)); }
+__device__ __forceinline__ uint2 quad_shfl_down(uint2 v) { return make_uint2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1)); }
+
+// S and the (|dx|,|dy|,|dz|) key of the four voxels of quad q; val[] = the voxels themselves.  All 32 lanes call.
+template <typename T>
+__device__ __forceinline__ void quad_grad(const RowCtx<T>& rc, uint32_t q, uint32_t nq, uint32_t lane, bool act,
+                                          unsigned long long s[4], unsigned long long key[4], uint32_t val[4]) {
+  typedef typename QuadOf<T>::type Q;
+  const Q z = quad_zero(Q());
+  const Q c = act ? quad_load<T>(rc.line, q) : z;
+  Q prev = quad_shfl_up(c), next = quad_shfl_down(c);
+  if (lane == 0) prev = (act && q > 0) ? quad_load<T>(rc.line, q - 1) : z;
+  if (lane == 31 || q + 1 >= nq) next = (act && q + 1 < nq) ? quad_load<T>(rc.line, q + 1) : z;
+  const Q up = act ? quad_load<T>(rc.up, q) : z, dn = act ? quad_load<T>(rc.down, q) : z;
+  const Q fr = act ? quad_load<T>(rc.front, q) : z, bk = act ? quad_load<T>(rc.back, q) : z;
+  if constexpr (sizeof(T) == 1) {
+    const uint32_t l = __byte_perm(prev, c, 0x6543), r = __byte_perm(c, next, 0x4321);
+    const uint32_t adx = __vabsdiffu4(l, r), ady = __vabsdiffu4(up, dn), adz = __vabsdiffu4(fr, bk);
+    const uint32_t t0 = __byte_perm(adx, ady, 0x5140), t1 = __byte_perm(adx, ady, 0x7362);
+    const uint32_t u0 = __byte_perm(adz, 0u, 0x4140), u1 = __byte_perm(adz, 0u, 0x4342);
+    const uint32_t k0 = __byte_perm(t0, u0, 0x5410), k1 = __byte_perm(t0, u0, 0x7632);
+    const uint32_t k2 = __byte_perm(t1, u1, 0x5410), k3 = __byte_perm(t1, u1, 0x7632);
+    key[0] = k0; key[1] = k1; key[2] = k2; key[3] = k3;
+    s[0] = __dp4a(k0, k0, 0u); s[1] = __dp4a(k1, k1, 0u); s[2] = __dp4a(k2, k2, 0u); s[3] = __dp4a(k3, k3, 0u);
+    val[0] = c & 0xffu; val[1] = (c >> 8) & 0xffu; val[2] = (c >> 16) & 0xffu; val[3] = c >> 24;
+  } else {
+    const uint32_t lx = __byte_perm(prev.y, c.x, 0x5432), ly = __byte_perm(c.x, c.y, 0x5432), ry = __byte_perm(c.y, next.x, 0x5432);
+    const uint32_t ax[2] = {__vabsdiffu2(lx, ly), __vabsdiffu2(ly, ry)};
+    const uint32_t ay[2] = {__vabsdiffu2(up.x, dn.x), __vabsdiffu2(up.y, dn.y)};
+    const uint32_t az[2] = {__vabsdiffu2(fr.x, bk.x), __vabsdiffu2(fr.y, bk.y)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t dx = (i & 1) ? ax[i >> 1] >> 16 : ax[i >> 1] & 0xffffu;
+      const uint32_t dy = (i & 1) ? ay[i >> 1] >> 16 : ay[i >> 1] & 0xffffu;
+      const uint32_t dz = (i & 1) ? az[i >> 1] >> 16 : az[i >> 1] & 0xffffu;
+      s[i] = (unsigned long long)dx * dx + (unsigned long long)dy * dy + (unsigned long long)dz * dz;
+      key[i] = (unsigned long long)(dx | (dy << 16)) | ((unsigned long long)dz << 32);
+    }
+    val[0] = c.x & 0xffffu; val[1] = c.x >> 16; val[2] = c.y & 0xffffu; val[3] = c.y >> 16;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) grad_max_vec_kernel(const T* __restrict__ raw, uint32_t sx, uint32_t sy, uint32_t sz,
+                                                            double norm2, GradBest* __restrict__ partial,
+                                                            unsigned long long* __restrict__ shared_best) {
+  const uint32_t rows = sy * sz, lane = threadIdx.x & 31u, nq = sx / 4u;
+  unsigned long long best_s = 0, best_bits = 0, last_key = ~0ull;
+  for (uint32_t row = blockIdx.x * 8u + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8u) {
+    const uint32_t y = row % sy, z = row / sy;
+    const RowCtx<T> rc = row_ctx(raw, y, z, sx, sy, sz);
+    // only voxels that tie or beat the LARGEST S seen anywhere can hold the maximum: adopt the grid-wide bound once
+    // per row, so that the exact chain stops running for every thread's local records and ties
+    const unsigned long long gb = *reinterpret_cast<volatile unsigned long long*>(shared_best);
+    if (gb > best_s) { best_s = gb; best_bits = 0; }
+    for (uint32_t q0 = 0; q0 < nq; q0 += 32u) {
+      const uint32_t q = q0 + lane;
+      const bool act = q < nq;
+      unsigned long long s[4], key[4];
+      uint32_t val[4];
+      quad_grad<T>(rc, q, nq, lane, act, s, key, val);
+      const unsigned long long m = max(max(s[0], s[1]), max(s[2], s[3]));
+      if (m == 0 || m < best_s) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (s[i] == 0 || s[i] < best_s || key[i] == last_key) continue;
+        last_key = key[i];
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(grad_mag(raw, 4u * q + i, y, z, sx, sy, sz, norm2));
+        if (s[i] > best_s) { best_s = s[i]; best_bits = bits; atomicMax(shared_best, best_s); }
+        else if (bits > best_bits) best_bits = bits;
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long os = __shfl_xor_sync(0xffffffffu, best_s, o), ob = __shfl_xor_sync(0xffffffffu, best_bits, o);
+    if (os > best_s || (os == best_s && ob > best_bits)) { best_s = os; best_bits = ob; }
+  }
+  __shared__ GradBest sh[8];
+  if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5].s = best_s; sh[threadIdx.x >> 5].len_bits = best_bits; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    GradBest g = sh[0];
+    for (int w = 1; w < 8; ++w) if (sh[w].s > g.s || (sh[w].s == g.s && sh[w].len_bits > g.len_bits)) g = sh[w];
+    partial[blockIdx.x] = g;
+  }
+}
+
+// exact bin of one voxel (the chain of hist2d_kernel's fall-back) and its vote
+template <typename T>
+__device__ __forceinline__ void hist2d_exact_vote(const T* __restrict__ raw, unsigned long long idx, uint32_t sx, uint32_t sy, uint32_t sz,
+                                                  double norm2, double max_grad, const uint16_t* __restrict__ vlut,
+                                                  unsigned long long* __restrict__ bins) {
+  const uint32_t x = (uint32_t)(idx % sx), y = (uint32_t)((idx / sx) % sy), z = (uint32_t)(idx / ((unsigned long long)sx * sy));
+  const double e = __dmul_rn(__ddiv_rn(grad_mag(raw, x, y, z, sx, sy, sz, norm2), max_grad), 255.0);
+  const uint32_t gi = (e >= 255.0) ? 255u : ((e > 0.0) ? (uint32_t)e : 0u);
+  atomicAdd(&bins[(uint32_t)vlut[raw[idx]] * 256u + gi], 1ull);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) hist2d_vec_kernel(const T* __restrict__ raw, uint32_t sx, uint32_t sy, uint32_t sz,
+                                                          double norm2, double max_grad, unsigned long long smax, float inv_smax,
+                                                          const uint16_t* __restrict__ vlut,
+                                                          unsigned long long* __restrict__ bins) {
+  __shared__ unsigned long long queue[8][64];
+  unsigned long long* wq = queue[threadIdx.x >> 5];
+  uint32_t qn = 0;                                      // queued voxels of this warp (same value in every lane)
+  uint32_t pend_bin = 0xFFFFFFFFu, pend_cnt = 0;
+  const uint32_t rows = sy * sz, lane = threadIdx.x & 31u, nq = sx / 4u;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (uint32_t row = blockIdx.x * 8u + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8u) {
+    const uint32_t y = row % sy, z = row / sy;
+    const RowCtx<T> rc = row_ctx(raw, y, z, sx, sy, sz);
+    const unsigned long long row_base = (unsigned long long)row * sx;
+    for (uint32_t q0 = 0; q0 < nq; q0 += 32u) {
+      const uint32_t q = q0 + lane;
+      const bool act = q < nq;
+      unsigned long long s[4], key[4];
+      uint32_t val[4], bin[4];
+      quad_grad<T>(rc, q, nq, lane, act, s, key, val);
+      uint32_t need = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t gi = 0;
+        if (s[i] != 0) {
+          // 255*sqrt(S/Smax) in fp32 (relative error < 5e-7, i.e. < 1.3e-4 absolute); floor by a round-down magic add
+          const float t = (float)s[i] * inv_smax;
+          const float qf = 255.0f * (t * rsqrtf(t));
+          const float mg = __fadd_rd(qf, 8388608.0f);
+          const float fl = mg - 8388608.0f;
+          // S < Smax: everything from 254.5 up lands in bin 254 (see hist2d_kernel); ties with the maximum and
+          // estimates within 5e-4 of a bin boundary take the exact chain
+          if (s[i] == smax) need |= 1u << i;
+          else if (qf >= 254.5f) gi = 254u;
+          else if (qf - fl > 5e-4f && fl + 1.0f - qf > 5e-4f) gi = __float_as_uint(mg) & 0x7FFFFFu;
+          else need |= 1u << i;
+        }
+        bin[i] = (uint32_t)vlut[val[i]] * 256u + gi;
+      }
+      if (!act) need = 0;
+      // ---- exact-chain queue
+      if (__any_sync(0xffffffffu, need != 0)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const unsigned m = __ballot_sync(0xffffffffu, (need >> i) & 1u);
+          if (!m) continue;
+          if ((need >> i) & 1u) wq[qn + __popc(m & lt)] = row_base + 4u * q + i;
+          qn += __popc(m);
+          __syncwarp();
+          if (qn >= 32u) {
+            hist2d_exact_vote<T>(raw, wq[lane], sx, sy, sz, norm2, max_grad, vlut, bins);
+            const unsigned long long mv = (lane + 32u < qn) ? wq[lane + 32u] : 0ull;
+            __syncwarp();
+            wq[lane] = mv;
+            qn -= 32u;
+            __syncwarp();
+          }
+        }
+      }
+      // ---- votes of the decided voxels: one atomic per distinct bin of the warp, repeated bins kept in a register.
+      // (Measured on B200: the L2 atomics are what bounds this pass -- merging only runs of neighbouring lanes, or
+      // voting per thread, issues more of them and is slower than MATCH.ANY over the whole warp.)
+      const bool uni = act && need == 0 && bin[0] == bin[1] && bin[1] == bin[2] && bin[2] == bin[3];
+      const unsigned um = __ballot_sync(0xffffffffu, uni), am = __ballot_sync(0xffffffffu, act);
+      if (um == am) {                                    // every active thread votes four times for one bin
+        if (act) {
+          const unsigned peers = __match_any_sync(am, bin[0]);
+          if (lane == (unsigned)(__ffs(peers) - 1)) {
+            const uint32_t n = 4u * __popc(peers);
+            if (bin[0] == pend_bin) pend_cnt += n;
+            else { if (pend_cnt) atomicAdd(&bins[pend_bin], (unsigned long long)pend_cnt); pend_bin = bin[0]; pend_cnt = n; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool v = act && !((need >> i) & 1u);
+          const unsigned vm = __ballot_sync(0xffffffffu, v);
+          if (!v) continue;
+          const unsigned peers = __match_any_sync(vm, bin[i]);
+          if (lane == (unsigned)(__ffs(peers) - 1)) {
+            const uint32_t n = __popc(peers);
+            if (bin[i] == pend_bin) pend_cnt += n;
+            else { if (pend_cnt) atomicAdd(&bins[pend_bin], (unsigned long long)pend_cnt); pend_bin = bin[i]; pend_cnt = n; }
+          }
+        }
+      }
+    }
+  }
+  if (pend_cnt) atomicAdd(&bins[pend_bin], (unsigned long long)pend_cnt);
+  if (lane < qn) hist2d_exact_vote<T>(raw, wq[lane], sx, sy, sz, norm2, max_grad, vlut, bins);
 }
 
 static void release(tvk_ctx* c) {
@@ -1256,7 +1468,11 @@ static int run_hist2d(tvk_ctx* c, uint32_t bins_x, double max_nonzero, uint64_t*
   TVK_CHECK_CUDA(c, cudaMalloc(&d_lut, sizeof(uint16_t) * range));
   TVK_CHECK_CUDA(c, cudaMemsetAsync(d_bins, 0, sizeof(unsigned long long) * 256 * bins_x, c->stream));
   TVK_CHECK_CUDA(c, cudaEventRecord(c->bev0, c->stream));
-  grad_max_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_part);
+  // 4 voxels per thread when rows are whole quads (cudaMalloc'ed / caller-aligned base); TVK_HIST2D_SCALAR=1 forces the
+  // one-voxel-per-thread kernels
+  const bool vec = (s[0] % 4u) == 0 && (reinterpret_cast<uintptr_t>(b.d_lod[0]) % (4 * sizeof(T))) == 0 && !getenv("TVK_HIST2D_SCALAR");
+  if (vec) grad_max_vec_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_part, d_bins);   // d_bins[0]: zeroed scratch, re-zeroed below
+  else grad_max_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_part);
   hist2d_value_lut_kernel<<<(range + 255) / 256, 256, 0, c->stream>>>(range, bins_x, max_nonzero, d_lut);
   c->launches += 2;
   std::vector<GradBest> part(blocks);
@@ -1267,7 +1483,9 @@ static int run_hist2d(tvk_ctx* c, uint32_t bins_x, double max_nonzero, uint64_t*
   double mg;
   memcpy(&mg, &g.len_bits, sizeof(mg));
   const float inv_smax = g.s ? 1.0f / (float)g.s : 0.0f;
-  hist2d_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, mg, g.s, inv_smax, d_lut, d_bins);
+  if (vec) TVK_CHECK_CUDA(c, cudaMemsetAsync(d_bins, 0, sizeof(unsigned long long), c->stream));
+  if (vec) hist2d_vec_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, mg, g.s, inv_smax, d_lut, d_bins);
+  else hist2d_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, mg, g.s, inv_smax, d_lut, d_bins);
   c->launches++;
   TVK_CHECK_CUDA(c, cudaGetLastError());
   TVK_CHECK_CUDA(c, cudaEventRecord(c->bev1, c->stream));

@@ -117,3 +117,44 @@ def test_fused_lod0_pass_is_bit_exact(vol, dtype, median, monkeypatch):
     ref = ref[:np.nonzero(ref)[0][-1] + 1]
     assert h1.size == ref.size and (h1 == ref).all()
     t.close()
+
+
+def _hist2d_volumes():
+    rng = np.random.default_rng(11)
+    out = []
+    out.append(("u8 noise", H.synth_noise((132, 37, 21), np.uint8, seed=3, maxval=255)))
+    out.append(("u8 sphere", H.synth_sphere((64, 64, 64), np.uint8)))
+    z, y, x = np.meshgrid(np.arange(20), np.arange(24), np.arange(128), indexing="ij")
+    out.append(("u8 ramp (every voxel ties with the maximum)", ((x + 2 * y + z) % 256).astype(np.uint8)))
+    out.append(("u8 flat", np.full((9, 10, 32), 77, np.uint8)))
+    out.append(("u16 noise", H.synth_noise((136, 30, 17), np.uint16, seed=9, maxval=65535)))
+    out.append(("u16 12-bit blobs", (H.synth_blobs((96, 52, 40), np.uint16) >> 4).astype(np.uint16)))
+    sm = rng.integers(0, 4096, (12, 16, 64)).astype(np.uint16)
+    sm[:, :, 20:40] = 4000                                   # runs of equal bins inside a thread's four voxels
+    out.append(("u16 runs", sm))
+    return out
+
+
+@pytest.mark.parametrize("case", range(7))
+def test_hist2d_four_voxels_per_thread_is_bit_exact(case, monkeypatch):
+    """The vectorised 2-D histogram kernels (rows of whole quads) against the oracle AND the one-voxel-per-thread
+    kernels (TVK_HIST2D_SCALAR=1)."""
+    from imagevis3d_b200.context import TvkContext
+    name, raw = _hist2d_volumes()[case]
+    raw = np.ascontiguousarray(raw)
+    assert raw.shape[2] % 4 == 0
+    oc = O.build_octree(raw, 64, 2, False)
+    bins_x = 256 if raw.dtype == np.uint8 else 4096
+    maxv = float(oc["minmax"][:, 1].max())
+    h_ref, mg_ref = O.hist2d(oc, bins_x, maxv)
+    t = TvkContext(0)
+    t.build_octree(raw, 64, 2)
+    h_vec, mg_vec = t.build_hist2d(bins_x, maxv)
+    monkeypatch.setenv("TVK_HIST2D_SCALAR", "1")
+    h_sc, mg_sc = t.build_hist2d(bins_x, maxv)
+    t.close()
+    assert h_vec.sum() == raw.size, name
+    assert np.float32(mg_vec) == np.float32(mg_ref) == np.float32(mg_sc), name
+    assert (h_sc == h_ref).all(), name
+    bad = np.argwhere(h_vec != h_ref)
+    assert bad.size == 0, (name, bad[:5], h_vec[tuple(bad[0])], h_ref[tuple(bad[0])])
