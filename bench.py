@@ -433,6 +433,21 @@ def run_gpu(args, rank, world):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))[os.environ.get("TVK_SAMPLER", "q4")]["dram_bytes_per_launch"]
     except Exception:       # noqa: BLE001
         traffic = None
+    # instruction-issue view of the same kernel (what actually bounds it): warp instructions per sample from the committed
+    # ncu capture x the samples of this run, against 4 warp instructions per clock per SM
+    issue = None
+    try:
+        if world == 1:
+            k = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))[os.environ.get("TVK_SAMPLER", "q4")]
+            per_sample = k["warp_instructions_per_launch"] / k["samples_in_capture"]
+            sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965
+            issue_peak = sm_count * 4 * sm_mhz * 1e6
+            issue_rate = per_sample * samples / (kernel_ms * 1e-3)
+            issue = {"achieved": issue_rate / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instr/s", "frac": issue_rate / issue_peak,
+                     "warp_instructions_per_sample": per_sample, "source": "profiles/k1_traffic.json (ncu smsp__inst_executed.sum)"}
+    except Exception:       # noqa: BLE001
+        issue = None
     ms_step = kernel_ms / args.steps
     if world > 1:
         # a step = render + exchange + blend + gather: the ray-march kernel alone is not the step
@@ -450,7 +465,8 @@ def run_gpu(args, rank, world):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "0.6068 B/sample + 16 B/ray (SURVEY 8d); the kernel is L1/TEX-issue bound, see DESIGN.md"},
+                         "note": "0.6068 B/sample + 16 B/ray (SURVEY 8d); the kernel is instruction-issue bound, see `issue` and DESIGN.md",
+                         "issue": issue},
             "e2e": {"value": e2e_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
                     "result": "RGBA8 frame (glReadPixels GL_UNSIGNED_BYTE, as captureSingleFrame reads it)"},

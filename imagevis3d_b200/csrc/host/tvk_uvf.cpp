@@ -11,6 +11,7 @@
 #include "tvk_cuda.h"
 
 #include <zlib.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -140,6 +141,73 @@ bool z_decompress(const uint8_t* src, size_t srclen, uint8_t* dst, size_t n) {
   const bool ok = ret == Z_STREAM_END && s.avail_out == 0;
   inflateEnd(&s);
   return ok;
+}
+
+// bzip2 and LZMA bricks (ExtendedOctree.cpp:344-353 -> BzlibCompression.cpp:60-77, LzmaCompression.cpp:130-150): the
+// reference links its vendored bzip2 / LZMA SDK; here the system's libbz2 / liblzma are opened on first use (no
+// headers in the image, so the few public declarations needed are restated below).
+bool bz_decompress(const uint8_t* src, size_t srclen, uint8_t* dst, size_t n) {
+  typedef int (*fn_t)(char*, unsigned int*, char*, unsigned int, int, int);      // BZ2_bzBuffToBuffDecompress
+  static fn_t fn = [] {
+    void* h = dlopen("libbz2.so.1.0", RTLD_NOW);
+    if (!h) h = dlopen("libbz2.so.1", RTLD_NOW);
+    return h ? reinterpret_cast<fn_t>(dlsym(h, "BZ2_bzBuffToBuffDecompress")) : nullptr;
+  }();
+  if (!fn) return false;
+  unsigned int out = (unsigned int)n;
+  const int rc = fn(reinterpret_cast<char*>(dst), &out, reinterpret_cast<char*>(const_cast<uint8_t*>(src)), (unsigned int)srclen, 0, 0);
+  return rc == 0 && out == n;
+}
+
+// liblzma public ABI (lzma/base.h, lzma/filter.h, lzma/lzma12.h)
+struct xz_stream {
+  const uint8_t* next_in; size_t avail_in; uint64_t total_in;
+  uint8_t* next_out; size_t avail_out; uint64_t total_out;
+  const void* allocator; void* internal;
+  void* reserved_ptr[4]; uint64_t reserved_int12[2]; size_t reserved_int34[2]; int reserved_enum[2];
+};
+struct xz_filter { uint64_t id; void* options; };
+struct xz_options_lzma {
+  uint32_t dict_size; const uint8_t* preset_dict; uint32_t preset_dict_size;
+  uint32_t lc, lp, pb; int mode; uint32_t nice_len; int mf; uint32_t depth;
+  uint8_t reserved[128];                                  // ext_* and reserved members of newer versions, zero
+};
+// A raw LZMA1 stream without end marker, as LzmaEncode(writeEndMark = 0) writes it.  The reader takes the
+// properties from the compression level in the header (ExtendedOctree.cpp:54): lc 3, lp 0, pb 2 for every level
+// (LzmaEncProps_Normalize); the dictionary only has to cover the brick.
+bool lzma_decompress(const uint8_t* src, size_t srclen, uint8_t* dst, size_t n) {
+  typedef int (*dec_t)(xz_stream*, const xz_filter*);
+  typedef int (*code_t)(xz_stream*, int);
+  typedef void (*end_t)(xz_stream*);
+  static dec_t dec; static code_t code; static end_t end;
+  static bool ok = [] {
+    void* h = dlopen("liblzma.so.5", RTLD_NOW);
+    if (!h) return false;
+    dec = reinterpret_cast<dec_t>(dlsym(h, "lzma_raw_decoder"));
+    code = reinterpret_cast<code_t>(dlsym(h, "lzma_code"));
+    end = reinterpret_cast<end_t>(dlsym(h, "lzma_end"));
+    return dec && code && end;
+  }();
+  if (!ok) return false;
+  xz_options_lzma opt;
+  memset(&opt, 0, sizeof(opt));
+  uint32_t dict = 4096;
+  while (dict < n && dict < (1u << 30)) dict <<= 1;
+  opt.dict_size = dict; opt.lc = 3; opt.lp = 0; opt.pb = 2;
+  xz_filter filters[2] = {{0x4000000000000001ull /* LZMA_FILTER_LZMA1 */, &opt}, {~0ull /* LZMA_VLI_UNKNOWN */, nullptr}};
+  xz_stream st;
+  memset(&st, 0, sizeof(st));
+  if (dec(&st, filters) != 0) return false;
+  st.next_in = src; st.avail_in = srclen; st.next_out = dst; st.avail_out = n;
+  bool good = false;
+  for (;;) {
+    const size_t before_in = st.avail_in, before_out = st.avail_out;
+    const int rc = code(&st, 0 /* LZMA_RUN */);
+    if (st.avail_out == 0 && (rc == 0 || rc == 1)) { good = true; break; }
+    if (rc != 0 || (st.avail_in == before_in && st.avail_out == before_out)) break;
+  }
+  end(&st);
+  return good;
 }
 
 // LZ4 block format with a known decompressed size (what LZ4_decompress_fast consumes), bounds checked
@@ -572,7 +640,9 @@ extern "C" int tvk_uvf_read_bricks(tvk_uvf* u, uint64_t first, uint64_t count, v
     bool ok;
     if (u->t_comp[i] == TVK_UVF_COMP_ZLIB) ok = z_decompress(tmp.data(), tmp.size(), o, n);
     else if (u->t_comp[i] == TVK_UVF_COMP_LZ4) ok = lz4_decompress(tmp.data(), tmp.size(), o, n);
-    else { u->err = "brick compression not supported (lzma / bzip2)"; return TVK_ERR_UNSUPPORTED; }
+    else if (u->t_comp[i] == TVK_UVF_COMP_LZMA) ok = lzma_decompress(tmp.data(), tmp.size(), o, n);
+    else if (u->t_comp[i] == TVK_UVF_COMP_BZIP) ok = bz_decompress(tmp.data(), tmp.size(), o, n);
+    else { u->err = "unknown brick compression"; return TVK_ERR_UNSUPPORTED; }
     if (!ok) { u->err = "brick decompression failed"; return TVK_ERR_INVALID; }
   }
   return TVK_OK;

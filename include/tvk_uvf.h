@@ -16,7 +16,8 @@
  *           zDecompress / lz4Decompress, the *DataBlock::GetHeaderFromFile readers, and what
  *           UVFDataset::Open pulls out of them (uvfDataset.cpp:83-216)
  * Little-endian files only (the reference writes the byte order of the machine it runs on).
- * Supported brick compression: none, zlib, lz4 (reading); none, zlib (writing).  Blocks of other kinds
+ * Supported brick compression: none, zlib, lz4, lzma, bzip2 (reading; the last two through the system's liblzma /
+ * libbz2, opened on first use); none, zlib (writing).  Blocks of other kinds
  * (legacy RasterDataBlock, geometry) are listed by tvk_uvf_info but not decoded.
  * All functions return 0 on success; on failure `err` (if given) receives a message.
  */

@@ -17,7 +17,8 @@ from oracle import oracle as O
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 CASES = {"ref_u8_none": ((50, 41, 33), np.uint8, 16, 2, 0, 0), "ref_u8_zlib": ((50, 41, 33), np.uint8, 16, 2, 1, 1),
-         "ref_u16_zlib": ((37, 20, 45), np.uint16, 20, 2, 1, 1), "ref_u8_lz4": ((50, 41, 33), np.uint8, 16, 2, 3, 1)}
+         "ref_u16_zlib": ((37, 20, 45), np.uint16, 20, 2, 1, 1), "ref_u8_lz4": ((50, 41, 33), np.uint8, 16, 2, 3, 1),
+         "ref_u8_lzma": ((50, 41, 33), np.uint8, 16, 2, 2, 4), "ref_u16_bzip": ((37, 20, 45), np.uint16, 20, 2, 4, 5)}
 
 
 def case_volume(name):
