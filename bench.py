@@ -363,6 +363,10 @@ def run_gpu(args, rank, world):
     t0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()
+        if world > 1:
+            # the untimed L2 flush lets the ranks drift apart; without re-aligning them a rank's step time would include
+            # the wait for the latest rank's flush, which is not part of the step
+            dist.barrier()
         torch.cuda.synchronize()
         ts = time.perf_counter()
         step(k)
