@@ -72,7 +72,7 @@ class ClassicParams(C.Structure):
                 ("light_diffuse", C.c_float * 3), ("light_specular", C.c_float * 3), ("light_dir", C.c_float * 3),
                 ("domain_scale", C.c_float * 3), ("bytes_per_voxel", C.c_uint32), ("render_mode", C.c_uint32),
                 ("gradient_scale", C.c_float), ("isoval", C.c_float), ("proj_param", C.c_float * 2),
-                ("iso_color", C.c_float * 3)]
+                ("iso_color", C.c_float * 3), ("clip_enabled", C.c_uint32), ("clip_plane", C.c_float * 4)]
 
 
 class QuantizeResult(C.Structure):

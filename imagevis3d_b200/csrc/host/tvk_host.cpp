@@ -847,6 +847,7 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
   // the 2D gradient test passes for every brick), isosurface: isovalue <= max
   const double smin = (m_mode == RM_2DTRANS) ? m_tf2dLimits[0] * resc : double(m_tf1d.NonZeroMin()) * resc;
   const double smax = (m_mode == RM_2DTRANS) ? m_tf2dLimits[1] * resc : double(m_tf1d.NonZeroMax()) * resc;
+  const Matrix4 world = m_rotation * m_translation;
   struct Item { float dist; uint64_t idx; tvk_classic_brick b; };
   std::vector<Item> items;
   for (uint32_t x = 0; x < nb[0]; ++x)
@@ -867,6 +868,18 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
               -(0.5f * be[0] * fabsf(pl[0]) + 0.5f * be[1] * fabsf(pl[1]) + 0.5f * be[2] * fabsf(pl[2]))) vis = false;
         }
         if (!vis) continue;
+        if (m_clipEnabled) {                               // AbstrRenderer::Clipped (:923-948): all eight world-space corners beyond the plane
+          bool all = true;
+          for (int k = 0; k < 8 && all; ++k) {
+            const float pt[4] = {bcn[0] + ((k & 4) ? 0.5f : -0.5f) * be[0], bcn[1] + ((k & 2) ? 0.5f : -0.5f) * be[1],
+                                 bcn[2] + ((k & 1) ? 0.5f : -0.5f) * be[2], 1.0f};
+            float w4[4];
+            world.transform(pt, w4);
+            const float wx = w4[0] / w4[3], wy = w4[1] / w4[3], wz = w4[2] / w4[3];
+            if (!(m_clipPlane[0] * wx + m_clipPlane[1] * wy + m_clipPlane[2] * wz + m_clipPlane[3] >= 0)) all = false;
+          }
+          if (all) continue;
+        }
         const bool contains = (m_mode == RM_ISOSURFACE) ? (m_isoValue <= v.minmax[2 * idx + 1])
                             : (m_mode == RM_2DTRANS)  ? (smax >= v.minmax[2 * idx] && smin <= v.minmax[2 * idx + 1] &&
                                                          m_tf2dLimits[3] >= -DBL_MAX && m_tf2dLimits[2] <= DBL_MAX)
@@ -928,6 +941,18 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
   p.proj_param[0] = m_zfar / (m_zfar - m_znear);                                           // CullingLOD::GetDepthScaleParams
   p.proj_param[1] = m_zfar * m_znear / (m_znear - m_zfar);
   p.iso_color[0] = m_isoColor.x; p.iso_color[1] = m_isoColor.y; p.iso_color[2] = m_isoColor.z;
+  if (m_clipEnabled) {
+    // RenderBox (GLRaycaster.cpp:327-337): world-space plane back to model space, PLANE::operator* divides all four
+    // components by |normal| (Vectors.h:1460-1477), then the normal is normalised once more (a no-op)
+    const Matrix4 rt = world.transposed();
+    float q[4];
+    rt.transform(m_clipPlane, q);
+    const float len = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    if (len > 0.0f) {
+      p.clip_enabled = 1;
+      for (int a = 0; a < 4; ++a) p.clip_plane[a] = q[a] / len;
+    }
+  }
   return true;
 }
 

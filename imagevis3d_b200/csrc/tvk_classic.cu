@@ -126,6 +126,15 @@ __global__ void __launch_bounds__(128) classic_kernel(const __grid_constant__ Cl
       if (ta > tb) { const float t = ta; ta = tb; tb = t; }
       s0 = fmaxf(s0, ta); s1 = fminf(s1, tb);
     }
+    if (p.clip_enabled && !miss) {                          // the box clipped by the plane (Clipper::BoxPlane), as in ray_setup of K1
+      const float dn = c_dot3(p.clip_plane[0], p.clip_plane[1], p.clip_plane[2], d[0], d[1], d[2]);
+      const float on = c_dot3(p.clip_plane[0], p.clip_plane[1], p.clip_plane[2], o[0], o[1], o[2]) + p.clip_plane[3];
+      if (dn == 0.0f) { if (on > 0.0f) miss = true; }
+      else {
+        const float t = -on / dn;
+        if (dn > 0.0f) s1 = fminf(s1, t); else s0 = fmaxf(s0, t);
+      }
+    }
     const float se = fmaxf(s0, 1.0f);                       // front face, or the near plane if that lies behind it
     if (miss || !(s1 > se)) continue;
     // ray entry through the RGBA16F buffer, ray exit from the interpolated varying

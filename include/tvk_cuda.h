@@ -330,6 +330,8 @@ typedef struct tvk_classic_params {
   float isoval;                      /* fIsoval = GetNormalizedIsovalue()                              */
   float proj_param[2];               /* vProjParam (CullingLOD::GetDepthScaleParams, CullingLOD.cpp:69-72) */
   float iso_color[3];                /* isosurface colour (ComposeSurfaceImage multiplies the diffuse by it) */
+  uint32_t clip_enabled;             /* m_bClipPlaneOn: RenderBox clips the brick's box with the plane (GLRaycaster.cpp:327-337) */
+  float clip_plane[4];               /* model-space plane, unit normal; n.p + d <= 0 is kept (Clipper::BoxPlane)         */
 } tvk_classic_params;
 /* bricks: host array, front to back.  Result: the context's image (tvk_read_image). */
 int tvk_raycast_classic(tvk_ctx* ctx, const tvk_classic_params* p, const tvk_classic_brick* bricks, uint32_t n,

@@ -491,11 +491,11 @@ class ClassicParams(C.Structure):                    # tvk_classic_params
                 ("light_diffuse", C.c_float * 3), ("light_specular", C.c_float * 3), ("light_dir", C.c_float * 3),
                 ("domain_scale", C.c_float * 3), ("bytes_per_voxel", C.c_uint32), ("render_mode", C.c_uint32),
                 ("gradient_scale", C.c_float), ("isoval", C.c_float), ("proj_param", C.c_float * 2),
-                ("iso_color", C.c_float * 3)]
+                ("iso_color", C.c_float * 3), ("clip_enabled", C.c_uint32), ("clip_plane", C.c_float * 4)]
 
 
 def classic_plan(oc, cam, width, height, tf_limits, lighting=False, sample_rate=1.0, scale=(1, 1, 1), trans_scale=1.0,
-                 capture=False, lod=None, render_mode=0, gradient_scale=1.0, iso_value=None):
+                 capture=False, lod=None, render_mode=0, gradient_scale=1.0, iso_value=None, clip_plane=None):
     """What AbstrRenderer::PlanFrame / BuildSubFrameBrickList (AbstrRenderer.cpp:1125-1212, 999-1100) and
     GLRaycaster::SetBrickDepShaderVars / ComputeEyeToTextureMatrix hand to the shaders for the FINAL sub-frame of a
     view: (ClassicParams, [ClassicBrick...] front to back, lod).  oc: oracle octree (tight store offsets).
@@ -567,6 +567,19 @@ def classic_plan(oc, cam, width, height, tf_limits, lighting=False, sample_rate=
                           -float(half[0] * abs(pl[0]) + half[1] * abs(pl[1]) + half[2] * abs(pl[2])) for pl in planes)
                 if not vis:
                     continue
+                if clip_plane is not None:            # AbstrRenderer::Clipped (:923-948)
+                    cpl = np.asarray(clip_plane, f32)
+                    world = (cam.rotation @ cam.translation).astype(f32)
+                    all_clipped = True
+                    for k in range(8):
+                        sgn = np.array([0.5 if k & 4 else -0.5, 0.5 if k & 2 else -0.5, 0.5 if k & 1 else -0.5], f32)
+                        w4 = np.append((b_cen + sgn * b_ext).astype(f32), f32(1)) @ world
+                        wp = (w4[:3] / w4[3]).astype(f32)
+                        if not (float(cpl[0] * wp[0] + cpl[1] * wp[1] + cpl[2] * wp[2] + cpl[3]) >= 0):
+                            all_clipped = False
+                            break
+                    if all_clipped:
+                        continue
                 mn, mx = oc["minmax"][idx]
                 if render_mode == 2:
                     contains = float(iso_value) <= mx
@@ -617,6 +630,12 @@ def classic_plan(oc, cam, width, height, tf_limits, lighting=False, sample_rate=
     zn, zf = f32(cam.znear), f32(cam.zfar)
     p.proj_param[:] = [float(f32(zf / f32(zf - zn))), float(f32(f32(zf * zn) / f32(zn - zf)))]
     p.iso_color[:] = cam.iso_color.tolist()
+    if clip_plane is not None:                        # GLRaycaster::RenderBox (:327-337)
+        q = (np.asarray(clip_plane, f32) @ (cam.rotation @ cam.translation).astype(f32).T).astype(f32)
+        ln = f32(np.sqrt(f32(q[0] * q[0] + q[1] * q[1] + q[2] * q[2])))
+        if ln > 0:
+            p.clip_enabled = 1
+            p.clip_plane[:] = (q / ln).tolist()
     return p, [t[2] for t in out], lod
 
 

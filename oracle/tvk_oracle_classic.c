@@ -155,6 +155,15 @@ int orc_raycast_classic(const tvk_classic_params* p, const tvk_classic_brick* br
           if (ta > tb) { const float t = ta; ta = tb; tb = t; }
           s0 = fmaxf(s0, ta); s1 = fminf(s1, tb);
         }
+        if (p->clip_enabled && !miss) {       /* RenderBox + Clipper::BoxPlane (GLRaycaster.cpp:327-337): n.p + d <= 0 is kept */
+          const float dn = dot3c(p->clip_plane[0], p->clip_plane[1], p->clip_plane[2], D[0], D[1], D[2]);
+          const float on = dot3c(p->clip_plane[0], p->clip_plane[1], p->clip_plane[2], O[0], O[1], O[2]) + p->clip_plane[3];
+          if (dn == 0.0f) { if (on > 0.0f) miss = 1; }
+          else {
+            const float t = -on / dn;
+            if (dn > 0.0f) s1 = fminf(s1, t); else s0 = fmaxf(s0, t);
+          }
+        }
         const float se = fmaxf(s0, 1.0f);
         if (miss || !(s1 > se)) continue;
         const float enx = half_round(ex * se), eny = half_round(ey * se), enz = half_round(ez * se);

@@ -226,3 +226,51 @@ def test_config1_c60_classic_raycaster(lighting):
     psnr, err = image_errors(got, want)
     assert want[..., 3].max() > 0.3 and psnr >= 45.0 and err <= 2.0 / 255.0, (psnr, err)
     r.cleanup()
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_classic_clip_plane(mode):
+    """m_bClipPlaneOn on the classic path: AbstrRenderer::Clipped drops bricks, RenderBox clips the rest
+    (GLRaycaster.cpp:327-337)."""
+    from imagevis3d_b200.renderer import Renderer, RT_HEADLESS
+    vol = H.synth_blobs((150, 131, 97), np.uint8)
+    r = Renderer(0)
+    r.loadRawVolume(vol, brick_size=32)
+    r.setRendererType(True)
+    info = r.datasetInfo()
+    tf = _tf(info.tf_size)
+    r.set1DTransFloat(tf)
+    r.setRenderMode(mode)
+    iso = 0.25 * float(vol.max())
+    r.setIsoValue(iso)
+    r.resize((203, 149))
+    r.setRendererTarget(RT_HEADLESS)
+    rot = H.rotation_y(0.6) @ H.rotation_x(0.3)
+    r.setRotation4x4(rot)
+    p0, bricks0, _ = r.planClassicFrame()
+    r.paintUntilConverged()
+    full = r.frameFloat()
+    plane = (0.6, 0.3, 0.74, 0.05)
+    r.setClipPlane(plane)
+    r.enableClipPlane(True)
+    p, bricks, lod = r.planClassicFrame()
+    assert p.clip_enabled == 1 and 0 < len(bricks) < len(bricks0)
+    r.paintUntilConverged()
+    got = r.frameFloat()
+    q, ob = _to_oracle(p, bricks)
+    want, _ = H.classic_render(q, ob, _device_store(r), H.tf_bytes(tf))
+    psnr, err = image_errors(got, want)
+    assert psnr >= 45.0, (psnr, err)
+    assert np.abs(got - full).max() > 0.05                  # the plane cuts something away
+    # the host's plan against the oracle's independent one
+    cam = H.Camera()
+    cam.rotation = rot
+    oc = O.build_octree(vol, 32, 2)
+    lo, hi = H.tf_nonzero_limits(tf)
+    po, bo, _ = H.classic_plan(oc, cam, 203, 149, (lo, hi, len(tf)), trans_scale=255.0 / float(vol.max()), render_mode=mode,
+                               gradient_scale=p.gradient_scale, iso_value=iso, clip_plane=plane)
+    assert len(bo) == len(bricks) and po.clip_enabled == 1
+    assert np.allclose(np.array(p.clip_plane[:]), np.array(po.clip_plane[:]), rtol=2e-5, atol=2e-6)
+    for x, y in zip(bricks, bo):
+        assert list(x.voxels) == list(y.voxels) and np.allclose(np.array(x.center[:]), np.array(y.center[:]), rtol=3e-5, atol=3e-6)
+    r.cleanup()
