@@ -47,6 +47,10 @@ class TvkContext:
         self._ck(self.lib.tvk_device_synchronize(self.h), "tvk_device_synchronize")
 
     # ------------------------------------------------------------------ pool
+    def set_march_occupancy(self, ctas_per_sm):
+        """resident ray-march CTAs per SM (0 = full occupancy); fewer leaves room for concurrent paging"""
+        self._ck(self.lib.tvk_set_march_occupancy(self.h, C.c_uint32(int(ctas_per_sm))), "tvk_set_march_occupancy")
+
     def pool_create(self, volume_size, max_brick_size, overlap, bytes_per_voxel, capacity, lod_count,
                     sampler=L.SAMPLER_EXACT):
         d = L.PoolDesc()

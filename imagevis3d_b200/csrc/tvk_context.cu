@@ -122,6 +122,12 @@ extern "C" int tvk_set_stream(tvk_ctx* c, void* cuda_stream) {
   return TVK_OK;
 }
 
+extern "C" int tvk_set_march_occupancy(tvk_ctx* c, uint32_t ctas_per_sm) {
+  if (!c) return TVK_ERR_INVALID;
+  c->march_ctas_per_sm = ctas_per_sm;
+  return TVK_OK;
+}
+
 extern "C" int tvk_device_synchronize(tvk_ctx* c) {
   if (!c) return TVK_ERR_INVALID;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));

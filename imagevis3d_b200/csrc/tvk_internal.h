@@ -66,6 +66,7 @@ struct tvk_ctx {
   cudaStream_t copy_stream = nullptr;  // pager side stream
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, copy_done = nullptr, render_done = nullptr, bev0 = nullptr, bev1 = nullptr;
   std::string err;
+  uint32_t march_ctas_per_sm = 0;      // tvk_set_march_occupancy (0 = occupancy calculator)
 
   // pool
   bool has_pool = false;

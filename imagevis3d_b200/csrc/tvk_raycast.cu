@@ -856,6 +856,7 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   int sms = 0, per_sm = 0;
   TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
   TVK_CHECK_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 128, 0));
+  if (c->march_ctas_per_sm && (int)c->march_ctas_per_sm < per_sm) per_sm = (int)c->march_ctas_per_sm;
   if (per_sm < 1) per_sm = 1;
   const uint32_t ntiles = rp.tiles_x * rp.tiles_y;
   uint32_t grid = (uint32_t)(sms * per_sm);

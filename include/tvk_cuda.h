@@ -70,6 +70,11 @@ int  tvk_device_synchronize(tvk_ctx* ctx);
  * (e.g. the caller's, so that NCCL collectives and these kernels are ordered without host
  * synchronisation).  cuda_stream is a cudaStream_t; NULL restores the context's own stream. */
 int  tvk_set_stream(tvk_ctx* ctx, void* cuda_stream);
+/* Upper bound on the resident CTAs per SM of the persistent ray-march grid (0 = what the occupancy calculator
+ * allows, the default).  At full occupancy K1 holds every register of an SM until the frame is done; one CTA less per
+ * SM leaves room for the pager's gather / placement kernels, so that the paging of the NEXT frame's bricks (side
+ * stream) proceeds while this frame marches. */
+int  tvk_set_march_occupancy(tvk_ctx* ctx, uint32_t ctas_per_sm);
 
 /* --------------------------------------------------------------- brick pool */
 /* replaces GLVolumePool ctor + CreateGLResources (GLVolumePool.cpp:119-259,
