@@ -14,6 +14,7 @@ struct ClassicArgs {
   const uint8_t* store;
   const float4* tf_f;                // 1D table as floats
   const uchar4* tf;                  // RGBA8 table (2D: [tf_h][tf_w])
+  const uint32_t* tf_colmask;        // bit x: column x has a non-zero alpha in some row
   uint32_t tf_w, tf_h;
   float4* image;
   unsigned long long* stats;
@@ -185,20 +186,29 @@ __global__ void __launch_bounds__(128) classic_kernel(const __grid_constant__ Cl
     }
     for (int i = 0; i < steps; ++i) {
       const float v = brick_sample<BPV>(data, b.voxels, ptx, pty, ptz);
+      // samples the transfer function makes fully transparent add nothing to the ray ((1-a)*0*rgb): their gradient
+      // and shading are skipped (1D: alpha of the entry; 2D: a column that is transparent in every gradient row)
       float4 c;
       float g[3];
-      if (MODE == TVK_RM_2DTRANS || LIT) brick_gradient<BPV>(data, b.voxels, ptx, pty, ptz, g);
+      bool shade = LIT;
       if (MODE == TVK_RM_2DTRANS) {                          // GLRaycaster-2D[-light]-FS.glsl
-        const float gm = sqrtf(c_dot3(g[0], g[1], g[2], g[0], g[1], g[2]));
-        const uchar4 t = __ldg(a.tf + (size_t)c_nearest(fmaf(-gm, p.gradient_scale, 1.0f), a.tf_h) * a.tf_w + c_nearest(v * p.trans_scale, a.tf_w));
-        const float k = 1.0f / 255.0f;
-        c = make_float4((float)t.x * k, (float)t.y * k, (float)t.z * k, (float)t.w * k);
+        const int cx = c_nearest(v * p.trans_scale, a.tf_w);
+        if ((__ldg(a.tf_colmask + (cx >> 5)) >> (cx & 31)) & 1u) {
+          brick_gradient<BPV>(data, b.voxels, ptx, pty, ptz, g);
+          const float gm = sqrtf(c_dot3(g[0], g[1], g[2], g[0], g[1], g[2]));
+          const uchar4 t = __ldg(a.tf + (size_t)c_nearest(fmaf(-gm, p.gradient_scale, 1.0f), a.tf_h) * a.tf_w + cx);
+          const float k = 1.0f / 255.0f;
+          c = make_float4((float)t.x * k, (float)t.y * k, (float)t.z * k, (float)t.w * k);
+          shade = LIT && c.w != 0.0f;
+        } else { c = make_float4(0.f, 0.f, 0.f, 0.f); shade = false; }
       } else {
         const int ti = min(max(__float2int_rz(v * p.trans_scale * (float)a.tf_w), 0), (int)a.tf_w - 1);
         c = __ldg(a.tf_f + ti);
+        shade = LIT && c.w != 0.0f;
+        if (shade) brick_gradient<BPV>(data, b.voxels, ptx, pty, ptz, g);
       }
       nsamples++;
-      if (LIT) {
+      if (LIT && shade) {
         float Nx, Ny, Nz;
         classic_normal(p, g, Nx, Ny, Nz);
         // Lighting(vec3(0), position, ...), lighting.glsl
@@ -249,7 +259,7 @@ extern "C" int tvk_raycast_classic(tvk_ctx* c, const tvk_classic_params* p, cons
   if (n) TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_bricks, bricks, sizeof(tvk_classic_brick) * n, cudaMemcpyHostToDevice, c->stream));
   ClassicArgs a;
   a.p = *p; a.bricks = d_bricks; a.nbricks = n; a.store = static_cast<const uint8_t*>(store);
-  a.tf_f = c->d_tf_f; a.tf = c->d_tf; a.tf_w = c->tf_w; a.tf_h = c->tf_h; a.image = c->d_image; a.stats = c->d_stats;
+  a.tf_f = c->d_tf_f; a.tf = c->d_tf; a.tf_colmask = c->d_tf_colmask; a.tf_w = c->tf_w; a.tf_h = c->tf_h; a.image = c->d_image; a.stats = c->d_stats;
   const uint32_t tiles = ((p->width + 7) / 8) * ((p->height + 3) / 4);
   const uint32_t blocks = (tiles + 3) / 4;
   TVK_CHECK_CUDA(c, cudaEventRecord(c->ev0, c->stream));

@@ -106,7 +106,7 @@ extern "C" void tvk_destroy(tvk_ctx* c) {
   tvk_build_release(c);
   tvk_pool_destroy(c);
   free_frame(c);
-  cudaFree(c->d_tf); cudaFree(c->d_tf_f); cudaFree(c->d_hash); cudaFree(c->d_tile_counter); cudaFree(c->d_stats); cudaFree(c->d_counts);
+  cudaFree(c->d_tf); cudaFree(c->d_tf_f); cudaFree(c->d_tf_colmask); cudaFree(c->d_hash); cudaFree(c->d_tile_counter); cudaFree(c->d_stats); cudaFree(c->d_counts);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->bev0); cudaEventDestroy(c->bev1); cudaEventDestroy(c->copy_done); cudaEventDestroy(c->render_done);
   cudaStreamDestroy(c->own_stream); cudaStreamDestroy(c->copy_stream);
   delete c;
@@ -566,6 +566,14 @@ static int set_tf(tvk_ctx* c, const uint8_t* rgba, uint32_t w, uint32_t h) {
   for (size_t i = 0; i < f.size(); ++i) f[i] = (float)rgba[i] * (1.0f / 255.0f);
   TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf, rgba, sizeof(uchar4) * (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
   TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf_f, f.data(), sizeof(float4) * (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
+  // per value column: does ANY gradient row give the sample a non-zero alpha?  (2D modes skip the gradient where not)
+  std::vector<uint32_t> mask((w + 31) / 32, 0u);
+  for (uint32_t y = 0; y < h; ++y)
+    for (uint32_t x = 0; x < w; ++x)
+      if (rgba[4 * ((size_t)y * w + x) + 3]) mask[x >> 5] |= 1u << (x & 31);
+  cudaFree(c->d_tf_colmask); c->d_tf_colmask = nullptr;
+  TVK_CHECK_CUDA(c, cudaMalloc(&c->d_tf_colmask, sizeof(uint32_t) * mask.size()));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf_colmask, mask.data(), sizeof(uint32_t) * mask.size(), cudaMemcpyHostToDevice, c->stream));
   TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
   return TVK_OK;
 }

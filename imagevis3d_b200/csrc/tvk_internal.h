@@ -84,6 +84,7 @@ struct tvk_ctx {
   // transfer functions
   uchar4* d_tf = nullptr;
   float4* d_tf_f = nullptr;            // float copy of the table (byte * (1/255))
+  uint32_t* d_tf_colmask = nullptr;    // bit x: column x of the table holds a non-zero alpha (any row); 4096 bits max... sized tf_w
   uint32_t tf_w = 0, tf_h = 0;
 
   // frame state

@@ -48,6 +48,7 @@ struct RayParams {
   const uint32_t* meta;
   const uchar4* tf;
   const float4* tf_f;   // the same table pre-converted to float (byte * (1/255)), 1D mode
+  const uint32_t* tf_colmask;   // bit x: some row of column x has alpha != 0
   uint32_t tf_w, tf_h;
   uint32_t* hash;
   float4* pos;      // rayStartPoint / rayResumePos
@@ -423,24 +424,28 @@ __device__ __forceinline__ float4 color_from_volume(const RayParams& rp, const S
   f3 n;
   if (MODE == TVK_RM_1DTRANS) {
     col = __ldg(rp.tf_f + nearest_index(data * p.trans_scale, rp.tf_w));
-    if (LIT) {
+    if (LIT && col.w != 0.0f) {                       // (see below: transparent samples are not shaded)
       const f3 g = grad ? *grad : gradient<BPV, SAMP>(rp, sl, pc);
       n = mk3(g.x * p.domain_scale[0], g.y * p.domain_scale[1], g.z * p.domain_scale[2]);
       const float d = dot3(n, n);
       if (d > 0.0f) { const float il = rsqrtf(d); n = mk3(n.x * il, n.y * il, n.z * il); }
     }
   } else {
+    const int cx = nearest_index(data * p.trans_scale, rp.tf_w);
+    // a table column that is transparent in every gradient row: no gradient needed to know the sample adds nothing
+    if (!grad && !((__ldg(rp.tf_colmask + (cx >> 5)) >> (cx & 31)) & 1u)) return make_float4(0.f, 0.f, 0.f, 0.f);
     const f3 g = grad ? *grad : gradient<BPV, SAMP>(rp, sl, pc);
     const float gm = len3(g);
-    col = tf_fetch(rp, nearest_index(fmaf(-gm, p.gradient_scale, 1.0f), rp.tf_h) * (int)rp.tf_w +
-                           nearest_index(data * p.trans_scale, rp.tf_w));
+    col = tf_fetch(rp, nearest_index(fmaf(-gm, p.gradient_scale, 1.0f), rp.tf_h) * (int)rp.tf_w + cx);
     if (LIT) {
       const float ig = 1.0f / gm;
       const f3 gn = (gm > 0.0f) ? mk3(g.x * ig, g.y * ig, g.z * ig) : g;
       n = mk3(p.domain_scale[0] * gn.x, p.domain_scale[1] * gn.y, p.domain_scale[2] * gn.z);
     }
   }
-  if (LIT) {
+  // a sample the transfer function makes fully transparent adds (1-a_acc)*0*rgb = 0 to the ray whatever its shading
+  // (rgb is clamped to [0,1]): the lighting is skipped for it
+  if (LIT && col.w != 0.0f) {
     const f3 mp = mk3((pc.x - trans.x) * scale.x, (pc.y - trans.y) * scale.y, (pc.z - trans.z) * scale.z);   // scale = 1 / brick scale here
     const f3 lit = lighting(p, mp, n, mk3(col.x * p.light_diffuse[0], col.y * p.light_diffuse[1], col.z * p.light_diffuse[2]));
     col.x = lit.x; col.y = lit.y; col.z = lit.z;
@@ -576,11 +581,29 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
         }
         for (; i < steps; ++i) {
           float4 s0;
-          if (SAMP == TVK_SAMPLER_EXACT_Q4 && (LIT || MODE == TVK_RM_2DTRANS)) {
-            float data;
-            f3 g;
-            q4_center_gradient<BPV>(rp, b.slot, q, data, g);
-            s0 = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, data, q, b.inv_scale, b.trans, &g);
+          if (SAMP == TVK_SAMPLER_EXACT_Q4 && LIT && MODE == TVK_RM_1DTRANS) {
+            // 1D-TF lit: the table needs the centre sample only (2 quad loads); where it returns alpha 0 -- empty space
+            // inside visible bricks -- the gradient (10 more quad loads) and the shading are not needed either
+            const float data = sample_pool<BPV, SAMP>(rp, b.slot, q);
+            s0 = __ldg(rp.tf_f + nearest_index(data * p.trans_scale, rp.tf_w));
+            if (s0.w != 0.0f) {
+              float dc;
+              f3 g;
+              q4_center_gradient<BPV>(rp, b.slot, q, dc, g);
+              s0 = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, data, q, b.inv_scale, b.trans, &g);
+            }
+          } else if (SAMP == TVK_SAMPLER_EXACT_Q4 && MODE == TVK_RM_2DTRANS) {
+            // 2D-TF: the table row depends on the gradient, the column on the centre sample alone; a column that is
+            // transparent in every row makes the sample transparent whatever its gradient
+            const float data = sample_pool<BPV, SAMP>(rp, b.slot, q);
+            const int cx = nearest_index(data * p.trans_scale, rp.tf_w);
+            s0 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((__ldg(rp.tf_colmask + (cx >> 5)) >> (cx & 31)) & 1u) {
+              float dc;
+              f3 g;
+              q4_center_gradient<BPV>(rp, b.slot, q, dc, g);
+              s0 = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, data, q, b.inv_scale, b.trans, &g);
+            }
           } else {
             const float data = sample_pool<BPV, SAMP>(rp, b.slot, q);
             s0 = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, data, q, b.inv_scale, b.trans);
@@ -839,6 +862,7 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   rp.meta = c->d_meta;
   rp.tf = c->d_tf;
   rp.tf_f = c->d_tf_f;
+  rp.tf_colmask = c->d_tf_colmask;
   rp.tf_w = c->tf_w; rp.tf_h = c->tf_h;
   rp.hash = c->d_hash;
   rp.pos = c->d_pos[0]; rp.aux = c->d_aux[0]; rp.image = c->d_image;
