@@ -368,11 +368,20 @@ def run_gpu(args, rank, world):
             # the wait for the latest rank's flush, which is not part of the step
             dist.barrier()
         torch.cuda.synchronize()
-        ts = time.perf_counter()
-        step(k)
-        tvk.synchronize()
-        torch.cuda.synchronize()
-        step_s += time.perf_counter() - ts
+        if world > 1:
+            # device time of the whole step (march + exchange + blend + landing on rank 0): CUDA events on the one
+            # stream every kernel of the step is launched on
+            ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev_a.record(work_stream)
+            step(k)
+            ev_b.record(work_stream)
+            tvk.synchronize()
+            torch.cuda.synchronize()
+            step_s += ev_a.elapsed_time(ev_b) * 1e-3
+        else:
+            step(k)
+            tvk.synchronize()
+            torch.cuda.synchronize()
         kernel_ms += tvk.stats().last_raycast_ms
     torch.cuda.synchronize()
     wall_s = time.perf_counter() - t0
