@@ -68,6 +68,9 @@ extern "C" int tvk_create(int device, tvk_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->place_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_gather[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_gather[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_place[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_place[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
       cudaEventCreate(&c->bev0) != cudaSuccess || cudaEventCreate(&c->bev1) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming) != cudaSuccess ||
@@ -108,7 +111,8 @@ extern "C" void tvk_destroy(tvk_ctx* c) {
   free_frame(c);
   cudaFree(c->d_tf); cudaFree(c->d_tf_f); cudaFree(c->d_tf_colmask); cudaFree(c->d_hash); cudaFree(c->d_tile_counter); cudaFree(c->d_stats); cudaFree(c->d_counts);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->bev0); cudaEventDestroy(c->bev1); cudaEventDestroy(c->copy_done); cudaEventDestroy(c->render_done);
-  cudaStreamDestroy(c->own_stream); cudaStreamDestroy(c->copy_stream);
+  for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_gather[i]); cudaEventDestroy(c->ev_place[i]); }
+  cudaStreamDestroy(c->own_stream); cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->place_stream);
   delete c;
 }
 
@@ -442,7 +446,10 @@ extern "C" int tvk_pool_upload_bricks(tvk_ctx* c, uint32_t n, const uint32_t* sl
     const uint32_t batch = 256;
     uint8_t* staging = nullptr;
     const uint32_t cap = std::min(n, batch);
-    if (cap) TVK_CHECK_CUDA(c, cudaMallocAsync(&staging, slot_bytes * cap, st));
+    // two staging areas when there is more than one batch: the placement of batch b (place_stream) then runs beside
+    // the PCIe gather of batch b+1
+    const uint32_t nbuf = n > batch ? 2u : 1u;
+    if (cap) TVK_CHECK_CUDA(c, cudaMallocAsync(&staging, slot_bytes * cap * nbuf, st));
     // zero-copy gather when every source is pinned, device-mapped host memory; else one DMA per (run of) brick(s)
     std::vector<const uint8_t*> alias(n, nullptr);
     bool mapped = true;
@@ -455,11 +462,14 @@ extern "C" int tvk_pool_upload_bricks(tvk_ctx* c, uint32_t n, const uint32_t* sl
       const uint32_t bn = std::min(batch, n - b0);
       std::vector<PlaceJob> jobs(bn);
       if (mapped) {
+        const uint32_t bi = b0 / batch, buf = nbuf == 2 ? (bi & 1u) : 0u;
+        uint8_t* stg = staging + (size_t)buf * slot_bytes * cap;
+        if (nbuf == 2 && bi >= 2) TVK_CHECK_CUDA(c, cudaStreamWaitEvent(st, c->ev_place[buf], 0));   // batch b-2 has left this area
         std::vector<GatherJob> gj(bn);
         for (uint32_t i = 0; i < bn; ++i) {
           const uint32_t k = b0 + i;
-          gj[i] = GatherJob{alias[k], staging + slot_bytes * i, (uint64_t)sizes[3 * k] * sizes[3 * k + 1] * sizes[3 * k + 2] * c->pc.bpv};
-          jobs[i] = PlaceJob{staging + slot_bytes * i, slot[k], sizes[3 * k], sizes[3 * k + 1], sizes[3 * k + 2]};
+          gj[i] = GatherJob{alias[k], stg + slot_bytes * i, (uint64_t)sizes[3 * k] * sizes[3 * k + 1] * sizes[3 * k + 2] * c->pc.bpv};
+          jobs[i] = PlaceJob{stg + slot_bytes * i, slot[k], sizes[3 * k], sizes[3 * k + 1], sizes[3 * k + 2]};
         }
         GatherJob* d_gj = nullptr;
         TVK_CHECK_CUDA(c, cudaMallocAsync(&d_gj, sizeof(GatherJob) * bn, st));
@@ -468,8 +478,20 @@ extern "C" int tvk_pool_upload_bricks(tvk_ctx* c, uint32_t n, const uint32_t* sl
         c->launches++;
         TVK_CHECK_CUDA(c, cudaGetLastError());
         TVK_CHECK_CUDA(c, cudaFreeAsync(d_gj, st));
-        int rc = place_batch(c, jobs, st);
-        if (rc) return rc;
+        if (nbuf == 2) {
+          TVK_CHECK_CUDA(c, cudaEventRecord(c->ev_gather[buf], st));
+          TVK_CHECK_CUDA(c, cudaStreamWaitEvent(c->place_stream, c->ev_gather[buf], 0));
+          int rc = place_batch(c, jobs, c->place_stream);
+          if (rc) return rc;
+          TVK_CHECK_CUDA(c, cudaEventRecord(c->ev_place[buf], c->place_stream));
+          if (b0 + batch >= n) {                             // last batch: the side stream ends after both placements in flight
+            TVK_CHECK_CUDA(c, cudaStreamWaitEvent(st, c->ev_place[buf], 0));
+            TVK_CHECK_CUDA(c, cudaStreamWaitEvent(st, c->ev_place[buf ^ 1u], 0));
+          }
+        } else {
+          int rc = place_batch(c, jobs, st);
+          if (rc) return rc;
+        }
         continue;
       }
       for (uint32_t i = 0; i < bn;) {

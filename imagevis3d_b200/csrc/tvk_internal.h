@@ -64,6 +64,8 @@ struct tvk_ctx {
   cudaStream_t stream = nullptr;       // render / builder stream (own_stream unless tvk_set_stream)
   cudaStream_t own_stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // pager side stream
+  cudaStream_t place_stream = nullptr; // pager: placement of batch b runs beside the gather of batch b+1
+  cudaEvent_t ev_gather[2] = {nullptr, nullptr}, ev_place[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, copy_done = nullptr, render_done = nullptr, bev0 = nullptr, bev1 = nullptr;
   std::string err;
   uint32_t march_ctas_per_sm = 0;      // tvk_set_march_occupancy (0 = occupancy calculator)
