@@ -942,7 +942,9 @@ __global__ void __launch_bounds__(256) hist2d_kernel(const T* __restrict__ raw, 
       const unsigned am = __ballot_sync(0xffffffffu, act);
       if (!act) continue;
       const unsigned long long s = grad_s_row(rc, x, sx);
-      uint32_t gi = 0;
+      // a volume without any gradient (Smax == 0): 0/0 = NaN, and size_t(NaN) is what x86-64 makes of it -- 2^63, clamped to
+      // bin 255 by the std::min (Histogram2DDataBlock.cpp:428); every other zero gradient lands in bin 0
+      uint32_t gi = smax == 0 ? 255u : 0u;
       if (s != 0) {
         const float q = 255.0f * sqrtf((float)s * inv_smax);
         const float fl = floorf(q);
@@ -951,7 +953,7 @@ __global__ void __launch_bounds__(256) hist2d_kernel(const T* __restrict__ raw, 
         if (s != smax && q >= 254.5f) gi = 254u;
         else if (s != smax && q - fl > 1e-3f && fl + 1.0f - q > 1e-3f) gi = (uint32_t)fl;
         else {
-          // size_t(len/max*255.0f); NaN (constant volume) -> 0 here, undefined in the reference
+          // size_t(len/max*255.0f)
           const double e = __dmul_rn(__ddiv_rn(grad_mag(raw, x, y, z, sx, sy, sz, norm2), max_grad), 255.0);
           gi = (e >= 255.0) ? 255u : ((e > 0.0) ? (uint32_t)e : 0u);
         }
@@ -1154,7 +1156,7 @@ __global__ void __launch_bounds__(256) hist2d_vec_kernel(const T* __restrict__ r
       uint32_t need = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        uint32_t gi = 0;
+        uint32_t gi = smax == 0 ? 255u : 0u;             // (no gradient anywhere: NaN -> bin 255, see hist2d_kernel)
         if (s[i] != 0) {
           // 255*sqrt(S/Smax) in fp32 (relative error < 5e-7, i.e. < 1.3e-4 absolute); floor by a round-down magic add
           const float t = (float)s[i] * inv_smax;
