@@ -155,3 +155,24 @@ def test_reference_reads_the_synthesised_legacy_file(tmp_path):
     # AFTER the open + checksum verification succeeded -- which is the part pinned here
     rc = subprocess.run([O.ref_driver_path(), "uvfinfo", path, dump], capture_output=True, text=True)
     assert "open failed" not in rc.stderr and "missing blocks" in rc.stderr
+
+
+@pytest.mark.skipif(O.ref_driver_path() is None, reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("vol,dt,brick,comp", [((1, 1, 1), np.uint8, 16, 0), ((1, 1, 1), np.uint16, 16, 1), ((5, 4, 3), np.uint8, 16, 1),
+                                               ((13, 1, 1), np.uint16, 8, 0), ((12, 12, 12), np.uint8, 16, 1), ((17, 16, 15), np.uint8, 16, 0)])
+def test_degenerate_volumes_byte_identical_to_the_reference(vol, dt, brick, comp, tmp_path):
+    """one-voxel, one-brick and one-voxel-thick volumes: the reference writes the file (ref_driver writeuvf), ours must be
+    the same bytes, and both must read back to the same bricks"""
+    raw = H.synth_noise(vol, dt, seed=sum(vol) + brick, maxval=200 if dt == np.uint8 else 3000)
+    rawf, ref = str(tmp_path / "v.raw"), str(tmp_path / "ref.uvf")
+    raw.tofile(rawf)
+    subprocess.check_call([O.ref_driver_path(), "writeuvf", rawf, str(vol[0]), str(vol[1]), str(vol[2]), "u16" if raw.dtype.itemsize == 2 else "u8",
+                           str(brick), "2", "0", str(comp), "1", ref])
+    oc, h1, h2, mg, tight = _oracle_parts(raw, brick, 2)
+    out = str(tmp_path / "ours.uvf")
+    U.write_uvf(out, vol, raw.dtype.itemsize, brick, 2, tight[:-1], oc["sizes"], oc["store"], oc["minmax"], h1, h2, mg, compression=comp, level=1)
+    a, b = open(out, "rb").read(), open(ref, "rb").read()
+    assert len(a) == len(b) and a == b
+    with U.UvfFile(ref, verify=True) as f:
+        assert f.info.total_bricks == oc["plan"].total_bricks and (f.read_bricks() == oc["store"]).all()
+        assert (f.minmax()[:, :2] == oc["minmax"]).all()
