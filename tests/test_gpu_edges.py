@@ -69,3 +69,53 @@ def test_one_brick_dataset_through_the_renderer():
     psnr, err = image_errors(img, want)
     assert psnr >= 45.0 and err <= 2.0 / 255.0, (psnr, err)
     r.cleanup()
+
+
+@pytest.mark.parametrize("size", [(1, 1), (8, 4), (9, 5), (1, 37), (640, 1)])
+def test_render_target_sizes_off_the_tile_grid(size):
+    """render targets smaller than / not a multiple of the 8x4 pixel tiles a warp works on"""
+    from imagevis3d_b200.renderer import Renderer, RT_HEADLESS
+    from tests.test_gpu_host import _oracle_converged
+    vol = H.synth_sphere((40, 36, 28), np.uint8)
+    r = Renderer(0)
+    r.loadRawVolume(vol)
+    info = r.datasetInfo()
+    tf = H.tf1d_std(info.tf_size, 0.3, 0.3)
+    tf[:, 3] *= 0.2
+    r.set1DTransFloat(tf)
+    r.setLightingEnabled(False)
+    r.resize(size)
+    r.setRendererTarget(RT_HEADLESS)
+    assert r.paintUntilConverged() >= 1
+    img = r.frameFloat()
+    assert img.shape == (size[1], size[0], 4) and np.isfinite(img).all()
+    want, _, _, _ = _oracle_converged(vol, 64, tf, H.Camera(), size[0], size[1], tuple(info.pool_capacity))
+    assert np.abs(img - want).max() <= 2.0 / 255.0
+    rgba = r.frameRGBA8()
+    assert rgba.shape == (size[1], size[0], 4)
+    r.cleanup()
+
+
+def test_volume_scale_and_odd_aspect_through_the_renderer():
+    """anisotropic voxels (dataset scale) and a flat slab of a volume: brick extents, LOD and ray set-up all depend on them"""
+    from imagevis3d_b200.renderer import Renderer, RT_HEADLESS
+    from tests.test_gpu_host import _oracle_converged
+    vol = H.synth_blobs((97, 33, 150), np.uint8)
+    r = Renderer(0)
+    r.loadRawVolume(vol, brick_size=32, scale=(1.0, 2.5, 0.7))
+    info = r.datasetInfo()
+    tf = H.tf1d_std(info.tf_size, 0.3, 0.3)
+    tf[:, 3] *= 0.15
+    r.set1DTransFloat(tf)
+    r.setLightingEnabled(True)
+    r.resize((171, 133))
+    r.setRendererTarget(RT_HEADLESS)
+    rot = H.rotation_y(0.9) @ H.rotation_x(-0.5)
+    r.setRotation4x4(rot)
+    r.paintUntilConverged()
+    cam = H.Camera()
+    cam.rotation = rot
+    want, _, _, _ = _oracle_converged(vol, 32, tf, cam, 171, 133, tuple(info.pool_capacity), lighting=True, scale=(1.0, 2.5, 0.7))
+    psnr, err = image_errors(r.frameFloat(), want)
+    assert want[..., 3].max() > 0.2 and psnr >= 45.0 and err <= 2.0 / 255.0, (psnr, err)
+    r.cleanup()
