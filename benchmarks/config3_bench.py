@@ -50,7 +50,8 @@ def main():
         tf2[..., 0] = v[None, :]; tf2[..., 1] = 0.3 + 0.7 * g[:, None]; tf2[..., 2] = 0.4     # noqa: E702
         tf2[..., 3] = np.clip((v[None, :] - 0.25) * 0.2, 0, 1) * (0.5 + 0.5 * g[:, None])
         tf2 = (np.clip(tf2, 0, 1) * np.float32(255)).astype(np.uint8)
-        for mode in ("1d", "1d-lit", "2d-lit", "iso"):
+        modes = [a.split("=")[1] for a in sys.argv if a.startswith("--mode=")] or ["1d", "1d-lit", "2d-lit", "iso"]
+        for mode in modes:
             tvk.set_metadata(sc["slots"] + 3)
             if mode in ("1d", "1d-lit"):
                 tvk.set_tf1d(tf1)
@@ -63,7 +64,7 @@ def main():
             else:
                 tvk.recompute_visibility(2, rmax / 2.0)
                 kw = dict(render_mode=2, isoval=(rmax / 2.0) / 65536.0)
-            ms, samples, rays = 0.0, 0, 0
+            ms, samples, rays, nbricks = 0.0, 0, 0, 0
             for k in range(-2, steps):
                 cam = B.camera_for_step(HM, max(k, 0), steps)
                 p = HM.raycast_params(cam, 1920, 1080, (N, N, N), **kw)
@@ -71,11 +72,12 @@ def main():
                 tvk.raycast(p)
                 st = tvk.stats()
                 if k >= 0:
-                    ms += st.last_raycast_ms; samples += int(st.samples); rays += int(st.rays)     # noqa: E702
+                    ms += st.last_raycast_ms; samples += int(st.samples); rays += int(st.rays); nbricks += int(st.brick_steps)     # noqa: E702
             assert len(tvk.read_requests()) == 0
             alg = samples * 1.2136 + rays * 16.0
             print(json.dumps({"bench": "config3", "volume": [N, N, N], "dtype": "uint16", "resolution": [1920, 1080], "mode": mode,
-                              "sampler": sname, "ms_per_frame": ms / steps, "samples_per_frame": samples / steps,
+                              "sampler": sname, "ms_per_frame": ms / steps, "samples_per_frame": samples / steps, "rays_per_frame": rays / steps,
+                              "brick_visits_per_frame": nbricks / steps,
                               "samples_per_s": samples / (ms * 1e-3), "algorithmic_GBps": alg / (ms * 1e-3) / 1e9,
                               "hbm_roofline_frac": alg / (ms * 1e-3) / 1e9 / peak}), flush=True)
         tvk.close()

@@ -32,7 +32,7 @@ def build(specs):
         if p.wait():
             raise SystemExit("nvcc failed for " + name)
         subprocess.check_call([B._nvcc(), "-shared", "-o", os.path.join(VAR, "libtvk_%s.so" % name), obj] + others +
-                              ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
+                              ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lz", "-ldl"])
         os.remove(obj)
         print("built", name)
 
