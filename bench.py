@@ -442,7 +442,7 @@ def run_gpu(args, rank, world):
         def upload(k):
             ss = slot_sets[k & 1]
             e2._ck(e2.lib.tvk_pool_upload_bricks(e2.h, C.c_uint32(n), ss.ctypes.data_as(C.c_void_p), src_arr,
-                                                 size_arr.ctypes.data_as(C.c_void_p), C.c_int(0)), "upload")
+                                                 size_arr.ctypes.data_as(C.c_void_p), C.c_int(2)), "upload")   # 2: one pinned allocation
 
         def run_steps(count):
             upload(0)

@@ -274,7 +274,7 @@ int BrickPool::UploadFirstBrick() {
   s.brick = (int32_t)idx; s.time = UINT64_MAX;
   const void* src = m_vol->host_store ? (const void*)(m_vol->host_store + m_vol->offsets[t])
                                       : (const void*)((const uint8_t*)m_vol->device_store + m_vol->offsets[t]);
-  int rc = tvk_pool_upload_bricks(m_ctx, 1, &s.pos, &src, &m_vol->sizes[3 * t], m_vol->host_store ? 0 : 1);
+  int rc = tvk_pool_upload_bricks(m_ctx, 1, &s.pos, &src, &m_vol->sizes[3 * t], m_vol->host_store ? 2 : 1);   // 2: the pinned store is one allocation
   if (rc) return rc;
   rc = tvk_pool_upload_wait(m_ctx);
   if (rc) return rc;
@@ -310,7 +310,7 @@ int BrickPool::UploadBricks(const std::vector<uint32_t>& xyzl, uint32_t& paged) 
     ++m_insertPos;
     ++paged;
   }
-  int rc = tvk_pool_upload_bricks(m_ctx, (uint32_t)slot.size(), slot.data(), src.data(), sizes.data(), m_vol->host_store ? 0 : 1);
+  int rc = tvk_pool_upload_bricks(m_ctx, (uint32_t)slot.size(), slot.data(), src.data(), sizes.data(), m_vol->host_store ? 2 : 1);
   if (rc) return rc;
   rc = tvk_pool_upload_wait(m_ctx);
   if (rc) return rc;

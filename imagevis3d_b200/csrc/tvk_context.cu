@@ -435,7 +435,7 @@ extern "C" int tvk_pool_upload_bricks(tvk_ctx* c, uint32_t n, const uint32_t* sl
   // the side stream must not overwrite slots a ray-march in flight still samples
   TVK_CHECK_CUDA(c, cudaEventRecord(c->render_done, c->stream));
   TVK_CHECK_CUDA(c, cudaStreamWaitEvent(st, c->render_done, 0));
-  if (on_device) {
+  if (on_device == 1) {
     std::vector<PlaceJob> jobs(n);
     for (uint32_t i = 0; i < n; ++i) jobs[i] = PlaceJob{(const uint8_t*)src[i], slot[i], sizes[3 * i], sizes[3 * i + 1], sizes[3 * i + 2]};
     int rc = place_batch(c, jobs, st);
@@ -453,6 +453,14 @@ extern "C" int tvk_pool_upload_bricks(tvk_ctx* c, uint32_t n, const uint32_t* sl
     // zero-copy gather when every source is pinned, device-mapped host memory; else one DMA per (run of) brick(s)
     std::vector<const uint8_t*> alias(n, nullptr);
     bool mapped = true;
+    if (on_device == 2 && n) {
+      // one allocation (caller's promise): the device alias of every source is the host pointer plus one offset
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, src[0]) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+        const ptrdiff_t delta = static_cast<const uint8_t*>(at.devicePointer) - static_cast<const uint8_t*>(src[0]);
+        for (uint32_t i = 0; i < n; ++i) alias[i] = static_cast<const uint8_t*>(src[i]) + delta;
+      } else { mapped = false; (void)cudaGetLastError(); }
+    } else
     for (uint32_t i = 0; i < n && mapped; ++i) {
       cudaPointerAttributes at;
       if (cudaPointerGetAttributes(&at, src[i]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) { mapped = false; (void)cudaGetLastError(); }

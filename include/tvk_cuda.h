@@ -98,7 +98,10 @@ int tvk_pool_total_bricks(const tvk_ctx* ctx, uint32_t* out);
  * Copies n bricks (x-fastest voxels, sizes[3*i..] voxels each, possibly smaller
  * than max_brick_size) into pool slots slot[i] (linear slot index
  * x + y*Cx + z*Cx*Cy) on the pager's side stream.  src pointers may be pinned
- * host memory (asynchronous DMA) or device memory (on_device != 0).
+ * host memory (on_device == 0: gathered over PCIe by a kernel when the memory is mapped into the
+ * device address space, else one DMA per run of bricks) or device memory (on_device == 1).
+ * on_device == 2: the caller states that ALL sources lie in ONE pinned, device-mapped host
+ * allocation (e.g. the renderer's brick store): one pointer query instead of one per brick.
  * Metadata is NOT touched; patch it with tvk_pool_patch_metadata once
  * tvk_pool_upload_wait() has returned. */
 int tvk_pool_upload_bricks(tvk_ctx* ctx, uint32_t n, const uint32_t* slot,
