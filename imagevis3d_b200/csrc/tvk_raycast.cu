@@ -951,7 +951,9 @@ extern "C" int tvk_read_image_rgba8(tvk_ctx* c, uint8_t* rgba8, int flip_rows) {
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
   const size_t n = (size_t)c->width * c->height;
   if (!c->d_rgba8) TVK_CHECK_CUDA(c, cudaMalloc(&c->d_rgba8, n * sizeof(uchar4)));
-  const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
+  int sm_count = 0;
+  TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, c->device));
+  const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)sm_count * 8);
   image_to_rgba8_kernel<<<blocks, 256, 0, c->stream>>>(c->d_image, c->d_rgba8, c->width, c->height, flip_rows);
   TVK_CHECK_CUDA(c, cudaGetLastError());
   TVK_CHECK_CUDA(c, cudaMemcpyAsync(rgba8, c->d_rgba8, n * sizeof(uchar4), cudaMemcpyDeviceToHost, c->stream));
