@@ -223,7 +223,13 @@ __global__ void __launch_bounds__(256) downsample_vec_kernel(const T* __restrict
   const uint32_t ncx = sx / E;
   const uint64_t n = (uint64_t)ncx * dy * dz;
   const uint64_t rs = sx, ss = (uint64_t)sx * sy;
-  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (uint64_t)gridDim.x * blockDim.x) {
+  // uniform trip count: the 16-bit table needs a barrier per round (32 voxels x 1024 threads = 0x8000 adds)
+  const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t rounds = (n + gstride - 1) / gstride;
+  uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint64_t round = 0; round < rounds; ++round, idx += gstride) {
+    if (sizeof(T) == 2) __syncthreads();
+    if (idx >= n) continue;
     const uint32_t cx = (uint32_t)(idx % ncx);
     const uint64_t row = idx / ncx;
     const uint32_t y = (uint32_t)(row % dy), z = (uint32_t)(row / dy);
@@ -259,7 +265,36 @@ __global__ void __launch_bounds__(256) downsample_vec_kernel(const T* __restrict
 // read of the volume.  One CTA of 1024 threads per SM; the table lives in shared memory: 32 per-warp 256-bin tables
 // for 8-bit data, one 32768-bin window [0, 32768) for 16-bit data (values above it are counted afterwards by
 // hist16_window_kernel, which returns at once when the volume has none).
+// downsample_hist_kernel itself packs TWO 16-bit counters into each word of the same 128 KB, so its table spans all
+// 65536 bins and full-range 16-bit volumes are not read a second time (see hist_add16_packed).
 #define HIST_WINDOW 32768u
+// One packed 16-bit counter per bin (bin v lives in half v&1 of word v>>1).  A half may never reach 0x10000 (the
+// low one would carry into its neighbour), which the caller guarantees like this: the CTA adds at most 0x8000
+// voxels between two barriers, and the one add that takes a half from below 0x8000 to 0x8000 or above moves
+// 0x8000 counts to the global bin before its thread reaches the barrier.  While that move is pending the half stays
+// >= 0x8000, so no second add can cross (at most one move is pending per half, and it never borrows); at a barrier
+// every half is therefore < 0x8000, and inside a round it is at most 0x7FFF + 0x8000 = 0xFFFF.
+__device__ __forceinline__ void packed_hist_add(unsigned int* __restrict__ table, unsigned long long* __restrict__ bins,
+                                                uint32_t v, uint32_t cnt) {
+  const uint32_t sh = (v & 1u) << 4;
+  const uint32_t o = (atomicAdd(&table[v >> 1], cnt << sh) >> sh) & 0xFFFFu;
+  if (o < 0x8000u && o + cnt >= 0x8000u) {
+    atomicSub(&table[v >> 1], 0x8000u << sh);
+    atomicAdd(&bins[v], 0x8000ull);
+  }
+}
+__device__ __forceinline__ void hist_add16_packed(const uint4& q, unsigned int* __restrict__ table,
+                                                  unsigned long long* __restrict__ bins) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+  uint32_t cur = w[0] & 0xFFFFu, cnt = 0;          // equal neighbours are merged into one atomic
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const uint32_t v = (w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
+    if (v == cur) cnt++;
+    else { packed_hist_add(table, bins, cur, cnt); cur = v; cnt = 1; }
+  }
+  packed_hist_add(table, bins, cur, cnt);
+}
 template <typename T>
 __device__ __forceinline__ void hist_add16(const uint4& q, unsigned int* __restrict__ table) {
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
@@ -310,10 +345,17 @@ __global__ void __launch_bounds__(1024, 1) downsample_hist_kernel(const T* __res
     if (hz) b = __ldg(reinterpret_cast<const uint4*>(p + ss));
     if (hy) c = __ldg(reinterpret_cast<const uint4*>(p + rs));
     if (hy && hz) d = __ldg(reinterpret_cast<const uint4*>(p + rs + ss));
-    hist_add16<T>(a, mine);                      // only rows that exist: the stand-ins b = c = d = a are not counted
-    if (hz) hist_add16<T>(b, mine);
-    if (hy) hist_add16<T>(c, mine);
-    if (hy && hz) hist_add16<T>(d, mine);
+    if (sizeof(T) == 1) {
+      hist_add16<T>(a, mine);                    // only rows that exist: the stand-ins b = c = d = a are not counted
+      if (hz) hist_add16<T>(b, mine);
+      if (hy) hist_add16<T>(c, mine);
+      if (hy && hz) hist_add16<T>(d, mine);
+    } else {
+      hist_add16_packed(a, hsm, bins);
+      if (hz) hist_add16_packed(b, hsm, bins);
+      if (hy) hist_add16_packed(c, hsm, bins);
+      if (hy && hz) hist_add16_packed(d, hsm, bins);
+    }
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
     for (int m = 0; m < V; ++m) {
@@ -340,7 +382,8 @@ __global__ void __launch_bounds__(1024, 1) downsample_hist_kernel(const T* __res
   } else {
     for (uint32_t b = threadIdx.x; b < HIST_WINDOW; b += blockDim.x) {
       const unsigned int s = hsm[b];
-      if (s) atomicAdd(&bins[b], (unsigned long long)s);
+      if (s & 0xFFFFu) atomicAdd(&bins[2u * b], (unsigned long long)(s & 0xFFFFu));
+      if (s >> 16) atomicAdd(&bins[2u * b + 1u], (unsigned long long)(s >> 16));
     }
   }
 }
@@ -1274,7 +1317,7 @@ static int run_build(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms) {
   TVK_CHECK_CUDA(c, cudaEventRecord(c->bev0, st));
   TVK_CHECK_CUDA(c, cudaMemsetAsync(d_mn, 0xFF, sizeof(uint32_t) * info.total_bricks, st));
   TVK_CHECK_CUDA(c, cudaMemsetAsync(d_mx, 0, sizeof(uint32_t) * (info.total_bricks + 1), st));
-  bool hist_fused = false, lod0_fused = false;
+  bool hist_fused = false, lod0_fused = false, hist_full = false;   // hist_full: the fused pass counted every bin
   // ---- fused LOD-0 pass: bricks + min/max + 1-D histogram + flat LOD 1 from ONE read of the raw volume
   {
     const uint32_t* s0 = info.lod_size[0];
@@ -1338,7 +1381,7 @@ static int run_build(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms) {
       TVK_CHECK_CUDA(c, cudaMemsetAsync(b.d_hist1d, 0, sizeof(unsigned long long) * range, st));
       if (b.desc.use_median) downsample_hist_kernel<T, true><<<sms, 1024, smem, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2], b.d_hist1d);
       else downsample_hist_kernel<T, false><<<sms, 1024, smem, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2], b.d_hist1d);
-      hist_fused = true;
+      hist_fused = true; hist_full = true;
     } else if (vec) {
       if (b.desc.use_median) downsample_vec_kernel<T, true><<<blocks, 256, 0, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2]);
       else downsample_vec_kernel<T, false><<<blocks, 256, 0, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2]);
@@ -1384,7 +1427,9 @@ static int run_build(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms) {
   // 1-D histogram: whatever the fused LOD 0 -> 1 pass did not count
   const uint64_t n0 = (uint64_t)info.lod_size[0][0] * info.lod_size[0][1] * info.lod_size[0][2];
   if (!hist_fused) TVK_CHECK_CUDA(c, cudaMemsetAsync(b.d_hist1d, 0, sizeof(unsigned long long) * range, st));
-  if (sizeof(T) == 2 && n0 >= (1u << 18)) {
+  if (hist_full) {
+    // nothing left to count
+  } else if (sizeof(T) == 2 && n0 >= (1u << 18)) {
     static bool attr_set = false;
     if (!attr_set) {
       TVK_CHECK_CUDA(c, cudaFuncSetAttribute(hist16_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HIST_WINDOW * sizeof(uint32_t))));

@@ -67,6 +67,28 @@ def test_builder_u16_full_range_histogram(tvk, kind):
     tvk.build_release()
 
 
+def test_builder_u16_packed_histogram_spills(tvk):
+    """The LOD 0 -> 1 pass counts 16-bit volumes in packed 16-bit shared-memory counters; a counter that reaches
+    0x8000 moves that many counts to the global bin.  Large flat regions (both halves of one word, the top bin,
+    zero) make every CTA spill many times; the histogram must still be Histogram1DDataBlock::Compute's
+    (IO/UVF/Histogram1DDataBlock.cpp:60-160), i.e. a plain count of the voxels."""
+    vol = (512, 256, 192)
+    rng = np.random.default_rng(11)
+    raw = rng.integers(0, 65536, size=vol[::-1], dtype=np.uint16)
+    raw[:40] = 40000
+    raw[40:80, :, ::2] = 40001            # alternating with noise: no run-length merging
+    raw[80:110] = 65535
+    raw[110:130, :128] = 0
+    raw[130:150] = (np.arange(512) // 3 + 32760).astype(np.uint16)    # straddles the old window boundary
+    tvk.build_octree(raw, 64, 2)
+    h1 = tvk.build_hist1d()
+    ref = np.bincount(raw.reshape(-1), minlength=65536)
+    assert h1.size == 65536 and (h1 == ref).all()
+    mm = tvk.build_minmax()
+    assert mm[:, 1].max() == 65535 and mm[:, 0].min() == 0
+    tvk.build_release()
+
+
 def test_builder_rejects_unsupported(tvk):
     from imagevis3d_b200._lib import TvkError
     raw = np.zeros((8, 8, 8), np.uint8)
