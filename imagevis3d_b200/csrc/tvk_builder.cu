@@ -223,13 +223,7 @@ __global__ void __launch_bounds__(256) downsample_vec_kernel(const T* __restrict
   const uint32_t ncx = sx / E;
   const uint64_t n = (uint64_t)ncx * dy * dz;
   const uint64_t rs = sx, ss = (uint64_t)sx * sy;
-  // uniform trip count: the 16-bit table needs a barrier per round (32 voxels x 1024 threads = 0x8000 adds)
-  const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
-  const uint64_t rounds = (n + gstride - 1) / gstride;
-  uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (uint64_t round = 0; round < rounds; ++round, idx += gstride) {
-    if (sizeof(T) == 2) __syncthreads();
-    if (idx >= n) continue;
+  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t cx = (uint32_t)(idx % ncx);
     const uint64_t row = idx / ncx;
     const uint32_t y = (uint32_t)(row % dy), z = (uint32_t)(row / dy);
@@ -268,18 +262,22 @@ __global__ void __launch_bounds__(256) downsample_vec_kernel(const T* __restrict
 // downsample_hist_kernel itself packs TWO 16-bit counters into each word of the same 128 KB, so its table spans all
 // 65536 bins and full-range 16-bit volumes are not read a second time (see hist_add16_packed).
 #define HIST_WINDOW 32768u
-// One packed 16-bit counter per bin (bin v lives in half v&1 of word v>>1).  A half may never reach 0x10000 (the
-// low one would carry into its neighbour), which the caller guarantees like this: the CTA adds at most 0x8000
-// voxels between two barriers, and the one add that takes a half from below 0x8000 to 0x8000 or above moves
-// 0x8000 counts to the global bin before its thread reaches the barrier.  While that move is pending the half stays
-// >= 0x8000, so no second add can cross (at most one move is pending per half, and it never borrows); at a barrier
-// every half is therefore < 0x8000, and inside a round it is at most 0x7FFF + 0x8000 = 0xFFFF.
+// One packed 16-bit counter per bin: bin v lives in half v>>15 of word v&0x7FFF (neighbouring values, which smooth
+// data sends to the table together, stay in different words and banks).  A half may never reach 0x10000 (the low
+// one would carry into the other bin), which the caller guarantees like this: the CTA adds at most 0x8000 voxels
+// between two barriers, and the one add that takes a half from below 0x8000 to 0x8000 or above (bit 15 of the half
+// goes 0 -> 1: `~old & new & 0x80008000`) moves 0x8000 counts to the global bin before its thread reaches the
+// barrier.  While that move is pending the half stays >= 0x8000, so no second add can cross (at most one move is
+// pending per half, and it never borrows); at a barrier every half is therefore < 0x8000, and inside a round it is
+// at most 0x7FFF + 0x8000 = 0xFFFF.
 __device__ __forceinline__ void packed_hist_add(unsigned int* __restrict__ table, unsigned long long* __restrict__ bins,
                                                 uint32_t v, uint32_t cnt) {
-  const uint32_t sh = (v & 1u) << 4;
-  const uint32_t o = (atomicAdd(&table[v >> 1], cnt << sh) >> sh) & 0xFFFFu;
-  if (o < 0x8000u && o + cnt >= 0x8000u) {
-    atomicSub(&table[v >> 1], 0x8000u << sh);
+  const uint32_t inc = cnt << ((v >> 11) & 16u);
+  unsigned int* p = table + (v & 0x7FFFu);
+  const uint32_t old = atomicAdd(p, inc);
+  const uint32_t crossed = ~old & (old + inc) & 0x80008000u;
+  if (crossed) {
+    atomicSub(p, crossed);
     atomicAdd(&bins[v], 0x8000ull);
   }
 }
@@ -295,6 +293,7 @@ __device__ __forceinline__ void hist_add16_packed(const uint4& q, unsigned int* 
   }
   packed_hist_add(table, bins, cur, cnt);
 }
+__device__ __forceinline__ bool same16(const uint4& p, const uint4& q) { return p.x == q.x && p.y == q.y && p.z == q.z && p.w == q.w; }
 template <typename T>
 __device__ __forceinline__ void hist_add16(const uint4& q, unsigned int* __restrict__ table) {
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
@@ -333,28 +332,52 @@ __global__ void __launch_bounds__(1024, 1) downsample_hist_kernel(const T* __res
   const uint32_t ncx = sx / E;
   const uint64_t n = (uint64_t)ncx * dy * dz;
   const uint64_t rs = sx, ss = (uint64_t)sx * sy;
-  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t cx = (uint32_t)(idx % ncx);
-    const uint64_t row = idx / ncx;
-    const uint32_t y = (uint32_t)(row % dy), z = (uint32_t)(row / dy);
-    const uint32_t y0 = (sy > 1) ? 2 * y : y, z0 = (sz > 1) ? 2 * z : z;
-    const bool hy = (sy > 1) && (y0 + 1 < sy), hz = (sz > 1) && (z0 + 1 < sz);
-    const T* p = src + (uint64_t)cx * E + y0 * rs + z0 * ss;
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
-    uint4 b = a, c = a, d = a;
-    if (hz) b = __ldg(reinterpret_cast<const uint4*>(p + ss));
-    if (hy) c = __ldg(reinterpret_cast<const uint4*>(p + rs));
-    if (hy && hz) d = __ldg(reinterpret_cast<const uint4*>(p + rs + ss));
+  // uniform trip count: the 16-bit table needs a barrier per round (32 voxels x 1024 threads = 0x8000 adds at most)
+  const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t rounds = (n + gstride - 1) / gstride;
+  uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint64_t round = 0; round < rounds; ++round, idx += gstride) {
+    const bool act = idx < n;
+    uint32_t cx = 0, y = 0, z = 0;
+    bool hy = false, hz = false;
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a, c = a, d = a;
+    if (act) {
+      cx = (uint32_t)(idx % ncx);
+      const uint64_t row = idx / ncx;
+      y = (uint32_t)(row % dy); z = (uint32_t)(row / dy);
+      const uint32_t y0 = (sy > 1) ? 2 * y : y, z0 = (sz > 1) ? 2 * z : z;
+      hy = (sy > 1) && (y0 + 1 < sy); hz = (sz > 1) && (z0 + 1 < sz);
+      const T* p = src + (uint64_t)cx * E + y0 * rs + z0 * ss;
+      a = __ldg(reinterpret_cast<const uint4*>(p));
+      b = a; c = a; d = a;
+      if (hz) b = __ldg(reinterpret_cast<const uint4*>(p + ss));
+      if (hy) c = __ldg(reinterpret_cast<const uint4*>(p + rs));
+      if (hy && hz) d = __ldg(reinterpret_cast<const uint4*>(p + rs + ss));
+    }
+    if (sizeof(T) == 2) {
+      __syncthreads();                           // every move to the global bins of the previous round is done
+      // a warp whose 32 x 32 voxels are one single value (background, saturated regions) issues one atomic
+      const uint32_t v0 = a.x & 0xFFFFu;
+      const bool uni = act && a.x == (v0 | (v0 << 16)) && a.y == a.x && a.z == a.x && a.w == a.x &&
+                       same16(b, a) && same16(c, a) && same16(d, a);      // rows that do not exist are copies of a
+      const uint32_t first = __shfl_sync(0xffffffffu, v0, 0);
+      if (__all_sync(0xffffffffu, uni && v0 == first)) {
+        const uint32_t mine_cnt = 8u * (1u + (hz ? 1u : 0u) + (hy ? 1u : 0u) + ((hy && hz) ? 1u : 0u));
+        const uint32_t tot = __reduce_add_sync(0xffffffffu, mine_cnt);
+        if ((threadIdx.x & 31u) == 0u) packed_hist_add(hsm, bins, v0, tot);
+      } else if (act) {
+        hist_add16_packed(a, hsm, bins);
+        if (hz) hist_add16_packed(b, hsm, bins);
+        if (hy) hist_add16_packed(c, hsm, bins);
+        if (hy && hz) hist_add16_packed(d, hsm, bins);
+      }
+    }
+    if (!act) continue;
     if (sizeof(T) == 1) {
       hist_add16<T>(a, mine);                    // only rows that exist: the stand-ins b = c = d = a are not counted
       if (hz) hist_add16<T>(b, mine);
       if (hy) hist_add16<T>(c, mine);
       if (hy && hz) hist_add16<T>(d, mine);
-    } else {
-      hist_add16_packed(a, hsm, bins);
-      if (hz) hist_add16_packed(b, hsm, bins);
-      if (hy) hist_add16_packed(c, hsm, bins);
-      if (hy && hz) hist_add16_packed(d, hsm, bins);
     }
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
@@ -382,8 +405,8 @@ __global__ void __launch_bounds__(1024, 1) downsample_hist_kernel(const T* __res
   } else {
     for (uint32_t b = threadIdx.x; b < HIST_WINDOW; b += blockDim.x) {
       const unsigned int s = hsm[b];
-      if (s & 0xFFFFu) atomicAdd(&bins[2u * b], (unsigned long long)(s & 0xFFFFu));
-      if (s >> 16) atomicAdd(&bins[2u * b + 1u], (unsigned long long)(s >> 16));
+      if (s & 0xFFFFu) atomicAdd(&bins[b], (unsigned long long)(s & 0xFFFFu));
+      if (s >> 16) atomicAdd(&bins[b + HIST_WINDOW], (unsigned long long)(s >> 16));
     }
   }
 }

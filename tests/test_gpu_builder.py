@@ -45,10 +45,11 @@ def test_builder_matches_oracle(tvk, vol, dtype, brick, overlap, median):
     _compare(tvk, raw, brick, overlap, median, oc["store"], oc["sizes"], oc["minmax"], h1, h2, mg)
 
 
-@pytest.mark.parametrize("kind", ["noise", "smooth", "flat"])
+@pytest.mark.parametrize("kind", ["noise", "smooth", "flat", "flat_odd"])
 def test_builder_u16_full_range_histogram(tvk, kind):
-    """Full-range 16-bit volumes take the windowed shared-memory histogram (two 32768-bin passes)."""
-    vol = (128, 96, 72)
+    """Full-range 16-bit volumes: packed shared-memory histogram inside the LOD 0 -> 1 pass (all 65536 bins); flat
+    volumes take its one-atomic-per-warp path, odd sizes give the lanes of one warp different row counts."""
+    vol = (128, 97, 73) if kind == "flat_odd" else (128, 96, 72)
     if kind == "noise":
         raw = H.synth_noise(vol, np.uint16, seed=5, maxval=65535)
     elif kind == "smooth":
