@@ -400,7 +400,7 @@ def run_gpu(args, rank, world):
     slot_arr = np.ascontiguousarray(slots, np.uint32)
     size_arr = np.ascontiguousarray(sizes[:total], np.uint32).reshape(-1)
 
-    e2e_mode = "serial"
+    e2e_mode, e2e_extra = "serial", {}
     if world > 1:
         def e2e_step(k):
             tvk.set_metadata(meta_host)
@@ -439,31 +439,78 @@ def run_gpu(args, rank, world):
         mh = np.ascontiguousarray(meta_host, np.uint32)
         metas = [mh, np.ascontiguousarray(np.where(mh >= 3, mh + np.uint32(half), mh).astype(np.uint32))]
 
-        def upload(k):
-            ss = slot_sets[k & 1]
-            e2._ck(e2.lib.tvk_pool_upload_bricks(e2.h, C.c_uint32(n), ss.ctypes.data_as(C.c_void_p), src_arr,
-                                                 size_arr.ctypes.data_as(C.c_void_p), C.c_int(2)), "upload")   # 2: one pinned allocation
+        # What a step pages in: the bricks the visibility pass leaves non-empty under the transfer function.  A brick
+        # whose [min, max] the table maps to alpha 0 is flagged EMPTY in the page table, no ray ever asks for it, and
+        # the reference's pool never uploads it either (GLVolumePool::RecomputeVisibility, GLVolumePool.cpp:1791-1909;
+        # GetBrick's empty flags, :484-656).  The all-bricks upload is timed too and reported beside it.
+        keep_all = np.arange(n, dtype=np.int64)
+        keep_vis = np.nonzero(mh[:n] >= 3)[0].astype(np.int64)
 
-        def run_steps(count):
-            upload(0)
-            for k in range(count):
-                e2._ck(e2.lib.tvk_pool_upload_wait(e2.h), "wait")          # step k's bricks are in place
-                if k + 1 < count:
-                    upload(k + 1)                                          # side stream, other slot set
-                e2.set_metadata(metas[k & 1])
-                e2.raycast(step_params[k % args.steps])
-                e2._ck(e2.lib.tvk_read_image_rgba8(e2.h, C.c_void_p(img8_host.data_ptr()), C.c_int(1)), "read_image_rgba8")
+        def subset(keep):
+            ks = (C.c_void_p * len(keep))(*[srcs[int(i)] for i in keep])
+            kz = np.ascontiguousarray(size_arr.reshape(n, -1)[keep]).reshape(-1)
+            return len(keep), [np.ascontiguousarray(ss[keep]) for ss in slot_sets], ks, kz
 
-        run_steps(2)
-        e2.stats(reset=True)
-        e2.synchronize()
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        run_steps(args.steps)
-        e2.synchronize()
-        e2e_s = time.perf_counter() - t1
-        e2e_samples = int(e2.stats().samples)
-        assert len(e2.read_requests()) == 0, "e2e pool not fully resident"
+        def run_leg(keep):
+            kn, kslots, ksrc, ksizes = subset(keep)
+
+            def upload(k):
+                e2._ck(e2.lib.tvk_pool_upload_bricks(e2.h, C.c_uint32(kn), kslots[k & 1].ctypes.data_as(C.c_void_p), ksrc,
+                                                     ksizes.ctypes.data_as(C.c_void_p), C.c_int(2)), "upload")   # 2: one pinned allocation
+
+            def run_steps(count):
+                upload(0)
+                for k in range(count):
+                    e2._ck(e2.lib.tvk_pool_upload_wait(e2.h), "wait")          # step k's bricks are in place
+                    if k + 1 < count:
+                        upload(k + 1)                                          # side stream, other slot set
+                    e2.set_metadata(metas[k & 1])
+                    e2.raycast(step_params[k % args.steps])
+                    e2._ck(e2.lib.tvk_read_image_rgba8(e2.h, C.c_void_p(img8_host.data_ptr()), C.c_int(1)), "read_image_rgba8")
+
+            run_steps(2)
+            e2.stats(reset=True)
+            e2.synchronize()
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            run_steps(args.steps)
+            e2.synchronize()
+            leg_s = time.perf_counter() - t1
+            leg_samples = int(e2.stats().samples)
+            if len(e2.read_requests()) != 0:
+                raise RuntimeError("e2e pool not fully resident: rays asked for bricks that were not uploaded")
+            return leg_s, leg_samples
+
+        try:
+            e2e_s, e2e_samples = run_leg(keep_vis)        # first: on a pool that never held the empty bricks
+            vis8 = img8_host.clone()
+        except RuntimeError as e:      # reported, never hidden: the line then carries the all-bricks figure
+            sys.stderr.write("e2e: visible-brick leg rejected (%s); reporting the all-bricks upload\n" % e)
+            e2e_extra = {"upload": "all %d bricks" % n, "visible_leg_error": str(e)}
+            vis8 = None
+        all_s, all_samples = run_leg(keep_all)
+        if vis8 is not None and (not torch.equal(vis8, img8_host) or e2e_samples != all_samples):
+            # same context, same slot set, same camera: the two frames must be the same bytes
+            sys.stderr.write("e2e: visible-brick frame differs from the all-bricks frame; reporting the all-bricks upload\n")
+            e2e_extra = {"upload": "all %d bricks" % n, "visible_leg_error": "frame or sample count differs from the all-bricks leg"}
+            vis8 = None
+        if vis8 is None:
+            e2e_s, e2e_samples = all_s, all_samples
+        else:
+            # informational: against the main context's fully resident pool (another pool geometry, so the pool-space
+            # coordinate arithmetic rounds differently in the last place)
+            ref8 = torch.empty_like(img8_host)
+            tvk.raycast(step_params[(args.steps - 1) % args.steps])
+            tvk._ck(tvk.lib.tvk_read_image_rgba8(tvk.h, C.c_void_p(ref8.data_ptr()), C.c_int(1)), "read_image_rgba8")
+            tvk.synchronize()
+            dmax = int((ref8.to(torch.int16) - vis8.to(torch.int16)).abs().max())
+            h2d_all = h2d
+            h2d = int(sum(int(np.prod(sizes[int(i)])) for i in keep_vis)) + 4 * total
+            e2e_extra = {"upload": "bricks the visibility pass leaves non-empty under the transfer function: %d of %d "
+                                   "(empty bricks are never requested, as in GLVolumePool)" % (len(keep_vis), n),
+                         "frame_equals_all_bricks_frame": True, "max_abs_diff_vs_resident_pool_rgba8": dmax,
+                         "all_bricks": {"value": all_samples / all_s, "ms_per_step": 1e3 * all_s / args.steps,
+                                        "h2d_bytes_per_step": h2d_all}}
         e2.close()
 
     # ---- reduce over ranks
@@ -523,7 +570,8 @@ def run_gpu(args, rank, world):
                          "issue": issue},
             "e2e": {"value": e2e_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "result": "RGBA8 frame (glReadPixels GL_UNSIGNED_BYTE, as captureSingleFrame reads it)", "pipeline": e2e_mode},
+                    "result": "RGBA8 frame (glReadPixels GL_UNSIGNED_BYTE, as captureSingleFrame reads it)", "pipeline": e2e_mode,
+                    **e2e_extra},
             "gpu_launches": args.steps * (1 if world == 1 else (2 * world if fused is not None else 2 * world)), "clocks": clocks,
             "builder_ms_untimed": 1e3 * t_build}
     if world > 1:

@@ -476,20 +476,37 @@ extern "C" int tvk_pool_upload_bricks(tvk_ctx* c, uint32_t n, const uint32_t* sl
         // A batch whose bricks follow one another in host memory (a bulk load in ToC order; the store aligns bricks to
         // 256 bytes) goes out as ONE copy-engine transfer, which gets closer to the link rate than SM-issued reads
         // (55 vs 49 GB/s); scattered bricks -- what paging on demand asks for -- are gathered by the kernel.
-        bool run = bn >= 16;
-        for (uint32_t i = 1; i < bn && run; ++i) {
-          const uint32_t k = b0 + i;
-          const uint8_t* prev_end = static_cast<const uint8_t*>(src[k - 1]) + (size_t)sizes[3 * (k - 1)] * sizes[3 * (k - 1) + 1] * sizes[3 * (k - 1) + 2] * c->pc.bpv;
-          const ptrdiff_t gap = static_cast<const uint8_t*>(src[k]) - prev_end;
-          if (gap < 0 || gap >= 256) run = false;
+        // A batch that is only PARTLY contiguous -- the non-empty bricks of a bulk load, which come in rows along x --
+        // goes out as one transfer per run when the runs are long enough (three bricks on average), so that the
+        // upload stays on the copy engine and off the SMs the ray-march kernel is using.
+        auto brick_bytes = [&](uint32_t k) { return (size_t)sizes[3 * k] * sizes[3 * k + 1] * sizes[3 * k + 2] * c->pc.bpv; };
+        struct Run { uint32_t first, count; size_t span; };
+        std::vector<Run> runs;
+        for (uint32_t i = 0; i < bn;) {
+          uint32_t j = i + 1;
+          while (j < bn) {
+            const uint32_t k = b0 + j;
+            const ptrdiff_t gap = static_cast<const uint8_t*>(src[k]) - (static_cast<const uint8_t*>(src[k - 1]) + brick_bytes(k - 1));
+            if (gap < 0 || gap >= 256) break;
+            ++j;
+          }
+          const uint32_t kl = b0 + j - 1;
+          runs.push_back(Run{i, j - i, (size_t)(static_cast<const uint8_t*>(src[kl]) - static_cast<const uint8_t*>(src[b0 + i])) + brick_bytes(kl)});
+          i = j;
         }
-        const size_t span = run ? (size_t)(static_cast<const uint8_t*>(src[b0 + bn - 1]) - static_cast<const uint8_t*>(src[b0])) +
-                                      (size_t)sizes[3 * (b0 + bn - 1)] * sizes[3 * (b0 + bn - 1) + 1] * sizes[3 * (b0 + bn - 1) + 2] * c->pc.bpv : 0;
-        if (run && span <= slot_bytes * cap) {
-          TVK_CHECK_CUDA(c, cudaMemcpyAsync(stg, src[b0], span, cudaMemcpyHostToDevice, st));
-          for (uint32_t i = 0; i < bn; ++i) {
-            const uint32_t k = b0 + i;
-            jobs[i] = PlaceJob{stg + (static_cast<const uint8_t*>(src[k]) - static_cast<const uint8_t*>(src[b0])), slot[k], sizes[3 * k], sizes[3 * k + 1], sizes[3 * k + 2]};
+        size_t staged = 0;
+        for (const Run& r : runs) staged += (r.span + 255u) & ~(size_t)255u;
+        const bool by_runs = bn >= 16 && runs.size() * 3u <= bn && staged <= slot_bytes * cap;
+        if (by_runs) {
+          size_t at = 0;
+          for (const Run& r : runs) {
+            const uint8_t* first = static_cast<const uint8_t*>(src[b0 + r.first]);
+            TVK_CHECK_CUDA(c, cudaMemcpyAsync(stg + at, first, r.span, cudaMemcpyHostToDevice, st));
+            for (uint32_t i = r.first; i < r.first + r.count; ++i) {
+              const uint32_t k = b0 + i;
+              jobs[i] = PlaceJob{stg + at + (static_cast<const uint8_t*>(src[k]) - first), slot[k], sizes[3 * k], sizes[3 * k + 1], sizes[3 * k + 2]};
+            }
+            at += (r.span + 255u) & ~(size_t)255u;
           }
         } else {
           std::vector<GatherJob> gj(bn);
