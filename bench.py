@@ -50,6 +50,20 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+_REAL_STDOUT = None
+
+
+def emit_line(line):
+    """The one JSON line, on the process's real stdout (see the descriptor swap in the multi-rank set-up)."""
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, text.encode())
+
+
 def bench_tf():
     """TransferFunction1D::SetStdFunction(0.5,0.5) colours with a 10x thinner alpha."""
     from_oracle = False
@@ -240,6 +254,12 @@ def run_gpu(args, rank, world):
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) must not join it
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # ... and whatever a library still writes to file descriptor 1 goes to stderr: the JSON line is written to the
+        # saved descriptor at the end
+        sys.stdout.flush()
+        global _REAL_STDOUT
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     tvk = TvkContext(local)
     if world > 1:
@@ -402,10 +422,25 @@ def run_gpu(args, rank, world):
 
     e2e_mode, e2e_extra = "serial", {}
     if world > 1:
+        # every rank pages in the bricks of ITS box that visibility leaves non-empty under the transfer function (see the
+        # N=1 leg below, which also checks the frame against the all-bricks upload)
+        keep = np.nonzero(np.asarray(meta_host, np.uint32)[:n] >= 3)[0]
+        kn = len(keep)
+        ksrc = (C.c_void_p * kn)(*[srcs[int(i)] for i in keep])
+        kslots = np.ascontiguousarray(slot_arr[keep])
+        ksizes = np.ascontiguousarray(size_arr.reshape(n, -1)[keep]).reshape(-1)
+        h2d_rank = int(sum(int(np.prod(sizes[int(i)])) for i in keep)) + 4 * total
+        tot = torch.tensor([h2d_rank, kn, n], device=dev, dtype=torch.int64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        h2d = int(tot[0])
+        e2e_extra = {"upload": "per rank, the bricks of its box that the visibility pass leaves non-empty under the "
+                               "transfer function: %d of %d over all ranks" % (int(tot[1]), int(tot[2])),
+                     "h2d_bytes_scope": "sum over ranks"}
+
         def e2e_step(k):
             tvk.set_metadata(meta_host)
-            tvk._ck(tvk.lib.tvk_pool_upload_bricks(tvk.h, C.c_uint32(n), slot_arr.ctypes.data_as(C.c_void_p), src_arr,
-                                                   size_arr.ctypes.data_as(C.c_void_p), C.c_int(0)), "upload")
+            tvk._ck(tvk.lib.tvk_pool_upload_bricks(tvk.h, C.c_uint32(kn), kslots.ctypes.data_as(C.c_void_p), ksrc,
+                                                   ksizes.ctypes.data_as(C.c_void_p), C.c_int(0)), "upload")
             tvk._ck(tvk.lib.tvk_pool_upload_wait(tvk.h), "wait")
             tvk.set_metadata(meta_host)
             step(k)
@@ -598,7 +633,7 @@ def run_gpu(args, rank, world):
         line["cpu_baseline"] = {"value": cs / dt, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": "first %d steps of the same orbit at full %dx%d, %.1f s of CPU work"
                                           % (nsteps, w, h, dt)}
-    print(json.dumps(line))
+    emit_line(line)
     tvk.close()
     if world > 1:
         dist.destroy_process_group()
