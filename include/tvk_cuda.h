@@ -98,8 +98,10 @@ int tvk_pool_total_bricks(const tvk_ctx* ctx, uint32_t* out);
  * Copies n bricks (x-fastest voxels, sizes[3*i..] voxels each, possibly smaller
  * than max_brick_size) into pool slots slot[i] (linear slot index
  * x + y*Cx + z*Cx*Cy) on the pager's side stream.  src pointers may be pinned
- * host memory (on_device == 0: gathered over PCIe by a kernel when the memory is mapped into the
- * device address space, else one DMA per run of bricks) or device memory (on_device == 1).
+ * host memory (on_device == 0; when it is mapped into the device address space a 256-brick batch
+ * travels as copy-engine transfers -- one if its bricks follow one another in host memory, one per
+ * run of adjacent bricks if the runs average three bricks or more -- and is otherwise gathered over
+ * PCIe by a kernel; unmapped memory: one DMA per run of bricks) or device memory (on_device == 1).
  * on_device == 2: the caller states that ALL sources lie in ONE pinned, device-mapped host
  * allocation (e.g. the renderer's brick store): one pointer query instead of one per brick.
  * Metadata is NOT touched; patch it with tvk_pool_patch_metadata once
