@@ -45,12 +45,15 @@ def test_builder_matches_oracle(tvk, vol, dtype, brick, overlap, median):
     _compare(tvk, raw, brick, overlap, median, oc["store"], oc["sizes"], oc["minmax"], h1, h2, mg)
 
 
-@pytest.mark.parametrize("kind", ["noise", "smooth", "flat", "flat_odd"])
+@pytest.mark.parametrize("kind", ["noise", "smooth", "flat", "flat_odd", "noise_unaligned"])
 def test_builder_u16_full_range_histogram(tvk, kind):
     """Full-range 16-bit volumes: packed shared-memory histogram inside the LOD 0 -> 1 pass (all 65536 bins); flat
-    volumes take its one-atomic-per-warp path, odd sizes give the lanes of one warp different row counts."""
+    volumes take its one-atomic-per-warp path, odd sizes give the lanes of one warp different row counts; volumes whose
+    rows are not 16-byte multiples keep the windowed histogram kernel (two 32768-bin passes)."""
     vol = (128, 97, 73) if kind == "flat_odd" else (128, 96, 72)
-    if kind == "noise":
+    if kind == "noise_unaligned":
+        vol = (127, 96, 75)       # rows are not 16-byte multiples: separate reduction + two-window histogram kernels
+    if kind in ("noise", "noise_unaligned"):
         raw = H.synth_noise(vol, np.uint16, seed=5, maxval=65535)
     elif kind == "smooth":
         raw = (H.synth_sphere(vol, np.uint8).astype(np.uint32) * 257).astype(np.uint16)
