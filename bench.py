@@ -268,7 +268,7 @@ def run_gpu(args, rank, world):
         work_stream = torch.cuda.Stream(device=dev)
         torch.cuda.set_stream(work_stream)
         tvk.set_stream(work_stream.cuda_stream)
-    sampler = {"exact": L.SAMPLER_EXACT, "tex3d": L.SAMPLER_TEX3D, "q4": L.SAMPLER_EXACT_Q4}[os.environ.get("TVK_SAMPLER", "q4")]
+    sampler = {"exact": L.SAMPLER_EXACT, "tex3d": L.SAMPLER_TEX3D, "q4": L.SAMPLER_EXACT_Q4, "gather": L.SAMPLER_GATHER}[os.environ.get("TVK_SAMPLER", "q4")]
 
     # ---- untimed set-up: synthesize the (slab of the) volume in HBM, build bricks, fill the pool
     from imagevis3d_b200 import sortlast as SL

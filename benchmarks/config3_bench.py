@@ -28,7 +28,7 @@ def main():
     torch.cuda.empty_cache()                 # generator temporaries: the quad-packed pool (106 GB) needs the room
     peak, _ = B.peaks()
     steps = 8
-    samplers = [("exact", L.SAMPLER_EXACT), ("q4", L.SAMPLER_EXACT_Q4), ("tex3d", L.SAMPLER_TEX3D)]
+    samplers = [("gather", L.SAMPLER_GATHER), ("exact", L.SAMPLER_EXACT), ("q4", L.SAMPLER_EXACT_Q4), ("tex3d", L.SAMPLER_TEX3D)]
     only = [a.split("=")[1] for a in sys.argv if a.startswith("--sampler=")]
     for sname, sampler in samplers:
         if only and sname not in only:

@@ -14,7 +14,7 @@ TVK_MAX_LOD = 16
 TVK_OK, TVK_ERR_INVALID, TVK_ERR_CUDA, TVK_ERR_NOMEM, TVK_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 RM_1DTRANS, RM_2DTRANS, RM_ISOSURFACE = 0, 1, 2
 MBS_ONLY_NEEDED, MBS_REQUEST_ALL, MBS_SKIP_ONE_LEVEL, MBS_SKIP_TWO_LEVELS = 0, 1, 2, 3
-SAMPLER_EXACT, SAMPLER_TEX3D, SAMPLER_EXACT_Q4 = 0, 1, 2
+SAMPLER_EXACT, SAMPLER_TEX3D, SAMPLER_EXACT_Q4, SAMPLER_GATHER = 0, 1, 2, 3
 BI_MISSING, BI_CHILD_EMPTY, BI_EMPTY, BI_FLAG_COUNT = 0, 1, 2, 3
 
 

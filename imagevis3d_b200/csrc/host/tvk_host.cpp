@@ -427,10 +427,9 @@ bool CudaGridLeaper::FinishLoad(BrickedVolume* v, uint64_t gpuMemBytes, uint32_t
   m_pool = new BrickPool(m_ctx, v);
   uint32_t sampler = m_sampler;
   if (sampler == kSamplerAuto) {
-    // the quad-packed pool needs 4x the bytes; take it when that is at most half of the free HBM
-    size_t freeB = 0, totalB = 0;
-    const uint64_t q4 = 4ull * bs[0] * bs[1] * bs[2] * bpv * cap[0] * cap[1] * cap[2];
-    sampler = (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess && q4 <= freeB / 2) ? TVK_SAMPLER_EXACT_Q4 : TVK_SAMPLER_EXACT;
+    // the layered-array pool read with four-texel gathers: exact filter arithmetic, two fetches per sample and 1x the
+    // memory (the quad-packed pool needs 4x and turns memory-latency bound on large volumes)
+    sampler = TVK_SAMPLER_GATHER;
   }
   m_activeSampler = sampler;
   rc = m_pool->Create(cap, sampler);
@@ -1190,7 +1189,7 @@ int tvkr_set_2d_trans(tvkr_renderer* h, const uint8_t* rgba, uint32_t w, uint32_
   return h && R(h)->Set2DTrans(rgba, w, hh, nz) ? 0 : 1;
 }
 int tvkr_set_state(tvkr_renderer* h, uint32_t strategy, uint32_t hash_size, uint32_t rehash, uint32_t sampler) {
-  if (!h || hash_size == 0 || rehash == 0 || strategy > TVK_MBS_SKIP_TWO_LEVELS || (sampler > TVK_SAMPLER_EXACT_Q4 && sampler != tvk::kSamplerAuto)) return 1;
+  if (!h || hash_size == 0 || rehash == 0 || strategy > TVK_MBS_SKIP_TWO_LEVELS || (sampler > TVK_SAMPLER_GATHER && sampler != tvk::kSamplerAuto)) return 1;
   R(h)->SetMissingBrickStrategy(strategy); R(h)->SetHashTable(hash_size, rehash); R(h)->SetSampler(sampler);
   return 0;
 }

@@ -139,7 +139,7 @@ class BrickPool {
   uint64_t m_uploadedBytes = 0;
 };
 
-// host-level choice: EXACT_Q4 when the 4x pool fits comfortably in free HBM, else EXACT
+// host-level choice: the layered-array pool (TVK_SAMPLER_GATHER)
 static const uint32_t kSamplerAuto = 0xFFFFFFFFu;
 
 enum ERenderMode { RM_1DTRANS = 0, RM_2DTRANS = 1, RM_ISOSURFACE = 2 };

@@ -8,6 +8,13 @@
 //                       reference's texture so the shader constants carry over.
 //   TVK_SAMPLER_TEX3D : the same voxels in a cudaArray (surface-writable) bound
 //                       to a normalised-float, linear-filter texture object.
+//   TVK_SAMPLER_GATHER: the same voxels in a LAYERED 2-D cudaArray, one layer per pool z
+//                       plane, read with the four-texel gather (PTX tld4.a2d) through a point-
+//                       sampled, element-type texture object: the texture units do the 2-D
+//                       addressing and caching, the kernel does the exact fp32 trilinear filter.
+//                       1x the memory of the volume (the quad-packed pool needs 4x).  The slot
+//                       grid of the array is PHYSICAL (pc.phys_cap, <= 2048 layers); the logical
+//                       capacity the reference's shader arithmetic sees is unchanged.
 // Brick upload = contiguous DMA (pinned host -> staging ring in HBM, side stream)
 // followed by a placement kernel that scatters each brick into its slot with
 // 16-byte accesses; the reference does one synchronous glTexSubImage3D per brick
@@ -163,6 +170,17 @@ int tvk_ensure_frame(tvk_ctx* c, uint32_t w, uint32_t h, uint32_t hash_size) {
 // ---------------------------------------------------------------------------
 // pool
 // ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) clear_layered_kernel(cudaSurfaceObject_t surf, uint32_t row_bytes, uint32_t rows, uint32_t layers) {
+  const uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+  if (x >= row_bytes) return;
+  const bool whole = x + 4u <= row_bytes;                               // rows of odd-sized slots end in a partial word
+  for (uint32_t l = blockIdx.z; l < layers; l += gridDim.z)
+    for (uint32_t y = blockIdx.y; y < rows; y += gridDim.y) {
+      if (whole) surf2DLayeredwrite(0u, surf, (int)x, (int)y, (int)l);
+      else for (uint32_t k = x; k < row_bytes; ++k) surf2DLayeredwrite((uint8_t)0, surf, (int)k, (int)y, (int)l);
+    }
+}
+
 extern "C" int tvk_pool_create(tvk_ctx* c, const tvk_pool_desc* d) {
   if (!c || !d) return TVK_ERR_INVALID;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
@@ -171,7 +189,7 @@ extern "C" int tvk_pool_create(tvk_ctx* c, const tvk_pool_desc* d) {
   for (int a = 0; a < 3; ++a)
     if (d->max_brick_size[a] <= 2 * d->overlap || d->pool_capacity[a] == 0 || d->volume_size[a] == 0)
       TVK_FAIL(c, TVK_ERR_INVALID, "bad pool description");
-  if (d->sampler > TVK_SAMPLER_EXACT_Q4) TVK_FAIL(c, TVK_ERR_INVALID, "bad sampler");
+  if (d->sampler > TVK_SAMPLER_GATHER) TVK_FAIL(c, TVK_ERR_INVALID, "bad sampler");
   tvk_pool_destroy(c);
   c->pdesc = *d;
   tvk_compute_pool_const(*d, c->pc);
@@ -180,6 +198,46 @@ extern "C" int tvk_pool_create(tvk_ctx* c, const tvk_pool_desc* d) {
     const size_t elem = (d->sampler == TVK_SAMPLER_EXACT_Q4 ? 4 : 1) * (size_t)d->bytes_per_voxel;
     TVK_CHECK_CUDA(c, cudaMalloc(&c->d_pool, voxels * elem));
     TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_pool, 0, voxels * elem, c->stream));
+  } else if (d->sampler == TVK_SAMPLER_GATHER) {
+    // physical slot grid: as many layer groups as the 2048-layer limit allows, the rest spread over a near-square
+    // X x Y grid (<= 32768 texels per side)
+    int max_w = 0, max_h = 0, max_l = 0;
+    TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&max_w, cudaDevAttrMaxTexture2DLayeredWidth, c->device));
+    TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&max_h, cudaDevAttrMaxTexture2DLayeredHeight, c->device));
+    TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&max_l, cudaDevAttrMaxTexture2DLayeredLayers, c->device));
+    const uint64_t nslots = (uint64_t)d->pool_capacity[0] * d->pool_capacity[1] * d->pool_capacity[2];
+    uint64_t pz = std::max<uint64_t>(1, std::min<uint64_t>(nslots, (uint64_t)max_l / d->max_brick_size[2]));
+    // fewer layer groups than the limit when that keeps the grid closer to a cube (small pools)
+    while (pz > 1 && pz * pz * pz > nslots * 8) --pz;
+    const uint64_t per_layer = (nslots + pz - 1) / pz;
+    uint64_t px = (uint64_t)std::ceil(std::sqrt((double)per_layer));
+    px = std::max<uint64_t>(1, std::min<uint64_t>(px, (uint64_t)max_w / d->max_brick_size[0]));
+    const uint64_t py = (per_layer + px - 1) / px;
+    if (py * d->max_brick_size[1] > (uint64_t)max_h || d->max_brick_size[2] > (uint32_t)max_l)
+      TVK_FAIL(c, TVK_ERR_UNSUPPORTED, "pool too large for a layered array (use TVK_SAMPLER_EXACT)");
+    c->pc.phys_cap[0] = (uint32_t)px; c->pc.phys_cap[1] = (uint32_t)py; c->pc.phys_cap[2] = (uint32_t)pz;
+    cudaChannelFormatDesc fd = cudaCreateChannelDesc(8 * d->bytes_per_voxel, 0, 0, 0, cudaChannelFormatKindUnsigned);
+    // (cudaArrayTextureGather is rejected together with cudaArrayLayered; the gather instruction does not need it:
+    //  benchmarks/gather_probe.cu, 4 M gathers checked on a B200)
+    TVK_CHECK_CUDA(c, cudaMalloc3DArray(&c->pool_array, &fd,
+                                        make_cudaExtent(px * d->max_brick_size[0], py * d->max_brick_size[1], pz * d->max_brick_size[2]),
+                                        cudaArrayLayered | cudaArraySurfaceLoadStore));
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = c->pool_array;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    TVK_CHECK_CUDA(c, cudaCreateTextureObject(&c->pool_tex, &rd, &td, nullptr));
+    TVK_CHECK_CUDA(c, cudaCreateSurfaceObject(&c->pool_surf, &rd));
+    // arrays are not zero-initialised; the linear pools are, and a fresh slot must read as zeros in all of them
+    const uint32_t row_bytes = (uint32_t)(px * d->max_brick_size[0] * d->bytes_per_voxel);
+    const uint32_t rows = (uint32_t)(py * d->max_brick_size[1]), layers = (uint32_t)(pz * d->max_brick_size[2]);
+    clear_layered_kernel<<<dim3(((row_bytes + 3) / 4 + 255) / 256, std::min<uint32_t>(rows, 65535u), std::min<uint32_t>(layers, 65535u)), 256, 0, c->stream>>>(
+        c->pool_surf, row_bytes, rows, layers);
+    TVK_CHECK_CUDA(c, cudaGetLastError());
   } else {
     cudaChannelFormatDesc fd = cudaCreateChannelDesc(8 * d->bytes_per_voxel, 0, 0, 0, cudaChannelFormatKindUnsigned);
     TVK_CHECK_CUDA(c, cudaMalloc3DArray(&c->pool_array, &fd,
@@ -206,6 +264,7 @@ extern "C" int tvk_pool_destroy(tvk_ctx* c) {
   if (!c) return TVK_ERR_INVALID;
   cudaSetDevice(c->device);
   if (c->pool_tex) { cudaDestroyTextureObject(c->pool_tex); c->pool_tex = 0; }
+  if (c->pool_surf) { cudaDestroySurfaceObject(c->pool_surf); c->pool_surf = 0; }
   if (c->pool_array) { cudaFreeArray(c->pool_array); c->pool_array = nullptr; }
   cudaFree(c->d_pool); c->d_pool = nullptr;
   cudaFree(c->d_meta); c->d_meta = nullptr;
@@ -363,6 +422,28 @@ __global__ void __launch_bounds__(256) place_bricks_surface(const PlaceJob* __re
   }
 }
 
+// TVK_SAMPLER_GATHER: brick rows go into the layered array through surface stores; VEC bytes per store (16 when
+// the row length, the source and the slot pitch allow it).  Slot (physical) = (p0, p1, p2): texel origin
+// (p0, p1) * max_brick in every layer of the group p2 * max_brick.z ...
+template <int VEC>
+__global__ void __launch_bounds__(256) place_bricks_layered(const PlaceJob* __restrict__ jobs, cudaSurfaceObject_t surf,
+                                                             const __grid_constant__ PoolConst pc) {
+  const PlaceJob j = jobs[blockIdx.x];
+  const uint32_t bpv = pc.bpv;
+  const uint32_t p0 = j.slot % pc.phys_cap[0], p1 = (j.slot / pc.phys_cap[0]) % pc.phys_cap[1],
+                 p2 = j.slot / (pc.phys_cap[0] * pc.phys_cap[1]);
+  const uint32_t row_bytes = j.sx * bpv, units = row_bytes / VEC, rows = j.sy * j.sz, total = units * rows;
+  const int x0 = (int)(p0 * pc.max_brick[0] * bpv), y0 = (int)(p1 * pc.max_brick[1]), l0 = (int)(p2 * pc.max_brick[2]);
+  for (uint32_t i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
+    const uint32_t r = i / units, u = i - r * units;
+    const uint32_t y = r % j.sy, z = r / j.sy;
+    const uint8_t* s = j.src + (size_t)r * row_bytes + (size_t)u * VEC;
+    if (VEC == 16) surf2DLayeredwrite(*reinterpret_cast<const uint4*>(s), surf, x0 + (int)(u * 16), y0 + (int)y, l0 + (int)z);
+    else if (VEC == 2) surf2DLayeredwrite(*reinterpret_cast<const uint16_t*>(s), surf, x0 + (int)(u * 2), y0 + (int)y, l0 + (int)z);
+    else surf2DLayeredwrite(*s, surf, x0 + (int)u, y0 + (int)y, l0 + (int)z);
+  }
+}
+
 static int place_batch(tvk_ctx* c, std::vector<PlaceJob>& jobs, cudaStream_t st) {
   if (jobs.empty()) return TVK_OK;
   const uint32_t bpv = c->pc.bpv;
@@ -403,6 +484,17 @@ static int place_batch(tvk_ctx* c, std::vector<PlaceJob>& jobs, cudaStream_t st)
     if (nvec < jobs.size()) {
       place_bricks_linear<1><<<dim3((unsigned)(jobs.size() - nvec), 8), 256, 0, st>>>(d_jobs + nvec, (uint8_t*)c->d_pool, c->pc);
       c->launches++;
+    }
+  } else if (c->pdesc.sampler == TVK_SAMPLER_GATHER) {
+    size_t nvec = 0;
+    while (nvec < jobs.size() && can_vec(jobs[nvec])) ++nvec;
+    if (nvec) place_bricks_layered<16><<<dim3((unsigned)nvec, 8), 256, 0, st>>>(d_jobs, c->pool_surf, c->pc);
+    if (nvec < jobs.size()) {
+      const dim3 g2((unsigned)(jobs.size() - nvec), 8);
+      // element-sized stores: bricks are arrays of whole voxels, so a source is always bpv-aligned
+      if (bpv == 2) place_bricks_layered<2><<<g2, 256, 0, st>>>(d_jobs + nvec, c->pool_surf, c->pc);
+      else place_bricks_layered<1><<<g2, 256, 0, st>>>(d_jobs + nvec, c->pool_surf, c->pc);
+      if (nvec) c->launches++;
     }
   } else {
     cudaResourceDesc rd{};

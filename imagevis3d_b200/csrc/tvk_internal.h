@@ -24,6 +24,7 @@ struct PoolConst {
   float    overlap_tc[3];                // "overlap" in pool tex coords
   float    volume_size[3];               // volumeSize
   uint32_t bpv;
+  uint32_t phys_cap[3];                  // TVK_SAMPLER_GATHER: slots per axis of the layered array (z = layer groups)
 };
 
 struct BuildState {
@@ -77,6 +78,7 @@ struct tvk_ctx {
   void* d_pool = nullptr;              // linear pool (TVK_SAMPLER_EXACT)
   cudaArray_t pool_array = nullptr;    // 3-D array (TVK_SAMPLER_TEX3D)
   cudaTextureObject_t pool_tex = 0;
+  cudaSurfaceObject_t pool_surf = 0;   // TVK_SAMPLER_GATHER: placement target (kept for the life of the pool)
   uint32_t* d_meta = nullptr;
   double* d_minmax = nullptr;
   double* d_gminmax = nullptr;

@@ -38,6 +38,12 @@
 #ifndef TVK_OCC_LIT
 #define TVK_OCC_LIT 4
 #endif
+#ifndef TVK_NB_GATHER
+#define TVK_NB_GATHER 4
+#endif
+#ifndef TVK_OCC_GATHER
+#define TVK_OCC_GATHER 4
+#endif
 
 struct RayParams {
   tvk_raycast_params p;
@@ -128,6 +134,11 @@ __device__ __forceinline__ void hash_report(const RayParams& rp, uint4 bc) {
 struct SlotCtx {
   const uint8_t* base;
   int ox, oy, oz;
+  // TVK_SAMPLER_GATHER: the slot's LOGICAL origin as floats (in-slot coordinates are formed in fp32, exactly), its
+  // PHYSICAL texel origin in the layered array (+1: a gather at (i+1, j+1) returns texels i..i+1 x j..j+1) and
+  // its first layer
+  float lx, ly, fx, fy;
+  uint32_t lz;
 };
 
 struct BrickHit {
@@ -138,6 +149,7 @@ struct BrickHit {
 };
 
 // GetBrick, GLVolumePool.cpp:552-620
+template <int SAMP>
 __device__ __forceinline__ void get_brick(const RayParams& rp, f3 entry, uint32_t& lod, f3 dir, BrickHit& b) {
   const PoolConst& pc = rp.pc;
   const uint32_t max_lod = pc.lod_count - 1;
@@ -189,6 +201,12 @@ __device__ __forceinline__ void get_brick(const RayParams& rp, f3 entry, uint32_
     const size_t sx = pc.pool_dim[0], sxy = sx * pc.pool_dim[1];
     b.slot.base = static_cast<const uint8_t*>(rp.pool) + ((size_t)vx + (size_t)vy * sx + (size_t)vz * sxy) * rp.elem_bytes;
     b.slot.ox = 0x4B400000 + (int)vx; b.slot.oy = 0x4B400000 + (int)vy; b.slot.oz = 0x4B400000 + (int)vz;
+    if (SAMP == TVK_SAMPLER_GATHER) {
+      const uint32_t p0 = idx % pc.phys_cap[0], p1 = (idx / pc.phys_cap[0]) % pc.phys_cap[1], p2 = idx / (pc.phys_cap[0] * pc.phys_cap[1]);
+      b.slot.lx = (float)vx; b.slot.ly = (float)vy;
+      b.slot.fx = (float)(p0 * pc.max_brick[0]) + 1.0f; b.slot.fy = (float)(p1 * pc.max_brick[1]) + 1.0f;
+      b.slot.lz = p2 * pc.max_brick[2];
+    }
   }
   {
     const uint32_t v = s0 * pc.max_brick[0];
@@ -221,6 +239,17 @@ __device__ __forceinline__ void get_brick(const RayParams& rp, f3 entry, uint32_
 // mantissa of 2^23 and subtract 2^23 (PRMT/LOP3 + FADD).
 __device__ __forceinline__ float u2f(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
 
+// Four-texel gather from one layer of the layered pool array (PTX tld4, 2-D array geometry): returns the texels
+// around the shared corner (x, y) in the order  .x = (i, j+1)  .y = (i+1, j+1)  .z = (i+1, j)  .w = (i, j)  with
+// i = x - 1, j = y - 1 (unnormalised coordinates; the corner is half a texel away from every texel boundary, so the
+// hardware's fixed-point footprint selection cannot disagree with ours).  Raw integer texels, zero-extended.
+__device__ __forceinline__ uint4 gather4(cudaTextureObject_t t, uint32_t layer, float x, float y) {
+  uint4 r;
+  asm("tld4.r.a2d.v4.u32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}];"
+      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(t), "r"(layer), "f"(x), "f"(y));
+  return r;
+}
+
 // The 2x2x2 voxel footprint of one sample: raw values + lerp weights.
 struct Taps {
   float v[4];       // base taps 000 010 001 011 (the x = 0 corner of each x-edge)
@@ -241,6 +270,23 @@ __device__ __forceinline__ void fetch_taps(const RayParams& rp, const SlotCtx& s
   const float u = fmaf(p.x, pc.pool_size[0], -0.5f), v = fmaf(p.y, pc.pool_size[1], -0.5f), w = fmaf(p.z, pc.pool_size[2], -0.5f);
   const float tu = __fadd_rd(u, M), tv = __fadd_rd(v, M), tw = __fadd_rd(w, M);
   t.a = u - (tu - M); t.b = v - (tv - M); t.g = w - (tw - M);
+  if (SAMP == TVK_SAMPLER_GATHER) {
+    // in-slot base corner in fp32 (small integers: exact), clamped like the integer path below; two gathers
+    const float xs = fminf(fmaxf((tu - M) - sl.lx, 0.0f), (float)((int)pc.max_brick[0] - 2));
+    const float ys = fminf(fmaxf((tv - M) - sl.ly, 0.0f), (float)((int)pc.max_brick[1] - 2));
+    const int zs = min(max(__float_as_int(tw) - sl.oz, 0), (int)pc.max_brick[2] - 2);
+    const float gx = xs + sl.fx, gy = ys + sl.fy;
+    const uint32_t l = sl.lz + (uint32_t)zs;
+    const uint4 g0 = gather4(rp.tex, l, gx, gy), g1 = gather4(rp.tex, l + 1u, gx, gy);
+    // biased values 2^23 + texel: differences of biased values are exact, only the base taps drop the bias
+    const float b000 = __uint_as_float(0x4B000000u | g0.w), b100 = __uint_as_float(0x4B000000u | g0.z);
+    const float b010 = __uint_as_float(0x4B000000u | g0.x), b110 = __uint_as_float(0x4B000000u | g0.y);
+    const float b001 = __uint_as_float(0x4B000000u | g1.w), b101 = __uint_as_float(0x4B000000u | g1.z);
+    const float b011 = __uint_as_float(0x4B000000u | g1.x), b111 = __uint_as_float(0x4B000000u | g1.y);
+    t.d[0] = b100 - b000; t.d[1] = b110 - b010; t.d[2] = b101 - b001; t.d[3] = b111 - b011;
+    t.v[0] = b000 - 8388608.0f; t.v[1] = b010 - 8388608.0f; t.v[2] = b001 - 8388608.0f; t.v[3] = b011 - 8388608.0f;
+    return;
+  }
   // in-slot voxel coordinates of the footprint's base corner
   const int x = min(max(__float_as_int(tu) - sl.ox, 0), (int)pc.max_brick[0] - 2);
   const int y = min(max(__float_as_int(tv) - sl.oy, 0), (int)pc.max_brick[1] - 2);
@@ -350,29 +396,18 @@ __device__ __forceinline__ void unpack_quad(const void* __restrict__ base, uint3
 }
 __device__ __forceinline__ float lerpf(float t, float a, float b) { return fmaf(t, b - a, a); }
 
-template <int BPV>
-__device__ __forceinline__ void q4_center_gradient(const RayParams& rp, const SlotCtx& sl, f3 p, float& data, f3& grad) {
-  const PoolConst& pc = rp.pc;
-  const float M = 12582912.0f;   // 1.5 * 2^23
-  const float u = fmaf(p.x, pc.pool_size[0], -0.5f), v = fmaf(p.y, pc.pool_size[1], -0.5f), w = fmaf(p.z, pc.pool_size[2], -0.5f);
-  const float tu = __fadd_rd(u, M), tv = __fadd_rd(v, M), tw = __fadd_rd(w, M);
-  const float a = u - (tu - M), b = v - (tv - M), g = w - (tw - M);
-  const int mx = (int)pc.max_brick[0], my = (int)pc.max_brick[1], mz = (int)pc.max_brick[2];
-  const int x = min(max(__float_as_int(tu) - sl.ox, 0), mx - 2);
-  const int y = min(max(__float_as_int(tv) - sl.oy, 0), my - 2);
-  const int z = min(max(__float_as_int(tw) - sl.oz, 0), mz - 2);
-  const uint32_t sx = pc.pool_dim[0], sxy = sx * pc.pool_dim[1];
-  const uint32_t o = (uint32_t)x + (uint32_t)y * sx + (uint32_t)z * sxy;
-  const uint32_t oxm = o - (x > 0 ? 1u : 0u), oxp = o + (x + 2 < mx ? 2u : 1u);         // columns x-1 and x+2 (clamped)
-  const uint32_t dym = y > 0 ? sx : 0u, dyp = sx, dzm = z > 0 ? sxy : 0u, dzp = sxy;     // (y+1, z+1 <= dim-1 always)
-  float X0[4], X1[4], X2[4], X3[4], Ym0[4], Ym1[4], Yp0[4], Yp1[4], Zm0[4], Zm1[4], Zp0[4], Zp1[4];
-  unpack_quad<BPV>(sl.base, oxm, X0); unpack_quad<BPV>(sl.base, o, X1); unpack_quad<BPV>(sl.base, o + 1, X2); unpack_quad<BPV>(sl.base, oxp, X3);
-  unpack_quad<BPV>(sl.base, o - dym, Ym0); unpack_quad<BPV>(sl.base, o + 1 - dym, Ym1);
-  unpack_quad<BPV>(sl.base, o + dyp, Yp0); unpack_quad<BPV>(sl.base, o + 1 + dyp, Yp1);
-  unpack_quad<BPV>(sl.base, o - dzm, Zm0); unpack_quad<BPV>(sl.base, o + 1 - dzm, Zm1);
-  unpack_quad<BPV>(sl.base, o + dzp, Zp0); unpack_quad<BPV>(sl.base, o + 1 + dzp, Zp1);
-  const float scale = (BPV == 1 ? 1.0f / 255.0f : 1.0f / 65535.0f);
-  // centre: filter_taps order (quad = {v(y,z), v(y+1,z), v(y,z+1), v(y+1,z+1)})
+// The 32 voxels the centre sample and its six central-difference neighbours touch, named by what the arithmetic
+// below needs: four x-columns of (y,z) quads {v(y,z), v(y+1,z), v(y,z+1), v(y+1,z+1)} at x-1, x, x+1, x+2, and the
+// rows y-1 / y+2 and planes z-1 / z+2 over the 2x2 of the other two axes.
+struct Cross {
+  float X0[4], X1[4], X2[4], X3[4];
+  float ym[4], yp[4];     // (x,y-1,z) (x+1,y-1,z) (x,y-1,z+1) (x+1,y-1,z+1);  the same at y+2
+  float zm[4], zp[4];     // (x,y,z-1) (x+1,y,z-1) (x,y+1,z-1) (x+1,y+1,z-1);  the same at z+2
+};
+
+__device__ __forceinline__ void cross_filter(const Cross& k, float a, float b, float g, float scale, float& data, f3& grad) {
+  const float* X0 = k.X0; const float* X1 = k.X1; const float* X2 = k.X2; const float* X3 = k.X3;
+  // centre: filter_taps order
   const float c00 = fmaf(a, X2[0] - X1[0], X1[0]), c10 = fmaf(a, X2[1] - X1[1], X1[1]);
   const float c01 = fmaf(a, X2[2] - X1[2], X1[2]), c11 = fmaf(a, X2[3] - X1[3], X1[3]);
   const float c0 = fmaf(b, c10 - c00, c00), c1 = fmaf(b, c11 - c01, c01);
@@ -382,17 +417,74 @@ __device__ __forceinline__ void q4_center_gradient(const RayParams& rp, const Sl
   const float B2 = lerpf(g, lerpf(b, X2[0], X2[1]), lerpf(b, X2[2], X2[3])), B3 = lerpf(g, lerpf(b, X3[0], X3[1]), lerpf(b, X3[2], X3[3]));
   const float txm = lerpf(a, B0, B1), txp = lerpf(a, B2, B3);
   // y: rows y-1, y, y+1, y+2, each bilinear in (a, g)
-  const float R0 = lerpf(g, lerpf(a, y > 0 ? Ym0[0] : X1[0], y > 0 ? Ym1[0] : X2[0]), lerpf(a, y > 0 ? Ym0[2] : X1[2], y > 0 ? Ym1[2] : X2[2]));
+  const float R0 = lerpf(g, lerpf(a, k.ym[0], k.ym[1]), lerpf(a, k.ym[2], k.ym[3]));
   const float R1 = lerpf(g, c00, c01), R2 = lerpf(g, c10, c11);
-  const float R3 = lerpf(g, lerpf(a, Yp0[1], Yp1[1]), lerpf(a, Yp0[3], Yp1[3]));
+  const float R3 = lerpf(g, lerpf(a, k.yp[0], k.yp[1]), lerpf(a, k.yp[2], k.yp[3]));
   const float tym = lerpf(b, R0, R1), typ = lerpf(b, R2, R3);
   // z: planes z-1, z, z+1, z+2, each bilinear in (a, b)
-  const float P0 = lerpf(b, lerpf(a, z > 0 ? Zm0[0] : X1[0], z > 0 ? Zm1[0] : X2[0]), lerpf(a, z > 0 ? Zm0[1] : X1[1], z > 0 ? Zm1[1] : X2[1]));
+  const float P0 = lerpf(b, lerpf(a, k.zm[0], k.zm[1]), lerpf(a, k.zm[2], k.zm[3]));
   const float P1 = c0, P2 = c1;
-  const float P3 = lerpf(b, lerpf(a, Zp0[2], Zp1[2]), lerpf(a, Zp0[3], Zp1[3]));
+  const float P3 = lerpf(b, lerpf(a, k.zp[0], k.zp[1]), lerpf(a, k.zp[2], k.zp[3]));
   const float tzm = lerpf(g, P0, P1), tzp = lerpf(g, P2, P3);
   // ComputeGradient: (xm - xp, yp - ym, zm - zp) / 2 with yp = S(y - dy), ym = S(y + dy)  (GradientTools.glsl:6-16)
   grad = mk3((txm - txp) * scale / 2.0f, (tym - typ) * scale / 2.0f, (tzm - tzp) * scale / 2.0f);
+}
+
+template <int BPV, int SAMP>
+__device__ __forceinline__ void center_gradient(const RayParams& rp, const SlotCtx& sl, f3 p, float& data, f3& grad) {
+  const PoolConst& pc = rp.pc;
+  const float M = 12582912.0f;   // 1.5 * 2^23
+  const float u = fmaf(p.x, pc.pool_size[0], -0.5f), v = fmaf(p.y, pc.pool_size[1], -0.5f), w = fmaf(p.z, pc.pool_size[2], -0.5f);
+  const float tu = __fadd_rd(u, M), tv = __fadd_rd(v, M), tw = __fadd_rd(w, M);
+  const float a = u - (tu - M), b = v - (tv - M), g = w - (tw - M);
+  const int mx = (int)pc.max_brick[0], my = (int)pc.max_brick[1], mz = (int)pc.max_brick[2];
+  const float scale = (BPV == 1 ? 1.0f / 255.0f : 1.0f / 65535.0f);
+  Cross k;
+  if (SAMP == TVK_SAMPLER_GATHER) {
+    // the 4x4 block (x-1..x+2, y-1..y+2) of planes z and z+1 = four diagonal gathers each; planes z-1 and z+2
+    // need the centre 2x2 only: 10 gathers.  x / y neighbours are not clamped to the slot: a position the march
+    // can produce keeps its taps inside the brick's ghost layers (see fetch_taps).
+    const float xs = fminf(fmaxf((tu - M) - sl.lx, 0.0f), (float)(mx - 2));
+    const float ys = fminf(fmaxf((tv - M) - sl.ly, 0.0f), (float)(my - 2));
+    const int zs = min(max(__float_as_int(tw) - sl.oz, 0), mz - 2);
+    const float gx = xs + sl.fx, gy = ys + sl.fy;
+    const uint32_t l = sl.lz + (uint32_t)zs;
+    const uint4 mm0 = gather4(rp.tex, l, gx - 1.0f, gy - 1.0f), pm0 = gather4(rp.tex, l, gx + 1.0f, gy - 1.0f);
+    const uint4 mp0 = gather4(rp.tex, l, gx - 1.0f, gy + 1.0f), pp0 = gather4(rp.tex, l, gx + 1.0f, gy + 1.0f);
+    const uint4 mm1 = gather4(rp.tex, l + 1u, gx - 1.0f, gy - 1.0f), pm1 = gather4(rp.tex, l + 1u, gx + 1.0f, gy - 1.0f);
+    const uint4 mp1 = gather4(rp.tex, l + 1u, gx - 1.0f, gy + 1.0f), pp1 = gather4(rp.tex, l + 1u, gx + 1.0f, gy + 1.0f);
+    const uint4 zm = gather4(rp.tex, sl.lz + (uint32_t)max(zs - 1, 0), gx, gy), zp = gather4(rp.tex, sl.lz + (uint32_t)min(zs + 2, mz - 1), gx, gy);
+    // gather(gx-1, gy-1): .w (x-1,y-1) .z (x,y-1) .x (x-1,y) .y (x,y);   gather(gx+1, gy-1): .w (x+1,y-1) .z (x+2,y-1) .x (x+1,y) .y (x+2,y)
+    // gather(gx-1, gy+1): .w (x-1,y+1) .z (x,y+1) .x (x-1,y+2) .y (x,y+2); gather(gx+1, gy+1): .w (x+1,y+1) .z (x+2,y+1) .x (x+1,y+2) .y (x+2,y+2)
+    k.X0[0] = u2f(mm0.x); k.X0[1] = u2f(mp0.w); k.X0[2] = u2f(mm1.x); k.X0[3] = u2f(mp1.w);
+    k.X1[0] = u2f(mm0.y); k.X1[1] = u2f(mp0.z); k.X1[2] = u2f(mm1.y); k.X1[3] = u2f(mp1.z);
+    k.X2[0] = u2f(pm0.x); k.X2[1] = u2f(pp0.w); k.X2[2] = u2f(pm1.x); k.X2[3] = u2f(pp1.w);
+    k.X3[0] = u2f(pm0.y); k.X3[1] = u2f(pp0.z); k.X3[2] = u2f(pm1.y); k.X3[3] = u2f(pp1.z);
+    k.ym[0] = u2f(mm0.z); k.ym[1] = u2f(pm0.w); k.ym[2] = u2f(mm1.z); k.ym[3] = u2f(pm1.w);
+    k.yp[0] = u2f(mp0.y); k.yp[1] = u2f(pp0.x); k.yp[2] = u2f(mp1.y); k.yp[3] = u2f(pp1.x);
+    k.zm[0] = u2f(zm.w); k.zm[1] = u2f(zm.z); k.zm[2] = u2f(zm.x); k.zm[3] = u2f(zm.y);
+    k.zp[0] = u2f(zp.w); k.zp[1] = u2f(zp.z); k.zp[2] = u2f(zp.x); k.zp[3] = u2f(zp.y);
+  } else {
+    // (y,z)-quad pool: the cross arrives in 12 quad loads around one base address
+    const int x = min(max(__float_as_int(tu) - sl.ox, 0), mx - 2);
+    const int y = min(max(__float_as_int(tv) - sl.oy, 0), my - 2);
+    const int z = min(max(__float_as_int(tw) - sl.oz, 0), mz - 2);
+    const uint32_t sx = pc.pool_dim[0], sxy = sx * pc.pool_dim[1];
+    const uint32_t o = (uint32_t)x + (uint32_t)y * sx + (uint32_t)z * sxy;
+    const uint32_t oxm = o - (x > 0 ? 1u : 0u), oxp = o + (x + 2 < mx ? 2u : 1u);         // columns x-1 and x+2 (clamped)
+    const uint32_t dym = y > 0 ? sx : 0u, dyp = sx, dzm = z > 0 ? sxy : 0u, dzp = sxy;     // (y+1, z+1 <= dim-1 always)
+    float Ym0[4], Ym1[4], Yp0[4], Yp1[4], Zm0[4], Zm1[4], Zp0[4], Zp1[4];
+    unpack_quad<BPV>(sl.base, oxm, k.X0); unpack_quad<BPV>(sl.base, o, k.X1); unpack_quad<BPV>(sl.base, o + 1, k.X2); unpack_quad<BPV>(sl.base, oxp, k.X3);
+    unpack_quad<BPV>(sl.base, o - dym, Ym0); unpack_quad<BPV>(sl.base, o + 1 - dym, Ym1);
+    unpack_quad<BPV>(sl.base, o + dyp, Yp0); unpack_quad<BPV>(sl.base, o + 1 + dyp, Yp1);
+    unpack_quad<BPV>(sl.base, o - dzm, Zm0); unpack_quad<BPV>(sl.base, o + 1 - dzm, Zm1);
+    unpack_quad<BPV>(sl.base, o + dzp, Zp0); unpack_quad<BPV>(sl.base, o + 1 + dzp, Zp1);
+    k.ym[0] = y > 0 ? Ym0[0] : k.X1[0]; k.ym[1] = y > 0 ? Ym1[0] : k.X2[0]; k.ym[2] = y > 0 ? Ym0[2] : k.X1[2]; k.ym[3] = y > 0 ? Ym1[2] : k.X2[2];
+    k.yp[0] = Yp0[1]; k.yp[1] = Yp1[1]; k.yp[2] = Yp0[3]; k.yp[3] = Yp1[3];
+    k.zm[0] = z > 0 ? Zm0[0] : k.X1[0]; k.zm[1] = z > 0 ? Zm1[0] : k.X2[0]; k.zm[2] = z > 0 ? Zm0[1] : k.X1[1]; k.zm[3] = z > 0 ? Zm1[1] : k.X2[1];
+    k.zp[0] = Zp0[2]; k.zp[1] = Zp1[2]; k.zp[2] = Zp0[3]; k.zp[3] = Zp1[3];
+  }
+  cross_filter(k, a, b, g, scale, data, grad);
 }
 
 __device__ __forceinline__ float pow8(float x) { x *= x; x *= x; return x * x; }
@@ -524,7 +616,7 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
       const float depth = fmaf(exit_depth, t, entry_depth * (1.0f - t));
       uint32_t lod = compute_lod(depth, p.lod_factor, p.level_zero_wse, pc.lod_count - 1);
       BrickHit b;
-      get_brick(rp, cur, lod, dir, b);
+      get_brick<SAMP>(rp, cur, lod, dir, b);
       cn.bricks++;
       if (!b.found && optimal) {
         optimal = false;
@@ -540,7 +632,7 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
         // multiplies the memory-level parallelism of a ray without any register rotation.  Samples are
         // still classified, counted and composited strictly in order, with the ERT test after each.
         // The hardware-filtered path needs one register per sample in flight, so it batches deeper.
-        const int NB = ((MODE == TVK_RM_1DTRANS) && !LIT) ? (SAMP == TVK_SAMPLER_TEX3D ? TVK_NB_TEX : TVK_NB_LDG) : 1;
+        const int NB = ((MODE == TVK_RM_1DTRANS) && !LIT) ? (SAMP == TVK_SAMPLER_TEX3D ? TVK_NB_TEX : (SAMP == TVK_SAMPLER_GATHER ? TVK_NB_GATHER : TVK_NB_LDG)) : 1;
         int i = 0;
 #define TVK_COMPOSITE(S)                                                                     \
         {                                                                                    \
@@ -581,7 +673,7 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
         }
         for (; i < steps; ++i) {
           float4 s0;
-          if (SAMP == TVK_SAMPLER_EXACT_Q4 && LIT && MODE == TVK_RM_1DTRANS) {
+          if ((SAMP == TVK_SAMPLER_EXACT_Q4 || SAMP == TVK_SAMPLER_GATHER) && LIT && MODE == TVK_RM_1DTRANS) {
             // 1D-TF lit: the table needs the centre sample only (2 quad loads); where it returns alpha 0 -- empty space
             // inside visible bricks -- the gradient (10 more quad loads) and the shading are not needed either
             const float data = sample_pool<BPV, SAMP>(rp, b.slot, q);
@@ -589,10 +681,10 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
             if (s0.w != 0.0f) {
               float dc;
               f3 g;
-              q4_center_gradient<BPV>(rp, b.slot, q, dc, g);
+              center_gradient<BPV, SAMP>(rp, b.slot, q, dc, g);
               s0 = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, data, q, b.inv_scale, b.trans, &g);
             }
-          } else if (SAMP == TVK_SAMPLER_EXACT_Q4 && MODE == TVK_RM_2DTRANS) {
+          } else if ((SAMP == TVK_SAMPLER_EXACT_Q4 || SAMP == TVK_SAMPLER_GATHER) && MODE == TVK_RM_2DTRANS) {
             // 2D-TF: the table row depends on the gradient, the column on the centre sample alone; a column that is
             // transparent in every row makes the sample transparent whatever its gradient
             const float data = sample_pool<BPV, SAMP>(rp, b.slot, q);
@@ -601,7 +693,7 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
             if ((__ldg(rp.tf_colmask + (cx >> 5)) >> (cx & 31)) & 1u) {
               float dc;
               f3 g;
-              q4_center_gradient<BPV>(rp, b.slot, q, dc, g);
+              center_gradient<BPV, SAMP>(rp, b.slot, q, dc, g);
               s0 = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, data, q, b.inv_scale, b.trans, &g);
             }
           } else {
@@ -658,7 +750,7 @@ __device__ __forceinline__ void march_ray_iso(const RayParams& rp, float4 exitp,
       const float depth = fmaf(exit_depth, t, entry_depth * (1.0f - t));
       uint32_t lod = compute_lod(depth, p.lod_factor, p.level_zero_wse, pc.lod_count - 1);
       BrickHit b;
-      get_brick(rp, cur, lod, dir, b);
+      get_brick<SAMP>(rp, cur, lod, dir, b);
       cn.bricks++;
       if (!b.found && optimal) {
         optimal = false;
@@ -741,7 +833,7 @@ __device__ __forceinline__ void store_pixel(const RayParams& rp, uint32_t px, ui
 // SRM1: sampleRateModifier == 1 known at compile time (the opacity correction is then the identity
 // 1-(1-a) and the pow path is not even compiled in); instantiated for the 1D-TF kernels only.
 template <int MODE, bool LIT, int BPV, int SAMP, bool SRM1>
-__global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP == TVK_SAMPLER_TEX3D ? TVK_OCC_TEX : TVK_OCC_LDG) : TVK_OCC_LIT) raycast_kernel(const __grid_constant__ RayParams rp) {
+__global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP == TVK_SAMPLER_TEX3D ? TVK_OCC_TEX : (SAMP == TVK_SAMPLER_GATHER ? TVK_OCC_GATHER : TVK_OCC_LDG)) : TVK_OCC_LIT) raycast_kernel(const __grid_constant__ RayParams rp) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t ntiles = rp.tiles_x * rp.tiles_y;
   Counters cn;
@@ -833,6 +925,7 @@ template <int BPV>
 static raycast_fn pick_sampler(uint32_t sampler, uint32_t mode, bool lit, bool srm1) {
   if (sampler == TVK_SAMPLER_TEX3D) return pick_kernel<BPV, TVK_SAMPLER_TEX3D>(mode, lit, srm1);
   if (sampler == TVK_SAMPLER_EXACT_Q4) return pick_kernel<BPV, TVK_SAMPLER_EXACT_Q4>(mode, lit, srm1);
+  if (sampler == TVK_SAMPLER_GATHER) return pick_kernel<BPV, TVK_SAMPLER_GATHER>(mode, lit, srm1);
   return pick_kernel<BPV, TVK_SAMPLER_EXACT>(mode, lit, srm1);
 }
 

@@ -56,6 +56,10 @@ extern "C" {
 #define TVK_SAMPLER_TEX3D  1   /* cudaArray + hardware filtering (1.8 fixed-point weights) */
 #define TVK_SAMPLER_EXACT_Q4 2 /* EXACT arithmetic; pool stored as (y,z) 2x2 quads per voxel: 4x the
                                   memory, 2 loads per sample instead of 8 (same results as EXACT)   */
+#define TVK_SAMPLER_GATHER 3   /* EXACT arithmetic; pool = LAYERED 2-D array (one layer per pool z), a sample's
+                                  2x2x2 footprint = two four-texel gathers (tld4) through the texture units:
+                                  1x the memory, 2 fetches per sample, same results as EXACT.  Limits: pool
+                                  slots are laid out physically as X x Y x (<= 2048 / max_brick.z) layer groups */
 
 typedef struct tvk_ctx tvk_ctx;
 

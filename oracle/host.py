@@ -401,7 +401,7 @@ class OracleFrame:
         self.aux = np.zeros((h, w, 4), f32)
         self.image = np.zeros((h, w, 4), f32)
         self.hash = np.zeros(hash_size, np.uint32)
-        self.stats = np.zeros(3, np.uint64)
+        self.stats = np.zeros(4, np.uint64)     # samples, GetBrick calls, rays, dropped reports
 
 
 def raycast(params, pool, tf_rgba8, frame):

@@ -137,7 +137,7 @@ typedef struct ctx_t {
   const uint8_t* tf;
   uint32_t tf_w, tf_h;
   uint32_t* hash;
-  uint64_t samples, bricks, rays;
+  uint64_t samples, bricks, rays, drops;   /* drops: reports that found no free entry within rehash_count probes */
 } ctx_t;
 
 static inline float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
@@ -152,6 +152,7 @@ static void hash_report(ctx_t* c, const uint32_t bc[4]) {
     const uint32_t cur = __sync_val_compare_and_swap(&c->hash[h], 0u, serial); /* imageAtomicCompSwap */
     if (cur == 0 || cur == serial) return;
   } while (++rehash < c->p->rehash_count);
+  c->drops++;
 }
 
 static inline void brick_coords(const ctx_t* c, const float p[3], uint32_t lod, uint32_t bc[4]) {
@@ -597,16 +598,16 @@ static void compose_iso(const tvk_raycast_params* p, const float hit[4], const f
 
 /* One sub-frame (GLGridLeaper::Render3DRegion -> Raycast).  ray_pos / ray_aux are
  * the W*H*4 resume buffers (in/out; ignored on input when new_view), image the
- * W*H*4 result, hash the request table (cleared here), stats[3] = samples,
- * GetBrick calls, rays. */
+ * W*H*4 result, hash the request table (cleared here), stats[4] = samples,
+ * GetBrick calls, rays, dropped brick reports (table full within the probe limit). */
 int orc_raycast(const tvk_raycast_params* p, const orc_pool_t* pool, const uint8_t* tf,
                 uint32_t tf_w, uint32_t tf_h, float* ray_pos, float* ray_aux, float* image,
                 uint32_t* hash, uint64_t* stats) {
   uint32_t inner[3] = {pool->max_brick[0] - 2 * pool->overlap, pool->max_brick[1] - 2 * pool->overlap,
                        pool->max_brick[2] - 2 * pool->overlap};
   memset(hash, 0, sizeof(uint32_t) * p->hash_table_size);
-  uint64_t tot_s = 0, tot_b = 0, tot_r = 0;
-#pragma omp parallel for schedule(dynamic, 4) reduction(+ : tot_s, tot_b, tot_r)
+  uint64_t tot_s = 0, tot_b = 0, tot_r = 0, tot_d = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : tot_s, tot_b, tot_r, tot_d)
   for (uint32_t py = 0; py < p->height; ++py) {
     ctx_t c;
     memset(&c, 0, sizeof(c));
@@ -636,9 +637,9 @@ int orc_raycast(const tvk_raycast_params* p, const orc_pool_t* pool, const uint8
         march_ray(&c, exitp, ray_pos + i, ray_aux + i, image + i);
       }
     }
-    tot_s += c.samples; tot_b += c.bricks; tot_r += c.rays;
+    tot_s += c.samples; tot_b += c.bricks; tot_r += c.rays; tot_d += c.drops;
   }
-  if (stats) { stats[0] = tot_s; stats[1] = tot_b; stats[2] = tot_r; }
+  if (stats) { stats[0] = tot_s; stats[1] = tot_b; stats[2] = tot_r; stats[3] = tot_d; }
   return 0;
 }
 

@@ -48,6 +48,12 @@ def _check(r, expect_paging=True):
     assert psnr >= PSNR_MIN, "PSNR %.2f dB" % psnr
     assert err <= MAX_ERR, "max channel error %.5f" % err
     assert r["rays_cuda"] == r["rays_oracle"]
+    # brick requests are integer work: identical sets.  Only a sub-frame whose 509-entry table overflowed (reports
+    # dropped after rehash_count probes, GLHashTable.cpp:170-182) may differ, because WHICH reports are dropped then
+    # depends on the order of the atomics, on the GPU as in the reference
+    assert r["req_mismatch_nodrop"] == 0, r
+    if r["req_drops"] == 0:
+        assert r["req_mismatch"] == 0, r
     assert r["req_mismatch"] <= max(1, r["req_total"] // 200), r
     assert abs(r["samples_cuda"] - r["samples_oracle"]) <= max(64, r["samples_oracle"] // 1000)
     if expect_paging:
@@ -170,12 +176,15 @@ def test_tex3d_sampler_reports_its_error(tvk, oct_u8):
     r = lockstep_render(tvk, p, pool, H.tf_bytes(tf), sampler=1)
     psnr, err = image_errors(r["cuda"], r["oracle"])
     print("TEX3D sampler: PSNR %.2f dB, max err %.5f (%.2f/255)" % (psnr, err, err * 255))
-    assert psnr >= 40.0 and err <= 4.0 / 255.0
+    # the north-star tolerance, not a looser one: hardware filtering is only usable where it stays inside it
+    assert psnr >= PSNR_MIN and err <= MAX_ERR
 
 
+@pytest.mark.parametrize("sampler", [2, 3])
 @pytest.mark.parametrize("which", ["u8_lit", "u16_2d", "u8_iso"])
-def test_quad_packed_pool_is_exact_too(tvk, oct_u8, oct_u16, which):
-    """TVK_SAMPLER_EXACT_Q4 (pool stored as 2x2 (y,z) quads, 2 loads per sample) must give the EXACT results."""
+def test_quad_packed_pool_is_exact_too(tvk, oct_u8, oct_u16, which, sampler):
+    """TVK_SAMPLER_EXACT_Q4 (pool stored as 2x2 (y,z) quads, 2 loads per sample) and TVK_SAMPLER_GATHER (layered
+    array read with four-texel gathers, 1x the memory) must give the EXACT results."""
     if which == "u8_lit":
         tf = _tf(256)
         lo, hi = H.tf_nonzero_limits(tf)
@@ -183,7 +192,7 @@ def test_quad_packed_pool_is_exact_too(tvk, oct_u8, oct_u16, which):
         cam = H.Camera()
         cam.rotation = H.rotation_y(0.6) @ H.rotation_x(0.3)
         p = H.raycast_params(cam, 203, 149, oct_u8["vol"], lighting=True)
-        _check(lockstep_render(tvk, p, pool, H.tf_bytes(tf), sampler=2))
+        _check(lockstep_render(tvk, p, pool, H.tf_bytes(tf), sampler=sampler))
     elif which == "u16_2d":
         n = 256
         v = np.linspace(0, 1, n, dtype=np.float32)
@@ -200,16 +209,44 @@ def test_quad_packed_pool_is_exact_too(tvk, oct_u8, oct_u16, which):
         cam.rotation = H.rotation_x(0.5) @ H.rotation_y(0.4)
         p = H.raycast_params(cam, 144, 112, oct_u16["vol"], render_mode=1, lighting=True,
                              trans_scale=65535.0 / maxv, gradient_scale=8.0)
-        _check(lockstep_render(tvk, p, pool, tfb, sampler=2))
+        _check(lockstep_render(tvk, p, pool, tfb, sampler=sampler))
     else:
         pool = _cold_pool(oct_u8, (8, 8, 8), 2, 100.0, 0.0)
         cam = H.Camera()
         cam.rotation = H.rotation_y(2.1) @ H.rotation_x(-0.4)
         p = H.raycast_params(cam, 180, 140, oct_u8["vol"], render_mode=2, isoval=100.0 / 256.0)
-        r = lockstep_render(tvk, p, pool, H.tf_bytes(_tf(256)), sampler=2)
+        r = lockstep_render(tvk, p, pool, H.tf_bytes(_tf(256)), sampler=sampler)
         d = np.abs(r["cuda"] - r["oracle"]).max(axis=2)
         assert r["oracle"][..., 3].sum() > 500
         assert (d > MAX_ERR).sum() <= max(4, int(0.002 * d.size))
+
+
+@pytest.mark.parametrize("bits", [8, 16])
+def test_gather_pool_is_bitwise_the_exact_pool(tvk, oct_u8, oct_u16, bits):
+    """The layered-array pool (two tld4 gathers per sample) runs the SAME fp32 filter arithmetic as the linear pool:
+    unlit 1D-TF and isosurface frames must be the same bits, the lit frame the same bits as the quad-packed pool's
+    (both take centre + gradient from one shared footprint)."""
+    oc = oct_u8 if bits == 8 else oct_u16
+    maxv = float(oc["minmax"][:, 1].max())
+    n = 256 if bits == 8 else 1024
+    tf = _tf(n)
+    lo, hi = H.tf_nonzero_limits(tf)
+    scale = maxv / (n - 1)
+    cam = H.Camera()
+    cam.rotation = H.rotation_y(0.9) @ H.rotation_x(-0.35)
+    for mode, lighting, ref_sampler in ((0, False, 0), (2, False, 0), (0, True, 2)):
+        imgs = []
+        for sampler in (ref_sampler, 3):
+            if mode == 2:
+                pool = _cold_pool(oc, (8, 8, 8), 2, 0.4 * maxv, 0.0)
+                p = H.raycast_params(cam, 150, 110, oc["vol"], render_mode=2, isoval=0.4 * maxv / float(1 << bits))
+            else:
+                pool = _cold_pool(oc, (8, 8, 8), 0, float(lo) * scale, float(hi) * scale)
+                p = H.raycast_params(cam, 150, 110, oc["vol"], lighting=lighting, trans_scale=float((1 << bits) - 1) / maxv)
+            r = lockstep_render(tvk, p, pool, H.tf_bytes(tf), sampler=sampler)
+            imgs.append(r["cuda"])
+            assert r["oracle"].max() > 0.05
+        assert np.array_equal(imgs[0], imgs[1]), (mode, lighting, float(np.abs(imgs[0] - imgs[1]).max()))
 
 
 def test_api_errors(tvk, oct_u8):

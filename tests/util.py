@@ -97,10 +97,12 @@ def lockstep_render(tvk, params, pool, tf_rgba8, sampler=0, max_subframes=100):
     params.new_view = 1
     tvk.stats(reset=True)
     req_mismatch, req_total, subframes, samples_o, rays_o = 0, 0, 0, 0, 0
+    req_mismatch_nodrop, drops = 0, 0
     for sub in range(max_subframes):
         H.raycast(params, pool, tf_rgba8, frame)
         samples_o += int(frame.stats[0])
         rays_o += int(frame.stats[2])
+        drops += int(frame.stats[3])
         tvk.raycast(to_cuda_params(params))
         params.new_view = 0
         subframes += 1
@@ -108,6 +110,10 @@ def lockstep_render(tvk, params, pool, tf_rgba8, sampler=0, max_subframes=100):
         req_c = {tuple(int(v) for v in r) for r in tvk.read_requests()}
         req_total += len(req_o | req_c)
         req_mismatch += len(req_o ^ req_c)
+        if int(frame.stats[3]) == 0:
+            # no report was dropped for want of a free table entry: the table holds EVERY brick the rays asked for,
+            # whatever the order of the atomics -- the two request sets must then be the same set
+            req_mismatch_nodrop += len(req_o ^ req_c)
         if not req_o and not req_c:
             break
         pool.upload_requests(H.read_requests(pool, frame) if req_o else np.array(sorted(req_c), np.uint32))
@@ -118,7 +124,8 @@ def lockstep_render(tvk, params, pool, tf_rgba8, sampler=0, max_subframes=100):
     pos_c, aux_c = tvk.read_resume()
     st = tvk.stats()
     return dict(cuda=img_c, oracle=frame.image.copy(), subframes=subframes, req_total=req_total,
-                req_mismatch=req_mismatch, samples_cuda=int(st.samples), samples_oracle=samples_o,
+                req_mismatch=req_mismatch, req_mismatch_nodrop=req_mismatch_nodrop, req_drops=drops,
+                samples_cuda=int(st.samples), samples_oracle=samples_o,
                 pos_cuda=pos_c, pos_oracle=frame.pos.copy(), rays_cuda=int(st.rays), rays_oracle=rays_o)
 
 
