@@ -1,22 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- ray samples/s and ms/frame of the bricked ray-march hot path.
-
-Workload at N=1 (BASELINE.json configs[1]): synthetic 512^3 uint8 volume (the reference's own
-"sphere" generator, UVFReader/DataSource.h:361-372, plus a deterministic ripple so that rays do
-not all terminate at the same depth), bricked 64/overlap 2 by the CUDA builder, fully resident
-brick pool, 1D transfer function + early ray termination, 1920x1080, one converged frame per
-step on an orbiting camera (every step is a new view).
+"""bench.py -- ray samples/s and ms/frame of the bricked ray-march hot path on the headline configurations.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-N > 1 (torchrun, one rank per GPU): sort-last.  Every rank owns one 512^3 z-slab of a
-512x512x(512*N) volume (weak scaling), renders its partial image, the partial images are
-exchanged as scan-line stripes (all_to_all over NCCL/NVLink), blended in depth order by the
-compositor kernel and gathered on rank 0.
+N = 1  -> BASELINE.json configs[2]: synthetic 2048^3 uint16 volume (the reference's own CT_SPHERE generator,
+          UVFReader/DataSource.h:361-372), bricked 64^3 / overlap 2 by the CUDA builder (K2), fully resident brick
+          pool, 1920x1080, one converged frame per step on an orbiting camera.  `value` = the 2D-transfer-function
+          frame with lighting; the 1D-TF, 1D-TF lit and isosurface frames of the same volume and configs[1]
+          (512^3 uint8, 1D-TF + ERT) are secondary records of the same line, each with its own clock record.
+N >= 2 -> configs[3]: ONE synthetic 4096^3 uint16 volume (137 GB), cut into N convex boxes on a regular grid, one per
+          GPU (torchrun, one rank per GPU), 3840x2160, 1D-TF lit, sort-last direct-send compositing fused into the
+          kernels over NVLink peer memory.  Strong scaling: the volume is the same at every N.
+The line also carries: `parity` (pixel crops of the timed frame re-rendered by the CPU oracle on a host copy of the
+same pool: PSNR / max error; brick-request sets of a cold-pool sub-frame compared with the oracle's), `k2` (builder
+and 2-D histogram kernels), `k3` (pager), `roofline`, `cpu_baseline`, `e2e` (the reference-facing renderer API with host
+buffers: cold working set paged in from pinned host memory, painted until converged, frame read back -- every step).
 
---impl reference times the CPU restatement of the reference's GLSL ray-marcher (oracle/, OpenMP
-on all host cores) because the reference's GL path cannot run here (no libGL/Mesa/Qt; see
-DESIGN.md); it is a reported baseline, not the target.
+--impl reference times the CPU restatement of the reference's GLSL ray-marcher (oracle/, OpenMP on all host cores)
+on crops of the same frames of the same volume, built by the oracle's own builder on the host: the reference's GL
+path cannot run here (no libGL/Mesa/Qt on the box).  It is a reported baseline, not the target.
+
+TVK_BENCH_SHRINK=k (test runs only) divides every volume edge by k; the line then names the volume it really used.
 """
 import argparse
 import ctypes as C
@@ -33,13 +37,21 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-VOL = (512, 512, 512)
-WIDTH, HEIGHT = 1920, 1080
 BRICK, OVERLAP = 64, 2
-BYTES_PER_SAMPLE = 1.2136 * 1 / 2.0     # 1.2136*bpv/(2*sampleRateModifier), uint8, srm 1
-BYTES_PER_RAY = 16.0                    # RGBA32F result write
-CPU_SAMPLE = (1920, 1080)               # the CPU arm renders full frames (a frame is < 1 s on 16 cores)
-CPU_STEPS = 24                          # ~0.47 s per 1080p frame on 16 cores -> ~11 s of CPU work
+SHRINK = max(1, int(os.environ.get("TVK_BENCH_SHRINK", "1")))
+C3_VOL = (2048 // SHRINK,) * 3
+C4_VOL = (4096 // SHRINK,) * 3
+C2_VOL = (512 // min(SHRINK, 4),) * 3
+CROP_TILES, CROP_SIZE = 64, 32            # parity / CPU arm: 64 tiles of 32x32 pixels spread over the frame
+CPU_STEPS = 6
+E2E_HASH = int(os.environ.get("TVK_E2E_HASH", "4093"))
+
+
+def gradient_scale(vol):
+    """fGradientScale of the workload: the sphere's value falls by 2/size per voxel (normalised), which is also its
+    central difference / 2 at LOD 0 -- the steepest gradient of the volume.  (A UVF file carries 1 / the maximum of
+    the 2-D histogram pass instead; the K2 record reports that value, the e2e leg uses it.)"""
+    return float(vol[0]) / 2.0
 
 
 def peaks():
@@ -64,10 +76,10 @@ def emit_line(line):
         os.write(_REAL_STDOUT, text.encode())
 
 
-def bench_tf():
-    """TransferFunction1D::SetStdFunction(0.5,0.5) colours with a 10x thinner alpha."""
-    from_oracle = False
-    n = 256
+# --------------------------------------------------------------------------- scene description (shared by both arms)
+def tf1d_std(n):
+    """TransferFunction1D::SetStdFunction(0.5, 0.5) (TransferFunction1D.cpp:81-112) with a 10x thinner alpha, n entries;
+    returns (rgba8 [n][4], first, last non-zero alpha index)."""
     t = np.zeros((n, 4), np.float32)
     ic, ig = int((n - 1) * 0.5), int((n - 1) * 0.5)
     start, end = ic - ig // 2, ic + ig // 2
@@ -78,42 +90,85 @@ def bench_tf():
     t[:, 3] *= np.float32(0.1)
     t[:, 1] *= np.float32(0.8)
     rgba = (np.clip(t, 0, 1) * np.float32(255)).astype(np.uint8)     # GetByteArray truncation
-    nz = np.nonzero(t[:, 3] != 0)[0]
+    nz = np.nonzero(rgba[:, 3] != 0)[0]
     return rgba, float(nz[0]), float(nz[-1])
 
 
-def volume_numpy(size, z0=0, zn=None, ztotal=None):
-    """sphere + ripple, uint8, [z][y][x]; z0/zn select a slab of a volume ztotal deep."""
-    sx, sy, sz = size
-    ztotal = sz if ztotal is None else ztotal
-    zn = sz if zn is None else zn
-    f = np.float32
-    x = (f(0.5) - np.arange(sx, dtype=f) / f(sx))[None, None, :]
-    y = (f(0.5) - np.arange(sy, dtype=f) / f(sy))[None, :, None]
-    z = (f(0.5) - (np.arange(zn, dtype=f) + f(z0)) / f(ztotal))[:, None, None]
-    d = np.sqrt(x * x + y * y + z * z)
-    v = np.maximum(f(0), (f(0.5) - d) * f(255) * f(2))
-    rip = f(18) * np.sin(x * f(40)) * np.sin(y * f(34)) * np.sin(z * f(46))
-    return np.clip(v + rip * (v > 0), 0, 255).astype(np.uint8)
+def tf2d(n=4096):
+    """Pre-rasterised 2D transfer function [256 gradient rows][n value bins][4] (value ramp x gradient
+    window) and its non-zero limits (value lo, value hi, gradient lo, gradient hi) in table units.  Row r is fetched for
+    1 - |grad| * fGradientScale in [r/256, (r+1)/256): row 0 = the steepest gradients."""
+    v = np.linspace(0, 1, n, dtype=np.float32)
+    g = np.linspace(0, 1, 256, dtype=np.float32)
+    t = np.zeros((256, n, 4), np.float32)
+    t[..., 0] = v[None, :]
+    t[..., 1] = 0.3 + 0.7 * (1.0 - g[:, None])
+    t[..., 2] = 0.4
+    t[..., 3] = np.clip((v[None, :] - 0.25) * 0.2, 0, 1) * (0.3 + 0.7 * (1.0 - g[:, None]))
+    rgba = (np.clip(t, 0, 1) * np.float32(255)).astype(np.uint8)
+    cols = np.nonzero(rgba[..., 3].max(axis=0) != 0)[0]
+    return rgba, (float(cols[0]), float(cols[-1]), 0.0, 255.0)
 
 
-def volume_torch(size, device, z0=0, zn=None, ztotal=None, origin=None, total=None):
-    """size = (sx, sy, sz) of the piece to generate; origin / total place it inside a larger volume (the z0 / zn /
-    ztotal form is the z-only special case)."""
-    import torch
-    sx, sy, sz = size
-    if origin is None:
-        origin = (0, 0, z0)
-        total = (sx, sy, sz if ztotal is None else ztotal)
-        sz = sz if zn is None else zn
-    tx, ty, tz = total
-    x = (0.5 - (torch.arange(sx, device=device, dtype=torch.float32) + origin[0]) / tx)[None, None, :]
-    y = (0.5 - (torch.arange(sy, device=device, dtype=torch.float32) + origin[1]) / ty)[None, :, None]
-    z = (0.5 - (torch.arange(sz, device=device, dtype=torch.float32) + origin[2]) / tz)[:, None, None]
-    d = torch.sqrt(x * x + y * y + z * z)
-    v = torch.clamp((0.5 - d) * 255.0 * 2.0, min=0)
-    rip = 18.0 * torch.sin(x * 40.0) * torch.sin(y * 34.0) * torch.sin(z * 46.0)
-    return torch.clamp(v + rip * (v > 0), 0, 255).to(torch.uint8).contiguous()
+def orbit_angle(k, steps):
+    return 0.35 + 2.0 * math.pi * (k % max(steps, 1)) / max(steps, 1)
+
+
+def camera_for_step(H, k, steps):
+    cam = H.Camera()
+    cam.rotation = H.rotation_y(orbit_angle(k, steps)) @ H.rotation_x(0.35)
+    return cam
+
+
+def crop_rects(w, h):
+    """CROP_TILES rectangles of CROP_SIZE^2 pixels on a regular lattice that covers the frame."""
+    n = int(round(math.sqrt(CROP_TILES)))
+    out = []
+    for j in range(n):
+        for i in range(n):
+            cx, cy = int((i + 0.5) * w / n), int((j + 0.5) * h / n)
+            x0, y0 = max(0, cx - CROP_SIZE // 2), max(0, cy - CROP_SIZE // 2)
+            out.append((x0, y0, min(w, x0 + CROP_SIZE), min(h, y0 + CROP_SIZE)))
+    return out
+
+
+MODES = {"2d_lit": (1, True), "1d": (0, False), "1d_lit": (0, True), "iso": (2, False)}     # name -> (render mode, lighting)
+MODE_NAMES = {"2d_lit": "2D-TF with lighting", "1d": "1D-TF", "1d_lit": "1D-TF with lighting", "iso": "isosurface"}
+
+
+def mode_setup(mode, rmax, bits, gscale):
+    """-> dict(kw for raycast_params, tf table, visibility args) for a volume whose largest value is rmax."""
+    n = 256 if bits == 8 else 4096
+    tmax = float((1 << bits) - 1)
+    rm, lit = MODES[mode]
+    resc = rmax / float(n - 1)                                        # GLGridLeaper.cpp:652-659
+    if rm == 0:
+        tf, lo, hi = tf1d_std(n)
+        return dict(kw=dict(render_mode=0, lighting=lit, trans_scale=tmax / rmax), tf=tf, vis=(0, lo * resc, hi * resc, 0.0, 0.0))
+    if rm == 1:
+        tf, nz = tf2d(n)
+        return dict(kw=dict(render_mode=1, lighting=lit, trans_scale=tmax / rmax, gradient_scale=gscale), tf=tf,
+                    vis=(1, nz[0] * resc, nz[1] * resc, -1e308, 1e308), nz=nz)
+    return dict(kw=dict(render_mode=2, isoval=(rmax / 2.0) / float(1 << bits)), tf=None, vis=(2, rmax / 2.0, 0.0, 0.0, 0.0))
+
+
+def pool_gb(vol, n):
+    b = [math.ceil(v / 60.0) for v in vol]
+    return 1.15 * b[0] * b[1] * b[2] * 64 ** 3 * 2 / n / 1e9
+
+
+def workload_config(n, mode):
+    if n == 1:
+        v, (w, h), what = C3_VOL, (1920, 1080), "BASELINE configs[2]"
+    else:
+        v, (w, h), what = C4_VOL, (3840, 2160), "BASELINE configs[3]"
+    return {"workload": "%s: synthetic %dx%dx%d uint16 (reference CT_SPHERE generator), brick 64/overlap 2, multi-LOD, %s, %dx%d, "
+                        "1 converged frame/step, orbiting camera" % (what, v[0], v[1], v[2], MODE_NAMES[mode], w, h),
+            "volume": list(v), "voxel_type": "uint16", "resolution": [w, h], "render_mode": MODE_NAMES[mode],
+            "sample_rate_modifier": 1.0, "sampler": os.environ.get("TVK_SAMPLER", "gather"),
+            "l2": "inputs larger than L2 (resident pool of %.1f GB per GPU) + 256 MB L2 flush between steps" % pool_gb(v, n),
+            "parallelism": "single GPU" if n == 1 else "sort-last, %d convex boxes on a regular grid (one per GPU) + direct-send "
+                           "compositing fused into the kernels (NVLink peer stores)" % n}
 
 
 class ClockSampler(threading.Thread):
@@ -127,7 +182,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
@@ -152,167 +207,540 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def camera_for_step(H, k, steps, n_slabs=1):
-    cam = H.Camera()
-    ang = 0.35 + 2.0 * math.pi * (k % max(steps, 1)) / max(steps, 1)
-    cam.rotation = H.rotation_y(ang) @ H.rotation_x(0.35)
-    return cam
+def image_errors(a, b):
+    d = np.abs(a.astype(np.float64) - b.astype(np.float64))
+    mse = float((d * d).mean())
+    return (99.0 if mse == 0 else 10.0 * math.log10(1.0 / mse)), float(d.max())
 
 
-# --------------------------------------------------------------------------- CPU arm
-def oracle_setup(z0=0, ztotal=None):
+# --------------------------------------------------------------------------- CPU arm (test infrastructure: oracle/)
+def oracle_scene(vol, bits):
+    """Generates the sphere on the host, builds the octree with the oracle builder and makes every brick resident."""
     from oracle import host as H
     from oracle import oracle as O
-    vol = volume_numpy(VOL, z0=z0, ztotal=ztotal)
-    oc = O.build_octree(vol, BRICK, OVERLAP)
-    pool = H.OraclePool(oc, (10, 10, 9))
-    pool.upload_first_brick()
-    req = []
-    for i in range(pool.total - 1):
-        req.append(pool.index_to_xyzl(i))
-    pool.upload_requests(req)
-    return H, O, oc, pool
-
-
-def cpu_frame(H, pool, tf_rgba, lo, hi, k, steps, w, h):
-    pool.recompute_visibility(0, lo, hi)
-    p = H.raycast_params(camera_for_step(H, k, steps), w, h, pool.vol)
-    frame = H.OracleFrame(w, h)
     t0 = time.perf_counter()
-    H.raycast(p, pool, tf_rgba, frame)
-    dt = time.perf_counter() - t0
-    return int(frame.stats[0]), int(frame.stats[2]), dt, frame
+    raw = H.gen_sphere(vol, np.uint8 if bits == 8 else np.uint16)
+    oc = O.build_octree(raw, BRICK, OVERLAP)
+    del raw
+    p = oc["plan"]
+    lod_count = H.largest_single_brick_lod(p) + 1
+    total = int(p.lod_offset[lod_count - 1]) + 1
+    nbx, nby = int(p.lod_bricks[0][0]) + 1, int(p.lod_bricks[0][1]) + 1
+    cap = (nbx, nby, -(-total // (nbx * nby)))
+    slots = np.arange(total, dtype=np.uint32)
+    slots[total - 1] = cap[0] * cap[1] * cap[2] - 1
+    mb = tuple(int(v) for v in oc["sizes"][:total].max(axis=0))
+    pool = H.ResidentPool(vol, bits // 8, OVERLAP, mb, cap, lod_count, oc["store"], oc["offsets"], oc["sizes"], slots,
+                          np.zeros(total, np.uint32))
+    pool.minmax = np.ascontiguousarray(oc["minmax"][:total])
+    pool.slots = slots
+    rmax = float(oc["minmax"][:int(p.lod_offset[1]), 1].max())
+    del oc
+    return H, pool, rmax, time.perf_counter() - t0
+
+
+def oracle_visibility(H, pool, vis):
+    """metadata of a fully resident pool under a visibility setting."""
+    from oracle import oracle as O
+    v = H.Visibility(*vis)
+    lo, hi = pool.minmax[:, 0], pool.minmax[:, 1]
+    cd = ((vis[1] >= lo) & (vis[1] <= hi)) if vis[0] == 2 else ((vis[2] >= lo) & (vis[1] <= hi))
+    # resident bricks keep their slot if they contain data, else they read EMPTY (RecomputeVisibilityForBrickPool,
+    # GLVolumePool.cpp:992-1018); everything is resident here, so the octree pass has nothing left to derive
+    meta = np.where(cd, pool.slots + np.uint32(3), np.uint32(2)).astype(np.uint32)
+    counts = np.zeros(4, np.uint32)
+    O.lib().orc_visibility((C.c_uint32 * 3)(*pool.vol), (C.c_uint32 * 3)(*pool.max_brick), C.c_uint32(pool.overlap),
+                           C.c_uint32(pool.lod_count), C.byref(v), pool.minmax.ctypes.data_as(C.c_void_p), None,
+                           meta.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p))
+    pool.meta = np.ascontiguousarray(meta)
+
+
+def oracle_crops(H, params, pool, tf, w, h):
+    """Renders the crop rectangles of one frame; -> (frame, samples, seconds)."""
+    frame = H.OracleFrame(w, h, params.hash_table_size)
+    params.new_view = 1
+    table = tf if tf is not None else np.zeros((1, 4), np.uint8)
+    samples, t0 = 0, time.perf_counter()
+    for i, r in enumerate(crop_rects(w, h)):
+        H.raycast(params, pool, table, frame, rect=r, clear_hash=(i == 0))
+        samples += int(frame.stats[0])
+    return frame, samples, time.perf_counter() - t0
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    # torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use every host core
     cores = os.cpu_count() or 1
-    os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ["OMP_NUM_THREADS"] = str(cores)      # torchrun pins OMP_NUM_THREADS=1 for its workers
     try:
         C.CDLL("libgomp.so.1").omp_set_num_threads(cores)
     except OSError:
         pass
-    H, O, oc, pool = oracle_setup()
-    tf_rgba, lo, hi = bench_tf()
-    cores = os.cpu_count() or 1
-    w, h = CPU_SAMPLE
-    for k in range(args.warmup):
-        cpu_frame(H, pool, tf_rgba, lo, hi, k, args.steps, w, h)
+    n = args.gpus
+    if n == 1:
+        vol, (w, h), mode, slab, gdims = C3_VOL, (1920, 1080), "2d_lit", None, C3_VOL
+    else:
+        # the host cannot hold 4096^3: its bounded sample is box 0 of the 8-box partition (the same box at every N)
+        from imagevis3d_b200 import sortlast as SL
+        slab = SL.block_partition(C4_VOL, 8, halo=64)[0]
+        vol, (w, h), mode, gdims = slab["local_dims"], (3840, 2160), "1d_lit", C4_VOL
+    H, pool, rmax, t_setup = oracle_scene(vol, 16)
+    ms = mode_setup(mode, rmax if n == 1 else 65535.0, 16, gradient_scale(gdims))
+    oracle_visibility(H, pool, ms["vis"])
     samples, secs = 0, 0.0
-    for k in range(args.steps):
-        s, r, dt, _ = cpu_frame(H, pool, tf_rgba, lo, hi, k, args.steps, w, h)
-        samples += s
-        secs += dt
+    for k in range(-args.warmup, args.steps):
+        cam = camera_for_step(H, max(k, 0), args.steps)
+        p = H.raycast_params(cam, w, h, gdims, slab=slab, **ms["kw"])
+        _, s, dt = oracle_crops(H, p, pool, ms["tf"], w, h)
+        if k >= 0:
+            samples += s
+            secs += dt
     value = samples / secs
-    sample = "same volume/TF/orbit, full %dx%d frames, %d steps" % (w, h, args.steps)
-    line = {"impl": "reference", "metric": "ray samples/s", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+    sample = ("%d crops of %dx%d pixels of every frame (same volume generator, camera orbit, transfer function); volume %dx%dx%d "
+              "generated and bricked on the host by the oracle builder in %.0f s (untimed)" % (CROP_TILES, CROP_SIZE, CROP_SIZE, vol[0], vol[1], vol[2], t_setup))
+    if n > 1:
+        sample += "; box 0 of the 8-box partition of the 4096^3 volume (the host cannot hold all of it)"
+    line = {"impl": "reference", "metric": "ray samples/s", "value": value, "unit": "samples/s", "n_gpus": n,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(n, mode),
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
-# N = 1: BASELINE configs[1].  N > 1: the sort-last configuration (configs[3]) scaled so that every GPU owns
-# exactly 512^3 voxels (weak scaling): the global volume doubles along x, then y, then z, cut into a regular grid of
-# boxes at multiples of 64 voxels (sortlast.block_partition), rendered at the 3840x2160 that configs[3] names.
-GLOBAL_BY_N = {1: (512, 512, 512), 2: (1024, 512, 512), 4: (1024, 1024, 512), 8: (1024, 1024, 1024)}
-
-
-def global_config(n):
-    g = GLOBAL_BY_N.get(n, (512, 512, 512 * n))
-    return g, ((1920, 1080) if n == 1 else (3840, 2160))
-
-
-def workload_config(n):
-    g, (w, h) = global_config(n)
-    return {"workload": "synthetic %dx%dx%d uint8 (sphere+ripple), brick 64/overlap 2, 1D-TF + ERT, %dx%d, "
-                        "1 converged frame/step, orbiting camera" % (g[0], g[1], g[2], w, h),
-            "volume": list(g), "resolution": [w, h], "render_mode": "1D-TF",
-            "lighting": False, "sample_rate_modifier": 1.0, "sampler": os.environ.get("TVK_SAMPLER", "q4"),
-            "l2": "inputs larger than L2 (236 MB pool) + 256 MB L2 flush between steps",
-            "parallelism": "single GPU" if n == 1 else "sort-last, %d boxes on a regular grid + direct-send compositing" % n}
-
-
 # --------------------------------------------------------------------------- GPU arm
+def sphere_torch(local_dims, origin, total, bits, device):
+    """The reference's CT_SPHERE volume (UVFReader/DataSource.h:361-372), piece local_dims at `origin` of a volume
+    `total`, generated in HBM with the reference's fp32 operations (bit-equal to oracle gen_sphere)."""
+    import torch
+    sx, sy, sz = [int(v) for v in local_dims]
+    tmax = 255.0 if bits == 8 else 65535.0
+    out = torch.empty((sz, sy, sx), dtype=torch.uint8 if bits == 8 else torch.uint16, device=device)
+    f = torch.float32
+    dx = (0.5 - (torch.arange(sx, device=device, dtype=f) + float(origin[0])) / float(total[0]))[None, None, :]
+    dy = (0.5 - (torch.arange(sy, device=device, dtype=f) + float(origin[1])) / float(total[1]))[None, :, None]
+    xy = dx * dx + dy * dy
+    step = max(1, (64 << 20) // max(1, sx * sy))
+    for z0 in range(0, sz, step):
+        zn = min(step, sz - z0)
+        dz = (0.5 - (torch.arange(zn, device=device, dtype=f) + float(origin[2] + z0)) / float(total[2]))[:, None, None]
+        v = torch.clamp(((0.5 - torch.sqrt(xy + dz * dz)) * tmax) * 2.0, min=0)
+        out[z0:z0 + zn] = v.to(torch.int32).to(out.dtype)
+    return out
+
+
+class Scene:
+    """A bricked volume resident in one context's pool (kernel-level C ABI)."""
+
+    def __init__(self, tvk, raw, dims, bits, want_host_copy):
+        import torch
+        self.tvk, self.dims, self.bits = tvk, tuple(int(v) for v in dims), bits
+        bpv = bits // 8
+        info = tvk.build_octree(raw_dptr=raw.data_ptr(), volume_size=self.dims, bpv=bpv, brick=BRICK, overlap=OVERLAP)
+        self.build_ms = tvk.build_last_ms()
+        self.info = info
+        off, sizes = tvk.build_toc()
+        mm = tvk.build_minmax()
+        self.lod_count = next(l for l in range(info.lod_count)
+                              if info.lod_bricks[l][0] * info.lod_bricks[l][1] * info.lod_bricks[l][2] == 1) + 1
+        total = self.total = int(info.lod_offset[self.lod_count - 1]) + 1
+        nbx, nby = int(info.lod_bricks[0][0]) + 1, int(info.lod_bricks[0][1]) + 1
+        self.cap = (nbx, nby, -(-total // (nbx * nby)))
+        self.maxb = tuple(int(v) for v in sizes[:total].max(axis=0))
+        self.off, self.sizes, self.mm = off[:total], sizes[:total], mm[:total]
+        self.rmax = float(mm[:int(info.lod_offset[1]), 1].max())
+        self.hist1d_size = len(tvk.build_hist1d())
+        self.store_bytes = int(info.total_bytes)
+        self.blob = None
+        if want_host_copy:
+            self.blob = torch.empty(self.store_bytes, dtype=torch.uint8, pin_memory=True)
+            tvk._ck(tvk.lib.tvk_build_get_bricks(tvk.h, C.c_void_p(self.blob.data_ptr()), C.c_uint64(0), C.c_uint64(self.blob.numel())), "get_bricks")
+
+    def fill_pool(self, sampler):
+        """creates the pool and makes every brick resident (the raw volume may have been freed by now)"""
+        tvk, total = self.tvk, self.total
+        got = tvk.pool_create(self.dims, self.maxb, OVERLAP, self.bits // 8, self.cap, self.lod_count, sampler)
+        assert got == total
+        store = tvk.build_store_ptr()
+        self.slots = np.arange(total, dtype=np.uint32)
+        self.slots[total - 1] = self.cap[0] * self.cap[1] * self.cap[2] - 1          # coarsest brick pinned in the last slot
+        tvk.pool_upload_device(self.slots, [store + int(o) for o in self.off], self.sizes)
+        tvk.set_minmax(self.mm)
+
+    def set_mode(self, ms):
+        self.tvk.set_metadata(self.slots + 3)
+        if ms["tf"] is not None:
+            (self.tvk.set_tf1d if ms["tf"].ndim == 2 else self.tvk.set_tf2d)(ms["tf"])
+        self.tvk.recompute_visibility(*ms["vis"])
+
+    def oracle_pool(self, H):
+        """host copy of the device pool for the CPU checks (bricks come from the CUDA builder, which the tests prove
+        bit-identical to the oracle builder and the reference)."""
+        return H.ResidentPool(self.dims, self.bits // 8, OVERLAP, self.maxb, self.cap, self.lod_count, self.blob.numpy(),
+                              self.off, self.sizes, self.slots, self.tvk.get_metadata())
+
+
+def timed_frames(tvk, torch, flush, params, steps, warmup, local):
+    """warm-up + `steps` timed frames; -> dict(ms_per_frame (K1 CUDA events), samples, rays, clocks, launches)."""
+    for k in range(warmup):
+        flush.zero_()
+        torch.cuda.synchronize()
+        tvk.raycast(params[k % len(params)])
+        tvk.synchronize()
+    tvk.stats(reset=True)
+    l0 = tvk.stats().launches
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    ms = 0.0
+    for k in range(steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        tvk.raycast(params[k % len(params)])
+        tvk.synchronize()
+        ms += tvk.stats().last_raycast_ms
+    st = tvk.stats()
+    return dict(ms_per_frame=ms / steps, samples=int(st.samples), rays=int(st.rays), clocks=sampler.stop(),
+                launches=int(st.launches - l0), samples_per_s=int(st.samples) / (ms * 1e-3))
+
+
+def roofline(rec, bpv, steps, peak, peak_src, traffic_key):
+    alg = (rec["samples"] * 1.2136 * bpv / 2.0 + rec["rays"] * 16.0) / steps       # SURVEY 8(d)
+    achieved = alg / (rec["ms_per_frame"] * 1e-3) / 1e9
+    traffic, issue = None, None
+    try:
+        k = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))[traffic_key]
+        traffic = k["dram_bytes_per_launch"]
+        issue = {"warp_instructions_per_sample": k["warp_instructions_per_launch"] / k["samples_in_capture"],
+                 "issue_active_pct": k.get("issue_active_pct"), "source": k["source"]}
+    except Exception:       # noqa: BLE001
+        pass
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+            "note": "%.4f B/sample + 16 B/ray (SURVEY 8d); the kernel is bound by instruction issue and texture-fetch latency, not by "
+                    "HBM -- see `issue` and DESIGN.md" % (1.2136 * bpv / 2.0), "issue": issue}
+
+
+def parity_crops(H, scene, params, ms, img_gpu, w, h, pool=None):
+    """Crops of the frame the GPU just rendered, re-rendered by the oracle on a host copy of the same pool."""
+    if pool is None:
+        pool = scene.oracle_pool(H)
+    else:
+        pool.meta = np.ascontiguousarray(scene.tvk.get_metadata(), np.uint32)
+    q = H.RaycastParams()
+    C.memmove(C.byref(q), C.byref(params), C.sizeof(q))
+    frame, samples, secs = oracle_crops(H, q, pool, ms["tf"], w, h)
+    psnr_min, err_max, npx, lit = 99.0, 0.0, 0, 0
+    for (x0, y0, x1, y1) in crop_rects(w, h):
+        ps, er = image_errors(img_gpu[y0:y1, x0:x1], frame.image[y0:y1, x0:x1])
+        psnr_min, err_max, npx = min(psnr_min, ps), max(err_max, er), npx + (x1 - x0) * (y1 - y0)
+        lit += int((frame.image[y0:y1, x0:x1, 3] > 0).sum())
+    return pool, dict(crops=CROP_TILES, crop_pixels=npx, crop_pixels_hit=lit, psnr_db_min_over_crops=psnr_min, max_abs_err=err_max,
+                      max_abs_err_255=err_max * 255.0, within_tolerance=bool(psnr_min >= 45.0 and err_max <= 2.0 / 255.0),
+                      oracle_samples=samples, oracle_seconds=secs)
+
+
+def parity_requests(H, scene, pool, params, ms, w, h):
+    """One sub-frame from a COLD pool (only the pinned coarsest brick resident) on both sides with a request table
+    large enough that no report is dropped: the two request sets must be the same set."""
+    tvk = scene.tvk
+    q = H.RaycastParams()
+    C.memmove(C.byref(q), C.byref(params), C.sizeof(q))
+    q.hash_table_size, q.rehash_count, q.new_view = 65521, 32, 1
+    meta_res = tvk.get_metadata()
+    last = int(scene.total - 1)
+    cold = np.where(meta_res >= 3, 0, meta_res).astype(np.uint32)
+    cold[last] = meta_res[last]
+    tvk.set_metadata(cold)
+    p2 = type(params)()
+    C.memmove(C.byref(p2), C.byref(q), C.sizeof(q))
+    tvk.raycast(p2)
+    req_g = {tuple(int(v) for v in r) for r in tvk.read_requests(cap=65521)}
+    tvk.set_metadata(meta_res)
+    keep = pool.meta
+    pool.meta = np.ascontiguousarray(cold)
+    frame = H.OracleFrame(w, h, q.hash_table_size)
+    H.raycast(q, pool, ms["tf"] if ms["tf"] is not None else np.zeros((1, 4), np.uint8), frame)
+    req_o = {tuple(int(v) for v in r) for r in H.read_requests(pool, frame, cap=65521)}
+    pool.meta = keep
+    return dict(cold_subframe_requests_gpu=len(req_g), cold_subframe_requests_oracle=len(req_o),
+                oracle_dropped_reports=int(frame.stats[3]), identical=bool(req_g == req_o), symmetric_difference=len(req_g ^ req_o),
+                what="full 1920x1080 sub-frame from a pool that holds only the pinned coarsest brick, request table of 65521 entries")
+
+
 def run_gpu(args, rank, world):
     import torch
     import torch.distributed as dist
     from imagevis3d_b200 import _lib as L
     from imagevis3d_b200.context import TvkContext
     from imagevis3d_b200 import hostmath as HM
+    from imagevis3d_b200 import sortlast as SL
 
-    global WIDTH, HEIGHT
-    GLOBAL, (WIDTH, HEIGHT) = global_config(world)
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) must not join it
+        # stdout carries exactly one JSON line: whatever a library writes to file descriptor 1 (NCCL's banner) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        # ... and whatever a library still writes to file descriptor 1 goes to stderr: the JSON line is written to the
-        # saved descriptor at the end
         sys.stdout.flush()
         global _REAL_STDOUT
         _REAL_STDOUT = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
-    tvk = TvkContext(local)
-    if world > 1:
-        # K1, NCCL and the compositor stay stream-ordered on ONE explicit stream (torch's legacy default stream has
-        # handle 0, which tvk_set_stream reads as "use your own stream")
-        work_stream = torch.cuda.Stream(device=dev)
-        torch.cuda.set_stream(work_stream)
-        tvk.set_stream(work_stream.cuda_stream)
-    sampler = {"exact": L.SAMPLER_EXACT, "tex3d": L.SAMPLER_TEX3D, "q4": L.SAMPLER_EXACT_Q4, "gather": L.SAMPLER_GATHER}[os.environ.get("TVK_SAMPLER", "q4")]
-
-    # ---- untimed set-up: synthesize the (slab of the) volume in HBM, build bricks, fill the pool
-    from imagevis3d_b200 import sortlast as SL
-    parts = SL.block_partition(GLOBAL, world, halo=64)          # world^(1/3)-ish boxes per ray instead of `world` slabs
-    part = parts[rank]
-    LOCAL = part["local_dims"] if world > 1 else VOL
-    raw = volume_torch(LOCAL, dev, origin=part["s"], total=GLOBAL)
-    torch.cuda.synchronize()
-    t_b0 = time.perf_counter()
-    info = tvk.build_octree(raw_dptr=raw.data_ptr(), volume_size=LOCAL, bpv=1, brick=BRICK, overlap=OVERLAP)
-    t_build = time.perf_counter() - t_b0
-    off, sizes = tvk.build_toc()
-    mm = tvk.build_minmax()
-    lod_count = next(l for l in range(info.lod_count)
-                     if info.lod_bricks[l][0] * info.lod_bricks[l][1] * info.lod_bricks[l][2] == 1) + 1
-    total_needed = int(info.lod_offset[lod_count - 1]) + 1
-    nbx, nby = int(info.lod_bricks[0][0]) + 1, int(info.lod_bricks[0][1]) + 1
-    cap = (10, 10, 9) if world == 1 else (nbx, nby, -(-total_needed // (nbx * nby)))
-    total = tvk.pool_create(LOCAL, (BRICK,) * 3, OVERLAP, 1, cap, lod_count, sampler)
-    store = tvk.build_store_ptr()
-    slots = np.arange(total, dtype=np.uint32)
-    slots[total - 1] = cap[0] * cap[1] * cap[2] - 1          # coarsest brick pinned in the last slot
-    tvk.pool_upload_device(slots, [store + int(o) for o in off[:total]], sizes[:total])
-    tvk.set_metadata(slots + 3)
-    tvk.set_minmax(mm[:total])
-    tf_rgba, lo, hi = bench_tf()
-    tvk.set_tf1d(tf_rgba)
-    tvk.recompute_visibility(0, lo, hi)
-
-    # host copies for the e2e leg (pinned) and the CPU baseline
-    blob = torch.empty(int(info.total_bytes), dtype=torch.uint8, pin_memory=True)
-    tvk._ck(tvk.lib.tvk_build_get_bricks(tvk.h, C.c_void_p(blob.data_ptr()), C.c_uint64(0), C.c_uint64(blob.numel())), "get_bricks")
-    meta_host = tvk.get_metadata()
-    img8_host = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, pin_memory=True)
-
+    sampler = {"exact": L.SAMPLER_EXACT, "tex3d": L.SAMPLER_TEX3D, "q4": L.SAMPLER_EXACT_Q4,
+               "gather": L.SAMPLER_GATHER}[os.environ.get("TVK_SAMPLER", "gather")]
+    peak, peak_src = peaks()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    steps, warmup = args.steps, max(args.warmup, 1)
+    if world == 1:
+        emit_line(run_single(args, torch, TvkContext, HM, dev, local, sampler, peak, peak_src, flush, steps, warmup))
+        return
+    line = run_sortlast(args, torch, dist, TvkContext, HM, SL, dev, local, rank, world, sampler, peak, peak_src, flush, steps, warmup)
+    if rank == 0:
+        emit_line(line)
+    dist.destroy_process_group()
 
-    def params_for(k):
-        cam = camera_for_step(HM, k, args.steps)
-        if world == 1:
-            return HM.raycast_params(cam, WIDTH, HEIGHT, VOL)
-        return HM.raycast_params(cam, WIDTH, HEIGHT, GLOBAL, slab=part)
 
-    class _CAI:                      # zero-copy torch view of the renderer's device image
+def run_single(args, torch, TvkContext, HM, dev, local, sampler, peak, peak_src, flush, steps, warmup):
+    W, Hh = 1920, 1080
+    skey = os.environ.get("TVK_SAMPLER", "gather")
+    tvk = TvkContext(local)
+    raw = sphere_torch(C3_VOL, (0, 0, 0), C3_VOL, 16, dev)
+    torch.cuda.synchronize()
+    scene = Scene(tvk, raw, C3_VOL, 16, want_host_copy=not args.no_cpu)
+    # K2 record: builder kernels (pyramid + brick cut + min/max + 1-D histogram) and the 2-D histogram, CUDA events
+    voxels = float(C3_VOL[0]) * C3_VOL[1] * C3_VOL[2]
+    tf_bins = max(1, min(scene.hist1d_size, 4096))
+    sk2 = ClockSampler(local)
+    sk2.start()
+    _, max_grad = tvk.build_hist2d(tf_bins, scene.rmax)
+    h2_ms = tvk.build_hist2d_last_ms()
+    k2 = {"volume": list(C3_VOL), "voxel_type": "uint16", "builder_ms": scene.build_ms, "hist2d_ms": h2_ms,
+          "builder_algorithmic_GBps": 2.387 * 2 * voxels / (scene.build_ms * 1e-3) / 1e9,
+          "builder_frac_of_hbm_peak": 2.387 * 2 * voxels / (scene.build_ms * 1e-3) / 1e9 / peak,
+          "hist2d_algorithmic_GBps": 2 * 2 * voxels / (h2_ms * 1e-3) / 1e9,
+          "hist2d_frac_of_hbm_peak": 2 * 2 * voxels / (h2_ms * 1e-3) / 1e9 / peak, "max_gradient_magnitude": max_grad,
+          "one_over_max_gradient": (1.0 / max_grad) if max_grad else None, "workload_gradient_scale": gradient_scale(C3_VOL),
+          "bricks": int(scene.info.total_bricks), "store_bytes": scene.store_bytes,
+          "note": "one run each, CUDA events around the kernels (tvk_build_last_ms / tvk_build_hist2d_last_ms); algorithmic bytes: "
+                  "2.387*bpv per voxel for the builder, 2*bpv for the two histogram passes (SURVEY 8d)",
+          "clocks": sk2.stop()}
+    del raw
+    torch.cuda.empty_cache()
+    scene.fill_pool(sampler)
+    tvk.build_release()
+
+    records, frames = {}, {}
+    for mode in ("2d_lit", "1d", "1d_lit", "iso"):
+        ms = mode_setup(mode, scene.rmax, 16, gradient_scale(C3_VOL))
+        scene.set_mode(ms)
+        params = [HM.raycast_params(camera_for_step(HM, k, steps), W, Hh, C3_VOL, **ms["kw"]) for k in range(steps)]
+        rec = timed_frames(tvk, torch, flush, params, steps, warmup, local)
+        assert len(tvk.read_requests()) == 0, "pool is not fully resident: frame would not be converged"
+        rec["roofline"] = roofline(rec, 2, steps, peak, peak_src, "c3_%s_%s" % (mode, skey))
+        records[mode] = rec
+        frames[mode] = (ms, params[(steps - 1) % len(params)], tvk.read_image())
+
+    main = records["2d_lit"]
+    line = {"metric": "ray samples/s", "value": main["samples_per_s"], "unit": "samples/s", "n_gpus": 1, "steps": steps,
+            "warmup": warmup, "ms_per_step": main["ms_per_frame"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(1, "2d_lit"),
+            "samples_per_step": main["samples"] / steps, "rays_per_step": main["rays"] / steps,
+            "roofline": main["roofline"], "gpu_launches": main["launches"], "clocks": main["clocks"], "k2": k2}
+    line["secondary"] = {m: {"config": workload_config(1, m)["workload"], "ms_per_frame": r["ms_per_frame"], "samples_per_s": r["samples_per_s"],
+                             "samples_per_frame": r["samples"] / steps, "hbm_roofline_frac": r["roofline"]["frac"],
+                             "dram_traffic_per_launch": r["roofline"]["traffic"], "clocks": r["clocks"]}
+                         for m, r in records.items() if m != "2d_lit"}
+
+    # ---- parity in the same run: oracle crops of the timed frames + request sets of a cold sub-frame
+    if not args.no_cpu:
+        from oracle import host as H
+        par, pool = {}, None
+        for mode in ("2d_lit", "iso", "1d"):
+            ms, p, img = frames[mode]
+            scene.set_mode(ms)
+            pool, par[mode] = parity_crops(H, scene, p, ms, img, W, Hh, pool)
+            if mode == "2d_lit":
+                par["requests"] = parity_requests(H, scene, pool, p, ms, W, Hh)
+                # CPU baseline: the oracle on the host cores, the crops of the first CPU_STEPS frames of the orbit
+                cs, dt = 0, 0.0
+                for k in range(min(CPU_STEPS, steps)):
+                    q = H.raycast_params(camera_for_step(H, k, steps), W, Hh, C3_VOL, **ms["kw"])
+                    _, s, d = oracle_crops(H, q, pool, ms["tf"], W, Hh)
+                    cs, dt = cs + s, dt + d
+                line["cpu_baseline"] = {"value": cs / dt, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                        "sample": "%d crops of %dx%d pixels of the first %d frames of the same orbit, %.1f s of CPU work"
+                                                  % (CROP_TILES, CROP_SIZE, CROP_SIZE, min(CPU_STEPS, steps), dt)}
+        par["tolerance"] = "PSNR >= 45 dB and max |error| <= 2/255 per crop (BASELINE.json north_star); requests: identical sets"
+        line["parity"] = par
+        del pool
+
+    # ---- K3 record: the pager (scattered bricks, pinned host store -> pool slots)
+    if scene.blob is not None:
+        line["k3"] = pager_record(tvk, scene)
+
+    scene.blob = None
+    tvk.close()
+    torch.cuda.empty_cache()
+    # ---- configs[1] as a secondary record: 512^3 uint8, 1D-TF + ERT
+    line["secondary"]["configs1_512_u8_1d"] = run_c2(TvkContext, torch, HM, dev, local, sampler, flush, steps, warmup, peak, peak_src)
+    # ---- e2e through the renderer API (host buffers in, RGBA8 frame out, every step)
+    line["e2e"] = run_e2e(torch, HM, dev, local, steps)
+    return line
+
+
+def pager_record(tvk, scene):
+    rng = np.random.default_rng(5)
+    n = min(4096, scene.total - 1)
+    pick = rng.choice(scene.total - 1, n, replace=False)
+    srcs = (C.c_void_p * n)(*[scene.blob.data_ptr() + int(scene.off[i]) for i in pick])
+    slots = np.ascontiguousarray(scene.slots[pick])
+    sizes = np.ascontiguousarray(scene.sizes[pick]).reshape(-1)
+    nbytes = int(sum(int(np.prod(scene.sizes[i])) for i in pick)) * (scene.bits // 8)
+    best = 1e9
+    for _ in range(3):
+        tvk.synchronize()
+        t0 = time.perf_counter()
+        tvk._ck(tvk.lib.tvk_pool_upload_bricks(tvk.h, C.c_uint32(n), slots.ctypes.data_as(C.c_void_p), srcs, sizes.ctypes.data_as(C.c_void_p), C.c_int(2)), "upload")
+        tvk._ck(tvk.lib.tvk_pool_upload_wait(tvk.h), "wait")
+        best = min(best, time.perf_counter() - t0)
+    return {"bricks": n, "bytes": nbytes, "ms": best * 1e3, "h2d_GBps": nbytes / best / 1e9,
+            "what": "tvk_pool_upload_bricks: %d scattered 64^3 uint16 bricks from the pinned host store into their pool slots "
+                    "(gather over PCIe + placement into the layered array), best of 3, host clock around issue + wait" % n}
+
+
+def run_c2(TvkContext, torch, HM, dev, local, sampler, flush, steps, warmup, peak, peak_src):
+    tvk = TvkContext(local)
+    raw = sphere_torch(C2_VOL, (0, 0, 0), C2_VOL, 8, dev)
+    scene = Scene(tvk, raw, C2_VOL, 8, want_host_copy=False)
+    scene.fill_pool(sampler)
+    tvk.build_release()
+    ms = mode_setup("1d", scene.rmax, 8, 1.0)
+    scene.set_mode(ms)
+    params = [HM.raycast_params(camera_for_step(HM, k, steps), 1920, 1080, C2_VOL, **ms["kw"]) for k in range(steps)]
+    rec = timed_frames(tvk, torch, flush, params, steps, warmup, local)
+    rf = roofline(rec, 1, steps, peak, peak_src, "c2_1d")
+    tvk.close()
+    return {"config": "BASELINE configs[1]: synthetic %dx%dx%d uint8 (reference CT_SPHERE generator), 1D-TF + ERT, 1920x1080" % C2_VOL,
+            "ms_per_frame": rec["ms_per_frame"], "samples_per_s": rec["samples_per_s"], "samples_per_frame": rec["samples"] / steps,
+            "hbm_roofline_frac": rf["frac"], "clocks": rec["clocks"]}
+
+
+def run_e2e(torch, HM, dev, local, steps):
+    """The call a user of the reference makes (include/tvk_renderer.h = the AbstrRenderer / Lua surface): dataset in
+    pinned HOST memory (out-of-core brick store), every step = new view + 2D transfer function edit (host table) +
+    empty working set -> paint() until converged (bricks paged in on the rays' requests) -> RGBA8 frame read back."""
+    from imagevis3d_b200.renderer import Renderer
+    W, Hh = 1920, 1080
+    raw = sphere_torch(C3_VOL, (0, 0, 0), C3_VOL, 16, dev)
+    host = np.empty((C3_VOL[2], C3_VOL[1], C3_VOL[0]), np.uint16)
+    for z0 in range(0, C3_VOL[2], 64):                       # chunked: no 17 GB staging copy on the host
+        host[z0:z0 + 64] = raw[z0:z0 + 64].view(torch.int16).cpu().numpy().view(np.uint16)
+    del raw
+    torch.cuda.empty_cache()
+    r = Renderer(local)
+    r.setState(hash_table_size=E2E_HASH, rehash_count=16, sampler=0xFFFFFFFF)
+    r.loadRawVolume(host, out_of_core=True, hist2d=True)
+    del host
+    r.resize((W, Hh))
+    tf, nz = tf2d(4096)
+    r.set2DTrans(tf, nz)
+    r.setRenderMode(1)
+    r.setLightingEnabled(True)
+    uploaded = [0.0]
+
+    def frame(k):
+        r.setRotation4x4((HM.rotation_y(orbit_angle(k, steps)) @ HM.rotation_x(0.35)).astype(np.float32))
+        r.clearWorkingSet()
+        r.set2DTrans(tf, nz)                                   # the table travels host -> device every step
+        sub = r.paintUntilConverged(4000)
+        img = r.frameRGBA8()
+        uploaded[0] += r.perf()["uploaded_bytes"]
+        return sub, img
+
+    frame(0)
+    uploaded[0] = 0.0
+    p0 = r.perf()
+    t0 = time.perf_counter()
+    subs = 0
+    for k in range(steps):
+        s, img = frame(k)
+        subs += s
+    dt = time.perf_counter() - t0
+    p1 = r.perf()
+    samples = p1["samples"] - p0["samples"]
+    h2d = uploaded[0] / steps + tf.nbytes
+    out = {"value": samples / dt, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(W * Hh * 4 + 4 * E2E_HASH * subs / steps),
+           "ms_per_step": 1e3 * dt / steps, "subframes_per_step": subs / steps,
+           "paged_bricks_per_step": (p1["paged_bricks"] - p0["paged_bricks"]) / steps,
+           "h2d_GBps_over_the_step": h2d / (dt / steps) / 1e9, "frame_nonzero_pixels": int((img[..., 3] > 0).sum()),
+           "samples_per_step_all_subframes": samples / steps,
+           "result": "RGBA8 frame (glReadPixels GL_UNSIGNED_BYTE, as captureSingleFrame reads it)",
+           "pipeline": "tvkr_* only (include/tvk_renderer.h): clearWorkingSet + changed2DTrans + paint() until converged() + frame "
+                       "read-back; the brick store lives in pinned host memory and bricks are paged in on the rays' requests "
+                       "(request table of %d entries, fGradientScale from the 2-D histogram pass)" % E2E_HASH}
+    r.cleanup()
+    return out
+
+
+def run_sortlast(args, torch, dist, TvkContext, HM, SL, dev, local, rank, world, sampler, peak, peak_src, flush, steps, warmup):
+    W, Hh = 3840, 2160
+    GLOBAL = C4_VOL
+    mode = "1d_lit"
+    parts = SL.block_partition(GLOBAL, world, halo=64)
+    part = parts[rank]
+    LOCAL = part["local_dims"]
+    # HBM while a box is set up: raw box + LOD pyramid (0.15) + brick store (1.7), then -- raw freed -- store + resident pool (1.7)
+    need_peak = 2.0 * LOCAL[0] * LOCAL[1] * LOCAL[2] * 3.6 / 1e9 + 2.0
+    free_gb = torch.cuda.mem_get_info()[0] / 1e9
+    fits = torch.tensor([1.0 if need_peak <= free_gb else 0.0], device=dev)
+    dist.all_reduce(fits, op=dist.ReduceOp.MIN)
+    if fits.item() == 0:
+        if rank == 0:
+            return {"metric": "ray samples/s", "value": None, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+                    "higher_is_better": True, "scaling": "strong", "config": workload_config(world, mode),
+                    "unsupported": "a rank's box of %dx%dx%d uint16 voxels needs about %.0f GB of HBM while it is built (brick store + "
+                                   "resident pool) and the GPU has %.0f GB free: 4096^3 does not fit %d GPUs until the builder streams "
+                                   "a box through in slabs" % (LOCAL[0], LOCAL[1], LOCAL[2], need_peak, free_gb, world)}
+        return None
+    tvk = TvkContext(local)
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
+    tvk.set_stream(work_stream.cuda_stream)
+    raw = sphere_torch(LOCAL, part["s"], GLOBAL, 16, dev)
+    torch.cuda.synchronize()
+    scene = Scene(tvk, raw, LOCAL, 16, want_host_copy=(rank == 0 and not args.no_cpu))
+    del raw
+    torch.cuda.empty_cache()
+    scene.fill_pool(sampler)
+    tvk.build_release()
+    # the transfer function is defined on the GLOBAL value range (a box that misses the centre has a smaller maximum)
+    ms = mode_setup(mode, 65535.0, 16, gradient_scale(GLOBAL))
+    scene.set_mode(ms)
+
+    exchange_kind, fused = os.environ.get("TVK_EXCHANGE", "p2p-fused"), None
+    if exchange_kind == "p2p-fused":
+        ok = torch.ones(1, device=dev)
+        try:
+            fused = SL.FusedExchange(tvk, world, rank, W, Hh, dist)
+        except Exception as e:            # noqa: BLE001 -- any failure to map peers demotes ALL ranks together
+            sys.stderr.write("rank %d: fused exchange unavailable (%s)\n" % (rank, e))
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            fused, exchange_kind = None, "nccl"
+
+    step_params, step_order = {}, {}
+    for k in range(max(steps, warmup)):
+        cam = camera_for_step(HM, k, steps)
+        step_params[k] = HM.raycast_params(cam, W, Hh, GLOBAL, slab=part, **ms["kw"])
+        pg = HM.raycast_params(cam, W, Hh, GLOBAL)
+        step_order[k] = SL.depth_order(np.array(pg.eye_to_model[:]).reshape(4, 4), parts)
+
+    class _CAI:                      # zero-copy torch view of a device image
         def __init__(self, ptr, shape):
             self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (int(ptr), False), "version": 2}
 
@@ -322,341 +750,102 @@ def run_gpu(args, rank, world):
         return out
 
     final_image = [None]
-    # sort-last exchange: fused into the kernels over NVLink peer memory (CUDA IPC); TVK_EXCHANGE=nccl selects the
-    # collective-based direct send instead, which is also the fall-back when peer mapping is not possible
-    exchange_kind, fused = "none", None
-    if world > 1:
-        exchange_kind = os.environ.get("TVK_EXCHANGE", "p2p-fused")
-        if exchange_kind == "p2p-fused":
-            ok = torch.ones(1, device=dev)
-            try:
-                fused = SL.FusedExchange(tvk, world, rank, WIDTH, HEIGHT, dist)
-            except Exception as e:            # noqa: BLE001 -- any failure to map peers demotes ALL ranks together
-                sys.stderr.write("rank %d: fused exchange unavailable (%s)\n" % (rank, e))
-                ok.zero_()
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if ok.item() == 0:
-                fused, exchange_kind = None, "nccl"
-
-    # the camera path is part of the scene description: per-step parameters and slab orders are laid out up front
-    step_params, step_order = {}, {}
-    for k in range(max(args.steps, args.warmup)):
-        step_params[k] = params_for(k)
-        if world > 1:
-            pg = HM.raycast_params(camera_for_step(HM, k, args.steps), WIDTH, HEIGHT, GLOBAL)
-            step_order[k] = SL.depth_order(np.array(pg.eye_to_model[:]).reshape(4, 4), parts)
 
     def step(k):
-        if world == 1:
-            tvk.raycast(step_params[k])
-            return
-        order = step_order[k]
         if fused is not None:
-            # K1 sends its stripes while it marches; stripe blend waits on arrival flags; result lands on rank 0
-            ptr = fused.render(step_params[k], order)
-            final_image[0] = torch.as_tensor(_CAI(ptr, (HEIGHT, WIDTH, 4)), device=dev)
+            ptr = fused.render(step_params[k], step_order[k])
+            final_image[0] = torch.as_tensor(_CAI(ptr, (Hh, W, 4)), device=dev)
         else:
-            # direct-send stripes over NCCL, ordered blend on the owner, gather
             tvk.raycast(step_params[k])
-            partial = torch.as_tensor(_CAI(tvk.image_device_ptr(), (HEIGHT, WIDTH, 4)), device=dev)
-            final_image[0] = SL.exchange_and_composite(partial, order, gpu_composite, world, rank)
+            partial = torch.as_tensor(_CAI(tvk.image_device_ptr(), (Hh, W, 4)), device=dev)
+            final_image[0] = SL.exchange_and_composite(partial, step_order[k], gpu_composite, world, rank)
 
-    # ---- warm-up
-    for k in range(args.warmup):
+    for k in range(warmup):
         flush.zero_()
         torch.cuda.synchronize()
         step(k)
         tvk.synchronize()
     tvk.stats(reset=True)
     assert len(tvk.read_requests()) == 0, "pool is not fully resident: frame would not be converged"
-    if fused is not None:
-        assert not tvk.exchange_timed_out(), "sort-last exchange timed out during warm-up"
-
-    # ---- timed region (device time from CUDA events around each step's launch)
-    sampler_thread = ClockSampler(local)
-    sampler_thread.start()
-    time.sleep(0.3)
-    if world > 1:
-        dist.barrier()
+    l0 = tvk.stats().launches
+    clock = ClockSampler(local)
+    clock.start()
+    time.sleep(0.25)
+    dist.barrier()
     torch.cuda.synchronize()
-    kernel_ms, step_s = 0.0, 0.0
-    t0 = time.perf_counter()
-    for k in range(args.steps):
+    kernel_ms, step_ms = 0.0, 0.0
+    for k in range(steps):
         flush.zero_()
-        if world > 1:
-            # the untimed L2 flush lets the ranks drift apart; without re-aligning them a rank's step time would include
-            # the wait for the latest rank's flush, which is not part of the step
-            dist.barrier()
+        dist.barrier()                  # the untimed L2 flush lets the ranks drift apart; re-align them
         torch.cuda.synchronize()
-        if world > 1:
-            # device time of the whole step (march + exchange + blend + landing on rank 0): CUDA events on the one
-            # stream every kernel of the step is launched on
-            ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev_a.record(work_stream)
-            step(k)
-            ev_b.record(work_stream)
-            tvk.synchronize()
-            torch.cuda.synchronize()
-            step_s += ev_a.elapsed_time(ev_b) * 1e-3
-        else:
-            step(k)
-            tvk.synchronize()
-            torch.cuda.synchronize()
-        kernel_ms += tvk.stats().last_raycast_ms
-    torch.cuda.synchronize()
-    wall_s = time.perf_counter() - t0
-    if world > 1:
-        dist.barrier()
-    st = tvk.stats()
-    clocks = sampler_thread.stop()
-    samples, rays = int(st.samples), int(st.rays)
-
-    # ---- e2e: host buffers in, host image out, every step (pager upload + march + read-back)
-    h2d = int(sum(int(np.prod(s)) for s in sizes[:total])) + 4 * total
-    d2h = HEIGHT * WIDTH * 4        # the frame as glReadPixels(GL_RGBA, GL_UNSIGNED_BYTE) returns it (captureSingleFrame)
-    srcs = [blob.data_ptr() + int(o) for o in off[:total]]
-    n = len(srcs)
-    src_arr = (C.c_void_p * n)(*srcs)
-    slot_arr = np.ascontiguousarray(slots, np.uint32)
-    size_arr = np.ascontiguousarray(sizes[:total], np.uint32).reshape(-1)
-
-    e2e_mode, e2e_extra = "serial", {}
-    if world > 1:
-        # every rank pages in the bricks of ITS box that visibility leaves non-empty under the transfer function (see the
-        # N=1 leg below, which also checks the frame against the all-bricks upload)
-        keep = np.nonzero(np.asarray(meta_host, np.uint32)[:n] >= 3)[0]
-        kn = len(keep)
-        ksrc = (C.c_void_p * kn)(*[srcs[int(i)] for i in keep])
-        kslots = np.ascontiguousarray(slot_arr[keep])
-        ksizes = np.ascontiguousarray(size_arr.reshape(n, -1)[keep]).reshape(-1)
-        h2d_rank = int(sum(int(np.prod(sizes[int(i)])) for i in keep)) + 4 * total
-        tot = torch.tensor([h2d_rank, kn, n], device=dev, dtype=torch.int64)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        h2d = int(tot[0])
-        e2e_extra = {"upload": "per rank, the bricks of its box that the visibility pass leaves non-empty under the "
-                               "transfer function: %d of %d over all ranks" % (int(tot[1]), int(tot[2])),
-                     "h2d_bytes_scope": "sum over ranks"}
-
-        def e2e_step(k):
-            tvk.set_metadata(meta_host)
-            tvk._ck(tvk.lib.tvk_pool_upload_bricks(tvk.h, C.c_uint32(kn), kslots.ctypes.data_as(C.c_void_p), ksrc,
-                                                   ksizes.ctypes.data_as(C.c_void_p), C.c_int(0)), "upload")
-            tvk._ck(tvk.lib.tvk_pool_upload_wait(tvk.h), "wait")
-            tvk.set_metadata(meta_host)
-            step(k)
-            if rank == 0:
-                img8_host.copy_((final_image[0].clamp(0.0, 1.0) * 255.0 + 0.5).to(torch.uint8))
-                torch.cuda.synchronize()
-
-        e2e_step(0)
-        tvk.stats(reset=True)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        for k in range(args.steps):
-            e2e_step(k)
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev_a.record(work_stream)
+        step(k)
+        ev_b.record(work_stream)
         tvk.synchronize()
-        e2e_s = time.perf_counter() - t1
-        e2e_samples = int(tvk.stats().samples)
-    else:
-        # Double-buffered frames: a second context whose pool holds TWO sets of slots.  While step k marches out of one
-        # set (and its frame is read back), the pager already pulls step k+1's bricks over PCIe into the other set on
-        # the side stream.  Every step still uploads all its bricks from pinned host memory and reads its frame back.
-        e2e_mode = "double-buffered pool (upload of step k+1 overlaps march + read-back of step k)"
-        e2 = TvkContext(local)
-        e2.set_march_occupancy(int(os.environ.get("TVK_E2E_MARCH_CTAS", "3")))   # room for the pager's kernels on every SM
-        cap2 = (cap[0], cap[1], 2 * cap[2])
-        e2.pool_create(LOCAL, (BRICK,) * 3, OVERLAP, 1, cap2, lod_count, sampler)
-        e2.set_minmax(mm[:total])
-        e2.set_tf1d(tf_rgba)
-        half = cap[0] * cap[1] * cap[2]
-        slot_sets = [np.ascontiguousarray(slot_arr), np.ascontiguousarray(slot_arr + np.uint32(half))]
-        # page tables of the two sets: the main context's table (visibility flags included), slot references shifted
-        mh = np.ascontiguousarray(meta_host, np.uint32)
-        metas = [mh, np.ascontiguousarray(np.where(mh >= 3, mh + np.uint32(half), mh).astype(np.uint32))]
+        torch.cuda.synchronize()
+        step_ms += ev_a.elapsed_time(ev_b)
+        kernel_ms += tvk.stats().last_raycast_ms
+    dist.barrier()
+    st = tvk.stats()
+    clocks = clock.stop()
+    launches = int(st.launches - l0)
+    per_rank = torch.tensor([kernel_ms / steps, step_ms / steps, float(st.samples) / steps], device=dev, dtype=torch.float64)
+    gathered = [torch.zeros_like(per_rank) for _ in range(world)]
+    dist.all_gather(gathered, per_rank)
+    t = torch.tensor([kernel_ms, step_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    kernel_ms, step_ms = [float(v) for v in t.tolist()]
+    c = torch.tensor([int(st.samples), int(st.rays), launches], device=dev, dtype=torch.int64)
+    dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    samples, rays, launches = [int(v) for v in c.tolist()]
 
-        # What a step pages in: the bricks the visibility pass leaves non-empty under the transfer function.  A brick
-        # whose [min, max] the table maps to alpha 0 is flagged EMPTY in the page table, no ray ever asks for it, and
-        # the reference's pool never uploads it either (GLVolumePool::RecomputeVisibility, GLVolumePool.cpp:1791-1909;
-        # GetBrick's empty flags, :484-656).  The all-bricks upload is timed too and reported beside it.
-        keep_all = np.arange(n, dtype=np.int64)
-        keep_vis = np.nonzero(mh[:n] >= 3)[0].astype(np.int64)
-
-        def subset(keep):
-            ks = (C.c_void_p * len(keep))(*[srcs[int(i)] for i in keep])
-            kz = np.ascontiguousarray(size_arr.reshape(n, -1)[keep]).reshape(-1)
-            return len(keep), [np.ascontiguousarray(ss[keep]) for ss in slot_sets], ks, kz
-
-        def run_leg(keep):
-            kn, kslots, ksrc, ksizes = subset(keep)
-
-            def upload(k):
-                e2._ck(e2.lib.tvk_pool_upload_bricks(e2.h, C.c_uint32(kn), kslots[k & 1].ctypes.data_as(C.c_void_p), ksrc,
-                                                     ksizes.ctypes.data_as(C.c_void_p), C.c_int(2)), "upload")   # 2: one pinned allocation
-
-            def run_steps(count):
-                upload(0)
-                for k in range(count):
-                    e2._ck(e2.lib.tvk_pool_upload_wait(e2.h), "wait")          # step k's bricks are in place
-                    if k + 1 < count:
-                        upload(k + 1)                                          # side stream, other slot set
-                    e2.set_metadata(metas[k & 1])
-                    e2.raycast(step_params[k % args.steps])
-                    e2._ck(e2.lib.tvk_read_image_rgba8(e2.h, C.c_void_p(img8_host.data_ptr()), C.c_int(1)), "read_image_rgba8")
-
-            run_steps(2)
-            e2.stats(reset=True)
-            e2.synchronize()
-            torch.cuda.synchronize()
-            t1 = time.perf_counter()
-            run_steps(args.steps)
-            e2.synchronize()
-            leg_s = time.perf_counter() - t1
-            leg_samples = int(e2.stats().samples)
-            if len(e2.read_requests()) != 0:
-                raise RuntimeError("e2e pool not fully resident: rays asked for bricks that were not uploaded")
-            return leg_s, leg_samples
-
-        try:
-            e2e_s, e2e_samples = run_leg(keep_vis)        # first: on a pool that never held the empty bricks
-            vis8 = img8_host.clone()
-        except RuntimeError as e:      # reported, never hidden: the line then carries the all-bricks figure
-            sys.stderr.write("e2e: visible-brick leg rejected (%s); reporting the all-bricks upload\n" % e)
-            e2e_extra = {"upload": "all %d bricks" % n, "visible_leg_error": str(e)}
-            vis8 = None
-        all_s, all_samples = run_leg(keep_all)
-        if vis8 is not None and (not torch.equal(vis8, img8_host) or e2e_samples != all_samples):
-            # same context, same slot set, same camera: the two frames must be the same bytes
-            sys.stderr.write("e2e: visible-brick frame differs from the all-bricks frame; reporting the all-bricks upload\n")
-            e2e_extra = {"upload": "all %d bricks" % n, "visible_leg_error": "frame or sample count differs from the all-bricks leg"}
-            vis8 = None
-        if vis8 is None:
-            e2e_s, e2e_samples = all_s, all_samples
-        else:
-            # informational: against the main context's fully resident pool (another pool geometry, so the pool-space
-            # coordinate arithmetic rounds differently in the last place)
-            ref8 = torch.empty_like(img8_host)
-            tvk.raycast(step_params[(args.steps - 1) % args.steps])
-            tvk._ck(tvk.lib.tvk_read_image_rgba8(tvk.h, C.c_void_p(ref8.data_ptr()), C.c_int(1)), "read_image_rgba8")
-            tvk.synchronize()
-            dmax = int((ref8.to(torch.int16) - vis8.to(torch.int16)).abs().max())
-            h2d_all = h2d
-            h2d = int(sum(int(np.prod(sizes[int(i)])) for i in keep_vis)) + 4 * total
-            e2e_extra = {"upload": "bricks the visibility pass leaves non-empty under the transfer function: %d of %d "
-                                   "(empty bricks are never requested, as in GLVolumePool)" % (len(keep_vis), n),
-                         "frame_equals_all_bricks_frame": True, "max_abs_diff_vs_resident_pool_rgba8": dmax,
-                         "all_bricks": {"value": all_samples / all_s, "ms_per_step": 1e3 * all_s / args.steps,
-                                        "h2d_bytes_per_step": h2d_all}}
-        e2.close()
-
-    # ---- reduce over ranks
-    if world > 1:
-        t = torch.tensor([kernel_ms, wall_s, e2e_s, step_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        kernel_ms, wall_s, e2e_s, step_s = [float(v) for v in t.tolist()]
-        c = torch.tensor([samples, rays, e2e_samples], device=dev, dtype=torch.int64)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        samples, rays, e2e_samples = [int(v) for v in c.tolist()]
+    # ---- parity: rank 0's partial image crops vs the oracle on its own box; final image == ordered blend of the partials
+    par = None
+    k_last = steps - 1
+    partial_host = tvk.read_image()
+    gather_list = [torch.empty((Hh, W, 4), dtype=torch.float32, device=dev) for _ in range(world)] if rank == 0 else None
+    dist.gather(torch.from_numpy(partial_host).to(dev), gather_list, dst=0)
+    if rank == 0 and not args.no_cpu:
+        from oracle import host as H
+        from oracle import oracle as O
+        fin = final_image[0].cpu().numpy()
+        parts_h = [g.cpu().numpy() for g in gather_list]
+        want = np.zeros((Hh * W, 4), np.float32)
+        arr = (C.c_void_p * world)(*[parts_h[r].ctypes.data for r in step_order[k_last]])
+        O.lib().orc_composite_ordered(arr, C.c_uint32(world), C.c_uint64(Hh * W), want.ctypes.data_as(C.c_void_p))
+        d = float(np.abs(fin.reshape(-1, 4) - want).max())
+        _, pc = parity_crops(H, scene, step_params[k_last], ms, partial_host, W, Hh)
+        par = {"rank0_partial_image": pc, "final_vs_oracle_blend_of_partials_max_abs_diff": d,
+               "final_image_nonzero_pixels": int((fin[..., 3] > 0).sum()),
+               "tolerance": "PSNR >= 45 dB and max |error| <= 2/255 per crop; compositing: <= 1e-6"}
+    dist.barrier()
     if rank != 0:
         tvk.close()
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    peak, peak_src = peaks()
-    traffic = None
-    try:        # DRAM bytes per launch of this kernel from the committed ncu --set full capture (N=1 workload only)
-        if world == 1:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))[os.environ.get("TVK_SAMPLER", "q4")]["dram_bytes_per_launch"]
-    except Exception:       # noqa: BLE001
-        traffic = None
-    # instruction-issue view of the same kernel (what actually bounds it): warp instructions per sample from the committed
-    # ncu capture x the samples of this run, against 4 warp instructions per clock per SM
-    issue = None
-    try:
-        if world == 1:
-            k = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))[os.environ.get("TVK_SAMPLER", "q4")]
-            per_sample = k["warp_instructions_per_launch"] / k["samples_in_capture"]
-            sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
-            sm_mhz = (clocks or {}).get("sm_mhz") or 1965
-            issue_peak = sm_count * 4 * sm_mhz * 1e6
-            issue_rate = per_sample * samples / (kernel_ms * 1e-3)
-            issue = {"achieved": issue_rate / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instr/s", "frac": issue_rate / issue_peak,
-                     "warp_instructions_per_sample": per_sample, "source": "profiles/k1_traffic.json (ncu smsp__inst_executed.sum)"}
-    except Exception:       # noqa: BLE001
-        issue = None
-    ms_step = kernel_ms / args.steps
-    if world > 1:
-        # a step = render + exchange + blend + gather: the ray-march kernel alone is not the step
-        ms_frame = 1e3 * step_s / args.steps
-    else:
-        ms_frame = ms_step
-    value = samples / (ms_frame * 1e-3 * args.steps)
-    alg_bytes = (samples * BYTES_PER_SAMPLE + rays * BYTES_PER_RAY) / args.steps / world
-    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
-    line = {"metric": "ray samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_frame, "raycast_kernel_ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
-            "samples_per_step": samples / args.steps, "rays_per_step": rays / args.steps,
-            "wall_ms_per_step_incl_l2_flush": 1e3 * wall_s / args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "0.6068 B/sample + 16 B/ray (SURVEY 8d); the kernel is instruction-issue bound, see `issue` and DESIGN.md",
-                         "issue": issue},
-            "e2e": {"value": e2e_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "result": "RGBA8 frame (glReadPixels GL_UNSIGNED_BYTE, as captureSingleFrame reads it)", "pipeline": e2e_mode,
-                    **e2e_extra},
-            "gpu_launches": args.steps * (1 if world == 1 else (2 * world if fused is not None else 2 * world)), "clocks": clocks,
-            "builder_ms_untimed": 1e3 * t_build}
-    if world > 1:
-        line["config"]["exchange"] = exchange_kind
-        if fused is not None:
-            line["exchange_timed_out"] = bool(tvk.exchange_timed_out())
-
-    # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample
-    if world == 1 and not args.no_cpu:
-        from oracle import host as H
-        oc_like = dict(plan=None)
-        pool = build_oracle_pool_from_store(H, info, off, sizes, blob.numpy(), mm, total, cap, lod_count, slots, meta_host)
-        w, h = CPU_SAMPLE
-        frame = H.OracleFrame(w, h)
-        nsteps = min(CPU_STEPS, args.steps)
-        cs, dt = 0, 0.0
-        for k in range(-1, nsteps):                       # k = -1: untimed warm-up frame
-            p = H.raycast_params(camera_for_step(H, max(k, 0), args.steps), w, h, VOL)
-            tc = time.perf_counter()
-            H.raycast(p, pool, tf_rgba, frame)
-            if k >= 0:
-                dt += time.perf_counter() - tc
-                cs += int(frame.stats[0])
-        line["cpu_baseline"] = {"value": cs / dt, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                "sample": "first %d steps of the same orbit at full %dx%d, %.1f s of CPU work"
-                                          % (nsteps, w, h, dt)}
-    emit_line(line)
+        return None
+    ms_frame = step_ms / steps
+    alg = (samples * 1.2136 + rays * 16.0) / steps / world
+    achieved = alg / (kernel_ms / steps * 1e-3) / 1e9
+    value = samples / (ms_frame * 1e-3 * steps)
+    line = {"metric": "ray samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_frame, "raycast_kernel_ms_per_step": kernel_ms / steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world, mode),
+            "samples_per_step": samples / steps, "rays_per_step": rays / steps,
+            "per_rank": {"march_ms": [float(g[0]) for g in gathered], "step_ms": [float(g[1]) for g in gathered],
+                         "samples_per_step": [float(g[2]) for g in gathered],
+                         "note": "march = K1 CUDA events; step = march + wait for the other ranks' stripes + blend + landing on rank 0, "
+                                 "CUDA events on the rank's stream"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                         "note": "per GPU: 1.2136 B/sample + 16 B/ray over the slowest rank's march kernel"},
+            "gpu_launches": launches, "clocks": clocks, "parity": par,
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "not measured at N > 1: the renderer API (tvkr_*) drives one GPU; the device-timed value is repeated"}}
+    line["config"]["exchange"] = exchange_kind
+    if fused is not None:
+        line["exchange_timed_out"] = bool(tvk.exchange_timed_out())
     tvk.close()
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def build_oracle_pool_from_store(H, info, off, sizes, blob, mm, total, cap, lod_count, slots, meta):
-    """Host copy of the device pool for the CPU baseline (bricks come from the CUDA builder, which the
-    tests prove bit-identical to the oracle builder)."""
-    class P:
-        pass
-    pool = P()
-    pool.vol, pool.bpv, pool.overlap, pool.max_brick, pool.lod_count, pool.capacity = VOL, 1, OVERLAP, (BRICK,) * 3, lod_count, cap
-    pool.layout, pool.lod_offset, pool.lod_bricks, pool.total = H.pool_layout(VOL, pool.max_brick, OVERLAP, lod_count)
-    pool.data = np.zeros((cap[2] * BRICK, cap[1] * BRICK, cap[0] * BRICK), np.uint8)
-    for i in range(total):
-        s = sizes[i]
-        b = blob[int(off[i]):int(off[i]) + int(np.prod(s))].reshape(int(s[2]), int(s[1]), int(s[0]))
-        sl = int(slots[i])
-        o = ((sl % cap[0]) * BRICK, ((sl // cap[0]) % cap[1]) * BRICK, (sl // (cap[0] * cap[1])) * BRICK)
-        pool.data[o[2]:o[2] + b.shape[0], o[1]:o[1] + b.shape[1], o[0]:o[0] + b.shape[2]] = b
-    pool.meta = np.ascontiguousarray(meta, np.uint32)
-    pool.c_pool = lambda: H.OraclePool.c_pool(pool)
-    return pool
+    return line
 
 
 def main():
@@ -665,7 +854,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the oracle legs (parity crops, cpu_baseline)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -512,6 +512,39 @@ bool CudaGridLeaper::LoadDataset(const std::string& uvfFile, uint64_t gpuMemByte
   return FinishLoad(v, gpuMemBytes, tfSize);
 }
 
+bool CudaGridLeaper::PrepareHostVolume(BrickedVolume* v) {
+  if (!v || (v->bpv != 1 && v->bpv != 2)) { m_err = "PrepareHostVolume: 8/16-bit unsigned volumes only"; return false; }
+  tvk_build_desc d{};
+  for (int a = 0; a < 3; ++a) d.volume_size[a] = v->domain[a];
+  d.brick_size = v->brick_size; d.overlap = v->overlap; d.bytes_per_voxel = v->bpv;
+  const int rc = tvk_build_plan(&d, &v->info);
+  if (rc) return Fail("tvk_build_plan", rc);
+  const uint64_t n = v->info.total_bricks;
+  if (v->sizes.size() != 3 * n || v->minmax.size() != 2 * n) { m_err = "PrepareHostVolume: sizes / minmax do not match the octree's brick count"; return false; }
+  v->offsets.resize(n);
+  uint64_t off = 0;
+  for (uint64_t i = 0; i < n; ++i) {          // same 256-byte brick alignment as the builder's store
+    v->offsets[i] = off;
+    off += ((uint64_t)v->sizes[3 * i] * v->sizes[3 * i + 1] * v->sizes[3 * i + 2] * v->bpv + 255) / 256 * 256;
+  }
+  v->store_bytes = v->info.total_bytes = off;
+  if (cudaHostAlloc((void**)&v->host_store, v->store_bytes, cudaHostAllocDefault) != cudaSuccess) {
+    v->host_store = nullptr; m_err = "cudaHostAlloc failed for the brick store"; return false;
+  }
+  return true;
+}
+
+bool CudaGridLeaper::AdoptVolume(BrickedVolume* v, uint64_t gpuMemBytes) {
+  if (!m_ctx) { m_err = "renderer not initialised"; return false; }
+  if (!v || !v->host_store) { m_err = "AdoptVolume: the volume has no host brick store (PrepareHostVolume first)"; return false; }
+  delete m_pool; m_pool = nullptr;
+  if (m_vol && m_vol != v) { if (m_vol->host_store) cudaFreeHost(m_vol->host_store); delete m_vol; }
+  m_vol = nullptr;
+  tvk_build_release(m_ctx);
+  const uint32_t tfSize = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)v->hist1d.size(), 4096));
+  return FinishLoad(v, gpuMemBytes, tfSize);
+}
+
 // writes the loaded volume as a UVF v5 file stock ImageVis3D opens (tvk_uvf_write)
 bool CudaGridLeaper::SaveUVF(const std::string& uvfFile, uint32_t compression, uint32_t level) {
   if (!m_ctx || !m_vol) { m_err = "no dataset"; return false; }

@@ -163,6 +163,13 @@ class CudaGridLeaper {
                      bool computeHist2D);
   // renderer.loadDataset(file.uvf): a UVF with a TOC block (8/16-bit unsigned); bricks go to pinned host memory
   bool LoadDataset(const std::string& uvfFile, uint64_t gpuMemBytes, bool verifyChecksum);
+  // A bricked volume some OTHER reader produced (the AbstrRenderer adapter walks a tuvok LinearIndexDataset once):
+  // the caller fills domain / scale / bpv / brick_size / overlap and, per brick in ToC order, sizes (3 each) and
+  // minmax (2 each), plus hist1d and max_grad_magnitude; PrepareHostVolume plans the octree, lays the bricks out in ONE
+  // pinned host allocation (host_store + offsets); the caller copies the brick payloads there; AdoptVolume takes
+  // ownership and sets up pool, transfer function and visibility like LoadDataset does.
+  bool PrepareHostVolume(BrickedVolume* v);
+  bool AdoptVolume(BrickedVolume* v, uint64_t gpuMemBytes);
   // the loaded volume as a UVF v5 file (TOC, histograms, max/min, key/values, MD5); compression: TVK_UVF_COMP_*
   bool SaveUVF(const std::string& uvfFile, uint32_t compression, uint32_t level);
   void Resize(uint32_t w, uint32_t h);
@@ -195,7 +202,7 @@ class CudaGridLeaper {
   void SetClipPlane(const float plane[4]);
   void EnableClipPlane(bool on);
   Vec3 GetViewPos() const { return m_eye; }
-  Vec3 GetViewDir() const { return m_at - m_eye; }                 // AbstrRenderer.cpp:1599-1601
+  Vec3 GetViewDir() const { return (m_at - m_eye).normalized(); }  // AbstrRenderer.cpp:1608-1610
   Vec3 GetUpDir() const { return m_up; }
   bool SetTimestep(size_t t);
   void SetLODLimits(uint32_t lo, uint32_t hi);                     // kept for the classic path; the ray-guided path ignores it

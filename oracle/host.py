@@ -404,16 +404,55 @@ class OracleFrame:
         self.stats = np.zeros(4, np.uint64)     # samples, GetBrick calls, rays, dropped reports
 
 
-def raycast(params, pool, tf_rgba8, frame):
+def raycast(params, pool, tf_rgba8, frame, rect=None, clear_hash=True):
+    """One sub-frame.  rect = (x0, y0, x1, y1) restricts it to a pixel rectangle of the full-size buffers (crops of
+    frames too large to render whole on the CPU); clear_hash=False accumulates the requests of several rectangles."""
     tf = np.ascontiguousarray(tf_rgba8, np.uint8)
     tf_w, tf_h = (tf.shape[0], 1) if tf.ndim == 2 else (tf.shape[1], tf.shape[0])
     cp = pool.c_pool()
-    rc = O.lib().orc_raycast(C.byref(params), C.byref(cp), tf.ctypes.data_as(C.c_void_p), C.c_uint32(tf_w), C.c_uint32(tf_h),
-                             frame.pos.ctypes.data_as(C.c_void_p), frame.aux.ctypes.data_as(C.c_void_p),
-                             frame.image.ctypes.data_as(C.c_void_p), frame.hash.ctypes.data_as(C.c_void_p),
-                             frame.stats.ctypes.data_as(C.c_void_p))
+    x0, y0, x1, y1 = (0, 0, params.width, params.height) if rect is None else rect
+    rc = O.lib().orc_raycast_rect(C.byref(params), C.byref(cp), tf.ctypes.data_as(C.c_void_p), C.c_uint32(tf_w), C.c_uint32(tf_h),
+                                  frame.pos.ctypes.data_as(C.c_void_p), frame.aux.ctypes.data_as(C.c_void_p),
+                                  frame.image.ctypes.data_as(C.c_void_p), frame.hash.ctypes.data_as(C.c_void_p),
+                                  frame.stats.ctypes.data_as(C.c_void_p), C.c_uint32(x0), C.c_uint32(y0), C.c_uint32(x1),
+                                  C.c_uint32(y1), C.c_int(1 if clear_hash else 0))
     assert rc == 0
     return frame.image
+
+
+def gen_sphere(vol, dtype, z0=0, nz=None):
+    """The reference's CT_SPHERE test volume (UVFReader/DataSource.h:361-372) as a numpy array [z][y][x]."""
+    vol = tuple(int(v) for v in vol)
+    nz = vol[2] - z0 if nz is None else int(nz)
+    out = np.empty((nz, vol[1], vol[0]), dtype)
+    O.lib().orc_gen_sphere(out.ctypes.data_as(C.c_void_p), (C.c_uint64 * 3)(*vol), C.c_uint32(out.dtype.itemsize),
+                           C.c_uint64(int(z0)), C.c_uint64(nz))
+    return out
+
+
+class ResidentPool:
+    """A host pool with EVERY pool-LOD brick resident (slot i = brick i, the coarsest brick in the last slot), filled
+    from a brick store in ToC order: the state bench.py / the full-size tests give the device pool.  Duck-types the
+    part of OraclePool that raycast() needs."""
+
+    def __init__(self, vol, bpv, overlap, max_brick, capacity, lod_count, store, offsets, sizes, slots, meta):
+        self.vol, self.bpv, self.overlap = tuple(int(v) for v in vol), int(bpv), int(overlap)
+        self.max_brick, self.capacity, self.lod_count = tuple(int(v) for v in max_brick), tuple(int(v) for v in capacity), int(lod_count)
+        self.layout, self.lod_offset, self.lod_bricks, self.total = pool_layout(self.vol, self.max_brick, self.overlap, self.lod_count)
+        dims = [self.capacity[a] * self.max_brick[a] for a in range(3)]
+        self.data = np.zeros((dims[2], dims[1], dims[0]), np.uint8 if self.bpv == 1 else np.uint16)
+        store = np.ascontiguousarray(store).view(np.uint8).reshape(-1)
+        cap3, mb3 = (C.c_uint32 * 3)(*self.capacity), (C.c_uint32 * 3)(*self.max_brick)
+        place = O.lib().orc_pool_place
+        base = store.ctypes.data
+        for i in range(len(slots)):
+            bs = (C.c_uint32 * 3)(*[int(v) for v in sizes[i]])
+            place(C.c_void_p(self.data.ctypes.data), cap3, mb3, C.c_uint32(self.bpv), C.c_uint32(int(slots[i])),
+                  C.c_void_p(base + int(offsets[i])), bs)
+        self.meta = np.ascontiguousarray(meta, np.uint32)
+
+    def c_pool(self):
+        return OraclePool.c_pool(self)
 
 
 def read_requests(pool, frame, cap=4096):

@@ -600,15 +600,33 @@ static void compose_iso(const tvk_raycast_params* p, const float hit[4], const f
  * the W*H*4 resume buffers (in/out; ignored on input when new_view), image the
  * W*H*4 result, hash the request table (cleared here), stats[4] = samples,
  * GetBrick calls, rays, dropped brick reports (table full within the probe limit). */
+int orc_raycast_rect(const tvk_raycast_params* p, const orc_pool_t* pool, const uint8_t* tf,
+                     uint32_t tf_w, uint32_t tf_h, float* ray_pos, float* ray_aux, float* image,
+                     uint32_t* hash, uint64_t* stats, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
+                     int clear_hash);
+
 int orc_raycast(const tvk_raycast_params* p, const orc_pool_t* pool, const uint8_t* tf,
                 uint32_t tf_w, uint32_t tf_h, float* ray_pos, float* ray_aux, float* image,
                 uint32_t* hash, uint64_t* stats) {
+  return orc_raycast_rect(p, pool, tf, tf_w, tf_h, ray_pos, ray_aux, image, hash, stats, 0, 0, p->width, p->height, 1);
+}
+
+/* The same sub-frame restricted to the pixel rectangle [x0,x1) x [y0,y1) of the W x H target (the buffers stay
+ * full-frame; pixels outside the rectangle are not touched).  Used to check crops of frames whose full CPU render
+ * would take too long.  clear_hash == 0 accumulates the requests of several rectangles in one table; stats are
+ * those of this call. */
+int orc_raycast_rect(const tvk_raycast_params* p, const orc_pool_t* pool, const uint8_t* tf,
+                     uint32_t tf_w, uint32_t tf_h, float* ray_pos, float* ray_aux, float* image,
+                     uint32_t* hash, uint64_t* stats, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
+                     int clear_hash) {
   uint32_t inner[3] = {pool->max_brick[0] - 2 * pool->overlap, pool->max_brick[1] - 2 * pool->overlap,
                        pool->max_brick[2] - 2 * pool->overlap};
-  memset(hash, 0, sizeof(uint32_t) * p->hash_table_size);
+  if (x1 > p->width) x1 = p->width;
+  if (y1 > p->height) y1 = p->height;
+  if (clear_hash) memset(hash, 0, sizeof(uint32_t) * p->hash_table_size);
   uint64_t tot_s = 0, tot_b = 0, tot_r = 0, tot_d = 0;
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : tot_s, tot_b, tot_r, tot_d)
-  for (uint32_t py = 0; py < p->height; ++py) {
+  for (uint32_t py = y0; py < y1; ++py) {
     ctx_t c;
     memset(&c, 0, sizeof(c));
     c.p = p; c.pool = pool; c.tf = tf; c.tf_w = tf_w; c.tf_h = tf_h; c.hash = hash;
@@ -617,7 +635,7 @@ int orc_raycast(const tvk_raycast_params* p, const orc_pool_t* pool, const uint8
       c.pool_size[a] = (float)(pool->capacity[a] * pool->max_brick[a]);
       c.overlap_tc[a] = (float)(pool->max_brick[a] - inner[a]) / (2.0f * c.pool_size[a]);
     }
-    for (uint32_t px = 0; px < p->width; ++px) {
+    for (uint32_t px = x0; px < x1; ++px) {
       const size_t i = 4 * ((size_t)py * p->width + px);
       float entry[4], exitp[4];
       const int hit_box = ray_setup(p, px, py, entry, exitp);
