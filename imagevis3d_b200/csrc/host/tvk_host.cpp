@@ -7,6 +7,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <fstream>
 
@@ -259,9 +260,25 @@ bool BrickPool::IsBrickResident(uint32_t x, uint32_t y, uint32_t z, uint32_t lod
 }
 
 void BrickPool::PrepareForPaging() {
-  // std::sort by m_iTimeOfCreation (:946-959); stable here so that ties are deterministic
-  std::stable_sort(m_slots.begin(), m_slots.end(), [](const PoolSlot& a, const PoolSlot& b) { return a.time < b.time; });
+  // std::sort by m_iTimeOfCreation (:946-959); stable here so that ties are deterministic.  After a paging pass the
+  // vector is [the m_insertPos slots just filled, ascending][the rest, ascending]: rotating the new ones to the back
+  // IS the stable sort in the common case (no slot flagged empty or restored in between); anything else is sorted.
+  auto by_time = [](const PoolSlot& a, const PoolSlot& b) { return a.time < b.time; };
+  if (m_insertPos > 0 && m_insertPos < m_slots.size()) std::rotate(m_slots.begin(), m_slots.begin() + m_insertPos, m_slots.end());
+  if (!std::is_sorted(m_slots.begin(), m_slots.end(), by_time)) std::stable_sort(m_slots.begin(), m_slots.end(), by_time);
   m_insertPos = 0;
+}
+
+int BrickPool::Reset() {
+  // GLVolumePool::PH_Reset (:261-284): every slot unused again, page table all MISSING, then UploadFirstBrick; the
+  // device pool itself is kept (slots are overwritten as bricks arrive)
+  std::sort(m_slots.begin(), m_slots.end(), [](const PoolSlot& a, const PoolSlot& b) { return a.pos < b.pos; });
+  for (PoolSlot& s : m_slots) { const uint32_t pos = s.pos; s = PoolSlot(); s.pos = pos; }
+  m_time = 2; m_insertPos = 0; m_uploadedBytes = 0;
+  std::vector<uint32_t> zero(m_total, TVK_BI_MISSING);
+  int rc = tvk_pool_set_metadata(m_ctx, zero.data(), m_total);
+  if (rc) return rc;
+  return UploadFirstBrick();
 }
 
 int BrickPool::UploadFirstBrick() {
@@ -282,11 +299,17 @@ int BrickPool::UploadFirstBrick() {
   return tvk_pool_patch_metadata(m_ctx, 1, &idx, &val);
 }
 
-int BrickPool::UploadBricks(const std::vector<uint32_t>& xyzl, uint32_t& paged) {
+int BrickPool::UploadBricks(const std::vector<uint32_t>& xyzl, uint32_t& paged, bool wait) {
   paged = 0;
   const size_t n = xyzl.size() / 4;
+  m_lastMs[0] = m_lastMs[1] = m_lastMs[2] = m_lastMs[3] = 0.0;
   if (!n) return TVK_OK;
+  typedef std::chrono::steady_clock clk;
+  auto ms_since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
+  clk::time_point t0 = clk::now();
   PrepareForPaging();
+  m_lastMs[0] = ms_since(t0);
+  t0 = clk::now();
   std::vector<uint32_t> slot, sizes, pidx, pval;
   std::vector<const void*> src;
   for (size_t i = 0; i < n; ++i) {
@@ -310,12 +333,18 @@ int BrickPool::UploadBricks(const std::vector<uint32_t>& xyzl, uint32_t& paged) 
     ++m_insertPos;
     ++paged;
   }
+  m_lastMs[1] = ms_since(t0);
+  t0 = clk::now();
   int rc = tvk_pool_upload_bricks(m_ctx, (uint32_t)slot.size(), slot.data(), src.data(), sizes.data(), m_vol->host_store ? 2 : 1);
   if (rc) return rc;
-  rc = tvk_pool_upload_wait(m_ctx);
+  rc = wait ? tvk_pool_upload_wait(m_ctx) : tvk_pool_upload_fence(m_ctx);
   if (rc) return rc;
+  m_lastMs[2] = ms_since(t0);
+  t0 = clk::now();
   // a slot can be evicted and re-filled within one pass only across passes, so later patches win
-  return tvk_pool_patch_metadata(m_ctx, (uint32_t)pidx.size(), pidx.data(), pval.data());
+  rc = tvk_pool_patch_metadata(m_ctx, (uint32_t)pidx.size(), pidx.data(), pval.data());
+  m_lastMs[3] = ms_since(t0);
+  return rc;
 }
 
 bool BrickPool::ContainsData(const tvk_visibility& v, uint32_t i) const {     // :963-989
@@ -343,6 +372,15 @@ int BrickPool::RecomputeVisibility(const tvk_visibility& vis, uint32_t counts[4]
   return tvk_visibility_recompute(m_ctx, &vis, counts);
 }
 
+static void free_volume(tvk_ctx* ctx, BrickedVolume*& v) {
+  if (!v) return;
+  if (ctx) tvk_device_synchronize(ctx);          // an upload in flight may still read the pinned store
+  if (v->classic_store) cudaFree(v->classic_store);
+  if (v->host_store) cudaFreeHost(v->host_store);
+  delete v;
+  v = nullptr;
+}
+
 // ---------------------------------------------------------------------------- CudaGridLeaper
 CudaGridLeaper::CudaGridLeaper() : m_tf1d(256) { m_tf1d.SetStdFunction(); }
 CudaGridLeaper::~CudaGridLeaper() { Cleanup(); }
@@ -361,7 +399,7 @@ bool CudaGridLeaper::Initialize(int device) {
 
 void CudaGridLeaper::Cleanup() {
   delete m_pool; m_pool = nullptr;
-  if (m_vol) { if (m_vol->host_store) cudaFreeHost(m_vol->host_store); delete m_vol; m_vol = nullptr; }
+  free_volume(m_ctx, m_vol);
   if (m_ctx) { tvk_destroy(m_ctx); m_ctx = nullptr; }
 }
 
@@ -370,7 +408,7 @@ bool CudaGridLeaper::LoadRawVolume(const void* raw, const uint32_t size[3], uint
                                    uint64_t gpuMemBytes, bool computeHist2D) {
   if (!m_ctx) { m_err = "renderer not initialised"; return false; }
   delete m_pool; m_pool = nullptr;
-  if (m_vol) { if (m_vol->host_store) cudaFreeHost(m_vol->host_store); delete m_vol; m_vol = nullptr; }
+  free_volume(m_ctx, m_vol);
   tvk_build_desc d{};
   for (int a = 0; a < 3; ++a) d.volume_size[a] = size[a];
   d.brick_size = brickSize; d.overlap = overlap; d.bytes_per_voxel = bpv; d.use_median = median ? 1 : 0;
@@ -394,9 +432,10 @@ bool CudaGridLeaper::LoadRawVolume(const void* raw, const uint32_t size[3], uint
   if (computeHist2D) {
     double lo, hi;
     v->Range(lo, hi);
-    std::vector<uint64_t> h2((size_t)tfSize * 256);
-    rc = tvk_build_hist2d(m_ctx, tfSize, hi, h2.data(), &v->max_grad_magnitude);
+    v->hist2d.resize((size_t)tfSize * 256);
+    rc = tvk_build_hist2d(m_ctx, tfSize, hi, v->hist2d.data(), &v->max_grad_magnitude);
     if (rc) { delete v; return Fail("tvk_build_hist2d", rc); }
+    v->hist2d_x = tfSize; v->hist2d_y = 256;
   }
   v->store_bytes = v->info.total_bytes;
   if (outOfCore) {
@@ -478,7 +517,7 @@ bool CudaGridLeaper::LoadDataset(const std::string& uvfFile, uint64_t gpuMemByte
     return false;
   }
   delete m_pool; m_pool = nullptr;
-  if (m_vol) { if (m_vol->host_store) cudaFreeHost(m_vol->host_store); delete m_vol; m_vol = nullptr; }
+  free_volume(m_ctx, m_vol);
   tvk_build_release(m_ctx);
   BrickedVolume* v = new BrickedVolume();
   v->bpv = ui.vol.component_type == TVK_UVF_CT_UINT16 ? 2 : 1;
@@ -502,6 +541,11 @@ bool CudaGridLeaper::LoadDataset(const std::string& uvfFile, uint64_t gpuMemByte
   v->hist1d.resize(ui.hist1d_size);
   if (ui.hist1d_size) tvk_uvf_get_hist1d(u, v->hist1d.data(), ui.hist1d_size);
   v->max_grad_magnitude = ui.max_grad_magnitude;
+  if (ui.hist2d_x && ui.hist2d_y) {                        // kept so that SaveUVF writes the file's own 2-D histogram back
+    v->hist2d.resize((size_t)(ui.hist2d_x * ui.hist2d_y));
+    if (tvk_uvf_get_hist2d(u, v->hist2d.data(), v->hist2d.size()) == TVK_OK) { v->hist2d_x = ui.hist2d_x; v->hist2d_y = ui.hist2d_y; }
+    else v->hist2d.clear();
+  }
   if (cudaHostAlloc((void**)&v->host_store, v->store_bytes, cudaHostAllocDefault) != cudaSuccess) {
     tvk_uvf_close(u); delete v; m_err = "cudaHostAlloc failed for the brick store"; return false;
   }
@@ -538,7 +582,7 @@ bool CudaGridLeaper::AdoptVolume(BrickedVolume* v, uint64_t gpuMemBytes) {
   if (!m_ctx) { m_err = "renderer not initialised"; return false; }
   if (!v || !v->host_store) { m_err = "AdoptVolume: the volume has no host brick store (PrepareHostVolume first)"; return false; }
   delete m_pool; m_pool = nullptr;
-  if (m_vol && m_vol != v) { if (m_vol->host_store) cudaFreeHost(m_vol->host_store); delete m_vol; }
+  if (m_vol && m_vol != v) free_volume(m_ctx, m_vol);
   m_vol = nullptr;
   tvk_build_release(m_ctx);
   const uint32_t tfSize = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)v->hist1d.size(), 4096));
@@ -560,7 +604,9 @@ bool CudaGridLeaper::SaveUVF(const std::string& uvfFile, uint32_t compression, u
   const uint32_t tfSize = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)v.hist1d.size(), 4096));
   std::vector<uint64_t> h2;
   float mg = v.max_grad_magnitude;
-  if (!v.host_store) {                        // the builder state is alive: the 2-D histogram comes from it
+  if (!v.hist2d.empty()) {                    // the histogram the file (or the load) came with
+    h2 = v.hist2d;
+  } else if (!v.host_store) {                 // the builder state is alive: the 2-D histogram comes from it
     double lo, hi;
     v.Range(lo, hi);
     h2.resize((size_t)tfSize * 256);
@@ -575,7 +621,7 @@ bool CudaGridLeaper::SaveUVF(const std::string& uvfFile, uint32_t compression, u
   w.total_bricks = v.info.total_bricks;
   w.brick_offsets = v.offsets.data(); w.brick_sizes = v.sizes.data(); w.store = store; w.minmax = v.minmax.data();
   w.hist1d = v.hist1d.data(); w.hist1d_size = v.hist1d.size();
-  if (!h2.empty()) { w.hist2d = h2.data(); w.hist2d_x = tfSize; w.hist2d_y = 256; }
+  if (!h2.empty()) { w.hist2d = h2.data(); w.hist2d_x = v.hist2d.empty() ? tfSize : v.hist2d_x; w.hist2d_y = v.hist2d.empty() ? 256 : v.hist2d_y; }
   w.max_grad_magnitude = mg;
   const char* keys[3] = {"Source Endianness", "Source Type", "Source Bitwidth"};
   const char* vals[3] = {"little", "integer", v.bpv == 2 ? "16" : "8"};
@@ -701,11 +747,8 @@ bool CudaGridLeaper::RecalcVisibility() { const bool ok = RecomputeBrickVisibili
 
 void CudaGridLeaper::ClearWorkingSet() {                                     // GLVolumePool::PH_Reset (:261-284)
   if (!m_pool || !m_vol) return;
-  const uint32_t* cap = m_pool->Capacity();
-  const uint32_t c[3] = {cap[0], cap[1], cap[2]};
-  BrickPool* np = new BrickPool(m_ctx, m_vol);
-  if (np->Create(c, m_activeSampler) == TVK_OK && np->UploadFirstBrick() == TVK_OK) { delete m_pool; m_pool = np; }
-  else delete np;
+  const int rc = m_pool->Reset();
+  if (rc) Fail("BrickPool::Reset", rc);
   m_visValid = false;
   RecomputeBrickVisibility(true);
   ScheduleCompleteRedraw();
@@ -990,13 +1033,32 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
 
 bool CudaGridLeaper::PaintClassic() {
   if (!m_ctx || !m_vol) { m_err = "Paint() without dataset"; return false; }
-  if (!m_vol->device_store) { m_err = "the classic ray-caster needs the brick store in device memory (load in core)"; return false; }
+  const void* store = m_vol->device_store;
+  if (!store) {
+    // datasets loaded from a UVF file (or out of core) keep their bricks in pinned host memory: the classic path reads
+    // whole bricks from a device-resident store, so the store is copied up once when it fits
+    if (!m_vol->classic_store) {
+      size_t freeB = 0, totalB = 0;
+      if (!m_vol->host_store || cudaMemGetInfo(&freeB, &totalB) != cudaSuccess || m_vol->store_bytes + (1ull << 30) > freeB) {
+        m_err = "the classic ray-caster needs the brick store in device memory and it does not fit (use the ray-guided renderer)";
+        return false;
+      }
+      if (cudaMalloc(&m_vol->classic_store, m_vol->store_bytes) != cudaSuccess ||
+          cudaMemcpy(m_vol->classic_store, m_vol->host_store, m_vol->store_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        if (m_vol->classic_store) { cudaFree(m_vol->classic_store); m_vol->classic_store = nullptr; }
+        (void)cudaGetLastError();
+        m_err = "could not copy the brick store to the device for the classic ray-caster";
+        return false;
+      }
+    }
+    store = m_vol->classic_store;
+  }
   tvk_classic_params p;
   std::vector<tvk_classic_brick> bricks;
   uint32_t lod = 0;
   if (!PlanClassicFrame(p, bricks, lod)) return false;
   if (m_blank) m_perf.frames += 1;
-  const int rc = tvk_raycast_classic(m_ctx, &p, bricks.data(), (uint32_t)bricks.size(), m_vol->device_store);
+  const int rc = tvk_raycast_classic(m_ctx, &p, bricks.data(), (uint32_t)bricks.size(), store);
   if (rc) return Fail("tvk_raycast_classic", rc);
   m_blank = false;
   m_perf.subframes += 1;
@@ -1006,33 +1068,62 @@ bool CudaGridLeaper::PaintClassic() {
   return true;
 }
 
+double CudaGridLeaper::PerfQuery(int counter) {
+  if (counter < 0 || counter >= PERF_END) return 0.0;
+  const double v = m_perfTable[counter];
+  m_perfTable[counter] = 0.0;
+  return v;
+}
+
 bool CudaGridLeaper::Paint() {                                               // GLGridLeaper::Render3DRegion (:914-1154)
   if (m_classic) return PaintClassic();
   if (!m_ctx || !m_vol || !m_pool) { m_err = "Paint() without dataset"; return false; }
   if (!m_w || !m_h) { m_err = "Paint() on a zero-sized target"; return false; }
+  typedef std::chrono::steady_clock clk;
+  auto ms_since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
+  const clk::time_point tPaint = clk::now();
   if (!m_visValid) RecomputeBrickVisibility(true);
   tvk_raycast_params p;
   if (!ComputeRaycastParams(p)) return false;
   if (m_blank) { m_perf.frames += 1; }
+  // the march is queued behind whatever upload the previous sub-frame left in flight (tvk_pool_upload_fence)
   int rc = tvk_raycast_subframe(m_ctx, &p);
   if (rc) return Fail("tvk_raycast_subframe", rc);
   m_blank = false;
   m_perf.subframes += 1;
+  m_perfTable[PERF_SUBFRAMES] += 1;
+  // ONE host synchronisation per sub-frame: request table and counters come back together
+  clk::time_point t0 = clk::now();
   std::vector<uint32_t> req(4 * (size_t)m_hashSize);
   uint32_t n = 0;
   rc = tvk_read_requests(m_ctx, req.data(), m_hashSize, &n);
   if (rc) return Fail("tvk_read_requests", rc);
   req.resize(4 * (size_t)n);
+  const double tRead = ms_since(t0);
+  tvk_stats st;
+  double marchMs = 0.0;
+  if (tvk_get_stats(m_ctx, &st, 0) == TVK_OK) { marchMs = st.last_raycast_ms; m_perf.raycast_ms += marchMs; m_perf.samples = (double)st.samples; }
+  m_perfTable[PERF_RAYCAST] += marchMs;
+  m_perfTable[PERF_READ_HTABLE] += std::max(0.0, tRead - marchMs);          // the wait covers the march itself
   if (n) {
     uint32_t paged = 0;
-    rc = m_pool->UploadBricks(req, paged);
+    t0 = clk::now();
+    const uint64_t before = m_pool->UploadedBytes();
+    // the upload is issued and ordered before the next sub-frame; the host goes on (Paint() returns while PCIe works)
+    rc = m_pool->UploadBricks(req, paged, false);
     if (rc) return Fail("UploadBricks", rc);
     m_perf.paged_bricks += paged;
     m_perf.uploaded_bytes = (double)m_pool->UploadedBytes();
+    m_perfTable[PERF_UPLOAD_BRICKS] += ms_since(t0);
+    m_perfTable[PERF_POOL_SORT] += m_pool->LastSortMs();
+    m_perfTable[PERF_POOL_GET_BRICK] += m_pool->LastGetBrickMs();
+    m_perfTable[PERF_POOL_UPLOAD_BRICK] += m_pool->LastUploadMs();
+    m_perfTable[PERF_POOL_UPLOAD_METADATA] += m_pool->LastMetadataMs();
+    m_perfTable[PERF_POOL_UPLOADED_MEM] += (double)(m_pool->UploadedBytes() - before);
+    m_perfTable[PERF_EO_BRICKS] += paged;
   }
-  tvk_stats st;
-  if (tvk_get_stats(m_ctx, &st, 0) == TVK_OK) { m_perf.raycast_ms += st.last_raycast_ms; m_perf.samples = (double)st.samples; }
   m_converged = (n == 0);
+  m_perfTable[PERF_RENDER] += ms_since(tPaint);
   return true;
 }
 
@@ -1280,5 +1371,6 @@ int tvkr_get_perf(tvkr_renderer* h, double out[6]) {
   out[0] = p.subframes; out[1] = p.raycast_ms; out[2] = p.paged_bricks; out[3] = p.uploaded_bytes; out[4] = p.samples; out[5] = p.frames;
   return 0;
 }
+double tvkr_perf_query(tvkr_renderer* h, int counter) { return h ? R(h)->PerfQuery(counter) : 0.0; }
 tvk_ctx* tvkr_context(tvkr_renderer* h) { return h ? R(h)->Context() : nullptr; }
 }

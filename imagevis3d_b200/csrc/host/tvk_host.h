@@ -84,6 +84,9 @@ struct BrickedVolume {
   std::vector<double>   minmax;         // 2 per brick
   std::vector<uint64_t> hist1d;
   float    max_grad_magnitude = 0.0f;   // 0 = unknown (2-D histogram not computed)
+  std::vector<uint64_t> hist2d;         // [hist2d_x][hist2d_y] when the file (or the builder) provided one
+  uint64_t hist2d_x = 0, hist2d_y = 0;
+  void*    classic_store = nullptr;     // device copy of host_store, made on demand for the classic ray-caster
   uint8_t* host_store = nullptr;        // pinned (cudaHostAlloc) when out of core
   void*    device_store = nullptr;      // owned by the tvk_ctx build state when in core
   uint64_t store_bytes = 0;
@@ -111,7 +114,10 @@ class BrickPool {
   static void ComputePoolCapacity(const BrickedVolume& v, uint64_t gpuMemBytes, uint32_t max3d, uint32_t cap[3]);
   int  Create(const uint32_t capacity[3], uint32_t sampler);
   int  UploadFirstBrick();                                       // :763-766
-  int  UploadBricks(const std::vector<uint32_t>& xyzl, uint32_t& paged);   // :1720-1789
+  // wait = false: the upload and the page-table patch are only ORDERED before later work on the render stream (the
+  // next sub-frame), the host does not block on the PCIe transfer (sources live in the pinned brick store)
+  int  UploadBricks(const std::vector<uint32_t>& xyzl, uint32_t& paged, bool wait = true);   // :1720-1789
+  int  Reset();                                                  // PH_Reset (:261-284): empty pool, coarsest brick pinned again
   int  RecomputeVisibility(const tvk_visibility& vis, uint32_t counts[4]); // :1580-1718
   bool IsBrickResident(uint32_t x, uint32_t y, uint32_t z, uint32_t lod) const;
   uint32_t BrickIndex(uint32_t x, uint32_t y, uint32_t z, uint32_t lod) const;   // GetIntegerBrickID
@@ -122,6 +128,11 @@ class BrickPool {
   const uint32_t* Capacity() const { return m_cap; }
   const uint32_t* MaxBrick() const { return m_maxBrick; }
   uint64_t UploadedBytes() const { return m_uploadedBytes; }
+  // host milliseconds of the last UploadBricks: slot sort, source look-up, transfer issue, page-table patch
+  double LastSortMs() const { return m_lastMs[0]; }
+  double LastGetBrickMs() const { return m_lastMs[1]; }
+  double LastUploadMs() const { return m_lastMs[2]; }
+  double LastMetadataMs() const { return m_lastMs[3]; }
 
  private:
   bool ContainsData(const tvk_visibility& vis, uint32_t index) const;
@@ -137,6 +148,7 @@ class BrickPool {
   uint64_t m_time = 2;                   // m_iTimeOfCreation
   size_t   m_insertPos = 0;
   uint64_t m_uploadedBytes = 0;
+  double   m_lastMs[4] = {0, 0, 0, 0};
 };
 
 // host-level choice: the layered-array pool (TVK_SAMPLER_GATHER)
@@ -145,8 +157,21 @@ static const uint32_t kSamplerAuto = 0xFFFFFFFFu;
 enum ERenderMode { RM_1DTRANS = 0, RM_2DTRANS = 1, RM_ISOSURFACE = 2 };
 enum ERendererTarget { RT_INTERACTIVE = 0, RT_CAPTURE = 1, RT_HEADLESS = 2 };
 
-struct PerfCounters {                     // subset of Basics/PerfCounter.h:7-44 we can fill
+struct PerfCounters {                     // running totals (tvkr_get_perf)
   double subframes = 0, raycast_ms = 0, paged_bricks = 0, uploaded_bytes = 0, samples = 0, frames = 0;
+};
+
+// enum PerfCounter of the reference, same order and values (Basics/PerfCounter.h:7-44): what `tuvok.perf(id)` takes.
+// PerfQuery returns the amount accumulated since the last query of that counter and resets it
+// (MasterController::PerfQuery, MasterController.cpp:305-310).  Filled here: SUBFRAMES, RENDER, RAYCAST, READ_HTABLE,
+// CONDENSE_HTABLE, UPLOAD_BRICKS, POOL_SORT, POOL_UPLOADED_MEM, POOL_GET_BRICK (host time of resolving the brick sources),
+// POOL_UPLOAD_BRICK (issue of the transfers), POOL_UPLOAD_METADATA, EO_BRICKS; the DY_* / disk counters stay 0.
+enum EPerfCounter {
+  PERF_SUBFRAMES = 0, PERF_RENDER, PERF_RAYCAST, PERF_READ_HTABLE, PERF_CONDENSE_HTABLE, PERF_SORT_HTABLE, PERF_UPLOAD_BRICKS,
+  PERF_POOL_SORT, PERF_POOL_UPLOADED_MEM, PERF_POOL_GET_BRICK, PERF_DY_GET_BRICK, PERF_DY_CACHE_LOOKUPS, PERF_DY_CACHE_LOOKUP,
+  PERF_DY_RESERVE_BRICK, PERF_DY_LOAD_BRICK, PERF_DY_CACHE_ADDS, PERF_DY_CACHE_ADD, PERF_DY_BRICK_COPIED, PERF_DY_BRICK_COPY,
+  PERF_POOL_UPLOAD_BRICK, PERF_POOL_UPLOAD_TEXEL, PERF_POOL_UPLOAD_METADATA, PERF_EO_BRICKS, PERF_EO_DISK_READ,
+  PERF_EO_DECOMPRESSION, PERF_MM_PRECOMPUTE, PERF_SOMETHING, PERF_END
 };
 
 class CudaGridLeaper {
@@ -236,6 +261,8 @@ class CudaGridLeaper {
   BrickPool* Pool() { return m_pool; }
   tvk_ctx* Context() { return m_ctx; }
   PerfCounters& Perf() { return m_perf; }
+  double PerfQuery(int counter);                        // tuvok.perf(id): value since the last query, then reset
+  void IncrementPerfCounter(int counter, double amount) { if (counter >= 0 && counter < PERF_END) m_perfTable[counter] += amount; }
   uint32_t Width() const { return m_w; }
   uint32_t Height() const { return m_h; }
 
@@ -267,6 +294,7 @@ class CudaGridLeaper {
   tvk_visibility m_lastVis{};
   bool m_visValid = false;
   PerfCounters m_perf;
+  double m_perfTable[PERF_END] = {};
   bool m_classic = false;
   bool m_clipEnabled = false;
   float m_clipPlane[4] = {0, 0, 1, 0};

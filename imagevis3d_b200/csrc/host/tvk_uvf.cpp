@@ -18,6 +18,7 @@
 #include <cfloat>
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -132,6 +133,7 @@ size_t z_compress(const uint8_t* src, size_t n, uint8_t* dst, uint32_t level) {
 }
 
 bool z_decompress(const uint8_t* src, size_t srclen, uint8_t* dst, size_t n) {
+  if (srclen > 0xFFFFFFFFull || n > 0xFFFFFFFFull) return false;       // zlib's one-shot interface counts in 32 bits
   z_stream s;
   memset(&s, 0, sizeof(s));
   if (inflateInit(&s) != Z_OK) return false;
@@ -147,6 +149,7 @@ bool z_decompress(const uint8_t* src, size_t srclen, uint8_t* dst, size_t n) {
 // reference links its vendored bzip2 / LZMA SDK; here the system's libbz2 / liblzma are opened on first use (no
 // headers in the image, so the few public declarations needed are restated below).
 bool bz_decompress(const uint8_t* src, size_t srclen, uint8_t* dst, size_t n) {
+  if (srclen > 0xFFFFFFFFull || n > 0xFFFFFFFFull) return false;       // unsigned int lengths in the bzip2 API
   typedef int (*fn_t)(char*, unsigned int*, char*, unsigned int, int, int);      // BZ2_bzBuffToBuffDecompress
   static fn_t fn = [] {
     void* h = dlopen("libbz2.so.1.0", RTLD_NOW);
@@ -426,6 +429,7 @@ struct tvk_uvf {
   std::vector<std::pair<std::string, std::string>> kv;
   uint32_t bpv = 0;
   uint64_t rdb_data_pos = 0;                  // file offset of the finest level's first brick
+  uint64_t file_size = 0;
 };
 
 namespace {
@@ -442,16 +446,34 @@ struct Rd {
 };
 }  // namespace
 
+// No C++ exception may cross the C ABI: every entry point that allocates from sizes found in the FILE runs inside this
+// guard (std::bad_alloc -> TVK_ERR_NOMEM, anything else -> TVK_ERR_INVALID).  On-disk sizes are checked against the
+// file size before they are trusted (a UVF's MD5 only guards against accidental corruption, and verifying it is optional).
+#define TVK_UVF_GUARD(expr_on_error, ...)                                                         \
+  try { __VA_ARGS__ }                                                                             \
+  catch (const std::bad_alloc&) { expr_on_error; return TVK_ERR_NOMEM; }                          \
+  catch (...) { expr_on_error; return TVK_ERR_INVALID; }
+
+static int uvf_open_impl(const char* path, int verify, tvk_uvf** out, char* err, size_t errlen, tvk_uvf*& u);
+
 extern "C" int tvk_uvf_open(const char* path, int verify, tvk_uvf** out, char* err, size_t errlen) {
   if (!path || !out) return TVK_ERR_INVALID;
   *out = nullptr;
+  tvk_uvf* u = nullptr;
+  TVK_UVF_GUARD({ if (u) tvk_uvf_close(u); *out = nullptr; set_err(err, errlen, "out of memory or corrupt file while parsing the UVF headers"); },
+                return uvf_open_impl(path, verify, out, err, errlen, u);)
+}
+
+static int uvf_open_impl(const char* path, int verify, tvk_uvf** out, char* err, size_t errlen, tvk_uvf*& u) {
   FILE* f = fopen(path, "rb");
   if (!f) { set_err(err, errlen, "file not found or access denied"); return TVK_ERR_INVALID; }
-  tvk_uvf* u = new tvk_uvf();
+  u = new tvk_uvf();
   u->f = f;
+  if (fseeko(f, 0, SEEK_END) == 0) u->file_size = (uint64_t)ftello(f);
+  fseeko(f, 0, SEEK_SET);
   u->info.toc_block = -1;
   u->info.rdb_block = -1;
-  auto fail = [&](const std::string& m, int code) { set_err(err, errlen, m); tvk_uvf_close(u); return code; };
+  auto fail = [&](const std::string& m, int code) { set_err(err, errlen, m); tvk_uvf_close(u); u = nullptr; return code; };
   Rd r{f};
   char magic[8];
   if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "UVF-DATA", 8) != 0) return fail("file magic not found", TVK_ERR_INVALID);
@@ -508,13 +530,20 @@ extern "C" int tvk_uvf_open(const char* path, int verify, tvk_uvf** out, char* e
       u->info.lod_count = bi2.lod_count;
       u->info.total_bricks = bi2.total_bricks;
       const uint64_t nb = bi2.total_bricks;
+      if (nb == 0 || nb > u->file_size / 36) return fail("brick table larger than the file", TVK_ERR_INVALID);   // 36 bytes per ToC entry
       u->t_off.resize(nb); u->t_len.resize(nb); u->t_comp.resize(nb);
       for (uint64_t i = 0; i < nb; ++i) {
-        u->t_off[i] = u->oct_pos + r.get<uint64_t>();
+        const uint64_t rel = r.get<uint64_t>();
+        u->t_off[i] = u->oct_pos + rel;
         u->t_len[i] = r.get<uint64_t>();
         u->t_comp[i] = r.get<uint32_t>();
         (void)r.get<uint64_t>(); (void)r.get<uint32_t>(); (void)r.get<uint32_t>();
-        u->info.store_bytes += (uint64_t)u->sizes[3 * i] * u->sizes[3 * i + 1] * u->sizes[3 * i + 2] * u->bpv;
+        const uint64_t raw = (uint64_t)u->sizes[3 * i] * u->sizes[3 * i + 1] * u->sizes[3 * i + 2] * u->bpv;
+        u->info.store_bytes += raw;
+        // a brick lies inside the file, and a stored (possibly compressed) brick is never much larger than its voxels
+        if (!r.ok || rel > u->file_size || u->t_len[i] > u->file_size || u->t_off[i] + u->t_len[i] > u->file_size ||
+            u->t_len[i] > raw + raw / 2 + 65536 || raw > 0xFFFFFFFFull)
+          return fail("corrupt brick table (entry outside the file or larger than its brick)", TVK_ERR_INVALID);
       }
       if (!r.ok) return fail("truncated brick table", TVK_ERR_INVALID);
       v.compression = u->t_comp[0];
@@ -534,7 +563,10 @@ extern "C" int tvk_uvf_open(const char* path, int verify, tvk_uvf** out, char* e
         uint64_t lodIdx = 1;
         for (int a = 0; a < 3; ++a) if (groups[a] >= lodIdx) lodIdx = groups[a] + 1;
         uint64_t levels = 0;
-        for (uint64_t i = 0; i < lodIdx; ++i) levels = std::max<uint64_t>(levels, r.get<uint64_t>());
+        usable = lodIdx <= 64;                                                // a LOD group index beyond that is a corrupt header
+        for (uint64_t i = 0; usable && i < lodIdx && r.ok; ++i) levels = std::max<uint64_t>(levels, r.get<uint64_t>());
+        usable = usable && r.ok;
+        if (!usable) { r.ok = true; if (next == 0) break; pos += next; continue; }
         const uint64_t edim = r.get<uint64_t>();
         usable = r.ok && edim == 1;
         if (usable) {
@@ -547,7 +579,8 @@ extern "C" int tvk_uvf_open(const char* path, int verify, tvk_uvf** out, char* e
             const uint8_t sgn = r.get<uint8_t>();
             const uint64_t toData = r.get<uint64_t>();
             usable = r.ok && (bits == 8 || bits == 16);
-            for (int a = 0; a < 3; ++a) usable = usable && dom[a] > 0 && brick[a] > ovl[a];
+            for (int a = 0; a < 3; ++a) usable = usable && dom[a] > 0 && dom[a] <= (1ull << 20) && brick[a] > ovl[a];
+            usable = usable && dom[0] * dom[1] * dom[2] * (bits / 8) <= u->file_size;      // the finest level is stored in full
             if (usable) {
               u->info.rdb_block = (int32_t)bi;
               u->info.rdb_bits = (uint32_t)bits; u->info.rdb_signed = sgn ? 1u : 0u; u->info.rdb_lod_levels = levels;
@@ -573,7 +606,7 @@ extern "C" int tvk_uvf_open(const char* path, int verify, tvk_uvf** out, char* e
       u->info.hist2d_x = nx; u->info.hist2d_y = ny;
     } else if (sem == BS_MAXMIN && u->minmax.empty()) {
       const uint64_t n = r.get<uint64_t>(), comps = r.get<uint64_t>();
-      if (!r.ok || comps == 0 || n > (1ull << 32)) return fail("corrupt max/min block", TVK_ERR_INVALID);
+      if (!r.ok || comps == 0 || comps > 64 || n > u->file_size / (32 * comps)) return fail("corrupt max/min block", TVK_ERR_INVALID);
       u->minmax.resize((size_t)(4 * n));
       std::vector<double> row(4 * comps);
       for (uint64_t i = 0; i < n; ++i) {
@@ -583,6 +616,7 @@ extern "C" int tvk_uvf_open(const char* path, int verify, tvk_uvf** out, char* e
       u->info.maxmin_bricks = n;
     } else if (sem == BS_KEY_VALUE && u->kv.empty()) {
       const uint64_t n = r.get<uint64_t>();
+      if (n > u->file_size / 16) return fail("corrupt key/value block", TVK_ERR_INVALID);
       for (uint64_t i = 0; i < n && r.ok; ++i) {
         const std::string k = r.str(r.get<uint64_t>());
         const std::string v = r.str(r.get<uint64_t>());
@@ -621,8 +655,12 @@ extern "C" int tvk_uvf_get_toc(const tvk_uvf* u, uint64_t* off, uint64_t* len, u
   return TVK_OK;
 }
 
+static int uvf_read_bricks_impl(tvk_uvf* u, uint64_t first, uint64_t count, void* dst, const uint64_t* dst_offsets);
 extern "C" int tvk_uvf_read_bricks(tvk_uvf* u, uint64_t first, uint64_t count, void* dst, const uint64_t* dst_offsets) {
-  if (!u || u->info.toc_block < 0 || !dst || first + count > u->info.total_bricks) return TVK_ERR_INVALID;
+  if (!u || u->info.toc_block < 0 || !dst || first > u->info.total_bricks || count > u->info.total_bricks - first) return TVK_ERR_INVALID;
+  TVK_UVF_GUARD({ u->err = "out of memory or corrupt data while reading bricks"; }, return uvf_read_bricks_impl(u, first, count, dst, dst_offsets);)
+}
+static int uvf_read_bricks_impl(tvk_uvf* u, uint64_t first, uint64_t count, void* dst, const uint64_t* dst_offsets) {
   std::vector<uint8_t> tmp;
   uint64_t packed = 0;
   for (uint64_t k = 0; k < count; ++k) {
@@ -660,8 +698,12 @@ static std::vector<uint64_t> rdb_axis_bricks(uint64_t size, uint64_t brick, uint
   return v;
 }
 
+static int uvf_read_rdb_impl(tvk_uvf* u, void* dst, uint64_t dst_bytes);
 extern "C" int tvk_uvf_read_rdb_volume(tvk_uvf* u, void* dst, uint64_t dst_bytes) {
   if (!u || !dst || u->info.rdb_block < 0) return TVK_ERR_INVALID;
+  TVK_UVF_GUARD({ u->err = "out of memory or corrupt data while reading the RasterDataBlock"; }, return uvf_read_rdb_impl(u, dst, dst_bytes);)
+}
+static int uvf_read_rdb_impl(tvk_uvf* u, void* dst, uint64_t dst_bytes) {
   const tvk_uvf_info& i = u->info;
   const uint64_t bpe = i.rdb_bits / 8;
   if (dst_bytes != i.rdb_domain[0] * i.rdb_domain[1] * i.rdb_domain[2] * bpe) { u->err = "destination size does not match the domain"; return TVK_ERR_INVALID; }

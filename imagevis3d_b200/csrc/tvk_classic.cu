@@ -275,6 +275,7 @@ extern "C" int tvk_raycast_classic(tvk_ctx* c, const tvk_classic_params* p, cons
   TVK_CHECK_CUDA(c, cudaGetLastError());
   TVK_CHECK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   c->launches++;
+  c->k1_serial++;
   TVK_CHECK_CUDA(c, cudaFreeAsync(d_bricks, c->stream));
   return TVK_OK;
 }

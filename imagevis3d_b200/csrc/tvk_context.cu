@@ -89,6 +89,11 @@ extern "C" int tvk_create(int device, tvk_ctx** out) {
     return TVK_ERR_CUDA;
   }
   c->own_stream = c->stream;
+  if (cudaHostAlloc((void**)&c->ring.base, (size_t)TVK_RING_SEGMENTS * TVK_RING_SEGMENT_BYTES, cudaHostAllocDefault) != cudaSuccess) {
+    c->ring.base = nullptr;                     // not fatal: parameter blocks then travel from pageable memory
+    (void)cudaGetLastError();
+  }
+  for (int i = 0; i < TVK_RING_SEGMENTS; ++i) cudaEventCreateWithFlags(&c->ring.done[i], cudaEventDisableTiming);
   cudaMemset(c->d_tile_counter, 0, 64);
   cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
   // keep stream-ordered allocations (pager staging ring, job lists) cached between frames
@@ -98,6 +103,24 @@ extern "C" int tvk_create(int device, tvk_ctx** out) {
     cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   *out = c;
+  return TVK_OK;
+}
+
+int tvk_copy_params_async(tvk_ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (!bytes) return TVK_OK;
+  PinnedRing& r = c->ring;
+  if (bytes > TVK_RING_SEGMENT_BYTES || !r.base) {
+    TVK_CHECK_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return TVK_OK;
+  }
+  const int k = r.next;
+  r.next = (r.next + 1) % TVK_RING_SEGMENTS;
+  if (r.in_flight[k]) TVK_CHECK_CUDA(c, cudaEventSynchronize(r.done[k]));     // 16 blocks ago: long finished in practice
+  uint8_t* seg = r.base + (size_t)k * TVK_RING_SEGMENT_BYTES;
+  memcpy(seg, src, bytes);
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(dst, seg, bytes, cudaMemcpyHostToDevice, st));
+  TVK_CHECK_CUDA(c, cudaEventRecord(r.done[k], st));
+  r.in_flight[k] = true;
   return TVK_OK;
 }
 
@@ -116,10 +139,13 @@ extern "C" void tvk_destroy(tvk_ctx* c) {
   tvk_build_release(c);
   tvk_pool_destroy(c);
   free_frame(c);
-  cudaFree(c->d_tf); cudaFree(c->d_tf_f); cudaFree(c->d_tf_colmask); cudaFree(c->d_hash); cudaFree(c->d_tile_counter); cudaFree(c->d_stats); cudaFree(c->d_counts);
+  cudaFree(c->d_tf); cudaFree(c->d_tf_f); cudaFree(c->d_tf_f1); cudaFree(c->d_tf_colmask); cudaFree(c->d_hash); cudaFree(c->d_tile_counter); cudaFree(c->d_stats); cudaFree(c->d_counts);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->bev0); cudaEventDestroy(c->bev1); cudaEventDestroy(c->copy_done); cudaEventDestroy(c->render_done);
   for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_gather[i]); cudaEventDestroy(c->ev_place[i]); }
   cudaStreamDestroy(c->own_stream); cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->place_stream);
+  for (int i = 0; i < TVK_RING_SEGMENTS; ++i) if (c->ring.done[i]) cudaEventDestroy(c->ring.done[i]);
+  if (c->ring.base) cudaFreeHost(c->ring.base);
+  if (c->h_readback) cudaFreeHost(c->h_readback);
   delete c;
 }
 
@@ -455,7 +481,7 @@ static int place_batch(tvk_ctx* c, std::vector<PlaceJob>& jobs, cudaStream_t st)
   std::stable_partition(jobs.begin(), jobs.end(), can_vec);
   PlaceJob* d_jobs = nullptr;
   TVK_CHECK_CUDA(c, cudaMallocAsync(&d_jobs, sizeof(PlaceJob) * jobs.size(), st));
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(PlaceJob) * jobs.size(), cudaMemcpyHostToDevice, st));
+  if (c->pdesc.sampler != TVK_SAMPLER_EXACT_Q4) { int rc = tvk_copy_params_async(c, d_jobs, jobs.data(), sizeof(PlaceJob) * jobs.size(), st); if (rc) return rc; }
   const dim3 grid((unsigned)jobs.size(), 8);
   if (c->pdesc.sampler == TVK_SAMPLER_EXACT_Q4) {
     // jobs with rows of a multiple of four voxels (and a source aligned to four voxels) take the vector kernel
@@ -464,8 +490,7 @@ static int place_batch(tvk_ctx* c, std::vector<PlaceJob>& jobs, cudaStream_t st)
     };
     std::vector<PlaceJob> sorted(jobs);
     const size_t nv = std::stable_partition(sorted.begin(), sorted.end(), q4_vec) - sorted.begin();
-    TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_jobs, sorted.data(), sizeof(PlaceJob) * sorted.size(), cudaMemcpyHostToDevice, st));
-    // (a cudaMemcpyAsync from pageable memory returns once the source has been staged: the locals may go)
+    { int rc = tvk_copy_params_async(c, d_jobs, sorted.data(), sizeof(PlaceJob) * sorted.size(), st); if (rc) return rc; }
     if (nv) {
       if (bpv == 1) place_bricks_q4_vec<uint8_t><<<dim3((unsigned)nv, 8), 256, 0, st>>>(d_jobs, c->d_pool, c->pc);
       else place_bricks_q4_vec<uint16_t><<<dim3((unsigned)nv, 8), 256, 0, st>>>(d_jobs, c->d_pool, c->pc);
@@ -609,7 +634,7 @@ extern "C" int tvk_pool_upload_bricks(tvk_ctx* c, uint32_t n, const uint32_t* sl
           }
           GatherJob* d_gj = nullptr;
           TVK_CHECK_CUDA(c, cudaMallocAsync(&d_gj, sizeof(GatherJob) * bn, st));
-          TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_gj, gj.data(), sizeof(GatherJob) * bn, cudaMemcpyHostToDevice, st));
+          { int rc = tvk_copy_params_async(c, d_gj, gj.data(), sizeof(GatherJob) * bn, st); if (rc) return rc; }
           gather_from_host_kernel<<<dim3(bn, 8), 256, 0, st>>>(d_gj);
           c->launches++;
           TVK_CHECK_CUDA(c, cudaGetLastError());
@@ -657,6 +682,14 @@ extern "C" int tvk_pool_upload_bricks(tvk_ctx* c, uint32_t n, const uint32_t* sl
   return TVK_OK;
 }
 
+extern "C" int tvk_pool_upload_fence(tvk_ctx* c) {
+  if (!c) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  // device-side ordering only: work issued on the render stream from now on sees the placed bricks; the host does not wait
+  TVK_CHECK_CUDA(c, cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+  return TVK_OK;
+}
+
 extern "C" int tvk_pool_upload_wait(tvk_ctx* c) {
   if (!c) return TVK_ERR_INVALID;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
@@ -689,13 +722,14 @@ extern "C" int tvk_pool_patch_metadata(tvk_ctx* c, uint32_t n, const uint32_t* b
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
   uint32_t* d = nullptr;
   TVK_CHECK_CUDA(c, cudaMallocAsync(&d, sizeof(uint32_t) * 2 * n, c->stream));
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(d, brick_index, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(d + n, value, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
+  { int rc = tvk_copy_params_async(c, d, brick_index, sizeof(uint32_t) * n, c->stream); if (rc) return rc; }
+  { int rc = tvk_copy_params_async(c, d + n, value, sizeof(uint32_t) * n, c->stream); if (rc) return rc; }
   patch_meta_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_meta, d, d + n, n, c->pc.total_bricks);
   c->launches++;
   TVK_CHECK_CUDA(c, cudaGetLastError());
   TVK_CHECK_CUDA(c, cudaFreeAsync(d, c->stream));
-  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));   // host arrays may be reused by the caller
+  // no host synchronisation: both arrays have been copied into the pinned parameter ring (or staged by the runtime), so
+  // the caller may reuse them; the patch itself is ordered on the render stream
   return TVK_OK;
 }
 
@@ -713,25 +747,41 @@ extern "C" int tvk_pool_get_metadata(tvk_ctx* c, uint32_t* meta, uint32_t n) {
 static int set_tf(tvk_ctx* c, const uint8_t* rgba, uint32_t w, uint32_t h) {
   if (!c || !rgba || w == 0 || h == 0) return TVK_ERR_INVALID;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
-  if ((size_t)w * h != (size_t)c->tf_w * c->tf_h) {
+  const size_t n = (size_t)w * h;
+  if (n != (size_t)c->tf_w * c->tf_h || (h == 1) != (c->d_tf_f != nullptr)) {
+    TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));            // a march in flight may still read the old tables
     cudaFree(c->d_tf); c->d_tf = nullptr;
     cudaFree(c->d_tf_f); c->d_tf_f = nullptr;
-    TVK_CHECK_CUDA(c, cudaMalloc(&c->d_tf, sizeof(uchar4) * (size_t)w * h));
-    TVK_CHECK_CUDA(c, cudaMalloc(&c->d_tf_f, sizeof(float4) * (size_t)w * h));
+    cudaFree(c->d_tf_f1); c->d_tf_f1 = nullptr;
+    TVK_CHECK_CUDA(c, cudaMalloc(&c->d_tf, sizeof(uchar4) * n));
+    // float copy with the kernel's own conversion (byte * (1/255)): one 16-byte fetch per sample -- 1D tables only
+    // (the 2D modes fetch the byte table; a 4096x256 table would be 16 MB more to convert and upload per edit)
+    if (h == 1) { TVK_CHECK_CUDA(c, cudaMalloc(&c->d_tf_f, sizeof(float4) * n)); TVK_CHECK_CUDA(c, cudaMalloc(&c->d_tf_f1, sizeof(float4) * n)); }
+  }
+  if (((w + 31) / 32) != ((c->tf_w + 31) / 32) || !c->d_tf_colmask) {
+    TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_tf_colmask); c->d_tf_colmask = nullptr;
+    TVK_CHECK_CUDA(c, cudaMalloc(&c->d_tf_colmask, sizeof(uint32_t) * ((w + 31) / 32)));
   }
   c->tf_w = w; c->tf_h = h;
-  // float copy with the kernel's own conversion (byte * (1/255)): one 16-byte fetch per sample
-  std::vector<float> f(4 * (size_t)w * h);
-  for (size_t i = 0; i < f.size(); ++i) f[i] = (float)rgba[i] * (1.0f / 255.0f);
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf, rgba, sizeof(uchar4) * (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf_f, f.data(), sizeof(float4) * (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf, rgba, sizeof(uchar4) * n, cudaMemcpyHostToDevice, c->stream));
+  std::vector<float> f;
+  if (h == 1) {
+    f.resize(4 * n);
+    for (size_t i = 0; i < f.size(); ++i) f[i] = (float)rgba[i] * (1.0f / 255.0f);
+    TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf_f, f.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
+    // OpacityCorrectColor for sampleRateModifier == 1 (blend.glsl:37-39): 1 - pow(1 - a, 1) = 1 - (1 - a), which is not
+    // always a in fp32 -- evaluated once per table entry here instead of once per sample in the kernel
+    for (size_t i = 0; i < n; ++i) { volatile float om = 1.0f - f[4 * i + 3]; f[4 * i + 3] = 1.0f - om; }
+    TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf_f1, f.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
+  }
   // per value column: does ANY gradient row give the sample a non-zero alpha?  (2D modes skip the gradient where not)
   std::vector<uint32_t> mask((w + 31) / 32, 0u);
-  for (uint32_t y = 0; y < h; ++y)
+  for (uint32_t y = 0; y < h; ++y) {
+    const uint8_t* row = rgba + 4 * (size_t)y * w;
     for (uint32_t x = 0; x < w; ++x)
-      if (rgba[4 * ((size_t)y * w + x) + 3]) mask[x >> 5] |= 1u << (x & 31);
-  cudaFree(c->d_tf_colmask); c->d_tf_colmask = nullptr;
-  TVK_CHECK_CUDA(c, cudaMalloc(&c->d_tf_colmask, sizeof(uint32_t) * mask.size()));
+      if (row[4 * x + 3]) mask[x >> 5] |= 1u << (x & 31);
+  }
   TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf_colmask, mask.data(), sizeof(uint32_t) * mask.size(), cudaMemcpyHostToDevice, c->stream));
   TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
   return TVK_OK;

@@ -60,8 +60,21 @@ struct ExchangeSend {                             // what K1 needs; world == 0: 
   uint32_t world, rank, rows, frame;
 };
 
+// Pinned host ring for the small parameter blocks that accompany asynchronous work (placement / gather job lists,
+// page-table patches).  A cudaMemcpyAsync FROM PAGEABLE memory first synchronises the host with the stream; from this
+// ring it does not, so issuing an upload never waits for the ray-march in flight.
+#define TVK_RING_SEGMENTS 16
+#define TVK_RING_SEGMENT_BYTES (256u << 10)
+struct PinnedRing {
+  uint8_t* base = nullptr;
+  cudaEvent_t done[TVK_RING_SEGMENTS] = {};
+  bool in_flight[TVK_RING_SEGMENTS] = {};
+  int next = 0;
+};
+
 struct tvk_ctx {
   int device = 0;
+  PinnedRing ring;
   cudaStream_t stream = nullptr;       // render / builder stream (own_stream unless tvk_set_stream)
   cudaStream_t own_stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // pager side stream
@@ -88,6 +101,7 @@ struct tvk_ctx {
   // transfer functions
   uchar4* d_tf = nullptr;
   float4* d_tf_f = nullptr;            // float copy of the table (byte * (1/255))
+  float4* d_tf_f1 = nullptr;           // the same with alpha already opacity-corrected for sampleRateModifier == 1: 1 - (1 - a)
   uint32_t* d_tf_colmask = nullptr;    // bit x: column x of the table holds a non-zero alpha (any row); 4096 bits max... sized tf_w
   uint32_t tf_w = 0, tf_h = 0;
 
@@ -104,6 +118,12 @@ struct tvk_ctx {
   unsigned long long* d_stats = nullptr;   // samples, rays, brick steps
   float last_raycast_ms = 0.f;
   uint32_t launches = 0;
+  // request read-back: one pinned staging block for the table AND the counters, so that a sub-frame costs ONE host
+  // synchronisation (tvk_read_requests); tvk_get_stats right after it is answered from the cached copy
+  uint32_t* h_readback = nullptr;
+  uint32_t h_readback_words = 0;
+  uint64_t k1_serial = 0, stats_serial = ~0ull;
+  unsigned long long cached_stats[3] = {0, 0, 0};
 
   BuildState build;
   ExchangeState xchg;
@@ -123,3 +143,5 @@ struct tvk_ctx {
 void tvk_compute_pool_const(const tvk_pool_desc& d, PoolConst& pc);
 int  tvk_ensure_frame(tvk_ctx* ctx, uint32_t w, uint32_t h, uint32_t hash_size);
 void tvk_exchange_fill(const tvk_ctx* ctx, ExchangeSend& s);
+// H2D copy of a small host block on stream st through the pinned ring (falls back to a plain copy for large blocks)
+int  tvk_copy_params_async(tvk_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t st);

@@ -44,6 +44,10 @@
 #ifndef TVK_OCC_GATHER
 #define TVK_OCC_GATHER 4
 #endif
+// lit / 2D-TF modes: centre samples whose footprints (and table look-ups) are in flight together
+#ifndef TVK_NB_LIT
+#define TVK_NB_LIT 2
+#endif
 
 struct RayParams {
   tvk_raycast_params p;
@@ -134,11 +138,11 @@ __device__ __forceinline__ void hash_report(const RayParams& rp, uint4 bc) {
 struct SlotCtx {
   const uint8_t* base;
   int ox, oy, oz;
-  // TVK_SAMPLER_GATHER: the slot's LOGICAL origin as floats (in-slot coordinates are formed in fp32, exactly), its
-  // PHYSICAL texel origin in the layered array (+1: a gather at (i+1, j+1) returns texels i..i+1 x j..j+1) and
-  // its first layer
-  float lx, ly, fx, fy;
-  uint32_t lz;
+  // TVK_SAMPLER_GATHER: what turns a LOGICAL pool voxel coordinate (the reference's texture addressing) into the
+  // PHYSICAL position of that voxel in the layered array: gather coordinate = floor(u) + gdx (exact in fp32: small
+  // integers; includes the +1 that makes a gather at (i+1, j+1) return texels i..i+1 x j..j+1), layer = floor(w) + ldz.
+  float gdx, gdy;
+  int ldz;               // added to the float BITS of floor(w) + 1.5*2^23 (the round-down trick's raw result)
 };
 
 struct BrickHit {
@@ -203,9 +207,9 @@ __device__ __forceinline__ void get_brick(const RayParams& rp, f3 entry, uint32_
     b.slot.ox = 0x4B400000 + (int)vx; b.slot.oy = 0x4B400000 + (int)vy; b.slot.oz = 0x4B400000 + (int)vz;
     if (SAMP == TVK_SAMPLER_GATHER) {
       const uint32_t p0 = idx % pc.phys_cap[0], p1 = (idx / pc.phys_cap[0]) % pc.phys_cap[1], p2 = idx / (pc.phys_cap[0] * pc.phys_cap[1]);
-      b.slot.lx = (float)vx; b.slot.ly = (float)vy;
-      b.slot.fx = (float)(p0 * pc.max_brick[0]) + 1.0f; b.slot.fy = (float)(p1 * pc.max_brick[1]) + 1.0f;
-      b.slot.lz = p2 * pc.max_brick[2];
+      b.slot.gdx = ((float)(p0 * pc.max_brick[0]) + 1.0f) - (float)vx;
+      b.slot.gdy = ((float)(p1 * pc.max_brick[1]) + 1.0f) - (float)vy;
+      b.slot.ldz = (int)(p2 * pc.max_brick[2]) - b.slot.oz;
     }
   }
   {
@@ -271,12 +275,11 @@ __device__ __forceinline__ void fetch_taps(const RayParams& rp, const SlotCtx& s
   const float tu = __fadd_rd(u, M), tv = __fadd_rd(v, M), tw = __fadd_rd(w, M);
   t.a = u - (tu - M); t.b = v - (tv - M); t.g = w - (tw - M);
   if (SAMP == TVK_SAMPLER_GATHER) {
-    // in-slot base corner in fp32 (small integers: exact), clamped like the integer path below; two gathers
-    const float xs = fminf(fmaxf((tu - M) - sl.lx, 0.0f), (float)((int)pc.max_brick[0] - 2));
-    const float ys = fminf(fmaxf((tv - M) - sl.ly, 0.0f), (float)((int)pc.max_brick[1] - 2));
-    const int zs = min(max(__float_as_int(tw) - sl.oz, 0), (int)pc.max_brick[2] - 2);
-    const float gx = xs + sl.fx, gy = ys + sl.fy;
-    const uint32_t l = sl.lz + (uint32_t)zs;
+    // Two gathers at the footprint's base corner.  No clamp to the slot: a position the march can produce keeps its
+    // footprint inside the brick's ghost layers (the integer path below clamps only to be able to share one
+    // address), and the texture unit itself clamps coordinates and layer index at the borders of the array.
+    const float gx = (tu - M) + sl.gdx, gy = (tv - M) + sl.gdy;
+    const uint32_t l = (uint32_t)(__float_as_int(tw) + sl.ldz);
     const uint4 g0 = gather4(rp.tex, l, gx, gy), g1 = gather4(rp.tex, l + 1u, gx, gy);
     // biased values 2^23 + texel: differences of biased values are exact, only the base taps drop the bias
     const float b000 = __uint_as_float(0x4B000000u | g0.w), b100 = __uint_as_float(0x4B000000u | g0.z);
@@ -444,16 +447,15 @@ __device__ __forceinline__ void center_gradient(const RayParams& rp, const SlotC
     // the 4x4 block (x-1..x+2, y-1..y+2) of planes z and z+1 = four diagonal gathers each; planes z-1 and z+2
     // need the centre 2x2 only: 10 gathers.  x / y neighbours are not clamped to the slot: a position the march
     // can produce keeps its taps inside the brick's ghost layers (see fetch_taps).
-    const float xs = fminf(fmaxf((tu - M) - sl.lx, 0.0f), (float)(mx - 2));
-    const float ys = fminf(fmaxf((tv - M) - sl.ly, 0.0f), (float)(my - 2));
-    const int zs = min(max(__float_as_int(tw) - sl.oz, 0), mz - 2);
-    const float gx = xs + sl.fx, gy = ys + sl.fy;
-    const uint32_t l = sl.lz + (uint32_t)zs;
+    const float gx = (tu - M) + sl.gdx, gy = (tv - M) + sl.gdy;
+    const int zs = min(max(__float_as_int(tw) - sl.oz, 0), mz - 2);          // in-slot plane (the z-1 / z+2 planes are clamped to the slot)
+    const int lz0 = sl.ldz + sl.oz;                                           // first layer of the slot
+    const uint32_t l = (uint32_t)(lz0 + zs);
     const uint4 mm0 = gather4(rp.tex, l, gx - 1.0f, gy - 1.0f), pm0 = gather4(rp.tex, l, gx + 1.0f, gy - 1.0f);
     const uint4 mp0 = gather4(rp.tex, l, gx - 1.0f, gy + 1.0f), pp0 = gather4(rp.tex, l, gx + 1.0f, gy + 1.0f);
     const uint4 mm1 = gather4(rp.tex, l + 1u, gx - 1.0f, gy - 1.0f), pm1 = gather4(rp.tex, l + 1u, gx + 1.0f, gy - 1.0f);
     const uint4 mp1 = gather4(rp.tex, l + 1u, gx - 1.0f, gy + 1.0f), pp1 = gather4(rp.tex, l + 1u, gx + 1.0f, gy + 1.0f);
-    const uint4 zm = gather4(rp.tex, sl.lz + (uint32_t)max(zs - 1, 0), gx, gy), zp = gather4(rp.tex, sl.lz + (uint32_t)min(zs + 2, mz - 1), gx, gy);
+    const uint4 zm = gather4(rp.tex, (uint32_t)(lz0 + max(zs - 1, 0)), gx, gy), zp = gather4(rp.tex, (uint32_t)(lz0 + min(zs + 2, mz - 1)), gx, gy);
     // gather(gx-1, gy-1): .w (x-1,y-1) .z (x,y-1) .x (x-1,y) .y (x,y);   gather(gx+1, gy-1): .w (x+1,y-1) .z (x+2,y-1) .x (x+1,y) .y (x+2,y)
     // gather(gx-1, gy+1): .w (x-1,y+1) .z (x,y+1) .x (x-1,y+2) .y (x,y+2); gather(gx+1, gy+1): .w (x+1,y+1) .z (x+2,y+1) .x (x+1,y+2) .y (x+2,y+2)
     k.X0[0] = u2f(mm0.x); k.X0[1] = u2f(mp0.w); k.X0[2] = u2f(mm1.x); k.X0[3] = u2f(mp1.w);
@@ -637,7 +639,7 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
 #define TVK_COMPOSITE(S)                                                                     \
         {                                                                                    \
           cn.samples++;                                                                      \
-          (S).w = (SRM1 || oc == 1.0f) ? 1.0f - (1.0f - (S).w) : 1.0f - powf(1.0f - (S).w, oc); \
+          if (!SRM1) (S).w = (oc == 1.0f) ? 1.0f - (1.0f - (S).w) : 1.0f - powf(1.0f - (S).w, oc);   /* SRM1: the table holds 1-(1-a) */ \
           const float w_ = (1.0f - acc.w) * (S).w;    /* UnderCompositing, Compositing.glsl:33-38 */ \
           acc.x = fmaf((S).x, w_, acc.x); acc.y = fmaf((S).y, w_, acc.y); acc.z = fmaf((S).z, w_, acc.z); \
           acc.w = fmaf((S).w, 1.0f - acc.w, acc.w);                                          \
@@ -669,6 +671,47 @@ __device__ __forceinline__ void march_ray(const RayParams& rp, float4 exitp, flo
 #pragma unroll
             for (int k = 0; k < NB; ++k) TVK_COMPOSITE(sc[k])
             q = mk3(qs[NB - 1].x + vdir.x, qs[NB - 1].y + vdir.y, qs[NB - 1].z + vdir.z);
+          }
+        }
+        if ((SAMP == TVK_SAMPLER_EXACT_Q4 || SAMP == TVK_SAMPLER_GATHER) && TVK_NB_LIT > 1 && ((LIT && MODE == TVK_RM_1DTRANS) || MODE == TVK_RM_2DTRANS)) {
+          // Lit and 2D-TF modes, pipelined: the CENTRE samples of NL consecutive steps (two fetches each) are issued
+          // together, then their table look-ups (1D: the entry itself, 2D: the column's "some row is visible" bit), and
+          // only then -- per sample, in order -- the gradient footprint and the shading of the samples that are not
+          // transparent.  Same arithmetic per sample as the scalar loop below, same order of compositing, early ray
+          // termination after each sample (later samples of the group were fetched speculatively and are dropped).
+          const int NL = TVK_NB_LIT;
+          for (; i + NL <= steps; i += NL) {
+            f3 qs[NL];
+            float d[NL];
+            qs[0] = q;
+#pragma unroll
+            for (int k = 1; k < NL; ++k) qs[k] = mk3(qs[k - 1].x + vdir.x, qs[k - 1].y + vdir.y, qs[k - 1].z + vdir.z);
+            {
+              Taps tp[NL];
+#pragma unroll
+              for (int k = 0; k < NL; ++k) fetch_taps<BPV, SAMP>(rp, b.slot, qs[k], tp[k]);
+#pragma unroll
+              for (int k = 0; k < NL; ++k) d[k] = filter_taps<BPV>(tp[k]);
+            }
+            float4 sc[NL];
+            bool vis[NL];
+#pragma unroll
+            for (int k = 0; k < NL; ++k) {
+              const int cx = nearest_index(d[k] * p.trans_scale, rp.tf_w);
+              if (MODE == TVK_RM_1DTRANS) { sc[k] = __ldg(rp.tf_f + cx); vis[k] = sc[k].w != 0.0f; }
+              else { sc[k] = make_float4(0.f, 0.f, 0.f, 0.f); vis[k] = ((__ldg(rp.tf_colmask + (cx >> 5)) >> (cx & 31)) & 1u) != 0u; }
+            }
+#pragma unroll
+            for (int k = 0; k < NL; ++k) {
+              if (vis[k]) {
+                float dc;
+                f3 g;
+                center_gradient<BPV, SAMP>(rp, b.slot, qs[k], dc, g);
+                sc[k] = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, d[k], qs[k], b.inv_scale, b.trans, &g);
+              }
+              TVK_COMPOSITE(sc[k])
+            }
+            q = mk3(qs[NL - 1].x + vdir.x, qs[NL - 1].y + vdir.y, qs[NL - 1].z + vdir.z);
           }
         }
         for (; i < steps; ++i) {
@@ -830,6 +873,276 @@ __device__ __forceinline__ void store_pixel(const RayParams& rp, uint32_t px, ui
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Transfer-function modes: LANES REFILL THEIR OWN RAYS.
+//
+// In the tile kernel below a warp owns an 8x4 pixel tile until its LAST ray has finished; rays of one tile end at
+// very different depths (early ray termination, silhouettes, bricks clipped at a corner), and ncu showed only 18-20
+// of 32 lanes active in the sample loop.  Here every lane carries its own ray through a small state machine --
+//   idle -> (fetch a pixel, set the ray up) -> need brick -> (GetBrick) -> sampling -> need brick -> ... -> finished -> idle
+// -- and a lane whose ray has finished fetches the next pixel while the others go on.  Pixels are handed out from one
+// global counter in tile-major order (32 consecutive numbers = one 8x4 tile), so the lanes of a warp stay on
+// neighbouring pixels.  The two divergent phases (ray set-up, page-table walk) only run when at least
+// TVK_REFILL_MIN / TVK_BRICK_MIN lanes wait for them (or nobody can sample), which keeps them from running with one
+// or two lanes.  The arithmetic of a ray -- and so every pixel, request and counter -- is that of march_ray.
+#ifndef TVK_REFILL_MIN
+#define TVK_REFILL_MIN 8
+#endif
+#ifndef TVK_BRICK_MIN
+#define TVK_BRICK_MIN 8
+#endif
+
+template <int MODE, bool LIT, int BPV, int SAMP, bool SRM1>
+__global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP == TVK_SAMPLER_TEX3D ? TVK_OCC_TEX : (SAMP == TVK_SAMPLER_GATHER ? TVK_OCC_GATHER : TVK_OCC_LDG)) : TVK_OCC_LIT) raycast_refill_kernel(const __grid_constant__ RayParams rp) {
+  const tvk_raycast_params& p = rp.p;
+  const PoolConst& pc = rp.pc;
+  const uint32_t lane = threadIdx.x & 31u;
+  const unsigned FULL = 0xffffffffu;
+  const uint32_t total_slots = rp.tiles_x * rp.tiles_y * 32u;
+  const float voxel_size = 0.125f / 2000.0f;
+  const float oc = 1.0f / p.sample_rate_modifier;
+  const float den = 2.0f * p.sample_rate_modifier;
+  unsigned long long nrays = 0, nsamples = 0, nbricks = 0;
+
+  // ---- per-lane ray state
+  bool active = false, optimal = true;
+  size_t pi = 0;
+  uint32_t px = 0, py = 0, j = 0, cn_samples = 0, cn_bricks = 0;
+  int steps_left = 0;
+  float4 exitp = make_float4(0.f, 0.f, 0.f, 0.f), pos = exitp, col = exitp, acc = exitp;
+  f3 entry = mk3(0.f, 0.f, 0.f), dir = entry, vdir = entry, cur = entry, q = entry;
+  float ray_len = 1.0f, step_size = 1.0f, t = 0.0f, entry_depth = 0.0f;
+  uint4 last_bc = make_uint4(0, 0, 0, 9999);
+  BrickHit b;
+  b.scale = b.trans = b.inv_scale = b.norm_exit = entry;
+  b.bc = last_bc;
+  b.slot.base = nullptr; b.slot.ox = b.slot.oy = b.slot.oz = 0; b.slot.gdx = b.slot.gdy = 0.f; b.slot.ldz = 0;
+  bool exhausted = false;                         // warp-uniform: the pixel counter has run past the image
+
+  // a finished ray writes its pixel and resume state (rayResumePos.w = 1000 when it was optimal all the way)
+#define TVK_FINISH_RAY()                                                   \
+  {                                                                        \
+    if (optimal) { pos.w = 1000.0f; col = acc; }                           \
+    store_pixel(rp, px, py, pi, acc);                                      \
+    rp.pos[pi] = pos;                                                      \
+    rp.aux[pi] = col;                                                      \
+    nsamples += cn_samples; nbricks += cn_bricks;                          \
+    active = false; steps_left = 0;                                        \
+  }
+  // what GLGridLeaper-blend.glsl does after a brick: new position, brick bookkeeping, progress along the ray
+#define TVK_AFTER_BRICK()                                                                                  \
+  {                                                                                                        \
+    last_bc = b.bc;                                                                                        \
+    t = len3(mk3(entry.x - b.norm_exit.x, entry.y - b.norm_exit.y, entry.z - b.norm_exit.z)) / ray_len;   \
+    ++j;                                                                                                   \
+    if (t > 0.9999f || j >= 100u) TVK_FINISH_RAY()                                                        \
+  }
+
+  for (;;) {
+    // ------------------------------------------------------------------ refill: idle lanes fetch pixels
+    const unsigned idle = __ballot_sync(FULL, !active);
+    if (!exhausted && (idle == FULL || __popc(idle) >= TVK_REFILL_MIN)) {
+      const int n = __popc(idle), leader = __ffs(idle) - 1;
+      uint32_t base = 0;
+      if ((int)lane == leader) base = atomicAdd(rp.tile_counter, (uint32_t)n);
+      base = __shfl_sync(FULL, base, leader);
+      if (base + (uint32_t)n >= total_slots) exhausted = true;
+      if (!active) {
+        const uint32_t slot = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+        if (slot < total_slots) {
+          const uint32_t tile = slot >> 5, l = slot & 31u;
+          px = (tile % rp.tiles_x) * 8u + (l & 7u); py = (tile / rp.tiles_x) * 4u + (l >> 3);
+          if (px < p.width && py < p.height) {
+            pi = (size_t)py * p.width + px;
+            float4 e4;
+            if (!ray_setup(p, px, py, e4, exitp)) {
+              if (p.new_view) {
+                store_pixel(rp, px, py, pi, make_float4(0.f, 0.f, 0.f, 0.f));
+                rp.aux[pi] = make_float4(0.f, 0.f, 0.f, 0.f);
+                rp.pos[pi] = make_float4(0.f, 0.f, 0.f, 1000.0f);
+              } else if (rp.xs.world) {
+                store_pixel(rp, px, py, pi, rp.image[pi]);       // the stripe owner needs every pixel of every frame
+              }
+            } else {
+              bool go = true;
+              if (p.new_view) { pos = e4; col = make_float4(0.f, 0.f, 0.f, 0.f); }
+              else {
+                pos = rp.pos[pi];
+                if (pos.w == 1000.0f) {                           // finished: image already holds rayResumeColor
+                  go = false;
+                  if (rp.xs.world) store_pixel(rp, px, py, pi, rp.image[pi]);
+                } else col = rp.aux[pi];
+              }
+              nrays++;
+              if (go) {
+                // GLGridLeaper-blend.glsl main(), the part before the brick loop
+                acc = col;
+                entry = mk3(pos.x, pos.y, pos.z);
+                entry_depth = pos.w;
+                dir = mk3(exitp.x - entry.x, exitp.y - entry.y, exitp.z - entry.z);
+                ray_len = len3(dir);
+                vdir = mk3(dir.x * pc.volume_size[0], dir.y * pc.volume_size[1], dir.z * pc.volume_size[2]);
+                const float vl = len3(vdir);
+                vdir = mk3(vdir.x / vl / pc.pool_size[0] / den, vdir.y / vl / pc.pool_size[1] / den, vdir.z / vl / pc.pool_size[2] / den);
+                step_size = len3(vdir);
+                t = 0.0f; optimal = true; cur = entry; last_bc = make_uint4(0, 0, 0, 9999); j = 0; steps_left = 0;
+                cn_samples = 0; cn_bricks = 0;
+                active = true;
+                if (!(ray_len > voxel_size)) TVK_FINISH_RAY()
+              }
+            }
+          }
+        }
+      }
+    }
+    const unsigned act = __ballot_sync(FULL, active);
+    if (act == 0u) { if (exhausted) break; continue; }
+
+    // ------------------------------------------------------------------ brick phase: GetBrick for the lanes that need one
+    const bool need_brick = active && steps_left == 0;
+    const unsigned nb = __ballot_sync(FULL, need_brick);
+    const unsigned can_sample = act & ~nb;
+    if (nb != 0u && (can_sample == 0u || __popc(nb) >= TVK_BRICK_MIN)) {
+      if (need_brick) {
+        const float depth = fmaf(exitp.w, t, entry_depth * (1.0f - t));
+        uint32_t lod = compute_lod(depth, p.lod_factor, p.level_zero_wse, pc.lod_count - 1);
+        get_brick<SAMP>(rp, cur, lod, dir, b);
+        cn_bricks++;
+        if (!b.found && optimal) {
+          optimal = false;
+          pos = make_float4(cur.x, cur.y, cur.z, depth);
+          col = acc;
+        }
+        if (!b.empty && (last_bc.x != b.bc.x || last_bc.y != b.bc.y || last_bc.z != b.bc.z || last_bc.w != b.bc.w)) {
+          int steps = (int)ceilf(len3(mk3(b.pool_exit.x - b.pool_entry.x, b.pool_exit.y - b.pool_entry.y, b.pool_exit.z - b.pool_entry.z)) / step_size);
+          const int s2 = (int)ceilf(len3(mk3((exitp.x - cur.x) * b.scale.x, (exitp.y - cur.y) * b.scale.y, (exitp.z - cur.z) * b.scale.z)) / step_size);
+          steps = min(steps, s2);
+          q = b.pool_entry;
+          steps_left = max(steps, 0);
+          if (steps_left == 0) {
+            cur = mk3((q.x - b.trans.x) / b.scale.x, (q.y - b.trans.y) / b.scale.y, (q.z - b.trans.z) / b.scale.z);
+            TVK_AFTER_BRICK()
+          }
+        } else {
+          cur = mk3(b.norm_exit.x + voxel_size * dir.x / ray_len, b.norm_exit.y + voxel_size * dir.y / ray_len,
+                    b.norm_exit.z + voxel_size * dir.z / ray_len);
+          TVK_AFTER_BRICK()
+        }
+      }
+      continue;                                   // lanes may have finished: give the refill a look before sampling
+    }
+
+    // ------------------------------------------------------------------ sample phase: one group of samples per lane
+    if (active && steps_left > 0) {
+      bool ended = false;                         // early ray termination inside this group
+#define TVK_COMPOSITE_L(S)                                                                   \
+      {                                                                                      \
+        cn_samples++;                                                                        \
+        if (!SRM1) (S).w = (oc == 1.0f) ? 1.0f - (1.0f - (S).w) : 1.0f - powf(1.0f - (S).w, oc);   /* SRM1: the table holds 1-(1-a) */ \
+        const float w_ = (1.0f - acc.w) * (S).w;    /* UnderCompositing, Compositing.glsl:33-38 */ \
+        acc.x = fmaf((S).x, w_, acc.x); acc.y = fmaf((S).y, w_, acc.y); acc.z = fmaf((S).z, w_, acc.z); \
+        acc.w = fmaf((S).w, 1.0f - acc.w, acc.w);                                            \
+        if (acc.w > 0.99f) ended = true;                                                     \
+      }
+      const bool shaded = (SAMP == TVK_SAMPLER_EXACT_Q4 || SAMP == TVK_SAMPLER_GATHER) && ((LIT && MODE == TVK_RM_1DTRANS) || MODE == TVK_RM_2DTRANS);
+      const int NG = shaded ? TVK_NB_LIT : (((MODE == TVK_RM_1DTRANS) && !LIT) ? (SAMP == TVK_SAMPLER_TEX3D ? TVK_NB_TEX : (SAMP == TVK_SAMPLER_GATHER ? TVK_NB_GATHER : TVK_NB_LDG)) : 1);
+      f3 qs[NG + 1];
+      float d[NG];
+      qs[0] = q;
+#pragma unroll
+      for (int k = 1; k <= NG; ++k) qs[k] = mk3(qs[k - 1].x + vdir.x, qs[k - 1].y + vdir.y, qs[k - 1].z + vdir.z);
+      // the footprints of the whole group are in flight together (positions past the brick's last step are fetched
+      // speculatively -- addresses stay inside the slot -- and never composited)
+      if (SAMP == TVK_SAMPLER_TEX3D) {
+#pragma unroll
+        for (int k = 0; k < NG; ++k) d[k] = tex3D<float>(rp.tex, qs[k].x, qs[k].y, qs[k].z);
+      } else {
+        Taps tp[NG];
+#pragma unroll
+        for (int k = 0; k < NG; ++k) fetch_taps<BPV, SAMP>(rp, b.slot, qs[k], tp[k]);
+#pragma unroll
+        for (int k = 0; k < NG; ++k) d[k] = filter_taps<BPV>(tp[k]);
+      }
+      float4 sc[NG];
+      const int n_do = min(NG, steps_left);
+      int done = 0;
+      if (shaded) {
+        bool vis[NG];
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+          const int cx = nearest_index(d[k] * p.trans_scale, rp.tf_w);
+          if (MODE == TVK_RM_1DTRANS) { sc[k] = __ldg(rp.tf_f + cx); vis[k] = sc[k].w != 0.0f; }
+          else { sc[k] = make_float4(0.f, 0.f, 0.f, 0.f); vis[k] = ((__ldg(rp.tf_colmask + (cx >> 5)) >> (cx & 31)) & 1u) != 0u; }
+        }
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+          if (k < n_do && !ended) {
+            if (vis[k]) {
+              float dc;
+              f3 g;
+              center_gradient<BPV, SAMP>(rp, b.slot, qs[k], dc, g);
+              sc[k] = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, d[k], qs[k], b.inv_scale, b.trans, &g);
+            }
+            TVK_COMPOSITE_L(sc[k])
+            done = k + 1;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < NG; ++k) sc[k] = color_from_volume<MODE, LIT, BPV, SAMP>(rp, b.slot, d[k], qs[k], b.inv_scale, b.trans);
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+          if (k < n_do && !ended) {
+            TVK_COMPOSITE_L(sc[k])
+            done = k + 1;
+          }
+        }
+      }
+#undef TVK_COMPOSITE_L
+      if (ended) {
+        TVK_FINISH_RAY()
+      } else {
+        // q after `done` samples: qs[done] (built by repeated addition, exactly like the scalar loop's q += step)
+        f3 qn = qs[0];
+#pragma unroll
+        for (int k = 1; k <= NG; ++k) if (k == done) qn = qs[k];
+        q = qn;
+        steps_left -= done;
+        if (steps_left == 0) {
+          cur = mk3((q.x - b.trans.x) / b.scale.x, (q.y - b.trans.y) / b.scale.y, (q.z - b.trans.z) / b.scale.z);
+          TVK_AFTER_BRICK()
+        }
+      }
+    }
+  }
+#undef TVK_FINISH_RAY
+#undef TVK_AFTER_BRICK
+  if (p.count_samples) {
+    for (int o = 16; o > 0; o >>= 1) {
+      nsamples += __shfl_down_sync(FULL, nsamples, o);
+      nbricks += __shfl_down_sync(FULL, nbricks, o);
+      nrays += __shfl_down_sync(FULL, nrays, o);
+    }
+    if (lane == 0) {
+      atomicAdd(rp.stats + 0, nsamples);
+      atomicAdd(rp.stats + 1, nrays);
+      atomicAdd(rp.stats + 2, nbricks);
+    }
+  }
+  if (rp.xs.world) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned prev = atomicAdd(rp.tile_counter + 1, 1u);
+      if (prev == gridDim.x - 1) {
+        rp.tile_counter[1] = 0u;
+        __threadfence_system();
+        for (uint32_t o = 0; o < rp.xs.world; ++o) *reinterpret_cast<volatile uint32_t*>(rp.xs.flag[o]) = rp.xs.frame;
+      }
+    }
+  }
+}
+
 // SRM1: sampleRateModifier == 1 known at compile time (the opacity correction is then the identity
 // 1-(1-a) and the pow path is not even compiled in); instantiated for the 1D-TF kernels only.
 template <int MODE, bool LIT, int BPV, int SAMP, bool SRM1>
@@ -855,6 +1168,8 @@ __global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP 
         store_pixel(rp, px, py, i, make_float4(0.f, 0.f, 0.f, 0.f));
         rp.aux[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         rp.pos[i] = make_float4(0.f, 0.f, 0.f, 1000.0f);
+      } else if (rp.xs.world) {
+        store_pixel(rp, px, py, i, rp.image[i]);      // sort-last: the stripe owner needs EVERY pixel of every frame
       }
       continue;
     }
@@ -864,7 +1179,10 @@ __global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP 
     nrays++;
     if (MODE == TVK_RM_ISOSURFACE) {
       if (!rp.p.new_view) {
-        if (floorf(pos.w) == 1000.0f) continue;      // finished without a hit: image stays 0
+        if (floorf(pos.w) == 1000.0f) {              // finished without a hit: image stays 0
+          if (rp.xs.world) store_pixel(rp, px, py, i, rp.image[i]);
+          continue;
+        }
         aux = rp.aux[i];
       }
       float4 hit, hitn;
@@ -872,7 +1190,10 @@ __global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP 
       store_pixel(rp, px, py, i, compose_iso(rp.p, hit, hitn));
     } else {
       if (!rp.p.new_view) {
-        if (pos.w == 1000.0f) continue;              // finished: image already holds rayResumeColor
+        if (pos.w == 1000.0f) {                      // finished: image already holds rayResumeColor
+          if (rp.xs.world) store_pixel(rp, px, py, i, rp.image[i]);
+          continue;
+        }
         aux = rp.aux[i];
       }
       float4 acc;
@@ -912,14 +1233,23 @@ __global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP 
 
 typedef void (*raycast_fn)(const RayParams);
 
+// Transfer-function modes run the tile kernel.  -DTVK_K1_REFILL builds the ray-refill kernel instead: same images
+// (the GPU tests pass with it), but measured SLOWER on the B200 -- 2048^3 2D-TF lit 5.7-7.5 ms against 3.9 ms, 1D-TF
+// 1.9-2.5 ms against 1.3 ms over the threshold sweep (profiles/r02_k1_sweep2.jsonl): the page-table walk and the ray
+// set-up then run many times with a quarter of the lanes, which costs more than the idle lanes it removes.
+#ifdef TVK_K1_REFILL
+#define TVK_TF_KERNEL raycast_refill_kernel
+#else
+#define TVK_TF_KERNEL raycast_kernel
+#endif
 template <int BPV, int SAMP>
 static raycast_fn pick_kernel(uint32_t mode, bool lit, bool srm1) {
   if (mode == TVK_RM_ISOSURFACE) return raycast_kernel<TVK_RM_ISOSURFACE, false, BPV, SAMP, false>;
   if (mode == TVK_RM_1DTRANS) {
-    if (srm1) return lit ? raycast_kernel<TVK_RM_1DTRANS, true, BPV, SAMP, true> : raycast_kernel<TVK_RM_1DTRANS, false, BPV, SAMP, true>;
-    return lit ? raycast_kernel<TVK_RM_1DTRANS, true, BPV, SAMP, false> : raycast_kernel<TVK_RM_1DTRANS, false, BPV, SAMP, false>;
+    if (srm1) return lit ? TVK_TF_KERNEL<TVK_RM_1DTRANS, true, BPV, SAMP, true> : TVK_TF_KERNEL<TVK_RM_1DTRANS, false, BPV, SAMP, true>;
+    return lit ? TVK_TF_KERNEL<TVK_RM_1DTRANS, true, BPV, SAMP, false> : TVK_TF_KERNEL<TVK_RM_1DTRANS, false, BPV, SAMP, false>;
   }
-  return lit ? raycast_kernel<TVK_RM_2DTRANS, true, BPV, SAMP, false> : raycast_kernel<TVK_RM_2DTRANS, false, BPV, SAMP, false>;
+  return lit ? TVK_TF_KERNEL<TVK_RM_2DTRANS, true, BPV, SAMP, false> : TVK_TF_KERNEL<TVK_RM_2DTRANS, false, BPV, SAMP, false>;
 }
 template <int BPV>
 static raycast_fn pick_sampler(uint32_t sampler, uint32_t mode, bool lit, bool srm1) {
@@ -954,7 +1284,7 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   rp.tex = c->pool_tex;
   rp.meta = c->d_meta;
   rp.tf = c->d_tf;
-  rp.tf_f = c->d_tf_f;
+  rp.tf_f = c->d_tf_f;       // (replaced below by the opacity-corrected copy when the SRM1 kernels run)
   rp.tf_colmask = c->d_tf_colmask;
   rp.tf_w = c->tf_w; rp.tf_h = c->tf_h;
   rp.hash = c->d_hash;
@@ -967,6 +1297,7 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
     TVK_FAIL(c, TVK_ERR_INVALID, "exchange was created for another image size");
 
   const bool srm1 = (1.0f / p->sample_rate_modifier == 1.0f);
+  if (srm1 && p->render_mode == TVK_RM_1DTRANS) rp.tf_f = c->d_tf_f1;
   const raycast_fn fn = (c->pc.bpv == 1) ? pick_sampler<1>(c->pdesc.sampler, p->render_mode, p->lighting != 0, srm1)
                                          : pick_sampler<2>(c->pdesc.sampler, p->render_mode, p->lighting != 0, srm1);
 
@@ -988,15 +1319,27 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   TVK_CHECK_CUDA(c, cudaGetLastError());
   TVK_CHECK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   c->launches++;
+  c->k1_serial++;
   return TVK_OK;
 }
 
 extern "C" int tvk_read_requests(tvk_ctx* c, uint32_t* xyzl, uint32_t cap, uint32_t* count) {
   if (!c || !count || (cap && !xyzl) || !c->d_hash || !c->has_pool) return TVK_ERR_INVALID;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
-  std::vector<uint32_t> h(c->hash_size);
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(h.data(), c->d_hash, sizeof(uint32_t) * c->hash_size, cudaMemcpyDeviceToHost, c->stream));
+  const uint32_t words = c->hash_size + 8;
+  if (c->h_readback_words < words) {
+    if (c->h_readback) cudaFreeHost(c->h_readback);
+    c->h_readback = nullptr; c->h_readback_words = 0;
+    TVK_CHECK_CUDA(c, cudaHostAlloc((void**)&c->h_readback, sizeof(uint32_t) * words, cudaHostAllocDefault));
+    c->h_readback_words = words;
+  }
+  uint32_t* h = c->h_readback;
+  unsigned long long* hs = reinterpret_cast<unsigned long long*>(h + ((c->hash_size + 1) & ~1u));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(h, c->d_hash, sizeof(uint32_t) * c->hash_size, cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(hs, c->d_stats, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->cached_stats[0] = hs[0]; c->cached_stats[1] = hs[1]; c->cached_stats[2] = hs[2];
+  c->stats_serial = c->k1_serial;
   // GLHashTable::GetData + Int2Vector (GLHashTable.cpp:65-77,90-104)
   const uint32_t* B = c->pc.l0_bricks;
   const uint32_t vol = B[0] * B[1] * B[2];
@@ -1074,9 +1417,14 @@ extern "C" int tvk_get_stats(tvk_ctx* c, tvk_stats* out, int reset) {
   if (!c || !out) return TVK_ERR_INVALID;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
   unsigned long long h[3];
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-  if (reset) TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_stats, 0, sizeof(h), c->stream));
-  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (!reset && c->stats_serial == c->k1_serial) {
+    // counters were fetched together with the request table after the last ray-march: no device access needed
+    h[0] = c->cached_stats[0]; h[1] = c->cached_stats[1]; h[2] = c->cached_stats[2];
+  } else {
+    TVK_CHECK_CUDA(c, cudaMemcpyAsync(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    if (reset) { TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_stats, 0, sizeof(h), c->stream)); c->stats_serial = ~0ull; }
+    TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
   float ms = 0.f;
   if (c->launches && cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_raycast_ms = ms;
   (void)cudaGetLastError();

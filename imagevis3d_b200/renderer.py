@@ -217,7 +217,7 @@ class Renderer:
         self._ck(self._lib.tvkr_set_2d_trans(self._h, a.ctypes.data_as(C.c_void_p), C.c_uint32(a.shape[1]),
                                              C.c_uint32(a.shape[0]), nz), "changed2DTrans")
 
-    def setState(self, brick_strategy=3, hash_table_size=509, rehash_count=10, sampler=0):
+    def setState(self, brick_strategy=3, hash_table_size=509, rehash_count=10, sampler=0xFFFFFFFF):
         """tuvok.state.brickStrategy / hashTableSize / rehashCount"""
         self._ck(self._lib.tvkr_set_state(self._h, C.c_uint32(brick_strategy), C.c_uint32(hash_table_size),
                                           C.c_uint32(rehash_count), C.c_uint32(sampler)), "setState")
@@ -277,6 +277,12 @@ class Renderer:
         self._ck(self._lib.tvkr_get_pool_slots(self._h, brick.ctypes.data_as(C.c_void_p), time.ctypes.data_as(C.c_void_p),
                                                C.c_uint32(n), C.byref(cnt)), "poolSlots")
         return brick, time
+
+    def perfQuery(self, counter):
+        """tuvok.perf(id): enum PerfCounter of Basics/PerfCounter.h (0 subframes, 2 raycast ms, 6 upload ms, 8 uploaded bytes ...);
+        returns the amount since the last query of that counter and resets it"""
+        self._lib.tvkr_perf_query.restype = C.c_double
+        return float(self._lib.tvkr_perf_query(self._h, C.c_int(int(counter))))
 
     def perf(self):
         out = (C.c_double * 6)()

@@ -114,6 +114,10 @@ int tvk_pool_upload_bricks(tvk_ctx* ctx, uint32_t n, const uint32_t* slot,
                            const void* const* src, const uint32_t* sizes,
                            int on_device);
 int tvk_pool_upload_wait(tvk_ctx* ctx);
+/* The same ordering without blocking the host: everything issued on the render stream after this call (metadata
+ * patches, the next ray-march) runs after the upload in flight has been placed.  Only for sources that stay valid
+ * until then (the renderer's pinned brick store). */
+int tvk_pool_upload_fence(tvk_ctx* ctx);
 
 /* replaces UploadMetadataTexture / UploadMetadataTexel (GLVolumePool.cpp:912-953) */
 int tvk_pool_set_metadata(tvk_ctx* ctx, const uint32_t* meta, uint32_t n);

@@ -117,6 +117,11 @@ int tvkr_set_lod_limits(tvkr_renderer* r, uint32_t lo, uint32_t hi);            
 int tvkr_set_bg_colors(tvkr_renderer* r, const float top[3], const float bottom[3]);   /* renderer.setBGColors */
 int tvkr_set_blend_precision(tvkr_renderer* r, int precision);   /* renderer.setBlendPrecision: accumulation is always fp32 here */
 int tvkr_get_perf(tvkr_renderer* r, double out[6]);     /* tuvok.perf: subframes, raycast ms, paged bricks, uploaded bytes, samples, frames */
+/* tuvok.perf(id) (MasterController::PerfQuery, MasterController.cpp:305-310, registered :502): id = enum PerfCounter of
+ * Basics/PerfCounter.h:7-44 (0 PERF_SUBFRAMES, 1 PERF_RENDER, 2 PERF_RAYCAST, 3 PERF_READ_HTABLE, 6 PERF_UPLOAD_BRICKS,
+ * 7 PERF_POOL_SORT, 8 PERF_POOL_UPLOADED_MEM, 9 PERF_POOL_GET_BRICK, 19 PERF_POOL_UPLOAD_BRICK,
+ * 21 PERF_POOL_UPLOAD_METADATA, 22 PERF_EO_BRICKS ...): the amount since the last query of that counter, which is reset */
+double tvkr_perf_query(tvkr_renderer* r, int counter);
 tvk_ctx* tvkr_context(tvkr_renderer* r);
 
 #ifdef __cplusplus

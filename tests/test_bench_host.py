@@ -31,10 +31,24 @@ def test_emit_line_plain_stdout():
 
 
 def test_bench_tf_visible_range():
-    """The bench transfer function is transparent below value 65: bricks whose maximum stays below it are the ones
-    the e2e leg never uploads."""
+    """The bench transfer functions have a transparent low end: bricks whose maximum stays below the first non-zero
+    alpha entry are the ones visibility flags empty and the e2e leg never pages in."""
     sys.path.insert(0, ROOT)
     import bench
-    rgba, lo, hi = bench.bench_tf()
-    assert rgba.shape == (256, 4) and (rgba[:int(lo), 3] == 0).all() and rgba[int(lo), 3] >= 0 and hi == 255.0
-    assert lo == 65.0
+    for n in (256, 4096):
+        rgba, lo, hi = bench.tf1d_std(n)
+        assert rgba.shape == (n, 4) and (rgba[:int(lo), 3] == 0).all() and rgba[int(lo), 3] > 0 and hi == n - 1
+        assert 0.25 * n <= lo <= 0.4 * n
+    t2, nz = bench.tf2d(4096)
+    assert t2.shape == (256, 4096, 4) and (t2[:, :int(nz[0]), 3] == 0).all() and t2[:, int(nz[0]), 3].max() > 0
+    assert nz[2:] == (0.0, 255.0)
+
+
+def test_bench_workloads_name_the_baseline_configs():
+    """N=1 is configs[2] (2048^3 u16, 1080p, 2D-TF lit), N>1 is configs[3] (4096^3 u16, 4K): the line says which."""
+    sys.path.insert(0, ROOT)
+    import bench
+    c = bench.workload_config(1, "2d_lit")
+    assert "configs[2]" in c["workload"] and c["volume"] == [2048] * 3 and c["resolution"] == [1920, 1080]
+    c = bench.workload_config(8, "1d_lit")
+    assert "configs[3]" in c["workload"] and c["volume"] == [4096] * 3 and c["resolution"] == [3840, 2160]

@@ -257,3 +257,35 @@ def test_clip_plane_through_the_host():
     with pytest.raises(Exception):
         r.setTimestep(3)
     r.cleanup()
+
+
+def test_clear_working_set_repaints_the_same_frame_and_perf_counters_reset():
+    """renderer.clearWorkingSet() (GLVolumePool::PH_Reset) empties the pool WITHOUT re-creating it; painting the same
+    view again pages the same bricks in and gives the same bits.  tuvok.perf(id) returns the amount since the last
+    query and resets the counter (MasterController::PerfQuery)."""
+    from imagevis3d_b200.renderer import Renderer
+    vol = H.synth_blobs((150, 131, 97), np.uint8)
+    r = Renderer(0)
+    r.loadRawVolume(vol, brick_size=20, out_of_core=True)
+    r.set1DTransFloat(_tf(r.datasetInfo().tf_size))
+    r.resize((160, 120))
+    r.setRotation4x4(H.rotation_y(0.6) @ H.rotation_x(0.3))
+    for k in range(8):                                      # drain whatever loading counted
+        r.perfQuery(k)
+    s1 = r.paintUntilConverged()
+    a = r.frameFloat()
+    slots1, _ = r.poolSlots()
+    assert r.perfQuery(0) == s1 and r.perfQuery(0) == 0          # PERF_SUBFRAMES
+    assert r.perfQuery(2) > 0 and r.perfQuery(2) == 0            # PERF_RAYCAST (ms)
+    up = r.perfQuery(8)                                          # PERF_POOL_UPLOADED_MEM (bytes)
+    assert up > 0 and r.perfQuery(22) > 0                        # PERF_EO_BRICKS
+    r.clearWorkingSet()
+    slots_c, _ = r.poolSlots()
+    assert (slots_c >= 0).sum() == 1                             # only the pinned coarsest brick
+    assert r.checkForRedraw()
+    s2 = r.paintUntilConverged()
+    b = r.frameFloat()
+    slots2, _ = r.poolSlots()
+    assert s1 == s2 and np.array_equal(a, b) and np.array_equal(slots1, slots2)
+    assert r.perfQuery(8) == up
+    r.cleanup()

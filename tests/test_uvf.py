@@ -104,6 +104,55 @@ def test_reader_rejects_corruption(tmp_path):
         U.UvfFile(str(tmp_path / "missing.uvf"))
 
 
+def test_reader_survives_hostile_sizes(tmp_path):
+    """Sizes found in the file are checked against the file before anything is allocated from them, and no C++
+    exception crosses the C ABI: a brick-table entry of 2^62 bytes, an entry pointing behind the end of the file, a
+    max/min block announcing 2^40 bricks and a RasterDataBlock header with an absurd LOD index all come back as
+    errors (or as an unusable block) -- the process must not abort or hang."""
+    import struct
+    from imagevis3d_b200._lib import TvkError
+    good = bytearray(open(golden_file("ref_u8_zlib", tmp_path), "rb").read())
+    f = U.UvfFile(golden_file("ref_u8_zlib", tmp_path), verify=False)
+    off, length, comp, sizes = f.toc()
+    n = len(off)
+    f.close()
+    # the ToC (36-byte entries: u64 offset, u64 length, u32 compression, u64 valid length, 2 x u32) ends where the
+    # first brick starts; entry k's length field sits at table + 36*k + 8
+    table = int(off.min()) - 36 * n
+    assert struct.unpack_from("<Q", good, table + 8)[0] == int(length[0])
+    for value, field in ((1 << 62, 8), (len(good) + 12345, 0)):
+        bad = bytearray(good)
+        struct.pack_into("<Q", bad, table + 36 * (n // 2) + field, value)
+        path = str(tmp_path / ("hostile_%d.uvf" % field))
+        open(path, "wb").write(bytes(bad))
+        with pytest.raises(TvkError):
+            U.UvfFile(path, verify=False)
+    # max/min block: brick count 2^40
+    pat = b"Brick Max/Min Values"
+    at = bytes(good).find(pat)
+    assert at > 0
+    bad = bytearray(good)
+    struct.pack_into("<Q", bad, at + len(pat) + 24, 1 << 40)        # after id: semantics, compression, offset-to-next, then n
+    path = str(tmp_path / "hostile_mm.uvf")
+    open(path, "wb").write(bytes(bad))
+    with pytest.raises(TvkError):
+        U.UvfFile(path, verify=False)
+    # legacy RasterDataBlock: LOD group count 2^60 (the header loop must not run 2^60 times)
+    from tests.util import write_rdb_uvf
+    path = str(tmp_path / "rdb.uvf")
+    write_rdb_uvf(path, H.synth_blobs((40, 30, 20), np.uint8, seed=3), brick=32, overlap=4)
+    raw = bytearray(open(path, "rb").read())
+    at = bytes(raw).find(b"Qvis data volume converted by ImageVis3D") + 40 + 24
+    groups = at + 8 + 24 + 128 + 24 + 24 + 24 + 24                    # dims, semantics, transform, domain, brick, overlap, decimation
+    assert struct.unpack_from("<3Q", raw, groups) == (0, 0, 0)
+    struct.pack_into("<Q", raw, groups, 1 << 60)
+    open(path, "wb").write(bytes(raw))
+    g = U.UvfFile(path, verify=False)                               # opens; the undecodable grid block is skipped
+    with pytest.raises(TvkError):
+        g.read_rdb_volume()
+    g.close()
+
+
 @pytest.mark.skipif(O.ref_driver_path() is None, reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("comp", [0, 1])
 def test_reference_reads_our_file(comp, tmp_path):
