@@ -361,7 +361,7 @@ static void xform_point(const float m[16], const float v[3], float w, float out[
 /* Analytic ray set-up for pixel (px,py): replaces the rasterised near-plane quad
  * and bbox faces (GLGridLeaper.cpp:579-620, 835-843).  Returns 0 if the ray
  * misses the box.  entry/exit = (normalised volume coords, eye-space z). */
-static int ray_setup(const tvk_raycast_params* p, uint32_t px, uint32_t py, float entry[4], float exitp[4]) {
+static int ray_setup_eye(const tvk_raycast_params* p, uint32_t px, uint32_t py, float entry[4], float exitp[4], float* exit_eye) {
   const float ndc[3] = {fmaf(((float)px + 0.5f) / (float)p->width, 2.0f, -1.0f),
                         fmaf(((float)py + 0.5f) / (float)p->height, 2.0f, -1.0f), -1.0f};
   float n4[4];
@@ -402,7 +402,29 @@ static int ray_setup(const tvk_raycast_params* p, uint32_t px, uint32_t py, floa
   entry[0] = t4[0]; entry[1] = t4[1]; entry[2] = t4[2]; entry[3] = pe[2];
   xform_point(p->eye_to_model, px1, 1.0f, t4);
   exitp[0] = t4[0]; exitp[1] = t4[1]; exitp[2] = t4[2]; exitp[3] = px1[2];
+  if (exit_eye) { exit_eye[0] = px1[0]; exit_eye[1] = px1[1]; exit_eye[2] = px1[2]; }
   return 1;
+}
+static int ray_setup(const tvk_raycast_params* p, uint32_t px, uint32_t py, float entry[4], float exitp[4]) {
+  return ray_setup_eye(p, px, py, entry, exitp, NULL);
+}
+
+/* The rasteriser's part of a sub-frame for the GLSL harness (oracle/glslref.py): per pixel, whether the bbox back faces
+ * cover it, the ray entry (what FillRayEntryBuffer leaves in rayStartPoint) and the back-face position in EYE space
+ * (the vertex shader's vPosInViewCoords; the fragment shader transforms it itself). */
+void orc_ray_setup_image(const tvk_raycast_params* p, float* entry, float* exit_eye, uint8_t* covered) {
+  for (uint32_t py = 0; py < p->height; ++py)
+    for (uint32_t px = 0; px < p->width; ++px) {
+      const size_t q = (size_t)py * p->width + px;
+      float e[4], x[4];
+      float xe[3];
+      covered[q] = (uint8_t)ray_setup_eye(p, px, py, e, x, xe);
+      memset(entry + 4 * q, 0, 16);
+      memset(exit_eye + 3 * q, 0, 12);
+      if (!covered[q]) continue;
+      memcpy(entry + 4 * q, e, 16);
+      memcpy(exit_eye + 3 * q, xe, 12);
+    }
 }
 
 static void under(const float src[4], float dst[4]) {   /* Compositing.glsl:33-38 */
