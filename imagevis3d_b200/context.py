@@ -208,6 +208,40 @@ class TvkContext:
         self.build_bpv = bpv
         return info
 
+    # ---- streamed build: LOD 0 fed in z-slabs of whole brick rows (tvk_build_stream_*)
+    def _desc(self, volume_size, bpv, brick, overlap, median=False):
+        d = L.BuildDesc()
+        d.volume_size[:] = [int(v) for v in volume_size]
+        d.brick_size, d.overlap, d.bytes_per_voxel = brick, overlap, bpv
+        d.use_median, d.clamp_to_edge = int(median), 0
+        return d
+
+    def build_stream_begin(self, volume_size, bpv, brick=64, overlap=2, median=False, store_ptr=None):
+        """store_ptr: None = device store owned by the context; else caller-owned device / mapped pinned host memory"""
+        self._stream_desc = self._desc(volume_size, bpv, brick, overlap, median)
+        info = L.BuildInfo()
+        self._ck(self.lib.tvk_build_stream_begin(self.h, C.byref(self._stream_desc), C.c_void_p(int(store_ptr) if store_ptr else None),
+                                                 C.byref(info)), "tvk_build_stream_begin")
+        self.build_info, self.build_bpv = info, bpv
+        return info
+
+    def build_stream_rows(self, bz0, bz1):
+        """raw rows (z0, count) the slab for LOD-0 brick rows [bz0, bz1) must hold"""
+        z0, rows = C.c_uint32(), C.c_uint32()
+        self._ck(self.lib.tvk_build_stream_rows(C.byref(self._stream_desc), C.c_uint32(bz0), C.c_uint32(bz1), C.byref(z0), C.byref(rows)),
+                 "tvk_build_stream_rows")
+        return int(z0.value), int(rows.value)
+
+    def build_stream_slab(self, slab_dptr, z0, rows, bz0, bz1):
+        self._ck(self.lib.tvk_build_stream_slab(self.h, C.c_void_p(int(slab_dptr)), C.c_uint32(z0), C.c_uint32(rows), C.c_uint32(bz0),
+                                                C.c_uint32(bz1)), "tvk_build_stream_slab")
+
+    def build_stream_end(self):
+        info = L.BuildInfo()
+        self._ck(self.lib.tvk_build_stream_end(self.h, C.byref(info)), "tvk_build_stream_end")
+        self.build_info = info
+        return info
+
     def build_toc(self):
         n = int(self.build_info.total_bricks)
         off = np.zeros(n, np.uint64)

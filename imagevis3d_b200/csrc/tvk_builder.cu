@@ -69,6 +69,10 @@ struct BuildConst {
   uint32_t brick, overlap, core;
 };
 
+// What a brick-cut kernel sees of its source: rows [z0, z0 + rows) of the flat LOD volume (all of it: z0 = 0, rows =
+// the LOD's depth) and the first brick row of the launch -- so that LOD 0 can be fed through in z-slabs.
+struct SlabView { uint32_t z0, rows, bz_first; };
+
 __host__ __device__ inline uint32_t brick_dim(const BuildConst& bc, uint32_t lod, int axis, uint32_t coord) {
   const bool last = coord >= bc.lod_bricks[lod][axis] - 1;
   const uint32_t rem = bc.lod_size[lod][axis] % bc.core;
@@ -466,13 +470,13 @@ __global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ f
                                                           const uint64_t* __restrict__ offsets, uint64_t first_brick,
                                                           uint32_t lod, const __grid_constant__ BuildConst bc,
                                                           uint32_t* __restrict__ mn, uint32_t* __restrict__ mx,
-                                                          uint32_t x_first, uint32_t x_count) {
+                                                          uint32_t x_first, uint32_t x_count, SlabView sv) {
   const uint32_t nbx = bc.lod_bricks[lod][0], nby = bc.lod_bricks[lod][1];
-  const int bx = (int)(x_first + blockIdx.x % x_count), by = (int)((blockIdx.x / x_count) % nby), bz = (int)(blockIdx.x / (x_count * nby));
+  const int bx = (int)(x_first + blockIdx.x % x_count), by = (int)((blockIdx.x / x_count) % nby), bz = (int)(sv.bz_first + blockIdx.x / (x_count * nby));
   const uint32_t b = (uint32_t)bx + (uint32_t)by * nbx + (uint32_t)bz * nbx * nby;
   const uint32_t tx = brick_dim(bc, lod, 0, bx), ty = brick_dim(bc, lod, 1, by), tz = brick_dim(bc, lod, 2, bz);
-  const uint32_t sx = bc.lod_size[lod][0], sy = bc.lod_size[lod][1], sz = bc.lod_size[lod][2];
-  const uint64_t nvox = (uint64_t)sx * sy * sz;
+  const uint32_t sx = bc.lod_size[lod][0], sy = bc.lod_size[lod][1];
+  const uint64_t nvox = (uint64_t)sx * sy * sv.rows;
   T* dst = reinterpret_cast<T*>(store + offsets[first_brick + b]);
   const int o = (int)bc.overlap;
   uint32_t lo = 0xFFFFFFFFu, hi = 0u;
@@ -494,7 +498,7 @@ __global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ f
       const bool in_z = k >= (fz ? o : 0) && k < (int)tz - (lz ? o : 0);
       const int xa = fx ? o : 0, xb = (int)tx - (lx ? o : 0);
       const uint64_t lin0 = (uint64_t)(int64_t)(bx * (int)bc.core - o) + (uint64_t)(by * (int)bc.core - o + j) * sx +
-                            (uint64_t)(bz * (int)bc.core - o + k) * sx * sy;      // wraps for i < xa only; never read there
+                            (uint64_t)(int64_t)(bz * (int)bc.core - o + k - (int)sv.z0) * sx * sy;      // wraps for i < xa only; never read there
       for (int i = (int)lane; i < (int)tx; i += 32) {
         T val = 0;
         if (in_y && in_z && i >= xa && i < xb) {
@@ -556,15 +560,15 @@ __global__ void __launch_bounds__(256) cut_bricks_vec_kernel(const T* __restrict
                                                               const uint64_t* __restrict__ offsets, uint64_t first_brick,
                                                               uint32_t lod, const __grid_constant__ BuildConst bc,
                                                               uint32_t* __restrict__ mn, uint32_t* __restrict__ mx,
-                                                              uint32_t x_first, uint32_t x_count) {
+                                                              uint32_t x_first, uint32_t x_count, SlabView sv) {
   constexpr int E = CB / (int)sizeof(T), NW = CB / 4;
   const uint32_t nbx = bc.lod_bricks[lod][0], nby = bc.lod_bricks[lod][1];
   const int nbz = (int)bc.lod_bricks[lod][2];
-  const int bx = (int)(x_first + blockIdx.x % x_count), by = (int)((blockIdx.x / x_count) % nby), bz = (int)(blockIdx.x / (x_count * nby));
+  const int bx = (int)(x_first + blockIdx.x % x_count), by = (int)((blockIdx.x / x_count) % nby), bz = (int)(sv.bz_first + blockIdx.x / (x_count * nby));
   const uint32_t b = (uint32_t)bx + (uint32_t)by * nbx + (uint32_t)bz * nbx * nby;
   const uint32_t tx = brick_dim(bc, lod, 0, bx), ty = brick_dim(bc, lod, 1, by), tz = brick_dim(bc, lod, 2, bz);
   const uint32_t sx = bc.lod_size[lod][0], sy = bc.lod_size[lod][1], sz = bc.lod_size[lod][2];
-  const uint64_t nbytes = (uint64_t)sx * sy * sz * sizeof(T);
+  const uint64_t nbytes = (uint64_t)sx * sy * sv.rows * sizeof(T);      // of the buffer `flat` points at (a z-slab of the LOD or all of it)
   const uint8_t* fb = reinterpret_cast<const uint8_t*>(flat);
   typename Chunk<CB>::type* dst = reinterpret_cast<typename Chunk<CB>::type*>(store + offsets[first_brick + b]);
   const int o = (int)bc.overlap, core = (int)bc.core;
@@ -591,7 +595,7 @@ __global__ void __launch_bounds__(256) cut_bricks_vec_kernel(const T* __restrict
     lo = max(lo, i0); hi = min(hi, i0 + E);
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (row_ok && lo < hi) {
-      const int64_t lin = (int64_t)(bx * core - o + i0) + (int64_t)(by * core - o + j) * sx + (int64_t)(bz * core - o + k) * sx * sy;
+      const int64_t lin = (int64_t)(bx * core - o + i0) + (int64_t)(by * core - o + j) * sx + (int64_t)(bz * core - o + k - (int)sv.z0) * sx * sy;
       v = load_chunk<CB>(fb, lin * (int64_t)sizeof(T), nbytes);
       if (lo > i0 || hi < i0 + E) v = keep16(v, (lo - i0) * (int)sizeof(T), (hi - i0) * (int)sizeof(T));
     }
@@ -1317,7 +1321,9 @@ __global__ void __launch_bounds__(256) hist2d_vec_kernel(const T* __restrict__ r
 
 static void release(tvk_ctx* c) {
   BuildState& b = c->build;
-  cudaFree(b.d_store); cudaFree(b.d_offsets); cudaFree(b.d_sizes); cudaFree(b.d_minmax); cudaFree(b.d_hist1d);
+  if (b.own_store) cudaFree(b.d_store);
+  cudaFree(b.d_mn);
+  cudaFree(b.d_offsets); cudaFree(b.d_sizes); cudaFree(b.d_minmax); cudaFree(b.d_hist1d);
   for (uint32_t l = 0; l < TVK_MAX_LOD; ++l) {
     if (l > 0 || b.own_lod0) cudaFree(b.d_lod[l]);
     b.d_lod[l] = nullptr;
@@ -1332,163 +1338,206 @@ extern "C" int tvk_build_release(tvk_ctx* c) {
   return TVK_OK;
 }
 
+// ------------------------------------------------------------------ host side of a build
+// A build is begin -> LOD-0 rows -> finish.  tvk_build_octree feeds the whole raw volume as one "slab";
+// tvk_build_stream_* feeds it in z-slabs of whole brick rows (raw volumes that do not fit next to their brick store).
+static BuildConst make_const(const BuildState& b) {
+  BuildConst bc{};
+  memcpy(bc.lod_size, b.info.lod_size, sizeof(bc.lod_size));
+  memcpy(bc.lod_bricks, b.info.lod_bricks, sizeof(bc.lod_bricks));
+  bc.brick = b.desc.brick_size; bc.overlap = b.desc.overlap; bc.core = b.desc.brick_size - 2 * b.desc.overlap;
+  return bc;
+}
+
 template <typename T>
-static int run_build(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms) {
+static int build_begin(tvk_ctx* c, BuildState& b) {
   const tvk_build_info& info = b.info;
   cudaStream_t st = c->stream;
-  constexpr uint32_t E = 16 / sizeof(T);
-  // all allocations first, so that the event-timed region below holds kernels only
+  // all allocations first, so that the event-timed regions below hold kernels only
   for (uint32_t l = 1; l < info.lod_count; ++l) {
     const uint64_t n = (uint64_t)info.lod_size[l][0] * info.lod_size[l][1] * info.lod_size[l][2];
     TVK_CHECK_CUDA(c, cudaMalloc(&b.d_lod[l], n * sizeof(T)));
   }
-  uint32_t *d_mn = nullptr, *d_mx = nullptr;
-  TVK_CHECK_CUDA(c, cudaMalloc(&d_mn, sizeof(uint32_t) * (2 * info.total_bricks + 1)));
-  d_mx = d_mn + info.total_bricks;
-  uint32_t* d_gmax = d_mx + info.total_bricks;
+  TVK_CHECK_CUDA(c, cudaMalloc(&b.d_mn, sizeof(uint32_t) * (2 * info.total_bricks + 1)));
   const uint32_t range = 1u << (8 * sizeof(T));
   TVK_CHECK_CUDA(c, cudaMalloc(&b.d_hist1d, sizeof(unsigned long long) * range));
-  TVK_CHECK_CUDA(c, cudaEventRecord(c->bev0, st));
-  TVK_CHECK_CUDA(c, cudaMemsetAsync(d_mn, 0xFF, sizeof(uint32_t) * info.total_bricks, st));
-  TVK_CHECK_CUDA(c, cudaMemsetAsync(d_mx, 0, sizeof(uint32_t) * (info.total_bricks + 1), st));
-  bool hist_fused = false, lod0_fused = false, hist_full = false;   // hist_full: the fused pass counted every bin
-  // ---- fused LOD-0 pass: bricks + min/max + 1-D histogram + flat LOD 1 from ONE read of the raw volume
-  {
-    const uint32_t* s0 = info.lod_size[0];
-    const uint32_t nbx = info.lod_bricks[0][0];
-    const uint32_t last_tx = brick_dim(bc, 0, 0, nbx - 1);
-    const uint32_t groups[2][3] = {{0u, last_tx == bc.brick ? nbx : nbx - 1, bc.brick}, {nbx - 1, last_tx == bc.brick ? 0u : 1u, last_tx}};
-    bool can = info.lod_count >= 2 && s0[0] > 1 && s0[1] > 1 && s0[2] > 1 && (bc.overlap % 2) == 0 && bc.core >= bc.overlap &&
-               (reinterpret_cast<uintptr_t>(b.d_lod[0]) & 3) == 0 && (uint64_t)s0[0] * s0[1] * s0[2] >= (1u << 18) &&
-               getenv("TVK_BUILD_FUSED") != nullptr;    // opt-in: measured SLOWER than the separate kernels, see DESIGN.md
-    for (int g = 0; g < 2; ++g) if (groups[g][1] && (groups[g][2] * sizeof(T)) % 4 != 0) can = false;
-    if (can) {
-      const size_t smem = sizeof(unsigned int) * (sizeof(T) == 1 ? 32u * 256u : HIST_WINDOW);
-      TVK_CHECK_CUDA(c, cudaMemsetAsync(b.d_hist1d, 0, sizeof(unsigned long long) * range, st));
-      for (int g = 0; g < 2; ++g) {
-        const uint32_t x_first = groups[g][0], x_count = groups[g][1], row_bytes = groups[g][2] * (uint32_t)sizeof(T);
-        if (!x_count) continue;
-        const uint64_t nb = (uint64_t)x_count * info.lod_bricks[0][1] * info.lod_bricks[0][2];
-        const unsigned grid = (unsigned)std::min<uint64_t>(nb, (uint64_t)sms);
-        const T* src = (const T*)b.d_lod[0];
-        uint8_t* store = (uint8_t*)b.d_store;
-        T* l1 = (T*)b.d_lod[1];
-#define TVK_LAUNCH_FUSED(CBV)                                                                                                  \
-        do {                                                                                                                   \
-          if (b.desc.use_median) {                                                                                             \
-            TVK_CHECK_CUDA(c, cudaFuncSetAttribute(lod0_fused_kernel<T, CBV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            lod0_fused_kernel<T, CBV, true><<<grid, 1024, smem, st>>>(src, store, b.d_offsets, bc, d_mn, d_mx, x_first, x_count, l1, b.d_hist1d); \
-          } else {                                                                                                             \
-            TVK_CHECK_CUDA(c, cudaFuncSetAttribute(lod0_fused_kernel<T, CBV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            lod0_fused_kernel<T, CBV, false><<<grid, 1024, smem, st>>>(src, store, b.d_offsets, bc, d_mn, d_mx, x_first, x_count, l1, b.d_hist1d); \
-          }                                                                                                                    \
-        } while (0)
-        if (row_bytes % 16 == 0) TVK_LAUNCH_FUSED(16);
-        else if (row_bytes % 8 == 0) TVK_LAUNCH_FUSED(8);
-        else TVK_LAUNCH_FUSED(4);
-#undef TVK_LAUNCH_FUSED
-        c->launches++;
-      }
-      TVK_CHECK_CUDA(c, cudaGetLastError());
-      hist_fused = true; lod0_fused = true;
-    }
-  }
-  // flat pyramid
-  for (uint32_t l = lod0_fused ? 2u : 1u; l < info.lod_count; ++l) {
-    const uint32_t* s = info.lod_size[l - 1];
-    const uint32_t* d = info.lod_size[l];
-    const bool vec = (s[0] % E) == 0 && (reinterpret_cast<uintptr_t>(b.d_lod[l - 1]) & 15) == 0;
-    const uint64_t n = vec ? (uint64_t)(s[0] / E) * d[1] * d[2] : (uint64_t)d[0] * d[1] * d[2];
-    const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 32);
-    const T* src = (const T*)b.d_lod[l - 1];
-    T* dst = (T*)b.d_lod[l];
-    // LOD 0 -> 1 also counts the 1-D histogram (bins [0, 32768) for 16-bit data)
-    const bool fuse_hist = vec && l == 1 && ((uint64_t)s[0] * s[1] * s[2]) >= (1u << 18);
-    if (fuse_hist) {
-      const size_t smem = sizeof(unsigned int) * (sizeof(T) == 1 ? 32u * 256u : HIST_WINDOW);
-      static bool attr_set = false;
-      if (!attr_set) {
-        TVK_CHECK_CUDA(c, cudaFuncSetAttribute(downsample_hist_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TVK_CHECK_CUDA(c, cudaFuncSetAttribute(downsample_hist_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-      }
-      TVK_CHECK_CUDA(c, cudaMemsetAsync(b.d_hist1d, 0, sizeof(unsigned long long) * range, st));
-      if (b.desc.use_median) downsample_hist_kernel<T, true><<<sms, 1024, smem, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2], b.d_hist1d);
-      else downsample_hist_kernel<T, false><<<sms, 1024, smem, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2], b.d_hist1d);
-      hist_fused = true; hist_full = true;
-    } else if (vec) {
-      if (b.desc.use_median) downsample_vec_kernel<T, true><<<blocks, 256, 0, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2]);
-      else downsample_vec_kernel<T, false><<<blocks, 256, 0, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2]);
-    } else {
-      if (b.desc.use_median) downsample_kernel<T, true><<<blocks, 256, 0, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2]);
-      else downsample_kernel<T, false><<<blocks, 256, 0, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2]);
-    }
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(b.d_mn, 0xFF, sizeof(uint32_t) * info.total_bricks, st));
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(b.d_mn + info.total_bricks, 0, sizeof(uint32_t) * (info.total_bricks + 1), st));
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(b.d_hist1d, 0, sizeof(unsigned long long) * range, st));
+  b.hist_fused = false; b.hist_full = false; b.lod0_fused = false; b.hist_pending = false; b.hist_upper_pending = false;
+  b.kernels_ms = 0.f;
+  return TVK_OK;
+}
+
+// launches one brick-cut pass: bricks bz in [bz0, bz1) of LOD `l`, read from `src` = rows [z0, z0 + rows) of the LOD
+template <typename T>
+static int cut_rows(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms, uint32_t l, const T* src, uint32_t z0, uint32_t rows,
+                    uint32_t bz0, uint32_t bz1) {
+  const tvk_build_info& info = b.info;
+  cudaStream_t st = c->stream;
+  uint32_t* d_mn = b.d_mn;
+  uint32_t* d_mx = b.d_mn + info.total_bricks;
+  // one launch for the full-width bricks, one for the last column if it is narrower
+  const uint32_t nbx = info.lod_bricks[l][0];
+  const uint32_t last_tx = brick_dim(bc, l, 0, nbx - 1);
+  const uint32_t groups[2][3] = {{0u, last_tx == bc.brick ? nbx : nbx - 1, bc.brick}, {nbx - 1, last_tx == bc.brick ? 0u : 1u, last_tx}};
+  const SlabView sv{z0, rows, bz0};
+  for (int g = 0; g < 2; ++g) {
+    const uint32_t x_first = groups[g][0], x_count = groups[g][1], tx = groups[g][2];
+    if (!x_count) continue;
+    const uint64_t nb = (uint64_t)x_count * info.lod_bricks[l][1] * (bz1 - bz0);
+    // a few z-chunks per brick when there are few bricks, to fill the machine
+    const unsigned chunks = nb >= (uint64_t)sms * 8 ? 2 : (nb >= (uint64_t)sms ? 8 : 32);
+    const dim3 grid((unsigned)nb, chunks);
+    const uint32_t row_bytes = tx * (uint32_t)sizeof(T);
+    // word-granular path: needs a 4-byte aligned volume, and core >= overlap for the closed-form ghosts
+    const bool vec = (reinterpret_cast<uintptr_t>(src) & 3) == 0 && bc.core >= bc.overlap && row_bytes % 4 == 0;
+    uint8_t* store = (uint8_t*)b.d_store;
+    if (vec && row_bytes % 16 == 0)
+      cut_bricks_vec_kernel<T, 16><<<grid, 256, 0, st>>>(src, store, b.d_offsets, info.lod_offset[l], l, bc, d_mn, d_mx, x_first, x_count, sv);
+    else if (vec && row_bytes % 8 == 0)
+      cut_bricks_vec_kernel<T, 8><<<grid, 256, 0, st>>>(src, store, b.d_offsets, info.lod_offset[l], l, bc, d_mn, d_mx, x_first, x_count, sv);
+    else if (vec)
+      cut_bricks_vec_kernel<T, 4><<<grid, 256, 0, st>>>(src, store, b.d_offsets, info.lod_offset[l], l, bc, d_mn, d_mx, x_first, x_count, sv);
+    else
+      cut_bricks_kernel<T><<<grid, 256, 0, st>>>(src, store, b.d_offsets, info.lod_offset[l], l, bc, d_mn, d_mx, x_first, x_count, sv);
     c->launches++;
   }
   TVK_CHECK_CUDA(c, cudaGetLastError());
-  // bricks + stats
-  for (uint32_t l = lod0_fused ? 1u : 0u; l < info.lod_count; ++l) {
-    // one launch for the full-width bricks, one for the last column if it is narrower
-    const uint32_t nbx = info.lod_bricks[l][0];
-    const uint32_t last_tx = brick_dim(bc, l, 0, nbx - 1);
-    const uint32_t groups[2][3] = {{0u, last_tx == bc.brick ? nbx : nbx - 1, bc.brick}, {nbx - 1, last_tx == bc.brick ? 0u : 1u, last_tx}};
-    for (int g = 0; g < 2; ++g) {
-      const uint32_t x_first = groups[g][0], x_count = groups[g][1], tx = groups[g][2];
-      if (!x_count) continue;
-      const uint64_t nb = (uint64_t)x_count * info.lod_bricks[l][1] * info.lod_bricks[l][2];
-      // a few z-chunks per brick when there are few bricks, to fill the machine
-      const unsigned chunks = nb >= (uint64_t)sms * 8 ? 2 : (nb >= (uint64_t)sms ? 8 : 32);
-      const dim3 grid((unsigned)nb, chunks);
-      const uint32_t row_bytes = tx * (uint32_t)sizeof(T);
-      // word-granular path: needs a 4-byte aligned volume, and core >= overlap for the closed-form ghosts
-      const bool vec = (reinterpret_cast<uintptr_t>(b.d_lod[l]) & 3) == 0 && bc.core >= bc.overlap && row_bytes % 4 == 0;
-      const T* src = (const T*)b.d_lod[l];
-      uint8_t* store = (uint8_t*)b.d_store;
-      if (vec && row_bytes % 16 == 0)
-        cut_bricks_vec_kernel<T, 16><<<grid, 256, 0, st>>>(src, store, b.d_offsets, info.lod_offset[l], l, bc, d_mn, d_mx, x_first, x_count);
-      else if (vec && row_bytes % 8 == 0)
-        cut_bricks_vec_kernel<T, 8><<<grid, 256, 0, st>>>(src, store, b.d_offsets, info.lod_offset[l], l, bc, d_mn, d_mx, x_first, x_count);
-      else if (vec)
-        cut_bricks_vec_kernel<T, 4><<<grid, 256, 0, st>>>(src, store, b.d_offsets, info.lod_offset[l], l, bc, d_mn, d_mx, x_first, x_count);
-      else
-        cut_bricks_kernel<T><<<grid, 256, 0, st>>>(src, store, b.d_offsets, info.lod_offset[l], l, bc, d_mn, d_mx, x_first, x_count);
-      c->launches++;
-    }
-  }
-  TVK_CHECK_CUDA(c, cudaGetLastError());
-  minmax_to_double_kernel<<<(unsigned)((info.total_bricks + 255) / 256), 256, 0, st>>>(d_mn, d_mx, b.d_minmax, info.total_bricks, d_gmax);
-  c->launches++;
-  // 1-D histogram: whatever the fused LOD 0 -> 1 pass did not count
-  const uint64_t n0 = (uint64_t)info.lod_size[0][0] * info.lod_size[0][1] * info.lod_size[0][2];
-  if (!hist_fused) TVK_CHECK_CUDA(c, cudaMemsetAsync(b.d_hist1d, 0, sizeof(unsigned long long) * range, st));
-  if (hist_full) {
-    // nothing left to count
-  } else if (sizeof(T) == 2 && n0 >= (1u << 18)) {
+  return TVK_OK;
+}
+
+// launches the reduction of rows [s_z0, s_z0 + s_rows) of LOD l-1 (at `src`) into LOD l (rows from s_z0 / 2 on); for
+// l == 1 it also counts the 1-D histogram of those rows when the fused kernel applies
+template <typename T>
+static int downsample_rows(tvk_ctx* c, BuildState& b, int sms, uint32_t l, const T* src, uint32_t s_z0, uint32_t s_rows, bool* counted) {
+  const tvk_build_info& info = b.info;
+  cudaStream_t st = c->stream;
+  constexpr uint32_t E = 16 / sizeof(T);
+  const uint32_t s[3] = {info.lod_size[l - 1][0], info.lod_size[l - 1][1], s_rows};
+  const uint32_t d[3] = {info.lod_size[l][0], info.lod_size[l][1], info.lod_size[l - 1][2] > 1 ? (s_rows + 1) / 2 : s_rows};
+  const uint32_t d_z0 = info.lod_size[l - 1][2] > 1 ? s_z0 / 2 : s_z0;
+  T* dst = (T*)b.d_lod[l] + (uint64_t)d_z0 * d[0] * d[1];
+  const bool vec = (s[0] % E) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  const uint64_t n = vec ? (uint64_t)(s[0] / E) * d[1] * d[2] : (uint64_t)d[0] * d[1] * d[2];
+  const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 32);
+  // LOD 0 -> 1 also counts the 1-D histogram (all 65536 bins for 16-bit data: packed shared-memory counters)
+  const bool fuse_hist = vec && l == 1 && ((uint64_t)s[0] * s[1] * s[2]) >= (1u << 18) && info.lod_size[0][2] > 1;
+  if (counted) *counted = fuse_hist;
+  if (fuse_hist) {
+    const size_t smem = sizeof(unsigned int) * (sizeof(T) == 1 ? 32u * 256u : HIST_WINDOW);
     static bool attr_set = false;
     if (!attr_set) {
-      TVK_CHECK_CUDA(c, cudaFuncSetAttribute(hist16_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HIST_WINDOW * sizeof(uint32_t))));
+      TVK_CHECK_CUDA(c, cudaFuncSetAttribute(downsample_hist_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TVK_CHECK_CUDA(c, cudaFuncSetAttribute(downsample_hist_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set = true;
     }
-    for (uint32_t lo = hist_fused ? HIST_WINDOW : 0u; lo < range; lo += HIST_WINDOW) {
+    if (b.desc.use_median) downsample_hist_kernel<T, true><<<sms, 1024, smem, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2], b.d_hist1d);
+    else downsample_hist_kernel<T, false><<<sms, 1024, smem, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2], b.d_hist1d);
+  } else if (vec) {
+    if (b.desc.use_median) downsample_vec_kernel<T, true><<<blocks, 256, 0, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2]);
+    else downsample_vec_kernel<T, false><<<blocks, 256, 0, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2]);
+  } else {
+    if (b.desc.use_median) downsample_kernel<T, true><<<blocks, 256, 0, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2]);
+    else downsample_kernel<T, false><<<blocks, 256, 0, st>>>(src, dst, s[0], s[1], s[2], d[0], d[1], d[2]);
+  }
+  c->launches++;
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  return TVK_OK;
+}
+
+// LOD-0 work for brick rows [bz0, bz1): `slab` holds raw rows [z0, z0 + rows), which must include the rows those bricks
+// touch.  whole == true: the slab is the entire volume (one-shot build) and the histogram may be finished later from it.
+template <typename T>
+static int build_lod0_rows(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms, const T* slab, uint32_t z0, uint32_t rows,
+                           uint32_t bz0, uint32_t bz1, bool whole) {
+  const tvk_build_info& info = b.info;
+  cudaStream_t st = c->stream;
+  const uint32_t* s0 = info.lod_size[0];
+  const uint32_t cz0 = bz0 * bc.core, cz1 = std::min<uint32_t>(bz1 * bc.core, s0[2]);   // inner rows of these bricks
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->bev0, st));
+  bool counted = false;
+  if (info.lod_count > 1 && cz1 > cz0) {
+    int rc = downsample_rows<T>(c, b, sms, 1, slab + (uint64_t)(cz0 - z0) * s0[0] * s0[1], cz0, cz1 - cz0, &counted);
+    if (rc) return rc;
+  }
+  int rc = cut_rows<T>(c, b, bc, sms, 0, slab, z0, rows, bz0, bz1);
+  if (rc) return rc;
+  if (counted) { b.hist_fused = true; }
+  else if (!whole && cz1 > cz0) {
+    // streamed slab the fused kernel does not take (unaligned rows / tiny slab): plain global-atomic histogram of its inner rows
+    const uint64_t n = (uint64_t)(cz1 - cz0) * s0[0] * s0[1];
+    hist1d_kernel<T><<<(unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 8), 256, 0, st>>>(slab + (uint64_t)(cz0 - z0) * s0[0] * s0[1], n, b.d_hist1d);
+    c->launches++;
+    TVK_CHECK_CUDA(c, cudaGetLastError());
+  } else if (whole) {
+    b.hist_pending = true;                       // finished in build_finish from the whole volume
+  }
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->bev1, st));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->bev0, c->bev1) == cudaSuccess) b.kernels_ms += ms;
+  return TVK_OK;
+}
+
+template <typename T>
+static int build_finish(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms) {
+  const tvk_build_info& info = b.info;
+  cudaStream_t st = c->stream;
+  uint32_t* d_mn = b.d_mn;
+  uint32_t* d_mx = d_mn + info.total_bricks;
+  uint32_t* d_gmax = d_mx + info.total_bricks;
+  const uint32_t range = 1u << (8 * sizeof(T));
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->bev0, st));
+  // the rest of the flat pyramid, then its bricks
+  for (uint32_t l = 2; l < info.lod_count; ++l) {
+    int rc = downsample_rows<T>(c, b, sms, l, (const T*)b.d_lod[l - 1], 0, info.lod_size[l - 1][2], nullptr);
+    if (rc) return rc;
+  }
+  for (uint32_t l = 1; l < info.lod_count; ++l) {
+    int rc = cut_rows<T>(c, b, bc, sms, l, (const T*)b.d_lod[l], 0, info.lod_size[l][2], 0, info.lod_bricks[l][2]);
+    if (rc) return rc;
+  }
+  minmax_to_double_kernel<<<(unsigned)((info.total_bricks + 255) / 256), 256, 0, st>>>(d_mn, d_mx, b.d_minmax, info.total_bricks, d_gmax);
+  c->launches++;
+  if (b.hist_upper_pending) {                    // fused LOD-0 pass, 16-bit: bins [HIST_WINDOW, 65536) from a second read
+    const uint64_t n0 = (uint64_t)info.lod_size[0][0] * info.lod_size[0][1] * info.lod_size[0][2];
+    for (uint32_t lo = HIST_WINDOW; lo < range; lo += HIST_WINDOW) {
       hist16_window_kernel<<<sms, 1024, HIST_WINDOW * sizeof(uint32_t), st>>>((const uint16_t*)b.d_lod[0], n0, lo, d_gmax, b.d_hist1d);
       c->launches++;
     }
-  } else if (!hist_fused) {
-    hist1d_kernel<T><<<(unsigned)std::min<uint64_t>((n0 + 255) / 256, (uint64_t)sms * 8), 256, 0, st>>>((const T*)b.d_lod[0], n0, b.d_hist1d);
-    c->launches++;
+    b.hist_upper_pending = false;
+  }
+  // 1-D histogram of a one-shot build that the fused LOD 0 -> 1 pass did not count
+  if (b.hist_pending && !b.hist_fused) {
+    const uint64_t n0 = (uint64_t)info.lod_size[0][0] * info.lod_size[0][1] * info.lod_size[0][2];
+    if (sizeof(T) == 2 && n0 >= (1u << 18)) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        TVK_CHECK_CUDA(c, cudaFuncSetAttribute(hist16_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HIST_WINDOW * sizeof(uint32_t))));
+        attr_set = true;
+      }
+      for (uint32_t lo = 0u; lo < range; lo += HIST_WINDOW) {
+        hist16_window_kernel<<<sms, 1024, HIST_WINDOW * sizeof(uint32_t), st>>>((const uint16_t*)b.d_lod[0], n0, lo, d_gmax, b.d_hist1d);
+        c->launches++;
+      }
+    } else {
+      hist1d_kernel<T><<<(unsigned)std::min<uint64_t>((n0 + 255) / 256, (uint64_t)sms * 8), 256, 0, st>>>((const T*)b.d_lod[0], n0, b.d_hist1d);
+      c->launches++;
+    }
   }
   TVK_CHECK_CUDA(c, cudaGetLastError());
   TVK_CHECK_CUDA(c, cudaEventRecord(c->bev1, st));
   TVK_CHECK_CUDA(c, cudaStreamSynchronize(st));
   float ms = 0.f;
-  if (cudaEventElapsedTime(&ms, c->bev0, c->bev1) == cudaSuccess) b.kernels_ms = ms;
-  cudaFree(d_mn);
+  if (cudaEventElapsedTime(&ms, c->bev0, c->bev1) == cudaSuccess) b.kernels_ms += ms;
+  cudaFree(b.d_mn); b.d_mn = nullptr;
   return TVK_OK;
 }
 
-extern "C" int tvk_build_octree(tvk_ctx* c, const tvk_build_desc* d, const void* raw, int raw_on_device, tvk_build_info* info_out) {
-  if (!c || !d || !raw) return TVK_ERR_INVALID;
-  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+// plan + ToC + the allocations every build needs; `store` != nullptr: caller-owned brick store (device memory, or pinned
+// host memory mapped into the device address space -- bricks are then written over PCIe)
+static int build_setup(tvk_ctx* c, const tvk_build_desc* d, void* store) {
   if (d->clamp_to_edge) TVK_FAIL(c, TVK_ERR_UNSUPPORTED, "clamp-to-edge borders are not built yet (reference default is off)");
   tvk_build_info info;
   if (tvk_build_plan(d, &info) != TVK_OK) TVK_FAIL(c, TVK_ERR_INVALID, "bad build description");
@@ -1497,10 +1546,7 @@ extern "C" int tvk_build_octree(tvk_ctx* c, const tvk_build_desc* d, const void*
   BuildState& b = c->build;
   b.desc = *d;
   b.info = info;
-  BuildConst bc{};
-  memcpy(bc.lod_size, info.lod_size, sizeof(bc.lod_size));
-  memcpy(bc.lod_bricks, info.lod_bricks, sizeof(bc.lod_bricks));
-  bc.brick = d->brick_size; bc.overlap = d->overlap; bc.core = d->brick_size - 2 * d->overlap;
+  const BuildConst bc = make_const(b);
   // ToC
   b.offsets.resize(info.total_bricks);
   b.sizes.resize(3 * info.total_bricks);
@@ -1515,6 +1561,101 @@ extern "C" int tvk_build_octree(tvk_ctx* c, const tvk_build_desc* d, const void*
           off += ((uint64_t)s[0] * s[1] * s[2] * d->bytes_per_voxel + kBrickAlign - 1) / kBrickAlign * kBrickAlign;
         }
   b.info.total_bytes = off;
+  if (store) { b.d_store = store; b.own_store = false; }
+  else { TVK_CHECK_CUDA(c, cudaMalloc(&b.d_store, off)); b.own_store = true; }
+  TVK_CHECK_CUDA(c, cudaMalloc(&b.d_offsets, sizeof(uint64_t) * info.total_bricks));
+  TVK_CHECK_CUDA(c, cudaMalloc(&b.d_sizes, sizeof(uint32_t) * 3 * info.total_bricks));
+  TVK_CHECK_CUDA(c, cudaMalloc(&b.d_minmax, sizeof(double) * 2 * info.total_bricks));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(b.d_offsets, b.offsets.data(), sizeof(uint64_t) * info.total_bricks, cudaMemcpyHostToDevice, c->stream));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(b.d_sizes, b.sizes.data(), sizeof(uint32_t) * 3 * info.total_bricks, cudaMemcpyHostToDevice, c->stream));
+  return TVK_OK;
+}
+
+// Opt-in (TVK_BUILD_FUSED=1) fused LOD-0 pass of a one-shot build: bricks + min/max + 1-D histogram (bins below
+// HIST_WINDOW for 16-bit data) + flat LOD 1 from ONE read of the raw volume.  Measured slower than the separate kernels
+// (DESIGN.md); kept because it is the lower-traffic variant.  *done = false: conditions not met, nothing launched.
+template <typename T>
+static int lod0_fused_pass(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms, bool* done) {
+  const tvk_build_info& info = b.info;
+  cudaStream_t st = c->stream;
+  *done = false;
+  const uint32_t* s0 = info.lod_size[0];
+  const uint32_t nbx = info.lod_bricks[0][0];
+  const uint32_t last_tx = brick_dim(bc, 0, 0, nbx - 1);
+  const uint32_t groups[2][3] = {{0u, last_tx == bc.brick ? nbx : nbx - 1, bc.brick}, {nbx - 1, last_tx == bc.brick ? 0u : 1u, last_tx}};
+  bool can = info.lod_count >= 2 && s0[0] > 1 && s0[1] > 1 && s0[2] > 1 && (bc.overlap % 2) == 0 && bc.core >= bc.overlap &&
+             (reinterpret_cast<uintptr_t>(b.d_lod[0]) & 3) == 0 && (uint64_t)s0[0] * s0[1] * s0[2] >= (1u << 18) &&
+             getenv("TVK_BUILD_FUSED") != nullptr;
+  for (int g = 0; g < 2; ++g) if (groups[g][1] && (groups[g][2] * sizeof(T)) % 4 != 0) can = false;
+  if (!can) return TVK_OK;
+  uint32_t* d_mn = b.d_mn;
+  uint32_t* d_mx = b.d_mn + info.total_bricks;
+  const size_t smem = sizeof(unsigned int) * (sizeof(T) == 1 ? 32u * 256u : HIST_WINDOW);
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->bev0, st));
+  for (int g = 0; g < 2; ++g) {
+    const uint32_t x_first = groups[g][0], x_count = groups[g][1], row_bytes = groups[g][2] * (uint32_t)sizeof(T);
+    if (!x_count) continue;
+    const uint64_t nb = (uint64_t)x_count * info.lod_bricks[0][1] * info.lod_bricks[0][2];
+    const unsigned grid = (unsigned)std::min<uint64_t>(nb, (uint64_t)sms);
+    const T* src = (const T*)b.d_lod[0];
+    uint8_t* store = (uint8_t*)b.d_store;
+    T* l1 = (T*)b.d_lod[1];
+#define TVK_LAUNCH_FUSED(CBV)                                                                                                  \
+    do {                                                                                                                   \
+      if (b.desc.use_median) {                                                                                             \
+        TVK_CHECK_CUDA(c, cudaFuncSetAttribute(lod0_fused_kernel<T, CBV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        lod0_fused_kernel<T, CBV, true><<<grid, 1024, smem, st>>>(src, store, b.d_offsets, bc, d_mn, d_mx, x_first, x_count, l1, b.d_hist1d); \
+      } else {                                                                                                             \
+        TVK_CHECK_CUDA(c, cudaFuncSetAttribute(lod0_fused_kernel<T, CBV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        lod0_fused_kernel<T, CBV, false><<<grid, 1024, smem, st>>>(src, store, b.d_offsets, bc, d_mn, d_mx, x_first, x_count, l1, b.d_hist1d); \
+      }                                                                                                                    \
+    } while (0)
+    if (row_bytes % 16 == 0) TVK_LAUNCH_FUSED(16);
+    else if (row_bytes % 8 == 0) TVK_LAUNCH_FUSED(8);
+    else TVK_LAUNCH_FUSED(4);
+#undef TVK_LAUNCH_FUSED
+    c->launches++;
+  }
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  if (sizeof(T) == 2) {                          // the fused table holds the bins below HIST_WINDOW: count the rest in a second pass
+    static bool attr_set = false;
+    if (!attr_set) {
+      TVK_CHECK_CUDA(c, cudaFuncSetAttribute(hist16_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HIST_WINDOW * sizeof(uint32_t))));
+      attr_set = true;
+    }
+    b.hist_upper_pending = true;                 // launched in build_finish, once the global maximum is known
+  }
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->bev1, st));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->bev0, c->bev1) == cudaSuccess) b.kernels_ms += ms;
+  b.hist_fused = true; b.lod0_fused = true;
+  *done = true;
+  return TVK_OK;
+}
+
+template <typename T>
+static int run_build(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms) {
+  int rc = build_begin<T>(c, b);
+  if (rc) return rc;
+  const tvk_build_info& info = b.info;
+  bool fused = false;
+  rc = lod0_fused_pass<T>(c, b, bc, sms, &fused);
+  if (rc) return rc;
+  if (!fused) {
+    rc = build_lod0_rows<T>(c, b, bc, sms, (const T*)b.d_lod[0], 0, info.lod_size[0][2], 0, info.lod_bricks[0][2], true);
+    if (rc) return rc;
+  }
+  return build_finish<T>(c, b, bc, sms);
+}
+
+extern "C" int tvk_build_octree(tvk_ctx* c, const tvk_build_desc* d, const void* raw, int raw_on_device, tvk_build_info* info_out) {
+  if (!c || !d || !raw) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  int rc = build_setup(c, d, nullptr);
+  if (rc) { release(c); return rc; }
+  BuildState& b = c->build;
+  const BuildConst bc = make_const(b);
   int sms = 0;
   TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
   const uint64_t n0 = (uint64_t)d->volume_size[0] * d->volume_size[1] * d->volume_size[2];
@@ -1524,15 +1665,71 @@ extern "C" int tvk_build_octree(tvk_ctx* c, const tvk_build_desc* d, const void*
     b.own_lod0 = true;
     TVK_CHECK_CUDA(c, cudaMemcpyAsync(b.d_lod[0], raw, n0 * d->bytes_per_voxel, cudaMemcpyHostToDevice, c->stream));
   }
-  TVK_CHECK_CUDA(c, cudaMalloc(&b.d_store, off));
-  TVK_CHECK_CUDA(c, cudaMalloc(&b.d_offsets, sizeof(uint64_t) * info.total_bricks));
-  TVK_CHECK_CUDA(c, cudaMalloc(&b.d_sizes, sizeof(uint32_t) * 3 * info.total_bricks));
-  TVK_CHECK_CUDA(c, cudaMalloc(&b.d_minmax, sizeof(double) * 2 * info.total_bricks));
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(b.d_offsets, b.offsets.data(), sizeof(uint64_t) * info.total_bricks, cudaMemcpyHostToDevice, c->stream));
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(b.d_sizes, b.sizes.data(), sizeof(uint32_t) * 3 * info.total_bricks, cudaMemcpyHostToDevice, c->stream));
-  int rc = (d->bytes_per_voxel == 1) ? run_build<uint8_t>(c, b, bc, sms) : run_build<uint16_t>(c, b, bc, sms);
+  rc = (d->bytes_per_voxel == 1) ? run_build<uint8_t>(c, b, bc, sms) : run_build<uint16_t>(c, b, bc, sms);
   if (rc) { release(c); return rc; }
   b.valid = true;
+  if (info_out) *info_out = b.info;
+  return TVK_OK;
+}
+
+// ---- streamed build: LOD 0 arrives in z-slabs of whole brick rows
+extern "C" int tvk_build_stream_begin(tvk_ctx* c, const tvk_build_desc* d, void* store, tvk_build_info* info_out) {
+  if (!c || !d) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  int rc = build_setup(c, d, store);
+  if (rc) { release(c); return rc; }
+  BuildState& b = c->build;
+  rc = (d->bytes_per_voxel == 1) ? build_begin<uint8_t>(c, b) : build_begin<uint16_t>(c, b);
+  if (rc) { release(c); return rc; }
+  b.streaming = true; b.next_bz = 0;
+  if (info_out) *info_out = b.info;
+  return TVK_OK;
+}
+
+extern "C" int tvk_build_stream_rows(const tvk_build_desc* d, uint32_t bz0, uint32_t bz1, uint32_t* z0, uint32_t* rows) {
+  tvk_build_info info;
+  if (!d || !z0 || !rows || tvk_build_plan(d, &info) != TVK_OK || bz0 >= bz1 || bz1 > info.lod_bricks[0][2]) return TVK_ERR_INVALID;
+  const uint32_t core = d->brick_size - 2 * d->overlap, sz = d->volume_size[2];
+  const uint32_t lo = bz0 * core >= d->overlap ? bz0 * core - d->overlap : 0u;
+  const uint32_t hi = std::min<uint64_t>((uint64_t)bz1 * core + d->overlap, sz);
+  *z0 = lo; *rows = hi - lo;
+  return TVK_OK;
+}
+
+extern "C" int tvk_build_stream_slab(tvk_ctx* c, const void* raw_slab, uint32_t z0, uint32_t rows, uint32_t bz0, uint32_t bz1) {
+  if (!c || !raw_slab) return TVK_ERR_INVALID;
+  BuildState& b = c->build;
+  if (!b.streaming) TVK_FAIL(c, TVK_ERR_INVALID, "tvk_build_stream_slab without tvk_build_stream_begin");
+  if (bz0 != b.next_bz || bz1 <= bz0 || bz1 > b.info.lod_bricks[0][2]) TVK_FAIL(c, TVK_ERR_INVALID, "slabs must cover the brick rows in ascending order, without gaps");
+  uint32_t need_z0 = 0, need_rows = 0;
+  tvk_build_stream_rows(&b.desc, bz0, bz1, &need_z0, &need_rows);
+  if (z0 > need_z0 || (uint64_t)z0 + rows < (uint64_t)need_z0 + need_rows || (uint64_t)z0 + rows > b.info.lod_size[0][2])
+    TVK_FAIL(c, TVK_ERR_INVALID, "the slab does not hold the raw rows its brick rows read (tvk_build_stream_rows)");
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  int sms = 0;
+  TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  const BuildConst bc = make_const(b);
+  const int rc = (b.desc.bytes_per_voxel == 1)
+      ? build_lod0_rows<uint8_t>(c, b, bc, sms, (const uint8_t*)raw_slab, z0, rows, bz0, bz1, false)
+      : build_lod0_rows<uint16_t>(c, b, bc, sms, (const uint16_t*)raw_slab, z0, rows, bz0, bz1, false);
+  if (rc) return rc;
+  b.next_bz = bz1;
+  return TVK_OK;
+}
+
+extern "C" int tvk_build_stream_end(tvk_ctx* c, tvk_build_info* info_out) {
+  if (!c) return TVK_ERR_INVALID;
+  BuildState& b = c->build;
+  if (!b.streaming) TVK_FAIL(c, TVK_ERR_INVALID, "tvk_build_stream_end without tvk_build_stream_begin");
+  if (b.next_bz != b.info.lod_bricks[0][2]) TVK_FAIL(c, TVK_ERR_INVALID, "not every brick row of LOD 0 has been fed");
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  int sms = 0;
+  TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  const BuildConst bc = make_const(b);
+  const int rc = (b.desc.bytes_per_voxel == 1) ? build_finish<uint8_t>(c, b, bc, sms) : build_finish<uint16_t>(c, b, bc, sms);
+  if (rc) { release(c); return rc; }
+  b.streaming = false;
+  b.valid = true;                                // no flat LOD 0: tvk_build_hist2d needs the raw volume and refuses
   if (info_out) *info_out = b.info;
   return TVK_OK;
 }
@@ -1644,6 +1841,7 @@ static int run_hist2d(tvk_ctx* c, uint32_t bins_x, double max_nonzero, uint64_t*
 
 extern "C" int tvk_build_hist2d(tvk_ctx* c, uint32_t bins_x, double max_nonzero_value, uint64_t* bins, float* max_grad_magnitude) {
   if (!c || !c->build.valid || !bins || !max_grad_magnitude || bins_x == 0) return TVK_ERR_INVALID;
+  if (!c->build.d_lod[0]) TVK_FAIL(c, TVK_ERR_UNSUPPORTED, "the 2-D histogram reads the flat raw volume, which a streamed build does not keep");
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
   int sms = 0;
   TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));

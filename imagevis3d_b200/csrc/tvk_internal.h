@@ -39,6 +39,11 @@ struct BuildState {
   unsigned long long* d_hist1d = nullptr;
   void*     d_lod[TVK_MAX_LOD] = {}; // flat LOD volumes (lod 0 = raw when raw_on_device)
   bool      own_lod0 = false;
+  bool      own_store = true;        // false: caller-owned store (tvk_build_stream_begin)
+  uint32_t* d_mn = nullptr;          // packed min | max | global max scratch while a build is in progress
+  bool      hist_fused = false, hist_full = false, lod0_fused = false, hist_pending = false, hist_upper_pending = false;
+  bool      streaming = false;       // between tvk_build_stream_begin and _end
+  uint32_t  next_bz = 0;             // first LOD-0 brick row not fed yet
   bool      valid = false;
   float     kernels_ms = 0.f;        // CUDA-event time of the builder kernels of the last tvk_build_octree
   float     hist2d_ms = 0.f;         // ... and of the last tvk_build_hist2d

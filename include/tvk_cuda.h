@@ -259,6 +259,25 @@ int tvk_build_plan(const tvk_build_desc* desc, tvk_build_info* info);
 int tvk_build_octree(tvk_ctx* ctx, const tvk_build_desc* desc, const void* raw,
                      int raw_on_device, tvk_build_info* info);
 /* per brick: offset into the store (bytes) and size in voxels */
+/* Streamed build for raw volumes that do not fit in device memory next to their brick store (replaces the
+ * out-of-core loop of ExtendedOctreeConverter::Convert, ExtendedOctreeConverter.cpp:118-300, which pages raw data
+ * through a brick cache): LOD 0 is fed in z-slabs of WHOLE BRICK ROWS, in ascending order; every slab yields its LOD-0
+ * bricks (ghost cells, min/max), its share of the 1-D histogram and of the flat LOD-1 volume; tvk_build_stream_end builds
+ * the coarser levels from LOD 1, which stays resident (1/7 of the raw size for the whole pyramid).  The result is the
+ * state tvk_build_octree leaves (same ToC, bricks, min/max, histogram), except that no flat LOD 0 is kept, so
+ * tvk_build_hist2d is not available.
+ *   store: NULL = the brick store is allocated in device memory; otherwise caller-owned memory of
+ *          info.total_bytes bytes -- device memory, or pinned host memory mapped into the device address space
+ *          (cudaHostAlloc), in which case bricks are written over PCIe as they are cut.
+ *   tvk_build_stream_rows: the raw rows [z0, z0 + rows) a slab must hold to build brick rows [bz0, bz1)
+ *          (inner rows plus `overlap` ghost rows either side, clipped to the volume).
+ *   tvk_build_stream_slab: raw_slab = device pointer to rows [z0, z0 + rows), x fastest; builds brick rows
+ *          [bz0, bz1); bz0 must be where the previous slab stopped. */
+int tvk_build_stream_begin(tvk_ctx* ctx, const tvk_build_desc* desc, void* store, tvk_build_info* info);
+int tvk_build_stream_rows(const tvk_build_desc* desc, uint32_t bz0, uint32_t bz1, uint32_t* z0, uint32_t* rows);
+int tvk_build_stream_slab(tvk_ctx* ctx, const void* raw_slab, uint32_t z0, uint32_t rows, uint32_t bz0, uint32_t bz1);
+int tvk_build_stream_end(tvk_ctx* ctx, tvk_build_info* info);
+
 int tvk_build_get_toc(tvk_ctx* ctx, uint64_t* offsets, uint32_t* sizes3, uint64_t n);
 int tvk_build_get_minmax(tvk_ctx* ctx, double* minmax2, uint64_t n);
 int tvk_build_get_bricks(tvk_ctx* ctx, void* host_dst, uint64_t offset, uint64_t bytes);

@@ -184,3 +184,86 @@ def test_hist2d_four_voxels_per_thread_is_bit_exact(case, monkeypatch):
     assert (h_sc == h_ref).all(), name
     bad = np.argwhere(h_vec != h_ref)
     assert bad.size == 0, (name, bad[:5], h_vec[tuple(bad[0])], h_ref[tuple(bad[0])])
+
+
+def _streamed(tvk, raw, brick, overlap, median, splits, host_store=False):
+    """Feeds `raw` through tvk_build_stream_* with the given brick-row split points; -> (tight store, sizes, minmax, hist1d)"""
+    import torch
+    dims = raw.shape[::-1]
+    pinned = None
+    if host_store:
+        info = tvk.build_stream_begin(dims, raw.dtype.itemsize, brick, overlap, median)     # plan only, to learn the size
+        nbytes = int(info.total_bytes)
+        tvk.build_release()
+        pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        info = tvk.build_stream_begin(dims, raw.dtype.itemsize, brick, overlap, median, store_ptr=pinned.data_ptr())
+    else:
+        info = tvk.build_stream_begin(dims, raw.dtype.itemsize, brick, overlap, median)
+    nbz = int(info.lod_bricks[0][2])
+    cuts = [0] + [c for c in splits if 0 < c < nbz] + [nbz]
+    for b0, b1 in zip(cuts[:-1], cuts[1:]):
+        z0, rows = tvk.build_stream_rows(b0, b1)
+        slab = torch.from_numpy(np.ascontiguousarray(raw[z0:z0 + rows]).view(np.uint8).reshape(-1).copy()).cuda()
+        tvk.build_stream_slab(slab.data_ptr(), z0, rows, b0, b1)
+        del slab
+    tvk.build_stream_end()
+    off, sizes = tvk.build_toc()
+    if host_store:
+        tvk.synchronize()
+        blob = pinned.numpy()
+        bpv = raw.dtype.itemsize
+        store = np.concatenate([blob[int(o):int(o) + int(s[0]) * int(s[1]) * int(s[2]) * bpv] for o, s in zip(off, sizes)])
+    else:
+        store, sizes = cuda_store_tight(tvk)
+    mm, h1 = tvk.build_minmax(), tvk.build_hist1d()
+    tvk.build_release()
+    return store, sizes, mm, h1
+
+
+@pytest.mark.parametrize("vol,dtype,brick,overlap,median,splits", [
+    ((128, 96, 200), np.uint16, 24, 2, False, [1, 4, 5]),          # fused reduction + histogram per slab
+    ((128, 96, 200), np.uint8, 24, 2, True, [3]),
+    ((127, 61, 133), np.uint16, 20, 2, False, [2, 7]),              # unaligned rows: scalar reduction, plain histogram
+    ((64, 64, 61), np.uint8, 64, 2, False, []),                      # one brick row: the whole volume as one slab
+    ((130, 70, 129), np.uint16, 64, 2, False, [1, 2]),               # last brick row thinner than the overlap + odd depth
+    ((96, 80, 97), np.uint8, 12, 4, False, [1, 2, 3, 5, 8, 13])])
+def test_streamed_build_equals_one_shot(tvk, vol, dtype, brick, overlap, median, splits):
+    """tvk_build_stream_*: LOD 0 fed in z-slabs gives the same store, min/max and histogram as tvk_build_octree, byte for byte."""
+    raw = H.synth_noise(vol, dtype, seed=sum(vol), maxval=255 if dtype == np.uint8 else 65535)
+    tvk.build_octree(raw, brick, overlap, median=bool(median))
+    ref_store, ref_sizes = cuda_store_tight(tvk)
+    ref_mm, ref_h1 = tvk.build_minmax(), tvk.build_hist1d()
+    tvk.build_release()
+    store, sizes, mm, h1 = _streamed(tvk, raw, brick, overlap, median, splits)
+    assert (sizes == ref_sizes).all() and store.size == ref_store.size
+    bad = np.nonzero(store != ref_store)[0]
+    assert bad.size == 0, "first mismatching byte %d of %d" % (bad[0], store.size)
+    assert (mm == ref_mm).all()
+    assert h1.size == ref_h1.size and (h1 == ref_h1).all()
+
+
+def test_streamed_build_into_pinned_host_store(tvk):
+    """The brick store may be caller-owned pinned host memory: bricks are written over PCIe as they are cut (how a volume
+    larger than HBM is bricked)."""
+    raw = H.synth_noise((128, 96, 150), np.uint16, seed=11, maxval=65535)
+    oc = O.build_octree(raw, 24, 2, False)
+    store, sizes, mm, h1 = _streamed(tvk, raw, 24, 2, False, [2, 5], host_store=True)
+    assert (sizes == oc["sizes"]).all() and (store == oc["store"]).all() and (mm == oc["minmax"]).all()
+    assert (h1 == O.hist1d(oc)).all()
+
+
+def test_streamed_build_rejects_gaps_and_short_slabs(tvk):
+    import torch
+    from imagevis3d_b200._lib import TvkError
+    raw = H.synth_noise((64, 64, 100), np.uint8, seed=2, maxval=255)
+    tvk.build_stream_begin((64, 64, 100), 1, 24, 2)
+    z0, rows = tvk.build_stream_rows(0, 2)
+    slab = torch.from_numpy(raw[z0:z0 + rows].reshape(-1).copy()).cuda()
+    with pytest.raises(TvkError):
+        tvk.build_stream_slab(slab.data_ptr(), z0, rows, 1, 2)          # does not start at brick row 0
+    with pytest.raises(TvkError):
+        tvk.build_stream_slab(slab.data_ptr(), z0, rows - 1, 0, 2)      # a row short
+    tvk.build_stream_slab(slab.data_ptr(), z0, rows, 0, 2)
+    with pytest.raises(TvkError):
+        tvk.build_stream_end()                                          # rows 2.. missing
+    tvk.build_release()
