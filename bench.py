@@ -172,14 +172,40 @@ def workload_config(n, mode):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of one GPU, sampled DURING a timed region through NVML in this process (the library
+    nvidia-smi itself calls; `nvidia-smi -lms` as a child process is the fall-back).  TVK_CLOCK_SAMPLER=off|smi|nvml."""
     Q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    PERIOD = 0.1
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+        self.kind = os.environ.get("TVK_CLOCK_SAMPLER", "nvml")
+
+    def _run_nvml(self):
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        bits = (("hw_slowdown", N.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", N.nvmlClocksEventReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", N.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", N.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag:
+            sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+            r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+            self.rows.append([str(self.index), str(sm), str(mx)] + [("Active" if r & b else "Not Active") for _, b in bits])
+            time.sleep(self.PERIOD)
 
     def run(self):
+        if self.kind == "off":
+            return
+        if self.kind == "nvml":
+            try:
+                self._run_nvml()
+                return
+            except Exception:
+                if self.rows:
+                    return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"],
@@ -204,7 +230,7 @@ class ClockSampler(threading.Thread):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.kind}
 
 
 def image_errors(a, b):
@@ -334,11 +360,30 @@ def sphere_torch(local_dims, origin, total, bits, device):
 class Scene:
     """A bricked volume resident in one context's pool (kernel-level C ABI)."""
 
-    def __init__(self, tvk, raw, dims, bits, want_host_copy):
+    def __init__(self, tvk, raw, dims, bits, want_host_copy, gen=None, slab_bytes=4 << 30):
+        """raw: the whole LOD-0 volume in HBM (one-shot build), or None with gen(z0, rows) -> device tensor of those raw
+        rows: the volume is then fed through the streamed builder in z-slabs of about slab_bytes and never exists whole."""
         import torch
         self.tvk, self.dims, self.bits = tvk, tuple(int(v) for v in dims), bits
         bpv = bits // 8
-        info = tvk.build_octree(raw_dptr=raw.data_ptr(), volume_size=self.dims, bpv=bpv, brick=BRICK, overlap=OVERLAP)
+        if raw is not None:
+            info = tvk.build_octree(raw_dptr=raw.data_ptr(), volume_size=self.dims, bpv=bpv, brick=BRICK, overlap=OVERLAP)
+            self.slabs = 1
+        else:
+            tvk.build_stream_begin(self.dims, bpv, BRICK, OVERLAP)
+            nbz = int(tvk.build_info.lod_bricks[0][2])
+            per = max(1, int(slab_bytes // (self.dims[0] * self.dims[1] * bpv * (BRICK - 2 * OVERLAP))))
+            self.slabs = 0
+            for b0 in range(0, nbz, per):
+                b1 = min(nbz, b0 + per)
+                z0, rows = tvk.build_stream_rows(b0, b1)
+                slab = gen(z0, rows)
+                torch.cuda.synchronize()
+                tvk.build_stream_slab(slab.data_ptr(), z0, rows, b0, b1)
+                del slab
+                self.slabs += 1
+            info = tvk.build_stream_end()
+            torch.cuda.empty_cache()
         self.build_ms = tvk.build_last_ms()
         self.info = info
         off, sizes = tvk.build_toc()
@@ -369,7 +414,37 @@ class Scene:
         tvk.pool_upload_device(self.slots, [store + int(o) for o in self.off], self.sizes)
         tvk.set_minmax(self.mm)
 
+    def fill_pool_visible(self, sampler, vis):
+        """The pool holds only the bricks the transfer function leaves non-empty (plus the pinned coarsest one): a brick
+        whose [min, max] misses the table's non-zero range is flagged EMPTY by the visibility pass, rays skip it without
+        asking for it and the reference never uploads it (GLVolumePool::RecomputeVisibility, GLVolumePool.cpp:1580-1718)."""
+        tvk, total = self.tvk, self.total
+        lo, hi = self.mm[:, 0], self.mm[:, 1]
+        cd = ((vis[1] >= lo) & (vis[1] <= hi)) if vis[0] == 2 else ((vis[2] >= lo) & (vis[1] <= hi))
+        cd[total - 1] = True                                  # the coarsest brick is always resident (UploadFirstBrick)
+        pick = np.nonzero(cd)[0]
+        n = len(pick)
+        cx = int(math.ceil(n ** (1.0 / 3.0)))
+        self.cap = (cx, cx, -(-n // (cx * cx)))
+        got = tvk.pool_create(self.dims, self.maxb, OVERLAP, self.bits // 8, self.cap, self.lod_count, sampler)
+        assert got == total
+        store = tvk.build_store_ptr()
+        slot_of = np.arange(n, dtype=np.uint32)
+        slot_of[-1] = self.cap[0] * self.cap[1] * self.cap[2] - 1                     # pick[-1] == total - 1
+        tvk.pool_upload_device(slot_of, [store + int(self.off[i]) for i in pick], self.sizes[pick])
+        tvk.set_minmax(self.mm)
+        self.resident_meta = np.zeros(total, np.uint32)       # MISSING everywhere else; visibility turns those into EMPTY flags
+        self.resident_meta[pick] = slot_of + 3
+        self.slots = None
+        self.resident_bricks, self.pool_bytes = n, n * self.maxb[0] * self.maxb[1] * self.maxb[2] * (self.bits // 8)
+
     def set_mode(self, ms):
+        if self.slots is None:
+            self.tvk.set_metadata(self.resident_meta)
+            if ms["tf"] is not None:
+                (self.tvk.set_tf1d if ms["tf"].ndim == 2 else self.tvk.set_tf2d)(ms["tf"])
+            self.tvk.recompute_visibility(*ms["vis"])
+            return
         self.tvk.set_metadata(self.slots + 3)
         if ms["tf"] is not None:
             (self.tvk.set_tf1d if ms["tf"].ndim == 2 else self.tvk.set_tf2d)(ms["tf"])
@@ -380,6 +455,64 @@ class Scene:
         bit-identical to the oracle builder and the reference)."""
         return H.ResidentPool(self.dims, self.bits // 8, OVERLAP, self.maxb, self.cap, self.lod_count, self.blob.numpy(),
                               self.off, self.sizes, self.slots, self.tvk.get_metadata())
+
+
+class MirrorPool:
+    """Host mirror of a device pool that copies a brick down (from the device brick store, into the SAME slot) only when
+    the oracle asks for it: the check of a few crops of a 4K frame touches a few thousand of the ~10^5 resident bricks.
+    Duck-types what oracle.host.raycast needs.  The numpy pool is calloc'ed: untouched slots cost no host memory."""
+
+    def __init__(self, H, scene):
+        from oracle import oracle as O
+        self.H, self.O, self.scene = H, O, scene
+        self.vol, self.bpv, self.overlap = scene.dims, scene.bits // 8, OVERLAP
+        self.max_brick, self.capacity, self.lod_count = scene.maxb, scene.cap, scene.lod_count
+        self.layout, self.lod_offset, self.lod_bricks, self.total = H.pool_layout(self.vol, self.max_brick, self.overlap, self.lod_count)
+        dims = [self.capacity[a] * self.max_brick[a] for a in range(3)]
+        self.data = np.zeros((dims[2], dims[1], dims[0]), np.uint8 if self.bpv == 1 else np.uint16)
+        self.dev_meta = np.ascontiguousarray(scene.tvk.get_metadata(), np.uint32)
+        self.meta = np.where(self.dev_meta >= 3, 0, self.dev_meta).astype(np.uint32)      # resident on the device = not fetched yet
+        self.fetched = 0
+        self.fetch(self.total - 1)
+
+    def c_pool(self):
+        return self.H.OraclePool.c_pool(self)
+
+    def fetch(self, idx):
+        sc, O = self.scene, self.O
+        s = sc.sizes[idx]
+        n = int(s[0]) * int(s[1]) * int(s[2]) * self.bpv
+        brick = sc.tvk.build_bricks(int(sc.off[idx]), n)
+        O.lib().orc_pool_place(C.c_void_p(self.data.ctypes.data), (C.c_uint32 * 3)(*self.capacity), (C.c_uint32 * 3)(*self.max_brick),
+                               C.c_uint32(self.bpv), C.c_uint32(int(self.dev_meta[idx]) - 3), C.c_void_p(brick.ctypes.data),
+                               (C.c_uint32 * 3)(*[int(v) for v in s]))
+        self.meta[idx] = self.dev_meta[idx]
+        self.fetched += 1
+
+    def render_crops(self, params, tf, w, h, max_passes=64):
+        """paints the crop rectangles until the oracle asks for nothing more; -> (frame, samples of the last pass, seconds)"""
+        H = self.H
+        q = H.RaycastParams()
+        C.memmove(C.byref(q), C.byref(params), C.sizeof(q))
+        q.hash_table_size, q.rehash_count = 65521, 32
+        table = tf if tf is not None else np.zeros((1, 4), np.uint8)
+        t0 = time.perf_counter()
+        for _ in range(max_passes):
+            frame = H.OracleFrame(w, h, q.hash_table_size)
+            q.new_view = 1
+            samples = 0
+            for i, r in enumerate(crop_rects(w, h)):
+                H.raycast(q, self, table, frame, rect=r, clear_hash=(i == 0))
+                samples += int(frame.stats[0])
+            req = H.read_requests(self, frame, cap=65521)
+            if len(req) == 0:
+                return frame, samples, time.perf_counter() - t0
+            for x, y, z, lod in req:
+                b = self.lod_bricks[int(lod)]
+                idx = int(self.lod_offset[int(lod)]) + int(x) + int(y) * int(b[0]) + int(z) * int(b[0]) * int(b[1])
+                assert self.dev_meta[idx] >= 3, "the oracle asks for a brick the device pool does not hold"
+                self.fetch(idx)
+        raise AssertionError("oracle crops did not converge")
 
 
 def timed_frames(tvk, torch, flush, params, steps, warmup, local):
@@ -687,14 +820,28 @@ def run_e2e(torch, HM, dev, local, steps):
 
 
 def run_sortlast(args, torch, dist, TvkContext, HM, SL, dev, local, rank, world, sampler, peak, peak_src, flush, steps, warmup):
+    """configs[3]: one 4096^3 uint16 volume over `world` GPUs (strong scaling), 3840x2160, 1D-TF with lighting.
+    Every GPU renders an ANTIPODAL PAIR of boxes (sortlast.antipodal_boxes): view-independent load balance; each box is a
+    member of the fused direct-send exchange.  TVK_BOXES_PER_GPU=1 gives one box per GPU, TVK_EXCHANGE=nccl (one box per
+    GPU only) the NCCL all_to_all cross-check path."""
     W, Hh = 3840, 2160
     GLOBAL = C4_VOL
     mode = "1d_lit"
-    parts = SL.block_partition(GLOBAL, world, halo=64)
-    part = parts[rank]
-    LOCAL = part["local_dims"]
-    # HBM while a box is set up: raw box + LOD pyramid (0.15) + brick store (1.7), then -- raw freed -- store + resident pool (1.7)
-    need_peak = 2.0 * LOCAL[0] * LOCAL[1] * LOCAL[2] * 3.6 / 1e9 + 2.0
+    exchange_kind = os.environ.get("TVK_EXCHANGE", "p2p-fused")
+    # two GPUs: one cut across the up axis has no box behind another at any azimuth (lowest ms/frame measured); from four
+    # GPUs on the one-box grids cut in depth anyway and antipodal pairs win (4 GPUs: 6.2 against 7.5 ms/frame)
+    per_gpu = 1 if exchange_kind != "p2p-fused" else int(os.environ.get("TVK_BOXES_PER_GPU", "1" if world == 2 else "2"))
+    if per_gpu == 1:
+        parts, owner = SL.block_partition(GLOBAL, world, halo=64), list(range(world))
+    else:
+        parts, owner = SL.antipodal_boxes(GLOBAL, world, per_gpu, halo=64)
+    V = len(parts)
+    mine = [i for i in range(V) if owner[i] == rank]
+    # HBM while a box is set up: the box is generated and bricked in z-slabs (streamed builder), so what is resident is the
+    # brick store (1.39 x the raw bytes: ghost cells + pyramid), the flat LOD >= 1 pyramid (0.15), one raw slab, and then the
+    # pool of the bricks the transfer function leaves non-empty (< the store); a finished box keeps only its pool
+    raw_gb = [2.0 * parts[i]["local_dims"][0] * parts[i]["local_dims"][1] * parts[i]["local_dims"][2] / 1e9 for i in mine]
+    need_peak = max(raw_gb) * (1.39 + 0.15) + 8.0 + sum(raw_gb) * 0.7
     free_gb = torch.cuda.mem_get_info()[0] / 1e9
     fits = torch.tensor([1.0 if need_peak <= free_gb else 0.0], device=dev)
     dist.all_reduce(fits, op=dist.ReduceOp.MIN)
@@ -702,41 +849,50 @@ def run_sortlast(args, torch, dist, TvkContext, HM, SL, dev, local, rank, world,
         if rank == 0:
             return {"metric": "ray samples/s", "value": None, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
                     "higher_is_better": True, "scaling": "strong", "config": workload_config(world, mode),
-                    "unsupported": "a rank's box of %dx%dx%d uint16 voxels needs about %.0f GB of HBM while it is built (brick store + "
-                                   "resident pool) and the GPU has %.0f GB free: 4096^3 does not fit %d GPUs until the builder streams "
-                                   "a box through in slabs" % (LOCAL[0], LOCAL[1], LOCAL[2], need_peak, free_gb, world)}
+                    "unsupported": "the boxes of a rank need about %.0f GB of HBM (brick store + pools) and the GPU has %.0f GB free"
+                                   % (need_peak, free_gb)}
         return None
-    tvk = TvkContext(local)
     work_stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(work_stream)
-    tvk.set_stream(work_stream.cuda_stream)
-    raw = sphere_torch(LOCAL, part["s"], GLOBAL, 16, dev)
-    torch.cuda.synchronize()
-    scene = Scene(tvk, raw, LOCAL, 16, want_host_copy=(rank == 0 and not args.no_cpu))
-    del raw
-    torch.cuda.empty_cache()
-    scene.fill_pool(sampler)
-    tvk.build_release()
     # the transfer function is defined on the GLOBAL value range (a box that misses the centre has a smaller maximum)
     ms = mode_setup(mode, 65535.0, 16, gradient_scale(GLOBAL))
-    scene.set_mode(ms)
+    t_setup = time.perf_counter()
+    ctxs, scenes = [], []
+    for n, i in enumerate(mine):
+        tvk = TvkContext(local)
+        tvk.set_stream(work_stream.cuda_stream)
+        part = parts[i]
+        L, origin = part["local_dims"], part["s"]
+        scene = Scene(tvk, None, L, 16, want_host_copy=False,
+                      gen=lambda z0, rows, L=L, origin=origin: sphere_torch((L[0], L[1], rows), (origin[0], origin[1], origin[2] + z0),
+                                                                            GLOBAL, 16, dev))
+        scene.fill_pool_visible(sampler, ms["vis"])
+        scene.set_mode(ms)
+        if not (rank == 0 and not args.no_cpu):
+            tvk.build_release()          # rank 0 keeps its brick stores until the oracle check has copied the bricks it marches
+        ctxs.append(tvk)
+        scenes.append(scene)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
 
-    exchange_kind, fused = os.environ.get("TVK_EXCHANGE", "p2p-fused"), None
+    fused = None
     if exchange_kind == "p2p-fused":
         ok = torch.ones(1, device=dev)
         try:
-            fused = SL.FusedExchange(tvk, world, rank, W, Hh, dist)
+            fused = SL.MultiBoxExchange(ctxs, mine, V, W, Hh, dist)
         except Exception as e:            # noqa: BLE001 -- any failure to map peers demotes ALL ranks together
             sys.stderr.write("rank %d: fused exchange unavailable (%s)\n" % (rank, e))
             ok.zero_()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if ok.item() == 0:
+            if per_gpu != 1:
+                raise SystemExit("peer memory is not available and the NCCL path renders one box per GPU: rerun with TVK_EXCHANGE=nccl")
             fused, exchange_kind = None, "nccl"
 
     step_params, step_order = {}, {}
     for k in range(max(steps, warmup)):
         cam = camera_for_step(HM, k, steps)
-        step_params[k] = HM.raycast_params(cam, W, Hh, GLOBAL, slab=part, **ms["kw"])
+        step_params[k] = [HM.raycast_params(cam, W, Hh, GLOBAL, slab=parts[i], **ms["kw"]) for i in mine]
         pg = HM.raycast_params(cam, W, Hh, GLOBAL)
         step_order[k] = SL.depth_order(np.array(pg.eye_to_model[:]).reshape(4, 4), parts)
 
@@ -746,28 +902,66 @@ def run_sortlast(args, torch, dist, TvkContext, HM, SL, dev, local, rank, world,
 
     def gpu_composite(stripes):
         out = torch.empty_like(stripes[0])
-        tvk.composite_ordered([t.data_ptr() for t in stripes], stripes[0].shape[0] * stripes[0].shape[1], out.data_ptr())
+        ctxs[0].composite_ordered([t.data_ptr() for t in stripes], stripes[0].shape[0] * stripes[0].shape[1], out.data_ptr())
         return out
 
     final_image = [None]
+    stage_ev = []                    # per timed step: events after the march launches, the stripe blends and the landing wait
+    box_streams = [torch.cuda.Stream(device=dev) for _ in ctxs] if (fused is not None and len(ctxs) > 1) else [work_stream] * len(ctxs)
+    for t, st in zip(ctxs, box_streams):
+        t.set_stream(st.cuda_stream)
 
-    def step(k):
+    def step(k, timed=False):
         if fused is not None:
-            ptr = fused.render(step_params[k], step_order[k])
-            final_image[0] = torch.as_tensor(_CAI(ptr, (Hh, W, 4)), device=dev)
+            # MultiBoxExchange.render with the boxes' marches on their own streams (the persistent grids overlap: CTAs of the
+            # second march fill the SMs the first one's tail leaves idle), and an event after each of the three stages
+            fused.frame += 1
+            start = torch.cuda.Event()
+            start.record(work_stream)
+            done = []
+            for t, p, st in zip(ctxs, step_params[k], box_streams):
+                st.wait_event(start)
+                t.exchange_begin_frame(fused.frame)
+                t.raycast(p)
+                e = torch.cuda.Event()
+                e.record(st)
+                done.append(e)
+            for e in done:
+                work_stream.wait_event(e)
+            e1 = torch.cuda.Event(enable_timing=True); e1.record(work_stream)
+            # the stripe blends spin on arrival flags: they run one after the other, after ALL local marches
+            for t in ctxs:
+                t.set_stream(work_stream.cuda_stream)
+                t.exchange_composite(step_order[k], fused.frame)
+            e2 = torch.cuda.Event(enable_timing=True); e2.record(work_stream)
+            ptr = ctxs[0].exchange_final(fused.frame) if mine[0] == 0 else None
+            e3 = torch.cuda.Event(enable_timing=True); e3.record(work_stream)
+            for t, st in zip(ctxs, box_streams):
+                st.wait_event(e3)
+                t.set_stream(st.cuda_stream)
+            if timed:
+                stage_ev.append((e1, e2, e3))
+            if ptr is not None:
+                final_image[0] = torch.as_tensor(_CAI(ptr, (Hh, W, 4)), device=dev)
         else:
-            tvk.raycast(step_params[k])
-            partial = torch.as_tensor(_CAI(tvk.image_device_ptr(), (Hh, W, 4)), device=dev)
+            ctxs[0].raycast(step_params[k][0])
+            partial = torch.as_tensor(_CAI(ctxs[0].image_device_ptr(), (Hh, W, 4)), device=dev)
             final_image[0] = SL.exchange_and_composite(partial, step_order[k], gpu_composite, world, rank)
+
+    def sync_all():
+        for t in ctxs:
+            t.synchronize()
+        torch.cuda.synchronize()
 
     for k in range(warmup):
         flush.zero_()
         torch.cuda.synchronize()
         step(k)
-        tvk.synchronize()
-    tvk.stats(reset=True)
-    assert len(tvk.read_requests()) == 0, "pool is not fully resident: frame would not be converged"
-    l0 = tvk.stats().launches
+        sync_all()
+    for t in ctxs:
+        t.stats(reset=True)
+        assert len(t.read_requests()) == 0, "pool is not fully resident: frame would not be converged"
+    l0 = sum(t.stats().launches for t in ctxs)
     clock = ClockSampler(local)
     clock.start()
     time.sleep(0.25)
@@ -780,48 +974,83 @@ def run_sortlast(args, torch, dist, TvkContext, HM, SL, dev, local, rank, world,
         torch.cuda.synchronize()
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev_a.record(work_stream)
-        step(k)
+        step(k, timed=True)
         ev_b.record(work_stream)
-        tvk.synchronize()
-        torch.cuda.synchronize()
+        sync_all()
         step_ms += ev_a.elapsed_time(ev_b)
-        kernel_ms += tvk.stats().last_raycast_ms
+        if stage_ev and len(stage_ev[-1]) == 3 and not isinstance(stage_ev[-1][0], float):
+            e1, e2, e3 = stage_ev[-1]
+            stage_ev[-1] = (ev_a.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3))
+        # one box: K1's own events; several boxes march concurrently: the span from the start to the last march's end
+        kernel_ms += ctxs[0].stats().last_raycast_ms if len(ctxs) == 1 or not stage_ev else stage_ev[-1][0]
     dist.barrier()
-    st = tvk.stats()
+    sts = [t.stats() for t in ctxs]
     clocks = clock.stop()
-    launches = int(st.launches - l0)
-    per_rank = torch.tensor([kernel_ms / steps, step_ms / steps, float(st.samples) / steps], device=dev, dtype=torch.float64)
+    launches = int(sum(st.launches for st in sts) - l0)
+    my_samples, my_rays = sum(int(st.samples) for st in sts), sum(int(st.rays) for st in sts)
+    stage = [sum(v[i] for v in stage_ev) / max(1, len(stage_ev)) for i in range(3)] if stage_ev else [0.0, 0.0, 0.0]
+    if os.environ.get("TVK_BENCH_DEBUG"):
+        sys.stderr.write("rank %d per-step (march+send, wait+blend, landing) ms: %s\n" % (rank, " ".join("(%.2f %.2f %.2f)" % v for v in stage_ev)))
+    per_rank = torch.tensor([kernel_ms / steps, step_ms / steps, float(my_samples) / steps] + stage, device=dev, dtype=torch.float64)
     gathered = [torch.zeros_like(per_rank) for _ in range(world)]
     dist.all_gather(gathered, per_rank)
     t = torch.tensor([kernel_ms, step_ms], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     kernel_ms, step_ms = [float(v) for v in t.tolist()]
-    c = torch.tensor([int(st.samples), int(st.rays), launches], device=dev, dtype=torch.int64)
+    c = torch.tensor([my_samples, my_rays, launches], device=dev, dtype=torch.int64)
     dist.all_reduce(c, op=dist.ReduceOp.SUM)
     samples, rays, launches = [int(v) for v in c.tolist()]
 
-    # ---- parity: rank 0's partial image crops vs the oracle on its own box; final image == ordered blend of the partials
+    # ---- parity: box 0's partial image crops vs the oracle on a mirror of its pool; final image == ordered blend of ALL partials
     par = None
     k_last = steps - 1
-    partial_host = tvk.read_image()
-    gather_list = [torch.empty((Hh, W, 4), dtype=torch.float32, device=dev) for _ in range(world)] if rank == 0 else None
-    dist.gather(torch.from_numpy(partial_host).to(dev), gather_list, dst=0)
+    partials = [t.read_image() for t in ctxs]
+    for t in ctxs:
+        assert not t.exchange_timed_out() if fused is not None else True
+    box_images = [None] * V if rank == 0 else None
+    for i in range(V):                   # box i's partial image travels to rank 0 (untimed)
+        if owner[i] == rank:
+            img = torch.from_numpy(partials[mine.index(i)]).to(dev)
+        else:
+            img = torch.empty((Hh, W, 4), dtype=torch.float32, device=dev)
+        if owner[i] != 0:
+            if rank == owner[i]:
+                dist.send(img, dst=0)
+            elif rank == 0:
+                dist.recv(img, src=owner[i])
+        if rank == 0:
+            box_images[i] = img.cpu().numpy()
+        del img
     if rank == 0 and not args.no_cpu:
         from oracle import host as H
         from oracle import oracle as O
         fin = final_image[0].cpu().numpy()
-        parts_h = [g.cpu().numpy() for g in gather_list]
         want = np.zeros((Hh * W, 4), np.float32)
-        arr = (C.c_void_p * world)(*[parts_h[r].ctypes.data for r in step_order[k_last]])
-        O.lib().orc_composite_ordered(arr, C.c_uint32(world), C.c_uint64(Hh * W), want.ctypes.data_as(C.c_void_p))
+        arr = (C.c_void_p * V)(*[box_images[r].ctypes.data for r in step_order[k_last]])
+        O.lib().orc_composite_ordered(arr, C.c_uint32(V), C.c_uint64(Hh * W), want.ctypes.data_as(C.c_void_p))
         d = float(np.abs(fin.reshape(-1, 4) - want).max())
-        _, pc = parity_crops(H, scene, step_params[k_last], ms, partial_host, W, Hh)
-        par = {"rank0_partial_image": pc, "final_vs_oracle_blend_of_partials_max_abs_diff": d,
+        chk = max(range(len(scenes)), key=lambda n: scenes[n].resident_bricks)      # the local box with the most to show
+        mirror = MirrorPool(H, scenes[chk])
+        frame_o, o_samples, o_secs = mirror.render_crops(step_params[k_last][chk], ms["tf"], W, Hh)
+        psnr_min, err_max, npx, lit = 99.0, 0.0, 0, 0
+        for (x0, y0, x1, y1) in crop_rects(W, Hh):
+            ps, er = image_errors(partials[chk][y0:y1, x0:x1], frame_o.image[y0:y1, x0:x1])
+            psnr_min, err_max, npx = min(psnr_min, ps), max(err_max, er), npx + (x1 - x0) * (y1 - y0)
+            lit += int((frame_o.image[y0:y1, x0:x1, 3] > 0).sum())
+        pc = dict(crops=CROP_TILES, crop_pixels=npx, crop_pixels_hit=lit, psnr_db_min_over_crops=psnr_min, max_abs_err=err_max,
+                  max_abs_err_255=err_max * 255.0, within_tolerance=bool(psnr_min >= 45.0 and err_max <= 2.0 / 255.0),
+                  oracle_samples=o_samples, oracle_seconds=o_secs, oracle_bricks_fetched=mirror.fetched,
+                  box=int(mine[chk]),
+                  what="partial image of rank 0's fullest box: the oracle marches the crops on a host mirror of that box's pool (same "
+                       "slots; bricks copied down from the device store as the oracle's own requests name them)")
+        del mirror
+        par = {"rank0_partial_image": pc, "final_vs_oracle_blend_of_partials_max_abs_diff": d, "partials_blended": V,
                "final_image_nonzero_pixels": int((fin[..., 3] > 0).sum()),
                "tolerance": "PSNR >= 45 dB and max |error| <= 2/255 per crop; compositing: <= 1e-6"}
     dist.barrier()
     if rank != 0:
-        tvk.close()
+        for t in ctxs:
+            t.close()
         return None
     ms_frame = step_ms / steps
     alg = (samples * 1.2136 + rays * 16.0) / steps / world
@@ -833,18 +1062,33 @@ def run_sortlast(args, torch, dist, TvkContext, HM, SL, dev, local, rank, world,
             "samples_per_step": samples / steps, "rays_per_step": rays / steps,
             "per_rank": {"march_ms": [float(g[0]) for g in gathered], "step_ms": [float(g[1]) for g in gathered],
                          "samples_per_step": [float(g[2]) for g in gathered],
-                         "note": "march = K1 CUDA events; step = march + wait for the other ranks' stripes + blend + landing on rank 0, "
-                                 "CUDA events on the rank's stream"},
+                         "stage_ms": {"march_and_send": [float(g[3]) for g in gathered], "wait_and_blend": [float(g[4]) for g in gathered],
+                                      "landing_wait": [float(g[5]) for g in gathered]},
+                         "note": "march = K1 CUDA events summed over the rank's boxes; step = marches + wait for the other ranks' stripes + "
+                                 "blend + landing on rank 0, CUDA events on the rank's stream; wait_and_blend is almost all waiting for "
+                                 "the slowest rank (the blend of a stripe takes ~0.05 ms)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                         "note": "per GPU: 1.2136 B/sample + 16 B/ray over the slowest rank's march kernel"},
+                         "note": "per GPU: 1.2136 B/sample + 16 B/ray over the slowest rank's march kernels"},
             "gpu_launches": launches, "clocks": clocks, "parity": par,
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                     "note": "not measured at N > 1: the renderer API (tvkr_*) drives one GPU; the device-timed value is repeated"}}
     line["config"]["exchange"] = exchange_kind
+    line["config"]["parallelism"] = ("sort-last, %d convex boxes on a %s grid, %d per GPU%s + direct-send compositing fused into the "
+                                     "kernels (NVLink peer stores)" % (V, "x".join(str(v) for v in SL.block_grid(GLOBAL, V)), per_gpu,
+                                                                        " as antipodal pairs" if per_gpu > 1 else ""))
+    sc0 = scenes[0]
+    line["config"]["l2"] = ("inputs larger than L2 (box 0: %d of %d bricks non-empty under the transfer function and resident, pool of %.1f GB) "
+                            "+ 256 MB L2 flush between steps" % (sc0.resident_bricks, sc0.total, sc0.pool_bytes / 1e9))
+    line["setup"] = {"seconds": t_setup, "boxes_per_gpu": per_gpu, "slabs_per_box": sc0.slabs, "builder_kernel_ms_box0": sc0.build_ms,
+                     "box": list(parts[mine[0]]["local_dims"]), "store_bytes_box0": sc0.store_bytes, "resident_bricks_box0": sc0.resident_bricks,
+                     "pool_bytes_box0": sc0.pool_bytes,
+                     "what": "rank 0: every box generated in HBM slab by slab (reference CT_SPHERE arithmetic) and fed through the streamed "
+                             "builder (tvk_build_stream_*); a pool holds the bricks visibility leaves non-empty"}
     if fused is not None:
-        line["exchange_timed_out"] = bool(tvk.exchange_timed_out())
-    tvk.close()
+        line["exchange_timed_out"] = bool(any(t.exchange_timed_out() for t in ctxs))
+    for t in ctxs:
+        t.close()
     return line
 
 

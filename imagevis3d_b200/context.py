@@ -354,6 +354,25 @@ class TvkContext:
         arr = (C.c_void_p * len(bases))(*[int(b) for b in bases])
         self._ck(self.lib.tvk_exchange_set_peers(self.h, arr), "tvk_exchange_set_peers")
 
+    def exchange_connect(self, handles=None, bases=None):
+        """handles: list of 64-byte IPC handles (None entries allowed where bases gives a pointer); bases: list of pointers
+        valid in this process (None where the handle is to be opened)"""
+        w = self._xchg_world
+        hb = None
+        if handles is not None:
+            hb = b"".join(h if h is not None else b"\0" * 64 for h in handles)
+            assert len(hb) == 64 * w
+        arr = None
+        if bases is not None:
+            assert len(bases) == w
+            arr = (C.c_void_p * w)(*[int(b) if b else None for b in bases])
+        self._ck(self.lib.tvk_exchange_connect(self.h, C.c_char_p(hb) if hb is not None else None, arr), "tvk_exchange_connect")
+
+    def exchange_peer_base(self, r):
+        p = C.c_void_p()
+        self._ck(self.lib.tvk_exchange_peer_base(self.h, C.c_uint32(r), C.byref(p)), "tvk_exchange_peer_base")
+        return p.value
+
     def exchange_begin_frame(self, frame_id):
         self._ck(self.lib.tvk_exchange_begin_frame(self.h, C.c_uint32(frame_id)), "tvk_exchange_begin_frame")
 

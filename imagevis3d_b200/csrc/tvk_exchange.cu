@@ -7,7 +7,11 @@
 //     final[world][rows][W]   float4   the finished image (filled on rank 0 and, stripe-wise, locally)
 //     flags[64]               uint32   arrival flags: [parity*16 + src] partial stripe of `src` is complete,
 //                                      [32 + parity*16 + src] finished stripe of `src` has landed (rank 0),
-//                                      [63] a wait timed out
+//                                      [192] a wait timed out (after the rectangle table: [63] is the landed flag
+//                                      of member 15 with 16 members)
+//     rects[2*16][4]          uint32   [parity*16 + src] = the pixel rectangle (x0, y0, x1, y1) rank `src` sent this frame:
+//                                      the screen rectangle of its box; its partial image is zero everywhere else and those
+//                                      pixels are neither marched nor sent
 // * K1 (tvk_raycast.cu) stores each finished pixel straight into the owner's recv buffer with a peer
 //   store over NVLink while it is still marching other tiles, so the exchange overlaps the render; the
 //   last CTA to retire publishes the arrival flag on every peer (fence.sys + flag store).
@@ -15,15 +19,18 @@
 //   stripes front to back (same arithmetic as composite_kernel) reading them past L1 (ld.cg), and stores the
 //   result into the local final image and into rank 0's; its last CTA raises the "landed" flag on rank 0.
 // * exchange_wait_kernel (rank 0) orders the stream behind the arrival of all finished stripes.
-// No NCCL call is on this path.  A wait that exceeds TVK_XCHG_TIMEOUT_NS sets flags[63] instead of hanging.
+// No NCCL call is on this path.  A wait that exceeds TVK_XCHG_TIMEOUT_NS sets flags[192] instead of hanging.
+#include <cstdio>
+#include <cstdlib>
 #include "tvk_internal.h"
 #include <cstring>
 
 #define TVK_XCHG_TIMEOUT_NS 4000000000ull
+#define TVK_XCHG_ERR_FLAG 192u       // word index after flags[64] and rects[32][4]
 
 static inline uint64_t stripe_px(const ExchangeState& x) { return (uint64_t)x.rows * x.width; }
 static inline uint64_t recv_bytes(const ExchangeState& x) { return stripe_px(x) * x.world * sizeof(float4); }
-static inline uint64_t region_bytes(const ExchangeState& x) { return 3 * recv_bytes(x) + 256; }
+static inline uint64_t region_bytes(const ExchangeState& x) { return 3 * recv_bytes(x) + 1024; }   // + flags[64] + rects[2*16][4] + error flag
 
 static void derive_pointers(ExchangeState& x) {
   for (uint32_t r = 0; r < x.world; ++r) {
@@ -96,6 +103,34 @@ extern "C" int tvk_exchange_set_peers(tvk_ctx* c, void* const* bases) {
   return TVK_OK;
 }
 
+// Mixed connection for several exchange members per process (a GPU that renders more than one box): bases[r] != NULL is a
+// region already addressable in this process (a sibling context's own region, or a peer mapping another sibling opened);
+// the others are opened from their IPC handles.  A mapping is owned -- and closed -- by the context that opened it.
+extern "C" int tvk_exchange_connect(tvk_ctx* c, const void* handles, void* const* bases) {
+  if (!c || !c->xchg.world || (!handles && !bases)) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  ExchangeState& x = c->xchg;
+  close_peers(x);
+  for (uint32_t r = 0; r < x.world; ++r) {
+    if (r == x.rank) { x.base[r] = x.local; continue; }
+    if (bases && bases[r]) { x.base[r] = bases[r]; continue; }
+    if (!handles) TVK_FAIL(c, TVK_ERR_INVALID, "no base pointer and no IPC handle for an exchange member");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const uint8_t*>(handles) + 64 * r, 64);
+    void* p = nullptr;
+    TVK_CHECK_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    x.base[r] = p; x.ipc_opened[r] = true;
+  }
+  derive_pointers(x);
+  return TVK_OK;
+}
+
+extern "C" int tvk_exchange_peer_base(tvk_ctx* c, uint32_t r, void** base) {
+  if (!c || !c->xchg.world || r >= c->xchg.world || !base) return TVK_ERR_INVALID;
+  *base = c->xchg.base[r];
+  return TVK_OK;
+}
+
 extern "C" int tvk_exchange_local_base(tvk_ctx* c, void** base) {
   if (!c || !c->xchg.world || !base) return TVK_ERR_INVALID;
   *base = c->xchg.local;
@@ -115,6 +150,7 @@ void tvk_exchange_fill(const tvk_ctx* c, ExchangeSend& s) {
   memset(&s, 0, sizeof(s));
   if (!x.world || !x.send_frame) return;
   s.world = x.world; s.rank = x.rank; s.rows = x.rows; s.frame = x.send_frame;
+  s.flag_index = (x.send_frame & 1u) * 16u + x.rank;
   const uint32_t parity = x.send_frame & 1u;
   for (uint32_t r = 0; r < x.world; ++r) {
     // stripe slot `rank` of the owner's receive buffer of this parity
@@ -142,25 +178,39 @@ struct CompositeArgs {
   uint32_t* flags_local;
   uint32_t* landed_root;       // rank 0's flags[32 + parity*16 + rank]
   uint32_t* done_counter;
+  unsigned long long* debug_ts;  // != nullptr: CTA 0 records globaltimer at start / after the flag wait / at its end
   uint32_t order[TVK_XCHG_MAX_WORLD];
   uint32_t world, parity, frame;
+  uint32_t width, first_row;   // image width; first scan line of this stripe
   uint64_t stripe_px, stripe_offset;
 };
 
 __global__ void __launch_bounds__(256) exchange_composite_kernel(const __grid_constant__ CompositeArgs a) {
   __shared__ int ok;
+  __shared__ uint4 srect[TVK_XCHG_MAX_WORLD];
+  if (a.debug_ts && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.debug_ts[0] = t; }
   if (threadIdx.x == 0) {
     int good = 1;
-    for (uint32_t s = 0; s < a.world && good; ++s) good = wait_flag(a.flags_local + a.parity * 16u + s, a.frame, a.flags_local + 63) ? 1 : 0;
+    for (uint32_t s = 0; s < a.world && good; ++s) good = wait_flag(a.flags_local + a.parity * 16u + s, a.frame, a.flags_local + TVK_XCHG_ERR_FLAG) ? 1 : 0;
     ok = good;
     __threadfence_system();
+    if (good)                                    // published before the flags by the sender's last CTA
+      for (uint32_t s = 0; s < a.world; ++s) {
+        const volatile uint32_t* r = a.flags_local + 64u + 4u * (a.parity * 16u + s);
+        srect[s] = make_uint4(r[0], r[1], r[2], r[3]);
+      }
   }
   __syncthreads();
+  if (a.debug_ts && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.debug_ts[1] = t; }
   if (ok) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.stripe_px; i += (uint64_t)gridDim.x * blockDim.x) {
       float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+      const uint32_t row = (uint32_t)(i / a.width), px = (uint32_t)(i - (uint64_t)row * a.width), py = a.first_row + row;
       for (uint32_t k = 0; k < a.world; ++k) {
-        const float4 s = __ldcg(a.recv + (uint64_t)a.order[k] * a.stripe_px + i);      // written by a peer: never from L1
+        const uint32_t src = a.order[k];
+        const uint4 r = srect[src];
+        if (px < r.x || px >= r.z || py < r.y || py >= r.w) continue;                    // outside what `src` sent: zero
+        const float4 s = __ldcg(a.recv + (uint64_t)src * a.stripe_px + i);              // written by a peer: never from L1
         const float w = 1.0f - d.w;
         d.x += w * s.x; d.y += w * s.y; d.z += w * s.z; d.w += w * s.w;
       }
@@ -168,9 +218,11 @@ __global__ void __launch_bounds__(256) exchange_composite_kernel(const __grid_co
       if (a.final_root) a.final_root[a.stripe_offset + i] = d;
     }
   }
-  __threadfence_system();
+  // ONE system-scope fence per CTA, after the CTA barrier: it is cumulative over the stores the barrier ordered before it
   __syncthreads();
+  if (a.debug_ts && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.debug_ts[2] = t; }
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned prev = atomicAdd(a.done_counter, 1u);
     if (prev == gridDim.x - 1) {
       *a.done_counter = 0u;
@@ -181,7 +233,7 @@ __global__ void __launch_bounds__(256) exchange_composite_kernel(const __grid_co
 }
 
 __global__ void exchange_wait_kernel(uint32_t* flags, uint32_t world, uint32_t parity, uint32_t frame) {
-  if (threadIdx.x < world) wait_flag(flags + 32u + parity * 16u + threadIdx.x, frame, flags + 63);
+  if (threadIdx.x < world) wait_flag(flags + 32u + parity * 16u + threadIdx.x, frame, flags + TVK_XCHG_ERR_FLAG);
   __threadfence_system();
 }
 
@@ -195,15 +247,18 @@ extern "C" int tvk_exchange_composite(tvk_ctx* c, const uint32_t* order, uint32_
   a.recv = reinterpret_cast<const float4*>(lb + parity * recv_bytes(x));
   a.final_local = reinterpret_cast<float4*>(lb + 2 * recv_bytes(x));
   a.final_root = x.rank == 0 ? nullptr : reinterpret_cast<float4*>(static_cast<uint8_t*>(x.base[0]) + 2 * recv_bytes(x));
+  if (getenv("TVK_XCHG_NO_LANDING")) a.final_root = nullptr;          // experiment: leave the image distributed
   a.flags_local = x.flags[x.rank];
   a.landed_root = x.flags[0] + 32u + parity * 16u + x.rank;
   a.done_counter = c->d_tile_counter + 2;
+  a.debug_ts = getenv("TVK_XCHG_DEBUG") ? reinterpret_cast<unsigned long long*>(c->d_tile_counter + 4) : nullptr;
   for (uint32_t k = 0; k < x.world; ++k) {
     if (order[k] >= x.world) TVK_FAIL(c, TVK_ERR_INVALID, "bad compositing order");
     a.order[k] = order[k];
   }
   a.world = x.world; a.parity = parity; a.frame = frame_id;
   a.stripe_px = stripe_px(x); a.stripe_offset = (uint64_t)x.rank * stripe_px(x);
+  a.width = x.width; a.first_row = x.rank * x.rows;
   int sms = 0;
   TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
   uint64_t blocks = (a.stripe_px + 255) / 256;
@@ -212,6 +267,12 @@ extern "C" int tvk_exchange_composite(tvk_ctx* c, const uint32_t* order, uint32_
   c->launches++;
   TVK_CHECK_CUDA(c, cudaGetLastError());
   x.send_frame = 0;
+  if (a.debug_ts) {
+    unsigned long long ts[3] = {0, 0, 0};
+    cudaStreamSynchronize(c->stream);
+    cudaMemcpy(ts, a.debug_ts, sizeof(ts), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[xchg rank %u frame %u] flag wait %.3f ms, blend %.3f ms (CTA 0)\n", x.rank, frame_id, (ts[1] - ts[0]) * 1e-6, (ts[2] - ts[1]) * 1e-6);
+  }
   return TVK_OK;
 }
 
@@ -232,6 +293,6 @@ extern "C" int tvk_exchange_status(tvk_ctx* c, uint32_t* timed_out) {
   if (!c || !c->xchg.world || !timed_out) return TVK_ERR_INVALID;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
   TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
-  TVK_CHECK_CUDA(c, cudaMemcpy(timed_out, c->xchg.flags[c->xchg.rank] + 63, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  TVK_CHECK_CUDA(c, cudaMemcpy(timed_out, c->xchg.flags[c->xchg.rank] + TVK_XCHG_ERR_FLAG, sizeof(uint32_t), cudaMemcpyDeviceToHost));
   return TVK_OK;
 }

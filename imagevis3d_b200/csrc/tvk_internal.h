@@ -63,6 +63,8 @@ struct ExchangeSend {                             // what K1 needs; world == 0: 
   float4* recv[TVK_XCHG_MAX_WORLD];               // owner r's buffer for this rank's stripe (rows*W pixels)
   uint32_t* flag[TVK_XCHG_MAX_WORLD];             // owner r's arrival flag for this rank
   uint32_t world, rank, rows, frame;
+  uint32_t flag_index;                            // parity*16 + rank: this rank's entry in an owner's flag / rectangle tables
+  uint32_t rect[4];                               // x0, y0, x1, y1: the pixels this rank sends (everything else reads as zero)
 };
 
 // Pinned host ring for the small parameter blocks that accompany asynchronous work (placement / gather job lists,

@@ -66,7 +66,8 @@ struct RayParams {
   float4* image;    // accRayColor (iso: composed image)
   uint32_t* tile_counter;
   unsigned long long* stats;
-  uint32_t tiles_x, tiles_y;
+  uint32_t tiles_x, tiles_y;     // 8x4-pixel tiles the launch covers ...
+  uint32_t tile_x0, tile_y0;     // ... starting at this tile: the screen rectangle of the (clipped) volume box
   ExchangeSend xs;       // sort-last: finished pixels also go to the stripe owner's receive buffer (peer store)
 };
 
@@ -951,7 +952,7 @@ __global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP 
         const uint32_t slot = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
         if (slot < total_slots) {
           const uint32_t tile = slot >> 5, l = slot & 31u;
-          px = (tile % rp.tiles_x) * 8u + (l & 7u); py = (tile / rp.tiles_x) * 4u + (l >> 3);
+          px = (rp.tile_x0 + tile % rp.tiles_x) * 8u + (l & 7u); py = (rp.tile_y0 + tile / rp.tiles_x) * 4u + (l >> 3);
           if (px < p.width && py < p.height) {
             pi = (size_t)py * p.width + px;
             float4 e4;
@@ -1130,12 +1131,18 @@ __global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP 
     }
   }
   if (rp.xs.world) {
-    __threadfence_system();
+    // one system-scope fence per CTA (cumulative over the peer stores the barrier orders before it), see tvk_exchange.cu
     __syncthreads();
     if (threadIdx.x == 0) {
+      __threadfence_system();
       const unsigned prev = atomicAdd(rp.tile_counter + 1, 1u);
       if (prev == gridDim.x - 1) {
         rp.tile_counter[1] = 0u;
+        // the rectangle this rank sent goes next to the flag (rects[parity*16 + rank] follow the 64 flag words)
+        for (uint32_t o = 0; o < rp.xs.world; ++o) {
+          volatile uint32_t* r = reinterpret_cast<volatile uint32_t*>(rp.xs.flag[o] - rp.xs.flag_index + 64u + 4u * rp.xs.flag_index);
+          r[0] = rp.xs.rect[0]; r[1] = rp.xs.rect[1]; r[2] = rp.xs.rect[2]; r[3] = rp.xs.rect[3];
+        }
         __threadfence_system();
         for (uint32_t o = 0; o < rp.xs.world; ++o) *reinterpret_cast<volatile uint32_t*>(rp.xs.flag[o]) = rp.xs.frame;
       }
@@ -1159,7 +1166,7 @@ __global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP 
     if (lane == 0) tile = atomicAdd(rp.tile_counter, 1u);
     tile = __shfl_sync(0xffffffffu, tile, 0);
     if (tile >= ntiles) break;
-    const uint32_t px = (tile % rp.tiles_x) * 8u + (lane & 7u), py = (tile / rp.tiles_x) * 4u + (lane >> 3);
+    const uint32_t px = (rp.tile_x0 + tile % rp.tiles_x) * 8u + (lane & 7u), py = (rp.tile_y0 + tile / rp.tiles_x) * 4u + (lane >> 3);
     if (px >= rp.p.width || py >= rp.p.height) continue;
     const size_t i = (size_t)py * rp.p.width + px;
     float4 entry, exitp;
@@ -1216,14 +1223,19 @@ __global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP 
     }
   }
   if (rp.xs.world) {
-    // all peer stores of this CTA are performed system-wide; the last CTA to retire raises this rank's
-    // arrival flag on every stripe owner
-    __threadfence_system();
+    // all peer stores of this CTA are performed system-wide (one cumulative fence after the CTA barrier); the last CTA
+    // to retire raises this rank's arrival flag on every stripe owner
     __syncthreads();
     if (threadIdx.x == 0) {
+      __threadfence_system();
       const unsigned prev = atomicAdd(rp.tile_counter + 1, 1u);
       if (prev == gridDim.x - 1) {
         rp.tile_counter[1] = 0u;
+        // the rectangle this rank sent goes next to the flag (rects[parity*16 + rank] follow the 64 flag words)
+        for (uint32_t o = 0; o < rp.xs.world; ++o) {
+          volatile uint32_t* r = reinterpret_cast<volatile uint32_t*>(rp.xs.flag[o] - rp.xs.flag_index + 64u + 4u * rp.xs.flag_index);
+          r[0] = rp.xs.rect[0]; r[1] = rp.xs.rect[1]; r[2] = rp.xs.rect[2]; r[3] = rp.xs.rect[3];
+        }
         __threadfence_system();
         for (uint32_t o = 0; o < rp.xs.world; ++o) *reinterpret_cast<volatile uint32_t*>(rp.xs.flag[o]) = rp.xs.frame;
       }
@@ -1259,6 +1271,76 @@ static raycast_fn pick_sampler(uint32_t sampler, uint32_t mode, bool lit, bool s
   return pick_kernel<BPV, TVK_SAMPLER_EXACT>(mode, lit, srm1);
 }
 
+// ---- screen rectangle of the ray-marched box -----------------------------------------------------------------
+static bool invert4(const double m[16], double inv[16]) {
+  double a[4][8];
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { a[i][j] = m[4 * i + j]; a[i][4 + j] = i == j ? 1.0 : 0.0; }
+  for (int col = 0; col < 4; ++col) {
+    int piv = col;
+    for (int r = col + 1; r < 4; ++r) if (fabs(a[r][col]) > fabs(a[piv][col])) piv = r;
+    if (fabs(a[piv][col]) < 1e-300) return false;
+    if (piv != col) for (int j = 0; j < 8; ++j) std::swap(a[piv][j], a[col][j]);
+    const double d = a[col][col];
+    for (int j = 0; j < 8; ++j) a[col][j] /= d;
+    for (int r = 0; r < 4; ++r) if (r != col) { const double f = a[r][col]; for (int j = 0; j < 8; ++j) a[r][j] -= f * a[col][j]; }
+  }
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) inv[4 * i + j] = a[i][4 + j];
+  return true;
+}
+
+// Conservative pixel rectangle [x0, x1) x [y0, y1) that contains the projection of the box [box_min, box_max] (normalised
+// volume coordinates): the box is convex, so with all eight corners in front of the eye its image lies inside the bounding
+// rectangle of the projected corners (+2 pixels of slack for the fp32 arithmetic of ray_setup).  Anything else -- a corner
+// beside or behind the eye, a singular matrix -- falls back to the whole frame.  TVK_FULL_FRAME=1 forces the fall-back.
+static void box_screen_rect(const tvk_raycast_params* p, uint32_t rect[4]) {
+  rect[0] = 0; rect[1] = 0; rect[2] = p->width; rect[3] = p->height;
+  static const bool full = getenv("TVK_FULL_FRAME") != nullptr;
+  if (full) return;
+  double ip[16], proj[16];
+  for (int i = 0; i < 16; ++i) ip[i] = p->inv_projection[i];
+  if (!invert4(ip, proj)) return;
+  double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+  for (int k = 0; k < 8; ++k) {
+    const double v[4] = {(k & 1) ? p->box_max[0] : p->box_min[0], (k & 2) ? p->box_max[1] : p->box_min[1],
+                         (k & 4) ? p->box_max[2] : p->box_min[2], 1.0};
+    double e[4], c[4];                                     // row vector times matrix, as xform_point
+    for (int j = 0; j < 4; ++j) e[j] = v[0] * p->model_to_eye[j] + v[1] * p->model_to_eye[4 + j] + v[2] * p->model_to_eye[8 + j] + v[3] * p->model_to_eye[12 + j];
+    for (int j = 0; j < 4; ++j) c[j] = e[0] * proj[j] + e[1] * proj[4 + j] + e[2] * proj[8 + j] + e[3] * proj[12 + j];
+    if (!(c[3] > 1e-6) || !(fabs(e[3]) > 1e-12)) return;   // at or behind the eye plane
+    const double sx = (c[0] / c[3] * 0.5 + 0.5) * p->width, sy = (c[1] / c[3] * 0.5 + 0.5) * p->height;
+    if (!(sx == sx) || !(sy == sy)) return;
+    x0 = std::min(x0, sx); x1 = std::max(x1, sx); y0 = std::min(y0, sy); y1 = std::max(y1, sy);
+  }
+  const double W = p->width, H = p->height;
+  x0 = std::max(0.0, floor(x0) - 2.0); y0 = std::max(0.0, floor(y0) - 2.0);
+  x1 = std::min(W, ceil(x1) + 2.0); y1 = std::min(H, ceil(y1) + 2.0);
+  if (x1 <= x0 || y1 <= y0) { rect[0] = rect[1] = rect[2] = rect[3] = 0; return; }      // the box is off screen
+  rect[0] = (uint32_t)x0; rect[1] = (uint32_t)y0; rect[2] = (uint32_t)x1; rect[3] = (uint32_t)y1;
+}
+
+// new view: the values the march leaves at a pixel no ray of which meets the box (cleared targets, ray finished)
+__global__ void __launch_bounds__(256) fill_outside_kernel(float4* __restrict__ image, float4* __restrict__ pos, float4* __restrict__ aux,
+                                                          uint32_t w, uint32_t h, uint32_t rx0, uint32_t ry0, uint32_t rx1, uint32_t ry1) {
+  const size_t n = (size_t)w * h;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f), done = make_float4(0.f, 0.f, 0.f, 1000.0f);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t y = (uint32_t)(i / w), x = (uint32_t)(i - (size_t)y * w);
+    if (x >= rx0 && x < rx1 && y >= ry0 && y < ry1) continue;
+    image[i] = zero; aux[i] = zero; pos[i] = done;
+  }
+}
+
+// sort-last with an empty rectangle: no march is launched, but the stripe owners still wait for this rank's flag
+__global__ void publish_empty_kernel(const ExchangeSend xs) {
+  if (threadIdx.x != 0) return;
+  for (uint32_t o = 0; o < xs.world; ++o) {
+    volatile uint32_t* r = reinterpret_cast<volatile uint32_t*>(xs.flag[o] - xs.flag_index + 64u + 4u * xs.flag_index);
+    r[0] = 0u; r[1] = 0u; r[2] = 0u; r[3] = 0u;
+  }
+  __threadfence_system();
+  for (uint32_t o = 0; o < xs.world; ++o) *reinterpret_cast<volatile uint32_t*>(xs.flag[o]) = xs.frame;
+}
+
 extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   if (!c || !p) return TVK_ERR_INVALID;
   if (!c->has_pool) TVK_FAIL(c, TVK_ERR_INVALID, "no brick pool");
@@ -1291,8 +1373,17 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   rp.pos = c->d_pos[0]; rp.aux = c->d_aux[0]; rp.image = c->d_image;
   rp.tile_counter = c->d_tile_counter;
   rp.stats = c->d_stats;
-  rp.tiles_x = (p->width + 7) / 8; rp.tiles_y = (p->height + 3) / 4;
+  // Screen rectangle of the (sort-last clipped) volume box: the reference rasterises the box's faces, so its fragment
+  // shader only runs where the box projects; pixels outside get their cleared values from a fill kernel on a new view and
+  // are not visited again
+  uint32_t rect[4];
+  box_screen_rect(p, rect);
+  rp.tile_x0 = rect[0] / 8u; rp.tile_y0 = rect[1] / 4u;
+  rp.tiles_x = (rect[2] + 7u) / 8u - rp.tile_x0; rp.tiles_y = (rect[3] + 3u) / 4u - rp.tile_y0;
+  const uint32_t rx0 = rp.tile_x0 * 8u, ry0 = rp.tile_y0 * 4u;
+  const uint32_t rx1 = std::min(p->width, (rp.tile_x0 + rp.tiles_x) * 8u), ry1 = std::min(p->height, (rp.tile_y0 + rp.tiles_y) * 4u);
   tvk_exchange_fill(c, rp.xs);
+  rp.xs.rect[0] = rx0; rp.xs.rect[1] = ry0; rp.xs.rect[2] = rx1; rp.xs.rect[3] = ry1;
   if (rp.xs.world && (c->xchg.width != p->width || c->xchg.height != p->height))
     TVK_FAIL(c, TVK_ERR_INVALID, "exchange was created for another image size");
 
@@ -1315,7 +1406,14 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_hash, 0, sizeof(uint32_t) * p->hash_table_size, c->stream));
   TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(uint32_t), c->stream));
   TVK_CHECK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-  fn<<<grid, 128, 0, c->stream>>>(rp);
+  if (p->new_view && (rx0 > 0 || ry0 > 0 || rx1 < p->width || ry1 < p->height)) {
+    const size_t npx = (size_t)p->width * p->height;
+    fill_outside_kernel<<<(unsigned)std::min<size_t>((npx + 255) / 256, (size_t)sms * 8), 256, 0, c->stream>>>(
+        rp.image, rp.pos, rp.aux, p->width, p->height, rx0, ry0, rx1, ry1);
+    c->launches++;
+  }
+  if (ntiles) fn<<<grid, 128, 0, c->stream>>>(rp);
+  else if (rp.xs.world) publish_empty_kernel<<<1, 32, 0, c->stream>>>(rp.xs);     // nothing to march: the owners still wait for the flag
   TVK_CHECK_CUDA(c, cudaGetLastError());
   TVK_CHECK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   c->launches++;

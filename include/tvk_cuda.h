@@ -388,6 +388,11 @@ int tvk_exchange_create(tvk_ctx* ctx, uint32_t world, uint32_t rank, uint32_t wi
                         void* ipc_handle64);
 int tvk_exchange_open_peers(tvk_ctx* ctx, const void* handles);
 int tvk_exchange_set_peers(tvk_ctx* ctx, void* const* bases);
+/* Several exchange members in one process (one GPU rendering more than one box): bases[r] != NULL = region r is already
+ * addressable here (a sibling context's region from tvk_exchange_local_base, or a mapping a sibling opened, from
+ * tvk_exchange_peer_base); every other region is opened from handles[r] (64 bytes each).  Either argument may be NULL. */
+int tvk_exchange_connect(tvk_ctx* ctx, const void* handles, void* const* bases);
+int tvk_exchange_peer_base(tvk_ctx* ctx, uint32_t r, void** base);
 int tvk_exchange_local_base(tvk_ctx* ctx, void** base);
 int tvk_exchange_begin_frame(tvk_ctx* ctx, uint32_t frame_id);
 int tvk_exchange_composite(tvk_ctx* ctx, const uint32_t* order, uint32_t frame_id);

@@ -122,7 +122,7 @@ def test_block_partition_composites_like_one_volume(tvk, world, angle):
     assert whole.max() > 0.05 and psnr >= 38.0 and err <= 12.0 / 255.0, (psnr, err)
 
 
-@pytest.mark.parametrize("world,angle", [(3, 0.3), (3, 3.5), (4, 1.9)])
+@pytest.mark.parametrize("world,angle", [(3, 0.3), (3, 3.5), (4, 1.9), (16, 0.8)])      # 16 = the most members the flag tables hold
 def test_fused_exchange_equals_separate_compositor(world, angle):
     """The fused direct-send path (K1 peer stores + arrival flags + stripe compositor, csrc/tvk_exchange.cu)
     with the ranks emulated inside one process on one GPU: its image must equal, bit for bit, the ordered
@@ -130,7 +130,7 @@ def test_fused_exchange_equals_separate_compositor(world, angle):
     import torch
     from imagevis3d_b200.context import TvkContext
     from tests.util import resident_pool, to_cuda_params
-    G = (64, 64, 64 * world)
+    G = (64, 64, 64 * world) if world <= 4 else (48, 48, 40 * world)
     vol = H.synth_blobs(G, np.uint8, seed=23)
     parts = SL.slab_partition(G, world, halo=32)
     tf = _tf()

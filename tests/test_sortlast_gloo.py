@@ -72,6 +72,8 @@ def test_block_partition_and_visibility_order():
     increasing position of the order."""
     assert SL.block_grid((1024, 1024, 1024), 8) == (2, 2, 2) and SL.block_grid((1024, 512, 512), 2) == (2, 1, 1)
     assert SL.block_grid((1024, 1024, 512), 4) == (2, 2, 1) and SL.block_grid((64, 64, 192), 3) == (1, 1, 3)
+    # ties: y (the up axis views orbit about) is cut first, then x, then z
+    assert SL.block_grid((512, 512, 512), 2) == (1, 2, 1) and SL.block_grid((512, 512, 512), 4) == (2, 2, 1)
     rng = np.random.default_rng(7)
     for dims, world in [((1024, 1024, 1024), 8), ((1024, 1024, 512), 4), ((768, 512, 640), 6), ((512, 512, 512), 12)]:
         parts = SL.block_partition(dims, world, halo=64)
