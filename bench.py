@@ -1001,10 +1001,51 @@ def run_sortlast(args, torch, dist, TvkContext, HM, SL, dev, local, rank, world,
     dist.all_reduce(c, op=dist.ReduceOp.SUM)
     samples, rays, launches = [int(v) for v in c.tolist()]
 
+    # what the last TIMED step left: every box's partial image and the composited frame (the e2e leg below renders on)
+    partials = [t.read_image() for t in ctxs]
+    fin_timed = final_image[0].cpu().numpy() if (rank == 0 and final_image[0] is not None) else None
+
+    # ---- e2e at N GPUs: what a caller of the renderer does per frame with the volume resident -- the transfer function and
+    # the camera come from the host (table re-uploaded every step), the boxes march, the exchange composites, and the
+    # finished frame is read back as RGBA8 on rank 0; device-timed on every rank's stream, max over ranks
+    e2e = None
+    if fused is not None:
+        frame_host = torch.empty((Hh, W, 4), dtype=torch.uint8, pin_memory=True) if mine[0] == 0 else None
+        e2e_ms = 0.0
+        for k in range(warmup + steps):
+            flush.zero_()
+            dist.barrier()
+            torch.cuda.synchronize()
+            ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev_a.record(work_stream)
+            for t, st in zip(ctxs, box_streams):
+                st.wait_event(ev_a)
+                t.set_tf1d(ms["tf"])                                         # host table -> device, every step
+            step(k % max(steps, 1))
+            if mine[0] == 0:
+                ctxs[0].set_stream(work_stream.cuda_stream)
+                ctxs[0].exchange_read_final_rgba8(fused.frame, frame_host.numpy())
+                ctxs[0].set_stream(box_streams[0].cuda_stream)
+            ev_b.record(work_stream)
+            sync_all()
+            if k >= warmup:
+                e2e_ms += ev_a.elapsed_time(ev_b)
+        tt = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tf_bytes = int(ms["tf"].nbytes) * len(mine)
+        hb = torch.tensor([tf_bytes], device=dev, dtype=torch.int64)
+        dist.all_reduce(hb, op=dist.ReduceOp.SUM)
+        e2e = {"ms_per_step": float(tt.item()) / steps, "h2d_bytes_per_step": int(hb.item()) * 9, "d2h_bytes_per_step": W * Hh * 4,
+               "frame_nonzero_pixels": int((frame_host.numpy()[..., 3] > 0).sum()) if frame_host is not None else None,
+               "pipeline": "per step, on every GPU: transfer-function table from host memory (byte table + its two float copies, per "
+                           "box), march of the resident boxes, fused exchange + blend; on rank 0 the finished 3840x2160 frame converted "
+                           "to RGBA8 on the device and copied to pinned host memory (tvk_exchange_read_final_rgba8).  The volume stays "
+                           "resident: its 191 GB brick store does not fit this box's host RAM to page from (the paging path is the "
+                           "single-GPU e2e leg).  CUDA events on each rank's stream, max over ranks"}
+
     # ---- parity: box 0's partial image crops vs the oracle on a mirror of its pool; final image == ordered blend of ALL partials
     par = None
     k_last = steps - 1
-    partials = [t.read_image() for t in ctxs]
     for t in ctxs:
         assert not t.exchange_timed_out() if fused is not None else True
     box_images = [None] * V if rank == 0 else None
@@ -1024,7 +1065,7 @@ def run_sortlast(args, torch, dist, TvkContext, HM, SL, dev, local, rank, world,
     if rank == 0 and not args.no_cpu:
         from oracle import host as H
         from oracle import oracle as O
-        fin = final_image[0].cpu().numpy()
+        fin = fin_timed
         want = np.zeros((Hh * W, 4), np.float32)
         arr = (C.c_void_p * V)(*[box_images[r].ctypes.data for r in step_order[k_last]])
         O.lib().orc_composite_ordered(arr, C.c_uint32(V), C.c_uint64(Hh * W), want.ctypes.data_as(C.c_void_p))
@@ -1072,7 +1113,10 @@ def run_sortlast(args, torch, dist, TvkContext, HM, SL, dev, local, rank, world,
                          "note": "per GPU: 1.2136 B/sample + 16 B/ray over the slowest rank's march kernels"},
             "gpu_launches": launches, "clocks": clocks, "parity": par,
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                    "note": "not measured at N > 1: the renderer API (tvkr_*) drives one GPU; the device-timed value is repeated"}}
+                    "note": "not measured (NCCL cross-check path): the device-timed value is repeated"}}
+    if e2e is not None:
+        e2e["value"], e2e["unit"] = (samples / steps) / (e2e["ms_per_step"] * 1e-3), "samples/s"
+        line["e2e"] = e2e
     line["config"]["exchange"] = exchange_kind
     line["config"]["parallelism"] = ("sort-last, %d convex boxes on a %s grid, %d per GPU%s + direct-send compositing fused into the "
                                      "kernels (NVLink peer stores)" % (V, "x".join(str(v) for v in SL.block_grid(GLOBAL, V)), per_gpu,

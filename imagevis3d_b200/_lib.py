@@ -98,7 +98,7 @@ EXPORTS = [
     "tvk_build_stream_begin", "tvk_build_stream_rows", "tvk_build_stream_slab", "tvk_build_stream_end",
     "tvk_composite_ordered", "tvk_raycast_classic",
     "tvk_exchange_create", "tvk_exchange_open_peers", "tvk_exchange_connect", "tvk_exchange_peer_base", "tvk_exchange_set_peers", "tvk_exchange_local_base",
-    "tvk_exchange_begin_frame", "tvk_exchange_composite", "tvk_exchange_final", "tvk_exchange_status", "tvk_exchange_destroy",
+    "tvk_exchange_begin_frame", "tvk_exchange_composite", "tvk_exchange_final", "tvk_exchange_read_final_rgba8", "tvk_exchange_status", "tvk_exchange_destroy",
 ]
 
 _lib = None

@@ -385,6 +385,13 @@ class TvkContext:
         self._ck(self.lib.tvk_exchange_final(self.h, C.c_uint32(frame_id), C.byref(p)), "tvk_exchange_final")
         return p.value
 
+    def exchange_read_final_rgba8(self, frame_id, out, flip_rows=False):
+        """rank 0: the finished sort-last frame as RGBA8 into `out` ([h][w][4] uint8 numpy array or a pinned torch tensor's
+        data pointer wrapped in numpy)"""
+        self._ck(self.lib.tvk_exchange_read_final_rgba8(self.h, C.c_uint32(frame_id), _p(out), C.c_int(int(flip_rows))),
+                 "tvk_exchange_read_final_rgba8")
+        return out
+
     def exchange_timed_out(self):
         t = C.c_uint32()
         self._ck(self.lib.tvk_exchange_status(self.h, C.byref(t)), "tvk_exchange_status")

@@ -116,6 +116,7 @@ struct tvk_ctx {
   uint32_t width = 0, height = 0;
   float4* d_image = nullptr;           // accRayColor / composed iso image
   uchar4* d_rgba8 = nullptr;           // tvk_read_image_rgba8 staging (allocated on first use)
+  size_t rgba8_px = 0;                 // pixels d_rgba8 holds
   float4* d_pos[2] = {nullptr, nullptr};   // rayStartPoint ping-pong
   float4* d_aux[2] = {nullptr, nullptr};   // rayStartColor (iso: normal) ping-pong
   int cur = 0;

@@ -1484,11 +1484,40 @@ extern "C" int tvk_read_image_rgba8(tvk_ctx* c, uint8_t* rgba8, int flip_rows) {
   if (!c || !rgba8 || !c->d_image) return TVK_ERR_INVALID;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
   const size_t n = (size_t)c->width * c->height;
-  if (!c->d_rgba8) TVK_CHECK_CUDA(c, cudaMalloc(&c->d_rgba8, n * sizeof(uchar4)));
+  if (!c->d_rgba8 || c->rgba8_px < n) {
+    cudaFree(c->d_rgba8); c->d_rgba8 = nullptr;
+    TVK_CHECK_CUDA(c, cudaMalloc(&c->d_rgba8, n * sizeof(uchar4)));
+    c->rgba8_px = n;
+  }
   int sm_count = 0;
   TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, c->device));
   const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)sm_count * 8);
   image_to_rgba8_kernel<<<blocks, 256, 0, c->stream>>>(c->d_image, c->d_rgba8, c->width, c->height, flip_rows);
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(rgba8, c->d_rgba8, n * sizeof(uchar4), cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TVK_OK;
+}
+
+// The same read-back for the sort-last result: the finished image of the fused exchange (rank 0, tvk_exchange_final) goes
+// through the same conversion kernel and ONE device-to-host copy of width*height*4 bytes.
+extern "C" int tvk_exchange_read_final_rgba8(tvk_ctx* c, uint32_t frame_id, uint8_t* rgba8, int flip_rows) {
+  if (!c || !rgba8 || !c->xchg.world) return TVK_ERR_INVALID;
+  void* fin = nullptr;
+  int rc = tvk_exchange_final(c, frame_id, &fin);            // rank 0: orders the stream behind the landing of every stripe
+  if (rc) return rc;
+  const uint32_t w = c->xchg.width, h = c->xchg.height;
+  const size_t n = (size_t)w * h;
+  if (!c->d_rgba8 || c->rgba8_px < n) {
+    cudaFree(c->d_rgba8); c->d_rgba8 = nullptr;
+    TVK_CHECK_CUDA(c, cudaMalloc(&c->d_rgba8, n * sizeof(uchar4)));
+    c->rgba8_px = n;
+  }
+  int sm_count = 0;
+  TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, c->device));
+  const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)sm_count * 8);
+  image_to_rgba8_kernel<<<blocks, 256, 0, c->stream>>>(static_cast<const float4*>(fin), c->d_rgba8, w, h, flip_rows);
+  c->launches++;
   TVK_CHECK_CUDA(c, cudaGetLastError());
   TVK_CHECK_CUDA(c, cudaMemcpyAsync(rgba8, c->d_rgba8, n * sizeof(uchar4), cudaMemcpyDeviceToHost, c->stream));
   TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));

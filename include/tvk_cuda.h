@@ -397,6 +397,9 @@ int tvk_exchange_local_base(tvk_ctx* ctx, void** base);
 int tvk_exchange_begin_frame(tvk_ctx* ctx, uint32_t frame_id);
 int tvk_exchange_composite(tvk_ctx* ctx, const uint32_t* order, uint32_t frame_id);
 int tvk_exchange_final(tvk_ctx* ctx, uint32_t frame_id, void** final_dptr);
+/* glReadPixels(GL_RGBA, GL_UNSIGNED_BYTE) of the sort-last result (rank 0): tvk_exchange_final + the conversion of
+ * tvk_read_image_rgba8 + one device-to-host copy of width*height*4 bytes; blocks until the frame is in rgba8. */
+int tvk_exchange_read_final_rgba8(tvk_ctx* ctx, uint32_t frame_id, uint8_t* rgba8, int flip_rows);
 int tvk_exchange_status(tvk_ctx* ctx, uint32_t* timed_out);
 int tvk_exchange_destroy(tvk_ctx* ctx);
 
