@@ -143,6 +143,65 @@ void TransferFunction1D::GetByteArray(std::vector<uint8_t>& out, uint8_t used) c
   for (size_t i = 0; i < m_color.size(); ++i)
     out[i] = (uint8_t)(std::max(0.0f, std::min(m_color[i], 1.0f)) * used);
 }
+void TransferFunction1D::Resample(size_t iTargetSize) {                      // TransferFunction1D.cpp:198-231
+  size_t iSourceSize = GetSize();
+  if (iTargetSize == iSourceSize) return;
+  std::vector<float> tmp(4 * iTargetSize, 0.0f);
+  const size_t n = iTargetSize;
+  if (iTargetSize < iSourceSize) {
+    // the reference shrinks BOTH counters as it goes, so that the bucket width adapts to what is left
+    size_t iFrom = 0;
+    for (size_t i = 0; i < n; ++i) {
+      const size_t iTo = iFrom + iSourceSize / iTargetSize;
+      for (int c = 0; c < 4; ++c) {
+        float acc = 0.0f;
+        for (size_t j = iFrom; j < iTo; ++j) acc += m_color[4 * j + c];
+        tmp[4 * i + c] = acc / float(iTo - iFrom);
+      }
+      iTargetSize -= 1;
+      iSourceSize -= iTo - iFrom;
+      iFrom = iTo;
+    }
+  } else {
+    for (size_t i = 0; i < n; ++i) {
+      const float fPos = float(i) * float(iSourceSize - 1) / float(iTargetSize);
+      const size_t iFloor = size_t(std::floor(fPos));
+      const size_t iCeil = std::min(iFloor + 1, iSourceSize - 1);
+      const float fInterp = fPos - float(iFloor);
+      for (int c = 0; c < 4; ++c) tmp[4 * i + c] = m_color[4 * iFloor + c] * (1 - fInterp) + m_color[4 * iCeil + c] * fInterp;
+    }
+  }
+  m_color.swap(tmp);
+  ComputeNonZeroLimits();
+}
+
+void ResampleHistogram1D(const std::vector<uint64_t>& in, size_t target, std::vector<uint32_t>& out) {   // uvfDataset.cpp:747-800
+  out.assign(target, 0u);
+  if (!target) return;
+  if (target == in.size()) { for (size_t i = 0; i < target; ++i) out[i] = uint32_t(in[i]); return; }
+  const float sampleFactor = static_cast<float>(in.size()) / static_cast<float>(target);
+  float accWeight = 0.0f, currWeight = 1.0f, accValue = 0.0f;
+  size_t j = 0;
+  bool bLast = false;
+  for (size_t i = 0; i < in.size(); i++) {
+    if (bLast) {
+      out[j] = uint32_t(accValue);
+      currWeight = 1.0f - currWeight;
+      j++;
+      i--;
+      bLast = false;
+      accValue = 0;
+      accWeight = 0;
+    } else {
+      if (sampleFactor - accWeight > 1) currWeight = 1.0f;
+      else { currWeight = sampleFactor - accWeight; bLast = true; }
+    }
+    accValue += static_cast<float>(in[i]) * currWeight;
+    accWeight += currWeight;
+    if (j == target - 1) break;
+  }
+}
+
 void TransferFunction1D::ComputeNonZeroLimits() {                                        // :362-370
   m_lo = GetSize(); m_hi = 0;
   for (size_t i = 0; i < GetSize(); ++i)
@@ -172,8 +231,13 @@ void BrickedVolume::Range(double& lo, double& hi) const {
 void BrickPool::ComputePoolCapacity(const BrickedVolume& v, uint64_t gpuMem, uint32_t max3d, uint32_t cap[3]) {
   uint32_t bs[3];
   v.MaxUsedBrickSizes(bs);
+  ComputePoolCapacity(bs, v.bpv, v.info.total_bricks, gpuMem, max3d, cap);
+}
+
+void BrickPool::ComputePoolCapacity(const uint32_t bs[3], uint32_t bpv, uint64_t totalBricks, uint64_t gpuMem, uint32_t max3d,
+                                    uint32_t cap[3]) {
   // the layout the GPU memory allows (GPUMemMan.cpp:780-803)
-  const uint64_t maxVoxels = gpuMem / v.bpv;
+  const uint64_t maxVoxels = gpuMem / bpv;
   const uint64_t r3 = (uint64_t)std::pow((double)maxVoxels, 1.0 / 3.0);
   uint64_t gx = uint64_t(((float)r3 / bs[0]) + 0.5f) * bs[0];
   if (gx > max3d) gx = (max3d / bs[0]) * bs[0];
@@ -185,7 +249,7 @@ void BrickPool::ComputePoolCapacity(const BrickedVolume& v, uint64_t gpuMem, uin
   if (gz > max3d) gz = (max3d / bs[2]) * bs[2];
   if (gz < bs[2]) gz = bs[2];
   // the layout the dataset needs (:805-826)
-  const uint64_t nb = v.info.total_bricks;                 // GetTotalBrickCount: all LODs of the file
+  const uint64_t nb = totalBricks;                         // GetTotalBrickCount: all LODs of the file
   const uint64_t r3b = (uint64_t)std::pow((double)nb, 1.0 / 3.0);
   uint64_t dx = (uint64_t)bs[0] * std::max<uint64_t>(r3b, 1);
   if (dx > max3d) dx = (max3d / bs[0]) * bs[0];
@@ -1369,6 +1433,41 @@ int tvkr_get_perf(tvkr_renderer* h, double out[6]) {
   if (!h || !out) return 1;
   const tvk::PerfCounters& p = R(h)->Perf();
   out[0] = p.subframes; out[1] = p.raycast_ms; out[2] = p.paged_bricks; out[3] = p.uploaded_bytes; out[4] = p.samples; out[5] = p.frames;
+  return 0;
+}
+int tvkr_tf1d_resample(const float* rgba, uint32_t n, uint32_t target, float* out) {
+  if (!rgba || !out || !n || !target) return -1;
+  tvk::TransferFunction1D tf(n);
+  tf.Set(rgba, n);
+  tf.Resample(target);
+  memcpy(out, tf.ColorData().data(), sizeof(float) * 4 * target);
+  return 0;
+}
+int tvkr_get_histogram1d(tvkr_renderer* h, uint32_t* out, uint32_t cap, uint32_t* n) {
+  // Dataset::Get1DHistogram as the TF editor reads it: min(file bins, 4096, 2^bits) bins (uvfDataset.cpp:755-757)
+  if (!h || !n || !R(h)->Volume()) return 1;
+  const tvk::BrickedVolume& v = *R(h)->Volume();
+  const size_t target = std::min<size_t>(v.hist1d.size(), std::min<size_t>(4096, size_t(1) << (8 * v.bpv)));
+  *n = (uint32_t)target;
+  if (!out) return 0;
+  if (cap < target) return 1;
+  std::vector<uint32_t> o;
+  tvk::ResampleHistogram1D(v.hist1d, target, o);
+  memcpy(out, o.data(), sizeof(uint32_t) * target);
+  return 0;
+}
+int tvkr_resample_hist1d(const uint64_t* bins, uint64_t n, uint32_t target, uint32_t* out) {
+  if (!bins || !out || !target) return -1;
+  std::vector<uint64_t> in(bins, bins + n);
+  std::vector<uint32_t> o;
+  tvk::ResampleHistogram1D(in, target, o);
+  memcpy(out, o.data(), sizeof(uint32_t) * target);
+  return 0;
+}
+int tvkr_compute_pool_capacity(const uint32_t max_brick[3], uint32_t bytes_per_voxel, uint64_t total_bricks, uint64_t gpu_mem_bytes,
+                               uint32_t max_3d_texture, uint32_t capacity[3]) {
+  if (!max_brick || !capacity || !bytes_per_voxel || !max_brick[0] || !max_brick[1] || !max_brick[2] || !max_3d_texture) return -1;
+  tvk::BrickPool::ComputePoolCapacity(max_brick, bytes_per_voxel, total_bricks, gpu_mem_bytes, max_3d_texture, capacity);
   return 0;
 }
 double tvkr_perf_query(tvkr_renderer* h, int counter) { return h ? R(h)->PerfQuery(counter) : 0.0; }

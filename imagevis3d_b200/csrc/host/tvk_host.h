@@ -55,6 +55,7 @@ class TransferFunction1D {
   explicit TransferFunction1D(size_t n = 0) : m_color(4 * n, 0.0f) { ComputeNonZeroLimits(); }
   size_t GetSize() const { return m_color.size() / 4; }
   void Resize(size_t n) { m_color.resize(4 * n, 0.0f); ComputeNonZeroLimits(); }
+  void Resample(size_t n);                                 // TransferFunction1D::Resample (box filter down, linear up)
   bool Load(const std::string& filename);                  // ".1dt" text format
   bool Save(const std::string& filename) const;
   void Set(const float* rgba, size_t n);
@@ -70,6 +71,11 @@ class TransferFunction1D {
   std::vector<float> m_color;     // r g b a per entry
   uint64_t m_lo = 0, m_hi = 0;
 };
+
+// The 1-D histogram the transfer-function editor draws: the file's histogram, "resampled" to at most
+// MAX_TRANSFERFUNCTION_SIZE (4096) bins when it is larger (UVFDataset::GetHistograms, uvfDataset.cpp:747-800).
+// The reference's loop stops before it writes the last bin (which stays an uninitialised new[] value there): it is 0 here.
+void ResampleHistogram1D(const std::vector<uint64_t>& in, size_t target, std::vector<uint32_t>& out);
 
 // A bricked multi-resolution volume in ExtendedOctree layout (ToC order).
 // Brick payloads live EITHER in the device brick store left by tvk_build_octree
@@ -112,6 +118,8 @@ class BrickPool {
   BrickPool(tvk_ctx* ctx, const BrickedVolume* vol) : m_ctx(ctx), m_vol(vol) {}
   // GPUMemMan::GetVolumePool (GPUMemMan.cpp:766-844); max3d = GL_MAX_3D_TEXTURE_SIZE stand-in
   static void ComputePoolCapacity(const BrickedVolume& v, uint64_t gpuMemBytes, uint32_t max3d, uint32_t cap[3]);
+  static void ComputePoolCapacity(const uint32_t maxBrick[3], uint32_t bpv, uint64_t totalBricks, uint64_t gpuMemBytes, uint32_t max3d,
+                                  uint32_t cap[3]);
   int  Create(const uint32_t capacity[3], uint32_t sampler);
   int  UploadFirstBrick();                                       // :763-766
   // wait = false: the upload and the page-table patch are only ORDERED before later work on the render stream (the

@@ -122,6 +122,19 @@ int tvkr_get_perf(tvkr_renderer* r, double out[6]);     /* tuvok.perf: subframes
  * 7 PERF_POOL_SORT, 8 PERF_POOL_UPLOADED_MEM, 9 PERF_POOL_GET_BRICK, 19 PERF_POOL_UPLOAD_BRICK,
  * 21 PERF_POOL_UPLOAD_METADATA, 22 PERF_EO_BRICKS ...): the amount since the last query of that counter, which is reset */
 double tvkr_perf_query(tvkr_renderer* r, int counter);
+/* TransferFunction1D::Resample (IO/TransferFunction1D.cpp:198-231): n RGBA float entries -> target entries (adaptive box
+ * filter down, linear interpolation up); no device needed. */
+int tvkr_tf1d_resample(const float* rgba, uint32_t n, uint32_t target, float* out);
+/* The 1-D histogram as the transfer-function editor gets it (UVFDataset::GetHistograms, IO/uvfDataset.cpp:747-800): the
+ * file's bins weighted into `target` bins; the last bin, which the reference's loop never writes, is 0. */
+int tvkr_resample_hist1d(const uint64_t* bins, uint64_t n, uint32_t target, uint32_t* out);
+/* Dataset::Get1DHistogram of the loaded dataset: *n = min(file bins, 4096, 2^bits); out == NULL only queries n. */
+int tvkr_get_histogram1d(tvkr_renderer* r, uint32_t* out, uint32_t cap, uint32_t* n);
+/* GPUMemMan::GetVolumePool's pool sizing (GPUMemMan.cpp:766-830) on its own, no device needed: slots per axis of the
+ * brick pool for bricks of max_brick voxels, total_bricks bricks in the dataset, gpu_mem_bytes of pool memory and a
+ * 3-D texture limit of max_3d_texture texels per axis. */
+int tvkr_compute_pool_capacity(const uint32_t max_brick[3], uint32_t bytes_per_voxel, uint64_t total_bricks, uint64_t gpu_mem_bytes,
+                               uint32_t max_3d_texture, uint32_t capacity[3]);
 tvk_ctx* tvkr_context(tvkr_renderer* r);
 
 #ifdef __cplusplus

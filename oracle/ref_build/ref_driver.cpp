@@ -206,6 +206,24 @@ static int do_tf1d(int argc, char** argv) {
   return 0;
 }
 
+// ref_driver tfresample <in.f32 (n*4 floats)> <n> <target> <out.f32>: TransferFunction1D::Resample on caller data
+static int do_tfresample(int argc, char** argv) {
+  if (argc < 6) return 2;
+  const size_t n = strtoull(argv[3], 0, 10), target = strtoull(argv[4], 0, 10);
+  TransferFunction1D tf(n);
+  std::vector<FLOATVECTOR4>* data = tf.GetColorData().get();
+  FILE* f = fopen(argv[2], "rb");
+  if (!f) return 1;
+  for (size_t i = 0; i < n; ++i) { float v[4]; if (fread(v, 4, 4, f) != 4) return 1; (*data)[i] = FLOATVECTOR4(v[0], v[1], v[2], v[3]); }
+  fclose(f);
+  tf.Resample(target);
+  data = tf.GetColorData().get();
+  f = fopen(argv[5], "wb");
+  for (size_t i = 0; i < data->size(); ++i) { float v[4] = {(*data)[i].x, (*data)[i].y, (*data)[i].z, (*data)[i].w}; fwrite(v, 4, 4, f); }
+  fclose(f);
+  return 0;
+}
+
 // ref_driver writeuvf <in.raw> <sx> <sy> <sz> <u8|u16> <brick> <overlap> <median> <compression> <level> <out.uvf>
 //   the file assembly of RAWConverter::ConvertRAWDataset (IO/RAWConverter.cpp:527-681) for an input that
 //   needs no quantisation: TOC block, 1-D / 2-D histogram, max/min, key/value block, MD5.
@@ -384,6 +402,7 @@ int main(int argc, char** argv) {
   if (!strcmp(argv[1], "convert")) return do_convert(argc, argv);
   if (!strcmp(argv[1], "uvfinfo")) return do_uvfinfo(argc, argv);
   if (!strcmp(argv[1], "tf1d")) return do_tf1d(argc, argv);
+  if (!strcmp(argv[1], "tfresample")) return do_tfresample(argc, argv);
   if (!strcmp(argv[1], "quantize")) return do_quantize(argc, argv);
   if (!strcmp(argv[1], "writeuvf")) return do_writeuvf(argc, argv);
   if (!strcmp(argv[1], "readuvf")) return do_readuvf(argc, argv);
