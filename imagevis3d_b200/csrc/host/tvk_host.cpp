@@ -908,7 +908,8 @@ void CudaGridLeaper::SetBGColors(const float top[3], const float bottom[3]) { me
 // (uvfDataset.cpp:242-288,1747-1774) and the per-brick uniforms of GLRaycaster::SetBrickDepShaderVars /
 // ComputeEyeToTextureMatrix (GLRaycaster.cpp:239-300,589-612).  The final sub-frame of a view (LOD =
 // m_iMinLODForCurrentView, or 0 for RT_CAPTURE) is rendered in one launch of tvk_raycast_classic.
-bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_classic_brick>& bricks, uint32_t& lodOut) {
+bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_classic_brick>& bricks, uint32_t& lodOut, int forceLod,
+                                      uint32_t* minLodOut) {
   if (!m_vol || !m_w || !m_h) { m_err = "no dataset / render target"; return false; }
   const BrickedVolume& v = *m_vol;
   memset(&p, 0, sizeof(p));
@@ -932,7 +933,10 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
   const int level = (int)floor(log(lodFactor * fz / wse) / log(2.0f));
   const int lodCount = (int)v.info.lod_count;
   const int minLod = std::min(std::max(level, (int)m_lodLimits[1]), lodCount - 1);
-  const uint32_t lod = (m_target == RT_CAPTURE) ? 0u : (uint32_t)minLod;
+  if (minLodOut) *minLodOut = (uint32_t)minLod;
+  // GLRaycaster::SetBrickDepShaderVars (:253-254): a "decrease sampling rate now" pass halves the rate (m_fSampleDecFactor = 2)
+  const float effRate = m_sampleRate / (m_decRateNow ? 2.0f : 1.0f);
+  const uint32_t lod = forceLod >= 0 ? (uint32_t)std::min(forceLod, lodCount - 1) : ((m_target == RT_CAPTURE) ? 0u : (uint32_t)minLod);
   lodOut = lod;
   // CullingLOD::Update: planes from modelView * projection
   const Matrix4 mvp = mv * proj;
@@ -1031,7 +1035,7 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
           const float n = float(v.sizes[3 * idx + a]);
           tmin[a] = float(v.overlap) / n;
           tmax[a] = (1.0f - tmin[a]) * float(asp[a]);
-          rs = std::min(rs, be[a] * (1.0f / n) * 0.5f * 1.0f / m_sampleRate);
+          rs = std::min(rs, be[a] * (1.0f / n) * 0.5f * 1.0f / effRate);
           it.b.center[a] = bcn[a]; it.b.extension[a] = be[a]; it.b.voxels[a] = v.sizes[3 * idx + a];
         }
         it.b.ray_step = rs;
@@ -1062,7 +1066,7 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
   memcpy(p.inv_projection, proj.inverse().m, 64);
   float ratio = 0;
   for (int a = 0; a < 3; ++a) ratio = std::max(ratio, dom0[a] / dl[a]);
-  p.step_scale = 1.0f / m_sampleRate * ratio;
+  p.step_scale = 1.0f / effRate * ratio;
   const uint32_t iMax = (1u << (8 * v.bpv)) - 1;
   p.trans_scale = float(iMax / maxValue);
   p.lighting = m_lighting ? 1u : 0u;
@@ -1095,6 +1099,51 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
   return true;
 }
 
+// AbstrRenderer::ComputeMaxLODForCurrentView (AbstrRenderer.cpp:681-787): at which (coarse) LOD offset a new view starts,
+// from how long the first two sub-frames of the previous view took.
+void CudaGridLeaper::ComputeMaxLODForCurrentView(tvkr_lod_state& s) {
+  if (s.target != RT_CAPTURE && s.msec_passed[0] >= 0.0f) {
+    if (s.msec_passed[0] > s.max_ms_per_frame) {
+      // too slow: after three such views, start one LOD coarser; at the coarsest, fall back on resolution / sampling rate
+      if (s.lod_not_ok_counter < 3) {
+        s.lod_not_ok_counter++;
+      } else {
+        s.lod_not_ok_counter = 0;
+        const uint64_t skip = std::max<uint64_t>(1, s.perf_lod_skip) - 1;
+        if (s.perf_lod_skip != skip) {
+          s.msec_passed[0] = s.msec_passed[1];
+          s.perf_lod_skip = skip;
+        } else if (s.low_res_intermediate) {
+          if (!(s.decrease_sampling_rate && s.decrease_screen_res)) {
+            if (!s.decrease_screen_res) s.decrease_screen_res = 1;
+            else s.decrease_sampling_rate = 1;
+          }
+        }
+      }
+    } else {
+      // the last view finished its sub-frame, and its second sub-frame was fast enough: step the quality up
+      if (s.brick_list_size == s.bricks_rendered && s.msec_passed[1] >= 0.0f && s.msec_passed[1] <= s.max_ms_per_frame) {
+        s.lod_not_ok_counter = 0;
+        if (s.decrease_sampling_rate || s.decrease_screen_res) {
+          if (s.decrease_sampling_rate) s.decrease_sampling_rate = 0;
+          else if (s.decrease_screen_res) s.decrease_screen_res = 0;
+        } else {
+          const uint64_t skip = std::min<uint64_t>(s.max_lod_index - s.min_lod_for_view, s.perf_lod_skip + 1);
+          if (s.perf_lod_skip != skip) s.perf_lod_skip = skip;
+        }
+      }
+    }
+    s.start_lod_offset = std::max(s.min_lod_for_view, s.max_lod_index - s.perf_lod_skip);
+  } else if (s.target != RT_INTERACTIVE) {
+    s.start_lod_offset = s.min_lod_for_view;
+  } else {
+    s.start_lod_offset = s.max_lod_index;          // the very first frame: take it easy
+  }
+  s.start_lod_offset = std::min(s.start_lod_offset, static_cast<uint64_t>(s.max_lod_index - s.lod_limit_x));
+  s.current_lod_offset = s.start_lod_offset;
+  s.msec_passed[0] = s.msec_passed[1] = -1.0f;     // RestartTimers
+}
+
 bool CudaGridLeaper::PaintClassic() {
   if (!m_ctx || !m_vol) { m_err = "Paint() without dataset"; return false; }
   const void* store = m_vol->device_store;
@@ -1119,16 +1168,48 @@ bool CudaGridLeaper::PaintClassic() {
   }
   tvk_classic_params p;
   std::vector<tvk_classic_brick> bricks;
-  uint32_t lod = 0;
-  if (!PlanClassicFrame(p, bricks, lod)) return false;
-  if (m_blank) m_perf.frames += 1;
+  uint32_t lod = 0, minLod = 0;
+  // ---- AbstrRenderer::PlanFrame (:1125-1212).  One Paint() renders one whole sub-frame = the brick list of one LOD (the
+  // reference's RT_HEADLESS time slice: GLRenderer::Render3DView, GLRenderer.cpp:2662-2675, stops early only for
+  // interactive targets; a list that one kernel launch walks has nothing to slice).
+  tvkr_lod_state& L = m_ladder;
+  L.target = (int32_t)m_target;
+  L.max_lod_index = m_vol->info.lod_count - 1;
+  L.lod_limit_x = std::min<uint64_t>(m_lodLimits[0], L.max_lod_index);
+  if (m_blank) {
+    if (!PlanClassicFrame(p, bricks, lod, -1, &minLod)) return false;       // ComputeMinLODForCurrentView
+    L.min_lod_for_view = minLod;
+    ComputeMaxLODForCurrentView(L);
+    m_decRateNow = L.decrease_sampling_rate != 0;
+    m_decResNow = L.decrease_screen_res != 0;
+    m_perf.frames += 1;
+  } else if (m_decRateNow || m_decResNow) {
+    m_decRateNow = m_decResNow = false;                                     // the low-quality pass is done: same LOD, full quality
+  } else if (L.current_lod_offset > L.min_lod_for_view) {
+    L.current_lod_offset--;                                                 // the sub-frame is complete: next finer LOD
+  }
+  m_currentLOD = (m_target == RT_CAPTURE) ? 0u : (uint32_t)std::min<uint64_t>(L.current_lod_offset, L.max_lod_index);
+  if (!PlanClassicFrame(p, bricks, lod, (int)m_currentLOD)) return false;   // BuildSubFrameBrickList
+  L.brick_list_size = bricks.size();
+  L.bricks_rendered = 0;
   const int rc = tvk_raycast_classic(m_ctx, &p, bricks.data(), (uint32_t)bricks.size(), store);
   if (rc) return Fail("tvk_raycast_classic", rc);
+  L.bricks_rendered = bricks.size();
   m_blank = false;
   m_perf.subframes += 1;
   tvk_stats st;
-  if (tvk_get_stats(m_ctx, &st, 0) == TVK_OK) { m_perf.raycast_ms += st.last_raycast_ms; m_perf.samples = (double)st.samples; }
-  m_converged = true;
+  float ms = 0.0f;
+  if (tvk_get_stats(m_ctx, &st, 0) == TVK_OK) { ms = st.last_raycast_ms; m_perf.raycast_ms += ms; m_perf.samples = (double)st.samples; }
+  if (m_msOverride >= 0.0f) ms = m_msOverride;
+  // AbstrRenderer::CompletedASubframe (:640-669): the first sub-frame's time tells whether the start LOD is affordable,
+  // the second one's whether a finer start would be
+  const bool first = (L.current_lod_offset == L.start_lod_offset) && (!L.decrease_screen_res || m_decResNow) &&
+                     (!L.decrease_sampling_rate || m_decRateNow);
+  const bool second = !first && (L.current_lod_offset == L.start_lod_offset ||
+                                 (L.current_lod_offset + 1 == L.start_lod_offset && !(L.decrease_screen_res || L.decrease_sampling_rate)));
+  if (first) L.msec_passed[0] = ms;
+  else if (second) L.msec_passed[1] = ms;
+  m_converged = (m_target == RT_CAPTURE) || (L.current_lod_offset <= L.min_lod_for_view && !m_decRateNow && !m_decResNow);
   return true;
 }
 
@@ -1433,6 +1514,24 @@ int tvkr_get_perf(tvkr_renderer* h, double out[6]) {
   if (!h || !out) return 1;
   const tvk::PerfCounters& p = R(h)->Perf();
   out[0] = p.subframes; out[1] = p.raycast_ms; out[2] = p.paged_bricks; out[3] = p.uploaded_bytes; out[4] = p.samples; out[5] = p.frames;
+  return 0;
+}
+int tvkr_compute_max_lod_for_view(tvkr_lod_state* s) {
+  if (!s) return -1;
+  tvk::CudaGridLeaper::ComputeMaxLODForCurrentView(*s);
+  return 0;
+}
+int tvkr_set_renderer_target(tvkr_renderer* h, int target) {
+  if (!h || target < tvk::RT_INTERACTIVE || target > tvk::RT_HEADLESS) return 1;
+  R(h)->SetRendererTarget(target);
+  return 0;
+}
+int tvkr_set_max_ms_per_frame(tvkr_renderer* h, float ms) { if (!h) return 1; R(h)->SetMaxMSPerFrame(ms); return 0; }
+int tvkr_override_subframe_ms(tvkr_renderer* h, float ms) { if (!h) return 1; R(h)->OverrideSubframeMs(ms); return 0; }
+int tvkr_get_lod_state(tvkr_renderer* h, tvkr_lod_state* out, uint32_t* lod) {
+  if (!h || !out) return 1;
+  *out = R(h)->LodState();
+  if (lod) *lod = R(h)->CurrentLOD();
   return 0;
 }
 int tvkr_tf1d_resample(const float* rgba, uint32_t n, uint32_t target, float* out) {

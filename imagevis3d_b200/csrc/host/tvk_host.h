@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 #include "tvk_cuda.h"
+#include "tvk_renderer.h"
 
 namespace tvk {
 
@@ -248,7 +249,15 @@ class CudaGridLeaper {
 
   // --- renderer type: false = ray-guided GLGridLeaper path (default), true = classic per-brick GLRaycaster path
   void SetClassic(bool on) { m_classic = on; ScheduleCompleteRedraw(); }
-  bool PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_classic_brick>& bricks, uint32_t& lod);
+  // forceLod < 0: the LOD the view needs (m_iMinLODForCurrentView; 0 for RT_CAPTURE); else the brick list of that LOD.
+  // minLodOut: m_iMinLODForCurrentView of the view.
+  bool PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_classic_brick>& bricks, uint32_t& lod, int forceLod = -1,
+                        uint32_t* minLodOut = nullptr);
+  static void ComputeMaxLODForCurrentView(tvkr_lod_state& s);        // AbstrRenderer.cpp:681-787
+  void SetMaxMSPerFrame(float ms) { m_ladder.max_ms_per_frame = ms; }
+  void OverrideSubframeMs(float ms) { m_msOverride = ms; }
+  const tvkr_lod_state& LodState() const { return m_ladder; }
+  uint32_t CurrentLOD() const { return m_currentLOD; }
   bool PaintClassic();
 
   // --- frame loop
@@ -307,6 +316,12 @@ class CudaGridLeaper {
   bool m_clipEnabled = false;
   float m_clipPlane[4] = {0, 0, 1, 0};
   uint32_t m_lodLimits[2] = {0, 0};
+  tvkr_lod_state m_ladder{0, {-1.0f, -1.0f}, 10000.0f, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t m_currentLOD = 0;
+  float m_msOverride = -1.0f, m_msCurrentFrame = 0.0f;
+  // a view whose start LOD is already the coarsest and still too slow first renders a pass at half the sampling rate
+  // (decreaseSamplingRateNow); the reduced-resolution pass (decreaseScreenResNow) is counted but rendered at full size
+  bool m_decRateNow = false, m_decResNow = false;
   float m_bg[2][3] = {{0, 0, 0}, {0, 0, 0}};
 };
 

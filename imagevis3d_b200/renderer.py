@@ -98,6 +98,38 @@ class Renderer:
 
     def setRendererTarget(self, t):
         self._target = t
+        self._ck(self._lib.tvkr_set_renderer_target(self._h, C.c_int(int(t))), "setRendererTarget")
+
+    def setMaxMSPerFrame(self, ms):
+        """frame-time budget of the classic renderer's coarse-to-fine ladder (m_fMaxMSPerFrame)"""
+        self._ck(self._lib.tvkr_set_max_ms_per_frame(self._h, C.c_float(ms)), "setMaxMSPerFrame")
+
+    def overrideSubframeMs(self, ms):
+        """test hook: the ladder sees this time for the next sub-frames instead of the measured kernel time (ms < 0: measure)"""
+        self._ck(self._lib.tvkr_override_subframe_ms(self._h, C.c_float(ms)), "overrideSubframeMs")
+
+    def lodState(self):
+        """-> dict of the ladder's state (tvkr_lod_state) + the LOD of the last sub-frame"""
+        class S(C.Structure):
+            _fields_ = [("target", C.c_int32), ("msec_passed", C.c_float * 2), ("max_ms_per_frame", C.c_float), ("lod_not_ok_counter", C.c_uint32),
+                        ("perf_lod_skip", C.c_uint64), ("low_res_intermediate", C.c_int32), ("decrease_sampling_rate", C.c_int32),
+                        ("decrease_screen_res", C.c_int32), ("brick_list_size", C.c_uint64), ("bricks_rendered", C.c_uint64),
+                        ("max_lod_index", C.c_uint64), ("min_lod_for_view", C.c_uint64), ("lod_limit_x", C.c_uint64),
+                        ("start_lod_offset", C.c_uint64), ("current_lod_offset", C.c_uint64)]
+        s, lod = S(), C.c_uint32()
+        self._ck(self._lib.tvkr_get_lod_state(self._h, C.byref(s), C.byref(lod)), "lodState")
+        d = {n: getattr(s, n) for n, _ in S._fields_ if n != "msec_passed"}
+        d["msec_passed"] = (float(s.msec_passed[0]), float(s.msec_passed[1]))
+        d["current_lod"] = int(lod.value)
+        return d
+
+    def histogram1D(self):
+        """Dataset::Get1DHistogram as the transfer-function editor reads it (at most 4096 bins)"""
+        n = C.c_uint32()
+        self._ck(self._lib.tvkr_get_histogram1d(self._h, None, C.c_uint32(0), C.byref(n)), "histogram1D")
+        out = np.zeros(n.value, np.uint32)
+        self._ck(self._lib.tvkr_get_histogram1d(self._h, out.ctypes.data_as(C.c_void_p), C.c_uint32(n.value), C.byref(n)), "histogram1D")
+        return out
 
     def setRenderMode(self, mode):
         self._ck(self._lib.tvkr_set_render_mode(self._h, C.c_int(mode)), "setRenderMode")

@@ -122,6 +122,32 @@ int tvkr_get_perf(tvkr_renderer* r, double out[6]);     /* tuvok.perf: subframes
  * 7 PERF_POOL_SORT, 8 PERF_POOL_UPLOADED_MEM, 9 PERF_POOL_GET_BRICK, 19 PERF_POOL_UPLOAD_BRICK,
  * 21 PERF_POOL_UPLOAD_METADATA, 22 PERF_EO_BRICKS ...): the amount since the last query of that counter, which is reset */
 double tvkr_perf_query(tvkr_renderer* r, int counter);
+/* The coarse-to-fine sub-frame ladder of AbstrRenderer (classic renderer): which LOD a view starts at
+ * (ComputeMaxLODForCurrentView, AbstrRenderer.cpp:681-787, fed by the times the first two sub-frames of the previous view
+ * took) and how PlanFrame steps down to the LOD the view needs (:1125-1212).  The state is a POD so that the logic can be
+ * driven -- and checked against the reference's statements -- without a device. */
+typedef struct tvkr_lod_state {
+  int32_t  target;               /* ERendererTarget: 0 interactive, 1 capture, 2 headless                              */
+  float    msec_passed[2];       /* time of the first / second sub-frame of the last view, -1 = none (RestartTimer)     */
+  float    max_ms_per_frame;     /* m_fMaxMSPerFrame (default 10000)                                                   */
+  uint32_t lod_not_ok_counter;   /* m_iLODNotOKCounter                                                                 */
+  uint64_t perf_lod_skip;        /* m_iPerformanceBasedLODSkip                                                         */
+  int32_t  low_res_intermediate; /* m_bRenderLowResIntermediateResults ("use all means")                               */
+  int32_t  decrease_sampling_rate, decrease_screen_res;
+  uint64_t brick_list_size, bricks_rendered;   /* m_vCurrentBrickList.size(), m_iBricksRenderedInThisSubFrame            */
+  uint64_t max_lod_index;        /* m_iMaxLODIndex = LOD level count - 1                                               */
+  uint64_t min_lod_for_view;     /* m_iMinLODForCurrentView                                                            */
+  uint64_t lod_limit_x;          /* m_iLODLimits.x                                                                     */
+  uint64_t start_lod_offset, current_lod_offset;   /* out: m_iStartLODOffset, m_iCurrentLODOffset                        */
+} tvkr_lod_state;
+int tvkr_compute_max_lod_for_view(tvkr_lod_state* s);
+/* classic renderer: frame-time budget of the ladder, a time to use instead of the measured kernel time of the next
+ * sub-frames (ms < 0: measure again; for deterministic tests), and the ladder's state */
+int tvkr_set_renderer_target(tvkr_renderer* r, int target);   /* AbstrRenderer::SetRendererTarget: 0 interactive, 1 capture, 2 headless */
+int tvkr_set_max_ms_per_frame(tvkr_renderer* r, float ms);
+int tvkr_override_subframe_ms(tvkr_renderer* r, float ms);
+int tvkr_get_lod_state(tvkr_renderer* r, tvkr_lod_state* out, uint32_t* current_lod);
+
 /* TransferFunction1D::Resample (IO/TransferFunction1D.cpp:198-231): n RGBA float entries -> target entries (adaptive box
  * filter down, linear interpolation up); no device needed. */
 int tvkr_tf1d_resample(const float* rgba, uint32_t n, uint32_t target, float* out);

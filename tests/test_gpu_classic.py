@@ -274,3 +274,61 @@ def test_classic_clip_plane(mode):
     for x, y in zip(bricks, bo):
         assert list(x.voxels) == list(y.voxels) and np.allclose(np.array(x.center[:]), np.array(y.center[:]), rtol=3e-5, atol=3e-6)
     r.cleanup()
+
+
+def test_classic_coarse_to_fine_ladder():
+    """AbstrRenderer::PlanFrame + ComputeMaxLODForCurrentView on the classic path: an interactive view starts coarse and
+    every paint() renders the brick list of the next finer LOD down to the one the view needs; the times of the first two
+    sub-frames move the start LOD of the NEXT view (three views of grace before it gets coarser).  The last sub-frame is the
+    image a headless renderer produces in one paint."""
+    from imagevis3d_b200.renderer import Renderer, RT_HEADLESS, RT_INTERACTIVE
+    vol = H.synth_blobs((150, 131, 97), np.uint8)
+    tf = None
+    frames = {}
+    for target in (RT_HEADLESS, RT_INTERACTIVE):
+        r = Renderer(0)
+        r.loadRawVolume(vol, brick_size=20)
+        r.setRendererType(True)
+        info = r.datasetInfo()
+        tf = _tf(info.tf_size)
+        r.set1DTransFloat(tf)
+        r.resize((203, 149))
+        r.setRendererTarget(target)
+        r.setRotation4x4(H.rotation_y(0.6) @ H.rotation_x(0.3))
+        if target == RT_HEADLESS:
+            assert r.paintUntilConverged() == 1
+            frames["headless"] = r.frameFloat()
+            r.cleanup()
+            continue
+        r.setMaxMSPerFrame(100.0)
+        r.overrideSubframeMs(1.0)                    # "fast": deterministic, whatever the kernel really took
+        # ---- view 1: no timings yet -> start at the coarsest LOD, one LOD finer per paint
+        lods = []
+        while True:
+            r.paint()
+            st = r.lodState()
+            lods.append(st["current_lod"])
+            if r.converged():
+                break
+        top = st["max_lod_index"]
+        assert top >= 3 and lods == list(range(top, st["min_lod_for_view"] - 1, -1)), lods
+        assert st["min_lod_for_view"] == 0
+        assert np.array_equal(r.frameFloat(), frames["headless"])
+        # ---- views 2..: both timed sub-frames were fast -> the skip grows by one per view, the start LOD gets finer
+        starts = []
+        for k in range(3):
+            r.setRotation4x4(H.rotation_y(0.7 + 0.1 * k) @ H.rotation_x(0.3))
+            n = r.paintUntilConverged()
+            st = r.lodState()
+            starts.append(int(st["start_lod_offset"]))
+            assert n == st["start_lod_offset"] - st["min_lod_for_view"] + 1
+        assert starts == [top - 1, top - 2, top - 3], starts
+        # ---- slow first sub-frames: three views of grace, the fourth starts one LOD coarser
+        r.overrideSubframeMs(500.0)
+        starts = []
+        for k in range(5):
+            r.setRotation4x4(H.rotation_y(1.2 + 0.1 * k) @ H.rotation_x(0.3))
+            r.paintUntilConverged()
+            starts.append(int(r.lodState()["start_lod_offset"]))
+        assert starts[0] == starts[1] == starts[2] == starts[3] and starts[4] == starts[3] + 1, starts
+        r.cleanup()
