@@ -355,7 +355,8 @@ int BrickPool::UploadFirstBrick() {
   s.brick = (int32_t)idx; s.time = UINT64_MAX;
   const void* src = m_vol->host_store ? (const void*)(m_vol->host_store + m_vol->offsets[t])
                                       : (const void*)((const uint8_t*)m_vol->device_store + m_vol->offsets[t]);
-  int rc = tvk_pool_upload_bricks(m_ctx, 1, &s.pos, &src, &m_vol->sizes[3 * t], m_vol->host_store ? 2 : 1);   // 2: the pinned store is one allocation
+  int rc = m_vol->lz4_store ? tvk_pool_upload_bricks_lz4(m_ctx, 1, &s.pos, &src, &m_vol->comp_len[t], &m_vol->sizes[3 * t])
+                            : tvk_pool_upload_bricks(m_ctx, 1, &s.pos, &src, &m_vol->sizes[3 * t], m_vol->host_store ? 2 : 1);   // 2: the pinned store is one allocation
   if (rc) return rc;
   rc = tvk_pool_upload_wait(m_ctx);
   if (rc) return rc;
@@ -374,7 +375,7 @@ int BrickPool::UploadBricks(const std::vector<uint32_t>& xyzl, uint32_t& paged, 
   PrepareForPaging();
   m_lastMs[0] = ms_since(t0);
   t0 = clk::now();
-  std::vector<uint32_t> slot, sizes, pidx, pval;
+  std::vector<uint32_t> slot, sizes, pidx, pval, clen;
   std::vector<const void*> src;
   for (size_t i = 0; i < n; ++i) {
     // "in this frame we already replaced all bricks (except the single low-res brick)" (:768-778)
@@ -393,13 +394,17 @@ int BrickPool::UploadBricks(const std::vector<uint32_t>& xyzl, uint32_t& paged, 
     src.push_back(m_vol->host_store ? (const void*)(m_vol->host_store + m_vol->offsets[t])
                                     : (const void*)((const uint8_t*)m_vol->device_store + m_vol->offsets[t]));
     for (int a = 0; a < 3; ++a) sizes.push_back(m_vol->sizes[3 * t + a]);
+    if (m_vol->lz4_store) clen.push_back(m_vol->comp_len[t]);
     m_uploadedBytes += (uint64_t)m_vol->sizes[3 * t] * m_vol->sizes[3 * t + 1] * m_vol->sizes[3 * t + 2] * m_vol->bpv;
     ++m_insertPos;
     ++paged;
   }
   m_lastMs[1] = ms_since(t0);
   t0 = clk::now();
-  int rc = tvk_pool_upload_bricks(m_ctx, (uint32_t)slot.size(), slot.data(), src.data(), sizes.data(), m_vol->host_store ? 2 : 1);
+  // compressed store: the LZ4 bytes cross PCIe and the device inflates them (blocks until placed)
+  int rc = m_vol->lz4_store
+               ? tvk_pool_upload_bricks_lz4(m_ctx, (uint32_t)slot.size(), slot.data(), src.data(), clen.data(), sizes.data())
+               : tvk_pool_upload_bricks(m_ctx, (uint32_t)slot.size(), slot.data(), src.data(), sizes.data(), m_vol->host_store ? 2 : 1);
   if (rc) return rc;
   rc = wait ? tvk_pool_upload_wait(m_ctx) : tvk_pool_upload_fence(m_ctx);
   if (rc) return rc;
@@ -553,7 +558,7 @@ bool CudaGridLeaper::FinishLoad(BrickedVolume* v, uint64_t gpuMemBytes, uint32_t
 
 // renderer.loadDataset(file.uvf): UVFDataset::Open (uvfDataset.cpp:83-216) through the reader of tvk_uvf.h.
 // The bricks are read (and inflated) once into pinned host memory, which is the pager's source.
-bool CudaGridLeaper::LoadDataset(const std::string& uvfFile, uint64_t gpuMemBytes, bool verifyChecksum) {
+bool CudaGridLeaper::LoadDataset(const std::string& uvfFile, uint64_t gpuMemBytes, bool verifyChecksum, bool keepCompressed) {
   if (!m_ctx) { m_err = "renderer not initialised"; return false; }
   char err[256] = {0};
   tvk_uvf* u = nullptr;
@@ -610,10 +615,26 @@ bool CudaGridLeaper::LoadDataset(const std::string& uvfFile, uint64_t gpuMemByte
     if (tvk_uvf_get_hist2d(u, v->hist2d.data(), v->hist2d.size()) == TVK_OK) { v->hist2d_x = ui.hist2d_x; v->hist2d_y = ui.hist2d_y; }
     else v->hist2d.clear();
   }
+  if (keepCompressed) {
+    // all bricks LZ4? then the store keeps what the file holds and the device inflates (ExtendedOctree.cpp:313-360 does
+    // it on the host, brick by brick, before the upload)
+    std::vector<uint64_t> flen(n);
+    std::vector<uint32_t> comp(n);
+    bool all = tvk_uvf_get_toc(u, nullptr, flen.data(), comp.data(), nullptr, n) == TVK_OK;
+    for (uint64_t i = 0; i < n && all; ++i) all = comp[i] == TVK_UVF_COMP_LZ4 && flen[i] <= 0xFFFFFFFFull;
+    if (all) {
+      v->lz4_store = true;
+      v->comp_len.resize(n);
+      uint64_t coff = 0;
+      for (uint64_t i = 0; i < n; ++i) { v->offsets[i] = coff; v->comp_len[i] = (uint32_t)flen[i]; coff += flen[i]; }
+      v->store_bytes = coff;                               // (info.total_bytes stays the inflated size)
+    }
+  }
   if (cudaHostAlloc((void**)&v->host_store, v->store_bytes, cudaHostAllocDefault) != cudaSuccess) {
     tvk_uvf_close(u); delete v; m_err = "cudaHostAlloc failed for the brick store"; return false;
   }
-  const int rc = tvk_uvf_read_bricks(u, 0, n, v->host_store, v->offsets.data());
+  const int rc = v->lz4_store ? tvk_uvf_read_bricks_raw(u, 0, n, v->host_store, v->offsets.data())
+                              : tvk_uvf_read_bricks(u, 0, n, v->host_store, v->offsets.data());
   if (rc) { m_err = std::string("UVF brick read failed: ") + tvk_uvf_last_error(u); tvk_uvf_close(u); cudaFreeHost(v->host_store); delete v; return false; }
   tvk_uvf_close(u);
   const uint32_t tfSize = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)v->hist1d.size(), 4096));
@@ -656,6 +677,7 @@ bool CudaGridLeaper::AdoptVolume(BrickedVolume* v, uint64_t gpuMemBytes) {
 // writes the loaded volume as a UVF v5 file stock ImageVis3D opens (tvk_uvf_write)
 bool CudaGridLeaper::SaveUVF(const std::string& uvfFile, uint32_t compression, uint32_t level) {
   if (!m_ctx || !m_vol) { m_err = "no dataset"; return false; }
+  if (m_vol->lz4_store) { m_err = "the dataset was loaded with its bricks kept compressed; reload it with loadDataset to save a copy"; return false; }
   const BrickedVolume& v = *m_vol;
   std::vector<uint8_t> tmp;
   const uint8_t* store = v.host_store;
@@ -1152,7 +1174,7 @@ bool CudaGridLeaper::PaintClassic() {
     // whole bricks from a device-resident store, so the store is copied up once when it fits
     if (!m_vol->classic_store) {
       size_t freeB = 0, totalB = 0;
-      if (!m_vol->host_store || cudaMemGetInfo(&freeB, &totalB) != cudaSuccess || m_vol->store_bytes + (1ull << 30) > freeB) {
+      if (!m_vol->host_store || m_vol->lz4_store || cudaMemGetInfo(&freeB, &totalB) != cudaSuccess || m_vol->store_bytes + (1ull << 30) > freeB) {
         m_err = "the classic ray-caster needs the brick store in device memory and it does not fit (use the ray-guided renderer)";
         return false;
       }
@@ -1388,6 +1410,10 @@ int tvkr_load_raw_volume(tvkr_renderer* h, const void* raw, const uint32_t size[
 int tvkr_load_dataset(tvkr_renderer* h, const char* uvf_file, uint64_t gpu_mem_bytes, int verify_checksum) {
   return h && uvf_file && R(h)->LoadDataset(uvf_file, gpu_mem_bytes, verify_checksum != 0) ? 0 : 1;
 }
+int tvkr_load_dataset_compressed(tvkr_renderer* h, const char* uvf_file, uint64_t gpu_mem_bytes, int verify_checksum) {
+  return h && uvf_file && R(h)->LoadDataset(uvf_file, gpu_mem_bytes, verify_checksum != 0, true) ? 0 : 1;
+}
+int tvkr_store_is_compressed(tvkr_renderer* h) { return h && R(h)->Volume() && R(h)->Volume()->lz4_store ? 1 : 0; }
 int tvkr_save_uvf(tvkr_renderer* h, const char* uvf_file, uint32_t compression, uint32_t level) {
   return h && uvf_file && R(h)->SaveUVF(uvf_file, compression, level) ? 0 : 1;
 }

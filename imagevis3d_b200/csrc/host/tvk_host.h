@@ -94,6 +94,10 @@ struct BrickedVolume {
   std::vector<uint64_t> hist2d;         // [hist2d_x][hist2d_y] when the file (or the builder) provided one
   uint64_t hist2d_x = 0, hist2d_y = 0;
   void*    classic_store = nullptr;     // device copy of host_store, made on demand for the classic ray-caster
+  // host_store holds the bricks STILL LZ4-COMPRESSED (as the file stores them): offsets[] index the compressed store,
+  // comp_len[] are their lengths, and the pager inflates on the device (tvk_pool_upload_bricks_lz4)
+  bool     lz4_store = false;
+  std::vector<uint32_t> comp_len;
   uint8_t* host_store = nullptr;        // pinned (cudaHostAlloc) when out of core
   void*    device_store = nullptr;      // owned by the tvk_ctx build state when in core
   uint64_t store_bytes = 0;
@@ -196,7 +200,9 @@ class CudaGridLeaper {
                      uint32_t brickSize, uint32_t overlap, bool median, bool outOfCore, uint64_t gpuMemBytes,
                      bool computeHist2D);
   // renderer.loadDataset(file.uvf): a UVF with a TOC block (8/16-bit unsigned); bricks go to pinned host memory
-  bool LoadDataset(const std::string& uvfFile, uint64_t gpuMemBytes, bool verifyChecksum);
+  // keepCompressed: a file whose bricks are all LZ4 keeps them compressed in the pinned store; they cross PCIe compressed
+  // and are inflated on the device (ray-guided renderer only; any other file loads as usual)
+  bool LoadDataset(const std::string& uvfFile, uint64_t gpuMemBytes, bool verifyChecksum, bool keepCompressed = false);
   // A bricked volume some OTHER reader produced (the AbstrRenderer adapter walks a tuvok LinearIndexDataset once):
   // the caller fills domain / scale / bpv / brick_size / overlap and, per brick in ToC order, sizes (3 each) and
   // minmax (2 each), plus hist1d and max_grad_magnitude; PrepareHostVolume plans the octree, lays the bricks out in ONE

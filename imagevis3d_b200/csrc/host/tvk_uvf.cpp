@@ -686,6 +686,20 @@ static int uvf_read_bricks_impl(tvk_uvf* u, uint64_t first, uint64_t count, void
   return TVK_OK;
 }
 
+// the bricks as the file stores them (compressed or not): what a GPU-side inflate pages from
+extern "C" int tvk_uvf_read_bricks_raw(tvk_uvf* u, uint64_t first, uint64_t count, void* dst, const uint64_t* dst_offsets) {
+  if (!u || u->info.toc_block < 0 || !dst || first > u->info.total_bricks || count > u->info.total_bricks - first) return TVK_ERR_INVALID;
+  uint64_t packed = 0;
+  for (uint64_t k = 0; k < count; ++k) {
+    const uint64_t i = first + k;
+    uint8_t* o = static_cast<uint8_t*>(dst) + (dst_offsets ? dst_offsets[k] : packed);
+    packed += u->t_len[i];
+    if (fseeko(u->f, (off_t)u->t_off[i], SEEK_SET)) { u->err = "seek failed"; return TVK_ERR_INVALID; }
+    if (fread(o, 1, (size_t)u->t_len[i], u->f) != (size_t)u->t_len[i]) { u->err = "short read"; return TVK_ERR_INVALID; }
+  }
+  return TVK_OK;
+}
+
 // RasterDataBlock::ComputeBricks (RasterDataBlock.cpp:321-349): brick sizes along one axis
 static std::vector<uint64_t> rdb_axis_bricks(uint64_t size, uint64_t brick, uint64_t overlap) {
   std::vector<uint64_t> v;

@@ -682,6 +682,144 @@ extern "C" int tvk_pool_upload_bricks(tvk_ctx* c, uint32_t n, const uint32_t* sl
   return TVK_OK;
 }
 
+// ------------------------------------------------------------------ LZ4 bricks inflated on the device
+// ExtendedOctree::GetBrickData inflates a compressed brick on the host (ExtendedOctree.cpp:313-360, lz4Decompress ->
+// LZ4_decompress_fast: raw LZ4 BLOCK format, decompressed size known from the ToC).  Here the COMPRESSED bytes cross
+// PCIe -- the link is what bounds paging -- and one warp per brick inflates them in HBM: every lane parses the sequence
+// header (token, length bytes, offset: uniform, broadcast loads), the 32 lanes share the literal copy and the match
+// copy.  A match whose offset is shorter than 32 bytes repeats a pattern that is already complete (out[i] = m[i % off]), a
+// longer one is copied 32 bytes per trip with a warp barrier between trips, so that no lane reads a byte another lane of
+// the same trip writes.  Malformed input (a length or offset that leaves the buffers) raises the error flag.
+struct Lz4Job { const uint8_t* src; uint8_t* dst; uint32_t src_len, dst_len; };
+
+__global__ void __launch_bounds__(128) lz4_inflate_kernel(const Lz4Job* __restrict__ jobs, uint32_t njobs, uint32_t* __restrict__ err) {
+  const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+  if (warp >= njobs) return;
+  const Lz4Job j = jobs[warp];
+  const uint8_t* ip = j.src;
+  const uint8_t* const iend = j.src + j.src_len;
+  uint8_t* op = j.dst;
+  uint8_t* const oend = j.dst + j.dst_len;
+  bool bad = false;
+  for (;;) {
+    if (ip >= iend) { bad = true; break; }
+    const uint32_t token = *ip++;
+    size_t lit = token >> 4;
+    if (lit == 15) { uint32_t b; do { if (ip >= iend) { bad = true; break; } b = *ip++; lit += b; } while (b == 255); if (bad) break; }
+    if (lit > (size_t)(iend - ip) || lit > (size_t)(oend - op)) { bad = true; break; }
+    for (size_t i = lane; i < lit; i += 32) op[i] = ip[i];
+    op += lit; ip += lit;
+    if (op == oend) break;                               // the last sequence has literals only
+    if (iend - ip < 2) { bad = true; break; }
+    const size_t off = (size_t)ip[0] | ((size_t)ip[1] << 8);
+    ip += 2;
+    if (off == 0 || off > (size_t)(op - j.dst)) { bad = true; break; }
+    size_t ml = token & 15u;
+    if (ml == 15) { uint32_t b; do { if (ip >= iend) { bad = true; break; } b = *ip++; ml += b; } while (b == 255); if (bad) break; }
+    ml += 4;
+    if (ml > (size_t)(oend - op)) { bad = true; break; }
+    const uint8_t* m = op - off;
+    __syncwarp();                                        // the literals just written may be the match source
+    if (off < 32) {
+      for (size_t i = lane; i < ml; i += 32) op[i] = m[i % off];
+    } else {
+      for (size_t i0 = 0; i0 < ml; i0 += 32) {
+        if (i0 + lane < ml) op[i0 + lane] = m[i0 + lane];
+        __syncwarp();
+      }
+    }
+    op += ml;
+    __syncwarp();
+  }
+  if (bad && lane == 0) atomicExch(err, 1u);
+}
+
+extern "C" int tvk_pool_upload_bricks_lz4(tvk_ctx* c, uint32_t n, const uint32_t* slot, const void* const* src, const uint32_t* comp_len,
+                                          const uint32_t* sizes) {
+  if (!c || !c->has_pool || (n && (!slot || !src || !comp_len || !sizes))) return TVK_ERR_INVALID;
+  if (!n) return TVK_OK;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->copy_stream;
+  // staging: [compressed bricks, 16-byte aligned][inflated bricks, 256-byte aligned][jobs][error flag]
+  std::vector<size_t> coff(n), doff(n);
+  size_t cbytes = 0, dbytes = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    coff[i] = cbytes; cbytes += ((size_t)comp_len[i] + 15) & ~(size_t)15;
+    doff[i] = dbytes; dbytes += (((size_t)sizes[3 * i] * sizes[3 * i + 1] * sizes[3 * i + 2] * c->pc.bpv) + 255) & ~(size_t)255;
+  }
+  uint8_t* d_comp = nullptr; uint8_t* d_out = nullptr; Lz4Job* d_jobs = nullptr; uint32_t* d_err = nullptr;
+  TVK_CHECK_CUDA(c, cudaMallocAsync(&d_comp, cbytes + 16, st));
+  TVK_CHECK_CUDA(c, cudaMallocAsync(&d_out, dbytes, st));
+  TVK_CHECK_CUDA(c, cudaMallocAsync(&d_jobs, sizeof(Lz4Job) * n, st));
+  TVK_CHECK_CUDA(c, cudaMallocAsync(&d_err, sizeof(uint32_t), st));
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(d_err, 0, sizeof(uint32_t), st));
+  std::vector<Lz4Job> jobs(n);
+  std::vector<const void*> dsrc(n);
+  for (uint32_t i = 0; i < n; ) {
+    // bricks that follow one another in host memory (a ToC-order bulk load) travel as one transfer
+    uint32_t k = i + 1;
+    while (k < n && static_cast<const uint8_t*>(src[k]) == static_cast<const uint8_t*>(src[k - 1]) + comp_len[k - 1] &&
+           coff[k] == coff[k - 1] + comp_len[k - 1]) ++k;
+    size_t span = 0;
+    for (uint32_t q = i; q < k; ++q) span += comp_len[q];
+    TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_comp + coff[i], src[i], span, cudaMemcpyHostToDevice, st));
+    i = k;
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    jobs[i].src = d_comp + coff[i]; jobs[i].dst = d_out + doff[i]; jobs[i].src_len = comp_len[i];
+    jobs[i].dst_len = sizes[3 * i] * sizes[3 * i + 1] * sizes[3 * i + 2] * c->pc.bpv;
+    dsrc[i] = jobs[i].dst;
+  }
+  { int rc = tvk_copy_params_async(c, d_jobs, jobs.data(), sizeof(Lz4Job) * n, st); if (rc) return rc; }
+  lz4_inflate_kernel<<<(n + 3) / 4, 128, 0, st>>>(d_jobs, n, d_err);
+  c->launches++;
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  uint32_t h_err = 0;
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(&h_err, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(st));          // the inflated bricks are placement sources from here on
+  c->lz4_bytes_in += cbytes; c->lz4_bytes_out += dbytes;
+  int rc = TVK_OK;
+  if (h_err) { c->err = "corrupt LZ4 brick"; rc = TVK_ERR_INVALID; }
+  else rc = tvk_pool_upload_bricks(c, n, slot, dsrc.data(), sizes, 1);
+  if (rc == TVK_OK) rc = tvk_pool_upload_wait(c);
+  cudaFreeAsync(d_comp, st); cudaFreeAsync(d_out, st); cudaFreeAsync(d_jobs, st); cudaFreeAsync(d_err, st);
+  return rc;
+}
+
+// the same kernel without a pool: n LZ4 blocks (host pointers) -> their inflated bytes in host memory (tests, tools)
+extern "C" int tvk_lz4_inflate(tvk_ctx* c, uint32_t n, const void* const* src, const uint32_t* comp_len, void* const* dst, const uint32_t* dst_len) {
+  if (!c || (n && (!src || !comp_len || !dst || !dst_len))) return TVK_ERR_INVALID;
+  if (!n) return TVK_OK;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->copy_stream;
+  std::vector<size_t> coff(n), doff(n);
+  size_t cbytes = 0, dbytes = 0;
+  for (uint32_t i = 0; i < n; ++i) { coff[i] = cbytes; cbytes += ((size_t)comp_len[i] + 15) & ~(size_t)15; doff[i] = dbytes; dbytes += ((size_t)dst_len[i] + 255) & ~(size_t)255; }
+  uint8_t* d_comp = nullptr; uint8_t* d_out = nullptr; Lz4Job* d_jobs = nullptr; uint32_t* d_err = nullptr;
+  TVK_CHECK_CUDA(c, cudaMalloc(&d_comp, cbytes + 16));
+  TVK_CHECK_CUDA(c, cudaMalloc(&d_out, dbytes));
+  TVK_CHECK_CUDA(c, cudaMalloc(&d_jobs, sizeof(Lz4Job) * n));
+  TVK_CHECK_CUDA(c, cudaMalloc(&d_err, sizeof(uint32_t)));
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(d_err, 0, sizeof(uint32_t), st));
+  std::vector<Lz4Job> jobs(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_comp + coff[i], src[i], comp_len[i], cudaMemcpyHostToDevice, st));
+    jobs[i].src = d_comp + coff[i]; jobs[i].dst = d_out + doff[i]; jobs[i].src_len = comp_len[i]; jobs[i].dst_len = dst_len[i];
+  }
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(Lz4Job) * n, cudaMemcpyHostToDevice, st));
+  lz4_inflate_kernel<<<(n + 3) / 4, 128, 0, st>>>(d_jobs, n, d_err);
+  c->launches++;
+  uint32_t h_err = 0;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h_err, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+  for (uint32_t i = 0; i < n && e == cudaSuccess; ++i) e = cudaMemcpyAsync(dst[i], d_out + doff[i], dst_len[i], cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_comp); cudaFree(d_out); cudaFree(d_jobs); cudaFree(d_err);
+  if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return TVK_ERR_CUDA; }
+  if (h_err) { c->err = "corrupt LZ4 block"; return TVK_ERR_INVALID; }
+  return TVK_OK;
+}
+
 extern "C" int tvk_pool_upload_fence(tvk_ctx* c) {
   if (!c) return TVK_ERR_INVALID;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));

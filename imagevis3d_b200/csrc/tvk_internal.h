@@ -117,6 +117,7 @@ struct tvk_ctx {
   float4* d_image = nullptr;           // accRayColor / composed iso image
   uchar4* d_rgba8 = nullptr;           // tvk_read_image_rgba8 staging (allocated on first use)
   size_t rgba8_px = 0;                 // pixels d_rgba8 holds
+  uint64_t lz4_bytes_in = 0, lz4_bytes_out = 0;   // compressed bytes moved over PCIe / bytes inflated on the device
   float4* d_pos[2] = {nullptr, nullptr};   // rayStartPoint ping-pong
   float4* d_aux[2] = {nullptr, nullptr};   // rayStartColor (iso: normal) ping-pong
   int cur = 0;

@@ -76,11 +76,16 @@ class Renderer:
                  "loadRawVolume")
         return True
 
-    def loadDataset(self, filename, gpu_mem_bytes=0, verify=True):
-        """renderer.loadDataset("file.uvf") -- UVF v5 with a TOC block (tvkr_load_dataset)"""
-        self._ck(self._lib.tvkr_load_dataset(self._h, filename.encode(), C.c_uint64(int(gpu_mem_bytes)), C.c_int(int(verify))),
+    def loadDataset(self, filename, gpu_mem_bytes=0, verify=True, keep_compressed=False):
+        """renderer.loadDataset("file.uvf") -- UVF v5 with a TOC block (tvkr_load_dataset); keep_compressed: LZ4 files keep their
+        bricks compressed in host memory and the device inflates them while paging"""
+        fn = self._lib.tvkr_load_dataset_compressed if keep_compressed else self._lib.tvkr_load_dataset
+        self._ck(fn(self._h, filename.encode(), C.c_uint64(int(gpu_mem_bytes)), C.c_int(int(verify))),
                  "loadDataset")
         return True
+
+    def storeIsCompressed(self):
+        return bool(self._lib.tvkr_store_is_compressed(self._h))
 
     def saveUVF(self, filename, compression=0, level=1):
         self._ck(self._lib.tvkr_save_uvf(self._h, filename.encode(), C.c_uint32(compression), C.c_uint32(level)), "saveUVF")

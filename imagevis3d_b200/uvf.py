@@ -132,6 +132,14 @@ class UvfFile:
         self._ck(self.lib.tvk_uvf_read_bricks(self.h, C.c_uint64(first), C.c_uint64(count), _p(out), None), "tvk_uvf_read_bricks")
         return out
 
+    def read_bricks_raw(self, first=0, count=None):
+        """the same bricks as the file stores them (still compressed), packed; lengths = toc()[1]"""
+        count = int(self.info.total_bricks) - first if count is None else count
+        _, ln, _, _ = self.toc()
+        out = np.zeros(int(ln[first:first + count].sum()), np.uint8)
+        self._ck(self.lib.tvk_uvf_read_bricks_raw(self.h, C.c_uint64(first), C.c_uint64(count), _p(out), None), "tvk_uvf_read_bricks_raw")
+        return out
+
     def read_rdb_volume(self):
         """finest level of a legacy RasterDataBlock file as a [z][y][x] array"""
         i = self.info

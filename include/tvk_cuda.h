@@ -114,6 +114,15 @@ int tvk_pool_upload_bricks(tvk_ctx* ctx, uint32_t n, const uint32_t* slot,
                            const void* const* src, const uint32_t* sizes,
                            int on_device);
 int tvk_pool_upload_wait(tvk_ctx* ctx);
+/* LZ4-compressed bricks (raw LZ4 block format, as lz4Compress writes them into a UVF file, ExtendedOctree/Lz4Compression.cpp)
+ * inflated ON THE DEVICE: replaces the host-side decompression of ExtendedOctree::GetBrickData (ExtendedOctree.cpp:313-360)
+ * for paging.  src[i] = the comp_len[i] compressed bytes of brick i in (pinned) host memory; only those bytes cross PCIe, a
+ * kernel (one warp per brick) inflates them in HBM and the placement kernels put them into slot[i].  Blocks until the
+ * bricks are in the pool; corrupt data -> TVK_ERR_INVALID, pool untouched.  Metadata as for tvk_pool_upload_bricks. */
+int tvk_pool_upload_bricks_lz4(tvk_ctx* ctx, uint32_t n, const uint32_t* slot, const void* const* src, const uint32_t* comp_len,
+                               const uint32_t* sizes);
+/* the same kernel without a pool: n LZ4 blocks in host memory -> dst[i] (dst_len[i] bytes each, host memory) */
+int tvk_lz4_inflate(tvk_ctx* ctx, uint32_t n, const void* const* src, const uint32_t* comp_len, void* const* dst, const uint32_t* dst_len);
 /* The same ordering without blocking the host: everything issued on the render stream after this call (metadata
  * patches, the next ray-march) runs after the upload in flight has been placed.  Only for sources that stay valid
  * until then (the renderer's pinned brick store). */

@@ -49,6 +49,11 @@ int tvkr_load_raw_volume(tvkr_renderer* r, const void* raw, const uint32_t size[
  * uvfDataset.cpp:83-216): a UVF v5 file with a TOC block; bricks are read (zlib / lz4 inflated) into pinned
  * host memory and paged from there.  gpu_mem_bytes as above. */
 int tvkr_load_dataset(tvkr_renderer* r, const char* uvf_file, uint64_t gpu_mem_bytes, int verify_checksum);
+/* the same, but a file whose bricks are all LZ4-compressed keeps them COMPRESSED in the pinned host store: paging moves the
+ * compressed bytes over PCIe and the device inflates them (tvk_pool_upload_bricks_lz4); replaces the host-side inflate of
+ * ExtendedOctree::GetBrickData (ExtendedOctree.cpp:313-360).  Other files load exactly as tvkr_load_dataset. */
+int tvkr_load_dataset_compressed(tvkr_renderer* r, const char* uvf_file, uint64_t gpu_mem_bytes, int verify_checksum);
+int tvkr_store_is_compressed(tvkr_renderer* r);
 /* what IOManager::ConvertDataset leaves on disk (RAWConverter::ConvertRAWDataset, RAWConverter.cpp:412-681):
  * the loaded volume as a UVF v5 file; compression = TVK_UVF_COMP_NONE / _ZLIB (tvk_uvf.h) */
 int tvkr_save_uvf(tvkr_renderer* r, const char* uvf_file, uint32_t compression, uint32_t level);

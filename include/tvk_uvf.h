@@ -103,6 +103,8 @@ int  tvk_uvf_read_bricks(tvk_uvf* u, uint64_t first, uint64_t count, void* dst, 
 /* RasterDataBlock::GetData over all bricks of the finest level, stitched back into the flat x-fastest volume
  * (rdb_domain voxels of rdb_bits/8 bytes): what DynamicBrickingDS (IO/DynamicBrickingDS.cpp) starts from when it
  * re-bricks a legacy / large-brick file for the ray-guided renderer. */
+/* the same bricks AS STORED (still compressed): lengths from tvk_uvf_get_toc; dst_offsets NULL = packed */
+int  tvk_uvf_read_bricks_raw(tvk_uvf* u, uint64_t first, uint64_t count, void* dst, const uint64_t* dst_offsets);
 int  tvk_uvf_read_rdb_volume(tvk_uvf* u, void* dst, uint64_t dst_bytes);
 int  tvk_uvf_get_minmax(const tvk_uvf* u, double* minmax4, uint64_t n);   /* min, max, minGrad, maxGrad per brick */
 int  tvk_uvf_get_hist1d(const tvk_uvf* u, uint64_t* bins, uint64_t n);

@@ -114,3 +114,89 @@ def test_batch_renderer_script(kind, tmp_path):
     assert (rows[:, 0] == 0).all()                                       # filter type 0 on every row
     img = rows[:, 1:].reshape(h, w, 4)
     assert img[..., 3].max() == 255 and 0.05 < (img[..., 3] > 0).mean() < 0.9
+
+
+def _gpu_inflate(tvk, blocks, sizes):
+    import ctypes as C
+    n = len(blocks)
+    bufs = [np.frombuffer(b, np.uint8).copy() for b in blocks]
+    outs = [np.zeros(s, np.uint8) for s in sizes]
+    src = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+    dst = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    rc = tvk.lib.tvk_lz4_inflate(tvk.h, C.c_uint32(n), src, (C.c_uint32 * n)(*[len(b) for b in blocks]), dst, (C.c_uint32 * n)(*sizes))
+    return rc, outs
+
+
+def test_lz4_inflate_on_the_device(tvk):
+    """tvk_lz4_inflate (one warp per block): random, run-length (matches that overlap their own output, offsets 1..40), smooth
+    volume data and an incompressible block -- against the bytes that went in."""
+    from tests.util import lz4_compress_block
+    rng = np.random.default_rng(3)
+    datas = [rng.integers(0, 4, 70000, dtype=np.uint8).tobytes(),                       # short alphabet: many matches
+             bytes(20000),                                                              # one long run (offset 1)
+             (bytes(range(37)) * 900),                                                  # period 37 > 32: the chunked copy
+             (bytes(range(7)) * 3000) + rng.integers(0, 256, 999, dtype=np.uint8).tobytes(),
+             H.synth_blobs((64, 64, 40), np.uint8).tobytes(),
+             rng.integers(0, 256, 50000, dtype=np.uint8).tobytes(), b"abc", b""]
+    blocks = [lz4_compress_block(d) for d in datas]
+    assert len(blocks[1]) < 200 and len(blocks[2]) < 400                                 # they really are matches
+    rc, outs = _gpu_inflate(tvk, blocks, [len(d) for d in datas])
+    assert rc == 0
+    for d, o in zip(datas, outs):
+        assert o.tobytes() == d
+
+
+def test_lz4_inflate_rejects_corrupt_blocks(tvk):
+    from tests.util import lz4_compress_block
+    good = lz4_compress_block(bytes(range(50)) * 100)
+    bad_offset = bytearray(good)
+    bad_offset[len(bytes(range(50))) + 2:len(bytes(range(50))) + 4] = b"\xff\xff"       # a match before the start of the output
+    for blk, size in ((bytes(bad_offset), 5000), (good[:len(good) // 2], 5000), (good, 9000)):
+        rc, _ = _gpu_inflate(tvk, [blk], [size])
+        assert rc != 0
+
+
+def test_reference_lz4_file_inflates_on_the_device(tvk, tmp_path):
+    """the bricks of a reference-written LZ4 UVF, taken from the file still compressed and inflated by the kernel, equal the
+    host decode of the same file"""
+    from imagevis3d_b200 import uvf as U
+    path = golden_file("ref_u8_lz4", tmp_path)
+    f = U.UvfFile(path)
+    off, ln, comp, sizes = f.toc()
+    assert (comp == 2).all()
+    want = f.read_bricks()
+    raw = f.read_bricks_raw()
+    blocks, pos = [], 0
+    for k in ln:
+        blocks.append(raw[pos:pos + int(k)].tobytes())
+        pos += int(k)
+    nbytes = [int(s[0]) * int(s[1]) * int(s[2]) for s in sizes]
+    rc, outs = _gpu_inflate(tvk, blocks, nbytes)
+    assert rc == 0
+    assert np.array_equal(np.concatenate(outs), want)
+    f.close()
+
+
+def test_paging_from_a_compressed_store_renders_the_same(tmp_path):
+    """renderer.loadDataset(keep_compressed=True): the pinned store holds the LZ4 bytes of the file, paging moves them
+    over PCIe compressed and the device inflates them -- same frame, bit for bit, as the host-inflated load."""
+    from imagevis3d_b200.renderer import Renderer, RT_HEADLESS
+    path = golden_file("ref_u8_lz4", tmp_path)
+    imgs = []
+    for keep in (False, True):
+        r = Renderer(0)
+        r.loadDataset(path, gpu_mem_bytes=24 * 36 ** 3, keep_compressed=keep)      # a pool smaller than the dataset: real paging
+        assert r.storeIsCompressed() == keep
+        info = r.datasetInfo()
+        tf = H.tf1d_std(info.tf_size, 0.4, 0.4)
+        tf[:, 3] *= 0.2
+        r.set1DTransFloat(tf)
+        r.setLightingEnabled(True)
+        r.resize((160, 120))
+        r.setRendererTarget(RT_HEADLESS)
+        r.setRotation4x4(H.rotation_y(0.5) @ H.rotation_x(0.2))
+        n = r.paintUntilConverged()
+        assert n > 1 and r.perf()["paged_bricks"] > 0
+        imgs.append(r.frameFloat().copy())
+        r.cleanup()
+    assert imgs[0].max() > 0.05 and np.array_equal(imgs[0], imgs[1])

@@ -194,3 +194,51 @@ def write_rdb_uvf(path, vol, brick=256, overlap=4, block_id="Qvis data volume co
     digest = hashlib.md5(body).digest()
     with open(path, "wb") as f:
         f.write(b"UVF-DATA" + b"\x00" + q(2) + q(2) + q(16) + digest + body)
+
+
+def lz4_compress_block(data, min_match=4):
+    """TEST HELPER: a small greedy LZ4 BLOCK compressor (raw block format, what lz4Compress / LZ4_compress write for a brick):
+    valid for any LZ4 decoder -- the last five bytes are literals and no match starts within the last twelve."""
+    src = bytes(data)
+    n = len(src)
+    out = bytearray()
+    table = {}
+    anchor = i = 0
+
+    def emit(lit_from, lit_to, off, mlen):
+        lit = lit_to - lit_from
+        token_l = 15 if lit >= 15 else lit
+        token_m = 0 if mlen is None else (15 if mlen - 4 >= 15 else mlen - 4)
+        out.append((token_l << 4) | token_m)
+        if lit >= 15:
+            r = lit - 15
+            while r >= 255:
+                out.append(255)
+                r -= 255
+            out.append(r)
+        out.extend(src[lit_from:lit_to])
+        if mlen is not None:
+            out.extend((off & 0xFF, off >> 8))
+            if mlen - 4 >= 15:
+                r = mlen - 4 - 15
+                while r >= 255:
+                    out.append(255)
+                    r -= 255
+                out.append(r)
+
+    limit = n - 12
+    while i < limit:
+        key = src[i:i + 4]
+        j = table.get(key)
+        table[key] = i
+        if j is not None and i - j <= 65535:
+            m = 4
+            while i + m < n - 5 and src[j + m] == src[i + m]:
+                m += 1
+            emit(anchor, i, i - j, m)
+            i += m
+            anchor = i
+        else:
+            i += 1
+    emit(anchor, n, 0, None)
+    return bytes(out)
