@@ -472,9 +472,49 @@ void CudaGridLeaper::Cleanup() {
   if (m_ctx) { tvk_destroy(m_ctx); m_ctx = nullptr; }
 }
 
+bool CudaGridLeaper::LoadVolumeFile(const std::string& path, uint32_t brickSize, uint32_t overlap, bool median, bool outOfCore,
+                                    uint64_t gpuMemBytes, bool computeHist2D) {
+  if (!m_ctx) { m_err = "renderer not initialised"; return false; }
+  tvk_raw_desc d;
+  char err[512] = {0};
+  if (tvk_raw_probe(path.c_str(), &d, err, sizeof(err))) { m_err = err; return false; }
+  if (d.component_count != 1) { m_err = "multi-component (colour) volumes are not supported"; return false; }
+  for (int a = 0; a < 3; ++a) if (d.size[a] == 0 || d.size[a] > 0xFFFFFFFFull) { m_err = "bad volume size"; return false; }
+  const uint64_t n = d.size[0] * d.size[1] * d.size[2];
+  const uint32_t bytes = d.component_bits / 8;
+  std::vector<uint8_t> host((size_t)(n * bytes));
+  if (tvk_raw_read(&d, host.data(), host.size(), err, sizeof(err))) { m_err = err; return false; }
+  // element type of RAWConverter::ConvertRAWDataset's dispatcher (RAWConverter.cpp:196-352)
+  uint32_t type;
+  if (d.is_float) type = bytes == 4 ? TVK_DT_F32 : TVK_DT_F64;
+  else if (bytes == 1) type = d.is_signed ? TVK_DT_I8 : TVK_DT_U8;
+  else if (bytes == 2) type = d.is_signed ? TVK_DT_I16 : TVK_DT_U16;
+  else if (bytes == 4) type = d.is_signed ? TVK_DT_I32 : TVK_DT_U32;
+  else type = d.is_signed ? TVK_DT_I64 : TVK_DT_U64;
+  void* d_q = nullptr;
+  if (cudaMalloc(&d_q, (size_t)(2 * n + 16)) != cudaSuccess) { (void)cudaGetLastError(); m_err = "out of device memory for the quantised volume"; return false; }
+  std::vector<uint64_t> hist(4096);
+  tvk_quantize_result qr{};
+  int rc = tvk_quantize(m_ctx, type, n, host.data(), 0, 0, d_q, hist.data(), &qr);
+  if (rc) { cudaFree(d_q); return Fail("tvk_quantize", rc); }
+  const uint32_t size[3] = {(uint32_t)d.size[0], (uint32_t)d.size[1], (uint32_t)d.size[2]};
+  bool ok;
+  if (qr.generated) {
+    std::vector<uint8_t>().swap(host);
+    ok = LoadRawVolume(d_q, size, qr.out_bits / 8, d.aspect, brickSize, overlap, median, outOfCore, gpuMemBytes, computeHist2D, true);
+  } else {
+    ok = LoadRawVolume(host.data(), size, bytes, d.aspect, brickSize, overlap, median, outOfCore, gpuMemBytes, computeHist2D, false);
+  }
+  // (an in-core build keeps reading the flat volume for the 2-D histogram only inside LoadRawVolume: safe to free now)
+  tvk_device_synchronize(m_ctx);
+  tvk_build_forget_raw(m_ctx);
+  cudaFree(d_q);
+  return ok;
+}
+
 bool CudaGridLeaper::LoadRawVolume(const void* raw, const uint32_t size[3], uint32_t bpv, const float scale[3],
                                    uint32_t brickSize, uint32_t overlap, bool median, bool outOfCore,
-                                   uint64_t gpuMemBytes, bool computeHist2D) {
+                                   uint64_t gpuMemBytes, bool computeHist2D, bool rawOnDevice) {
   if (!m_ctx) { m_err = "renderer not initialised"; return false; }
   delete m_pool; m_pool = nullptr;
   free_volume(m_ctx, m_vol);
@@ -482,7 +522,7 @@ bool CudaGridLeaper::LoadRawVolume(const void* raw, const uint32_t size[3], uint
   for (int a = 0; a < 3; ++a) d.volume_size[a] = size[a];
   d.brick_size = brickSize; d.overlap = overlap; d.bytes_per_voxel = bpv; d.use_median = median ? 1 : 0;
   BrickedVolume* v = new BrickedVolume();
-  int rc = tvk_build_octree(m_ctx, &d, raw, 0, &v->info);
+  int rc = tvk_build_octree(m_ctx, &d, raw, rawOnDevice ? 1 : 0, &v->info);
   if (rc) { delete v; return Fail("tvk_build_octree", rc); }
   for (int a = 0; a < 3; ++a) { v->domain[a] = size[a]; v->scale[a] = scale ? scale[a] : 1.0f; }
   v->bpv = bpv; v->brick_size = brickSize; v->overlap = overlap;
@@ -1409,6 +1449,10 @@ int tvkr_load_raw_volume(tvkr_renderer* h, const void* raw, const uint32_t size[
 }
 int tvkr_load_dataset(tvkr_renderer* h, const char* uvf_file, uint64_t gpu_mem_bytes, int verify_checksum) {
   return h && uvf_file && R(h)->LoadDataset(uvf_file, gpu_mem_bytes, verify_checksum != 0) ? 0 : 1;
+}
+int tvkr_load_volume_file(tvkr_renderer* h, const char* path, uint32_t brick, uint32_t overlap, int median, int out_of_core,
+                          uint64_t gpu_mem_bytes, int hist2d) {
+  return h && path && R(h)->LoadVolumeFile(path, brick, overlap, median != 0, out_of_core != 0, gpu_mem_bytes, hist2d != 0) ? 0 : 1;
 }
 int tvkr_load_dataset_compressed(tvkr_renderer* h, const char* uvf_file, uint64_t gpu_mem_bytes, int verify_checksum) {
   return h && uvf_file && R(h)->LoadDataset(uvf_file, gpu_mem_bytes, verify_checksum != 0, true) ? 0 : 1;

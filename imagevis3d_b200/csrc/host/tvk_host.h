@@ -198,7 +198,11 @@ class CudaGridLeaper {
   // brick store to pinned host memory and sizes the pool by gpuMemBytes (0 = whole dataset).
   bool LoadRawVolume(const void* raw, const uint32_t size[3], uint32_t bytesPerVoxel, const float scale[3],
                      uint32_t brickSize, uint32_t overlap, bool median, bool outOfCore, uint64_t gpuMemBytes,
-                     bool computeHist2D);
+                     bool computeHist2D, bool rawOnDevice = false);
+  // "open a .dat / .nrrd file": raw front end (tvk_raw_probe / tvk_raw_read) -> quantisation on the device (tvk_quantize)
+  // -> LoadRawVolume; single-component volumes of any of the ten element types
+  bool LoadVolumeFile(const std::string& path, uint32_t brickSize, uint32_t overlap, bool median, bool outOfCore, uint64_t gpuMemBytes,
+                      bool computeHist2D);
   // renderer.loadDataset(file.uvf): a UVF with a TOC block (8/16-bit unsigned); bricks go to pinned host memory
   // keepCompressed: a file whose bricks are all LZ4 keeps them compressed in the pinned store; they cross PCIe compressed
   // and are inflated on the device (ray-guided renderer only; any other file loads as usual)

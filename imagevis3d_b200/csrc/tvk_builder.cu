@@ -1734,6 +1734,13 @@ extern "C" int tvk_build_stream_end(tvk_ctx* c, tvk_build_info* info_out) {
   return TVK_OK;
 }
 
+extern "C" int tvk_build_forget_raw(tvk_ctx* c) {
+  if (!c) return TVK_ERR_INVALID;
+  BuildState& b = c->build;
+  if (!b.own_lod0) b.d_lod[0] = nullptr;           // caller-owned flat volume: it may be freed from now on
+  return TVK_OK;
+}
+
 extern "C" int tvk_build_get_toc(tvk_ctx* c, uint64_t* offsets, uint32_t* sizes3, uint64_t n) {
   if (!c || !c->build.valid || n != c->build.info.total_bricks) return TVK_ERR_INVALID;
   if (offsets) memcpy(offsets, c->build.offsets.data(), sizeof(uint64_t) * n);

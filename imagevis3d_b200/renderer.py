@@ -84,6 +84,11 @@ class Renderer:
                  "loadDataset")
         return True
 
+    def loadVolumeFile(self, filename, brick_size=64, overlap=2, median=False, out_of_core=False, gpu_mem_bytes=0, hist2d=True):
+        """opens a QVIS .dat or a NRRD .nrrd/.nhdr volume: header parse, quantisation to 8/16 bit on the device, octree build"""
+        self._ck(self._lib.tvkr_load_volume_file(self._h, filename.encode(), C.c_uint32(brick_size), C.c_uint32(overlap), C.c_int(int(median)),
+                                                 C.c_int(int(out_of_core)), C.c_uint64(int(gpu_mem_bytes)), C.c_int(int(hist2d))), "loadVolumeFile")
+
     def storeIsCompressed(self):
         return bool(self._lib.tvkr_store_is_compressed(self._h))
 

@@ -287,6 +287,9 @@ int tvk_build_stream_rows(const tvk_build_desc* desc, uint32_t bz0, uint32_t bz1
 int tvk_build_stream_slab(tvk_ctx* ctx, const void* raw_slab, uint32_t z0, uint32_t rows, uint32_t bz0, uint32_t bz1);
 int tvk_build_stream_end(tvk_ctx* ctx, tvk_build_info* info);
 
+/* the caller is about to free the device volume it passed with raw_on_device = 1: the build state drops its pointer
+ * (tvk_build_hist2d is refused afterwards) */
+int tvk_build_forget_raw(tvk_ctx* ctx);
 int tvk_build_get_toc(tvk_ctx* ctx, uint64_t* offsets, uint32_t* sizes3, uint64_t n);
 int tvk_build_get_minmax(tvk_ctx* ctx, double* minmax2, uint64_t n);
 int tvk_build_get_bricks(tvk_ctx* ctx, void* host_dst, uint64_t offset, uint64_t bytes);

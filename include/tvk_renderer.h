@@ -127,6 +127,31 @@ int tvkr_get_perf(tvkr_renderer* r, double out[6]);     /* tuvok.perf: subframes
  * 7 PERF_POOL_SORT, 8 PERF_POOL_UPLOADED_MEM, 9 PERF_POOL_GET_BRICK, 19 PERF_POOL_UPLOAD_BRICK,
  * 21 PERF_POOL_UPLOAD_METADATA, 22 PERF_EO_BRICKS ...): the amount since the last query of that counter, which is reset */
 double tvkr_perf_query(tvkr_renderer* r, int counter);
+/* ---- raw-volume front ends: QVIS .dat/.raw (IO/QVISConverter.cpp) and NRRD .nrrd/.nhdr, raw or gzip encoded
+ * (IO/NRRDConverter.cpp).  tvk_raw_probe fills what AbstrConverter::ConvertToRAW returns; tvk_raw_read delivers the voxels
+ * in host byte order; tvkr_load_volume_file = probe + read + quantisation on the device (RAWConverter::ConvertRAWDataset's
+ * dispatcher, tvk_quantize) + octree build, i.e. what "open a .dat / .nrrd file" does in ImageVis3D.  No device needed for
+ * the first two. */
+#define TVK_RAW_ENC_RAW  0
+#define TVK_RAW_ENC_GZIP 1
+typedef struct tvk_raw_desc {
+  uint64_t header_skip;          /* iHeaderSkip: bytes before the voxels in data_file                              */
+  uint64_t inflated_skip;        /* gzip encoding: bytes to drop at the start of the INFLATED stream ("byte skip")   */
+  uint32_t component_bits;       /* iComponentSize: 8, 16, 32, 64                                                  */
+  uint32_t component_count;      /* iComponentCount                                                                */
+  int32_t  convert_endianness;   /* bConvertEndianess: the file's byte order is not the host's                     */
+  int32_t  is_signed, is_float;
+  uint32_t encoding;             /* TVK_RAW_ENC_*                                                                  */
+  uint64_t size[3];              /* vVolumeSize                                                                    */
+  float    aspect[3];            /* vVolumeAspect                                                                  */
+  char     title[64];
+  char     data_file[1024];      /* strIntermediateFile: where the voxels are                                      */
+} tvk_raw_desc;
+int tvk_raw_probe(const char* path, tvk_raw_desc* out, char* err, size_t errlen);
+int tvk_raw_read(const tvk_raw_desc* d, void* dst, uint64_t dst_bytes, char* err, size_t errlen);
+int tvkr_load_volume_file(tvkr_renderer* r, const char* path, uint32_t brick_size, uint32_t overlap, int median, int out_of_core,
+                          uint64_t gpu_mem_bytes, int compute_hist2d);
+
 /* The coarse-to-fine sub-frame ladder of AbstrRenderer (classic renderer): which LOD a view starts at
  * (ComputeMaxLODForCurrentView, AbstrRenderer.cpp:681-787, fed by the times the first two sub-frames of the previous view
  * took) and how PlanFrame steps down to the LOD the view needs (:1125-1212).  The state is a POD so that the logic can be

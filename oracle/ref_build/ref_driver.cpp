@@ -45,6 +45,9 @@
 #include "IO/UVF/Histogram2DDataBlock.h"
 #include "IO/UVF/RasterDataBlock.h"
 #include "IO/TransferFunction1D.h"
+#include "IO/QVISConverter.h"
+#include "IO/NRRDConverter.h"
+#include "Basics/SysTools.h"
 #include "Basics/LargeRAWFile.h"
 #include "IO/AbstrConverter.h"
 #include "IO/Quantize.h"
@@ -203,6 +206,24 @@ static int do_tf1d(int argc, char** argv) {
   uint64_t lo = tf.GetNonZeroLimits().x; uint64_t hi = tf.GetNonZeroLimits().y;
   put(f, lo); put(f, hi);
   fclose(f);
+  return 0;
+}
+
+// ref_driver rawinfo <file.dat | file.nrrd | file.nhdr>: what the reference's converter reports for the file
+// (QVISConverter / NRRDConverter::ConvertToRAW), one "key value" per line
+static int do_rawinfo(int argc, char** argv) {
+  if (argc < 3) return 2;
+  const std::string fn(argv[2]);
+  const std::string ext = SysTools::ToUpperCase(SysTools::GetExt(fn));
+  uint64_t skip = 0; unsigned bits = 0; uint64_t comps = 0; bool conv = false, sgn = false, flt = false, del = false;
+  UINT64VECTOR3 size; FLOATVECTOR3 aspect; std::string title, inter;
+  bool ok;
+  if (ext == "DAT") { QVISConverter c; ok = c.ConvertToRAW(fn, "/tmp/", true, skip, bits, comps, conv, sgn, flt, size, aspect, title, inter, del); }
+  else { NRRDConverter c; ok = c.ConvertToRAW(fn, "/tmp/", true, skip, bits, comps, conv, sgn, flt, size, aspect, title, inter, del); }
+  if (!ok) { printf("ok 0\n"); return 0; }
+  printf("ok 1\nskip %llu\nbits %u\ncomps %llu\nconv %d\nsigned %d\nfloat %d\nsize %llu %llu %llu\naspect %.9g %.9g %.9g\nfile %s\ndelete %d\n",
+         (unsigned long long)skip, bits, (unsigned long long)comps, (int)conv, (int)sgn, (int)flt, (unsigned long long)size.x,
+         (unsigned long long)size.y, (unsigned long long)size.z, aspect.x, aspect.y, aspect.z, inter.c_str(), (int)del);
   return 0;
 }
 
@@ -403,6 +424,7 @@ int main(int argc, char** argv) {
   if (!strcmp(argv[1], "uvfinfo")) return do_uvfinfo(argc, argv);
   if (!strcmp(argv[1], "tf1d")) return do_tf1d(argc, argv);
   if (!strcmp(argv[1], "tfresample")) return do_tfresample(argc, argv);
+  if (!strcmp(argv[1], "rawinfo")) return do_rawinfo(argc, argv);
   if (!strcmp(argv[1], "quantize")) return do_quantize(argc, argv);
   if (!strcmp(argv[1], "writeuvf")) return do_writeuvf(argc, argv);
   if (!strcmp(argv[1], "readuvf")) return do_readuvf(argc, argv);
