@@ -469,7 +469,90 @@ bool CudaGridLeaper::Initialize(int device) {
 void CudaGridLeaper::Cleanup() {
   delete m_pool; m_pool = nullptr;
   free_volume(m_ctx, m_vol);
+  free_volume(m_ctx, m_streamVol);
   if (m_ctx) { tvk_destroy(m_ctx); m_ctx = nullptr; }
+}
+
+bool CudaGridLeaper::LoadStreamedBegin(const uint32_t size[3], uint32_t bpv, const float scale[3], uint32_t brickSize, uint32_t overlap,
+                                       bool median) {
+  if (!m_ctx) { m_err = "renderer not initialised"; return false; }
+  delete m_pool; m_pool = nullptr;
+  free_volume(m_ctx, m_vol);
+  if (m_streamVol) free_volume(m_ctx, m_streamVol);
+  tvk_build_release(m_ctx);
+  tvk_build_desc& d = m_streamDesc;
+  d = tvk_build_desc{};
+  for (int a = 0; a < 3; ++a) d.volume_size[a] = size[a];
+  d.brick_size = brickSize; d.overlap = overlap; d.bytes_per_voxel = bpv; d.use_median = median ? 1 : 0;
+  BrickedVolume* v = new BrickedVolume();
+  for (int a = 0; a < 3; ++a) { v->domain[a] = size[a]; v->scale[a] = scale ? scale[a] : 1.0f; }
+  v->bpv = bpv; v->brick_size = brickSize; v->overlap = overlap;
+  int rc = tvk_build_plan(&d, &v->info);
+  if (rc) { delete v; return Fail("tvk_build_plan", rc); }
+  // the store's size is the sum of the 256-byte aligned bricks: learn it from a ToC-only begin (no store yet)
+  const uint64_t n = v->info.total_bricks;
+  const uint32_t core = brickSize - 2 * overlap;
+  uint64_t bytes = 0;
+  for (uint32_t l = 0; l < v->info.lod_count; ++l)
+    for (uint32_t z = 0; z < v->info.lod_bricks[l][2]; ++z)
+      for (uint32_t y = 0; y < v->info.lod_bricks[l][1]; ++y)
+        for (uint32_t x = 0; x < v->info.lod_bricks[l][0]; ++x) {
+          const uint32_t c[3] = {x, y, z};
+          uint64_t vox = 1;
+          for (int a = 0; a < 3; ++a) {
+            const bool last = c[a] >= v->info.lod_bricks[l][a] - 1;
+            const uint32_t rem = v->info.lod_size[l][a] % core;
+            vox *= (last && rem) ? (2 * overlap + rem) : brickSize;
+          }
+          bytes += (vox * bpv + 255) / 256 * 256;
+        }
+  v->store_bytes = bytes;
+  if (cudaHostAlloc((void**)&v->host_store, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    (void)cudaGetLastError(); delete v; m_err = "cudaHostAlloc failed for the out-of-core brick store"; return false;
+  }
+  rc = tvk_build_stream_begin(m_ctx, &d, v->host_store, &v->info);
+  if (rc || v->info.total_bytes != bytes) {
+    cudaFreeHost(v->host_store); delete v;
+    if (!rc) { m_err = "store size mismatch"; return false; }
+    return Fail("tvk_build_stream_begin", rc);
+  }
+  (void)n;
+  m_streamVol = v;
+  m_lastBuildMs = 0.0f;
+  return true;
+}
+
+bool CudaGridLeaper::LoadStreamedRows(uint32_t bz0, uint32_t bz1, uint32_t& z0, uint32_t& rows) const {
+  return m_streamVol && tvk_build_stream_rows(&m_streamDesc, bz0, bz1, &z0, &rows) == TVK_OK;
+}
+
+bool CudaGridLeaper::LoadStreamedSlab(const void* slab, uint32_t z0, uint32_t rows, uint32_t bz0, uint32_t bz1) {
+  if (!m_streamVol) { m_err = "LoadStreamedSlab without LoadStreamedBegin"; return false; }
+  const int rc = tvk_build_stream_slab(m_ctx, slab, z0, rows, bz0, bz1);
+  return rc ? Fail("tvk_build_stream_slab", rc) : true;
+}
+
+bool CudaGridLeaper::LoadStreamedEnd(uint64_t gpuMemBytes) {
+  if (!m_streamVol) { m_err = "LoadStreamedEnd without LoadStreamedBegin"; return false; }
+  BrickedVolume* v = m_streamVol;
+  int rc = tvk_build_stream_end(m_ctx, &v->info);
+  if (rc) return Fail("tvk_build_stream_end", rc);
+  tvk_device_synchronize(m_ctx);                         // every brick has landed in the pinned store
+  const uint64_t n = v->info.total_bricks;
+  v->offsets.resize(n); v->sizes.resize(3 * n); v->minmax.resize(2 * n);
+  rc = tvk_build_get_toc(m_ctx, v->offsets.data(), v->sizes.data(), n);
+  if (!rc) rc = tvk_build_get_minmax(m_ctx, v->minmax.data(), n);
+  if (rc) return Fail("tvk_build_get_*", rc);
+  v->hist1d.resize(1u << (8 * v->bpv));
+  uint32_t hn = 0;
+  rc = tvk_build_hist1d(m_ctx, v->hist1d.data(), (uint32_t)v->hist1d.size(), &hn);
+  if (rc) return Fail("tvk_build_hist1d", rc);
+  v->hist1d.resize(hn);
+  tvk_build_last_ms(m_ctx, &m_lastBuildMs);
+  tvk_build_release(m_ctx);                              // (the store is caller-owned: it stays)
+  m_streamVol = nullptr;
+  const uint32_t tfSize = std::max<uint32_t>(1, std::min<uint32_t>(hn, 4096));
+  return FinishLoad(v, gpuMemBytes, tfSize);
 }
 
 bool CudaGridLeaper::LoadVolumeFile(const std::string& path, uint32_t brickSize, uint32_t overlap, bool median, bool outOfCore,
@@ -1449,6 +1532,20 @@ int tvkr_load_raw_volume(tvkr_renderer* h, const void* raw, const uint32_t size[
 }
 int tvkr_load_dataset(tvkr_renderer* h, const char* uvf_file, uint64_t gpu_mem_bytes, int verify_checksum) {
   return h && uvf_file && R(h)->LoadDataset(uvf_file, gpu_mem_bytes, verify_checksum != 0) ? 0 : 1;
+}
+int tvkr_load_streamed_begin(tvkr_renderer* h, const uint32_t size[3], uint32_t bpv, const float scale[3], uint32_t brick, uint32_t overlap, int median) {
+  return h && size && R(h)->LoadStreamedBegin(size, bpv, scale, brick, overlap, median != 0) ? 0 : 1;
+}
+int tvkr_load_streamed_rows(tvkr_renderer* h, uint32_t bz0, uint32_t bz1, uint32_t* z0, uint32_t* rows) {
+  return h && z0 && rows && R(h)->LoadStreamedRows(bz0, bz1, *z0, *rows) ? 0 : 1;
+}
+int tvkr_load_streamed_slab(tvkr_renderer* h, const void* device_slab, uint32_t z0, uint32_t rows, uint32_t bz0, uint32_t bz1) {
+  return h && device_slab && R(h)->LoadStreamedSlab(device_slab, z0, rows, bz0, bz1) ? 0 : 1;
+}
+int tvkr_load_streamed_end(tvkr_renderer* h, uint64_t gpu_mem_bytes, float* builder_kernel_ms) {
+  if (!h || !R(h)->LoadStreamedEnd(gpu_mem_bytes)) return 1;
+  if (builder_kernel_ms) *builder_kernel_ms = R(h)->LastBuildMs();
+  return 0;
 }
 int tvkr_load_volume_file(tvkr_renderer* h, const char* path, uint32_t brick, uint32_t overlap, int median, int out_of_core,
                           uint64_t gpu_mem_bytes, int hist2d) {

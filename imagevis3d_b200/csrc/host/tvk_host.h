@@ -199,6 +199,15 @@ class CudaGridLeaper {
   bool LoadRawVolume(const void* raw, const uint32_t size[3], uint32_t bytesPerVoxel, const float scale[3],
                      uint32_t brickSize, uint32_t overlap, bool median, bool outOfCore, uint64_t gpuMemBytes,
                      bool computeHist2D, bool rawOnDevice = false);
+  // Volumes larger than device memory: the flat volume arrives in z-slabs of whole brick rows (device pointers), the streamed
+  // builder (tvk_build_stream_*) cuts the bricks STRAIGHT INTO THE PINNED HOST STORE the pager reads from; nothing but one
+  // slab, the coarser flat levels (1/7 of the raw size) and the pool is ever resident.  Begin -> Rows/Slab... -> End.
+  bool LoadStreamedBegin(const uint32_t size[3], uint32_t bytesPerVoxel, const float scale[3], uint32_t brickSize, uint32_t overlap,
+                         bool median);
+  bool LoadStreamedRows(uint32_t bz0, uint32_t bz1, uint32_t& z0, uint32_t& rows) const;
+  bool LoadStreamedSlab(const void* deviceSlab, uint32_t z0, uint32_t rows, uint32_t bz0, uint32_t bz1);
+  bool LoadStreamedEnd(uint64_t gpuMemBytes);
+  float LastBuildMs() const { return m_lastBuildMs; }
   // "open a .dat / .nrrd file": raw front end (tvk_raw_probe / tvk_raw_read) -> quantisation on the device (tvk_quantize)
   // -> LoadRawVolume; single-component volumes of any of the ten element types
   bool LoadVolumeFile(const std::string& path, uint32_t brickSize, uint32_t overlap, bool median, bool outOfCore, uint64_t gpuMemBytes,
@@ -326,6 +335,9 @@ class CudaGridLeaper {
   bool m_clipEnabled = false;
   float m_clipPlane[4] = {0, 0, 1, 0};
   uint32_t m_lodLimits[2] = {0, 0};
+  BrickedVolume* m_streamVol = nullptr;      // between LoadStreamedBegin and LoadStreamedEnd
+  tvk_build_desc m_streamDesc{};
+  float m_lastBuildMs = 0.0f;
   tvkr_lod_state m_ladder{0, {-1.0f, -1.0f}, 10000.0f, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   uint32_t m_currentLOD = 0;
   float m_msOverride = -1.0f, m_msCurrentFrame = 0.0f;

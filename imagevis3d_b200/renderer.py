@@ -89,6 +89,27 @@ class Renderer:
         self._ck(self._lib.tvkr_load_volume_file(self._h, filename.encode(), C.c_uint32(brick_size), C.c_uint32(overlap), C.c_int(int(median)),
                                                  C.c_int(int(out_of_core)), C.c_uint64(int(gpu_mem_bytes)), C.c_int(int(hist2d))), "loadVolumeFile")
 
+    def loadStreamed(self, size, bpv, gen, scale=(1, 1, 1), brick_size=64, overlap=2, median=False, gpu_mem_bytes=0, slab_bytes=4 << 30):
+        """Volumes larger than device memory: gen(z0, rows) -> object with .data_ptr() holding raw rows [z0, z0 + rows) in device
+        memory (e.g. a torch tensor); the streamed builder cuts the bricks into the pinned host store.  -> builder kernel ms"""
+        size = [int(v) for v in size]
+        self._ck(self._lib.tvkr_load_streamed_begin(self._h, (C.c_uint32 * 3)(*size), C.c_uint32(bpv), (C.c_float * 3)(*scale),
+                                                    C.c_uint32(brick_size), C.c_uint32(overlap), C.c_int(int(median))), "loadStreamed begin")
+        core = brick_size - 2 * overlap
+        nbz = -(-size[2] // core)
+        per = max(1, int(slab_bytes // (size[0] * size[1] * bpv * core)))
+        for b0 in range(0, nbz, per):
+            b1 = min(nbz, b0 + per)
+            z0, rows = C.c_uint32(), C.c_uint32()
+            self._ck(self._lib.tvkr_load_streamed_rows(self._h, C.c_uint32(b0), C.c_uint32(b1), C.byref(z0), C.byref(rows)), "loadStreamed rows")
+            slab = gen(z0.value, rows.value)
+            self._ck(self._lib.tvkr_load_streamed_slab(self._h, C.c_void_p(int(slab.data_ptr())), z0, rows, C.c_uint32(b0), C.c_uint32(b1)),
+                     "loadStreamed slab")
+            del slab
+        ms = C.c_float()
+        self._ck(self._lib.tvkr_load_streamed_end(self._h, C.c_uint64(int(gpu_mem_bytes)), C.byref(ms)), "loadStreamed end")
+        return float(ms.value)
+
     def storeIsCompressed(self):
         return bool(self._lib.tvkr_store_is_compressed(self._h))
 

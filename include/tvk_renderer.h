@@ -147,6 +147,15 @@ typedef struct tvk_raw_desc {
   char     title[64];
   char     data_file[1024];      /* strIntermediateFile: where the voxels are                                      */
 } tvk_raw_desc;
+/* Volumes larger than device memory (configs[4]): the flat volume is fed in z-slabs of whole LOD-0 brick rows (DEVICE
+ * pointers; tvkr_load_streamed_rows tells which raw rows a slab must hold), the streamed builder cuts the bricks straight into
+ * the pinned host store the pager reads from.  _end finishes the coarser levels, creates the pool (gpu_mem_bytes budget) and
+ * reports the builder's kernel time.  No 2-D histogram (it needs the flat volume). */
+int tvkr_load_streamed_begin(tvkr_renderer* r, const uint32_t size[3], uint32_t bytes_per_voxel, const float scale[3], uint32_t brick_size,
+                             uint32_t overlap, int median);
+int tvkr_load_streamed_rows(tvkr_renderer* r, uint32_t bz0, uint32_t bz1, uint32_t* z0, uint32_t* rows);
+int tvkr_load_streamed_slab(tvkr_renderer* r, const void* device_slab, uint32_t z0, uint32_t rows, uint32_t bz0, uint32_t bz1);
+int tvkr_load_streamed_end(tvkr_renderer* r, uint64_t gpu_mem_bytes, float* builder_kernel_ms);
 int tvk_raw_probe(const char* path, tvk_raw_desc* out, char* err, size_t errlen);
 int tvk_raw_read(const tvk_raw_desc* d, void* dst, uint64_t dst_bytes, char* err, size_t errlen);
 int tvkr_load_volume_file(tvkr_renderer* r, const char* path, uint32_t brick_size, uint32_t overlap, int median, int out_of_core,

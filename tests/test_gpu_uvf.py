@@ -163,7 +163,7 @@ def test_reference_lz4_file_inflates_on_the_device(tvk, tmp_path):
     path = golden_file("ref_u8_lz4", tmp_path)
     f = U.UvfFile(path)
     off, ln, comp, sizes = f.toc()
-    assert (comp == 2).all()
+    assert (comp == 3).all()                     # TVK_UVF_COMP_LZ4
     want = f.read_bricks()
     raw = f.read_bricks_raw()
     blocks, pos = [], 0
