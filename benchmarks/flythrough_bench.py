@@ -59,29 +59,40 @@ def camera_path(keys, frames):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--size", default="1024", help="N or XxYxZ")
+    ap.add_argument("--bits", type=int, default=8)
     ap.add_argument("--frames", type=int, default=120)
     ap.add_argument("--pool-mb", type=int, default=384)
     ap.add_argument("--res", default="1920x1080")
+    ap.add_argument("--streamed", action="store_true",
+                    help="generate and brick the volume slab by slab straight into pinned host memory (volumes larger than HBM)")
     args = ap.parse_args()
     import torch
     import bench as B
     from imagevis3d_b200.renderer import Renderer, RT_HEADLESS
     w, h = [int(v) for v in args.res.split("x")]
-    n = args.size
+    dims = [int(v) for v in args.size.split("x")]
+    dims = dims * 3 if len(dims) == 1 else dims
+    bits = args.bits
     dev = torch.device("cuda", 0)
-    raw = torch.empty((n, n, n), dtype=torch.uint8, device=dev)
-    for z0 in range(0, n, 64):
-        raw[z0:z0 + 64] = B.volume_torch((n, n, n), dev, z0=z0, zn=min(64, n - z0), ztotal=n)
-    vol = raw.cpu().numpy()
-    del raw
-    torch.cuda.empty_cache()
     r = Renderer(0)
+    r.setState(hash_table_size=4093, rehash_count=16)
     t0 = time.perf_counter()
-    r.loadRawVolume(vol, brick_size=64, overlap=2, out_of_core=True, gpu_mem_bytes=args.pool_mb << 20)
+    build_ms = None
+    if args.streamed:
+        build_ms = r.loadStreamed(dims, bits // 8, lambda z0, rows: B.sphere_torch((dims[0], dims[1], rows), (0, 0, z0), dims, bits, dev),
+                                  gpu_mem_bytes=args.pool_mb << 20)
+    else:
+        raw = B.sphere_torch(dims, (0, 0, 0), dims, bits, dev)
+        vol = raw.cpu().numpy() if bits == 8 else raw.view(torch.int16).cpu().numpy().view(np.uint16)
+        del raw
+        torch.cuda.empty_cache()
+        r.loadRawVolume(vol, brick_size=64, overlap=2, out_of_core=True, gpu_mem_bytes=args.pool_mb << 20)
+        del vol
     t_load = time.perf_counter() - t0
+    torch.cuda.empty_cache()
     info = r.datasetInfo()
-    tf, lo, hi = B.bench_tf()
+    tf, lo, hi = B.tf1d_std(info.tf_size)
     r.set1DTrans(tf)
     r.setLightingEnabled(False)
     r.resize((w, h))
@@ -96,6 +107,8 @@ def main():
             dict(eye=V(-0.9, 0.1, -1.4), ref=V(0.6, -0.1, 1), vup=V(0, 1, 0))]
     path = camera_path(keys, args.frames)
     passes = {}
+    clock = B.ClockSampler(0)
+    clock.start()
     for name in ("cold", "warm"):
         if name == "cold":
             r.clearWorkingSet()
@@ -116,11 +129,23 @@ def main():
                         "paged_bricks_per_frame": paged / len(path), "uploaded_GB": up / 1e9,
                         "h2d_GBps_over_pass": up / dt / 1e9, "raycast_ms_per_frame": (p1["raycast_ms"] - p0["raycast_ms"]) / len(path),
                         "samples_per_s": (p1["samples"] - p0["samples"]) / dt}
+    clocks = clock.stop()
     cap = list(info.pool_capacity)
-    print(json.dumps({"bench": "out-of-core fly-through", "volume": [n, n, n], "bpv": 1, "resolution": [w, h], "frames": len(path),
-                      "total_bricks": int(info.total_bricks), "pool_slots": cap[0] * cap[1] * cap[2],
-                      "pool_capacity": cap, "pool_budget_MB": args.pool_mb, "load_s_incl_build_and_pinned_copy": t_load,
-                      "cold": passes["cold"], "warm": passes["warm"]}))
+    voxels = float(dims[0]) * dims[1] * dims[2]
+    host = {}
+    try:
+        with open("/proc/meminfo") as f:
+            host = {ln.split(":")[0]: int(ln.split()[1]) for ln in f if ln.split(":")[0] in ("MemTotal", "MemAvailable")}
+    except OSError:
+        pass
+    out = {"bench": "out-of-core fly-through (BASELINE configs[4], FlyThroughAnimator.lua path)", "volume": dims, "bpv": bits // 8,
+           "raw_GB": voxels * bits / 8 / 1e9, "resolution": [w, h], "frames": len(path), "total_bricks": int(info.total_bricks),
+           "pool_slots": cap[0] * cap[1] * cap[2], "pool_capacity": cap, "pool_budget_MB": args.pool_mb,
+           "load_s_incl_generation_build_and_host_store": t_load, "streamed_build": bool(args.streamed),
+           "builder_kernel_ms": build_ms,
+           "builder_algorithmic_GBps": (2.387 * bits / 8 * voxels / (build_ms * 1e-3) / 1e9) if build_ms else None,
+           "host_mem_kB": host, "clocks": clocks, "cold": passes["cold"], "warm": passes["warm"]}
+    print(json.dumps(out))
     r.cleanup()
 
 
