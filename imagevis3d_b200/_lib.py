@@ -41,7 +41,8 @@ class RaycastParams(C.Structure):
                 ("iso_color", C.c_float * 3), ("compose_light_dir", C.c_float * 3),
                 ("new_view", C.c_uint32), ("missing_strategy", C.c_uint32), ("rehash_count", C.c_uint32),
                 ("hash_table_size", C.c_uint32), ("clip_enabled", C.c_uint32), ("clip_plane", C.c_float * 4),
-                ("box_min", C.c_float * 3), ("box_max", C.c_float * 3), ("count_samples", C.c_uint32)]
+                ("box_min", C.c_float * 3), ("box_max", C.c_float * 3), ("count_samples", C.c_uint32),
+                ("model_pos_scale_m1", C.c_float * 3), ("model_pos_offset", C.c_float * 3)]
 
 
 class Stats(C.Structure):

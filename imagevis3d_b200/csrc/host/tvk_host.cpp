@@ -473,6 +473,84 @@ void CudaGridLeaper::Cleanup() {
   if (m_ctx) { tvk_destroy(m_ctx); m_ctx = nullptr; }
 }
 
+// ---------------------------------------------------------------------------- sort-last members
+bool CudaGridLeaper::SortLastConfigure(uint32_t members, uint32_t member, const uint32_t g[3], const uint32_t lo[3], const uint32_t hi[3],
+                                       const uint32_t start[3], double globalMaxValue) {
+  if (!m_vol) { m_err = "sort-last: load the box first"; return false; }
+  if (!members || member >= members) { m_err = "sort-last: bad member index"; return false; }
+  for (int a = 0; a < 3; ++a)
+    if (!(start[a] <= lo[a] && lo[a] < hi[a] && hi[a] <= start[a] + m_vol->domain[a] && start[a] + m_vol->domain[a] <= g[a])) {
+      m_err = "sort-last: the owned box must lie inside the loaded box, and that inside the global volume"; return false;
+    }
+  m_sl = SortLast();
+  m_sl.on = true; m_sl.members = members; m_sl.member = member; m_sl.maxValue = globalMaxValue;
+  m_visValid = false;
+  for (int a = 0; a < 3; ++a) { m_sl.global[a] = g[a]; m_sl.lo[a] = lo[a]; m_sl.hi[a] = hi[a]; m_sl.start[a] = start[a]; }
+  ScheduleCompleteRedraw();
+  return true;
+}
+
+bool CudaGridLeaper::SortLastExchangeCreate(void* handle64) {
+  if (!m_sl.on || !m_w || !m_h) { m_err = "sort-last: configure and resize first"; return false; }
+  const int rc = tvk_exchange_create(m_ctx, m_sl.members, m_sl.member, m_w, m_h, handle64);
+  if (rc) return Fail("tvk_exchange_create", rc);
+  m_sl.exchange = false;
+  return true;
+}
+
+bool CudaGridLeaper::SortLastExchangeConnect(const void* handles, void* const* bases) {
+  if (!m_sl.on) { m_err = "sort-last: not configured"; return false; }
+  const int rc = tvk_exchange_connect(m_ctx, handles, bases);
+  if (rc) return Fail("tvk_exchange_connect", rc);
+  m_sl.exchange = true;
+  return true;
+}
+
+bool CudaGridLeaper::SortLastBeginFrame() {
+  if (!m_sl.on || !m_sl.exchange) { m_err = "sort-last: exchange not connected"; return false; }
+  m_sl.frame++;
+  return true;
+}
+
+bool CudaGridLeaper::SortLastComposite(const uint32_t* order) {
+  if (!m_sl.on || !m_sl.exchange || !m_sl.frame || !order) { m_err = "sort-last: nothing to composite"; return false; }
+  const int rc = tvk_exchange_composite(m_ctx, order, m_sl.frame);
+  return rc ? Fail("tvk_exchange_composite", rc) : true;
+}
+
+// sortlast.depth_order: along every axis a ray moves monotonically, so sorting the boxes by the per-axis distances of their
+// intervals from the eye (a tuple, lexicographic) is a linear extension of the visibility order of a regular grid of boxes
+void CudaGridLeaper::SortLastDepthOrder(const uint32_t* b, uint32_t* order) {
+  float ext[3], mx = 0;
+  for (int a = 0; a < 3; ++a) { ext[a] = float(m_sl.global[a]) * (m_vol ? m_vol->scale[a] : 1.0f); mx = std::max(mx, ext[a]); }
+  for (int a = 0; a < 3; ++a) ext[a] /= mx;
+  const Matrix4 mv = m_rotation * m_translation * Matrix4::LookAt(m_eye, m_at, m_up);
+  const Matrix4 emm = mv.inverse() * Matrix4::Scaling(1.0f / ext[0], 1.0f / ext[1], 1.0f / ext[2]) * Matrix4::Translation(0.5f, 0.5f, 0.5f);
+  const float o4[4] = {0, 0, 0, 1};
+  float eye[4];
+  emm.transform(o4, eye);                                 // the eye in global normalised coordinates
+  struct Key { double k[3]; uint32_t r; };
+  std::vector<Key> keys(m_sl.members);
+  for (uint32_t r = 0; r < m_sl.members; ++r) {
+    keys[r].r = r;
+    for (int a = 0; a < 3; ++a) {
+      const double lo = double(b[6 * r + a]) / m_sl.global[a], hi = double(b[6 * r + 3 + a]) / m_sl.global[a];
+      keys[r].k[a] = std::max(std::max(lo - double(eye[a]), 0.0), double(eye[a]) - hi);
+    }
+  }
+  std::sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) {
+    for (int a = 0; a < 3; ++a) if (x.k[a] != y.k[a]) return x.k[a] < y.k[a];
+    return x.r < y.r;
+  });
+  for (uint32_t i = 0; i < m_sl.members; ++i) order[i] = keys[i].r;
+}
+
+bool CudaGridLeaper::SortLastReadFrameRGBA8(uint8_t* out, bool flipRows) {
+  if (!m_sl.on || !m_sl.exchange || !m_sl.frame || m_sl.member != 0) { m_err = "sort-last: the finished frame lands on member 0"; return false; }
+  const int rc = tvk_exchange_read_final_rgba8(m_ctx, m_sl.frame, out, flipRows ? 1 : 0);
+  return rc ? Fail("tvk_exchange_read_final_rgba8", rc) : true;
+}
+
 bool CudaGridLeaper::LoadStreamedBegin(const uint32_t size[3], uint32_t bpv, const float scale[3], uint32_t brickSize, uint32_t overlap,
                                        bool median) {
   if (!m_ctx) { m_err = "renderer not initialised"; return false; }
@@ -933,7 +1011,8 @@ bool CudaGridLeaper::RecomputeBrickVisibility(bool force) {                  // 
   if (!m_pool || !m_vol) return false;
   double lo, hi;
   m_vol->Range(lo, hi);
-  const double maxValue = (lo > hi) ? double(m_tf1d.GetSize()) : hi;
+  double maxValue = (lo > hi) ? double(m_tf1d.GetSize()) : hi;
+  if (m_sl.on && m_sl.maxValue > 0) maxValue = m_sl.maxValue;          // sort-last: the table spans the global value range
   const double rescale = maxValue / double(m_tf1d.GetSize() - 1);
   tvk_visibility v{};
   v.render_mode = (uint32_t)m_mode;
@@ -968,8 +1047,9 @@ bool CudaGridLeaper::ComputeRaycastParams(tvk_raycast_params& p) {
   memset(&p, 0, sizeof(p));
   p.width = m_w; p.height = m_h;
   // GetVolumeAABB (AbstrRenderer.cpp:1102-1109)
-  float ext[3], mx = 0;
-  for (int a = 0; a < 3; ++a) { ext[a] = float(m_vol->domain[a]) * m_vol->scale[a]; mx = std::max(mx, ext[a]); }
+  // (sort-last: the volume the camera sees is the GLOBAL one; this member holds a box of it)
+  float dom[3], ext[3], mx = 0;
+  for (int a = 0; a < 3; ++a) { dom[a] = m_sl.on ? float(m_sl.global[a]) : float(m_vol->domain[a]); ext[a] = dom[a] * m_vol->scale[a]; mx = std::max(mx, ext[a]); }
   for (int a = 0; a < 3; ++a) ext[a] /= mx;
   // GLRenderer::ComputeViewAndProjection (:888-920) and Paint (:627)
   const float aspect = float(m_w) / float(m_h);
@@ -977,8 +1057,19 @@ bool CudaGridLeaper::ComputeRaycastParams(tvk_raycast_params& p) {
   const Matrix4 proj = Matrix4::Perspective(m_fov, aspect, m_znear, m_zfar);
   const Matrix4 mv = m_rotation * m_translation * view;
   // ComputeEyeToModelMatrix (GLGridLeaper.cpp:560-573), centre = 0
-  const Matrix4 emm = mv.inverse() * Matrix4::Translation(0, 0, 0) * Matrix4::Scaling(1.0f / ext[0], 1.0f / ext[1], 1.0f / ext[2]) *
-                      Matrix4::Translation(0.5f, 0.5f, 0.5f);
+  Matrix4 emm = mv.inverse() * Matrix4::Translation(0, 0, 0) * Matrix4::Scaling(1.0f / ext[0], 1.0f / ext[1], 1.0f / ext[2]) *
+                Matrix4::Translation(0.5f, 0.5f, 0.5f);
+  const Matrix4 emmGlobal = emm;                        // lighting lives in the global volume's model space
+  if (m_sl.on) {
+    // global normalised coordinates -> this box's: scale by global / local size, shift by the box's start
+    const float ld[3] = {float(m_vol->domain[0]), float(m_vol->domain[1]), float(m_vol->domain[2])};
+    emm = emm * Matrix4::Scaling(dom[0] / ld[0], dom[1] / ld[1], dom[2] / ld[2]) *
+          Matrix4::Translation(-float(m_sl.start[0]) / ld[0], -float(m_sl.start[1]) / ld[1], -float(m_sl.start[2]) / ld[2]);
+    for (int a = 0; a < 3; ++a) {
+      p.model_pos_scale_m1[a] = float(double(ld[a]) / double(dom[a]) - 1.0);
+      p.model_pos_offset[a] = float(double(m_sl.start[a]) / double(dom[a]));
+    }
+  }
   memcpy(p.eye_to_model, emm.m, 64);
   memcpy(p.model_to_eye, emm.inverse().m, 64);
   memcpy(p.model_view_it, mv.inverse().transposed().m, 64);
@@ -986,13 +1077,14 @@ bool CudaGridLeaper::ComputeRaycastParams(tvk_raycast_params& p) {
   // CullingLOD::SetScreenParams (CullingLOD.cpp:65-66), screen space error 1
   p.lod_factor = 2.0f * (float)tan(m_fov * ((3.1416f / 180.0f) / 2.0f)) * 1.0f / float(m_h);
   float wse = 0;
-  for (int a = 0; a < 3; ++a) wse = std::max(wse, ext[a] / float(m_vol->domain[a]));   // GLVolumePool.cpp:801
+  for (int a = 0; a < 3; ++a) wse = std::max(wse, ext[a] / dom[a]);   // GLVolumePool.cpp:801 (sort-last: of the global volume)
   p.level_zero_wse = wse;
   p.sample_rate_modifier = m_sampleRate;
   // CalculateScaling (GLRenderer.cpp:1813-1819) / MaxValue (AbstrRenderer.cpp:860-866)
   double lo, hi;
   m_vol->Range(lo, hi);
-  const double maxValue = (lo > hi) ? double(m_tf1d.GetSize()) : hi;
+  double maxValue = (lo > hi) ? double(m_tf1d.GetSize()) : hi;
+  if (m_sl.on && m_sl.maxValue > 0) maxValue = m_sl.maxValue;          // the transfer function spans the GLOBAL value range
   const uint32_t iMax = (1u << (8 * m_vol->bpv)) - 1;
   p.trans_scale = float(iMax / maxValue);
   p.gradient_scale = (m_vol->max_grad_magnitude == 0) ? 1.0f : 1.0f / m_vol->max_grad_magnitude;
@@ -1008,10 +1100,10 @@ bool CudaGridLeaper::ComputeRaycastParams(tvk_raycast_params& p) {
   }
   const float l4[4] = {m_lightDir.x, m_lightDir.y, m_lightDir.z, 0.0f}, e4[4] = {m_eye.x, m_eye.y, m_eye.z, 1.0f};
   float o[4];
-  emm.transform(l4, o);
+  emmGlobal.transform(l4, o);
   const Vec3 ml = Vec3(o[0], o[1], o[2]).normalized();
   p.model_light_dir[0] = ml.x; p.model_light_dir[1] = ml.y; p.model_light_dir[2] = ml.z;
-  emm.transform(e4, o);                                 // sic: the world-space eye through eye->model (:735)
+  emmGlobal.transform(e4, o);                           // sic: the world-space eye through eye->model (:735)
   p.model_eye_pos[0] = o[0]; p.model_eye_pos[1] = o[1]; p.model_eye_pos[2] = o[2];
   p.iso_color[0] = m_isoColor.x; p.iso_color[1] = m_isoColor.y; p.iso_color[2] = m_isoColor.z;
   p.compose_light_dir[0] = m_lightDir.x; p.compose_light_dir[1] = m_lightDir.y; p.compose_light_dir[2] = m_lightDir.z;
@@ -1035,6 +1127,11 @@ bool CudaGridLeaper::ComputeRaycastParams(tvk_raycast_params& p) {
     }
   }
   for (int a = 0; a < 3; ++a) { p.box_min[a] = 0.0f; p.box_max[a] = 1.0f; }
+  if (m_sl.on)
+    for (int a = 0; a < 3; ++a) {
+      p.box_min[a] = float((double(m_sl.lo[a]) - double(m_sl.start[a])) / double(m_vol->domain[a]));
+      p.box_max[a] = float((double(m_sl.hi[a]) - double(m_sl.start[a])) / double(m_vol->domain[a]));
+    }
   p.count_samples = 1;
   return true;
 }
@@ -1376,6 +1473,13 @@ bool CudaGridLeaper::Paint() {                                               // 
   tvk_raycast_params p;
   if (!ComputeRaycastParams(p)) return false;
   if (m_blank) { m_perf.frames += 1; }
+  if (m_sl.on && m_sl.exchange) {
+    // every sub-frame of the displayed frame sends its pixels (tagged with the frame number) to the stripe owners; the
+    // owners blend when the application says every member has converged (SortLastComposite)
+    if (!m_sl.frame) { m_err = "sort-last: Paint() before SortLastBeginFrame()"; return false; }
+    const int xr = tvk_exchange_begin_frame(m_ctx, m_sl.frame);
+    if (xr) return Fail("tvk_exchange_begin_frame", xr);
+  }
   // the march is queued behind whatever upload the previous sub-frame left in flight (tvk_pool_upload_fence)
   int rc = tvk_raycast_subframe(m_ctx, &p);
   if (rc) return Fail("tvk_raycast_subframe", rc);
@@ -1533,6 +1637,24 @@ int tvkr_load_raw_volume(tvkr_renderer* h, const void* raw, const uint32_t size[
 int tvkr_load_dataset(tvkr_renderer* h, const char* uvf_file, uint64_t gpu_mem_bytes, int verify_checksum) {
   return h && uvf_file && R(h)->LoadDataset(uvf_file, gpu_mem_bytes, verify_checksum != 0) ? 0 : 1;
 }
+int tvkr_sortlast_configure(tvkr_renderer* h, uint32_t members, uint32_t member, const uint32_t global_size[3], const uint32_t lo[3],
+                            const uint32_t hi[3], const uint32_t start[3], double global_max_value) {
+  return h && global_size && lo && hi && start && R(h)->SortLastConfigure(members, member, global_size, lo, hi, start, global_max_value) ? 0 : 1;
+}
+int tvkr_sortlast_exchange_create(tvkr_renderer* h, void* handle64) { return h && R(h)->SortLastExchangeCreate(handle64) ? 0 : 1; }
+int tvkr_sortlast_exchange_connect(tvkr_renderer* h, const void* handles, void* const* bases) { return h && R(h)->SortLastExchangeConnect(handles, bases) ? 0 : 1; }
+int tvkr_sortlast_exchange_base(tvkr_renderer* h, uint32_t member, void** base) {
+  if (!h || !base) return 1;
+  return tvk_exchange_peer_base(R(h)->Context(), member, base) == TVK_OK ? 0 : 1;
+}
+int tvkr_sortlast_begin_frame(tvkr_renderer* h) { return h && R(h)->SortLastBeginFrame() ? 0 : 1; }
+int tvkr_sortlast_composite(tvkr_renderer* h, const uint32_t* order) { return h && R(h)->SortLastComposite(order) ? 0 : 1; }
+int tvkr_sortlast_depth_order(tvkr_renderer* h, const uint32_t* boxes_lo_hi, uint32_t* order) {
+  if (!h || !boxes_lo_hi || !order || !R(h)->SortLastActive()) return 1;
+  R(h)->SortLastDepthOrder(boxes_lo_hi, order);
+  return 0;
+}
+int tvkr_sortlast_read_frame_rgba8(tvkr_renderer* h, uint8_t* out, int flip_rows) { return h && out && R(h)->SortLastReadFrameRGBA8(out, flip_rows != 0) ? 0 : 1; }
 int tvkr_load_streamed_begin(tvkr_renderer* h, const uint32_t size[3], uint32_t bpv, const float scale[3], uint32_t brick, uint32_t overlap, int median) {
   return h && size && R(h)->LoadStreamedBegin(size, bpv, scale, brick, overlap, median != 0) ? 0 : 1;
 }

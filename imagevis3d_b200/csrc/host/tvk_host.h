@@ -199,6 +199,21 @@ class CudaGridLeaper {
   bool LoadRawVolume(const void* raw, const uint32_t size[3], uint32_t bytesPerVoxel, const float scale[3],
                      uint32_t brickSize, uint32_t overlap, bool median, bool outOfCore, uint64_t gpuMemBytes,
                      bool computeHist2D, bool rawOnDevice = false);
+  // ---- sort-last over several GPUs (`tuvok.state.gpuCount` / compositor in MasterController terms): the loaded
+  // volume is ONE BOX of a larger global volume -- voxels [start, start + domain) of it, of which this member owns [lo, hi)
+  // (the rest is halo) -- and the member is one of `members` exchange members (one per box; several per process are fine).
+  // The camera, the LOD selection and the transfer-function scaling then refer to the GLOBAL volume, rays are clipped to the
+  // owned box, every Paint() sends its pixels to the scan-line stripe owners (fused direct send, tvk_exchange_*), and
+  // SortLastComposite blends this member's stripe once every member has converged.
+  bool SortLastConfigure(uint32_t members, uint32_t member, const uint32_t globalSize[3], const uint32_t lo[3], const uint32_t hi[3],
+                         const uint32_t start[3], double globalMaxValue);
+  bool SortLastExchangeCreate(void* handle64);                         // after Resize: tvk_exchange_create
+  bool SortLastExchangeConnect(const void* handles, void* const* bases);
+  bool SortLastBeginFrame();                                           // once per displayed frame, on every member
+  bool SortLastComposite(const uint32_t* order);                       // after all members have converged
+  void SortLastDepthOrder(const uint32_t* boxesLoHi, uint32_t* order); // members x 6 (lo xyz, hi xyz) -> front-to-back order
+  bool SortLastReadFrameRGBA8(uint8_t* out, bool flipRows);            // member 0: the finished frame
+  bool SortLastActive() const { return m_sl.on; }
   // Volumes larger than device memory: the flat volume arrives in z-slabs of whole brick rows (device pointers), the streamed
   // builder (tvk_build_stream_*) cuts the bricks STRAIGHT INTO THE PINNED HOST STORE the pager reads from; nothing but one
   // slab, the coarser flat levels (1/7 of the raw size) and the pool is ever resident.  Begin -> Rows/Slab... -> End.
@@ -335,6 +350,8 @@ class CudaGridLeaper {
   bool m_clipEnabled = false;
   float m_clipPlane[4] = {0, 0, 1, 0};
   uint32_t m_lodLimits[2] = {0, 0};
+  struct SortLast { bool on = false; uint32_t members = 1, member = 0, global[3] = {0, 0, 0}, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0},
+                    start[3] = {0, 0, 0}, frame = 0; double maxValue = 0; bool exchange = false; } m_sl;
   BrickedVolume* m_streamVol = nullptr;      // between LoadStreamedBegin and LoadStreamedEnd
   tvk_build_desc m_streamDesc{};
   float m_lastBuildMs = 0.0f;

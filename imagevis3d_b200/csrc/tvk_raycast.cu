@@ -494,6 +494,9 @@ __device__ __forceinline__ float pow8(float x) { x *= x; x *= x; return x * x; }
 
 // Lighting, lighting.glsl:33-43
 __device__ __forceinline__ f3 lighting(const tvk_raycast_params& p, f3 pos, f3 n, f3 diffuse) {
+  // (sort-last: box-local model position -> the global volume's; identity when the fields are zero: fmaf(x, 1, 0) == x)
+  pos = mk3(fmaf(pos.x, 1.0f + p.model_pos_scale_m1[0], p.model_pos_offset[0]), fmaf(pos.y, 1.0f + p.model_pos_scale_m1[1], p.model_pos_offset[1]),
+            fmaf(pos.z, 1.0f + p.model_pos_scale_m1[2], p.model_pos_offset[2]));
   f3 v = mk3(p.model_eye_pos[0] - pos.x, p.model_eye_pos[1] - pos.y, p.model_eye_pos[2] - pos.z);
   float il = rsqrtf(dot3(v, v));
   v = mk3(v.x * il, v.y * il, v.z * il);

@@ -107,6 +107,8 @@ def raycast_params(cam, width, height, domain_size, scale=(1, 1, 1), render_mode
     emm = (inverse(mv) @ scaling(*(f32(1) / extent)) @ translation(0.5, 0.5, 0.5)).astype(f32)
     box_min, box_max = [0.0, 0.0, 0.0], [1.0, 1.0, 1.0]
     wse = float((extent / dom).max())
+    emm_global = emm
+    pos_scale_m1, pos_offset = [0.0, 0.0, 0.0], [0.0, 0.0, 0.0]
     if slab is not None:
         # sort-last partition: this rank holds voxels [zs, ze) of the global volume (its own slab
         # [z0, z1) plus a halo) as ITS volume; map global normalised coords to the local ones and
@@ -122,6 +124,8 @@ def raycast_params(cam, width, height, domain_size, scale=(1, 1, 1), render_mode
                translation(-s3[0] / float(ld[0]), -s3[1] / float(ld[1]), -s3[2] / float(ld[2]))).astype(f32)
         for a in range(3):
             box_min[a], box_max[a] = (lo3[a] - s3[a]) / float(ld[a]), (hi3[a] - s3[a]) / float(ld[a])
+            # lighting happens in the GLOBAL volume's model space: local position * ld/dom + s/dom
+            pos_scale_m1[a], pos_offset[a] = float(ld[a]) / float(dom[a]) - 1.0, float(s3[a]) / float(dom[a])
     p.eye_to_model[:] = emm.reshape(-1).tolist()
     p.model_to_eye[:] = inverse(emm).reshape(-1).tolist()
     p.model_view_it[:] = inverse(mv).T.reshape(-1).tolist()
@@ -134,9 +138,11 @@ def raycast_params(cam, width, height, domain_size, scale=(1, 1, 1), render_mode
     p.light_ambient[:] = (cam.ambient[:3] * cam.ambient[3]).tolist()
     p.light_diffuse[:] = (cam.diffuse[:3] * cam.diffuse[3]).tolist()
     p.light_specular[:] = (cam.specular[:3] * cam.specular[3]).tolist()
-    ld = (np.append(cam.light_dir, f32(0)) @ emm)[:3]
+    ld = (np.append(cam.light_dir, f32(0)) @ emm_global)[:3]
     p.model_light_dir[:] = (ld / f32(np.sqrt(f32(np.dot(ld, ld))))).tolist()
-    p.model_eye_pos[:] = (np.append(cam.eye, f32(1)) @ emm)[:3].tolist()
+    p.model_eye_pos[:] = (np.append(cam.eye, f32(1)) @ emm_global)[:3].tolist()
+    p.model_pos_scale_m1[:] = pos_scale_m1
+    p.model_pos_offset[:] = pos_offset
     p.domain_scale[:] = (f32(1) / (sc / sc.min())).tolist()
     p.iso_color[:] = cam.iso_color.tolist()
     p.compose_light_dir[:] = cam.light_dir.tolist()

@@ -351,3 +351,73 @@ class Renderer:
         out = (C.c_double * 6)()
         self._ck(self._lib.tvkr_get_perf(self._h, out), "perf")
         return dict(zip(("subframes", "raycast_ms", "paged_bricks", "uploaded_bytes", "samples", "frames"), list(out)))
+
+
+class SortLastGroup:
+    """Sort-last rendering through the renderer API only (tvkr_sortlast_*): one Renderer per box ("member"), any number of
+    them in this process (several boxes per GPU, or ranks emulated on one GPU); members of other processes join through their
+    IPC handles.  Mirrors what `tuvok.state.gpuCount = N` + a compositor choice would switch on in a Tuvok build."""
+
+    def __init__(self, renderers, member_ids, total_members, global_size, boxes, global_max_value, all_gather=None):
+        """boxes: for EVERY member i a dict lo / hi / s (as sortlast.block_partition gives them); renderers: the local members,
+        each with its box loaded and resized; all_gather(obj) -> list over processes (None: single process)"""
+        self.r, self.ids, self.n, self.boxes = list(renderers), list(member_ids), int(total_members), boxes
+        u3 = C.c_uint32 * 3
+        handles = {}
+        for r, m in zip(self.r, self.ids):
+            b = boxes[m]
+            r._ck(r._lib.tvkr_sortlast_configure(r._h, C.c_uint32(self.n), C.c_uint32(m), u3(*global_size), u3(*b["lo"]), u3(*b["hi"]),
+                                                 u3(*b["s"]), C.c_double(global_max_value)), "sortlast configure")
+            h = C.create_string_buffer(64)
+            r._ck(r._lib.tvkr_sortlast_exchange_create(r._h, h), "sortlast exchange create")
+            handles[m] = h.raw
+        table = [None] * self.n
+        for g in (all_gather(handles) if all_gather else [handles]):
+            for m, h in g.items():
+                table[m] = h
+        local = {}
+        for r, m in zip(self.r, self.ids):
+            p = C.c_void_p()
+            r._ck(r._lib.tvkr_sortlast_exchange_base(r._h, C.c_uint32(m), C.byref(p)), "sortlast base")
+            local[m] = p.value
+        first = self.r[0]
+        hb = b"".join((b"\0" * 64) if (m in local or table[m] is None) else table[m] for m in range(self.n))
+        bases = (C.c_void_p * self.n)(*[local.get(m) for m in range(self.n)])
+        first._ck(first._lib.tvkr_sortlast_exchange_connect(first._h, C.c_char_p(hb), bases), "sortlast connect")
+        allb = []
+        for m in range(self.n):
+            p = C.c_void_p()
+            first._ck(first._lib.tvkr_sortlast_exchange_base(first._h, C.c_uint32(m), C.byref(p)), "sortlast base")
+            allb.append(p.value)
+        for r in self.r[1:]:
+            r._ck(r._lib.tvkr_sortlast_exchange_connect(r._h, None, (C.c_void_p * self.n)(*allb)), "sortlast connect")
+        self._boxes6 = (C.c_uint32 * (6 * self.n))(*[int(v) for m in range(self.n) for v in list(boxes[m]["lo"]) + list(boxes[m]["hi"])])
+
+    def depth_order(self):
+        order = (C.c_uint32 * self.n)()
+        r = self.r[0]
+        r._ck(r._lib.tvkr_sortlast_depth_order(r._h, self._boxes6, order), "sortlast depth order")
+        return list(order)
+
+    def render(self, all_converged=None):
+        """one displayed frame: every local member paints until converged (its pixels travel while it marches), then -- once
+        all_converged() says the members of the other processes are done too -- the stripes are blended.  -> sub-frames painted"""
+        subs = 0
+        for r in self.r:
+            r._ck(r._lib.tvkr_sortlast_begin_frame(r._h), "sortlast begin frame")
+        for r in self.r:
+            subs += r.paintUntilConverged(4000)
+        if all_converged:
+            all_converged()
+        order = (C.c_uint32 * self.n)(*self.depth_order())
+        for r in self.r:
+            r._ck(r._lib.tvkr_sortlast_composite(r._h, order), "sortlast composite")
+        return subs
+
+    def frame_rgba8(self, flip_rows=True):
+        """member 0's process: the finished frame, top row first like Renderer.frameRGBA8 (FrameCapture::SaveImage's flip)"""
+        assert self.ids[0] == 0
+        r = self.r[0]
+        out = np.empty((r._size[1], r._size[0], 4), np.uint8)
+        r._ck(r._lib.tvkr_sortlast_read_frame_rgba8(r._h, out.ctypes.data_as(C.c_void_p), C.c_int(int(flip_rows))), "sortlast read frame")
+        return out

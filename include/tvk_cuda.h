@@ -195,6 +195,11 @@ typedef struct tvk_raycast_params {
   float box_min[3];                /* rays are clipped to this sub-box of the unit cube (normalised   */
   float box_max[3];                /* volume coords): {0,0,0}-{1,1,1}, or a sort-last partition       */
   uint32_t count_samples;          /* accumulate executed samples into the stats      */
+  /* sort-last: the volume of this context is one box of a larger one.  Lighting is evaluated in the GLOBAL volume's model
+   * space -- model_light_dir / model_eye_pos refer to it -- so a sample's (box-local) model position p is first taken there:
+   * p * (1 + model_pos_scale_m1) + model_pos_offset.  All zero = one volume, positions used as they are (bit-identical). */
+  float model_pos_scale_m1[3];
+  float model_pos_offset[3];
 } tvk_raycast_params;
 
 /* One sub-frame = one GLGridLeaper::Render3DRegion pass: clears the request

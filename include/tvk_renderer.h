@@ -147,6 +147,26 @@ typedef struct tvk_raw_desc {
   char     title[64];
   char     data_file[1024];      /* strIntermediateFile: where the voxels are                                      */
 } tvk_raw_desc;
+/* ---- sort-last over several GPUs: what `tuvok.state.gpuCount` + a compositor setting stand for.  Every GPU (or
+ * every box, when a GPU renders several) runs one renderer = one MEMBER; the dataset it loaded is one box of a global volume:
+ * voxels [start, start + domain) of it, of which the member owns [lo, hi) (the rest is halo for the filter, the gradients and
+ * the coarser LODs).  After tvkr_sortlast_configure the camera, LOD selection and TF scaling refer to the global volume and
+ * rays are clipped to the owned box.  Exchange = fused direct send (tvk_exchange_*): _exchange_create returns this member's
+ * 64-byte CUDA IPC handle, _exchange_connect takes all members' handles and / or base pointers already valid in this process
+ * (bases[i] != NULL wins; a sibling member's base comes from _exchange_base), exactly as tvk_exchange_connect.
+ * Per displayed frame, on every member: _begin_frame; paint() until converged() -- each sub-frame's pixels travel to the stripe
+ * owners while it marches; when the APPLICATION knows every member has converged: _composite(order) with the front-to-back
+ * order _depth_order gives for the current view (boxes: members x {lo xyz, hi xyz}); member 0 reads the frame. */
+int tvkr_sortlast_configure(tvkr_renderer* r, uint32_t members, uint32_t member, const uint32_t global_size[3], const uint32_t lo[3],
+                            const uint32_t hi[3], const uint32_t start[3], double global_max_value);
+int tvkr_sortlast_exchange_create(tvkr_renderer* r, void* handle64);
+int tvkr_sortlast_exchange_connect(tvkr_renderer* r, const void* handles, void* const* bases);
+int tvkr_sortlast_exchange_base(tvkr_renderer* r, uint32_t member, void** base);
+int tvkr_sortlast_begin_frame(tvkr_renderer* r);
+int tvkr_sortlast_composite(tvkr_renderer* r, const uint32_t* order);
+int tvkr_sortlast_depth_order(tvkr_renderer* r, const uint32_t* boxes_lo_hi, uint32_t* order);
+int tvkr_sortlast_read_frame_rgba8(tvkr_renderer* r, uint8_t* rgba8, int flip_rows);
+
 /* Volumes larger than device memory (configs[4]): the flat volume is fed in z-slabs of whole LOD-0 brick rows (DEVICE
  * pointers; tvkr_load_streamed_rows tells which raw rows a slab must hold), the streamed builder cuts the bricks straight into
  * the pinned host store the pager reads from.  _end finishes the coarser levels, creates the pool (gpu_mem_bytes budget) and

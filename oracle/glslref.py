@@ -43,6 +43,7 @@ def _load(pool, strategy, table_size, rehash):
         out = os.path.join(B.OUT, key)
         lib = os.path.join(out, "libglslref.so")
         srcs = [os.path.join(_HERE, "glsl", f) for f in os.listdir(os.path.join(_HERE, "glsl"))]
+        srcs.append(os.path.join(os.path.dirname(_HERE), "include", "tvk_cuda.h"))
         if not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs if os.path.isfile(s)):
             B.build({"key": key, "args": args})
         _LIBS[key] = (C.CDLL(lib), json.load(open(os.path.join(out, "meta.json"))), out)

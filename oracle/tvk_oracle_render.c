@@ -310,7 +310,11 @@ static void gradient(const ctx_t* c, const float p[3], float g[3]) {
 static void lighting(const ctx_t* c, const float pos[3], const float n[3], const float diffuse[3],
                      float out[3]) {
   const tvk_raycast_params* p = c->p;
-  float v[3] = {p->model_eye_pos[0] - pos[0], p->model_eye_pos[1] - pos[1], p->model_eye_pos[2] - pos[2]};
+  /* sort-last: box-local model position -> the global volume's (identity when the fields are zero) */
+  const float gp[3] = {fmaf(pos[0], 1.0f + p->model_pos_scale_m1[0], p->model_pos_offset[0]),
+                       fmaf(pos[1], 1.0f + p->model_pos_scale_m1[1], p->model_pos_offset[1]),
+                       fmaf(pos[2], 1.0f + p->model_pos_scale_m1[2], p->model_pos_offset[2])};
+  float v[3] = {p->model_eye_pos[0] - gp[0], p->model_eye_pos[1] - gp[1], p->model_eye_pos[2] - gp[2]};
   float l = len3(v);
   for (int a = 0; a < 3; ++a) v[a] /= l;
   /* reflect(I,N) = I - 2*dot(N,I)*N */

@@ -172,3 +172,54 @@ def test_fused_exchange_equals_separate_compositor(world, angle):
         assert want.max() > 0.05 and np.array_equal(got, want), frame
     for t in ctxs:
         t.close()
+
+
+@pytest.mark.parametrize("members,mode", [(2, "1d"), (4, "1d_lit"), (8, "1d")])
+def test_sort_last_through_the_renderer_api(members, mode):
+    """tvkr_sortlast_*: every box is a Renderer (its part of the volume loaded as its own dataset, out of core, paged on
+    request); the group's frame -- members emulated on one GPU -- equals the frame ONE renderer paints of the whole volume
+    within the image tolerance (boxes resolve their bricks against their own pyramids: the cut faces see the halo)."""
+    from imagevis3d_b200.renderer import Renderer, SortLastGroup, RT_HEADLESS
+    G = (128, 128, 128)
+    vol = H.synth_blobs(G, np.uint8, seed=23)
+    tf = _tf()
+    cam = H.rotation_y(0.7) @ H.rotation_x(0.3)
+    W, Hh = 200, 150
+
+    def setup(r, tf_size):
+        t = H.tf1d_std(tf_size, 0.3, 0.3)
+        t[:, 3] *= 0.15
+        r.set1DTransFloat(t)
+        r.setLightingEnabled(mode == "1d_lit")
+        r.resize((W, Hh))
+        r.setRendererTarget(RT_HEADLESS)
+        r.setRotation4x4(cam)
+
+    whole = Renderer(0)
+    whole.loadRawVolume(vol, brick_size=32, out_of_core=True)
+    setup(whole, whole.datasetInfo().tf_size)
+    whole.paintUntilConverged()
+    want = whole.frameRGBA8().astype(np.int32)
+    vmax = float(whole.datasetInfo().range[1])
+    whole.cleanup()
+
+    parts = SL.block_partition(G, members, halo=32, align=32)
+    rs = []
+    for part in parts:
+        r = Renderer(0)
+        s, e = part["s"], part["e"]
+        r.loadRawVolume(np.ascontiguousarray(vol[s[2]:e[2], s[1]:e[1], s[0]:e[0]]), brick_size=32, out_of_core=True)
+        setup(r, 256)
+        rs.append(r)
+    grp = SortLastGroup(rs, list(range(members)), members, G, parts, vmax)
+    assert sorted(grp.depth_order()) == list(range(members))
+    for frame in range(2):                                     # both buffer parities
+        subs = grp.render()
+        assert subs >= members
+        got = grp.frame_rgba8().astype(np.int32)
+        err = np.abs(got - want)
+        psnr = 10 * np.log10(255.0 ** 2 / max(float((err.astype(np.float64) ** 2).mean()), 1e-12))
+        print("members %d %s frame %d: PSNR %.1f dB, max err %d/255, lit pixels %d" % (members, mode, frame, psnr, err.max(), int((want[..., 3] > 0).sum())))
+        assert want[..., 3].max() > 30 and psnr >= 48.0 and err.max() <= 6, (psnr, err.max())
+    for r in rs:
+        r.cleanup()
