@@ -783,13 +783,14 @@ def run_e2e(torch, HM, dev, local, steps):
     r.setRenderMode(1)
     r.setLightingEnabled(True)
     uploaded = [0.0]
+    frame_buf = np.zeros((Hh, W, 4), np.uint8)                # the application's frame buffer (host, pageable)
 
     def frame(k):
         r.setRotation4x4((HM.rotation_y(orbit_angle(k, steps)) @ HM.rotation_x(0.35)).astype(np.float32))
         r.clearWorkingSet()
         r.set2DTrans(tf, nz)                                   # the table travels host -> device every step
         sub = r.paintUntilConverged(4000)
-        img = r.frameRGBA8()
+        img = r.frameRGBA8(frame_buf)
         uploaded[0] += r.perf()["uploaded_bytes"]
         return sub, img
 

@@ -328,7 +328,10 @@ void BrickPool::PrepareForPaging() {
   // vector is [the m_insertPos slots just filled, ascending][the rest, ascending]: rotating the new ones to the back
   // IS the stable sort in the common case (no slot flagged empty or restored in between); anything else is sorted.
   auto by_time = [](const PoolSlot& a, const PoolSlot& b) { return a.time < b.time; };
-  if (m_insertPos > 0 && m_insertPos < m_slots.size()) std::rotate(m_slots.begin(), m_slots.begin() + m_insertPos, m_slots.end());
+  // The pinned coarsest brick (time UINT64_MAX) sits at the very end and stays there: the rotation leaves it out, or every
+  // pass after a PH_Reset would fall into the full sort (48k slots, 1.1 ms) because of that one element.
+  const size_t movable = m_slots.size() - ((!m_slots.empty() && m_slots.back().time == UINT64_MAX) ? 1 : 0);
+  if (m_insertPos > 0 && m_insertPos < movable) std::rotate(m_slots.begin(), m_slots.begin() + m_insertPos, m_slots.begin() + movable);
   if (!std::is_sorted(m_slots.begin(), m_slots.end(), by_time)) std::stable_sort(m_slots.begin(), m_slots.end(), by_time);
   m_insertPos = 0;
 }
@@ -336,16 +339,15 @@ void BrickPool::PrepareForPaging() {
 int BrickPool::Reset() {
   // GLVolumePool::PH_Reset (:261-284): every slot unused again, page table all MISSING, then UploadFirstBrick; the
   // device pool itself is kept (slots are overwritten as bricks arrive)
-  std::sort(m_slots.begin(), m_slots.end(), [](const PoolSlot& a, const PoolSlot& b) { return a.pos < b.pos; });
-  for (PoolSlot& s : m_slots) { const uint32_t pos = s.pos; s = PoolSlot(); s.pos = pos; }
+  // (slot positions are a permutation of 0..n-1: writing them out in order IS the sort by position)
+  for (size_t i = 0; i < m_slots.size(); ++i) { m_slots[i] = PoolSlot(); m_slots[i].pos = (uint32_t)i; }
   m_time = 2; m_insertPos = 0; m_uploadedBytes = 0;
-  std::vector<uint32_t> zero(m_total, TVK_BI_MISSING);
-  int rc = tvk_pool_set_metadata(m_ctx, zero.data(), m_total);
+  int rc = tvk_pool_clear_metadata(m_ctx);                  // page table all MISSING, on the stream (no host wait)
   if (rc) return rc;
-  return UploadFirstBrick();
+  return UploadFirstBrick(false);
 }
 
-int BrickPool::UploadFirstBrick() {
+int BrickPool::UploadFirstBrick(bool wait) {
   // coarsest brick -> last slot, time = UINT64_MAX so that it is never evicted (:763-766)
   const uint32_t idx = m_lodOffset[m_lodCount - 1];
   uint32_t c[4];
@@ -358,7 +360,7 @@ int BrickPool::UploadFirstBrick() {
   int rc = m_vol->lz4_store ? tvk_pool_upload_bricks_lz4(m_ctx, 1, &s.pos, &src, &m_vol->comp_len[t], &m_vol->sizes[3 * t])
                             : tvk_pool_upload_bricks(m_ctx, 1, &s.pos, &src, &m_vol->sizes[3 * t], m_vol->host_store ? 2 : 1);   // 2: the pinned store is one allocation
   if (rc) return rc;
-  rc = tvk_pool_upload_wait(m_ctx);
+  rc = wait ? tvk_pool_upload_wait(m_ctx) : tvk_pool_upload_fence(m_ctx);    // fence: the next march is ordered behind it
   if (rc) return rc;
   const uint32_t val = s.pos + TVK_BI_FLAG_COUNT;
   return tvk_pool_patch_metadata(m_ctx, 1, &idx, &val);
@@ -1024,8 +1026,7 @@ bool CudaGridLeaper::RecomputeBrickVisibility(bool force) {                  // 
   if (!force && m_visValid && v.render_mode == m_lastVis.render_mode && v.smin == m_lastVis.smin && v.smax == m_lastVis.smax &&
       v.gmin == m_lastVis.gmin && v.gmax == m_lastVis.gmax)
     return true;
-  uint32_t counts[4];
-  const int rc = m_pool->RecomputeVisibility(v, counts);
+  const int rc = m_pool->RecomputeVisibility(v, nullptr);   // the counts are not used here: no read-back, no host wait
   if (rc) return Fail("RecomputeVisibility", rc);
   m_lastVis = v; m_visValid = true;
   return true;
@@ -1542,9 +1543,14 @@ bool CudaGridLeaper::GetFrameFloat(std::vector<float>& out) {
 bool CudaGridLeaper::GetFrameRGBA8(std::vector<uint8_t>& out) {
   if (!m_ctx || !m_w || !m_h) return false;
   out.resize((size_t)m_w * m_h * 4);
+  return GetFrameRGBA8(out.data());
+}
+
+bool CudaGridLeaper::GetFrameRGBA8(uint8_t* out) {                           // width*height*4 bytes, caller-owned
+  if (!m_ctx || !m_w || !m_h || !out) return false;
   // glReadPixels(GL_RGBA, GL_UNSIGNED_BYTE): clamp, scale, round to nearest; then the vertical flip of
   // FrameCapture::SaveImage (FrameCapture.h:90-98) -- both done on the device, a quarter of the bytes come back
-  const int rc = tvk_read_image_rgba8(m_ctx, out.data(), 1);
+  const int rc = tvk_read_image_rgba8(m_ctx, out, 1);
   return rc ? Fail("tvk_read_image_rgba8", rc) : true;
 }
 
@@ -1763,10 +1769,7 @@ int tvkr_paint_until_converged(tvkr_renderer* h, uint32_t max_subframes, uint32_
 int tvkr_clear_working_set(tvkr_renderer* h) { if (!h) return 1; R(h)->ClearWorkingSet(); return 0; }
 int tvkr_recalc_visibility(tvkr_renderer* h) { return h && R(h)->RecalcVisibility() ? 0 : 1; }
 int tvkr_get_frame_rgba8(tvkr_renderer* h, uint8_t* out) {
-  std::vector<uint8_t> v;
-  if (!h || !out || !R(h)->GetFrameRGBA8(v)) return 1;
-  memcpy(out, v.data(), v.size());
-  return 0;
+  return (h && out && R(h)->GetFrameRGBA8(out)) ? 0 : 1;
 }
 int tvkr_get_frame_float(tvkr_renderer* h, float* out) {
   if (!h || !out) return 1;

@@ -126,7 +126,7 @@ class BrickPool {
   static void ComputePoolCapacity(const uint32_t maxBrick[3], uint32_t bpv, uint64_t totalBricks, uint64_t gpuMemBytes, uint32_t max3d,
                                   uint32_t cap[3]);
   int  Create(const uint32_t capacity[3], uint32_t sampler);
-  int  UploadFirstBrick();                                       // :763-766
+  int  UploadFirstBrick(bool wait = true);                                     // :763-766
   // wait = false: the upload and the page-table patch are only ORDERED before later work on the render stream (the
   // next sub-frame), the host does not block on the PCIe transfer (sources live in the pinned brick store)
   int  UploadBricks(const std::vector<uint32_t>& xyzl, uint32_t& paged, bool wait = true);   // :1720-1789
@@ -303,6 +303,7 @@ class CudaGridLeaper {
   bool RecalcVisibility();           // PH_RecalculateVisibility
   // GLFrameCapture.cpp:47-86 + FrameCapture.h:83-159: RGBA8, top row first
   bool GetFrameRGBA8(std::vector<uint8_t>& out);
+  bool GetFrameRGBA8(uint8_t* out);
   bool GetFrameFloat(std::vector<float>& out);             // premultiplied RGBA32F, bottom row first
   bool CaptureSingleFrame(const std::string& filename, bool preserveTransparency);
 

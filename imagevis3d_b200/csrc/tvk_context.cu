@@ -146,6 +146,9 @@ extern "C" void tvk_destroy(tvk_ctx* c) {
   for (int i = 0; i < TVK_RING_SEGMENTS; ++i) if (c->ring.done[i]) cudaEventDestroy(c->ring.done[i]);
   if (c->ring.base) cudaFreeHost(c->ring.base);
   if (c->h_readback) cudaFreeHost(c->h_readback);
+  if (c->h_tf_stage) cudaFreeHost(c->h_tf_stage);
+  if (c->tf_stage_done) cudaEventDestroy(c->tf_stage_done);
+  if (c->h_rgba8) cudaFreeHost(c->h_rgba8);
   delete c;
 }
 
@@ -854,6 +857,14 @@ extern "C" int tvk_pool_set_metadata(tvk_ctx* c, const uint32_t* meta, uint32_t 
   return TVK_OK;
 }
 
+extern "C" int tvk_pool_clear_metadata(tvk_ctx* c) {
+  if (!c || !c->has_pool) return TVK_ERR_INVALID;
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  static_assert(TVK_BI_MISSING == 0u, "the clear is a memset");
+  TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_meta, 0, sizeof(uint32_t) * c->pc.total_bricks, c->stream));
+  return TVK_OK;
+}
+
 extern "C" int tvk_pool_patch_metadata(tvk_ctx* c, uint32_t n, const uint32_t* brick_index, const uint32_t* value) {
   if (!c || !c->has_pool || (n && (!brick_index || !value))) return TVK_ERR_INVALID;
   if (!n) return TVK_OK;
@@ -882,6 +893,17 @@ extern "C" int tvk_pool_get_metadata(tvk_ctx* c, uint32_t* meta, uint32_t n) {
 // ---------------------------------------------------------------------------
 // transfer functions (RGBA8, fetched NEAREST in the kernels)
 // ---------------------------------------------------------------------------
+// per value column of a 2-D table: does ANY gradient row give the sample a non-zero alpha?  (the 2D modes skip the
+// gradient where not)  One warp per 32 columns, lanes read adjacent entries of a row.
+__global__ void tf_colmask_kernel(const uchar4* __restrict__ tf, uint32_t w, uint32_t h, uint32_t* __restrict__ mask) {
+  const uint32_t x = blockIdx.x * 32 + threadIdx.x;
+  bool any = false;
+  if (x < w)
+    for (uint32_t y = 0; y < h; ++y) any |= (tf[(size_t)y * w + x].w != 0);
+  const uint32_t m = __ballot_sync(0xFFFFFFFFu, any);
+  if (threadIdx.x == 0) mask[blockIdx.x] = m;
+}
+
 static int set_tf(tvk_ctx* c, const uint8_t* rgba, uint32_t w, uint32_t h) {
   if (!c || !rgba || w == 0 || h == 0) return TVK_ERR_INVALID;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
@@ -902,24 +924,38 @@ static int set_tf(tvk_ctx* c, const uint8_t* rgba, uint32_t w, uint32_t h) {
     TVK_CHECK_CUDA(c, cudaMalloc(&c->d_tf_colmask, sizeof(uint32_t) * ((w + 31) / 32)));
   }
   c->tf_w = w; c->tf_h = h;
+  if (h > 1) {
+    // 2-D table: the bytes go through the pinned staging block and the column mask is built on the device, so the edit
+    // returns without waiting for the stream (the march in flight keeps the old table until the copy is reached)
+    const size_t bytes = sizeof(uchar4) * n;
+    if (c->tf_stage_busy) { TVK_CHECK_CUDA(c, cudaEventSynchronize(c->tf_stage_done)); c->tf_stage_busy = false; }
+    if (c->tf_stage_bytes < bytes) {
+      if (c->h_tf_stage) cudaFreeHost(c->h_tf_stage);
+      c->h_tf_stage = nullptr; c->tf_stage_bytes = 0;
+      TVK_CHECK_CUDA(c, cudaMallocHost(&c->h_tf_stage, bytes));
+      c->tf_stage_bytes = bytes;
+    }
+    if (!c->tf_stage_done) TVK_CHECK_CUDA(c, cudaEventCreateWithFlags(&c->tf_stage_done, cudaEventDisableTiming));
+    memcpy(c->h_tf_stage, rgba, bytes);
+    TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf, c->h_tf_stage, bytes, cudaMemcpyHostToDevice, c->stream));
+    TVK_CHECK_CUDA(c, cudaEventRecord(c->tf_stage_done, c->stream));
+    c->tf_stage_busy = true;
+    tf_colmask_kernel<<<(w + 31) / 32, 32, 0, c->stream>>>(c->d_tf, w, h, c->d_tf_colmask);
+    c->launches++;
+    TVK_CHECK_CUDA(c, cudaGetLastError());
+    return TVK_OK;
+  }
   TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf, rgba, sizeof(uchar4) * n, cudaMemcpyHostToDevice, c->stream));
-  std::vector<float> f;
-  if (h == 1) {
-    f.resize(4 * n);
-    for (size_t i = 0; i < f.size(); ++i) f[i] = (float)rgba[i] * (1.0f / 255.0f);
-    TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf_f, f.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
-    // OpacityCorrectColor for sampleRateModifier == 1 (blend.glsl:37-39): 1 - pow(1 - a, 1) = 1 - (1 - a), which is not
-    // always a in fp32 -- evaluated once per table entry here instead of once per sample in the kernel
-    for (size_t i = 0; i < n; ++i) { volatile float om = 1.0f - f[4 * i + 3]; f[4 * i + 3] = 1.0f - om; }
-    TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf_f1, f.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
-  }
-  // per value column: does ANY gradient row give the sample a non-zero alpha?  (2D modes skip the gradient where not)
+  std::vector<float> f(4 * n);
+  for (size_t i = 0; i < f.size(); ++i) f[i] = (float)rgba[i] * (1.0f / 255.0f);
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf_f, f.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
+  // OpacityCorrectColor for sampleRateModifier == 1 (blend.glsl:37-39): 1 - pow(1 - a, 1) = 1 - (1 - a), which is not
+  // always a in fp32 -- evaluated once per table entry here instead of once per sample in the kernel
+  for (size_t i = 0; i < n; ++i) { volatile float om = 1.0f - f[4 * i + 3]; f[4 * i + 3] = 1.0f - om; }
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf_f1, f.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
   std::vector<uint32_t> mask((w + 31) / 32, 0u);
-  for (uint32_t y = 0; y < h; ++y) {
-    const uint8_t* row = rgba + 4 * (size_t)y * w;
-    for (uint32_t x = 0; x < w; ++x)
-      if (row[4 * x + 3]) mask[x >> 5] |= 1u << (x & 31);
-  }
+  for (uint32_t x = 0; x < w; ++x)
+    if (rgba[4 * x + 3]) mask[x >> 5] |= 1u << (x & 31);
   TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf_colmask, mask.data(), sizeof(uint32_t) * mask.size(), cudaMemcpyHostToDevice, c->stream));
   TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
   return TVK_OK;

@@ -111,12 +111,20 @@ struct tvk_ctx {
   float4* d_tf_f1 = nullptr;           // the same with alpha already opacity-corrected for sampleRateModifier == 1: 1 - (1 - a)
   uint32_t* d_tf_colmask = nullptr;    // bit x: column x of the table holds a non-zero alpha (any row); 4096 bits max... sized tf_w
   uint32_t tf_w = 0, tf_h = 0;
+  // pinned staging for table edits (a 4096x256 2-D table is 4 MB): the caller's bytes are copied here and travel
+  // asynchronously, so that an edit costs no host synchronisation; tf_stage_done guards the buffer's reuse
+  uint8_t* h_tf_stage = nullptr;
+  size_t tf_stage_bytes = 0;
+  cudaEvent_t tf_stage_done = nullptr;
+  bool tf_stage_busy = false;
 
   // frame state
   uint32_t width = 0, height = 0;
   float4* d_image = nullptr;           // accRayColor / composed iso image
   uchar4* d_rgba8 = nullptr;           // tvk_read_image_rgba8 staging (allocated on first use)
   size_t rgba8_px = 0;                 // pixels d_rgba8 holds
+  uint8_t* h_rgba8 = nullptr;          // pinned landing buffer of the RGBA8 read-back (the caller's memory may be pageable)
+  size_t h_rgba8_px = 0;
   uint64_t lz4_bytes_in = 0, lz4_bytes_out = 0;   // compressed bytes moved over PCIe / bytes inflated on the device
   float4* d_pos[2] = {nullptr, nullptr};   // rayStartPoint ping-pong
   float4* d_aux[2] = {nullptr, nullptr};   // rayStartColor (iso: normal) ping-pong

@@ -20,6 +20,7 @@
 // planes and is updated in place: each pixel only ever touches its own entry.
 #include "tvk_internal.h"
 #include <cmath>
+#include <cstring>
 
 // Tuning knobs of the 1D-TF sample loop (swept on a B200, see profiles/README.md): samples in flight
 // per ray and resident CTAs per SM, for the hardware-filtered and the exact (LDG) samplers.
@@ -1483,6 +1484,22 @@ __global__ void __launch_bounds__(256) image_to_rgba8_kernel(const float4* __res
   }
 }
 
+// d_rgba8 -> the caller's buffer.  The caller's memory is usually pageable (a std::vector, a numpy array): a direct
+// cudaMemcpy from the device to it is staged by the runtime in small pieces; one DMA into a pinned block the context
+// keeps + one host memcpy is 3-4x quicker for a 1080p frame.
+static int rgba8_to_host(tvk_ctx* c, uint8_t* rgba8, size_t n) {
+  if (!c->h_rgba8 || c->h_rgba8_px < n) {
+    if (c->h_rgba8) cudaFreeHost(c->h_rgba8);
+    c->h_rgba8 = nullptr; c->h_rgba8_px = 0;
+    TVK_CHECK_CUDA(c, cudaMallocHost(&c->h_rgba8, n * sizeof(uchar4)));
+    c->h_rgba8_px = n;
+  }
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->h_rgba8, c->d_rgba8, n * sizeof(uchar4), cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  memcpy(rgba8, c->h_rgba8, n * sizeof(uchar4));
+  return TVK_OK;
+}
+
 extern "C" int tvk_read_image_rgba8(tvk_ctx* c, uint8_t* rgba8, int flip_rows) {
   if (!c || !rgba8 || !c->d_image) return TVK_ERR_INVALID;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
@@ -1497,9 +1514,7 @@ extern "C" int tvk_read_image_rgba8(tvk_ctx* c, uint8_t* rgba8, int flip_rows) {
   const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)sm_count * 8);
   image_to_rgba8_kernel<<<blocks, 256, 0, c->stream>>>(c->d_image, c->d_rgba8, c->width, c->height, flip_rows);
   TVK_CHECK_CUDA(c, cudaGetLastError());
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(rgba8, c->d_rgba8, n * sizeof(uchar4), cudaMemcpyDeviceToHost, c->stream));
-  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
-  return TVK_OK;
+  return rgba8_to_host(c, rgba8, n);
 }
 
 // The same read-back for the sort-last result: the finished image of the fused exchange (rank 0, tvk_exchange_final) goes
@@ -1522,9 +1537,7 @@ extern "C" int tvk_exchange_read_final_rgba8(tvk_ctx* c, uint32_t frame_id, uint
   image_to_rgba8_kernel<<<blocks, 256, 0, c->stream>>>(static_cast<const float4*>(fin), c->d_rgba8, w, h, flip_rows);
   c->launches++;
   TVK_CHECK_CUDA(c, cudaGetLastError());
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(rgba8, c->d_rgba8, n * sizeof(uchar4), cudaMemcpyDeviceToHost, c->stream));
-  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
-  return TVK_OK;
+  return rgba8_to_host(c, rgba8, n);
 }
 
 extern "C" int tvk_read_resume(tvk_ctx* c, float* pos, float* color) {

@@ -313,9 +313,14 @@ class Renderer:
                  "captureSingleFrame")
         return True
 
-    def frameRGBA8(self):
+    def frameRGBA8(self, out=None):
+        """the frame as glReadPixels(GL_RGBA, GL_UNSIGNED_BYTE) returns it; `out`: a (h, w, 4) uint8 array to fill
+        (an application reads every frame into the same buffer)"""
         w, h = self._size
-        out = np.zeros((h, w, 4), np.uint8)
+        if out is None:
+            out = np.empty((h, w, 4), np.uint8)
+        elif out.shape != (h, w, 4) or out.dtype != np.uint8 or not out.flags.c_contiguous:
+            raise ValueError("frameRGBA8: out must be a contiguous (%d, %d, 4) uint8 array" % (h, w))
         self._ck(self._lib.tvkr_get_frame_rgba8(self._h, out.ctypes.data_as(C.c_void_p)), "frameRGBA8")
         return out
 

@@ -130,6 +130,9 @@ int tvk_pool_upload_fence(tvk_ctx* ctx);
 
 /* replaces UploadMetadataTexture / UploadMetadataTexel (GLVolumePool.cpp:912-953) */
 int tvk_pool_set_metadata(tvk_ctx* ctx, const uint32_t* meta, uint32_t n);
+/* every entry TVK_BI_MISSING, ordered on the render stream, no host wait (GLVolumePool::PH_Reset, GLVolumePool.cpp:261-284,
+ * clears m_vBrickMetadata and re-uploads it) */
+int tvk_pool_clear_metadata(tvk_ctx* ctx);
 int tvk_pool_patch_metadata(tvk_ctx* ctx, uint32_t n, const uint32_t* brick_index,
                             const uint32_t* value);
 int tvk_pool_get_metadata(tvk_ctx* ctx, uint32_t* meta, uint32_t n);
