@@ -1319,6 +1319,262 @@ __global__ void __launch_bounds__(256) hist2d_vec_kernel(const T* __restrict__ r
   }
 }
 
+
+// ---- 8 voxels per thread, squares in fp32 (rows a multiple of 8 voxels long, base 16-byte aligned) ---------
+// What the 4-voxel kernels above spend their instructions on is the exact 64-bit S of EVERY voxel (three 32x32->64
+// multiplies, 64-bit adds, a 64-bit int->float conversion) and a MATCH.ANY + 64-bit shared-memory CAS loop per vote.
+// Neither is needed:
+//  * a voxel value v becomes the float 2^23 + v with ONE byte permute (0x4B000000 | v); the difference of two such
+//    floats is the exact central difference, and S' = dx*dx + dy*dy + dz*dz in fp32 is S to within 1.8e-7 relative
+//    (exactly S below 2^24).  Pass 1 keeps the fp32 maximum as a FILTER: only voxels with S' >= best*(1 - 4e-7) --
+//    the ones that can tie or beat the exact maximum -- evaluate the exact integer S and the fp64 chain.  Pass 2 bins
+//    on S' and sends the voxels within 5e-4 of a bin boundary or within 1e-6 of the maximum down the exact chain, as
+//    before (fp32 error of the estimate < 1.5e-4);
+//  * votes go to a per-CTA table of (tag, count) pairs whose tags cannot change within a PHASE (= one tile): a slot is
+//    claimed once (32-bit CAS on an empty tag) and then counted with plain 32-bit shared-memory adds; a vote whose slot
+//    belongs to another bin goes to the global table directly.  Slots are flushed and cleared between tiles.
+//  * a warp whose 5 x 32 x 16 bytes are all one value (empty background, saturated regions) votes once.
+template <typename T> struct V8;
+template <> struct V8<uint16_t> {
+  typedef uint4 type;
+  static __device__ __forceinline__ float m(const uint4& v, int i) {           // 2^23 + voxel i as a float
+    const uint32_t w = (i >> 1) == 0 ? v.x : (i >> 1) == 1 ? v.y : (i >> 1) == 2 ? v.z : v.w;
+    return __uint_as_float(__byte_perm(w, 0x4B00u, (i & 1) ? 0x5432 : 0x5410));
+  }
+  static __device__ __forceinline__ uint4 zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  static __device__ __forceinline__ uint4 load(const uint16_t* row, uint32_t o) { return __ldg(reinterpret_cast<const uint4*>(row) + o); }
+  static __device__ __forceinline__ uint32_t first(const uint4& v) { return v.x & 0xffffu; }
+  static __device__ __forceinline__ uint32_t last(const uint4& v) { return v.w >> 16; }
+  static __device__ __forceinline__ bool all_equal(const uint4& v, uint32_t val) {
+    const uint32_t rep = val | (val << 16);
+    return ((v.x ^ rep) | (v.y ^ rep) | (v.z ^ rep) | (v.w ^ rep)) == 0u;
+  }
+  static __device__ __forceinline__ uint32_t shfl_last_up(const uint4& v) { return __shfl_up_sync(0xffffffffu, v.w, 1) >> 16; }
+  static __device__ __forceinline__ uint32_t shfl_first_down(const uint4& v) { return __shfl_down_sync(0xffffffffu, v.x, 1) & 0xffffu; }
+};
+template <> struct V8<uint8_t> {
+  typedef uint2 type;
+  static __device__ __forceinline__ float m(const uint2& v, int i) {
+    return __uint_as_float(__byte_perm((i >> 2) ? v.y : v.x, 0x4B000000u, 0x7440 | (i & 3)));
+  }
+  static __device__ __forceinline__ uint2 zero() { return make_uint2(0u, 0u); }
+  static __device__ __forceinline__ uint2 load(const uint8_t* row, uint32_t o) { return __ldg(reinterpret_cast<const uint2*>(row) + o); }
+  static __device__ __forceinline__ uint32_t first(const uint2& v) { return v.x & 0xffu; }
+  static __device__ __forceinline__ uint32_t last(const uint2& v) { return v.y >> 24; }
+  static __device__ __forceinline__ bool all_equal(const uint2& v, uint32_t val) {
+    const uint32_t rep = val * 0x01010101u;
+    return ((v.x ^ rep) | (v.y ^ rep)) == 0u;
+  }
+  static __device__ __forceinline__ uint32_t shfl_last_up(const uint2& v) { return __shfl_up_sync(0xffffffffu, v.y, 1) >> 24; }
+  static __device__ __forceinline__ uint32_t shfl_first_down(const uint2& v) { return __shfl_down_sync(0xffffffffu, v.x, 1) & 0xffu; }
+};
+
+// The 8 voxels of octet o of row rc (all 32 lanes call; inactive lanes get zeros): S' per voxel, 2^23 + value per voxel.
+// `uniform` = every byte this thread looked at (own octet, x halo, four neighbouring octets) is the value `v0`.
+template <typename T>
+__device__ __forceinline__ void octet_grad(const RowCtx<T>& rc, uint32_t o, uint32_t o_first, uint32_t o_end, uint32_t no, uint32_t lane,
+                                           bool act, float sf[8], float cm[8], bool& uniform, uint32_t& v0) {
+  typedef V8<T> V;
+  typedef typename V::type Q;
+  const Q z = V::zero();
+  const Q c = act ? V::load(rc.line, o) : z;
+  const Q up = (act && rc.up) ? V::load(rc.up, o) : z, dn = (act && rc.down) ? V::load(rc.down, o) : z;
+  const Q fr = (act && rc.front) ? V::load(rc.front, o) : z, bk = (act && rc.back) ? V::load(rc.back, o) : z;
+  uint32_t prev = V::shfl_last_up(c), next = V::shfl_first_down(c);
+  // the x halo of the first / last lane of the chunk comes from memory (zero outside the row)
+  if (lane == 0 || o == o_first) prev = (act && o > 0) ? (uint32_t)__ldg(rc.line + 8u * o - 1u) : 0u;
+  if (lane == 31 || o + 1 == o_end) next = (act && o + 1 < no) ? (uint32_t)__ldg(rc.line + 8u * o + 8u) : 0u;
+  if (!act) prev = next = 0u;                           // (an idle lane next to the row's last octet: S' stays 0)
+  v0 = V::first(c);
+  uniform = V::all_equal(c, v0) && V::all_equal(up, v0) && V::all_equal(dn, v0) && V::all_equal(fr, v0) && V::all_equal(bk, v0) &&
+            prev == v0 && next == v0;
+  float xm[10];
+  xm[0] = __uint_as_float(0x4B000000u | prev);
+  xm[9] = __uint_as_float(0x4B000000u | next);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { cm[i] = V::m(c, i); xm[i + 1] = cm[i]; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float dx = __fsub_rn(xm[i], xm[i + 2]);                 // exact: both are 2^23 + integer
+    const float dy = __fsub_rn(V::m(up, i), V::m(dn, i));
+    const float dz = __fsub_rn(V::m(fr, i), V::m(bk, i));
+    sf[i] = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) grad_max_v8_kernel(const T* __restrict__ raw, uint32_t sx, uint32_t sy, uint32_t sz,
+                                                           double norm2, GradBest* __restrict__ partial,
+                                                           unsigned long long* __restrict__ shared_best) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, no = sx / 8u;
+  unsigned long long best_s = 0, best_bits = 0, last_key = ~0ull;
+  float thr = 0.0f;                                     // a voxel below it cannot tie or beat best_s
+  const uint32_t nyb = (sy + 7u) / 8u, nzb = (sz + 15u) / 16u, ntiles = nyb * nzb;
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+  for (uint32_t z = (tile / nyb) * 16u; z < min(sz, (tile / nyb) * 16u + 16u); ++z) {
+    const uint32_t y = (tile % nyb) * 8u + warp;
+    const bool row_valid = y < sy;
+    const RowCtx<T> rc = row_ctx(raw, min(y, sy - 1u), z, sx, sy, sz);
+    const unsigned long long gb = *reinterpret_cast<volatile unsigned long long*>(shared_best);
+    if (gb > best_s) { best_s = gb; best_bits = 0; thr = __fmul_rd(__ull2float_rd(best_s), 1.0f - 4e-7f); }
+    for (uint32_t o0 = 0; o0 < no; o0 += 32u) {
+      const uint32_t o = o0 + lane;
+      const bool act = row_valid && o < no;
+      float sf[8], cm[8];
+      bool uni; uint32_t v0;
+      octet_grad<T>(rc, o, o0, no, no, lane, act, sf, cm, uni, v0);
+      const float m = fmaxf(fmaxf(fmaxf(sf[0], sf[1]), fmaxf(sf[2], sf[3])), fmaxf(fmaxf(sf[4], sf[5]), fmaxf(sf[6], sf[7])));
+      if (m == 0.0f || m < thr) continue;
+      uint32_t cand = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cand |= (sf[i] != 0.0f && sf[i] >= thr) ? (1u << i) : 0u;
+      while (cand) {
+        const uint32_t i = __ffs(cand) - 1u;
+        cand &= cand - 1u;
+        const uint32_t x = 8u * o + i;
+        unsigned long long key;
+        const unsigned long long s = grad_s_row(rc, x, sx, &key);
+        if (s == 0 || s < best_s || key == last_key) continue;
+        last_key = key;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(grad_mag(raw, x, y, z, sx, sy, sz, norm2));
+        if (s > best_s) {
+          best_s = s; best_bits = bits; atomicMax(shared_best, best_s);
+          thr = __fmul_rd(__ull2float_rd(best_s), 1.0f - 4e-7f);
+        } else if (bits > best_bits) best_bits = bits;
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long os = __shfl_xor_sync(0xffffffffu, best_s, o), ob = __shfl_xor_sync(0xffffffffu, best_bits, o);
+    if (os > best_s || (os == best_s && ob > best_bits)) { best_s = os; best_bits = ob; }
+  }
+  __shared__ GradBest sh[8];
+  if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5].s = best_s; sh[threadIdx.x >> 5].len_bits = best_bits; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    GradBest g = sh[0];
+    for (int w = 1; w < 8; ++w) if (sh[w].s > g.s || (sh[w].s == g.s && sh[w].len_bits > g.len_bits)) g = sh[w];
+    partial[blockIdx.x] = g;
+  }
+}
+
+#ifndef TVK_H2D8_SLOTS
+#define TVK_H2D8_SLOTS 8192u
+#endif
+#ifndef TVK_H2D8_XO
+#define TVK_H2D8_XO 32u          // tile width in octets (one warp trip = 256 voxels)
+#endif
+#ifndef TVK_H2D8_ZT
+#define TVK_H2D8_ZT 16u
+#endif
+__device__ __forceinline__ void h2d8_vote(uint32_t* tags, uint32_t* cnts, unsigned long long* __restrict__ bins, uint32_t bin, uint32_t w) {
+  const uint32_t h = (bin * 2654435761u) >> (32 - 13 + (TVK_H2D8_SLOTS == 8192u ? 0 : TVK_H2D8_SLOTS == 4096u ? 1 : 2));
+  uint32_t t = *reinterpret_cast<volatile uint32_t*>(tags + h);
+  if (t == 0u) { t = atomicCAS(tags + h, 0u, bin + 1u); if (t == 0u) t = bin + 1u; }
+  if (t == bin + 1u) atomicAdd(cnts + h, w);            // the tag cannot change before the end of the phase
+  else atomicAdd(&bins[bin], (unsigned long long)w);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) hist2d_v8_kernel(const T* __restrict__ raw, uint32_t sx, uint32_t sy, uint32_t sz,
+                                                         double norm2, double max_grad, unsigned long long smax, float k_smax, float tie_thr,
+                                                         const uint16_t* __restrict__ vlut,
+                                                         unsigned long long* __restrict__ bins) {
+  static_assert(TVK_H2D8_SLOTS == 8192u || TVK_H2D8_SLOTS == 4096u || TVK_H2D8_SLOTS == 2048u, "slot count");
+  extern __shared__ unsigned long long h2d8_smem[];       // 8 x 64 queue entries, then the tags, then the counts
+  uint32_t* tags = reinterpret_cast<uint32_t*>(h2d8_smem + 8 * 64);
+  uint32_t* cnts = tags + TVK_H2D8_SLOTS;
+  for (uint32_t i = threadIdx.x; i < TVK_H2D8_SLOTS; i += blockDim.x) { tags[i] = 0u; cnts[i] = 0u; }
+  __syncthreads();
+  unsigned long long* wq = h2d8_smem + 64 * (threadIdx.x >> 5);
+  uint32_t qn = 0;                                      // queued voxels of this warp (same value in every lane)
+  uint32_t pend_bin = 0xFFFFFFFFu;
+  unsigned long long pend_cnt = 0;                      // lane 0: votes of uniform warps, kept across tiles
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, no = sx / 8u;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t nxc = (no + TVK_H2D8_XO - 1u) / TVK_H2D8_XO, nyb = (sy + 7u) / 8u, nzb = (sz + TVK_H2D8_ZT - 1u) / TVK_H2D8_ZT;
+  const uint32_t ntiles = nxc * nyb * nzb;
+  const uint32_t gi_zero = smax == 0 ? 255u : 0u;       // (no gradient anywhere: NaN -> bin 255, see hist2d_kernel)
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t xc = tile % nxc, yb = (tile / nxc) % nyb, zb = tile / (nxc * nyb);
+    const uint32_t y = yb * 8u + warp;
+    const uint32_t z_end = min(sz, (zb + 1u) * TVK_H2D8_ZT), o_end = min(no, (xc + 1u) * TVK_H2D8_XO);
+    for (uint32_t z = zb * TVK_H2D8_ZT; z < z_end; ++z)
+    for (uint32_t o0 = xc * TVK_H2D8_XO; o0 < o_end; o0 += 32u) {
+      const uint32_t o = o0 + lane;
+      const bool act = y < sy && o < o_end;
+      const RowCtx<T> rc = row_ctx(raw, min(y, sy - 1u), z, sx, sy, sz);
+      float sf[8], cm[8];
+      bool uni; uint32_t v0;
+      octet_grad<T>(rc, o, o0, o_end, no, lane, act, sf, cm, uni, v0);
+      const unsigned am = __ballot_sync(0xffffffffu, act);
+      if (am == 0u) continue;
+      // ---- one value everywhere the warp looked: one vote for the lot
+      const uint32_t lead = __ffs(am) - 1;
+      const uint32_t vl = __shfl_sync(0xffffffffu, v0, lead);
+      if (__all_sync(0xffffffffu, !act || (uni && v0 == vl))) {
+        if (lane == 0) {
+          const uint32_t bin = (uint32_t)vlut[vl] * 256u + gi_zero;
+          const uint32_t n = 8u * __popc(am);
+          if (bin == pend_bin) pend_cnt += n;
+          else { if (pend_cnt) atomicAdd(&bins[pend_bin], pend_cnt); pend_bin = bin; pend_cnt = n; }
+        }
+        continue;
+      }
+      const unsigned long long row_base = ((unsigned long long)z * sy + y) * sx + 8ull * o;
+      uint32_t need = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint32_t gi = gi_zero;
+        if (sf[i] != 0.0f) {
+          // 255*sqrt(S/Smax) = sqrt(t), t = S' * (65025/Smax); floor by a round-down magic add
+          const float t = sf[i] * k_smax;
+          const float qf = t * rsqrtf(t);
+          const float mg = __fadd_rd(qf, 8388608.0f);
+          const float fr = qf - (mg - 8388608.0f);
+          if (sf[i] >= tie_thr) need |= 1u << i;                                  // may tie with the maximum
+          else if (qf >= 254.5f) gi = 254u;                                       // S < Smax: bin 254 (see hist2d_kernel)
+          else if (fabsf(fr - 0.5f) < 0.4995f) gi = __float_as_uint(mg) & 0x7FFFFFu;
+          else need |= 1u << i;
+        }
+        if (act && !((need >> i) & 1u)) {
+          const uint32_t v = __float_as_uint(cm[i]) & 0xFFFFu;
+          h2d8_vote(tags, cnts, bins, (uint32_t)vlut[v] * 256u + gi, 1u);
+        }
+      }
+      if (!act) need = 0;
+      // ---- exact-chain queue
+      if (__any_sync(0xffffffffu, need != 0)) {
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+          const unsigned m = __ballot_sync(0xffffffffu, (need >> i) & 1u);
+          if (!m) continue;
+          if ((need >> i) & 1u) wq[qn + __popc(m & lt)] = row_base + i;
+          qn += __popc(m);
+          __syncwarp();
+          if (qn >= 32u) {
+            hist2d_exact_vote<T>(raw, wq[lane], sx, sy, sz, norm2, max_grad, vlut, bins);
+            const unsigned long long mv = (lane + 32u < qn) ? wq[lane + 32u] : 0ull;
+            __syncwarp();
+            wq[lane] = mv;
+            qn -= 32u;
+            __syncwarp();
+          }
+        }
+      }
+    }
+    // ---- end of the phase: counts go to the global table, slots are free again
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < TVK_H2D8_SLOTS; i += blockDim.x) {
+      const uint32_t t = tags[i];
+      if (t) { atomicAdd(&bins[t - 1u], (unsigned long long)cnts[i]); tags[i] = 0u; cnts[i] = 0u; }
+    }
+    __syncthreads();
+  }
+  if (lane == 0 && pend_cnt) atomicAdd(&bins[pend_bin], pend_cnt);
+  if (lane < qn) hist2d_exact_vote<T>(raw, wq[lane], sx, sy, sz, norm2, max_grad, vlut, bins);
+}
+
 static void release(tvk_ctx* c) {
   BuildState& b = c->build;
   if (b.own_store) cudaFree(b.d_store);
@@ -1814,7 +2070,10 @@ static int run_hist2d(tvk_ctx* c, uint32_t bins_x, double max_nonzero, uint64_t*
   // 4 voxels per thread when rows are whole quads (cudaMalloc'ed / caller-aligned base); TVK_HIST2D_SCALAR=1 forces the
   // one-voxel-per-thread kernels
   const bool vec = (s[0] % 4u) == 0 && (reinterpret_cast<uintptr_t>(b.d_lod[0]) % (4 * sizeof(T))) == 0 && !getenv("TVK_HIST2D_SCALAR");
-  if (vec) grad_max_vec_kernel<T><<<(unsigned)std::min<uint64_t>((uint64_t)((s[1] + 7) / 8) * ((s[2] + 15) / 16), (uint64_t)sms * 8), 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_part, d_bins);   // d_bins[0]: zeroed scratch, re-zeroed below
+  // 8 voxels per thread + fp32 squares when rows are whole octets and 16-byte aligned (TVK_HIST2D_V4=1: the 4-voxel kernels)
+  const bool v8 = vec && (s[0] % 8u) == 0 && (reinterpret_cast<uintptr_t>(b.d_lod[0]) % (8 * sizeof(T))) == 0 && !getenv("TVK_HIST2D_V4");
+  if (v8) grad_max_v8_kernel<T><<<(unsigned)std::min<uint64_t>((uint64_t)((s[1] + 7) / 8) * ((s[2] + 15) / 16), (uint64_t)sms * 8), 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_part, d_bins);
+  else if (vec) grad_max_vec_kernel<T><<<(unsigned)std::min<uint64_t>((uint64_t)((s[1] + 7) / 8) * ((s[2] + 15) / 16), (uint64_t)sms * 8), 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_part, d_bins);   // d_bins[0]: zeroed scratch, re-zeroed below
   else grad_max_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_part);
   hist2d_value_lut_kernel<<<(range + 255) / 256, 256, 0, c->stream>>>(range, bins_x, max_nonzero, d_lut);
   c->launches += 2;
@@ -1827,7 +2086,18 @@ static int run_hist2d(tvk_ctx* c, uint32_t bins_x, double max_nonzero, uint64_t*
   memcpy(&mg, &g.len_bits, sizeof(mg));
   const float inv_smax = g.s ? 1.0f / (float)g.s : 0.0f;
   if (vec) TVK_CHECK_CUDA(c, cudaMemsetAsync(d_bins, 0, sizeof(unsigned long long), c->stream));
-  if (vec) {
+  if (v8) {
+    const uint64_t tiles = (uint64_t)((s[0] / 8 + TVK_H2D8_XO - 1) / TVK_H2D8_XO) * ((s[1] + 7) / 8) * ((s[2] + TVK_H2D8_ZT - 1) / TVK_H2D8_ZT);
+    const size_t smem = sizeof(unsigned long long) * 8 * 64 + 2 * sizeof(uint32_t) * TVK_H2D8_SLOTS;
+    TVK_CHECK_CUDA(c, cudaFuncSetAttribute(hist2d_v8_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    TVK_CHECK_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hist2d_v8_kernel<T>, 256, smem));
+    const unsigned tb = (unsigned)std::min<uint64_t>(tiles, (uint64_t)sms * std::max(per_sm, 1));
+    const float k_smax = g.s ? (float)(65025.0 / (double)g.s) : 0.0f;
+    const float tie_thr = (float)((double)g.s * (1.0 - 1e-6));
+    hist2d_v8_kernel<T><<<tb, 256, smem, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, mg, g.s, k_smax, tie_thr, d_lut, d_bins);
+  }
+  else if (vec) {
     const uint32_t xq = TVK_H2D_XQ ? TVK_H2D_XQ : s[0] / 4;
     const uint64_t tiles = (uint64_t)((s[0] / 4 + xq - 1) / xq) * ((s[1] + 7) / 8) * ((s[2] + TVK_H2D_ZT - 1) / TVK_H2D_ZT);
     const unsigned tb = (unsigned)std::min<uint64_t>(tiles, (uint64_t)sms * (sizeof(T) == 1 ? 16 : 6));

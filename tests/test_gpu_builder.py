@@ -158,13 +158,23 @@ def _hist2d_volumes():
     sm = rng.integers(0, 4096, (12, 16, 64)).astype(np.uint16)
     sm[:, :, 20:40] = 4000                                   # runs of equal bins inside a thread's four voxels
     out.append(("u16 runs", sm))
+    # rows of several 256-voxel chunks, the last one a single octet: x halos at chunk borders come from memory
+    out.append(("u16 wide noise", rng.integers(0, 65536, (5, 9, 520)).astype(np.uint16)))
+    out.append(("u8 wide noise", rng.integers(0, 256, (5, 11, 776)).astype(np.uint8)))
+    out.append(("u16 sphere (the bench generator: S nearly constant, many ties with the maximum)", H.synth_sphere((72, 80, 64), np.uint16)))
+    flat = np.zeros((20, 18, 512), np.uint16)
+    flat[4:9, 3:12, 100:300] = 51234                         # uniform warps next to edges of a constant block
+    out.append(("u16 constant block in empty space", flat))
+    # the maximum sits on the last voxel of a row that ends inside the warp (idle lanes to its right)
+    out.append(("u16 ramp, one octet per row", np.arange(64, dtype=np.uint16).reshape(1, 8, 8)))
     return out
 
 
-@pytest.mark.parametrize("case", range(7))
+@pytest.mark.parametrize("case", range(12))
 def test_hist2d_four_voxels_per_thread_is_bit_exact(case, monkeypatch):
-    """The vectorised 2-D histogram kernels (rows of whole quads) against the oracle AND the one-voxel-per-thread
-    kernels (TVK_HIST2D_SCALAR=1)."""
+    """The vectorised 2-D histogram kernels (8 voxels per thread with fp32 squares where rows are whole octets, 4 voxels
+    per thread with TVK_HIST2D_V4=1 / rows of whole quads) against the oracle AND the one-voxel-per-thread kernels
+    (TVK_HIST2D_SCALAR=1)."""
     from imagevis3d_b200.context import TvkContext
     name, raw = _hist2d_volumes()[case]
     raw = np.ascontiguousarray(raw)
@@ -176,6 +186,9 @@ def test_hist2d_four_voxels_per_thread_is_bit_exact(case, monkeypatch):
     t = TvkContext(0)
     t.build_octree(raw, 64, 2)
     h_vec, mg_vec = t.build_hist2d(bins_x, maxv)
+    monkeypatch.setenv("TVK_HIST2D_V4", "1")
+    h_v4, mg_v4 = t.build_hist2d(bins_x, maxv)
+    assert np.float32(mg_v4) == np.float32(mg_ref) and (h_v4 == h_ref).all(), name
     monkeypatch.setenv("TVK_HIST2D_SCALAR", "1")
     h_sc, mg_sc = t.build_hist2d(bins_x, maxv)
     t.close()
