@@ -1458,8 +1458,8 @@ __global__ void __launch_bounds__(256) grad_max_v8_kernel(const T* __restrict__ 
   }
 }
 
-#ifndef TVK_H2D8_SLOTS
-#define TVK_H2D8_SLOTS 8192u
+#ifndef TVK_H2D8_LOG_SLOTS
+#define TVK_H2D8_LOG_SLOTS 13u   // 8192 slots of 4 bytes
 #endif
 #ifndef TVK_H2D8_XO
 #define TVK_H2D8_XO 32u          // tile width in octets (one warp trip = 256 voxels)
@@ -1467,12 +1467,46 @@ __global__ void __launch_bounds__(256) grad_max_v8_kernel(const T* __restrict__ 
 #ifndef TVK_H2D8_ZT
 #define TVK_H2D8_ZT 16u
 #endif
-__device__ __forceinline__ void h2d8_vote(uint32_t* tags, uint32_t* cnts, unsigned long long* __restrict__ bins, uint32_t bin, uint32_t w) {
-  const uint32_t h = (bin * 2654435761u) >> (32 - 13 + (TVK_H2D8_SLOTS == 8192u ? 0 : TVK_H2D8_SLOTS == 4096u ? 1 : 2));
-  uint32_t t = *reinterpret_cast<volatile uint32_t*>(tags + h);
-  if (t == 0u) { t = atomicCAS(tags + h, 0u, bin + 1u); if (t == 0u) t = bin + 1u; }
-  if (t == bin + 1u) atomicAdd(cnts + h, w);            // the tag cannot change before the end of the phase
-  else atomicAdd(&bins[bin], (unsigned long long)w);
+#define TVK_H2D8_SLOTS (1u << TVK_H2D8_LOG_SLOTS)
+#define TVK_H2D8_BIN_BITS 20u                           // bins_x * 256 <= 2^20 (4096 value columns), else the 4-voxel kernels
+static_assert(TVK_H2D8_XO * 8u * 8u * TVK_H2D8_ZT < 65536u, "a tile's votes must fit the 16-bit count of a slot");
+// A slot is ONE 32-bit word: tag << 16 | count.  bin -> m = bin * K mod 2^20 is a bijection (K odd); the slot index is the
+// top bits of m, the tag the remaining low bits + 1 (never 0), so (slot, tag) names the bin and the flush can invert it.
+constexpr uint32_t kH2d8K = 0x779B1u;
+constexpr uint32_t h2d8_inverse(uint32_t k) { uint32_t x = k; for (int i = 0; i < 6; ++i) x *= 2u - k * x; return x & ((1u << TVK_H2D8_BIN_BITS) - 1u); }
+constexpr uint32_t kH2d8Kinv = h2d8_inverse(kH2d8K);
+static_assert(((kH2d8K * kH2d8Kinv) & ((1u << TVK_H2D8_BIN_BITS) - 1u)) == 1u, "modular inverse");
+constexpr uint32_t kH2d8TagBits = TVK_H2D8_BIN_BITS - TVK_H2D8_LOG_SLOTS;
+
+__device__ __forceinline__ float rsqrt_ftz(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// One vote.  The tag of a slot cannot change before the end of the phase (tile), so "tag matches" followed by a plain
+// shared-memory add is safe; an empty slot is claimed with one CAS; a slot owned by another bin sends the vote to the
+// global table.  Tags carry a valid bit (0x80), so a word with count 0 still names its bin: at the end of a phase the
+// counts are flushed and the tags of the slots that were voted for STAY (the next tile of the CTA is its neighbour and
+// mostly votes for the same bins -- re-claiming them cost a divergent CAS path in two warps out of three), slots that
+// saw no vote are freed.
+// Shared-state-space instructions on 32-bit addresses (no generic-address arithmetic).
+__device__ __forceinline__ uint32_t lds_volatile(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void reds_inc(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(a) : "memory"); }
+__device__ __forceinline__ uint32_t atoms_cas(uint32_t a, uint32_t cmp, uint32_t val) {
+  uint32_t o; asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(o) : "r"(a), "r"(cmp), "r"(val) : "memory"); return o;
+}
+__device__ __noinline__ void h2d8_vote_slow(uint32_t addr, uint32_t tagw, uint32_t w, unsigned long long* __restrict__ bins, uint32_t bin) {
+  if (w == 0u) {
+    w = atoms_cas(addr, 0u, tagw | 1u);
+    if (w == 0u) return;
+    if ((w ^ tagw) < 0x10000u) { reds_inc(addr); return; }
+  }
+  atomicAdd(&bins[bin], 1ull);
+}
+__device__ __forceinline__ void h2d8_vote(uint32_t slots_saddr, unsigned long long* __restrict__ bins, uint32_t bin) {
+  const uint32_t m = bin * kH2d8K;                                       // low 20 bits: the bijective mix
+  const uint32_t addr = slots_saddr + ((m >> (kH2d8TagBits - 2u)) & ((TVK_H2D8_SLOTS - 1u) << 2));
+  const uint32_t tagw = ((m << 16) & (((1u << kH2d8TagBits) - 1u) << 16)) | (1u << (16 + kH2d8TagBits));
+  const uint32_t w = lds_volatile(addr);
+  if ((w ^ tagw) < 0x10000u) reds_inc(addr);                             // same tag
+  else h2d8_vote_slow(addr, tagw, w, bins, bin);
 }
 
 template <typename T>
@@ -1480,12 +1514,11 @@ __global__ void __launch_bounds__(256) hist2d_v8_kernel(const T* __restrict__ ra
                                                          double norm2, double max_grad, unsigned long long smax, float k_smax, float tie_thr,
                                                          const uint16_t* __restrict__ vlut,
                                                          unsigned long long* __restrict__ bins) {
-  static_assert(TVK_H2D8_SLOTS == 8192u || TVK_H2D8_SLOTS == 4096u || TVK_H2D8_SLOTS == 2048u, "slot count");
-  extern __shared__ unsigned long long h2d8_smem[];       // 8 x 64 queue entries, then the tags, then the counts
-  uint32_t* tags = reinterpret_cast<uint32_t*>(h2d8_smem + 8 * 64);
-  uint32_t* cnts = tags + TVK_H2D8_SLOTS;
-  for (uint32_t i = threadIdx.x; i < TVK_H2D8_SLOTS; i += blockDim.x) { tags[i] = 0u; cnts[i] = 0u; }
+  extern __shared__ unsigned long long h2d8_smem[];       // 8 x 64 queue entries, then the slots
+  uint32_t* slots = reinterpret_cast<uint32_t*>(h2d8_smem + 8 * 64);
+  for (uint32_t i = threadIdx.x; i < TVK_H2D8_SLOTS; i += blockDim.x) slots[i] = 0u;
   __syncthreads();
+  const uint32_t slots_saddr = (uint32_t)__cvta_generic_to_shared(slots);
   unsigned long long* wq = h2d8_smem + 64 * (threadIdx.x >> 5);
   uint32_t qn = 0;                                      // queued voxels of this warp (same value in every lane)
   uint32_t pend_bin = 0xFFFFFFFFu;
@@ -1495,7 +1528,10 @@ __global__ void __launch_bounds__(256) hist2d_v8_kernel(const T* __restrict__ ra
   const uint32_t nxc = (no + TVK_H2D8_XO - 1u) / TVK_H2D8_XO, nyb = (sy + 7u) / 8u, nzb = (sz + TVK_H2D8_ZT - 1u) / TVK_H2D8_ZT;
   const uint32_t ntiles = nxc * nyb * nzb;
   const uint32_t gi_zero = smax == 0 ? 255u : 0u;       // (no gradient anywhere: NaN -> bin 255, see hist2d_kernel)
-  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  // a CTA takes a run of consecutive tiles (neighbours along x, then y): the bins of one tile are mostly those of the next
+  const uint32_t per_cta = (ntiles + gridDim.x - 1u) / gridDim.x;
+  const uint32_t tile_end = min(ntiles, (blockIdx.x + 1u) * per_cta);
+  for (uint32_t tile = blockIdx.x * per_cta; tile < tile_end; ++tile) {
     const uint32_t xc = tile % nxc, yb = (tile / nxc) % nyb, zb = tile / (nxc * nyb);
     const uint32_t y = yb * 8u + warp;
     const uint32_t z_end = min(sz, (zb + 1u) * TVK_H2D8_ZT), o_end = min(no, (xc + 1u) * TVK_H2D8_XO);
@@ -1521,30 +1557,35 @@ __global__ void __launch_bounds__(256) hist2d_v8_kernel(const T* __restrict__ ra
         }
         continue;
       }
-      const unsigned long long row_base = ((unsigned long long)z * sy + y) * sx + 8ull * o;
+      // ---- value columns: eight table reads in flight while the gradient bins are worked out
+      uint32_t vb[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) vb[i] = (uint32_t)__ldg(vlut + (__float_as_uint(cm[i]) & 0xFFFFu)) << 8;
       uint32_t need = 0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        uint32_t gi = gi_zero;
-        if (sf[i] != 0.0f) {
-          // 255*sqrt(S/Smax) = sqrt(t), t = S' * (65025/Smax); floor by a round-down magic add
-          const float t = sf[i] * k_smax;
-          const float qf = t * rsqrtf(t);
-          const float mg = __fadd_rd(qf, 8388608.0f);
-          const float fr = qf - (mg - 8388608.0f);
-          if (sf[i] >= tie_thr) need |= 1u << i;                                  // may tie with the maximum
-          else if (qf >= 254.5f) gi = 254u;                                       // S < Smax: bin 254 (see hist2d_kernel)
-          else if (fabsf(fr - 0.5f) < 0.4995f) gi = __float_as_uint(mg) & 0x7FFFFFu;
-          else need |= 1u << i;
-        }
-        if (act && !((need >> i) & 1u)) {
-          const uint32_t v = __float_as_uint(cm[i]) & 0xFFFFu;
-          h2d8_vote(tags, cnts, bins, (uint32_t)vlut[v] * 256u + gi, 1u);
-        }
+        // 255*sqrt(S/Smax) = sqrt(t), t = S' * (65025/Smax); floor by a round-down magic add.  Branch-free: S' == 0
+        // makes t * rsqrt(t) a NaN, which every comparison below rejects before the zero case overrides the result.
+        const float t = sf[i] * k_smax;
+        const float qf = t * rsqrt_ftz(t);
+        const float mg = __fadd_rd(qf, 8388608.0f);
+        const float fr = qf - (mg - 8388608.0f);
+        const bool top = qf >= 254.5f;                                       // S < Smax: bin 254 (see hist2d_kernel)
+        const bool ok = sf[i] < tie_thr && (top || fabsf(fr - 0.5f) < 0.4995f);   // else: boundary or may tie with the maximum
+        uint32_t gi = top ? 254u : (__float_as_uint(mg) & 0x7FFFFFu);
+        const bool zero = sf[i] == 0.0f;
+        gi = zero ? gi_zero : gi;
+        vb[i] |= gi;
+        need |= (zero || ok) ? 0u : (1u << i);
       }
+      if (!act) need = 0xFFu;                            // idle lanes: no votes (the queue below takes active lanes only)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (!((need >> i) & 1u)) h2d8_vote(slots_saddr, bins, vb[i]);
       if (!act) need = 0;
       // ---- exact-chain queue
       if (__any_sync(0xffffffffu, need != 0)) {
+        const unsigned long long row_base = ((unsigned long long)z * sy + y) * sx + 8ull * o;
 #pragma unroll 1
         for (int i = 0; i < 8; ++i) {
           const unsigned m = __ballot_sync(0xffffffffu, (need >> i) & 1u);
@@ -1566,8 +1607,12 @@ __global__ void __launch_bounds__(256) hist2d_v8_kernel(const T* __restrict__ ra
     // ---- end of the phase: counts go to the global table, slots are free again
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < TVK_H2D8_SLOTS; i += blockDim.x) {
-      const uint32_t t = tags[i];
-      if (t) { atomicAdd(&bins[t - 1u], (unsigned long long)cnts[i]); tags[i] = 0u; cnts[i] = 0u; }
+      const uint32_t w = slots[i];
+      if (w & 0xFFFFu) {
+        const uint32_t m = (i << kH2d8TagBits) | ((w >> 16) & ((1u << kH2d8TagBits) - 1u));
+        atomicAdd(&bins[(m * kH2d8Kinv) & ((1u << TVK_H2D8_BIN_BITS) - 1u)], (unsigned long long)(w & 0xFFFFu));
+        slots[i] = w & 0xFFFF0000u;                     // the bin keeps its slot
+      } else if (w) slots[i] = 0u;                      // no vote in this phase: the slot is free again
     }
     __syncthreads();
   }
@@ -2054,7 +2099,6 @@ template <typename T>
 static int run_hist2d(tvk_ctx* c, uint32_t bins_x, double max_nonzero, uint64_t* bins, float* max_grad, int sms) {
   BuildState& b = c->build;
   const uint32_t* s = b.info.lod_size[0];
-  const uint64_t n = (uint64_t)s[0] * s[1] * s[2];
   const double norm2 = (sizeof(T) == 1 ? 255.0 : 65535.0) * 2;
   const uint32_t range = 1u << (8 * sizeof(T));
   const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)s[1] * s[2] + 7) / 8, (uint64_t)sms * 16);
@@ -2071,7 +2115,8 @@ static int run_hist2d(tvk_ctx* c, uint32_t bins_x, double max_nonzero, uint64_t*
   // one-voxel-per-thread kernels
   const bool vec = (s[0] % 4u) == 0 && (reinterpret_cast<uintptr_t>(b.d_lod[0]) % (4 * sizeof(T))) == 0 && !getenv("TVK_HIST2D_SCALAR");
   // 8 voxels per thread + fp32 squares when rows are whole octets and 16-byte aligned (TVK_HIST2D_V4=1: the 4-voxel kernels)
-  const bool v8 = vec && (s[0] % 8u) == 0 && (reinterpret_cast<uintptr_t>(b.d_lod[0]) % (8 * sizeof(T))) == 0 && !getenv("TVK_HIST2D_V4");
+  const bool v8 = vec && (s[0] % 8u) == 0 && (reinterpret_cast<uintptr_t>(b.d_lod[0]) % (8 * sizeof(T))) == 0 &&
+                  (uint64_t)bins_x * 256u <= (1ull << TVK_H2D8_BIN_BITS) && !getenv("TVK_HIST2D_V4");
   if (v8) grad_max_v8_kernel<T><<<(unsigned)std::min<uint64_t>((uint64_t)((s[1] + 7) / 8) * ((s[2] + 15) / 16), (uint64_t)sms * 8), 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_part, d_bins);
   else if (vec) grad_max_vec_kernel<T><<<(unsigned)std::min<uint64_t>((uint64_t)((s[1] + 7) / 8) * ((s[2] + 15) / 16), (uint64_t)sms * 8), 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_part, d_bins);   // d_bins[0]: zeroed scratch, re-zeroed below
   else grad_max_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_part);
@@ -2088,11 +2133,12 @@ static int run_hist2d(tvk_ctx* c, uint32_t bins_x, double max_nonzero, uint64_t*
   if (vec) TVK_CHECK_CUDA(c, cudaMemsetAsync(d_bins, 0, sizeof(unsigned long long), c->stream));
   if (v8) {
     const uint64_t tiles = (uint64_t)((s[0] / 8 + TVK_H2D8_XO - 1) / TVK_H2D8_XO) * ((s[1] + 7) / 8) * ((s[2] + TVK_H2D8_ZT - 1) / TVK_H2D8_ZT);
-    const size_t smem = sizeof(unsigned long long) * 8 * 64 + 2 * sizeof(uint32_t) * TVK_H2D8_SLOTS;
+    const size_t smem = sizeof(unsigned long long) * 8 * 64 + sizeof(uint32_t) * TVK_H2D8_SLOTS;
     TVK_CHECK_CUDA(c, cudaFuncSetAttribute(hist2d_v8_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     TVK_CHECK_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hist2d_v8_kernel<T>, 256, smem));
-    const unsigned tb = (unsigned)std::min<uint64_t>(tiles, (uint64_t)sms * std::max(per_sm, 1));
+    // runs of consecutive tiles per CTA; 4 waves of CTAs, so that runs through empty space do not leave SMs idle
+    const unsigned tb = (unsigned)std::min<uint64_t>(tiles, (uint64_t)sms * std::max(per_sm, 1) * 4);
     const float k_smax = g.s ? (float)(65025.0 / (double)g.s) : 0.0f;
     const float tie_thr = (float)((double)g.s * (1.0 - 1e-6));
     hist2d_v8_kernel<T><<<tb, 256, smem, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, mg, g.s, k_smax, tie_thr, d_lut, d_bins);
