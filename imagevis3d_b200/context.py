@@ -377,6 +377,8 @@ class TvkContext:
         self._ck(self.lib.tvk_exchange_begin_frame(self.h, C.c_uint32(frame_id)), "tvk_exchange_begin_frame")
 
     def exchange_composite(self, order, frame_id):
+        if len(order) != self._xchg_world:                   # tvk_exchange_composite reads exactly `world` entries
+            raise ValueError("exchange_composite: order has %d entries, the exchange has %d members" % (len(order), self._xchg_world))
         arr = (C.c_uint32 * len(order))(*[int(o) for o in order])
         self._ck(self.lib.tvk_exchange_composite(self.h, arr, C.c_uint32(frame_id)), "tvk_exchange_composite")
 
