@@ -10,7 +10,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtvk_cuda.so")
 
-CU_SOURCES = ["tvk_context.cu", "tvk_raycast.cu", "tvk_visibility.cu", "tvk_builder.cu", "tvk_quantize.cu", "tvk_exchange.cu", "tvk_classic.cu"]
+CU_SOURCES = ["tvk_context.cu", "tvk_raycast.cu", "tvk_visibility.cu", "tvk_builder.cu", "tvk_quantize.cu", "tvk_exchange.cu", "tvk_classic.cu", "tvk_rebrick.cu"]
 CPP_SOURCES = ["host/tvk_host.cpp", "host/tvk_uvf.cpp", "host/tvk_rawio.cpp"]
 # -fmad=false: multiply-adds are fused only where the source says fmaf(), so that the ray-marcher
 # rounds exactly like the CPU oracle (see the floating-point contract in tvk_raycast.cu)

@@ -22,6 +22,7 @@ class TvkContext:
         rc = self.lib.tvk_create(C.c_int(device), C.byref(self.h))
         if rc != L.TVK_OK:
             raise L.TvkError("tvk_create(device=%d) failed with status %d (no CUDA device?)" % (device, rc))
+        self.device = device
         self.total_bricks = 0
         self.build_info = None
 
@@ -188,6 +189,55 @@ class TvkContext:
         if rc != L.TVK_OK:
             raise L.TvkError("tvk_build_plan failed with status %d" % rc)
         return info
+
+    # ---------------------------------------------------------- re-bricking (DynamicBrickingDS)
+    @staticmethod
+    def rebrick_desc(lod_sizes, src_brick, tgt_brick, overlap=2, bpv=1):
+        d = L.RebrickDesc()
+        d.lod_count = len(lod_sizes)
+        for l, s in enumerate(lod_sizes):
+            d.lod_size[l][:] = [int(v) for v in s]
+        d.src_brick[:] = [int(v) for v in src_brick]
+        d.tgt_brick[:] = [int(v) for v in tgt_brick]
+        d.overlap, d.bytes_per_voxel = overlap, bpv
+        return d
+
+    @staticmethod
+    def rebrick_plan(desc):
+        """-> RebrickInfo (layout only, no device needed); TvkError when the reference would refuse the sizes"""
+        info = L.RebrickInfo()
+        rc = L.load().tvk_rebrick_plan(C.byref(desc), C.byref(info))
+        if rc != L.TVK_OK:
+            raise L.TvkError("tvk_rebrick_plan failed with status %d (target core must divide source core, overlap 2)" % rc)
+        return info
+
+    @staticmethod
+    def rebrick_toc(desc):
+        """-> (offsets u64[n], sizes u32[n,3], src_index u64[n], src_offset u32[n,3]) of the target bricks"""
+        info = TvkContext.rebrick_plan(desc)
+        n = int(info.total_bricks)
+        off, sz = np.zeros(n, np.uint64), np.zeros((n, 3), np.uint32)
+        si, so = np.zeros(n, np.uint64), np.zeros((n, 3), np.uint32)
+        rc = L.load().tvk_rebrick_toc(C.byref(desc), _p(off), _p(sz), _p(si), _p(so), C.c_uint64(n))
+        if rc != L.TVK_OK:
+            raise L.TvkError("tvk_rebrick_toc failed with status %d" % rc)
+        return off, sz, si, so
+
+    def rebrick(self, desc, src_store, src_offsets, src_sizes):
+        """src_store: numpy uint8 array holding every source brick (brick i at src_offsets[i], src_sizes[i] voxels).
+        -> (target store as numpy uint8 [256-byte aligned bricks], offsets, sizes, minmax f64[n,2])"""
+        import torch
+        info = self.rebrick_plan(desc)
+        off, sz, _, _ = self.rebrick_toc(desc)
+        dev = torch.device("cuda", self.device)
+        src = torch.from_numpy(np.ascontiguousarray(src_store)).to(dev)
+        dst = torch.zeros(int(info.total_bytes), dtype=torch.uint8, device=dev)
+        so = np.ascontiguousarray(src_offsets, np.uint64)
+        ss = np.ascontiguousarray(src_sizes, np.uint32).reshape(-1)
+        mm = np.zeros((int(info.total_bricks), 2), np.float64)
+        self._ck(self.lib.tvk_rebrick(self.h, C.byref(desc), C.c_void_p(src.data_ptr()), _p(so), _p(ss), C.c_uint64(so.size),
+                                      C.c_void_p(dst.data_ptr()), _p(mm)), "tvk_rebrick")
+        return dst.cpu().numpy(), off, sz, mm
 
     def build_octree(self, raw=None, brick=64, overlap=2, median=False, clamp=False, raw_dptr=None,
                      volume_size=None, bpv=None):

@@ -840,8 +840,74 @@ bool CudaGridLeaper::LoadDataset(const std::string& uvfFile, uint64_t gpuMemByte
                               : tvk_uvf_read_bricks(u, 0, n, v->host_store, v->offsets.data());
   if (rc) { m_err = std::string("UVF brick read failed: ") + tvk_uvf_last_error(u); tvk_uvf_close(u); cudaFreeHost(v->host_store); delete v; return false; }
   tvk_uvf_close(u);
+  if (m_rebrickSize) {                                     // LoadRebricked: present the file with smaller bricks
+    BrickedVolume* r = Rebrick(v, m_rebrickSize, m_rebrickMinMax);
+    cudaFreeHost(v->host_store);
+    delete v;
+    if (!r) return false;
+    v = r;
+  }
   const uint32_t tfSize = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)v->hist1d.size(), 4096));
   return FinishLoad(v, gpuMemBytes, tfSize);
+}
+
+// AbstrRenderer::LoadRebricked (AbstrRenderer.cpp:266-273) -> IOManager::LoadRebrickedDataset (IOManager.cpp:1281-1320) ->
+// DynamicBrickingDS.  The reference wraps the source dataset and cuts target bricks one GetBrick() at a time; here the
+// whole target store is cut by one kernel that reads the source bricks straight out of the pinned host store
+// (tvk_rebrick), and the result is an ordinary paged volume.  Because an ExtendedOctree pyramid always runs down to
+// 1x1x1, the target has the layout a direct build with the small brick size would have (single-brick coarsest level
+// included), so both renderers take it as it is.
+bool CudaGridLeaper::LoadRebricked(const std::string& uvfFile, uint32_t brickSize, int minmaxMode, uint64_t gpuMemBytes, bool verifyChecksum) {
+  if (minmaxMode < TVK_MM_SOURCE || minmaxMode > TVK_MM_DYNAMIC) { m_err = "minmaxType too large"; return false; }   // IOManager.cpp:1290-1292
+  if (!brickSize) { m_err = "null brick size"; return false; }
+  m_rebrickSize = brickSize; m_rebrickMinMax = minmaxMode;
+  const bool ok = LoadDataset(uvfFile, gpuMemBytes, verifyChecksum, false);
+  m_rebrickSize = 0;
+  return ok;
+}
+
+BrickedVolume* CudaGridLeaper::Rebrick(const BrickedVolume* src, uint32_t brickSize, int minmaxMode) {
+  tvk_rebrick_desc d{};
+  d.lod_count = src->info.lod_count;
+  for (uint32_t l = 0; l < d.lod_count; ++l) for (int a = 0; a < 3; ++a) d.lod_size[l][a] = src->info.lod_size[l][a];
+  for (int a = 0; a < 3; ++a) { d.src_brick[a] = src->brick_size; d.tgt_brick[a] = brickSize; }
+  d.overlap = src->overlap; d.bytes_per_voxel = src->bpv;
+  tvk_rebrick_info ri;
+  if (tvk_rebrick_plan(&d, &ri) != TVK_OK) {
+    m_err = "target brick size (" + std::to_string(brickSize) + ") without ghost voxels is not a divisor of the source brick size (" +
+            std::to_string(src->brick_size) + ") without ghost voxels, or the overlap is not 2";
+    return nullptr;
+  }
+  BrickedVolume* v = new BrickedVolume();
+  for (int a = 0; a < 3; ++a) { v->domain[a] = src->domain[a]; v->scale[a] = src->scale[a]; }
+  v->bpv = src->bpv; v->brick_size = ri.tgt_brick[0]; v->overlap = src->overlap;
+  tvk_build_desc bd{};
+  for (int a = 0; a < 3; ++a) bd.volume_size[a] = v->domain[a];
+  bd.brick_size = v->brick_size; bd.overlap = v->overlap; bd.bytes_per_voxel = v->bpv;
+  tvk_build_plan(&bd, &v->info);
+  const uint64_t n = ri.total_bricks;
+  if (v->info.total_bricks != n || v->info.lod_count != d.lod_count) { delete v; m_err = "re-bricked layout differs from the octree layout of the target brick size"; return nullptr; }
+  v->offsets.resize(n); v->sizes.resize(3 * n); v->minmax.resize(2 * n);
+  std::vector<uint64_t> sidx(n);
+  tvk_rebrick_toc(&d, v->offsets.data(), v->sizes.data(), sidx.data(), nullptr, n);
+  v->store_bytes = v->info.total_bytes = ri.total_bytes;
+  v->hist1d = src->hist1d; v->max_grad_magnitude = src->max_grad_magnitude;
+  v->hist2d = src->hist2d; v->hist2d_x = src->hist2d_x; v->hist2d_y = src->hist2d_y;
+  void* d_dst = nullptr;
+  if (cudaMalloc(&d_dst, ri.total_bytes) != cudaSuccess) { delete v; m_err = "re-bricking: no device memory for the target store"; return nullptr; }
+  cudaMemset(d_dst, 0, ri.total_bytes);                     // (alignment padding between bricks)
+  std::vector<double> mm(2 * n);
+  int rc = tvk_rebrick(m_ctx, &d, src->host_store, src->offsets.data(), src->sizes.data(), src->info.total_bricks, d_dst, mm.data());
+  if (rc == TVK_OK && cudaHostAlloc((void**)&v->host_store, v->store_bytes, cudaHostAllocDefault) != cudaSuccess) rc = TVK_ERR_NOMEM;
+  if (rc == TVK_OK && cudaMemcpy(v->host_store, d_dst, v->store_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = TVK_ERR_CUDA;
+  cudaFree(d_dst);
+  if (rc) { Fail("tvk_rebrick", rc); if (v->host_store) cudaFreeHost(v->host_store); delete v; return nullptr; }
+  // MaxMinForKey (DynamicBrickingDS.cpp:862-876)
+  for (uint64_t i = 0; i < n; ++i) {
+    if (minmaxMode == TVK_MM_SOURCE) { v->minmax[2 * i] = src->minmax[2 * sidx[i]]; v->minmax[2 * i + 1] = src->minmax[2 * sidx[i] + 1]; }
+    else { v->minmax[2 * i] = mm[2 * i]; v->minmax[2 * i + 1] = mm[2 * i + 1]; }
+  }
+  return v;
 }
 
 bool CudaGridLeaper::PrepareHostVolume(BrickedVolume* v) {
@@ -1678,6 +1744,9 @@ int tvkr_load_streamed_end(tvkr_renderer* h, uint64_t gpu_mem_bytes, float* buil
 int tvkr_load_volume_file(tvkr_renderer* h, const char* path, uint32_t brick, uint32_t overlap, int median, int out_of_core,
                           uint64_t gpu_mem_bytes, int hist2d) {
   return h && path && R(h)->LoadVolumeFile(path, brick, overlap, median != 0, out_of_core != 0, gpu_mem_bytes, hist2d != 0) ? 0 : 1;
+}
+int tvkr_load_rebricked(tvkr_renderer* h, const char* uvf_file, uint32_t brick_size, int minmax_mode, uint64_t gpu_mem_bytes, int verify_checksum) {
+  return h && uvf_file && R(h)->LoadRebricked(uvf_file, brick_size, minmax_mode, gpu_mem_bytes, verify_checksum != 0) ? 0 : 1;
 }
 int tvkr_load_dataset_compressed(tvkr_renderer* h, const char* uvf_file, uint64_t gpu_mem_bytes, int verify_checksum) {
   return h && uvf_file && R(h)->LoadDataset(uvf_file, gpu_mem_bytes, verify_checksum != 0, true) ? 0 : 1;

@@ -236,6 +236,9 @@ class CudaGridLeaper {
   // minmax (2 each), plus hist1d and max_grad_magnitude; PrepareHostVolume plans the octree, lays the bricks out in ONE
   // pinned host allocation (host_store + offsets); the caller copies the brick payloads there; AdoptVolume takes
   // ownership and sets up pool, transfer function and visibility like LoadDataset does.
+  // renderer.loadRebricked(file, {bs,bs,bs}, minmaxMode) (AbstrRenderer.cpp:266-273): brickSize includes the ghost voxels;
+  // minmaxMode = TVK_MM_SOURCE / _PRECOMPUTE / _DYNAMIC
+  bool LoadRebricked(const std::string& uvfFile, uint32_t brickSize, int minmaxMode, uint64_t gpuMemBytes, bool verifyChecksum);
   bool PrepareHostVolume(BrickedVolume* v);
   bool AdoptVolume(BrickedVolume* v, uint64_t gpuMemBytes);
   // the loaded volume as a UVF v5 file (TOC, histograms, max/min, key/values, MD5); compression: TVK_UVF_COMP_*
@@ -321,6 +324,9 @@ class CudaGridLeaper {
  private:
   bool Fail(const std::string& what, int rc);
   bool FinishLoad(BrickedVolume* v, uint64_t gpuMemBytes, uint32_t tfSize);
+  BrickedVolume* Rebrick(const BrickedVolume* src, uint32_t brickSize, int minmaxMode);
+  uint32_t m_rebrickSize = 0;          // != 0 while LoadRebricked runs LoadDataset
+  int m_rebrickMinMax = 0;
   bool RecomputeBrickVisibility(bool force);            // GLGridLeaper.cpp:632-688
   tvk_ctx* m_ctx = nullptr;
   BrickedVolume* m_vol = nullptr;

@@ -84,6 +84,13 @@ class Renderer:
                  "loadDataset")
         return True
 
+    def loadRebricked(self, filename, brick_size, minmax_mode=0, gpu_mem_bytes=0, verify=True):
+        """renderer.loadRebricked(file, {bs,bs,bs}, minmaxMode): the file's bricks presented as bricks of brick_size (ghost
+        voxels included); minmax_mode 0 source / 1 precompute / 2 dynamic (DynamicBrickingDS::MinMaxMode)"""
+        self._ck(self._lib.tvkr_load_rebricked(self._h, filename.encode(), C.c_uint32(int(brick_size)), C.c_int(int(minmax_mode)),
+                                               C.c_uint64(int(gpu_mem_bytes)), C.c_int(int(verify))), "loadRebricked")
+        return True
+
     def loadVolumeFile(self, filename, brick_size=64, overlap=2, median=False, out_of_core=False, gpu_mem_bytes=0, hist2d=True):
         """opens a QVIS .dat or a NRRD .nrrd/.nhdr volume: header parse, quantisation to 8/16 bit on the device, octree build"""
         self._ck(self._lib.tvkr_load_volume_file(self._h, filename.encode(), C.c_uint32(brick_size), C.c_uint32(overlap), C.c_int(int(median)),

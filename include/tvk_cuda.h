@@ -295,6 +295,45 @@ int tvk_build_stream_rows(const tvk_build_desc* desc, uint32_t bz0, uint32_t bz1
 int tvk_build_stream_slab(tvk_ctx* ctx, const void* raw_slab, uint32_t z0, uint32_t rows, uint32_t bz0, uint32_t bz1);
 int tvk_build_stream_end(tvk_ctx* ctx, tvk_build_info* info);
 
+/* ------------------------------------------------------------------ re-bricking */
+/* replaces DynamicBrickingDS (IO/DynamicBrickingDS.cpp; IOManager::LoadRebrickedDataset, IOManager.cpp:1281-1320):
+ * a dataset with large bricks is presented with smaller ones.  Every target brick is a sub-box of ONE source brick
+ * (ghost voxels included: the target's ghost cells are the source brick's own voxels), target index / source index /
+ * offset as SourceBrickIndex (:273-303), OffsetIntoSource (:305-336) and ComputedTargetBrickSize (:414-435) define
+ * them; the LOD pyramid is the source's (Rebrick(), :1090-1180, adds no level).  The reference serves target bricks one
+ * GetBrick() at a time from a host cache of source bricks; here the whole target store is cut on the device in one
+ * launch.  Brick sizes INCLUDE the 2*overlap ghost voxels; overlap must be 2 (the reference hard-codes 4 ghost voxels in
+ * BrickSansGhost, :208-218).  Target bricks are ordered LOD by LOD, x fastest (BrickKey index order, :1148). */
+#define TVK_MM_SOURCE      0   /* a target brick reports its source brick's min/max (DynamicBrickingDS.h MinMaxMode) */
+#define TVK_MM_PRECOMPUTE  1   /* min/max of the target brick's voxels, computed when the dataset is opened          */
+#define TVK_MM_DYNAMIC     2   /* the same values, computed when asked for (identical here: one kernel does both)    */
+typedef struct tvk_rebrick_desc {
+  uint32_t lod_count;
+  uint32_t lod_size[TVK_MAX_LOD][3];   /* voxels per LOD of the SOURCE dataset (GetDomainSize)     */
+  uint32_t src_brick[3];               /* GetMaxBrickSize() of the source, ghost voxels included   */
+  uint32_t tgt_brick[3];               /* wanted brick size, ghost voxels included                 */
+  uint32_t overlap;                    /* 2                                                         */
+  uint32_t bytes_per_voxel;            /* 1 or 2                                                    */
+} tvk_rebrick_desc;
+typedef struct tvk_rebrick_info {
+  uint32_t tgt_brick[3];                   /* min(tgt, src) per axis (IOManager.cpp:1300-1304)   */
+  uint32_t lod_bricks[TVK_MAX_LOD][3];     /* target layout                                      */
+  uint64_t lod_offset[TVK_MAX_LOD];        /* first target index of each LOD                     */
+  uint32_t src_lod_bricks[TVK_MAX_LOD][3]; /* source layout                                      */
+  uint64_t src_lod_offset[TVK_MAX_LOD];
+  uint64_t total_bricks, src_total_bricks;
+  uint64_t total_bytes;                    /* target store, every brick 256-byte aligned         */
+} tvk_rebrick_info;
+/* layout only; TVK_ERR_INVALID if a target core size does not divide the source core size (the reference throws) */
+int tvk_rebrick_plan(const tvk_rebrick_desc* desc, tvk_rebrick_info* info);
+/* per target brick: byte offset in the target store, size, index of its source brick, voxel offset inside it */
+int tvk_rebrick_toc(const tvk_rebrick_desc* desc, uint64_t* offsets, uint32_t* sizes3, uint64_t* src_index, uint32_t* src_offset3, uint64_t n);
+/* Cuts the target store.  src_store: all source bricks (device memory, or pinned host memory mapped into the device),
+ * brick i at src_offsets[i] with src_sizes3[3*i..]; dst_store: device memory of info.total_bytes bytes.
+ * minmax2 (host, 2 doubles per target brick, may be NULL): min/max of each target brick's voxels. */
+int tvk_rebrick(tvk_ctx* ctx, const tvk_rebrick_desc* desc, const void* src_store, const uint64_t* src_offsets,
+                const uint32_t* src_sizes3, uint64_t n_src, void* dst_store, double* minmax2);
+
 /* the caller is about to free the device volume it passed with raw_on_device = 1: the build state drops its pointer
  * (tvk_build_hist2d is refused afterwards) */
 int tvk_build_forget_raw(tvk_ctx* ctx);

@@ -54,6 +54,13 @@ int tvkr_load_dataset(tvkr_renderer* r, const char* uvf_file, uint64_t gpu_mem_b
  * ExtendedOctree::GetBrickData (ExtendedOctree.cpp:313-360).  Other files load exactly as tvkr_load_dataset. */
 int tvkr_load_dataset_compressed(tvkr_renderer* r, const char* uvf_file, uint64_t gpu_mem_bytes, int verify_checksum);
 int tvkr_store_is_compressed(tvkr_renderer* r);
+/* renderer.loadRebricked("file.uvf", {bs,bs,bs}, minmaxMode) (AbstrRenderer::LoadRebricked, AbstrRenderer.cpp:266-273 ->
+ * IOManager::LoadRebrickedDataset, IOManager.cpp:1281-1320 -> DynamicBrickingDS): the file's bricks (e.g. 256^3) are
+ * presented as bricks of brick_size (ghost voxels included; clamped to the file's brick size; its core must divide the
+ * file's core).  minmax_mode: TVK_MM_SOURCE / TVK_MM_PRECOMPUTE / TVK_MM_DYNAMIC (tvk_cuda.h).  The target store is cut on
+ * the device (tvk_rebrick) and paged like any loaded dataset. */
+int tvkr_load_rebricked(tvkr_renderer* r, const char* uvf_file, uint32_t brick_size, int minmax_mode, uint64_t gpu_mem_bytes,
+                        int verify_checksum);
 /* what IOManager::ConvertDataset leaves on disk (RAWConverter::ConvertRAWDataset, RAWConverter.cpp:412-681):
  * the loaded volume as a UVF v5 file; compression = TVK_UVF_COMP_NONE / _ZLIB (tvk_uvf.h) */
 int tvkr_save_uvf(tvkr_renderer* r, const char* uvf_file, uint32_t compression, uint32_t level);

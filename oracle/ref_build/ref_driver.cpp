@@ -53,6 +53,8 @@
 #include "IO/Quantize.h"
 #include "IO/UVF/KeyValuePairDataBlock.h"
 #include "Basics/nonstd.h"
+#include "IO/uvfDataset.h"
+#include "IO/DynamicBrickingDS.h"
 
 using namespace tuvok;
 
@@ -294,6 +296,59 @@ static int do_writeuvf(int argc, char** argv) {
 // ref_driver readuvf <file.uvf> <out.bin>: UVF::Open with checksum verification, then the TVKREF1 dump of
 // the first TOC block with the file's own histogram / max-min blocks, followed by u64 nkv and, per pair,
 // u64 len, key, u64 len, value.
+
+// ref_driver rebrick <file.uvf> <bx> <by> <bz> <mm 0|1|2> <out.bin>
+//   opens the file with the reference's UVFDataset, wraps it in the reference's DynamicBrickingDS (target brick size
+//   INCLUDING ghost voxels, min/max mode MM_SOURCE / MM_PRECOMPUTE / MM_DYNAMIC -- IO/DynamicBrickingDS.h) and dumps
+//     char[8] "TVKRBK1\0"; u32 lods; per LOD: u32 layout[3], u64 domain[3]; u64 total;
+//     per brick (LOD-major, index order): u32 size[3]; f64 min; f64 max   (MaxMinForKey)
+//     then per brick: payload (GetBrick)
+static int do_rebrick(int argc, char** argv) {
+  if (argc < 8) return 2;
+  std::shared_ptr<UVFDataset> ds(new UVFDataset(argv[2], 1024, false));
+  const unsigned mode = (unsigned)atoi(argv[6]);
+  std::array<size_t, 3> bs = {{(size_t)atoi(argv[3]), (size_t)atoi(argv[4]), (size_t)atoi(argv[5])}};
+  std::unique_ptr<DynamicBrickingDS> dyn;
+  try { dyn.reset(new DynamicBrickingDS(ds, bs, 1u << 30, (DynamicBrickingDS::MinMaxMode)mode)); }
+  catch (const std::exception& e) { fprintf(stderr, "rebrick refused: %s\n", e.what()); return 3; }
+  FILE* f = fopen(argv[7], "wb");
+  if (!f) return 1;
+  fwrite("TVKRBK1\0", 1, 8, f);
+  const uint32_t lods = (uint32_t)dyn->GetLODLevelCount();
+  put(f, lods);
+  uint64_t total = 0;
+  std::vector<uint64_t> per_lod(lods);
+  for (uint32_t l = 0; l < lods; ++l) {
+    const UINTVECTOR3 lay = dyn->GetBrickLayout(l, 0);
+    const UINT64VECTOR3 dom = dyn->GetDomainSize(l, 0);
+    put(f, (uint32_t)lay[0]); put(f, (uint32_t)lay[1]); put(f, (uint32_t)lay[2]);
+    put(f, (uint64_t)dom[0]); put(f, (uint64_t)dom[1]); put(f, (uint64_t)dom[2]);
+    per_lod[l] = (uint64_t)lay[0] * lay[1] * lay[2];
+    total += per_lod[l];
+  }
+  put(f, total);
+  for (uint32_t l = 0; l < lods; ++l)
+    for (uint64_t i = 0; i < per_lod[l]; ++i) {
+      const BrickKey k(0, l, i);
+      const UINTVECTOR3 n = dyn->GetBrickMetadata(k).n_voxels;
+      put(f, (uint32_t)n[0]); put(f, (uint32_t)n[1]); put(f, (uint32_t)n[2]);
+      const MinMaxBlock mm = dyn->MaxMinForKey(k);
+      put(f, mm.minScalar); put(f, mm.maxScalar);
+    }
+  std::vector<uint8_t> data;
+  std::vector<uint16_t> data16;                              // (GetBrick is typed: the 8-bit overload copies 8-bit elements)
+  const bool wide = dyn->GetBitWidth() == 16;
+  for (uint32_t l = 0; l < lods; ++l)
+    for (uint64_t i = 0; i < per_lod[l]; ++i) {
+      const BrickKey k(0, l, i);
+      if (!(wide ? dyn->GetBrick(k, data16) : dyn->GetBrick(k, data))) { fprintf(stderr, "GetBrick failed\n"); fclose(f); return 1; }
+      if (wide) fwrite(data16.data(), 2, data16.size(), f);
+      else fwrite(data.data(), 1, data.size(), f);
+    }
+  fclose(f);
+  return 0;
+}
+
 static int do_readuvf(int argc, char** argv) {
   if (argc < 4) return 2;
   std::string fn(argv[2]);
@@ -428,5 +483,6 @@ int main(int argc, char** argv) {
   if (!strcmp(argv[1], "quantize")) return do_quantize(argc, argv);
   if (!strcmp(argv[1], "writeuvf")) return do_writeuvf(argc, argv);
   if (!strcmp(argv[1], "readuvf")) return do_readuvf(argc, argv);
+  if (!strcmp(argv[1], "rebrick")) return do_rebrick(argc, argv);
   return 2;
 }

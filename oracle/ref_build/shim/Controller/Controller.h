@@ -28,6 +28,8 @@ public:
 class ShimIOMan {
 public:
   unsigned long long GetIncoresize() const { return 1ull << 20; }
+  unsigned long long GetMaxBrickSize() const { return 256; }     // UVFDataset::Crop only
+  unsigned long long GetBrickOverlap() const { return 2; }
 };
 
 class ShimMasterController {
