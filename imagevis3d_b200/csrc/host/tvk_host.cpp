@@ -765,9 +765,13 @@ bool CudaGridLeaper::LoadDataset(const std::string& uvfFile, uint64_t gpuMemByte
   if (!m_ctx) { m_err = "renderer not initialised"; return false; }
   char err[256] = {0};
   tvk_uvf* u = nullptr;
-  if (tvk_uvf_open(uvfFile.c_str(), verifyChecksum ? 1 : 0, &u, err, sizeof(err))) { m_err = std::string("UVF open failed: ") + err; return false; }
+  if (tvk_uvf_open_timestep(uvfFile.c_str(), verifyChecksum ? 1 : 0, (uint32_t)m_loadTimestep, &u, err, sizeof(err))) { m_err = std::string("UVF open failed: ") + err; return false; }
   tvk_uvf_info ui;
   tvk_uvf_get_info(u, &ui);
+  // what SetTimestep needs to come back for another time step of the same file
+  m_file = uvfFile; m_fileGpuMem = gpuMemBytes; m_fileVerify = verifyChecksum; m_fileKeepCompressed = keepCompressed;
+  m_fileRebrick = m_rebrickSize; m_fileRebrickMinMax = m_rebrickMinMax;
+  m_timesteps = std::max<uint32_t>(1u, ui.timesteps); m_timestep = m_loadTimestep;
   if (ui.toc_block < 0 && ui.rdb_block >= 0 && !ui.rdb_signed) {
     // legacy RasterDataBlock file (e.g. DemoData/c60.uvf: one 128^3 brick): stitch the finest level back together
     // and re-brick it for the ray-guided path, as IOManager::LoadRebrickedDataset / DynamicBrickingDS do
@@ -1205,7 +1209,28 @@ bool CudaGridLeaper::ComputeRaycastParams(tvk_raycast_params& p) {
 
 void CudaGridLeaper::SetClipPlane(const float plane[4]) { memcpy(m_clipPlane, plane, 16); if (m_clipEnabled) ScheduleCompleteRedraw(); }
 void CudaGridLeaper::EnableClipPlane(bool on) { if (on != m_clipEnabled) { m_clipEnabled = on; ScheduleCompleteRedraw(); } }
-bool CudaGridLeaper::SetTimestep(size_t t) { if (t != 0) { m_err = "the dataset has one time step"; return false; } return true; }
+// AbstrRenderer::SetTimestep (AbstrRenderer.cpp:1345-1361): time steps of a time-dependent UVF are separate octrees; the
+// renderer swaps the brick store for the requested step's (read from the file again) and starts with an empty working
+// set.  Transfer functions, iso value, mode and view are the renderer's and stay.
+bool CudaGridLeaper::SetTimestep(size_t t) {
+  if (t == m_timestep) return true;
+  if (m_file.empty() || t >= m_timesteps) { m_err = "time step " + std::to_string(t) + " requested, the dataset has " + std::to_string(m_timesteps); return false; }
+  const TransferFunction1D tf = m_tf1d;
+  const float iso = m_isoValue;
+  m_loadTimestep = t;
+  m_rebrickSize = m_fileRebrick; m_rebrickMinMax = m_fileRebrickMinMax;
+  const std::string file = m_file;
+  const bool ok = LoadDataset(file, m_fileGpuMem, m_fileVerify, m_fileKeepCompressed);
+  m_rebrickSize = 0;
+  m_loadTimestep = 0;
+  if (!ok) return false;
+  m_tf1d = tf; m_isoValue = iso;
+  Changed1DTrans();
+  if (m_has2d && m_mode == RM_2DTRANS) { const int rc = tvk_set_tf2d(m_ctx, m_tf2dBytes.data(), m_tf2dW, m_tf2dH); if (rc) return Fail("tvk_set_tf2d", rc); }
+  m_visValid = false;
+  ScheduleCompleteRedraw();
+  return true;
+}
 void CudaGridLeaper::SetLODLimits(uint32_t lo, uint32_t hi) { m_lodLimits[0] = lo; m_lodLimits[1] = hi; }
 void CudaGridLeaper::SetBGColors(const float top[3], const float bottom[3]) { memcpy(m_bg[0], top, 12); memcpy(m_bg[1], bottom, 12); }
 
@@ -1781,6 +1806,12 @@ int tvkr_get_view(tvkr_renderer* h, float pos[3], float dir[3], float up[3]) {
 }
 int tvkr_reset_view(tvkr_renderer* h) { if (!h) return 1; R(h)->ResetViewPos(); R(h)->ResetViewDir(); R(h)->ResetUpDir(); return 0; }
 int tvkr_set_timestep(tvkr_renderer* h, uint64_t t) { return h && R(h)->SetTimestep((size_t)t) ? 0 : 1; }
+int tvkr_get_timesteps(tvkr_renderer* h, uint64_t* count, uint64_t* current) {
+  if (!h) return 1;
+  if (count) *count = R(h)->Timesteps();
+  if (current) *current = R(h)->Timestep();
+  return 0;
+}
 int tvkr_set_lod_limits(tvkr_renderer* h, uint32_t lo, uint32_t hi) { if (!h) return 1; R(h)->SetLODLimits(lo, hi); return 0; }
 int tvkr_set_bg_colors(tvkr_renderer* h, const float top[3], const float bottom[3]) { if (!h || !top || !bottom) return 1; R(h)->SetBGColors(top, bottom); return 0; }
 int tvkr_set_blend_precision(tvkr_renderer* h, int) { return h ? 0 : 1; }

@@ -276,6 +276,8 @@ class CudaGridLeaper {
   Vec3 GetViewDir() const { return (m_at - m_eye).normalized(); }  // AbstrRenderer.cpp:1608-1610
   Vec3 GetUpDir() const { return m_up; }
   bool SetTimestep(size_t t);
+  size_t Timesteps() const { return m_timesteps; }
+  size_t Timestep() const { return m_timestep; }
   void SetLODLimits(uint32_t lo, uint32_t hi);                     // kept for the classic path; the ray-guided path ignores it
   void SetBGColors(const float top[3], const float bottom[3]);     // display path only (captures read the FBO)
   void SetRendererTarget(int t) { m_target = t; }
@@ -325,6 +327,12 @@ class CudaGridLeaper {
   bool Fail(const std::string& what, int rc);
   bool FinishLoad(BrickedVolume* v, uint64_t gpuMemBytes, uint32_t tfSize);
   BrickedVolume* Rebrick(const BrickedVolume* src, uint32_t brickSize, int minmaxMode);
+  std::string m_file;                  // the UVF the dataset came from (SetTimestep reads another step of it)
+  uint64_t m_fileGpuMem = 0;
+  bool m_fileVerify = false, m_fileKeepCompressed = false;
+  uint32_t m_fileRebrick = 0;
+  int m_fileRebrickMinMax = 0;
+  size_t m_timestep = 0, m_timesteps = 1, m_loadTimestep = 0;
   uint32_t m_rebrickSize = 0;          // != 0 while LoadRebricked runs LoadDataset
   int m_rebrickMinMax = 0;
   bool RecomputeBrickVisibility(bool force);            // GLGridLeaper.cpp:632-688

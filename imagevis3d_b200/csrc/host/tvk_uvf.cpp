@@ -430,6 +430,7 @@ struct tvk_uvf {
   uint32_t bpv = 0;
   uint64_t rdb_data_pos = 0;                  // file offset of the finest level's first brick
   uint64_t file_size = 0;
+  uint32_t want_ts = 0;                       // which time step's blocks this handle reads (UVFDataset::FindSuitableDataBlocks)
 };
 
 namespace {
@@ -454,21 +455,28 @@ struct Rd {
   catch (const std::bad_alloc&) { expr_on_error; return TVK_ERR_NOMEM; }                          \
   catch (...) { expr_on_error; return TVK_ERR_INVALID; }
 
-static int uvf_open_impl(const char* path, int verify, tvk_uvf** out, char* err, size_t errlen, tvk_uvf*& u);
+static int uvf_open_impl(const char* path, int verify, uint32_t timestep, tvk_uvf** out, char* err, size_t errlen, tvk_uvf*& u);
 
-extern "C" int tvk_uvf_open(const char* path, int verify, tvk_uvf** out, char* err, size_t errlen) {
+extern "C" int tvk_uvf_open_timestep(const char* path, int verify, uint32_t timestep, tvk_uvf** out, char* err, size_t errlen) {
   if (!path || !out) return TVK_ERR_INVALID;
   *out = nullptr;
   tvk_uvf* u = nullptr;
   TVK_UVF_GUARD({ if (u) tvk_uvf_close(u); *out = nullptr; set_err(err, errlen, "out of memory or corrupt file while parsing the UVF headers"); },
-                return uvf_open_impl(path, verify, out, err, errlen, u);)
+                return uvf_open_impl(path, verify, timestep, out, err, errlen, u);)
+}
+extern "C" int tvk_uvf_open(const char* path, int verify, tvk_uvf** out, char* err, size_t errlen) {
+  return tvk_uvf_open_timestep(path, verify, 0, out, err, errlen);
 }
 
-static int uvf_open_impl(const char* path, int verify, tvk_uvf** out, char* err, size_t errlen, tvk_uvf*& u) {
+static int uvf_open_impl(const char* path, int verify, uint32_t timestep, tvk_uvf** out, char* err, size_t errlen, tvk_uvf*& u) {
   FILE* f = fopen(path, "rb");
   if (!f) { set_err(err, errlen, "file not found or access denied"); return TVK_ERR_INVALID; }
   u = new tvk_uvf();
   u->f = f;
+  u->want_ts = timestep;
+  // UVFDataset::FindSuitableDataBlocks (uvfDataset.cpp:635-745) hands the k-th volume / 1-D histogram / 2-D histogram /
+  // max-min block of the file to time step k, in file order
+  uint32_t toc_seen = 0, h1_seen = 0, h2_seen = 0, mm_seen = 0;
   if (fseeko(f, 0, SEEK_END) == 0) u->file_size = (uint64_t)ftello(f);
   fseeko(f, 0, SEEK_SET);
   u->info.toc_block = -1;
@@ -503,7 +511,7 @@ static int uvf_open_impl(const char* path, int verify, tvk_uvf** out, char* err,
     if (!r.ok) return fail("corrupt block header", TVK_ERR_INVALID);
     const uint32_t bi = u->info.block_count++;
     if (bi < 16) u->info.block_semantics[bi] = (uint32_t)sem;
-    if (sem == BS_TOC && u->info.toc_block < 0) {
+    if (sem == BS_TOC && toc_seen++ == u->want_ts) {
       u->info.toc_block = (int32_t)bi;
       u->oct_pos = (uint64_t)ftello(f);
       tvk_uvf_volume& v = u->info.vol;
@@ -591,20 +599,20 @@ static int uvf_open_impl(const char* path, int verify, tvk_uvf** out, char* err,
         }
       }
       r.ok = true;                                                            // an undecodable grid block is skipped, not fatal
-    } else if (sem == BS_HIST1D && u->hist1d.empty()) {
+    } else if (sem == BS_HIST1D && h1_seen++ == u->want_ts) {
       const uint64_t n = r.get<uint64_t>();
       if (!r.ok || n > (1u << 24)) return fail("corrupt 1D histogram", TVK_ERR_INVALID);
       u->hist1d.resize((size_t)n);
       if (n && fread(u->hist1d.data(), 8, (size_t)n, f) != n) return fail("corrupt 1D histogram", TVK_ERR_INVALID);
       u->info.hist1d_size = n;
-    } else if (sem == BS_HIST2D && u->hist2d.empty()) {
+    } else if (sem == BS_HIST2D && h2_seen++ == u->want_ts) {
       u->info.max_grad_magnitude = r.get<float>();
       const uint64_t nx = r.get<uint64_t>(), ny = r.get<uint64_t>();
       if (!r.ok || nx * ny > (1u << 26)) return fail("corrupt 2D histogram", TVK_ERR_INVALID);
       u->hist2d.resize((size_t)(nx * ny));
       if (nx * ny && fread(u->hist2d.data(), 8, (size_t)(nx * ny), f) != nx * ny) return fail("corrupt 2D histogram", TVK_ERR_INVALID);
       u->info.hist2d_x = nx; u->info.hist2d_y = ny;
-    } else if (sem == BS_MAXMIN && u->minmax.empty()) {
+    } else if (sem == BS_MAXMIN && mm_seen++ == u->want_ts) {
       const uint64_t n = r.get<uint64_t>(), comps = r.get<uint64_t>();
       if (!r.ok || comps == 0 || comps > 64 || n > u->file_size / (32 * comps)) return fail("corrupt max/min block", TVK_ERR_INVALID);
       u->minmax.resize((size_t)(4 * n));
@@ -628,6 +636,8 @@ static int uvf_open_impl(const char* path, int verify, tvk_uvf** out, char* err,
     if (next == 0) break;
     pos += next;
   }
+  u->info.timesteps = toc_seen;
+  if (toc_seen && u->want_ts >= toc_seen) return fail("time step " + std::to_string(u->want_ts) + " requested, the file has " + std::to_string(toc_seen), TVK_ERR_INVALID);
   *out = u;
   return TVK_OK;
 }

@@ -243,6 +243,12 @@ class Renderer:
     def resetView(self):
         self._ck(self._lib.tvkr_reset_view(self._h), "resetView")
 
+    def timesteps(self):
+        """(number of time steps of the loaded dataset, the one being shown)"""
+        n, cur = C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.tvkr_get_timesteps(self._h, C.byref(n), C.byref(cur)), "timesteps")
+        return int(n.value), int(cur.value)
+
     def setTimestep(self, t):
         self._ck(self._lib.tvkr_set_timestep(self._h, C.c_uint64(int(t))), "setTimestep")
 

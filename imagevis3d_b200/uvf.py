@@ -34,7 +34,7 @@ class UvfInfo(C.Structure):
                 ("maxmin_bricks", C.c_uint64), ("kv_count", C.c_uint32), ("checksum_ok", C.c_uint32),
                 ("rdb_block", C.c_int32), ("rdb_bits", C.c_uint32), ("rdb_signed", C.c_uint32),
                 ("rdb_domain", C.c_uint64 * 3), ("rdb_brick", C.c_uint64 * 3), ("rdb_overlap", C.c_uint64 * 3),
-                ("rdb_lod_levels", C.c_uint64)]
+                ("rdb_lod_levels", C.c_uint64), ("timesteps", C.c_uint32)]
 
 
 def _p(a):
@@ -89,11 +89,12 @@ def write_uvf(path, volume_size, bpv, brick, overlap, offsets, sizes, store, min
 
 
 class UvfFile:
-    def __init__(self, path, verify=True):
+    def __init__(self, path, verify=True, timestep=0):
         self.lib = L.load()
         self.h = C.c_void_p()
         err = C.create_string_buffer(256)
-        rc = self.lib.tvk_uvf_open(path.encode(), C.c_int(1 if verify else 0), C.byref(self.h), err, C.c_size_t(256))
+        rc = self.lib.tvk_uvf_open_timestep(path.encode(), C.c_int(1 if verify else 0), C.c_uint32(int(timestep)), C.byref(self.h), err,
+                                            C.c_size_t(256))
         if rc:
             raise L.TvkError("tvk_uvf_open(%s): %s" % (path, err.value.decode()))
         self.info = UvfInfo()

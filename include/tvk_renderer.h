@@ -125,6 +125,9 @@ int tvkr_set_light_colors(tvkr_renderer* r, const float ambient[4], const float 
 int tvkr_get_view(tvkr_renderer* r, float pos[3], float dir[3], float up[3]);    /* getViewPos/Dir/UpDir      */
 int tvkr_reset_view(tvkr_renderer* r);                                           /* resetViewPos/Dir/UpDir    */
 int tvkr_set_timestep(tvkr_renderer* r, uint64_t t);                             /* renderer.setTimestep      */
+/* dataset.getNumberOfTimesteps (UVFDataset::GetNumberOfTimesteps, uvfDataset.cpp:621-623) and the step being shown; a
+ * dataset loaded from memory has one */
+int tvkr_get_timesteps(tvkr_renderer* r, uint64_t* count, uint64_t* current);
 int tvkr_set_lod_limits(tvkr_renderer* r, uint32_t lo, uint32_t hi);             /* renderer.setLODLimits     */
 int tvkr_set_bg_colors(tvkr_renderer* r, const float top[3], const float bottom[3]);   /* renderer.setBGColors */
 int tvkr_set_blend_precision(tvkr_renderer* r, int precision);   /* renderer.setBlendPrecision: accumulation is always fp32 here */

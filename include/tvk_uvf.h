@@ -89,9 +89,13 @@ typedef struct tvk_uvf_info {
   int32_t  rdb_block;               /* index of the first 3-D scalar RasterDataBlock, -1 if none */
   uint32_t rdb_bits, rdb_signed;    /* element width (8 / 16) and signedness                */
   uint64_t rdb_domain[3], rdb_brick[3], rdb_overlap[3], rdb_lod_levels;
+  uint32_t timesteps;               /* TOC blocks in the file = time steps (UVFDataset::GetNumberOfTimesteps, uvfDataset.cpp:621-623) */
 } tvk_uvf_info;
 
 int  tvk_uvf_open(const char* path, int verify_checksum, tvk_uvf** out, char* err, size_t errlen);
+/* the same for time step `timestep` of a time-dependent file: every getter below then answers for the k-th volume /
+ * histogram / max-min block of the file (UVFDataset::FindSuitableDataBlocks, uvfDataset.cpp:635-745); tvk_uvf_open = step 0 */
+int  tvk_uvf_open_timestep(const char* path, int verify_checksum, uint32_t timestep, tvk_uvf** out, char* err, size_t errlen);
 void tvk_uvf_close(tvk_uvf* u);
 int  tvk_uvf_get_info(const tvk_uvf* u, tvk_uvf_info* info);
 /* per brick: position / stored length in the file, compression, size in voxels */

@@ -297,6 +297,91 @@ static int do_writeuvf(int argc, char** argv) {
 // the first TOC block with the file's own histogram / max-min blocks, followed by u64 nkv and, per pair,
 // u64 len, key, u64 len, value.
 
+// ref_driver writeuvfts <out.uvf> <sx> <sy> <sz> <u8|u16> <brick> <overlap> <raw0> <raw1> ...
+//   a TIME-DEPENDENT file, block order as the time-step loop of RAWConverter::ConvertRAWDataset writes it
+//   (IO/RAWConverter.cpp:548-661): per step a TOC block, the 1-D histogram block (the loop computes it for the first step
+//   only and stores the same object again for every later step, :630-637), a 2-D histogram and a max/min block; the
+//   key/value block once at the end.
+static int do_writeuvfts(int argc, char** argv) {
+  if (argc < 10) return 2;
+  const std::string out = argv[2];
+  const uint64_t sx = strtoull(argv[3], 0, 10), sy = strtoull(argv[4], 0, 10), sz = strtoull(argv[5], 0, 10);
+  const bool u16 = !strcmp(argv[6], "u16");
+  const uint64_t brick = strtoull(argv[7], 0, 10);
+  const uint32_t overlap = (uint32_t)strtoul(argv[8], 0, 10);
+  UVF uvfFile(std::wstring(out.begin(), out.end()));
+  GlobalHeader gh;
+  gh.bIsBigEndian = EndianConvert::IsBigEndian();
+  gh.ulChecksumSemanticsEntry = UVFTables::CS_MD5;
+  uvfFile.SetGlobalHeader(gh);
+  Histogram1DDataBlock h1;
+  std::vector<std::shared_ptr<TOCBlock>> keep;
+  for (int t = 9; t < argc; ++t) {
+    LargeRAWFile_ptr src(new LargeRAWFile(std::string(argv[t])));
+    if (!src->Open(false)) return 1;
+    std::shared_ptr<MaxMinDataBlock> mm(new MaxMinDataBlock(1));
+    std::shared_ptr<Histogram2DDataBlock> h2(new Histogram2DDataBlock());
+    std::shared_ptr<TOCBlock> toc(new TOCBlock(UVF::ms_ulReaderVersion));
+    toc->strBlockID = "Volume converted by ImageVis3D";
+    const std::string tmp = out + "." + std::to_string(t) + ".octree.tmp";
+    if (!toc->FlatDataToBrickedLOD(src, tmp, u16 ? ExtendedOctree::CT_UINT16 : ExtendedOctree::CT_UINT8, 1,
+                                   UINT64VECTOR3(sx, sy, sz), DOUBLEVECTOR3(1, 1, 1), UINT64VECTOR3(brick, brick, brick), overlap,
+                                   false, false, size_t(1) << 31, mm, &Controller::Debug::Out(), CT_NONE, 1, LT_SCANLINE)) return 1;
+    if (!uvfFile.AddDataBlock(toc)) return 1;
+    keep.push_back(toc);
+    if (h1.GetHistogram().empty() && !h1.Compute(toc.get(), 0)) return 1;
+    if (!h2->Compute(toc.get(), 0, h1.GetHistogram().size(), mm->GetGlobalValue().maxScalar)) return 1;
+    uvfFile.AddDataBlock(std::shared_ptr<Histogram1DDataBlock>(&h1, nonstd::null_deleter()));
+    uvfFile.AddDataBlock(h2);
+    uvfFile.AddDataBlock(mm);
+    src->Close();
+  }
+  std::shared_ptr<KeyValuePairDataBlock> meta(new KeyValuePairDataBlock());
+  meta->AddPair("Source Type", "integer");
+  uvfFile.AddDataBlock(meta);
+  uvfFile.Create();
+  uvfFile.Close();
+  return 0;
+}
+
+// ref_driver dsdump <file.uvf> <timestep> <out.bin>: the file through the reference's UVFDataset (uvfDataset.cpp)
+//     char[8] "TVKDSD1\0"; u64 timesteps; u32 lods; u64 total; per brick (LOD-major, index order): u32 size[3];
+//     f64 min; f64 max (MaxMinForKey); then the payloads (GetBrick); u64 n1; u64 hist1d[n1] (Get1DHistogram of step 0 --
+//     the dataset only ever exposes m_timesteps[0]'s histograms, uvfDataset.cpp:747-750); f32 maxGradMagnitude(timestep)
+static int do_dsdump(int argc, char** argv) {
+  if (argc < 5) return 2;
+  UVFDataset ds(argv[2], 1024, false);
+  const size_t ts = (size_t)atoi(argv[3]);
+  FILE* f = fopen(argv[4], "wb");
+  if (!f) return 1;
+  fwrite("TVKDSD1\0", 1, 8, f);
+  put(f, (uint64_t)ds.GetNumberOfTimesteps());
+  const uint32_t lods = (uint32_t)ds.GetLODLevelCount();
+  put(f, lods);
+  std::vector<uint64_t> per_lod(lods);
+  uint64_t total = 0;
+  for (uint32_t l = 0; l < lods; ++l) { const UINTVECTOR3 lay = ds.GetBrickLayout(l, ts); per_lod[l] = (uint64_t)lay[0] * lay[1] * lay[2]; total += per_lod[l]; }
+  put(f, total);
+  for (uint32_t l = 0; l < lods; ++l)
+    for (uint64_t i = 0; i < per_lod[l]; ++i) {
+      const BrickKey k(ts, l, i);
+      const UINTVECTOR3 n = ds.GetBrickVoxelCounts(k);
+      put(f, (uint32_t)n[0]); put(f, (uint32_t)n[1]); put(f, (uint32_t)n[2]);
+      const MinMaxBlock mm = ds.MaxMinForKey(k);
+      put(f, mm.minScalar); put(f, mm.maxScalar);
+    }
+  std::vector<uint8_t> d8; std::vector<uint16_t> d16;
+  const bool wide = ds.GetBitWidth() == 16;
+  for (uint32_t l = 0; l < lods; ++l)
+    for (uint64_t i = 0; i < per_lod[l]; ++i) {
+      const BrickKey k(ts, l, i);
+      if (!(wide ? ds.GetBrick(k, d16) : ds.GetBrick(k, d8))) { fclose(f); return 1; }
+      if (wide) fwrite(d16.data(), 2, d16.size(), f); else fwrite(d8.data(), 1, d8.size(), f);
+    }
+  fclose(f);
+  return 0;
+}
+
 // ref_driver rebrick <file.uvf> <bx> <by> <bz> <mm 0|1|2> <out.bin>
 //   opens the file with the reference's UVFDataset, wraps it in the reference's DynamicBrickingDS (target brick size
 //   INCLUDING ghost voxels, min/max mode MM_SOURCE / MM_PRECOMPUTE / MM_DYNAMIC -- IO/DynamicBrickingDS.h) and dumps
@@ -484,5 +569,7 @@ int main(int argc, char** argv) {
   if (!strcmp(argv[1], "writeuvf")) return do_writeuvf(argc, argv);
   if (!strcmp(argv[1], "readuvf")) return do_readuvf(argc, argv);
   if (!strcmp(argv[1], "rebrick")) return do_rebrick(argc, argv);
+  if (!strcmp(argv[1], "writeuvfts")) return do_writeuvfts(argc, argv);
+  if (!strcmp(argv[1], "dsdump")) return do_dsdump(argc, argv);
   return 2;
 }
