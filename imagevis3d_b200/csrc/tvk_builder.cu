@@ -537,6 +537,77 @@ __global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ f
   }
 }
 
+// Clamp-to-edge borders (bClampToEdge, ExtendedOctreeConverter.cpp:288-373 GetInputBrick + :376-462 ClampToEdge, and
+// FillOverlap + ClampToEdge for the coarser levels, :1203-1372).  What the reference's sequence of neighbour copies
+// followed by the x, y, z replications leaves in a brick is, voxel for voxel, the LOD's flat volume at the brick voxel's
+// global coordinate CLAMPED to the domain (checked against the compiled reference, tests/test_gpu_builder.py) -- with one
+// exception: the ghost corners FillOverlap never writes (high ghost on two axes, low ghost on the third, all neighbours
+// present; 8 voxels each) keep whatever the converter's reused, un-cleared temp buffer held from an earlier brick in
+// that mode (ExtendedOctreeConverter.inc:261).  That content is an accident of processing history; this kernel writes
+// the voxel at the global coordinate there as everywhere else.
+template <typename T>
+__global__ void __launch_bounds__(256) cut_bricks_clamp_kernel(const T* __restrict__ flat, uint8_t* __restrict__ store,
+                                                                const uint64_t* __restrict__ offsets, uint64_t first_brick,
+                                                                uint32_t lod, const __grid_constant__ BuildConst bc,
+                                                                uint32_t* __restrict__ mn, uint32_t* __restrict__ mx,
+                                                                uint32_t x_first, uint32_t x_count, SlabView sv) {
+  const uint32_t nbx = bc.lod_bricks[lod][0], nby = bc.lod_bricks[lod][1];
+  const int bx = (int)(x_first + blockIdx.x % x_count), by = (int)((blockIdx.x / x_count) % nby), bz = (int)(sv.bz_first + blockIdx.x / (x_count * nby));
+  const uint32_t b = (uint32_t)bx + (uint32_t)by * nbx + (uint32_t)bz * nbx * nby;
+  const uint32_t tx = brick_dim(bc, lod, 0, bx), ty = brick_dim(bc, lod, 1, by), tz = brick_dim(bc, lod, 2, bz);
+  const int sx = (int)bc.lod_size[lod][0], sy = (int)bc.lod_size[lod][1], sz = (int)bc.lod_size[lod][2];
+  T* dst = reinterpret_cast<T*>(store + offsets[first_brick + b]);
+  const int o = (int)bc.overlap;
+  uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.y * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.y * blockDim.x) >> 5;
+  const uint32_t rows = ty * tz;
+  const int nbz = (int)bc.lod_bricks[lod][2];
+  const bool fx = bx == 0, fy = by == 0, fz = bz == 0;
+  const bool lx = bx == (int)nbx - 1, ly = by == (int)nby - 1, lz = bz == nbz - 1;
+  const uint64_t nvox = (uint64_t)sx * sy * sv.rows;
+  for (uint32_t r = warp; r < rows; r += nwarps) {
+    const int j = (int)(r % ty), k = (int)(r / ty);
+    const int gy = min(max(by * (int)bc.core - o + j, 0), sy - 1);
+    const int gz = min(max(bz * (int)bc.core - o + k, 0), sz - 1) - (int)sv.z0;      // (the slab holds every row the bricks' clamped range needs)
+    const T* srow = flat + (uint64_t)gy * sx + (uint64_t)gz * sx * sy;
+    T* drow = dst + (size_t)r * tx;
+    const int x0 = bx * (int)bc.core - o;
+    if (lod == 0) {
+      // GetInputBrick reads scan lines by LINEAR file offset (a line towards a neighbour whose interior is thinner than
+      // the overlap runs on into the next row / slice), then ClampToEdge replicates on the domain faces: the brick
+      // voxel clamped into the box the copy loops fill, read at its linear offset; past the end of the file (where the
+      // reference's buffer keeps stale bytes) the voxel at the clamped coordinate.
+      const int jc = min(max(j, fy ? o : 0), (int)ty - (ly ? o : 0) - 1), kc = min(max(k, fz ? o : 0), (int)tz - (lz ? o : 0) - 1);
+      const int xa = fx ? o : 0, xb = (int)tx - (lx ? o : 0);
+      const uint64_t lin0 = (uint64_t)(int64_t)x0 + (uint64_t)(by * (int)bc.core - o + jc) * sx +
+                            (uint64_t)(int64_t)(bz * (int)bc.core - o + kc - (int)sv.z0) * sx * sy;
+      for (int i = (int)lane; i < (int)tx; i += 32) {
+        const uint64_t lin = lin0 + (uint64_t)min(max(i, xa), xb - 1);
+        const T val = lin < nvox ? flat[lin] : srow[min(max(x0 + i, 0), sx - 1)];
+        drow[i] = val;
+        lo = min(lo, (uint32_t)val);
+        hi = max(hi, (uint32_t)val);
+      }
+      continue;
+    }
+    for (int i = (int)lane; i < (int)tx; i += 32) {
+      const T val = srow[min(max(x0 + i, 0), sx - 1)];
+      drow[i] = val;
+      lo = min(lo, (uint32_t)val);
+      hi = max(hi, (uint32_t)val);
+    }
+  }
+  for (int s = 16; s > 0; s >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+  }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) {
+    atomicMin(mn + first_brick + b, lo);
+    atomicMax(mx + first_brick + b, hi);
+  }
+}
+
 // Vector form of cut_bricks_kernel: a thread produces one aligned CB-byte chunk (16, 8 or 4 bytes,
 // whatever divides the brick's row length) per trip, so loads and stores are word-granular.
 //  * LOD 0: the chunk is CB bytes at a linear file offset, masked to the x range GetInputBrick copies;
@@ -902,14 +973,17 @@ __global__ void __launch_bounds__(256) hist1d_kernel(const T* __restrict__ raw, 
 // inner LOD-0 brick voxel are the raw neighbours, zero outside the domain.
 // All arithmetic in fp64 with explicit round-to-nearest ops (no FMA contraction)
 // so that it matches the reference's x86-64 doubles bit for bit.
+// `clamp`: the LOD-0 bricks were built with clamp-to-edge borders, so a neighbour outside the domain is the voxel itself
+// (Histogram2DDataBlock reads the bricks' ghost cells, whatever the converter put there) instead of zero.
 template <typename T>
 __device__ __forceinline__ double grad_mag(const T* __restrict__ raw, uint32_t x, uint32_t y, uint32_t z,
-                                           uint32_t sx, uint32_t sy, uint32_t sz, double norm2) {
+                                           uint32_t sx, uint32_t sy, uint32_t sz, double norm2, bool clamp = false) {
   const uint64_t rs = sx, ss = (uint64_t)sx * sy;
   const uint64_t c = x + y * rs + z * ss;
-  const double l = x > 0 ? (double)raw[c - 1] : 0.0, r = x + 1 < sx ? (double)raw[c + 1] : 0.0;
-  const double t = y > 0 ? (double)raw[c - rs] : 0.0, b = y + 1 < sy ? (double)raw[c + rs] : 0.0;
-  const double f = z > 0 ? (double)raw[c - ss] : 0.0, k = z + 1 < sz ? (double)raw[c + ss] : 0.0;
+  const double e = clamp ? (double)raw[c] : 0.0;
+  const double l = x > 0 ? (double)raw[c - 1] : e, r = x + 1 < sx ? (double)raw[c + 1] : e;
+  const double t = y > 0 ? (double)raw[c - rs] : e, b = y + 1 < sy ? (double)raw[c + rs] : e;
+  const double f = z > 0 ? (double)raw[c - ss] : e, k = z + 1 < sz ? (double)raw[c + ss] : e;
   const double gx = __ddiv_rn(__dsub_rn(l, r), norm2), gy = __ddiv_rn(__dsub_rn(t, b), norm2), gz = __ddiv_rn(__dsub_rn(f, k), norm2);
   return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), __dmul_rn(gz, gz)));
 }
@@ -935,19 +1009,23 @@ __device__ __forceinline__ unsigned long long grad_s(const T* __restrict__ raw, 
 
 // the same S with everything that depends on (y,z) hoisted out of the row loop: pointers to the four
 // neighbouring rows (nullptr outside the domain) and 32-bit arithmetic (a difference is < 2^16)
-template <typename T> struct RowCtx { const T *line, *up, *down, *front, *back; };
+template <typename T> struct RowCtx { const T *line, *up, *down, *front, *back; bool clamp; };
 template <typename T>
-__device__ __forceinline__ RowCtx<T> row_ctx(const T* __restrict__ raw, uint32_t y, uint32_t z, uint32_t sx, uint32_t sy, uint32_t sz) {
+__device__ __forceinline__ RowCtx<T> row_ctx(const T* __restrict__ raw, uint32_t y, uint32_t z, uint32_t sx, uint32_t sy, uint32_t sz,
+                                             bool clamp = false) {
   const uint64_t rs = sx, ss = (uint64_t)sx * sy;
   RowCtx<T> r;
   r.line = raw + y * rs + z * ss;
-  r.up = y > 0 ? r.line - rs : nullptr; r.down = y + 1 < sy ? r.line + rs : nullptr;
-  r.front = z > 0 ? r.line - ss : nullptr; r.back = z + 1 < sz ? r.line + ss : nullptr;
+  const T* outside = clamp ? r.line : nullptr;          // clamp-to-edge: the missing neighbour row is the row itself
+  r.up = y > 0 ? r.line - rs : outside; r.down = y + 1 < sy ? r.line + rs : outside;
+  r.front = z > 0 ? r.line - ss : outside; r.back = z + 1 < sz ? r.line + ss : outside;
+  r.clamp = clamp;
   return r;
 }
 template <typename T>
 __device__ __forceinline__ unsigned long long grad_s_row(const RowCtx<T>& r, uint32_t x, uint32_t sx, unsigned long long* key = nullptr) {
-  const int l = x > 0 ? (int)r.line[x - 1] : 0, rr = x + 1 < sx ? (int)r.line[x + 1] : 0;
+  const int e = r.clamp ? (int)r.line[x] : 0;
+  const int l = x > 0 ? (int)r.line[x - 1] : e, rr = x + 1 < sx ? (int)r.line[x + 1] : e;
   const int t = r.up ? (int)r.up[x] : 0, b = r.down ? (int)r.down[x] : 0;
   const int f = r.front ? (int)r.front[x] : 0, k = r.back ? (int)r.back[x] : 0;
   const int dx = l - rr, dy = t - b, dz = f - k;
@@ -964,19 +1042,19 @@ struct GradBest { unsigned long long s; unsigned long long len_bits; };
 
 template <typename T>
 __global__ void __launch_bounds__(256) grad_max_kernel(const T* __restrict__ raw, uint32_t sx, uint32_t sy, uint32_t sz,
-                                                        double norm2, GradBest* __restrict__ partial) {
+                                                        double norm2, GradBest* __restrict__ partial, bool clamp) {
   // a warp walks one row (y,z) at a time, 32 voxels per trip: no per-voxel index division
   const uint32_t rows = sy * sz, lane = threadIdx.x & 31u;
   unsigned long long best_s = 0, best_bits = 0, last_key = ~0ull;
   for (uint32_t row = blockIdx.x * 8u + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8u) {
     const uint32_t y = row % sy, z = row / sy;
-    const RowCtx<T> rc = row_ctx(raw, y, z, sx, sy, sz);
+    const RowCtx<T> rc = row_ctx(raw, y, z, sx, sy, sz, clamp);
     for (uint32_t x = lane; x < sx; x += 32u) {
       unsigned long long key;
       const unsigned long long s = grad_s_row(rc, x, sx, &key);
       if (s == 0 || s < best_s || key == last_key) continue;      // (a tie with the triple just evaluated adds nothing)
       last_key = key;
-      const unsigned long long bits = (unsigned long long)__double_as_longlong(grad_mag(raw, x, y, z, sx, sy, sz, norm2));
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(grad_mag(raw, x, y, z, sx, sy, sz, norm2, clamp));
       if (s > best_s) { best_s = s; best_bits = bits; }
       else if (bits > best_bits) best_bits = bits;          // non-negative doubles order like integers
     }
@@ -1008,14 +1086,14 @@ template <typename T>
 __global__ void __launch_bounds__(256) hist2d_kernel(const T* __restrict__ raw, uint32_t sx, uint32_t sy, uint32_t sz,
                                                       double norm2, double max_grad, unsigned long long smax, float inv_smax,
                                                       const uint16_t* __restrict__ vlut,
-                                                      unsigned long long* __restrict__ bins) {
+                                                      unsigned long long* __restrict__ bins, bool clamp) {
   // a warp's votes for one bin go out as one atomic; a leader whose bin repeats from trip to trip (the empty
   // background sends every warp to bin 0) keeps counting in a register and flushes when the bin changes
   uint32_t pend_bin = 0xFFFFFFFFu, pend_cnt = 0;
   const uint32_t rows = sy * sz, lane = threadIdx.x & 31u;
   for (uint32_t row = blockIdx.x * 8u + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8u) {
     const uint32_t y = row % sy, z = row / sy;
-    const RowCtx<T> rc = row_ctx(raw, y, z, sx, sy, sz);
+    const RowCtx<T> rc = row_ctx(raw, y, z, sx, sy, sz, clamp);
     const T* line = rc.line;
     for (uint32_t x0 = 0; x0 < sx; x0 += 32u) {
       const uint32_t x = x0 + lane;
@@ -1035,7 +1113,7 @@ __global__ void __launch_bounds__(256) hist2d_kernel(const T* __restrict__ raw, 
         else if (s != smax && q - fl > 1e-3f && fl + 1.0f - q > 1e-3f) gi = (uint32_t)fl;
         else {
           // size_t(len/max*255.0f)
-          const double e = __dmul_rn(__ddiv_rn(grad_mag(raw, x, y, z, sx, sy, sz, norm2), max_grad), 255.0);
+          const double e = __dmul_rn(__ddiv_rn(grad_mag(raw, x, y, z, sx, sy, sz, norm2, clamp), max_grad), 255.0);
           gi = (e >= 255.0) ? 255u : ((e > 0.0) ? (uint32_t)e : 0u);
         }
       }
@@ -1694,7 +1772,9 @@ static int cut_rows(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms, ui
     // word-granular path: needs a 4-byte aligned volume, and core >= overlap for the closed-form ghosts
     const bool vec = (reinterpret_cast<uintptr_t>(src) & 3) == 0 && bc.core >= bc.overlap && row_bytes % 4 == 0;
     uint8_t* store = (uint8_t*)b.d_store;
-    if (vec && row_bytes % 16 == 0)
+    if (b.desc.clamp_to_edge)
+      cut_bricks_clamp_kernel<T><<<grid, 256, 0, st>>>(src, store, b.d_offsets, info.lod_offset[l], l, bc, d_mn, d_mx, x_first, x_count, sv);
+    else if (vec && row_bytes % 16 == 0)
       cut_bricks_vec_kernel<T, 16><<<grid, 256, 0, st>>>(src, store, b.d_offsets, info.lod_offset[l], l, bc, d_mn, d_mx, x_first, x_count, sv);
     else if (vec && row_bytes % 8 == 0)
       cut_bricks_vec_kernel<T, 8><<<grid, 256, 0, st>>>(src, store, b.d_offsets, info.lod_offset[l], l, bc, d_mn, d_mx, x_first, x_count, sv);
@@ -1839,7 +1919,6 @@ static int build_finish(tvk_ctx* c, BuildState& b, const BuildConst& bc, int sms
 // plan + ToC + the allocations every build needs; `store` != nullptr: caller-owned brick store (device memory, or pinned
 // host memory mapped into the device address space -- bricks are then written over PCIe)
 static int build_setup(tvk_ctx* c, const tvk_build_desc* d, void* store) {
-  if (d->clamp_to_edge) TVK_FAIL(c, TVK_ERR_UNSUPPORTED, "clamp-to-edge borders are not built yet (reference default is off)");
   tvk_build_info info;
   if (tvk_build_plan(d, &info) != TVK_OK) TVK_FAIL(c, TVK_ERR_INVALID, "bad build description");
   if ((d->brick_size - 2 * d->overlap) % 2) TVK_FAIL(c, TVK_ERR_UNSUPPORTED, "odd inner brick size");
@@ -1886,7 +1965,7 @@ static int lod0_fused_pass(tvk_ctx* c, BuildState& b, const BuildConst& bc, int 
   const uint32_t groups[2][3] = {{0u, last_tx == bc.brick ? nbx : nbx - 1, bc.brick}, {nbx - 1, last_tx == bc.brick ? 0u : 1u, last_tx}};
   bool can = info.lod_count >= 2 && s0[0] > 1 && s0[1] > 1 && s0[2] > 1 && (bc.overlap % 2) == 0 && bc.core >= bc.overlap &&
              (reinterpret_cast<uintptr_t>(b.d_lod[0]) & 3) == 0 && (uint64_t)s0[0] * s0[1] * s0[2] >= (1u << 18) &&
-             getenv("TVK_BUILD_FUSED") != nullptr;
+             getenv("TVK_BUILD_FUSED") != nullptr && !b.desc.clamp_to_edge;
   for (int g = 0; g < 2; ++g) if (groups[g][1] && (groups[g][2] * sizeof(T)) % 4 != 0) can = false;
   if (!can) return TVK_OK;
   uint32_t* d_mn = b.d_mn;
@@ -2113,13 +2192,15 @@ static int run_hist2d(tvk_ctx* c, uint32_t bins_x, double max_nonzero, uint64_t*
   TVK_CHECK_CUDA(c, cudaEventRecord(c->bev0, c->stream));
   // 4 voxels per thread when rows are whole quads (cudaMalloc'ed / caller-aligned base); TVK_HIST2D_SCALAR=1 forces the
   // one-voxel-per-thread kernels
-  const bool vec = (s[0] % 4u) == 0 && (reinterpret_cast<uintptr_t>(b.d_lod[0]) % (4 * sizeof(T))) == 0 && !getenv("TVK_HIST2D_SCALAR");
+  // (clamp-to-edge volumes: the one-voxel-per-thread kernels, which know that a neighbour outside the domain is the voxel itself)
+  const bool clamp = b.desc.clamp_to_edge != 0;
+  const bool vec = (s[0] % 4u) == 0 && (reinterpret_cast<uintptr_t>(b.d_lod[0]) % (4 * sizeof(T))) == 0 && !getenv("TVK_HIST2D_SCALAR") && !clamp;
   // 8 voxels per thread + fp32 squares when rows are whole octets and 16-byte aligned (TVK_HIST2D_V4=1: the 4-voxel kernels)
   const bool v8 = vec && (s[0] % 8u) == 0 && (reinterpret_cast<uintptr_t>(b.d_lod[0]) % (8 * sizeof(T))) == 0 &&
                   (uint64_t)bins_x * 256u <= (1ull << TVK_H2D8_BIN_BITS) && !getenv("TVK_HIST2D_V4");
   if (v8) grad_max_v8_kernel<T><<<(unsigned)std::min<uint64_t>((uint64_t)((s[1] + 7) / 8) * ((s[2] + 15) / 16), (uint64_t)sms * 8), 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_part, d_bins);
   else if (vec) grad_max_vec_kernel<T><<<(unsigned)std::min<uint64_t>((uint64_t)((s[1] + 7) / 8) * ((s[2] + 15) / 16), (uint64_t)sms * 8), 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_part, d_bins);   // d_bins[0]: zeroed scratch, re-zeroed below
-  else grad_max_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_part);
+  else grad_max_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, d_part, clamp);
   hist2d_value_lut_kernel<<<(range + 255) / 256, 256, 0, c->stream>>>(range, bins_x, max_nonzero, d_lut);
   c->launches += 2;
   std::vector<GradBest> part(blocks);
@@ -2149,7 +2230,7 @@ static int run_hist2d(tvk_ctx* c, uint32_t bins_x, double max_nonzero, uint64_t*
     const unsigned tb = (unsigned)std::min<uint64_t>(tiles, (uint64_t)sms * (sizeof(T) == 1 ? 16 : 6));
     hist2d_vec_kernel<T><<<tb, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, mg, g.s, inv_smax, d_lut, d_bins);
   }
-  else hist2d_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, mg, g.s, inv_smax, d_lut, d_bins);
+  else hist2d_kernel<T><<<blocks, 256, 0, c->stream>>>((const T*)b.d_lod[0], s[0], s[1], s[2], norm2, mg, g.s, inv_smax, d_lut, d_bins, clamp);
   c->launches++;
   TVK_CHECK_CUDA(c, cudaGetLastError());
   TVK_CHECK_CUDA(c, cudaEventRecord(c->bev1, c->stream));

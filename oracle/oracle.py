@@ -64,7 +64,7 @@ def toc(p, bpv):
     return int(total), offsets, sizes
 
 
-def build_octree(raw, brick=64, overlap=2, median=False):
+def build_octree(raw, brick=64, overlap=2, median=False, clamp=False):
     """raw: numpy array [z][y][x] of uint8/uint16.  Returns dict with plan, toc and data."""
     raw = np.ascontiguousarray(raw)
     bpv = raw.dtype.itemsize
@@ -73,9 +73,9 @@ def build_octree(raw, brick=64, overlap=2, median=False):
     total, offsets, sizes = toc(p, bpv)
     store = np.zeros(total, np.uint8)
     minmax = np.zeros((int(p.total_bricks), 2), np.float64)
-    rc = lib().orc_build(raw.ctypes.data_as(C.c_void_p), _vol3(vol), C.c_uint32(bpv),
-                         C.c_uint64(brick), C.c_uint32(overlap), C.c_int(1 if median else 0),
-                         store.ctypes.data_as(C.c_void_p), minmax.ctypes.data_as(C.c_void_p))
+    rc = lib().orc_build_ex(raw.ctypes.data_as(C.c_void_p), _vol3(vol), C.c_uint32(bpv),
+                            C.c_uint64(brick), C.c_uint32(overlap), C.c_int(1 if median else 0), C.c_int(1 if clamp else 0),
+                            store.ctypes.data_as(C.c_void_p), minmax.ctypes.data_as(C.c_void_p))
     if rc:
         raise ValueError("orc_build failed (%d)" % rc)
     return dict(plan=p, offsets=offsets, sizes=sizes, store=store, minmax=minmax, bpv=bpv,

@@ -97,9 +97,32 @@ def test_builder_rejects_unsupported(tvk):
     from imagevis3d_b200._lib import TvkError
     raw = np.zeros((8, 8, 8), np.uint8)
     with pytest.raises(TvkError):
-        tvk.build_octree(raw, 64, 2, clamp=True)
-    with pytest.raises(TvkError):
         tvk.build_octree(raw, 4, 2)
+
+
+@pytest.mark.parametrize("vol,dtype,brick,overlap,median", [
+    ((70, 45, 38), np.uint8, 16, 2, False), ((37, 29, 23), np.uint8, 12, 2, True), ((50, 26, 40), np.uint16, 16, 2, False),
+    ((9, 7, 5), np.uint8, 12, 2, False), ((8, 8, 6), np.uint8, 16, 2, False), ((130, 121, 70), np.uint16, 64, 2, False)])
+def test_builder_clamp_to_edge_matches_oracle(tvk, vol, dtype, brick, overlap, median):
+    """bClampToEdge (ExtendedOctreeConverter.cpp:376-462): bricks, min/max and both histograms equal to the oracle's, which
+    tests/test_oracle_builder.py pins to the compiled reference on every voxel the reference defines in that mode."""
+    raw = H.synth_noise(vol, dtype, seed=sum(vol) + 7, maxval=255 if dtype == np.uint8 else 60000)
+    raw[raw == 0] = 1                                          # a zero in a ghost cell would be a border that was not clamped
+    oc = O.build_octree(raw, brick, overlap, median, clamp=True)
+    tvk.build_octree(raw, brick, overlap, median=median, clamp=True)
+    store, sizes = cuda_store_tight(tvk)
+    assert (sizes == oc["sizes"]).all()
+    bad = np.nonzero(store != oc["store"])[0]
+    assert bad.size == 0, "first mismatching byte %d of %d" % (bad[0], store.size)
+    assert store.view(dtype).min() > 0
+    assert (tvk.build_minmax() == oc["minmax"]).all()
+    h1 = tvk.build_hist1d()
+    ref1 = O.hist1d(oc)
+    assert h1.size == ref1.size and (h1 == ref1).all()
+    h2, mg = tvk.build_hist2d(len(h1), float(oc["minmax"][:, 1].max()))
+    r2, rmg = O.hist2d(oc, len(h1), oc["minmax"][:, 1].max())
+    assert np.float32(mg) == np.float32(rmg) and (h2 == r2).all()
+    tvk.build_release()
 
 
 def test_builder_full_size_properties(tvk):
