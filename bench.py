@@ -642,14 +642,18 @@ def run_single(args, torch, TvkContext, HM, dev, local, sampler, peak, peak_src,
     tvk = TvkContext(local)
     raw = sphere_torch(C3_VOL, (0, 0, 0), C3_VOL, 16, dev)
     torch.cuda.synchronize()
-    scene = Scene(tvk, raw, C3_VOL, 16, want_host_copy=not args.no_cpu)
-    # K2 record: builder kernels (pyramid + brick cut + min/max + 1-D histogram) and the 2-D histogram, CUDA events
-    voxels = float(C3_VOL[0]) * C3_VOL[1] * C3_VOL[2]
-    tf_bins = max(1, min(scene.hist1d_size, 4096))
+    # K2 record: builder kernels (pyramid + brick cut + min/max + 1-D histogram) and the 2-D histogram, CUDA events; the
+    # clock sampler covers the build and three runs of the histogram (the best is reported)
     sk2 = ClockSampler(local)
     sk2.start()
-    _, max_grad = tvk.build_hist2d(tf_bins, scene.rmax)
-    h2_ms = tvk.build_hist2d_last_ms()
+    time.sleep(0.3)                                           # (NVML start-up: the first sample lands before the build starts)
+    scene = Scene(tvk, raw, C3_VOL, 16, want_host_copy=not args.no_cpu)
+    voxels = float(C3_VOL[0]) * C3_VOL[1] * C3_VOL[2]
+    tf_bins = max(1, min(scene.hist1d_size, 4096))
+    h2_ms = 1e30
+    for _ in range(3):
+        _, max_grad = tvk.build_hist2d(tf_bins, scene.rmax)
+        h2_ms = min(h2_ms, tvk.build_hist2d_last_ms())
     k2 = {"volume": list(C3_VOL), "voxel_type": "uint16", "builder_ms": scene.build_ms, "hist2d_ms": h2_ms,
           "builder_algorithmic_GBps": 2.387 * 2 * voxels / (scene.build_ms * 1e-3) / 1e9,
           "builder_frac_of_hbm_peak": 2.387 * 2 * voxels / (scene.build_ms * 1e-3) / 1e9 / peak,
@@ -657,7 +661,7 @@ def run_single(args, torch, TvkContext, HM, dev, local, sampler, peak, peak_src,
           "hist2d_frac_of_hbm_peak": 2 * 2 * voxels / (h2_ms * 1e-3) / 1e9 / peak, "max_gradient_magnitude": max_grad,
           "one_over_max_gradient": (1.0 / max_grad) if max_grad else None, "workload_gradient_scale": gradient_scale(C3_VOL),
           "bricks": int(scene.info.total_bricks), "store_bytes": scene.store_bytes,
-          "note": "one run each, CUDA events around the kernels (tvk_build_last_ms / tvk_build_hist2d_last_ms); algorithmic bytes: "
+          "note": "builder: one run; 2-D histogram: best of three; CUDA events around the kernels (tvk_build_last_ms / tvk_build_hist2d_last_ms); algorithmic bytes: "
                   "2.387*bpv per voxel for the builder, 2*bpv for the two histogram passes (SURVEY 8d)",
           "clocks": sk2.stop()}
     del raw
