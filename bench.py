@@ -810,12 +810,31 @@ def run_e2e(torch, HM, dev, local, steps):
     p1 = r.perf()
     samples = p1["samples"] - p0["samples"]
     h2d = uploaded[0] / steps + tf.nbytes
+    # secondary: the same orbit WITHOUT emptying the working set -- what an interactive session does between two views: only
+    # the bricks the new view adds are paged in (the headline above is the cold case, every brick of every frame over PCIe)
+    def warm_frame(k):
+        r.setRotation4x4((HM.rotation_y(orbit_angle(k, steps)) @ HM.rotation_x(0.35)).astype(np.float32))
+        r.set2DTrans(tf, nz)
+        sub = r.paintUntilConverged(4000)
+        r.frameRGBA8(frame_buf)
+        return sub
+    warm_frame(0)
+    w0 = r.perf()
+    tw = time.perf_counter()
+    wsubs = sum(warm_frame(k) for k in range(1, steps + 1))
+    dtw = time.perf_counter() - tw
+    w1 = r.perf()
+    warm = {"ms_per_step": 1e3 * dtw / steps, "value": (w1["samples"] - w0["samples"]) / dtw, "unit": "samples/s",
+            "subframes_per_step": wsubs / steps, "paged_bricks_per_step": (w1["paged_bricks"] - w0["paged_bricks"]) / steps,
+            "h2d_bytes_per_step": int((w1["uploaded_bytes"] - w0["uploaded_bytes"]) / steps + tf.nbytes),
+            "what": "same calls without clearWorkingSet(): the pool keeps the bricks of the previous view (orbit of %d views, "
+                    "%.0f degrees apart)" % (steps, 360.0 / steps)}
     out = {"value": samples / dt, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(W * Hh * 4 + 4 * E2E_HASH * subs / steps),
            "ms_per_step": 1e3 * dt / steps, "subframes_per_step": subs / steps,
            "paged_bricks_per_step": (p1["paged_bricks"] - p0["paged_bricks"]) / steps,
            "h2d_GBps_over_the_step": h2d / (dt / steps) / 1e9, "frame_nonzero_pixels": int((img[..., 3] > 0).sum()),
-           "samples_per_step_all_subframes": samples / steps,
+           "samples_per_step_all_subframes": samples / steps, "warm_working_set": warm,
            "result": "RGBA8 frame (glReadPixels GL_UNSIGNED_BYTE, as captureSingleFrame reads it)",
            "pipeline": "tvkr_* only (include/tvk_renderer.h): clearWorkingSet + changed2DTrans + paint() until converged() + frame "
                        "read-back; the brick store lives in pinned host memory and bricks are paged in on the rays' requests "

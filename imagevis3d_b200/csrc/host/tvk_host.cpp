@@ -103,24 +103,180 @@ void Matrix4::transform(const float v[4], float out[4]) const {
 // ---------------------------------------------------------------------------- TransferFunction1D
 void TransferFunction1D::Set(const float* rgba, size_t n) { m_color.assign(rgba, rgba + 4 * n); ComputeNonZeroLimits(); }
 
-bool TransferFunction1D::Load(const std::string& filename) {                  // TransferFunction1D.cpp:279-293
-  std::ifstream f(filename.c_str());
-  if (!f.is_open()) return false;
+bool TransferFunction1D::Load(std::istream& f) {                              // TransferFunction1D.cpp:279-295
   uint32_t n = 0;
   f >> n;
-  if (!f || n == 0) return false;
+  if (!f || n == 0 || n > (1u << 24)) return false;
   m_color.assign(4 * (size_t)n, 0.0f);
   for (size_t i = 0; i < 4 * (size_t)n; ++i) if (!(f >> m_color[i])) return false;
   ComputeNonZeroLimits();
   return true;
 }
+bool TransferFunction1D::Save(std::ostream& f) const {                        // :298-309 ("r g b a " + endl per entry)
+  f << GetSize() << std::endl;
+  for (size_t i = 0; i < GetSize(); ++i) {
+    for (int j = 0; j < 4; ++j) f << m_color[4 * i + j] << " ";
+    f << std::endl;
+  }
+  return (bool)f;
+}
+bool TransferFunction1D::Load(const std::string& filename) {
+  std::ifstream f(filename.c_str());
+  return f.is_open() && Load(f);
+}
 bool TransferFunction1D::Save(const std::string& filename) const {
   std::ofstream f(filename.c_str());
-  if (!f.is_open()) return false;
-  f << GetSize() << "\n";
-  for (size_t i = 0; i < GetSize(); ++i)
-    f << m_color[4 * i] << " " << m_color[4 * i + 1] << " " << m_color[4 * i + 2] << " " << m_color[4 * i + 3] << "\n";
+  return f.is_open() && Save(f);
+}
+
+// ---------------------------------------------------------------------------- TransferFunction2D
+static bool LoadSwatch(std::istream& f, TFPolygon& p) {                       // TFPolygon::Load, TransferFunction2D.cpp:511-543
+  uint32_t n = 0;
+  f >> p.radial;
+  f >> n;
+  if (!f || n > (1u << 20)) return false;
+  p.points.resize(n);
+  for (auto& q : p.points) f >> q[0] >> q[1];
+  f >> p.gradientCoords[0][0] >> p.gradientCoords[0][1];
+  f >> p.gradientCoords[1][0] >> p.gradientCoords[1][1];
+  f >> n;
+  if (!f || n > (1u << 20)) return false;
+  p.stops.resize(n);
+  for (auto& s : p.stops) { f >> s.first; for (int j = 0; j < 4; ++j) f >> s.second[j]; }
+  return !f.fail();
+}
+static void SaveSwatch(std::ostream& f, const TFPolygon& p) {                 // TFPolygon::Save, :545-568
+  f << p.radial << std::endl;
+  f << uint32_t(p.points.size()) << std::endl;
+  for (const auto& q : p.points) { f << q[0] << " " << q[1] << " "; f << std::endl; }
+  f << p.gradientCoords[0][0] << " " << p.gradientCoords[0][1] << " ";
+  f << p.gradientCoords[1][0] << " " << p.gradientCoords[1][1];
+  f << std::endl;
+  f << p.stops.size() << std::endl;
+  for (const auto& s : p.stops) {
+    f << s.first << "  ";
+    for (int j = 0; j < 4; ++j) f << s.second[j] << " ";
+    f << std::endl;
+  }
+}
+bool TransferFunction2D::LoadRest(std::istream& f, bool allowNoSwatch) {
+  uint32_t n = 0;
+  f >> n;
+  if (!f || n > (1u << 20)) return false;
+  m_swatches.assign(n, TFPolygon());
+  if (n == 0 && !allowNoSwatch) return false;                                 // "No swatches?!  Ridiculous 2D TFqn, bailing..." (:181-184)
+  for (auto& s : m_swatches) if (!LoadSwatch(f, s)) return false;
   return true;
+}
+bool TransferFunction2D::Load(const std::string& filename) {
+  std::ifstream f(filename.c_str());
+  if (!f.is_open()) return false;
+  f >> m_w >> m_h;
+  if (!f || !m_w || !m_h) return false;
+  if (!m_trans1d.Load(f)) return false;
+  m_trans1d.Resample(m_w);
+  return LoadRest(f, false);
+}
+bool TransferFunction2D::Load(const std::string& filename, size_t targetW, size_t targetH) {
+  std::ifstream f(filename.c_str());
+  if (!f.is_open() || !targetW || !targetH) return false;
+  m_w = targetW; m_h = targetH;
+  size_t fw = 0, fh = 0;
+  f >> fw >> fh;                                                              // "ignore the size in the file" (:109-111)
+  if (!f) return false;
+  if (!m_trans1d.Load(f)) return false;
+  m_trans1d.Resample(targetW);
+  return LoadRest(f, true);
+}
+bool TransferFunction2D::Save(const std::string& filename) const {
+  std::ofstream f(filename.c_str());
+  if (!f.is_open()) return false;
+  f << m_w << " " << m_h << std::endl;
+  m_trans1d.Save(f);
+  f << m_swatches.size() << std::endl;
+  for (const auto& s : m_swatches) SaveSwatch(f, s);
+  return (bool)f;
+}
+
+void TransferFunction2D::Render(std::vector<uint8_t>& rgba, double limits[4]) const {
+  // GetRenderSize (TransferFunction2D.h:136-144): a 2:1 canvas of at most 4096 pixels, scaled to the table afterwards
+  const size_t cw0 = std::min<size_t>(m_w, 4096), ch0 = std::min<size_t>(m_h, 4096);
+  const size_t W = cw0 > ch0 ? cw0 : ch0 * 2, H = cw0 > ch0 ? size_t(cw0 / 2.0) : ch0;
+  std::vector<float> canvas(4 * W * std::max<size_t>(H, 1), 0.0f);              // straight (non-premultiplied) RGBA in [0,1]
+  // the 1-D function, one pixel per entry, stretched over the canvas (Update1DTrans :399-424 + drawImage :311)
+  TransferFunction1D t1 = m_trans1d;
+  const size_t n1 = std::min<size_t>(m_w, t1.GetSize());
+  std::vector<uint8_t> row;
+  t1.GetByteArray(row);
+  for (size_t y = 0; y < H; ++y)
+    for (size_t x = 0; x < W && n1; ++x) {
+      const size_t i = std::min<size_t>(n1 - 1, x * n1 / W);
+      for (int c = 0; c < 4; ++c) canvas[4 * (y * W + x) + c] = row[4 * i + c] / 255.0f;
+    }
+  for (const TFPolygon& sw : m_swatches) {
+    const size_t np = sw.points.size();
+    if (np < 3 || sw.stops.empty()) continue;
+    // Normalized2Offscreen (:288-291): int(coord * size)
+    std::vector<std::array<int, 2>> pt(np);
+    for (size_t j = 0; j < np; ++j) pt[j] = {int(sw.points[j][0] * int(W)), int(sw.points[j][1] * int(H))};
+    const int g0[2] = {int(sw.gradientCoords[0][0] * int(W)), int(sw.gradientCoords[0][1] * int(H))};
+    const int g1[2] = {int(sw.gradientCoords[1][0] * int(W)), int(sw.gradientCoords[1][1] * int(H))};
+    const double dx = g1[0] - g0[0], dy = g1[1] - g0[1], len2 = dx * dx + dy * dy, rad = std::sqrt(len2);
+    // stops as Qt keeps them: sorted by position, colours quantised to 8 bits (QColor(int(c*255)...), :333-339)
+    std::vector<std::pair<float, std::array<float, 4>>> st = sw.stops;
+    std::stable_sort(st.begin(), st.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    for (auto& s : st) for (int c = 0; c < 4; ++c) s.second[c] = float(std::min(255, std::max(0, int(s.second[c] * 255)))) / 255.0f;
+    auto colour = [&](double t, float out[4]) {
+      t = std::min(1.0, std::max(0.0, t));                                     // pad spread
+      if (t <= st.front().first) { for (int c = 0; c < 4; ++c) out[c] = st.front().second[c]; return; }
+      if (t >= st.back().first) { for (int c = 0; c < 4; ++c) out[c] = st.back().second[c]; return; }
+      for (size_t k = 1; k < st.size(); ++k)
+        if (t <= st[k].first) {
+          const double span = st[k].first - st[k - 1].first, u = span > 0 ? (t - st[k - 1].first) / span : 1.0;
+          for (int c = 0; c < 4; ++c) out[c] = float(st[k - 1].second[c] * (1.0 - u) + st[k].second[c] * u);
+          return;
+        }
+    };
+    int ymin = INT32_MAX, ymax = INT32_MIN;
+    for (const auto& q : pt) { ymin = std::min(ymin, q[1]); ymax = std::max(ymax, q[1]); }
+    for (int y = std::max(ymin, 0); y < std::min<int>(ymax, (int)H); ++y) {
+      const double cy = y + 0.5;
+      std::vector<double> xs;                                                  // odd-even fill: crossings of the scan line through pixel centres
+      for (size_t j = 0; j < np; ++j) {
+        const auto& a = pt[j]; const auto& b = pt[(j + 1) % np];
+        if ((a[1] <= cy) != (b[1] <= cy)) xs.push_back(a[0] + (cy - a[1]) * double(b[0] - a[0]) / double(b[1] - a[1]));
+      }
+      std::sort(xs.begin(), xs.end());
+      for (size_t k = 0; k + 1 < xs.size(); k += 2) {
+        const int x0 = std::max(0, (int)std::ceil(xs[k] - 0.5)), x1 = std::min<int>((int)W, (int)std::ceil(xs[k + 1] - 0.5));
+        for (int x = x0; x < x1; ++x) {
+          const double px = x + 0.5, py = cy;
+          double t;
+          if (sw.radial) t = rad > 0 ? std::sqrt((px - g0[0]) * (px - g0[0]) + (py - g0[1]) * (py - g0[1])) / rad : 1.0;
+          else t = len2 > 0 ? ((px - g0[0]) * dx + (py - g0[1]) * dy) / len2 : 0.0;
+          float src[4];
+          colour(t, src);
+          float* d = &canvas[4 * ((size_t)y * W + x)];
+          const float sa = src[3], da = d[3], oa = sa + da * (1.0f - sa);          // source-over on straight alpha
+          for (int c = 0; c < 3; ++c) d[c] = oa > 0 ? (src[c] * sa + d[c] * da * (1.0f - sa)) / oa : 0.0f;
+          d[3] = oa;
+        }
+      }
+    }
+  }
+  // scaled(m_iSize) (:355, fast transformation = nearest) + 8-bit RGBA
+  rgba.assign(4 * m_w * m_h, 0);
+  uint64_t lim[4] = {m_w, 0, m_h, 0};
+  for (size_t y = 0; y < m_h; ++y)
+    for (size_t x = 0; x < m_w; ++x) {
+      const size_t sx = std::min(W - 1, x * W / m_w), sy = std::min(std::max<size_t>(H, 1) - 1, y * H / m_h);
+      for (int c = 0; c < 4; ++c) rgba[4 * (y * m_w + x) + c] = (uint8_t)std::lround(std::min(1.0f, std::max(0.0f, canvas[4 * (sy * W + sx) + c])) * 255.0f);
+      if (rgba[4 * (y * m_w + x) + 3]) {
+        lim[0] = std::min<uint64_t>(lim[0], x); lim[1] = std::max<uint64_t>(lim[1], x);
+        lim[2] = std::min<uint64_t>(lim[2], y); lim[3] = std::max<uint64_t>(lim[3], y);
+      }
+    }
+  for (int i = 0; i < 4; ++i) limits[i] = double(lim[i]);
 }
 static float Smoothstep(float x) { return 3 * x * x - 2 * x * x * x; }
 void TransferFunction1D::SetStdFunction(float c, float g, int comp) {        // TransferFunction1D.cpp:81-112
@@ -1063,6 +1219,16 @@ void CudaGridLeaper::Changed1DTrans() {                                      // 
   ScheduleCompleteRedraw();
 }
 
+bool CudaGridLeaper::Load2DTrans(const std::string& filename) {
+  // AbstrRenderer::LoadFile sizes the 2-D function like the 1-D one: value bins x 256 gradient bins (AbstrRenderer.cpp:236-244)
+  TransferFunction2D tf;
+  if (!tf.Load(filename, std::max<size_t>(1, m_tf1d.GetSize()), 256)) { m_err = "could not load 2D transfer function " + filename; return false; }
+  std::vector<uint8_t> table;
+  double nz[4];
+  tf.Render(table, nz);
+  return Set2DTrans(table.data(), (uint32_t)tf.Width(), (uint32_t)tf.Height(), nz);
+}
+
 bool CudaGridLeaper::Set2DTrans(const uint8_t* rgba, uint32_t w, uint32_t h, double nz[4]) {
   // the swatch rasterisation of TransferFunction2D needs Qt (TransferFunction2D.cpp:294-361);
   // the renderer takes the rasterised RGBA8 table and its non-zero limits instead
@@ -1846,6 +2012,20 @@ int tvkr_set_1d_trans_float(tvkr_renderer* h, const float* rgba, uint32_t n) {
 int tvkr_load_1d_trans(tvkr_renderer* h, const char* filename) {
   if (!h || !filename || !R(h)->Get1DTrans().Load(filename)) return 1;
   R(h)->Changed1DTrans();
+  return 0;
+}
+int tvkr_load_2d_trans(tvkr_renderer* h, const char* filename) { return h && filename && R(h)->Load2DTrans(filename) ? 0 : 1; }
+int tvkr_tf2d_render(const char* filename, uint32_t w, uint32_t hh, uint8_t* rgba, double nz_limits[4], const char* save_as) {
+  if (!filename || !rgba || !nz_limits || !w || !hh) return 1;
+  tvk::TransferFunction2D tf;
+  if (!tf.Load(filename, w, hh)) return 1;
+  std::vector<uint8_t> t;
+  tf.Render(t, nz_limits);
+  memcpy(rgba, t.data(), t.size());
+  if (save_as && *save_as) {                                                  // Load(file) keeps the file's own size: the round trip Save writes
+    tvk::TransferFunction2D own;
+    if (!own.Load(filename) || !own.Save(save_as)) return 1;
+  }
   return 0;
 }
 int tvkr_set_2d_trans(tvkr_renderer* h, const uint8_t* rgba, uint32_t w, uint32_t hh, const double nz_limits[4]) {

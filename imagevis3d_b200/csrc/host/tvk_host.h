@@ -14,6 +14,7 @@
 //                           frame loop (Render3DRegion :914-1154) + GLRenderer camera set-up
 #pragma once
 #include <cstdint>
+#include <array>
 #include <string>
 #include <vector>
 #include "tvk_cuda.h"
@@ -59,6 +60,8 @@ class TransferFunction1D {
   void Resample(size_t n);                                 // TransferFunction1D::Resample (box filter down, linear up)
   bool Load(const std::string& filename);                  // ".1dt" text format
   bool Save(const std::string& filename) const;
+  bool Load(std::istream& in);                             // TransferFunction1D.cpp:279-295 (the 1-D part of a ".2dt" file)
+  bool Save(std::ostream& out) const;                      // :298-309, byte for byte
   void Set(const float* rgba, size_t n);
   void SetStdFunction(float center = 0.5f, float invGradient = 0.5f);
   void GetByteArray(std::vector<uint8_t>& out, uint8_t usedRange = 255) const;
@@ -71,6 +74,40 @@ class TransferFunction1D {
   void SetStdFunction(float center, float invGradient, int component);
   std::vector<float> m_color;     // r g b a per entry
   uint64_t m_lo = 0, m_hi = 0;
+};
+
+// One swatch of a 2-D transfer function (TFPolygon, TransferFunction2D.h:52-66): a polygon in normalised (value,
+// gradient) coordinates filled with a linear or radial colour gradient.
+struct TFPolygon {
+  bool radial = false;
+  std::vector<std::array<float, 2>> points;
+  float gradientCoords[2][2] = {{0, 0}, {0, 0}};
+  std::vector<std::pair<float, std::array<float, 4>>> stops;
+};
+
+// TransferFunction2D (IO/TransferFunction2D.cpp): the ".2dt" file (size, a 1-D function, the swatch list) with the
+// reference's Load / Save, and a rasteriser for the table the GPU samples.  The reference rasterises with Qt's QPainter
+// (RenderTransferFunction8Bit, :295-361: the 1-D function stretched over every row, then each swatch as a polygon without
+// pen or anti-aliasing, QLinearGradient / QRadialGradient brush, source-over); Qt is not available here, so Render()
+// restates those rules (pixel-centre coverage, odd-even fill, pad spread, stops interpolated linearly) -- equal in
+// structure, not guaranteed equal in the last bit to what a particular Qt version paints.
+class TransferFunction2D {
+ public:
+  bool Load(const std::string& filename);                                  // :156-198 (size from the file)
+  bool Load(const std::string& filename, size_t targetW, size_t targetH);  // :102-152 (1-D part resampled to the target)
+  bool Save(const std::string& filename) const;                            // :200-220, byte for byte
+  // GetByteArray (:222-236, RGBA8 rows) + ComputeNonZeroLimits (:376-397: min x, max x, min y, max y of alpha != 0)
+  void Render(std::vector<uint8_t>& rgba, double limits[4]) const;
+  size_t Width() const { return m_w; }
+  size_t Height() const { return m_h; }
+  TransferFunction1D& Trans1D() { return m_trans1d; }
+  std::vector<TFPolygon>& Swatches() { return m_swatches; }
+
+ private:
+  bool LoadRest(std::istream& in, bool allowNoSwatch);
+  size_t m_w = 0, m_h = 0;
+  TransferFunction1D m_trans1d;
+  std::vector<TFPolygon> m_swatches;
 };
 
 // The 1-D histogram the transfer-function editor draws: the file's histogram, "resampled" to at most
@@ -238,6 +275,8 @@ class CudaGridLeaper {
   // ownership and sets up pool, transfer function and visibility like LoadDataset does.
   // renderer.loadRebricked(file, {bs,bs,bs}, minmaxMode) (AbstrRenderer.cpp:266-273): brickSize includes the ghost voxels;
   // minmaxMode = TVK_MM_SOURCE / _PRECOMPUTE / _DYNAMIC
+  // renderer.load2DTrans(file.2dt): Load with the renderer's table size + rasterisation + Set2DTrans
+  bool Load2DTrans(const std::string& filename);
   bool LoadRebricked(const std::string& uvfFile, uint32_t brickSize, int minmaxMode, uint64_t gpuMemBytes, bool verifyChecksum);
   bool PrepareHostVolume(BrickedVolume* v);
   bool AdoptVolume(BrickedVolume* v, uint64_t gpuMemBytes);

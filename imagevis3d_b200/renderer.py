@@ -287,6 +287,23 @@ class Renderer:
     def load1DTrans(self, filename):
         self._ck(self._lib.tvkr_load_1d_trans(self._h, filename.encode()), "load1DTrans")
 
+    def load2DTrans(self, filename):
+        """renderer.load2DTrans(file.2dt): swatches rasterised on the host into a (1-D table size) x 256 table"""
+        self._ck(self._lib.tvkr_load_2d_trans(self._h, filename.encode()), "load2DTrans")
+
+    @staticmethod
+    def renderTF2D(filename, w, h, save_as=None):
+        """-> (RGBA8 table [h][w][4], non-zero limits) of a .2dt file, no device needed; save_as: write it back out"""
+        from . import _lib as L2
+        lib = L2.load()
+        out = np.zeros((h, w, 4), np.uint8)
+        nz = (C.c_double * 4)()
+        rc = lib.tvkr_tf2d_render(filename.encode(), C.c_uint32(w), C.c_uint32(h), out.ctypes.data_as(C.c_void_p), nz,
+                                  (save_as or "").encode())
+        if rc:
+            raise RuntimeError("tvkr_tf2d_render(%s) failed" % filename)
+        return out, list(nz)
+
     def set2DTrans(self, rgba8, nz_limits):
         a = np.ascontiguousarray(rgba8, np.uint8)           # [256 gradient rows][value bins][4]
         nz = (C.c_double * 4)(*[float(v) for v in nz_limits])

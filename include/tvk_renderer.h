@@ -90,6 +90,14 @@ int tvkr_load_1d_trans(tvkr_renderer* r, const char* filename_1dt);
 /* 2-D TF as a rasterised RGBA8 table (w = value bins, h = 256 gradient bins) + its non-zero
  * limits (TransferFunction2D::GetNonZeroLimits); + tuvok.gpu.changed2DTrans */
 int tvkr_set_2d_trans(tvkr_renderer* r, const uint8_t* rgba, uint32_t w, uint32_t h, const double nz_limits[4]);
+/* renderer.load2DTrans("file.2dt") (TransferFunction2D::Load(file, size), TransferFunction2D.cpp:102-152): the swatch list is
+ * rasterised on the host (the reference paints it with Qt's QPainter, :295-361; here: the same rules without Qt -- 1-D
+ * function stretched over every row, polygons filled without anti-aliasing, linear / radial gradient, source-over) into a
+ * table of (1-D table size) x 256 entries, then as tvkr_set_2d_trans */
+int tvkr_load_2d_trans(tvkr_renderer* r, const char* filename_2dt);
+/* the same without a renderer: rasterises file.2dt into a w x h RGBA8 table + its non-zero limits; save_as != NULL/"" also
+ * writes the function back out with the file's own size (TransferFunction2D::Load(file) + Save, :156-220: the text round trip) */
+int tvkr_tf2d_render(const char* filename_2dt, uint32_t w, uint32_t h, uint8_t* rgba, double nz_limits[4], const char* save_as);
 /* tuvok.state.brickStrategy / hashTableSize / rehashCount (MasterController.cpp:458-496) + sampler */
 int tvkr_set_state(tvkr_renderer* r, uint32_t brick_strategy, uint32_t hash_table_size, uint32_t rehash_count,
                    uint32_t sampler);

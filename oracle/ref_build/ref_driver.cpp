@@ -45,6 +45,7 @@
 #include "IO/UVF/Histogram2DDataBlock.h"
 #include "IO/UVF/RasterDataBlock.h"
 #include "IO/TransferFunction1D.h"
+#include "IO/TransferFunction2D.h"
 #include "IO/QVISConverter.h"
 #include "IO/NRRDConverter.h"
 #include "Basics/SysTools.h"
@@ -382,6 +383,15 @@ static int do_dsdump(int argc, char** argv) {
   return 0;
 }
 
+// ref_driver tf2d <in.2dt> <out.2dt>: TransferFunction2D::Load(file) + Save(file) of the reference (the text round trip;
+//   the swatch rasterisation needs Qt and is compiled out)
+static int do_tf2d(int argc, char** argv) {
+  if (argc < 4) return 2;
+  TransferFunction2D tf;
+  if (!tf.Load(std::string(argv[2]))) return 1;
+  return tf.Save(std::string(argv[3])) ? 0 : 1;
+}
+
 // ref_driver rebrick <file.uvf> <bx> <by> <bz> <mm 0|1|2> <out.bin>
 //   opens the file with the reference's UVFDataset, wraps it in the reference's DynamicBrickingDS (target brick size
 //   INCLUDING ghost voxels, min/max mode MM_SOURCE / MM_PRECOMPUTE / MM_DYNAMIC -- IO/DynamicBrickingDS.h) and dumps
@@ -569,6 +579,7 @@ int main(int argc, char** argv) {
   if (!strcmp(argv[1], "writeuvf")) return do_writeuvf(argc, argv);
   if (!strcmp(argv[1], "readuvf")) return do_readuvf(argc, argv);
   if (!strcmp(argv[1], "rebrick")) return do_rebrick(argc, argv);
+  if (!strcmp(argv[1], "tf2d")) return do_tf2d(argc, argv);
   if (!strcmp(argv[1], "writeuvfts")) return do_writeuvfts(argc, argv);
   if (!strcmp(argv[1], "dsdump")) return do_dsdump(argc, argv);
   return 2;
