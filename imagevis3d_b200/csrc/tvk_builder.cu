@@ -1447,35 +1447,46 @@ template <> struct V8<uint8_t> {
   static __device__ __forceinline__ uint32_t shfl_first_down(const uint2& v) { return __shfl_down_sync(0xffffffffu, v.x, 1) & 0xffu; }
 };
 
-// The 8 voxels of octet o of row rc (all 32 lanes call; inactive lanes get zeros): S' per voxel, 2^23 + value per voxel.
+// The 8 voxels of octet o of row rc and everything around them, as loaded (all 32 lanes call; inactive lanes get zeros).
 // `uniform` = every byte this thread looked at (own octet, x halo, four neighbouring octets) is the value `v0`.
+template <typename T> struct Octet {
+  typename V8<T>::type c, up, dn, fr, bk;
+  uint32_t prev, next, v0;
+  bool uniform;
+};
 template <typename T>
-__device__ __forceinline__ void octet_grad(const RowCtx<T>& rc, uint32_t o, uint32_t o_first, uint32_t o_end, uint32_t no, uint32_t lane,
-                                           bool act, float sf[8], float cm[8], bool& uniform, uint32_t& v0) {
+__device__ __forceinline__ Octet<T> octet_load(const RowCtx<T>& rc, uint32_t o, uint32_t o_first, uint32_t o_end, uint32_t no, uint32_t lane, bool act) {
   typedef V8<T> V;
   typedef typename V::type Q;
   const Q z = V::zero();
-  const Q c = act ? V::load(rc.line, o) : z;
-  const Q up = (act && rc.up) ? V::load(rc.up, o) : z, dn = (act && rc.down) ? V::load(rc.down, o) : z;
-  const Q fr = (act && rc.front) ? V::load(rc.front, o) : z, bk = (act && rc.back) ? V::load(rc.back, o) : z;
-  uint32_t prev = V::shfl_last_up(c), next = V::shfl_first_down(c);
+  Octet<T> r;
+  r.c = act ? V::load(rc.line, o) : z;
+  r.up = (act && rc.up) ? V::load(rc.up, o) : z; r.dn = (act && rc.down) ? V::load(rc.down, o) : z;
+  r.fr = (act && rc.front) ? V::load(rc.front, o) : z; r.bk = (act && rc.back) ? V::load(rc.back, o) : z;
+  r.prev = V::shfl_last_up(r.c); r.next = V::shfl_first_down(r.c);
   // the x halo of the first / last lane of the chunk comes from memory (zero outside the row)
-  if (lane == 0 || o == o_first) prev = (act && o > 0) ? (uint32_t)__ldg(rc.line + 8u * o - 1u) : 0u;
-  if (lane == 31 || o + 1 == o_end) next = (act && o + 1 < no) ? (uint32_t)__ldg(rc.line + 8u * o + 8u) : 0u;
-  if (!act) prev = next = 0u;                           // (an idle lane next to the row's last octet: S' stays 0)
-  v0 = V::first(c);
-  uniform = V::all_equal(c, v0) && V::all_equal(up, v0) && V::all_equal(dn, v0) && V::all_equal(fr, v0) && V::all_equal(bk, v0) &&
-            prev == v0 && next == v0;
+  if (lane == 0 || o == o_first) r.prev = (act && o > 0) ? (uint32_t)__ldg(rc.line + 8u * o - 1u) : 0u;
+  if (lane == 31 || o + 1 == o_end) r.next = (act && o + 1 < no) ? (uint32_t)__ldg(rc.line + 8u * o + 8u) : 0u;
+  if (!act) r.prev = r.next = 0u;                       // (an idle lane next to the row's last octet: S' stays 0)
+  r.v0 = V::first(r.c);
+  r.uniform = V::all_equal(r.c, r.v0) && V::all_equal(r.up, r.v0) && V::all_equal(r.dn, r.v0) && V::all_equal(r.fr, r.v0) &&
+              V::all_equal(r.bk, r.v0) && r.prev == r.v0 && r.next == r.v0;
+  return r;
+}
+// S' per voxel and 2^23 + value per voxel of a loaded octet
+template <typename T>
+__device__ __forceinline__ void octet_s(const Octet<T>& q, float sf[8], float cm[8]) {
+  typedef V8<T> V;
   float xm[10];
-  xm[0] = __uint_as_float(0x4B000000u | prev);
-  xm[9] = __uint_as_float(0x4B000000u | next);
+  xm[0] = __uint_as_float(0x4B000000u | q.prev);
+  xm[9] = __uint_as_float(0x4B000000u | q.next);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { cm[i] = V::m(c, i); xm[i + 1] = cm[i]; }
+  for (int i = 0; i < 8; ++i) { cm[i] = V::m(q.c, i); xm[i + 1] = cm[i]; }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float dx = __fsub_rn(xm[i], xm[i + 2]);                 // exact: both are 2^23 + integer
-    const float dy = __fsub_rn(V::m(up, i), V::m(dn, i));
-    const float dz = __fsub_rn(V::m(fr, i), V::m(bk, i));
+    const float dy = __fsub_rn(V::m(q.up, i), V::m(q.dn, i));
+    const float dz = __fsub_rn(V::m(q.fr, i), V::m(q.bk, i));
     sf[i] = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
   }
 }
@@ -1498,9 +1509,10 @@ __global__ void __launch_bounds__(256) grad_max_v8_kernel(const T* __restrict__ 
     for (uint32_t o0 = 0; o0 < no; o0 += 32u) {
       const uint32_t o = o0 + lane;
       const bool act = row_valid && o < no;
+      const Octet<T> oc = octet_load<T>(rc, o, o0, no, no, lane, act);
+      if (__all_sync(0xffffffffu, oc.uniform)) continue;            // one value everywhere the warp looked: no gradient
       float sf[8], cm[8];
-      bool uni; uint32_t v0;
-      octet_grad<T>(rc, o, o0, no, no, lane, act, sf, cm, uni, v0);
+      octet_s<T>(oc, sf, cm);
       const float m = fmaxf(fmaxf(fmaxf(sf[0], sf[1]), fmaxf(sf[2], sf[3])), fmaxf(fmaxf(sf[4], sf[5]), fmaxf(sf[6], sf[7])));
       if (m == 0.0f || m < thr) continue;
       uint32_t cand = 0;
@@ -1618,15 +1630,13 @@ __global__ void __launch_bounds__(256) hist2d_v8_kernel(const T* __restrict__ ra
       const uint32_t o = o0 + lane;
       const bool act = y < sy && o < o_end;
       const RowCtx<T> rc = row_ctx(raw, min(y, sy - 1u), z, sx, sy, sz);
-      float sf[8], cm[8];
-      bool uni; uint32_t v0;
-      octet_grad<T>(rc, o, o0, o_end, no, lane, act, sf, cm, uni, v0);
+      const Octet<T> oc = octet_load<T>(rc, o, o0, o_end, no, lane, act);
       const unsigned am = __ballot_sync(0xffffffffu, act);
       if (am == 0u) continue;
-      // ---- one value everywhere the warp looked: one vote for the lot
+      // ---- one value everywhere the warp looked: one vote for the lot (before any of the per-voxel arithmetic)
       const uint32_t lead = __ffs(am) - 1;
-      const uint32_t vl = __shfl_sync(0xffffffffu, v0, lead);
-      if (__all_sync(0xffffffffu, !act || (uni && v0 == vl))) {
+      const uint32_t vl = __shfl_sync(0xffffffffu, oc.v0, lead);
+      if (__all_sync(0xffffffffu, !act || (oc.uniform && oc.v0 == vl))) {
         if (lane == 0) {
           const uint32_t bin = (uint32_t)vlut[vl] * 256u + gi_zero;
           const uint32_t n = 8u * __popc(am);
@@ -1635,6 +1645,8 @@ __global__ void __launch_bounds__(256) hist2d_v8_kernel(const T* __restrict__ ra
         }
         continue;
       }
+      float sf[8], cm[8];
+      octet_s<T>(oc, sf, cm);
       // ---- value columns: eight table reads in flight while the gradient bins are worked out
       uint32_t vb[8];
 #pragma unroll

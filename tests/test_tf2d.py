@@ -82,12 +82,12 @@ def test_renderer_load_2d_trans(tmp_path):
         r = Renderer(0)
         r.loadRawVolume(raw, hist2d=True)
         r.resize((160, 120))
-        r.setRenderMode(1)
         if how == "file":
             r.load2DTrans(f)
         else:
             t, nz = Renderer.renderTF2D(f, 256, 256)
             r.set2DTrans(t, nz)
+        r.setRenderMode(1)
         r.paintUntilConverged(100)
         frames.append(r.frameFloat())
         r.cleanup()
