@@ -992,11 +992,22 @@ def run_sortlast(args, torch, dist, TvkContext, HM, SL, dev, local, rank, world,
     dist.barrier()
     torch.cuda.synchronize()
     kernel_ms, step_ms = 0.0, 0.0
+    align = torch.zeros(1, device=dev)
+
+    def align_ranks_on_device():
+        # The host-side barrier above releases the ranks' HOSTS within a scheduling quantum of each other (eight processes
+        # on sixteen host threads: up to a millisecond), and a rank that starts its march late makes every other rank wait
+        # for its stripes inside the timed region.  A one-element all-reduce on the work stream, with the step's start event
+        # recorded BEHIND it, makes every rank's timed region start when the last rank's GPU has arrived.
+        with torch.cuda.stream(work_stream):
+            dist.all_reduce(align)
+
     for k in range(steps):
         flush.zero_()
         dist.barrier()                  # the untimed L2 flush lets the ranks drift apart; re-align them
         torch.cuda.synchronize()
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        align_ranks_on_device()
         ev_a.record(work_stream)
         step(k, timed=True)
         ev_b.record(work_stream)
@@ -1041,7 +1052,7 @@ def run_sortlast(args, torch, dist, TvkContext, HM, SL, dev, local, rank, world,
             dist.barrier()
             torch.cuda.synchronize()
             ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev_a.record(work_stream)
+            ev_a.record(work_stream)       # (no device-side alignment here: the host work of a step is part of what e2e measures)
             for t, st in zip(ctxs, box_streams):
                 st.wait_event(ev_a)
                 t.set_tf1d(ms["tf"])                                         # host table -> device, every step
