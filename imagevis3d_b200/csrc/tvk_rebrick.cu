@@ -155,8 +155,11 @@ extern "C" int tvk_rebrick(tvk_ctx* c, const tvk_rebrick_desc* d, const void* sr
   // the source may be pinned host memory: the kernel needs its device alias
   const uint8_t* src = static_cast<const uint8_t*>(src_store);
   cudaPointerAttributes at;
-  if (cudaPointerGetAttributes(&at, src_store) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) src = static_cast<const uint8_t*>(at.devicePointer);
-  else (void)cudaGetLastError();
+  const bool known = cudaPointerGetAttributes(&at, src_store) == cudaSuccess;
+  if (!known) (void)cudaGetLastError();
+  if (known && at.type == cudaMemoryTypeHost && at.devicePointer) src = static_cast<const uint8_t*>(at.devicePointer);
+  else if (!known || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged))
+    TVK_FAIL(c, TVK_ERR_INVALID, "re-bricking: the source store must be device memory or pinned (mapped) host memory");
   RebrickJob* d_jobs = nullptr;
   uint32_t* d_mm = nullptr;
   TVK_CHECK_CUDA(c, cudaMalloc(&d_jobs, sizeof(RebrickJob) * n));

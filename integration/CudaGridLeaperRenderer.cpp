@@ -16,7 +16,7 @@ namespace tuvok {
 CudaGridLeaperRenderer::CudaGridLeaperRenderer(MasterController* pMasterController, bool bUseOnlyPowerOfTwo,
                                                bool bDownSampleTo8Bits, bool bDisableBorder)
     : AbstrRenderer(pMasterController, bUseOnlyPowerOfTwo, bDownSampleTo8Bits, bDisableBorder),
-      m_pToCDataset(NULL), m_bUploaded(false) {}
+      m_pToCDataset(NULL), m_bUploaded(false), m_iUploadedTimestep(0) {}
 
 CudaGridLeaperRenderer::~CudaGridLeaperRenderer() { m_impl.Cleanup(); }
 
@@ -104,6 +104,7 @@ bool CudaGridLeaperRenderer::UploadDataset() {
     return false;
   }
   m_bUploaded = true;
+  m_iUploadedTimestep = ts;
   m_impl.Resize(m_vWinSize.x, m_vWinSize.y);
   Changed1DTrans();
   return true;
@@ -195,6 +196,9 @@ void CudaGridLeaperRenderer::PushState() {
 bool CudaGridLeaperRenderer::Paint() {                                     // GLRenderer::Paint + GLGridLeaper::Render3DRegion
   if (!AbstrRenderer::Paint()) return false;
   if (m_bDatasetIsInvalid || !m_bUploaded) return true;
+  // AbstrRenderer::SetTimestep (AbstrRenderer.h:573) is not virtual: it only records m_iTimestep and schedules a redraw.
+  // The brick store here holds ONE time step, so a change is picked up where the redraw arrives.
+  if (m_iTimestep != m_iUploadedTimestep && !UploadDataset()) return false;
   std::shared_ptr<RenderRegion3D> rr = GetFirst3DRegion();
   if (rr && rr->isBlank) {                                                 // a new view: everything may have changed
     PushState();

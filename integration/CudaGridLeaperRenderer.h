@@ -87,6 +87,7 @@ class CudaGridLeaperRenderer : public AbstrRenderer {
   mutable tvk::CudaGridLeaper m_impl;
   LinearIndexDataset* m_pToCDataset;
   bool m_bUploaded;
+  size_t m_iUploadedTimestep;   ///< the time step whose bricks the CUDA renderer holds
 };
 
 }  // namespace tuvok
