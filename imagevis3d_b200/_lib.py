@@ -72,6 +72,13 @@ class RebrickInfo(C.Structure):
                 ("total_bricks", C.c_uint64), ("src_total_bricks", C.c_uint64), ("total_bytes", C.c_uint64)]
 
 
+class SliceParams(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("window_mode", C.c_uint32), ("use_mip", C.c_uint32),
+                ("slice", C.c_float), ("voxels", C.c_uint32 * 3), ("bytes_per_voxel", C.c_uint32), ("min_coords", C.c_float * 3),
+                ("max_coords", C.c_float * 3), ("quad", C.c_float * 2), ("render_mode", C.c_uint32), ("trans_scale", C.c_float),
+                ("gradient_scale", C.c_float)]
+
+
 class ClassicBrick(C.Structure):
     _fields_ = [("center", C.c_float * 3), ("extension", C.c_float * 3), ("eye_to_tex", C.c_float * 16),
                 ("ray_step", C.c_float), ("voxels", C.c_uint32 * 3), ("store_offset", C.c_uint64)]
@@ -109,7 +116,7 @@ EXPORTS = [
     "tvk_build_store_device_ptr", "tvk_build_hist1d", "tvk_build_hist2d", "tvk_build_release", "tvk_build_last_ms", "tvk_build_hist2d_last_ms", "tvk_quantize",
     "tvk_build_forget_raw", "tvk_build_stream_begin", "tvk_build_stream_rows", "tvk_build_stream_slab", "tvk_build_stream_end",
     "tvk_rebrick_plan", "tvk_rebrick_toc", "tvk_rebrick",
-    "tvk_composite_ordered", "tvk_raycast_classic",
+    "tvk_composite_ordered", "tvk_raycast_classic", "tvk_render_slice",
     "tvk_exchange_create", "tvk_exchange_open_peers", "tvk_exchange_connect", "tvk_exchange_peer_base", "tvk_exchange_set_peers", "tvk_exchange_local_base",
     "tvk_exchange_begin_frame", "tvk_exchange_composite", "tvk_exchange_final", "tvk_exchange_read_final_rgba8", "tvk_exchange_status", "tvk_exchange_destroy",
 ]

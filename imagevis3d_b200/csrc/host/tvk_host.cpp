@@ -1219,6 +1219,66 @@ void CudaGridLeaper::Changed1DTrans() {                                      // 
   ScheduleCompleteRedraw();
 }
 
+// GLRenderer::Render2DView (GLRenderer.cpp:1057-1176), slice and MIP-preview path: the whole target is ONE 2-D render
+// region showing the finest LOD that is a single brick.  windowMode / sliceIndex / useMIP / flipView are the fields of
+// RenderRegion2D (RenderRegion.h:53-140); the result is the frame (GetFrameFloat / GetFrameRGBA8 / CaptureSingleFrame).
+bool CudaGridLeaper::ComputeSliceParams(int windowMode, uint64_t sliceIndex, bool useMIP, bool flipX, bool flipY, tvk_slice_params& p, uint64_t& toc) const {
+  if (!m_vol || !m_w || !m_h || windowMode < TVK_WM_SAGITTAL || windowMode > TVK_WM_CORONAL) return false;
+  const BrickedVolume& v = *m_vol;
+  memset(&p, 0, sizeof(p));
+  p.width = m_w; p.height = m_h; p.window_mode = (uint32_t)windowMode; p.use_mip = useMIP ? 1u : 0u;
+  const uint32_t lod = v.LargestSingleBrickLOD();          // "the LOD level with just one brick" (:1095-1105)
+  toc = v.TocIndex(0, 0, 0, lod);
+  double aspect[3];
+  for (int a = 0; a < 3; ++a) {
+    p.voxels[a] = v.sizes[3 * toc + a];                    // vVoxelCount (= vRealVoxelCount: no power-of-two padding)
+    // vMinCoords = (vVoxelCount - domain(lod) + 1) / (2 * vRealVoxelCount); vMaxCoords = vVoxelCount / vRealVoxelCount - vMinCoords (:1141-1142)
+    p.min_coords[a] = (float(p.voxels[a]) - float(v.info.lod_size[lod][a]) + 1.0f) / (2.0f * float(p.voxels[a]));
+    p.max_coords[a] = (float(p.voxels[a]) / float(p.voxels[a])) - p.min_coords[a];
+    aspect[a] = double(v.scale[a]) * double(v.domain[a]);  // GetScale() * GetDomainSize() (:1144-1145)
+  }
+  p.bytes_per_voxel = v.bpv;
+  // vWinAspectRatio = 1 / region size, normalised by its largest component (:1147-1149)
+  double win[2] = {1.0 / double(m_w), 1.0 / double(m_h)};
+  const double wm = std::max(win[0], win[1]);
+  win[0] /= wm; win[1] /= wm;
+  // RenderSlice (:922-1014): which volume axes the quad shows, and what flipView swaps
+  const int ah = windowMode == TVK_WM_SAGITTAL ? 1 : 0, av = windowMode == TVK_WM_CORONAL ? 1 : 2;
+  if (flipX) std::swap(p.min_coords[ah], p.max_coords[ah]);
+  if (flipY) std::swap(p.min_coords[av], p.max_coords[av]);
+  double q[2] = {aspect[ah] * win[0], aspect[av] * win[1]};
+  const double qm = std::max(q[0], q[1]);
+  p.quad[0] = float(q[0] / qm); p.quad[1] = float(q[1] / qm);
+  p.slice = float(double(sliceIndex) / double(v.domain[windowMode]));        // sliceDir == windowMode (:1151, :1170-1171)
+  double lo, hi;
+  v.Range(lo, hi);
+  const double maxValue = (lo > hi) ? double(m_tf1d.GetSize()) : hi;
+  p.trans_scale = float(((1u << (8 * v.bpv)) - 1) / maxValue);
+  p.gradient_scale = (v.max_grad_magnitude == 0) ? 1.0f : 1.0f / v.max_grad_magnitude;
+  p.render_mode = (!useMIP && m_mode == RM_2DTRANS && m_has2d) ? TVK_RM_2DTRANS : TVK_RM_1DTRANS;   // `default:` = the 1-D slice shader (:1072-1079)
+  return true;
+}
+
+bool CudaGridLeaper::Render2DView(int windowMode, uint64_t sliceIndex, bool useMIP, bool flipX, bool flipY) {
+  if (!m_ctx || !m_vol) { m_err = "Render2DView() without dataset"; return false; }
+  tvk_slice_params p;
+  uint64_t toc = 0;
+  if (!ComputeSliceParams(windowMode, sliceIndex, useMIP, flipX, flipY, p, toc)) { m_err = "bad 2-D view (window mode, or no render target)"; return false; }
+  if (sliceIndex >= m_vol->domain[windowMode]) { m_err = "slice index beyond the domain"; return false; }
+  const void* brick = m_vol->host_store ? (const void*)(m_vol->host_store + m_vol->offsets[toc])
+                                        : (const void*)((const uint8_t*)m_vol->device_store + m_vol->offsets[toc]);
+  if (m_vol->lz4_store) { m_err = "2-D views need an uncompressed brick store"; return false; }
+  // the context holds ONE table: the slice shaders of the 1-D path (and Transfer-MIP) want the 1-D function
+  const bool swapTF = p.render_mode == TVK_RM_1DTRANS && m_mode == RM_2DTRANS && m_has2d;
+  std::vector<uint8_t> bytes;
+  if (swapTF) { m_tf1d.GetByteArray(bytes); const int rc = tvk_set_tf1d(m_ctx, bytes.data(), (uint32_t)m_tf1d.GetSize()); if (rc) return Fail("tvk_set_tf1d", rc); }
+  int rc = tvk_render_slice(m_ctx, &p, brick);
+  if (swapTF) { const int r2 = tvk_set_tf2d(m_ctx, m_tf2dBytes.data(), m_tf2dW, m_tf2dH); if (!rc && r2) rc = r2; }
+  if (rc) return Fail("tvk_render_slice", rc);
+  m_blank = true; m_converged = false;                     // the 3-D frame has to be redrawn from scratch afterwards
+  return true;
+}
+
 bool CudaGridLeaper::Load2DTrans(const std::string& filename) {
   // AbstrRenderer::LoadFile sizes the 2-D function like the 1-D one: value bins x 256 gradient bins (AbstrRenderer.cpp:236-244)
   TransferFunction2D tf;
@@ -2013,6 +2073,13 @@ int tvkr_load_1d_trans(tvkr_renderer* h, const char* filename) {
   if (!h || !filename || !R(h)->Get1DTrans().Load(filename)) return 1;
   R(h)->Changed1DTrans();
   return 0;
+}
+int tvkr_render_2d_view(tvkr_renderer* h, int window_mode, uint64_t slice_index, int use_mip, int flip_x, int flip_y) {
+  return h && R(h)->Render2DView(window_mode, slice_index, use_mip != 0, flip_x != 0, flip_y != 0) ? 0 : 1;
+}
+int tvkr_get_slice_params(tvkr_renderer* h, int window_mode, uint64_t slice_index, int use_mip, int flip_x, int flip_y, tvk_slice_params* out) {
+  uint64_t toc = 0;
+  return h && out && R(h)->ComputeSliceParams(window_mode, slice_index, use_mip != 0, flip_x != 0, flip_y != 0, *out, toc) ? 0 : 1;
 }
 int tvkr_load_2d_trans(tvkr_renderer* h, const char* filename) { return h && filename && R(h)->Load2DTrans(filename) ? 0 : 1; }
 int tvkr_tf2d_render(const char* filename, uint32_t w, uint32_t hh, uint8_t* rgba, double nz_limits[4], const char* save_as) {

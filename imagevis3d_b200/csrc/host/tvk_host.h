@@ -275,6 +275,9 @@ class CudaGridLeaper {
   // ownership and sets up pool, transfer function and visibility like LoadDataset does.
   // renderer.loadRebricked(file, {bs,bs,bs}, minmaxMode) (AbstrRenderer.cpp:266-273): brickSize includes the ghost voxels;
   // minmaxMode = TVK_MM_SOURCE / _PRECOMPUTE / _DYNAMIC
+  // a 2-D render region over the whole target: slice view or MIP preview (GLRenderer::Render2DView)
+  bool Render2DView(int windowMode, uint64_t sliceIndex, bool useMIP, bool flipX, bool flipY);
+  bool ComputeSliceParams(int windowMode, uint64_t sliceIndex, bool useMIP, bool flipX, bool flipY, tvk_slice_params& p, uint64_t& toc) const;
   // renderer.load2DTrans(file.2dt): Load with the renderer's table size + rasterisation + Set2DTrans
   bool Load2DTrans(const std::string& filename);
   bool LoadRebricked(const std::string& uvfFile, uint32_t brickSize, int minmaxMode, uint64_t gpuMemBytes, bool verifyChecksum);

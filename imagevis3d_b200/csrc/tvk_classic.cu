@@ -279,3 +279,128 @@ extern "C" int tvk_raycast_classic(tvk_ctx* c, const tvk_classic_params* p, cons
   TVK_CHECK_CUDA(c, cudaFreeAsync(d_bricks, c->stream));
   return TVK_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------
+// 2-D slice / MIP views (GLRenderer::Render2DView, GLRenderer.cpp:1057-1176; RenderSlice :922-1014; 1D-slice-FS.glsl,
+// 2D-slice-FS.glsl, MIP-slice-FS.glsl, Transfer-MIP-FS.glsl).  The reference draws ONE quad textured with the finest
+// single-brick LOD; here every pixel computes the texture coordinate the rasteriser would interpolate for its centre.
+// ---------------------------------------------------------------------------------------------------------
+struct SliceArgs {
+  tvk_slice_params p;
+  const uint8_t* brick;
+  const uchar4* tf;
+  uint32_t tf_w, tf_h;
+  float4* image;
+};
+
+// texture3D(texVolume, c): GL_LINEAR, GL_CLAMP_TO_EDGE, UNORM
+template <int BPV>
+__device__ __forceinline__ float slice_sample(const SliceArgs& a, float cx, float cy, float cz) {
+  const uint32_t* n = a.p.voxels;
+  const float u = fmaf(cx, (float)n[0], -0.5f), v = fmaf(cy, (float)n[1], -0.5f), w = fmaf(cz, (float)n[2], -0.5f);
+  const float fu = floorf(u), fv = floorf(v), fw = floorf(w);
+  const float ta = u - fu, tb = v - fv, tg = w - fw;
+  const int x0 = min(max((int)fu, 0), (int)n[0] - 1), x1 = min(max((int)fu + 1, 0), (int)n[0] - 1);
+  const int y0 = min(max((int)fv, 0), (int)n[1] - 1), y1 = min(max((int)fv + 1, 0), (int)n[1] - 1);
+  const int z0 = min(max((int)fw, 0), (int)n[2] - 1), z1 = min(max((int)fw + 1, 0), (int)n[2] - 1);
+  auto at = [&](int x, int y, int z) -> float {
+    const size_t i = (size_t)x + (size_t)y * n[0] + (size_t)z * n[0] * n[1];
+    return BPV == 1 ? (float)a.brick[i] : (float)reinterpret_cast<const uint16_t*>(a.brick)[i];
+  };
+  const float c00 = fmaf(ta, at(x1, y0, z0) - at(x0, y0, z0), at(x0, y0, z0)), c10 = fmaf(ta, at(x1, y1, z0) - at(x0, y1, z0), at(x0, y1, z0));
+  const float c01 = fmaf(ta, at(x1, y0, z1) - at(x0, y0, z1), at(x0, y0, z1)), c11 = fmaf(ta, at(x1, y1, z1) - at(x0, y1, z1), at(x0, y1, z1));
+  const float c0 = fmaf(tb, c10 - c00, c00), c1 = fmaf(tb, c11 - c01, c01);
+  return fmaf(tg, c1 - c0, c0) * (BPV == 1 ? 1.0f / 255.0f : 1.0f / 65535.0f);
+}
+__device__ __forceinline__ int slice_nearest(float s, uint32_t n) { return min(max(__float2int_rz(s * (float)n), 0), (int)n - 1); }
+__device__ __forceinline__ float4 slice_tf(const SliceArgs& a, int x, int y) {
+  const uchar4 t = a.tf[(size_t)y * a.tf_w + x];
+  return make_float4(t.x * (1.0f / 255.0f), t.y * (1.0f / 255.0f), t.z * (1.0f / 255.0f), t.w * (1.0f / 255.0f));
+}
+
+template <int BPV>
+__global__ void __launch_bounds__(256) slice_kernel(const __grid_constant__ SliceArgs a) {
+  const tvk_slice_params& p = a.p;
+  const uint32_t px = blockIdx.x * 16u + (threadIdx.x & 15u), py = blockIdx.y * 16u + (threadIdx.x >> 4);
+  if (px >= p.width || py >= p.height) return;
+  // pixel centre in normalised device coordinates; the quad spans [-quad.x, quad.x] x [-quad.y, quad.y]
+  const float nx = (2.0f * ((float)px + 0.5f)) / (float)p.width - 1.0f, ny = (2.0f * ((float)py + 0.5f)) / (float)p.height - 1.0f;
+  float4 out = make_float4(0.f, 0.f, 0.f, 1.f);                             // glClearColor(0,0,0,1)
+  const bool inside = fabsf(nx) <= p.quad[0] && fabsf(ny) <= p.quad[1];
+  // horizontal / vertical position on the quad in [0,1] (left -> right, bottom -> top)
+  const float sx = inside ? (nx + p.quad[0]) / (2.0f * p.quad[0]) : 0.f, sy = inside ? (ny + p.quad[1]) / (2.0f * p.quad[1]) : 0.f;
+  // which texture axes the screen axes run along (RenderSlice's glTexCoord3d calls)
+  const int ah = p.window_mode == TVK_WM_SAGITTAL ? 1 : 0;                  // sagittal: screen x = texture y; axial, coronal: texture x
+  const int av = p.window_mode == TVK_WM_CORONAL ? 1 : 2;                   // coronal: screen y = texture y; sagittal, axial: texture z
+  const int ad = (int)p.window_mode == TVK_WM_SAGITTAL ? 0 : (p.window_mode == TVK_WM_AXIAL ? 1 : 2);
+  float c[3];
+  c[ah] = fmaf(sx, p.max_coords[ah] - p.min_coords[ah], p.min_coords[ah]);
+  c[av] = fmaf(sy, p.max_coords[av] - p.min_coords[av], p.min_coords[av]);
+  c[ad] = p.slice;
+  if (!p.use_mip) {
+    if (inside) {
+      const float val = slice_sample<BPV>(a, c[0], c[1], c[2]);
+      float4 t;
+      if (p.render_mode == TVK_RM_2DTRANS) {
+        const float hx = 1.0f / (float)p.voxels[0], hy = 1.0f / (float)p.voxels[1], hz = 1.0f / (float)p.voxels[2];   // vVoxelStepsize
+        const float xp = slice_sample<BPV>(a, c[0] + hx, c[1], c[2]), xm = slice_sample<BPV>(a, c[0] - hx, c[1], c[2]);
+        const float yp = slice_sample<BPV>(a, c[0], c[1] - hy, c[2]), ym = slice_sample<BPV>(a, c[0], c[1] + hy, c[2]);
+        const float zp = slice_sample<BPV>(a, c[0], c[1], c[2] + hz), zm = slice_sample<BPV>(a, c[0], c[1], c[2] - hz);
+        const float gx = (xm - xp) / 2.0f, gy = (yp - ym) / 2.0f, gz = (zm - zp) / 2.0f;
+        const float gm = sqrtf(fmaf(gz, gz, fmaf(gy, gy, gx * gx)));
+        t = slice_tf(a, slice_nearest(val * p.trans_scale, a.tf_w), slice_nearest(1.0f - gm * p.gradient_scale, a.tf_h));
+      } else {
+        t = slice_tf(a, slice_nearest(val * p.trans_scale, a.tf_w), 0);
+      }
+      out = make_float4(t.x * t.w, t.y * t.w, t.z * t.w, 1.0f);             // rgb *= a; a = 1
+    }
+  } else {
+    // MIP preview: GL_MAX blend of sampleVolume().xxxx over the brick's slices; outside the quad the cleared 0 remains
+    float m = 0.0f;
+    if (inside) {
+      const uint32_t ns = p.voxels[ad];
+      for (uint32_t i = 0; i < ns; ++i) {
+        c[ad] = (float)((double)i / (double)ns);
+        m = fmaxf(m, slice_sample<BPV>(a, c[0], c[1], c[2]));
+      }
+    }
+    // Transfer-MIP-FS.glsl: the cleared alpha of 1 marks every pixel of the region -> vec4(tf(max).rgb, 1)
+    const float4 t = slice_tf(a, slice_nearest(m * p.trans_scale, a.tf_w), 0);
+    out = make_float4(t.x, t.y, t.z, 1.0f);
+  }
+  a.image[(size_t)py * p.width + px] = out;
+}
+
+extern "C" int tvk_render_slice(tvk_ctx* c, const tvk_slice_params* p, const void* brick) {
+  if (!c || !p || !brick) return TVK_ERR_INVALID;
+  if (p->window_mode > TVK_WM_CORONAL || !p->width || !p->height || !p->voxels[0] || !p->voxels[1] || !p->voxels[2] ||
+      (p->bytes_per_voxel != 1 && p->bytes_per_voxel != 2) || !(p->quad[0] > 0.f) || !(p->quad[1] > 0.f))
+    TVK_FAIL(c, TVK_ERR_INVALID, "bad slice parameters");
+  const bool two_d = !p->use_mip && p->render_mode == TVK_RM_2DTRANS;
+  if (!p->use_mip && p->render_mode != TVK_RM_1DTRANS && p->render_mode != TVK_RM_2DTRANS) TVK_FAIL(c, TVK_ERR_INVALID, "slice views classify with the 1-D or the 2-D transfer function");
+  if (!c->d_tf || (two_d ? c->tf_h < 2 : c->tf_h != 1)) TVK_FAIL(c, TVK_ERR_INVALID, "the transfer function of the slice view's mode is not set");
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  int rc = tvk_ensure_frame(c, p->width, p->height, c->hash_size ? c->hash_size : 509);
+  if (rc) return rc;
+  const size_t bytes = (size_t)p->voxels[0] * p->voxels[1] * p->voxels[2] * p->bytes_per_voxel;
+  const void* d_brick = brick;
+  void* tmp = nullptr;
+  cudaPointerAttributes at;
+  const bool known = cudaPointerGetAttributes(&at, brick) == cudaSuccess;
+  if (!known) (void)cudaGetLastError();
+  if (!known || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {   // host memory: the brick is small, copy it up
+    TVK_CHECK_CUDA(c, cudaMallocAsync(&tmp, bytes, c->stream));
+    TVK_CHECK_CUDA(c, cudaMemcpyAsync(tmp, brick, bytes, cudaMemcpyHostToDevice, c->stream));
+    d_brick = tmp;
+  }
+  SliceArgs a;
+  a.p = *p; a.brick = static_cast<const uint8_t*>(d_brick); a.tf = c->d_tf; a.tf_w = c->tf_w; a.tf_h = c->tf_h; a.image = c->d_image;
+  const dim3 grid((p->width + 15) / 16, (p->height + 15) / 16);
+  if (p->bytes_per_voxel == 1) slice_kernel<1><<<grid, 256, 0, c->stream>>>(a);
+  else slice_kernel<2><<<grid, 256, 0, c->stream>>>(a);
+  c->launches++;
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  if (tmp) TVK_CHECK_CUDA(c, cudaFreeAsync(tmp, c->stream));
+  return TVK_OK;
+}

@@ -287,6 +287,18 @@ class Renderer:
     def load1DTrans(self, filename):
         self._ck(self._lib.tvkr_load_1d_trans(self._h, filename.encode()), "load1DTrans")
 
+    def render2DView(self, window_mode, slice_index, mip=False, flip=(False, False)):
+        """a 2-D render region over the whole target: window_mode 0 sagittal / 1 axial / 2 coronal, slice index in voxels,
+        mip = MIP preview (GLRenderer::Render2DView); read the picture with frameFloat() / frameRGBA8()"""
+        self._ck(self._lib.tvkr_render_2d_view(self._h, C.c_int(int(window_mode)), C.c_uint64(int(slice_index)), C.c_int(int(mip)),
+                                               C.c_int(int(flip[0])), C.c_int(int(flip[1]))), "render2DView")
+
+    def sliceParams(self, window_mode, slice_index, mip=False, flip=(False, False)):
+        p = L.SliceParams()
+        self._ck(self._lib.tvkr_get_slice_params(self._h, C.c_int(int(window_mode)), C.c_uint64(int(slice_index)), C.c_int(int(mip)),
+                                                 C.c_int(int(flip[0])), C.c_int(int(flip[1])), C.byref(p)), "sliceParams")
+        return p
+
     def load2DTrans(self, filename):
         """renderer.load2DTrans(file.2dt): swatches rasterised on the host into a (1-D table size) x 256 table"""
         self._ck(self._lib.tvkr_load_2d_trans(self._h, filename.encode()), "load2DTrans")

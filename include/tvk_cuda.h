@@ -433,6 +433,34 @@ typedef struct tvk_classic_params {
 int tvk_raycast_classic(tvk_ctx* ctx, const tvk_classic_params* p, const tvk_classic_brick* bricks, uint32_t n,
                         const void* store_dptr);
 
+/* ------------------------------------------------------------ 2-D slice / MIP views */
+/* replaces GLRenderer::Render2DView's slice and MIP-preview path (GLRenderer.cpp:1057-1176: the finest LOD that is ONE
+ * brick, GLRenderer::RenderSlice :922-1014 for the textured quad, and the shaders 1D-slice-FS.glsl / 2D-slice-FS.glsl /
+ * MIP-slice-FS.glsl + Transfer-MIP-FS.glsl).  One launch: every pixel of the region finds its texture coordinate on the
+ * quad, samples the brick (GL_LINEAR, clamp to edge) and classifies -- slice: transfer function, colour multiplied by
+ * its opacity, alpha 1; MIP: maximum over all slices of the brick along the view axis, then the 1-D transfer function's
+ * colour with alpha 1 (Transfer-MIP ignores opacity).  Pixels outside the quad keep the clear colour (0,0,0,1).
+ * The full-resolution rotating MIP of capture mode (RenderHQMIP*, GLRenderer.cpp:1177-1216) is not built. */
+#define TVK_WM_SAGITTAL 0   /* slices along x (RenderRegion::EWindowMode, RenderRegion.h:53-59) */
+#define TVK_WM_AXIAL    1   /* along y */
+#define TVK_WM_CORONAL  2   /* along z */
+typedef struct tvk_slice_params {
+  uint32_t width, height;        /* the region = the whole target                                              */
+  uint32_t window_mode;          /* TVK_WM_*                                                                   */
+  uint32_t use_mip;              /* 0 slice, 1 MIP preview                                                     */
+  float    slice;                /* fSliceIndex: texture coordinate along the view axis (slice index / domain) */
+  uint32_t voxels[3];            /* vVoxelCount: size of the brick, ghost voxels included                      */
+  uint32_t bytes_per_voxel;
+  float    min_coords[3];        /* vMinCoords / vMaxCoords (:1141-1142), already swapped for flipView          */
+  float    max_coords[3];
+  float    quad[2];              /* v2AspectRatio: half extent of the quad in normalised device coordinates    */
+  uint32_t render_mode;          /* slice: TVK_RM_1DTRANS or TVK_RM_2DTRANS; MIP always uses the 1-D function  */
+  float    trans_scale;          /* fTransScale                                                                */
+  float    gradient_scale;       /* fGradientScale (2-D function)                                              */
+} tvk_slice_params;
+/* brick: the single brick (x fastest), device memory or host memory (copied up).  Result: the context's image. */
+int tvk_render_slice(tvk_ctx* ctx, const tvk_slice_params* p, const void* brick);
+
 /* ---------------------------------------------- sort-last exchange over peer memory */
 /* Direct-send compositing fused into the kernels (no reference counterpart): rank r owns scan-line
  * stripe r.  After tvk_exchange_begin_frame the next tvk_raycast_subframe stores every finished pixel into the

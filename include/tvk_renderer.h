@@ -90,6 +90,14 @@ int tvkr_load_1d_trans(tvkr_renderer* r, const char* filename_1dt);
 /* 2-D TF as a rasterised RGBA8 table (w = value bins, h = 256 gradient bins) + its non-zero
  * limits (TransferFunction2D::GetNonZeroLimits); + tuvok.gpu.changed2DTrans */
 int tvkr_set_2d_trans(tvkr_renderer* r, const uint8_t* rgba, uint32_t w, uint32_t h, const double nz_limits[4]);
+/* A 2-D render region over the whole target (RenderRegion2D: windowMode TVK_WM_SAGITTAL / _AXIAL / _CORONAL, slice index in
+ * voxels of the finest level, MIP flag, flipView): GLRenderer::Render2DView's slice view and MIP preview
+ * (GLRenderer.cpp:1057-1176) of the finest single-brick LOD, classified with the 1-D transfer function (the 2-D one in 2-D
+ * mode; MIP: 1-D colour only).  The result is the frame (tvkr_get_frame_*, tvkr_capture_single_frame); the next
+ * tvkr_paint() starts the 3-D view again.  tvkr_get_slice_params: what the view would be drawn with (tests). */
+int tvkr_render_2d_view(tvkr_renderer* r, int window_mode, uint64_t slice_index, int use_mip, int flip_x, int flip_y);
+int tvkr_get_slice_params(tvkr_renderer* r, int window_mode, uint64_t slice_index, int use_mip, int flip_x, int flip_y,
+                          tvk_slice_params* out);
 /* renderer.load2DTrans("file.2dt") (TransferFunction2D::Load(file, size), TransferFunction2D.cpp:102-152): the swatch list is
  * rasterised on the host (the reference paints it with Qt's QPainter, :295-361; here: the same rules without Qt -- 1-D
  * function stretched over every row, polygons filled without anti-aliasing, linear / radial gradient, source-over) into a

@@ -700,3 +700,105 @@ def classic_render(p, bricks, store_tight, tf_rgba8):
     if rc:
         raise ValueError("orc_raycast_classic failed")
     return img, int(n.value)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 2-D slice / MIP views: GLRenderer::Render2DView (GLRenderer.cpp:1057-1176), RenderSlice (:922-1014) and the shaders
+# 1D-slice-FS.glsl, 2D-slice-FS.glsl, MIP-slice-FS.glsl, Transfer-MIP-FS.glsl.  TEST INFRASTRUCTURE (restatement; the GL
+# rasteriser's interpolation of the quad is replaced by the texture coordinate at the pixel centre).
+# ---------------------------------------------------------------------------------------------------------------
+def slice_params(vol_dims, scale, lod_size, brick_voxels, bpv, width, height, window_mode, slice_index, mip, flip, render_mode,
+                 max_value, max_grad):
+    """Render2DView's set-up for one 2-D region covering a width x height target.  vol_dims: LOD-0 domain; lod_size /
+    brick_voxels: domain and brick size (ghost voxels included) of the finest single-brick LOD."""
+    f = np.float32
+    mn = [(f(brick_voxels[a]) - f(lod_size[a]) + f(1.0)) / (f(2.0) * f(brick_voxels[a])) for a in range(3)]
+    mx = [f(brick_voxels[a]) / f(brick_voxels[a]) - mn[a] for a in range(3)]
+    aspect = [float(f(scale[a])) * float(vol_dims[a]) for a in range(3)]
+    win = [1.0 / width, 1.0 / height]
+    wm = max(win)
+    win = [w / wm for w in win]
+    ah = 1 if window_mode == 0 else 0
+    av = 1 if window_mode == 2 else 2
+    if flip[0]:
+        mn[ah], mx[ah] = mx[ah], mn[ah]
+    if flip[1]:
+        mn[av], mx[av] = mx[av], mn[av]
+    q = [aspect[ah] * win[0], aspect[av] * win[1]]
+    qm = max(q)
+    return dict(width=width, height=height, window_mode=window_mode, use_mip=int(bool(mip)), slice=f(float(slice_index) / float(vol_dims[window_mode])),
+                voxels=[int(v) for v in brick_voxels], bpv=bpv, min_coords=mn, max_coords=mx, quad=[f(q[0] / qm), f(q[1] / qm)],
+                render_mode=(1 if (render_mode == 1 and not mip) else 0), trans_scale=f(((1 << (8 * bpv)) - 1) / max_value),
+                gradient_scale=f(1.0) if max_grad == 0 else f(1.0) / f(max_grad))
+
+
+def _slice_sample(brick, c):
+    """texture3D: GL_LINEAR, clamp to edge, UNORM; brick [z][y][x], c = (cx, cy, cz) arrays"""
+    f = np.float32
+    nz, ny, nx = brick.shape
+    b = brick.astype(f)
+    def taps(cc, n):
+        u = cc.astype(f) * f(n) + f(-0.5)
+        fl = np.floor(u).astype(f)
+        return (u - fl).astype(f), np.clip(fl.astype(np.int64), 0, n - 1), np.clip(fl.astype(np.int64) + 1, 0, n - 1)
+    ta, x0, x1 = taps(c[0], nx)
+    tb, y0, y1 = taps(c[1], ny)
+    tg, z0, z1 = taps(c[2], nz)
+    lerp = lambda t, a0, a1: (t * (a1 - a0).astype(f) + a0).astype(f)   # one rounding for the product-sum is an fma; numpy rounds twice:
+    def lerp_fma(t, a0, a1):                                            # evaluate in float64 and round once (exact for these magnitudes)
+        return (t.astype(np.float64) * (a1 - a0).astype(f).astype(np.float64) + a0.astype(np.float64)).astype(f)
+    c00, c10 = lerp_fma(ta, b[z0, y0, x0], b[z0, y0, x1]), lerp_fma(ta, b[z0, y1, x0], b[z0, y1, x1])
+    c01, c11 = lerp_fma(ta, b[z1, y0, x0], b[z1, y0, x1]), lerp_fma(ta, b[z1, y1, x0], b[z1, y1, x1])
+    c0, c1 = lerp_fma(tb, c00, c10), lerp_fma(tb, c01, c11)
+    return (lerp_fma(tg, c0, c1) * (f(1.0) / f(255.0) if brick.dtype == np.uint8 else f(1.0) / f(65535.0))).astype(f)
+
+
+def slice_view(p, brick, tf_rgba8):
+    """-> float32 image [h][w][4].  tf_rgba8: [n][4] (1-D) or [rows][n][4] (2-D, slice mode with render_mode 1)"""
+    f = np.float32
+    w, h = p["width"], p["height"]
+    px, py = np.meshgrid(np.arange(w), np.arange(h))
+    nx = ((f(2.0) * (px.astype(f) + f(0.5))) / f(w) - f(1.0)).astype(f)
+    ny = ((f(2.0) * (py.astype(f) + f(0.5))) / f(h) - f(1.0)).astype(f)
+    qx, qy = f(p["quad"][0]), f(p["quad"][1])
+    inside = (np.abs(nx) <= qx) & (np.abs(ny) <= qy)
+    sx = np.where(inside, ((nx + qx) / (f(2.0) * qx)).astype(f), f(0))
+    sy = np.where(inside, ((ny + qy) / (f(2.0) * qy)).astype(f), f(0))
+    wm = p["window_mode"]
+    ah, av, ad = (1 if wm == 0 else 0), (1 if wm == 2 else 2), wm
+    mn, mx = [f(v) for v in p["min_coords"]], [f(v) for v in p["max_coords"]]
+    fma = lambda t, d, a0: (t.astype(np.float64) * np.float64(d) + np.float64(a0)).astype(f)
+    c = [None, None, None]
+    c[ah] = fma(sx, f(mx[ah] - mn[ah]), mn[ah])
+    c[av] = fma(sy, f(mx[av] - mn[av]), mn[av])
+    c[ad] = np.full(sx.shape, f(p["slice"]), f)
+    tf = np.asarray(tf_rgba8)
+    tfw = tf.shape[-2]
+    nearest = lambda s, n: np.clip((s * f(n)).astype(f).astype(np.int64), 0, n - 1)
+    img = np.zeros((h, w, 4), f)
+    img[..., 3] = 1.0
+    if not p["use_mip"]:
+        val = _slice_sample(brick, c)
+        if p["render_mode"] == 1:
+            hx, hy, hz = [f(1.0) / f(v) for v in p["voxels"]]
+            s = lambda dx, dy, dz: _slice_sample(brick, [(c[0] + f(dx)).astype(f), (c[1] + f(dy)).astype(f), (c[2] + f(dz)).astype(f)])
+            gx = ((s(-hx, 0, 0) - s(hx, 0, 0)) / f(2.0)).astype(f)
+            gy = ((s(0, -hy, 0) - s(0, hy, 0)) / f(2.0)).astype(f)
+            gz = ((s(0, 0, -hz) - s(0, 0, hz)) / f(2.0)).astype(f)
+            gm = np.sqrt((gz.astype(np.float64) * gz + (gy.astype(np.float64) * gy + (gx * gx).astype(f)).astype(f)).astype(f)).astype(f)
+            t = tf[nearest((f(1.0) - gm * f(p["gradient_scale"])).astype(f), tf.shape[0]), nearest(val * f(p["trans_scale"]), tfw)]
+        else:
+            t = tf.reshape(-1, tfw, 4)[0][nearest(val * f(p["trans_scale"]), tfw)]
+        t = t.astype(f) * (f(1.0) / f(255.0))
+        rgb = t[..., :3] * t[..., 3:4]
+        img[..., :3] = np.where(inside[..., None], rgb, f(0))
+    else:
+        m = np.zeros(sx.shape, f)
+        ns = p["voxels"][ad]
+        for i in range(ns):
+            c[ad] = np.full(sx.shape, f(np.float64(i) / np.float64(ns)), f)
+            m = np.maximum(m, _slice_sample(brick, c))
+        m = np.where(inside, m, f(0))
+        t = tf.reshape(-1, tfw, 4)[0][nearest(m * f(p["trans_scale"]), tfw)].astype(f) * (f(1.0) / f(255.0))
+        img[..., :3] = t[..., :3]
+    return img
