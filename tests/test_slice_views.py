@@ -47,7 +47,7 @@ def test_slice_and_mip_views_match_the_restated_shaders(dtype, vol, scale):
     for wm in (0, 1, 2):
         for mip in (False, True):
             for flip in ((False, False), (True, False), (True, True)):
-                si = vol[wm] // 3
+                si = vol[wm] // 2
                 want = H.slice_params(vol, scale, [int(v) for v in oc["plan"].lod_size[lod]], brick.shape[::-1], raw.dtype.itemsize, w, h,
                                       wm, si, mip, flip, 0, mm, 0.0)
                 got = r.sliceParams(wm, si, mip, flip)
