@@ -116,7 +116,7 @@ EXPORTS = [
     "tvk_build_store_device_ptr", "tvk_build_hist1d", "tvk_build_hist2d", "tvk_build_release", "tvk_build_last_ms", "tvk_build_hist2d_last_ms", "tvk_quantize",
     "tvk_build_forget_raw", "tvk_build_stream_begin", "tvk_build_stream_rows", "tvk_build_stream_slab", "tvk_build_stream_end",
     "tvk_rebrick_plan", "tvk_rebrick_toc", "tvk_rebrick",
-    "tvk_composite_ordered", "tvk_raycast_classic", "tvk_render_slice",
+    "tvk_composite_ordered", "tvk_raycast_classic", "tvk_render_slice", "tvk_select_eye", "tvk_read_eye_image", "tvk_compose_stereo",
     "tvk_exchange_create", "tvk_exchange_open_peers", "tvk_exchange_connect", "tvk_exchange_peer_base", "tvk_exchange_set_peers", "tvk_exchange_local_base",
     "tvk_exchange_begin_frame", "tvk_exchange_composite", "tvk_exchange_final", "tvk_exchange_read_final_rgba8", "tvk_exchange_status", "tvk_exchange_destroy",
 ]

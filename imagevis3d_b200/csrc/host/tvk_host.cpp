@@ -96,6 +96,28 @@ Matrix4 Matrix4::Perspective(float fovy, float aspect, float n, float f) {    //
   r.m[11] = -1.0f;
   return r;
 }
+Matrix4 Matrix4::PerspectiveOffCenter(float left, float right, float bottom, float top, float n, float f) {   // Vectors.h:1286-1291
+  Matrix4 r;
+  for (int i = 0; i < 16; ++i) r.m[i] = 0;
+  r.m[0] = 2.0f * n / (right - left); r.m[8] = (right + left) / (right - left);
+  r.m[5] = 2.0f * n / (top - bottom); r.m[9] = (top + bottom) / (top - bottom);
+  r.m[10] = -(f + n) / (f - n); r.m[14] = -2.0f * (f * n) / (f - n);
+  r.m[11] = -1.0f;
+  return r;
+}
+void Matrix4::StereoLookAtAndProjection(const Vec3& eye, const Vec3& at, const Vec3& up, float fovy, float aspect, float n, float f,
+                                        float focalLength, float eyeDist, Matrix4 view[2], Matrix4 proj[2]) {
+  const float radians = float(3.14159265358979323846 / 180.0) * fovy / 2;
+  const float wd2 = n * float(std::tan(radians));
+  const float nfdl = n / focalLength;
+  const float shift = eyeDist * nfdl;
+  const float top = wd2, bottom = -wd2;
+  proj[0] = PerspectiveOffCenter(-aspect * wd2 + shift, aspect * wd2 + shift, bottom, top, n, f);
+  proj[1] = PerspectiveOffCenter(-aspect * wd2 - shift, aspect * wd2 - shift, bottom, top, n, f);
+  const Matrix4 look = LookAt(eye, at, up);
+  view[0] = Translation(eyeDist, 0.0f, 0.0f) * look;
+  view[1] = Translation(-eyeDist, 0.0f, 0.0f) * look;
+}
 void Matrix4::transform(const float v[4], float out[4]) const {
   for (int j = 0; j < 4; ++j) out[j] = v[0] * m[j] + v[1] * m[4 + j] + v[2] * m[8 + j] + v[3] * m[12 + j];
 }
@@ -1339,7 +1361,7 @@ void CudaGridLeaper::ClearWorkingSet() {                                     // 
   ScheduleCompleteRedraw();
 }
 
-bool CudaGridLeaper::ComputeRaycastParams(tvk_raycast_params& p) {
+bool CudaGridLeaper::ComputeRaycastParams(tvk_raycast_params& p, int eye) {
   if (!m_vol || !m_w || !m_h) { m_err = "no dataset / render target"; return false; }
   memset(&p, 0, sizeof(p));
   p.width = m_w; p.height = m_h;
@@ -1350,8 +1372,13 @@ bool CudaGridLeaper::ComputeRaycastParams(tvk_raycast_params& p) {
   for (int a = 0; a < 3; ++a) ext[a] /= mx;
   // GLRenderer::ComputeViewAndProjection (:888-920) and Paint (:627)
   const float aspect = float(m_w) / float(m_h);
-  const Matrix4 view = Matrix4::LookAt(m_eye, m_at, m_up);
-  const Matrix4 proj = Matrix4::Perspective(m_fov, aspect, m_znear, m_zfar);
+  Matrix4 view = Matrix4::LookAt(m_eye, m_at, m_up);
+  Matrix4 proj = Matrix4::Perspective(m_fov, aspect, m_znear, m_zfar);
+  if (m_stereo) {
+    Matrix4 views[2], projs[2];
+    Matrix4::StereoLookAtAndProjection(m_eye, m_at, m_up, m_fov, aspect, m_znear, m_zfar, m_stereoFocalLength, m_stereoEyeDist, views, projs);
+    view = views[eye ? 1 : 0]; proj = projs[eye ? 1 : 0];
+  }
   const Matrix4 mv = m_rotation * m_translation * view;
   // ComputeEyeToModelMatrix (GLGridLeaper.cpp:560-573), centre = 0
   Matrix4 emm = mv.inverse() * Matrix4::Translation(0, 0, 0) * Matrix4::Scaling(1.0f / ext[0], 1.0f / ext[1], 1.0f / ext[2]) *
@@ -1801,6 +1828,16 @@ bool CudaGridLeaper::Paint() {                                               // 
   // the march is queued behind whatever upload the previous sub-frame left in flight (tvk_pool_upload_fence)
   int rc = tvk_raycast_subframe(m_ctx, &p);
   if (rc) return Fail("tvk_raycast_subframe", rc);
+  if (m_stereo) {
+    // the second eye (GLGridLeaper.cpp:950-958): its own frame state, the same pool and request table
+    if (m_sl.on) { m_err = "stereo is not available for a sort-last member"; return false; }
+    tvk_raycast_params pr;
+    if (!ComputeRaycastParams(pr, 1)) return false;
+    rc = tvk_select_eye(m_ctx, 1);
+    if (!rc) rc = tvk_raycast_subframe(m_ctx, &pr);
+    const int rc2 = tvk_select_eye(m_ctx, 0);
+    if (rc || rc2) return Fail("tvk_raycast_subframe (right eye)", rc ? rc : rc2);
+  }
   m_blank = false;
   m_perf.subframes += 1;
   m_perfTable[PERF_SUBFRAMES] += 1;
@@ -1835,7 +1872,26 @@ bool CudaGridLeaper::Paint() {                                               // 
     m_perfTable[PERF_EO_BRICKS] += paged;
   }
   m_converged = (n == 0);
+  if (m_converged && m_stereo && !ComposeStereo()) return false;        // GLRenderer::EndFrame (:757-812)
   m_perfTable[PERF_RENDER] += ms_since(tPaint);
+  return true;
+}
+
+bool CudaGridLeaper::ComposeStereo() {
+  if (!m_ctx) return false;
+  const int rc = tvk_compose_stereo(m_ctx, (uint32_t)m_stereoMode, m_stereoEyeSwap ? 1u : 0u, 0.5f, m_afId);
+  return rc ? Fail("tvk_compose_stereo", rc) : true;
+}
+bool CudaGridLeaper::SetStereoMode(int mode) {
+  if (mode < TVK_SM_RB || mode > TVK_SM_AF) { m_err = "bad stereo mode"; return false; }
+  m_stereoMode = mode;
+  if (m_stereo) ScheduleCompleteRedraw();
+  return true;
+}
+void CudaGridLeaper::SetStereoEyeSwap(bool swap) { m_stereoEyeSwap = swap; if (m_stereo) ScheduleCompleteRedraw(); }
+bool CudaGridLeaper::ToggleStereoFrame() {                            // AbstrRenderer.cpp:1582-1585: recompose only
+  m_afId = 1 - m_afId;
+  if (m_stereo && m_converged && !m_blank && !m_classic) return ComposeStereo();
   return true;
 }
 
@@ -2017,6 +2073,27 @@ int tvkr_plan_classic_frame(tvkr_renderer* h, tvk_classic_params* p, tvk_classic
 }
 int tvkr_set_clip_plane(tvkr_renderer* h, const float plane[4]) { if (!h || !plane) return 1; R(h)->SetClipPlane(plane); return 0; }
 int tvkr_enable_clip_plane(tvkr_renderer* h, int on) { if (!h) return 1; R(h)->EnableClipPlane(on != 0); return 0; }
+int tvkr_set_stereo(tvkr_renderer* h, int on) { if (!h) return 1; R(h)->SetStereo(on != 0); return 0; }
+int tvkr_get_stereo(tvkr_renderer* h) { return h && R(h)->GetStereo() ? 1 : 0; }
+int tvkr_set_stereo_eye_dist(tvkr_renderer* h, float d) { if (!h) return 1; R(h)->SetStereoEyeDist(d); return 0; }
+int tvkr_set_stereo_focal_length(tvkr_renderer* h, float f) { if (!h || !(f > 0.0f)) return 1; R(h)->SetStereoFocalLength(f); return 0; }
+int tvkr_set_stereo_mode(tvkr_renderer* h, int mode) { return h && R(h)->SetStereoMode(mode) ? 0 : 1; }
+int tvkr_set_stereo_eye_swap(tvkr_renderer* h, int swap) { if (!h) return 1; R(h)->SetStereoEyeSwap(swap != 0); return 0; }
+int tvkr_init_stereo_frame(tvkr_renderer* h) { if (!h) return 1; R(h)->InitStereoFrame(); return 0; }
+int tvkr_toggle_stereo_frame(tvkr_renderer* h) { return h && R(h)->ToggleStereoFrame() ? 0 : 1; }
+int tvkr_get_raycast_params_eye(tvkr_renderer* h, int eye, tvk_raycast_params* p) { return h && p && (eye == 0 || eye == 1) && R(h)->ComputeRaycastParams(*p, eye) ? 0 : 1; }
+int tvkr_get_eye_frame_float(tvkr_renderer* h, int eye, float* out) {
+  return h && out && (eye == 0 || eye == 1) && R(h)->Context() && tvk_read_eye_image(R(h)->Context(), (uint32_t)eye, out) == TVK_OK ? 0 : 1;
+}
+int tvkr_stereo_matrices(const float eye[3], const float at[3], const float up[3], float fovy, float aspect, float znear, float zfar,
+                         float focal_length, float eye_dist, float out[64]) {
+  if (!eye || !at || !up || !out) return 1;
+  Matrix4 v[2], p[2];
+  Matrix4::StereoLookAtAndProjection(Vec3(eye[0], eye[1], eye[2]), Vec3(at[0], at[1], at[2]), Vec3(up[0], up[1], up[2]), fovy, aspect, znear, zfar,
+                                     focal_length, eye_dist, v, p);
+  memcpy(out, v[0].m, 64); memcpy(out + 16, v[1].m, 64); memcpy(out + 32, p[0].m, 64); memcpy(out + 48, p[1].m, 64);
+  return 0;
+}
 int tvkr_set_light_colors(tvkr_renderer* h, const float ambient[4], const float diffuse[4], const float specular[4], const float dir[3]) {
   if (!h || !ambient || !diffuse || !specular || !dir) return 1;
   R(h)->SetLightColors(ambient, diffuse, specular, Vec3(dir[0], dir[1], dir[2]));

@@ -49,6 +49,10 @@ struct Matrix4 {
   static Matrix4 RotationZ(double a);
   static Matrix4 LookAt(const Vec3& eye, const Vec3& at, const Vec3& up);
   static Matrix4 Perspective(float fovy, float aspect, float n, float f);
+  static Matrix4 PerspectiveOffCenter(float left, float right, float bottom, float top, float n, float f);
+  // FLOATMATRIX4::BuildStereoLookAtAndProjection (Vectors.h:1215-1248): [0] = left eye, [1] = right eye
+  static void StereoLookAtAndProjection(const Vec3& eye, const Vec3& at, const Vec3& up, float fovy, float aspect, float n, float f,
+                                        float focalLength, float eyeDist, Matrix4 view[2], Matrix4 proj[2]);
   void transform(const float v[4], float out[4]) const;   // v*M
 };
 
@@ -314,6 +318,18 @@ class CudaGridLeaper {
   // RenderRegion::SetClipPlane / EnableClipPlane (world-space plane a,b,c,d; n.p + d <= 0 is kept)
   void SetClipPlane(const float plane[4]);
   void EnableClipPlane(bool on);
+  // stereo (AbstrRenderer.cpp:1387-1410, :1577-1585; the Lua names setStereoEnabled, setStereoEyeDist, setStereoFocalLength,
+  // setStereoMode, setStereoEyeSwap, initStereoFrame, toggleStereoFrame): both eyes are marched in every sub-frame, share the
+  // request table and the pool, and are composed into one picture when the frame has converged (GLRenderer::EndFrame)
+  void SetStereo(bool on) { if (on != m_stereo) { m_stereo = on; ScheduleCompleteRedraw(); } }
+  bool GetStereo() const { return m_stereo; }
+  void SetStereoEyeDist(float d) { m_stereoEyeDist = d; if (m_stereo) ScheduleCompleteRedraw(); }
+  void SetStereoFocalLength(float f) { m_stereoFocalLength = f; if (m_stereo) ScheduleCompleteRedraw(); }
+  bool SetStereoMode(int mode);
+  void SetStereoEyeSwap(bool swap);
+  void InitStereoFrame() { m_afId = 0; ScheduleCompleteRedraw(); }
+  bool ToggleStereoFrame();
+  bool ComposeStereo();
   Vec3 GetViewPos() const { return m_eye; }
   Vec3 GetViewDir() const { return (m_at - m_eye).normalized(); }  // AbstrRenderer.cpp:1608-1610
   Vec3 GetUpDir() const { return m_up; }
@@ -355,7 +371,7 @@ class CudaGridLeaper {
   bool CaptureSingleFrame(const std::string& filename, bool preserveTransparency);
 
   // --- introspection used by tests / the C wrapper
-  bool ComputeRaycastParams(tvk_raycast_params& p);
+  bool ComputeRaycastParams(tvk_raycast_params& p, int eye = 0);    // eye: which of the two stereo views (ignored in mono)
   const BrickedVolume* Volume() const { return m_vol; }
   BrickPool* Pool() { return m_pool; }
   tvk_ctx* Context() { return m_ctx; }
@@ -406,6 +422,10 @@ class CudaGridLeaper {
   bool m_classic = false;
   bool m_clipEnabled = false;
   float m_clipPlane[4] = {0, 0, 1, 0};
+  bool m_stereo = false, m_stereoEyeSwap = false;                 // AbstrRenderer.cpp:141-145
+  float m_stereoEyeDist = 0.02f, m_stereoFocalLength = 1.0f;
+  int m_stereoMode = TVK_SM_RB;
+  uint32_t m_afId = 0;
   uint32_t m_lodLimits[2] = {0, 0};
   struct SortLast { bool on = false; uint32_t members = 1, member = 0, global[3] = {0, 0, 0}, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0},
                     start[3] = {0, 0, 0}, frame = 0; double maxValue = 0; bool exchange = false; } m_sl;

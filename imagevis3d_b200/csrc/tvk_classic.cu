@@ -254,6 +254,7 @@ extern "C" int tvk_raycast_classic(tvk_ctx* c, const tvk_classic_params* p, cons
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
   int rc = tvk_ensure_frame(c, p->width, p->height, c->hash_size ? c->hash_size : 509);
   if (rc) return rc;
+  c->show_stereo = false;
   tvk_classic_brick* d_bricks = nullptr;
   TVK_CHECK_CUDA(c, cudaMallocAsync(&d_bricks, sizeof(tvk_classic_brick) * (n ? n : 1), c->stream));
   if (n) TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_bricks, bricks, sizeof(tvk_classic_brick) * n, cudaMemcpyHostToDevice, c->stream));
@@ -383,6 +384,7 @@ extern "C" int tvk_render_slice(tvk_ctx* c, const tvk_slice_params* p, const voi
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
   int rc = tvk_ensure_frame(c, p->width, p->height, c->hash_size ? c->hash_size : 509);
   if (rc) return rc;
+  c->show_stereo = false;
   const size_t bytes = (size_t)p->voxels[0] * p->voxels[1] * p->voxels[2] * p->bytes_per_voxel;
   const void* d_brick = brick;
   void* tmp = nullptr;

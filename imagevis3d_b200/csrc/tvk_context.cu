@@ -139,6 +139,9 @@ extern "C" void tvk_destroy(tvk_ctx* c) {
   tvk_build_release(c);
   tvk_pool_destroy(c);
   free_frame(c);
+  cudaFree(c->other_eye.image);
+  for (int i = 0; i < 2; ++i) { cudaFree(c->other_eye.pos[i]); cudaFree(c->other_eye.aux[i]); }
+  cudaFree(c->d_stereo);
   cudaFree(c->d_tf); cudaFree(c->d_tf_f); cudaFree(c->d_tf_f1); cudaFree(c->d_tf_colmask); cudaFree(c->d_hash); cudaFree(c->d_tile_counter); cudaFree(c->d_stats); cudaFree(c->d_counts);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->bev0); cudaEventDestroy(c->bev1); cudaEventDestroy(c->copy_done); cudaEventDestroy(c->render_done);
   for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_gather[i]); cudaEventDestroy(c->ev_place[i]); }

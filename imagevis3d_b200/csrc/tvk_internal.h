@@ -142,9 +142,24 @@ struct tvk_ctx {
   uint64_t k1_serial = 0, stats_serial = ~0ull;
   unsigned long long cached_stats[3] = {0, 0, 0};
 
+  // stereo (tvk_select_eye): the frame state of the eye that is NOT selected, and the composed picture
+  struct EyeState {
+    float4* image = nullptr;
+    float4* pos[2] = {nullptr, nullptr};
+    float4* aux[2] = {nullptr, nullptr};
+    uint32_t width = 0, height = 0;
+  } other_eye;
+  uint32_t eye = 0;
+  float4* d_stereo = nullptr;          // tvk_compose_stereo target
+  size_t stereo_px = 0;
+  bool show_stereo = false;            // the read-back calls return d_stereo (until the next launch that draws)
+
   BuildState build;
   ExchangeState xchg;
 };
+
+// the picture the read-back calls return
+static inline float4* tvk_display_image(const tvk_ctx* c) { return c->show_stereo ? c->d_stereo : c->d_image; }
 
 #define TVK_CHECK_CUDA(ctx, call)                                                       \
   do {                                                                                  \

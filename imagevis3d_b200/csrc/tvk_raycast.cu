@@ -1407,8 +1407,10 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   if (grid < 1) grid = 1;
 
   // GLHashTable::ClearData (:106-110) + tile counter reset, then the march; timed with events
-  TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_hash, 0, sizeof(uint32_t) * p->hash_table_size, c->stream));
+  // (stereo: the second eye's march adds its requests to the table the first eye's left, GLGridLeaper.cpp:947-958)
+  if (c->eye == 0) TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_hash, 0, sizeof(uint32_t) * p->hash_table_size, c->stream));
   TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(uint32_t), c->stream));
+  c->show_stereo = false;
   TVK_CHECK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
   if (p->new_view && (rx0 > 0 || ry0 > 0 || rx1 < p->width || ry1 < p->height)) {
     const size_t npx = (size_t)p->width * p->height;
@@ -1462,7 +1464,7 @@ extern "C" int tvk_read_requests(tvk_ctx* c, uint32_t* xyzl, uint32_t cap, uint3
 extern "C" int tvk_read_image(tvk_ctx* c, float* rgba) {
   if (!c || !rgba || !c->d_image) return TVK_ERR_INVALID;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(rgba, c->d_image, sizeof(float4) * (size_t)c->width * c->height, cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(rgba, tvk_display_image(c), sizeof(float4) * (size_t)c->width * c->height, cudaMemcpyDeviceToHost, c->stream));
   TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
   return TVK_OK;
 }
@@ -1512,7 +1514,7 @@ extern "C" int tvk_read_image_rgba8(tvk_ctx* c, uint8_t* rgba8, int flip_rows) {
   int sm_count = 0;
   TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, c->device));
   const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)sm_count * 8);
-  image_to_rgba8_kernel<<<blocks, 256, 0, c->stream>>>(c->d_image, c->d_rgba8, c->width, c->height, flip_rows);
+  image_to_rgba8_kernel<<<blocks, 256, 0, c->stream>>>(tvk_display_image(c), c->d_rgba8, c->width, c->height, flip_rows);
   TVK_CHECK_CUDA(c, cudaGetLastError());
   return rgba8_to_host(c, rgba8, n);
 }
@@ -1552,7 +1554,7 @@ extern "C" int tvk_read_resume(tvk_ctx* c, float* pos, float* color) {
 
 extern "C" int tvk_image_device_ptr(tvk_ctx* c, void** dptr) {
   if (!c || !dptr || !c->d_image) return TVK_ERR_INVALID;
-  *dptr = c->d_image;
+  *dptr = tvk_display_image(c);
   return TVK_OK;
 }
 
@@ -1629,5 +1631,96 @@ extern "C" int tvk_probe_brick_index(tvk_ctx* c, const float* norm_xyz, const ui
   TVK_CHECK_CUDA(c, cudaMemcpyAsync(serial_out, d_s, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
   TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
   cudaFree(d_xyz); cudaFree(d_lod); cudaFree(d_i); cudaFree(d_s);
+  return TVK_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Stereo (GLGridLeaper::Render3DRegion's loop over EStereoID, GLGridLeaper.cpp:922-958; GLRenderer::EndFrame :757-812;
+// Compose-Anaglyphs-FS.glsl, Compose-Scanline-FS.glsl, Compose-SBS-FS.glsl, Compose-AF-FS.glsl).  The reference keeps one
+// set of frame buffers per eye (m_pFBO3DImageNext[2], m_pFBORayStart[2], m_pFBOStartColor[2]) and ONE request table.
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int tvk_select_eye(tvk_ctx* c, uint32_t eye) {
+  if (!c || eye > 1) return TVK_ERR_INVALID;
+  if (eye == c->eye) return TVK_OK;
+  tvk_ctx::EyeState& o = c->other_eye;
+  std::swap(c->d_image, o.image);
+  for (int i = 0; i < 2; ++i) { std::swap(c->d_pos[i], o.pos[i]); std::swap(c->d_aux[i], o.aux[i]); }
+  std::swap(c->width, o.width);
+  std::swap(c->height, o.height);
+  c->eye = eye;
+  return TVK_OK;
+}
+
+extern "C" int tvk_read_eye_image(tvk_ctx* c, uint32_t eye, float* rgba) {
+  if (!c || eye > 1 || !rgba) return TVK_ERR_INVALID;
+  const float4* src = eye == c->eye ? c->d_image : c->other_eye.image;
+  const uint32_t w = eye == c->eye ? c->width : c->other_eye.width, h = eye == c->eye ? c->height : c->other_eye.height;
+  if (!src || !w || !h) TVK_FAIL(c, TVK_ERR_INVALID, "that eye has no picture yet");
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(rgba, src, sizeof(float4) * (size_t)w * h, cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TVK_OK;
+}
+
+struct StereoArgs {
+  const float4* left;
+  const float4* right;
+  float4* out;
+  uint32_t w, h, mode, af_id;
+  double right_shift;                  // SBS: 2 * fSplitCoord * width
+  float split;
+};
+
+__global__ void __launch_bounds__(256) compose_stereo_kernel(const __grid_constant__ StereoArgs a) {
+  const uint32_t n = a.w * a.h;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t y = i / a.w, x = i - y * a.w;
+    float4 o;
+    if (a.mode == TVK_SM_RB) {
+      const float4 l = a.left[i], r = a.right[i];
+      const float gl = fmaf(l.z, 0.11f, fmaf(l.y, 0.59f, l.x * 0.3f)), gr = fmaf(r.z, 0.11f, fmaf(r.y, 0.59f, r.x * 0.3f));
+      o = make_float4(gl, gr * 0.5f, gr, fmaxf(l.w, r.w));
+    } else if (a.mode == TVK_SM_SCANLINE) {
+      o = (y & 1u) ? a.right[i] : a.left[i];                           // fLine/2 == floor(fLine/2): even lines show the left eye
+    } else if (a.mode == TVK_SM_SBS) {
+      // both halves show a whole eye image squeezed to half the width: GL_NEAREST at x*2 is texel 2x+1
+      const float tx = ((float)x + 0.5f) / (float)a.w;
+      const bool lhs = tx < a.split;
+      const double t = lhs ? (double)(2u * x + 1u) : (double)(2u * x + 1u) - a.right_shift;
+      const int sx = min(max((int)floor(t), 0), (int)a.w - 1);
+      o = (lhs ? a.left : a.right)[(size_t)y * a.w + sx];
+    } else {
+      o = a.af_id == 0 ? a.left[i] : a.right[i];
+    }
+    a.out[i] = o;
+  }
+}
+
+extern "C" int tvk_compose_stereo(tvk_ctx* c, uint32_t mode, uint32_t swap_eyes, float split_coord, uint32_t alternating_frame_id) {
+  if (!c || mode > TVK_SM_AF) return TVK_ERR_INVALID;
+  if (!c->d_image || !c->other_eye.image) TVK_FAIL(c, TVK_ERR_INVALID, "stereo compose needs a picture for each eye (tvk_select_eye)");
+  if (c->width != c->other_eye.width || c->height != c->other_eye.height) TVK_FAIL(c, TVK_ERR_INVALID, "the two eyes' pictures differ in size");
+  if (mode == TVK_SM_SBS && !(split_coord > 0.0f && split_coord <= 0.5f)) TVK_FAIL(c, TVK_ERR_INVALID, "bad split coordinate");
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)c->width * c->height;
+  if (!c->d_stereo || c->stereo_px < n) {
+    cudaFree(c->d_stereo); c->d_stereo = nullptr; c->stereo_px = 0;
+    TVK_CHECK_CUDA(c, cudaMalloc(&c->d_stereo, n * sizeof(float4)));
+    c->stereo_px = n;
+  }
+  const float4* eye0 = c->eye == 0 ? c->d_image : c->other_eye.image;
+  const float4* eye1 = c->eye == 0 ? c->other_eye.image : c->d_image;
+  StereoArgs a;
+  a.left = swap_eyes ? eye1 : eye0;                                   // m_bStereoEyeSwap binds the textures the other way round
+  a.right = swap_eyes ? eye0 : eye1;
+  a.out = c->d_stereo; a.w = c->width; a.h = c->height; a.mode = mode; a.af_id = alternating_frame_id;
+  a.split = split_coord; a.right_shift = 2.0 * (double)split_coord * (double)c->width;
+  int sm_count = 0;
+  TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, c->device));
+  compose_stereo_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, (size_t)sm_count * 8), 256, 0, c->stream>>>(a);
+  c->launches++;
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  c->show_stereo = true;
   return TVK_OK;
 }

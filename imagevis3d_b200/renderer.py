@@ -222,6 +222,41 @@ class Renderer:
     def enableClipPlane(self, on=True):
         self._ck(self._lib.tvkr_enable_clip_plane(self._h, C.c_int(int(on))), "enableClipPlane")
 
+    # -- stereo (AbstrRenderer.cpp:1387-1410, :1577-1585)
+    STEREO_MODES = {"rb": 0, "scanline": 1, "sbs": 2, "af": 3}
+
+    def setStereoEnabled(self, on=True):
+        self._ck(self._lib.tvkr_set_stereo(self._h, C.c_int(int(on))), "setStereoEnabled")
+
+    def getStereoEnabled(self):
+        return bool(self._lib.tvkr_get_stereo(self._h))
+
+    def setStereoEyeDist(self, d):
+        self._ck(self._lib.tvkr_set_stereo_eye_dist(self._h, C.c_float(d)), "setStereoEyeDist")
+
+    def setStereoFocalLength(self, f):
+        self._ck(self._lib.tvkr_set_stereo_focal_length(self._h, C.c_float(f)), "setStereoFocalLength")
+
+    def setStereoMode(self, mode):
+        """0 / "rb" red-blue anaglyph, 1 / "scanline", 2 / "sbs" side by side, 3 / "af" alternating frames"""
+        self._ck(self._lib.tvkr_set_stereo_mode(self._h, C.c_int(self.STEREO_MODES.get(mode, mode))), "setStereoMode")
+
+    def setStereoEyeSwap(self, swap=True):
+        self._ck(self._lib.tvkr_set_stereo_eye_swap(self._h, C.c_int(int(swap))), "setStereoEyeSwap")
+
+    def initStereoFrame(self):
+        self._ck(self._lib.tvkr_init_stereo_frame(self._h), "initStereoFrame")
+
+    def toggleStereoFrame(self):
+        self._ck(self._lib.tvkr_toggle_stereo_frame(self._h), "toggleStereoFrame")
+
+    def eyeFrameFloat(self, eye):
+        """one eye's own picture of a stereo frame (before the composition)"""
+        w, h = self._size
+        out = np.zeros((h, w, 4), np.float32)
+        self._ck(self._lib.tvkr_get_eye_frame_float(self._h, C.c_int(int(eye)), out.ctypes.data_as(C.c_void_p)), "eyeFrameFloat")
+        return out
+
     def setLightColors(self, ambient, diffuse, specular, direction):
         f4 = lambda v: (C.c_float * 4)(*[float(x) for x in v])      # noqa: E731
         self._ck(self._lib.tvkr_set_light_colors(self._h, f4(ambient), f4(diffuse), f4(specular), _f3(direction)), "setLightColors")
@@ -373,9 +408,13 @@ class Renderer:
         return out
 
     # -- introspection
-    def raycastParams(self):
+    def raycastParams(self, eye=None):
+        """eye: None = the (mono or left) view; 0 / 1 = the left / right view of a stereo pair"""
         p = L.RaycastParams()
-        self._ck(self._lib.tvkr_get_raycast_params(self._h, C.byref(p)), "raycastParams")
+        if eye is None:
+            self._ck(self._lib.tvkr_get_raycast_params(self._h, C.byref(p)), "raycastParams")
+        else:
+            self._ck(self._lib.tvkr_get_raycast_params_eye(self._h, C.c_int(int(eye)), C.byref(p)), "raycastParams")
         return p
 
     def poolSlots(self):

@@ -461,6 +461,29 @@ typedef struct tvk_slice_params {
 /* brick: the single brick (x fastest), device memory or host memory (copied up).  Result: the context's image. */
 int tvk_render_slice(tvk_ctx* ctx, const tvk_slice_params* p, const void* brick);
 
+/* ------------------------------------------------------------------------ stereo */
+/* replaces the per-eye frame buffers of GLGridLeaper / GLRenderer (m_pFBO3DImageNext[2], m_pFBORayStart[2],
+ * m_pFBOStartColor[2]; GLGridLeaper.cpp:922-958) and GLRenderer::EndFrame's stereo compose (GLRenderer.cpp:757-812 with
+ * Compose-Anaglyphs-FS.glsl, Compose-Scanline-FS.glsl, Compose-SBS-FS.glsl, Compose-AF-FS.glsl).
+ * tvk_select_eye: the following sub-frames, read-backs and resume state refer to that eye's frame state (eye 0 = left is
+ * what a context starts with; eye 1's buffers appear with its first sub-frame, which must be a new view).  Both eyes share
+ * ONE request table: a sub-frame of eye 0 clears it, a sub-frame of eye 1 adds to what eye 0's left, and
+ * tvk_read_requests after the pair returns the union -- as Render3DRegion clears the table once, marches both eyes and
+ * reads it once.
+ * tvk_compose_stereo: both eyes' pictures -> one, which tvk_read_image / _rgba8 / tvk_image_device_ptr return until the
+ * next launch that draws.  swap_eyes = m_bStereoEyeSwap; split_coord = fSplitCoord of the side-by-side mode (0.5 at full
+ * resolution); alternating_frame_id = m_iAlternatingFrameID of the alternating-frame mode.  The eye pictures are
+ * GL_NEAREST textures drawn one to one; the side-by-side mode reads at twice the x coordinate, i.e. texel 2x+1 of the
+ * left picture in the left half, texel 2x+1-2*split*width of the right one in the right half. */
+#define TVK_SM_RB       0   /* red/blue anaglyph: (grey(left), grey(right)/2, grey(right), max alpha), grey = (0.3,0.59,0.11).rgb */
+#define TVK_SM_SCANLINE 1   /* even lines left, odd lines right */
+#define TVK_SM_SBS      2   /* side by side */
+#define TVK_SM_AF       3   /* alternating frames */
+int tvk_select_eye(tvk_ctx* ctx, uint32_t eye);
+/* one eye's own picture (m_pFBO3DImageNext[eye]), whichever eye is selected and whether or not a composition is shown */
+int tvk_read_eye_image(tvk_ctx* ctx, uint32_t eye, float* rgba);
+int tvk_compose_stereo(tvk_ctx* ctx, uint32_t mode, uint32_t swap_eyes, float split_coord, uint32_t alternating_frame_id);
+
 /* ---------------------------------------------- sort-last exchange over peer memory */
 /* Direct-send compositing fused into the kernels (no reference counterpart): rank r owns scan-line
  * stripe r.  After tvk_exchange_begin_frame the next tvk_raycast_subframe stores every finished pixel into the

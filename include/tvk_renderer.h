@@ -136,6 +136,26 @@ int tvkr_plan_classic_frame(tvkr_renderer* r, tvk_classic_params* p, tvk_classic
  * (GLGridLeaper::FillBBoxVBO, GLGridLeaper.cpp:515-526 + Clipper::BoxPlane) */
 int tvkr_set_clip_plane(tvkr_renderer* r, const float plane[4]);
 int tvkr_enable_clip_plane(tvkr_renderer* r, int on);
+/* Stereo (renderer.setStereoEnabled / setStereoEyeDist / setStereoFocalLength / setStereoMode / setStereoEyeSwap /
+ * initStereoFrame / toggleStereoFrame; AbstrRenderer.cpp:1387-1410,1577-1585): every paint() marches the left and the right
+ * eye (views and off-axis projections of FLOATMATRIX4::BuildStereoLookAtAndProjection, Vectors.h:1215-1248), both report
+ * into one request table, and the converged frame is the composition GLRenderer::EndFrame draws (GLRenderer.cpp:757-812):
+ * mode TVK_SM_RB anaglyph (default), _SCANLINE, _SBS, _AF.  Defaults: eye distance 0.02, focal length 1.  Ray-guided
+ * renderer only; not for sort-last members.  tvkr_get_raycast_params_eye: the parameters of eye 0 (left) / 1 (right).
+ * tvkr_stereo_matrices: the four matrices (left view, right view, left projection, right projection; 16 floats each, as
+ * the reference stores them), no renderer needed. */
+int tvkr_set_stereo(tvkr_renderer* r, int on);
+int tvkr_get_stereo(tvkr_renderer* r);
+int tvkr_set_stereo_eye_dist(tvkr_renderer* r, float dist);
+int tvkr_set_stereo_focal_length(tvkr_renderer* r, float focal_length);
+int tvkr_set_stereo_mode(tvkr_renderer* r, int mode);
+int tvkr_set_stereo_eye_swap(tvkr_renderer* r, int swap);
+int tvkr_init_stereo_frame(tvkr_renderer* r);
+int tvkr_toggle_stereo_frame(tvkr_renderer* r);
+int tvkr_get_raycast_params_eye(tvkr_renderer* r, int eye, tvk_raycast_params* out);
+int tvkr_get_eye_frame_float(tvkr_renderer* r, int eye, float* out);   /* one eye's own picture, premultiplied RGBA32F */
+int tvkr_stereo_matrices(const float eye[3], const float at[3], const float up[3], float fovy, float aspect, float znear, float zfar,
+                         float focal_length, float eye_dist, float out[64]);
 int tvkr_set_light_colors(tvkr_renderer* r, const float ambient[4], const float diffuse[4], const float specular[4],
                           const float dir[3]);                                    /* renderer.setLightColors   */
 int tvkr_get_view(tvkr_renderer* r, float pos[3], float dir[3], float up[3]);    /* getViewPos/Dir/UpDir      */

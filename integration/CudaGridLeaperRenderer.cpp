@@ -190,6 +190,13 @@ void CudaGridLeaperRenderer::PushState() {
   m_impl.SetClipPlane(plane);
   m_impl.EnableClipPlane(m_bClipPlaneOn);
   m_impl.SetRendererTarget(int(m_eRendererTarget));
+  // stereo: AbstrRenderer's setters only record the state (AbstrRenderer.cpp:1387-1410); m_bDoStereoRendering is the
+  // request restricted to a single 3-D region (AbstrRenderer.h:444)
+  m_impl.SetStereo(m_bDoStereoRendering);
+  m_impl.SetStereoEyeDist(m_fStereoEyeDist);
+  m_impl.SetStereoFocalLength(m_fStereoFocalLength);
+  m_impl.SetStereoMode(int(m_eStereoMode));
+  m_impl.SetStereoEyeSwap(m_bStereoEyeSwap);
 }
 
 // ---------------------------------------------------------------------------------------------- frame loop

@@ -141,7 +141,7 @@ class Camera:
 
 def raycast_params(cam, width, height, domain_size, scale=(1, 1, 1), render_mode=0, lighting=False,
                    sample_rate=1.0, trans_scale=1.0, gradient_scale=1.0, isoval=0.5, new_view=True,
-                   strategy=3, rehash=10, hash_size=509, count_samples=True, slab=None, clip_plane=None):
+                   strategy=3, rehash=10, hash_size=509, count_samples=True, slab=None, clip_plane=None, view_proj=None):
     p = RaycastParams()
     p.width, p.height = width, height
     dom = np.asarray(domain_size, f32)
@@ -151,6 +151,8 @@ def raycast_params(cam, width, height, domain_size, scale=(1, 1, 1), render_mode
     aspect = f32(width) / f32(height)
     view = look_at(cam.eye, cam.at, cam.up)
     proj = perspective(cam.fov, aspect, cam.znear, cam.zfar)
+    if view_proj is not None:                            # one eye of a stereo pair (stereo_matrices)
+        view, proj = view_proj
     mv = (cam.rotation @ cam.translation @ view).astype(f32)     # GLRenderer.cpp:627
     emm = (inverse(mv) @ translation(0, 0, 0) @ scaling(*(f32(1) / extent)) @ translation(0.5, 0.5, 0.5)).astype(f32)
     box_min, box_max = [0.0, 0.0, 0.0], [1.0, 1.0, 1.0]
@@ -485,6 +487,80 @@ def render_converged(params, pool, tf_rgba8, max_subframes=200):
             return frame.image.copy(), sub + 1, paged, total_samples
         paged += pool.upload_requests(req)
     raise RuntimeError("oracle render did not converge")
+
+
+# ---------------------------------------------------------------- stereo (TEST INFRASTRUCTURE, restatement)
+def perspective_off_center(left, right, bottom, top, n, f):
+    """MATRIX4::MatrixPerspectiveOffCenter (Basics/Vectors.h:1286-1291), row-vector storage like perspective()"""
+    left, right, bottom, top, n, f = [f32(v) for v in (left, right, bottom, top, n, f)]
+    m = np.zeros((4, 4), f32)
+    m[0, 0] = f32(2) * n / (right - left)
+    m[2, 0] = (right + left) / (right - left)
+    m[1, 1] = f32(2) * n / (top - bottom)
+    m[2, 1] = (top + bottom) / (top - bottom)
+    m[2, 2] = -(f + n) / (f - n)
+    m[3, 2] = f32(-2) * (f * n) / (f - n)
+    m[2, 3] = f32(-1)
+    return m
+
+
+def stereo_matrices(cam, aspect, focal_length=1.0, eye_dist=0.02):
+    """FLOATMATRIX4::BuildStereoLookAtAndProjection (Basics/Vectors.h:1215-1248) -> ((view L, proj L), (view R, proj R))"""
+    radians = f32(3.14159265358979323846 / 180.0) * f32(cam.fov) / f32(2)
+    wd2 = f32(cam.znear) * f32(math.tan(float(radians)))
+    shift = f32(eye_dist) * (f32(cam.znear) / f32(focal_length))
+    a = f32(aspect)
+    pl = perspective_off_center(-a * wd2 + shift, a * wd2 + shift, -wd2, wd2, cam.znear, cam.zfar)
+    pr = perspective_off_center(-a * wd2 - shift, a * wd2 - shift, -wd2, wd2, cam.znear, cam.zfar)
+    look = look_at(cam.eye, cam.at, cam.up)
+    vl = (translation(f32(eye_dist), 0, 0) @ look).astype(f32)
+    vr = (translation(-f32(eye_dist), 0, 0) @ look).astype(f32)
+    return (vl, pl), (vr, pr)
+
+
+def render_converged_stereo(p_left, p_right, pool, tf_rgba8, max_subframes=200):
+    """GLGridLeaper::Render3DRegion with m_bDoStereoRendering (GLGridLeaper.cpp:922-958): per sub-frame the table is cleared
+    once, both eyes march (each with its own resume buffers) and the table is read once.  -> (left, right, subframes)"""
+    fl = OracleFrame(p_left.width, p_left.height, p_left.hash_table_size)
+    fr = OracleFrame(p_right.width, p_right.height, p_right.hash_table_size)
+    fr.hash = fl.hash
+    p_left.new_view = p_right.new_view = 1
+    for sub in range(max_subframes):
+        raycast(p_left, pool, tf_rgba8, fl)
+        raycast(p_right, pool, tf_rgba8, fr, clear_hash=False)
+        p_left.new_view = p_right.new_view = 0
+        req = read_requests(pool, fl)
+        if len(req) == 0:
+            return fl.image.copy(), fr.image.copy(), sub + 1
+        pool.upload_requests(req)
+    raise RuntimeError("oracle stereo render did not converge")
+
+
+def stereo_compose(eye0, eye1, mode, swap=False, split=0.5, af_id=0):
+    """GLRenderer::EndFrame's stereo pass (GLRenderer.cpp:770-812) with Compose-Anaglyphs-FS.glsl (mode 0),
+    Compose-Scanline-FS.glsl (1), Compose-SBS-FS.glsl (2), Compose-AF-FS.glsl (3); images [h][w][4], GL_NEAREST"""
+    left, right = (eye1, eye0) if swap else (eye0, eye1)
+    h, w = left.shape[:2]
+    if mode == 0:
+        g = np.array([0.3, 0.59, 0.11], f32)
+        gl = (left[..., :3].astype(np.float64) * g).sum(axis=2).astype(f32)
+        gr = (right[..., :3].astype(np.float64) * g).sum(axis=2).astype(f32)
+        return np.stack([gl, gr * f32(0.5), gr, np.maximum(left[..., 3], right[..., 3])], axis=2).astype(f32)
+    if mode == 1:
+        out = left.copy()
+        out[1::2] = right[1::2]
+        return out
+    if mode == 2:
+        out = np.empty_like(left)
+        x = np.arange(w)
+        tx = (x.astype(f32) + f32(0.5)) / f32(w)
+        lhs = tx < f32(split)
+        t = np.where(lhs, 2.0 * x + 1.0, 2.0 * x + 1.0 - 2.0 * float(f32(split)) * w)
+        sx = np.clip(np.floor(t).astype(np.int64), 0, w - 1)
+        out[:, lhs] = left[:, sx[lhs]]
+        out[:, ~lhs] = right[:, sx[~lhs]]
+        return out
+    return (left if af_id == 0 else right).copy()
 
 
 def psnr(a, b, peak=1.0):
