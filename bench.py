@@ -787,7 +787,10 @@ def run_e2e(torch, HM, dev, local, steps):
     r.setRenderMode(1)
     r.setLightingEnabled(True)
     uploaded = [0.0]
-    frame_buf = np.zeros((Hh, W, 4), np.uint8)                # the application's frame buffer (host, pageable)
+    # the application's frame buffer: page-locked host memory, so that the read-back is one DMA into it (a pageable buffer is
+    # accepted too and costs a host copy out of the library's landing block)
+    frame_pin = torch.empty((Hh, W, 4), dtype=torch.uint8, pin_memory=True)
+    frame_buf = frame_pin.numpy()
 
     def frame(k):
         r.setRotation4x4((HM.rotation_y(orbit_angle(k, steps)) @ HM.rotation_x(0.35)).astype(np.float32))

@@ -201,6 +201,7 @@ class BrickPool {
   std::vector<PoolSlot> m_slots;
   uint64_t m_time = 2;                   // m_iTimeOfCreation
   size_t   m_insertPos = 0;
+  bool     m_sorted = false;             // m_slots is in PrepareForPaging's order and m_insertPos has been folded in
   uint64_t m_uploadedBytes = 0;
   double   m_lastMs[4] = {0, 0, 0, 0};
 };
@@ -405,7 +406,9 @@ class CudaGridLeaper {
   Vec3 m_eye{0, 0, 1.6f}, m_at{0, 0, 0}, m_up{0, 1, 0};
   Matrix4 m_rotation, m_translation;
   Vec3 m_lightDir{0, 0, -1}, m_isoColor{0.5f, 0.5f, 0.5f};
-  std::vector<uint8_t> m_tf2dBytes;                                   // host copy of the rasterised 2D table
+  std::vector<uint8_t> m_tf2dBytes;                                   // host copy of the rasterised 2D table while the context does not hold it
+  bool m_tf2dInCtx = false;                                           // the context's staging block holds the table (tvk_tf2d_staging)
+  int Upload2DTable();
   uint32_t m_tf2dW = 0, m_tf2dH = 0;
   float m_ambient[4] = {1, 1, 1, 0.1f}, m_diffuse[4] = {1, 1, 1, 1}, m_specular[4] = {1, 1, 1, 1};
   double m_isoValue = 0.5;

@@ -939,7 +939,8 @@ static int set_tf(tvk_ctx* c, const uint8_t* rgba, uint32_t w, uint32_t h) {
       c->tf_stage_bytes = bytes;
     }
     if (!c->tf_stage_done) TVK_CHECK_CUDA(c, cudaEventCreateWithFlags(&c->tf_stage_done, cudaEventDisableTiming));
-    memcpy(c->h_tf_stage, rgba, bytes);
+    if (rgba != c->h_tf_stage) memcpy(c->h_tf_stage, rgba, bytes);   // (tvk_tf2d_staging: the block itself may be handed back)
+    c->tf_stage_w = w; c->tf_stage_h = h;
     TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf, c->h_tf_stage, bytes, cudaMemcpyHostToDevice, c->stream));
     TVK_CHECK_CUDA(c, cudaEventRecord(c->tf_stage_done, c->stream));
     c->tf_stage_busy = true;
@@ -965,3 +966,9 @@ static int set_tf(tvk_ctx* c, const uint8_t* rgba, uint32_t w, uint32_t h) {
 }
 extern "C" int tvk_set_tf1d(tvk_ctx* c, const uint8_t* rgba, uint32_t n) { return set_tf(c, rgba, n, 1); }
 extern "C" int tvk_set_tf2d(tvk_ctx* c, const uint8_t* rgba, uint32_t w, uint32_t h) { return set_tf(c, rgba, w, h); }
+extern "C" int tvk_tf2d_staging(tvk_ctx* c, const uint8_t** rgba, uint32_t* w, uint32_t* h) {
+  if (!c || !rgba || !w || !h) return TVK_ERR_INVALID;
+  if (!c->h_tf_stage || !c->tf_stage_w || !c->tf_stage_h) TVK_FAIL(c, TVK_ERR_INVALID, "no 2-D transfer function has been set");
+  *rgba = c->h_tf_stage; *w = c->tf_stage_w; *h = c->tf_stage_h;
+  return TVK_OK;
+}

@@ -115,6 +115,7 @@ struct tvk_ctx {
   // asynchronously, so that an edit costs no host synchronisation; tf_stage_done guards the buffer's reuse
   uint8_t* h_tf_stage = nullptr;
   size_t tf_stage_bytes = 0;
+  uint32_t tf_stage_w = 0, tf_stage_h = 0;   // the 2-D table the block holds (tvk_tf2d_staging)
   cudaEvent_t tf_stage_done = nullptr;
   bool tf_stage_busy = false;
 

@@ -1490,6 +1490,15 @@ __global__ void __launch_bounds__(256) image_to_rgba8_kernel(const float4* __res
 // cudaMemcpy from the device to it is staged by the runtime in small pieces; one DMA into a pinned block the context
 // keeps + one host memcpy is 3-4x quicker for a 1080p frame.
 static int rgba8_to_host(tvk_ctx* c, uint8_t* rgba8, size_t n) {
+  // a caller whose frame buffer is page-locked (cudaHostAlloc / cudaHostRegister) gets the frame by DMA, without the
+  // landing block and the host copy out of it
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, rgba8) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+    TVK_CHECK_CUDA(c, cudaMemcpyAsync(rgba8, c->d_rgba8, n * sizeof(uchar4), cudaMemcpyDeviceToHost, c->stream));
+    TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TVK_OK;
+  }
+  (void)cudaGetLastError();
   if (!c->h_rgba8 || c->h_rgba8_px < n) {
     if (c->h_rgba8) cudaFreeHost(c->h_rgba8);
     c->h_rgba8 = nullptr; c->h_rgba8_px = 0;

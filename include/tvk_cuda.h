@@ -162,6 +162,11 @@ int tvk_visibility_recompute(tvk_ctx* ctx, const tvk_visibility* vis, uint32_t* 
  * (GLRenderer.cpp:465-472, GPUMemMan.cpp:421-427): RGBA8, NEAREST, clamp. */
 int tvk_set_tf1d(tvk_ctx* ctx, const uint8_t* rgba, uint32_t n);
 int tvk_set_tf2d(tvk_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t h);
+/* The context keeps the bytes of the last 2-D table it was given in a page-locked block (they travel to the device from
+ * there).  tvk_tf2d_staging returns that block; passing it back to tvk_set_tf2d uploads the table again without a host
+ * copy -- what a host that switches between the 1-D and the 2-D function does (the device holds ONE table), instead of
+ * keeping a second copy of a 4 MB table and copying it twice per edit. */
+int tvk_tf2d_staging(tvk_ctx* ctx, const uint8_t** rgba, uint32_t* w, uint32_t* h);
 
 /* ------------------------------------------------------------------ ray-march */
 /* replaces GLGridLeaper::Raycast + SetupRaycastShader + FillRayEntryBuffer
