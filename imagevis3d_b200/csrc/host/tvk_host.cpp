@@ -482,7 +482,7 @@ int BrickPool::Create(const uint32_t capacity[3], uint32_t sampler) {
   const uint32_t nslots = capacity[0] * capacity[1] * capacity[2];
   m_slots.assign(nslots, PoolSlot());
   for (uint32_t i = 0; i < nslots; ++i) m_slots[i].pos = i;
-  m_sorted = false;
+  m_order = ORDER_TOUCHED; m_head = 0; m_movable = 0;
   m_time = 2; m_insertPos = 0; m_uploadedBytes = 0;
   return TVK_OK;
 }
@@ -504,19 +504,26 @@ bool BrickPool::IsBrickResident(uint32_t x, uint32_t y, uint32_t z, uint32_t lod
 
 void BrickPool::PrepareForPaging() {
   // std::sort by m_iTimeOfCreation (:946-959); stable here so that ties are deterministic.  After a paging pass the
-  // vector is [the m_insertPos slots just filled, ascending][the rest, ascending]: rotating the new ones to the back
-  // IS the stable sort in the common case (no slot flagged empty or restored in between); anything else is sorted.
+  // order is [the m_insertPos slots just filled, ascending][the rest, ascending]: moving the new ones to the back IS the
+  // stable sort in the common case (no slot flagged empty or restored in between).  The pinned coarsest brick (time
+  // UINT64_MAX) sits at the very end and stays there.  The slots in front of it are kept as a RING (SlotAt): moving the
+  // first m_insertPos of them to the back is advancing its head -- no slot moves (rotating 48k slots took 0.3 ms per
+  // sub-frame, in the gap between a march and the upload it asked for).  Anything else -- a slot flagged empty or restored,
+  // a reset, the pinned brick arriving -- puts the ring back at the vector's start and sorts.
   auto by_time = [](const PoolSlot& a, const PoolSlot& b) { return a.time < b.time; };
-  // The pinned coarsest brick (time UINT64_MAX) sits at the very end and stays there: the rotation leaves it out, or every
-  // pass after a PH_Reset would fall into the full sort (48k slots, 1.1 ms) because of that one element.
-  // The order is already the sorted one when the previous pass sorted behind its own upload (see UploadBricks) and no slot's
-  // time has changed since.
-  if (m_sorted) { m_insertPos = 0; return; }
+  if (m_order == ORDER_SORTED) { m_insertPos = 0; return; }
   const size_t movable = m_slots.size() - ((!m_slots.empty() && m_slots.back().time == UINT64_MAX) ? 1 : 0);
-  if (m_insertPos > 0 && m_insertPos < movable) std::rotate(m_slots.begin(), m_slots.begin() + m_insertPos, m_slots.begin() + movable);
-  if (!std::is_sorted(m_slots.begin(), m_slots.end(), by_time)) std::stable_sort(m_slots.begin(), m_slots.end(), by_time);
+  if (m_order == ORDER_INSERTED && movable == m_movable && m_insertPos <= movable) {
+    if (movable) m_head = (m_head + m_insertPos) % movable;
+  } else {
+    if (m_head && m_head < m_movable) std::rotate(m_slots.begin(), m_slots.begin() + m_head, m_slots.begin() + m_movable);
+    m_head = 0;
+    m_movable = movable;
+    if (m_insertPos > 0 && m_insertPos < movable) std::rotate(m_slots.begin(), m_slots.begin() + m_insertPos, m_slots.begin() + movable);
+    if (!std::is_sorted(m_slots.begin(), m_slots.end(), by_time)) std::stable_sort(m_slots.begin(), m_slots.end(), by_time);
+  }
   m_insertPos = 0;
-  m_sorted = true;
+  m_order = ORDER_SORTED;
 }
 
 int BrickPool::Reset() {
@@ -524,7 +531,7 @@ int BrickPool::Reset() {
   // device pool itself is kept (slots are overwritten as bricks arrive)
   // (slot positions are a permutation of 0..n-1: writing them out in order IS the sort by position)
   for (size_t i = 0; i < m_slots.size(); ++i) { m_slots[i] = PoolSlot(); m_slots[i].pos = (uint32_t)i; }
-  m_time = 2; m_insertPos = 0; m_uploadedBytes = 0; m_sorted = false;
+  m_time = 2; m_insertPos = 0; m_uploadedBytes = 0; m_order = ORDER_TOUCHED; m_head = 0; m_movable = 0;
   int rc = tvk_pool_clear_metadata(m_ctx);                  // page table all MISSING, on the stream (no host wait)
   if (rc) return rc;
   return UploadFirstBrick(false);
@@ -536,8 +543,10 @@ int BrickPool::UploadFirstBrick(bool wait) {
   uint32_t c[4];
   BrickCoords(idx, c);
   const uint64_t t = m_vol->TocIndex(c[0], c[1], c[2], c[3]);
+  if (m_head && m_head < m_movable) std::rotate(m_slots.begin(), m_slots.begin() + m_head, m_slots.begin() + m_movable);   // ring back to the start
+  m_head = 0;
   PoolSlot& s = m_slots[m_slots.size() - 1];
-  s.brick = (int32_t)idx; s.time = UINT64_MAX; m_sorted = false;
+  s.brick = (int32_t)idx; s.time = UINT64_MAX; m_order = ORDER_TOUCHED;
   const void* src = m_vol->host_store ? (const void*)(m_vol->host_store + m_vol->offsets[t])
                                       : (const void*)((const uint8_t*)m_vol->device_store + m_vol->offsets[t]);
   int rc = m_vol->lz4_store ? tvk_pool_upload_bricks_lz4(m_ctx, 1, &s.pos, &src, &m_vol->comp_len[t], &m_vol->sizes[3 * t])
@@ -569,11 +578,11 @@ int BrickPool::UploadBricks(const std::vector<uint32_t>& xyzl, uint32_t& paged, 
     if (b[3] >= m_lodCount || b[0] >= m_lodBricks[3 * b[3]] || b[1] >= m_lodBricks[3 * b[3] + 1] || b[2] >= m_lodBricks[3 * b[3] + 2])
       return TVK_ERR_INVALID;
     const uint32_t idx = BrickIndex(b[0], b[1], b[2], b[3]);
-    PoolSlot& s = m_slots[m_insertPos];
+    PoolSlot& s = SlotAt(m_insertPos);
     if (s.ContainsVisibleBrick()) { pidx.push_back((uint32_t)s.brick); pval.push_back(TVK_BI_MISSING); }   // evicted
     s.brick = (int32_t)idx;
     s.time = m_time++;
-    m_sorted = false;
+    if (m_order == ORDER_SORTED) m_order = ORDER_INSERTED;
     pidx.push_back(idx); pval.push_back(s.pos + TVK_BI_FLAG_COUNT);
     const uint64_t t = m_vol->TocIndex(b[0], b[1], b[2], b[3]);
     slot.push_back(s.pos);
@@ -600,7 +609,7 @@ int BrickPool::UploadBricks(const std::vector<uint32_t>& xyzl, uint32_t& paged, 
   rc = tvk_pool_patch_metadata(m_ctx, (uint32_t)pidx.size(), pidx.data(), pval.data());
   m_lastMs[3] = ms_since(t0);
   // The sort the NEXT pass starts with, done now: the transfer just issued keeps the device busy, whereas at the start of
-  // the next pass the device would sit idle behind it (0.3 ms per sub-frame on a 48k-slot pool).  Same order either way.
+  // the next pass the device would sit idle behind it.  Same order either way.
   if (!rc && !wait) PrepareForPaging();
   return rc;
 }
@@ -624,7 +633,7 @@ int BrickPool::RecomputeVisibility(const tvk_visibility& vis, uint32_t counts[4]
     if (cd) { if (!had) s.Restore(); pidx.push_back((uint32_t)s.brick); pval.push_back(s.pos + TVK_BI_FLAG_COUNT); }
     else { if (had) s.FlagEmpty(); pidx.push_back((uint32_t)s.brick); pval.push_back(TVK_BI_EMPTY); }
   }
-  m_sorted = false;
+  m_order = ORDER_TOUCHED;
   int rc = tvk_pool_patch_metadata(m_ctx, (uint32_t)pidx.size(), pidx.data(), pval.data());
   if (rc) return rc;
   // RecomputeVisibilityForOctree (:1021-1359) on the device

@@ -201,7 +201,11 @@ class BrickPool {
   std::vector<PoolSlot> m_slots;
   uint64_t m_time = 2;                   // m_iTimeOfCreation
   size_t   m_insertPos = 0;
-  bool     m_sorted = false;             // m_slots is in PrepareForPaging's order and m_insertPos has been folded in
+  // LRU order = the ring m_slots[m_head .. m_movable) ++ m_slots[0 .. m_head), then the pinned tail (PrepareForPaging)
+  enum { ORDER_SORTED = 0, ORDER_INSERTED = 1, ORDER_TOUCHED = 2 };
+  int      m_order = ORDER_TOUCHED;      // what happened to the slots' times since the order was last established
+  size_t   m_head = 0, m_movable = 0;
+  PoolSlot& SlotAt(size_t i) { return m_slots[i < m_movable ? (m_head + i) % m_movable : i]; }
   uint64_t m_uploadedBytes = 0;
   double   m_lastMs[4] = {0, 0, 0, 0};
 };

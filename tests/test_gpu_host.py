@@ -296,3 +296,45 @@ def test_clear_working_set_repaints_the_same_frame_and_perf_counters_reset():
         assert (slots1 != slots2).sum() <= 8 and np.abs(a - b).max() < 2e-3
     assert r.perfQuery(8) == up
     r.cleanup()
+
+
+def test_lru_eviction_follows_the_oracle_pool_over_several_views():
+    """A pool far smaller than the dataset, five views in a row, NO reset in between: after every view the set of resident
+    bricks must be the one the restated GLVolumePool (std::sort by time of creation, oldest slots refilled first) holds
+    after the same views.  Pins the order the slots are reused in (kept as a ring on the host, no physical sort)."""
+    from imagevis3d_b200.renderer import Renderer
+    vol = H.synth_blobs((120, 100, 90), np.uint16, seed=9)
+    r = Renderer(0)
+    r.setState(hash_table_size=65521, rehash_count=16)          # (a large table: hardly any colliding requests, whose order is a race)
+    r.loadRawVolume(vol, brick_size=20, out_of_core=True, gpu_mem_bytes=40 * 20 ** 3 * 2)
+    info = r.datasetInfo()
+    cap = tuple(info.pool_capacity)
+    tf = _tf(info.tf_size)
+    r.set1DTransFloat(tf)
+    r.setLightingEnabled(False)
+    w, h = 160, 120
+    r.resize((w, h))
+    oc = O.build_octree(vol, 20, 2)
+    pool = H.OraclePool(oc, cap)
+    pool.upload_first_brick()
+    maxv = float(oc["minmax"][:int(np.prod(oc["plan"].lod_bricks[0][:])), 1].max())
+    lo, hi = H.tf_nonzero_limits(tf)
+    pool.recompute_visibility(0, lo * maxv / (len(tf) - 1), hi * maxv / (len(tf) - 1))
+    views = [(0.0, 0.0, 3.0), (0.6, 0.1, 2.6), (-0.5, 0.3, 2.7), (0.0, -0.4, 2.4), (0.0, 0.0, 3.0)]
+    evicted_something = False
+    for eye in views:
+        r.setViewPos(eye)
+        subs = r.paintUntilConverged(300)
+        cam = H.Camera()
+        cam.at = cam.at + (np.array(eye, np.float32) - cam.eye)
+        cam.eye = np.array(eye, np.float32)
+        p = H.raycast_params(cam, w, h, oc["vol"], trans_scale=65535.0 / maxv, hash_size=65521, rehash=16)
+        before = set(pool.slot_brick[pool.slot_brick >= 0].tolist())
+        _, subs_o, _, _ = H.render_converged(p, pool, H.tf_bytes(tf))
+        after = set(pool.slot_brick[pool.slot_brick >= 0].tolist())
+        evicted_something |= bool(before - after)
+        bricks, _ = r.poolSlots()
+        got = set(bricks[bricks >= 0].tolist())
+        assert subs == subs_o and len(got ^ after) <= 2, (eye, subs, subs_o, sorted(got ^ after))
+    assert evicted_something, "the views never filled the pool: nothing was evicted, the test would be vacuous"
+    r.cleanup()
