@@ -1532,16 +1532,26 @@ void CudaGridLeaper::SetBGColors(const float top[3], const float bottom[3]) { me
 // ComputeEyeToTextureMatrix (GLRaycaster.cpp:239-300,589-612).  The final sub-frame of a view (LOD =
 // m_iMinLODForCurrentView, or 0 for RT_CAPTURE) is rendered in one launch of tvk_raycast_classic.
 bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_classic_brick>& bricks, uint32_t& lodOut, int forceLod,
-                                      uint32_t* minLodOut) {
+                                      uint32_t* minLodOut, int eye) {
   if (!m_vol || !m_w || !m_h) { m_err = "no dataset / render target"; return false; }
   const BrickedVolume& v = *m_vol;
   memset(&p, 0, sizeof(p));
   bricks.clear();
   const float aspect = float(m_w) / float(m_h);
-  const Matrix4 view = Matrix4::LookAt(m_eye, m_at, m_up);
-  const Matrix4 proj = Matrix4::Perspective(m_fov, aspect, m_znear, m_zfar);
+  // Stereo (AbstrRenderer::PlanFrame :1196-1201, BuildLeftEyeSubFrameBrickList :843-858, GLRaycaster::Render3DInLoop :389):
+  // LOD, frustum culling and the brick set come from eye 0's matrices; the other eye draws the SAME bricks in its own
+  // front-to-back order with its own model-view and projection.
+  Matrix4 view = Matrix4::LookAt(m_eye, m_at, m_up), proj = Matrix4::Perspective(m_fov, aspect, m_znear, m_zfar);
+  Matrix4 viewE = view, projE = proj;
+  if (m_stereo) {
+    Matrix4 views[2], projs[2];
+    Matrix4::StereoLookAtAndProjection(m_eye, m_at, m_up, m_fov, aspect, m_znear, m_zfar, m_stereoFocalLength, m_stereoEyeDist, views, projs);
+    view = views[0]; proj = projs[0];
+    viewE = views[eye ? 1 : 0]; projE = projs[eye ? 1 : 0];
+  }
   const Matrix4 mv = m_rotation * m_translation * view;
-  const Matrix4 invMv = mv.inverse();
+  const Matrix4 mvE = m_rotation * m_translation * viewE;
+  const Matrix4 invMv = mvE.inverse();                      // everything drawn uses the eye's own matrices
   float dom0[3], ext[3], mx = 0;
   for (int a = 0; a < 3; ++a) { dom0[a] = float(v.domain[a]); ext[a] = dom0[a] * v.scale[a]; mx = std::max(mx, ext[a]); }
   for (int a = 0; a < 3; ++a) ext[a] /= mx;
@@ -1667,7 +1677,7 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
         for (int sx = -1; sx <= 1; sx += 2) for (int sy = -1; sy <= 1; sy += 2) for (int sz = -1; sz <= 1; sz += 2) {
           const float pt[4] = {bcn[0] + float(sx) * be[0] * 0.4999f, bcn[1] + float(sy) * be[1] * 0.4999f, bcn[2] + float(sz) * be[2] * 0.4999f, 1.0f};
           float e4[4];
-          mv.transform(pt, e4);
+          mvE.transform(pt, e4);
           dist = std::min(dist, sqrtf(e4[0] * e4[0] + e4[1] * e4[1] + e4[2] * e4[2]));
         }
         it.dist = dist; it.idx = idx;
@@ -1686,7 +1696,7 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
   memcpy(p.inv_model_view, invMv.m, 64);
   const Matrix4 nmT = invMv.transposed();
   for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) p.normal_matrix[3 * r + c] = nmT.m[4 * r + c];
-  memcpy(p.inv_projection, proj.inverse().m, 64);
+  memcpy(p.inv_projection, projE.inverse().m, 64);
   float ratio = 0;
   for (int a = 0; a < 3; ++a) ratio = std::max(ratio, dom0[a] / dl[a]);
   p.step_scale = 1.0f / effRate * ratio;
@@ -1815,8 +1825,20 @@ bool CudaGridLeaper::PaintClassic() {
   if (!PlanClassicFrame(p, bricks, lod, (int)m_currentLOD)) return false;   // BuildSubFrameBrickList
   L.brick_list_size = bricks.size();
   L.bricks_rendered = 0;
-  const int rc = tvk_raycast_classic(m_ctx, &p, bricks.data(), (uint32_t)bricks.size(), store);
+  int rc = tvk_raycast_classic(m_ctx, &p, bricks.data(), (uint32_t)bricks.size(), store);
   if (rc) return Fail("tvk_raycast_classic", rc);
+  if (m_stereo) {
+    // the other eye: the same bricks in its own order, into its own picture; then GLRenderer::EndFrame's composition
+    tvk_classic_params pr;
+    std::vector<tvk_classic_brick> br;
+    uint32_t lodR = 0;
+    if (!PlanClassicFrame(pr, br, lodR, (int)m_currentLOD, nullptr, 1)) return false;
+    rc = tvk_select_eye(m_ctx, 1);
+    if (!rc) rc = tvk_raycast_classic(m_ctx, &pr, br.data(), (uint32_t)br.size(), store);
+    const int rc2 = tvk_select_eye(m_ctx, 0);
+    if (rc || rc2) return Fail("tvk_raycast_classic (right eye)", rc ? rc : rc2);
+    if (!ComposeStereo()) return false;
+  }
   L.bricks_rendered = bricks.size();
   m_blank = false;
   m_perf.subframes += 1;
@@ -1847,6 +1869,7 @@ bool CudaGridLeaper::Paint() {                                               // 
   if (m_classic) return PaintClassic();
   if (!m_ctx || !m_vol || !m_pool) { m_err = "Paint() without dataset"; return false; }
   if (!m_w || !m_h) { m_err = "Paint() on a zero-sized target"; return false; }
+  if (m_stereo && m_sl.on) { m_err = "stereo is not available for a sort-last member"; return false; }
   typedef std::chrono::steady_clock clk;
   auto ms_since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
   const clk::time_point tPaint = clk::now();
@@ -1866,7 +1889,6 @@ bool CudaGridLeaper::Paint() {                                               // 
   if (rc) return Fail("tvk_raycast_subframe", rc);
   if (m_stereo) {
     // the second eye (GLGridLeaper.cpp:950-958): its own frame state, the same pool and request table
-    if (m_sl.on) { m_err = "stereo is not available for a sort-last member"; return false; }
     tvk_raycast_params pr;
     if (!ComputeRaycastParams(pr, 1)) return false;
     rc = tvk_select_eye(m_ctx, 1);
@@ -1927,7 +1949,7 @@ bool CudaGridLeaper::SetStereoMode(int mode) {
 void CudaGridLeaper::SetStereoEyeSwap(bool swap) { m_stereoEyeSwap = swap; if (m_stereo) ScheduleCompleteRedraw(); }
 bool CudaGridLeaper::ToggleStereoFrame() {                            // AbstrRenderer.cpp:1582-1585: recompose only
   m_afId = 1 - m_afId;
-  if (m_stereo && m_converged && !m_blank && !m_classic) return ComposeStereo();
+  if (m_stereo && !m_blank && (m_converged || m_classic)) return ComposeStereo();
   return true;
 }
 
@@ -2118,6 +2140,16 @@ int tvkr_set_stereo_eye_swap(tvkr_renderer* h, int swap) { if (!h) return 1; R(h
 int tvkr_init_stereo_frame(tvkr_renderer* h) { if (!h) return 1; R(h)->InitStereoFrame(); return 0; }
 int tvkr_toggle_stereo_frame(tvkr_renderer* h) { return h && R(h)->ToggleStereoFrame() ? 0 : 1; }
 int tvkr_get_raycast_params_eye(tvkr_renderer* h, int eye, tvk_raycast_params* p) { return h && p && (eye == 0 || eye == 1) && R(h)->ComputeRaycastParams(*p, eye) ? 0 : 1; }
+int tvkr_plan_classic_frame_eye(tvkr_renderer* h, int eye, tvk_classic_params* p, tvk_classic_brick* bricks, uint32_t cap, uint32_t* n, uint32_t* lod) {
+  if (!h || !p || !n || (eye != 0 && eye != 1)) return 1;
+  std::vector<tvk_classic_brick> b;
+  uint32_t l = 0;
+  if (!R(h)->PlanClassicFrame(*p, b, l, -1, nullptr, eye)) return 1;
+  *n = (uint32_t)b.size();
+  if (lod) *lod = l;
+  if (bricks) { if (cap < b.size()) return 1; memcpy(bricks, b.data(), b.size() * sizeof(tvk_classic_brick)); }
+  return 0;
+}
 int tvkr_get_eye_frame_float(tvkr_renderer* h, int eye, float* out) {
   return h && out && (eye == 0 || eye == 1) && R(h)->Context() && tvk_read_eye_image(R(h)->Context(), (uint32_t)eye, out) == TVK_OK ? 0 : 1;
 }

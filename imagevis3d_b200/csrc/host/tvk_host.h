@@ -354,7 +354,7 @@ class CudaGridLeaper {
   // forceLod < 0: the LOD the view needs (m_iMinLODForCurrentView; 0 for RT_CAPTURE); else the brick list of that LOD.
   // minLodOut: m_iMinLODForCurrentView of the view.
   bool PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_classic_brick>& bricks, uint32_t& lod, int forceLod = -1,
-                        uint32_t* minLodOut = nullptr);
+                        uint32_t* minLodOut = nullptr, int eye = 0);
   static void ComputeMaxLODForCurrentView(tvkr_lod_state& s);        // AbstrRenderer.cpp:681-787
   void SetMaxMSPerFrame(float ms) { m_ladder.max_ms_per_frame = ms; }
   void OverrideSubframeMs(float ms) { m_msOverride = ms; }

@@ -206,12 +206,17 @@ class Renderer:
         """False: ray-guided (OpenGL_GridLeaper-like, default); True: classic per-brick (OpenGL_Raycaster-like)"""
         self._ck(self._lib.tvkr_set_renderer_type(self._h, C.c_int(1 if classic else 0)), "setRendererType")
 
-    def planClassicFrame(self, cap=65536):
+    def planClassicFrame(self, cap=65536, eye=None):
+        """eye: None = the (mono or left) view; 0 / 1 = the left / right view of a stereo pair"""
         from . import _lib
         p = _lib.ClassicParams()
         arr = (_lib.ClassicBrick * cap)()
         n, lod = C.c_uint32(), C.c_uint32()
-        self._ck(self._lib.tvkr_plan_classic_frame(self._h, C.byref(p), arr, C.c_uint32(cap), C.byref(n), C.byref(lod)), "planClassicFrame")
+        if eye is None:
+            self._ck(self._lib.tvkr_plan_classic_frame(self._h, C.byref(p), arr, C.c_uint32(cap), C.byref(n), C.byref(lod)), "planClassicFrame")
+        else:
+            self._ck(self._lib.tvkr_plan_classic_frame_eye(self._h, C.c_int(int(eye)), C.byref(p), arr, C.c_uint32(cap), C.byref(n),
+                                                           C.byref(lod)), "planClassicFrame")
         return p, [arr[i] for i in range(n.value)], lod.value
 
     def setClipPlane(self, plane):

@@ -140,8 +140,8 @@ int tvkr_enable_clip_plane(tvkr_renderer* r, int on);
  * initStereoFrame / toggleStereoFrame; AbstrRenderer.cpp:1387-1410,1577-1585): every paint() marches the left and the right
  * eye (views and off-axis projections of FLOATMATRIX4::BuildStereoLookAtAndProjection, Vectors.h:1215-1248), both report
  * into one request table, and the converged frame is the composition GLRenderer::EndFrame draws (GLRenderer.cpp:757-812):
- * mode TVK_SM_RB anaglyph (default), _SCANLINE, _SBS, _AF.  Defaults: eye distance 0.02, focal length 1.  Ray-guided
- * renderer only; not for sort-last members.  tvkr_get_raycast_params_eye: the parameters of eye 0 (left) / 1 (right).
+ * mode TVK_SM_RB anaglyph (default), _SCANLINE, _SBS, _AF.  Defaults: eye distance 0.02, focal length 1.  Both renderer
+ * types (the classic one draws eye 0's brick set in each eye's own front-to-back order); not for sort-last members.  tvkr_get_raycast_params_eye: the parameters of eye 0 (left) / 1 (right).
  * tvkr_stereo_matrices: the four matrices (left view, right view, left projection, right projection; 16 floats each, as
  * the reference stores them), no renderer needed. */
 int tvkr_set_stereo(tvkr_renderer* r, int on);
@@ -153,6 +153,10 @@ int tvkr_set_stereo_eye_swap(tvkr_renderer* r, int swap);
 int tvkr_init_stereo_frame(tvkr_renderer* r);
 int tvkr_toggle_stereo_frame(tvkr_renderer* r);
 int tvkr_get_raycast_params_eye(tvkr_renderer* r, int eye, tvk_raycast_params* out);
+/* the classic path's frame plan of one eye of a stereo pair (tvkr_plan_classic_frame = eye 0): the same bricks as eye 0,
+ * sorted front to back for this eye (AbstrRenderer::BuildLeftEyeSubFrameBrickList, AbstrRenderer.cpp:843-858) */
+int tvkr_plan_classic_frame_eye(tvkr_renderer* r, int eye, tvk_classic_params* p, tvk_classic_brick* bricks, uint32_t cap,
+                                uint32_t* n, uint32_t* lod);
 int tvkr_get_eye_frame_float(tvkr_renderer* r, int eye, float* out);   /* one eye's own picture, premultiplied RGBA32F */
 int tvkr_stereo_matrices(const float eye[3], const float at[3], const float up[3], float fovy, float aspect, float znear, float zfar,
                          float focal_length, float eye_dist, float out[64]);

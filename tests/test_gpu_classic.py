@@ -332,3 +332,65 @@ def test_classic_coarse_to_fine_ladder():
             starts.append(int(r.lodState()["start_lod_offset"]))
         assert starts[0] == starts[1] == starts[2] == starts[3] and starts[4] == starts[3] + 1, starts
         r.cleanup()
+
+
+def test_classic_stereo_pair():
+    """Stereo on the classic path (AbstrRenderer::PlanFrame :1196-1201, BuildLeftEyeSubFrameBrickList :843-858,
+    GLRaycaster::Render3DInLoop :389): the right eye draws the left eye's brick SET in its own front-to-back order with its
+    own matrices; each eye's picture equals the oracle's restated shaders on that eye's plan, the frame is the composition."""
+    from imagevis3d_b200.renderer import Renderer, RT_HEADLESS
+    vol = H.synth_blobs((150, 131, 97), np.uint8)
+    r = Renderer(0)
+    r.loadRawVolume(vol, brick_size=32)
+    r.setRendererType(True)
+    info = r.datasetInfo()
+    tf = _tf(info.tf_size)
+    r.set1DTransFloat(tf)
+    r.setLightingEnabled(True)
+    w, h = 203, 149
+    r.resize((w, h))
+    r.setRendererTarget(RT_HEADLESS)
+    rot = H.rotation_y(0.6) @ H.rotation_x(0.3)
+    r.setRotation4x4(rot)
+    p_mono, bricks_mono, _ = r.planClassicFrame()
+    r.setStereoEnabled(True)
+    r.setStereoEyeDist(0.08)
+    r.setStereoMode("rb")
+    plans = [r.planClassicFrame(eye=e) for e in (0, 1)]
+    key = lambda b: int(b.store_offset)                                                # noqa: E731
+    assert sorted(map(key, plans[0][1])) == sorted(map(key, plans[1][1])) == sorted(map(key, bricks_mono))
+    # each eye's list is sorted by ITS distance to the bricks (nearest corner, pulled in by 0.4999 of the extension)
+    cam = H.Camera()
+    cam.rotation = rot
+    eyes = H.stereo_matrices(cam, np.float32(w) / np.float32(h), 1.0, 0.08)
+    for e in (0, 1):
+        mv = (cam.rotation @ cam.translation @ eyes[e][0]).astype(np.float32)
+        d = []
+        for b in plans[e][1]:
+            c, ext = np.array(b.center[:], np.float32), np.array(b.extension[:], np.float32)
+            corners = np.array([[c[0] + sx * ext[0] * 0.4999, c[1] + sy * ext[1] * 0.4999, c[2] + sz * ext[2] * 0.4999, 1.0]
+                                for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], np.float32)
+            d.append(np.sqrt(((corners @ mv)[:, :3] ** 2).sum(axis=1)).min())
+        d = np.array(d)
+        assert (np.diff(d) >= -1e-5).all(), e
+        assert np.allclose(np.array(plans[e][0].inv_model_view[:]), np.linalg.inv(mv.astype(np.float64)).reshape(-1), atol=2e-5)
+        assert np.allclose(np.array(plans[e][0].inv_projection[:]), np.linalg.inv(eyes[e][1].astype(np.float64)).reshape(-1), rtol=1e-4, atol=1e-4)
+    assert [key(b) for b in plans[0][1]] != [key(b) for b in plans[1][1]] or len(bricks_mono) < 3
+    assert r.paintUntilConverged() == 1 and r.converged()
+    store = _device_store(r)
+    pics = []
+    for e in (0, 1):
+        q, ob = _to_oracle(*plans[e][:2])
+        want, _ = H.classic_render(q, ob, store, H.tf_bytes(tf))
+        got = r.eyeFrameFloat(e)
+        psnr, err = image_errors(got, want)
+        assert want[..., 3].max() > 0.3 and psnr >= 45.0 and err <= 2.0 / 255.0, (e, psnr, err)
+        pics.append(got)
+    assert np.abs(pics[0] - pics[1]).max() > 0.05
+    assert np.abs(r.frameFloat() - H.stereo_compose(pics[0], pics[1], 0)).max() <= 1e-6
+    r.setStereoMode("af")
+    r.paintUntilConverged()
+    assert np.array_equal(r.frameFloat(), r.eyeFrameFloat(0))
+    r.toggleStereoFrame()
+    assert np.array_equal(r.frameFloat(), r.eyeFrameFloat(1))
+    r.cleanup()
