@@ -105,6 +105,13 @@ Matrix4 Matrix4::PerspectiveOffCenter(float left, float right, float bottom, flo
   r.m[11] = -1.0f;
   return r;
 }
+Matrix4 Matrix4::Ortho(float left, float right, float bottom, float top, float n, float f) {   // Vectors.h:1279-1284
+  Matrix4 r;
+  r.m[0] = 2.0f / (right - left); r.m[12] = -(right + left) / (right - left);
+  r.m[5] = 2.0f / (top - bottom); r.m[13] = -(top + bottom) / (top - bottom);
+  r.m[10] = -2.0f / (f - n); r.m[14] = -(f + n) / (f - n);
+  return r;
+}
 void Matrix4::StereoLookAtAndProjection(const Vec3& eye, const Vec3& at, const Vec3& up, float fovy, float aspect, float n, float f,
                                         float focalLength, float eyeDist, Matrix4 view[2], Matrix4 proj[2]) {
   const float radians = float(3.14159265358979323846 / 180.0) * fovy / 2;
@@ -1320,6 +1327,73 @@ bool CudaGridLeaper::Render2DView(int windowMode, uint64_t sliceIndex, bool useM
   return true;
 }
 
+// The full-resolution MIP of the capture mode (GLRenderer::Render2DView :1182-1250 with m_eRendererTarget == RT_CAPTURE):
+// AbstrRenderer::PlanHQMIPFrame (:1214-1245) picks the LOD and lists EVERY brick of it (a 2-D region needs them all,
+// RegionNeedsBrick :879-882), GLRenderer::RenderHQMIPPreLoop (:1256-1283) builds m_maMIPRotation, GLRaycaster's Pre/InLoop
+// (GLRaycaster.cpp:481-529) set the model-view and fRayStepsize.  region.rotation of the 2-D region is the identity here.
+bool CudaGridLeaper::PlanHQMIP(int windowMode, bool flipX, bool flipY, float angleDeg, bool ortho, bool mipLOD, tvk_mip_params& p,
+                               std::vector<tvk_classic_brick>& bricks, uint32_t& lod) {
+  if (!m_vol || !m_w || !m_h || windowMode < TVK_WM_SAGITTAL || windowMode > TVK_WM_CORONAL) { m_err = "bad MIP view (window mode, dataset or render target)"; return false; }
+  const BrickedVolume& v = *m_vol;
+  // PlanHQMIPFrame: halve until the smallest domain side is below the largest window side, then one level back
+  uint64_t vc[3] = {v.domain[0], v.domain[1], v.domain[2]};
+  uint64_t l = 0;
+  if (mipLOD)
+    while (std::min(vc[0], std::min(vc[1], vc[2])) >= std::max<uint64_t>(m_w, m_h)) { for (int a = 0; a < 3; ++a) vc[a] /= 2; ++l; }
+  if (l > 0) l = std::min<uint64_t>(v.info.lod_count - 1, l - 1);
+  lod = (uint32_t)l;
+  const double PI = 3.141592653589793238462643383;
+  Matrix4 rotDir, flipXm, flipYm;
+  if (windowMode == TVK_WM_SAGITTAL) rotDir = Matrix4::RotationX(-PI / 2.0) * Matrix4::RotationY(-PI / 2.0);
+  else if (windowMode == TVK_WM_AXIAL) rotDir = Matrix4::RotationX(-PI / 2.0);
+  if (flipX) flipYm = Matrix4::Scaling(-1, 1, 1);
+  if (flipY) flipXm = Matrix4::Scaling(1, -1, 1);
+  const Matrix4 mipRot = rotDir * Matrix4() * flipXm * flipYm * Matrix4::RotationY(PI * double(angleDeg) / 180.0);
+  ClassicPlanOverride ov;
+  ov.allBricks = true;
+  const float aspect = float(m_w) / float(m_h);
+  if (ortho) {
+    // GLRenderer.cpp:1183-1197
+    double wa[2] = {1.0 / double(m_w), 1.0 / double(m_h)};
+    const double wm = std::max(wa[0], wa[1]);
+    wa[0] /= wm; wa[1] /= wm;
+    const float r2 = (wa[0] < wa[1]) ? std::max(1.0f, 1.414213f * float(wa[0] / wa[1])) : 1.414213f;
+    ov.proj = Matrix4::Ortho(-0.5f * r2 / float(wa[0]), +0.5f * r2 / float(wa[0]), -0.5f * r2 / float(wa[1]), +0.5f * r2 / float(wa[1]), -100.0f, 100.0f);
+    ov.mv = mipRot;
+  } else {
+    ov.proj = Matrix4::Perspective(m_fov, aspect, m_znear, m_zfar);
+    ov.mv = mipRot * Matrix4::LookAt(m_eye, m_at, m_up);
+  }
+  tvk_classic_params cp;
+  uint32_t lodOut = 0;
+  if (!PlanClassicFrame(cp, bricks, lodOut, (int)lod, nullptr, 0, &ov)) return false;
+  memset(&p, 0, sizeof(p));
+  p.width = m_w; p.height = m_h;
+  memcpy(p.inv_model_view, cp.inv_model_view, 64);
+  memcpy(p.inv_projection, cp.inv_projection, 64);
+  p.bytes_per_voxel = v.bpv;
+  p.trans_scale = cp.trans_scale;
+  return true;
+}
+
+bool CudaGridLeaper::RenderHQMIP(int windowMode, bool flipX, bool flipY, float angleDeg, bool ortho, bool mipLOD) {
+  if (!m_ctx || !m_vol) { m_err = "RenderHQMIP() without dataset"; return false; }
+  const void* store = ClassicStore();
+  if (!store) return false;
+  tvk_mip_params p;
+  std::vector<tvk_classic_brick> bricks;
+  uint32_t lod = 0;
+  if (!PlanHQMIP(windowMode, flipX, flipY, angleDeg, ortho, mipLOD, p, bricks, lod)) return false;
+  const bool swapTF = m_mode == RM_2DTRANS && m_has2d;      // the context holds ONE table; the MIP wants the 1-D function
+  std::vector<uint8_t> bytes;
+  if (swapTF) { m_tf1d.GetByteArray(bytes); const int rc = tvk_set_tf1d(m_ctx, bytes.data(), (uint32_t)m_tf1d.GetSize()); if (rc) return Fail("tvk_set_tf1d", rc); }
+  int rc = tvk_raycast_mip(m_ctx, &p, bricks.data(), (uint32_t)bricks.size(), store);
+  if (swapTF) { const int r2 = Upload2DTable(); if (!rc && r2) rc = r2; }
+  if (rc) return Fail("tvk_raycast_mip", rc);
+  m_blank = true; m_converged = false;                     // the 3-D frame has to be redrawn from scratch afterwards
+  return true;
+}
+
 bool CudaGridLeaper::Load2DTrans(const std::string& filename) {
   // AbstrRenderer::LoadFile sizes the 2-D function like the 1-D one: value bins x 256 gradient bins (AbstrRenderer.cpp:236-244)
   TransferFunction2D tf;
@@ -1532,7 +1606,7 @@ void CudaGridLeaper::SetBGColors(const float top[3], const float bottom[3]) { me
 // ComputeEyeToTextureMatrix (GLRaycaster.cpp:239-300,589-612).  The final sub-frame of a view (LOD =
 // m_iMinLODForCurrentView, or 0 for RT_CAPTURE) is rendered in one launch of tvk_raycast_classic.
 bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_classic_brick>& bricks, uint32_t& lodOut, int forceLod,
-                                      uint32_t* minLodOut, int eye) {
+                                      uint32_t* minLodOut, int eye, const ClassicPlanOverride* ov) {
   if (!m_vol || !m_w || !m_h) { m_err = "no dataset / render target"; return false; }
   const BrickedVolume& v = *m_vol;
   memset(&p, 0, sizeof(p));
@@ -1549,8 +1623,9 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
     view = views[0]; proj = projs[0];
     viewE = views[eye ? 1 : 0]; projE = projs[eye ? 1 : 0];
   }
-  const Matrix4 mv = m_rotation * m_translation * view;
-  const Matrix4 mvE = m_rotation * m_translation * viewE;
+  if (ov) projE = proj = ov->proj;                          // (the full-resolution MIP brings its own matrices)
+  const Matrix4 mv = ov ? ov->mv : m_rotation * m_translation * view;
+  const Matrix4 mvE = ov ? ov->mv : m_rotation * m_translation * viewE;
   const Matrix4 invMv = mvE.inverse();                      // everything drawn uses the eye's own matrices
   float dom0[3], ext[3], mx = 0;
   for (int a = 0; a < 3; ++a) { dom0[a] = float(v.domain[a]); ext[a] = dom0[a] * v.scale[a]; mx = std::max(mx, ext[a]); }
@@ -1568,7 +1643,7 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
   const int minLod = std::min(std::max(level, (int)m_lodLimits[1]), lodCount - 1);
   if (minLodOut) *minLodOut = (uint32_t)minLod;
   // GLRaycaster::SetBrickDepShaderVars (:253-254): a "decrease sampling rate now" pass halves the rate (m_fSampleDecFactor = 2)
-  const float effRate = m_sampleRate / (m_decRateNow ? 2.0f : 1.0f);
+  const float effRate = ov ? m_sampleRate : m_sampleRate / (m_decRateNow ? 2.0f : 1.0f);
   const uint32_t lod = forceLod >= 0 ? (uint32_t)std::min(forceLod, lodCount - 1) : ((m_target == RT_CAPTURE) ? 0u : (uint32_t)minLod);
   lodOut = lod;
   // CullingLOD::Update: planes from modelView * projection
@@ -1638,13 +1713,13 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
           be[a] = e * vscale[a]; bcn[a] = cen * vscale[a];
         }
         bool vis = true;
-        for (int k = 0; k < 6 && vis; ++k) {
+        for (int k = 0; k < 6 && vis && !(ov && ov->allBricks); ++k) {
           const float* pl = planes[k];
           if (pl[0] * bcn[0] + pl[1] * bcn[1] + pl[2] * bcn[2] + pl[3] <=
               -(0.5f * be[0] * fabsf(pl[0]) + 0.5f * be[1] * fabsf(pl[1]) + 0.5f * be[2] * fabsf(pl[2]))) vis = false;
         }
         if (!vis) continue;
-        if (m_clipEnabled) {                               // AbstrRenderer::Clipped (:923-948): all eight world-space corners beyond the plane
+        if (m_clipEnabled && !(ov && ov->allBricks)) {     // AbstrRenderer::Clipped (:923-948): all eight world-space corners beyond the plane
           bool all = true;
           for (int k = 0; k < 8 && all; ++k) {
             const float pt[4] = {bcn[0] + ((k & 4) ? 0.5f : -0.5f) * be[0], bcn[1] + ((k & 2) ? 0.5f : -0.5f) * be[1],
@@ -1660,7 +1735,7 @@ bool CudaGridLeaper::PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_cla
                             : (m_mode == RM_2DTRANS)  ? (smax >= v.minmax[2 * idx] && smin <= v.minmax[2 * idx + 1] &&
                                                          m_tf2dLimits[3] >= -DBL_MAX && m_tf2dLimits[2] <= DBL_MAX)
                                                       : (smax >= v.minmax[2 * idx] && smin <= v.minmax[2 * idx + 1]);
-        if (!contains) continue;                                                          // bIsEmpty: never drawn
+        if (!contains && !(ov && ov->allBricks)) continue;                                // bIsEmpty: never drawn
         Item it;
         memset(&it.b, 0, sizeof(it.b));
         float tmin[3], tmax[3], rs = FLT_MAX;
@@ -1779,6 +1854,15 @@ void CudaGridLeaper::ComputeMaxLODForCurrentView(tvkr_lod_state& s) {
 
 bool CudaGridLeaper::PaintClassic() {
   if (!m_ctx || !m_vol) { m_err = "Paint() without dataset"; return false; }
+  const void* store = ClassicStore();
+  if (!store) return false;
+  tvk_classic_params p;
+  std::vector<tvk_classic_brick> bricks;
+  uint32_t lod = 0, minLod = 0;
+  return PaintClassicWith(store, p, bricks, lod, minLod);
+}
+
+const void* CudaGridLeaper::ClassicStore() {
   const void* store = m_vol->device_store;
   if (!store) {
     // datasets loaded from a UVF file (or out of core) keep their bricks in pinned host memory: the classic path reads
@@ -1787,21 +1871,22 @@ bool CudaGridLeaper::PaintClassic() {
       size_t freeB = 0, totalB = 0;
       if (!m_vol->host_store || m_vol->lz4_store || cudaMemGetInfo(&freeB, &totalB) != cudaSuccess || m_vol->store_bytes + (1ull << 30) > freeB) {
         m_err = "the classic ray-caster needs the brick store in device memory and it does not fit (use the ray-guided renderer)";
-        return false;
+        return nullptr;
       }
       if (cudaMalloc(&m_vol->classic_store, m_vol->store_bytes) != cudaSuccess ||
           cudaMemcpy(m_vol->classic_store, m_vol->host_store, m_vol->store_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
         if (m_vol->classic_store) { cudaFree(m_vol->classic_store); m_vol->classic_store = nullptr; }
         (void)cudaGetLastError();
         m_err = "could not copy the brick store to the device for the classic ray-caster";
-        return false;
+        return nullptr;
       }
     }
     store = m_vol->classic_store;
   }
-  tvk_classic_params p;
-  std::vector<tvk_classic_brick> bricks;
-  uint32_t lod = 0, minLod = 0;
+  return store;
+}
+
+bool CudaGridLeaper::PaintClassicWith(const void* store, tvk_classic_params& p, std::vector<tvk_classic_brick>& bricks, uint32_t& lod, uint32_t& minLod) {
   // ---- AbstrRenderer::PlanFrame (:1125-1212).  One Paint() renders one whole sub-frame = the brick list of one LOD (the
   // reference's RT_HEADLESS time slice: GLRenderer::Render3DView, GLRenderer.cpp:2662-2675, stops early only for
   // interactive targets; a list that one kernel launch walks has nothing to slice).
@@ -2221,6 +2306,20 @@ int tvkr_load_1d_trans(tvkr_renderer* h, const char* filename) {
 }
 int tvkr_render_2d_view(tvkr_renderer* h, int window_mode, uint64_t slice_index, int use_mip, int flip_x, int flip_y) {
   return h && R(h)->Render2DView(window_mode, slice_index, use_mip != 0, flip_x != 0, flip_y != 0) ? 0 : 1;
+}
+int tvkr_render_hq_mip(tvkr_renderer* h, int window_mode, int flip_x, int flip_y, float angle_deg, int ortho, int mip_lod) {
+  return h && R(h)->RenderHQMIP(window_mode, flip_x != 0, flip_y != 0, angle_deg, ortho != 0, mip_lod != 0) ? 0 : 1;
+}
+int tvkr_plan_hq_mip(tvkr_renderer* h, int window_mode, int flip_x, int flip_y, float angle_deg, int ortho, int mip_lod, tvk_mip_params* p,
+                     tvk_classic_brick* bricks, uint32_t cap, uint32_t* n, uint32_t* lod) {
+  if (!h || !p || !n) return 1;
+  std::vector<tvk_classic_brick> b;
+  uint32_t l = 0;
+  if (!R(h)->PlanHQMIP(window_mode, flip_x != 0, flip_y != 0, angle_deg, ortho != 0, mip_lod != 0, *p, b, l)) return 1;
+  *n = (uint32_t)b.size();
+  if (lod) *lod = l;
+  if (bricks) { if (cap < b.size()) return 1; memcpy(bricks, b.data(), b.size() * sizeof(tvk_classic_brick)); }
+  return 0;
 }
 int tvkr_get_slice_params(tvkr_renderer* h, int window_mode, uint64_t slice_index, int use_mip, int flip_x, int flip_y, tvk_slice_params* out) {
   uint64_t toc = 0;

@@ -49,6 +49,7 @@ struct Matrix4 {
   static Matrix4 RotationZ(double a);
   static Matrix4 LookAt(const Vec3& eye, const Vec3& at, const Vec3& up);
   static Matrix4 Perspective(float fovy, float aspect, float n, float f);
+  static Matrix4 Ortho(float left, float right, float bottom, float top, float n, float f);
   static Matrix4 PerspectiveOffCenter(float left, float right, float bottom, float top, float n, float f);
   // FLOATMATRIX4::BuildStereoLookAtAndProjection (Vectors.h:1215-1248): [0] = left eye, [1] = right eye
   static void StereoLookAtAndProjection(const Vec3& eye, const Vec3& at, const Vec3& up, float fovy, float aspect, float n, float f,
@@ -353,14 +354,23 @@ class CudaGridLeaper {
   void SetClassic(bool on) { m_classic = on; ScheduleCompleteRedraw(); }
   // forceLod < 0: the LOD the view needs (m_iMinLODForCurrentView; 0 for RT_CAPTURE); else the brick list of that LOD.
   // minLodOut: m_iMinLODForCurrentView of the view.
+  // ov: model-view / projection of the caller instead of the camera's, and (allBricks) every brick of the LOD without the
+  // frustum, clip-plane and contains-data tests -- the brick list of the full-resolution MIP
+  struct ClassicPlanOverride { Matrix4 mv, proj; bool allBricks = false; };
   bool PlanClassicFrame(tvk_classic_params& p, std::vector<tvk_classic_brick>& bricks, uint32_t& lod, int forceLod = -1,
-                        uint32_t* minLodOut = nullptr, int eye = 0);
+                        uint32_t* minLodOut = nullptr, int eye = 0, const ClassicPlanOverride* ov = nullptr);
+  // the capture mode's full-resolution MIP of a 2-D region (window mode, flipView, m_fMIPRotationAngle, m_bOrthoView, m_bMIPLOD)
+  bool PlanHQMIP(int windowMode, bool flipX, bool flipY, float angleDeg, bool ortho, bool mipLOD, tvk_mip_params& p,
+                 std::vector<tvk_classic_brick>& bricks, uint32_t& lod);
+  bool RenderHQMIP(int windowMode, bool flipX, bool flipY, float angleDeg, bool ortho, bool mipLOD);
   static void ComputeMaxLODForCurrentView(tvkr_lod_state& s);        // AbstrRenderer.cpp:681-787
   void SetMaxMSPerFrame(float ms) { m_ladder.max_ms_per_frame = ms; }
   void OverrideSubframeMs(float ms) { m_msOverride = ms; }
   const tvkr_lod_state& LodState() const { return m_ladder; }
   uint32_t CurrentLOD() const { return m_currentLOD; }
   bool PaintClassic();
+  const void* ClassicStore();        // the brick store in device memory (copied up once for datasets kept in pinned host memory)
+  bool PaintClassicWith(const void* store, tvk_classic_params& p, std::vector<tvk_classic_brick>& bricks, uint32_t& lod, uint32_t& minLod);
 
   // --- frame loop
   bool Paint();                      // one sub-frame (GLGridLeaper::Render3DRegion, or the classic path's final sub-frame)

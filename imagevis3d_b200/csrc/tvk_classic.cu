@@ -406,3 +406,112 @@ extern "C" int tvk_render_slice(tvk_ctx* c, const tvk_slice_params* p, const voi
   if (tmp) TVK_CHECK_CUDA(c, cudaFreeAsync(tmp, c->stream));
   return TVK_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Full-resolution MIP of the capture mode ("MIP rotation"): GLRenderer::Render2DView's other branch (GLRenderer.cpp:1182-1250),
+// GLRaycaster::RenderHQMIPPreLoop / RenderHQMIPInLoop (GLRaycaster.cpp:481-529), GLRaycaster-MIP-Rot-FS.glsl and
+// Transfer-MIP-FS.glsl.  The reference draws every brick of the chosen LOD (front faces into the RGBA16F entry buffer, back
+// faces with the MIP shader, GL_MAX blending) and classifies the result; here one thread per pixel walks the brick list --
+// the maximum does not depend on the order.  Rays are general (near point -> far point through the inverse projection), so
+// that the orthographic view of m_bOrthoView and the perspective one share the code.
+// ---------------------------------------------------------------------------------------------------------
+struct MipArgs {
+  tvk_mip_params p;
+  const tvk_classic_brick* bricks;
+  uint32_t nbricks;
+  const uint8_t* store;
+  const uchar4* tf;
+  uint32_t tf_w;
+  float4* image;
+  unsigned long long* stats;
+};
+
+template <int BPV>
+__global__ void __launch_bounds__(128) mip_kernel(const __grid_constant__ MipArgs a) {
+  const uint32_t lane = threadIdx.x & 31u, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t tiles_x = (a.p.width + 7) / 8;
+  const uint32_t px = (warp % tiles_x) * 8u + (lane & 7u), py = (warp / tiles_x) * 4u + (lane >> 3);
+  if (px >= a.p.width || py >= a.p.height) return;
+  const tvk_mip_params& p = a.p;
+  const float nx = fmaf(((float)px + 0.5f) / (float)p.width, 2.0f, -1.0f), ny = fmaf(((float)py + 0.5f) / (float)p.height, 2.0f, -1.0f);
+  const float4 n4 = c_xform(p.inv_projection, nx, ny, -1.0f, 1.0f), f4 = c_xform(p.inv_projection, nx, ny, 1.0f, 1.0f);
+  const float e0[3] = {n4.x / n4.w, n4.y / n4.w, n4.z / n4.w};                // near point, eye space
+  const float ed[3] = {f4.x / f4.w - e0[0], f4.y / f4.w - e0[1], f4.z / f4.w - e0[2]};   // near -> far
+  const float4 O = c_xform(p.inv_model_view, e0[0], e0[1], e0[2], 1.0f);
+  const float4 D = c_xform(p.inv_model_view, ed[0], ed[1], ed[2], 0.0f);
+  const float o[3] = {O.x, O.y, O.z}, d[3] = {D.x, D.y, D.z};
+  float vmax = 0.0f;
+  bool covered = false;
+  unsigned long long nsamples = 0;
+  for (uint32_t bi = 0; bi < a.nbricks; ++bi) {
+    const tvk_classic_brick& b = a.bricks[bi];
+    float s0 = -INFINITY, s1 = INFINITY;
+    bool miss = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float lo = b.center[k] - b.extension[k] / 2.0f, hi = b.center[k] + b.extension[k] / 2.0f;
+      if (d[k] == 0.0f) { if (o[k] < lo || o[k] > hi) miss = true; continue; }
+      const float inv = 1.0f / d[k];
+      float ta = (lo - o[k]) * inv, tb = (hi - o[k]) * inv;
+      if (ta > tb) { const float t = ta; ta = tb; tb = t; }
+      s0 = fmaxf(s0, ta); s1 = fminf(s1, tb);
+    }
+    const float se = fmaxf(s0, 0.0f);                       // front face (the near plane when it lies behind it)
+    s1 = fminf(s1, 1.0f);
+    if (miss || !(s1 > se)) continue;
+    covered = true;
+    // ray entry through the RGBA16F buffer (m_pFBORayEntry), ray exit from the interpolated varying
+    const float enx = __half2float(__float2half_rn(fmaf(ed[0], se, e0[0]))), eny = __half2float(__float2half_rn(fmaf(ed[1], se, e0[1]))),
+                enz = __half2float(__float2half_rn(fmaf(ed[2], se, e0[2])));
+    const float xx = fmaf(ed[0], s1, e0[0]), xy = fmaf(ed[1], s1, e0[1]), xz = fmaf(ed[2], s1, e0[2]);
+    const float4 te = c_xform(b.eye_to_tex, enx, eny, enz, 1.0f), tx = c_xform(b.eye_to_tex, xx, xy, xz, 1.0f);
+    const float dx = xx - enx, dy = xy - eny, dz = xz - enz;
+    const float len = sqrtf(c_dot3(dx, dy, dz, dx, dy, dz));
+    const int steps = (int)(len / b.ray_step) + 1;
+    const float q = len / b.ray_step;
+    const float itx = (tx.x - te.x) / q, ity = (tx.y - te.y) / q, itz = (tx.z - te.z) / q;
+    const uint8_t* data = a.store + b.store_offset;
+    float ptx = te.x, pty = te.y, ptz = te.z;
+    for (int i = 0; i < steps; ++i) {                       // GLRaycaster-MIP-Rot-FS.glsl:60-66
+      vmax = fmaxf(vmax, brick_sample<BPV>(data, b.voxels, ptx, pty, ptz));
+      ptx += itx; pty += ity; ptz += itz;
+    }
+    nsamples += (unsigned long long)steps;
+  }
+  // Transfer-MIP-FS.glsl: colour of the 1-D function, opacity ignored; pixels no brick covers are black; alpha 1 everywhere
+  float4 out = make_float4(0.f, 0.f, 0.f, 1.f);
+  if (covered) {
+    const uchar4 t = __ldg(a.tf + c_nearest(vmax * p.trans_scale, a.tf_w));
+    out = make_float4((float)t.x * (1.0f / 255.0f), (float)t.y * (1.0f / 255.0f), (float)t.z * (1.0f / 255.0f), 1.0f);
+  }
+  a.image[(size_t)py * p.width + px] = out;
+  for (int s = 16; s > 0; s >>= 1) nsamples += __shfl_down_sync(__activemask(), nsamples, s);
+  if (lane == 0 && a.stats) atomicAdd(a.stats, nsamples);
+}
+
+extern "C" int tvk_raycast_mip(tvk_ctx* c, const tvk_mip_params* p, const tvk_classic_brick* bricks, uint32_t n, const void* store) {
+  if (!c || !p || (n && !bricks) || !store) return TVK_ERR_INVALID;
+  if (!c->d_tf || c->tf_h != 1) TVK_FAIL(c, TVK_ERR_INVALID, "the MIP is classified with the 1-D transfer function");
+  if (p->bytes_per_voxel != 1 && p->bytes_per_voxel != 2) TVK_FAIL(c, TVK_ERR_INVALID, "bad voxel size");
+  if (!p->width || !p->height) TVK_FAIL(c, TVK_ERR_INVALID, "bad image size");
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  int rc = tvk_ensure_frame(c, p->width, p->height, c->hash_size ? c->hash_size : 509);
+  if (rc) return rc;
+  c->show_stereo = false;
+  tvk_classic_brick* d_bricks = nullptr;
+  TVK_CHECK_CUDA(c, cudaMallocAsync(&d_bricks, sizeof(tvk_classic_brick) * (n ? n : 1), c->stream));
+  if (n) TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_bricks, bricks, sizeof(tvk_classic_brick) * n, cudaMemcpyHostToDevice, c->stream));
+  MipArgs a;
+  a.p = *p; a.bricks = d_bricks; a.nbricks = n; a.store = static_cast<const uint8_t*>(store);
+  a.tf = c->d_tf; a.tf_w = c->tf_w; a.image = c->d_image; a.stats = c->d_stats;
+  const uint32_t tiles = ((p->width + 7) / 8) * ((p->height + 3) / 4);
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  if (p->bytes_per_voxel == 1) mip_kernel<1><<<(tiles + 3) / 4, 128, 0, c->stream>>>(a);
+  else mip_kernel<2><<<(tiles + 3) / 4, 128, 0, c->stream>>>(a);
+  c->launches++;
+  TVK_CHECK_CUDA(c, cudaGetLastError());
+  TVK_CHECK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  TVK_CHECK_CUDA(c, cudaFreeAsync(d_bricks, c->stream));
+  return TVK_OK;
+}

@@ -333,6 +333,22 @@ class Renderer:
         self._ck(self._lib.tvkr_render_2d_view(self._h, C.c_int(int(window_mode)), C.c_uint64(int(slice_index)), C.c_int(int(mip)),
                                                C.c_int(int(flip[0])), C.c_int(int(flip[1]))), "render2DView")
 
+    def renderHQMIP(self, window_mode, angle=0.0, flip=(False, False), ortho=True, mip_lod=True):
+        """the capture mode's full-resolution MIP of a 2-D region (ImageVis3D's rotating MIP): angle = the MIP rotation angle in
+        degrees, ortho = orthographic view, mip_lod = let the window size pick the level of detail; read the picture with
+        frameFloat() / frameRGBA8()"""
+        self._ck(self._lib.tvkr_render_hq_mip(self._h, C.c_int(int(window_mode)), C.c_int(int(flip[0])), C.c_int(int(flip[1])),
+                                              C.c_float(angle), C.c_int(int(ortho)), C.c_int(int(mip_lod))), "renderHQMIP")
+
+    def planHQMIP(self, window_mode, angle=0.0, flip=(False, False), ortho=True, mip_lod=True, cap=65536):
+        p = L.MipParams()
+        arr = (L.ClassicBrick * cap)()
+        n, lod = C.c_uint32(), C.c_uint32()
+        self._ck(self._lib.tvkr_plan_hq_mip(self._h, C.c_int(int(window_mode)), C.c_int(int(flip[0])), C.c_int(int(flip[1])), C.c_float(angle),
+                                            C.c_int(int(ortho)), C.c_int(int(mip_lod)), C.byref(p), arr, C.c_uint32(cap), C.byref(n),
+                                            C.byref(lod)), "planHQMIP")
+        return p, [arr[i] for i in range(n.value)], lod.value
+
     def sliceParams(self, window_mode, slice_index, mip=False, flip=(False, False)):
         p = L.SliceParams()
         self._ck(self._lib.tvkr_get_slice_params(self._h, C.c_int(int(window_mode)), C.c_uint64(int(slice_index)), C.c_int(int(mip)),

@@ -445,7 +445,7 @@ int tvk_raycast_classic(tvk_ctx* ctx, const tvk_classic_params* p, const tvk_cla
  * quad, samples the brick (GL_LINEAR, clamp to edge) and classifies -- slice: transfer function, colour multiplied by
  * its opacity, alpha 1; MIP: maximum over all slices of the brick along the view axis, then the 1-D transfer function's
  * colour with alpha 1 (Transfer-MIP ignores opacity).  Pixels outside the quad keep the clear colour (0,0,0,1).
- * The full-resolution rotating MIP of capture mode (RenderHQMIP*, GLRenderer.cpp:1177-1216) is not built. */
+ * The full-resolution rotating MIP of capture mode is tvk_raycast_mip below. */
 #define TVK_WM_SAGITTAL 0   /* slices along x (RenderRegion::EWindowMode, RenderRegion.h:53-59) */
 #define TVK_WM_AXIAL    1   /* along y */
 #define TVK_WM_CORONAL  2   /* along z */
@@ -465,6 +465,25 @@ typedef struct tvk_slice_params {
 } tvk_slice_params;
 /* brick: the single brick (x fastest), device memory or host memory (copied up).  Result: the context's image. */
 int tvk_render_slice(tvk_ctx* ctx, const tvk_slice_params* p, const void* brick);
+
+/* ------------------------------------------------------------ full-resolution MIP (capture mode) */
+/* replaces the other branch of GLRenderer::Render2DView (GLRenderer.cpp:1182-1250): RenderHQMIPPreLoop (:1256-1283),
+ * GLRaycaster::RenderHQMIPPreLoop / RenderHQMIPInLoop (GLRaycaster.cpp:481-529: per brick the front faces into the RGBA16F
+ * entry buffer, the back faces with GLRaycaster-MIP-Rot-FS.glsl under GL_MAX blending) and Transfer-MIP-FS.glsl.  One launch
+ * walks the brick list per pixel (the maximum does not depend on the order) and classifies: colour of the 1-D transfer
+ * function at the maximum, opacity ignored, alpha 1; pixels no brick covers are black.  bricks: every brick of the LOD
+ * AbstrRenderer::PlanHQMIPFrame picks (AbstrRenderer.cpp:1214-1245), described like the classic path's
+ * (tvk_classic_brick: centre, extension, eye-to-texture matrix, fRayStepsize, voxel counts, offset in the store).
+ * inv_projection: the inverse of the orthographic projection of m_bOrthoView (:1183-1197) or of the perspective one;
+ * inv_model_view: (m_maMIPRotation [* m_mView[0]])^-1. */
+typedef struct tvk_mip_params {
+  uint32_t width, height;
+  float inv_model_view[16];
+  float inv_projection[16];
+  uint32_t bytes_per_voxel;
+  float trans_scale;             /* fTransScale */
+} tvk_mip_params;
+int tvk_raycast_mip(tvk_ctx* ctx, const tvk_mip_params* p, const tvk_classic_brick* bricks, uint32_t n, const void* store_dptr);
 
 /* ------------------------------------------------------------------------ stereo */
 /* replaces the per-eye frame buffers of GLGridLeaper / GLRenderer (m_pFBO3DImageNext[2], m_pFBORayStart[2],

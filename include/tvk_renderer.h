@@ -98,6 +98,15 @@ int tvkr_set_2d_trans(tvkr_renderer* r, const uint8_t* rgba, uint32_t w, uint32_
 int tvkr_render_2d_view(tvkr_renderer* r, int window_mode, uint64_t slice_index, int use_mip, int flip_x, int flip_y);
 int tvkr_get_slice_params(tvkr_renderer* r, int window_mode, uint64_t slice_index, int use_mip, int flip_x, int flip_y,
                           tvk_slice_params* out);
+/* The full-resolution MIP a 2-D region shows in capture mode (the rotating MIP of ImageVis3D's capture dialog;
+ * GLRenderer::Render2DView :1182-1250, AbstrRenderer::PlanHQMIPFrame :1214-1245, GLRenderer::RenderHQMIPPreLoop :1256-1283,
+ * GLRaycaster.cpp:481-529): every brick of the LOD PlanHQMIPFrame picks (mip_lod = m_bMIPLOD, default on in the reference)
+ * is marched for its maximum under the rotation windowMode / flipView / angle_deg (= m_fMIPRotationAngle) define, with
+ * the orthographic projection of m_bOrthoView (ortho != 0) or the camera's perspective one; the maximum is classified with
+ * the 1-D transfer function's colour (opacity ignored).  The result is the frame.  tvkr_plan_hq_mip: what it is drawn with. */
+int tvkr_render_hq_mip(tvkr_renderer* r, int window_mode, int flip_x, int flip_y, float angle_deg, int ortho, int mip_lod);
+int tvkr_plan_hq_mip(tvkr_renderer* r, int window_mode, int flip_x, int flip_y, float angle_deg, int ortho, int mip_lod,
+                     tvk_mip_params* p, tvk_classic_brick* bricks, uint32_t cap, uint32_t* n, uint32_t* lod);
 /* renderer.load2DTrans("file.2dt") (TransferFunction2D::Load(file, size), TransferFunction2D.cpp:102-152): the swatch list is
  * rasterised on the host (the reference paints it with Qt's QPainter, :295-361; here: the same rules without Qt -- 1-D
  * function stretched over every row, polygons filled without anti-aliasing, linear / radial gradient, source-over) into a

@@ -878,3 +878,114 @@ def slice_view(p, brick, tf_rgba8):
         t = tf.reshape(-1, tfw, 4)[0][nearest(m * f(p["trans_scale"]), tfw)].astype(f) * (f(1.0) / f(255.0))
         img[..., :3] = t[..., :3]
     return img
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Full-resolution MIP of the capture mode: GLRaycaster::RenderHQMIPInLoop (GLRaycaster.cpp:494-529), GLRaycaster-MIP-Rot-FS.glsl,
+# Transfer-MIP-FS.glsl, on the plan the host made (model-view, projection, brick list).  TEST INFRASTRUCTURE (numpy
+# restatement; the rasterised front / back faces of a brick are the analytic entry / exit of the pixel-centre ray).
+# ---------------------------------------------------------------------------------------------------------------
+def _fma(a, b, c):
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(np.float32)
+
+
+def _xform(m, x, y, z, w):
+    """(x, y, z, w) * M in the kernel's order of operations; m: 16 floats, FLOATMATRIX4 memory order"""
+    f = np.float32
+    m = [f(v) for v in m]
+    return [_fma(w, m[12 + j], _fma(z, m[8 + j], _fma(y, m[4 + j], (np.asarray(x, f) * m[j]).astype(f)))) for j in range(4)]
+
+
+def hq_mip(p, bricks, store, tf_rgba8):
+    """p: the plan's parameters (width, height, inv_model_view, inv_projection, bytes_per_voxel, trans_scale); bricks: objects
+    with center / extension / eye_to_tex / ray_step / voxels / store_offset; store: the brick store as bytes -> [h][w][4]"""
+    f = np.float32
+    w, h = int(p.width), int(p.height)
+    px, py = np.meshgrid(np.arange(w), np.arange(h))
+    nx = _fma(((px.astype(f) + f(0.5)) / f(w)).astype(f), f(2.0), f(-1.0))
+    ny = _fma(((py.astype(f) + f(0.5)) / f(h)).astype(f), f(2.0), f(-1.0))
+    one, mone = np.ones_like(nx), -np.ones_like(nx)
+    n4, f4 = _xform(p.inv_projection[:], nx, ny, mone, one), _xform(p.inv_projection[:], nx, ny, one, one)
+    e0 = [(n4[k] / n4[3]).astype(f) for k in range(3)]
+    ed = [((f4[k] / f4[3]).astype(f) - e0[k]).astype(f) for k in range(3)]
+    O = _xform(p.inv_model_view[:], e0[0], e0[1], e0[2], one)
+    D = _xform(p.inv_model_view[:], ed[0], ed[1], ed[2], np.zeros_like(nx))
+    vmax = np.zeros((h, w), f)
+    covered = np.zeros((h, w), bool)
+    bpv = int(p.bytes_per_voxel)
+    dt = np.uint8 if bpv == 1 else np.uint16
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        for b in bricks:
+            s0 = np.full((h, w), -np.inf, f)
+            s1 = np.full((h, w), np.inf, f)
+            miss = np.zeros((h, w), bool)
+            for k in range(3):
+                lo, hi = f(b.center[k]) - f(b.extension[k]) / f(2.0), f(b.center[k]) + f(b.extension[k]) / f(2.0)
+                zero = D[k] == 0
+                miss |= zero & ((O[k] < lo) | (O[k] > hi))
+                inv = (f(1.0) / D[k]).astype(f)
+                ta, tb = ((lo - O[k]) * inv).astype(f), ((hi - O[k]) * inv).astype(f)
+                ta, tb = np.minimum(ta, tb), np.maximum(ta, tb)
+                s0 = np.where(zero, s0, np.maximum(s0, ta))
+                s1 = np.where(zero, s1, np.minimum(s1, tb))
+            se = np.maximum(s0, f(0.0))
+            s1 = np.minimum(s1, f(1.0))
+            act = ~miss & (s1 > se)
+            if not act.any():
+                continue
+            covered |= act
+            en = [_fma(ed[k], se, e0[k]).astype(np.float16).astype(f) for k in range(3)]
+            ex = [_fma(ed[k], s1, e0[k]) for k in range(3)]
+            te = _xform(b.eye_to_tex[:], en[0], en[1], en[2], one)
+            tx = _xform(b.eye_to_tex[:], ex[0], ex[1], ex[2], one)
+            dd = [(ex[k] - en[k]).astype(f) for k in range(3)]
+            ln = np.sqrt(_fma(dd[2], dd[2], _fma(dd[1], dd[1], (dd[0] * dd[0]).astype(f)))).astype(f)
+            q = (ln / f(b.ray_step)).astype(f)
+            steps = np.where(act, q.astype(np.int64) + 1, 0)
+            it = [((tx[k] - te[k]) / q).astype(f) for k in range(3)]
+            vox = [int(v) for v in b.voxels]
+            n = vox[0] * vox[1] * vox[2]
+            data = np.frombuffer(store, np.uint8, n * bpv, int(b.store_offset)).view(dt).reshape(vox[2], vox[1], vox[0])
+            pt = [te[k].copy() for k in range(3)]
+            for i in range(int(steps.max())):
+                m = steps > i
+                if not m.any():
+                    break
+                val = _slice_sample(data, [pt[0][m], pt[1][m], pt[2][m]])
+                vmax[m] = np.maximum(vmax[m], val)
+                for k in range(3):
+                    pt[k] = (pt[k] + it[k]).astype(f)
+    tf = np.asarray(tf_rgba8).reshape(-1, 4)
+    idx = np.clip(((vmax * f(p.trans_scale)).astype(f) * f(len(tf))).astype(f).astype(np.int64), 0, len(tf) - 1)
+    img = np.zeros((h, w, 4), f)
+    img[..., 3] = 1.0
+    rgb = tf[idx][..., :3].astype(f) * (f(1.0) / f(255.0))
+    img[..., :3] = np.where(covered[..., None], rgb, f(0))
+    return img, vmax
+
+
+def hq_mip_matrices(window_mode, flip, angle_deg, ortho, width, height, cam):
+    """GLRenderer::RenderHQMIPPreLoop (:1256-1283) + the orthographic projection of Render2DView (:1183-1197) /
+    GLRaycaster::RenderHQMIPPreLoop (GLRaycaster.cpp:481-492) -> (model-view, projection), row-vector convention"""
+    f = np.float32
+    rot_dir = np.eye(4, dtype=f)
+    if window_mode == 0:
+        rot_dir = (rotation_x(-math.pi / 2.0) @ rotation_y(-math.pi / 2.0)).astype(f)
+    elif window_mode == 1:
+        rot_dir = rotation_x(-math.pi / 2.0)
+    flip_y = scaling(-1, 1, 1) if flip[0] else np.eye(4, dtype=f)
+    flip_x = scaling(1, -1, 1) if flip[1] else np.eye(4, dtype=f)
+    mip_rot = (rot_dir @ np.eye(4, dtype=f) @ flip_x @ flip_y @ rotation_y(math.pi * float(f(angle_deg)) / 180.0)).astype(f)
+    if ortho:
+        wa = np.array([1.0 / width, 1.0 / height])
+        wa = wa / wa.max()
+        r2 = max(f(1.0), f(1.414213) * f(wa[0] / wa[1])) if wa[0] < wa[1] else f(1.414213)
+        l, r = f(-0.5) * r2 / f(wa[0]), f(0.5) * r2 / f(wa[0])
+        bt, tp = f(-0.5) * r2 / f(wa[1]), f(0.5) * r2 / f(wa[1])
+        zn, zf = f(-100.0), f(100.0)
+        proj = np.eye(4, dtype=f)
+        proj[0, 0] = f(2) / (r - l); proj[3, 0] = -(r + l) / (r - l)       # noqa: E702
+        proj[1, 1] = f(2) / (tp - bt); proj[3, 1] = -(tp + bt) / (tp - bt)  # noqa: E702
+        proj[2, 2] = -f(2) / (zf - zn); proj[3, 2] = -(zf + zn) / (zf - zn)  # noqa: E702
+        return mip_rot, proj
+    return (mip_rot @ look_at(cam.eye, cam.at, cam.up)).astype(f), perspective(cam.fov, f(width) / f(height), cam.znear, cam.zfar)
