@@ -79,6 +79,11 @@ class SliceParams(C.Structure):
                 ("gradient_scale", C.c_float)]
 
 
+class ClearViewParams(C.Structure):
+    _fields_ = [("cv_isoval", C.c_float), ("cv_color", C.c_float * 3), ("size", C.c_float), ("context_scale", C.c_float),
+                ("border_scale", C.c_float), ("pick_pos", C.c_float * 3)]
+
+
 class MipParams(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("inv_model_view", C.c_float * 16), ("inv_projection", C.c_float * 16),
                 ("bytes_per_voxel", C.c_uint32), ("trans_scale", C.c_float)]
@@ -121,7 +126,7 @@ EXPORTS = [
     "tvk_build_store_device_ptr", "tvk_build_hist1d", "tvk_build_hist2d", "tvk_build_release", "tvk_build_last_ms", "tvk_build_hist2d_last_ms", "tvk_quantize",
     "tvk_build_forget_raw", "tvk_build_stream_begin", "tvk_build_stream_rows", "tvk_build_stream_slab", "tvk_build_stream_end",
     "tvk_rebrick_plan", "tvk_rebrick_toc", "tvk_rebrick",
-    "tvk_composite_ordered", "tvk_raycast_classic", "tvk_raycast_mip", "tvk_render_slice", "tvk_select_eye", "tvk_read_eye_image", "tvk_compose_stereo",
+    "tvk_composite_ordered", "tvk_raycast_classic", "tvk_raycast_classic_cv", "tvk_read_iso_hit", "tvk_raycast_mip", "tvk_render_slice", "tvk_select_eye", "tvk_read_eye_image", "tvk_compose_stereo",
     "tvk_exchange_create", "tvk_exchange_open_peers", "tvk_exchange_connect", "tvk_exchange_peer_base", "tvk_exchange_set_peers", "tvk_exchange_local_base",
     "tvk_exchange_begin_frame", "tvk_exchange_composite", "tvk_exchange_final", "tvk_exchange_read_final_rgba8", "tvk_exchange_status", "tvk_exchange_destroy",
 ]

@@ -955,6 +955,7 @@ bool CudaGridLeaper::FinishLoad(BrickedVolume* v, uint64_t gpuMemBytes, uint32_t
   double lo, hi;
   v->Range(lo, hi);
   m_isoValue = float(hi - lo) / 2.0f;
+  m_cvIsoValue = float(m_isoValue + m_isoValue / 2.0);       // AbstrRenderer.cpp:261
   m_tf1d.Resize(tfSize);
   m_tf1d.SetStdFunction();
   m_visValid = false;
@@ -1910,16 +1911,25 @@ bool CudaGridLeaper::PaintClassicWith(const void* store, tvk_classic_params& p, 
   if (!PlanClassicFrame(p, bricks, lod, (int)m_currentLOD)) return false;   // BuildSubFrameBrickList
   L.brick_list_size = bricks.size();
   L.bricks_rendered = 0;
-  int rc = tvk_raycast_classic(m_ctx, &p, bricks.data(), (uint32_t)bricks.size(), store);
+  // ClearView: isosurface mode with the lens (GLRaycaster::Render3DInLoop's second pass + the ClearView composition)
+  const bool clearView = m_cv && m_mode == RM_ISOSURFACE;
+  tvk_clearview_params cv;
+  if (clearView && !ComputeClearViewParams(cv, 0)) return false;
+  int rc = clearView ? tvk_raycast_classic_cv(m_ctx, &p, &cv, bricks.data(), (uint32_t)bricks.size(), store)
+                     : tvk_raycast_classic(m_ctx, &p, bricks.data(), (uint32_t)bricks.size(), store);
   if (rc) return Fail("tvk_raycast_classic", rc);
+  m_cvFrame = clearView;
   if (m_stereo) {
     // the other eye: the same bricks in its own order, into its own picture; then GLRenderer::EndFrame's composition
     tvk_classic_params pr;
     std::vector<tvk_classic_brick> br;
     uint32_t lodR = 0;
     if (!PlanClassicFrame(pr, br, lodR, (int)m_currentLOD, nullptr, 1)) return false;
+    tvk_clearview_params cvr;
+    if (clearView && !ComputeClearViewParams(cvr, 1)) return false;
     rc = tvk_select_eye(m_ctx, 1);
-    if (!rc) rc = tvk_raycast_classic(m_ctx, &pr, br.data(), (uint32_t)br.size(), store);
+    if (!rc) rc = clearView ? tvk_raycast_classic_cv(m_ctx, &pr, &cvr, br.data(), (uint32_t)br.size(), store)
+                            : tvk_raycast_classic(m_ctx, &pr, br.data(), (uint32_t)br.size(), store);
     const int rc2 = tvk_select_eye(m_ctx, 0);
     if (rc || rc2) return Fail("tvk_raycast_classic (right eye)", rc ? rc : rc2);
     if (!ComposeStereo()) return false;
@@ -2017,6 +2027,48 @@ bool CudaGridLeaper::Paint() {                                               // 
   m_converged = (n == 0);
   if (m_converged && m_stereo && !ComposeStereo()) return false;        // GLRenderer::EndFrame (:757-812)
   m_perfTable[PERF_RENDER] += ms_since(tPaint);
+  return true;
+}
+
+// the model-view matrix of an eye (rotation * translation * view, GLRenderer.cpp:627-629)
+Matrix4 CudaGridLeaper::ModelView(int eye) const {
+  Matrix4 view = Matrix4::LookAt(m_eye, m_at, m_up);
+  if (m_stereo) {
+    Matrix4 views[2], projs[2];
+    Matrix4::StereoLookAtAndProjection(m_eye, m_at, m_up, m_fov, float(m_w) / float(m_h), m_znear, m_zfar, m_stereoFocalLength, m_stereoEyeDist, views, projs);
+    view = views[eye ? 1 : 0];
+  }
+  return m_rotation * m_translation * view;
+}
+
+bool CudaGridLeaper::ComputeClearViewParams(tvk_clearview_params& cv, int eye) {
+  if (!m_vol || !m_w || !m_h) { m_err = "no dataset / render target"; return false; }
+  memset(&cv, 0, sizeof(cv));
+  cv.cv_isoval = float(double(m_cvIsoValue) / double(1u << (8 * m_vol->bpv)));          // GetNormalizedCVIsovalue
+  cv.cv_color[0] = m_cvColor.x; cv.cv_color[1] = m_cvColor.y; cv.cv_color[2] = m_cvColor.z;
+  cv.size = m_cvSize; cv.context_scale = m_cvContextScale; cv.border_scale = m_cvBorderScale;
+  float t[4];
+  ModelView(eye).transform(m_cvPos, t);                    // transPos = m_vCVPos * modelView (GLRenderer.cpp:2789)
+  cv.pick_pos[0] = t[0]; cv.pick_pos[1] = t[1]; cv.pick_pos[2] = t[2];
+  return true;
+}
+
+// AbstrRenderer::SetCVFocusPos (:1354-1361) + GLRenderer::CVFocusHasChanged (GLRenderer.cpp:2833-2851): the first surface's hit
+// under the mouse goes back to world space through the inverse model-view; no hit there sends the lens to "nirvana"
+bool CudaGridLeaper::SetCVFocusPos(int x, int y) {
+  if (!m_ctx || !m_w || !m_h) { m_err = "no render target"; return false; }
+  if (x < 0 || y < 0 || x >= (int)m_w || y >= (int)m_h) { m_err = "focus position outside the window"; return false; }
+  float hit[4] = {0, 0, 0, 0};
+  // (the reference reads row m_vWinSize.y - mouse.y; the last row is clamped here)
+  const uint32_t row = (uint32_t)std::min<int>((int)m_h - y, (int)m_h - 1);
+  if (!m_cvFrame || tvk_read_iso_hit(m_ctx, (uint32_t)x, row, hit) != TVK_OK) { m_err = "no ClearView frame to pick from"; return false; }
+  if (hit[3] != 0.0f) {
+    const float h4[4] = {hit[0], hit[1], hit[2], 1.0f};
+    ModelView(0).inverse().transform(h4, m_cvPos);
+  } else {
+    m_cvPos[0] = m_cvPos[1] = m_cvPos[2] = 10000000.0f; m_cvPos[3] = 0.0f;
+  }
+  CVChanged();
   return true;
 }
 
@@ -2216,6 +2268,19 @@ int tvkr_plan_classic_frame(tvkr_renderer* h, tvk_classic_params* p, tvk_classic
 }
 int tvkr_set_clip_plane(tvkr_renderer* h, const float plane[4]) { if (!h || !plane) return 1; R(h)->SetClipPlane(plane); return 0; }
 int tvkr_enable_clip_plane(tvkr_renderer* h, int on) { if (!h) return 1; R(h)->EnableClipPlane(on != 0); return 0; }
+int tvkr_set_clearview(tvkr_renderer* h, int on) { if (!h) return 1; R(h)->SetCV(on != 0); return 0; }
+int tvkr_get_clearview(tvkr_renderer* h) { return h && R(h)->GetCV() ? 1 : 0; }
+int tvkr_set_cv_iso_value(tvkr_renderer* h, float v) { if (!h) return 1; R(h)->SetCVIsoValue(v); return 0; }
+int tvkr_get_cv_iso_value(tvkr_renderer* h, float* v) { if (!h || !v) return 1; *v = R(h)->GetCVIsoValue(); return 0; }
+int tvkr_set_cv_color(tvkr_renderer* h, const float c[3]) { if (!h || !c) return 1; R(h)->SetCVColor(Vec3(c[0], c[1], c[2])); return 0; }
+int tvkr_set_cv_size(tvkr_renderer* h, float f) { if (!h) return 1; R(h)->SetCVSize(f); return 0; }
+int tvkr_set_cv_context_scale(tvkr_renderer* h, float f) { if (!h) return 1; R(h)->SetCVContextScale(f); return 0; }
+int tvkr_set_cv_border_scale(tvkr_renderer* h, float f) { if (!h) return 1; R(h)->SetCVBorderScale(f); return 0; }
+int tvkr_set_cv_focus_pos(tvkr_renderer* h, int x, int y) { return h && R(h)->SetCVFocusPos(x, y) ? 0 : 1; }
+int tvkr_set_cv_focus_pos_fvec(tvkr_renderer* h, const float p[4]) { if (!h || !p) return 1; R(h)->SetCVFocusPosFVec(p); return 0; }
+int tvkr_get_clearview_params(tvkr_renderer* h, int eye, tvk_clearview_params* out) {
+  return h && out && (eye == 0 || eye == 1) && R(h)->ComputeClearViewParams(*out, eye) ? 0 : 1;
+}
 int tvkr_set_stereo(tvkr_renderer* h, int on) { if (!h) return 1; R(h)->SetStereo(on != 0); return 0; }
 int tvkr_get_stereo(tvkr_renderer* h) { return h && R(h)->GetStereo() ? 1 : 0; }
 int tvkr_set_stereo_eye_dist(tvkr_renderer* h, float d) { if (!h) return 1; R(h)->SetStereoEyeDist(d); return 0; }

@@ -19,6 +19,7 @@
 #include <vector>
 #include "tvk_cuda.h"
 #include "tvk_renderer.h"
+#include <cstring>
 
 namespace tvk {
 
@@ -327,6 +328,20 @@ class CudaGridLeaper {
   // stereo (AbstrRenderer.cpp:1387-1410, :1577-1585; the Lua names setStereoEnabled, setStereoEyeDist, setStereoFocalLength,
   // setStereoMode, setStereoEyeSwap, initStereoFrame, toggleStereoFrame): both eyes are marched in every sub-frame, share the
   // request table and the pool, and are composed into one picture when the frame has converged (GLRenderer::EndFrame)
+  // ClearView (classic renderer, isosurface mode; AbstrRenderer.cpp:1247-1256,1304-1361, GLRenderer.cpp:2833-2851; the Lua names
+  // setClearViewEnabled, setCVIsoValue, setCVColor, setCVSize, setCVContextScale, setCVBorderScale, setCVFocusPos)
+  void SetCV(bool on) { if (on != m_cv) { m_cv = on; if (m_mode == RM_ISOSURFACE) ScheduleCompleteRedraw(); } }
+  bool GetCV() const { return m_cv && m_classic; }                           // SupportsClearView: the classic renderer only
+  void SetCVIsoValue(float v) { if (v != m_cvIsoValue) { m_cvIsoValue = v; if (m_cv && m_mode == RM_ISOSURFACE) ScheduleCompleteRedraw(); } }
+  float GetCVIsoValue() const { return m_cvIsoValue; }
+  void SetCVColor(const Vec3& c) { m_cvColor = c; CVChanged(); }
+  void SetCVSize(float f) { m_cvSize = f; CVChanged(); }
+  void SetCVContextScale(float f) { m_cvContextScale = f; CVChanged(); }
+  void SetCVBorderScale(float f) { m_cvBorderScale = f; CVChanged(); }
+  void SetCVFocusPosFVec(const float p[4]) { memcpy(m_cvPos, p, 16); CVChanged(); }
+  bool SetCVFocusPos(int x, int y);                 // window coordinates, y from the top (the mouse position)
+  bool ComputeClearViewParams(tvk_clearview_params& cv, int eye = 0);
+  Matrix4 ModelView(int eye = 0) const;
   void SetStereo(bool on) { if (on != m_stereo) { m_stereo = on; ScheduleCompleteRedraw(); } }
   bool GetStereo() const { return m_stereo; }
   void SetStereoEyeDist(float d) { m_stereoEyeDist = d; if (m_stereo) ScheduleCompleteRedraw(); }
@@ -439,6 +454,12 @@ class CudaGridLeaper {
   bool m_classic = false;
   bool m_clipEnabled = false;
   float m_clipPlane[4] = {0, 0, 1, 0};
+  bool m_cv = false;                                              // AbstrRenderer.cpp:130-136,171
+  bool m_cvFrame = false;                                         // the last classic frame was a ClearView one (hit buffers readable)
+  float m_cvIsoValue = 0.8f, m_cvSize = 5.5f, m_cvContextScale = 1.0f, m_cvBorderScale = 60.0f;
+  Vec3 m_cvColor{1, 0, 0};
+  float m_cvPos[4] = {0, 0, 0.5f, 1.0f};
+  void CVChanged() { if (m_cv && m_mode == RM_ISOSURFACE) ScheduleCompleteRedraw(); }   // (the reference only recomposes)
   bool m_stereo = false, m_stereoEyeSwap = false;                 // AbstrRenderer.cpp:141-145
   float m_stereoEyeDist = 0.02f, m_stereoFocalLength = 1.0f;
   int m_stereoMode = TVK_SM_RB;

@@ -18,6 +18,10 @@ struct ClassicArgs {
   uint32_t tf_w, tf_h;
   float4* image;
   unsigned long long* stats;
+  // ClearView (isosurface mode only): second surface per brick, hit buffers instead of the fused composition
+  uint32_t cv_on;
+  tvk_clearview_params cv;
+  float4* cvb[4];                    // m_pFBOIsoHit buffers 0 / 1 (fp32), m_pFBOCVHit buffers 0 / 1 (half precision)
 };
 
 __device__ __forceinline__ float c_dot3(float ax, float ay, float az, float bx, float by, float bz) { return fmaf(az, bz, fmaf(ay, by, ax * bx)); }
@@ -114,6 +118,8 @@ __global__ void __launch_bounds__(128) classic_kernel(const __grid_constant__ Cl
   // isosurface: the two hit targets and the depth buffer (cleared to 0 / 1.0, depth test GL_LESS)
   float4 hit = make_float4(0.f, 0.f, 0.f, 0.f);
   float hnx = 0.f, hny = 0.f, hnz = 0.f, best_depth = 1.0f;
+  float4 hit2 = make_float4(0.f, 0.f, 0.f, 0.f);            // ClearView: the same for the second surface
+  float h2nx = 0.f, h2ny = 0.f, h2nz = 0.f, best_depth2 = 1.0f, best_tile = 0.0f;
   for (uint32_t bi = 0; bi < a.nbricks; ++bi) {
     const tvk_classic_brick& b = a.bricks[bi];
     float s0 = -INFINITY, s1 = INFINITY;
@@ -160,27 +166,71 @@ __global__ void __launch_bounds__(128) classic_kernel(const __grid_constant__ Cl
         if (v >= p.isoval) { found = true; break; }
         ptx += itx; pty += ity; ptz += itz;
       }
-      if (!found) continue;                                 // discard
-      // RefineIsosurface.glsl:37-53
-      float rx = itx / 2.0f, ry = ity / 2.0f, rz = itz / 2.0f;
-      ptx -= rx; pty -= ry; ptz -= rz;
-      for (int i = 0; i < 5; ++i) {
-        rx /= 2.0f; ry /= 2.0f; rz /= 2.0f;
-        const float v = brick_sample<BPV>(data, b.voxels, ptx, pty, ptz);
-        if (v >= p.isoval) { ptx -= rx; pty -= ry; ptz -= rz; } else { ptx += rx; pty += ry; ptz += rz; }
+      if (found) {                                          // (else: discard)
+        // RefineIsosurface.glsl:37-53
+        float rx = itx / 2.0f, ry = ity / 2.0f, rz = itz / 2.0f;
+        ptx -= rx; pty -= ry; ptz -= rz;
+        for (int i = 0; i < 5; ++i) {
+          rx /= 2.0f; ry /= 2.0f; rz /= 2.0f;
+          const float v = brick_sample<BPV>(data, b.voxels, ptx, pty, ptz);
+          if (v >= p.isoval) { ptx -= rx; pty -= ry; ptz -= rz; } else { ptx += rx; pty += ry; ptz += rz; }
+        }
+        const float ltx = tx.x - te.x, lty = tx.y - te.y, ltz = tx.z - te.z;
+        const float len_tex = sqrtf(c_dot3(ltx, lty, ltz, ltx, lty, ltz));
+        const float hx = ptx - te.x, hy = pty - te.y, hz = ptz - te.z;
+        const float f = sqrtf(c_dot3(hx, hy, hz, hx, hy, hz)) / len_tex;
+        const float hpx = fmaf(xx, f, enx * (1.0f - f)), hpy = fmaf(xy, f, eny * (1.0f - f)), hpz = fmaf(xz, f, enz * (1.0f - f));
+        const float depth = c_clamp01(p.proj_param[0] + p.proj_param[1] / (0.0f - hpz));
+        if (depth < best_depth) {
+          best_depth = depth;
+          hit = make_float4(hpx, hpy, hpz, f);
+          float g[3];
+          brick_gradient<BPV>(data, b.voxels, ptx, pty, ptz, g);
+          classic_normal(p, g, hnx, hny, hnz);
+          best_tile = (float)bi;                            // gl_FragData[1].w = float(iTileID)
+        }
       }
-      const float ltx = tx.x - te.x, lty = tx.y - te.y, ltz = tx.z - te.z;
-      const float len_tex = sqrtf(c_dot3(ltx, lty, ltz, ltx, lty, ltz));
-      const float hx = ptx - te.x, hy = pty - te.y, hz = ptz - te.z;
-      const float f = sqrtf(c_dot3(hx, hy, hz, hx, hy, hz)) / len_tex;
-      const float hpx = fmaf(xx, f, enx * (1.0f - f)), hpy = fmaf(xy, f, eny * (1.0f - f)), hpz = fmaf(xz, f, enz * (1.0f - f));
-      const float depth = c_clamp01(p.proj_param[0] + p.proj_param[1] / (0.0f - hpz));
-      if (depth < best_depth) {
-        best_depth = depth;
-        hit = make_float4(hpx, hpy, hpz, f);
-        float g[3];
-        brick_gradient<BPV>(data, b.voxels, ptx, pty, ptz, g);
-        classic_normal(p, g, hnx, hny, hnz);
+      if (a.cv_on) {
+        // ClearView's second surface in the same brick (GLRaycaster::Render3DInLoop, GLRaycaster.cpp:438-452;
+        // GLRaycaster-ISO-CV-FS.glsl:57-115).  If the first surface recorded for this pixel lies in THIS brick the search
+        // starts there.  As in the shader, only the texture-space start moves: the step count and the step length still come
+        // from the whole eye-space segment, and the hit position is interpolated between the brick's entry and exit.
+        float sx = te.x, sy = te.y, sz = te.z;
+        if ((float)bi == best_tile) {                       // (cleared buffer: tile 0 with a hit parameter of 0)
+          const float pp = hit.w;
+          sx = fmaf(tx.x, pp, te.x * (1.0f - pp)); sy = fmaf(tx.y, pp, te.y * (1.0f - pp)); sz = fmaf(tx.z, pp, te.z * (1.0f - pp));
+        }
+        const float l2x = tx.x - sx, l2y = tx.y - sy, l2z = tx.z - sz;
+        const float len_tex2 = sqrtf(c_dot3(l2x, l2y, l2z, l2x, l2y, l2z));
+        const float i2x = l2x / q, i2y = l2y / q, i2z = l2z / q;
+        float cx = sx, cy = sy, cz = sz;
+        bool found2 = false;
+        for (int i = 0; i < steps; ++i) {
+          const float v = brick_sample<BPV>(data, b.voxels, cx, cy, cz);
+          nsamples++;
+          if (v >= a.cv.cv_isoval) { found2 = true; break; }
+          cx += i2x; cy += i2y; cz += i2z;
+        }
+        if (found2) {
+          float rx = i2x / 2.0f, ry = i2y / 2.0f, rz = i2z / 2.0f;
+          cx -= rx; cy -= ry; cz -= rz;
+          for (int i = 0; i < 5; ++i) {
+            rx /= 2.0f; ry /= 2.0f; rz /= 2.0f;
+            const float v = brick_sample<BPV>(data, b.voxels, cx, cy, cz);
+            if (v >= a.cv.cv_isoval) { cx -= rx; cy -= ry; cz -= rz; } else { cx += rx; cy += ry; cz += rz; }
+          }
+          const float hx = cx - sx, hy = cy - sy, hz = cz - sz;
+          const float f2 = sqrtf(c_dot3(hx, hy, hz, hx, hy, hz)) / len_tex2;
+          // "as the surface maybe transparent set depth to the ray exit pos"
+          const float depth2 = c_clamp01(p.proj_param[0] + p.proj_param[1] / (0.0f - xz));
+          if (depth2 < best_depth2) {
+            best_depth2 = depth2;
+            hit2 = make_float4(fmaf(xx, f2, enx * (1.0f - f2)), fmaf(xy, f2, eny * (1.0f - f2)), fmaf(xz, f2, enz * (1.0f - f2)), f2);
+            float g[3];
+            brick_gradient<BPV>(data, b.voxels, cx, cy, cz, g);
+            classic_normal(p, g, h2nx, h2ny, h2nz);
+          }
+        }
       }
       continue;
     }
@@ -237,13 +287,106 @@ __global__ void __launch_bounds__(128) classic_kernel(const __grid_constant__ Cl
     const float k = 1.0f - dst.w;                          // frame buffer blend: ONE_MINUS_DST_ALPHA, ONE
     dst.x = fmaf(col.x, k, dst.x); dst.y = fmaf(col.y, k, dst.y); dst.z = fmaf(col.z, k, dst.z); dst.w = fmaf(col.w, k, dst.w);
   }
-  if (MODE == TVK_RM_ISOSURFACE) dst = classic_compose(p, hit, hnx, hny, hnz);
-  a.image[(size_t)py * p.width + px] = dst;
+  if (MODE == TVK_RM_ISOSURFACE && a.cv_on) {
+    // the four hit targets, composed by cv_compose_kernel (it reads the neighbours' normals); the ClearView targets are RGBA16F
+    const size_t i = (size_t)py * p.width + px;
+    a.cvb[0][i] = hit;
+    a.cvb[1][i] = make_float4(hnx, hny, hnz, best_tile);
+    a.cvb[2][i] = make_float4(__half2float(__float2half_rn(hit2.x)), __half2float(__float2half_rn(hit2.y)), __half2float(__float2half_rn(hit2.z)),
+                              __half2float(__float2half_rn(hit2.w)));
+    a.cvb[3][i] = make_float4(__half2float(__float2half_rn(h2nx)), __half2float(__float2half_rn(h2ny)), __half2float(__float2half_rn(h2nz)), 0.0f);
+  } else {
+    if (MODE == TVK_RM_ISOSURFACE) dst = classic_compose(p, hit, hnx, hny, hnz);
+    a.image[(size_t)py * p.width + px] = dst;
+  }
   for (int s = 16; s > 0; s >>= 1) nsamples += __shfl_down_sync(__activemask(), nsamples, s);
   if (lane == 0 && a.stats) atomicAdd(a.stats, nsamples);
 }
 
+// Compose-CV-FS.glsl:52-108 with the uniforms of GLRenderer::ComposeSurfaceImage (GLRenderer.cpp:2776-2795)
+__device__ __forceinline__ void cv_lighting(const tvk_classic_params& p, float4 pos, float nx, float ny, float nz, const float diffuse[3], float out[3]) {
+  nz = fabsf(nz);
+  float vx = 0.0f - pos.x, vy = 0.0f - pos.y, vz = 0.0f - pos.z;
+  float l = sqrtf(c_dot3(vx, vy, vz, vx, vy, vz));
+  vx /= l; vy /= l; vz /= l;
+  const float d2 = 2.0f * c_dot3(nx, ny, nz, vx, vy, vz);
+  float rx = fmaf(-d2, nx, vx), ry = fmaf(-d2, ny, vy), rz = fmaf(-d2, nz, vz);
+  l = sqrtf(c_dot3(rx, ry, rz, rx, ry, rz));
+  rx /= l; ry /= l; rz /= l;
+  const float ndl = fmaxf(fabsf(c_dot3(nx, ny, nz, -p.light_dir[0], -p.light_dir[1], -p.light_dir[2])), 0.0f);
+  float sp = fmaxf(c_dot3(rx, ry, rz, p.light_dir[0], p.light_dir[1], p.light_dir[2]), 0.0f);
+  sp *= sp; sp *= sp; sp *= sp;
+  for (int k = 0; k < 3; ++k) out[k] = c_clamp01(fmaf(p.light_specular[k], sp, fmaf(diffuse[k], ndl, p.light_ambient[k])));
+}
+
+__global__ void __launch_bounds__(256) cv_compose_kernel(const __grid_constant__ ClassicArgs a) {
+  const tvk_classic_params& p = a.p;
+  const uint32_t n = p.width * p.height;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int y = (int)(i / p.width), x = (int)(i - (uint32_t)y * p.width);
+    const float4 pos = a.cvb[0][i];
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pos.w != 0.0f) {                                    // (else: discard)
+      const float4 nrm = a.cvb[1][i];
+      const float d1[3] = {p.light_diffuse[0] * p.iso_color[0], p.light_diffuse[1] * p.iso_color[1], p.light_diffuse[2] * p.iso_color[2]};
+      const float d2c[3] = {p.light_diffuse[0] * a.cv.cv_color[0], p.light_diffuse[1] * a.cv.cv_color[1], p.light_diffuse[2] * a.cv.cv_color[2]};
+      float ctx[3];
+      cv_lighting(p, pos, nrm.x, nrm.y, nrm.z, d1, ctx);
+      // curvature estimate of the context surface: the normals one pixel away (GL_NEAREST, clamped at the border)
+      const int xs[4] = {min(x + 1, (int)p.width - 1), max(x - 1, 0), x, x}, ys[4] = {y, y, min(y + 1, (int)p.height - 1), max(y - 1, 0)};
+      float sx = 0.f, sy = 0.f, sz = 0.f;
+      for (int k = 0; k < 4; ++k) {
+        const float4 nb = a.cvb[1][(size_t)ys[k] * p.width + xs[k]];
+        sx += fabsf(nb.x - nrm.x); sy += fabsf(nb.y - nrm.y); sz += fabsf(nb.z - nrm.z);
+      }
+      const float curv = sqrtf(c_dot3(sx, sy, sz, sx, sy, sz));
+      const float qx = pos.x - a.cv.pick_pos[0], qy = pos.y - a.cv.pick_pos[1], qz = pos.z - a.cv.pick_pos[2];
+      const float dist_w = sqrtf(c_dot3(qx, qy, qz, qx, qy, qz)) * a.cv.size;
+      const float blend = c_clamp01(fmaxf(curv * a.cv.context_scale, c_clamp01(dist_w)));
+      const float4 pos2 = a.cvb[2][i];
+      float foc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (pos2.w != 0.0f) {
+        const float4 n2 = a.cvb[3][i];
+        cv_lighting(p, pos2, n2.x, n2.y, n2.z, d2c, foc);
+        foc[3] = 1.0f;
+      }
+      const float ib = 1.0f - blend;
+      float col[4];
+      for (int k = 0; k < 3; ++k) col[k] = c_clamp01(fmaf(foc[k], ib, ctx[k] * blend));
+      col[3] = c_clamp01(fmaf(foc[3], ib, 1.0f * blend));
+      const float border = 0.5f * (1.0f - c_clamp01(fabsf(dist_w - 1.0f) * a.cv.border_scale));
+      out = make_float4(col[0] - border, col[1] - border, col[2] - border, col[3]);
+    }
+    a.image[i] = out;
+  }
+}
+
+static int classic_launch(tvk_ctx* c, const tvk_classic_params* p, const tvk_clearview_params* cv, const tvk_classic_brick* bricks, uint32_t n,
+                          const void* store);
+
 extern "C" int tvk_raycast_classic(tvk_ctx* c, const tvk_classic_params* p, const tvk_classic_brick* bricks, uint32_t n, const void* store) {
+  return classic_launch(c, p, nullptr, bricks, n, store);
+}
+
+extern "C" int tvk_raycast_classic_cv(tvk_ctx* c, const tvk_classic_params* p, const tvk_clearview_params* cv, const tvk_classic_brick* bricks,
+                                      uint32_t n, const void* store) {
+  if (!cv) return TVK_ERR_INVALID;
+  if (p && p->render_mode != TVK_RM_ISOSURFACE) TVK_FAIL(c, TVK_ERR_INVALID, "ClearView belongs to the isosurface mode");
+  return classic_launch(c, p, cv, bricks, n, store);
+}
+
+// the first surface's hit buffer of the last ClearView frame at one pixel (GLRenderer::CVFocusHasChanged reads m_pFBOIsoHit there)
+extern "C" int tvk_read_iso_hit(tvk_ctx* c, uint32_t x, uint32_t y, float out[4]) {
+  if (!c || !out || !c->d_pos[0] || x >= c->width || y >= c->height) return TVK_ERR_INVALID;
+  if (!c->cv_hits_valid) TVK_FAIL(c, TVK_ERR_INVALID, "no ClearView frame has been drawn");
+  TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(out, c->d_pos[0] + (size_t)y * c->width + x, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TVK_OK;
+}
+
+static int classic_launch(tvk_ctx* c, const tvk_classic_params* p, const tvk_clearview_params* cv, const tvk_classic_brick* bricks, uint32_t n,
+                          const void* store) {
   if (!c || !p || (n && !bricks) || !store) return TVK_ERR_INVALID;
   if (p->render_mode != TVK_RM_1DTRANS && p->render_mode != TVK_RM_2DTRANS && p->render_mode != TVK_RM_ISOSURFACE)
     TVK_FAIL(c, TVK_ERR_INVALID, "bad render mode");
@@ -261,6 +404,10 @@ extern "C" int tvk_raycast_classic(tvk_ctx* c, const tvk_classic_params* p, cons
   ClassicArgs a;
   a.p = *p; a.bricks = d_bricks; a.nbricks = n; a.store = static_cast<const uint8_t*>(store);
   a.tf_f = c->d_tf_f; a.tf = c->d_tf; a.tf_colmask = c->d_tf_colmask; a.tf_w = c->tf_w; a.tf_h = c->tf_h; a.image = c->d_image; a.stats = c->d_stats;
+  a.cv_on = cv ? 1u : 0u;
+  if (cv) { a.cv = *cv; a.cvb[0] = c->d_pos[0]; a.cvb[1] = c->d_aux[0]; a.cvb[2] = c->d_pos[1]; a.cvb[3] = c->d_aux[1]; }
+  else { memset(&a.cv, 0, sizeof(a.cv)); a.cvb[0] = a.cvb[1] = a.cvb[2] = a.cvb[3] = nullptr; }
+  c->cv_hits_valid = cv != nullptr;                         // (the ray-guided path reuses these buffers as its resume state)
   const uint32_t tiles = ((p->width + 7) / 8) * ((p->height + 3) / 4);
   const uint32_t blocks = (tiles + 3) / 4;
   TVK_CHECK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
@@ -274,6 +421,14 @@ extern "C" int tvk_raycast_classic(tvk_ctx* c, const tvk_classic_params* p, cons
 #undef TVK_PICK
   fn<<<blocks, 128, 0, c->stream>>>(a);
   TVK_CHECK_CUDA(c, cudaGetLastError());
+  if (cv) {
+    int sm_count = 0;
+    TVK_CHECK_CUDA(c, cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, c->device));
+    const size_t npx = (size_t)p->width * p->height;
+    cv_compose_kernel<<<(unsigned)std::min<size_t>((npx + 255) / 256, (size_t)sm_count * 8), 256, 0, c->stream>>>(a);
+    c->launches++;
+    TVK_CHECK_CUDA(c, cudaGetLastError());
+  }
   TVK_CHECK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   c->launches++;
   c->k1_serial++;

@@ -1411,6 +1411,7 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   if (c->eye == 0) TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_hash, 0, sizeof(uint32_t) * p->hash_table_size, c->stream));
   TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(uint32_t), c->stream));
   c->show_stereo = false;
+  c->cv_hits_valid = false;
   TVK_CHECK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
   if (p->new_view && (rx0 > 0 || ry0 > 0 || rx1 < p->width || ry1 < p->height)) {
     const size_t npx = (size_t)p->width * p->height;

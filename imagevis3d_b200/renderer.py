@@ -227,6 +227,45 @@ class Renderer:
     def enableClipPlane(self, on=True):
         self._ck(self._lib.tvkr_enable_clip_plane(self._h, C.c_int(int(on))), "enableClipPlane")
 
+    # -- ClearView (classic renderer, isosurface mode; AbstrRenderer.cpp:1247-1256,1304-1361)
+    def setClearViewEnabled(self, on=True):
+        self._ck(self._lib.tvkr_set_clearview(self._h, C.c_int(int(on))), "setClearViewEnabled")
+
+    def getClearViewEnabled(self):
+        return bool(self._lib.tvkr_get_clearview(self._h))
+
+    def setCVIsoValue(self, v):
+        self._ck(self._lib.tvkr_set_cv_iso_value(self._h, C.c_float(v)), "setCVIsoValue")
+
+    def getCVIsoValue(self):
+        v = C.c_float()
+        self._ck(self._lib.tvkr_get_cv_iso_value(self._h, C.byref(v)), "getCVIsoValue")
+        return v.value
+
+    def setCVColor(self, rgb):
+        self._ck(self._lib.tvkr_set_cv_color(self._h, _f3(rgb)), "setCVColor")
+
+    def setCVSize(self, f):
+        self._ck(self._lib.tvkr_set_cv_size(self._h, C.c_float(f)), "setCVSize")
+
+    def setCVContextScale(self, f):
+        self._ck(self._lib.tvkr_set_cv_context_scale(self._h, C.c_float(f)), "setCVContextScale")
+
+    def setCVBorderScale(self, f):
+        self._ck(self._lib.tvkr_set_cv_border_scale(self._h, C.c_float(f)), "setCVBorderScale")
+
+    def setCVFocusPos(self, xy):
+        """window coordinates of the mouse (y from the top): the first surface's hit there becomes the lens' focus"""
+        self._ck(self._lib.tvkr_set_cv_focus_pos(self._h, C.c_int(int(xy[0])), C.c_int(int(xy[1]))), "setCVFocusPos")
+
+    def setCVFocusPosFVec(self, pos):
+        self._ck(self._lib.tvkr_set_cv_focus_pos_fvec(self._h, (C.c_float * 4)(*[float(v) for v in pos])), "setCVFocusPosFVec")
+
+    def clearViewParams(self, eye=0):
+        p = L.ClearViewParams()
+        self._ck(self._lib.tvkr_get_clearview_params(self._h, C.c_int(int(eye)), C.byref(p)), "clearViewParams")
+        return p
+
     # -- stereo (AbstrRenderer.cpp:1387-1410, :1577-1585)
     STEREO_MODES = {"rb": 0, "scanline": 1, "sbs": 2, "af": 3}
 

@@ -438,6 +438,27 @@ typedef struct tvk_classic_params {
 int tvk_raycast_classic(tvk_ctx* ctx, const tvk_classic_params* p, const tvk_classic_brick* bricks, uint32_t n,
                         const void* store_dptr);
 
+/* ClearView (isosurface mode of the classic renderer): replaces the second pass of GLRaycaster::Render3DInLoop
+ * (GLRaycaster.cpp:438-452, GLRaycaster-ISO-CV-FS.glsl: per brick a second surface at the ClearView isovalue, searched from
+ * the first surface's hit when that lies in the same brick; its own depth test on the ray EXIT depth; hit targets in half
+ * precision like m_pFBOCVHit) and the ClearView branch of GLRenderer::ComposeSurfaceImage (GLRenderer.cpp:2776-2795,
+ * Compose-CV-FS.glsl: context surface, focus surface, blended by the distance to the picked point and by a screen-space
+ * curvature estimate of the context surface's normals, dark ring at the lens border).  The march writes four hit buffers,
+ * a second launch composes. */
+typedef struct tvk_clearview_params {
+  float cv_isoval;               /* GetNormalizedCVIsovalue (AbstrRenderer.cpp:426-438)                        */
+  float cv_color[3];             /* m_vCVColor (vLightDiffuse2 = diffuse * colour)                             */
+  float size;                    /* vCVParam.x = m_fCVSize (default 5.5)                                       */
+  float context_scale;           /* vCVParam.y = m_fCVContextScale (1)                                         */
+  float border_scale;            /* vCVParam.z = m_fCVBorderScale (60)                                         */
+  float pick_pos[3];             /* vCVPickPos = m_vCVPos * modelView (eye space)                              */
+} tvk_clearview_params;
+int tvk_raycast_classic_cv(tvk_ctx* ctx, const tvk_classic_params* p, const tvk_clearview_params* cv, const tvk_classic_brick* bricks,
+                           uint32_t n, const void* store_dptr);
+/* the first surface's hit (eye-space position, w != 0: hit) of the last ClearView frame at pixel (x, y), y from the bottom:
+ * what GLRenderer::CVFocusHasChanged (GLRenderer.cpp:2833-2851) reads back under the mouse */
+int tvk_read_iso_hit(tvk_ctx* ctx, uint32_t x, uint32_t y, float out[4]);
+
 /* ------------------------------------------------------------ 2-D slice / MIP views */
 /* replaces GLRenderer::Render2DView's slice and MIP-preview path (GLRenderer.cpp:1057-1176: the finest LOD that is ONE
  * brick, GLRenderer::RenderSlice :922-1014 for the textured quad, and the shaders 1D-slice-FS.glsl / 2D-slice-FS.glsl /

@@ -145,6 +145,24 @@ int tvkr_plan_classic_frame(tvkr_renderer* r, tvk_classic_params* p, tvk_classic
  * (GLGridLeaper::FillBBoxVBO, GLGridLeaper.cpp:515-526 + Clipper::BoxPlane) */
 int tvkr_set_clip_plane(tvkr_renderer* r, const float plane[4]);
 int tvkr_enable_clip_plane(tvkr_renderer* r, int on);
+/* ClearView (renderer.setClearViewEnabled / setCVIsoValue / setCVColor / setCVSize / setCVContextScale / setCVBorderScale /
+ * setCVFocusPos; AbstrRenderer.cpp:1247-1256,1304-1361): the classic renderer's isosurface mode draws a second surface at the
+ * ClearView isovalue (data units, default 1.5 x the isovalue) and shows it through a lens around the focus point (defaults:
+ * colour (1,0,0), size 5.5, context scale 1, border scale 60, focus (0,0,0.5,1)).  tvkr_set_cv_focus_pos: window
+ * coordinates of the mouse, y from the top -- the first surface's hit there becomes the focus (needs a ClearView frame;
+ * GLRenderer::CVFocusHasChanged, GLRenderer.cpp:2833-2851); tvkr_set_cv_focus_pos_fvec: the world-space point itself.
+ * The ray-guided renderer has no ClearView (GLGridLeaper::SupportsClearView is false); it ignores the switch. */
+int tvkr_set_clearview(tvkr_renderer* r, int on);
+int tvkr_get_clearview(tvkr_renderer* r);
+int tvkr_set_cv_iso_value(tvkr_renderer* r, float iso);
+int tvkr_get_cv_iso_value(tvkr_renderer* r, float* iso);
+int tvkr_set_cv_color(tvkr_renderer* r, const float rgb[3]);
+int tvkr_set_cv_size(tvkr_renderer* r, float size);
+int tvkr_set_cv_context_scale(tvkr_renderer* r, float scale);
+int tvkr_set_cv_border_scale(tvkr_renderer* r, float scale);
+int tvkr_set_cv_focus_pos(tvkr_renderer* r, int x, int y);
+int tvkr_set_cv_focus_pos_fvec(tvkr_renderer* r, const float pos[4]);
+int tvkr_get_clearview_params(tvkr_renderer* r, int eye, tvk_clearview_params* out);
 /* Stereo (renderer.setStereoEnabled / setStereoEyeDist / setStereoFocalLength / setStereoMode / setStereoEyeSwap /
  * initStereoFrame / toggleStereoFrame; AbstrRenderer.cpp:1387-1410,1577-1585): every paint() marches the left and the right
  * eye (views and off-axis projections of FLOATMATRIX4::BuildStereoLookAtAndProjection, Vectors.h:1215-1248), both report

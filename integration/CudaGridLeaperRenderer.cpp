@@ -197,6 +197,14 @@ void CudaGridLeaperRenderer::PushState() {
   m_impl.SetStereoFocalLength(m_fStereoFocalLength);
   m_impl.SetStereoMode(int(m_eStereoMode));
   m_impl.SetStereoEyeSwap(m_bStereoEyeSwap);
+  // ClearView (classic renderer type only): state AbstrRenderer's setters recorded (AbstrRenderer.cpp:1247-1256,1304-1361)
+  m_impl.SetCV(m_bDoClearView);
+  m_impl.SetCVIsoValue(GetCVIsoValue());
+  m_impl.SetCVColor(tvk::Vec3(m_vCVColor.x, m_vCVColor.y, m_vCVColor.z));
+  m_impl.SetCVSize(m_fCVSize);
+  m_impl.SetCVContextScale(m_fCVContextScale);
+  m_impl.SetCVBorderScale(m_fCVBorderScale);
+  m_impl.SetCVFocusPosFVec(&m_vCVPos.x);
 }
 
 // ---------------------------------------------------------------------------------------------- frame loop

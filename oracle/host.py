@@ -778,6 +778,26 @@ def classic_render(p, bricks, store_tight, tf_rgba8):
     return img, int(n.value)
 
 
+class ClearViewParams(C.Structure):
+    _fields_ = [("cv_isoval", C.c_float), ("cv_color", C.c_float * 3), ("size", C.c_float), ("context_scale", C.c_float),
+                ("border_scale", C.c_float), ("pick_pos", C.c_float * 3)]
+
+
+def classic_render_cv(p, cv, bricks, store_tight):
+    """orc_raycast_classic_cv (isosurface mode with ClearView): (image, hit buffers [4][H][W][4], samples)"""
+    from . import oracle as O
+    arr = (ClassicBrick * max(len(bricks), 1))(*bricks)
+    img = np.zeros((p.height, p.width, 4), f32)
+    hits = np.zeros((4, p.height, p.width, 4), f32)
+    n = C.c_uint64()
+    st = np.ascontiguousarray(store_tight, np.uint8)
+    rc = O.lib().orc_raycast_classic_cv(C.byref(p), C.byref(cv), arr, C.c_uint32(len(bricks)), st.ctypes.data_as(C.c_void_p),
+                                        hits.ctypes.data_as(C.c_void_p), img.ctypes.data_as(C.c_void_p), C.byref(n))
+    if rc:
+        raise ValueError("orc_raycast_classic_cv failed")
+    return img, hits, int(n.value)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # 2-D slice / MIP views: GLRenderer::Render2DView (GLRenderer.cpp:1057-1176), RenderSlice (:922-1014) and the shaders
 # 1D-slice-FS.glsl, 2D-slice-FS.glsl, MIP-slice-FS.glsl, Transfer-MIP-FS.glsl.  TEST INFRASTRUCTURE (restatement; the GL

@@ -127,8 +127,78 @@ static void classic_compose(const tvk_classic_params* p, const float hit[4], con
 }
 
 /* tf_rgba8: [tf_h][tf_w][4]; tf_h == 1 for the 1D modes */
+/* Compose-CV-FS.glsl:52-62 */
+static void cv_lighting(const tvk_classic_params* p, const float pos[4], const float nrm[3], const float diffuse[3], float out[3]) {
+  const float nx = nrm[0], ny = nrm[1], nz = fabsf(nrm[2]);
+  float vx = 0.0f - pos[0], vy = 0.0f - pos[1], vz = 0.0f - pos[2];
+  float l = sqrtf(dot3c(vx, vy, vz, vx, vy, vz));
+  vx /= l; vy /= l; vz /= l;
+  const float d2 = 2.0f * dot3c(nx, ny, nz, vx, vy, vz);
+  float rx = fmaf(-d2, nx, vx), ry = fmaf(-d2, ny, vy), rz = fmaf(-d2, nz, vz);
+  l = sqrtf(dot3c(rx, ry, rz, rx, ry, rz));
+  rx /= l; ry /= l; rz /= l;
+  const float ndl = fmaxf(fabsf(dot3c(nx, ny, nz, -p->light_dir[0], -p->light_dir[1], -p->light_dir[2])), 0.0f);
+  float sp = fmaxf(dot3c(rx, ry, rz, p->light_dir[0], p->light_dir[1], p->light_dir[2]), 0.0f);
+  sp *= sp; sp *= sp; sp *= sp;
+  for (int k = 0; k < 3; ++k) out[k] = clamp01c(fmaf(p->light_specular[k], sp, fmaf(diffuse[k], ndl, p->light_ambient[k])));
+}
+
+/* cv != NULL (isosurface mode): ClearView -- the second pass of GLRaycaster::Render3DInLoop (GLRaycaster.cpp:438-452) with
+ * GLRaycaster-ISO-CV-FS.glsl:57-115 per brick, then Compose-CV-FS.glsl:65-108 with the uniforms of
+ * GLRenderer::ComposeSurfaceImage (GLRenderer.cpp:2776-2795).  hits: 4 * width * height * 4 floats of scratch (m_pFBOIsoHit
+ * buffers 0 / 1 in fp32, m_pFBOCVHit buffers 0 / 1 rounded to half precision, GLRenderer.cpp:1788-1796). */
+static int classic_impl(const tvk_classic_params* p, const tvk_clearview_params* cv, float* hits, const tvk_classic_brick* bricks, uint32_t n,
+                        const uint8_t* store, const uint8_t* tf_rgba8, uint32_t tf_n, uint32_t tf_h, float* image, uint64_t* samples_out);
+
 int orc_raycast_classic(const tvk_classic_params* p, const tvk_classic_brick* bricks, uint32_t n, const uint8_t* store,
                         const uint8_t* tf_rgba8, uint32_t tf_n, uint32_t tf_h, float* image, uint64_t* samples_out) {
+  return classic_impl(p, NULL, NULL, bricks, n, store, tf_rgba8, tf_n, tf_h, image, samples_out);
+}
+
+int orc_raycast_classic_cv(const tvk_classic_params* p, const tvk_clearview_params* cv, const tvk_classic_brick* bricks, uint32_t n,
+                           const uint8_t* store, float* hits, float* image, uint64_t* samples_out) {
+  static const uint8_t no_tf[4] = {0, 0, 0, 0};
+  if (!p || !cv || !hits || p->render_mode != TVK_RM_ISOSURFACE) return 1;
+  int rc = classic_impl(p, cv, hits, bricks, n, store, no_tf, 1, 1, image, samples_out);
+  if (rc) return rc;
+  const size_t npx = (size_t)p->width * p->height;
+  const float *H0 = hits, *H1 = hits + 4 * npx, *H2 = hits + 8 * npx, *H3 = hits + 12 * npx;
+  const float d1[3] = {p->light_diffuse[0] * p->iso_color[0], p->light_diffuse[1] * p->iso_color[1], p->light_diffuse[2] * p->iso_color[2]};
+  const float d2[3] = {p->light_diffuse[0] * cv->cv_color[0], p->light_diffuse[1] * cv->cv_color[1], p->light_diffuse[2] * cv->cv_color[2]};
+  for (int64_t y = 0; y < (int64_t)p->height; ++y)
+    for (int64_t x = 0; x < (int64_t)p->width; ++x) {
+      const size_t i = (size_t)y * p->width + (size_t)x;
+      float* o = image + 4 * i;
+      o[0] = o[1] = o[2] = o[3] = 0.0f;
+      const float* pos = H0 + 4 * i;
+      if (pos[3] == 0.0f) continue;
+      const float* nrm = H1 + 4 * i;
+      float ctx[3];
+      cv_lighting(p, pos, nrm, d1, ctx);
+      const int64_t xs[4] = {x + 1 < (int64_t)p->width ? x + 1 : x, x > 0 ? x - 1 : 0, x, x};
+      const int64_t ys[4] = {y, y, y + 1 < (int64_t)p->height ? y + 1 : y, y > 0 ? y - 1 : 0};
+      float sx = 0.f, sy = 0.f, sz = 0.f;
+      for (int k = 0; k < 4; ++k) {
+        const float* nb = H1 + 4 * ((size_t)ys[k] * p->width + (size_t)xs[k]);
+        sx += fabsf(nb[0] - nrm[0]); sy += fabsf(nb[1] - nrm[1]); sz += fabsf(nb[2] - nrm[2]);
+      }
+      const float curv = sqrtf(dot3c(sx, sy, sz, sx, sy, sz));
+      const float qx = pos[0] - cv->pick_pos[0], qy = pos[1] - cv->pick_pos[1], qz = pos[2] - cv->pick_pos[2];
+      const float dist_w = sqrtf(dot3c(qx, qy, qz, qx, qy, qz)) * cv->size;
+      const float blend = clamp01c(fmaxf(curv * cv->context_scale, clamp01c(dist_w)));
+      const float* pos2 = H2 + 4 * i;
+      float foc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (pos2[3] != 0.0f) { cv_lighting(p, pos2, H3 + 4 * i, d2, foc); foc[3] = 1.0f; }
+      const float ib = 1.0f - blend;
+      const float border = 0.5f * (1.0f - clamp01c(fabsf(dist_w - 1.0f) * cv->border_scale));
+      for (int k = 0; k < 3; ++k) o[k] = clamp01c(fmaf(foc[k], ib, ctx[k] * blend)) - border;
+      o[3] = clamp01c(fmaf(foc[3], ib, 1.0f * blend));
+    }
+  return 0;
+}
+
+static int classic_impl(const tvk_classic_params* p, const tvk_clearview_params* cv, float* hits, const tvk_classic_brick* bricks, uint32_t n,
+                        const uint8_t* store, const uint8_t* tf_rgba8, uint32_t tf_n, uint32_t tf_h, float* image, uint64_t* samples_out) {
   if (!p || (n && !bricks) || !store || !tf_rgba8 || !image || !tf_h) return 1;
   const int lit = p->lighting && p->render_mode != TVK_RM_ISOSURFACE;
   uint64_t total = 0;
@@ -143,6 +213,7 @@ int orc_raycast_classic(const tvk_classic_params* p, const tvk_classic_brick* br
       xformc(p->inv_model_view, ex, ey, ez, 0.0f, D);
       float dst[4] = {0.f, 0.f, 0.f, 0.f};
       float hit[4] = {0.f, 0.f, 0.f, 0.f}, hn[3] = {0.f, 0.f, 0.f}, best_depth = 1.0f;
+      float hit2[4] = {0.f, 0.f, 0.f, 0.f}, hn2[3] = {0.f, 0.f, 0.f}, best_depth2 = 1.0f, best_tile = 0.0f;
       for (uint32_t bi = 0; bi < n; ++bi) {
         const tvk_classic_brick* b = &bricks[bi];
         float s0 = -INFINITY, s1 = INFINITY;
@@ -190,26 +261,69 @@ int orc_raycast_classic(const tvk_classic_params* p, const tvk_classic_brick* br
             if (v >= p->isoval) { found = 1; break; }
             ptx += itx; pty += ity; ptz += itz;
           }
-          if (!found) continue;
-          float rx = itx / 2.0f, ry = ity / 2.0f, rz = itz / 2.0f;
-          ptx -= rx; pty -= ry; ptz -= rz;
-          for (int i = 0; i < 5; ++i) {
-            rx /= 2.0f; ry /= 2.0f; rz /= 2.0f;
-            const float v = brick_sample(data, bpv, b->voxels, ptx, pty, ptz);
-            if (v >= p->isoval) { ptx -= rx; pty -= ry; ptz -= rz; } else { ptx += rx; pty += ry; ptz += rz; }
+          if (found) {
+            float rx = itx / 2.0f, ry = ity / 2.0f, rz = itz / 2.0f;
+            ptx -= rx; pty -= ry; ptz -= rz;
+            for (int i = 0; i < 5; ++i) {
+              rx /= 2.0f; ry /= 2.0f; rz /= 2.0f;
+              const float v = brick_sample(data, bpv, b->voxels, ptx, pty, ptz);
+              if (v >= p->isoval) { ptx -= rx; pty -= ry; ptz -= rz; } else { ptx += rx; pty += ry; ptz += rz; }
+            }
+            const float ltx = tx[0] - te[0], lty = tx[1] - te[1], ltz = tx[2] - te[2];
+            const float len_tex = sqrtf(dot3c(ltx, lty, ltz, ltx, lty, ltz));
+            const float hx = ptx - te[0], hy = pty - te[1], hz = ptz - te[2];
+            const float f = sqrtf(dot3c(hx, hy, hz, hx, hy, hz)) / len_tex;
+            const float hpx = fmaf(xx, f, enx * (1.0f - f)), hpy = fmaf(xy, f, eny * (1.0f - f)), hpz = fmaf(xz, f, enz * (1.0f - f));
+            const float depth = clamp01c(p->proj_param[0] + p->proj_param[1] / (0.0f - hpz));
+            if (depth < best_depth) {
+              best_depth = depth;
+              hit[0] = hpx; hit[1] = hpy; hit[2] = hpz; hit[3] = f;
+              float g[3];
+              brick_gradient(data, bpv, b->voxels, ptx, pty, ptz, g);
+              classic_normal(p, g, hn);
+              best_tile = (float)bi;                     /* gl_FragData[1].w = float(iTileID), GLRaycaster-ISO-FS.glsl */
+            }
           }
-          const float ltx = tx[0] - te[0], lty = tx[1] - te[1], ltz = tx[2] - te[2];
-          const float len_tex = sqrtf(dot3c(ltx, lty, ltz, ltx, lty, ltz));
-          const float hx = ptx - te[0], hy = pty - te[1], hz = ptz - te[2];
-          const float f = sqrtf(dot3c(hx, hy, hz, hx, hy, hz)) / len_tex;
-          const float hpx = fmaf(xx, f, enx * (1.0f - f)), hpy = fmaf(xy, f, eny * (1.0f - f)), hpz = fmaf(xz, f, enz * (1.0f - f));
-          const float depth = clamp01c(p->proj_param[0] + p->proj_param[1] / (0.0f - hpz));
-          if (depth < best_depth) {
-            best_depth = depth;
-            hit[0] = hpx; hit[1] = hpy; hit[2] = hpz; hit[3] = f;
-            float g[3];
-            brick_gradient(data, bpv, b->voxels, ptx, pty, ptz, g);
-            classic_normal(p, g, hn);
+          if (cv) {
+            /* GLRaycaster-ISO-CV-FS.glsl:66-115.  fLastTileID comes from the (possibly just updated) first-pass target;
+             * a cleared target reads tile 0 / parameter 0.  Only vRayEntryTex is advanced (:71-72 advance vRayEntry by
+             * itself): fRayLength, iStepCount and the interpolation end points stay those of the whole brick segment. */
+            float sx = te[0], sy = te[1], sz = te[2];
+            if ((float)bi == best_tile) {
+              const float pp = hit[3];
+              sx = fmaf(tx[0], pp, te[0] * (1.0f - pp)); sy = fmaf(tx[1], pp, te[1] * (1.0f - pp)); sz = fmaf(tx[2], pp, te[2] * (1.0f - pp));
+            }
+            const float l2x = tx[0] - sx, l2y = tx[1] - sy, l2z = tx[2] - sz;
+            const float len_tex2 = sqrtf(dot3c(l2x, l2y, l2z, l2x, l2y, l2z));
+            const float i2x = l2x / q, i2y = l2y / q, i2z = l2z / q;
+            float cx = sx, cy = sy, cz = sz;
+            int found2 = 0;
+            for (int i = 0; i < steps; ++i) {
+              const float v = brick_sample(data, bpv, b->voxels, cx, cy, cz);
+              total++;
+              if (v >= cv->cv_isoval) { found2 = 1; break; }
+              cx += i2x; cy += i2y; cz += i2z;
+            }
+            if (found2) {
+              float rx = i2x / 2.0f, ry = i2y / 2.0f, rz = i2z / 2.0f;
+              cx -= rx; cy -= ry; cz -= rz;
+              for (int i = 0; i < 5; ++i) {
+                rx /= 2.0f; ry /= 2.0f; rz /= 2.0f;
+                const float v = brick_sample(data, bpv, b->voxels, cx, cy, cz);
+                if (v >= cv->cv_isoval) { cx -= rx; cy -= ry; cz -= rz; } else { cx += rx; cy += ry; cz += rz; }
+              }
+              const float hx = cx - sx, hy = cy - sy, hz = cz - sz;
+              const float f2 = sqrtf(dot3c(hx, hy, hz, hx, hy, hz)) / len_tex2;
+              const float depth2 = clamp01c(p->proj_param[0] + p->proj_param[1] / (0.0f - xz));   /* depth of the ray EXIT (:106) */
+              if (depth2 < best_depth2) {
+                best_depth2 = depth2;
+                hit2[0] = fmaf(xx, f2, enx * (1.0f - f2)); hit2[1] = fmaf(xy, f2, eny * (1.0f - f2)); hit2[2] = fmaf(xz, f2, enz * (1.0f - f2));
+                hit2[3] = f2;
+                float g[3];
+                brick_gradient(data, bpv, b->voxels, cx, cy, cz, g);
+                classic_normal(p, g, hn2);
+              }
+            }
           }
           continue;
         }
@@ -253,6 +367,14 @@ int orc_raycast_classic(const tvk_classic_params* p, const tvk_classic_brick* br
         }
         const float k = 1.0f - dst[3];
         dst[0] = fmaf(col[0], k, dst[0]); dst[1] = fmaf(col[1], k, dst[1]); dst[2] = fmaf(col[2], k, dst[2]); dst[3] = fmaf(col[3], k, dst[3]);
+      }
+      if (cv) {
+        const size_t npx = (size_t)p->width * p->height, i = (size_t)py * p->width + px;
+        float* h0 = hits + 4 * i; float* h1 = hits + 4 * (npx + i); float* h2 = hits + 4 * (2 * npx + i); float* h3 = hits + 4 * (3 * npx + i);
+        for (int k = 0; k < 4; ++k) { h0[k] = hit[k]; h2[k] = half_round(hit2[k]); }
+        for (int k = 0; k < 3; ++k) { h1[k] = hn[k]; h3[k] = half_round(hn2[k]); }
+        h1[3] = best_tile; h3[3] = 0.0f;
+        continue;
       }
       if (p->render_mode == TVK_RM_ISOSURFACE) classic_compose(p, hit, hn, dst);
       float* o = image + 4 * ((size_t)py * p->width + px);

@@ -394,3 +394,79 @@ def test_classic_stereo_pair():
     r.toggleStereoFrame()
     assert np.array_equal(r.frameFloat(), r.eyeFrameFloat(1))
     r.cleanup()
+
+
+def test_clearview_lens_on_the_classic_isosurface():
+    """ClearView (GLRaycaster::Render3DInLoop's second pass + GLRaycaster-ISO-CV-FS.glsl, Compose-CV-FS.glsl): the picture
+    against the oracle's restatement on the same plan; outside the lens it is the plain isosurface picture; the focus set
+    from a window position is the first surface's hit there; a position without a hit takes the lens away."""
+    from imagevis3d_b200.renderer import Renderer, RT_HEADLESS, RM_ISOSURFACE
+    vol = H.synth_blobs((150, 131, 97), np.uint8)
+    r = Renderer(0)
+    r.loadRawVolume(vol, brick_size=32)
+    r.setRendererType(True)
+    w, h = 203, 149
+    r.resize((w, h))
+    r.setRendererTarget(RT_HEADLESS)
+    r.setRotation4x4(H.rotation_y(0.6) @ H.rotation_x(0.3))
+    r.setRenderMode(RM_ISOSURFACE)
+    iso = 0.12 * float(vol.max())
+    r.setIsoValue(iso)
+    r.paintUntilConverged()
+    plain = r.frameFloat()
+    assert (plain[..., 3] == 1.0).mean() > 0.08
+    r.setClearViewEnabled(True)
+    r.setCVIsoValue(1.6 * iso)
+    r.setCVColor((1.0, 0.2, 0.1))
+    r.setCVSize(3.0)
+    assert r.getClearViewEnabled() and abs(r.getCVIsoValue() - 1.6 * iso) < 1e-3 and r.checkForRedraw()
+    store = _device_store(r)
+
+    def both():
+        p, bricks, _ = r.planClassicFrame()
+        cv = r.clearViewParams()
+        r.paintUntilConverged()
+        got = r.frameFloat()
+        q, ob = _to_oracle(p, bricks)
+        cq = H.ClearViewParams()
+        assert C.sizeof(cq) == C.sizeof(cv)
+        C.memmove(C.byref(cq), C.byref(cv), C.sizeof(cv))
+        want, hits, _ = H.classic_render_cv(q, cq, ob, store)
+        d = np.abs(got - want).max(axis=2)
+        # (a hit / miss flip on a silhouette pixel is a full-scale difference, and the curvature term reads the neighbours' normals)
+        assert (d > 2.0 / 255.0).sum() <= max(6, int(0.004 * d.size)), int((d > 2.0 / 255.0).sum())
+        return got, want, hits, cv
+
+    got, want, hits, cv = both()
+    assert abs(cv.cv_isoval - 1.6 * iso / 256.0) < 1e-6 and cv.size == 3.0 and cv.border_scale == 60.0
+    hit = hits[0][..., 3] != 0
+    # focus from a window position: the first surface's hit under it
+    ys, xs = np.nonzero(hit & (hits[2][..., 3] != 0))
+    k = len(ys) // 2
+    x, row = int(xs[k]), int(ys[k])                         # row counted from the bottom
+    r.setCVFocusPos((x, h - row))
+    cv2 = r.clearViewParams()
+    assert np.allclose(np.array(cv2.pick_pos[:]), hits[0][row, x, :3], atol=2e-4), (cv2.pick_pos[:], hits[0][row, x])
+    assert r.checkForRedraw()
+    got2, _, hits2, _ = both()
+    assert np.abs(got2 - got).max() > 0.05                   # the lens moved
+    dist_w = np.sqrt(((hits2[0][..., :3] - np.array(cv2.pick_pos[:], np.float32)) ** 2).sum(axis=2)) * cv2.size
+    outside = hit & (dist_w > 1.0 + 1.5 / 60.0)
+    inside = hit & (dist_w < 0.5) & (hits2[2][..., 3] != 0)
+    assert outside.sum() > 200 and inside.sum() > 50, (int(outside.sum()), int(inside.sum()))
+    # curvature can pull the focus colour in outside the lens too; where it does not, the picture is the plain isosurface
+    same = outside & (np.abs(got2 - plain).max(axis=2) <= 1e-6)
+    assert same.sum() > 0.5 * outside.sum(), (int(same.sum()), int(outside.sum()))
+    # inside the lens the focus surface's colour (red) dominates
+    assert (got2[inside][:, 0] > got2[inside][:, 2] + 0.05).mean() > 0.8
+    # a window position without a hit sends the lens away: the plain isosurface picture wherever the curvature term is quiet
+    ys0, xs0 = np.nonzero(~hit[1:])                         # (row 0 is window y == height, which no mouse position has)
+    r.setCVFocusPos((int(xs0[0]), h - (int(ys0[0]) + 1)))
+    got3, _, _, cv3 = both()
+    assert max(abs(v) for v in cv3.pick_pos[:]) > 1e6
+    assert (np.abs(got3 - plain).max(axis=2) <= 1e-6).mean() > 0.9
+    # ClearView off: the plain picture again, bit for bit
+    r.setClearViewEnabled(False)
+    r.paintUntilConverged()
+    assert np.array_equal(r.frameFloat(), plain)
+    r.cleanup()
