@@ -101,6 +101,7 @@ template <class T> struct vec<T, 4> {
     swz<T, 4, 0, 1> xy; swz<T, 4, 2, 3> zw; swz<T, 4, 0, 1> rg;
     swz<T, 4, 0, 1, 2> xyz; swz<T, 4, 0, 1, 2> rgb; swz<T, 4, 1, 2, 3> yzw;
     swz<T, 4, 0, 1, 2, 3> xyzw; swz<T, 4, 0, 1, 2, 3> rgba;
+    swz<T, 4, 0, 0, 0, 0> xxxx; swz<T, 4, 0, 3> xw;          // (read-only uses in MIP-slice-FS.glsl / Transfer-MIP-FS.glsl)
   };
   GLSL_VEC_COMMON(4)
 };

@@ -801,7 +801,8 @@ def classic_render_cv(p, cv, bricks, store_tight):
 # ---------------------------------------------------------------------------------------------------------------
 # 2-D slice / MIP views: GLRenderer::Render2DView (GLRenderer.cpp:1057-1176), RenderSlice (:922-1014) and the shaders
 # 1D-slice-FS.glsl, 2D-slice-FS.glsl, MIP-slice-FS.glsl, Transfer-MIP-FS.glsl.  TEST INFRASTRUCTURE (restatement; the GL
-# rasteriser's interpolation of the quad is replaced by the texture coordinate at the pixel centre).
+# rasteriser's interpolation of the quad is replaced by the texture coordinate at the pixel centre).  Pinned to the shader
+# text by oracle/classicref.py (tests/test_glsl_classic_reference.py).
 # ---------------------------------------------------------------------------------------------------------------
 def slice_params(vol_dims, scale, lod_size, brick_voxels, bpv, width, height, window_mode, slice_index, mip, flip, render_mode,
                  max_value, max_grad):

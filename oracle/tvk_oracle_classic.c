@@ -16,7 +16,10 @@
  *   Shaders/VRender1D.glsl, VRender1DLit.glsl, Volume3D.glsl (sampleVolume, ComputeGradient, ComputeNormal),
  *   Shaders/lighting.glsl, Shaders/Compositing.glsl:33-38
  *   Renderer/GL/GLRenderer.cpp:152-153    frame-buffer blend ONE_MINUS_DST_ALPHA / ONE between bricks
- * Parity status: "parity unpinned" like the ray-guided restatement (the reference's pixels need an OpenGL driver).
+ * Parity status: PINNED to the reference's own shader text -- oracle/classicref.py compiles GLRaycaster-*-FS.glsl, Volume3D,
+ * VRender1D*, lighting, Compositing, RefineIsosurface, Compose-FS and Compose-CV-FS with g++ against the GLSL shim and
+ * tests/test_glsl_classic_reference.py requires this restatement to agree with it (120-158 dB; 1D / 2D, lit / unlit,
+ * isosurface, ClearView, clip plane, u8 / u16).  The reference's pixels themselves need an OpenGL driver.
  * Restatement choices: brick faces are intersected analytically with the pixel-centre ray instead of being
  * rasterised; a brick whose front face lies behind the near plane starts at the near plane (the reference reads
  * whatever the previous brick left in the entry buffer there); the entry point is rounded to half precision as the
