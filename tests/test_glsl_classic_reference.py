@@ -12,45 +12,10 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.skipif(not R.available(), reason="/root/reference (the shader sources) is not mounted")
 
-W, Hh = 96, 72
+from tests import classic_scenes as S
+from tests.classic_scenes import CASES, W, Hh
 
-
-def _tf(n):
-    t = H.tf1d_std(n, 0.3, 0.3)
-    t[:, 3] *= 0.15
-    t[:, 2] *= 0.5
-    return t
-
-
-def _scene(dtype, mode, lighting, clip=None):
-    vol = H.synth_blobs((70, 61, 47), dtype)
-    oc = O.build_octree(vol, 32, 2)
-    cam = H.Camera()
-    cam.rotation = H.rotation_y(0.6) @ H.rotation_x(0.3)
-    n = 256 if dtype == np.uint8 else 4096
-    maxv = float(oc["minmax"][:int(np.prod(oc["plan"].lod_bricks[0][:])), 1].max())
-    bits = 8 * np.dtype(dtype).itemsize
-    kw = dict(lighting=lighting, trans_scale=((1 << bits) - 1) / maxv, lod=0, render_mode=mode, clip_plane=clip)
-    if mode == 0:
-        tf = H.tf_bytes(_tf(n))
-        lo, hi = H.tf_nonzero_limits(_tf(n))
-        p, bricks, _ = H.classic_plan(oc, cam, W, Hh, (lo, hi, n), **kw)
-    elif mode == 1:
-        v, g = np.linspace(0, 1, n, dtype=np.float32), np.linspace(0, 1, 256, dtype=np.float32)
-        t2 = np.zeros((256, n, 4), np.float32)
-        t2[..., 0] = v[None, :]; t2[..., 1] = 0.3 + 0.7 * g[:, None]; t2[..., 2] = 0.4          # noqa: E702
-        t2[..., 3] = np.clip((v[None, :] - 0.2) * 0.3, 0, 1) * (0.5 + 0.5 * g[:, None])
-        tf = (np.clip(t2, 0, 1) * np.float32(255)).astype(np.uint8)
-        p, bricks, _ = H.classic_plan(oc, cam, W, Hh, (int(0.2 * n), n - 1, n), gradient_scale=4.0, **kw)
-    else:
-        tf = np.zeros((n, 4), np.uint8)
-        p, bricks, _ = H.classic_plan(oc, cam, W, Hh, (0, n - 1, n), iso_value=0.15 * maxv, **kw)
-    return p, bricks, oc["store"], tf
-
-
-CASES = [("u8_1d", np.uint8, 0, False, None), ("u8_1d_lit", np.uint8, 0, True, None), ("u16_1d_lit", np.uint16, 0, True, None),
-         ("u8_2d", np.uint8, 1, False, None), ("u16_2d_lit", np.uint16, 1, True, None), ("u8_iso", np.uint8, 2, False, None),
-         ("u16_iso", np.uint16, 2, False, None), ("u8_1d_clip", np.uint8, 0, True, (0.3, 0.2, 1.0, 0.05))]
+_scene = S.scene
 
 
 @pytest.mark.parametrize("name,dtype,mode,lighting,clip", CASES)
