@@ -118,7 +118,7 @@ DTYPE_CODES = {"int8": 0, "uint8": 1, "int16": 2, "uint16": 3, "int32": 4, "uint
 EXPORTS = [
     "tvk_create", "tvk_destroy", "tvk_last_error", "tvk_device_synchronize", "tvk_set_stream", "tvk_set_march_occupancy",
     "tvk_pool_create", "tvk_pool_destroy", "tvk_pool_total_bricks", "tvk_pool_upload_bricks",
-    "tvk_pool_upload_wait", "tvk_pool_upload_bricks_lz4", "tvk_lz4_inflate", "tvk_pool_upload_fence", "tvk_pool_set_metadata", "tvk_pool_clear_metadata", "tvk_pool_patch_metadata", "tvk_pool_get_metadata",
+    "tvk_pool_upload_wait", "tvk_pool_upload_bricks_lz4", "tvk_lz4_inflate", "tvk_zlib_inflate", "tvk_pool_upload_bricks_compressed", "tvk_pool_upload_fence", "tvk_pool_set_metadata", "tvk_pool_clear_metadata", "tvk_pool_patch_metadata", "tvk_pool_get_metadata",
     "tvk_visibility_set_minmax", "tvk_visibility_recompute", "tvk_set_tf1d", "tvk_set_tf2d", "tvk_tf2d_staging",
     "tvk_raycast_subframe", "tvk_read_requests", "tvk_read_image", "tvk_read_image_rgba8", "tvk_read_resume", "tvk_image_device_ptr",
     "tvk_get_stats", "tvk_probe_lod", "tvk_probe_brick_index",

@@ -556,7 +556,7 @@ int BrickPool::UploadFirstBrick(bool wait) {
   s.brick = (int32_t)idx; s.time = UINT64_MAX; m_order = ORDER_TOUCHED;
   const void* src = m_vol->host_store ? (const void*)(m_vol->host_store + m_vol->offsets[t])
                                       : (const void*)((const uint8_t*)m_vol->device_store + m_vol->offsets[t]);
-  int rc = m_vol->lz4_store ? tvk_pool_upload_bricks_lz4(m_ctx, 1, &s.pos, &src, &m_vol->comp_len[t], &m_vol->sizes[3 * t])
+  int rc = m_vol->lz4_store ? tvk_pool_upload_bricks_compressed(m_ctx, m_vol->store_codec, 1, &s.pos, &src, &m_vol->comp_len[t], &m_vol->sizes[3 * t])
                             : tvk_pool_upload_bricks(m_ctx, 1, &s.pos, &src, &m_vol->sizes[3 * t], m_vol->host_store ? 2 : 1);   // 2: the pinned store is one allocation
   if (rc) return rc;
   rc = wait ? tvk_pool_upload_wait(m_ctx) : tvk_pool_upload_fence(m_ctx);    // fence: the next march is ordered behind it
@@ -605,7 +605,7 @@ int BrickPool::UploadBricks(const std::vector<uint32_t>& xyzl, uint32_t& paged, 
   t0 = clk::now();
   // compressed store: the LZ4 bytes cross PCIe and the device inflates them (blocks until placed)
   int rc = m_vol->lz4_store
-               ? tvk_pool_upload_bricks_lz4(m_ctx, (uint32_t)slot.size(), slot.data(), src.data(), clen.data(), sizes.data())
+               ? tvk_pool_upload_bricks_compressed(m_ctx, m_vol->store_codec, (uint32_t)slot.size(), slot.data(), src.data(), clen.data(), sizes.data())
                : tvk_pool_upload_bricks(m_ctx, (uint32_t)slot.size(), slot.data(), src.data(), sizes.data(), m_vol->host_store ? 2 : 1);
   if (rc) return rc;
   rc = wait ? tvk_pool_upload_wait(m_ctx) : tvk_pool_upload_fence(m_ctx);
@@ -1028,14 +1028,17 @@ bool CudaGridLeaper::LoadDataset(const std::string& uvfFile, uint64_t gpuMemByte
     else v->hist2d.clear();
   }
   if (keepCompressed) {
-    // all bricks LZ4? then the store keeps what the file holds and the device inflates (ExtendedOctree.cpp:313-360 does
-    // it on the host, brick by brick, before the upload)
+    // all bricks LZ4, or all zlib? then the store keeps what the file holds and the device inflates (ExtendedOctree.cpp:313-360
+    // does it on the host, brick by brick, before the upload)
     std::vector<uint64_t> flen(n);
     std::vector<uint32_t> comp(n);
-    bool all = tvk_uvf_get_toc(u, nullptr, flen.data(), comp.data(), nullptr, n) == TVK_OK;
-    for (uint64_t i = 0; i < n && all; ++i) all = comp[i] == TVK_UVF_COMP_LZ4 && flen[i] <= 0xFFFFFFFFull;
+    bool all = n > 0 && tvk_uvf_get_toc(u, nullptr, flen.data(), comp.data(), nullptr, n) == TVK_OK;
+    const uint32_t codec = all ? comp[0] : 0u;
+    all = all && (codec == TVK_UVF_COMP_LZ4 || codec == TVK_UVF_COMP_ZLIB);
+    for (uint64_t i = 0; i < n && all; ++i) all = comp[i] == codec && flen[i] <= 0xFFFFFFFFull;
     if (all) {
-      v->lz4_store = true;
+      v->lz4_store = true;                                 // (the flag's name is older than the zlib decoder: "kept compressed")
+      v->store_codec = codec;
       v->comp_len.resize(n);
       uint64_t coff = 0;
       for (uint64_t i = 0; i < n; ++i) { v->offsets[i] = coff; v->comp_len[i] = (uint32_t)flen[i]; coff += flen[i]; }

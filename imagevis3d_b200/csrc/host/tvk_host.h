@@ -140,6 +140,7 @@ struct BrickedVolume {
   // host_store holds the bricks STILL LZ4-COMPRESSED (as the file stores them): offsets[] index the compressed store,
   // comp_len[] are their lengths, and the pager inflates on the device (tvk_pool_upload_bricks_lz4)
   bool     lz4_store = false;
+  uint32_t store_codec = 0;                // TVK_CODEC_LZ4 / TVK_CODEC_ZLIB when the store holds the compressed bricks of the file
   std::vector<uint32_t> comp_len;
   uint8_t* host_store = nullptr;        // pinned (cudaHostAlloc) when out of core
   void*    device_store = nullptr;      // owned by the tvk_ctx build state when in core

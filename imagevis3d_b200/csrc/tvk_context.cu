@@ -740,8 +740,226 @@ __global__ void __launch_bounds__(128) lz4_inflate_kernel(const Lz4Job* __restri
   if (bad && lane == 0) atomicExch(err, 1u);
 }
 
+// ------------------------------------------------------------------ zlib bricks inflated on the device
+// A brick stored CT_ZLIB is one zlib stream (RFC 1950: 2 header bytes, DEFLATE blocks, Adler-32; zCompress / zDecompress,
+// ExtendedOctree/ZlibCompression.cpp:14-70 -- the reference inflates it on the host).  One warp per brick, same job
+// layout as the LZ4 kernel.  DEFLATE (RFC 1951) is a serial bit stream: EVERY lane reads it (private, identical bit
+// position; the loads are broadcasts), so control flow stays uniform without any shuffle; lane 0 alone writes literals
+// and the shared-memory Huffman tables (canonical codes decoded by counting, one bit at a time); the 32 lanes share the
+// copy of every match and of stored blocks, as in the LZ4 kernel.  The Adler-32 trailer is not checked (the UVF carries an
+// MD5 of the whole file).  Throughput is that of a serial decoder per brick (a batch of bricks inflates in parallel); what it
+// buys is that the compressed bytes, not the inflated ones, sit in pinned memory and cross PCIe.
+__constant__ unsigned short lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ unsigned short lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ unsigned short dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ unsigned short dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ unsigned char zorder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+struct ZTables {
+  unsigned short lencnt[16], lensym[288], distcnt[16], distsym[32];
+  unsigned char lengths[320];
+};
+struct ZBits { const uint8_t* ip; const uint8_t* iend; unsigned long long buf; int cnt; bool bad; };
+
+// at least 32 bits in the buffer (zeros behind the end of the input: reading them is an error only once they are CONSUMED)
+__device__ __forceinline__ void z_fill(ZBits& z) {
+  while (z.cnt <= 56) {
+    const unsigned long long b = z.ip < z.iend ? (unsigned long long)(*z.ip) : 0ull;
+    z.ip++;
+    z.buf |= b << z.cnt;
+    z.cnt += 8;
+  }
+}
+__device__ __forceinline__ void z_drop(ZBits& z, int n) {
+  z.buf >>= n; z.cnt -= n;
+  // bits taken from behind the end of the stream: ip ran past iend by more bytes than the buffer still holds
+  if (z.ip > z.iend && (long long)(z.ip - z.iend) * 8 > (long long)z.cnt) z.bad = true;
+}
+__device__ __forceinline__ uint32_t z_bits(ZBits& z, int need) {             // need <= 16
+  z_fill(z);
+  const uint32_t v = (uint32_t)z.buf & ((1u << need) - 1u);
+  z_drop(z, need);
+  return v;
+}
+// Canonical Huffman decode by counting (one bit per length), with the 15 per-length counts in REGISTERS (packed two per word,
+// the loop is unrolled so that every access has a constant index): the only shared-memory access is the symbol fetch.
+struct ZCounts { uint32_t w[8]; };
+__device__ __forceinline__ void z_load_counts(ZCounts& c, const unsigned short* cnt) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) c.w[k] = (uint32_t)cnt[2 * k] | ((uint32_t)cnt[2 * k + 1] << 16);
+}
+__device__ __forceinline__ int z_decode(ZBits& z, const ZCounts& c, const unsigned short* sym) {
+  z_fill(z);
+  uint32_t bits = (uint32_t)z.buf;
+  int code = 0, first = 0, index = 0;
+#pragma unroll
+  for (int len = 1; len <= 15; ++len) {
+    code |= (int)(bits & 1u);
+    bits >>= 1;
+    const int count = (int)((c.w[len >> 1] >> (16 * (len & 1))) & 0xFFFFu);
+    if (code - count < first) { z_drop(z, len); return z.bad ? -1 : (int)sym[index + (code - first)]; }
+    index += count; first += count; first <<= 1; code <<= 1;
+  }
+  z.bad = true;
+  return -1;
+}
+// canonical Huffman table from code lengths (lane 0 only); returns < 0 for an over-subscribed set
+__device__ int z_construct(unsigned short* cnt, unsigned short* sym, const unsigned char* length, int n) {
+  unsigned short offs[16];
+  for (int l = 0; l <= 15; ++l) cnt[l] = 0;
+  for (int s = 0; s < n; ++s) cnt[length[s]]++;
+  if (cnt[0] == n) return 0;
+  int left = 1;
+  for (int l = 1; l <= 15; ++l) { left <<= 1; left -= cnt[l]; if (left < 0) return left; }
+  offs[1] = 0;
+  for (int l = 1; l < 15; ++l) offs[l + 1] = offs[l] + cnt[l];
+  for (int s = 0; s < n; ++s) if (length[s]) sym[offs[length[s]]++] = (unsigned short)s;
+  return left;
+}
+
+__global__ void __launch_bounds__(128) zlib_inflate_kernel(const Lz4Job* __restrict__ jobs, uint32_t njobs, uint32_t* __restrict__ err) {
+  __shared__ ZTables tables[4];
+  const uint32_t wib = threadIdx.x >> 5, warp = blockIdx.x * (blockDim.x >> 5) + wib, lane = threadIdx.x & 31u;
+  if (warp >= njobs) return;
+  ZTables& T = tables[wib];
+  const Lz4Job j = jobs[warp];
+  uint8_t* op = j.dst;
+  uint8_t* const oend = j.dst + j.dst_len;
+  ZBits z;
+  z.ip = j.src; z.iend = j.src + j.src_len; z.buf = 0ull; z.cnt = 0; z.bad = false;
+  bool bad = false;
+  // zlib header: CM = 8 (deflate), no preset dictionary, (CMF * 256 + FLG) % 31 == 0
+  if (j.src_len < 2 || (j.src[0] & 0x0F) != 8 || (j.src[1] & 0x20) || ((((uint32_t)j.src[0]) << 8) | j.src[1]) % 31u) bad = true;
+  z.ip += 2;
+  uint32_t last = 0;
+  while (!bad && !last) {
+    last = z_bits(z, 1);
+    const uint32_t type = z_bits(z, 2);
+    if (z.bad || type == 3) { bad = true; break; }
+    if (type == 0) {                                       // stored
+      // back to the byte boundary: drop the bits left of the current byte, then hand the whole bytes still buffered back
+      z_drop(z, z.cnt & 7);
+      z.ip -= z.cnt >> 3; z.buf = 0ull; z.cnt = 0;
+      if (z.bad || z.ip > z.iend || z.iend - z.ip < 4) { bad = true; break; }
+      const uint32_t len = (uint32_t)z.ip[0] | ((uint32_t)z.ip[1] << 8), nlen = (uint32_t)z.ip[2] | ((uint32_t)z.ip[3] << 8);
+      z.ip += 4;
+      if (len != (~nlen & 0xFFFFu) || len > (size_t)(z.iend - z.ip) || len > (size_t)(oend - op)) { bad = true; break; }
+      for (uint32_t i = lane; i < len; i += 32) op[i] = z.ip[i];
+      op += len; z.ip += len;
+      __syncwarp();
+      continue;
+    }
+    __syncwarp();                                          // nobody still reads the previous block's tables
+    if (type == 1) {                                       // fixed codes
+      if (lane == 0) {
+        int s = 0;
+        for (; s < 144; ++s) T.lengths[s] = 8;
+        for (; s < 256; ++s) T.lengths[s] = 9;
+        for (; s < 280; ++s) T.lengths[s] = 7;
+        for (; s < 288; ++s) T.lengths[s] = 8;
+        z_construct(T.lencnt, T.lensym, T.lengths, 288);
+        for (s = 0; s < 30; ++s) T.lengths[s] = 5;
+        z_construct(T.distcnt, T.distsym, T.lengths, 30);
+      }
+    } else {                                               // dynamic codes
+      const int nlen = (int)z_bits(z, 5) + 257, ndist = (int)z_bits(z, 5) + 1, ncode = (int)z_bits(z, 4) + 4;
+      if (z.bad || nlen > 286 || ndist > 30) { bad = true; break; }
+      unsigned char cl[19];
+      for (int i = 0; i < 19; ++i) cl[i] = 0;
+      for (int i = 0; i < ncode; ++i) cl[zorder[i]] = (unsigned char)z_bits(z, 3);
+      if (z.bad) { bad = true; break; }
+      int ok = 0;
+      if (lane == 0) ok = z_construct(T.lencnt, T.lensym, cl, 19);       // the code-length code, in the literal/length table's place
+      ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
+      if (ok != 0) { bad = true; break; }                  // must be complete
+      __syncwarp();
+      int index = 0;
+      int prev = 0;
+      bool hdr_bad = false;
+      ZCounts cc;
+      z_load_counts(cc, T.lencnt);
+      while (index < nlen + ndist) {
+        int sym = z_decode(z, cc, T.lensym);
+        if (sym < 0) { hdr_bad = true; break; }
+        if (sym < 16) { if (lane == 0) T.lengths[index] = (unsigned char)sym; prev = sym; ++index; }
+        else {
+          int len = 0, rep;
+          if (sym == 16) { if (index == 0) { hdr_bad = true; break; } len = prev; rep = 3 + (int)z_bits(z, 2); }
+          else if (sym == 17) rep = 3 + (int)z_bits(z, 3);
+          else rep = 11 + (int)z_bits(z, 7);
+          if (z.bad || index + rep > nlen + ndist) { hdr_bad = true; break; }
+          if (lane == 0) for (int k = 0; k < rep; ++k) T.lengths[index + k] = (unsigned char)len;
+          index += rep;
+          prev = len;
+        }
+      }
+      if (hdr_bad) { bad = true; break; }
+      __syncwarp();                                        // lengths complete; the code-length table is no longer read
+      int e1 = 0, e2 = 0, eob = 0;
+      if (lane == 0) {
+        eob = T.lengths[256];
+        e1 = z_construct(T.lencnt, T.lensym, T.lengths, nlen);
+        e2 = z_construct(T.distcnt, T.distsym, T.lengths + nlen, ndist);
+        // incomplete codes are allowed only for a single code of length one (RFC 1951 / zlib)
+        if (e1 < 0 || (e1 > 0 && nlen - T.lencnt[0] != 1)) e1 = -1; else e1 = 0;
+        if (e2 < 0 || (e2 > 0 && ndist - T.distcnt[0] != 1)) e2 = -1; else e2 = 0;
+        if (eob == 0) e1 = -1;
+      }
+      e1 = __shfl_sync(0xFFFFFFFFu, e1 | e2, 0);
+      if (e1 != 0) { bad = true; break; }
+    }
+    __syncwarp();
+    ZCounts lc, dc;
+    z_load_counts(lc, T.lencnt);
+    z_load_counts(dc, T.distcnt);
+    for (;;) {                                             // the block's symbols
+      const int sym = z_decode(z, lc, T.lensym);
+      if (sym < 0) { bad = true; break; }
+      if (sym < 256) {
+        if (op >= oend) { bad = true; break; }
+        if (lane == 0) *op = (uint8_t)sym;
+        ++op;
+      } else if (sym == 256) {
+        break;
+      } else {
+        const int ls = sym - 257;
+        if (ls >= 29) { bad = true; break; }
+        const uint32_t ml = lbase[ls] + z_bits(z, lext[ls]);
+        const int ds = z_decode(z, dc, T.distsym);
+        if (ds < 0 || ds >= 30) { bad = true; break; }
+        const size_t off = dbase[ds] + z_bits(z, dext[ds]);
+        if (z.bad || off > (size_t)(op - j.dst) || ml > (size_t)(oend - op)) { bad = true; break; }
+        const uint8_t* m = op - off;
+        __syncwarp();                                      // the literals lane 0 wrote may be the match source
+        if (off < 32) {
+          for (uint32_t i = lane; i < ml; i += 32) op[i] = m[i % off];
+        } else {
+          for (uint32_t i0 = 0; i0 < ml; i0 += 32) {
+            if (i0 + lane < ml) op[i0 + lane] = m[i0 + lane];
+            __syncwarp();
+          }
+        }
+        op += ml;
+        __syncwarp();
+      }
+    }
+  }
+  if (!bad && op != oend) bad = true;                      // the ToC's brick size is the inflated size
+  if (bad && lane == 0) atomicExch(err, 1u);
+}
+
+static int upload_bricks_compressed(tvk_ctx* c, uint32_t codec, uint32_t n, const uint32_t* slot, const void* const* src, const uint32_t* comp_len,
+                                    const uint32_t* sizes);
 extern "C" int tvk_pool_upload_bricks_lz4(tvk_ctx* c, uint32_t n, const uint32_t* slot, const void* const* src, const uint32_t* comp_len,
                                           const uint32_t* sizes) {
+  return upload_bricks_compressed(c, TVK_CODEC_LZ4, n, slot, src, comp_len, sizes);
+}
+extern "C" int tvk_pool_upload_bricks_compressed(tvk_ctx* c, uint32_t codec, uint32_t n, const uint32_t* slot, const void* const* src,
+                                                 const uint32_t* comp_len, const uint32_t* sizes) {
+  if (codec != TVK_CODEC_LZ4 && codec != TVK_CODEC_ZLIB) return TVK_ERR_INVALID;
+  return upload_bricks_compressed(c, codec, n, slot, src, comp_len, sizes);
+}
+static int upload_bricks_compressed(tvk_ctx* c, uint32_t codec, uint32_t n, const uint32_t* slot, const void* const* src, const uint32_t* comp_len,
+                                    const uint32_t* sizes) {
   if (!c || !c->has_pool || (n && (!slot || !src || !comp_len || !sizes))) return TVK_ERR_INVALID;
   if (!n) return TVK_OK;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
@@ -777,7 +995,8 @@ extern "C" int tvk_pool_upload_bricks_lz4(tvk_ctx* c, uint32_t n, const uint32_t
     dsrc[i] = jobs[i].dst;
   }
   { int rc = tvk_copy_params_async(c, d_jobs, jobs.data(), sizeof(Lz4Job) * n, st); if (rc) return rc; }
-  lz4_inflate_kernel<<<(n + 3) / 4, 128, 0, st>>>(d_jobs, n, d_err);
+  if (codec == TVK_CODEC_ZLIB) zlib_inflate_kernel<<<(n + 3) / 4, 128, 0, st>>>(d_jobs, n, d_err);
+  else lz4_inflate_kernel<<<(n + 3) / 4, 128, 0, st>>>(d_jobs, n, d_err);
   c->launches++;
   TVK_CHECK_CUDA(c, cudaGetLastError());
   uint32_t h_err = 0;
@@ -785,7 +1004,7 @@ extern "C" int tvk_pool_upload_bricks_lz4(tvk_ctx* c, uint32_t n, const uint32_t
   TVK_CHECK_CUDA(c, cudaStreamSynchronize(st));          // the inflated bricks are placement sources from here on
   c->lz4_bytes_in += cbytes; c->lz4_bytes_out += dbytes;
   int rc = TVK_OK;
-  if (h_err) { c->err = "corrupt LZ4 brick"; rc = TVK_ERR_INVALID; }
+  if (h_err) { c->err = codec == TVK_CODEC_ZLIB ? "corrupt zlib brick" : "corrupt LZ4 brick"; rc = TVK_ERR_INVALID; }
   else rc = tvk_pool_upload_bricks(c, n, slot, dsrc.data(), sizes, 1);
   if (rc == TVK_OK) rc = tvk_pool_upload_wait(c);
   cudaFreeAsync(d_comp, st); cudaFreeAsync(d_out, st); cudaFreeAsync(d_jobs, st); cudaFreeAsync(d_err, st);
@@ -793,7 +1012,14 @@ extern "C" int tvk_pool_upload_bricks_lz4(tvk_ctx* c, uint32_t n, const uint32_t
 }
 
 // the same kernel without a pool: n LZ4 blocks (host pointers) -> their inflated bytes in host memory (tests, tools)
+static int inflate_blocks(tvk_ctx* c, uint32_t codec, uint32_t n, const void* const* src, const uint32_t* comp_len, void* const* dst, const uint32_t* dst_len);
 extern "C" int tvk_lz4_inflate(tvk_ctx* c, uint32_t n, const void* const* src, const uint32_t* comp_len, void* const* dst, const uint32_t* dst_len) {
+  return inflate_blocks(c, TVK_CODEC_LZ4, n, src, comp_len, dst, dst_len);
+}
+extern "C" int tvk_zlib_inflate(tvk_ctx* c, uint32_t n, const void* const* src, const uint32_t* comp_len, void* const* dst, const uint32_t* dst_len) {
+  return inflate_blocks(c, TVK_CODEC_ZLIB, n, src, comp_len, dst, dst_len);
+}
+static int inflate_blocks(tvk_ctx* c, uint32_t codec, uint32_t n, const void* const* src, const uint32_t* comp_len, void* const* dst, const uint32_t* dst_len) {
   if (!c || (n && (!src || !comp_len || !dst || !dst_len))) return TVK_ERR_INVALID;
   if (!n) return TVK_OK;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
@@ -813,7 +1039,8 @@ extern "C" int tvk_lz4_inflate(tvk_ctx* c, uint32_t n, const void* const* src, c
     jobs[i].src = d_comp + coff[i]; jobs[i].dst = d_out + doff[i]; jobs[i].src_len = comp_len[i]; jobs[i].dst_len = dst_len[i];
   }
   TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(Lz4Job) * n, cudaMemcpyHostToDevice, st));
-  lz4_inflate_kernel<<<(n + 3) / 4, 128, 0, st>>>(d_jobs, n, d_err);
+  if (codec == TVK_CODEC_ZLIB) zlib_inflate_kernel<<<(n + 3) / 4, 128, 0, st>>>(d_jobs, n, d_err);
+  else lz4_inflate_kernel<<<(n + 3) / 4, 128, 0, st>>>(d_jobs, n, d_err);
   c->launches++;
   uint32_t h_err = 0;
   cudaError_t e = cudaGetLastError();
@@ -822,7 +1049,7 @@ extern "C" int tvk_lz4_inflate(tvk_ctx* c, uint32_t n, const void* const* src, c
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFree(d_comp); cudaFree(d_out); cudaFree(d_jobs); cudaFree(d_err);
   if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return TVK_ERR_CUDA; }
-  if (h_err) { c->err = "corrupt LZ4 block"; return TVK_ERR_INVALID; }
+  if (h_err) { c->err = codec == TVK_CODEC_ZLIB ? "corrupt zlib stream" : "corrupt LZ4 block"; return TVK_ERR_INVALID; }
   return TVK_OK;
 }
 

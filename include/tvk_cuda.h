@@ -123,6 +123,14 @@ int tvk_pool_upload_bricks_lz4(tvk_ctx* ctx, uint32_t n, const uint32_t* slot, c
                                const uint32_t* sizes);
 /* the same kernel without a pool: n LZ4 blocks in host memory -> dst[i] (dst_len[i] bytes each, host memory) */
 int tvk_lz4_inflate(tvk_ctx* ctx, uint32_t n, const void* const* src, const uint32_t* comp_len, void* const* dst, const uint32_t* dst_len);
+/* zlib-compressed bricks (CT_ZLIB: one RFC 1950 stream per brick, zCompress, ExtendedOctree/ZlibCompression.cpp) inflated on
+ * the device the same way: one warp per brick runs a DEFLATE decoder (stored, fixed and dynamic blocks; every lane follows
+ * the bit stream, lane 0 writes literals, the warp shares the match copies).  codec = TVK_CODEC_LZ4 / TVK_CODEC_ZLIB. */
+#define TVK_CODEC_LZ4  3u   /* = TVK_UVF_COMP_LZ4  */
+#define TVK_CODEC_ZLIB 1u   /* = TVK_UVF_COMP_ZLIB */
+int tvk_pool_upload_bricks_compressed(tvk_ctx* ctx, uint32_t codec, uint32_t n, const uint32_t* slot, const void* const* src,
+                                      const uint32_t* comp_len, const uint32_t* sizes);
+int tvk_zlib_inflate(tvk_ctx* ctx, uint32_t n, const void* const* src, const uint32_t* comp_len, void* const* dst, const uint32_t* dst_len);
 /* The same ordering without blocking the host: everything issued on the render stream after this call (metadata
  * patches, the next ray-march) runs after the upload in flight has been placed.  Only for sources that stay valid
  * until then (the renderer's pinned brick store). */

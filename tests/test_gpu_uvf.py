@@ -116,14 +116,15 @@ def test_batch_renderer_script(kind, tmp_path):
     assert img[..., 3].max() == 255 and 0.05 < (img[..., 3] > 0).mean() < 0.9
 
 
-def _gpu_inflate(tvk, blocks, sizes):
+def _gpu_inflate(tvk, blocks, sizes, codec="lz4"):
     import ctypes as C
     n = len(blocks)
     bufs = [np.frombuffer(b, np.uint8).copy() for b in blocks]
     outs = [np.zeros(s, np.uint8) for s in sizes]
     src = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
     dst = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
-    rc = tvk.lib.tvk_lz4_inflate(tvk.h, C.c_uint32(n), src, (C.c_uint32 * n)(*[len(b) for b in blocks]), dst, (C.c_uint32 * n)(*sizes))
+    fn = tvk.lib.tvk_zlib_inflate if codec == "zlib" else tvk.lib.tvk_lz4_inflate
+    rc = fn(tvk.h, C.c_uint32(n), src, (C.c_uint32 * n)(*[len(b) for b in blocks]), dst, (C.c_uint32 * n)(*sizes))
     return rc, outs
 
 
@@ -186,6 +187,96 @@ def test_paging_from_a_compressed_store_renders_the_same(tmp_path):
     for keep in (False, True):
         r = Renderer(0)
         r.loadDataset(path, gpu_mem_bytes=24 * 36 ** 3, keep_compressed=keep)      # a pool smaller than the dataset: real paging
+        assert r.storeIsCompressed() == keep
+        info = r.datasetInfo()
+        tf = H.tf1d_std(info.tf_size, 0.4, 0.4)
+        tf[:, 3] *= 0.2
+        r.set1DTransFloat(tf)
+        r.setLightingEnabled(True)
+        r.resize((160, 120))
+        r.setRendererTarget(RT_HEADLESS)
+        r.setRotation4x4(H.rotation_y(0.5) @ H.rotation_x(0.2))
+        n = r.paintUntilConverged()
+        assert n > 1 and r.perf()["paged_bricks"] > 0
+        imgs.append(r.frameFloat().copy())
+        r.cleanup()
+    assert imgs[0].max() > 0.05 and np.array_equal(imgs[0], imgs[1])
+
+
+def test_zlib_inflate_on_the_device(tvk):
+    """tvk_zlib_inflate (one warp per stream, DEFLATE on the device): stored, fixed-code and dynamic-code blocks, long and
+    short match distances, several blocks per stream, brick-sized volume data -- against the bytes that went in."""
+    import zlib
+    rng = np.random.default_rng(7)
+    vol8 = H.synth_blobs((64, 64, 64), np.uint8).tobytes()
+    vol16 = H.synth_blobs((64, 64, 64), np.uint16).tobytes()                             # a whole 64^3 uint16 brick: 512 KB
+    datas = [rng.integers(0, 4, 70000, dtype=np.uint8).tobytes(), bytes(20000), bytes(range(37)) * 900,
+             (bytes(range(7)) * 3000) + rng.integers(0, 256, 999, dtype=np.uint8).tobytes(), vol8, vol16,
+             rng.integers(0, 256, 50000, dtype=np.uint8).tobytes(), b"abc", b"a" * 300]
+    blocks, sizes, want = [], [], []
+    for d in datas:
+        for level in (0, 1, 6, 9):                                                       # 0: stored blocks
+            blocks.append(zlib.compress(d, level))
+            sizes.append(len(d))
+            want.append(d)
+    co = zlib.compressobj(9, zlib.DEFLATED, 15, 9, zlib.Z_FIXED)                         # fixed Huffman codes only
+    blocks.append(co.compress(vol8) + co.flush()); sizes.append(len(vol8)); want.append(vol8)      # noqa: E702
+    co = zlib.compressobj(6)                                                             # several blocks, sync flushes in between
+    parts = b"".join(co.compress(vol16[i:i + 50000]) + co.flush(zlib.Z_FULL_FLUSH) for i in range(0, len(vol16), 50000)) + co.flush()
+    blocks.append(parts); sizes.append(len(vol16)); want.append(vol16)                   # noqa: E702
+    rc, outs = _gpu_inflate(tvk, blocks, sizes, "zlib")
+    assert rc == 0, tvk.lib.tvk_last_error(tvk.h)
+    for k, (d, o) in enumerate(zip(want, outs)):
+        assert o.tobytes() == d, k
+
+
+def test_zlib_inflate_rejects_corrupt_streams(tvk):
+    import zlib
+    d = H.synth_blobs((40, 40, 40), np.uint8).tobytes()
+    good = zlib.compress(d, 6)
+    flipped = bytearray(good)
+    flipped[len(good) // 2] ^= 0x5A
+    assert _gpu_inflate(tvk, [good[:len(good) // 2]], [len(d)], "zlib")[0] != 0          # truncated
+    assert _gpu_inflate(tvk, [good], [len(d) + 100], "zlib")[0] != 0                     # the ToC promises more bytes than the stream holds
+    assert _gpu_inflate(tvk, [good], [len(d) - 100], "zlib")[0] != 0                     # ... or fewer
+    assert _gpu_inflate(tvk, [b"\x00\x00" + good[2:]], [len(d)], "zlib")[0] != 0         # not a zlib header
+    rc, outs = _gpu_inflate(tvk, [bytes(flipped)], [len(d)], "zlib")                     # a flipped byte: an error, or different bytes --
+    assert rc != 0 or outs[0].tobytes() != d                                             # never a crash (bounds are checked)
+    assert _gpu_inflate(tvk, [good], [len(d)], "zlib")[0] == 0
+
+
+@pytest.mark.parametrize("name", ["ref_u8_zlib", "ref_u16_zlib"])
+def test_reference_zlib_file_inflates_on_the_device(tvk, tmp_path, name):
+    """the bricks of a reference-written zlib UVF, taken from the file still compressed and inflated by the kernel, equal the
+    host decode of the same file"""
+    from imagevis3d_b200 import uvf as U
+    path = golden_file(name, tmp_path)
+    f = U.UvfFile(path)
+    off, ln, comp, sizes = f.toc()
+    assert (comp == 1).all()                     # TVK_UVF_COMP_ZLIB
+    want = f.read_bricks()
+    raw = f.read_bricks_raw()
+    blocks, pos = [], 0
+    for k in ln:
+        blocks.append(raw[pos:pos + int(k)].tobytes())
+        pos += int(k)
+    bpv = 2 if "u16" in name else 1
+    nbytes = [int(s[0]) * int(s[1]) * int(s[2]) * bpv for s in sizes]
+    rc, outs = _gpu_inflate(tvk, blocks, nbytes, "zlib")
+    assert rc == 0
+    assert np.array_equal(np.concatenate(outs), np.asarray(want).view(np.uint8).reshape(-1))
+    f.close()
+
+
+def test_paging_from_a_zlib_store_renders_the_same(tmp_path):
+    """renderer.loadDataset(keep_compressed=True) on a zlib file: the pinned store holds the file's zlib streams, paging moves
+    them over PCIe compressed and the device inflates them -- same frame, bit for bit, as the host-inflated load."""
+    from imagevis3d_b200.renderer import Renderer, RT_HEADLESS
+    path = golden_file("ref_u8_zlib", tmp_path)
+    imgs = []
+    for keep in (False, True):
+        r = Renderer(0)
+        r.loadDataset(path, gpu_mem_bytes=24 * 36 ** 3, keep_compressed=keep)
         assert r.storeIsCompressed() == keep
         info = r.datasetInfo()
         tf = H.tf1d_std(info.tf_size, 0.4, 0.4)
