@@ -754,9 +754,13 @@ __constant__ unsigned short lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2
 __constant__ unsigned short dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
 __constant__ unsigned short dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __constant__ unsigned char zorder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+#define TVK_Z_LITBITS 10
+#define TVK_Z_DISTBITS 8
 struct ZTables {
   unsigned short lencnt[16], lensym[288], distcnt[16], distsym[32];
   unsigned char lengths[320];
+  // first-level look-up: the next TVK_Z_*BITS bits of the stream -> (code length << 9) | symbol, 0 = a longer code (decoded by counting)
+  unsigned short litfast[1 << TVK_Z_LITBITS], distfast[1 << TVK_Z_DISTBITS];
 };
 struct ZBits { const uint8_t* ip; const uint8_t* iend; unsigned long long buf; int cnt; bool bad; };
 
@@ -801,6 +805,31 @@ __device__ __forceinline__ int z_decode(ZBits& z, const ZCounts& c, const unsign
   }
   z.bad = true;
   return -1;
+}
+// the look-up table of one code: every lane decodes its share of the 2^nbits bit patterns by counting
+__device__ __forceinline__ void z_build_fast(unsigned short* fast, int nbits, const ZCounts& c, const unsigned short* sym, uint32_t lane) {
+  for (uint32_t e = lane; e < (1u << nbits); e += 32u) {
+    uint32_t bits = e;
+    int code = 0, first = 0, index = 0;
+    unsigned short out = 0;
+#pragma unroll
+    for (int len = 1; len <= 15; ++len) {
+      if (len <= nbits && !out) {
+        code |= (int)(bits & 1u);
+        bits >>= 1;
+        const int count = (int)((c.w[len >> 1] >> (16 * (len & 1))) & 0xFFFFu);
+        if (code - count < first) out = (unsigned short)((len << 9) | sym[index + (code - first)]);
+        index += count; first += count; first <<= 1; code <<= 1;
+      }
+    }
+    fast[e] = out;
+  }
+}
+__device__ __forceinline__ int z_decode_fast(ZBits& z, const unsigned short* fast, int nbits, const ZCounts& c, const unsigned short* sym) {
+  z_fill(z);
+  const uint32_t e = fast[(uint32_t)z.buf & ((1u << nbits) - 1u)];
+  if (e) { z_drop(z, (int)(e >> 9)); return z.bad ? -1 : (int)(e & 511u); }
+  return z_decode(z, c, sym);
 }
 // canonical Huffman table from code lengths (lane 0 only); returns < 0 for an over-subscribed set
 __device__ int z_construct(unsigned short* cnt, unsigned short* sym, const unsigned char* length, int n) {
@@ -911,8 +940,11 @@ __global__ void __launch_bounds__(128) zlib_inflate_kernel(const Lz4Job* __restr
     ZCounts lc, dc;
     z_load_counts(lc, T.lencnt);
     z_load_counts(dc, T.distcnt);
+    z_build_fast(T.litfast, TVK_Z_LITBITS, lc, T.lensym, lane);
+    z_build_fast(T.distfast, TVK_Z_DISTBITS, dc, T.distsym, lane);
+    __syncwarp();
     for (;;) {                                             // the block's symbols
-      const int sym = z_decode(z, lc, T.lensym);
+      const int sym = z_decode_fast(z, T.litfast, TVK_Z_LITBITS, lc, T.lensym);
       if (sym < 0) { bad = true; break; }
       if (sym < 256) {
         if (op >= oend) { bad = true; break; }
@@ -924,7 +956,7 @@ __global__ void __launch_bounds__(128) zlib_inflate_kernel(const Lz4Job* __restr
         const int ls = sym - 257;
         if (ls >= 29) { bad = true; break; }
         const uint32_t ml = lbase[ls] + z_bits(z, lext[ls]);
-        const int ds = z_decode(z, dc, T.distsym);
+        const int ds = z_decode_fast(z, T.distfast, TVK_Z_DISTBITS, dc, T.distsym);
         if (ds < 0 || ds >= 30) { bad = true; break; }
         const size_t off = dbase[ds] + z_bits(z, dext[ds]);
         if (z.bad || off > (size_t)(op - j.dst) || ml > (size_t)(oend - op)) { bad = true; break; }
