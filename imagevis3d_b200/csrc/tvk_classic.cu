@@ -775,6 +775,7 @@ extern "C" int tvk_raycast_mip(tvk_ctx* c, const tvk_mip_params* p, const tvk_cl
   if (p->bytes_per_voxel == 1) mip_kernel<1><<<(tiles + 3) / 4, 128, 0, c->stream>>>(a);
   else mip_kernel<2><<<(tiles + 3) / 4, 128, 0, c->stream>>>(a);
   c->launches++;
+  c->k1_serial++;                                          // (the sample counter moved: cached statistics are stale)
   TVK_CHECK_CUDA(c, cudaGetLastError());
   TVK_CHECK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   TVK_CHECK_CUDA(c, cudaFreeAsync(d_bricks, c->stream));
