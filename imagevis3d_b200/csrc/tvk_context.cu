@@ -764,13 +764,18 @@ struct ZTables {
 };
 struct ZBits { const uint8_t* ip; const uint8_t* iend; unsigned long long buf; int cnt; bool bad; };
 
-// at least 32 bits in the buffer (zeros behind the end of the input: reading them is an error only once they are CONSUMED)
+// more than 32 bits in the buffer (zeros behind the end of the input: reading them is an error only once they are CONSUMED)
 __device__ __forceinline__ void z_fill(ZBits& z) {
-  while (z.cnt <= 56) {
-    const unsigned long long b = z.ip < z.iend ? (unsigned long long)(*z.ip) : 0ull;
-    z.ip++;
-    z.buf |= b << z.cnt;
-    z.cnt += 8;
+  if (z.cnt <= 32) {                                       // four bytes at a time: one load latency per ~3 symbols, not per symbol
+    uint32_t w;
+    if (z.iend - z.ip >= 4) w = (uint32_t)z.ip[0] | ((uint32_t)z.ip[1] << 8) | ((uint32_t)z.ip[2] << 16) | ((uint32_t)z.ip[3] << 24);
+    else {
+      w = 0u;
+      for (int k = 0; k < 4; ++k) if (z.ip + k < z.iend) w |= (uint32_t)z.ip[k] << (8 * k);
+    }
+    z.ip += 4;
+    z.buf |= (unsigned long long)w << z.cnt;
+    z.cnt += 32;
   }
 }
 __device__ __forceinline__ void z_drop(ZBits& z, int n) {
