@@ -151,6 +151,8 @@ extern "C" void tvk_destroy(tvk_ctx* c) {
   if (c->h_readback) cudaFreeHost(c->h_readback);
   if (c->h_tf_stage) cudaFreeHost(c->h_tf_stage);
   if (c->tf_stage_done) cudaEventDestroy(c->tf_stage_done);
+  if (c->h_tf1_stage) cudaFreeHost(c->h_tf1_stage);
+  if (c->tf1_stage_done) cudaEventDestroy(c->tf1_stage_done);
   if (c->h_rgba8) cudaFreeHost(c->h_rgba8);
   delete c;
 }
@@ -1171,6 +1173,21 @@ __global__ void tf_colmask_kernel(const uchar4* __restrict__ tf, uint32_t w, uin
   if (threadIdx.x == 0) mask[blockIdx.x] = m;
 }
 
+// 1-D table: the float copies the march fetches (byte * (1/255); and the same with the opacity already corrected for
+// sampleRateModifier == 1: 1 - (1 - a), which is not always a in fp32 -- OpacityCorrectColor, blend.glsl:37-39, evaluated
+// once per table entry instead of once per sample), made on the device from the bytes
+__global__ void __launch_bounds__(256) tf1d_expand_kernel(const uchar4* __restrict__ tf, uint32_t n, float4* __restrict__ tf_f,
+                                                         float4* __restrict__ tf_f1) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uchar4 b = tf[i];
+  const float k = 1.0f / 255.0f;
+  const float4 f = make_float4((float)b.x * k, (float)b.y * k, (float)b.z * k, (float)b.w * k);
+  tf_f[i] = f;
+  const float om = __fsub_rn(1.0f, f.w);
+  tf_f1[i] = make_float4(f.x, f.y, f.z, __fsub_rn(1.0f, om));
+}
+
 static int set_tf(tvk_ctx* c, const uint8_t* rgba, uint32_t w, uint32_t h) {
   if (!c || !rgba || w == 0 || h == 0) return TVK_ERR_INVALID;
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
@@ -1213,19 +1230,27 @@ static int set_tf(tvk_ctx* c, const uint8_t* rgba, uint32_t w, uint32_t h) {
     TVK_CHECK_CUDA(c, cudaGetLastError());
     return TVK_OK;
   }
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf, rgba, sizeof(uchar4) * n, cudaMemcpyHostToDevice, c->stream));
-  std::vector<float> f(4 * n);
-  for (size_t i = 0; i < f.size(); ++i) f[i] = (float)rgba[i] * (1.0f / 255.0f);
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf_f, f.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
-  // OpacityCorrectColor for sampleRateModifier == 1 (blend.glsl:37-39): 1 - pow(1 - a, 1) = 1 - (1 - a), which is not
-  // always a in fp32 -- evaluated once per table entry here instead of once per sample in the kernel
-  for (size_t i = 0; i < n; ++i) { volatile float om = 1.0f - f[4 * i + 3]; f[4 * i + 3] = 1.0f - om; }
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf_f1, f.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
-  std::vector<uint32_t> mask((w + 31) / 32, 0u);
-  for (uint32_t x = 0; x < w; ++x)
-    if (rgba[4 * x + 3]) mask[x >> 5] |= 1u << (x & 31);
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf_colmask, mask.data(), sizeof(uint32_t) * mask.size(), cudaMemcpyHostToDevice, c->stream));
-  TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
+  // 1-D table: the bytes travel through their own page-locked block (the 2-D block doubles as the host's copy of the 2-D
+  // table) and the float copies + the column mask are made on the device: no host loop over the table, no stream wait
+  {
+    const size_t bytes = sizeof(uchar4) * n;
+    if (c->tf1_stage_busy) { TVK_CHECK_CUDA(c, cudaEventSynchronize(c->tf1_stage_done)); c->tf1_stage_busy = false; }
+    if (c->tf1_stage_bytes < bytes) {
+      if (c->h_tf1_stage) cudaFreeHost(c->h_tf1_stage);
+      c->h_tf1_stage = nullptr; c->tf1_stage_bytes = 0;
+      TVK_CHECK_CUDA(c, cudaMallocHost(&c->h_tf1_stage, bytes));
+      c->tf1_stage_bytes = bytes;
+    }
+    if (!c->tf1_stage_done) TVK_CHECK_CUDA(c, cudaEventCreateWithFlags(&c->tf1_stage_done, cudaEventDisableTiming));
+    memcpy(c->h_tf1_stage, rgba, bytes);
+    TVK_CHECK_CUDA(c, cudaMemcpyAsync(c->d_tf, c->h_tf1_stage, bytes, cudaMemcpyHostToDevice, c->stream));
+    TVK_CHECK_CUDA(c, cudaEventRecord(c->tf1_stage_done, c->stream));
+    c->tf1_stage_busy = true;
+    tf1d_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_tf, (uint32_t)n, c->d_tf_f, c->d_tf_f1);
+    tf_colmask_kernel<<<(w + 31) / 32, 32, 0, c->stream>>>(c->d_tf, w, 1, c->d_tf_colmask);
+    c->launches += 2;
+    TVK_CHECK_CUDA(c, cudaGetLastError());
+  }
   return TVK_OK;
 }
 extern "C" int tvk_set_tf1d(tvk_ctx* c, const uint8_t* rgba, uint32_t n) { return set_tf(c, rgba, n, 1); }

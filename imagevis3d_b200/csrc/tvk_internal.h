@@ -118,6 +118,10 @@ struct tvk_ctx {
   uint32_t tf_stage_w = 0, tf_stage_h = 0;   // the 2-D table the block holds (tvk_tf2d_staging)
   cudaEvent_t tf_stage_done = nullptr;
   bool tf_stage_busy = false;
+  uint8_t* h_tf1_stage = nullptr;      // the same for 1-D tables (their own block: the 2-D one doubles as the host's copy of the 2-D table)
+  size_t tf1_stage_bytes = 0;
+  cudaEvent_t tf1_stage_done = nullptr;
+  bool tf1_stage_busy = false;
 
   // frame state
   uint32_t width = 0, height = 0;
