@@ -1073,10 +1073,10 @@ def run_sortlast(args, torch, dist, TvkContext, HM, SL, dev, local, rank, world,
         tf_bytes = int(ms["tf"].nbytes) * len(mine)
         hb = torch.tensor([tf_bytes], device=dev, dtype=torch.int64)
         dist.all_reduce(hb, op=dist.ReduceOp.SUM)
-        e2e = {"ms_per_step": float(tt.item()) / steps, "h2d_bytes_per_step": int(hb.item()) * 9, "d2h_bytes_per_step": W * Hh * 4,
+        e2e = {"ms_per_step": float(tt.item()) / steps, "h2d_bytes_per_step": int(hb.item()), "d2h_bytes_per_step": W * Hh * 4,
                "frame_nonzero_pixels": int((frame_host.numpy()[..., 3] > 0).sum()) if frame_host is not None else None,
-               "pipeline": "per step, on every GPU: transfer-function table from host memory (byte table + its two float copies, per "
-                           "box), march of the resident boxes, fused exchange + blend; on rank 0 the finished 3840x2160 frame converted "
+               "pipeline": "per step, on every GPU: transfer-function table from host memory (the byte table, per box; its float "
+                           "copies are made on the device), march of the resident boxes, fused exchange + blend; on rank 0 the finished 3840x2160 frame converted "
                            "to RGBA8 on the device and copied to pinned host memory (tvk_exchange_read_final_rgba8).  The volume stays "
                            "resident: its 191 GB brick store does not fit this box's host RAM to page from (the paging path is the "
                            "single-GPU e2e leg).  CUDA events on each rank's stream, max over ranks"}
