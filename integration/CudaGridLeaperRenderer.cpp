@@ -214,6 +214,24 @@ bool CudaGridLeaperRenderer::Paint() {                                     // GL
   // AbstrRenderer::SetTimestep (AbstrRenderer.h:573) is not virtual: it only records m_iTimestep and schedules a redraw.
   // The brick store here holds ONE time step, so a change is picked up where the redraw arrives.
   if (m_iTimestep != m_iUploadedTimestep && !UploadDataset()) return false;
+  // A window that shows ONE 2-D region (slice view / MIP): GLRenderer::Render2DView's job.  The region covers the whole
+  // target here; ImageVis3D's 2x2 layout of several regions per window is not mapped.
+  if (renderRegions.size() == 1 && renderRegions[0]->is2D()) {
+    RenderRegion* r2 = renderRegions[0].get();
+    if (r2->isBlank) {
+      PushState();
+      bool fx = false, fy = false;
+      Get2DFlipMode(r2, fx, fy);
+      const bool mip = GetUseMIP(r2);
+      const bool ok = (mip && m_eRendererTarget == RT_CAPTURE)
+                          ? m_impl.RenderHQMIP(int(r2->windowMode), fx, fy, m_fMIPRotationAngle, m_bOrthoView, m_bMIPLOD)
+                          : m_impl.Render2DView(int(r2->windowMode), GetSliceDepth(r2), mip, fx, fy);
+      if (!ok) { T_ERROR("CUDA renderer: %s", m_impl.LastError()); return false; }
+      r2->isBlank = false; r2->isTargetBlank = false; r2->redrawMask = false;
+      ++m_iFrameCounter;
+    }
+    return true;
+  }
   std::shared_ptr<RenderRegion3D> rr = GetFirst3DRegion();
   if (rr && rr->isBlank) {                                                 // a new view: everything may have changed
     PushState();
