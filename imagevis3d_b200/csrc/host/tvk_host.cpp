@@ -1921,7 +1921,7 @@ bool CudaGridLeaper::PaintClassicWith(const void* store, tvk_classic_params& p, 
   int rc = clearView ? tvk_raycast_classic_cv(m_ctx, &p, &cv, bricks.data(), (uint32_t)bricks.size(), store)
                      : tvk_raycast_classic(m_ctx, &p, bricks.data(), (uint32_t)bricks.size(), store);
   if (rc) return Fail("tvk_raycast_classic", rc);
-  m_cvFrame = clearView;
+  m_cvFrame = m_mode == RM_ISOSURFACE;                   // the first surface's hit buffer is readable (Pick, ClearView focus)
   if (m_stereo) {
     // the other eye: the same bricks in its own order, into its own picture; then GLRenderer::EndFrame's composition
     tvk_classic_params pr;
@@ -2064,7 +2064,7 @@ bool CudaGridLeaper::SetCVFocusPos(int x, int y) {
   float hit[4] = {0, 0, 0, 0};
   // (the reference reads row m_vWinSize.y - mouse.y; the last row is clamped here)
   const uint32_t row = (uint32_t)std::min<int>((int)m_h - y, (int)m_h - 1);
-  if (!m_cvFrame || tvk_read_iso_hit(m_ctx, (uint32_t)x, row, hit) != TVK_OK) { m_err = "no ClearView frame to pick from"; return false; }
+  if (!m_cvFrame || tvk_read_iso_hit(m_ctx, (uint32_t)x, row, hit) != TVK_OK) { m_err = "no isosurface frame of the classic renderer to pick from"; return false; }
   if (hit[3] != 0.0f) {
     const float h4[4] = {hit[0], hit[1], hit[2], 1.0f};
     ModelView(0).inverse().transform(h4, m_cvPos);
@@ -2072,6 +2072,21 @@ bool CudaGridLeaper::SetCVFocusPos(int x, int y) {
     m_cvPos[0] = m_cvPos[1] = m_cvPos[2] = 10000000.0f; m_cvPos[3] = 0.0f;
   }
   CVChanged();
+  return true;
+}
+
+// GLRenderer::Pick (GLRenderer.cpp:2856-2872): the eye-space position of the isosurface under a window position (y from the top)
+bool CudaGridLeaper::Pick(int x, int y, float out[3]) {
+  if (m_mode != RM_ISOSURFACE) { m_err = "Can only determine pick locations in isosurface rendering mode."; return false; }
+  if (!m_ctx || x < 0 || y < 0 || x >= (int)m_w || y >= (int)m_h) { m_err = "pick position outside the window"; return false; }
+  float hit[4] = {0, 0, 0, 0};
+  const uint32_t row = (uint32_t)std::min<int>((int)m_h - y, (int)m_h - 1);
+  if (!m_classic || !m_cvFrame || tvk_read_iso_hit(m_ctx, (uint32_t)x, row, hit) != TVK_OK) {
+    m_err = "picking reads the hit buffer of the classic renderer's last isosurface frame";
+    return false;
+  }
+  if (hit[3] == 0.0f) { m_err = "No intersection."; return false; }
+  out[0] = hit[0]; out[1] = hit[1]; out[2] = hit[2];
   return true;
 }
 
@@ -2271,6 +2286,7 @@ int tvkr_plan_classic_frame(tvkr_renderer* h, tvk_classic_params* p, tvk_classic
 }
 int tvkr_set_clip_plane(tvkr_renderer* h, const float plane[4]) { if (!h || !plane) return 1; R(h)->SetClipPlane(plane); return 0; }
 int tvkr_enable_clip_plane(tvkr_renderer* h, int on) { if (!h) return 1; R(h)->EnableClipPlane(on != 0); return 0; }
+int tvkr_pick(tvkr_renderer* h, int x, int y, float out[3]) { return h && out && R(h)->Pick(x, y, out) ? 0 : 1; }
 int tvkr_set_clearview(tvkr_renderer* h, int on) { if (!h) return 1; R(h)->SetCV(on != 0); return 0; }
 int tvkr_get_clearview(tvkr_renderer* h) { return h && R(h)->GetCV() ? 1 : 0; }
 int tvkr_set_cv_iso_value(tvkr_renderer* h, float v) { if (!h) return 1; R(h)->SetCVIsoValue(v); return 0; }

@@ -340,6 +340,7 @@ class CudaGridLeaper {
   void SetCVContextScale(float f) { m_cvContextScale = f; CVChanged(); }
   void SetCVBorderScale(float f) { m_cvBorderScale = f; CVChanged(); }
   void SetCVFocusPosFVec(const float p[4]) { memcpy(m_cvPos, p, 16); CVChanged(); }
+  bool Pick(int x, int y, float out[3]);            // GLRenderer::Pick: eye-space isosurface position under a window position
   bool SetCVFocusPos(int x, int y);                 // window coordinates, y from the top (the mouse position)
   bool ComputeClearViewParams(tvk_clearview_params& cv, int eye = 0);
   Matrix4 ModelView(int eye = 0) const;

@@ -381,7 +381,10 @@ __global__ void __launch_bounds__(128) classic_kernel(const __grid_constant__ Cl
                               __half2float(__float2half_rn(hit2.w)));
     a.cvb[3][i] = make_float4(__half2float(__float2half_rn(h2nx)), __half2float(__float2half_rn(h2ny)), __half2float(__float2half_rn(h2nz)), 0.0f);
   } else {
-    if (MODE == TVK_RM_ISOSURFACE) dst = classic_compose(p, hit, hnx, hny, hnz);
+    if (MODE == TVK_RM_ISOSURFACE) {
+      if (a.cvb[0]) a.cvb[0][(size_t)py * p.width + px] = hit;     // m_pFBOIsoHit buffer 0: what Pick / the ClearView focus read back
+      dst = classic_compose(p, hit, hnx, hny, hnz);
+    }
     a.image[(size_t)py * p.width + px] = dst;
   }
   for (int s = 16; s > 0; s >>= 1) nsamples += __shfl_down_sync(0xFFFFFFFFu, nsamples, s);
@@ -463,7 +466,7 @@ extern "C" int tvk_raycast_classic_cv(tvk_ctx* c, const tvk_classic_params* p, c
 // the first surface's hit buffer of the last ClearView frame at one pixel (GLRenderer::CVFocusHasChanged reads m_pFBOIsoHit there)
 extern "C" int tvk_read_iso_hit(tvk_ctx* c, uint32_t x, uint32_t y, float out[4]) {
   if (!c || !out || !c->d_pos[0] || x >= c->width || y >= c->height) return TVK_ERR_INVALID;
-  if (!c->cv_hits_valid) TVK_FAIL(c, TVK_ERR_INVALID, "no ClearView frame has been drawn");
+  if (!c->cv_hits_valid) TVK_FAIL(c, TVK_ERR_INVALID, "no isosurface frame of the classic renderer has been drawn");
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
   TVK_CHECK_CUDA(c, cudaMemcpyAsync(out, c->d_pos[0] + (size_t)y * c->width + x, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
   TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -491,8 +494,12 @@ static int classic_launch(tvk_ctx* c, const tvk_classic_params* p, const tvk_cle
   a.tf_f = c->d_tf_f; a.tf = c->d_tf; a.tf_colmask = c->d_tf_colmask; a.tf_w = c->tf_w; a.tf_h = c->tf_h; a.image = c->d_image; a.stats = c->d_stats;
   a.cv_on = cv ? 1u : 0u;
   if (cv) { a.cv = *cv; a.cvb[0] = c->d_pos[0]; a.cvb[1] = c->d_aux[0]; a.cvb[2] = c->d_pos[1]; a.cvb[3] = c->d_aux[1]; }
-  else { memset(&a.cv, 0, sizeof(a.cv)); a.cvb[0] = a.cvb[1] = a.cvb[2] = a.cvb[3] = nullptr; }
-  c->cv_hits_valid = cv != nullptr;                         // (the ray-guided path reuses these buffers as its resume state)
+  else {
+    memset(&a.cv, 0, sizeof(a.cv));
+    a.cvb[0] = p->render_mode == TVK_RM_ISOSURFACE ? c->d_pos[0] : nullptr;      // the first surface's hits are kept in any isosurface frame
+    a.cvb[1] = a.cvb[2] = a.cvb[3] = nullptr;
+  }
+  c->cv_hits_valid = p->render_mode == TVK_RM_ISOSURFACE;   // (the ray-guided path reuses these buffers as its resume state)
   const uint32_t tiles = ((p->width + 7) / 8) * ((p->height + 3) / 4);
   const uint32_t blocks = (tiles + 3) / 4;
   TVK_CHECK_CUDA(c, cudaEventRecord(c->ev0, c->stream));

@@ -227,6 +227,12 @@ class Renderer:
     def enableClipPlane(self, on=True):
         self._ck(self._lib.tvkr_enable_clip_plane(self._h, C.c_int(int(on))), "enableClipPlane")
 
+    def pick(self, xy):
+        """eye-space position of the isosurface under a window position (y from the top); classic renderer, isosurface mode"""
+        out = (C.c_float * 3)()
+        self._ck(self._lib.tvkr_pick(self._h, C.c_int(int(xy[0])), C.c_int(int(xy[1])), out), "pick")
+        return tuple(out[:])
+
     # -- ClearView (classic renderer, isosurface mode; AbstrRenderer.cpp:1247-1256,1304-1361)
     def setClearViewEnabled(self, on=True):
         self._ck(self._lib.tvkr_set_clearview(self._h, C.c_int(int(on))), "setClearViewEnabled")

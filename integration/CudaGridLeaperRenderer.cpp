@@ -256,8 +256,11 @@ bool CudaGridLeaperRenderer::CaptureSingleFrame(const std::string& strFilename, 
   return m_impl.CaptureSingleFrame(strFilename, bPreserveTransparency);
 }
 
-FLOATVECTOR3 CudaGridLeaperRenderer::Pick(const UINTVECTOR2&) const {
-  throw std::runtime_error("picking needs the isosurface hit buffer, which this renderer composes on the device");
+FLOATVECTOR3 CudaGridLeaperRenderer::Pick(const UINTVECTOR2& mousePos) const {      // GLRenderer.cpp:2856-2872
+  float p[3];
+  if (!const_cast<tvk::CudaGridLeaper&>(m_impl).Pick(int(mousePos.x), int(mousePos.y), p))
+    throw std::runtime_error(m_impl.LastError());          // "Can only determine pick locations in isosurface ..." / "No intersection."
+  return FLOATVECTOR3(p[0], p[1], p[2]);
 }
 
 void CudaGridLeaperRenderer::NewFrameClear(const RenderRegion&) {}         // the march kernel clears what it rewrites

@@ -465,8 +465,14 @@ def test_clearview_lens_on_the_classic_isosurface():
     got3, _, _, cv3 = both()
     assert max(abs(v) for v in cv3.pick_pos[:]) > 1e6
     assert (np.abs(got3 - plain).max(axis=2) <= 1e-6).mean() > 0.9
-    # ClearView off: the plain picture again, bit for bit
+    # ClearView off: the plain picture again, bit for bit; GLRenderer::Pick reads the same hit buffer
     r.setClearViewEnabled(False)
     r.paintUntilConverged()
     assert np.array_equal(r.frameFloat(), plain)
+    assert np.allclose(np.array(r.pick((x, h - row))), hits[0][row, x, :3], atol=1e-5)
+    with pytest.raises(Exception, match="No intersection"):
+        r.pick((int(xs0[0]), h - (int(ys0[0]) + 1)))
+    r.setRenderMode(0)
+    with pytest.raises(Exception, match="isosurface"):
+        r.pick((x, h - row))
     r.cleanup()
