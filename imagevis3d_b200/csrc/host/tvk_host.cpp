@@ -2081,10 +2081,7 @@ bool CudaGridLeaper::Pick(int x, int y, float out[3]) {
   if (!m_ctx || x < 0 || y < 0 || x >= (int)m_w || y >= (int)m_h) { m_err = "pick position outside the window"; return false; }
   float hit[4] = {0, 0, 0, 0};
   const uint32_t row = (uint32_t)std::min<int>((int)m_h - y, (int)m_h - 1);
-  if (!m_classic || !m_cvFrame || tvk_read_iso_hit(m_ctx, (uint32_t)x, row, hit) != TVK_OK) {
-    m_err = "picking reads the hit buffer of the classic renderer's last isosurface frame";
-    return false;
-  }
+  if (tvk_read_iso_hit(m_ctx, (uint32_t)x, row, hit) != TVK_OK) { m_err = "picking reads the hit buffer of the last isosurface frame: paint first"; return false; }
   if (hit[3] == 0.0f) { m_err = "No intersection."; return false; }
   out[0] = hit[0]; out[1] = hit[1]; out[2] = hit[2];
   return true;

@@ -465,10 +465,10 @@ extern "C" int tvk_raycast_classic_cv(tvk_ctx* c, const tvk_classic_params* p, c
 
 // the first surface's hit buffer of the last ClearView frame at one pixel (GLRenderer::CVFocusHasChanged reads m_pFBOIsoHit there)
 extern "C" int tvk_read_iso_hit(tvk_ctx* c, uint32_t x, uint32_t y, float out[4]) {
-  if (!c || !out || !c->d_pos[0] || x >= c->width || y >= c->height) return TVK_ERR_INVALID;
-  if (!c->cv_hits_valid) TVK_FAIL(c, TVK_ERR_INVALID, "no isosurface frame of the classic renderer has been drawn");
+  if (!c || !out || x >= c->width || y >= c->height) return TVK_ERR_INVALID;
+  if (!c->iso_hits) TVK_FAIL(c, TVK_ERR_INVALID, "no isosurface frame has been drawn");
   TVK_CHECK_CUDA(c, cudaSetDevice(c->device));
-  TVK_CHECK_CUDA(c, cudaMemcpyAsync(out, c->d_pos[0] + (size_t)y * c->width + x, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  TVK_CHECK_CUDA(c, cudaMemcpyAsync(out, c->iso_hits + (size_t)y * c->width + x, sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
   TVK_CHECK_CUDA(c, cudaStreamSynchronize(c->stream));
   return TVK_OK;
 }
@@ -486,6 +486,7 @@ static int classic_launch(tvk_ctx* c, const tvk_classic_params* p, const tvk_cle
   int rc = tvk_ensure_frame(c, p->width, p->height, c->hash_size ? c->hash_size : 509);
   if (rc) return rc;
   c->show_stereo = false;
+  if (c->eye == 0) c->iso_hits = nullptr;
   tvk_classic_brick* d_bricks = nullptr;
   TVK_CHECK_CUDA(c, cudaMallocAsync(&d_bricks, sizeof(tvk_classic_brick) * (n ? n : 1), c->stream));
   if (n) TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_bricks, bricks, sizeof(tvk_classic_brick) * n, cudaMemcpyHostToDevice, c->stream));
@@ -499,7 +500,7 @@ static int classic_launch(tvk_ctx* c, const tvk_classic_params* p, const tvk_cle
     a.cvb[0] = p->render_mode == TVK_RM_ISOSURFACE ? c->d_pos[0] : nullptr;      // the first surface's hits are kept in any isosurface frame
     a.cvb[1] = a.cvb[2] = a.cvb[3] = nullptr;
   }
-  c->cv_hits_valid = p->render_mode == TVK_RM_ISOSURFACE;   // (the ray-guided path reuses these buffers as its resume state)
+  if (c->eye == 0) c->iso_hits = p->render_mode == TVK_RM_ISOSURFACE ? c->d_pos[0] : nullptr;   // (m_pFBOIsoHit[0]: the first eye's)
   const uint32_t tiles = ((p->width + 7) / 8) * ((p->height + 3) / 4);
   const uint32_t blocks = (tiles + 3) / 4;
   TVK_CHECK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
@@ -632,6 +633,7 @@ extern "C" int tvk_render_slice(tvk_ctx* c, const tvk_slice_params* p, const voi
   int rc = tvk_ensure_frame(c, p->width, p->height, c->hash_size ? c->hash_size : 509);
   if (rc) return rc;
   c->show_stereo = false;
+  if (c->eye == 0) c->iso_hits = nullptr;
   const size_t bytes = (size_t)p->voxels[0] * p->voxels[1] * p->voxels[2] * p->bytes_per_voxel;
   const void* d_brick = brick;
   void* tmp = nullptr;
@@ -771,6 +773,7 @@ extern "C" int tvk_raycast_mip(tvk_ctx* c, const tvk_mip_params* p, const tvk_cl
   int rc = tvk_ensure_frame(c, p->width, p->height, c->hash_size ? c->hash_size : 509);
   if (rc) return rc;
   c->show_stereo = false;
+  if (c->eye == 0) c->iso_hits = nullptr;
   tvk_classic_brick* d_bricks = nullptr;
   TVK_CHECK_CUDA(c, cudaMallocAsync(&d_bricks, sizeof(tvk_classic_brick) * (n ? n : 1), c->stream));
   if (n) TVK_CHECK_CUDA(c, cudaMemcpyAsync(d_bricks, bricks, sizeof(tvk_classic_brick) * n, cudaMemcpyHostToDevice, c->stream));

@@ -125,6 +125,7 @@ int tvk_copy_params_async(tvk_ctx* c, void* dst, const void* src, size_t bytes, 
 }
 
 static void free_frame(tvk_ctx* c) {
+  c->iso_hits = nullptr;
   cudaFree(c->d_image); c->d_image = nullptr;
   cudaFree(c->d_rgba8); c->d_rgba8 = nullptr; c->rgba8_px = 0;
   for (int i = 0; i < 2; ++i) { cudaFree(c->d_pos[i]); cudaFree(c->d_aux[i]); c->d_pos[i] = c->d_aux[i] = nullptr; }

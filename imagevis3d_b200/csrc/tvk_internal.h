@@ -158,7 +158,7 @@ struct tvk_ctx {
   float4* d_stereo = nullptr;          // tvk_compose_stereo target
   size_t stereo_px = 0;
   bool show_stereo = false;            // the read-back calls return d_stereo (until the next launch that draws)
-  bool cv_hits_valid = false;          // d_pos / d_aux hold the hit buffers of a ClearView frame (tvk_read_iso_hit)
+  const float4* iso_hits = nullptr;    // the first surface's hit positions of the last isosurface frame (tvk_read_iso_hit), or nullptr
 
   BuildState build;
   ExchangeState xchg;

@@ -65,6 +65,7 @@ struct RayParams {
   float4* pos;      // rayStartPoint / rayResumePos
   float4* aux;      // rayStartColor / rayResumeColor (iso: normal)
   float4* image;    // accRayColor (iso: composed image)
+  float4* hit_buf;  // iso: rayHitPos (m_pFBOIsoHit buffer 0) kept for Pick; nullptr otherwise
   uint32_t* tile_counter;
   unsigned long long* stats;
   uint32_t tiles_x, tiles_y;     // 8x4-pixel tiles the launch covers ...
@@ -1198,6 +1199,7 @@ __global__ void __launch_bounds__(128, (MODE == TVK_RM_1DTRANS && !LIT) ? (SAMP 
       }
       float4 hit, hitn;
       march_ray_iso<BPV, SAMP>(rp, exitp, pos, aux, hit, hitn, cn);
+      if (rp.hit_buf) rp.hit_buf[i] = hit;           // (rays that found the surface march again in every sub-frame: the buffer is current)
       store_pixel(rp, px, py, i, compose_iso(rp.p, hit, hitn));
     } else {
       if (!rp.p.new_view) {
@@ -1375,6 +1377,9 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   rp.tf_w = c->tf_w; rp.tf_h = c->tf_h;
   rp.hash = c->d_hash;
   rp.pos = c->d_pos[0]; rp.aux = c->d_aux[0]; rp.image = c->d_image;
+  // isosurface mode: the hit positions (eye space; w == 0: no hit) are kept in the second position buffer, which this path
+  // does not use otherwise -- GLRenderer::Pick reads them back (m_pFBOIsoHit[0]: the first eye's)
+  rp.hit_buf = (p->render_mode == TVK_RM_ISOSURFACE && c->eye == 0) ? c->d_pos[1] : nullptr;
   rp.tile_counter = c->d_tile_counter;
   rp.stats = c->d_stats;
   // Screen rectangle of the (sort-last clipped) volume box: the reference rasterises the box's faces, so its fragment
@@ -1411,7 +1416,8 @@ extern "C" int tvk_raycast_subframe(tvk_ctx* c, const tvk_raycast_params* p) {
   if (c->eye == 0) TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_hash, 0, sizeof(uint32_t) * p->hash_table_size, c->stream));
   TVK_CHECK_CUDA(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(uint32_t), c->stream));
   c->show_stereo = false;
-  c->cv_hits_valid = false;
+  if (c->eye == 0) c->iso_hits = rp.hit_buf;
+  if (rp.hit_buf && p->new_view) TVK_CHECK_CUDA(c, cudaMemsetAsync(rp.hit_buf, 0, sizeof(float4) * (size_t)p->width * p->height, c->stream));
   TVK_CHECK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
   if (p->new_view && (rx0 > 0 || ry0 > 0 || rx1 < p->width || ry1 < p->height)) {
     const size_t npx = (size_t)p->width * p->height;

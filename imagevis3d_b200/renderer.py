@@ -228,7 +228,7 @@ class Renderer:
         self._ck(self._lib.tvkr_enable_clip_plane(self._h, C.c_int(int(on))), "enableClipPlane")
 
     def pick(self, xy):
-        """eye-space position of the isosurface under a window position (y from the top); classic renderer, isosurface mode"""
+        """eye-space position of the isosurface under a window position (y from the top); isosurface mode, after a frame"""
         out = (C.c_float * 3)()
         self._ck(self._lib.tvkr_pick(self._h, C.c_int(int(xy[0])), C.c_int(int(xy[1])), out), "pick")
         return tuple(out[:])

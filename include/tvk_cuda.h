@@ -463,8 +463,8 @@ typedef struct tvk_clearview_params {
 } tvk_clearview_params;
 int tvk_raycast_classic_cv(tvk_ctx* ctx, const tvk_classic_params* p, const tvk_clearview_params* cv, const tvk_classic_brick* bricks,
                            uint32_t n, const void* store_dptr);
-/* the first surface's hit (eye-space position, w != 0: hit) of the last isosurface frame of the classic renderer (with or
- * without ClearView) at pixel (x, y), y from the bottom: what GLRenderer::Pick (GLRenderer.cpp:2856-2872) and
+/* the first surface's hit (eye-space position, w != 0: hit) of the last isosurface frame -- classic renderer with or without
+ * ClearView, or the ray-guided renderer (rayHitPos of GLGridLeaper-iso.glsl) -- at pixel (x, y), y from the bottom: what GLRenderer::Pick (GLRenderer.cpp:2856-2872) and
  * GLRenderer::CVFocusHasChanged (:2833-2851) read back from m_pFBOIsoHit under the mouse */
 int tvk_read_iso_hit(tvk_ctx* ctx, uint32_t x, uint32_t y, float out[4]);
 

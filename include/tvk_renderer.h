@@ -152,7 +152,7 @@ int tvkr_enable_clip_plane(tvkr_renderer* r, int on);
  * coordinates of the mouse, y from the top -- the first surface's hit there becomes the focus (needs a ClearView frame;
  * GLRenderer::CVFocusHasChanged, GLRenderer.cpp:2833-2851); tvkr_set_cv_focus_pos_fvec: the world-space point itself.
  * The ray-guided renderer has no ClearView (GLGridLeaper::SupportsClearView is false); it ignores the switch. */
-/* renderer.pick (GLRenderer::Pick, GLRenderer.cpp:2856-2872): isosurface mode of the classic renderer, after a frame: the
+/* renderer.pick (GLRenderer::Pick, GLRenderer.cpp:2856-2872): isosurface mode (either renderer type), after a frame: the
  * eye-space position of the surface under window position (x, y from the top); 1 = no intersection / not available
  * (tvkr_last_error says which) */
 int tvkr_pick(tvkr_renderer* r, int x, int y, float out[3]);

@@ -338,3 +338,53 @@ def test_lru_eviction_follows_the_oracle_pool_over_several_views():
         assert subs == subs_o and len(got ^ after) <= 2, (eye, subs, subs_o, sorted(got ^ after))
     assert evicted_something, "the views never filled the pool: nothing was evicted, the test would be vacuous"
     r.cleanup()
+
+
+@pytest.mark.parametrize("classic", [False, True])
+def test_pick_returns_a_point_on_the_isosurface(classic):
+    """GLRenderer::Pick (GLRenderer.cpp:2856-2872): the eye-space hit under a window position, both renderer types.  Checked
+    without any restatement: taken back to volume coordinates, the raw volume has the isovalue there."""
+    from imagevis3d_b200.renderer import Renderer, RM_ISOSURFACE, RT_CAPTURE
+    vol = H.synth_blobs((120, 100, 90), np.uint8, seed=9)
+    r = Renderer(0)
+    r.loadRawVolume(vol, brick_size=32)
+    r.setRendererType(classic)
+    if classic:
+        r.setRendererTarget(RT_CAPTURE)
+    w, h = 160, 120
+    r.resize((w, h))
+    r.setRotation4x4(H.rotation_y(0.4) @ H.rotation_x(0.2))
+    r.setRenderMode(RM_ISOSURFACE)
+    iso = 0.3 * float(vol.max())
+    r.setIsoValue(iso)
+    r.paintUntilConverged(200)
+    img = r.frameFloat()
+    ys, xs = np.nonzero(img[..., 3] > 0)
+    assert len(ys) > 300
+    p = r.raycastParams()
+    e2m = np.array(p.eye_to_model[:], np.float64).reshape(4, 4)           # eye space -> normalised volume coordinates (row vectors)
+    v = vol.astype(np.float64)
+    errs = []
+    for k in range(0, len(ys), max(1, len(ys) // 40)):
+        x, row = int(xs[k]), int(ys[k])
+        if row == 0:
+            continue
+        hit = np.array(r.pick((x, h - row)) + (1.0,))
+        q = hit @ e2m
+        c = q[:3] / q[3] * np.array(vol.shape[::-1]) - 0.5                 # voxel coordinates (x, y, z)
+        i0 = np.clip(np.floor(c).astype(int), 0, np.array(vol.shape[::-1]) - 2)
+        t = c - i0
+        cube = v[i0[2]:i0[2] + 2, i0[1]:i0[1] + 2, i0[0]:i0[0] + 2]
+        val = (((cube[0, 0, 0] * (1 - t[0]) + cube[0, 0, 1] * t[0]) * (1 - t[1]) + (cube[0, 1, 0] * (1 - t[0]) + cube[0, 1, 1] * t[0]) * t[1]) * (1 - t[2]) +
+               ((cube[1, 0, 0] * (1 - t[0]) + cube[1, 0, 1] * t[0]) * (1 - t[1]) + (cube[1, 1, 0] * (1 - t[0]) + cube[1, 1, 1] * t[0]) * t[1]) * t[2])
+        errs.append(abs(val - iso))
+    errs = np.array(errs)
+    # the refined hit lies within a fraction of a step of the surface: the value there is the isovalue to a few grey levels
+    assert len(errs) >= 20 and np.median(errs) < 1.5 and (errs < 6.0).mean() > 0.9, (np.median(errs), errs.max())
+    ys0, xs0 = np.nonzero(img[1:, :, 3] == 0)
+    with pytest.raises(Exception, match="No intersection"):
+        r.pick((int(xs0[0]), h - (int(ys0[0]) + 1)))
+    r.setRenderMode(0)
+    with pytest.raises(Exception, match="isosurface"):
+        r.pick((w // 2, h // 2))
+    r.cleanup()
