@@ -13,6 +13,10 @@ binary (BatchRenderer/main.cpp) with the same call sequence on the Lua-named sur
 
 Usage:  python -m imagevis3d_b200.batch DATASET.uvf OUT.png [--tf FILE.1dt] [--size WxH] [--renderer gridleaper|raycaster]
                                          [--lighting 0|1] [--rotate-y DEG] [--rotate-x DEG] [--device N]
+                                         [--iso VALUE [--clearview CVISO]] [--stereo rb|scanline|sbs|af [--eye-dist D]]
+                                         [--slice sagittal|axial|coronal:INDEX | --mip sagittal|axial|coronal[:ANGLE]]
+--iso: isosurface mode (ClearView needs the raycaster); --stereo: both eyes, composed; --slice: a 2-D slice view of the finest
+single-brick level of detail; --mip: the capture mode's full-resolution MIP, rotated by ANGLE degrees (orthographic).
 Prints one JSON line with the timings."""
 import argparse
 import json
@@ -46,6 +50,12 @@ def main(argv=None):
     ap.add_argument("--rotate-y", type=float, default=0.0)
     ap.add_argument("--rotate-x", type=float, default=0.0)
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--iso", type=float, default=None, help="isosurface mode with this isovalue (data units)")
+    ap.add_argument("--clearview", type=float, default=None, help="ClearView lens showing the surface at this isovalue (raycaster, with --iso)")
+    ap.add_argument("--stereo", default=None, choices=["rb", "scanline", "sbs", "af"])
+    ap.add_argument("--eye-dist", type=float, default=0.02)
+    ap.add_argument("--slice", default=None, help="sagittal|axial|coronal:INDEX -- a 2-D slice view instead of the 3-D one")
+    ap.add_argument("--mip", default=None, help="sagittal|axial|coronal[:ANGLE] -- full-resolution MIP instead of the 3-D view")
     args = ap.parse_args(argv)
     from .renderer import Renderer, RT_CAPTURE, RT_HEADLESS
     w, h = [int(v) for v in args.size.lower().split("x")]
@@ -61,17 +71,40 @@ def main(argv=None):
     renderer.resize((w, h))
     if args.rotate_y or args.rotate_x:
         renderer.setRotation4x4(rotation("y", args.rotate_y) @ rotation("x", args.rotate_x))
+    modes = {"sagittal": 0, "axial": 1, "coronal": 2}
+    if args.iso is not None:
+        from .renderer import RM_ISOSURFACE
+        renderer.setRenderMode(RM_ISOSURFACE)
+        renderer.setIsoValue(args.iso)
+        if args.clearview is not None:
+            renderer.setClearViewEnabled(True)
+            renderer.setCVIsoValue(args.clearview)
+    if args.stereo:
+        renderer.setStereoEnabled(True)
+        renderer.setStereoMode(args.stereo)
+        renderer.setStereoEyeDist(args.eye_dist)
     t1 = time.perf_counter()
-    renderer.setRendererTarget(RT_HEADLESS)
     subframes = 0
-    while True:
-        renderer.paint()
-        subframes += 1
-        if renderer.converged() or subframes >= 10000:
-            break
+    if args.slice or args.mip:
+        name, _, val = (args.slice or args.mip).partition(":")
+        if name not in modes:
+            raise SystemExit("--slice / --mip: sagittal, axial or coronal")
+        if args.slice:
+            renderer.render2DView(modes[name], int(val or 0))
+        else:
+            renderer.setRendererTarget(RT_CAPTURE)
+            renderer.renderHQMIP(modes[name], float(val or 0.0))
+        subframes = 1
+    else:
+        renderer.setRendererTarget(RT_HEADLESS)
+        while True:
+            renderer.paint()
+            subframes += 1
+            if renderer.converged() or subframes >= 10000:
+                break
     t2 = time.perf_counter()
     renderer.setRendererTarget(RT_CAPTURE)
-    renderer.captureSingleFrame(args.output, True)
+    renderer.captureSingleFrame(args.output, not (args.slice or args.mip or args.stereo))
     perf = renderer.perf()
     info = renderer.datasetInfo()
     print(json.dumps({"dataset": args.dataset, "domain": list(info.domain), "renderer": args.renderer, "size": [w, h],

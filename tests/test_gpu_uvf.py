@@ -291,3 +291,24 @@ def test_paging_from_a_zlib_store_renders_the_same(tmp_path):
         imgs.append(r.frameFloat().copy())
         r.cleanup()
     assert imgs[0].max() > 0.05 and np.array_equal(imgs[0], imgs[1])
+
+
+def test_batch_renderer_script_views(tmp_path):
+    """the other things the script can write: an isosurface with the ClearView lens (raycaster), a stereo frame, a slice view
+    and the capture mode's MIP -- every call must produce a PNG of the requested size with something in it"""
+    import os
+    import struct
+    from imagevis3d_b200 import batch
+    from tests.util import write_rdb_uvf
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c60.npz"))
+    path = str(tmp_path / "c60.uvf")
+    write_rdb_uvf(path, np.ascontiguousarray(z["brick"]), 256, 4)
+    tfb = np.ascontiguousarray(z["tf1d_rgba8"]).astype(np.float32) / 255.0
+    with open(str(tmp_path / "c60.1dt"), "w") as f:
+        f.write("%d\n" % len(tfb) + "".join("%.9g %.9g %.9g %.9g\n" % tuple(r) for r in tfb))
+    for k, extra in enumerate((["--renderer", "raycaster", "--iso", "60", "--clearview", "110"], ["--stereo", "rb", "--eye-dist", "0.05"],
+                               ["--slice", "axial:64"], ["--mip", "coronal:30"], ["--iso", "60"])):
+        out = str(tmp_path / ("view%d.png" % k))
+        assert batch.main([path, out, "--size", "200x160", "--rotate-y", "25"] + extra) == 0
+        raw = open(out, "rb").read()
+        assert raw[:8] == b"\x89PNG\r\n\x1a\n" and struct.unpack(">II", raw[16:24]) == (200, 160) and len(raw) > 2000, extra
