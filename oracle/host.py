@@ -985,6 +985,20 @@ def hq_mip(p, bricks, store, tf_rgba8):
     return img, vmax
 
 
+def hq_mip_lod(domain, win, lod_count, mip_lod=True):
+    """AbstrRenderer::PlanHQMIPFrame (AbstrRenderer.cpp:1220-1235): the domain is halved while its smallest side is not below the
+    largest window side, then one level back (pinned to the reference's statements: tests/test_slice_mip_host_pins.py)"""
+    vc = [int(v) for v in domain]
+    lod = 0
+    if mip_lod:
+        while min(vc) >= max(win):
+            vc = [v // 2 for v in vc]
+            lod += 1
+    if lod > 0:
+        lod = min(int(lod_count) - 1, lod - 1)
+    return lod
+
+
 def hq_mip_matrices(window_mode, flip, angle_deg, ortho, width, height, cam):
     """GLRenderer::RenderHQMIPPreLoop (:1256-1283) + the orthographic projection of Render2DView (:1183-1197) /
     GLRaycaster::RenderHQMIPPreLoop (GLRaycaster.cpp:481-492) -> (model-view, projection), row-vector convention"""

@@ -6,6 +6,9 @@ and compiled into oracle/_ref/ref_extract.  Nothing of the reference is copied i
   poolsize      GPUMemMan::GetVolumePool's pool sizing, Renderer/GPUMemMan/GPUMemMan.cpp:769-830
   histresample  the 1-D histogram "resampling" loop of UVFDataset::GetHistograms, IO/uvfDataset.cpp:762-798
   maxlod        AbstrRenderer::ComputeMaxLODForCurrentView (whole body), Renderer/AbstrRenderer.cpp:681-787
+  slice2d       the set-up of a 2-D slice view in GLRenderer::Render2DView (texture window of the single brick, aspect ratios,
+                slice coordinate), Renderer/GL/GLRenderer.cpp:1129-1171
+  hqmiplod      the level-of-detail rule of AbstrRenderer::PlanHQMIPFrame, Renderer/AbstrRenderer.cpp:1220-1235
 """
 import os
 import subprocess
@@ -41,6 +44,65 @@ def _hist_statements():
 def _maxlod_body():
     ar = B.read(os.path.join(B.T, "Renderer/AbstrRenderer.cpp"))
     return B.cut_body(ar, r"void AbstrRenderer::ComputeMaxLODForCurrentView\(\)")
+
+
+def _slice2d_statements():
+    gl = B.read(os.path.join(B.T, "Renderer/GL/GLRenderer.cpp"))
+    body = B.cut_body(gl, r"bool GLRenderer::Render2DView\(RenderRegion2D& renderRegion\)")
+    a = body.index("UINTVECTOR3 vRealVoxelCount;")
+    b = body.index("const int sliceDir = static_cast<size_t>(renderRegion.windowMode);")
+    c = body.index("double fSliceIndex = static_cast<double>(renderRegion.GetSliceIndex())")
+    d = body.index("RenderSlice(renderRegion, fSliceIndex", c)
+    return body[a:b], body[c:d]
+
+
+def _hqmiplod_statements():
+    ar = B.read(os.path.join(B.T, "Renderer/AbstrRenderer.cpp"))
+    body = B.cut_body(ar, r"void AbstrRenderer::PlanHQMIPFrame\(RenderRegion& renderRegion\)")
+    return body[body.index("UINTVECTOR3  viVoxelCount"):body.index("// build new brick todo-list")]
+
+
+def _f3_source():
+    first, second = _slice2d_statements()
+    return (r"""// ref_extract slice2d <domain xyz> <lod domain xyz> <brick voxels xyz> <scale xyz> <win w h> <window mode> <slice index>
+namespace MathTools { static inline uint32_t NextPow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; } }   // (branch not taken: m_bUseOnlyPowerOfTwo is false)
+struct Stub2DDataset {
+  UINT64VECTOR3 dom, lod; DOUBLEVECTOR3 scale; uint64_t lodCount;
+  UINT64VECTOR3 GetDomainSize(size_t l = 0) const { return l ? lod : dom; } DOUBLEVECTOR3 GetScale() const { return scale; }
+  uint64_t GetLODLevelCount() const { return lodCount; }
+};
+struct StubRegion2D { UINTVECTOR2 minCoord, maxCoord; int windowMode; uint64_t slice; uint64_t GetSliceIndex() const { return slice; } };
+static int slice2d(char** a) {
+  Stub2DDataset ds; Stub2DDataset* m_pDataset = &ds;
+  ds.dom = UINT64VECTOR3(strtoull(a[2], 0, 10), strtoull(a[3], 0, 10), strtoull(a[4], 0, 10));
+  ds.lod = UINT64VECTOR3(strtoull(a[5], 0, 10), strtoull(a[6], 0, 10), strtoull(a[7], 0, 10));
+  UINTVECTOR3 vVoxelCount((uint32_t)strtoul(a[8], 0, 10), (uint32_t)strtoul(a[9], 0, 10), (uint32_t)strtoul(a[10], 0, 10));
+  ds.scale = DOUBLEVECTOR3(atof(a[11]), atof(a[12]), atof(a[13]));
+  StubRegion2D renderRegion; renderRegion.minCoord = UINTVECTOR2(0, 0);
+  renderRegion.maxCoord = UINTVECTOR2((uint32_t)strtoul(a[14], 0, 10), (uint32_t)strtoul(a[15], 0, 10));
+  renderRegion.windowMode = atoi(a[16]); renderRegion.slice = strtoull(a[17], 0, 10);
+  const bool m_bUseOnlyPowerOfTwo = false; const size_t iCurrentLOD = 1;
+""" + first + """
+  const int sliceDir = renderRegion.windowMode;
+""" + second + r"""
+  printf("%.9g %.9g %.9g %.9g %.9g %.9g %.17g %.17g %.17g %.17g %.17g %.17g\n", vMinCoords.x, vMinCoords.y, vMinCoords.z, vMaxCoords.x, vMaxCoords.y,
+         vMaxCoords.z, vAspectRatio.x, vAspectRatio.y, vAspectRatio.z, vWinAspectRatio.x, vWinAspectRatio.y, fSliceIndex);
+  return 0;
+}
+// ref_extract q <domain xyz> <win w h> <lod count> <mip lod 0|1>
+static int hqmiplod(char** a) {
+  Stub2DDataset ds; Stub2DDataset* m_pDataset = &ds;
+  ds.dom = UINT64VECTOR3(strtoull(a[2], 0, 10), strtoull(a[3], 0, 10), strtoull(a[4], 0, 10));
+  const UINTVECTOR2 m_vWinSize((uint32_t)strtoul(a[5], 0, 10), (uint32_t)strtoul(a[6], 0, 10));
+  ds.lodCount = strtoull(a[7], 0, 10);
+  const bool m_bMIPLOD = atoi(a[8]) != 0;
+  uint64_t m_iCurrentLODOffset = 0, m_iCurrentLOD = 0;
+  using std::min;
+""" + _hqmiplod_statements() + r"""
+  printf("%llu\n", (unsigned long long)m_iCurrentLOD);
+  return 0;
+}
+""")
 
 
 def _source():
@@ -112,6 +174,7 @@ static int maxlod_loop() {
   return 0;
 }
 
+@@F3@@
 #define Controller StubController
 #define m_iAllocatedGPUMemory uint64_t(0)
 #define GL(stmt) iMaxVolumeDims = g_max3d
@@ -119,6 +182,8 @@ static int maxlod_loop() {
 int main(int argc, char** argv) {
   if (argc == 6 && argv[1][0] == 'h') return hist_resample(argv);
   if (argc == 2 && argv[1][0] == 'm') return maxlod_loop();
+  if (argc == 18 && argv[1][0] == 's') return slice2d(argv);
+  if (argc == 9 && argv[1][0] == 'q') return hqmiplod(argv);
   if (argc != 9) return 2;
   StubDataset ds; StubDataset* dataSet = &ds;
   ds.bits = strtoull(argv[1], 0, 10); ds.comps = strtoull(argv[2], 0, 10);
@@ -128,7 +193,7 @@ int main(int argc, char** argv) {
   printf("%u %u %u\n", poolSize.x, poolSize.y, poolSize.z);
   return 0;
 }
-''').replace("@@MAXLOD@@", _maxlod_body())
+''').replace("@@MAXLOD@@", _maxlod_body()).replace("@@F3@@", _f3_source())
 
 
 def build():
@@ -172,3 +237,17 @@ def max_lod_for_view(states):
             f = line.split()
             res.append((float(f[0]), float(f[1]), int(f[2]), int(f[3]), int(f[4]), int(f[5]), int(f[6]), int(f[7])))
     return res
+
+
+def slice2d(domain, lod_domain, brick_voxels, scale, win, window_mode, slice_index):
+    """the reference's own statements of GLRenderer::Render2DView for a slice view -> dict(min_coords, max_coords, aspect, win_aspect, slice)"""
+    args = [str(int(v)) for v in domain] + [str(int(v)) for v in lod_domain] + [str(int(v)) for v in brick_voxels] + \
+           [repr(float(v)) for v in scale] + [str(int(win[0])), str(int(win[1])), str(int(window_mode)), str(int(slice_index))]
+    f = [float(t) for t in subprocess.check_output([build(), "slice2d"] + args).decode().split()]
+    return dict(min_coords=f[0:3], max_coords=f[3:6], aspect=f[6:9], win_aspect=f[9:11], slice=f[11])
+
+
+def hq_mip_lod(domain, win, lod_count, mip_lod=True):
+    """m_iCurrentLOD as AbstrRenderer::PlanHQMIPFrame's statements leave it"""
+    args = [str(int(v)) for v in domain] + [str(int(win[0])), str(int(win[1])), str(int(lod_count)), "1" if mip_lod else "0"]
+    return int(subprocess.check_output([build(), "q"] + args).decode().split()[0])

@@ -102,6 +102,12 @@ def test_hq_mip_lod_follows_the_window():
     r.set1DTrans(H.tf_bytes(H.tf1d_std(256, 0.4, 0.5)))
     _, bricks, lod = r.planHQMIP(2)
     assert lod == 1                                            # 38 >= 16 -> 19 >= 16 -> 9: two halvings, one back
+    lods = r.datasetInfo().lod_count
+    for size in ((16, 12), (9, 9), (40, 30), (37, 80), (5, 4), (200, 100)):
+        r.resize(size)                                         # the numpy rule is pinned to the reference's statements (CPU test)
+        assert r.planHQMIP(2)[2] == H.hq_mip_lod((70, 45, 38), size, lods), size
+        assert r.planHQMIP(2, mip_lod=False)[2] == 0
+    r.resize((16, 12))
     _, bricks0, lod0 = r.planHQMIP(2, mip_lod=False)
     assert lod0 == 0 and len(bricks0) > len(bricks)
     r.renderHQMIP(2)
