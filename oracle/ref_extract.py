@@ -9,6 +9,9 @@ and compiled into oracle/_ref/ref_extract.  Nothing of the reference is copied i
   slice2d       the set-up of a 2-D slice view in GLRenderer::Render2DView (texture window of the single brick, aspect ratios,
                 slice coordinate), Renderer/GL/GLRenderer.cpp:1129-1171
   hqmiplod      the level-of-detail rule of AbstrRenderer::PlanHQMIPFrame, Renderer/AbstrRenderer.cpp:1220-1235
+  mipmatrices   (second program, oracle/_ref/ref_extract_gl: Vectors.h's USEGL section is needed for MATRIX4::Ortho) the
+                orthographic projection of the MIP view, Renderer/GL/GLRenderer.cpp:1184-1196, and the whole body of
+                GLRenderer::RenderHQMIPPreLoop, :1256-1283 (m_maMIPRotation)
 """
 import os
 import subprocess
@@ -251,3 +254,78 @@ def hq_mip_lod(domain, win, lod_count, mip_lod=True):
     """m_iCurrentLOD as AbstrRenderer::PlanHQMIPFrame's statements leave it"""
     args = [str(int(v)) for v in domain] + [str(int(win[0])), str(int(win[1])), str(int(lod_count)), "1" if mip_lod else "0"]
     return int(subprocess.check_output([build(), "q"] + args).decode().split()[0])
+
+
+BIN_GL = os.path.join(OUT, "ref_extract_gl")
+
+
+def _gl_source():
+    gl = B.read(os.path.join(B.T, "Renderer/GL/GLRenderer.cpp"))
+    body = B.cut_body(gl, r"bool GLRenderer::Render2DView\(RenderRegion2D& renderRegion\)")
+    a = body.index("FLOATMATRIX4 maOrtho;")
+    ortho = body[a:body.index("maOrtho.setProjection();", a)]
+    preloop = B.cut_body(gl, r"void GLRenderer::RenderHQMIPPreLoop\(RenderRegion2D& region\)")
+    return (r"""// GENERATED by oracle/ref_extract.py from the reference's GLRenderer.cpp -- do not commit
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+typedef float GLfloat;
+typedef unsigned GLenum;
+enum { GL_MODELVIEW = 1, GL_MODELVIEW_MATRIX, GL_PROJECTION, GL_PROJECTION_MATRIX, GL_TEXTURE, GL_TEXTURE0_ARB };
+static void glGetFloatv(GLenum, GLfloat*) { abort(); }
+static void glLoadMatrixf(const GLfloat*) { abort(); }
+static void glMultMatrixf(const GLfloat*) { abort(); }
+static void glMatrixMode(GLenum) { abort(); }
+static void glActiveTextureARB(GLenum) { abort(); }
+static void glNormal3f(GLfloat, GLfloat, GLfloat) { abort(); }
+static void glVertex2f(GLfloat, GLfloat) { abort(); }
+static void glVertex3f(GLfloat, GLfloat, GLfloat) { abort(); }
+static void glVertex4f(GLfloat, GLfloat, GLfloat, GLfloat) { abort(); }
+#define USEGL
+#include "Basics/Vectors.h"
+#define T_ERROR(...)
+using std::max;
+struct RenderRegion { enum EWindowMode { WM_SAGITTAL = 0, WM_AXIAL = 1, WM_CORONAL = 2, WM_3D, WM_INVALID }; };
+struct RenderRegion2D { int windowMode; VECTOR2<bool> flipView; FLOATMATRIX4 rotation; };
+struct StubGLRenderer {
+  float m_fMIPRotationAngle; FLOATMATRIX4 m_maMIPRotation;
+  void RenderHQMIPPreLoop(RenderRegion2D& region);
+};
+void StubGLRenderer::RenderHQMIPPreLoop(RenderRegion2D& region) {
+""" + preloop + r"""
+}
+// ref_extract_gl <win w> <win h> <window mode> <flip x> <flip y> <angle>: the orthographic projection, then m_maMIPRotation
+int main(int argc, char** argv) {
+  if (argc != 7) return 2;
+  const UINTVECTOR2 m_vWinSize((unsigned)atoi(argv[1]), (unsigned)atoi(argv[2]));
+""" + ortho + r"""
+  StubGLRenderer r; r.m_fMIPRotationAngle = (float)atof(argv[6]);
+  RenderRegion2D region; region.windowMode = atoi(argv[3]); region.flipView = VECTOR2<bool>(atoi(argv[4]) != 0, atoi(argv[5]) != 0);
+  r.RenderHQMIPPreLoop(region);
+  for (int i = 0; i < 16; ++i) printf("%.9g ", maOrtho.array[i]);
+  printf("\n");
+  for (int i = 0; i < 16; ++i) printf("%.9g ", r.m_maMIPRotation.array[i]);
+  printf("\n");
+  return 0;
+}
+""")
+
+
+def build_gl():
+    os.makedirs(OUT, exist_ok=True)
+    src = _gl_source()
+    cpp = os.path.join(OUT, "ref_extract_gl.cpp")
+    if not os.path.exists(BIN_GL) or not os.path.exists(cpp) or B.read(cpp) != src:
+        with open(cpp, "w") as f:
+            f.write(src)
+        subprocess.check_call(["g++", "-O1", "-std=c++14", "-fpermissive", "-w", "-I" + B.T, "-I" + os.path.join(B.T, "Basics"), cpp, "-o", BIN_GL])
+    return BIN_GL
+
+
+def mip_matrices(win, window_mode, flip, angle_deg):
+    """(orthographic projection, m_maMIPRotation) as the reference's statements compute them, 4x4 float32 each (row-vector storage)"""
+    import numpy as np
+    out = subprocess.check_output([build_gl(), str(int(win[0])), str(int(win[1])), str(int(window_mode)), "1" if flip[0] else "0",
+                                   "1" if flip[1] else "0", repr(float(angle_deg))]).decode().strip().splitlines()
+    rows = [np.array([float(t) for t in line.split()], np.float32).reshape(4, 4) for line in out]
+    return rows[0], rows[1]

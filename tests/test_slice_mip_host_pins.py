@@ -44,3 +44,19 @@ def test_hq_mip_lod_rule_equals_the_reference_statements():
         for mip_lod in (True, False):
             assert H.hq_mip_lod(dom, win, lods, mip_lod) == X.hq_mip_lod(dom, win, lods, mip_lod), (dom, win, lods, mip_lod)
     assert H.hq_mip_lod((2048, 2048, 2048), (1920, 1080), 7) == 0 and H.hq_mip_lod((70, 45, 38), (16, 12), 3) == 1
+
+
+def test_hq_mip_matrices_equal_the_reference_statements():
+    """the orthographic projection of the MIP view (GLRenderer.cpp:1184-1196) and m_maMIPRotation (the whole body of
+    GLRenderer::RenderHQMIPPreLoop, :1256-1283), run from the reference's text, against oracle.host.hq_mip_matrices -- which the
+    GPU test compares the product's plan with"""
+    rng = np.random.default_rng(13)
+    for _ in range(30):
+        w, h = int(rng.integers(16, 4000)), int(rng.integers(16, 2200))
+        wm = int(rng.integers(0, 3))
+        flip = (bool(rng.integers(0, 2)), bool(rng.integers(0, 2)))
+        ang = float(np.float32(rng.uniform(-360, 360)))
+        po, mr = X.mip_matrices((w, h), wm, flip, ang)
+        mv, proj = H.hq_mip_matrices(wm, flip, ang, True, w, h, H.Camera())
+        assert np.allclose(po, proj, rtol=1e-6, atol=1e-7), np.abs(po - proj).max()
+        assert np.allclose(mr, mv, rtol=1e-6, atol=1e-7), np.abs(mr - mv).max()
