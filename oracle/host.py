@@ -850,8 +850,11 @@ def _slice_sample(brick, c):
     return (lerp_fma(tg, c0, c1) * (f(1.0) / f(255.0) if brick.dtype == np.uint8 else f(1.0) / f(65535.0))).astype(f)
 
 
-def slice_view(p, brick, tf_rgba8):
-    """-> float32 image [h][w][4].  tf_rgba8: [n][4] (1-D) or [rows][n][4] (2-D, slice mode with render_mode 1)"""
+def slice_texcoords(p):
+    """the texture coordinate of every pixel centre on the quad GLRenderer::RenderSlice draws (GLRenderer.cpp:922-1014): which
+    volume axes run along the screen axes in each window mode, flipView already folded into min / max coords.
+    -> (inside [h][w] bool, [cx, cy, cz] float32 arrays); pinned to the reference's glTexCoord3d / glVertex3d calls by
+    tests/test_slice_mip_host_pins.py"""
     f = np.float32
     w, h = p["width"], p["height"]
     px, py = np.meshgrid(np.arange(w), np.arange(h))
@@ -869,6 +872,17 @@ def slice_view(p, brick, tf_rgba8):
     c[ah] = fma(sx, f(mx[ah] - mn[ah]), mn[ah])
     c[av] = fma(sy, f(mx[av] - mn[av]), mn[av])
     c[ad] = np.full(sx.shape, f(p["slice"]), f)
+    return inside, c
+
+
+def slice_view(p, brick, tf_rgba8):
+    """-> float32 image [h][w][4].  tf_rgba8: [n][4] (1-D) or [rows][n][4] (2-D, slice mode with render_mode 1)"""
+    f = np.float32
+    w, h = p["width"], p["height"]
+    inside, c = slice_texcoords(p)
+    sx = c[0]
+    wm = p["window_mode"]
+    ad = wm
     tf = np.asarray(tf_rgba8)
     tfw = tf.shape[-2]
     nearest = lambda s, n: np.clip((s * f(n)).astype(f).astype(np.int64), 0, n - 1)

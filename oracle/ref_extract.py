@@ -11,7 +11,8 @@ and compiled into oracle/_ref/ref_extract.  Nothing of the reference is copied i
   hqmiplod      the level-of-detail rule of AbstrRenderer::PlanHQMIPFrame, Renderer/AbstrRenderer.cpp:1220-1235
   mipmatrices   (second program, oracle/_ref/ref_extract_gl: Vectors.h's USEGL section is needed for MATRIX4::Ortho) the
                 orthographic projection of the MIP view, Renderer/GL/GLRenderer.cpp:1184-1196, and the whole body of
-                GLRenderer::RenderHQMIPPreLoop, :1256-1283 (m_maMIPRotation)
+                GLRenderer::RenderHQMIPPreLoop, :1256-1283 (m_maMIPRotation); and the whole body of GLRenderer::RenderSlice,
+                :922-1014, with glTexCoord3d / glVertex3d recording the quad it draws
 """
 import os
 import subprocess
@@ -290,12 +291,32 @@ struct RenderRegion2D { int windowMode; VECTOR2<bool> flipView; FLOATMATRIX4 rot
 struct StubGLRenderer {
   float m_fMIPRotationAngle; FLOATMATRIX4 m_maMIPRotation;
   void RenderHQMIPPreLoop(RenderRegion2D& region);
+  void RenderSlice(const RenderRegion2D& region, double fSliceIndex, FLOATVECTOR3 vMinCoords, FLOATVECTOR3 vMaxCoords,
+                   DOUBLEVECTOR3 vAspectRatio, DOUBLEVECTOR2 vWinAspectRatio);
 };
+enum { GL_QUADS = 7 };
+static double g_tc[3]; static int g_nv = 0;
+static void glBegin(int) {}
+static void glEnd() {}
+static void glTexCoord3d(double a, double b, double c) { g_tc[0] = a; g_tc[1] = b; g_tc[2] = c; }
+static void glVertex3d(double x, double y, double z) { printf("%.9g %.9g %.9g %.9g %.9g\n", x, y, g_tc[0], g_tc[1], g_tc[2]); ++g_nv; }
+void StubGLRenderer::RenderSlice(const RenderRegion2D& region, double fSliceIndex, FLOATVECTOR3 vMinCoords, FLOATVECTOR3 vMaxCoords,
+                                 DOUBLEVECTOR3 vAspectRatio, DOUBLEVECTOR2 vWinAspectRatio) {
+""" + B.cut_body(gl, r"void GLRenderer::RenderSlice\(const RenderRegion2D& region, double fSliceIndex,") + r"""
+}
 void StubGLRenderer::RenderHQMIPPreLoop(RenderRegion2D& region) {
 """ + preloop + r"""
 }
 // ref_extract_gl <win w> <win h> <window mode> <flip x> <flip y> <angle>: the orthographic projection, then m_maMIPRotation
 int main(int argc, char** argv) {
+  if (argc == 17) {   // slice <mode> <flip x> <flip y> <slice> <min xyz> <max xyz> <aspect xyz> <win aspect xy>: the quad RenderSlice draws
+    RenderRegion2D region; region.windowMode = atoi(argv[2]); region.flipView = VECTOR2<bool>(atoi(argv[3]) != 0, atoi(argv[4]) != 0);
+    StubGLRenderer r;
+    r.RenderSlice(region, atof(argv[5]), FLOATVECTOR3((float)atof(argv[6]), (float)atof(argv[7]), (float)atof(argv[8])),
+                  FLOATVECTOR3((float)atof(argv[9]), (float)atof(argv[10]), (float)atof(argv[11])),
+                  DOUBLEVECTOR3(atof(argv[12]), atof(argv[13]), atof(argv[14])), DOUBLEVECTOR2(atof(argv[15]), atof(argv[16])));
+    return g_nv == 4 ? 0 : 1;
+  }
   if (argc != 7) return 2;
   const UINTVECTOR2 m_vWinSize((unsigned)atoi(argv[1]), (unsigned)atoi(argv[2]));
 """ + ortho + r"""
@@ -329,3 +350,14 @@ def mip_matrices(win, window_mode, flip, angle_deg):
                                    "1" if flip[1] else "0", repr(float(angle_deg))]).decode().strip().splitlines()
     rows = [np.array([float(t) for t in line.split()], np.float32).reshape(4, 4) for line in out]
     return rows[0], rows[1]
+
+
+def slice_quad(window_mode, flip, slice_coord, min_coords, max_coords, aspect, win_aspect):
+    """the quad GLRenderer::RenderSlice draws, from the reference's own text: four (x, y, s, t, r) rows -- vertex position in
+    normalised device coordinates and its 3-D texture coordinate"""
+    import numpy as np
+    args = ["slice", str(int(window_mode)), "1" if flip[0] else "0", "1" if flip[1] else "0", repr(float(slice_coord))] + \
+           [repr(float(v)) for v in min_coords] + [repr(float(v)) for v in max_coords] + [repr(float(v)) for v in aspect] + \
+           [repr(float(v)) for v in win_aspect]
+    out = subprocess.check_output([build_gl()] + args).decode().strip().splitlines()
+    return np.array([[float(t) for t in line.split()] for line in out], np.float64)

@@ -60,3 +60,33 @@ def test_hq_mip_matrices_equal_the_reference_statements():
         mv, proj = H.hq_mip_matrices(wm, flip, ang, True, w, h, H.Camera())
         assert np.allclose(po, proj, rtol=1e-6, atol=1e-7), np.abs(po - proj).max()
         assert np.allclose(mr, mv, rtol=1e-6, atol=1e-7), np.abs(mr - mv).max()
+
+
+def test_slice_texture_coordinates_equal_the_quad_the_reference_draws():
+    """GLRenderer::RenderSlice (GLRenderer.cpp:922-1014), run from the reference's text with glTexCoord3d / glVertex3d recording
+    the quad: its extent and the texture coordinates interpolated over it at the pixel centres against
+    oracle.host.slice_texcoords -- which volume axes run along the screen axes in each window mode, and what flipView swaps"""
+    rng = np.random.default_rng(14)
+    for _ in range(20):
+        dom = [int(v) for v in rng.integers(20, 600, 3)]
+        lod = [max(1, d >> 3) for d in dom]
+        brick = [l + 4 for l in lod]
+        scale = [float(v) for v in rng.choice([0.5, 1.0, 1.0, 2.0], 3)]
+        w, h = int(rng.integers(40, 160)), int(rng.integers(40, 120))
+        for wm in (0, 1, 2):
+            flip = (bool(rng.integers(0, 2)), bool(rng.integers(0, 2)))
+            si = int(rng.integers(0, dom[wm]))
+            ref = X.slice2d(dom, lod, brick, scale, (w, h), wm, si)
+            quad = X.slice_quad(wm, flip, ref["slice"], ref["min_coords"], ref["max_coords"], ref["aspect"], ref["win_aspect"])
+            p = H.slice_params(dom, scale, lod, brick, 1, w, h, wm, si, False, flip, 0, 255.0, 0.0)
+            tl, tr, br, bl = quad                              # (-x,+y) (+x,+y) (+x,-y) (-x,-y)
+            assert tl[0] == -tr[0] == bl[0] == -br[0] and tl[1] == tr[1] == -br[1] == -bl[1]
+            assert abs(tr[0] - float(p["quad"][0])) <= 2e-7 and abs(tr[1] - float(p["quad"][1])) <= 2e-7    # (printed with nine digits)
+            inside, c = H.slice_texcoords(p)
+            px, py = np.meshgrid(np.arange(w), np.arange(h))
+            nx, ny = 2.0 * (px + 0.5) / w - 1.0, 2.0 * (py + 0.5) / h - 1.0
+            u, v = (nx + tr[0]) / (2.0 * tr[0]), (ny + tr[1]) / (2.0 * tr[1])
+            assert inside.sum() > 100
+            for k in range(3):
+                want = (1 - u) * (1 - v) * bl[2 + k] + u * (1 - v) * br[2 + k] + (1 - u) * v * tl[2 + k] + u * v * tr[2 + k]
+                assert np.abs(c[k][inside] - want[inside]).max() <= 2e-6, (wm, flip, k, np.abs(c[k][inside] - want[inside]).max())
